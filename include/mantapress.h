@@ -1,0 +1,211 @@
+/* mantapress.h -- C-ABI of the B200-native (sm_100a) pressure-projection path of mantaflow.
+ *
+ * This is the drop-in boundary: everything the reference's plugin/pressure.cpp, conjugategrad.{h,cpp},
+ * multigrid.{h,cpp} and the Grid storage of grid.cpp need from the device is reachable through the
+ * entry points below (plain pointers and sizes, int status codes, no C++ / torch types).  Each entry
+ * point cites the reference interface (file:line, relative to the mantaflow tree) it replaces.
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Layout is the reference's (grid.h:70): idx = i + sx*(j + sy*k), x fastest; flags are int32 bit
+ *    masks (grid.h:292-304); MAC grids are AoS {x,y,z} (vectorbase.h:199-213). 2-D grids have sz == 1.
+ *  - "Real" is chosen per grid at run time: prec = 4 (float, reference build fp1) or 8 (double, fp2,
+ *    -DDOUBLEPRECISION).  All grids of one call must share size and precision.  Scalars cross the ABI
+ *    as double and are narrowed to Real inside, exactly like the reference's Python->Real conversion.
+ *  - Every function returns MP_OK (0) or an error code; mp_last_error() gives the message of the last
+ *    failure on the calling thread.  Nothing throws across the ABI.  The host mirror turns codes into
+ *    Manta::Error / RuntimeError (general.h:42-57, pclass.cpp:57-61).
+ *  - All work is enqueued on the context's CUDA stream; functions that return host-visible results
+ *    synchronise that stream.  A context is bound to one device; one host thread drives it
+ *    (the reference runs plugins on the interpreter thread).
+ *  - There is NO CPU fallback: without a CUDA device mp_context_create fails with MP_ERR_CUDA.
+ */
+#ifndef MANTAPRESS_H
+#define MANTAPRESS_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP_VERSION 100
+
+enum mp_status {
+	MP_OK = 0,
+	MP_ERR_INVALID = 1,      /* bad argument / size or precision mismatch / fluid cell on the outer layer */
+	MP_ERR_CUDA = 2,         /* CUDA runtime error (message has file:line) */
+	MP_ERR_DIVERGED = 3,     /* "GridCg::iterate: The CG solver diverged" conjugategrad.cpp:288-295 */
+	MP_ERR_NOT_SET = 4,      /* "GridMg::setRhs Error: A has not been set." multigrid.cpp:428,:453 */
+	MP_ERR_UNSUPPORTED = 5,
+	MP_ERR_COMM = 6          /* NCCL / peer-memory error in the multi-GPU path */
+};
+
+/* Grid element kinds (GridBase::GridType grid.h:29) */
+enum mp_grid_kind { MP_GRID_REAL = 1, MP_GRID_FLAGS = 2, MP_GRID_MAC = 8 };
+
+/* enum Preconditioner plugin/pressure.cpp:27, python/defines.py:46-50 */
+enum mp_preconditioner { MP_PC_NONE = 0, MP_PC_MIC = 1, MP_PC_MG_DYNAMIC = 2, MP_PC_MG_STATIC = 3 };
+
+/* GridCgInterface::PreconditionType conjugategrad.h:29 */
+enum mp_cg_pc_type { MP_CG_PC_NONE = 0, MP_CG_PC_ICP = 1, MP_CG_PC_MICP = 2, MP_CG_PC_MGP = 3 };
+
+typedef struct mp_context mp_context;   /* device, stream, scratch; also plays FluidSolver for gMapMG (pressure.cpp:250) */
+typedef struct mp_grid mp_grid;         /* device-resident mirror of Grid<Real> / MACGrid / FlagGrid storage */
+typedef struct mp_cg mp_cg;             /* GridCg<ApplyMatrix|ApplyMatrix2D> conjugategrad.h:65-114 */
+typedef struct mp_mg mp_mg;             /* GridMg multigrid.h:31-137 */
+
+/* The keyword tail shared by the four pressure plugins (pressure.cpp:277-292,:312-326,:455-468,:480-495).
+ * Defaults are the reference's: see mp_pressure_params_default(). */
+typedef struct mp_pressure_params {
+	double cgAccuracy;            /* 1e-3 */
+	double gfClamp;               /* 1e-4 */
+	double cgMaxIterFac;          /* 1.5  */
+	int    precondition;          /* true; deprecated switch: false forces PcNone (pressure.cpp:328) */
+	int    preconditioner;        /* PcMIC */
+	int    enforceCompatibility;  /* false */
+	int    useL2Norm;             /* false */
+	int    zeroPressureFixing;    /* false */
+	double surfTens;              /* 0. */
+} mp_pressure_params;
+
+/* What the reference only prints (pressure.cpp:440 debMsg level 2) plus device timings. */
+typedef struct mp_solve_info {
+	int       iterations;         /* gcg->getIterations() */
+	double    resNorm;            /* gcg->getResNorm() */
+	int       maxIter;            /* the cap that was applied (pressure.cpp:408,:419) */
+	long long fixedCell;          /* pinned cell index or -1 (pressure.cpp:383-387) */
+	int       mgLevels;           /* GridMg levels (0 unless PcMG*) */
+	float     msRhs, msMatrix, msSolve, msCorrect, msTotal;  /* CUDA-event times of the stages */
+	float     msH2D, msD2H;       /* only filled by the *_host entry points */
+} mp_solve_info;
+
+/* ---- library / errors ---- */
+int         mp_version(void);
+const char* mp_last_error(void);
+const char* mp_status_string(int status);
+int         mp_device_count(int* count);                       /* 0 devices is MP_OK with *count = 0 */
+void        mp_pressure_params_default(mp_pressure_params* p);
+
+/* ---- context ---- */
+int   mp_context_create(int device, mp_context** out);
+int   mp_context_destroy(mp_context* ctx);
+int   mp_context_synchronize(mp_context* ctx);
+void* mp_context_stream(mp_context* ctx);                      /* cudaStream_t all work is enqueued on */
+int   mp_context_device(const mp_context* ctx);
+int   mp_context_sm_count(const mp_context* ctx);
+int   mp_context_kernel_launches(const mp_context* ctx, long long* count);  /* kernels launched so far */
+
+/* ---- Grid storage mirror: Grid<T> ctor/dtor grid.cpp:47-91, FluidSolver::GridStorage fluidsolver.cpp:33-50 ---- */
+int   mp_grid_create(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, mp_grid** out);  /* zero-filled like Grid<T>(parent) */
+int   mp_grid_destroy(mp_grid* g);
+int   mp_grid_upload(mp_grid* g, const void* host);            /* host: sx*sy*sz (*3 for MAC) elements, reference layout */
+int   mp_grid_download(const mp_grid* g, void* host);
+int   mp_grid_upload_async(mp_grid* g, const void* pinned_host);
+int   mp_grid_download_async(const mp_grid* g, void* pinned_host);
+int   mp_grid_clear(mp_grid* g);                               /* Grid<T>::clear grid.cpp:93-96 */
+int   mp_grid_copy_from(mp_grid* dst, const mp_grid* src);     /* Grid<T>::copyFrom grid.cpp:205-210 */
+void* mp_grid_device_ptr(mp_grid* g);
+int   mp_grid_info(const mp_grid* g, int* kind, int* prec, int* sx, int* sy, int* sz);
+/* pinned host staging for plugin-boundary transfers */
+int   mp_host_alloc(void** out, unsigned long long bytes);
+int   mp_host_free(void* p);
+
+/* ---- Grid<Real> reductions / BLAS-1 used by GridCg ---- */
+int mp_grid_dot(mp_context* ctx, const mp_grid* a, const mp_grid* b, double* out);        /* GridDotProduct conjugategrad.cpp:175-178 */
+int mp_grid_max_abs(mp_context* ctx, const mp_grid* a, double* out);                      /* Grid<Real>::getMaxAbs grid.cpp:319-323 */
+int mp_grid_sum_sqr(mp_context* ctx, const mp_grid* a, double* out);                      /* GridSumSqr commonkernels.h:32-35 */
+int mp_grid_scaled_add(mp_context* ctx, mp_grid* me, const mp_grid* other, double factor);/* gridScaledAdd grid.h:478 */
+int mp_grid_add_const(mp_context* ctx, mp_grid* me, double value);                        /* Grid<T>::operator+=(S) grid.h:490 */
+
+/* ---- assembly kernels ---- */
+/* MakeRhs pressure.cpp:32-84 (+ the optional mean subtraction of computePressureRhs :297-298 is NOT
+ * applied here, see mp_compute_pressure_rhs).  Optional grids may be NULL. */
+int mp_make_rhs(mp_context* ctx, const mp_grid* flags, mp_grid* rhs, const mp_grid* vel,
+                const mp_grid* perCellCorr, const mp_grid* fractions, const mp_grid* obvel,
+                const mp_grid* phi, const mp_grid* curv, double surfTens, double gfClamp,
+                double* sum, int* cnt);
+/* MakeLaplaceMatrix conjugategrad.h:154-187; writes every cell (the reference relies on cleared grids) */
+int mp_make_laplace_matrix(mp_context* ctx, const mp_grid* flags, mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak,
+                           const mp_grid* fractions);
+/* ApplyGhostFluidDiagonal pressure.cpp:136-151 */
+int mp_apply_ghost_fluid_diagonal(mp_context* ctx, mp_grid* A0, const mp_grid* flags, const mp_grid* phi, double gfClamp);
+/* CountEmptyCells pressure.cpp:217-220 */
+int mp_count_empty_cells(mp_context* ctx, const mp_grid* flags, long long* numEmpty);
+/* the cell choice of pressure.cpp:352-382: -1 when an empty cell exists or no fluid cell is found */
+int mp_choose_fix_cell(mp_context* ctx, const mp_grid* flags, long long* fixPidx);
+/* fixPressure pressure.cpp:226-245 */
+int mp_fix_pressure(mp_context* ctx, long long fixPidx, double value, mp_grid* rhs, mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak);
+/* ApplyMatrix / ApplyMatrix2D conjugategrad.h:118-151 (chosen by sz) */
+int mp_apply_matrix(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const mp_grid* src,
+                    const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
+/* InitPreconditionModifiedIncompCholesky2 / ApplyPreconditionModifiedIncompCholesky2 conjugategrad.cpp:66-97,:135-159 */
+int mp_mic_init(mp_context* ctx, const mp_grid* flags, mp_grid* Aprecond, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
+int mp_mic_apply(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* flags, const mp_grid* Aprecond,
+                 const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
+
+/* ---- GridCg conjugategrad.h:65-114 ---- */
+int mp_cg_create(mp_context* ctx, mp_grid* dst, mp_grid* rhs, mp_grid* residual, mp_grid* search, const mp_grid* flags, mp_grid* tmp,
+                 mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak, mp_cg** out);                 /* ctor conjugategrad.cpp:201-207 */
+int mp_cg_destroy(mp_cg* cg);
+int mp_cg_set_accuracy(mp_cg* cg, double accuracy);                                                /* setAccuracy :87 */
+int mp_cg_set_use_l2_norm(mp_cg* cg, int useL2);                                                   /* setUseL2Norm :52 */
+int mp_cg_set_ic_preconditioner(mp_cg* cg, int method, mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak); /* :310-326; MP_CG_PC_NONE accepted */
+int mp_cg_set_mg_preconditioner(mp_cg* cg, int method, mp_mg* mg);                                 /* :328-335 */
+int mp_cg_force_reinit(mp_cg* cg);                                                                 /* forceReinit :79 */
+int mp_cg_iterate(mp_cg* cg, int* keepGoing);                                                      /* iterate :237-299 (one iteration, synchronous) */
+int mp_cg_solve(mp_cg* cg, int maxIter);                                                           /* solve :301-307 (whole loop on the device) */
+int mp_cg_get(mp_cg* cg, int* iterations, double* resNorm, double* sigma);                         /* getIterations/getResNorm/getSigma :82-85 */
+
+/* ---- GridMg multigrid.h:31-137 ---- */
+int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out);                  /* GridMg::GridMg multigrid.cpp:220-319 */
+int mp_mg_destroy(mp_mg* mg);
+int mp_mg_set_a(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);  /* setA :386-415 */
+int mp_mg_set_rhs(mp_mg* mg, const mp_grid* rhs);                                                  /* setRhs :426-433 */
+int mp_mg_is_a_set(const mp_mg* mg, int* isSet);
+int mp_mg_do_vcycle(mp_mg* mg, mp_grid* dst, const mp_grid* src /* may be NULL */, double* resNorm /* may be NULL */); /* doVCycle :448-504 */
+int mp_mg_set_coarsest_level_accuracy(mp_mg* mg, double accuracy);
+int mp_mg_set_smoothing(mp_mg* mg, int numPreSmooth, int numPostSmooth);
+int mp_mg_num_levels(const mp_mg* mg, int* levels);
+int mp_mg_level_info(const mp_mg* mg, int level, int* sx, int* sy, int* sz, int* stencil);
+/* parity probes: copy one level's vertex types (int8) / operator (interleaved, multigrid.cpp:208-218) / x,b,r to the host */
+int mp_mg_download(const mp_mg* mg, int level, const char* what /* "type","a","x","b","r" */, void* host);
+
+/* ---- the plugins, device-resident grids (fields stay in HBM for the whole projection) ---- */
+/* releaseMG pressure.cpp:252-266 (the context plays the FluidSolver key of gMapMG) */
+int mp_release_mg(mp_context* ctx);
+/* computePressureRhs pressure.cpp:277-299 */
+int mp_compute_pressure_rhs(mp_context* ctx, mp_grid* rhs, const mp_grid* vel, const mp_grid* pressure, const mp_grid* flags,
+                            const mp_grid* phi, const mp_grid* perCellCorr, const mp_grid* fractions, const mp_grid* obvel,
+                            const mp_grid* curv, const mp_pressure_params* params);
+/* solvePressureSystem pressure.cpp:312-452 */
+int mp_solve_pressure_system(mp_context* ctx, mp_grid* rhs, mp_grid* vel, mp_grid* pressure, const mp_grid* flags,
+                             const mp_grid* phi, const mp_grid* perCellCorr, const mp_grid* fractions,
+                             const mp_grid* curv, const mp_pressure_params* params, mp_solve_info* info);
+/* correctVelocity pressure.cpp:455-476 */
+int mp_correct_velocity(mp_context* ctx, mp_grid* vel, const mp_grid* pressure, const mp_grid* flags,
+                        const mp_grid* phi, const mp_grid* curv, const mp_pressure_params* params);
+/* solvePressure pressure.cpp:480-521 */
+int mp_solve_pressure(mp_context* ctx, mp_grid* vel, mp_grid* pressure, const mp_grid* flags,
+                      const mp_grid* phi, const mp_grid* perCellCorr, const mp_grid* fractions, const mp_grid* obvel,
+                      const mp_grid* curv, mp_grid* retRhs, const mp_pressure_params* params, mp_solve_info* info);
+
+/* ---- the plugin with HOST buffers (what pressure.cpp calls when grids have no device mirror yet):
+ * uploads flags/vel(/phi...), runs mp_solve_pressure, downloads vel/pressure(/retRhs).  Optional
+ * pointers may be NULL.  Buffers may be pageable or pinned (mp_host_alloc). ---- */
+int mp_solve_pressure_host(mp_context* ctx, int prec, int sx, int sy, int sz,
+                           void* vel, void* pressure, const int* flags,
+                           const void* phi, const void* perCellCorr, const void* fractions, const void* obvel,
+                           const void* curv, void* retRhs, const mp_pressure_params* params, mp_solve_info* info);
+
+/* ---- multi-GPU: z-slab sharding of one solve over the GPUs of one box (one process per GPU) ----
+ * The host (torch.distributed or anything else) only moves the opaque unique id; halo exchange and
+ * the per-iteration scalar all-reduce run over NCCL/NVLink inside the library. */
+int mp_dist_unique_id(void* out128 /* 128 bytes */);
+int mp_dist_init(mp_context* ctx, int rank, int world, const void* id128, const char* nccl_library_path /* NULL: search */);
+int mp_dist_shutdown(mp_context* ctx);
+/* slab of rank r: global planes [k0, k1), computed exactly like the library does */
+int mp_dist_slab(int sz_global, int rank, int world, int* k0, int* k1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

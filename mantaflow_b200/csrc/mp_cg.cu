@@ -1,0 +1,445 @@
+// GridCg on the device: conjugategrad.h:65-151, conjugategrad.cpp:170-339.
+//
+// One PCG iteration of the reference is 9 full-grid passes.  Here it is
+//   k_matvec_dot    t = A s  fused with  dp = t.s           -> alpha          (R flags,s,A0,Ai,Aj,Ak  W t : 4+6w B/cell)
+//   k_axpy2_norm    x += alpha s ; r -= alpha t  fused with |r|_inf (or sum r^2) and, for PcNone, r.r -> beta
+//                                                                             (R x,s,r,t W x,r : 6w B/cell)
+//   [preconditioner z = M^-1 r : MIC sweeps (mp_mic.cu) or a GridMg V-cycle (mp_mg.cu), then k_dot_zr -> beta]
+//   k_update_search s = z + beta s                                            (R z,s W s : 3w B/cell)
+// All scalars (sigma, alpha, beta, dp, resNorm are `Real`, accumulators double, conjugategrad.h:108-113,
+// conjugategrad.cpp:250-252,279-280) live on the device; the host only polls a pinned copy every few
+// iterations, so the loop of solvePressureSystem (pressure.cpp:436-439) never stalls the stream.
+// Kernels early-out once `done` is set, which makes the overshoot of the lagged poll free of side effects.
+#include "mp_common.cuh"
+#include "mp_cg.cuh"
+
+// ---------------------------------------------------------------- vector access helpers
+template <typename T, int V> struct alignas(sizeof(T) * V) VecT { T v[V]; };
+template <typename T, int V> __device__ __forceinline__ VecT<T, V> ldv(const T* p) { return *reinterpret_cast<const VecT<T, V>*>(p); }
+template <typename T, int V> __device__ __forceinline__ void stv(T* p, const VecT<T, V>& x) { *reinterpret_cast<VecT<T, V>*>(p) = x; }
+
+// ---------------------------------------------------------------- k_matvec_dot
+// ApplyMatrix / ApplyMatrix2D (conjugategrad.h:118-151) over ALL cells: identity rows on non-fluid cells,
+// same left-to-right summation order as the reference (bit-identical t with -fmad=false), fused with
+// GridDotProduct(t, s) (product in Real, double accumulation, conjugategrad.cpp:175-178).
+// Each thread owns V consecutive x-cells (V=4 float / 2 double when sx % V == 0 -> 16-byte loads along x);
+// +-Y / +-Z neighbours are re-read through L1/L2 (a z-plane of the whole chip's working window stays in the
+// 126 MB L2, so DRAM traffic is the compulsory 4+6w B/cell).
+template <typename Real, int V, bool IS3D>
+__global__ void __launch_bounds__(256) k_matvec_dot(Dims d, const int* __restrict__ flags, Real* __restrict__ dst, const Real* __restrict__ src,
+	const Real* __restrict__ A0, const Real* __restrict__ Ai, const Real* __restrict__ Aj, const Real* __restrict__ Ak,
+	CgScal<Real>* sc, double* partials, unsigned int* ticket, int finalize)
+{
+	if (sc && sc->done) return;
+	const IndexInt Y = d.Y, Z = d.Z;
+	const IndexInt nv = d.n / V;                 // d.n % V == 0 is guaranteed by the launcher
+	double acc = 0.0;
+	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
+		const IndexInt idx = vi * V;
+		const VecT<int, V> f = ldv<int, V>(flags + idx);
+		const VecT<Real, V> s = ldv<Real, V>(src + idx);
+		bool any = false;
+		#pragma unroll
+		for (int q = 0; q < V; q++) any |= (f.v[q] & TypeFluid) != 0;
+		VecT<Real, V> out = s;
+		if (any) {
+			// a vector holding a fluid cell lies in an interior row/plane, so the +-Y/+-Z vectors are in range
+			const VecT<Real, V> a0 = ldv<Real, V>(A0 + idx), ai = ldv<Real, V>(Ai + idx), aj = ldv<Real, V>(Aj + idx);
+			const VecT<Real, V> ajm = ldv<Real, V>(Aj + idx - Y), sym = ldv<Real, V>(src + idx - Y), syp = ldv<Real, V>(src + idx + Y);
+			VecT<Real, V> ak, akm, szm, szp;
+			if (IS3D) { ak = ldv<Real, V>(Ak + idx); akm = ldv<Real, V>(Ak + idx - Z); szm = ldv<Real, V>(src + idx - Z); szp = ldv<Real, V>(src + idx + Z); }
+			// x neighbours: inside the vector, plus one scalar on each side (only read when that lane is fluid)
+			Real sxm0 = 0, aim0 = 0, sxpL = 0;
+			if (f.v[0] & TypeFluid) { sxm0 = src[idx - 1]; aim0 = Ai[idx - 1]; }
+			if (f.v[V - 1] & TypeFluid) sxpL = src[idx + V];
+			#pragma unroll
+			for (int q = 0; q < V; q++) {
+				if (f.v[q] & TypeFluid) {
+					const Real sm = (q == 0) ? sxm0 : s.v[q - 1 < 0 ? 0 : q - 1];
+					const Real am = (q == 0) ? aim0 : ai.v[q - 1 < 0 ? 0 : q - 1];
+					const Real sp = (q == V - 1) ? sxpL : s.v[q + 1 > V - 1 ? V - 1 : q + 1];
+					Real t = s.v[q] * a0.v[q] + sm * am + sp * ai.v[q] + sym.v[q] * ajm.v[q] + syp.v[q] * aj.v[q];
+					if (IS3D) t = t + szm.v[q] * akm.v[q] + szp.v[q] * ak.v[q];
+					out.v[q] = t;
+				}
+			}
+		}
+		stv<Real, V>(dst + idx, out);
+		#pragma unroll
+		for (int q = 0; q < V; q++) acc += (double)(out.v[q] * s.v[q]);
+	}
+	if (!finalize) return;
+	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
+	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
+		// iterate(): mIterations++ ; dp ; alpha (conjugategrad.cpp:241,:250-252)
+		const Real dp = (Real)fin[0];
+		Real alpha = (Real)0.;
+		if (fabs((double)dp) > 0.) alpha = sc->sigma / dp;
+		sc->alpha = alpha; sc->dp = dp;
+		sc->iterations += 1;
+	}
+}
+
+// ---------------------------------------------------------------- k_axpy2_norm
+// gridScaledAdd x2 (conjugategrad.cpp:254-255) + residual norm (:267-271) [+ for PcNone z==r: sigmaNew = r.r, :279]
+// MODE 0: PcNone (z = r, finalises beta/sigma here), MODE 1: preconditioned (only the norm / stop test here)
+template <typename Real, int V, int MODE>
+__global__ void __launch_bounds__(256) k_axpy2_norm(IndexInt n, Real* __restrict__ x, const Real* __restrict__ s, Real* __restrict__ r, const Real* __restrict__ t,
+	CgScal<Real>* sc, double* partials, unsigned int* ticket)
+{
+	if (sc->done) return;
+	const Real alpha = sc->alpha, nalpha = -alpha;
+	const bool useL2 = sc->useL2 != 0;
+	const IndexInt nv = n / V;
+	double nrm = useL2 ? 0.0 : -1.0, rr = 0.0;
+	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
+		const IndexInt idx = vi * V;
+		VecT<Real, V> xv = ldv<Real, V>(x + idx), rv = ldv<Real, V>(r + idx);
+		const VecT<Real, V> sv = ldv<Real, V>(s + idx), tv = ldv<Real, V>(t + idx);
+		#pragma unroll
+		for (int q = 0; q < V; q++) {
+			xv.v[q] += alpha * sv.v[q];
+			rv.v[q] += nalpha * tv.v[q];
+			const double rd = (double)rv.v[q];
+			if (useL2) nrm += rd * rd; else nrm = fmax(nrm, fabs(rd));
+			if (MODE == 0) rr += (double)(rv.v[q] * rv.v[q]);
+		}
+		stv<Real, V>(x + idx, xv); stv<Real, V>(r + idx, rv);
+	}
+	double v[2] = { nrm, rr }; const bool isMax[2] = { !useL2, false }; double fin[2];
+	if (blockReduceFinal<2>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
+		const Real resNorm = (Real)fin[0];
+		sc->resNorm = resNorm;
+		if (resNorm < sc->accuracy) { sc->sigma = resNorm; sc->done = 1; }          // :274-277
+		else {
+			if (MODE == 0) {
+				const Real sigmaNew = (Real)fin[1];
+				sc->beta = sigmaNew / sc->sigma;                                      // :279-280
+				sc->sigma = sigmaNew;                                                 // :286
+			}
+			if (!(resNorm < (Real)1e35)) { sc->diverged = 1; sc->done = 1; }          // :288-295
+		}
+	}
+}
+
+// sigmaNew = z.r after a preconditioner application -> beta, sigma (conjugategrad.cpp:279-286); also used by doInit (:234)
+template <typename Real, int V>
+__global__ void __launch_bounds__(256) k_dot_zr(IndexInt n, const Real* __restrict__ z, const Real* __restrict__ r,
+	CgScal<Real>* sc, double* partials, unsigned int* ticket, int isInit)
+{
+	if (sc->done) return;
+	const IndexInt nv = n / V;
+	double acc = 0.0;
+	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
+		const VecT<Real, V> zv = ldv<Real, V>(z + vi * V), rv = ldv<Real, V>(r + vi * V);
+		#pragma unroll
+		for (int q = 0; q < V; q++) acc += (double)(zv.v[q] * rv.v[q]);
+	}
+	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
+	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
+		const Real sigmaNew = (Real)fin[0];
+		if (isInit) sc->sigma = sigmaNew;
+		else { sc->beta = sigmaNew / sc->sigma; sc->sigma = sigmaNew; }
+	}
+}
+
+// UpdateSearchVec conjugategrad.cpp:193-196: s = z + beta s
+template <typename Real, int V>
+__global__ void __launch_bounds__(256) k_update_search(IndexInt n, Real* __restrict__ s, const Real* __restrict__ z, const CgScal<Real>* sc)
+{
+	if (sc->done) return;
+	const Real beta = sc->beta;
+	const IndexInt nv = n / V;
+	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
+		VecT<Real, V> sv = ldv<Real, V>(s + vi * V); const VecT<Real, V> zv = ldv<Real, V>(z + vi * V);
+		#pragma unroll
+		for (int q = 0; q < V; q++) sv.v[q] = zv.v[q] + beta * sv.v[q];
+		stv<Real, V>(s + vi * V, sv);
+	}
+}
+
+// doInit (conjugategrad.cpp:209-235) for PcNone: x = 0, r = b, s = b, sigma = b.b  (one pass)
+template <typename Real, int V, int MODE>   // MODE 0: PcNone; MODE 1: only x = 0, r = b (preconditioner follows)
+__global__ void __launch_bounds__(256) k_cg_init(IndexInt n, Real* __restrict__ x, const Real* __restrict__ b, Real* __restrict__ r, Real* __restrict__ s,
+	CgScal<Real>* sc, double* partials, unsigned int* ticket)
+{
+	const IndexInt nv = n / V;
+	double acc = 0.0;
+	VecT<Real, V> zero;
+	#pragma unroll
+	for (int q = 0; q < V; q++) zero.v[q] = (Real)0;
+	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
+		const VecT<Real, V> bv = ldv<Real, V>(b + vi * V);
+		stv<Real, V>(x + vi * V, zero); stv<Real, V>(r + vi * V, bv);
+		if (MODE == 0) {
+			stv<Real, V>(s + vi * V, bv);
+			#pragma unroll
+			for (int q = 0; q < V; q++) acc += (double)(bv.v[q] * bv.v[q]);
+		}
+	}
+	if (MODE != 0) return;
+	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
+	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) sc->sigma = (Real)fin[0];
+}
+
+template <typename Real>
+__global__ void k_scal_reset(CgScal<Real>* sc, Real accuracy, int useL2) {
+	sc->sigma = (Real)0; sc->alpha = (Real)0; sc->beta = (Real)0; sc->dp = (Real)0; sc->resNorm = (Real)1e20; sc->accuracy = accuracy;
+	sc->iterations = 0; sc->done = 0; sc->diverged = 0; sc->useL2 = useL2;
+}
+
+// ================================================================ launch helpers
+static inline int vecWidth(const mp_grid* g) {   // 16-byte vectors along x when every row start stays aligned
+	const int V = (g->prec == 4) ? 4 : 2;
+	return (g->sx % V == 0) ? V : 1;
+}
+static inline unsigned int streamBlocks(mp_context* ctx, IndexInt work) {
+	unsigned int b = gridFor(work, 256);
+	const unsigned int cap = (unsigned int)ctx->smCount * 8;      // 148 SMs x 8 CTAs of 256 threads = one full wave
+	return b < cap ? b : cap;
+}
+
+#define DISPATCH_RV(g, ...) do { \
+	const int V_ = vecWidth(g); \
+	if ((g)->prec == 4) { typedef float Real; if (V_ == 4) { constexpr int V = 4; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; } } \
+	else { typedef double Real; if (V_ == 2) { constexpr int V = 2; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; } } } while (0)
+
+int mp_launch_matvec(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const mp_grid* src,
+	const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, void* sc, int finalize)
+{
+	const Dims d = dimsOf(flags);
+	DISPATCH_RV(dst, {
+		const unsigned int blocks = streamBlocks(ctx, d.n / V);
+		if (d.is3D) k_matvec_dot<Real, V, true><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (Real*)dst->d, (const Real*)src->d,
+			(const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d, (const Real*)Ak->d, (CgScal<Real>*)sc, ctx->partials, ctx->tickets + 2, finalize);
+		else k_matvec_dot<Real, V, false><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (Real*)dst->d, (const Real*)src->d,
+			(const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d, (const Real*)Ak->d, (CgScal<Real>*)sc, ctx->partials, ctx->tickets + 2, finalize);
+	});
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+extern "C" int mp_apply_matrix(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const mp_grid* src,
+                               const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak)
+{
+	if (!ctx || !flags || !dst || !src || !A0 || !Ai || !Aj || !Ak) MP_FAIL(MP_ERR_INVALID, "mp_apply_matrix: NULL argument");
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "mp_apply_matrix: flags is not a FlagGrid");
+	if (dst == src) MP_FAIL(MP_ERR_INVALID, "mp_apply_matrix: dst must not alias src");
+	MP_TRY(mp_check_same(flags, dst, MP_GRID_REAL, "dst", false)); MP_TRY(mp_check_same(dst, src, MP_GRID_REAL, "src", false));
+	MP_TRY(mp_check_same(dst, A0, MP_GRID_REAL, "A0", false)); MP_TRY(mp_check_same(dst, Ai, MP_GRID_REAL, "Ai", false));
+	MP_TRY(mp_check_same(dst, Aj, MP_GRID_REAL, "Aj", false)); MP_TRY(mp_check_same(dst, Ak, MP_GRID_REAL, "Ak", false));
+	MP_CUDA(cudaSetDevice(ctx->device));
+	MP_TRY(mp_check_flags_interior(ctx, flags));
+	return mp_launch_matvec(ctx, flags, dst, src, A0, Ai, Aj, Ak, nullptr, 0);
+}
+
+// ================================================================ GridCg object
+struct mp_cg {
+	mp_context* ctx;
+	mp_grid *dst, *rhs, *residual, *search, *tmp, *A0, *Ai, *Aj, *Ak; const mp_grid* flags;
+	int pcMethod;                 // mp_cg_pc_type
+	mp_grid* pcA0; mp_mg* mg;
+	bool inited; bool useL2; double accuracy;
+	void* dSc;                    // CgScal<Real> on the device
+	CgScalHost* hSc;              // pinned mirror (2 slots for the lagged poll)
+	cudaEvent_t pollEv[2];
+	int iterations; double resNorm, sigma; bool diverged, finished;
+	bool flagsChecked;
+};
+
+template <typename Real>
+__global__ void k_scal_export(const CgScal<Real>* sc, CgScalHost* out) {
+	out->sigma = (double)sc->sigma; out->resNorm = (double)sc->resNorm; out->iterations = sc->iterations; out->done = sc->done; out->diverged = sc->diverged;
+}
+
+static int cgPollAsync(mp_cg* cg, int slot) {
+	mp_context* ctx = cg->ctx;
+	// the scalar block is exported by a 1-thread kernel straight into pinned host memory (mapped), then an event marks it
+	if (cg->dst->prec == 4) k_scal_export<float><<<1, 1, 0, ctx->stream>>>((const CgScal<float>*)cg->dSc, cg->hSc + slot);
+	else                    k_scal_export<double><<<1, 1, 0, ctx->stream>>>((const CgScal<double>*)cg->dSc, cg->hSc + slot);
+	MP_CHECK_LAUNCH(ctx);
+	MP_CUDA(cudaEventRecord(cg->pollEv[slot], ctx->stream));
+	return MP_OK;
+}
+static int cgPollWait(mp_cg* cg, int slot) {
+	MP_CUDA(cudaEventSynchronize(cg->pollEv[slot]));
+	const CgScalHost& h = cg->hSc[slot];
+	cg->iterations = h.iterations; cg->resNorm = h.resNorm; cg->sigma = h.sigma; cg->diverged = h.diverged != 0; cg->finished = h.done != 0;
+	return MP_OK;
+}
+
+int mp_mic_init_launch(mp_context* ctx, const mp_grid* flags, mp_grid* P, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
+int mp_mic_apply_launch(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* flags, const mp_grid* P,
+                        const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, const int* doneFlag);
+int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, double accuracy);
+int mp_mg_precond_apply(mp_mg* mg, mp_grid* dst, const mp_grid* rhs, const int* doneFlag);
+
+static int cgApplyPrecond(mp_cg* cg, const int* doneFlag) {
+	mp_context* ctx = cg->ctx;
+	if (cg->pcMethod == MP_CG_PC_MICP) return mp_mic_apply_launch(ctx, cg->tmp, cg->residual, cg->flags, cg->pcA0, cg->Ai, cg->Aj, cg->Ak, doneFlag);
+	if (cg->pcMethod == MP_CG_PC_MGP) return mp_mg_precond_apply(cg->mg, cg->tmp, cg->residual, doneFlag);
+	MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: preconditioner %d not implemented on the device (PC_ICP is not reachable from solvePressure)", cg->pcMethod);
+}
+
+static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
+	mp_context* ctx = cg->ctx;
+	const Dims d = dimsOf(cg->flags);
+	if (!cg->flagsChecked) { MP_TRY(mp_check_flags_interior(ctx, cg->flags)); cg->flagsChecked = true; }
+	if (cg->pcMethod == MP_CG_PC_MICP && !d.is3D) MP_FAIL(MP_ERR_INVALID, "mICP only supports 3D grids so far");   // :222
+	if (cg->pcMethod == MP_CG_PC_ICP) MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: PC_ICP is not implemented on the device");
+	cg->inited = true; cg->iterations = 0; cg->finished = false; cg->diverged = false; cg->resNorm = 1e20;
+	const bool none = cg->pcMethod == MP_CG_PC_NONE;
+	DISPATCH_RV(cg->dst, {
+		k_scal_reset<Real><<<1, 1, 0, ctx->stream>>>((CgScal<Real>*)cg->dSc, (Real)cg->accuracy, cg->useL2 ? 1 : 0);
+		MP_CHECK_LAUNCH(ctx);
+		const unsigned int blocks = streamBlocks(ctx, d.n / V);
+		if (none) k_cg_init<Real, V, 0><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->rhs->d, (Real*)cg->residual->d, (Real*)cg->search->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 3);
+		else      k_cg_init<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->rhs->d, (Real*)cg->residual->d, (Real*)cg->search->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 3);
+		MP_CHECK_LAUNCH(ctx);
+	});
+	if (!none) {
+		if (cg->pcMethod == MP_CG_PC_MICP) MP_TRY(mp_mic_init_launch(ctx, cg->flags, cg->pcA0, cg->A0, cg->Ai, cg->Aj, cg->Ak));
+		else MP_TRY(mp_mg_precond_init(cg->mg, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->accuracy));
+		MP_TRY(cgApplyPrecond(cg, nullptr));
+		MP_TRY(mp_grid_copy_from(cg->search, cg->tmp));                     // mSearch.copyFrom(mTmp) :232
+		DISPATCH_RV(cg->dst, {
+			const unsigned int blocks = streamBlocks(ctx, d.n / V);
+			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (const Real*)cg->tmp->d, (const Real*)cg->residual->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 4, 1);
+			MP_CHECK_LAUNCH(ctx);
+		});
+	}
+	return MP_OK;
+}
+
+static int cgEnqueueIteration(mp_cg* cg) {   // iterate conjugategrad.cpp:237-299, no host synchronisation
+	mp_context* ctx = cg->ctx;
+	const Dims d = dimsOf(cg->flags);
+	const bool none = cg->pcMethod == MP_CG_PC_NONE;
+	MP_TRY(mp_launch_matvec(ctx, cg->flags, cg->tmp, cg->search, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->dSc, 1));
+	DISPATCH_RV(cg->dst, {
+		const unsigned int blocks = streamBlocks(ctx, d.n / V);
+		CgScal<Real>* sc = (CgScal<Real>*)cg->dSc;
+		if (none) {
+			k_axpy2_norm<Real, V, 0><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->search->d, (Real*)cg->residual->d, (const Real*)cg->tmp->d, sc, ctx->partials, ctx->tickets + 5);
+			MP_CHECK_LAUNCH(ctx);
+			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->search->d, (const Real*)cg->residual->d, sc);
+			MP_CHECK_LAUNCH(ctx);
+		} else {
+			k_axpy2_norm<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->search->d, (Real*)cg->residual->d, (const Real*)cg->tmp->d, sc, ctx->partials, ctx->tickets + 5);
+			MP_CHECK_LAUNCH(ctx);
+			MP_TRY(cgApplyPrecond(cg, &sc->done));
+			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (const Real*)cg->tmp->d, (const Real*)cg->residual->d, sc, ctx->partials, ctx->tickets + 4, 0);
+			MP_CHECK_LAUNCH(ctx);
+			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->search->d, (const Real*)cg->tmp->d, sc);
+			MP_CHECK_LAUNCH(ctx);
+		}
+	});
+	return MP_OK;
+}
+
+static int cgFinishCheck(mp_cg* cg) {
+	if (cg->diverged) MP_FAIL(MP_ERR_DIVERGED, "GridCg::iterate: The CG solver diverged, residual norm > 1e30, stopping.");
+	return MP_OK;
+}
+
+int mp_cg_run(mp_cg* cg, int maxIter) {
+	mp_context* ctx = cg->ctx;
+	MP_CUDA(cudaSetDevice(ctx->device));
+	if (!cg->inited) MP_TRY(cgDoInit(cg));
+	if (cg->finished) return cgFinishCheck(cg);
+	// batches of iterations; the poll of batch b is awaited only after batch b+1 has been enqueued
+	const IndexInt n = cg->dst->n;
+	int batch = n >= (IndexInt)1 << 24 ? 4 : (n >= (IndexInt)1 << 21 ? 8 : 16);
+	if (cg->pcMethod != MP_CG_PC_NONE) batch = (batch + 3) / 4;
+	int enq = 0, slot = 0; bool pending[2] = { false, false };
+	while (enq < maxIter) {
+		const int nb = (maxIter - enq) < batch ? (maxIter - enq) : batch;
+		for (int q = 0; q < nb; q++) MP_TRY(cgEnqueueIteration(cg));
+		enq += nb;
+		MP_TRY(cgPollAsync(cg, slot)); pending[slot] = true;
+		const int other = slot ^ 1;
+		if (pending[other]) { MP_TRY(cgPollWait(cg, other)); pending[other] = false; if (cg->finished) break; }
+		slot = other;
+	}
+	for (int q = 0; q < 2; q++) { const int sl = (slot + 1 + q) & 1; if (pending[sl]) { MP_TRY(cgPollWait(cg, sl)); pending[sl] = false; } }
+	// the most recent export is the one recorded last
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));
+	return cgFinishCheck(cg);
+}
+
+extern "C" {
+
+int mp_cg_create(mp_context* ctx, mp_grid* dst, mp_grid* rhs, mp_grid* residual, mp_grid* search, const mp_grid* flags, mp_grid* tmp,
+                 mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak, mp_cg** out)
+{
+	if (!ctx || !dst || !rhs || !residual || !search || !flags || !tmp || !A0 || !Ai || !Aj || !Ak || !out) MP_FAIL(MP_ERR_INVALID, "mp_cg_create: NULL argument");
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "mp_cg_create: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, dst, MP_GRID_REAL, "dst", false));
+	const mp_grid* gs[] = { rhs, residual, search, tmp, A0, Ai, Aj, Ak }; const char* nm[] = { "rhs", "residual", "search", "tmp", "A0", "Ai", "Aj", "Ak" };
+	for (int q = 0; q < 8; q++) MP_TRY(mp_check_same(dst, gs[q], MP_GRID_REAL, nm[q], false));
+	MP_CUDA(cudaSetDevice(ctx->device));
+	mp_cg* cg = new mp_cg();
+	cg->ctx = ctx; cg->dst = dst; cg->rhs = rhs; cg->residual = residual; cg->search = search; cg->flags = flags; cg->tmp = tmp;
+	cg->A0 = A0; cg->Ai = Ai; cg->Aj = Aj; cg->Ak = Ak;
+	cg->pcMethod = MP_CG_PC_NONE; cg->pcA0 = nullptr; cg->mg = nullptr;
+	cg->inited = false; cg->useL2 = true;            // GridCgInterface() : mUseL2Norm(true), conjugategrad.h:31
+	cg->accuracy = 1e-8;                             // mAccuracy(VECTOR_EPSILON) conjugategrad.cpp:206, vectorbase.h
+	cg->iterations = 0; cg->resNorm = 1e20; cg->sigma = 0; cg->diverged = false; cg->finished = false; cg->flagsChecked = false;
+	MP_CUDA(cudaMalloc(&cg->dSc, 256));
+	MP_CUDA(cudaHostAlloc((void**)&cg->hSc, sizeof(CgScalHost) * 2, cudaHostAllocMapped));
+	memset(cg->hSc, 0, sizeof(CgScalHost) * 2);
+	MP_CUDA(cudaEventCreateWithFlags(&cg->pollEv[0], cudaEventDisableTiming));
+	MP_CUDA(cudaEventCreateWithFlags(&cg->pollEv[1], cudaEventDisableTiming));
+	*out = cg; return MP_OK;
+}
+int mp_cg_destroy(mp_cg* cg) {
+	if (!cg) return MP_OK;
+	cudaSetDevice(cg->ctx->device);
+	cudaStreamSynchronize(cg->ctx->stream);
+	cudaFree(cg->dSc); cudaFreeHost(cg->hSc); cudaEventDestroy(cg->pollEv[0]); cudaEventDestroy(cg->pollEv[1]);
+	delete cg; return MP_OK;
+}
+int mp_cg_set_accuracy(mp_cg* cg, double accuracy) { cg->accuracy = accuracy; return MP_OK; }
+int mp_cg_set_use_l2_norm(mp_cg* cg, int useL2) { cg->useL2 = useL2 != 0; return MP_OK; }
+int mp_cg_set_ic_preconditioner(mp_cg* cg, int method, mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak) {
+	// conjugategrad.cpp:310-326.  The reference asserts method is PC_ICP|PC_mICP, which makes PcNone unreachable from
+	// solvePressure in 3-D; north_star requires PcNone, so PC_None is accepted here and documented.
+	if (method != MP_CG_PC_NONE && method != MP_CG_PC_ICP && method != MP_CG_PC_MICP)
+		MP_FAIL(MP_ERR_INVALID, "GridCg<APPLYMAT>::setICPreconditioner: Invalid method specified.");
+	if (method != MP_CG_PC_NONE) {
+		if (!A0) MP_FAIL(MP_ERR_INVALID, "setICPreconditioner: preconditioner grid A0 is NULL");
+		MP_TRY(mp_check_same(cg->dst, A0, MP_GRID_REAL, "pcA0", false));
+	}
+	cg->pcMethod = method;
+	if (method != MP_CG_PC_NONE && cg->dst->sz == 1) cg->pcMethod = MP_CG_PC_NONE;   // "only supported in 3D for now, disabling it" :315-321
+	cg->pcA0 = A0; (void)Ai; (void)Aj; (void)Ak;
+	return MP_OK;
+}
+int mp_cg_set_mg_preconditioner(mp_cg* cg, int method, mp_mg* mg) {
+	if (method != MP_CG_PC_MGP) MP_FAIL(MP_ERR_INVALID, "GridCg<APPLYMAT>::setMGPreconditioner: Invalid method specified.");   // :330
+	if (!mg) MP_FAIL(MP_ERR_INVALID, "setMGPreconditioner: mg is NULL");
+	cg->pcMethod = method; cg->mg = mg; return MP_OK;
+}
+int mp_cg_force_reinit(mp_cg* cg) { cg->inited = false; cg->finished = false; return MP_OK; }
+
+int mp_cg_iterate(mp_cg* cg, int* keepGoing) {
+	mp_context* ctx = cg->ctx;
+	MP_CUDA(cudaSetDevice(ctx->device));
+	if (!cg->inited) MP_TRY(cgDoInit(cg));
+	MP_TRY(cgEnqueueIteration(cg));
+	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));
+	if (keepGoing) *keepGoing = cg->finished ? 0 : 1;
+	MP_TRY(cgFinishCheck(cg));
+	// the reference keeps iterating if the caller insists after convergence; re-arm like a fresh iterate() would see it
+	if (cg->finished && !cg->diverged) {
+		// keep `done` set: further iterate() calls are no-ops returning false, matching `iter = maxIter` in solve()
+	}
+	return MP_OK;
+}
+int mp_cg_solve(mp_cg* cg, int maxIter) { return mp_cg_run(cg, maxIter); }
+int mp_cg_get(mp_cg* cg, int* iterations, double* resNorm, double* sigma) {
+	if (iterations) *iterations = cg->iterations; if (resNorm) *resNorm = cg->resNorm; if (sigma) *sigma = cg->sigma; return MP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,144 @@
+// Shared internals of libmantapress (sm_100a).  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/mantapress.h"
+
+typedef long long IndexInt;   // general.h:88
+
+// FlagGrid::CellType grid.h:292-304
+enum : int { TypeFluid = 1, TypeObstacle = 2, TypeEmpty = 4, TypeInflow = 8, TypeOutflow = 16, TypeOpen = 32, TypeStick = 64 };
+
+// ---------------------------------------------------------------- errors
+void mp_set_error(const char* fmt, ...);
+#define MP_FAIL(code, ...) do { mp_set_error(__VA_ARGS__); return (code); } while (0)
+#define MP_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	mp_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); return MP_ERR_CUDA; } } while (0)
+#define MP_TRY(call) do { int rc_ = (call); if (rc_ != MP_OK) return rc_; } while (0)
+#define MP_CHECK_LAUNCH(ctx) do { (ctx)->launches++; MP_CUDA(cudaGetLastError()); } while (0)
+
+// ---------------------------------------------------------------- context / grid
+struct DistState;   // mp_dist.cu
+
+struct mp_context {
+	int device = 0;
+	int smCount = 0;
+	cudaStream_t stream = nullptr;
+	cudaStream_t copyStream = nullptr;
+	// reduction scratch: per-block partials (double) for up to kMaxPartials blocks x kSlots values, ticket counters
+	double* partials = nullptr;
+	unsigned int* tickets = nullptr;
+	// generic device result slots + pinned host mirror
+	double* dScal = nullptr;      // 64 doubles
+	double* hScal = nullptr;      // pinned, 64 doubles
+	long long launches = 0;
+	mp_mg* staticMg = nullptr;    // gMapMG[parent] pressure.cpp:250
+	DistState* dist = nullptr;
+	cudaEvent_t ev[8] = {};
+};
+static const int kMaxPartials = 1 << 16;   // max blocks of a reducing kernel
+static const int kSlots = 4;               // values reduced per kernel
+
+struct mp_grid {
+	mp_context* ctx;
+	int kind, prec, sx, sy, sz;
+	IndexInt n;          // cells
+	size_t bytes;
+	void* d;
+	bool owns;
+	int comps() const { return kind == MP_GRID_MAC ? 3 : 1; }
+	int elemSize() const { return kind == MP_GRID_FLAGS ? 4 : prec; }
+	bool is3D() const { return sz > 1; }
+};
+
+struct Dims {
+	int sx, sy, sz;
+	IndexInt X, Y, Z, n;     // strides (Z == 0 in 2-D, grid.cpp:55) and cell count
+	bool is3D;
+};
+static inline Dims dimsOf(const mp_grid* g) {
+	Dims d; d.sx = g->sx; d.sy = g->sy; d.sz = g->sz; d.is3D = g->sz > 1;
+	d.X = 1; d.Y = g->sx; d.Z = d.is3D ? (IndexInt)g->sx * g->sy : 0; d.n = (IndexInt)g->sx * g->sy * g->sz;
+	return d;
+}
+
+int mp_check_same(const mp_grid* ref, const mp_grid* g, int kind, const char* name, bool optional);
+int mp_check_flags_interior(mp_context* ctx, const mp_grid* flags);   // fluid cells must not touch the outer layer
+
+template <typename T> static inline T* dptr(const mp_grid* g) { return g ? (T*)g->d : (T*)nullptr; }
+
+static inline unsigned int gridFor(IndexInt work, int block) {
+	IndexInt b = (work + block - 1) / block;
+	if (b < 1) b = 1;
+	return (unsigned int)b;
+}
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ double warpSum(double v) {
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ double warpMax(double v) {
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// Block-level reduction of NV values (sum or max per slot), written to partials[slot*kMaxPartials + block];
+// the last block to arrive (ticket) reduces the partials in a fixed order -> deterministic result.
+// Returns true in ALL threads of the last block, with final[] valid in thread 0 only.
+template <int NV>
+__device__ __forceinline__ bool blockReduceFinal(double (&v)[NV], const bool (&isMax)[NV], double* partials, unsigned int* ticket,
+                                                 double (&fin)[NV]) {
+	__shared__ double sh[NV][32];
+	__shared__ bool amLast;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+	#pragma unroll
+	for (int q = 0; q < NV; q++) {
+		double w = isMax[q] ? warpMax(v[q]) : warpSum(v[q]);
+		if (lane == 0) sh[q][warp] = w;
+	}
+	__syncthreads();
+	if (warp == 0) {
+		#pragma unroll
+		for (int q = 0; q < NV; q++) {
+			double w = (lane < nwarps) ? sh[q][lane] : (isMax[q] ? -1.0 : 0.0);
+			w = isMax[q] ? warpMax(w) : warpSum(w);
+			if (lane == 0) partials[(size_t)q * kMaxPartials + blockIdx.x] = w;
+		}
+	}
+	if (threadIdx.x == 0) {
+		__threadfence();
+		unsigned int t = atomicAdd(ticket, 1u);
+		amLast = (t == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (!amLast) return false;
+	__threadfence();
+	#pragma unroll
+	for (int q = 0; q < NV; q++) {
+		double acc = isMax[q] ? -1.0 : 0.0;
+		for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+			double p = __ldcg(&partials[(size_t)q * kMaxPartials + b]);
+			acc = isMax[q] ? fmax(acc, p) : acc + p;
+		}
+		double w = isMax[q] ? warpMax(acc) : warpSum(acc);
+		__syncthreads();
+		if (lane == 0) sh[q][warp] = w;
+		__syncthreads();
+		if (warp == 0) {
+			double u = (lane < nwarps) ? sh[q][lane] : (isMax[q] ? -1.0 : 0.0);
+			u = isMax[q] ? warpMax(u) : warpSum(u);
+			if (lane == 0) fin[q] = u;
+		}
+	}
+	if (threadIdx.x == 0) *ticket = 0;   // re-arm for the next launch on this stream
+	return true;
+}
+#endif

@@ -1,0 +1,195 @@
+// The pressure plugins on device-resident grids: computePressureRhs, solvePressureSystem, correctVelocity,
+// solvePressure, releaseMG (plugin/pressure.cpp:252-521) and the host-buffer entry point that a maintainer's
+// pressure.cpp calls while grids have no device mirror.
+#include "mp_common.cuh"
+#include <cmath>
+
+int mp_make_matrix_fused(mp_context* ctx, const mp_grid* flags, mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak, const mp_grid* fractions, const mp_grid* phi, double gfClamp);
+int mp_fix_pressure_auto(mp_context* ctx, const mp_grid* flags, mp_grid* rhs, mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak);
+int mp_cg_run(mp_cg* cg, int maxIter);
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_add_mean_corr(Real* __restrict__ rhs, IndexInt n, const double* sumcnt) {
+	// rhs += (Real)(-sum / (Real)cnt)  on ALL cells (pressure.cpp:297-298); sum,cnt come from k_make_rhs on the device
+	const Real corr = (Real)(-sumcnt[0] / (double)(Real)(int)sumcnt[1]);
+	for (IndexInt i = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IndexInt)gridDim.x * blockDim.x) rhs[i] += corr;
+}
+
+struct GridHolder {   // RAII for the temp grids of one call (the reference takes them from the FluidSolver pool, pressure.cpp:331-338)
+	std::vector<mp_grid*> gs;
+	~GridHolder() { for (mp_grid* g : gs) mp_grid_destroy(g); }
+	int make(mp_context* ctx, int kind, int prec, const mp_grid* like, mp_grid** out) {
+		int rc = mp_grid_create(ctx, kind, prec, like->sx, like->sy, like->sz, out);
+		if (rc == MP_OK) gs.push_back(*out);
+		return rc;
+	}
+};
+
+extern "C" {
+
+int mp_release_mg(mp_context* ctx) {
+	if (ctx && ctx->staticMg) { mp_mg_destroy(ctx->staticMg); ctx->staticMg = nullptr; }
+	return MP_OK;
+}
+
+int mp_compute_pressure_rhs(mp_context* ctx, mp_grid* rhs, const mp_grid* vel, const mp_grid* pressure, const mp_grid* flags,
+                            const mp_grid* phi, const mp_grid* perCellCorr, const mp_grid* fractions, const mp_grid* obvel,
+                            const mp_grid* curv, const mp_pressure_params* params)
+{
+	(void)pressure;
+	mp_pressure_params def; if (!params) { mp_pressure_params_default(&def); params = &def; }
+	MP_TRY(mp_make_rhs(ctx, flags, rhs, vel, perCellCorr, fractions, obvel, phi, curv, params->surfTens, params->gfClamp, nullptr, nullptr));
+	if (params->enforceCompatibility) {
+		unsigned int blocks = gridFor(rhs->n, 256 * 4);
+		if (rhs->prec == 4) k_add_mean_corr<float><<<blocks, 256, 0, ctx->stream>>>((float*)rhs->d, rhs->n, ctx->dScal + 2);
+		else                k_add_mean_corr<double><<<blocks, 256, 0, ctx->stream>>>((double*)rhs->d, rhs->n, ctx->dScal + 2);
+		MP_CHECK_LAUNCH(ctx);
+	}
+	return MP_OK;
+}
+
+int mp_solve_pressure_system(mp_context* ctx, mp_grid* rhs, mp_grid* vel, mp_grid* pressure, const mp_grid* flags,
+                             const mp_grid* phi, const mp_grid* perCellCorr, const mp_grid* fractions,
+                             const mp_grid* curv, const mp_pressure_params* params, mp_solve_info* info)
+{
+	(void)vel; (void)perCellCorr; (void)curv;
+	if (!ctx || !rhs || !pressure || !flags) MP_FAIL(MP_ERR_INVALID, "mp_solve_pressure_system: NULL argument");
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "mp_solve_pressure_system: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, rhs, MP_GRID_REAL, "rhs", false));
+	MP_TRY(mp_check_same(rhs, pressure, MP_GRID_REAL, "pressure", false));
+	MP_TRY(mp_check_same(rhs, phi, MP_GRID_REAL, "phi", true));
+	MP_TRY(mp_check_same(rhs, fractions, MP_GRID_MAC, "fractions", true));
+	mp_pressure_params def; if (!params) { mp_pressure_params_default(&def); params = &def; }
+	MP_CUDA(cudaSetDevice(ctx->device));
+	int preconditioner = params->preconditioner;
+	if (!params->precondition) preconditioner = MP_PC_NONE;                       // pressure.cpp:328
+	if (preconditioner < MP_PC_NONE || preconditioner > MP_PC_MG_STATIC) MP_FAIL(MP_ERR_INVALID, "solvePressureSystem: invalid preconditioner %d", preconditioner);
+	const int prec = rhs->prec;
+	const bool is3D = flags->sz > 1;
+
+	GridHolder tmp;
+	mp_grid *residual, *search, *A0, *Ai, *Aj, *Ak, *t;                           // :331-338
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, rhs, &residual)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, rhs, &search));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, rhs, &A0)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, rhs, &Ai));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, rhs, &Aj)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, rhs, &Ak));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, rhs, &t));
+
+	MP_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+	MP_TRY(mp_make_matrix_fused(ctx, flags, A0, Ai, Aj, Ak, fractions, phi, params->gfClamp));   // :341-345
+
+	long long fixed = -1;
+	const bool wantFix = params->zeroPressureFixing || (prec == 4 ? (double)(float)params->cgAccuracy : params->cgAccuracy) < 1e-07;   // :349
+	if (wantFix) MP_TRY(mp_fix_pressure_auto(ctx, flags, rhs, A0, Ai, Aj, Ak));
+	MP_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+
+	mp_cg* cg = nullptr;
+	MP_TRY(mp_cg_create(ctx, pressure, rhs, residual, search, flags, t, A0, Ai, Aj, Ak, &cg));   // :392-396
+	struct CgGuard { mp_cg* c; ~CgGuard() { mp_cg_destroy(c); } } cgGuard{ cg };
+	mp_cg_set_accuracy(cg, prec == 4 ? (double)(float)params->cgAccuracy : params->cgAccuracy);
+	mp_cg_set_use_l2_norm(cg, params->useL2Norm);
+
+	int maxIter = 0;
+	mp_grid* pca0 = nullptr; mp_mg* pmg = nullptr;
+	if (preconditioner == MP_PC_NONE || preconditioner == MP_PC_MIC) {
+		const int maxDim = std::max(flags->sx, std::max(flags->sy, flags->sz));
+		// (int)(cgMaxIterFac * size.max()) with Real arithmetic (:408)
+		if (prec == 4) maxIter = (int)((float)params->cgMaxIterFac * (float)maxDim) * (is3D ? 1 : 4);
+		else           maxIter = (int)(params->cgMaxIterFac * (double)maxDim) * (is3D ? 1 : 4);
+		if (preconditioner == MP_PC_MIC) MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, rhs, &pca0));
+		MP_TRY(mp_cg_set_ic_preconditioner(cg, preconditioner == MP_PC_MIC ? MP_CG_PC_MICP : MP_CG_PC_NONE, pca0, nullptr, nullptr, nullptr));
+	} else {
+		maxIter = 100;                                                            // :419
+		pmg = ctx->staticMg;
+		if (pmg && preconditioner == MP_PC_MG_DYNAMIC) { mp_release_mg(ctx); pmg = nullptr; }   // :423-426
+		if (!pmg) { MP_TRY(mp_mg_create(ctx, prec, flags->sx, flags->sy, flags->sz, &pmg)); ctx->staticMg = pmg; }
+		MP_TRY(mp_cg_set_mg_preconditioner(cg, MP_CG_PC_MGP, pmg));
+	}
+
+	int rc = mp_cg_run(cg, maxIter);                                              // :436-439
+	MP_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+	if (info) {
+		mp_cg_get(cg, &info->iterations, &info->resNorm, nullptr);
+		info->maxIter = maxIter;
+		if (wantFix) {
+			cudaMemcpyAsync(ctx->hScal + 12, ctx->dScal + 12, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+			cudaStreamSynchronize(ctx->stream);
+			fixed = *(long long*)(ctx->hScal + 12);
+		}
+		info->fixedCell = fixed;
+		info->mgLevels = 0;
+		if (pmg) mp_mg_num_levels(pmg, &info->mgLevels);
+		cudaEventSynchronize(ctx->ev[3]);
+		cudaEventElapsedTime(&info->msMatrix, ctx->ev[1], ctx->ev[2]);
+		cudaEventElapsedTime(&info->msSolve, ctx->ev[2], ctx->ev[3]);
+	}
+	if (pmg && preconditioner == MP_PC_MG_DYNAMIC) mp_release_mg(ctx);            // :451
+	return rc;
+}
+
+int mp_solve_pressure(mp_context* ctx, mp_grid* vel, mp_grid* pressure, const mp_grid* flags,
+                      const mp_grid* phi, const mp_grid* perCellCorr, const mp_grid* fractions, const mp_grid* obvel,
+                      const mp_grid* curv, mp_grid* retRhs, const mp_pressure_params* params, mp_solve_info* info)
+{
+	if (!ctx || !vel || !pressure || !flags) MP_FAIL(MP_ERR_INVALID, "mp_solve_pressure: NULL argument");
+	mp_pressure_params def; if (!params) { mp_pressure_params_default(&def); params = &def; }
+	MP_CUDA(cudaSetDevice(ctx->device));
+	if (info) { memset(info, 0, sizeof *info); info->fixedCell = -1; }
+	GridHolder tmp; mp_grid* rhs;
+	MP_TRY(mp_check_same(flags, pressure, MP_GRID_REAL, "pressure", false));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, pressure->prec, pressure, &rhs));          // Grid<Real> rhs(parent) :497
+	MP_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	MP_TRY(mp_compute_pressure_rhs(ctx, rhs, vel, pressure, flags, phi, perCellCorr, fractions, obvel, curv, params));
+	MP_TRY(mp_solve_pressure_system(ctx, rhs, vel, pressure, flags, phi, perCellCorr, fractions, curv, params, info));
+	MP_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
+	MP_TRY(mp_correct_velocity(ctx, vel, pressure, flags, phi, curv, params));
+	if (retRhs) { MP_TRY(mp_check_same(pressure, retRhs, MP_GRID_REAL, "retRhs", false)); MP_TRY(mp_grid_copy_from(retRhs, rhs)); }   // :518-520
+	MP_CUDA(cudaEventRecord(ctx->ev[4], ctx->stream));
+	MP_CUDA(cudaEventSynchronize(ctx->ev[4]));
+	if (info) {
+		cudaEventElapsedTime(&info->msRhs, ctx->ev[0], ctx->ev[1]);
+		cudaEventElapsedTime(&info->msCorrect, ctx->ev[3], ctx->ev[4]);
+		cudaEventElapsedTime(&info->msTotal, ctx->ev[0], ctx->ev[4]);
+	}
+	return MP_OK;
+}
+
+int mp_solve_pressure_host(mp_context* ctx, int prec, int sx, int sy, int sz,
+                           void* vel, void* pressure, const int* flags,
+                           const void* phi, const void* perCellCorr, const void* fractions, const void* obvel,
+                           const void* curv, void* retRhs, const mp_pressure_params* params, mp_solve_info* info)
+{
+	if (!ctx || !vel || !pressure || !flags) MP_FAIL(MP_ERR_INVALID, "mp_solve_pressure_host: NULL argument");
+	MP_CUDA(cudaSetDevice(ctx->device));
+	GridHolder h;
+	mp_grid *gFlags, *gVel, *gP, *gPhi = nullptr, *gCorr = nullptr, *gFrac = nullptr, *gOb = nullptr, *gCurv = nullptr, *gRet = nullptr;
+	mp_grid like; like.sx = sx; like.sy = sy; like.sz = sz;
+	MP_TRY(h.make(ctx, MP_GRID_FLAGS, 4, &like, &gFlags)); MP_TRY(h.make(ctx, MP_GRID_MAC, prec, &like, &gVel)); MP_TRY(h.make(ctx, MP_GRID_REAL, prec, &like, &gP));
+	if (phi) MP_TRY(h.make(ctx, MP_GRID_REAL, prec, &like, &gPhi));
+	if (perCellCorr) MP_TRY(h.make(ctx, MP_GRID_REAL, prec, &like, &gCorr));
+	if (fractions) MP_TRY(h.make(ctx, MP_GRID_MAC, prec, &like, &gFrac));
+	if (obvel) MP_TRY(h.make(ctx, MP_GRID_MAC, prec, &like, &gOb));
+	if (curv) MP_TRY(h.make(ctx, MP_GRID_REAL, prec, &like, &gCurv));
+	if (retRhs) MP_TRY(h.make(ctx, MP_GRID_REAL, prec, &like, &gRet));
+	MP_CUDA(cudaEventRecord(ctx->ev[5], ctx->stream));
+	MP_TRY(mp_grid_upload_async(gFlags, flags)); MP_TRY(mp_grid_upload_async(gVel, vel));
+	if (phi) MP_TRY(mp_grid_upload_async(gPhi, phi));
+	if (perCellCorr) MP_TRY(mp_grid_upload_async(gCorr, perCellCorr));
+	if (fractions) MP_TRY(mp_grid_upload_async(gFrac, fractions));
+	if (obvel) MP_TRY(mp_grid_upload_async(gOb, obvel));
+	if (curv) MP_TRY(mp_grid_upload_async(gCurv, curv));
+	MP_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+	// the pressure grid is an output only: GridCg::doInit clears it (conjugategrad.cpp:214)
+	MP_TRY(mp_solve_pressure(ctx, gVel, gP, gFlags, gPhi, gCorr, gFrac, gOb, gCurv, gRet, params, info));
+	MP_CUDA(cudaEventRecord(ctx->ev[6 + 1], ctx->stream));
+	MP_TRY(mp_grid_download_async(gVel, vel)); MP_TRY(mp_grid_download_async(gP, pressure));
+	if (retRhs) MP_TRY(mp_grid_download_async(gRet, retRhs));
+	MP_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (info) {
+		cudaEventElapsedTime(&info->msH2D, ctx->ev[5], ctx->ev[6]);
+		cudaEventElapsedTime(&info->msD2H, ctx->ev[7], ctx->ev[0]);
+	}
+	return MP_OK;
+}
+
+} // extern "C"

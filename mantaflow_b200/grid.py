@@ -1,0 +1,200 @@
+"""Host-side mirror of the reference's FluidSolver / Grid<Real> / MACGrid / FlagGrid types for the pressure path
+(grid.h:92-365, fluidsolver.h:27-91) with a device-resident storage mirror: every grid owns a numpy array in the
+reference layout ([Z,Y,X] / [Z,Y,X,3], the convention of plugin/numpyconvert.cpp:145-183) AND an mp_grid in HBM.
+Two dirty bits keep them coherent lazily, so a sequence of pressure plugins never leaves the device.
+
+Only what the pressure path and its callers need is here; scene construction helpers (initDomain, fillGrid,
+updateFromLevelset, setConst) are the simple host loops of grid.cpp:732-861."""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import MP_GRID_FLAGS, MP_GRID_MAC, MP_GRID_REAL, check
+
+# FlagGrid::CellType grid.h:292-304 / python/defines.py
+FlagFluid, FlagObstacle, FlagEmpty, FlagInflow, FlagOutflow, FlagOpen, FlagStick = 1, 2, 4, 8, 16, 32, 64
+
+
+class Solver:
+    """FluidSolver (fluidsolver.h:27): grid size, dimension, precision, and the CUDA context that plays the
+    `parent` key of gMapMG (pressure.cpp:250).  `prec` 4 = the reference's float build, 8 = -DDOUBLEPRECISION."""
+
+    def __init__(self, gridSize, dim=3, prec=4, device=0, name="main"):
+        gs = tuple(int(v) for v in gridSize)
+        if dim not in (2, 3):
+            raise _lib.MantaError(1, "Only 2D and 3D solvers allowed.")
+        if dim == 2 and gs[2] != 1:
+            raise _lib.MantaError(1, "Trying to create 2D solver with size.z != 1")
+        self.gridSize, self.dim, self.prec, self.name = gs, dim, prec, name
+        self.real = np.float32 if prec == 4 else np.float64
+        self.timestep = 1.0
+        self.lib = _lib.load()
+        self._ctx = C.c_void_p()
+        check(self.lib.mp_context_create(C.c_int(device), C.byref(self._ctx)))
+
+    # solver.create(RealGrid) like the reference's Python API
+    def create(self, cls, **kw):
+        return cls(self, **kw)
+
+    def getGridSize(self):
+        return self.gridSize
+
+    def is3D(self):
+        return self.dim == 3
+
+    def synchronize(self):
+        check(self.lib.mp_context_synchronize(self._ctx))
+
+    def kernelLaunches(self):
+        n = C.c_longlong(0)
+        check(self.lib.mp_context_kernel_launches(self._ctx, C.byref(n)))
+        return n.value
+
+    def stream(self):
+        return self.lib.mp_context_stream(self._ctx)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.lib.mp_context_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _GridBase:
+    KIND = MP_GRID_REAL
+
+    def __init__(self, parent, data=None):
+        self.parent = parent
+        sx, sy, sz = parent.gridSize
+        self.size = (sx, sy, sz)
+        shape = (sz, sy, sx) + ((3,) if self.KIND == MP_GRID_MAC else ())
+        dtype = np.int32 if self.KIND == MP_GRID_FLAGS else parent.real
+        if data is None:
+            self._host = np.zeros(shape, dtype)
+        else:
+            self._host = np.ascontiguousarray(data, dtype=dtype).reshape(shape)
+        self._dev = C.c_void_p()
+        check(parent.lib.mp_grid_create(parent._ctx, C.c_int(self.KIND), C.c_int(parent.prec), C.c_int(sx), C.c_int(sy), C.c_int(sz), C.byref(self._dev)))
+        self._hostDirty = data is not None      # host holds newer data than the device
+        self._devDirty = False                  # device holds newer data than the host
+
+    # ---- coherence ----
+    def dev(self):
+        """mp_grid handle with the device copy made current (uploads only if the host copy is newer)."""
+        if self._hostDirty:
+            check(self.parent.lib.mp_grid_upload(self._dev, self._host.ctypes.data_as(C.c_void_p)))
+            self._hostDirty = False
+        return self._dev
+
+    def markDeviceWritten(self):
+        self._devDirty, self._hostDirty = True, False
+
+    def numpy(self, writable=False):
+        """numpy view of the host copy made current (downloads only if the device copy is newer)."""
+        if self._devDirty:
+            check(self.parent.lib.mp_grid_download(self._dev, self._host.ctypes.data_as(C.c_void_p)))
+            self._devDirty = False
+        if writable:
+            self._hostDirty = True
+        return self._host
+
+    def copyFromArray(self, arr):
+        self._host[...] = np.asarray(arr, dtype=self._host.dtype).reshape(self._host.shape)
+        self._hostDirty, self._devDirty = True, False
+
+    # ---- reference API subset ----
+    def getSizeX(self): return self.size[0]
+    def getSizeY(self): return self.size[1]
+    def getSizeZ(self): return self.size[2]
+    def getSize(self): return self.size
+    def is3D(self): return self.size[2] > 1
+
+    def clear(self):
+        self._host[...] = 0
+        self._hostDirty, self._devDirty = True, False
+
+    def setConst(self, value):
+        self._host[...] = value
+        self._hostDirty, self._devDirty = True, False
+
+    def copyFrom(self, other):
+        self.copyFromArray(other.numpy())
+
+    def close(self):
+        if getattr(self, "_dev", None) is not None and self._dev and self.parent._ctx:
+            self.parent.lib.mp_grid_destroy(self._dev)
+        self._dev = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RealGrid(_GridBase):
+    """Grid<Real> (grid.h:92-235)"""
+    KIND = MP_GRID_REAL
+
+    def getMaxAbs(self):
+        out = C.c_double(0)
+        check(self.parent.lib.mp_grid_max_abs(self.parent._ctx, self.dev(), C.byref(out)))
+        return out.value
+
+
+class LevelsetGrid(RealGrid):
+    pass
+
+
+class MACGrid(_GridBase):
+    """MACGrid (grid.h:243-281), AoS Vec3"""
+    KIND = MP_GRID_MAC
+
+
+class FlagGrid(_GridBase):
+    """FlagGrid (grid.h:284-365)"""
+    KIND = MP_GRID_FLAGS
+
+    def initDomain(self, boundaryWidth=0, wall="xXyYzZ", open="      ", inflow="      ", outflow="      "):
+        """grid.cpp:732-842: everything Empty, then the six boundary slabs typed wall/open/inflow/outflow."""
+        wall, open_, inflow, outflow = (s + "      " for s in (wall, open, inflow, outflow))
+        types = [0] * 6
+        for d, ch in enumerate("xXyYzZ"):
+            for i in range(6):
+                if types[d]:
+                    break
+                if open_[i] == ch: types[d] = FlagOpen
+                elif inflow[i] == ch: types[d] = FlagInflow
+                elif outflow[i] == ch: types[d] = FlagOutflow
+                elif wall[i] == ch: types[d] = FlagObstacle
+        f = self._host
+        f[...] = FlagEmpty
+        w = boundaryWidth
+        sx, sy, sz = self.size
+        # the reference overwrites in the order x, X, y, Y, z, Z per cell (initBoundaries grid.cpp:826-842)
+        f[:, :, :w + 1] = types[0]
+        f[:, :, sx - 1 - w:] = types[1]
+        f[:, :w + 1, :] = types[2]
+        f[:, sy - 1 - w:, :] = types[3]
+        if self.is3D():
+            f[:w + 1, :, :] = types[4]
+            f[sz - 1 - w:, :, :] = types[5]
+        self._hostDirty, self._devDirty = True, False
+
+    def fillGrid(self, type=FlagFluid):
+        """grid.cpp:856-861"""
+        f = self.numpy(writable=True)
+        m = (f & (FlagObstacle | FlagInflow | FlagOutflow | FlagOpen)) == 0
+        f[m] = (f[m] & ~(FlagEmpty | FlagFluid)) | type
+
+    def updateFromLevelset(self, levelset):
+        """grid.cpp:844-854 (invalidTimeValue = -1000, fastmarch.h:134)"""
+        f = self.numpy(writable=True)
+        phi = levelset.numpy()
+        m = ((f & (FlagObstacle | FlagOutflow)) == 0) & (phi > -1000)
+        f[m] = (f[m] & ~(FlagEmpty | FlagFluid)) | np.where(phi[m] <= 0, FlagFluid, FlagEmpty).astype(np.int32)

@@ -1,0 +1,1062 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of mantaflow's pressure-projection path.
+ *
+ * Nothing here is linked, imported or executed by the product path (mantaflow_b200/); only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it,
+ * and only as the checker.  It is a from-scratch plain-C restatement of the reference algorithm,
+ * each function citing the reference file:line (relative to the mantaflow tree) it follows.
+ *
+ * PARITY PIN: validated against the UNMODIFIED reference compiled from /root/reference
+ * (oracle/_ref/libmanta_ref_f{32,64}.so, see oracle/Makefile + oracle/ref_harness.cpp) by
+ * tests/test_oracle_vs_reference.py, and against golden vectors generated from that reference
+ * (tests/golden/, generator tests/golden/make_golden.py).  The reference ships no golden data of
+ * its own (tools/testdata/readme.txt:1).
+ *
+ * Precision: compiled twice, Real=float (reference default build "fp1") and Real=double ("fp2",
+ * -DDOUBLEPRECISION=ON).  Compiled with -ffp-contract=off: the reference build has no FMA.
+ *
+ * Layout (grid.h:70): idx = i + sx*(j + sy*k), x fastest; flags int32; MAC velocity AoS {x,y,z}.
+ * 2-D grids have sz==1 and Z-stride 0 (grid.cpp:55).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <stdint.h>
+
+#if MF_REAL_IS_DOUBLE
+typedef double Real;
+#define R_SQRT sqrt
+#define R_FABS fabs
+#else
+typedef float Real;
+#define R_SQRT sqrtf
+#define R_FABS fabsf
+#endif
+
+typedef long long IndexInt;
+
+enum { TypeFluid = 1, TypeObstacle = 2, TypeEmpty = 4, TypeInflow = 8, TypeOutflow = 16, TypeOpen = 32, TypeStick = 64 }; /* grid.h:292-304 */
+
+static char g_err[512];
+const char* mfo_last_error(void) { return g_err; }
+int mfo_real_size(void) { return (int)sizeof(Real); }
+int mfo_is_reference(void) { return 0; }
+int mfo_set_debug_level(int l) { (void)l; return 0; }
+
+#define IS3D (sz > 1)
+#define IDX(i, j, k) ((IndexInt)(i) + (IndexInt)sx * (j) + (IndexInt)SZ * (k))
+#define STRIDES const IndexInt X = 1, Y = sx, SZ = (sz > 1) ? (IndexInt)sx * sy : 0, Z = SZ; (void)X; (void)Y; (void)Z;
+
+static inline Real rmin(Real a, Real b) { return a < b ? a : b; }
+static inline Real rmax(Real a, Real b) { return a > b ? a : b; }
+
+/* ---------------------------------------------------------------------------------------------
+ * setWallBcs without obvel / fractions: plugin/extforces.cpp:186-218 (KnSetWallBcs), :307-316   */
+int mfo_set_wall_bcs(int sx, int sy, int sz, const int* flags, Real* vel)
+{
+	STRIDES
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		const int curFluid = flags[idx] & TypeFluid, curObs = flags[idx] & TypeObstacle;
+		if (!curFluid && !curObs) continue;
+		Real* v = vel + 3 * idx;
+		if (i > 0 && (flags[idx - X] & TypeObstacle)) v[0] = 0;
+		if (i > 0 && curObs && (flags[idx - X] & TypeFluid)) v[0] = 0;
+		if (j > 0 && (flags[idx - Y] & TypeObstacle)) v[1] = 0;
+		if (j > 0 && curObs && (flags[idx - Y] & TypeFluid)) v[1] = 0;
+		if (!IS3D) { v[2] = 0; } else {
+			if (k > 0 && (flags[idx - Z] & TypeObstacle)) v[2] = 0;
+			if (k > 0 && curObs && (flags[idx - Z] & TypeFluid)) v[2] = 0;
+		}
+		if (curFluid) {
+			if ((i > 0 && (flags[idx - X] & TypeStick)) || (i < sx - 1 && (flags[idx + X] & TypeStick))) v[1] = v[2] = 0;
+			if ((j > 0 && (flags[idx - Y] & TypeStick)) || (j < sy - 1 && (flags[idx + Y] & TypeStick))) v[0] = v[2] = 0;
+			if (IS3D && ((k > 0 && (flags[idx - Z] & TypeStick)) || (k < sz - 1 && (flags[idx + Z] & TypeStick)))) v[0] = v[1] = 0;
+		}
+	}
+	return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * ghost-fluid helpers: plugin/pressure.cpp:115-133                                              */
+static inline Real thetaHelper(Real inside, Real outside)
+{
+	const Real denom = inside - outside;
+	if ((double)denom > -1e-04) return (Real)0.5;           /* Real compared with a double literal (:118) */
+	return rmax((Real)0, rmin((Real)1, inside / denom));
+}
+static inline Real ghostFluidHelper(IndexInt idx, IndexInt offset, const Real* phi, Real gfClamp)
+{
+	Real alpha = thetaHelper(phi[idx], phi[idx + offset]);
+	if (alpha < gfClamp) return gfClamp;
+	return (Real)(1. - (1. / (double)alpha));                /* evaluated in double, then narrowed (:127) */
+}
+static inline Real surfTensHelper(IndexInt idx, IndexInt offset, const Real* phi, const Real* curv, Real surfTens, Real gfClamp)
+{
+	return surfTens * (curv[idx + offset] - ghostFluidHelper(idx, offset, phi, gfClamp) * curv[idx]);
+}
+static inline int ghostFluidWasClamped(IndexInt idx, IndexInt offset, const Real* phi, Real gfClamp)
+{
+	return thetaHelper(phi[idx], phi[idx + offset]) < gfClamp;   /* :191-196 */
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * computePressureRhs: plugin/pressure.cpp:277-299, kernel MakeRhs :32-84 (bnd=1)                */
+int mfo_compute_rhs(int sx, int sy, int sz, const int* flags, const Real* vel, Real* rhs,
+	const Real* phi, const Real* perCellCorr, const Real* fractions, const Real* obvel, const Real* curv,
+	double gfClamp_, double surfTens_, int enforceCompatibility, double* sum_out, int* cnt_out)
+{
+	STRIDES
+	const Real gfClamp = (Real)gfClamp_, surfTens = (Real)surfTens_;
+	double sum = 0; int cnt = 0;
+	const int k0 = IS3D ? 1 : 0, k1 = IS3D ? sz - 1 : 1;
+	for (int k = k0; k < k1; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) { rhs[idx] = 0; continue; }
+		const Real* v = vel + 3 * idx; const Real* vx = vel + 3 * (idx + X); const Real* vy = vel + 3 * (idx + Y); const Real* vz = vel + 3 * (idx + Z);
+		Real set = 0;
+		if (!fractions) {
+			set = v[0] - vx[0] + v[1] - vy[1];
+			if (IS3D) set += v[2] - vz[2];
+		} else {
+			const Real* f = fractions + 3 * idx; const Real* fx = fractions + 3 * (idx + X); const Real* fy = fractions + 3 * (idx + Y); const Real* fz = fractions + 3 * (idx + Z);
+			set = f[0] * v[0] - fx[0] * vx[0] + f[1] * v[1] - fy[1] * vy[1];
+			if (IS3D) set += f[2] * v[2] - fz[2] * vz[2];
+			if (obvel) {
+				const Real* o = obvel + 3 * idx; const Real* ox = obvel + 3 * (idx + X); const Real* oy = obvel + 3 * (idx + Y); const Real* oz = obvel + 3 * (idx + Z);
+				set += (1 - f[0]) * o[0] - (1 - fx[0]) * ox[0] + (1 - f[1]) * o[1] - (1 - fy[1]) * oy[1];
+				if (IS3D) set += (1 - f[2]) * o[2] - (1 - fz[2]) * oz[2];
+			}
+		}
+		if (phi && curv) {
+			if (flags[idx - X] & TypeEmpty) set += surfTensHelper(idx, -X, phi, curv, surfTens, gfClamp);
+			if (flags[idx + X] & TypeEmpty) set += surfTensHelper(idx, +X, phi, curv, surfTens, gfClamp);
+			if (flags[idx - Y] & TypeEmpty) set += surfTensHelper(idx, -Y, phi, curv, surfTens, gfClamp);
+			if (flags[idx + Y] & TypeEmpty) set += surfTensHelper(idx, +Y, phi, curv, surfTens, gfClamp);
+			if (IS3D) {
+				if (flags[idx - Z] & TypeEmpty) set += surfTensHelper(idx, -Z, phi, curv, surfTens, gfClamp);
+				if (flags[idx + Z] & TypeEmpty) set += surfTensHelper(idx, +Z, phi, curv, surfTens, gfClamp);
+			}
+		}
+		if (perCellCorr) set += perCellCorr[idx];
+		sum += set; cnt++;
+		rhs[idx] = set;
+	}
+	if (enforceCompatibility) {                               /* :297-298, applied to ALL cells */
+		const Real corr = (Real)(-sum / (Real)cnt);
+		const IndexInt n = (IndexInt)sx * sy * sz;
+		for (IndexInt q = 0; q < n; q++) rhs[q] += corr;
+	}
+	if (sum_out) *sum_out = sum;
+	if (cnt_out) *cnt_out = cnt;
+	return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * MakeLaplaceMatrix conjugategrad.h:154-187 (+ ApplyGhostFluidDiagonal pressure.cpp:136-151
+ * when phi != NULL).  A* must be zero on entry (the reference allocates cleared grids).          */
+int mfo_make_matrix(int sx, int sy, int sz, const int* flags, const Real* fractions, const Real* phi, double gfClamp_,
+	Real* A0, Real* Ai, Real* Aj, Real* Ak)
+{
+	STRIDES
+	const Real gfClamp = (Real)gfClamp_;
+	const int k0 = IS3D ? 1 : 0, k1 = IS3D ? sz - 1 : 1;
+	#pragma omp parallel for schedule(static)
+	for (int k = k0; k < k1; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		if (!fractions) {
+			if (!(flags[idx - X] & TypeObstacle)) A0[idx] += 1.;
+			if (!(flags[idx + X] & TypeObstacle)) A0[idx] += 1.;
+			if (!(flags[idx - Y] & TypeObstacle)) A0[idx] += 1.;
+			if (!(flags[idx + Y] & TypeObstacle)) A0[idx] += 1.;
+			if (IS3D && !(flags[idx - Z] & TypeObstacle)) A0[idx] += 1.;
+			if (IS3D && !(flags[idx + Z] & TypeObstacle)) A0[idx] += 1.;
+			if (flags[idx + X] & TypeFluid) Ai[idx] = -1.;
+			if (flags[idx + Y] & TypeFluid) Aj[idx] = -1.;
+			if (IS3D && (flags[idx + Z] & TypeFluid)) Ak[idx] = -1.;
+		} else {
+			A0[idx] += fractions[3 * idx + 0];
+			A0[idx] += fractions[3 * (idx + X) + 0];
+			A0[idx] += fractions[3 * idx + 1];
+			A0[idx] += fractions[3 * (idx + Y) + 1];
+			if (IS3D) A0[idx] += fractions[3 * idx + 2];
+			if (IS3D) A0[idx] += fractions[3 * (idx + Z) + 2];
+			if (flags[idx + X] & TypeFluid) Ai[idx] = -fractions[3 * (idx + X) + 0];
+			if (flags[idx + Y] & TypeFluid) Aj[idx] = -fractions[3 * (idx + Y) + 1];
+			if (IS3D && (flags[idx + Z] & TypeFluid)) Ak[idx] = -fractions[3 * (idx + Z) + 2];
+		}
+		if (phi) {
+			if (flags[idx - X] & TypeEmpty) A0[idx] -= ghostFluidHelper(idx, -X, phi, gfClamp);
+			if (flags[idx + X] & TypeEmpty) A0[idx] -= ghostFluidHelper(idx, +X, phi, gfClamp);
+			if (flags[idx - Y] & TypeEmpty) A0[idx] -= ghostFluidHelper(idx, -Y, phi, gfClamp);
+			if (flags[idx + Y] & TypeEmpty) A0[idx] -= ghostFluidHelper(idx, +Y, phi, gfClamp);
+			if (IS3D) {
+				if (flags[idx - Z] & TypeEmpty) A0[idx] -= ghostFluidHelper(idx, -Z, phi, gfClamp);
+				if (flags[idx + Z] & TypeEmpty) A0[idx] -= ghostFluidHelper(idx, +Z, phi, gfClamp);
+			}
+		}
+	}
+	return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * pressure pinning: cell choice plugin/pressure.cpp:349-382 (CountEmptyCells :217-220)          */
+long long mfo_choose_fix_cell(int sx, int sy, int sz, const int* flags)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	for (IndexInt q = 0; q < n; q++) if (flags[q] & TypeEmpty) return -1;
+	const int cx = sx / 2, cz = IS3D ? sz / 2 : 0;
+	for (int d = 0; d < 3; d++) {                          /* top centre, then one and two cells below */
+		const int cy = sy - 1 - d;
+		if (cy < 0) continue;
+		const IndexInt idx = IDX(cx, cy, cz);
+		if (flags[idx] & TypeFluid) return idx;
+	}
+	const int k0 = IS3D ? 1 : 0, k1 = IS3D ? sz - 1 : 1;
+	for (int k = k0; k < k1; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++)
+		if (flags[IDX(i, j, k)] & TypeFluid) return IDX(i, j, k);
+	return -1;
+}
+
+/* fixPressure plugin/pressure.cpp:226-245 */
+int mfo_fix_pressure(int sx, int sy, int sz, long long p, double value_, Real* rhs, Real* A0, Real* Ai, Real* Aj, Real* Ak)
+{
+	STRIDES
+	const Real value = (Real)value_;
+	rhs[p + X] -= Ai[p] * value;
+	rhs[p + Y] -= Aj[p] * value;
+	rhs[p - X] -= Ai[p - X] * value;
+	rhs[p - Y] -= Aj[p - Y] * value;
+	if (IS3D) { rhs[p + Z] -= Ak[p] * value; rhs[p - Z] -= Ak[p - Z] * value; }
+	rhs[p] = value;
+	A0[p] = (Real)1;
+	Ai[p] = Aj[p] = Ak[p] = (Real)0;
+	Ai[p - X] = (Real)0;
+	Aj[p - Y] = (Real)0;
+	if (IS3D) Ak[p - Z] = (Real)0;
+	return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * ApplyMatrix / ApplyMatrix2D conjugategrad.h:118-151 (idx mode over ALL cells)                 */
+static void apply_matrix(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	if (IS3D) {
+		#pragma omp parallel for schedule(static)
+		for (IndexInt idx = 0; idx < n; idx++) {
+			if (!(flags[idx] & TypeFluid)) { dst[idx] = src[idx]; continue; }
+			dst[idx] = src[idx] * A0[idx]
+				+ src[idx - X] * Ai[idx - X] + src[idx + X] * Ai[idx]
+				+ src[idx - Y] * Aj[idx - Y] + src[idx + Y] * Aj[idx]
+				+ src[idx - Z] * Ak[idx - Z] + src[idx + Z] * Ak[idx];
+		}
+	} else {
+		#pragma omp parallel for schedule(static)
+		for (IndexInt idx = 0; idx < n; idx++) {
+			if (!(flags[idx] & TypeFluid)) { dst[idx] = src[idx]; continue; }
+			dst[idx] = src[idx] * A0[idx]
+				+ src[idx - X] * Ai[idx - X] + src[idx + X] * Ai[idx]
+				+ src[idx - Y] * Aj[idx - Y] + src[idx + Y] * Aj[idx];
+		}
+	}
+}
+int mfo_apply_matrix(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ apply_matrix(sx, sy, sz, flags, dst, src, A0, Ai, Aj, Ak); return 0; }
+
+/* deterministic blocked reductions (the reference's OpenMP/TBB join order is unspecified,
+ * codegen_kernel.cpp:204-210,:462; accumulators are double as in the reference)              */
+#define RBLK 8192
+static double dot_product(const Real* a, const Real* b, IndexInt n)   /* GridDotProduct conjugategrad.cpp:175-178 */
+{
+	const IndexInt nb = (n + RBLK - 1) / RBLK;
+	double* part = (double*)malloc(sizeof(double) * (size_t)nb);
+	#pragma omp parallel for schedule(static)
+	for (IndexInt b_ = 0; b_ < nb; b_++) {
+		double s = 0; const IndexInt e = (b_ + 1) * RBLK < n ? (b_ + 1) * RBLK : n;
+		for (IndexInt q = b_ * RBLK; q < e; q++) s += (a[q] * b[q]);     /* product in Real, sum in double */
+		part[b_] = s;
+	}
+	double s = 0; for (IndexInt b_ = 0; b_ < nb; b_++) s += part[b_];
+	free(part); return s;
+}
+static double sum_sqr(const Real* a, IndexInt n)                       /* GridSumSqr commonkernels.h:32-35 */
+{
+	const IndexInt nb = (n + RBLK - 1) / RBLK;
+	double* part = (double*)malloc(sizeof(double) * (size_t)nb);
+	#pragma omp parallel for schedule(static)
+	for (IndexInt b_ = 0; b_ < nb; b_++) {
+		double s = 0; const IndexInt e = (b_ + 1) * RBLK < n ? (b_ + 1) * RBLK : n;
+		for (IndexInt q = b_ * RBLK; q < e; q++) s += (double)a[q] * (double)a[q];
+		part[b_] = s;
+	}
+	double s = 0; for (IndexInt b_ = 0; b_ < nb; b_++) s += part[b_];
+	free(part); return s;
+}
+static Real max_abs(const Real* a, IndexInt n)                         /* Grid<Real>::getMaxAbs grid.cpp:319-323 */
+{
+	Real m = 0;
+	#pragma omp parallel for reduction(max:m) schedule(static)
+	for (IndexInt q = 0; q < n; q++) { Real v = R_FABS(a[q]); if (v > m) m = v; }
+	return m;
+}
+static void scaled_add(Real* me, const Real* other, Real f, IndexInt n) /* gridScaledAdd grid.h:478 */
+{
+	#pragma omp parallel for schedule(static)
+	for (IndexInt q = 0; q < n; q++) me[q] += f * other[q];
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * MIC(0): InitPreconditionModifiedIncompCholesky2 conjugategrad.cpp:66-97 (serial, k/j/i order) */
+static void mic_init(int sx, int sy, int sz, const int* flags, Real* P, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	memset(P, 0, sizeof(Real) * (size_t)n);
+	const Real tau = (Real)0.97, sigma = (Real)0.25;
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		const IndexInt ix = idx - X, iy = idx - Y, iz = idx - Z;
+		const Real tx = Ai[ix] * P[ix], ty = Aj[iy] * P[iy], tz = Ak[iz] * P[iz];
+		Real e = A0[idx] - tx * tx - ty * ty - tz * tz;
+		/* the "+ 0." in the reference promotes the bracket, the product with tau and the
+		   subtraction to double before narrowing back to Real (:85-89) */
+		const Real inner = Ai[ix] * (Aj[ix] + Ak[ix]) * (P[ix] * P[ix])
+		                 + Aj[iy] * (Ai[iy] + Ak[iy]) * (P[iy] * P[iy])
+		                 + Ak[iz] * (Ai[iz] + Aj[iz]) * (P[iz] * P[iz]);
+		e = (Real)((double)e - (double)tau * ((double)inner + 0.));
+		if (e < sigma * A0[idx]) e = A0[idx];
+		P[idx] = (Real)(1. / (double)R_SQRT(e));
+	}
+}
+int mfo_mic_init(int sx, int sy, int sz, const int* flags, Real* P, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ mic_init(sx, sy, sz, flags, P, A0, Ai, Aj, Ak); return 0; }
+
+/* ApplyPreconditionModifiedIncompCholesky2 conjugategrad.cpp:135-159 */
+static void mic_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src, const Real* P,
+	const Real* Ai, const Real* Aj, const Real* Ak)
+{
+	STRIDES
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		const Real p = P[idx];
+		dst[idx] = p * (src[idx]
+			- dst[idx - X] * Ai[idx - X] * P[idx - X]
+			- dst[idx - Y] * Aj[idx - Y] * P[idx - Y]
+			- dst[idx - Z] * Ak[idx - Z] * P[idx - Z]);
+	}
+	for (int k = sz - 1; k >= 0; k--) for (int j = sy - 1; j >= 0; j--) for (int i = sx - 1; i >= 0; i--) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		const Real p = P[idx];
+		dst[idx] = p * (dst[idx]
+			- dst[idx + X] * Ai[idx] * p
+			- dst[idx + Y] * Aj[idx] * p
+			- dst[idx + Z] * Ak[idx] * p);
+	}
+}
+int mfo_mic_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src, const Real* P,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ (void)A0; mic_apply(sx, sy, sz, flags, dst, src, P, Ai, Aj, Ak); return 0; }
+
+/* =============================================================================================
+ * GridMg  (multigrid.h:31-137, multigrid.cpp)                                                   */
+enum { vtInactive = 0, vtActive = 1, vtActiveTrivial = 2, vtRemoved = 3, vtZero = 4, vtFree = 5 };  /* multigrid.h:87-94 */
+#define MG_MAXLVL 32
+
+typedef struct { int Ux, Uy, Uz, Wx, Wy, Wz, Nx, Ny, Nz, sc, sf, inU; Real rw, iw; } CoarseningPath;
+
+typedef struct MgState {
+	int is3D, dim, stencil, stencil0, nlev;
+	int smin[3], smax[3];
+	int size[MG_MAXLVL][3]; int pitch[MG_MAXLVL][3]; int n[MG_MAXLVL];
+	Real* A[MG_MAXLVL]; Real* x[MG_MAXLVL]; Real* b[MG_MAXLVL]; Real* r[MG_MAXLVL]; signed char* type[MG_MAXLVL];
+	double *cg1, *cg2, *cg3, *cg4;
+	CoarseningPath* paths; int npaths;
+	int numPre, numPost; Real coarsestAcc, trivialScale;
+	int isASet, isRhsSet;
+	int lastCoarseIters;
+} MgState;
+
+static int path_less(const void* a_, const void* b_)   /* multigrid.cpp:314-318 (key only; ties keep generation order) */
+{
+	const CoarseningPath* a = (const CoarseningPath*)a_; const CoarseningPath* b = (const CoarseningPath*)b_;
+	if (a->sc != b->sc) return a->sc < b->sc ? -1 : 1;
+	const int ka = (a->Ux + 1) + 3 * (a->Uy + 1) + 9 * (a->Uz + 1), kb = (b->Ux + 1) + 3 * (b->Uy + 1) + 9 * (b->Uz + 1);
+	if (ka != kb) return ka < kb ? -1 : 1;
+	return 0;
+}
+
+static MgState* mg_create(int sx, int sy, int sz)       /* GridMg::GridMg multigrid.cpp:220-319 */
+{
+	MgState* m = (MgState*)calloc(1, sizeof(MgState));
+	m->numPre = m->numPost = 1; m->coarsestAcc = (Real)1E-8; m->trivialScale = (Real)1E-6;
+	m->is3D = sz > 1; m->dim = m->is3D ? 3 : 2;
+	m->stencil = m->is3D ? 14 : 5; m->stencil0 = m->is3D ? 4 : 3;
+	m->smin[0] = m->smin[1] = -1; m->smin[2] = m->is3D ? -1 : 0;
+	m->smax[0] = m->smax[1] = 1;  m->smax[2] = m->is3D ? 1 : 0;
+	int l = 0;
+	m->size[0][0] = sx; m->size[0][1] = sy; m->size[0][2] = sz;
+	for (;;) {
+		const int* s = m->size[l];
+		m->pitch[l][0] = 1; m->pitch[l][1] = s[0]; m->pitch[l][2] = s[0] * s[1];
+		m->n[l] = s[0] * s[1] * s[2];
+		const int st = (l == 0) ? m->stencil0 : m->stencil;
+		m->A[l] = (Real*)calloc((size_t)m->n[l] * st, sizeof(Real));
+		m->x[l] = (Real*)calloc((size_t)m->n[l], sizeof(Real));
+		m->b[l] = (Real*)calloc((size_t)m->n[l], sizeof(Real));
+		m->r[l] = (Real*)calloc((size_t)m->n[l], sizeof(Real));
+		m->type[l] = (signed char*)calloc((size_t)m->n[l], 1);
+		m->nlev = l + 1;
+		if (l + 1 > 100) break;
+		if (s[0] <= 5 && s[1] <= 5 && s[2] <= 5) break;
+		if (m->n[l] <= 1000) break;
+		for (int d = 0; d < 3; d++) m->size[l + 1][d] = (s[d] + 2) / 2;
+		l++;
+	}
+	const int nc = m->n[m->nlev - 1];
+	m->cg1 = (double*)calloc((size_t)nc, sizeof(double)); m->cg2 = (double*)calloc((size_t)nc, sizeof(double));
+	m->cg3 = (double*)calloc((size_t)nc, sizeof(double)); m->cg4 = (double*)calloc((size_t)nc, sizeof(double));
+
+	/* coarsening paths (V)<-R-(U)<-A-(W)<-I-(N) for level 1, multigrid.cpp:286-318 */
+	static const int p7[7][3] = { {0,0,0}, {-1,0,0}, {1,0,0}, {0,-1,0}, {0,1,0}, {0,0,-1}, {0,0,1} };
+	m->paths = (CoarseningPath*)malloc(sizeof(CoarseningPath) * 27 * 7 * 8);
+	m->npaths = 0;
+	for (int uz = 2 + m->smin[2]; uz <= 2 + m->smax[2]; uz++) for (int uy = 1; uy <= 3; uy++) for (int ux = 1; ux <= 3; ux++) {
+		for (int i = 0; i < 1 + 2 * m->dim; i++) {
+			const int wx = ux + p7[i][0], wy = uy + p7[i][1], wz = uz + p7[i][2];
+			for (int nz = wz / 2; nz <= (wz + 1) / 2; nz++) for (int ny = wy / 2; ny <= (wy + 1) / 2; ny++) for (int nx = wx / 2; nx <= (wx + 1) / 2; nx++) {
+				const int s = nx + 3 * ny + 9 * nz;
+				if (s >= 13) {
+					CoarseningPath* p = &m->paths[m->npaths++];
+					p->Nx = nx - 1; p->Ny = ny - 1; p->Nz = nz - 1;
+					p->Ux = ux - 2; p->Uy = uy - 2; p->Uz = uz - 2;
+					p->Wx = wx - 2; p->Wy = wy - 2; p->Wz = wz - 2;
+					p->sc = s - 13; p->sf = (i + 1) / 2; p->inU = (i % 2 == 0);
+					p->rw = (Real)1 / (Real)(1 << ((ux % 2) + (uy % 2) + (uz % 2)));
+					p->iw = (Real)1 / (Real)(1 << ((wx % 2) + (wy % 2) + (wz % 2)));
+				}
+			}
+		}
+	}
+	/* stable insertion sort on the reference's key (std::sort's order among equal keys is unspecified) */
+	for (int a = 1; a < m->npaths; a++) {
+		CoarseningPath t = m->paths[a]; int b = a - 1;
+		while (b >= 0 && path_less(&t, &m->paths[b]) < 0) { m->paths[b + 1] = m->paths[b]; b--; }
+		m->paths[b + 1] = t;
+	}
+	return m;
+}
+
+static void mg_destroy(MgState* m)
+{
+	if (!m) return;
+	for (int l = 0; l < m->nlev; l++) { free(m->A[l]); free(m->x[l]); free(m->b[l]); free(m->r[l]); free(m->type[l]); }
+	free(m->cg1); free(m->cg2); free(m->cg3); free(m->cg4); free(m->paths); free(m);
+}
+
+#define VEC(v, l, V) int V[3]; { const int* s_ = m->size[l]; V[0] = (v) % s_[0]; V[1] = ((v) % (s_[0] * s_[1])) / s_[0]; V[2] = (v) / (s_[0] * s_[1]); }
+#define LIN(V0, V1, V2, l) ((V0) + (V1) * m->pitch[l][1] + (V2) * m->pitch[l][2])
+#define INGRID(V0, V1, V2, l) ((V0) >= 0 && (V1) >= 0 && (V2) >= 0 && (V0) < m->size[l][0] && (V1) < m->size[l][1] && (V2) < m->size[l][2])
+
+/* ---- bucket min-heap, multigrid.cpp:59-203 (pop order = LIFO within a key) ---- */
+typedef struct { int key, prev, next; } HEntry;
+typedef struct { int N, K, size, minKey; HEntry* e; } NKMinHeap;
+static void heap_init(NKMinHeap* h, int N, int K) { h->N = N; h->K = K; h->size = 0; h->minKey = -1; h->e = (HEntry*)malloc(sizeof(HEntry) * ((size_t)N + K)); for (int i = 0; i < N + K; i++) { h->e[i].key = -1; h->e[i].prev = -1; h->e[i].next = -1; } }
+static inline int heap_get(NKMinHeap* h, int id) { return h->e[h->K + id].key; }
+static void heap_set(NKMinHeap* h, int id, int key)
+{
+	const int kid = h->K + id; HEntry* e = h->e;
+	if (e[kid].key == key) return;
+	if (e[kid].key != -1) {
+		const int pred = e[kid].prev, succ = e[kid].next;
+		e[pred].next = succ; if (succ != -1) e[succ].prev = pred;
+		const int removed = e[kid].key;
+		if (removed == h->minKey) {
+			if (h->size == 1) h->minKey = -1;
+			else for (; h->minKey < h->K; h->minKey++) if (e[h->minKey].next != -1) break;
+		}
+		h->size--;
+	}
+	e[kid].key = key;
+	if (key == -1) { e[kid].next = e[kid].prev = -1; return; }
+	h->size++;
+	if (h->minKey == -1) h->minKey = key; else if (key < h->minKey) h->minKey = key;
+	const int tmp = e[key].next;
+	e[key].next = kid; e[kid].prev = key; e[kid].next = tmp; if (tmp != -1) e[tmp].prev = kid;
+}
+static int heap_pop(NKMinHeap* h)
+{
+	if (h->size == 0) return -1;
+	HEntry* e = h->e;
+	const int kid = e[h->minKey].next, id = kid - h->K;
+	const int pred = e[kid].prev, succ = e[kid].next;
+	e[pred].next = succ; if (succ != -1) e[succ].prev = pred;
+	e[kid].key = -1; e[kid].prev = -1; e[kid].next = -1;
+	h->size--;
+	if (h->size == 0) h->minKey = -1;
+	else for (; h->minKey < h->K; h->minKey++) if (e[h->minKey].next != -1) break;
+	return id;
+}
+
+/* genCoarseGrid multigrid.cpp:520-578 */
+static void mg_gen_coarse_grid(MgState* m, int l)
+{
+	signed char* tc = m->type[l]; const signed char* tf = m->type[l - 1];
+	memset(tc, vtFree, (size_t)m->n[l]);
+	NKMinHeap h; heap_init(&h, m->n[l - 1], m->is3D ? 9 : 5);
+	for (int v = 0; v < m->n[l - 1]; v++) if (tf[v] != vtInactive) {
+		VEC(v, l - 1, V)
+		heap_set(&h, v, 1 << ((V[0] % 2) + (V[1] % 2) + (V[2] % 2)));
+	}
+	while (h.size > 0) {
+		const int v = heap_pop(&h);
+		VEC(v, l - 1, V)
+		int vdone = 0;
+		for (int iz = V[2] / 2; iz <= (V[2] + 1) / 2; iz++) for (int iy = V[1] / 2; iy <= (V[1] + 1) / 2; iy++) for (int ix = V[0] / 2; ix <= (V[0] + 1) / 2; ix++) {
+			const int i = LIN(ix, iy, iz, l);
+			if (tc[i] == vtFree) {
+				if (vdone) tc[i] = vtRemoved; else { tc[i] = vtZero; vdone = 1; }
+				const int* sf = m->size[l - 1];
+				const int r0x = ix * 2 - 1 > 0 ? ix * 2 - 1 : 0, r0y = iy * 2 - 1 > 0 ? iy * 2 - 1 : 0, r0z = iz * 2 - 1 > 0 ? iz * 2 - 1 : 0;
+				const int r1x = ix * 2 + 1 < sf[0] - 1 ? ix * 2 + 1 : sf[0] - 1, r1y = iy * 2 + 1 < sf[1] - 1 ? iy * 2 + 1 : sf[1] - 1, r1z = iz * 2 + 1 < sf[2] - 1 ? iz * 2 + 1 : sf[2] - 1;
+				for (int rz = r0z; rz <= r1z; rz++) for (int ry = r0y; ry <= r1y; ry++) for (int rx = r0x; rx <= r1x; rx++) {
+					const int r = LIN(rx, ry, rz, l - 1);
+					const int key = heap_get(&h, r);
+					if (key > 1) heap_set(&h, r, key - 1);
+					else if (key > -1) heap_set(&h, r, -1);
+				}
+			}
+		}
+	}
+	free(h.e);
+	for (int i = 0; i < m->n[l]; i++) {                     /* knActivateCoarseVertices :507-516 */
+		if (tc[i] == vtFree) tc[i] = vtRemoved;
+		if (tc[i] == vtZero) tc[i] = vtActive;
+		if (tc[i] == vtRemoved) tc[i] = vtInactive;
+	}
+}
+
+/* knGenCoarseGridOperator multigrid.cpp:580-657: A_l = R A_{l-1} I */
+static void mg_gen_coarse_operator(MgState* m, int l)
+{
+	const int S = m->stencil, S0 = m->stencil0;
+	Real* A = m->A[l]; const Real* Af = m->A[l - 1];
+	const signed char* tc = m->type[l]; const signed char* tf = m->type[l - 1];
+	#pragma omp parallel for schedule(dynamic, 256)
+	for (int idx = 0; idx < m->n[l]; idx++) {
+		if (tc[idx] == vtInactive) continue;
+		for (int i = 0; i < S; i++) A[(size_t)idx * S + i] = (Real)0;
+		VEC(idx, l, V)
+		if (l == 1) {
+			for (int q = 0; q < m->npaths; q++) {
+				const CoarseningPath* p = &m->paths[q];
+				const int Nx = V[0] + p->Nx, Ny = V[1] + p->Ny, Nz = V[2] + p->Nz;
+				if (!INGRID(Nx, Ny, Nz, l) || tc[LIN(Nx, Ny, Nz, l)] == vtInactive) continue;
+				const int Ux = V[0] * 2 + p->Ux, Uy = V[1] * 2 + p->Uy, Uz = V[2] * 2 + p->Uz;
+				if (!INGRID(Ux, Uy, Uz, 0)) continue;
+				const int u = LIN(Ux, Uy, Uz, 0); if (tf[u] == vtInactive) continue;
+				const int Wx = V[0] * 2 + p->Wx, Wy = V[1] * 2 + p->Wy, Wz = V[2] * 2 + p->Wz;
+				if (!INGRID(Wx, Wy, Wz, 0)) continue;
+				const int w = LIN(Wx, Wy, Wz, 0); if (tf[w] == vtInactive) continue;
+				if (p->inU) A[(size_t)idx * S + p->sc] += p->rw * Af[(size_t)u * S0 + p->sf] * p->iw;
+				else        A[(size_t)idx * S + p->sc] += p->rw * Af[(size_t)w * S0 + p->sf] * p->iw;
+			}
+		} else {
+			const int* sf = m->size[l - 1]; const int* sc_ = m->size[l];
+			int u0[3], u1[3];
+			for (int d = 0; d < 3; d++) { u0[d] = V[d] * 2 - 1 > 0 ? V[d] * 2 - 1 : 0; u1[d] = V[d] * 2 + 1 < sf[d] - 1 ? V[d] * 2 + 1 : sf[d] - 1; }
+			for (int Uz = u0[2]; Uz <= u1[2]; Uz++) for (int Uy = u0[1]; Uy <= u1[1]; Uy++) for (int Ux = u0[0]; Ux <= u1[0]; Ux++) {
+				const int U[3] = { Ux, Uy, Uz };
+				const int u = LIN(Ux, Uy, Uz, l - 1);
+				if (tf[u] == vtInactive) continue;
+				const Real rw = (Real)1 / (Real)(1 << ((Ux % 2) + (Uy % 2) + (Uz % 2)));
+				int n0[3], n1[3];
+				/* C integer division truncates toward zero exactly like the reference's Vec3i '/' */
+				for (int d = 0; d < 3; d++) { n0[d] = (U[d] - 1) / 2; n1[d] = (U[d] + 2) / 2 < sc_[d] - 1 ? (U[d] + 2) / 2 : sc_[d] - 1; }
+				for (int Nz = n0[2]; Nz <= n1[2]; Nz++) for (int Ny = n0[1]; Ny <= n1[1]; Ny++) for (int Nx = n0[0]; Nx <= n1[0]; Nx++) {
+					const int N[3] = { Nx, Ny, Nz };
+					const int nn = LIN(Nx, Ny, Nz, l);
+					if (tc[nn] == vtInactive) continue;
+					const int sc = (Nx - V[0] + m->smax[0]) + 3 * (Ny - V[1] + m->smax[1]) + 9 * (Nz - V[2] + m->smax[2]);
+					if (sc < S - 1) continue;
+					int w0[3], w1[3];
+					for (int d = 0; d < 3; d++) {
+						int a = U[d] - 1 > N[d] * 2 - 1 ? U[d] - 1 : N[d] * 2 - 1; if (a < 0) a = 0;
+						int b = U[d] + 1 < N[d] * 2 + 1 ? U[d] + 1 : N[d] * 2 + 1; if (b > sf[d] - 1) b = sf[d] - 1;
+						w0[d] = a; w1[d] = b;
+					}
+					for (int Wz = w0[2]; Wz <= w1[2]; Wz++) for (int Wy = w0[1]; Wy <= w1[1]; Wy++) for (int Wx = w0[0]; Wx <= w1[0]; Wx++) {
+						const int w = LIN(Wx, Wy, Wz, l - 1);
+						if (tf[w] == vtInactive) continue;
+						const int sfi = (Wx - Ux + m->smax[0]) + 3 * (Wy - Uy + m->smax[1]) + 9 * (Wz - Uz + m->smax[2]);
+						const Real iw = (Real)1 / (Real)(1 << ((Wx % 2) + (Wy % 2) + (Wz % 2)));
+						if (sfi < S) A[(size_t)idx * S + sc - S + 1] += rw * Af[(size_t)w * S + S - 1 - sfi] * iw;
+						else         A[(size_t)idx * S + sc - S + 1] += rw * Af[(size_t)u * S + sfi - S + 1] * iw;
+					}
+				}
+			}
+		}
+	}
+}
+
+/* GridMg::setA multigrid.cpp:386-415 (knCopyA :350-358, knActivateVertices :360-384, analyzeStencil :321-348) */
+static void mg_set_a(MgState* m, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{
+	const int S0 = m->stencil0; Real* A = m->A[0]; const int n = m->n[0];
+	for (int idx = 0; idx < n; idx++) {
+		A[(size_t)idx * S0 + 0] = A0[idx]; A[(size_t)idx * S0 + 1] = Ai[idx]; A[(size_t)idx * S0 + 2] = Aj[idx];
+		if (m->is3D) A[(size_t)idx * S0 + 3] = Ak[idx];
+	}
+	for (int v = 0; v < n; v++) {
+		m->type[0][v] = vtInactive;
+		if (A[(size_t)v * S0 + 0] != (Real)0) {
+			m->type[0][v] = vtActive;
+			VEC(v, 0, V)
+			Real a[7];
+			a[0] = A[(size_t)v * S0 + 0]; a[1] = A[(size_t)v * S0 + 1]; a[2] = A[(size_t)v * S0 + 2];
+			a[3] = m->is3D ? A[(size_t)v * S0 + 3] : (Real)0;
+			a[4] = V[0] != 0 ? A[(size_t)(v - m->pitch[0][0]) * S0 + 1] : (Real)0;
+			a[5] = V[1] != 0 ? A[(size_t)(v - m->pitch[0][1]) * S0 + 2] : (Real)0;
+			a[6] = (V[2] != 0 && m->is3D) ? A[(size_t)(v - m->pitch[0][2]) * S0 + 3] : (Real)0;
+			const int trivial = a[0] == (Real)1 && a[1] == 0 && a[2] == 0 && a[3] == 0 && a[4] == 0 && a[5] == 0 && a[6] == 0;
+			if (trivial) { m->type[0][v] = vtActiveTrivial; A[(size_t)v * S0 + 0] *= m->trivialScale; }
+		}
+	}
+	for (int l = 1; l < m->nlev; l++) { mg_gen_coarse_grid(m, l); mg_gen_coarse_operator(m, l); }
+	m->isASet = 1; m->isRhsSet = 0;
+}
+
+/* NOTE on knActivateVertices' read-after-scale: the reference's kernel scales A0 of trivial rows
+ * in place while other threads may analyse neighbours; analyzeStencil only reads the *diagonal of
+ * its own row* and the *off-diagonals* of neighbours, and trivial rows have zero off-diagonals, so
+ * the result does not depend on the order.  Same here.                                            */
+
+static void mg_set_rhs(MgState* m, const Real* rhs)          /* multigrid.cpp:417-433 */
+{
+	for (int i = 0; i < m->n[0]; i++) { Real v = rhs[i]; if (m->type[0][i] == vtActiveTrivial) v *= m->trivialScale; m->b[0][i] = v; }
+	m->isRhsSet = 1;
+}
+
+/* knSmoothColor multigrid.cpp:668-711 + smoothGS :713-737 */
+static void mg_smooth(MgState* m, int l, int reversed)
+{
+	static const int a8[8][3] = { {0,0,0},{1,0,0},{0,1,0},{1,1,0},{0,0,1},{1,0,1},{0,1,1},{1,1,1} };
+	int colors[8][4]; int ncol, percol;
+	if (m->is3D) {
+		if (l == 0) { ncol = 2; percol = 4; int c0[4] = {0,3,5,6}, c1[4] = {1,2,4,7}; memcpy(colors[0], c0, sizeof c0); memcpy(colors[1], c1, sizeof c1); }
+		else { ncol = 8; percol = 1; for (int c = 0; c < 8; c++) colors[c][0] = c; }
+	} else {
+		if (l == 0) { ncol = 2; percol = 2; colors[0][0] = 0; colors[0][1] = 3; colors[1][0] = 1; colors[1][1] = 2; }
+		else { ncol = 4; percol = 1; for (int c = 0; c < 4; c++) colors[c][0] = c; }
+	}
+	const int* s = m->size[l];
+	const int bs[3] = { (s[0] + 1) / 2, (s[1] + 1) / 2, (s[2] + 1) / 2 };
+	const int nblocks = bs[0] * bs[1] * bs[2];
+	const int S = m->stencil, S0 = m->stencil0;
+	Real* x = m->x[l]; const Real* A = m->A[l]; const Real* b = m->b[l]; const signed char* type = m->type[l];
+	for (int c = 0; c < ncol; c++) {
+		const int color = reversed ? ncol - 1 - c : c;
+		#pragma omp parallel for schedule(static)
+		for (int blk = 0; blk < nblocks; blk++) {
+			const int bo[3] = { blk % bs[0], (blk % (bs[0] * bs[1])) / bs[0], blk / (bs[0] * bs[1]) };
+			for (int off = 0; off < percol; off++) {
+				const int* co = a8[colors[color][off]];
+				const int V[3] = { bo[0] * 2 + co[0], bo[1] * 2 + co[1], bo[2] * 2 + co[2] };
+				if (!INGRID(V[0], V[1], V[2], l)) continue;
+				const int v = LIN(V[0], V[1], V[2], l);
+				if (type[v] == vtInactive) continue;
+				Real sum = b[v];
+				if (l == 0) {
+					for (int d = 0; d < m->dim; d++) {
+						if (V[d] > 0)        { const int n = v - m->pitch[0][d]; sum -= A[(size_t)n * S0 + d + 1] * x[n]; }
+						if (V[d] < s[d] - 1) { const int n = v + m->pitch[0][d]; sum -= A[(size_t)v * S0 + d + 1] * x[n]; }
+					}
+					x[v] = sum / A[(size_t)v * S0 + 0];
+				} else {
+					int sidx = 0;
+					for (int dz = m->smin[2]; dz <= m->smax[2]; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++, sidx++) {
+						if (sidx == S - 1) continue;
+						const int N0 = V[0] + dx, N1 = V[1] + dy, N2 = V[2] + dz;
+						if (!INGRID(N0, N1, N2, l)) continue;
+						const int n = LIN(N0, N1, N2, l);
+						if (type[n] == vtInactive) continue;
+						if (sidx < S) sum -= A[(size_t)n * S + S - 1 - sidx] * x[n];
+						else          sum -= A[(size_t)v * S + sidx - S + 1] * x[n];
+					}
+					x[v] = sum / A[(size_t)v * S + 0];
+				}
+			}
+		}
+	}
+}
+
+/* knCalcResidual multigrid.cpp:739-771 */
+static void mg_residual(MgState* m, int l)
+{
+	const int* s = m->size[l]; const int S = m->stencil, S0 = m->stencil0;
+	const Real* x = m->x[l]; const Real* A = m->A[l]; const Real* b = m->b[l]; const signed char* type = m->type[l]; Real* r = m->r[l];
+	#pragma omp parallel for schedule(static)
+	for (int idx = 0; idx < m->n[l]; idx++) {
+		if (type[idx] == vtInactive) continue;
+		VEC(idx, l, V)
+		Real sum = b[idx];
+		if (l == 0) {
+			for (int d = 0; d < m->dim; d++) {
+				if (V[d] > 0)        { const int n = idx - m->pitch[0][d]; sum -= A[(size_t)n * S0 + d + 1] * x[n]; }
+				if (V[d] < s[d] - 1) { const int n = idx + m->pitch[0][d]; sum -= A[(size_t)idx * S0 + d + 1] * x[n]; }
+			}
+			sum -= A[(size_t)idx * S0 + 0] * x[idx];
+		} else {
+			int sidx = 0;
+			for (int dz = m->smin[2]; dz <= m->smax[2]; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++, sidx++) {
+				const int N0 = V[0] + dx, N1 = V[1] + dy, N2 = V[2] + dz;
+				if (!INGRID(N0, N1, N2, l)) continue;
+				const int n = LIN(N0, N1, N2, l);
+				if (type[n] == vtInactive) continue;
+				if (sidx < S) sum -= A[(size_t)n * S + S - 1 - sidx] * x[n];
+				else          sum -= A[(size_t)idx * S + sidx - S + 1] * x[n];
+			}
+		}
+		r[idx] = sum;
+	}
+}
+
+/* knRestrict multigrid.cpp:904-927 */
+static void mg_restrict(MgState* m, int ld, const Real* src, Real* dst)
+{
+	const int ls = ld - 1; const int* sf = m->size[ls];
+	#pragma omp parallel for schedule(static)
+	for (int idx = 0; idx < m->n[ld]; idx++) {
+		if (m->type[ld][idx] == vtInactive) continue;
+		VEC(idx, ld, V)
+		Real sum = (Real)0;
+		int r0[3], r1[3];
+		for (int d = 0; d < 3; d++) { r0[d] = V[d] * 2 - 1 > 0 ? V[d] * 2 - 1 : 0; r1[d] = V[d] * 2 + 1 < sf[d] - 1 ? V[d] * 2 + 1 : sf[d] - 1; }
+		for (int rz = r0[2]; rz <= r1[2]; rz++) for (int ry = r0[1]; ry <= r1[1]; ry++) for (int rx = r0[0]; rx <= r1[0]; rx++) {
+			const int r = LIN(rx, ry, rz, ls);
+			if (m->type[ls][r] == vtInactive) continue;
+			const Real rw = (Real)1 / (Real)(1 << ((rx % 2) + (ry % 2) + (rz % 2)));
+			sum += rw * src[r];
+		}
+		dst[idx] = sum;
+	}
+}
+
+/* knInterpolate multigrid.cpp:934-954 */
+static void mg_interpolate(MgState* m, int ld, const Real* src, Real* dst)
+{
+	const int ls = ld + 1;
+	#pragma omp parallel for schedule(static)
+	for (int idx = 0; idx < m->n[ld]; idx++) {
+		if (m->type[ld][idx] == vtInactive) continue;
+		VEC(idx, ld, V)
+		Real sum = (Real)0;
+		for (int iz = V[2] / 2; iz <= (V[2] + 1) / 2; iz++) for (int iy = V[1] / 2; iy <= (V[1] + 1) / 2; iy++) for (int ix = V[0] / 2; ix <= (V[0] + 1) / 2; ix++) {
+			const int i = LIN(ix, iy, iz, ls);
+			if (m->type[ls][i] != vtInactive) sum += src[i];
+		}
+		const Real iw = (Real)1 / (Real)(1 << ((V[0] % 2) + (V[1] % 2) + (V[2] % 2)));
+		dst[idx] = iw * sum;
+	}
+}
+
+/* GridMg::solveCG multigrid.cpp:796-902: serial double-precision Jacobi-PCG on the coarsest level */
+static double mg_apply_stencil(const MgState* m, int v, int l, const double* vec)
+{
+	const int* s = m->size[l]; const int S = m->stencil, S0 = m->stencil0; const Real* A = m->A[l];
+	VEC(v, l, V)
+	double sum = 0;
+	if (l == 0) {
+		for (int d = 0; d < m->dim; d++) {
+			if (V[d] > 0)        { const int n = v - m->pitch[0][d]; sum += A[(size_t)n * S0 + d + 1] * vec[n]; }
+			if (V[d] < s[d] - 1) { const int n = v + m->pitch[0][d]; sum += A[(size_t)v * S0 + d + 1] * vec[n]; }
+		}
+		sum += A[(size_t)v * S0 + 0] * vec[v];
+	} else {
+		int sidx = 0;
+		for (int dz = m->smin[2]; dz <= m->smax[2]; dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++, sidx++) {
+			const int N0 = V[0] + dx, N1 = V[1] + dy, N2 = V[2] + dz;
+			if (!INGRID(N0, N1, N2, l)) continue;
+			const int n = LIN(N0, N1, N2, l);
+			if (m->type[l][n] == vtInactive) continue;
+			if (sidx < S) sum += A[(size_t)n * S + S - 1 - sidx] * vec[n];
+			else          sum += A[(size_t)v * S + sidx - S + 1] * vec[n];
+		}
+	}
+	return sum;
+}
+static void mg_solve_cg(MgState* m, int l)
+{
+	double *z = m->cg1, *p = m->cg2, *x = m->cg3, *r = m->cg4;
+	const int n = m->n[l]; const signed char* type = m->type[l];
+	const int S = (l == 0) ? m->stencil0 : m->stencil; const Real* A = m->A[l];
+	double alphaTop = 0, initialResidual = 0;
+	for (int v = 0; v < n; v++) x[v] = m->x[l][v];
+	for (int v = 0; v < n; v++) {
+		if (type[v] == vtInactive) continue;
+		r[v] = m->b[l][v] - mg_apply_stencil(m, v, l, x);
+		z[v] = r[v] / A[(size_t)v * S + 0];
+		initialResidual += r[v] * r[v];
+		p[v] = z[v];
+		alphaTop += r[v] * z[v];
+	}
+	initialResidual = sqrt(initialResidual);
+	int iter = 0; const int maxIter = 10000; double residual = -1;
+	for (; iter < maxIter && initialResidual > 1E-12; iter++) {
+		double alphaBot = 0;
+		for (int v = 0; v < n; v++) { if (type[v] == vtInactive) continue; z[v] = mg_apply_stencil(m, v, l, p); alphaBot += p[v] * z[v]; }
+		const double alpha = alphaTop / alphaBot;
+		double alphaTopNew = 0; residual = 0;
+		for (int v = 0; v < n; v++) {
+			if (type[v] == vtInactive) continue;
+			x[v] += alpha * p[v];
+			r[v] -= alpha * z[v];
+			residual += r[v] * r[v];
+			z[v] = r[v] / A[(size_t)v * S + 0];
+			alphaTopNew += r[v] * z[v];
+		}
+		residual = sqrt(residual);
+		if (residual / initialResidual < m->coarsestAcc) break;
+		const double beta = alphaTopNew / alphaTop;
+		alphaTop = alphaTopNew;
+		for (int v = 0; v < n; v++) p[v] = z[v] + beta * p[v];
+	}
+	m->lastCoarseIters = iter;
+	for (int v = 0; v < n; v++) m->x[l][v] = (Real)x[v];
+}
+
+/* GridMg::doVCycle multigrid.cpp:448-504 with src == NULL (as the preconditioner calls it) */
+static void mg_vcycle(MgState* m, Real* dst)
+{
+	const int maxLevel = m->nlev - 1;
+	memset(m->x[0], 0, sizeof(Real) * (size_t)m->n[0]);
+	for (int l = 0; l < maxLevel; l++) {
+		for (int i = 0; i < m->numPre; i++) mg_smooth(m, l, 0);
+		mg_residual(m, l);
+		mg_restrict(m, l + 1, m->r[l], m->b[l + 1]);
+		memset(m->x[l + 1], 0, sizeof(Real) * (size_t)m->n[l + 1]);
+	}
+	mg_solve_cg(m, maxLevel);
+	for (int l = maxLevel - 1; l >= 0; l--) {
+		mg_interpolate(m, l, m->x[l + 1], m->r[l]);
+		for (int i = 0; i < m->n[l]; i++) m->x[l][i] += m->r[l][i];
+		for (int i = 0; i < m->numPost; i++) mg_smooth(m, l, 1);
+	}
+	mg_residual(m, 0);                                        /* result (norm) unused by the caller */
+	memcpy(dst, m->x[0], sizeof(Real) * (size_t)m->n[0]);
+}
+
+/* ---- exported GridMg probes (same shape as oracle/ref_harness.cpp) ---- */
+static MgState* g_mg = 0;
+int mfo_mg_create(int sx, int sy, int sz) { mg_destroy(g_mg); g_mg = mg_create(sx, sy, sz); return 0; }
+int mfo_mg_destroy(void) { mg_destroy(g_mg); g_mg = 0; return 0; }
+int mfo_mg_set_a(const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak) { mg_set_a(g_mg, A0, Ai, Aj, Ak); return 0; }
+int mfo_mg_num_levels(void) { return g_mg ? g_mg->nlev : 0; }
+int mfo_mg_level_size(int l, int* out3) { for (int d = 0; d < 3; d++) out3[d] = g_mg->size[l][d]; return 0; }
+int mfo_mg_stencil_size(int l) { return l == 0 ? g_mg->stencil0 : g_mg->stencil; }
+int mfo_mg_get_type(int l, signed char* out) { memcpy(out, g_mg->type[l], (size_t)g_mg->n[l]); return 0; }
+int mfo_mg_get_a(int l, Real* out) { memcpy(out, g_mg->A[l], sizeof(Real) * (size_t)g_mg->n[l] * (l == 0 ? g_mg->stencil0 : g_mg->stencil)); return 0; }
+int mfo_mg_get_x(int l, Real* out) { memcpy(out, g_mg->x[l], sizeof(Real) * (size_t)g_mg->n[l]); return 0; }
+int mfo_mg_get_b(int l, Real* out) { memcpy(out, g_mg->b[l], sizeof(Real) * (size_t)g_mg->n[l]); return 0; }
+int mfo_mg_get_r(int l, Real* out) { memcpy(out, g_mg->r[l], sizeof(Real) * (size_t)g_mg->n[l]); return 0; }
+int mfo_mg_vcycle(const Real* rhs, Real* dst, double coarsestAccuracy, int pre, int post)
+{
+	if (!g_mg || !g_mg->isASet) { snprintf(g_err, sizeof g_err, "GridMg::setRhs Error: A has not been set."); return 1; }
+	g_mg->coarsestAcc = (Real)coarsestAccuracy; g_mg->numPre = pre; g_mg->numPost = post;
+	mg_set_rhs(g_mg, rhs); mg_vcycle(g_mg, dst); return 0;
+}
+
+/* =============================================================================================
+ * GridCg<APPLYMAT>: conjugategrad.cpp:201-307 (doInit :209-235, iterate :237-299)
+ * pc: 0 PC_None, 1 PC_mICP, 2 PC_MGP.  `mg` may carry an already-set hierarchy (PcMGStatic).     */
+static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Real* x,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak,
+	int pc, Real accuracy, int useL2, int maxIter, MgState* mg, int* iterations, double* resNormOut)
+{
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	Real* residual = (Real*)calloc((size_t)n, sizeof(Real));
+	Real* search = (Real*)calloc((size_t)n, sizeof(Real));
+	Real* tmp = (Real*)calloc((size_t)n, sizeof(Real));
+	Real* P = 0;
+	int rc = 0;
+	if (pc == 1 && !IS3D) pc = 0;                              /* setICPreconditioner :315-321 */
+	/* doInit */
+	memset(x, 0, sizeof(Real) * (size_t)n);
+	memcpy(residual, rhs, sizeof(Real) * (size_t)n);
+	if (pc == 1) {
+		P = (Real*)calloc((size_t)n, sizeof(Real));
+		mic_init(sx, sy, sz, flags, P, A0, Ai, Aj, Ak);
+		mic_apply(sx, sy, sz, flags, tmp, residual, P, Ai, Aj, Ak);
+	} else if (pc == 2) {
+		if (!mg->isASet) mg_set_a(mg, A0, Ai, Aj, Ak);         /* InitPreconditionMultigrid :100-106 */
+		mg->coarsestAcc = (Real)(accuracy * 1E-4); mg->numPre = 1; mg->numPost = 1;
+		mg_set_rhs(mg, residual); mg_vcycle(mg, tmp);
+	} else memcpy(tmp, residual, sizeof(Real) * (size_t)n);
+	memcpy(search, tmp, sizeof(Real) * (size_t)n);
+	Real sigma = (Real)dot_product(tmp, residual, n);
+	Real resNorm = (Real)1e20;
+	int its = 0;
+	for (int iter = 0; iter < maxIter; iter++) {
+		its++;
+		apply_matrix(sx, sy, sz, flags, tmp, search, A0, Ai, Aj, Ak);
+		const Real dp = (Real)dot_product(tmp, search, n);
+		Real alpha = 0.;
+		if (R_FABS(dp) > 0.) alpha = sigma / dp;
+		scaled_add(x, search, alpha, n);
+		scaled_add(residual, tmp, -alpha, n);
+		if (pc == 1) mic_apply(sx, sy, sz, flags, tmp, residual, P, Ai, Aj, Ak);
+		else if (pc == 2) { mg_set_rhs(mg, residual); mg_vcycle(mg, tmp); }
+		else memcpy(tmp, residual, sizeof(Real) * (size_t)n);
+		if (useL2) resNorm = (Real)sum_sqr(residual, n); else resNorm = max_abs(residual, n);
+		if (resNorm < accuracy) { sigma = resNorm; break; }
+		const Real sigmaNew = (Real)dot_product(tmp, residual, n);
+		const Real beta = sigmaNew / sigma;
+		#pragma omp parallel for schedule(static)
+		for (IndexInt q = 0; q < n; q++) search[q] = tmp[q] + beta * search[q];   /* UpdateSearchVec :193-196 */
+		sigma = sigmaNew;
+		if (!(resNorm < 1e35)) { snprintf(g_err, sizeof g_err, "GridCg::iterate: The CG solver diverged, residual norm > 1e30, stopping."); rc = 1; break; }
+	}
+	if (iterations) *iterations = its;
+	if (resNormOut) *resNormOut = resNorm;
+	free(residual); free(search); free(tmp); free(P);
+	return rc;
+}
+
+int mfo_cg_solve(int sx, int sy, int sz, const int* flags, const Real* rhs, Real* x,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak,
+	int pc, double accuracy, int useL2, int maxIter, int* iterations, double* resNorm)
+{
+	MgState* mg = (pc == 2) ? mg_create(sx, sy, sz) : 0;
+	const int rc = cg_run(sx, sy, sz, flags, rhs, x, A0, Ai, Aj, Ak, pc, (Real)accuracy, useL2, maxIter, mg, iterations, resNorm);
+	mg_destroy(mg);
+	return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * correctVelocity plugin/pressure.cpp:455-476: knCorrectVelocity :87-109,
+ * knCorrectVelocityGhostFluid :154-187, knReplaceClampedGhostFluidVels :198-214                 */
+int mfo_correct_velocity(int sx, int sy, int sz, const int* flags, Real* vel, const Real* pressure,
+	const Real* phi, const Real* curv, double gfClamp_, double surfTens_)
+{
+	STRIDES
+	const Real gfClamp = (Real)gfClamp_, surfTens = (Real)surfTens_;
+	const int k0 = IS3D ? 1 : 0, k1 = IS3D ? sz - 1 : 1;
+	#pragma omp parallel for schedule(static)
+	for (int k = k0; k < k1; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++) {
+		const IndexInt idx = IDX(i, j, k); Real* v = vel + 3 * idx;
+		if (flags[idx] & TypeFluid) {
+			if (flags[idx - X] & TypeFluid) v[0] -= (pressure[idx] - pressure[idx - X]);
+			if (flags[idx - Y] & TypeFluid) v[1] -= (pressure[idx] - pressure[idx - Y]);
+			if (IS3D && (flags[idx - Z] & TypeFluid)) v[2] -= (pressure[idx] - pressure[idx - Z]);
+			if (flags[idx - X] & TypeEmpty) v[0] -= pressure[idx];
+			if (flags[idx - Y] & TypeEmpty) v[1] -= pressure[idx];
+			if (IS3D && (flags[idx - Z] & TypeEmpty)) v[2] -= pressure[idx];
+		} else if ((flags[idx] & TypeEmpty) && !(flags[idx] & TypeOutflow)) {
+			if (flags[idx - X] & TypeFluid) v[0] += pressure[idx - X]; else v[0] = 0.f;
+			if (flags[idx - Y] & TypeFluid) v[1] += pressure[idx - Y]; else v[1] = 0.f;
+			if (IS3D) { if (flags[idx - Z] & TypeFluid) v[2] += pressure[idx - Z]; else v[2] = 0.f; }
+		}
+	}
+	if (!phi) return 0;
+	#pragma omp parallel for schedule(static)
+	for (int k = k0; k < k1; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++) {
+		const IndexInt idx = IDX(i, j, k); Real* v = vel + 3 * idx;
+		const int fl = flags[idx] & TypeFluid, em = (flags[idx] & TypeEmpty) && !(flags[idx] & TypeOutflow);
+		if (fl) {
+			if (flags[idx - X] & TypeEmpty) v[0] += pressure[idx] * ghostFluidHelper(idx, -X, phi, gfClamp);
+			if (flags[idx - Y] & TypeEmpty) v[1] += pressure[idx] * ghostFluidHelper(idx, -Y, phi, gfClamp);
+			if (IS3D && (flags[idx - Z] & TypeEmpty)) v[2] += pressure[idx] * ghostFluidHelper(idx, -Z, phi, gfClamp);
+		} else if (em) {
+			if (flags[idx - X] & TypeFluid) v[0] -= pressure[idx - X] * ghostFluidHelper(idx - X, +X, phi, gfClamp); else v[0] = 0.f;
+			if (flags[idx - Y] & TypeFluid) v[1] -= pressure[idx - Y] * ghostFluidHelper(idx - Y, +Y, phi, gfClamp); else v[1] = 0.f;
+			if (IS3D) { if (flags[idx - Z] & TypeFluid) v[2] -= pressure[idx - Z] * ghostFluidHelper(idx - Z, +Z, phi, gfClamp); else v[2] = 0.f; }
+		}
+		if (curv) {
+			if (fl) {
+				if (flags[idx - X] & TypeEmpty) v[0] += surfTensHelper(idx, -X, phi, curv, surfTens, gfClamp);
+				if (flags[idx - Y] & TypeEmpty) v[1] += surfTensHelper(idx, -Y, phi, curv, surfTens, gfClamp);
+				if (IS3D && (flags[idx - Z] & TypeEmpty)) v[2] += surfTensHelper(idx, -Z, phi, curv, surfTens, gfClamp);
+			} else if (em) {
+				v[0] -= (flags[idx - X] & TypeFluid) ? surfTensHelper(idx - X, +X, phi, curv, surfTens, gfClamp) : 0.f;
+				v[1] -= (flags[idx - Y] & TypeFluid) ? surfTensHelper(idx - Y, +Y, phi, curv, surfTens, gfClamp) : 0.f;
+				if (IS3D) v[2] -= (flags[idx - Z] & TypeFluid) ? surfTensHelper(idx - Z, +Z, phi, curv, surfTens, gfClamp) : 0.f;
+			}
+		}
+	}
+	/* knReplaceClampedGhostFluidVels: reads neighbours' *updated* velocity; an empty cell only
+	   reads components of fluid cells, which this kernel never writes, so the order is immaterial */
+	#pragma omp parallel for schedule(static)
+	for (int k = k0; k < k1; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++) {
+		const IndexInt idx = IDX(i, j, k); Real* v = vel + 3 * idx;
+		if (!(flags[idx] & TypeEmpty)) continue;
+		if ((flags[idx - X] & TypeFluid) && ghostFluidWasClamped(idx - X, +X, phi, gfClamp)) v[0] = vel[3 * (idx - X) + 0];
+		if ((flags[idx - Y] & TypeFluid) && ghostFluidWasClamped(idx - Y, +Y, phi, gfClamp)) v[1] = vel[3 * (idx - Y) + 1];
+		if (IS3D && (flags[idx - Z] & TypeFluid) && ghostFluidWasClamped(idx - Z, +Z, phi, gfClamp)) v[2] = vel[3 * (idx - Z) + 2];
+		if ((flags[idx + X] & TypeFluid) && ghostFluidWasClamped(idx + X, -X, phi, gfClamp)) v[0] = vel[3 * (idx + X) + 0];
+		if ((flags[idx + Y] & TypeFluid) && ghostFluidWasClamped(idx + Y, -Y, phi, gfClamp)) v[1] = vel[3 * (idx + Y) + 1];
+		if (IS3D && (flags[idx + Z] & TypeFluid) && ghostFluidWasClamped(idx + Z, -Z, phi, gfClamp)) v[2] = vel[3 * (idx + Z) + 2];
+	}
+	return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * solvePressure plugin/pressure.cpp:480-521 = computePressureRhs + solvePressureSystem (:312-452)
+ * + correctVelocity.  `solver_key` != 0 keeps the PcMGStatic hierarchy across calls like gMapMG. */
+#define MAXKEYS 16
+static long long g_keys[MAXKEYS]; static MgState* g_static_mg[MAXKEYS];
+static MgState** static_slot(long long key)
+{
+	for (int i = 0; i < MAXKEYS; i++) if (g_keys[i] == key) return &g_static_mg[i];
+	for (int i = 0; i < MAXKEYS; i++) if (g_keys[i] == 0) { g_keys[i] = key; return &g_static_mg[i]; }
+	return 0;
+}
+int mfo_release_solver(long long key)
+{
+	for (int i = 0; i < MAXKEYS; i++) if (g_keys[i] == key) { mg_destroy(g_static_mg[i]); g_static_mg[i] = 0; g_keys[i] = 0; }
+	return 0;
+}
+
+int mfo_solve_pressure(long long solver_key, int sx, int sy, int sz, const int* flags, Real* vel, Real* pressure,
+	const Real* phi, const Real* perCellCorr, const Real* fractions, const Real* obvel, const Real* curv, Real* retRhs,
+	double cgAccuracy, double gfClamp, double cgMaxIterFac, int precondition, int preconditioner,
+	int enforceCompatibility, int useL2Norm, int zeroPressureFixing, double surfTens,
+	int* iterations, double* resNorm)
+{
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	Real* rhs = (Real*)calloc((size_t)n, sizeof(Real));
+	Real *A0 = (Real*)calloc((size_t)n, sizeof(Real)), *Ai = (Real*)calloc((size_t)n, sizeof(Real)), *Aj = (Real*)calloc((size_t)n, sizeof(Real)), *Ak = (Real*)calloc((size_t)n, sizeof(Real));
+	mfo_compute_rhs(sx, sy, sz, flags, vel, rhs, phi, perCellCorr, fractions, obvel, curv, gfClamp, surfTens, enforceCompatibility, 0, 0);
+	if (!precondition) preconditioner = 0;
+	mfo_make_matrix(sx, sy, sz, flags, fractions, phi, gfClamp, A0, Ai, Aj, Ak);
+	if (zeroPressureFixing || (Real)cgAccuracy < 1e-07) {
+		const long long fix = mfo_choose_fix_cell(sx, sy, sz, flags);
+		if (fix >= 0) mfo_fix_pressure(sx, sy, sz, fix, 0., rhs, A0, Ai, Aj, Ak);
+	}
+	int maxIter, pc, rc;
+	const int maxDim = sx > sy ? (sx > sz ? sx : sz) : (sy > sz ? sy : sz);
+	MgState* mg = 0; MgState** slot = 0;
+	if (preconditioner == 0 || preconditioner == 1) {
+		/* the reference asserts on PcNone here; the oracle (like the GPU build) runs plain CG */
+		maxIter = (int)((Real)cgMaxIterFac * maxDim) * (IS3D ? 1 : 4);
+		pc = preconditioner;
+	} else if (preconditioner == 2 || preconditioner == 3) {
+		maxIter = 100; pc = 2;
+		if (solver_key) { slot = static_slot(solver_key); mg = slot ? *slot : 0; }
+		if (mg && preconditioner == 2) { mg_destroy(mg); mg = 0; *slot = 0; }
+		if (!mg) { mg = mg_create(sx, sy, sz); if (slot) *slot = mg; }
+	} else { snprintf(g_err, sizeof g_err, "invalid preconditioner"); free(rhs); free(A0); free(Ai); free(Aj); free(Ak); return 1; }
+	rc = cg_run(sx, sy, sz, flags, rhs, pressure, A0, Ai, Aj, Ak, pc, (Real)cgAccuracy, useL2Norm, maxIter, mg, iterations, resNorm);
+	if (mg && (preconditioner == 2 || !slot)) { mg_destroy(mg); if (slot) *slot = 0; }
+	if (rc == 0) mfo_correct_velocity(sx, sy, sz, flags, vel, pressure, phi, curv, gfClamp, surfTens);
+	if (retRhs) memcpy(retRhs, rhs, sizeof(Real) * (size_t)n);
+	free(rhs); free(A0); free(Ai); free(Aj); free(Ak);
+	return rc;
+}

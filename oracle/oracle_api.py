@@ -1,0 +1,188 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes driver shared by the two CPU oracles.
+
+* ``Oracle("port", prec)``      -> oracle/libmf_oracle_f{32,64}.so  (plain-C restatement, mf_oracle.c)
+* ``Oracle("reference", prec)`` -> oracle/_ref/libmanta_ref_f{32,64}.so (the UNMODIFIED reference
+  compiled from /root/reference by oracle/Makefile, C entry points in ref_harness.cpp)
+
+Both export the same functions with prefix ``mfo_`` / ``ref_``.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / ``--impl reference`` legs may import this module; the product package
+(mantaflow_b200/) never does.
+
+Arrays follow the reference layout (grid.h:70): numpy shape [Z, Y, X] (C order) for Real/flag grids,
+[Z, Y, X, 3] for MAC grids -- the same convention as the reference's numpy bridge
+(plugin/numpyconvert.cpp:145-183).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path(kind, prec):
+    tag = "f32" if prec == 4 else "f64"
+    if kind == "port":
+        return os.path.join(_HERE, "libmf_oracle_%s.so" % tag)
+    return os.path.join(_HERE, "_ref", "libmanta_ref_%s.so" % tag)
+
+
+def available(kind, prec=4):
+    return os.path.exists(lib_path(kind, prec))
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    def __init__(self, kind="port", prec=4):
+        assert kind in ("port", "reference") and prec in (4, 8)
+        self.kind, self.prec = kind, prec
+        self.real = np.float32 if prec == 4 else np.float64
+        self.pfx = "mfo_" if kind == "port" else "ref_"
+        path = lib_path(kind, prec)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle`)")
+        self.lib = C.CDLL(path)
+        assert self._f("real_size", C.c_int)() == prec
+        self._f("set_debug_level")(C.c_int(0))   # the reference chats on stdout at level 1
+
+    def _f(self, name, restype=C.c_int):
+        f = getattr(self.lib, self.pfx + name)
+        f.restype = restype
+        return f
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise OracleError(self._f("last_error", C.c_char_p)().decode())
+
+    def _r(self, a, shape=None):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=self.real)
+        return a
+
+    @staticmethod
+    def dims(flags):
+        sz, sy, sx = flags.shape
+        return C.c_int(sx), C.c_int(sy), C.c_int(sz)
+
+    # -- plugin/extforces.cpp:307 setWallBcs (no obvel / fractions) --
+    def set_wall_bcs(self, flags, vel):
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        self._chk(self._f("set_wall_bcs")(*self.dims(flags), _p(flags), _p(vel)))
+        return vel
+
+    def compute_rhs(self, flags, vel, phi=None, perCellCorr=None, fractions=None, obvel=None, curv=None,
+                    gfClamp=1e-4, surfTens=0.0, enforceCompatibility=False):
+        vel, phi, perCellCorr, fractions, obvel, curv = map(self._r, (vel, phi, perCellCorr, fractions, obvel, curv))
+        rhs = np.zeros(flags.shape, self.real)
+        s, c = C.c_double(0), C.c_int(0)
+        self._chk(self._f("compute_rhs")(*self.dims(flags), _p(flags), _p(vel), _p(rhs), _p(phi), _p(perCellCorr),
+                                         _p(fractions), _p(obvel), _p(curv), C.c_double(gfClamp), C.c_double(surfTens),
+                                         C.c_int(int(enforceCompatibility)), C.byref(s), C.byref(c)))
+        return rhs, s.value, c.value
+
+    def make_matrix(self, flags, fractions=None, phi=None, gfClamp=1e-4):
+        fractions, phi = self._r(fractions), self._r(phi)
+        A = [np.zeros(flags.shape, self.real) for _ in range(4)]
+        self._chk(self._f("make_matrix")(*self.dims(flags), _p(flags), _p(fractions), _p(phi), C.c_double(gfClamp),
+                                         *[_p(a) for a in A]))
+        return A
+
+    def choose_fix_cell(self, flags):
+        assert self.kind == "port", "cell choice is only exposed by the restatement"
+        return self._f("choose_fix_cell", C.c_longlong)(*self.dims(flags), _p(flags))
+
+    def fix_pressure(self, flags, idx, value, rhs, A0, Ai, Aj, Ak):
+        self._chk(self._f("fix_pressure")(*self.dims(flags), C.c_longlong(idx), C.c_double(value), _p(rhs), _p(A0), _p(Ai), _p(Aj), _p(Ak)))
+
+    def apply_matrix(self, flags, src, A0, Ai, Aj, Ak):
+        dst = np.zeros(flags.shape, self.real)
+        self._chk(self._f("apply_matrix")(*self.dims(flags), _p(flags), _p(dst), _p(self._r(src)), _p(A0), _p(Ai), _p(Aj), _p(Ak)))
+        return dst
+
+    def mic_init(self, flags, A0, Ai, Aj, Ak):
+        P = np.zeros(flags.shape, self.real)
+        self._chk(self._f("mic_init")(*self.dims(flags), _p(flags), _p(P), _p(A0), _p(Ai), _p(Aj), _p(Ak)))
+        return P
+
+    def mic_apply(self, flags, src, P, A0, Ai, Aj, Ak, dst=None):
+        dst = np.zeros(flags.shape, self.real) if dst is None else dst
+        self._chk(self._f("mic_apply")(*self.dims(flags), _p(flags), _p(dst), _p(self._r(src)), _p(P), _p(A0), _p(Ai), _p(Aj), _p(Ak)))
+        return dst
+
+    def cg_solve(self, flags, rhs, A0, Ai, Aj, Ak, pc=0, accuracy=1e-4, useL2=False, maxIter=1000):
+        x = np.zeros(flags.shape, self.real)
+        it, rn = C.c_int(0), C.c_double(0)
+        self._chk(self._f("cg_solve")(*self.dims(flags), _p(flags), _p(self._r(rhs)), _p(x), _p(A0), _p(Ai), _p(Aj), _p(Ak),
+                                      C.c_int(pc), C.c_double(accuracy), C.c_int(int(useL2)), C.c_int(maxIter),
+                                      C.byref(it), C.byref(rn)))
+        return x, it.value, rn.value
+
+    def correct_velocity(self, flags, vel, pressure, phi=None, curv=None, gfClamp=1e-4, surfTens=0.0):
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        self._chk(self._f("correct_velocity")(*self.dims(flags), _p(flags), _p(vel), _p(self._r(pressure)), _p(self._r(phi)),
+                                              _p(self._r(curv)), C.c_double(gfClamp), C.c_double(surfTens)))
+        return vel
+
+    def solve_pressure(self, flags, vel, pressure=None, phi=None, perCellCorr=None, fractions=None, obvel=None, curv=None,
+                       cgAccuracy=1e-3, gfClamp=1e-4, cgMaxIterFac=1.5, precondition=True, preconditioner=1,
+                       enforceCompatibility=False, useL2Norm=False, zeroPressureFixing=False, surfTens=0.0,
+                       retRhs=False, solver_key=0):
+        """plugin/pressure.cpp:480-521; vel is updated in place; returns (pressure, iterations, resNorm[, rhs])"""
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        if pressure is None:
+            pressure = np.zeros(flags.shape, self.real)
+        rr = np.zeros(flags.shape, self.real) if retRhs else None
+        it, rn = C.c_int(-1), C.c_double(-1)
+        self._chk(self._f("solve_pressure")(C.c_longlong(solver_key), *self.dims(flags), _p(flags), _p(vel), _p(pressure),
+                                            _p(self._r(phi)), _p(self._r(perCellCorr)), _p(self._r(fractions)), _p(self._r(obvel)),
+                                            _p(self._r(curv)), _p(rr), C.c_double(cgAccuracy), C.c_double(gfClamp),
+                                            C.c_double(cgMaxIterFac), C.c_int(int(precondition)), C.c_int(preconditioner),
+                                            C.c_int(int(enforceCompatibility)), C.c_int(int(useL2Norm)),
+                                            C.c_int(int(zeroPressureFixing)), C.c_double(surfTens), C.byref(it), C.byref(rn)))
+        out = (pressure, it.value, rn.value)
+        return out + (rr,) if retRhs else out
+
+    def release_solver(self, key):
+        self._chk(self._f("release_solver")(C.c_longlong(key)))
+
+    # -- GridMg probes --
+    def mg_create(self, sx, sy, sz):
+        self._chk(self._f("mg_create")(C.c_int(sx), C.c_int(sy), C.c_int(sz)))
+
+    def mg_destroy(self):
+        self._f("mg_destroy")()
+
+    def mg_set_a(self, A0, Ai, Aj, Ak):
+        self._chk(self._f("mg_set_a")(_p(A0), _p(Ai), _p(Aj), _p(Ak)))
+
+    def mg_num_levels(self):
+        return self._f("mg_num_levels")()
+
+    def mg_level_size(self, l):
+        o = (C.c_int * 3)()
+        self._f("mg_level_size")(C.c_int(l), o)
+        return tuple(o)
+
+    def mg_get(self, what, l):
+        sx, sy, sz = self.mg_level_size(l)
+        n = sx * sy * sz
+        if what == "type":
+            out = np.zeros(n, np.int8)
+        elif what == "a":
+            out = np.zeros(n * self._f("mg_stencil_size")(C.c_int(l)), self.real)
+        else:
+            out = np.zeros(n, self.real)
+        self._f("mg_get_" + what)(C.c_int(l), _p(out))
+        return out
+
+    def mg_vcycle(self, rhs, coarsestAccuracy=1e-8, pre=1, post=1):
+        dst = np.zeros(rhs.shape, self.real)
+        self._chk(self._f("mg_vcycle")(_p(self._r(rhs)), _p(dst), C.c_double(coarsestAccuracy), C.c_int(pre), C.c_int(post)))
+        return dst

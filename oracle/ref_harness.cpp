@@ -1,0 +1,291 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product path.
+//
+// C entry points over the UNMODIFIED reference implementation (thunil/mantaflow, built
+// -DNOPYTHON from /root/reference by oracle/Makefile into oracle/_ref/).  The functions
+// here wrap caller-owned arrays in the reference's own Grid<T> objects (external-data
+// constructors, grid.cpp:62-72) and call the reference's own kernels / plugins:
+//   computePressureRhs      plugin/pressure.cpp:277-299
+//   MakeLaplaceMatrix       conjugategrad.h:154-187
+//   ApplyGhostFluidDiagonal plugin/pressure.cpp:136-151
+//   fixPressure             plugin/pressure.cpp:226-245
+//   GridCg<ApplyMatrix[2D]> conjugategrad.cpp:201-339
+//   GridMg                  multigrid.cpp
+//   correctVelocity         plugin/pressure.cpp:455-476
+//   solvePressure           plugin/pressure.cpp:480-521
+//   setWallBcs              plugin/extforces.cpp:307-316
+// Nothing of the reference is copied: its sources are compiled where they lie.
+//
+// The signatures are shared with oracle/mf_oracle.c (the restatement) so the same
+// python driver (tests/refapi.py) can run either.
+#include <vector>
+#include <string>
+#include <map>
+#include <sstream>
+#include <iostream>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include <algorithm>
+
+#define private public      // dump GridMg internals (levels, types, operators) for parity tests
+#include "multigrid.h"
+#undef private
+
+// pull in the preprocessed plugin so file-local kernels (ApplyGhostFluidDiagonal,
+// CountEmptyCells, MakeRhs, fixPressure, gMapMG ...) are visible to the harness
+#include "plugin/pressure.cpp"
+#include "commonkernels.h"
+#include "levelset.h"
+
+namespace Manta {
+// --- link stubs for I/O entry points referenced by grid.cpp but irrelevant here ---
+template<class T> int writeGridUni  (const std::string&, Grid<T>*) { return 0; }
+template<class T> int writeGridVol  (const std::string&, Grid<T>*) { return 0; }
+template<class T> int writeGridTxt  (const std::string&, Grid<T>*) { return 0; }
+template<class T> int writeGridRaw  (const std::string&, Grid<T>*) { return 0; }
+template<class T> int writeGridNumpy(const std::string&, Grid<T>*) { return 0; }
+template<class T> int readGridUni   (const std::string&, Grid<T>*) { return 0; }
+template<class T> int readGridVol   (const std::string&, Grid<T>*) { return 0; }
+template<class T> int readGridRaw   (const std::string&, Grid<T>*) { return 0; }
+template<class T> int readGridNumpy (const std::string&, Grid<T>*) { return 0; }
+#define INST(T) \
+ template int writeGridUni<T>(const std::string&, Grid<T>*);  template int writeGridVol<T>(const std::string&, Grid<T>*); \
+ template int writeGridTxt<T>(const std::string&, Grid<T>*);  template int writeGridRaw<T>(const std::string&, Grid<T>*); \
+ template int writeGridNumpy<T>(const std::string&, Grid<T>*); template int readGridUni<T>(const std::string&, Grid<T>*); \
+ template int readGridVol<T>(const std::string&, Grid<T>*);   template int readGridRaw<T>(const std::string&, Grid<T>*); \
+ template int readGridNumpy<T>(const std::string&, Grid<T>*);
+INST(int) INST(Real) INST(Vec3)
+int writeObjectsVDB(const std::string&, std::vector<PbClass*>*, float, bool, int, bool) { return 0; }
+int readObjectsVDB (const std::string&, std::vector<PbClass*>*, float) { return 0; }
+Real LevelsetGrid::invalidTimeValue() { return -1000; }   // levelset.cpp:103 -> fastmarch.h:134
+void setWallBcs(const FlagGrid& flags, MACGrid& vel, const MACGrid* obvel, const MACGrid* fractions, const Grid<Real>* phiObs, int boundaryWidth);
+void InitPreconditionModifiedIncompCholesky2(const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
+void ApplyPreconditionModifiedIncompCholesky2(Grid<Real>& dst, Grid<Real>& Var1, const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
+}
+
+using namespace Manta;
+
+static std::string gLastError;
+static thread_local std::stringstream gLog;
+
+struct CoutCapture {   // the reference reports iteration counts only through debMsg (pressure.cpp:440)
+	std::streambuf* old; std::stringstream ss;
+	CoutCapture() { old = std::cout.rdbuf(ss.rdbuf()); }
+	~CoutCapture() { std::cout.rdbuf(old); }
+};
+
+static FluidSolver* mkSolver(int sx, int sy, int sz) {
+	return new FluidSolver(Vec3i(sx, sy, sz), sz > 1 ? 3 : 2);
+}
+
+#define TRY try {
+#define CATCH } catch (std::exception& e) { gLastError = e.what(); return 1; } return 0;
+
+extern "C" {
+
+const char* ref_last_error() { return gLastError.c_str(); }
+int ref_real_size() { return (int)sizeof(Real); }
+int ref_is_reference() { return 1; }
+int ref_set_debug_level(int l) { gDebugLevel = l; return 0; }
+
+int ref_set_wall_bcs(int sx, int sy, int sz, const int* flags, Real* vel)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
+	  setWallBcs(F, V, 0, 0, 0, 0); }
+	delete s;
+  CATCH }
+
+int ref_compute_rhs(int sx, int sy, int sz, const int* flags, const Real* vel, Real* rhs,
+	const Real* phi, const Real* perCellCorr, const Real* fractions, const Real* obvel, const Real* curv,
+	double gfClamp, double surfTens, int enforceCompatibility, double* sum, int* cnt)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel); Grid<Real> R(s, rhs);
+	  Grid<Real>* P = phi ? new Grid<Real>(s, (Real*)phi) : 0;
+	  Grid<Real>* C = perCellCorr ? new Grid<Real>(s, (Real*)perCellCorr) : 0;
+	  MACGrid* Fr = fractions ? new MACGrid(s, (Vec3*)fractions) : 0;
+	  MACGrid* Ov = obvel ? new MACGrid(s, (Vec3*)obvel) : 0;
+	  Grid<Real>* Cu = curv ? new Grid<Real>(s, (Real*)curv) : 0;
+	  MakeRhs k(F, R, V, C, Fr, Ov, P, Cu, (Real)surfTens, (Real)gfClamp);
+	  if (enforceCompatibility) R += (Real)(-k.sum / (Real)k.cnt);
+	  if (sum) *sum = k.sum; if (cnt) *cnt = k.cnt;
+	  delete P; delete C; delete Fr; delete Ov; delete Cu; }
+	delete s;
+  CATCH }
+
+// MakeLaplaceMatrix (+ ApplyGhostFluidDiagonal when phi != NULL); A* must be zero-filled by the caller
+int ref_make_matrix(int sx, int sy, int sz, const int* flags, const Real* fractions, const Real* phi, double gfClamp,
+	Real* A0, Real* Ai, Real* Aj, Real* Ak)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); Grid<Real> a0(s, A0), ai(s, Ai), aj(s, Aj), ak(s, Ak);
+	  MACGrid* Fr = fractions ? new MACGrid(s, (Vec3*)fractions) : 0;
+	  MakeLaplaceMatrix(F, a0, ai, aj, ak, Fr);
+	  if (phi) { Grid<Real> P(s, (Real*)phi); ApplyGhostFluidDiagonal(a0, F, P, (Real)gfClamp); }
+	  delete Fr; }
+	delete s;
+  CATCH }
+
+int ref_fix_pressure(int sx, int sy, int sz, long long idx, double value, Real* rhs, Real* A0, Real* Ai, Real* Aj, Real* Ak)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ Grid<Real> r(s, rhs), a0(s, A0), ai(s, Ai), aj(s, Aj), ak(s, Ak);
+	  fixPressure((int)idx, (Real)value, r, a0, ai, aj, ak); }
+	delete s;
+  CATCH }
+
+int ref_apply_matrix(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); Grid<Real> d(s, dst), sr(s, (Real*)src), a0(s, (Real*)A0), ai(s, (Real*)Ai), aj(s, (Real*)Aj), ak(s, (Real*)Ak);
+	  if (sz > 1) ApplyMatrix(F, d, sr, a0, ai, aj, ak); else ApplyMatrix2D(F, d, sr, a0, ai, aj, ak); }
+	delete s;
+  CATCH }
+
+int ref_mic_init(int sx, int sy, int sz, const int* flags, Real* precond, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); Grid<Real> p(s, precond), a0(s, (Real*)A0), ai(s, (Real*)Ai), aj(s, (Real*)Aj), ak(s, (Real*)Ak);
+	  InitPreconditionModifiedIncompCholesky2(F, p, a0, ai, aj, ak); }
+	delete s;
+  CATCH }
+
+int ref_mic_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src, const Real* precond,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); Grid<Real> d(s, dst), sr(s, (Real*)src), p(s, (Real*)precond), a0(s, (Real*)A0), ai(s, (Real*)Ai), aj(s, (Real*)Aj), ak(s, (Real*)Ak);
+	  ApplyPreconditionModifiedIncompCholesky2(d, sr, F, p, a0, ai, aj, ak); }
+	delete s;
+  CATCH }
+
+// GridCg driven directly (the only unpatched route to PcNone in 3-D).
+// pc: 0 none, 1 mICP, 2 MG (fresh GridMg).  x is overwritten; returns iterations / resNorm.
+int ref_cg_solve(int sx, int sy, int sz, const int* flags, const Real* rhs, Real* x,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak,
+	int pc, double accuracy, int useL2, int maxIter, int* iterations, double* resNorm)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags);
+	  Grid<Real> X(s, x), B(s, (Real*)rhs), a0(s, (Real*)A0), ai(s, (Real*)Ai), aj(s, (Real*)Aj), ak(s, (Real*)Ak);
+	  Grid<Real> residual(s), search(s), tmp(s);
+	  GridCgInterface* gcg;
+	  if (sz > 1) gcg = new GridCg<ApplyMatrix>(X, B, residual, search, F, tmp, &a0, &ai, &aj, &ak);
+	  else        gcg = new GridCg<ApplyMatrix2D>(X, B, residual, search, F, tmp, &a0, &ai, &aj, &ak);
+	  gcg->setAccuracy((Real)accuracy);
+	  gcg->setUseL2Norm(useL2 != 0);
+	  Grid<Real>* pca0 = 0, *pca1 = 0, *pca2 = 0, *pca3 = 0; GridMg* mg = 0;
+	  if (pc == 1) {
+		pca0 = new Grid<Real>(s); pca1 = new Grid<Real>(s); pca2 = new Grid<Real>(s); pca3 = new Grid<Real>(s);
+		gcg->setICPreconditioner(GridCgInterface::PC_mICP, pca0, pca1, pca2, pca3);
+	  } else if (pc == 2) {
+		mg = new GridMg(Vec3i(sx, sy, sz));
+		gcg->setMGPreconditioner(GridCgInterface::PC_MGP, mg);
+	  }
+	  try {
+		for (int iter = 0; iter < maxIter; iter++) if (!gcg->iterate()) iter = maxIter;
+	  } catch (...) { delete gcg; delete pca0; delete pca1; delete pca2; delete pca3; delete mg; throw; }
+	  if (iterations) *iterations = (int)gcg->getIterations();
+	  if (resNorm) *resNorm = gcg->getResNorm();
+	  delete gcg; delete pca0; delete pca1; delete pca2; delete pca3; delete mg; }
+	delete s;
+  CATCH }
+
+int ref_correct_velocity(int sx, int sy, int sz, const int* flags, Real* vel, const Real* pressure,
+	const Real* phi, const Real* curv, double gfClamp, double surfTens)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel); Grid<Real> P(s, (Real*)pressure);
+	  Grid<Real>* Ph = phi ? new Grid<Real>(s, (Real*)phi) : 0;
+	  Grid<Real>* Cu = curv ? new Grid<Real>(s, (Real*)curv) : 0;
+	  correctVelocity(V, P, F, 1e-3, Ph, 0, 0, (Real)gfClamp, 1.5, true, PcMIC, false, false, false, Cu, (Real)surfTens);
+	  delete Ph; delete Cu; }
+	delete s;
+  CATCH }
+
+// the reference plugin itself; `solver_key` lets PcMGStatic reuse its hierarchy across calls
+// (gMapMG is keyed by FluidSolver*, pressure.cpp:250): pass the same key for the same scene.
+static std::map<long long, FluidSolver*> gSolvers;
+
+int ref_release_solver(long long key)
+{ TRY
+	auto it = gSolvers.find(key);
+	if (it != gSolvers.end()) { releaseMG(it->second); delete it->second; gSolvers.erase(it); }
+  CATCH }
+
+int ref_solve_pressure(long long solver_key, int sx, int sy, int sz, const int* flags, Real* vel, Real* pressure,
+	const Real* phi, const Real* perCellCorr, const Real* fractions, const Real* obvel, const Real* curv, Real* retRhs,
+	double cgAccuracy, double gfClamp, double cgMaxIterFac, int precondition, int preconditioner,
+	int enforceCompatibility, int useL2Norm, int zeroPressureFixing, double surfTens,
+	int* iterations, double* resNorm)
+{ TRY
+	FluidSolver* s;
+	if (solver_key) { auto it = gSolvers.find(solver_key); if (it == gSolvers.end()) { s = mkSolver(sx, sy, sz); gSolvers[solver_key] = s; } else s = it->second; }
+	else s = mkSolver(sx, sy, sz);
+	std::string log;
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel); Grid<Real> P(s, pressure);
+	  Grid<Real>* Ph = phi ? new Grid<Real>(s, (Real*)phi) : 0;
+	  Grid<Real>* C = perCellCorr ? new Grid<Real>(s, (Real*)perCellCorr) : 0;
+	  MACGrid* Fr = fractions ? new MACGrid(s, (Vec3*)fractions) : 0;
+	  MACGrid* Ov = obvel ? new MACGrid(s, (Vec3*)obvel) : 0;
+	  Grid<Real>* Cu = curv ? new Grid<Real>(s, (Real*)curv) : 0;
+	  Grid<Real>* RR = retRhs ? new Grid<Real>(s, retRhs) : 0;
+	  int oldLevel = gDebugLevel; gDebugLevel = 2;
+	  try {
+		CoutCapture cap;
+		try {
+			solvePressure(V, P, F, (Real)cgAccuracy, Ph, C, Fr, Ov, (Real)gfClamp, (Real)cgMaxIterFac, precondition != 0, preconditioner,
+				enforceCompatibility != 0, useL2Norm != 0, zeroPressureFixing != 0, Cu, (Real)surfTens, RR);
+		} catch (...) { log = cap.ss.str(); throw; }
+		log = cap.ss.str();
+	  } catch (...) { gDebugLevel = oldLevel; delete Ph; delete C; delete Fr; delete Ov; delete Cu; delete RR; if (!solver_key) { releaseMG(s); } throw; }
+	  gDebugLevel = oldLevel;
+	  delete Ph; delete C; delete Fr; delete Ov; delete Cu; delete RR; }
+	// parse "FluidSolver::solvePressure done. Iterations:<n>, residual:<r>"  (pressure.cpp:440)
+	size_t p = log.rfind("Iterations:");
+	if (p != std::string::npos) {
+		int it = 0; double rn = 0;
+		sscanf(log.c_str() + p, "Iterations:%d, residual:%lf", &it, &rn);
+		if (iterations) *iterations = it; if (resNorm) *resNorm = rn;
+	}
+	if (!solver_key) { releaseMG(s); delete s; }
+  CATCH }
+
+// ---------------- GridMg probes (hierarchy + V-cycle) ----------------
+static GridMg* gMg = 0; static FluidSolver* gMgSolver = 0;
+
+int ref_mg_create(int sx, int sy, int sz)
+{ TRY
+	delete gMg; delete gMgSolver;
+	gMgSolver = mkSolver(sx, sy, sz);
+	gMg = new GridMg(Vec3i(sx, sy, sz));
+  CATCH }
+int ref_mg_destroy() { delete gMg; gMg = 0; delete gMgSolver; gMgSolver = 0; return 0; }
+int ref_mg_set_a(const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ TRY
+	FluidSolver* s = gMgSolver;
+	Grid<Real> a0(s, (Real*)A0), ai(s, (Real*)Ai), aj(s, (Real*)Aj), ak(s, (Real*)Ak);
+	gMg->setA(&a0, &ai, &aj, &ak);
+  CATCH }
+int ref_mg_num_levels() { return gMg ? (int)gMg->mA.size() : 0; }
+int ref_mg_level_size(int l, int* out3) { out3[0] = gMg->mSize[l].x; out3[1] = gMg->mSize[l].y; out3[2] = gMg->mSize[l].z; return 0; }
+int ref_mg_stencil_size(int l) { return l == 0 ? gMg->mStencilSize0 : gMg->mStencilSize; }
+int ref_mg_get_type(int l, signed char* out) { for (size_t i = 0; i < gMg->mType[l].size(); i++) out[i] = (signed char)gMg->mType[l][i]; return 0; }
+int ref_mg_get_a(int l, Real* out) { memcpy(out, gMg->mA[l].data(), gMg->mA[l].size() * sizeof(Real)); return 0; }
+int ref_mg_get_x(int l, Real* out) { memcpy(out, gMg->mx[l].data(), gMg->mx[l].size() * sizeof(Real)); return 0; }
+int ref_mg_get_b(int l, Real* out) { memcpy(out, gMg->mb[l].data(), gMg->mb[l].size() * sizeof(Real)); return 0; }
+int ref_mg_get_r(int l, Real* out) { memcpy(out, gMg->mr[l].data(), gMg->mr[l].size() * sizeof(Real)); return 0; }
+// one V-cycle as the preconditioner applies it (conjugategrad.cpp:100-106, :162-167)
+int ref_mg_vcycle(const Real* rhs, Real* dst, double coarsestAccuracy, int pre, int post)
+{ TRY
+	FluidSolver* s = gMgSolver;
+	Grid<Real> b(s, (Real*)rhs), d(s, dst);
+	gMg->setCoarsestLevelAccuracy((Real)coarsestAccuracy);
+	gMg->setSmoothing(pre, post);
+	gMg->setRhs(b);
+	gMg->doVCycle(d);
+  CATCH }
+
+} // extern "C"

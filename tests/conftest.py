@@ -1,0 +1,53 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def _build_once():
+    # the C restatement is cheap to build; the CUDA library and oracle/_ref are built by __graft_entry__.build()
+    import subprocess
+    orc = os.path.join(ROOT, "oracle")
+    if not os.path.exists(os.path.join(orc, "libmf_oracle_f32.so")) or \
+            os.path.getmtime(os.path.join(orc, "libmf_oracle_f32.so")) < os.path.getmtime(os.path.join(orc, "mf_oracle.c")):
+        subprocess.check_call(["make", "-C", orc, "oracle"], stdout=subprocess.DEVNULL)
+
+
+_build_once()
+
+
+@pytest.fixture(scope="session")
+def port32():
+    from oracle.oracle_api import Oracle
+    return Oracle("port", 4)
+
+
+@pytest.fixture(scope="session")
+def port64():
+    from oracle.oracle_api import Oracle
+    return Oracle("port", 8)
+
+
+def _ref(prec):
+    from oracle.oracle_api import Oracle, available
+    if not available("reference", prec):
+        pytest.skip("oracle/_ref not built (needs /root/reference; run `make -C oracle ref`)")
+    return Oracle("reference", prec)
+
+
+@pytest.fixture(scope="session")
+def ref32():
+    return _ref(4)
+
+
+@pytest.fixture(scope="session")
+def ref64():
+    return _ref(8)
