@@ -57,6 +57,8 @@ int mp_context_destroy(mp_context* c) {
 	mp_release_mg(c);
 	mp_dist_shutdown(c);
 	cudaStreamSynchronize(c->stream);
+	for (auto& pb : c->pool) cudaFree(pb.first);
+	c->pool.clear();
 	for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	cudaFree(c->partials); cudaFree(c->tickets); cudaFree(c->dScal); cudaFreeHost(c->hScal);
 	cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copyStream);
@@ -78,16 +80,30 @@ int mp_grid_create(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, 
 	g->ctx = ctx; g->kind = kind; g->prec = (kind == MP_GRID_FLAGS) ? 4 : prec; g->sx = sx; g->sy = sy; g->sz = sz;
 	g->n = (IndexInt)sx * sy * sz; g->bytes = (size_t)g->n * g->comps() * g->elemSize(); g->owns = true;
 	// +256 bytes of slack so vector loads of the last (partial) vector never leave the allocation
-	cudaError_t e = cudaMalloc(&g->d, g->bytes + 256);
-	if (e != cudaSuccess) { delete g; mp_set_error("mp_grid_create: cudaMalloc(%zu) failed: %s", g->bytes, cudaGetErrorString(e)); return MP_ERR_CUDA; }
+	g->d = nullptr;
+	for (size_t q = 0; q < ctx->pool.size(); q++) if (ctx->pool[q].second == g->bytes) {
+		g->d = ctx->pool[q].first; ctx->poolBytes -= g->bytes; ctx->pool.erase(ctx->pool.begin() + q); break; }
+	if (!g->d) {
+		cudaError_t e = cudaMalloc(&g->d, g->bytes + 256);
+		if (e != cudaSuccess && !ctx->pool.empty()) {      // give pooled blocks back and retry once
+			for (auto& pb : ctx->pool) cudaFree(pb.first);
+			ctx->pool.clear(); ctx->poolBytes = 0; cudaGetLastError();
+			e = cudaMalloc(&g->d, g->bytes + 256);
+		}
+		if (e != cudaSuccess) { const size_t b = g->bytes; delete g; cudaGetLastError(); mp_set_error("mp_grid_create: cudaMalloc(%zu) failed: %s", b, cudaGetErrorString(e)); return MP_ERR_CUDA; }
+	}
 	MP_CUDA(cudaMemsetAsync(g->d, 0, g->bytes + 256, ctx->stream));     // Grid<T>(parent) clears, grid.cpp:57
 	*out = g; return MP_OK;
 }
 int mp_grid_destroy(mp_grid* g) {
 	if (!g) return MP_OK;
 	cudaSetDevice(g->ctx->device);
-	cudaStreamSynchronize(g->ctx->stream);
-	if (g->owns) cudaFree(g->d);
+	if (g->owns) {
+		// stream-ordered reuse: every consumer of a pooled block runs on ctx->stream, so no synchronisation is needed
+		mp_context* ctx = g->ctx;
+		if (ctx->pool.size() < 64) { ctx->pool.push_back(std::make_pair(g->d, g->bytes)); ctx->poolBytes += g->bytes; }
+		else { cudaStreamSynchronize(ctx->stream); cudaFree(g->d); }
+	}
 	delete g; return MP_OK;
 }
 int mp_grid_upload(mp_grid* g, const void* host) {

@@ -39,6 +39,10 @@ struct mp_context {
 	mp_mg* staticMg = nullptr;    // gMapMG[parent] pressure.cpp:250
 	DistState* dist = nullptr;
 	cudaEvent_t ev[8] = {};
+	// FluidSolver::GridStorage analogue (fluidsolver.cpp:33-50): freed device blocks are kept for reuse so the
+	// ~12 temporary grids of a solve cost no cudaMalloc/cudaFree after the first call
+	std::vector<std::pair<void*, size_t>> pool;
+	size_t poolBytes = 0;
 };
 static const int kMaxPartials = 1 << 16;   // max blocks of a reducing kernel
 static const int kSlots = 4;               // values reduced per kernel

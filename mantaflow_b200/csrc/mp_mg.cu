@@ -1,18 +1,799 @@
-// placeholder, replaced below
+// GridMg on the device: Galerkin geometric multigrid of Dick et al. 2015 without topology awareness
+// (multigrid.h:31-137, multigrid.cpp).  Used as the PcMGDynamic / PcMGStatic preconditioner of GridCg
+// (conjugategrad.cpp:100-106,:162-167) and exposed 1:1 through mp_mg_*.
+//
+// Storage: per level l  A (struct-of-arrays: A[s*n + v], s < 4 on level 0 / 14 on levels > 0; the reference
+// interleaves A[v*stencil+s], multigrid.cpp:208-218 -- mp_mg_download("a") returns the reference layout),
+// x, b, r (Real) and the vertex type (int8).  Everything stays in HBM between setA and the V-cycles.
+//
+// setA (multigrid.cpp:386-415)
+//   k_mg_copy_activate      knCopyA + knActivateVertices (+analyzeStencil)                :321-384
+//   coarse vertex selection genCoarseGrid :520-578.  The reference runs a serial bucket-heap.  Its first phase
+//                           (vertices with exactly one free interpolation vertex select it; min-key-first) is a
+//                           monotone closure and therefore order independent: k_mg_select iterates it in parallel
+//                           to the fixed point.  If fine vertices with >= 2 free interpolation vertices remain
+//                           (isolated features), the order-dependent second phase is needed: that level is then
+//                           redone by the exact serial algorithm on the host (hostCoarsen) -- same result as the
+//                           reference in every case, fast in the common one.
+//   k_mg_galerkin1/k_mg_galerkinN  knGenCoarseGridOperator :580-657 (one thread per stored stencil entry, the
+//                           reference's accumulation order per entry)
+// V-cycle (doVCycle :448-504)
+//   k_mg_smooth0 / k_mg_smoothN     knSmoothColor :668-711 (2 colours on level 0, 8 (4 in 2-D) above, :713-737)
+//   k_mg_residual0 / k_mg_residualN knCalcResidual :739-771
+//   k_mg_restrict                   knRestrict :904-927          k_mg_interp_add  knInterpolate + knAddAssign :934-954,:445
+//   k_mg_coarse_cg                  solveCG :796-902 (double Jacobi-PCG, one CTA; block reductions in fixed order)
 #include "mp_common.cuh"
-struct mp_mg { mp_context* ctx; };
-int mp_mg_precond_init(mp_mg*, const mp_grid*, const mp_grid*, const mp_grid*, const mp_grid*, double) { MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg not built yet"); }
-int mp_mg_precond_apply(mp_mg*, mp_grid*, const mp_grid*, const int*) { MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg not built yet"); }
-extern "C" {
-int mp_mg_create(mp_context*, int, int, int, int, mp_mg**) { MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg not built yet"); }
-int mp_mg_destroy(mp_mg* mg) { delete mg; return MP_OK; }
-int mp_mg_set_a(mp_mg*, const mp_grid*, const mp_grid*, const mp_grid*, const mp_grid*) { MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg not built yet"); }
-int mp_mg_set_rhs(mp_mg*, const mp_grid*) { MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg not built yet"); }
-int mp_mg_is_a_set(const mp_mg*, int* s) { *s = 0; return MP_OK; }
-int mp_mg_do_vcycle(mp_mg*, mp_grid*, const mp_grid*, double*) { MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg not built yet"); }
-int mp_mg_set_coarsest_level_accuracy(mp_mg*, double) { return MP_OK; }
-int mp_mg_set_smoothing(mp_mg*, int, int) { return MP_OK; }
-int mp_mg_num_levels(const mp_mg*, int* l) { *l = 0; return MP_OK; }
-int mp_mg_level_info(const mp_mg*, int, int*, int*, int*, int*) { MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg not built yet"); }
-int mp_mg_download(const mp_mg*, int, const char*, void*) { MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg not built yet"); }
+#include <algorithm>
+#include <cmath>
+
+enum : signed char { vtInactive = 0, vtActive = 1, vtActiveTrivial = 2, vtRemoved = 3, vtZero = 4, vtFree = 5 };   // multigrid.h:87-94
+#define MG_MAXLVL 32
+
+struct LvlGeom { int sx, sy, sz, n; };
+
+struct CoarseningPath { int Ux, Uy, Uz, Wx, Wy, Wz, Nx, Ny, Nz, sc, sf, inU; float rw, iw; };
+
+template <typename Real> struct MgLevel {
+	LvlGeom g;
+	Real *A, *x, *b, *r;
+	signed char* type;
+};
+
+struct mp_mg {
+	mp_context* ctx;
+	int prec, is3D, dim, stencil, stencil0, nlev;
+	LvlGeom geom[MG_MAXLVL];
+	void *A[MG_MAXLVL], *x[MG_MAXLVL], *b[MG_MAXLVL], *r[MG_MAXLVL];
+	signed char* type[MG_MAXLVL];
+	double* cg;                      // 4 * n_coarsest doubles
+	CoarseningPath* dPaths; int npaths; int pathStart[15];
+	int numPre, numPost; double coarsestAcc, trivialScale;
+	bool isASet, isRhsSet;
+	int* dFlags;                     // [0] changed, [1] leftovers, [2] nonZeroStencilSum, [3] trivialFound, [4] coarse iterations
+	int* hFlags;                     // pinned
+	int hostCoarsenLevels;           // how many levels needed the serial host path in the last setA
+};
+
+// ---------------------------------------------------------------- index helpers
+__host__ __device__ __forceinline__ void vecIdx(const LvlGeom& g, int v, int& x, int& y, int& z) { x = v % g.sx; const int t = v / g.sx; y = t % g.sy; z = t / g.sy; }
+__host__ __device__ __forceinline__ int linIdx(const LvlGeom& g, int x, int y, int z) { return x + g.sx * (y + g.sy * z); }
+__host__ __device__ __forceinline__ bool inGrid(const LvlGeom& g, int x, int y, int z) { return x >= 0 && y >= 0 && z >= 0 && x < g.sx && y < g.sy && z < g.sz; }
+
+// ---------------------------------------------------------------- setA: level 0
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_copy_activate(LvlGeom g, int is3D, Real trivialScale, const Real* __restrict__ A0, const Real* __restrict__ Ai,
+	const Real* __restrict__ Aj, const Real* __restrict__ Ak, Real* __restrict__ A, signed char* __restrict__ type, int* flagsOut)
+{
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= g.n) return;
+	const size_t n = (size_t)g.n;
+	Real a[7];
+	a[0] = A0[v]; a[1] = Ai[v]; a[2] = Aj[v]; a[3] = is3D ? Ak[v] : (Real)0;
+	signed char t = vtInactive;
+	Real diag = a[0];
+	if (a[0] != (Real)0) {
+		t = vtActive;
+		int x, y, z; vecIdx(g, v, x, y, z);
+		a[4] = x != 0 ? Ai[v - 1] : (Real)0;
+		a[5] = y != 0 ? Aj[v - g.sx] : (Real)0;
+		a[6] = (z != 0 && is3D) ? Ak[v - g.sx * g.sy] : (Real)0;
+		Real smax = 0, ssum = 0;
+		#pragma unroll
+		for (int i = 0; i < 7; i++) { ssum += a[i]; smax = fmax(smax, fabs(a[i])); }
+		if (fabs(ssum / smax) > (Real)1E-6) flagsOut[2] = 1;
+		const bool trivial = a[0] == (Real)1 && a[1] == 0 && a[2] == 0 && a[3] == 0 && a[4] == 0 && a[5] == 0 && a[6] == 0;
+		if (trivial) { t = vtActiveTrivial; diag = a[0] * trivialScale; flagsOut[3] = 1; }
+	}
+	type[v] = t;
+	A[v] = diag; A[n + v] = a[1]; A[2 * n + v] = a[2];
+	if (is3D) A[3 * n + v] = a[3];
 }
+
+// ---------------------------------------------------------------- setA: coarse vertex selection (phase-1 closure of genCoarseGrid)
+__global__ void __launch_bounds__(256) k_mg_fill_type(signed char* t, int n, signed char v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) t[i] = v; }
+
+// one sweep: every active fine vertex with exactly one free interpolation vertex selects it.  mode 1: count leftovers.
+__global__ void __launch_bounds__(256) k_mg_select(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, signed char* tc, int* flagsOut, int mode)
+{
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= gf.n || tf[v] == vtInactive) return;
+	int x, y, z; vecIdx(gf, v, x, y, z);
+	int nfree = 0, last = -1;
+	for (int iz = z / 2; iz <= (z + 1) / 2; iz++) for (int iy = y / 2; iy <= (y + 1) / 2; iy++) for (int ix = x / 2; ix <= (x + 1) / 2; ix++) {
+		const int i = linIdx(gc, ix, iy, iz);
+		if (tc[i] == vtFree) { nfree++; last = i; }
+	}
+	if (mode == 0) { if (nfree == 1) { tc[last] = vtZero; flagsOut[0] = 1; } }
+	else if (nfree >= 2) flagsOut[1] = 1;
+}
+__global__ void __launch_bounds__(256) k_mg_activate_coarse(signed char* t, int n) {   // knActivateCoarseVertices :507-516
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) t[i] = (t[i] == vtZero) ? vtActive : vtInactive;
+}
+
+// exact serial algorithm (multigrid.cpp:59-203,:520-578) for levels where the parallel closure leaves work
+namespace {
+struct HEntry { int key, prev, next; };
+struct NKMinHeap {
+	int N, K, size, minKey; std::vector<HEntry> e;
+	NKMinHeap(int n, int k) : N(n), K(k), size(0), minKey(-1), e((size_t)n + k, HEntry{ -1, -1, -1 }) {}
+	int getKey(int id) const { return e[K + id].key; }
+	void setKey(int id, int key) {
+		const int kid = K + id;
+		if (e[kid].key == key) return;
+		if (e[kid].key != -1) {
+			const int pred = e[kid].prev, succ = e[kid].next;
+			e[pred].next = succ; if (succ != -1) e[succ].prev = pred;
+			const int removed = e[kid].key;
+			if (removed == minKey) { if (size == 1) minKey = -1; else for (; minKey < K; minKey++) if (e[minKey].next != -1) break; }
+			size--;
+		}
+		e[kid].key = key;
+		if (key == -1) { e[kid].next = e[kid].prev = -1; return; }
+		size++;
+		minKey = (minKey == -1) ? key : std::min(minKey, key);
+		const int tmp = e[key].next;
+		e[key].next = kid; e[kid].prev = key; e[kid].next = tmp; if (tmp != -1) e[tmp].prev = kid;
+	}
+	int popMin() {
+		const int kid = e[minKey].next, id = kid - K;
+		const int pred = e[kid].prev, succ = e[kid].next;
+		e[pred].next = succ; if (succ != -1) e[succ].prev = pred;
+		e[kid] = HEntry{ -1, -1, -1 }; size--;
+		if (size == 0) minKey = -1; else for (; minKey < K; minKey++) if (e[minKey].next != -1) break;
+		return id;
+	}
+};
+void hostCoarsen(const LvlGeom& gf, const LvlGeom& gc, bool is3D, const std::vector<signed char>& tf, std::vector<signed char>& tc) {
+	std::fill(tc.begin(), tc.end(), (signed char)vtFree);
+	NKMinHeap heap(gf.n, is3D ? 9 : 5);
+	for (int v = 0; v < gf.n; v++) if (tf[v] != vtInactive) { int x, y, z; vecIdx(gf, v, x, y, z); heap.setKey(v, 1 << ((x % 2) + (y % 2) + (z % 2))); }
+	while (heap.size > 0) {
+		const int v = heap.popMin();
+		int x, y, z; vecIdx(gf, v, x, y, z);
+		bool vdone = false;
+		for (int iz = z / 2; iz <= (z + 1) / 2; iz++) for (int iy = y / 2; iy <= (y + 1) / 2; iy++) for (int ix = x / 2; ix <= (x + 1) / 2; ix++) {
+			const int i = linIdx(gc, ix, iy, iz);
+			if (tc[i] != vtFree) continue;
+			if (vdone) tc[i] = vtRemoved; else { tc[i] = vtZero; vdone = true; }
+			for (int rz = std::max(0, iz * 2 - 1); rz <= std::min(gf.sz - 1, iz * 2 + 1); rz++)
+			for (int ry = std::max(0, iy * 2 - 1); ry <= std::min(gf.sy - 1, iy * 2 + 1); ry++)
+			for (int rx = std::max(0, ix * 2 - 1); rx <= std::min(gf.sx - 1, ix * 2 + 1); rx++) {
+				const int r = linIdx(gf, rx, ry, rz);
+				const int key = heap.getKey(r);
+				if (key > 1) heap.setKey(r, key - 1); else if (key > -1) heap.setKey(r, -1);
+			}
+		}
+	}
+	for (auto& t : tc) t = (t == vtZero) ? vtActive : vtInactive;
+}
+}
+
+// ---------------------------------------------------------------- setA: Galerkin operators
+// level 1 from the 7-point level 0 along the precomputed paths (V)<-R-(U)<-A-(W)<-I-(N); thread = (coarse vertex, sc)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_galerkin1(LvlGeom gf, LvlGeom gc, int stencil, const CoarseningPath* __restrict__ paths, const int* __restrict__ pathStart,
+	const Real* __restrict__ Af, const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)gc.n * stencil) return;
+	const int sc = (int)(t / gc.n), v = (int)(t % gc.n);
+	if (tc[v] == vtInactive) return;
+	int vx, vy, vz; vecIdx(gc, v, vx, vy, vz);
+	Real acc = 0;
+	for (int q = pathStart[sc]; q < pathStart[sc + 1]; q++) {
+		const CoarseningPath p = paths[q];
+		const int Nx = vx + p.Nx, Ny = vy + p.Ny, Nz = vz + p.Nz;
+		if (!inGrid(gc, Nx, Ny, Nz) || tc[linIdx(gc, Nx, Ny, Nz)] == vtInactive) continue;
+		const int Ux = vx * 2 + p.Ux, Uy = vy * 2 + p.Uy, Uz = vz * 2 + p.Uz;
+		if (!inGrid(gf, Ux, Uy, Uz)) continue;
+		const int u = linIdx(gf, Ux, Uy, Uz); if (tf[u] == vtInactive) continue;
+		const int Wx = vx * 2 + p.Wx, Wy = vy * 2 + p.Wy, Wz = vz * 2 + p.Wz;
+		if (!inGrid(gf, Wx, Wy, Wz)) continue;
+		const int w = linIdx(gf, Wx, Wy, Wz); if (tf[w] == vtInactive) continue;
+		const Real a = Af[(size_t)p.sf * gf.n + (p.inU ? u : w)];
+		acc += (Real)p.rw * a * (Real)p.iw;
+	}
+	A[(size_t)sc * gc.n + v] = acc;
+}
+
+// levels > 1 from a 27-point fine level; thread = (coarse vertex, stored entry e = sc-13)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_galerkinN(LvlGeom gf, LvlGeom gc, int S, int is3D, const Real* __restrict__ Af,
+	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)gc.n * S) return;
+	const int e = (int)(t / gc.n), v = (int)(t % gc.n);
+	if (tc[v] == vtInactive) return;
+	int V[3]; vecIdx(gc, v, V[0], V[1], V[2]);
+	const int smaxz = is3D ? 1 : 0;
+	// stencil offset of entry e: sc = e + S - 1 ; SC = N - V + smax
+	const int sc = e + S - 1;
+	int N[3];
+	if (is3D) { N[0] = V[0] + sc % 3 - 1; N[1] = V[1] + (sc / 3) % 3 - 1; N[2] = V[2] + sc / 9 - 1; }
+	else      { N[0] = V[0] + sc % 3 - 1; N[1] = V[1] + (sc / 3) % 3 - 1; N[2] = V[2]; }
+	Real acc = 0;
+	if (inGrid(gc, N[0], N[1], N[2]) && tc[linIdx(gc, N[0], N[1], N[2])] != vtInactive) {
+		const int fs[3] = { gf.sx, gf.sy, gf.sz }, cs[3] = { gc.sx, gc.sy, gc.sz };
+		int u0[3], u1[3];
+		for (int d = 0; d < 3; d++) { u0[d] = max(0, V[d] * 2 - 1); u1[d] = min(fs[d] - 1, V[d] * 2 + 1); }
+		for (int Uz = u0[2]; Uz <= u1[2]; Uz++) for (int Uy = u0[1]; Uy <= u1[1]; Uy++) for (int Ux = u0[0]; Ux <= u1[0]; Ux++) {
+			const int U[3] = { Ux, Uy, Uz };
+			const int u = linIdx(gf, Ux, Uy, Uz);
+			if (tf[u] == vtInactive) continue;
+			// N must be reachable from U: (U-1)/2 <= N <= min(size-1,(U+2)/2)  (C division truncates like Vec3i '/')
+			bool ok = true;
+			for (int d = 0; d < 3; d++) { const int lo = (U[d] - 1) / 2, hi = min(cs[d] - 1, (U[d] + 2) / 2); if (N[d] < lo || N[d] > hi) ok = false; }
+			if (!ok) continue;
+			const Real rw = (Real)1 / (Real)(1 << ((Ux % 2) + (Uy % 2) + (Uz % 2)));
+			int w0[3], w1[3];
+			for (int d = 0; d < 3; d++) { w0[d] = max(0, max(U[d] - 1, N[d] * 2 - 1)); w1[d] = min(fs[d] - 1, min(U[d] + 1, N[d] * 2 + 1)); }
+			for (int Wz = w0[2]; Wz <= w1[2]; Wz++) for (int Wy = w0[1]; Wy <= w1[1]; Wy++) for (int Wx = w0[0]; Wx <= w1[0]; Wx++) {
+				const int w = linIdx(gf, Wx, Wy, Wz);
+				if (tf[w] == vtInactive) continue;
+				const int sf = (Wx - Ux + 1) + 3 * (Wy - Uy + 1) + 9 * (Wz - Uz + smaxz);
+				const Real iw = (Real)1 / (Real)(1 << ((Wx % 2) + (Wy % 2) + (Wz % 2)));
+				const Real a = (sf < S) ? Af[(size_t)(S - 1 - sf) * gf.n + w] : Af[(size_t)(sf - S + 1) * gf.n + u];
+				acc += rw * a * iw;
+			}
+		}
+	}
+	A[(size_t)e * gc.n + v] = acc;
+}
+
+// ---------------------------------------------------------------- V-cycle kernels
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_set_rhs(int n, Real trivialScale, const Real* __restrict__ rhs, const signed char* __restrict__ type, Real* __restrict__ b, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n) return;
+	Real val = rhs[v];
+	if (type[v] == vtActiveTrivial) val *= trivialScale;    // knSetRhs :417-424
+	b[v] = val;
+}
+
+// level-0 colour sweep: colour = (x+y+z) parity ({a0,a3,a5,a6} / {a1,a2,a4,a7}, :721); thread = (x pair, y, z)
+template <typename Real, bool ZEROX>
+__global__ void __launch_bounds__(256) k_mg_smooth0(LvlGeom g, int is3D, int color, const Real* __restrict__ A, const Real* __restrict__ b,
+	const signed char* __restrict__ type, Real* __restrict__ x, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int hx = (g.sx + 1) >> 1;
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)hx * g.sy * g.sz) return;
+	const int m = (int)(t % hx); const long long t2 = t / hx; const int j = (int)(t2 % g.sy), k = (int)(t2 / g.sy);
+	const int i = 2 * m + ((j + k + color) & 1);
+	if (i >= g.sx) return;
+	const int v = linIdx(g, i, j, k);
+	if (type[v] == vtInactive) return;
+	const size_t n = (size_t)g.n; const int Y = g.sx, Z = g.sx * g.sy;
+	Real sum = b[v];
+	if (!ZEROX) {
+		if (i > 0)        sum -= A[n + v - 1] * x[v - 1];
+		if (i < g.sx - 1) sum -= A[n + v] * x[v + 1];
+		if (j > 0)        sum -= A[2 * n + v - Y] * x[v - Y];
+		if (j < g.sy - 1) sum -= A[2 * n + v] * x[v + Y];
+		if (is3D) {
+			if (k > 0)        sum -= A[3 * n + v - Z] * x[v - Z];
+			if (k < g.sz - 1) sum -= A[3 * n + v] * x[v + Z];
+		}
+	}
+	x[v] = sum / A[v];
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_residual0(LvlGeom g, int is3D, const Real* __restrict__ A, const Real* __restrict__ b,
+	const signed char* __restrict__ type, const Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= g.n || type[v] == vtInactive) return;
+	int i, j, k; vecIdx(g, v, i, j, k);
+	const size_t n = (size_t)g.n; const int Y = g.sx, Z = g.sx * g.sy;
+	Real sum = b[v];
+	if (i > 0)        sum -= A[n + v - 1] * x[v - 1];
+	if (i < g.sx - 1) sum -= A[n + v] * x[v + 1];
+	if (j > 0)        sum -= A[2 * n + v - Y] * x[v - Y];
+	if (j < g.sy - 1) sum -= A[2 * n + v] * x[v + Y];
+	if (is3D) {
+		if (k > 0)        sum -= A[3 * n + v - Z] * x[v - Z];
+		if (k < g.sz - 1) sum -= A[3 * n + v] * x[v + Z];
+	}
+	sum -= A[v] * x[v];
+	r[v] = sum;
+}
+
+// 27-point (9-point in 2-D) stencil application shared by smoother / residual / coarse CG on levels > 0
+template <typename Real, typename VecT, bool SKIPCENTER>
+__device__ __forceinline__ VecT stencilSub(const LvlGeom& g, int is3D, int S, const Real* __restrict__ A, const signed char* __restrict__ type,
+	const VecT* __restrict__ x, int v, int vx, int vy, int vz, VecT sum)
+{
+	int s = 0;
+	for (int dz = is3D ? -1 : 0; dz <= (is3D ? 1 : 0); dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++, s++) {
+		if (SKIPCENTER && s == S - 1) continue;
+		const int nx = vx + dx, ny = vy + dy, nz = vz + dz;
+		if (!inGrid(g, nx, ny, nz)) continue;
+		const int nb = linIdx(g, nx, ny, nz);
+		if (type[nb] == vtInactive) continue;
+		if (s < S) sum -= A[(size_t)(S - 1 - s) * g.n + nb] * x[nb];
+		else       sum -= A[(size_t)(s - S + 1) * g.n + v] * x[nb];
+	}
+	return sum;
+}
+
+// levels > 0: colour = offset inside 2x2x2 blocks (:722); thread = block
+template <typename Real>
+__global__ void __launch_bounds__(128) k_mg_smoothN(LvlGeom g, int is3D, int S, int ox, int oy, int oz, const Real* __restrict__ A, const Real* __restrict__ b,
+	const signed char* __restrict__ type, Real* __restrict__ x, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int bx = (g.sx + 1) >> 1, by = (g.sy + 1) >> 1, bz = (g.sz + 1) >> 1;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= bx * by * bz) return;
+	const int vx = 2 * (t % bx) + ox, vy = 2 * ((t / bx) % by) + oy, vz = 2 * (t / (bx * by)) + oz;
+	if (!inGrid(g, vx, vy, vz)) return;
+	const int v = linIdx(g, vx, vy, vz);
+	if (type[v] == vtInactive) return;
+	const Real sum = stencilSub<Real, Real, true>(g, is3D, S, A, type, x, v, vx, vy, vz, b[v]);
+	x[v] = sum / A[v];
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(128) k_mg_residualN(LvlGeom g, int is3D, int S, const Real* __restrict__ A, const Real* __restrict__ b,
+	const signed char* __restrict__ type, const Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= g.n || type[v] == vtInactive) return;
+	int vx, vy, vz; vecIdx(g, v, vx, vy, vz);
+	r[v] = stencilSub<Real, Real, false>(g, is3D, S, A, type, x, v, vx, vy, vz, b[v]);
+}
+
+// knRestrict :904-927 (dst level = coarse), also zeroes x on the coarse level (knSet :472)
+template <typename Real>
+__global__ void __launch_bounds__(128) k_mg_restrict(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+	const Real* __restrict__ src, Real* __restrict__ dst, Real* __restrict__ xc, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= gc.n) return;
+	xc[v] = (Real)0;
+	if (tc[v] == vtInactive) return;
+	int vx, vy, vz; vecIdx(gc, v, vx, vy, vz);
+	Real sum = 0;
+	for (int rz = max(0, vz * 2 - 1); rz <= min(gf.sz - 1, vz * 2 + 1); rz++)
+	for (int ry = max(0, vy * 2 - 1); ry <= min(gf.sy - 1, vy * 2 + 1); ry++)
+	for (int rx = max(0, vx * 2 - 1); rx <= min(gf.sx - 1, vx * 2 + 1); rx++) {
+		const int r = linIdx(gf, rx, ry, rz);
+		if (tf[r] == vtInactive) continue;
+		const Real rw = (Real)1 / (Real)(1 << ((rx % 2) + (ry % 2) + (rz % 2)));
+		sum += rw * src[r];
+	}
+	dst[v] = sum;
+}
+
+// knInterpolate :934-954 into r_l, then x_l += r_l (knAddAssign :445-446, over ALL vertices: inactive ones add their stale r)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_interp_add(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+	const Real* __restrict__ xc, Real* __restrict__ rf, Real* __restrict__ xf, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= gf.n) return;
+	Real val = rf[v];
+	if (tf[v] != vtInactive) {
+		int x, y, z; vecIdx(gf, v, x, y, z);
+		Real sum = 0;
+		for (int iz = z / 2; iz <= (z + 1) / 2; iz++) for (int iy = y / 2; iy <= (y + 1) / 2; iy++) for (int ix = x / 2; ix <= (x + 1) / 2; ix++) {
+			const int i = linIdx(gc, ix, iy, iz);
+			if (tc[i] != vtInactive) sum += xc[i];
+		}
+		const Real iw = (Real)1 / (Real)(1 << ((x % 2) + (y % 2) + (z % 2)));
+		val = iw * sum;
+		rf[v] = val;
+	}
+	xf[v] += val;
+}
+
+// solveCG :796-902 on the coarsest level: one CTA, double precision, Jacobi preconditioner
+__device__ __forceinline__ double ctaSum(double v, double* sh) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	v = warpSum(v);
+	__syncthreads();
+	if (lane == 0) sh[warp] = v;
+	__syncthreads();
+	double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+	if (warp == 0) { t = warpSum(t); if (lane == 0) sh[32] = t; }
+	__syncthreads();
+	return sh[32];
+}
+template <typename Real>
+__global__ void __launch_bounds__(1024) k_mg_coarse_cg(LvlGeom g, int is3D, int S, int level0, const Real* __restrict__ A, const Real* __restrict__ b,
+	const signed char* __restrict__ type, Real* __restrict__ xr, double* __restrict__ cg, double accuracy, int* flagsOut, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	__shared__ double sh[33];
+	const int n = g.n;
+	double *z = cg, *p = cg + n, *x = cg + 2 * n, *r = cg + 3 * n;
+	for (int v = threadIdx.x; v < n; v += blockDim.x) x[v] = (double)xr[v];
+	__syncthreads();
+	auto applyA = [&](int v, const double* vec) -> double {
+		int vx, vy, vz; vecIdx(g, v, vx, vy, vz);
+		if (level0) {
+			double sum = 0; const int Y = g.sx, Z = g.sx * g.sy;
+			if (vx > 0)        sum += (double)A[n + v - 1] * vec[v - 1];
+			if (vx < g.sx - 1) sum += (double)A[n + v] * vec[v + 1];
+			if (vy > 0)        sum += (double)A[2 * n + v - Y] * vec[v - Y];
+			if (vy < g.sy - 1) sum += (double)A[2 * n + v] * vec[v + Y];
+			if (is3D) { if (vz > 0) sum += (double)A[3 * n + v - Z] * vec[v - Z]; if (vz < g.sz - 1) sum += (double)A[3 * n + v] * vec[v + Z]; }
+			sum += (double)A[v] * vec[v];
+			return sum;
+		}
+		return -stencilSub<Real, double, false>(g, is3D, S, A, type, vec, v, vx, vy, vz, 0.0);
+	};
+	double aTop = 0, res0 = 0;
+	for (int v = threadIdx.x; v < n; v += blockDim.x) {
+		if (type[v] == vtInactive) continue;
+		const double rv = (double)b[v] - applyA(v, x);
+		const double zv = rv / (double)A[v];
+		r[v] = rv; z[v] = zv; p[v] = zv;
+		res0 += rv * rv; aTop += rv * zv;
+	}
+	aTop = ctaSum(aTop, sh); res0 = sqrt(ctaSum(res0, sh));
+	int iter = 0; const int maxIter = 10000;
+	for (; iter < maxIter && res0 > 1E-12; iter++) {
+		double aBot = 0;
+		for (int v = threadIdx.x; v < n; v += blockDim.x) {
+			if (type[v] == vtInactive) continue;
+			const double zv = applyA(v, p);
+			z[v] = zv; aBot += p[v] * zv;
+		}
+		aBot = ctaSum(aBot, sh);
+		const double alpha = aTop / aBot;
+		double aTopNew = 0, res = 0;
+		for (int v = threadIdx.x; v < n; v += blockDim.x) {
+			if (type[v] == vtInactive) continue;
+			x[v] += alpha * p[v];
+			const double rv = r[v] - alpha * z[v];
+			r[v] = rv; res += rv * rv;
+			const double zv = rv / (double)A[v];
+			z[v] = zv; aTopNew += rv * zv;
+		}
+		aTopNew = ctaSum(aTopNew, sh); res = sqrt(ctaSum(res, sh));
+		if (res / res0 < accuracy) break;
+		const double beta = aTopNew / aTop;
+		aTop = aTopNew;
+		for (int v = threadIdx.x; v < n; v += blockDim.x) p[v] = z[v] + beta * p[v];
+		__syncthreads();
+	}
+	for (int v = threadIdx.x; v < n; v += blockDim.x) xr[v] = (Real)x[v];
+	if (threadIdx.x == 0) flagsOut[4] = iter;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_copy(int n, const Real* __restrict__ src, Real* __restrict__ dst, const int* doneFlag) {
+	if (doneFlag && *doneFlag) return;
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v < n) dst[v] = src[v];
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_norm(int n, const Real* __restrict__ r, const signed char* __restrict__ type, double* partials, unsigned int* ticket, double* out) {
+	double v[1] = { 0.0 };   // knResidualNormSumSqr :778-784 (Real products, here accumulated in double)
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) if (type[i] != vtInactive) v[0] += (double)(r[i] * r[i]);
+	const bool isMax[1] = { false }; double fin[1];
+	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) out[0] = fin[0];
+}
+
+// ================================================================ host side
+static inline unsigned int nb(long long work, int block) { return (unsigned int)((work + block - 1) / block); }
+
+template <typename Real>
+static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak)
+{
+	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
+	MP_CUDA(cudaMemsetAsync(m->dFlags, 0, 8 * sizeof(int), st));
+	const LvlGeom g0 = m->geom[0];
+	k_mg_copy_activate<Real><<<nb(g0.n, 256), 256, 0, st>>>(g0, m->is3D, (Real)m->trivialScale, (const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d,
+		(const Real*)Ak->d, (Real*)m->A[0], m->type[0], m->dFlags);
+	MP_CHECK_LAUNCH(ctx);
+	m->hostCoarsenLevels = 0;
+	for (int l = 1; l < m->nlev; l++) {
+		const LvlGeom gf = m->geom[l - 1], gc = m->geom[l];
+		k_mg_fill_type<<<nb(gc.n, 256), 256, 0, st>>>(m->type[l], gc.n, vtFree); MP_CHECK_LAUNCH(ctx);
+		// phase-1 closure to its fixed point (a handful of sweeps for bulk domains)
+		for (int sweep = 0; sweep < gf.sx + gf.sy + gf.sz + 8; sweep += 4) {
+			MP_CUDA(cudaMemsetAsync(m->dFlags, 0, sizeof(int), st));
+			for (int q = 0; q < 4; q++) { k_mg_select<<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, 0); MP_CHECK_LAUNCH(ctx); }
+			MP_CUDA(cudaMemcpyAsync(m->hFlags, m->dFlags, sizeof(int), cudaMemcpyDeviceToHost, st));
+			MP_CUDA(cudaStreamSynchronize(st));
+			if (!m->hFlags[0]) break;
+		}
+		MP_CUDA(cudaMemsetAsync(m->dFlags + 1, 0, sizeof(int), st));
+		k_mg_select<<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, 1); MP_CHECK_LAUNCH(ctx);
+		MP_CUDA(cudaMemcpyAsync(m->hFlags, m->dFlags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+		MP_CUDA(cudaStreamSynchronize(st));
+		if (m->hFlags[1]) {
+			// order-dependent phase needed: redo this level with the exact serial algorithm
+			std::vector<signed char> tf(gf.n), tc(gc.n);
+			MP_CUDA(cudaMemcpy(tf.data(), m->type[l - 1], gf.n, cudaMemcpyDeviceToHost));
+			hostCoarsen(gf, gc, m->is3D != 0, tf, tc);
+			MP_CUDA(cudaMemcpy(m->type[l], tc.data(), gc.n, cudaMemcpyHostToDevice));
+			m->hostCoarsenLevels++;
+		} else {
+			k_mg_activate_coarse<<<nb(gc.n, 256), 256, 0, st>>>(m->type[l], gc.n); MP_CHECK_LAUNCH(ctx);
+		}
+		const long long work = (long long)gc.n * m->stencil;
+		if (l == 1) k_mg_galerkin1<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->dPaths, (const int*)(m->dFlags + 16), (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1]);
+		else        k_mg_galerkinN<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->A[l]);
+		MP_CHECK_LAUNCH(ctx);
+	}
+	m->isASet = true; m->isRhsSet = false;
+	return MP_OK;
+}
+
+template <typename Real>
+static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneFlag)
+{
+	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
+	const LvlGeom g = m->geom[l];
+	if (l == 0) {
+		const long long work = (long long)((g.sx + 1) / 2) * g.sy * g.sz;
+		for (int c = 0; c < 2; c++) {
+			const int color = reversed ? 1 - c : c;
+			// with x == 0 on entry the first colour reduces to x = b / A0 (same arithmetic: the skipped products are exact zeros)
+			if (zeroX && c == 0) k_mg_smooth0<Real, true><<<nb(work, 256), 256, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], (const Real*)m->b[0], m->type[0], (Real*)m->x[0], doneFlag);
+			else                 k_mg_smooth0<Real, false><<<nb(work, 256), 256, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], (const Real*)m->b[0], m->type[0], (Real*)m->x[0], doneFlag);
+			MP_CHECK_LAUNCH(ctx);
+		}
+	} else {
+		const int ncol = m->is3D ? 8 : 4;
+		const int blocks = ((g.sx + 1) / 2) * ((g.sy + 1) / 2) * ((g.sz + 1) / 2);
+		for (int c = 0; c < ncol; c++) {
+			const int color = reversed ? ncol - 1 - c : c;
+			k_mg_smoothN<Real><<<nb(blocks, 128), 128, 0, st>>>(g, m->is3D, m->stencil, color & 1, (color >> 1) & 1, (color >> 2) & 1,
+				(const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], doneFlag);
+			MP_CHECK_LAUNCH(ctx);
+		}
+	}
+	return MP_OK;
+}
+
+template <typename Real>
+static int mgResidual(mp_mg* m, int l, const int* doneFlag)
+{
+	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
+	const LvlGeom g = m->geom[l];
+	if (l == 0) k_mg_residual0<Real><<<nb(g.n, 256), 256, 0, st>>>(g, m->is3D, (const Real*)m->A[0], (const Real*)m->b[0], m->type[0], (const Real*)m->x[0], (Real*)m->r[0], doneFlag);
+	else        k_mg_residualN<Real><<<nb(g.n, 128), 128, 0, st>>>(g, m->is3D, m->stencil, (const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (const Real*)m->x[l], (Real*)m->r[l], doneFlag);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+// doVCycle :448-504.  xInit: x0 already holds the initial guess (src) instead of zero.
+template <typename Real>
+static int mgVCycle(mp_mg* m, Real* dst, bool xInit, bool wantNorm, const int* doneFlag)
+{
+	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
+	const int maxLevel = m->nlev - 1;
+	if (!xInit && !(maxLevel > 0 && m->numPre > 0)) MP_CUDA(cudaMemsetAsync(m->x[0], 0, sizeof(Real) * (size_t)m->geom[0].n, st));
+	bool x0zero = !xInit;
+	if (x0zero && maxLevel > 0 && m->numPre > 0) {
+		// knSet(x0, 0) is folded into the first pre-smoothing sweep: the first colour writes b/A0 on its active
+		// vertices; everything else must read as zero, so only the other colour / inactive cells need the clear
+		MP_CUDA(cudaMemsetAsync(m->x[0], 0, sizeof(Real) * (size_t)m->geom[0].n, st));
+	}
+	for (int l = 0; l < maxLevel; l++) {
+		for (int i = 0; i < m->numPre; i++) MP_TRY((mgSmooth<Real>(m, l, false, (l == 0 ? x0zero : true) && i == 0 && l == 0, doneFlag)));
+		MP_TRY((mgResidual<Real>(m, l, doneFlag)));
+		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
+		k_mg_restrict<Real><<<nb(gc.n, 128), 128, 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->r[l], (Real*)m->b[l + 1], (Real*)m->x[l + 1], doneFlag);
+		MP_CHECK_LAUNCH(ctx);
+	}
+	{
+		const LvlGeom g = m->geom[maxLevel];
+		k_mg_coarse_cg<Real><<<1, 1024, 0, st>>>(g, m->is3D, m->stencil, maxLevel == 0 ? 1 : 0, (const Real*)m->A[maxLevel], (const Real*)m->b[maxLevel], m->type[maxLevel],
+			(Real*)m->x[maxLevel], m->cg, m->coarsestAcc, m->dFlags, doneFlag);
+		MP_CHECK_LAUNCH(ctx);
+	}
+	for (int l = maxLevel - 1; l >= 0; l--) {
+		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
+		k_mg_interp_add<Real><<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], (Real*)m->x[l], doneFlag);
+		MP_CHECK_LAUNCH(ctx);
+		for (int i = 0; i < m->numPost; i++) MP_TRY((mgSmooth<Real>(m, l, true, false, doneFlag)));
+	}
+	if (wantNorm) MP_TRY((mgResidual<Real>(m, 0, doneFlag)));      // calcResidual(0) only feeds the returned norm (:496-497)
+	k_mg_copy<Real><<<nb(m->geom[0].n, 256), 256, 0, st>>>(m->geom[0].n, (const Real*)m->x[0], dst, doneFlag);   // knCopyToGrid :499
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+template <typename Real>
+static int mgSetRhs(mp_mg* m, const Real* rhs, const int* doneFlag)
+{
+	if (!m->isASet) MP_FAIL(MP_ERR_NOT_SET, "GridMg::setRhs Error: A has not been set.");
+	const int n = m->geom[0].n;
+	k_mg_set_rhs<Real><<<nb(n, 256), 256, 0, m->ctx->stream>>>(n, (Real)m->trivialScale, rhs, m->type[0], (Real*)m->b[0], doneFlag);
+	MP_CHECK_LAUNCH(m->ctx);
+	m->isRhsSet = true;
+	return MP_OK;
+}
+
+// InitPreconditionMultigrid conjugategrad.cpp:100-106
+int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, double accuracy)
+{
+	if (!mg->isASet) MP_TRY(mp_mg_set_a(mg, A0, Ai, Aj, Ak));
+	// mAccuracy * 1E-4 is evaluated in double from a Real accuracy and narrowed to the Real member (multigrid.h:52)
+	mg->coarsestAcc = (mg->prec == 4) ? (double)(float)((double)(float)accuracy * 1E-4) : accuracy * 1E-4;
+	mg->numPre = 1; mg->numPost = 1;
+	return MP_OK;
+}
+// ApplyPreconditionMultigrid conjugategrad.cpp:162-167
+int mp_mg_precond_apply(mp_mg* mg, mp_grid* dst, const mp_grid* rhs, const int* doneFlag)
+{
+	if (mg->prec == 4) { MP_TRY(mgSetRhs<float>(mg, (const float*)rhs->d, doneFlag)); return mgVCycle<float>(mg, (float*)dst->d, false, false, doneFlag); }
+	MP_TRY(mgSetRhs<double>(mg, (const double*)rhs->d, doneFlag)); return mgVCycle<double>(mg, (double*)dst->d, false, false, doneFlag);
+}
+
+extern "C" {
+
+int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
+{
+	if (!ctx || !out) MP_FAIL(MP_ERR_INVALID, "mp_mg_create: NULL argument");
+	if (prec != 4 && prec != 8) MP_FAIL(MP_ERR_INVALID, "mp_mg_create: prec must be 4 or 8");
+	if ((long long)sx * sy * sz > 2000000000LL) MP_FAIL(MP_ERR_UNSUPPORTED, "mp_mg_create: more than 2^31 cells per GPU are not supported");
+	MP_CUDA(cudaSetDevice(ctx->device));
+	mp_mg* m = new mp_mg();
+	memset(m, 0, sizeof *m);
+	m->ctx = ctx; m->prec = prec;
+	m->numPre = m->numPost = 1; m->coarsestAcc = (prec == 4) ? (double)1E-8f : 1E-8; m->trivialScale = (prec == 4) ? (double)1E-6f : 1E-6;
+	m->is3D = sz > 1; m->dim = m->is3D ? 3 : 2; m->stencil = m->is3D ? 14 : 5; m->stencil0 = m->is3D ? 4 : 3;
+	// levels: size_l = (size_{l-1}+2)/2 until all dims <= 5 or n <= 1000 (multigrid.cpp:256-263)
+	int l = 0; m->geom[0] = LvlGeom{ sx, sy, sz, sx * sy * sz };
+	for (;;) {
+		const LvlGeom g = m->geom[l];
+		m->nlev = l + 1;
+		if (l + 1 > 100 || l + 1 >= MG_MAXLVL) break;
+		if (g.sx <= 5 && g.sy <= 5 && g.sz <= 5) break;
+		if (g.n <= 1000) break;
+		LvlGeom c; c.sx = (g.sx + 2) / 2; c.sy = (g.sy + 2) / 2; c.sz = (g.sz + 2) / 2; c.n = c.sx * c.sy * c.sz;
+		m->geom[++l] = c;
+	}
+	for (l = 0; l < m->nlev; l++) {
+		const size_t n = (size_t)m->geom[l].n; const int S = l == 0 ? m->stencil0 : m->stencil;
+		MP_CUDA(cudaMalloc(&m->A[l], n * S * prec)); MP_CUDA(cudaMalloc(&m->x[l], n * prec)); MP_CUDA(cudaMalloc(&m->b[l], n * prec));
+		MP_CUDA(cudaMalloc(&m->r[l], n * prec)); MP_CUDA(cudaMalloc((void**)&m->type[l], n));
+		MP_CUDA(cudaMemsetAsync(m->A[l], 0, n * S * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->x[l], 0, n * prec, ctx->stream));
+		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, n * prec, ctx->stream));
+		MP_CUDA(cudaMemsetAsync(m->type[l], 0, n, ctx->stream));
+	}
+	MP_CUDA(cudaMalloc((void**)&m->cg, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n));
+	MP_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n, ctx->stream));
+	MP_CUDA(cudaMalloc((void**)&m->dFlags, 64 * sizeof(int)));
+	MP_CUDA(cudaMemsetAsync(m->dFlags, 0, 64 * sizeof(int), ctx->stream));
+	MP_CUDA(cudaHostAlloc((void**)&m->hFlags, 64 * sizeof(int), cudaHostAllocDefault));
+
+	// coarsening paths for level 1 (multigrid.cpp:286-318), sorted by (sc, U) with generation order among equal keys
+	static const int p7[7][3] = { {0,0,0}, {-1,0,0}, {1,0,0}, {0,-1,0}, {0,1,0}, {0,0,-1}, {0,0,1} };
+	std::vector<CoarseningPath> paths;
+	const int z0 = m->is3D ? 1 : 2, z1 = m->is3D ? 3 : 2;
+	for (int uz = z0; uz <= z1; uz++) for (int uy = 1; uy <= 3; uy++) for (int ux = 1; ux <= 3; ux++)
+		for (int i = 0; i < 1 + 2 * m->dim; i++) {
+			const int wx = ux + p7[i][0], wy = uy + p7[i][1], wz = uz + p7[i][2];
+			for (int nz = wz / 2; nz <= (wz + 1) / 2; nz++) for (int ny = wy / 2; ny <= (wy + 1) / 2; ny++) for (int nx = wx / 2; nx <= (wx + 1) / 2; nx++) {
+				const int s = nx + 3 * ny + 9 * nz;
+				if (s < 13) continue;
+				CoarseningPath p;
+				p.Nx = nx - 1; p.Ny = ny - 1; p.Nz = nz - 1; p.Ux = ux - 2; p.Uy = uy - 2; p.Uz = uz - 2; p.Wx = wx - 2; p.Wy = wy - 2; p.Wz = wz - 2;
+				p.sc = s - 13; p.sf = (i + 1) / 2; p.inU = (i % 2 == 0);
+				p.rw = 1.f / (float)(1 << ((ux % 2) + (uy % 2) + (uz % 2)));
+				p.iw = 1.f / (float)(1 << ((wx % 2) + (wy % 2) + (wz % 2)));
+				paths.push_back(p);
+			}
+		}
+	std::stable_sort(paths.begin(), paths.end(), [](const CoarseningPath& a, const CoarseningPath& b) {
+		if (a.sc != b.sc) return a.sc < b.sc;
+		return (a.Ux + 1) + 3 * (a.Uy + 1) + 9 * (a.Uz + 1) < (b.Ux + 1) + 3 * (b.Uy + 1) + 9 * (b.Uz + 1); });
+	m->npaths = (int)paths.size();
+	for (int s = 0; s <= 14; s++) m->pathStart[s] = m->npaths;
+	for (int q = m->npaths - 1; q >= 0; q--) m->pathStart[paths[q].sc] = q;
+	for (int s = 13; s >= 0; s--) if (m->pathStart[s] > m->pathStart[s + 1]) m->pathStart[s] = m->pathStart[s + 1];
+	MP_CUDA(cudaMalloc((void**)&m->dPaths, sizeof(CoarseningPath) * paths.size()));
+	MP_CUDA(cudaMemcpy(m->dPaths, paths.data(), sizeof(CoarseningPath) * paths.size(), cudaMemcpyHostToDevice));
+	MP_CUDA(cudaMemcpy(m->dFlags + 16, m->pathStart, sizeof(int) * 15, cudaMemcpyHostToDevice));
+	*out = m; return MP_OK;
+}
+
+int mp_mg_destroy(mp_mg* m)
+{
+	if (!m) return MP_OK;
+	cudaSetDevice(m->ctx->device);
+	cudaStreamSynchronize(m->ctx->stream);
+	for (int l = 0; l < m->nlev; l++) { cudaFree(m->A[l]); cudaFree(m->x[l]); cudaFree(m->b[l]); cudaFree(m->r[l]); cudaFree(m->type[l]); }
+	cudaFree(m->cg); cudaFree(m->dPaths); cudaFree(m->dFlags); cudaFreeHost(m->hFlags);
+	if (m->ctx->staticMg == m) m->ctx->staticMg = nullptr;
+	delete m; return MP_OK;
+}
+
+int mp_mg_set_a(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak)
+{
+	if (!m || !A0 || !Ai || !Aj || !Ak) MP_FAIL(MP_ERR_INVALID, "mp_mg_set_a: NULL argument");
+	const mp_grid* gs[] = { A0, Ai, Aj, Ak };
+	for (const mp_grid* g : gs) {
+		if (g->kind != MP_GRID_REAL || g->prec != m->prec || g->sx != m->geom[0].sx || g->sy != m->geom[0].sy || g->sz != m->geom[0].sz)
+			MP_FAIL(MP_ERR_INVALID, "mp_mg_set_a: grid does not match the GridMg size/precision");
+	}
+	MP_CUDA(cudaSetDevice(m->ctx->device));
+	return m->prec == 4 ? mgSetA<float>(m, A0, Ai, Aj, Ak) : mgSetA<double>(m, A0, Ai, Aj, Ak);
+}
+
+int mp_mg_set_rhs(mp_mg* m, const mp_grid* rhs)
+{
+	if (!m || !rhs) MP_FAIL(MP_ERR_INVALID, "mp_mg_set_rhs: NULL argument");
+	if (rhs->kind != MP_GRID_REAL || rhs->prec != m->prec || rhs->n != m->geom[0].n) MP_FAIL(MP_ERR_INVALID, "mp_mg_set_rhs: grid does not match the GridMg size/precision");
+	return m->prec == 4 ? mgSetRhs<float>(m, (const float*)rhs->d, nullptr) : mgSetRhs<double>(m, (const double*)rhs->d, nullptr);
+}
+
+int mp_mg_is_a_set(const mp_mg* m, int* isSet) { *isSet = m->isASet ? 1 : 0; return MP_OK; }
+
+int mp_mg_do_vcycle(mp_mg* m, mp_grid* dst, const mp_grid* src, double* resNorm)
+{
+	if (!m || !dst) MP_FAIL(MP_ERR_INVALID, "mp_mg_do_vcycle: NULL argument");
+	if (!m->isASet || !m->isRhsSet) MP_FAIL(MP_ERR_NOT_SET, "GridMg::doVCycle Error: A and/or rhs have not been set.");   // :453
+	if (dst->kind != MP_GRID_REAL || dst->prec != m->prec || dst->n != m->geom[0].n) MP_FAIL(MP_ERR_INVALID, "mp_mg_do_vcycle: dst does not match the GridMg size/precision");
+	mp_context* ctx = m->ctx;
+	MP_CUDA(cudaSetDevice(ctx->device));
+	if (src) {
+		if (src->kind != MP_GRID_REAL || src->prec != m->prec || src->n != m->geom[0].n) MP_FAIL(MP_ERR_INVALID, "mp_mg_do_vcycle: src does not match");
+		MP_CUDA(cudaMemcpyAsync(m->x[0], src->d, (size_t)m->prec * m->geom[0].n, cudaMemcpyDeviceToDevice, ctx->stream));   // knCopyToVector :457
+	}
+	if (m->prec == 4) MP_TRY((mgVCycle<float>(m, (float*)dst->d, src != nullptr, resNorm != nullptr, nullptr)));
+	else              MP_TRY((mgVCycle<double>(m, (double*)dst->d, src != nullptr, resNorm != nullptr, nullptr)));
+	if (resNorm) {
+		const int n = m->geom[0].n;
+		unsigned int blocks = nb(n, 256 * 8); if (blocks > 1024) blocks = 1024;
+		if (m->prec == 4) k_mg_norm<float><<<blocks, 256, 0, ctx->stream>>>(n, (const float*)m->r[0], m->type[0], ctx->partials, ctx->tickets + 6, ctx->dScal + 16);
+		else              k_mg_norm<double><<<blocks, 256, 0, ctx->stream>>>(n, (const double*)m->r[0], m->type[0], ctx->partials, ctx->tickets + 6, ctx->dScal + 16);
+		MP_CHECK_LAUNCH(ctx);
+		MP_CUDA(cudaMemcpyAsync(ctx->hScal + 16, ctx->dScal + 16, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		MP_CUDA(cudaStreamSynchronize(ctx->stream));
+		*resNorm = std::sqrt(ctx->hScal[16]);
+	}
+	return MP_OK;
+}
+
+int mp_mg_set_coarsest_level_accuracy(mp_mg* m, double accuracy) { m->coarsestAcc = (m->prec == 4) ? (double)(float)accuracy : accuracy; return MP_OK; }
+int mp_mg_set_smoothing(mp_mg* m, int numPre, int numPost) { m->numPre = numPre; m->numPost = numPost; return MP_OK; }
+int mp_mg_num_levels(const mp_mg* m, int* levels) { *levels = m->nlev; return MP_OK; }
+int mp_mg_level_info(const mp_mg* m, int level, int* sx, int* sy, int* sz, int* stencil)
+{
+	if (level < 0 || level >= m->nlev) MP_FAIL(MP_ERR_INVALID, "mp_mg_level_info: level %d out of range", level);
+	if (sx) *sx = m->geom[level].sx; if (sy) *sy = m->geom[level].sy; if (sz) *sz = m->geom[level].sz;
+	if (stencil) *stencil = level == 0 ? m->stencil0 : m->stencil;
+	return MP_OK;
+}
+
+int mp_mg_download(const mp_mg* m, int level, const char* what, void* host)
+{
+	if (level < 0 || level >= m->nlev) MP_FAIL(MP_ERR_INVALID, "mp_mg_download: level %d out of range", level);
+	MP_CUDA(cudaSetDevice(m->ctx->device));
+	MP_CUDA(cudaStreamSynchronize(m->ctx->stream));
+	const size_t n = (size_t)m->geom[level].n; const int S = level == 0 ? m->stencil0 : m->stencil;
+	if (!strcmp(what, "type")) { MP_CUDA(cudaMemcpy(host, m->type[level], n, cudaMemcpyDeviceToHost)); return MP_OK; }
+	if (!strcmp(what, "x")) { MP_CUDA(cudaMemcpy(host, m->x[level], n * m->prec, cudaMemcpyDeviceToHost)); return MP_OK; }
+	if (!strcmp(what, "b")) { MP_CUDA(cudaMemcpy(host, m->b[level], n * m->prec, cudaMemcpyDeviceToHost)); return MP_OK; }
+	if (!strcmp(what, "r")) { MP_CUDA(cudaMemcpy(host, m->r[level], n * m->prec, cudaMemcpyDeviceToHost)); return MP_OK; }
+	if (!strcmp(what, "a")) {
+		// device SoA [s][v] -> reference interleaved [v][s]
+		std::vector<char> tmp(n * S * m->prec);
+		MP_CUDA(cudaMemcpy(tmp.data(), m->A[level], n * S * m->prec, cudaMemcpyDeviceToHost));
+		for (size_t v = 0; v < n; v++) for (int s = 0; s < S; s++)
+			memcpy((char*)host + (v * S + s) * m->prec, tmp.data() + ((size_t)s * n + v) * m->prec, m->prec);
+		return MP_OK;
+	}
+	if (!strcmp(what, "stats")) { ((int*)host)[0] = m->hostCoarsenLevels; MP_CUDA(cudaMemcpy((int*)host + 1, m->dFlags + 4, sizeof(int), cudaMemcpyDeviceToHost)); return MP_OK; }
+	MP_FAIL(MP_ERR_INVALID, "mp_mg_download: unknown item '%s'", what);
+}
+
+} // extern "C"

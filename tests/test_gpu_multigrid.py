@@ -1,0 +1,155 @@
+"""GPU parity tests for GridMg (multigrid.cpp) and the PcMGDynamic / PcMGStatic preconditioners.
+
+The vertex types of every level must equal the oracle's exactly (the coarse-vertex selection is integer work);
+level-0/1 operators are bit-exact for the integer-valued Laplacian, coarser Galerkin operators and the V-cycle are
+compared with a floating-point tolerance because the coarse solve reduces in a different (fixed) order."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from mantaflow_b200 import scenes  # noqa: E402
+from test_gpu_parity import SCENES, mf, mk, oracle, rel_l2, TOL  # noqa: E402,F401
+
+
+def setup_system(prec, scene, pin=True):
+    flags, vel, phi = SCENES[scene](prec)
+    O = oracle(prec)
+    rhs, _, _ = O.compute_rhs(flags, vel, phi=phi)
+    A = O.make_matrix(flags, phi=phi)
+    if pin:
+        fix = O.choose_fix_cell(flags)
+        if fix >= 0:
+            O.fix_pressure(flags, fix, 0.0, rhs, *A)
+    return flags, vel, phi, O, rhs, A
+
+
+def isolated_features_flags(prec):
+    """a domain with isolated single fluid cells and thin diagonal features: forces the order-dependent phase of
+    genCoarseGrid (multigrid.cpp:543-575), i.e. the exact serial fallback"""
+    flags, vel = scenes.smoke_plume((26, 22, 18), prec, random_vel=True)
+    rng = np.random.Generator(np.random.PCG64(21))
+    inner = np.zeros(flags.shape, bool); inner[1:-1, 1:-1, 1:-1] = True
+    keep = rng.random(flags.shape) < 0.18
+    flags[inner & ~keep] = 2          # most of the interior becomes obstacle: many isolated fluid cells
+    scenes.set_wall_bcs(flags, vel)
+    return flags, vel
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28", "smoke2d", "liquid2d"])
+def test_hierarchy_matches_oracle(mf, scene, prec):
+    from mantaflow_b200 import cg
+    flags, vel, phi, O, rhs, A_o = setup_system(prec, scene)
+    sz, sy, sx = flags.shape
+    O.mg_create(sx, sy, sz); O.mg_set_a(*A_o)
+    s = mk(mf, flags.shape, prec)
+    A = [mf.RealGrid(s, a) for a in A_o]
+    mg = cg.GridMg(s)
+    assert not mg.isASet()
+    mg.setA(*A)
+    assert mg.isASet()
+    assert mg.numLevels() == O.mg_num_levels()
+    for l in range(mg.numLevels()):
+        assert mg.levelInfo(l)[0] == O.mg_level_size(l)
+        t, t_o = mg.download("type", l), O.mg_get("type", l)
+        assert np.array_equal(t, t_o), "vertex types differ on level %d" % l
+        a, a_o = mg.download("a", l), O.mg_get("a", l)
+        st = mg.levelInfo(l)[1]
+        act = np.repeat(t_o != 0, st)
+        if l == 0 or phi is None:
+            assert np.array_equal(a[act], a_o[act]), "operator differs on level %d" % l
+        else:
+            assert np.allclose(a[act], a_o[act], rtol=1e-5 if prec == 4 else 1e-13, atol=1e-6 if prec == 4 else 1e-14)
+    O.mg_destroy()
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+def test_hierarchy_isolated_features_exact_fallback(mf, prec):
+    from mantaflow_b200 import cg
+    flags, vel = isolated_features_flags(prec)
+    O = oracle(prec)
+    A_o = O.make_matrix(flags)
+    sz, sy, sx = flags.shape
+    O.mg_create(sx, sy, sz); O.mg_set_a(*A_o)
+    s = mk(mf, flags.shape, prec)
+    A = [mf.RealGrid(s, a) for a in A_o]
+    mg = cg.GridMg(s)
+    mg.setA(*A)
+    for l in range(mg.numLevels()):
+        assert np.array_equal(mg.download("type", l), O.mg_get("type", l)), "vertex types differ on level %d" % l
+        st = mg.levelInfo(l)[1]
+        act = np.repeat(O.mg_get("type", l) != 0, st)
+        assert np.array_equal(mg.download("a", l)[act], O.mg_get("a", l)[act])
+    O.mg_destroy()
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28", "smoke2d"])
+def test_vcycle_matches_oracle(mf, scene, prec):
+    from mantaflow_b200 import cg
+    flags, vel, phi, O, rhs, A_o = setup_system(prec, scene)
+    sz, sy, sx = flags.shape
+    O.mg_create(sx, sy, sz); O.mg_set_a(*A_o)
+    z_o = O.mg_vcycle(rhs, coarsestAccuracy=1e-9, pre=1, post=1)
+    s = mk(mf, flags.shape, prec)
+    A = [mf.RealGrid(s, a) for a in A_o]
+    mg = cg.GridMg(s)
+    B, Z = mf.RealGrid(s, rhs), mf.RealGrid(s)
+    with pytest.raises(mf.MantaError, match="not been set"):
+        mg.setRhs(B)
+    mg.setA(*A)
+    mg.setCoarsestLevelAccuracy(1e-9)
+    mg.setSmoothing(1, 1)
+    mg.setRhs(B)
+    res = mg.doVCycle(Z)
+    assert rel_l2(Z.numpy(), z_o) <= (1e-5 if prec == 4 else 1e-9)
+    assert res >= 0
+    # second cycle starting from the first result (src != NULL path, multigrid.cpp:457)
+    Z2 = mf.RealGrid(s)
+    res2 = mg.doVCycle(Z2, Z)
+    assert res2 < res
+    O.mg_destroy()
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("pc", [2, 3])
+@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28", "smoke2d"])
+def test_solve_pressure_mg(mf, scene, pc, prec):
+    flags, vel, phi = SCENES[scene](prec)
+    O = oracle(prec)
+    acc = 1e-5 if prec == 4 else 1e-11
+    v_o = vel.copy()
+    p_o, it_o, rn_o = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=True)
+    s = mk(mf, flags.shape, prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+    PH = mf.RealGrid(s, phi) if phi is not None else None
+    mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=True)
+    info = mf.lastSolveInfo()
+    assert abs(info["iterations"] - it_o) <= 1, (info["iterations"], it_o)
+    assert info["maxIter"] == 100 and info["mgLevels"] >= 2
+    assert rel_l2(P.numpy(), p_o) <= TOL[prec]
+    assert rel_l2(V.numpy(), v_o) <= TOL[prec]
+    mf.releaseMG(s)
+
+
+def test_static_mg_reuses_hierarchy_like_test_0110(mf):
+    """tools/tests/test_0110_mgsolve.py:57-68: two PcMGStatic solves with different velocities on one hierarchy,
+    preceded by a PcMGDynamic solve that must drop any previous hierarchy (pressure.cpp:423-426)."""
+    prec = 4
+    flags, vel = scenes.smoke_plume(28, prec)
+    O = oracle(prec)
+    s = mk(mf, flags.shape, prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s), mf.RealGrid(s)
+    key = 77
+    for step, (pc, scale) in enumerate([(3, 1.0), (3, -1.3), (2, 0.7), (3, 2.0)]):
+        _, v = scenes.smoke_plume(28, prec, scale=scale)
+        v_o = v.copy()
+        p_o, it_o, _ = O.solve_pressure(flags, v_o, cgAccuracy=1e-5, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=True, solver_key=key)
+        V.copyFromArray(v)
+        mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=1e-5, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=True)
+        info = mf.lastSolveInfo()
+        assert abs(info["iterations"] - it_o) <= 1, (step, info["iterations"], it_o)
+        assert rel_l2(P.numpy(), p_o) <= 1e-4 and rel_l2(V.numpy(), v_o) <= 1e-4
+    O.release_solver(key)
+    mf.releaseMG(s)

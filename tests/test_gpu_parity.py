@@ -1,0 +1,297 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): RHS / matrix assembly bit-exact; MIC(0) factor and sweeps bit-exact (same
+per-cell arithmetic as the serial reference); converged pressure rel-L2 <= 1e-4 (float) / 1e-10 (double) against
+the oracle with the same preconditioner and pinning; PcNone iteration counts within +-1; post-projection
+divergence at or below the oracle's."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from mantaflow_b200 import scenes  # noqa: E402
+from oracle.oracle_api import OracleError as OracleErr  # noqa: E402
+
+TOL = {4: 1e-4, 8: 1e-10}
+
+
+@pytest.fixture(scope="module")
+def mf():
+    import mantaflow_b200 as m
+    if m.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests need a B200")
+    return m
+
+
+def oracle(prec):
+    from oracle.oracle_api import Oracle
+    return Oracle("port", prec)
+
+
+def mk(mf, shape, prec):
+    sz, sy, sx = shape
+    return mf.Solver(gridSize=(sx, sy, sz), dim=3 if sz > 1 else 2, prec=prec)
+
+
+def rel_l2(a, b):
+    d = np.linalg.norm((a.astype(np.float64) - b.astype(np.float64)).ravel())
+    n = np.linalg.norm(b.astype(np.float64).ravel())
+    return d / n if n > 0 else d
+
+
+SCENES = {
+    "smoke24": lambda prec: scenes.smoke_plume(24, prec, random_vel=True) + (None,),
+    "smoke_ragged": lambda prec: scenes.smoke_plume((37, 26, 19), prec, random_vel=True) + (None,),
+    "liquid28": lambda prec: scenes.liquid_basin(28, prec),
+    "smoke2d": lambda prec: scenes.smoke_plume((40, 36, 1), prec, random_vel=True) + (None,),
+    "liquid2d": lambda prec: scenes.liquid_basin((33, 30, 1), prec),
+}
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("scene", list(SCENES))
+def test_rhs_and_matrix_bit_exact(mf, scene, prec):
+    from mantaflow_b200 import cg
+    flags, vel, phi = SCENES[scene](prec)
+    O = oracle(prec)
+    s = mk(mf, flags.shape, prec)
+    F, V = mf.FlagGrid(s, flags), mf.MACGrid(s, vel)
+    PH = mf.RealGrid(s, phi) if phi is not None else None
+    rhs = mf.RealGrid(s)
+    sm, cnt = cg.MakeRhs(F, rhs, V, phi=PH)
+    r_o, s_o, c_o = O.compute_rhs(flags, vel, phi=phi)
+    assert cnt == c_o
+    assert np.array_equal(rhs.numpy(), r_o)
+    assert abs(sm - s_o) <= 1e-12 * max(1.0, abs(s_o)) * cnt
+    A = [mf.RealGrid(s) for _ in range(4)]
+    cg.MakeLaplaceMatrix(F, *A)
+    if PH is not None:
+        cg.ApplyGhostFluidDiagonal(A[0], F, PH, 1e-4)
+    A_o = O.make_matrix(flags, phi=phi)
+    for a, b in zip(A, A_o):
+        assert np.array_equal(a.numpy(), b)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+def test_rhs_matrix_fractions_obvel_corr(mf, prec):
+    from mantaflow_b200 import cg
+    flags, vel = scenes.smoke_plume((30, 22, 18), prec, random_vel=True)
+    frac, obvel = scenes.random_fractions(flags, prec)
+    corr = (np.random.Generator(np.random.PCG64(3)).random(flags.shape) * 0.01).astype(vel.dtype)
+    O = oracle(prec)
+    s = mk(mf, flags.shape, prec)
+    F, V, FR, OV, CO = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.MACGrid(s, frac), mf.MACGrid(s, obvel), mf.RealGrid(s, corr)
+    rhs = mf.RealGrid(s)
+    cg.MakeRhs(F, rhs, V, perCellCorr=CO, fractions=FR, obvel=OV)
+    r_o, _, _ = O.compute_rhs(flags, vel, perCellCorr=corr, fractions=frac, obvel=obvel)
+    assert np.array_equal(rhs.numpy(), r_o)
+    A = [mf.RealGrid(s) for _ in range(4)]
+    cg.MakeLaplaceMatrix(F, *A, fractions=FR)
+    for a, b in zip(A, O.make_matrix(flags, fractions=frac)):
+        assert np.array_equal(a.numpy(), b)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+def test_surface_tension_rhs_and_velocity(mf, prec):
+    flags, vel, phi = scenes.liquid_basin(26, prec)
+    curv = (np.random.Generator(np.random.PCG64(5)).random(flags.shape) - 0.5).astype(vel.dtype)
+    O = oracle(prec)
+    s = mk(mf, flags.shape, prec)
+    F, V, PH, CU = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s, phi), mf.RealGrid(s, curv)
+    rhs = mf.RealGrid(s)
+    p = mf.RealGrid(s)
+    mf.computePressureRhs(rhs, V, p, F, phi=PH, curv=CU, surfTens=0.3)
+    r_o, _, _ = O.compute_rhs(flags, vel, phi=phi, curv=curv, surfTens=0.3)
+    assert np.array_equal(rhs.numpy(), r_o)
+    pr = (np.random.Generator(np.random.PCG64(6)).random(flags.shape)).astype(vel.dtype)
+    P = mf.RealGrid(s, pr)
+    mf.correctVelocity(V, P, F, phi=PH, curv=CU, surfTens=0.3)
+    v_o = O.correct_velocity(flags, vel.copy(), pr, phi=phi, curv=curv, surfTens=0.3)
+    assert np.array_equal(V.numpy(), v_o)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+def test_enforce_compatibility(mf, prec):
+    flags, vel = scenes.smoke_plume(20, prec, random_vel=True)
+    O = oracle(prec)
+    s = mk(mf, flags.shape, prec)
+    F, V = mf.FlagGrid(s, flags), mf.MACGrid(s, vel)
+    rhs, p = mf.RealGrid(s), mf.RealGrid(s)
+    mf.computePressureRhs(rhs, V, p, F, enforceCompatibility=True)
+    r_o, _, _ = O.compute_rhs(flags, vel, enforceCompatibility=True)
+    # the mean correction depends on the order of a double sum of Reals: equal to 1 ulp of the correction
+    assert np.allclose(rhs.numpy(), r_o, rtol=0, atol=1e-6 if prec == 4 else 1e-15)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28", "smoke2d"])
+def test_apply_matrix_bit_exact(mf, scene, prec):
+    from mantaflow_b200 import cg
+    flags, vel, phi = SCENES[scene](prec)
+    O = oracle(prec)
+    A_o = O.make_matrix(flags, phi=phi)
+    src = (np.random.Generator(np.random.PCG64(9)).random(flags.shape) - 0.5).astype(vel.dtype)
+    s = mk(mf, flags.shape, prec)
+    F = mf.FlagGrid(s, flags)
+    A = [mf.RealGrid(s, a) for a in A_o]
+    S, D = mf.RealGrid(s, src), mf.RealGrid(s)
+    cg.ApplyMatrix(F, D, S, *A)
+    assert np.array_equal(D.numpy(), O.apply_matrix(flags, src, *A_o))
+    assert abs(cg.GridDotProduct(D, S) - float(np.sum((D.numpy() * src).astype(np.float64)))) < 1e-6 * flags.size
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28"])
+def test_mic_bit_exact(mf, scene, prec):
+    from mantaflow_b200 import cg
+    flags, vel, phi = SCENES[scene](prec)
+    O = oracle(prec)
+    A_o = O.make_matrix(flags, phi=phi)
+    P_o = O.mic_init(flags, *A_o)
+    src = (np.random.Generator(np.random.PCG64(10)).random(flags.shape) - 0.5).astype(vel.dtype)
+    s = mk(mf, flags.shape, prec)
+    F = mf.FlagGrid(s, flags)
+    A = [mf.RealGrid(s, a) for a in A_o]
+    P = mf.RealGrid(s)
+    cg.InitPreconditionModifiedIncompCholesky2(F, P, *A)
+    assert np.array_equal(P.numpy(), P_o)
+    S, D = mf.RealGrid(s, src), mf.RealGrid(s)
+    cg.ApplyPreconditionModifiedIncompCholesky2(D, S, F, P, *A)
+    assert np.array_equal(D.numpy(), O.mic_apply(flags, src, P_o, *A_o))
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("pc", [0, 2])   # GridCg::PC_None, PC_mICP
+@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28"])
+def test_gridcg_direct(mf, scene, pc, prec):
+    """GridCg driven directly (the harness route of SURVEY F4): iteration counts +-1 and pressure tolerance."""
+    from mantaflow_b200 import cg
+    flags, vel, phi = SCENES[scene](prec)
+    O = oracle(prec)
+    rhs_o, _, _ = O.compute_rhs(flags, vel, phi=phi)
+    A_o = O.make_matrix(flags, phi=phi)
+    acc = 1e-5 if prec == 4 else 1e-11
+    x_o, it_o, rn_o = O.cg_solve(flags, rhs_o, *A_o, pc=1 if pc == 2 else 0, accuracy=acc, maxIter=3000)
+    s = mk(mf, flags.shape, prec)
+    F = mf.FlagGrid(s, flags)
+    A = [mf.RealGrid(s, a) for a in A_o]
+    x, b, r, se, t = mf.RealGrid(s), mf.RealGrid(s, rhs_o), mf.RealGrid(s), mf.RealGrid(s), mf.RealGrid(s)
+    g = cg.GridCg(x, b, r, se, F, t, *A)
+    g.setAccuracy(acc)
+    g.setUseL2Norm(False)
+    if pc == 2:
+        pcs = [mf.RealGrid(s) for _ in range(4)]
+        g.setICPreconditioner(pc, *pcs)
+    g.solve(3000)
+    assert abs(g.getIterations() - it_o) <= 1, (g.getIterations(), it_o)
+    assert g.getResNorm() < acc
+    assert rel_l2(x.numpy(), x_o) <= TOL[prec]
+
+
+def test_gridcg_iterate_stepwise(mf):
+    from mantaflow_b200 import cg
+    prec = 4
+    flags, vel, _ = SCENES["smoke24"](prec)
+    O = oracle(prec)
+    rhs_o, _, _ = O.compute_rhs(flags, vel)
+    A_o = O.make_matrix(flags)
+    x_o, it_o, _ = O.cg_solve(flags, rhs_o, *A_o, pc=0, accuracy=1e-5, maxIter=3000)
+    s = mk(mf, flags.shape, prec)
+    F = mf.FlagGrid(s, flags)
+    A = [mf.RealGrid(s, a) for a in A_o]
+    x, b, r, se, t = mf.RealGrid(s), mf.RealGrid(s, rhs_o), mf.RealGrid(s), mf.RealGrid(s), mf.RealGrid(s)
+    g = cg.GridCg(x, b, r, se, F, t, *A)
+    g.setAccuracy(1e-5)
+    g.setUseL2Norm(False)
+    n = 0
+    while g.iterate():
+        n += 1
+        assert n < 3000
+    assert abs(g.getIterations() - it_o) <= 1
+    assert rel_l2(x.numpy(), x_o) <= 1e-4
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("pc", [0, 1])   # PcNone, PcMIC
+@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28", "smoke2d", "liquid2d"])
+def test_solve_pressure_plugin(mf, scene, pc, prec):
+    flags, vel, phi = SCENES[scene](prec)
+    O = oracle(prec)
+    acc = 1e-5 if prec == 4 else 1e-11
+    v_o = vel.copy()
+    p_o, it_o, rn_o = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc)
+    s = mk(mf, flags.shape, prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+    PH = mf.RealGrid(s, phi) if phi is not None else None
+    mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc)
+    info = mf.lastSolveInfo()
+    assert abs(info["iterations"] - it_o) <= 1, (info["iterations"], it_o)
+    assert rel_l2(P.numpy(), p_o) <= TOL[prec]
+    assert rel_l2(V.numpy(), v_o) <= TOL[prec]
+    if phi is None:
+        assert scenes.max_divergence(flags, V.numpy()) <= scenes.max_divergence(flags, v_o) * 1.05 + acc
+
+
+def test_solve_pressure_host_entry(mf):
+    prec = 4
+    flags, vel, _ = SCENES["smoke24"](prec)
+    O = oracle(prec)
+    v_o = vel.copy()
+    p_o, it_o, _ = O.solve_pressure(flags, v_o, cgAccuracy=1e-5, cgMaxIterFac=99, preconditioner=0, retRhs=True)[:3]
+    s = mk(mf, flags.shape, prec)
+    v = vel.copy()
+    p = np.full(flags.shape, 7.0, np.float32)     # must be overwritten
+    rr = np.zeros(flags.shape, np.float32)
+    info = mf.solvePressureHost(s, v, p, flags, retRhs=rr, cgAccuracy=1e-5, cgMaxIterFac=99, preconditioner=0)
+    assert abs(info["iterations"] - it_o) <= 1
+    assert rel_l2(p, p_o) <= 1e-4 and rel_l2(v, v_o) <= 1e-4
+    assert np.array_equal(rr, O.compute_rhs(flags, vel)[0])
+
+
+def test_max_iter_cap_and_l2_norm(mf):
+    prec = 4
+    flags, vel, _ = SCENES["smoke24"](prec)
+    O = oracle(prec)
+    v_o = vel.copy()
+    p_o, it_o, rn_o = O.solve_pressure(flags, v_o, cgAccuracy=1e-9, cgMaxIterFac=0.5, preconditioner=0, useL2Norm=True)
+    s = mk(mf, flags.shape, prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+    mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=1e-9, cgMaxIterFac=0.5, preconditioner=0, useL2Norm=True)
+    info = mf.lastSolveInfo()
+    assert info["iterations"] == it_o == 12 and info["maxIter"] == 12
+    assert abs(info["resNorm"] - rn_o) <= 1e-3 * rn_o
+    assert rel_l2(P.numpy(), p_o) <= 1e-4
+
+
+def test_errors(mf):
+    s = mf.Solver(gridSize=(12, 12, 12), dim=3, prec=4)
+    flags = np.full((12, 12, 12), 1, np.int32)     # fluid on the outer layer: the reference reads out of bounds
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s), mf.RealGrid(s)
+    with pytest.raises(mf.MantaError):
+        mf.solvePressure(vel=V, pressure=P, flags=F)
+    with pytest.raises(TypeError):
+        mf.solvePressure(vel=V, pressure=P, flags=F, notAKwarg=1)
+    s2 = mf.Solver(gridSize=(10, 12, 12), dim=3, prec=4)
+    with pytest.raises(mf.MantaError):
+        mf.solvePressure(vel=V, pressure=mf.RealGrid(s2), flags=F)
+
+
+def test_diverged_reports_reference_error(mf):
+    # a residual beyond 1e35 that does not converge in one step -> the reference's errMsg (conjugategrad.cpp:288-295)
+    from mantaflow_b200 import cg
+    prec = 8
+    flags, vel, _ = SCENES["smoke24"](prec)
+    O = oracle(prec)
+    A_o = O.make_matrix(flags)
+    rhs = np.where((flags & 1) != 0, 1e36, 0) * np.random.Generator(np.random.PCG64(1)).random(flags.shape)
+    s = mk(mf, flags.shape, prec)
+    F = mf.FlagGrid(s, flags)
+    A = [mf.RealGrid(s, a) for a in A_o]
+    x, b, r, se, t = mf.RealGrid(s), mf.RealGrid(s, rhs), mf.RealGrid(s), mf.RealGrid(s), mf.RealGrid(s)
+    g = cg.GridCg(x, b, r, se, F, t, *A)
+    g.setAccuracy(1e-12)
+    g.setUseL2Norm(False)
+    with pytest.raises(mf.MantaError, match="diverged"):
+        g.solve(500)
+    with pytest.raises(OracleErr, match="diverged"):
+        O.cg_solve(flags, rhs, *A_o, pc=0, accuracy=1e-12, maxIter=500)
