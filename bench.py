@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- the pressure-projection hot path on B200 (see DESIGN.md "Measurement").
+
+A step = ONE solvePressure (computePressureRhs + MakeLaplaceMatrix + GridCg to convergence + correctVelocity,
+plugin/pressure.cpp:480-521) over one synthetic smoke-plume grid:
+  N=1 : BASELINE.json configs[3] "synthetic 512^3 smoke plume single-GPU pressure projection", float build,
+        preconditioner PcNone by default (the memory-bound matvec/axpy path the north_star roofline is about),
+        cgAccuracy 1e-4, cgMaxIterFac 99.
+  N>1 : the same 512^3 cells PER GPU, z-slab sharded (global grid 512 x 512 x 512N; N=8 has the cell count of the
+        1024^3 config), one-plane halo exchange + per-iteration scalar all-reduce over NCCL -> "scaling": "weak".
+metric  = cells x CG iterations / second over the whole job ("Gcell-iter/s"); a 512^3 PcNone iteration at the HBM roofline
+          (64 B/cell, MEASURED_PEAKS hbm_gbs) is the ceiling.  cg_iter_per_s and solve_ms are reported beside it.
+value   = inputs resident in HBM when the timed region starts; e2e = same metric through mp_solve_pressure_host with
+          pinned HOST buffers (H2D of flags+vel and D2H of vel+pressure inside the timed region).
+--impl reference : the reference's own CPU code (oracle/_ref, the unmodified reference compiled here; else the C port)
+          on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PC_NAMES = {0: "PcNone", 1: "PcMIC", 2: "PcMGDynamic", 3: "PcMGStatic"}
+# algorithmic bytes per cell (SURVEY 8d / DESIGN.md): matvec 4+6w, axpy2+norms 6w, update 3w
+def bytes_per_cell(w):
+    return {"matvec": 4 + 6 * w, "axpy": 6 * w, "update": 3 * w, "iter_none": 4 + 15 * w}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(res, prec, n_slabs=1):
+    from mantaflow_b200 import scenes
+    sx = sy = res
+    sz = res * n_slabs
+    return scenes.smoke_plume((sx, sy, sz), prec)
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_step(O, flags, vel, pc, max_iter, accuracy):
+    """One bounded pass of the hot path on the CPU: rhs + matrix + GridCg capped at max_iter + correctVelocity.
+    GridCg is driven directly because solvePressure(PcNone) asserts in the reference."""
+    t0 = time.perf_counter()
+    rhs, _, _ = O.compute_rhs(flags, vel)
+    A = O.make_matrix(flags)
+    x, it, rn = O.cg_solve(flags, rhs, *A, pc={0: 0, 1: 1, 2: 2, 3: 2}[pc], accuracy=accuracy, maxIter=max_iter)
+    O.correct_velocity(flags, vel, x)
+    return time.perf_counter() - t0, it
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle_api import Oracle, available
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    kind = "reference" if available("reference", args.prec) else "port"
+    O = Oracle(kind, args.prec)
+    flags, vel = make_scene(args.res, args.prec)
+    cells = flags.size
+    cap = args.cpu_iters
+    times, its = [], 0
+    for s in range(args.warmup + args.steps):
+        v = vel.copy()
+        dt, its = cpu_step(O, flags, v, args.pc, cap, 1e-4)
+        if s >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = cells * its / (ms * 1e-3) / 1e9
+    sample = "%d^3 %s, GridCg capped at %d iterations per step (full solve needs ~%d)" % (args.res, PC_NAMES[args.pc], cap, 3.2 * args.res)
+    line = {"impl": "reference", "metric": "pressure-solve CG throughput (cells x iterations / s)", "value": value, "unit": "Gcell-iter/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.prec == 4 else "f64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cg_iter_per_s": its / (ms * 1e-3),
+            "cpu_baseline": {"value": value, "unit": "Gcell-iter/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "Gcell-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": "synthetic %d^3 smoke plume with sphere obstacle per GPU (global %dx%dx%d), solvePressure %s, cgAccuracy 1e-4, cgMaxIterFac 99, %s build"
+            % (args.res, args.res, args.res, args.res * n, PC_NAMES[args.pc], "float" if args.prec == 4 else "double"),
+            "preconditioner": PC_NAMES[args.pc], "grid": [args.res, args.res, args.res * n], "sharding": "z-slabs x%d" % n,
+            "l2": "inputs larger than L2 (one Real grid = %d MiB, 9 streamed per iteration)" % (args.res ** 3 * args.prec >> 20)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import mantaflow_b200 as mf
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run --nproc-per-node N)" % (args.gpus, world))
+    if not torch.cuda.is_available() or mf.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    prec, res, pc = args.prec, args.res, args.pc
+    real = np.float32 if prec == 4 else np.float64
+
+    if world > 1:
+        from mantaflow_b200 import sharded
+        runner = sharded.ShardedBench(args, rank, world, local, dist)
+    else:
+        runner = SingleBench(args, local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ----
+    for _ in range(args.warmup):
+        runner.step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = runner.launches()
+    barrier()
+    t0 = time.perf_counter()
+    ms_dev, iters = [], 0
+    for _ in range(args.steps):
+        info = runner.step_resident()
+        ms_dev.append(info["msTotal"]); iters = info["iterations"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    launches = runner.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = float(np.mean(ms_dev))          # CUDA-event time of the step on the launching stream
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = t.tolist()
+    prof = runner.last_info
+
+    # ---- end-to-end arm (host buffers through the C-ABI plugin entry point) ----
+    e2e_ms, bi, bo = runner.run_e2e(args.warmup, args.steps, barrier)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item()
+
+    if rank == 0:
+        cells = res ** 3 * world
+        peak, peak_src = load_peaks()
+        bpc = bytes_per_cell(prec)
+        mv_ms = prof.get("msMatvecAvg", 0.0)
+        cells_gpu = res ** 3
+        achieved = (bpc["matvec"] * cells_gpu / (mv_ms * 1e-3) / 1e9) if mv_ms > 0 else None
+        line = {"metric": "pressure-solve CG throughput (cells x iterations / s)", "value": cells * iters / (dev_ms * 1e-3) / 1e9, "unit": "Gcell-iter/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32" if prec == 4 else "f64", "data": "synthetic", "config": workload_config(args, world),
+                "solve_ms": dev_ms, "wall_ms_per_step": wall_ms, "iterations": iters, "cg_iter_per_s": iters / (dev_ms * 1e-3),
+                "stage_ms": {k: prof.get(k) for k in ("msRhs", "msMatrix", "msSolve", "msCorrect")},
+                "kernel_ms": {"matvec_dot": mv_ms, "axpy2_norm": prof.get("msAxpyAvg"), "update_search": prof.get("msUpdateAvg"),
+                              "precond": prof.get("msPrecondAvg"), "samples": prof.get("profSamples")},
+                "kernel_gbs": {"matvec_dot": achieved,
+                               "axpy2_norm": (bpc["axpy"] * cells_gpu / (prof["msAxpyAvg"] * 1e-3) / 1e9) if prof.get("msAxpyAvg") else None,
+                               "update_search": (bpc["update"] * cells_gpu / (prof["msUpdateAvg"] * 1e-3) / 1e9) if prof.get("msUpdateAvg") else None},
+                "roofline": {"bound": "hbm", "kernel": "k_matvec_dot", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": (achieved / peak) if achieved else None, "traffic": runner.ncu_traffic(), "peak_source": peak_src,
+                             "algorithmic_bytes_per_cell": bpc["matvec"]},
+                "e2e": {"value": cells * iters / (e2e_ms * 1e-3) / 1e9, "unit": "Gcell-iter/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+class SingleBench:
+    def __init__(self, args, device):
+        import ctypes as C
+        import mantaflow_b200 as mf
+        self.mf, self.args = mf, args
+        res, prec = args.res, args.prec
+        flags, vel = make_scene(res, prec)
+        self.s = mf.Solver(gridSize=(res, res, res), dim=3, prec=prec, device=device)
+        self.s.setProfiling(16)
+        self.F, self.V0, self.V, self.P = mf.FlagGrid(self.s, flags), mf.MACGrid(self.s, vel), mf.MACGrid(self.s), mf.RealGrid(self.s)
+        self.F.dev(); self.V0.dev()
+        self.kw = dict(cgAccuracy=1e-4, cgMaxIterFac=99, preconditioner=args.pc, zeroPressureFixing=(args.pc >= 2))
+        self.last_info = {}
+        # pinned host staging for the e2e arm
+        lib = self.s.lib
+        self._pinned = []
+
+        def pinned_like(a):
+            p = C.c_void_p()
+            mf._lib.check(lib.mp_host_alloc(C.byref(p), C.c_ulonglong(a.nbytes)))
+            self._pinned.append(p)
+            buf = (C.c_char * a.nbytes).from_address(p.value)
+            out = np.frombuffer(buf, dtype=a.dtype).reshape(a.shape)
+            out[...] = a
+            return out
+        self.h_flags, self.h_vel0 = pinned_like(flags), pinned_like(vel)
+        self.h_vel, self.h_p = pinned_like(vel), pinned_like(np.zeros(flags.shape, vel.dtype))
+
+    def launches(self):
+        return self.s.kernelLaunches()
+
+    def step_resident(self):
+        mf = self.mf
+        # restore the un-projected velocity on the device (D2D, part of the step) and project it
+        mf._lib.check(self.s.lib.mp_grid_copy_from(self.V.dev(), self.V0.dev()))
+        mf.solvePressure(vel=self.V, pressure=self.P, flags=self.F, **self.kw)
+        self.last_info = mf.lastSolveInfo()
+        return self.last_info
+
+    def run_e2e(self, warmup, steps, barrier):
+        mf = self.mf
+        ts = []
+        for i in range(warmup + steps):
+            self.h_vel[...] = self.h_vel0          # host-side reset, outside the timed region
+            barrier()
+            t0 = time.perf_counter()
+            mf.solvePressureHost(self.s, self.h_vel, self.h_p, self.h_flags, **self.kw)   # synchronous: returns after the D2H
+            float(self.h_p.ravel()[self.h_p.size // 2])
+            barrier()
+            if i >= warmup:
+                ts.append(1e3 * (time.perf_counter() - t0))
+        bi = self.h_flags.nbytes + self.h_vel.nbytes
+        bo = self.h_vel.nbytes + self.h_p.nbytes
+        return float(np.mean(ts)), bi, bo
+
+    def ncu_traffic(self):
+        p = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(p):
+            try:
+                return json.load(open(p)).get("k_matvec_dot_f%d_%d" % (self.args.prec * 8, self.args.res))
+            except Exception:
+                return None
+        return None
+
+
+def cpu_baseline(args):
+    from oracle.oracle_api import Oracle, available
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    kind = "reference" if available("reference", args.prec) else "port"
+    O = Oracle(kind, args.prec)
+    res = args.cpu_res or args.res
+    flags, vel = make_scene(res, args.prec)
+    cap = args.cpu_iters
+    cpu_step(O, flags, vel.copy(), args.pc, 2, 1e-4)       # warm-up (page faults, thread pool)
+    dt, its = cpu_step(O, flags, vel.copy(), args.pc, cap, 1e-4)
+    return {"value": flags.size * its / dt / 1e9, "unit": "Gcell-iter/s", "cores": cores, "kind": kind,
+            "sample": "%d^3 %s, rhs+matrix+GridCg capped at %d iterations+correctVelocity, %.1f s" % (res, PC_NAMES[args.pc], its, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=512)
+    ap.add_argument("--prec", type=int, default=4, choices=[4, 8])
+    ap.add_argument("--pc", type=int, default=0, choices=[0, 1, 2, 3], help="0 PcNone 1 PcMIC 2 PcMGDynamic 3 PcMGStatic")
+    ap.add_argument("--cpu-res", type=int, default=0, help="grid of the bounded cpu_baseline sample in our arm (0 = --res)")
+    ap.add_argument("--cpu-iters", type=int, default=24, help="GridCg iteration cap of a CPU step")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

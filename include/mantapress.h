@@ -76,6 +76,9 @@ typedef struct mp_solve_info {
 	int       mgLevels;           /* GridMg levels (0 unless PcMG*) */
 	float     msRhs, msMatrix, msSolve, msCorrect, msTotal;  /* CUDA-event times of the stages */
 	float     msH2D, msD2H;       /* only filled by the *_host entry points */
+	/* per-kernel averages over sampled launches of the CG loop (mp_context_set_profiling), 0 when off */
+	float     msMatvecAvg, msAxpyAvg, msUpdateAvg, msPrecondAvg;
+	int       profSamples;
 } mp_solve_info;
 
 /* ---- library / errors ---- */
@@ -93,6 +96,8 @@ void* mp_context_stream(mp_context* ctx);                      /* cudaStream_t a
 int   mp_context_device(const mp_context* ctx);
 int   mp_context_sm_count(const mp_context* ctx);
 int   mp_context_kernel_launches(const mp_context* ctx, long long* count);  /* kernels launched so far */
+/* every `period`-th CG iteration brackets its kernels with CUDA events (0 = off); results land in mp_solve_info */
+int   mp_context_set_profiling(mp_context* ctx, int period);
 
 /* ---- Grid storage mirror: Grid<T> ctor/dtor grid.cpp:47-91, FluidSolver::GridStorage fluidsolver.cpp:33-50 ---- */
 int   mp_grid_create(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, mp_grid** out);  /* zero-filled like Grid<T>(parent) */

@@ -59,6 +59,7 @@ int mp_context_destroy(mp_context* c) {
 	cudaStreamSynchronize(c->stream);
 	for (auto& pb : c->pool) cudaFree(pb.first);
 	c->pool.clear();
+	for (auto& e : c->profEv) cudaEventDestroy(e);
 	for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	cudaFree(c->partials); cudaFree(c->tickets); cudaFree(c->dScal); cudaFreeHost(c->hScal);
 	cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copyStream);
@@ -69,6 +70,11 @@ void* mp_context_stream(mp_context* c) { return (void*)c->stream; }
 int mp_context_device(const mp_context* c) { return c->device; }
 int mp_context_sm_count(const mp_context* c) { return c->smCount; }
 int mp_context_kernel_launches(const mp_context* c, long long* count) { *count = c->launches; return MP_OK; }
+int mp_context_set_profiling(mp_context* c, int period) {
+	c->profPeriod = period < 0 ? 0 : period;
+	if (period > 0 && c->profEv.empty()) { c->profEv.resize(5 * 128); for (auto& e : c->profEv) MP_CUDA(cudaEventCreate(&e)); }
+	return MP_OK;
+}
 
 int mp_grid_create(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, mp_grid** out) {
 	if (!ctx || !out) MP_FAIL(MP_ERR_INVALID, "mp_grid_create: NULL argument");

@@ -311,29 +311,40 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	return MP_OK;
 }
 
-static int cgEnqueueIteration(mp_cg* cg) {   // iterate conjugategrad.cpp:237-299, no host synchronisation
+static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conjugategrad.cpp:237-299, no host synchronisation
 	mp_context* ctx = cg->ctx;
 	const Dims d = dimsOf(cg->flags);
 	const bool none = cg->pcMethod == MP_CG_PC_NONE;
+	// sampled kernel timing: 5 events around the 4 stages of this iteration
+	cudaEvent_t* pe = nullptr;
+	if (ctx->profPeriod > 0 && iterIndex >= 0 && iterIndex % ctx->profPeriod == 0 && ctx->profCount < 128) pe = &ctx->profEv[5 * ctx->profCount++];
+	#define PROF(k) do { if (pe) MP_CUDA(cudaEventRecord(pe[k], ctx->stream)); } while (0)
+	PROF(0);
 	MP_TRY(mp_launch_matvec(ctx, cg->flags, cg->tmp, cg->search, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->dSc, 1));
+	PROF(1);
 	DISPATCH_RV(cg->dst, {
 		const unsigned int blocks = streamBlocks(ctx, d.n / V);
 		CgScal<Real>* sc = (CgScal<Real>*)cg->dSc;
 		if (none) {
 			k_axpy2_norm<Real, V, 0><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->search->d, (Real*)cg->residual->d, (const Real*)cg->tmp->d, sc, ctx->partials, ctx->tickets + 5);
 			MP_CHECK_LAUNCH(ctx);
+			PROF(2); PROF(3);
 			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->search->d, (const Real*)cg->residual->d, sc);
 			MP_CHECK_LAUNCH(ctx);
 		} else {
 			k_axpy2_norm<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->search->d, (Real*)cg->residual->d, (const Real*)cg->tmp->d, sc, ctx->partials, ctx->tickets + 5);
 			MP_CHECK_LAUNCH(ctx);
+			PROF(2);
 			MP_TRY(cgApplyPrecond(cg, &sc->done));
 			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (const Real*)cg->tmp->d, (const Real*)cg->residual->d, sc, ctx->partials, ctx->tickets + 4, 0);
 			MP_CHECK_LAUNCH(ctx);
+			PROF(3);
 			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->search->d, (const Real*)cg->tmp->d, sc);
 			MP_CHECK_LAUNCH(ctx);
 		}
 	});
+	PROF(4);
+	#undef PROF
 	return MP_OK;
 }
 
@@ -347,6 +358,7 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 	MP_CUDA(cudaSetDevice(ctx->device));
 	if (!cg->inited) MP_TRY(cgDoInit(cg));
 	if (cg->finished) return cgFinishCheck(cg);
+	ctx->profCount = 0;
 	// batches of iterations; the poll of batch b is awaited only after batch b+1 has been enqueued
 	const IndexInt n = cg->dst->n;
 	int batch = n >= (IndexInt)1 << 24 ? 4 : (n >= (IndexInt)1 << 21 ? 8 : 16);
@@ -354,7 +366,7 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 	int enq = 0, slot = 0; bool pending[2] = { false, false };
 	while (enq < maxIter) {
 		const int nb = (maxIter - enq) < batch ? (maxIter - enq) : batch;
-		for (int q = 0; q < nb; q++) MP_TRY(cgEnqueueIteration(cg));
+		for (int q = 0; q < nb; q++) MP_TRY(cgEnqueueIteration(cg, enq + q));
 		enq += nb;
 		MP_TRY(cgPollAsync(cg, slot)); pending[slot] = true;
 		const int other = slot ^ 1;
@@ -365,6 +377,17 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 	// the most recent export is the one recorded last
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));
+	if (ctx->profPeriod > 0) {
+		// only samples of iterations that really ran (before `done`) count
+		int used = 0; double acc[4] = {0, 0, 0, 0};
+		for (int q = 0; q < ctx->profCount; q++) {
+			if (q * ctx->profPeriod >= cg->iterations) break;
+			for (int k = 0; k < 4; k++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->profEv[5 * q + k], ctx->profEv[5 * q + k + 1]); acc[k] += ms; }
+			used++;
+		}
+		for (int k = 0; k < 4; k++) ctx->profMs[k] = used ? (float)(acc[k] / used) : 0.f;
+		ctx->profCount = used;
+	}
 	return cgFinishCheck(cg);
 }
 

@@ -43,6 +43,11 @@ struct mp_context {
 	// ~12 temporary grids of a solve cost no cudaMalloc/cudaFree after the first call
 	std::vector<std::pair<void*, size_t>> pool;
 	size_t poolBytes = 0;
+	// sampled per-kernel timing of the CG loop
+	int profPeriod = 0;
+	std::vector<cudaEvent_t> profEv;      // 5 events per sample: t0 | matvec | axpy | precond+dot | update
+	int profCount = 0;
+	float profMs[4] = {0, 0, 0, 0};
 };
 static const int kMaxPartials = 1 << 16;   // max blocks of a reducing kernel
 static const int kSlots = 4;               // values reduced per kernel

@@ -121,6 +121,10 @@ int mp_solve_pressure_system(mp_context* ctx, mp_grid* rhs, mp_grid* vel, mp_gri
 		cudaEventSynchronize(ctx->ev[3]);
 		cudaEventElapsedTime(&info->msMatrix, ctx->ev[1], ctx->ev[2]);
 		cudaEventElapsedTime(&info->msSolve, ctx->ev[2], ctx->ev[3]);
+		if (ctx->profPeriod > 0) {
+			info->msMatvecAvg = ctx->profMs[0]; info->msAxpyAvg = ctx->profMs[1]; info->msPrecondAvg = ctx->profMs[2]; info->msUpdateAvg = ctx->profMs[3];
+			info->profSamples = ctx->profCount;
+		}
 	}
 	if (pmg && preconditioner == MP_PC_MG_DYNAMIC) mp_release_mg(ctx);            // :451
 	return rc;

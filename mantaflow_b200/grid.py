@@ -50,6 +50,9 @@ class Solver:
         check(self.lib.mp_context_kernel_launches(self._ctx, C.byref(n)))
         return n.value
 
+    def setProfiling(self, period):
+        check(self.lib.mp_context_set_profiling(self._ctx, C.c_int(period)))
+
     def stream(self):
         return self.lib.mp_context_stream(self._ctx)
 
