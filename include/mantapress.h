@@ -209,6 +209,14 @@ int mp_dist_init(mp_context* ctx, int rank, int world, const void* id128, const 
 int mp_dist_shutdown(mp_context* ctx);
 /* slab of rank r: global planes [k0, k1), computed exactly like the library does */
 int mp_dist_slab(int sz_global, int rank, int world, int* k0, int* k1);
+/* switch the context to slab mode for a global grid of sz_global planes: from now on every 3-D grid of the context
+ * holds the rank's owned planes [k0,k1) plus one ghost plane on each side (local sz = k1-k0+2, local plane kl is global
+ * plane k0-1+kl; ghost planes outside the domain are ignored).  Inputs (flags, vel, phi ...) are uploaded WITH their ghost
+ * planes; outputs are valid on owned planes (and on ghosts after mp_dist_exchange_halo).  PcNone is sharded in this
+ * round; PcMIC / PcMG* return MP_ERR_UNSUPPORTED in slab mode. */
+int mp_dist_set_domain(mp_context* ctx, int sz_global);
+/* refresh the two ghost planes of a slab grid from the neighbouring ranks (NCCL send/recv on the context stream) */
+int mp_dist_exchange_halo(mp_context* ctx, mp_grid* g);
 
 #ifdef __cplusplus
 }

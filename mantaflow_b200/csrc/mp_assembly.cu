@@ -33,7 +33,7 @@ template <typename Real> __device__ __forceinline__ bool ghostFluidWasClamped(In
 __device__ __forceinline__ bool interior(const Dims& d, IndexInt idx, int& i, int& j, int& k) {
 	i = (int)(idx % d.sx); const IndexInt t = idx / d.sx; j = (int)(t % d.sy); k = (int)(t / d.sy);
 	if (i < 1 || i >= d.sx - 1 || j < 1 || j >= d.sy - 1) return false;
-	if (d.is3D) return k >= 1 && k < d.sz - 1;
+	if (d.is3D) { const int kg = k + d.kOff; return k >= d.kb && k < d.ke && kg >= 1 && kg < d.gsz - 1; }   // owned plane, global interior
 	return true;
 }
 
@@ -159,12 +159,13 @@ __global__ void __launch_bounds__(256) k_ghost_diag(Dims d, const int* __restric
 __global__ void __launch_bounds__(256) k_scan_flags(Dims d, const int* __restrict__ flags, unsigned long long* slots)
 {
 	unsigned long long nEmpty = 0, nBad = 0, minFluid = ~0ull;
-	for (IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; idx < d.n; idx += (IndexInt)gridDim.x * blockDim.x) {
+	for (IndexInt idx = d.i0 + (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; idx < d.i1; idx += (IndexInt)gridDim.x * blockDim.x) {
 		const int f = flags[idx];
 		if (f & TypeEmpty) nEmpty++;
 		if (f & TypeFluid) {
 			int i, j, k;
-			if (interior(d, idx, i, j, k)) { if ((unsigned long long)idx < minFluid) minFluid = (unsigned long long)idx; }
+			const unsigned long long gidx = (unsigned long long)(idx + (IndexInt)d.kOff * d.Z);      // index in the global grid
+			if (interior(d, idx, i, j, k)) { if (gidx < minFluid) minFluid = gidx; }
 			else nBad++;
 		}
 	}
@@ -181,19 +182,47 @@ __global__ void __launch_bounds__(256) k_scan_flags(Dims d, const int* __restric
 		if (nBad) atomicAdd(&slots[2], nBad);
 	}
 }
-__global__ void k_scan_init(unsigned long long* slots) { slots[0] = 0; slots[1] = ~0ull; slots[2] = 0; }
+__global__ void k_scan_init(unsigned long long* slots) { slots[0] = 0; slots[1] = ~0ull; slots[2] = 0; slots[3] = 0; }
 
-// pressure.cpp:352-382: -1 if any empty cell; else top centre, one below, two below; else first interior fluid cell
-__global__ void k_choose_fix(Dims d, const int* __restrict__ flags, const unsigned long long* slots, long long* outIdx)
+// the three preferred cells of pressure.cpp:357-367 (top centre, one below, two below): bit q of slots[3] = cell q is fluid
+__global__ void k_scan_preferred(Dims d, const int* __restrict__ flags, unsigned long long* slots)
+{
+	const int cx = d.sx / 2, czg = d.is3D ? d.gsz / 2 : 0, cz = czg - d.kOff;
+	if (d.is3D && (cz < d.kb || cz >= d.ke)) return;          // another rank owns that plane
+	unsigned long long bits = 0;
+	for (int q = 0; q < 3; q++) {
+		const int cy = d.sy - 1 - q;
+		if (cy < 0) continue;
+		if (flags[(IndexInt)cx + (IndexInt)d.sx * cy + d.Z * cz] & TypeFluid) bits |= 1ull << q;
+	}
+	slots[3] = bits;
+}
+
+// combine the ranks' scan results: gathered[r*8 + q] holds rank r's slots as doubles (exact below 2^53)
+__global__ void k_scan_to_double(const unsigned long long* slots, double* out) {
+	out[0] = (double)slots[0]; out[1] = slots[1] == ~0ull ? -1.0 : (double)slots[1]; out[2] = (double)slots[2]; out[3] = (double)slots[3];
+}
+__global__ void k_scan_combine(const double* gathered, int world, unsigned long long* slots) {
+	unsigned long long nEmpty = 0, nBad = 0, bits = 0, minFluid = ~0ull;
+	for (int r = 0; r < world; r++) {
+		const double* g = gathered + 8 * r;
+		nEmpty += (unsigned long long)g[0]; nBad += (unsigned long long)g[2]; bits |= (unsigned long long)g[3];
+		if (g[1] >= 0 && (unsigned long long)g[1] < minFluid) minFluid = (unsigned long long)g[1];
+	}
+	slots[0] = nEmpty; slots[1] = minFluid; slots[2] = nBad; slots[3] = bits;
+}
+
+// pressure.cpp:352-382: -1 if any empty cell; else top centre, one below, two below; else first interior fluid cell.
+// The result is an index into the GLOBAL grid.
+__global__ void k_choose_fix(Dims d, const unsigned long long* slots, long long* outIdx)
 {
 	long long fix = -1;
 	if (slots[0] == 0) {
-		const int cx = d.sx / 2, cz = d.is3D ? d.sz / 2 : 0;
+		const int cx = d.sx / 2, cz = d.is3D ? d.gsz / 2 : 0;
 		for (int q = 0; q < 3 && fix < 0; q++) {
 			const int cy = d.sy - 1 - q;
 			if (cy < 0) continue;
-			const IndexInt idx = (IndexInt)cx + (IndexInt)d.sx * cy + d.Z * cz;
-			if (flags[idx] & TypeFluid) fix = idx;
+			if (slots[3] & (1ull << q)) fix = (long long)cx + (long long)d.sx * cy + d.Z * cz;
 		}
 		if (fix < 0 && slots[1] != ~0ull) fix = (long long)slots[1];
 	}
@@ -204,20 +233,32 @@ __global__ void k_choose_fix(Dims d, const int* __restrict__ flags, const unsign
 template <typename Real>
 __global__ void k_fix_pressure(Dims d, const long long* pIdx, Real value, Real* rhs, Real* A0, Real* Ai, Real* Aj, Real* Ak)
 {
-	const long long p = *pIdx;
-	if (p < 0) return;
+	const long long pg = *pIdx;                               // index in the global grid
+	if (pg < 0) return;
 	const IndexInt X = d.X, Y = d.Y, Z = d.Z;
-	rhs[p + X] -= Ai[p] * value;
-	rhs[p + Y] -= Aj[p] * value;
-	rhs[p - X] -= Ai[p - X] * value;
-	rhs[p - Y] -= Aj[p - Y] * value;
-	if (d.is3D) { rhs[p + Z] -= Ak[p] * value; rhs[p - Z] -= Ak[p - Z] * value; }
-	rhs[p] = value;
-	A0[p] = (Real)1;
-	Ai[p] = Aj[p] = Ak[p] = (Real)0;
-	Ai[p - X] = (Real)0;
-	Aj[p - Y] = (Real)0;
-	if (d.is3D) Ak[p - Z] = (Real)0;
+	// local index; in slab mode every rank applies the edits that land on its planes (ghost copies included), so
+	// owned data and ghost copies stay consistent without another exchange
+	const long long p = pg - (long long)d.kOff * Z;
+	const int kp = d.is3D ? (int)(p >= 0 ? p / Z : -1 - (-p - 1) / Z) : 0;    // local plane of the pinned cell (floor division)
+	const bool here = kp >= 0 && kp < d.sz, below = kp - 1 >= 0 && kp - 1 < d.sz, above = kp + 1 >= 0 && kp + 1 < d.sz;
+	if (here) {
+		rhs[p + X] -= Ai[p] * value;
+		rhs[p + Y] -= Aj[p] * value;
+		rhs[p - X] -= Ai[p - X] * value;
+		rhs[p - Y] -= Aj[p - Y] * value;
+	}
+	if (d.is3D) {
+		if (here && above) rhs[p + Z] -= Ak[p] * value;
+		if (below) rhs[p - Z] -= Ak[p - Z] * value;
+	}
+	if (here) {
+		rhs[p] = value;
+		A0[p] = (Real)1;
+		Ai[p] = Aj[p] = Ak[p] = (Real)0;
+		Ai[p - X] = (Real)0;
+		Aj[p - Y] = (Real)0;
+	}
+	if (d.is3D && below) Ak[p - Z] = (Real)0;
 }
 
 // ---------------------------------------------------------------- correctVelocity
@@ -296,15 +337,22 @@ __global__ void __launch_bounds__(256) k_replace_clamped(Dims d, const int* __re
 static int scanFlags(mp_context* ctx, const mp_grid* flags) {
 	unsigned long long* slots = (unsigned long long*)(ctx->dScal + 8);
 	const Dims d = dimsOf(flags);
+	MP_TRY(mp_dist_check_grid(flags));
 	k_scan_init<<<1, 1, 0, ctx->stream>>>(slots); MP_CHECK_LAUNCH(ctx);
-	unsigned int blocks = gridFor(d.n, 256 * 8); if (blocks > (unsigned)ctx->smCount * 16) blocks = ctx->smCount * 16;
+	unsigned int blocks = gridFor(d.i1 - d.i0, 256 * 8); if (blocks > (unsigned)ctx->smCount * 16) blocks = ctx->smCount * 16;
 	k_scan_flags<<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, slots); MP_CHECK_LAUNCH(ctx);
+	k_scan_preferred<<<1, 1, 0, ctx->stream>>>(d, (const int*)flags->d, slots); MP_CHECK_LAUNCH(ctx);
+	if (d.world > 1) {
+		k_scan_to_double<<<1, 1, 0, ctx->stream>>>(slots, ctx->dist->dLocal); MP_CHECK_LAUNCH(ctx);
+		MP_TRY(mp_dist_allgather(ctx, 4));
+		k_scan_combine<<<1, 1, 0, ctx->stream>>>(ctx->dist->dGather, d.world, slots); MP_CHECK_LAUNCH(ctx);
+	}
 	return MP_OK;
 }
 
 int mp_check_flags_interior(mp_context* ctx, const mp_grid* flags) {
 	MP_TRY(scanFlags(ctx, flags));
-	MP_CUDA(cudaMemcpyAsync(ctx->hScal + 8, ctx->dScal + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	MP_CUDA(cudaMemcpyAsync(ctx->hScal + 8, ctx->dScal + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));
 	const unsigned long long nBad = ((unsigned long long*)(ctx->hScal + 8))[2];
 	if (nBad) MP_FAIL(MP_ERR_INVALID, "FlagGrid has %llu fluid cell(s) on the outer layer of the domain; the reference reads out of bounds there (conjugategrad.h:126-132)", nBad);
@@ -316,7 +364,7 @@ int mp_fix_pressure_auto(mp_context* ctx, const mp_grid* flags, mp_grid* rhs, mp
 	const Dims d = dimsOf(flags);
 	MP_TRY(scanFlags(ctx, flags));
 	long long* pIdx = (long long*)(ctx->dScal + 12);
-	k_choose_fix<<<1, 1, 0, ctx->stream>>>(d, (const int*)flags->d, (const unsigned long long*)(ctx->dScal + 8), pIdx); MP_CHECK_LAUNCH(ctx);
+	k_choose_fix<<<1, 1, 0, ctx->stream>>>(d, (const unsigned long long*)(ctx->dScal + 8), pIdx); MP_CHECK_LAUNCH(ctx);
 	if (rhs->prec == 4) k_fix_pressure<float><<<1, 1, 0, ctx->stream>>>(d, pIdx, 0.f, (float*)rhs->d, (float*)A0->d, (float*)Ai->d, (float*)Aj->d, (float*)Ak->d);
 	else                k_fix_pressure<double><<<1, 1, 0, ctx->stream>>>(d, pIdx, 0., (double*)rhs->d, (double*)A0->d, (double*)Ai->d, (double*)Aj->d, (double*)Ak->d);
 	MP_CHECK_LAUNCH(ctx);
@@ -349,6 +397,7 @@ int mp_make_rhs(mp_context* ctx, const mp_grid* flags, mp_grid* rhs, const mp_gr
 		k_make_rhs<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)rhs->d, (const double*)vel->d, dptr<double>(perCellCorr), dptr<double>(fractions),
 			dptr<double>(obvel), dptr<double>(phi), dptr<double>(curv), surfTens, gfClamp, ctx->partials, ctx->tickets + 1, ctx->dScal + 2);
 	MP_CHECK_LAUNCH(ctx);
+	MP_TRY(mp_dist_sum(ctx, ctx->dScal + 2, 2));          // slab mode: global sum / cnt
 	if (sum || cnt) {
 		MP_CUDA(cudaMemcpyAsync(ctx->hScal + 2, ctx->dScal + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 		MP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -397,7 +446,7 @@ int mp_count_empty_cells(mp_context* ctx, const mp_grid* flags, long long* numEm
 {
 	if (!flags || flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "mp_count_empty_cells: flags is not a FlagGrid");
 	MP_TRY(scanFlags(ctx, flags));
-	MP_CUDA(cudaMemcpyAsync(ctx->hScal + 8, ctx->dScal + 8, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	MP_CUDA(cudaMemcpyAsync(ctx->hScal + 8, ctx->dScal + 8, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));
 	*numEmpty = (long long)((unsigned long long*)(ctx->hScal + 8))[0];
 	return MP_OK;
@@ -409,7 +458,7 @@ int mp_choose_fix_cell(mp_context* ctx, const mp_grid* flags, long long* fixPidx
 	const Dims d = dimsOf(flags);
 	MP_TRY(scanFlags(ctx, flags));
 	long long* pIdx = (long long*)(ctx->dScal + 12);
-	k_choose_fix<<<1, 1, 0, ctx->stream>>>(d, (const int*)flags->d, (const unsigned long long*)(ctx->dScal + 8), pIdx); MP_CHECK_LAUNCH(ctx);
+	k_choose_fix<<<1, 1, 0, ctx->stream>>>(d, (const unsigned long long*)(ctx->dScal + 8), pIdx); MP_CHECK_LAUNCH(ctx);
 	MP_CUDA(cudaMemcpyAsync(ctx->hScal + 12, pIdx, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));
 	*fixPidx = *(long long*)(ctx->hScal + 12);
@@ -422,7 +471,8 @@ int mp_fix_pressure(mp_context* ctx, long long fixPidx, double value, mp_grid* r
 	MP_TRY(mp_check_same(rhs, A0, MP_GRID_REAL, "A0", false)); MP_TRY(mp_check_same(rhs, Ai, MP_GRID_REAL, "Ai", false));
 	MP_TRY(mp_check_same(rhs, Aj, MP_GRID_REAL, "Aj", false)); MP_TRY(mp_check_same(rhs, Ak, MP_GRID_REAL, "Ak", false));
 	const Dims d = dimsOf(rhs);
-	if (fixPidx < d.Y + (d.is3D ? d.Z : 0) + 1 || fixPidx >= d.n - d.Y - (d.is3D ? d.Z : 0) - 1) MP_FAIL(MP_ERR_INVALID, "mp_fix_pressure: cell %lld has neighbours outside the grid", fixPidx);
+	const IndexInt nGlobal = d.is3D ? d.Z * d.gsz : d.n;     // fixPidx indexes the GLOBAL grid
+	if (fixPidx < d.Y + (d.is3D ? d.Z : 0) + 1 || fixPidx >= nGlobal - d.Y - (d.is3D ? d.Z : 0) - 1) MP_FAIL(MP_ERR_INVALID, "mp_fix_pressure: cell %lld has neighbours outside the grid", fixPidx);
 	long long* pIdx = (long long*)(ctx->dScal + 13);
 	MP_CUDA(cudaMemcpyAsync(pIdx, &fixPidx, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));   // fixPidx lives on the caller's stack
@@ -444,13 +494,17 @@ int mp_correct_velocity(mp_context* ctx, mp_grid* vel, const mp_grid* pressure, 
 	MP_CUDA(cudaSetDevice(ctx->device));
 	const Dims d = dimsOf(flags);
 	const unsigned int blocks = gridFor(d.n, 256);
+	const size_t planeReal = (size_t)d.Z * pressure->prec;
+	if (d.world > 1) MP_TRY(mp_dist_halo(ctx, pressure->d, planeReal, pressure->sz));    // p(k-1) of the first owned plane
 	if (vel->prec == 4) {
 		k_correct_velocity<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, (const float*)pressure->d, dptr<float>(phi), dptr<float>(curv), (float)params->gfClamp, (float)params->surfTens);
 		MP_CHECK_LAUNCH(ctx);
+		if (phi && d.world > 1) MP_TRY(mp_dist_halo(ctx, vel->d, planeReal * 3, vel->sz));   // k_replace_clamped reads neighbours' updated velocity
 		if (phi) { k_replace_clamped<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, (const float*)phi->d, (float)params->gfClamp); MP_CHECK_LAUNCH(ctx); }
 	} else {
 		k_correct_velocity<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, (const double*)pressure->d, dptr<double>(phi), dptr<double>(curv), params->gfClamp, params->surfTens);
 		MP_CHECK_LAUNCH(ctx);
+		if (phi && d.world > 1) MP_TRY(mp_dist_halo(ctx, vel->d, planeReal * 3, vel->sz));
 		if (phi) { k_replace_clamped<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, (const double*)phi->d, params->gfClamp); MP_CHECK_LAUNCH(ctx); }
 	}
 	return MP_OK;

@@ -18,6 +18,51 @@ template <typename T, int V> struct alignas(sizeof(T) * V) VecT { T v[V]; };
 template <typename T, int V> __device__ __forceinline__ VecT<T, V> ldv(const T* p) { return *reinterpret_cast<const VecT<T, V>*>(p); }
 template <typename T, int V> __device__ __forceinline__ void stv(T* p, const VecT<T, V>& x) { *reinterpret_cast<VecT<T, V>*>(p) = x; }
 
+// ---------------------------------------------------------------- scalar updates of one iteration (conjugategrad.cpp:241-295)
+// Executed by the last block of the reducing kernel on a single GPU, or by k_cg_combine after the all-gather of the
+// ranks' partial sums in slab mode (same code, so both paths produce the same scalars).
+template <typename Real> __device__ __forceinline__ void cgFinA(CgScal<Real>* sc, double dpSum) {
+	const Real dp = (Real)dpSum;                       // iterate(): mIterations++ ; dp ; alpha (:241,:250-252)
+	Real alpha = (Real)0.;
+	if (fabs((double)dp) > 0.) alpha = sc->sigma / dp;
+	sc->alpha = alpha; sc->dp = dp;
+	sc->iterations += 1;
+}
+template <typename Real> __device__ __forceinline__ void cgFinB(CgScal<Real>* sc, double nrm, double rr, int mode) {
+	const Real resNorm = (Real)nrm;
+	sc->resNorm = resNorm;
+	if (resNorm < sc->accuracy) { sc->sigma = resNorm; sc->done = 1; }              // :274-277
+	else {
+		if (mode == 0) {
+			const Real sigmaNew = (Real)rr;
+			sc->beta = sigmaNew / sc->sigma;                                          // :279-280
+			sc->sigma = sigmaNew;                                                     // :286
+		}
+		if (!(resNorm < (Real)1e35)) { sc->diverged = 1; sc->done = 1; }              // :288-295
+	}
+}
+template <typename Real> __device__ __forceinline__ void cgFinZR(CgScal<Real>* sc, double zr, int isInit) {
+	const Real sigmaNew = (Real)zr;
+	if (isInit) sc->sigma = sigmaNew;                                                 // doInit :234
+	else { sc->beta = sigmaNew / sc->sigma; sc->sigma = sigmaNew; }                   // :279-286
+}
+// slab mode: combine the all-gathered partials (gathered[r*8 + q]) in rank order and apply the same update
+template <typename Real>
+__global__ void k_cg_combine(const double* __restrict__ gathered, int world, CgScal<Real>* sc, int stage, int mode) {
+	if (sc->done && stage != 3) return;
+	double a = 0.0, b = 0.0;
+	const bool useMax = (stage == 1) && !sc->useL2;
+	if (useMax) a = -1.0;
+	for (int r = 0; r < world; r++) {
+		const double g0 = gathered[8 * r], g1 = gathered[8 * r + 1];
+		a = useMax ? fmax(a, g0) : a + g0;
+		b += g1;
+	}
+	if (stage == 0) cgFinA<Real>(sc, a);
+	else if (stage == 1) cgFinB<Real>(sc, a, b, mode);
+	else cgFinZR<Real>(sc, a, stage == 3);
+}
+
 // ---------------------------------------------------------------- k_matvec_dot
 // ApplyMatrix / ApplyMatrix2D (conjugategrad.h:118-151) over ALL cells: identity rows on non-fluid cells,
 // same left-to-right summation order as the reference (bit-identical t with -fmad=false), fused with
@@ -28,13 +73,13 @@ template <typename T, int V> __device__ __forceinline__ void stv(T* p, const Vec
 template <typename Real, int V, bool IS3D>
 __global__ void __launch_bounds__(256) k_matvec_dot(Dims d, const int* __restrict__ flags, Real* __restrict__ dst, const Real* __restrict__ src,
 	const Real* __restrict__ A0, const Real* __restrict__ Ai, const Real* __restrict__ Aj, const Real* __restrict__ Ak,
-	CgScal<Real>* sc, double* partials, unsigned int* ticket, int finalize)
+	CgScal<Real>* sc, double* partials, unsigned int* ticket, int finalize, double* distLocal)
 {
 	if (sc && sc->done) return;
 	const IndexInt Y = d.Y, Z = d.Z;
-	const IndexInt nv = d.n / V;                 // d.n % V == 0 is guaranteed by the launcher
+	const IndexInt nv = d.i1 / V;                // owned range [i0,i1); both are multiples of V (launcher)
 	double acc = 0.0;
-	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
+	for (IndexInt vi = d.i0 / V + (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
 		const IndexInt idx = vi * V;
 		const VecT<int, V> f = ldv<int, V>(flags + idx);
 		const VecT<Real, V> s = ldv<Real, V>(src + idx);
@@ -71,12 +116,7 @@ __global__ void __launch_bounds__(256) k_matvec_dot(Dims d, const int* __restric
 	if (!finalize) return;
 	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
 	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
-		// iterate(): mIterations++ ; dp ; alpha (conjugategrad.cpp:241,:250-252)
-		const Real dp = (Real)fin[0];
-		Real alpha = (Real)0.;
-		if (fabs((double)dp) > 0.) alpha = sc->sigma / dp;
-		sc->alpha = alpha; sc->dp = dp;
-		sc->iterations += 1;
+		if (distLocal) distLocal[0] = fin[0]; else cgFinA<Real>(sc, fin[0]);
 	}
 }
 
@@ -85,7 +125,7 @@ __global__ void __launch_bounds__(256) k_matvec_dot(Dims d, const int* __restric
 // MODE 0: PcNone (z = r, finalises beta/sigma here), MODE 1: preconditioned (only the norm / stop test here)
 template <typename Real, int V, int MODE>
 __global__ void __launch_bounds__(256) k_axpy2_norm(IndexInt n, Real* __restrict__ x, const Real* __restrict__ s, Real* __restrict__ r, const Real* __restrict__ t,
-	CgScal<Real>* sc, double* partials, unsigned int* ticket)
+	CgScal<Real>* sc, double* partials, unsigned int* ticket, double* distLocal)
 {
 	if (sc->done) return;
 	const Real alpha = sc->alpha, nalpha = -alpha;
@@ -108,24 +148,14 @@ __global__ void __launch_bounds__(256) k_axpy2_norm(IndexInt n, Real* __restrict
 	}
 	double v[2] = { nrm, rr }; const bool isMax[2] = { !useL2, false }; double fin[2];
 	if (blockReduceFinal<2>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
-		const Real resNorm = (Real)fin[0];
-		sc->resNorm = resNorm;
-		if (resNorm < sc->accuracy) { sc->sigma = resNorm; sc->done = 1; }          // :274-277
-		else {
-			if (MODE == 0) {
-				const Real sigmaNew = (Real)fin[1];
-				sc->beta = sigmaNew / sc->sigma;                                      // :279-280
-				sc->sigma = sigmaNew;                                                 // :286
-			}
-			if (!(resNorm < (Real)1e35)) { sc->diverged = 1; sc->done = 1; }          // :288-295
-		}
+		if (distLocal) { distLocal[0] = fin[0]; distLocal[1] = fin[1]; } else cgFinB<Real>(sc, fin[0], fin[1], MODE);
 	}
 }
 
 // sigmaNew = z.r after a preconditioner application -> beta, sigma (conjugategrad.cpp:279-286); also used by doInit (:234)
 template <typename Real, int V>
 __global__ void __launch_bounds__(256) k_dot_zr(IndexInt n, const Real* __restrict__ z, const Real* __restrict__ r,
-	CgScal<Real>* sc, double* partials, unsigned int* ticket, int isInit)
+	CgScal<Real>* sc, double* partials, unsigned int* ticket, int isInit, double* distLocal)
 {
 	if (sc->done) return;
 	const IndexInt nv = n / V;
@@ -137,9 +167,7 @@ __global__ void __launch_bounds__(256) k_dot_zr(IndexInt n, const Real* __restri
 	}
 	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
 	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
-		const Real sigmaNew = (Real)fin[0];
-		if (isInit) sc->sigma = sigmaNew;
-		else { sc->beta = sigmaNew / sc->sigma; sc->sigma = sigmaNew; }
+		if (distLocal) distLocal[0] = fin[0]; else cgFinZR<Real>(sc, fin[0], isInit);
 	}
 }
 
@@ -161,7 +189,7 @@ __global__ void __launch_bounds__(256) k_update_search(IndexInt n, Real* __restr
 // doInit (conjugategrad.cpp:209-235) for PcNone: x = 0, r = b, s = b, sigma = b.b  (one pass)
 template <typename Real, int V, int MODE>   // MODE 0: PcNone; MODE 1: only x = 0, r = b (preconditioner follows)
 __global__ void __launch_bounds__(256) k_cg_init(IndexInt n, Real* __restrict__ x, const Real* __restrict__ b, Real* __restrict__ r, Real* __restrict__ s,
-	CgScal<Real>* sc, double* partials, unsigned int* ticket)
+	CgScal<Real>* sc, double* partials, unsigned int* ticket, double* distLocal)
 {
 	const IndexInt nv = n / V;
 	double acc = 0.0;
@@ -179,7 +207,9 @@ __global__ void __launch_bounds__(256) k_cg_init(IndexInt n, Real* __restrict__ 
 	}
 	if (MODE != 0) return;
 	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
-	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) sc->sigma = (Real)fin[0];
+	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
+		if (distLocal) distLocal[0] = fin[0]; else cgFinZR<Real>(sc, fin[0], 1);
+	}
 }
 
 template <typename Real>
@@ -198,24 +228,36 @@ static inline unsigned int streamBlocks(mp_context* ctx, IndexInt work) {
 	const unsigned int cap = (unsigned int)ctx->smCount * 8;      // 148 SMs x 8 CTAs of 256 threads = one full wave
 	return b < cap ? b : cap;
 }
+static inline double* distLocalOf(mp_context* ctx, const Dims& d) { return d.world > 1 ? ctx->dist->dLocal : nullptr; }
 
 #define DISPATCH_RV(g, ...) do { \
 	const int V_ = vecWidth(g); \
 	if ((g)->prec == 4) { typedef float Real; if (V_ == 4) { constexpr int V = 4; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; } } \
 	else { typedef double Real; if (V_ == 2) { constexpr int V = 2; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; } } } while (0)
 
+// slab mode: all-gather the ranks' partials and apply the scalar update of `stage` (0 alpha, 1 norm/beta, 2 z.r, 3 init sigma)
+static int cgCombine(mp_context* ctx, const mp_grid* g, void* sc, int stage, int mode) {
+	MP_TRY(mp_dist_allgather(ctx, 2));
+	if (g->prec == 4) k_cg_combine<float><<<1, 1, 0, ctx->stream>>>(ctx->dist->dGather, ctx->dist->world, (CgScal<float>*)sc, stage, mode);
+	else              k_cg_combine<double><<<1, 1, 0, ctx->stream>>>(ctx->dist->dGather, ctx->dist->world, (CgScal<double>*)sc, stage, mode);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
 int mp_launch_matvec(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const mp_grid* src,
 	const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, void* sc, int finalize)
 {
 	const Dims d = dimsOf(flags);
+	double* dl = (sc && finalize) ? distLocalOf(ctx, d) : nullptr;
 	DISPATCH_RV(dst, {
-		const unsigned int blocks = streamBlocks(ctx, d.n / V);
+		const unsigned int blocks = streamBlocks(ctx, (d.i1 - d.i0) / V);
 		if (d.is3D) k_matvec_dot<Real, V, true><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (Real*)dst->d, (const Real*)src->d,
-			(const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d, (const Real*)Ak->d, (CgScal<Real>*)sc, ctx->partials, ctx->tickets + 2, finalize);
+			(const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d, (const Real*)Ak->d, (CgScal<Real>*)sc, ctx->partials, ctx->tickets + 2, finalize, dl);
 		else k_matvec_dot<Real, V, false><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (Real*)dst->d, (const Real*)src->d,
-			(const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d, (const Real*)Ak->d, (CgScal<Real>*)sc, ctx->partials, ctx->tickets + 2, finalize);
+			(const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d, (const Real*)Ak->d, (CgScal<Real>*)sc, ctx->partials, ctx->tickets + 2, finalize, dl);
 	});
 	MP_CHECK_LAUNCH(ctx);
+	if (dl) MP_TRY(cgCombine(ctx, dst, sc, 0, 0));
 	return MP_OK;
 }
 
@@ -230,6 +272,7 @@ extern "C" int mp_apply_matrix(mp_context* ctx, const mp_grid* flags, mp_grid* d
 	MP_TRY(mp_check_same(dst, Aj, MP_GRID_REAL, "Aj", false)); MP_TRY(mp_check_same(dst, Ak, MP_GRID_REAL, "Ak", false));
 	MP_CUDA(cudaSetDevice(ctx->device));
 	MP_TRY(mp_check_flags_interior(ctx, flags));
+	// slab mode: the caller's src / Ak must have current ghost planes (mp_dist_exchange_halo)
 	return mp_launch_matvec(ctx, flags, dst, src, A0, Ai, Aj, Ak, nullptr, 0);
 }
 
@@ -254,7 +297,7 @@ __global__ void k_scal_export(const CgScal<Real>* sc, CgScalHost* out) {
 
 static int cgPollAsync(mp_cg* cg, int slot) {
 	mp_context* ctx = cg->ctx;
-	// the scalar block is exported by a 1-thread kernel straight into pinned host memory (mapped), then an event marks it
+	// the scalar block is exported by a 1-thread kernel straight into pinned (mapped) host memory, then an event marks it
 	if (cg->dst->prec == 4) k_scal_export<float><<<1, 1, 0, ctx->stream>>>((const CgScal<float>*)cg->dSc, cg->hSc + slot);
 	else                    k_scal_export<double><<<1, 1, 0, ctx->stream>>>((const CgScal<double>*)cg->dSc, cg->hSc + slot);
 	MP_CHECK_LAUNCH(ctx);
@@ -281,22 +324,34 @@ static int cgApplyPrecond(mp_cg* cg, const int* doneFlag) {
 	MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: preconditioner %d not implemented on the device (PC_ICP is not reachable from solvePressure)", cg->pcMethod);
 }
 
+static int cgHalo(mp_cg* cg, mp_grid* g) {       // one-plane ghost exchange of a Real slab grid (no-op on a single GPU)
+	return mp_dist_halo(cg->ctx, g->d, (size_t)g->sx * g->sy * g->prec, g->sz);
+}
+
 static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	mp_context* ctx = cg->ctx;
 	const Dims d = dimsOf(cg->flags);
+	MP_TRY(mp_dist_check_grid(cg->flags));
 	if (!cg->flagsChecked) { MP_TRY(mp_check_flags_interior(ctx, cg->flags)); cg->flagsChecked = true; }
 	if (cg->pcMethod == MP_CG_PC_MICP && !d.is3D) MP_FAIL(MP_ERR_INVALID, "mICP only supports 3D grids so far");   // :222
 	if (cg->pcMethod == MP_CG_PC_ICP) MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: PC_ICP is not implemented on the device");
+	if (d.world > 1 && cg->pcMethod != MP_CG_PC_NONE)
+		MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: only PcNone is sharded across GPUs in this round (the MIC sweeps and the MG hierarchy are single-GPU)");
 	cg->inited = true; cg->iterations = 0; cg->finished = false; cg->diverged = false; cg->resNorm = 1e20;
 	const bool none = cg->pcMethod == MP_CG_PC_NONE;
+	const IndexInt nOwn = d.i1 - d.i0;
+	double* dl = distLocalOf(ctx, d);
+	if (d.world > 1) MP_TRY(cgHalo(cg, cg->Ak));      // Ak[idx-Z] of the first owned plane lives on the lower neighbour
 	DISPATCH_RV(cg->dst, {
 		k_scal_reset<Real><<<1, 1, 0, ctx->stream>>>((CgScal<Real>*)cg->dSc, (Real)cg->accuracy, cg->useL2 ? 1 : 0);
 		MP_CHECK_LAUNCH(ctx);
-		const unsigned int blocks = streamBlocks(ctx, d.n / V);
-		if (none) k_cg_init<Real, V, 0><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->rhs->d, (Real*)cg->residual->d, (Real*)cg->search->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 3);
-		else      k_cg_init<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->rhs->d, (Real*)cg->residual->d, (Real*)cg->search->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 3);
+		const unsigned int blocks = streamBlocks(ctx, nOwn / V);
+		Real *x = (Real*)cg->dst->d + d.i0, *r = (Real*)cg->residual->d + d.i0, *s = (Real*)cg->search->d + d.i0; const Real* b = (const Real*)cg->rhs->d + d.i0;
+		if (none) k_cg_init<Real, V, 0><<<blocks, 256, 0, ctx->stream>>>(nOwn, x, b, r, s, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 3, dl);
+		else      k_cg_init<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(nOwn, x, b, r, s, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 3, dl);
 		MP_CHECK_LAUNCH(ctx);
 	});
+	if (none && dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 3, 0));
 	if (!none) {
 		if (cg->pcMethod == MP_CG_PC_MICP) MP_TRY(mp_mic_init_launch(ctx, cg->flags, cg->pcA0, cg->A0, cg->Ai, cg->Aj, cg->Ak));
 		else MP_TRY(mp_mg_precond_init(cg->mg, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->accuracy));
@@ -304,10 +359,11 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 		MP_TRY(mp_grid_copy_from(cg->search, cg->tmp));                     // mSearch.copyFrom(mTmp) :232
 		DISPATCH_RV(cg->dst, {
 			const unsigned int blocks = streamBlocks(ctx, d.n / V);
-			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (const Real*)cg->tmp->d, (const Real*)cg->residual->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 4, 1);
+			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (const Real*)cg->tmp->d, (const Real*)cg->residual->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 4, 1, nullptr);
 			MP_CHECK_LAUNCH(ctx);
 		});
 	}
+	if (d.world > 1) MP_TRY(cgHalo(cg, cg->search));  // the first matvec reads the neighbours' planes of s
 	return MP_OK;
 }
 
@@ -315,6 +371,8 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 	mp_context* ctx = cg->ctx;
 	const Dims d = dimsOf(cg->flags);
 	const bool none = cg->pcMethod == MP_CG_PC_NONE;
+	const IndexInt nOwn = d.i1 - d.i0;
+	double* dl = distLocalOf(ctx, d);
 	// sampled kernel timing: 5 events around the 4 stages of this iteration
 	cudaEvent_t* pe = nullptr;
 	if (ctx->profPeriod > 0 && iterIndex >= 0 && iterIndex % ctx->profPeriod == 0 && ctx->profCount < 128) pe = &ctx->profEv[5 * ctx->profCount++];
@@ -323,23 +381,26 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 	MP_TRY(mp_launch_matvec(ctx, cg->flags, cg->tmp, cg->search, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->dSc, 1));
 	PROF(1);
 	DISPATCH_RV(cg->dst, {
-		const unsigned int blocks = streamBlocks(ctx, d.n / V);
+		const unsigned int blocks = streamBlocks(ctx, nOwn / V);
 		CgScal<Real>* sc = (CgScal<Real>*)cg->dSc;
+		Real *x = (Real*)cg->dst->d + d.i0, *r = (Real*)cg->residual->d + d.i0, *s = (Real*)cg->search->d + d.i0, *t = (Real*)cg->tmp->d + d.i0;
 		if (none) {
-			k_axpy2_norm<Real, V, 0><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->search->d, (Real*)cg->residual->d, (const Real*)cg->tmp->d, sc, ctx->partials, ctx->tickets + 5);
+			k_axpy2_norm<Real, V, 0><<<blocks, 256, 0, ctx->stream>>>(nOwn, x, s, r, t, sc, ctx->partials, ctx->tickets + 5, dl);
 			MP_CHECK_LAUNCH(ctx);
+			if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 1, 0));
 			PROF(2); PROF(3);
-			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->search->d, (const Real*)cg->residual->d, sc);
+			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, s, r, sc);
 			MP_CHECK_LAUNCH(ctx);
+			if (dl) MP_TRY(cgHalo(cg, cg->search));
 		} else {
-			k_axpy2_norm<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->dst->d, (const Real*)cg->search->d, (Real*)cg->residual->d, (const Real*)cg->tmp->d, sc, ctx->partials, ctx->tickets + 5);
+			k_axpy2_norm<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(nOwn, x, s, r, t, sc, ctx->partials, ctx->tickets + 5, nullptr);
 			MP_CHECK_LAUNCH(ctx);
 			PROF(2);
 			MP_TRY(cgApplyPrecond(cg, &sc->done));
-			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (const Real*)cg->tmp->d, (const Real*)cg->residual->d, sc, ctx->partials, ctx->tickets + 4, 0);
+			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, t, r, sc, ctx->partials, ctx->tickets + 4, 0, nullptr);
 			MP_CHECK_LAUNCH(ctx);
 			PROF(3);
-			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (Real*)cg->search->d, (const Real*)cg->tmp->d, sc);
+			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, s, t, sc);
 			MP_CHECK_LAUNCH(ctx);
 		}
 	});
@@ -359,7 +420,8 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 	if (!cg->inited) MP_TRY(cgDoInit(cg));
 	if (cg->finished) return cgFinishCheck(cg);
 	ctx->profCount = 0;
-	// batches of iterations; the poll of batch b is awaited only after batch b+1 has been enqueued
+	// batches of iterations; the poll of batch b is awaited only after batch b+1 has been enqueued.  In slab mode every
+	// rank sees the same scalars at the same polls, so all ranks enqueue the same sequence of kernels and NCCL calls.
 	const IndexInt n = cg->dst->n;
 	int batch = n >= (IndexInt)1 << 24 ? 4 : (n >= (IndexInt)1 << 21 ? 8 : 16);
 	if (cg->pcMethod != MP_CG_PC_NONE) batch = (batch + 3) / 4;
@@ -373,10 +435,8 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 		if (pending[other]) { MP_TRY(cgPollWait(cg, other)); pending[other] = false; if (cg->finished) break; }
 		slot = other;
 	}
-	for (int q = 0; q < 2; q++) { const int sl = (slot + 1 + q) & 1; if (pending[sl]) { MP_TRY(cgPollWait(cg, sl)); pending[sl] = false; } }
-	// the most recent export is the one recorded last
-	MP_CUDA(cudaStreamSynchronize(ctx->stream));
-	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));
+	for (int q = 0; q < 2; q++) if (pending[q]) { MP_TRY(cgPollWait(cg, q)); pending[q] = false; }
+	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));      // the state after everything that was enqueued
 	if (ctx->profPeriod > 0) {
 		// only samples of iterations that really ran (before `done`) count
 		int used = 0; double acc[4] = {0, 0, 0, 0};
@@ -452,13 +512,8 @@ int mp_cg_iterate(mp_cg* cg, int* keepGoing) {
 	if (!cg->inited) MP_TRY(cgDoInit(cg));
 	MP_TRY(cgEnqueueIteration(cg));
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));
-	if (keepGoing) *keepGoing = cg->finished ? 0 : 1;
-	MP_TRY(cgFinishCheck(cg));
-	// the reference keeps iterating if the caller insists after convergence; re-arm like a fresh iterate() would see it
-	if (cg->finished && !cg->diverged) {
-		// keep `done` set: further iterate() calls are no-ops returning false, matching `iter = maxIter` in solve()
-	}
-	return MP_OK;
+	if (keepGoing) *keepGoing = cg->finished ? 0 : 1;      // once converged, further calls are no-ops returning false
+	return cgFinishCheck(cg);
 }
 int mp_cg_solve(mp_cg* cg, int maxIter) { return mp_cg_run(cg, maxIter); }
 int mp_cg_get(mp_cg* cg, int* iterations, double* resNorm, double* sigma) {

@@ -22,7 +22,7 @@ void mp_set_error(const char* fmt, ...);
 #define MP_CHECK_LAUNCH(ctx) do { (ctx)->launches++; MP_CUDA(cudaGetLastError()); } while (0)
 
 // ---------------------------------------------------------------- context / grid
-struct DistState;   // mp_dist.cu
+struct DistState;   // below
 
 struct mp_context {
 	int device = 0;
@@ -64,16 +64,41 @@ struct mp_grid {
 	bool is3D() const { return sz > 1; }
 };
 
+// z-slab sharding state of a context (mp_dist.cu).  A slab grid holds the owned planes [k0,k1) of the global grid
+// plus one ghost plane on each side: local plane kl <-> global plane k0 - 1 + kl, local sz = k1 - k0 + 2.
+struct DistState {
+	int rank = 0, world = 1;
+	void* comm = nullptr;        // ncclComm_t
+	void* nccl = nullptr;        // dlopen handle
+	bool active = false;         // mp_dist_set_domain called: 3-D grids of this context are slabs
+	int gsz = 0, k0 = 0, k1 = 0;
+	double* dGather = nullptr;   // world * 8 doubles: all-gathered partial results
+	double* dLocal = nullptr;    // 8 doubles: this rank's partial results
+};
+
 struct Dims {
 	int sx, sy, sz;
 	IndexInt X, Y, Z, n;     // strides (Z == 0 in 2-D, grid.cpp:55) and cell count
 	bool is3D;
+	// sharding: owned local planes [kb,ke), global plane of local plane 0, global sz, ranks (single GPU: 0,sz,0,sz,1)
+	int kb, ke, kOff, gsz, world;
+	IndexInt i0, i1;         // owned linear range [kb*Z, ke*Z) (whole grid on a single GPU / in 2-D)
 };
 static inline Dims dimsOf(const mp_grid* g) {
 	Dims d; d.sx = g->sx; d.sy = g->sy; d.sz = g->sz; d.is3D = g->sz > 1;
 	d.X = 1; d.Y = g->sx; d.Z = d.is3D ? (IndexInt)g->sx * g->sy : 0; d.n = (IndexInt)g->sx * g->sy * g->sz;
+	d.kb = 0; d.ke = g->sz; d.kOff = 0; d.gsz = g->sz; d.world = 1; d.i0 = 0; d.i1 = d.n;
+	const DistState* ds = g->ctx ? g->ctx->dist : nullptr;
+	if (ds && ds->active && d.is3D) {
+		d.kb = 1; d.ke = g->sz - 1; d.kOff = ds->k0 - 1; d.gsz = ds->gsz; d.world = ds->world;
+		d.i0 = d.kb * d.Z; d.i1 = d.ke * d.Z;
+	}
 	return d;
 }
+int mp_dist_check_grid(const mp_grid* g);                                  // slab grids must have sz == k1-k0+2
+int mp_dist_halo(mp_context* ctx, void* base, size_t planeBytes, int szLocal);   // exchange the two ghost planes (no-op when world == 1)
+int mp_dist_allgather(mp_context* ctx, int nvals);
+int mp_dist_sum(mp_context* ctx, double* deviceVals, int n);                   // in-place global sum of n <= 8 doubles (no-op when world == 1)                         // dLocal[0..nvals) of every rank -> dGather[rank*8 + q]
 
 int mp_check_same(const mp_grid* ref, const mp_grid* g, int kind, const char* name, bool optional);
 int mp_check_flags_interior(mp_context* ctx, const mp_grid* flags);   // fluid cells must not touch the outer layer

@@ -42,17 +42,32 @@ def set_wall_bcs(flags, vel):
     return vel
 
 
-def smoke_plume(res, prec=4, obstacle=True, random_vel=False, seed=1234, scale=1.0):
+def smoke_plume(res, prec=4, obstacle=True, random_vel=False, seed=1234, scale=1.0, zrange=None):
     """Closed box, sphere obstacle r=0.12 res at (0.5,0.6,0.5) res, velocity (0.15,0.3,0.21) inside the box
-    (0.3,0.1,0.3)-(0.7,0.3,0.7) res, then setWallBcs.  `res` is an int or (sx,sy,sz)."""
+    (0.3,0.1,0.3)-(0.7,0.3,0.7) res, then setWallBcs.  `res` is an int or (sx,sy,sz).
+    zrange=(za,zb) builds only the global planes [za,zb) (a z-slab with its ghost planes; planes outside the
+    domain are zero) without ever allocating the global grid."""
     sx, sy, sz = (res, res, res) if np.isscalar(res) else res
     real = np.float32 if prec == 4 else np.float64
-    flags = closed_box_flags(sx, sy, sz)
-    i, j, k = _coords(sx, sy, sz)
+    if zrange is None:
+        ks = np.arange(sz)
+    else:
+        assert sz > 1 and not random_vel
+        ks = np.arange(zrange[0] - 1, zrange[1])          # one extra plane below for the z wall condition, cropped at the end
+    nz = len(ks)
+    k = ks.reshape(nz, 1, 1)
+    j = np.arange(sy).reshape(1, sy, 1)
+    i = np.arange(sx).reshape(1, 1, sx)
+    flags = np.full((nz, sy, sx), FlagFluid, np.int32)
+    flags[:, :, 0] = FlagObstacle; flags[:, :, sx - 1] = FlagObstacle
+    flags[:, 0, :] = FlagObstacle; flags[:, sy - 1, :] = FlagObstacle
+    if sz > 1:
+        flags[(ks == 0) | (ks == sz - 1)] = FlagObstacle
+        flags[(ks < 0) | (ks >= sz)] = 0
     if obstacle:
         r2 = (i + 0.5 - 0.5 * sx) ** 2 + (j + 0.5 - 0.6 * sy) ** 2 + ((k + 0.5 - 0.5 * sz) ** 2 if sz > 1 else 0)
         flags[np.broadcast_to(r2 <= (0.12 * max(sx, sy, sz)) ** 2, flags.shape) & (flags == FlagFluid)] = FlagObstacle
-    vel = np.zeros((sz, sy, sx, 3), real)
+    vel = np.zeros((nz, sy, sx, 3), real)
     if random_vel:
         rng = np.random.Generator(np.random.PCG64(seed))
         vel[...] = (0.1 * (rng.random(vel.shape) - 0.5)).astype(real)
@@ -62,6 +77,9 @@ def smoke_plume(res, prec=4, obstacle=True, random_vel=False, seed=1234, scale=1
     inbox = np.broadcast_to(inbox, flags.shape)
     vel[inbox] = np.array([0.15, 0.3, 0.21 if sz > 1 else 0.0], real) * scale
     set_wall_bcs(flags, vel)
+    if zrange is not None:
+        flags, vel = np.ascontiguousarray(flags[1:]), np.ascontiguousarray(vel[1:])
+        vel[(flags == 0)] = 0
     return flags, vel
 
 
