@@ -1,0 +1,142 @@
+"""Adapter giving the CUDA path (through the C-ABI / host mirror) the same interface as oracle_api.Oracle, so the generic
+golden checkers of tests/helpers.py run unchanged against it."""
+import numpy as np
+
+import mantaflow_b200 as mf
+from mantaflow_b200 import cg
+
+
+class CudaImpl:
+    kind = "cuda"
+
+    def __init__(self, prec):
+        self.prec = prec
+        self.real = np.float32 if prec == 4 else np.float64
+        self._solvers = {}
+        self._mg = None
+
+    def _solver(self, flags, key=None):
+        sz, sy, sx = flags.shape
+        k = (sx, sy, sz, key)
+        if k not in self._solvers:
+            self._solvers[k] = mf.Solver(gridSize=(sx, sy, sz), dim=3 if sz > 1 else 2, prec=self.prec)
+        return self._solvers[k]
+
+    def _g(self, s, cls, a):
+        return None if a is None else cls(s, a)
+
+    def compute_rhs(self, flags, vel, phi=None, perCellCorr=None, fractions=None, obvel=None, curv=None, gfClamp=1e-4, surfTens=0.0, enforceCompatibility=False):
+        s = self._solver(flags)
+        F, V, rhs = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+        sm, cnt = cg.MakeRhs(F, rhs, V, perCellCorr=self._g(s, mf.RealGrid, perCellCorr), fractions=self._g(s, mf.MACGrid, fractions),
+                             obvel=self._g(s, mf.MACGrid, obvel), phi=self._g(s, mf.RealGrid, phi), curv=self._g(s, mf.RealGrid, curv),
+                             surfTens=surfTens, gfClamp=gfClamp)
+        return rhs.numpy().copy(), sm, cnt
+
+    def make_matrix(self, flags, fractions=None, phi=None, gfClamp=1e-4):
+        s = self._solver(flags)
+        F = mf.FlagGrid(s, flags)
+        A = [mf.RealGrid(s) for _ in range(4)]
+        cg.MakeLaplaceMatrix(F, *A, fractions=self._g(s, mf.MACGrid, fractions))
+        if phi is not None:
+            cg.ApplyGhostFluidDiagonal(A[0], F, mf.RealGrid(s, phi), gfClamp)
+        return [a.numpy().copy() for a in A]
+
+    def choose_fix_cell(self, flags):
+        s = self._solver(flags)
+        return cg.chooseFixCell(mf.FlagGrid(s, flags))
+
+    def fix_pressure(self, flags, idx, value, rhs, A0, Ai, Aj, Ak):
+        s = self._solver(flags)
+        gs = [mf.RealGrid(s, a) for a in (rhs, A0, Ai, Aj, Ak)]
+        cg.fixPressure(idx, value, *gs)
+        for a, g in zip((rhs, A0, Ai, Aj, Ak), gs):
+            a[...] = g.numpy()
+
+    def apply_matrix(self, flags, src, A0, Ai, Aj, Ak):
+        s = self._solver(flags)
+        D = mf.RealGrid(s)
+        cg.ApplyMatrix(mf.FlagGrid(s, flags), D, mf.RealGrid(s, src), *[mf.RealGrid(s, a) for a in (A0, Ai, Aj, Ak)])
+        return D.numpy().copy()
+
+    def mic_init(self, flags, A0, Ai, Aj, Ak):
+        s = self._solver(flags)
+        P = mf.RealGrid(s)
+        cg.InitPreconditionModifiedIncompCholesky2(mf.FlagGrid(s, flags), P, *[mf.RealGrid(s, a) for a in (A0, Ai, Aj, Ak)])
+        return P.numpy().copy()
+
+    def mic_apply(self, flags, src, P, A0, Ai, Aj, Ak):
+        s = self._solver(flags)
+        D = mf.RealGrid(s)
+        cg.ApplyPreconditionModifiedIncompCholesky2(D, mf.RealGrid(s, src), mf.FlagGrid(s, flags), mf.RealGrid(s, P), *[mf.RealGrid(s, a) for a in (A0, Ai, Aj, Ak)])
+        return D.numpy().copy()
+
+    def cg_solve(self, flags, rhs, A0, Ai, Aj, Ak, pc=0, accuracy=1e-4, useL2=False, maxIter=1000):
+        s = self._solver(flags)
+        F = mf.FlagGrid(s, flags)
+        A = [mf.RealGrid(s, a) for a in (A0, Ai, Aj, Ak)]
+        x, b, r, se, t = mf.RealGrid(s), mf.RealGrid(s, rhs), mf.RealGrid(s), mf.RealGrid(s), mf.RealGrid(s)
+        g = cg.GridCg(x, b, r, se, F, t, *A)
+        g.setAccuracy(accuracy); g.setUseL2Norm(useL2)
+        keep = None
+        if pc == 1:
+            keep = [mf.RealGrid(s) for _ in range(4)]
+            g.setICPreconditioner(cg.GridCg.PC_mICP, *keep)
+        elif pc == 2:
+            keep = cg.GridMg(s)
+            g.setMGPreconditioner(cg.GridCg.PC_MGP, keep)
+        g.solve(maxIter)
+        return x.numpy().copy(), g.getIterations(), g.getResNorm()
+
+    def correct_velocity(self, flags, vel, pressure, phi=None, curv=None, gfClamp=1e-4, surfTens=0.0):
+        s = self._solver(flags)
+        V = mf.MACGrid(s, vel)
+        mf.correctVelocity(V, mf.RealGrid(s, pressure), mf.FlagGrid(s, flags), phi=self._g(s, mf.RealGrid, phi), curv=self._g(s, mf.RealGrid, curv),
+                           gfClamp=gfClamp, surfTens=surfTens)
+        vel[...] = V.numpy()
+        return vel
+
+    def solve_pressure(self, flags, vel, pressure=None, phi=None, perCellCorr=None, fractions=None, obvel=None, curv=None, retRhs=False, solver_key=0, **kw):
+        s = self._solver(flags, solver_key or None)
+        F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+        RR = mf.RealGrid(s) if retRhs else None
+        mf.solvePressure(vel=V, pressure=P, flags=F, phi=self._g(s, mf.RealGrid, phi), perCellCorr=self._g(s, mf.RealGrid, perCellCorr),
+                         fractions=self._g(s, mf.MACGrid, fractions), obvel=self._g(s, mf.MACGrid, obvel), curv=self._g(s, mf.RealGrid, curv), retRhs=RR, **kw)
+        info = mf.lastSolveInfo()
+        vel[...] = V.numpy()
+        out = (P.numpy().copy(), info["iterations"], info["resNorm"])
+        return out + (RR.numpy().copy(),) if retRhs else out
+
+    def release_solver(self, key):
+        for k, s in list(self._solvers.items()):
+            if k[3] == key:
+                mf.releaseMG(s)
+
+    # GridMg probes
+    def mg_create(self, sx, sy, sz):
+        self._mg_solver = mf.Solver(gridSize=(sx, sy, sz), dim=3 if sz > 1 else 2, prec=self.prec)
+        self._mg = cg.GridMg(self._mg_solver)
+
+    def mg_destroy(self):
+        if self._mg is not None:
+            self._mg.close(); self._mg = None
+
+    def mg_set_a(self, A0, Ai, Aj, Ak):
+        self._mg.setA(*[mf.RealGrid(self._mg_solver, a) for a in (A0, Ai, Aj, Ak)])
+
+    def mg_num_levels(self):
+        return self._mg.numLevels()
+
+    def mg_level_size(self, l):
+        return self._mg.levelInfo(l)[0]
+
+    def mg_get(self, what, l):
+        return self._mg.download(what, l)
+
+    def mg_vcycle(self, rhs, coarsestAccuracy=1e-8, pre=1, post=1):
+        s = self._mg_solver
+        self._mg.setCoarsestLevelAccuracy(coarsestAccuracy); self._mg.setSmoothing(pre, post)
+        self._mg.setRhs(mf.RealGrid(s, rhs))
+        Z = mf.RealGrid(s)
+        self._mg.doVCycle(Z)
+        return Z.numpy().copy()

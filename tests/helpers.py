@@ -1,0 +1,124 @@
+"""Shared helpers of the parity tests: golden fixtures and one generic checker that runs any implementation with the
+oracle_api interface (the CPU restatement, the reference build, or the CUDA path through tests/cuda_impl.py)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, GOLDEN)
+
+KERNEL_FIXTURES = ["smoke16", "liquid14", "smoke2d"]
+
+
+def load_golden(name, prec):
+    return dict(np.load(os.path.join(GOLDEN, "kernels_%s_f%d.npz" % (name, prec * 8))))
+
+
+def rel_l2(a, b):
+    d = np.linalg.norm((np.asarray(a, np.float64) - np.asarray(b, np.float64)).ravel())
+    n = np.linalg.norm(np.asarray(b, np.float64).ravel())
+    return d / n if n > 0 else d
+
+
+def check_kernels_against_golden(I, g, prec, exact_reductions):
+    """I: implementation with the Oracle interface.  Integer / per-cell arithmetic must be bit-exact; whatever passes
+    through a global reduction (CG scalars) is bit-exact only when `exact_reductions` (serial float oracle)."""
+    flags, vel = g["flags"], g["vel"]
+    phi = g.get("phi")
+    sz = flags.shape[0]
+    tol = 1e-4 if prec == 4 else 1e-10
+    rhs, s, c = I.compute_rhs(flags, vel, phi=phi)
+    assert c == int(g["rhs_cnt"])
+    assert np.array_equal(rhs, g["rhs"]), "rhs not bit-exact"
+    assert abs(s - float(g["rhs_sum"])) <= 1e-10 * max(1.0, c)
+    A = I.make_matrix(flags, phi=phi)
+    for n, a in zip("A0 Ai Aj Ak".split(), A):
+        assert np.array_equal(a, g[n]), n + " not bit-exact"
+    assert np.array_equal(I.apply_matrix(flags, g["src"], *A), g["apply_matrix"]), "ApplyMatrix not bit-exact"
+    acc = 1e-5 if prec == 4 else 1e-11
+    x, it, rn = I.cg_solve(flags, rhs, *A, pc=0, accuracy=acc, maxIter=4000)
+    assert abs(it - int(g["cg_none_it"])) <= 1, ("PcNone iterations", it, int(g["cg_none_it"]))
+    assert rel_l2(x, g["cg_none_x"]) <= tol
+    if exact_reductions:
+        assert it == int(g["cg_none_it"]) and np.array_equal(x, g["cg_none_x"])
+    if sz > 1:
+        P = I.mic_init(flags, *A)
+        assert np.array_equal(P, g["mic_P"]), "MIC factor not bit-exact"
+        assert np.array_equal(I.mic_apply(flags, g["src"], P, *A), g["mic_apply"]), "MIC sweeps not bit-exact"
+        x, it, rn = I.cg_solve(flags, rhs, *A, pc=1, accuracy=acc, maxIter=4000)
+        assert abs(it - int(g["cg_mic_it"])) <= 1
+        assert rel_l2(x, g["cg_mic_x"]) <= tol
+    if "fix_idx" in g:
+        fix = int(g["fix_idx"])
+        if hasattr(I, "choose_fix_cell") and getattr(I, "kind", "") != "reference":
+            assert I.choose_fix_cell(flags) == fix, "pinned-cell choice differs from the reference"
+        rhs_f = rhs.copy(); Af = [a.copy() for a in A]
+        I.fix_pressure(flags, fix, 0.0, rhs_f, *Af)
+        assert np.array_equal(rhs_f, g["fix_rhs"])
+        for n, a in zip("fix_A0 fix_Ai fix_Aj fix_Ak".split(), Af):
+            assert np.array_equal(a, g[n]), n
+    else:
+        rhs_f, Af = rhs, A
+    sx, sy = flags.shape[2], flags.shape[1]
+    I.mg_create(sx, sy, sz)
+    I.mg_set_a(*Af)
+    assert I.mg_num_levels() == int(g["mg_levels"])
+    for l in range(int(g["mg_levels"])):
+        assert tuple(I.mg_level_size(l)) == tuple(g["mg_size_%d" % l])
+        t = I.mg_get("type", l)
+        assert np.array_equal(t, g["mg_type_%d" % l]), "GridMg vertex types differ on level %d" % l
+        a, a_g = I.mg_get("a", l), g["mg_a_%d" % l]
+        act = np.repeat(t != 0, a.size // t.size)
+        if l == 0 or phi is None:
+            assert np.array_equal(a[act], a_g[act]), "GridMg operator differs on level %d" % l
+        else:   # std::sort leaves the order of equal-key coarsening paths unspecified: last-bit differences allowed
+            assert np.allclose(a[act], a_g[act], rtol=1e-5 if prec == 4 else 1e-13, atol=1e-6 if prec == 4 else 1e-14)
+    z = I.mg_vcycle(rhs_f, coarsestAccuracy=1e-9, pre=1, post=1)
+    assert rel_l2(z, g["mg_vcycle"]) <= (1e-5 if prec == 4 else 1e-9)
+    I.mg_destroy()
+    v = I.correct_velocity(flags, vel.copy(), g["cv_pressure"], phi=phi)
+    assert np.array_equal(v, g["cv_vel"]), "correctVelocity not bit-exact"
+    # the plugin
+    v = vel.copy()
+    p, it, rn = I.solve_pressure(flags, v, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=2, zeroPressureFixing=True)
+    assert abs(it - int(g["plugin_mg_it"])) <= 1
+    assert rel_l2(p, g["plugin_mg_p"]) <= tol and rel_l2(v, g["plugin_mg_vel"]) <= tol
+    if sz > 1:
+        v = vel.copy()
+        p, it, rn = I.solve_pressure(flags, v, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=1)
+        assert abs(it - int(g["plugin_mic_it"])) <= 1
+        assert rel_l2(p, g["plugin_mic_p"]) <= tol and rel_l2(v, g["plugin_mic_vel"]) <= tol
+
+
+def check_psolve52(I, thr=1e-4):
+    """tools/tests/test_0100_psolve.py and test_0110_mgsolve.py: max abs per-cell difference (gridMaxDiff, grid.cpp:400-430)
+    against the reference's result below the float-build threshold 1e-4 (test_0100_psolve.py:40-41,:54-55)."""
+    from make_golden import box_source
+    from mantaflow_b200 import scenes
+    g = dict(np.load(os.path.join(GOLDEN, "psolve52_f32.npz")))
+    res, prec = 52, 4
+    flags = scenes.closed_box_flags(res, res, res)
+    kw = dict(cgMaxIterFac=99, cgAccuracy=1e-4)
+    md = lambda a, b: float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+    v = box_source(res, (0.15, 0.3, 0.21), prec)
+    p, it, _ = I.solve_pressure(flags, v, zeroPressureFixing=False, **kw)
+    assert md(p, g["t0100_pressure0"]) <= thr and md(v, g["t0100_vel0"]) <= thr and abs(it - int(g["t0100_it0"])) <= 1
+    v = box_source(res, (1.5, 3, 2.1), prec); scenes.set_wall_bcs(flags, v)
+    p, it, _ = I.solve_pressure(flags, v, zeroPressureFixing=False, **kw)
+    assert md(p, g["t0100_pressure"]) <= thr * 10 and md(v, g["t0100_vel"]) <= thr * 10 and abs(it - int(g["t0100_it1"])) <= 1   # 10x larger source
+    key = 4242
+    v = box_source(res, (0.15, 0.3, 0.21), prec)
+    p, it, _ = I.solve_pressure(flags, v, zeroPressureFixing=True, preconditioner=2, solver_key=key, **kw)
+    assert md(p, g["t0110_p0"]) <= thr and abs(it - int(g["t0110_it0"])) <= 1
+    v = box_source(res, (1.5, 3, 2.1), prec); scenes.set_wall_bcs(flags, v)
+    p, it, _ = I.solve_pressure(flags, v, zeroPressureFixing=True, preconditioner=2, solver_key=key, **kw)
+    assert md(p, g["t0110_p1"]) <= thr * 10 and abs(it - int(g["t0110_it1"])) <= 1
+    v = box_source(res, (1.1, 2, -2.1), prec); scenes.set_wall_bcs(flags, v)
+    p, it, _ = I.solve_pressure(flags, v, zeroPressureFixing=True, preconditioner=3, solver_key=key, **kw)
+    assert abs(it - int(g["t0110_it2"])) <= 1
+    v = g["t0110_vel_in3"].copy()
+    p, it, _ = I.solve_pressure(flags, v, zeroPressureFixing=True, preconditioner=3, solver_key=key, **kw)
+    assert md(p, g["t0110_p2"]) <= thr * 10 and md(v, g["t0110_v2"]) <= thr * 10 and abs(it - int(g["t0110_it3"])) <= 1
+    I.release_solver(key)

@@ -16,7 +16,6 @@ from oracle.oracle_api import Oracle  # noqa: E402
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-uid = sharded.exchange_unique_id(dist, rank)
 ok = True
 
 
@@ -39,6 +38,7 @@ for name, prec, extra in cases:
     else:
         flags, vel = scenes.smoke_plume(shape, prec, random_vel=True)
     acc = 1e-5 if prec == 4 else 1e-11
+    uid = sharded.exchange_unique_id(dist, rank)      # one NCCL communicator per solver
     s = sharded.ShardedSolver(shape, rank, world, uid, prec=prec, device=local)
     F = mf.FlagGrid(s, sharded.local_slab(flags, rank, world)); V = mf.MACGrid(s, sharded.local_slab(vel, rank, world)); P = mf.RealGrid(s)
     PH = mf.RealGrid(s, sharded.local_slab(phi, rank, world)) if phi is not None else None
