@@ -12,6 +12,7 @@
 // Kernels early-out once `done` is set, which makes the overshoot of the lagged poll free of side effects.
 #include "mp_common.cuh"
 #include "mp_cg.cuh"
+#include <cstdlib>
 
 // ---------------------------------------------------------------- vector access helpers
 template <typename T, int V> struct alignas(sizeof(T) * V) VecT { T v[V]; };
@@ -116,6 +117,69 @@ __global__ void __launch_bounds__(256) k_matvec_dot(Dims d, const int* __restric
 	if (!finalize) return;
 	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
 	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
+		if (distLocal) distLocal[0] = fin[0]; else cgFinA<Real>(sc, fin[0]);
+	}
+}
+
+// ---------------------------------------------------------------- k_matvec_zmarch (3-D, vectorised sizes)
+// Same arithmetic as k_matvec_dot, restructured so that NOTHING relies on the L2 for reuse along z: a CTA of 32 x 8
+// threads owns an x-y tile (32 vectors x 8 rows) and marches along z through a chunk of planes, carrying s(k-1), s(k),
+// s(k+1) and Ak(k-1) in registers; every plane of s, flags, A0, Ai, Aj, Ak is therefore requested once per tile.  The
+// +-Y rows were loaded by the neighbouring warps of the same CTA one step earlier (L1 hits); only tile edges go to L2.
+template <typename Real, int V>
+__global__ void __launch_bounds__(256) k_matvec_zmarch(Dims d, int nvx, int chunk, const int* __restrict__ flags, Real* __restrict__ dst, const Real* __restrict__ src,
+	const Real* __restrict__ A0, const Real* __restrict__ Ai, const Real* __restrict__ Aj, const Real* __restrict__ Ak,
+	CgScal<Real>* sc, double* partials, unsigned int* ticket, int finalize, double* distLocal)
+{
+	if (sc && sc->done) return;
+	const IndexInt Y = d.Y, Z = d.Z;
+	const int vx = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+	const int k0 = d.kb + blockIdx.z * chunk, k1 = min(d.ke, k0 + chunk);
+	double acc = 0.0;
+	if (vx < nvx && j < d.sy && k0 < k1) {
+		IndexInt idx = (IndexInt)vx * V + Y * j + Z * k0;
+		VecT<Real, V> sm, s0, sp, akm;
+		#pragma unroll
+		for (int q = 0; q < V; q++) { sm.v[q] = (Real)0; akm.v[q] = (Real)0; }
+		if (k0 > 0) { sm = ldv<Real, V>(src + idx - Z); akm = ldv<Real, V>(Ak + idx - Z); }
+		s0 = ldv<Real, V>(src + idx);
+		for (int k = k0; k < k1; k++, idx += Z) {
+			const VecT<int, V> f = ldv<int, V>(flags + idx);
+			const VecT<Real, V> ak = ldv<Real, V>(Ak + idx);
+			if (k + 1 < d.sz) sp = ldv<Real, V>(src + idx + Z);
+			bool any = false;
+			#pragma unroll
+			for (int q = 0; q < V; q++) any |= (f.v[q] & TypeFluid) != 0;
+			VecT<Real, V> out = s0;
+			if (any) {
+				const VecT<Real, V> a0 = ldv<Real, V>(A0 + idx), ai = ldv<Real, V>(Ai + idx), aj = ldv<Real, V>(Aj + idx);
+				const VecT<Real, V> ajm = ldv<Real, V>(Aj + idx - Y), sym = ldv<Real, V>(src + idx - Y), syp = ldv<Real, V>(src + idx + Y);
+				Real sxm0 = 0, aim0 = 0, sxpL = 0;
+				if (f.v[0] & TypeFluid) { sxm0 = src[idx - 1]; aim0 = Ai[idx - 1]; }
+				if (f.v[V - 1] & TypeFluid) sxpL = src[idx + V];
+				#pragma unroll
+				for (int q = 0; q < V; q++) {
+					if (f.v[q] & TypeFluid) {
+						const Real xm = (q == 0) ? sxm0 : s0.v[q - 1 < 0 ? 0 : q - 1];
+						const Real am = (q == 0) ? aim0 : ai.v[q - 1 < 0 ? 0 : q - 1];
+						const Real xp = (q == V - 1) ? sxpL : s0.v[q + 1 > V - 1 ? V - 1 : q + 1];
+						Real t = s0.v[q] * a0.v[q] + xm * am + xp * ai.v[q] + sym.v[q] * ajm.v[q] + syp.v[q] * aj.v[q];
+						t = t + sm.v[q] * akm.v[q] + sp.v[q] * ak.v[q];
+						out.v[q] = t;
+					}
+				}
+			}
+			stv<Real, V>(dst + idx, out);
+			#pragma unroll
+			for (int q = 0; q < V; q++) acc += (double)(out.v[q] * s0.v[q]);
+			sm = s0; s0 = sp; akm = ak;
+		}
+	}
+	if (!finalize) return;
+	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
+	const unsigned int tid = threadIdx.y * 32 + threadIdx.x;
+	const unsigned int blockLinear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z), numBlocks = gridDim.x * gridDim.y * gridDim.z;
+	if (blockReduceFinalL<1>(v, isMax, partials, ticket, fin, tid, 256, blockLinear, numBlocks) && tid == 0) {
 		if (distLocal) distLocal[0] = fin[0]; else cgFinA<Real>(sc, fin[0]);
 	}
 }
@@ -249,6 +313,26 @@ int mp_launch_matvec(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const 
 {
 	const Dims d = dimsOf(flags);
 	double* dl = (sc && finalize) ? distLocalOf(ctx, d) : nullptr;
+	static const int variant = getenv("MP_MATVEC") ? atoi(getenv("MP_MATVEC")) : 1;    // 0: L2-reuse kernel, 1: z-marching kernel
+	const int Vw = vecWidth(dst);
+	if (variant == 1 && d.is3D && Vw > 1) {
+		const int nvx = d.sx / Vw, planes = d.ke - d.kb;
+		// z-chunks: enough CTAs for >= 4 waves of 148 SMs x 3 resident CTAs, chunks of >= 16 planes
+		const int tiles = ((nvx + 31) / 32) * ((d.sy + 7) / 8);
+		int nchunk = (4 * 3 * ctx->smCount + tiles - 1) / tiles; if (nchunk < 1) nchunk = 1;
+		int chunk = (planes + nchunk - 1) / nchunk; if (chunk < 16) chunk = 16; if (chunk > planes) chunk = planes;
+		nchunk = (planes + chunk - 1) / chunk;
+		const dim3 grid((nvx + 31) / 32, (d.sy + 7) / 8, nchunk), block(32, 8, 1);
+		if ((long long)grid.x * grid.y * grid.z <= kMaxPartials) {
+			if (dst->prec == 4) k_matvec_zmarch<float, 4><<<grid, block, 0, ctx->stream>>>(d, nvx, chunk, (const int*)flags->d, (float*)dst->d, (const float*)src->d,
+				(const float*)A0->d, (const float*)Ai->d, (const float*)Aj->d, (const float*)Ak->d, (CgScal<float>*)sc, ctx->partials, ctx->tickets + 2, finalize, dl);
+			else k_matvec_zmarch<double, 2><<<grid, block, 0, ctx->stream>>>(d, nvx, chunk, (const int*)flags->d, (double*)dst->d, (const double*)src->d,
+				(const double*)A0->d, (const double*)Ai->d, (const double*)Aj->d, (const double*)Ak->d, (CgScal<double>*)sc, ctx->partials, ctx->tickets + 2, finalize, dl);
+			MP_CHECK_LAUNCH(ctx);
+			if (dl) MP_TRY(cgCombine(ctx, dst, sc, 0, 0));
+			return MP_OK;
+		}
+	}
 	DISPATCH_RV(dst, {
 		const unsigned int blocks = streamBlocks(ctx, (d.i1 - d.i0) / V);
 		if (d.is3D) k_matvec_dot<Real, V, true><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (Real*)dst->d, (const Real*)src->d,

@@ -128,11 +128,12 @@ __device__ __forceinline__ double warpMax(double v) {
 // the last block to arrive (ticket) reduces the partials in a fixed order -> deterministic result.
 // Returns true in ALL threads of the last block, with final[] valid in thread 0 only.
 template <int NV>
-__device__ __forceinline__ bool blockReduceFinal(double (&v)[NV], const bool (&isMax)[NV], double* partials, unsigned int* ticket,
-                                                 double (&fin)[NV]) {
+__device__ __forceinline__ bool blockReduceFinalL(double (&v)[NV], const bool (&isMax)[NV], double* partials, unsigned int* ticket,
+                                                  double (&fin)[NV], const unsigned int tid, const unsigned int nthreads,
+                                                  const unsigned int blockLinear, const unsigned int numBlocks) {
 	__shared__ double sh[NV][32];
 	__shared__ bool amLast;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+	const int lane = tid & 31, warp = tid >> 5, nwarps = (nthreads + 31) >> 5;
 	#pragma unroll
 	for (int q = 0; q < NV; q++) {
 		double w = isMax[q] ? warpMax(v[q]) : warpSum(v[q]);
@@ -144,13 +145,13 @@ __device__ __forceinline__ bool blockReduceFinal(double (&v)[NV], const bool (&i
 		for (int q = 0; q < NV; q++) {
 			double w = (lane < nwarps) ? sh[q][lane] : (isMax[q] ? -1.0 : 0.0);
 			w = isMax[q] ? warpMax(w) : warpSum(w);
-			if (lane == 0) partials[(size_t)q * kMaxPartials + blockIdx.x] = w;
+			if (lane == 0) partials[(size_t)q * kMaxPartials + blockLinear] = w;
 		}
 	}
-	if (threadIdx.x == 0) {
+	if (tid == 0) {
 		__threadfence();
 		unsigned int t = atomicAdd(ticket, 1u);
-		amLast = (t == gridDim.x - 1);
+		amLast = (t == numBlocks - 1);
 	}
 	__syncthreads();
 	if (!amLast) return false;
@@ -158,7 +159,7 @@ __device__ __forceinline__ bool blockReduceFinal(double (&v)[NV], const bool (&i
 	#pragma unroll
 	for (int q = 0; q < NV; q++) {
 		double acc = isMax[q] ? -1.0 : 0.0;
-		for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+		for (unsigned int b = tid; b < numBlocks; b += nthreads) {
 			double p = __ldcg(&partials[(size_t)q * kMaxPartials + b]);
 			acc = isMax[q] ? fmax(acc, p) : acc + p;
 		}
@@ -172,7 +173,12 @@ __device__ __forceinline__ bool blockReduceFinal(double (&v)[NV], const bool (&i
 			if (lane == 0) fin[q] = u;
 		}
 	}
-	if (threadIdx.x == 0) *ticket = 0;   // re-arm for the next launch on this stream
+	if (tid == 0) *ticket = 0;   // re-arm for the next launch on this stream
 	return true;
+}
+// 1-D launch convenience: result valid in threadIdx.x == 0 of the last block
+template <int NV>
+__device__ __forceinline__ bool blockReduceFinal(double (&v)[NV], const bool (&isMax)[NV], double* partials, unsigned int* ticket, double (&fin)[NV]) {
+	return blockReduceFinalL<NV>(v, isMax, partials, ticket, fin, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
 #endif
