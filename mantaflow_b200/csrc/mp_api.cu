@@ -55,6 +55,7 @@ int mp_context_destroy(mp_context* c) {
 	if (!c) return MP_OK;
 	cudaSetDevice(c->device);
 	mp_release_mg(c);
+	if (c->spareMg) { mp_mg_destroy(c->spareMg); c->spareMg = nullptr; }
 	mp_dist_shutdown(c);
 	cudaStreamSynchronize(c->stream);
 	for (auto& pb : c->pool) cudaFree(pb.first);

@@ -37,6 +37,7 @@ struct mp_context {
 	double* hScal = nullptr;      // pinned, 64 doubles
 	long long launches = 0;
 	mp_mg* staticMg = nullptr;    // gMapMG[parent] pressure.cpp:250
+	mp_mg* spareMg = nullptr;     // a released GridMg kept for reuse of its allocations (PcMGDynamic rebuilds every solve)
 	DistState* dist = nullptr;
 	cudaEvent_t ev[8] = {};
 	// FluidSolver::GridStorage analogue (fluidsolver.cpp:33-50): freed device blocks are kept for reuse so the

@@ -25,6 +25,7 @@
 #include "mp_common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 enum : signed char { vtInactive = 0, vtActive = 1, vtActiveTrivial = 2, vtRemoved = 3, vtZero = 4, vtFree = 5 };   // multigrid.h:87-94
 #define MG_MAXLVL 32
@@ -197,6 +198,58 @@ __global__ void __launch_bounds__(256) k_mg_galerkin1(LvlGeom gf, LvlGeom gc, in
 	A[(size_t)sc * gc.n + v] = acc;
 }
 
+// level 1, restructured: one thread per coarse vertex walks U (27 restriction vertices, z/y/x order) and W (the 7-point
+// stencil of U in the reference's order centre,-x,+x,-y,+y,-z,+z) once, loading each level-0 coefficient a single time,
+// and scatters rw*a*iw to the accumulators of the <= 8 coarse vertices N that W interpolates from.  For a fixed
+// accumulator the contributions arrive in exactly the order of the reference's sorted path list (U-major, then W), so
+// the sums are the same bit for bit as k_mg_galerkin1 / multigrid.cpp:594-614 -- with 189 instead of ~700 coefficient loads.
+template <typename Real>
+__global__ void __launch_bounds__(128) k_mg_galerkin1_v2(LvlGeom gf, LvlGeom gc, int is3D, const Real* __restrict__ Af,
+	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A)
+{
+	__shared__ Real acc[14][128];
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= gc.n || tc[v] == vtInactive) return;
+	const int S = is3D ? 14 : 5, t = threadIdx.x;
+	for (int e = 0; e < S; e++) acc[e][t] = (Real)0;
+	int vx, vy, vz; vecIdx(gc, v, vx, vy, vz);
+	// active coarse neighbours N = V + (nx-1, ny-1, nz-1), local code s = nx + 3 ny + 9 nz (>= 13 are the stored entries)
+	unsigned int nmask = 0;
+	for (int s = 13; s < 27; s++) {
+		const int nx = vx + s % 3 - 1, ny = vy + (s / 3) % 3 - 1, nz = vz + s / 9 - 1;
+		if ((is3D || s / 9 == 1) && inGrid(gc, nx, ny, nz) && tc[linIdx(gc, nx, ny, nz)] != vtInactive) nmask |= 1u << s;
+	}
+	const int p7[7][3] = { {0,0,0}, {-1,0,0}, {1,0,0}, {0,-1,0}, {0,1,0}, {0,0,-1}, {0,0,1} };
+	const int uz0 = is3D ? 1 : 2, uz1 = is3D ? 3 : 2, nW = is3D ? 7 : 5;
+	for (int uz = uz0; uz <= uz1; uz++) for (int uy = 1; uy <= 3; uy++) for (int ux = 1; ux <= 3; ux++) {     // local frame: V sits at (1,1,1), U = 2V + (u-2)
+		const int Ux = 2 * vx + ux - 2, Uy = 2 * vy + uy - 2, Uz = 2 * vz + uz - 2;
+		if (!inGrid(gf, Ux, Uy, Uz)) continue;
+		const int u = linIdx(gf, Ux, Uy, Uz);
+		if (tf[u] == vtInactive) continue;
+		const Real rw = (Real)1 / (Real)(1 << ((ux % 2) + (uy % 2) + (uz % 2)));
+		for (int i = 0; i < nW; i++) {
+			const int wx = ux + p7[i][0], wy = uy + p7[i][1], wz = uz + p7[i][2];
+			const int Wx = Ux + p7[i][0], Wy = Uy + p7[i][1], Wz = Uz + p7[i][2];
+			if (!inGrid(gf, Wx, Wy, Wz)) continue;
+			const int w = linIdx(gf, Wx, Wy, Wz);
+			if (tf[w] == vtInactive) continue;
+			const int sf = (i + 1) / 2;
+			const Real a = Af[(size_t)sf * gf.n + ((i % 2 == 0) ? u : w)];
+			const Real iw = (Real)1 / (Real)(1 << ((wx % 2) + (wy % 2) + (wz % 2)));
+			const Real contrib = rw * a * iw;
+			for (int nz = wz / 2; nz <= (wz + 1) / 2; nz++) for (int ny = wy / 2; ny <= (wy + 1) / 2; ny++) for (int nx = wx / 2; nx <= (wx + 1) / 2; nx++) {
+				const int sN = nx + 3 * ny + 9 * nz;
+				if (sN >= 13 && (nmask >> sN & 1u)) acc[sN - 13][t] += contrib;
+			}
+		}
+	}
+	if (is3D) { for (int e = 0; e < 14; e++) A[(size_t)e * gc.n + v] = acc[e][t]; }
+	else {
+		// 2-D: stored entries sc = s-13 with nz == 1: s in {13,14,15,16,17} -> e = 0..4
+		for (int e = 0; e < 5; e++) A[(size_t)e * gc.n + v] = acc[e][t];
+	}
+}
+
 // levels > 1 from a 27-point fine level; thread = (coarse vertex, stored entry e = sc-13)
 template <typename Real>
 __global__ void __launch_bounds__(256) k_mg_galerkinN(LvlGeom gf, LvlGeom gc, int S, int is3D, const Real* __restrict__ Af,
@@ -256,7 +309,7 @@ __global__ void __launch_bounds__(256) k_mg_set_rhs(int n, Real trivialScale, co
 
 // level-0 colour sweep: colour = (x+y+z) parity ({a0,a3,a5,a6} / {a1,a2,a4,a7}, :721); thread = (x pair, y, z)
 template <typename Real, bool ZEROX>
-__global__ void __launch_bounds__(256) k_mg_smooth0(LvlGeom g, int is3D, int color, const Real* __restrict__ A, const Real* __restrict__ b,
+__global__ void __launch_bounds__(256) k_mg_smooth0(LvlGeom g, int is3D, int color, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
 	const signed char* __restrict__ type, Real* __restrict__ x, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
@@ -267,9 +320,11 @@ __global__ void __launch_bounds__(256) k_mg_smooth0(LvlGeom g, int is3D, int col
 	const int i = 2 * m + ((j + k + color) & 1);
 	if (i >= g.sx) return;
 	const int v = linIdx(g, i, j, k);
-	if (type[v] == vtInactive) return;
+	const signed char ty = type[v];
+	if (ty == vtInactive) return;
 	const size_t n = (size_t)g.n; const int Y = g.sx, Z = g.sx * g.sy;
 	Real sum = b[v];
+	if (bscale != (Real)0 && ty == vtActiveTrivial) sum *= bscale;
 	if (!ZEROX) {
 		if (i > 0)        sum -= A[n + v - 1] * x[v - 1];
 		if (i < g.sx - 1) sum -= A[n + v] * x[v + 1];
@@ -284,15 +339,18 @@ __global__ void __launch_bounds__(256) k_mg_smooth0(LvlGeom g, int is3D, int col
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(256) k_mg_residual0(LvlGeom g, int is3D, const Real* __restrict__ A, const Real* __restrict__ b,
+__global__ void __launch_bounds__(256) k_mg_residual0(LvlGeom g, int is3D, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
 	const signed char* __restrict__ type, const Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
 	const int v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= g.n || type[v] == vtInactive) return;
+	if (v >= g.n) return;
+	const signed char ty = type[v];
+	if (ty == vtInactive) return;
 	int i, j, k; vecIdx(g, v, i, j, k);
 	const size_t n = (size_t)g.n; const int Y = g.sx, Z = g.sx * g.sy;
 	Real sum = b[v];
+	if (bscale != (Real)0 && ty == vtActiveTrivial) sum *= bscale;
 	if (i > 0)        sum -= A[n + v - 1] * x[v - 1];
 	if (i < g.sx - 1) sum -= A[n + v] * x[v + 1];
 	if (j > 0)        sum -= A[2 * n + v - Y] * x[v - Y];
@@ -382,19 +440,17 @@ __global__ void __launch_bounds__(256) k_mg_interp_add(LvlGeom gf, LvlGeom gc, c
 	if (doneFlag && *doneFlag) return;
 	const int v = blockIdx.x * blockDim.x + threadIdx.x;
 	if (v >= gf.n) return;
-	Real val = rf[v];
-	if (tf[v] != vtInactive) {
-		int x, y, z; vecIdx(gf, v, x, y, z);
-		Real sum = 0;
-		for (int iz = z / 2; iz <= (z + 1) / 2; iz++) for (int iy = y / 2; iy <= (y + 1) / 2; iy++) for (int ix = x / 2; ix <= (x + 1) / 2; ix++) {
-			const int i = linIdx(gc, ix, iy, iz);
-			if (tc[i] != vtInactive) sum += xc[i];
-		}
-		const Real iw = (Real)1 / (Real)(1 << ((x % 2) + (y % 2) + (z % 2)));
-		val = iw * sum;
-		rf[v] = val;
+	// inactive vertices: the reference adds their r entry, which is never written and stays 0 -> nothing to do;
+	// the interpolated value itself (mr[l] in the reference) is a temporary and is not stored
+	if (tf[v] == vtInactive) return;
+	int x, y, z; vecIdx(gf, v, x, y, z);
+	Real sum = 0;
+	for (int iz = z / 2; iz <= (z + 1) / 2; iz++) for (int iy = y / 2; iy <= (y + 1) / 2; iy++) for (int ix = x / 2; ix <= (x + 1) / 2; ix++) {
+		const int i = linIdx(gc, ix, iy, iz);
+		if (tc[i] != vtInactive) sum += xc[i];
 	}
-	xf[v] += val;
+	const Real iw = (Real)1 / (Real)(1 << ((x % 2) + (y % 2) + (z % 2)));
+	xf[v] += iw * sum;
 }
 
 // solveCG :796-902 on the coarsest level: one CTA, double precision, Jacobi preconditioner
@@ -411,7 +467,7 @@ __device__ __forceinline__ double ctaSum(double v, double* sh) {
 }
 template <typename Real>
 __global__ void __launch_bounds__(1024) k_mg_coarse_cg(LvlGeom g, int is3D, int S, int level0, const Real* __restrict__ A, const Real* __restrict__ b,
-	const signed char* __restrict__ type, Real* __restrict__ xr, double* __restrict__ cg, double accuracy, int* flagsOut, const int* doneFlag)
+	const signed char* __restrict__ type, Real* __restrict__ xr, double* __restrict__ cg, double accuracy, int* flagsOut, const int* doneFlag, Real bscale)
 {
 	if (doneFlag && *doneFlag) return;
 	__shared__ double sh[33];
@@ -436,7 +492,9 @@ __global__ void __launch_bounds__(1024) k_mg_coarse_cg(LvlGeom g, int is3D, int 
 	double aTop = 0, res0 = 0;
 	for (int v = threadIdx.x; v < n; v += blockDim.x) {
 		if (type[v] == vtInactive) continue;
-		const double rv = (double)b[v] - applyA(v, x);
+		Real bv = b[v];
+		if (bscale != (Real)0 && type[v] == vtActiveTrivial) bv *= bscale;
+		const double rv = (double)bv - applyA(v, x);
 		const double zv = rv / (double)A[v];
 		r[v] = rv; z[v] = zv; p[v] = zv;
 		res0 += rv * rv; aTop += rv * zv;
@@ -503,9 +561,9 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 		const LvlGeom gf = m->geom[l - 1], gc = m->geom[l];
 		k_mg_fill_type<<<nb(gc.n, 256), 256, 0, st>>>(m->type[l], gc.n, vtFree); MP_CHECK_LAUNCH(ctx);
 		// phase-1 closure to its fixed point (a handful of sweeps for bulk domains)
-		for (int sweep = 0; sweep < gf.sx + gf.sy + gf.sz + 8; sweep += 4) {
+		for (int sweep = 0; sweep < gf.sx + gf.sy + gf.sz + 8; sweep += 2) {
 			MP_CUDA(cudaMemsetAsync(m->dFlags, 0, sizeof(int), st));
-			for (int q = 0; q < 4; q++) { k_mg_select<<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, 0); MP_CHECK_LAUNCH(ctx); }
+			for (int q = 0; q < 2; q++) { k_mg_select<<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, 0); MP_CHECK_LAUNCH(ctx); }
 			MP_CUDA(cudaMemcpyAsync(m->hFlags, m->dFlags, sizeof(int), cudaMemcpyDeviceToHost, st));
 			MP_CUDA(cudaStreamSynchronize(st));
 			if (!m->hFlags[0]) break;
@@ -525,7 +583,9 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 			k_mg_activate_coarse<<<nb(gc.n, 256), 256, 0, st>>>(m->type[l], gc.n); MP_CHECK_LAUNCH(ctx);
 		}
 		const long long work = (long long)gc.n * m->stencil;
-		if (l == 1) k_mg_galerkin1<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->dPaths, (const int*)(m->dFlags + 16), (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1]);
+		static const int g1variant = getenv("MP_MG_GALERKIN1") ? atoi(getenv("MP_MG_GALERKIN1")) : 2;
+		if (l == 1 && g1variant == 2) k_mg_galerkin1_v2<Real><<<nb(gc.n, 128), 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1]);
+		else if (l == 1) k_mg_galerkin1<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->dPaths, (const int*)(m->dFlags + 16), (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1]);
 		else        k_mg_galerkinN<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->A[l]);
 		MP_CHECK_LAUNCH(ctx);
 	}
@@ -533,8 +593,12 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 	return MP_OK;
 }
 
+// level-0 vectors of the running V-cycle: x0 is the caller's dst grid (no copy at the end), b0 either the scaled copy made
+// by setRhs or the caller's rhs with trivial rows scaled on the fly (bscale != 0)
+template <typename Real> struct L0 { Real* x; const Real* b; Real bscale; };
+
 template <typename Real>
-static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneFlag)
+static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneFlag, const L0<Real>& l0)
 {
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	const LvlGeom g = m->geom[l];
@@ -543,8 +607,8 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 		for (int c = 0; c < 2; c++) {
 			const int color = reversed ? 1 - c : c;
 			// with x == 0 on entry the first colour reduces to x = b / A0 (same arithmetic: the skipped products are exact zeros)
-			if (zeroX && c == 0) k_mg_smooth0<Real, true><<<nb(work, 256), 256, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], (const Real*)m->b[0], m->type[0], (Real*)m->x[0], doneFlag);
-			else                 k_mg_smooth0<Real, false><<<nb(work, 256), 256, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], (const Real*)m->b[0], m->type[0], (Real*)m->x[0], doneFlag);
+			if (zeroX && c == 0) k_mg_smooth0<Real, true><<<nb(work, 256), 256, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, doneFlag);
+			else                 k_mg_smooth0<Real, false><<<nb(work, 256), 256, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, doneFlag);
 			MP_CHECK_LAUNCH(ctx);
 		}
 	} else {
@@ -561,51 +625,48 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 }
 
 template <typename Real>
-static int mgResidual(mp_mg* m, int l, const int* doneFlag)
+static int mgResidual(mp_mg* m, int l, const int* doneFlag, const L0<Real>& l0)
 {
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	const LvlGeom g = m->geom[l];
-	if (l == 0) k_mg_residual0<Real><<<nb(g.n, 256), 256, 0, st>>>(g, m->is3D, (const Real*)m->A[0], (const Real*)m->b[0], m->type[0], (const Real*)m->x[0], (Real*)m->r[0], doneFlag);
+	if (l == 0) k_mg_residual0<Real><<<nb(g.n, 256), 256, 0, st>>>(g, m->is3D, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], (const Real*)l0.x, (Real*)m->r[0], doneFlag);
 	else        k_mg_residualN<Real><<<nb(g.n, 128), 128, 0, st>>>(g, m->is3D, m->stencil, (const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (const Real*)m->x[l], (Real*)m->r[l], doneFlag);
 	MP_CHECK_LAUNCH(ctx);
 	return MP_OK;
 }
 
-// doVCycle :448-504.  xInit: x0 already holds the initial guess (src) instead of zero.
+// doVCycle :448-504.  The level-0 iterate lives directly in `dst` (knCopyToGrid :499 becomes a no-op); xInit: dst already
+// holds the initial guess (src) instead of zero.  rhsExt != NULL: use the caller's unscaled rhs (setRhs folded in).
 template <typename Real>
-static int mgVCycle(mp_mg* m, Real* dst, bool xInit, bool wantNorm, const int* doneFlag)
+static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wantNorm, const int* doneFlag)
 {
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	const int maxLevel = m->nlev - 1;
-	if (!xInit && !(maxLevel > 0 && m->numPre > 0)) MP_CUDA(cudaMemsetAsync(m->x[0], 0, sizeof(Real) * (size_t)m->geom[0].n, st));
-	bool x0zero = !xInit;
-	if (x0zero && maxLevel > 0 && m->numPre > 0) {
-		// knSet(x0, 0) is folded into the first pre-smoothing sweep: the first colour writes b/A0 on its active
-		// vertices; everything else must read as zero, so only the other colour / inactive cells need the clear
-		MP_CUDA(cudaMemsetAsync(m->x[0], 0, sizeof(Real) * (size_t)m->geom[0].n, st));
-	}
+	L0<Real> l0; l0.x = dst; l0.b = rhsExt ? rhsExt : (const Real*)m->b[0]; l0.bscale = rhsExt ? (Real)m->trivialScale : (Real)0;
+	// knSet(x0, 0) :458.  (If a preconditioner call was skipped because the solve is done, dst simply keeps zeros.)
+	if (!xInit) MP_CUDA(cudaMemsetAsync(dst, 0, sizeof(Real) * (size_t)m->geom[0].n, st));
 	for (int l = 0; l < maxLevel; l++) {
-		for (int i = 0; i < m->numPre; i++) MP_TRY((mgSmooth<Real>(m, l, false, (l == 0 ? x0zero : true) && i == 0 && l == 0, doneFlag)));
-		MP_TRY((mgResidual<Real>(m, l, doneFlag)));
+		// with x == 0 on entry the first colour of the first sweep reduces to x = b / A0 (the skipped products are exact zeros)
+		for (int i = 0; i < m->numPre; i++) MP_TRY((mgSmooth<Real>(m, l, false, l == 0 && i == 0 && !xInit, doneFlag, l0)));
+		MP_TRY((mgResidual<Real>(m, l, doneFlag, l0)));
 		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
 		k_mg_restrict<Real><<<nb(gc.n, 128), 128, 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->r[l], (Real*)m->b[l + 1], (Real*)m->x[l + 1], doneFlag);
 		MP_CHECK_LAUNCH(ctx);
 	}
 	{
 		const LvlGeom g = m->geom[maxLevel];
-		k_mg_coarse_cg<Real><<<1, 1024, 0, st>>>(g, m->is3D, m->stencil, maxLevel == 0 ? 1 : 0, (const Real*)m->A[maxLevel], (const Real*)m->b[maxLevel], m->type[maxLevel],
-			(Real*)m->x[maxLevel], m->cg, m->coarsestAcc, m->dFlags, doneFlag);
+		const bool lvl0 = maxLevel == 0;
+		k_mg_coarse_cg<Real><<<1, 1024, 0, st>>>(g, m->is3D, m->stencil, lvl0 ? 1 : 0, (const Real*)m->A[maxLevel], lvl0 ? l0.b : (const Real*)m->b[maxLevel], m->type[maxLevel],
+			lvl0 ? l0.x : (Real*)m->x[maxLevel], m->cg, m->coarsestAcc, m->dFlags, doneFlag, lvl0 ? l0.bscale : (Real)0);
 		MP_CHECK_LAUNCH(ctx);
 	}
 	for (int l = maxLevel - 1; l >= 0; l--) {
 		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
-		k_mg_interp_add<Real><<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], (Real*)m->x[l], doneFlag);
+		k_mg_interp_add<Real><<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], l == 0 ? l0.x : (Real*)m->x[l], doneFlag);
 		MP_CHECK_LAUNCH(ctx);
-		for (int i = 0; i < m->numPost; i++) MP_TRY((mgSmooth<Real>(m, l, true, false, doneFlag)));
+		for (int i = 0; i < m->numPost; i++) MP_TRY((mgSmooth<Real>(m, l, true, false, doneFlag, l0)));
 	}
-	if (wantNorm) MP_TRY((mgResidual<Real>(m, 0, doneFlag)));      // calcResidual(0) only feeds the returned norm (:496-497)
-	k_mg_copy<Real><<<nb(m->geom[0].n, 256), 256, 0, st>>>(m->geom[0].n, (const Real*)m->x[0], dst, doneFlag);   // knCopyToGrid :499
-	MP_CHECK_LAUNCH(ctx);
+	if (wantNorm) MP_TRY((mgResidual<Real>(m, 0, doneFlag, l0)));      // calcResidual(0) only feeds the returned norm (:496-497)
 	return MP_OK;
 }
 
@@ -620,6 +681,9 @@ static int mgSetRhs(mp_mg* m, const Real* rhs, const int* doneFlag)
 	return MP_OK;
 }
 
+void mp_mg_invalidate(mp_mg* mg) { mg->isASet = false; mg->isRhsSet = false; mg->numPre = mg->numPost = 1; mg->coarsestAcc = (mg->prec == 4) ? (double)1E-8f : 1E-8; }
+bool mp_mg_matches(const mp_mg* mg, int prec, int sx, int sy, int sz) { return mg->prec == prec && mg->geom[0].sx == sx && mg->geom[0].sy == sy && mg->geom[0].sz == sz; }
+
 // InitPreconditionMultigrid conjugategrad.cpp:100-106
 int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, double accuracy)
 {
@@ -632,8 +696,10 @@ int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp
 // ApplyPreconditionMultigrid conjugategrad.cpp:162-167
 int mp_mg_precond_apply(mp_mg* mg, mp_grid* dst, const mp_grid* rhs, const int* doneFlag)
 {
-	if (mg->prec == 4) { MP_TRY(mgSetRhs<float>(mg, (const float*)rhs->d, doneFlag)); return mgVCycle<float>(mg, (float*)dst->d, false, false, doneFlag); }
-	MP_TRY(mgSetRhs<double>(mg, (const double*)rhs->d, doneFlag)); return mgVCycle<double>(mg, (double*)dst->d, false, false, doneFlag);
+	if (!mg->isASet) MP_FAIL(MP_ERR_NOT_SET, "GridMg::setRhs Error: A has not been set.");
+	mg->isRhsSet = false;      // b0 is not materialised on this path (setRhs is folded into the level-0 kernels)
+	if (mg->prec == 4) return mgVCycle<float>(mg, (float*)dst->d, (const float*)rhs->d, false, false, doneFlag);
+	return mgVCycle<double>(mg, (double*)dst->d, (const double*)rhs->d, false, false, doneFlag);
 }
 
 extern "C" {
@@ -662,9 +728,10 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 	}
 	for (l = 0; l < m->nlev; l++) {
 		const size_t n = (size_t)m->geom[l].n; const int S = l == 0 ? m->stencil0 : m->stencil;
-		MP_CUDA(cudaMalloc(&m->A[l], n * S * prec)); MP_CUDA(cudaMalloc(&m->x[l], n * prec)); MP_CUDA(cudaMalloc(&m->b[l], n * prec));
+		MP_CUDA(cudaMalloc(&m->A[l], n * S * prec)); MP_CUDA(cudaMalloc(&m->b[l], n * prec));
+		if (l > 0) MP_CUDA(cudaMalloc(&m->x[l], n * prec));        // the level-0 iterate lives in the caller's dst grid
 		MP_CUDA(cudaMalloc(&m->r[l], n * prec)); MP_CUDA(cudaMalloc((void**)&m->type[l], n));
-		MP_CUDA(cudaMemsetAsync(m->A[l], 0, n * S * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->x[l], 0, n * prec, ctx->stream));
+		MP_CUDA(cudaMemsetAsync(m->A[l], 0, n * S * prec, ctx->stream)); if (l > 0) MP_CUDA(cudaMemsetAsync(m->x[l], 0, n * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, n * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->type[l], 0, n, ctx->stream));
 	}
@@ -713,6 +780,7 @@ int mp_mg_destroy(mp_mg* m)
 	for (int l = 0; l < m->nlev; l++) { cudaFree(m->A[l]); cudaFree(m->x[l]); cudaFree(m->b[l]); cudaFree(m->r[l]); cudaFree(m->type[l]); }
 	cudaFree(m->cg); cudaFree(m->dPaths); cudaFree(m->dFlags); cudaFreeHost(m->hFlags);
 	if (m->ctx->staticMg == m) m->ctx->staticMg = nullptr;
+	if (m->ctx->spareMg == m) m->ctx->spareMg = nullptr;
 	delete m; return MP_OK;
 }
 
@@ -746,10 +814,10 @@ int mp_mg_do_vcycle(mp_mg* m, mp_grid* dst, const mp_grid* src, double* resNorm)
 	MP_CUDA(cudaSetDevice(ctx->device));
 	if (src) {
 		if (src->kind != MP_GRID_REAL || src->prec != m->prec || src->n != m->geom[0].n) MP_FAIL(MP_ERR_INVALID, "mp_mg_do_vcycle: src does not match");
-		MP_CUDA(cudaMemcpyAsync(m->x[0], src->d, (size_t)m->prec * m->geom[0].n, cudaMemcpyDeviceToDevice, ctx->stream));   // knCopyToVector :457
+		if (src != dst) MP_CUDA(cudaMemcpyAsync(dst->d, src->d, (size_t)m->prec * m->geom[0].n, cudaMemcpyDeviceToDevice, ctx->stream));   // knCopyToVector :457
 	}
-	if (m->prec == 4) MP_TRY((mgVCycle<float>(m, (float*)dst->d, src != nullptr, resNorm != nullptr, nullptr)));
-	else              MP_TRY((mgVCycle<double>(m, (double*)dst->d, src != nullptr, resNorm != nullptr, nullptr)));
+	if (m->prec == 4) MP_TRY((mgVCycle<float>(m, (float*)dst->d, nullptr, src != nullptr, resNorm != nullptr, nullptr)));
+	else              MP_TRY((mgVCycle<double>(m, (double*)dst->d, nullptr, src != nullptr, resNorm != nullptr, nullptr)));
 	if (resNorm) {
 		const int n = m->geom[0].n;
 		unsigned int blocks = nb(n, 256 * 8); if (blocks > 1024) blocks = 1024;
@@ -781,7 +849,9 @@ int mp_mg_download(const mp_mg* m, int level, const char* what, void* host)
 	MP_CUDA(cudaStreamSynchronize(m->ctx->stream));
 	const size_t n = (size_t)m->geom[level].n; const int S = level == 0 ? m->stencil0 : m->stencil;
 	if (!strcmp(what, "type")) { MP_CUDA(cudaMemcpy(host, m->type[level], n, cudaMemcpyDeviceToHost)); return MP_OK; }
-	if (!strcmp(what, "x")) { MP_CUDA(cudaMemcpy(host, m->x[level], n * m->prec, cudaMemcpyDeviceToHost)); return MP_OK; }
+	if (!strcmp(what, "x")) {
+		if (level == 0) MP_FAIL(MP_ERR_INVALID, "mp_mg_download: the level-0 iterate lives in the caller's dst grid");
+		MP_CUDA(cudaMemcpy(host, m->x[level], n * m->prec, cudaMemcpyDeviceToHost)); return MP_OK; }
 	if (!strcmp(what, "b")) { MP_CUDA(cudaMemcpy(host, m->b[level], n * m->prec, cudaMemcpyDeviceToHost)); return MP_OK; }
 	if (!strcmp(what, "r")) { MP_CUDA(cudaMemcpy(host, m->r[level], n * m->prec, cudaMemcpyDeviceToHost)); return MP_OK; }
 	if (!strcmp(what, "a")) {

@@ -7,6 +7,8 @@
 int mp_make_matrix_fused(mp_context* ctx, const mp_grid* flags, mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak, const mp_grid* fractions, const mp_grid* phi, double gfClamp);
 int mp_fix_pressure_auto(mp_context* ctx, const mp_grid* flags, mp_grid* rhs, mp_grid* A0, mp_grid* Ai, mp_grid* Aj, mp_grid* Ak);
 int mp_cg_run(mp_cg* cg, int maxIter);
+void mp_mg_invalidate(mp_mg* mg);
+bool mp_mg_matches(const mp_mg* mg, int prec, int sx, int sy, int sz);
 
 template <typename Real>
 __global__ void __launch_bounds__(256) k_add_mean_corr(Real* __restrict__ rhs, IndexInt n, const double* sumcnt) {
@@ -28,7 +30,13 @@ struct GridHolder {   // RAII for the temp grids of one call (the reference take
 extern "C" {
 
 int mp_release_mg(mp_context* ctx) {
-	if (ctx && ctx->staticMg) { mp_mg_destroy(ctx->staticMg); ctx->staticMg = nullptr; }
+	// releaseMG pressure.cpp:252-266.  The hierarchy is invalidated (isASet = false); its device allocations are parked in
+	// the context so that the next `new GridMg(size)` of the same size costs no cudaMalloc/cudaFree (PcMGDynamic does this
+	// every solve, pressure.cpp:423-429,:451).
+	if (!ctx || !ctx->staticMg) return MP_OK;
+	if (ctx->spareMg) mp_mg_destroy(ctx->spareMg);
+	ctx->spareMg = ctx->staticMg; ctx->staticMg = nullptr;
+	mp_mg_invalidate(ctx->spareMg);
 	return MP_OK;
 }
 
@@ -101,7 +109,11 @@ int mp_solve_pressure_system(mp_context* ctx, mp_grid* rhs, mp_grid* vel, mp_gri
 		maxIter = 100;                                                            // :419
 		pmg = ctx->staticMg;
 		if (pmg && preconditioner == MP_PC_MG_DYNAMIC) { mp_release_mg(ctx); pmg = nullptr; }   // :423-426
-		if (!pmg) { MP_TRY(mp_mg_create(ctx, prec, flags->sx, flags->sy, flags->sz, &pmg)); ctx->staticMg = pmg; }
+		if (!pmg) {
+			if (ctx->spareMg && mp_mg_matches(ctx->spareMg, prec, flags->sx, flags->sy, flags->sz)) { pmg = ctx->spareMg; ctx->spareMg = nullptr; }
+			else MP_TRY(mp_mg_create(ctx, prec, flags->sx, flags->sy, flags->sz, &pmg));
+			ctx->staticMg = pmg;
+		}
 		MP_TRY(mp_cg_set_mg_preconditioner(cg, MP_CG_PC_MGP, pmg));
 	}
 

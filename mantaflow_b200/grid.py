@@ -80,7 +80,7 @@ class _GridBase:
         if data is None:
             self._host = np.zeros(shape, dtype)
         else:
-            self._host = np.ascontiguousarray(data, dtype=dtype).reshape(shape)
+            self._host = np.array(data, dtype=dtype, order="C", copy=True).reshape(shape)   # never alias the caller's array
         self._dev = C.c_void_p()
         check(parent.lib.mp_grid_create(parent._ctx, C.c_int(self.KIND), C.c_int(parent.prec), C.c_int(sx), C.c_int(sy), C.c_int(sz), C.byref(self._dev)))
         self._hostDirty = data is not None      # host holds newer data than the device
