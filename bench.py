@@ -6,8 +6,8 @@ plugin/pressure.cpp:480-521) over one synthetic smoke-plume grid:
   N=1 : BASELINE.json configs[3] "synthetic 512^3 smoke plume single-GPU pressure projection", float build,
         preconditioner PcNone by default (the memory-bound matvec/axpy path the north_star roofline is about),
         cgAccuracy 1e-4, cgMaxIterFac 99.
-  N>1 : the same 512^3 cells PER GPU, z-slab sharded (global grid 512 x 512 x 512N; N=8 has the cell count of the
-        1024^3 config), one-plane halo exchange + per-iteration scalar all-reduce over NCCL -> "scaling": "weak".
+  N>1 : the same 512^3 cells PER GPU, z-slab sharded (global grid 512x512x1024 / 512x1024x1024 / 1024^3 for N = 2 / 4 / 8;
+        N=8 is BASELINE.json's 1024^3 config), one-plane halo exchange + per-iteration scalar all-gather over NCCL -> "scaling": "weak".
 metric  = cells x CG iterations / second over the whole job ("Gcell-iter/s"); a 512^3 PcNone iteration at the HBM roofline
           (64 B/cell, MEASURED_PEAKS hbm_gbs) is the ceiling.  cg_iter_per_s and solve_ms are reported beside it.
 value   = inputs resident in HBM when the timed region starts; e2e = same metric through mp_solve_pressure_host with
@@ -129,11 +129,15 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+from mantaflow_b200.sharded import global_grid  # noqa: E402
+
+
 def workload_config(args, n):
-    return {"workload": "synthetic %d^3 smoke plume with sphere obstacle per GPU (global %dx%dx%d), solvePressure %s, cgAccuracy 1e-4, cgMaxIterFac 99, %s build"
-            % (args.res, args.res, args.res, args.res * n, PC_NAMES[args.pc], "float" if args.prec == 4 else "double"),
-            "preconditioner": PC_NAMES[args.pc], "grid": [args.res, args.res, args.res * n], "sharding": "z-slabs x%d" % n,
-            "l2": "inputs larger than L2 (one Real grid = %d MiB, 9 streamed per iteration)" % (args.res ** 3 * args.prec >> 20)}
+    gx, gy, gz = global_grid(args.res, n)
+    return {"workload": "synthetic smoke plume with sphere obstacle, %d^3 cells per GPU (global %dx%dx%d), solvePressure %s, cgAccuracy 1e-4, cgMaxIterFac 99, %s build"
+            % (args.res, gx, gy, gz, PC_NAMES[args.pc], "float" if args.prec == 4 else "double"),
+            "preconditioner": PC_NAMES[args.pc], "grid": [gx, gy, gz], "sharding": "z-slabs x%d (%d planes per GPU)" % (n, gz // n),
+            "l2": "inputs larger than L2 (one Real grid = %d MiB per GPU, 9 streamed per iteration)" % (args.res ** 3 * args.prec >> 20)}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -196,7 +200,7 @@ def run_ours(args):
     e2e_ms = t.item()
 
     if rank == 0:
-        cells = res ** 3 * world
+        cells = res ** 3 * world          # = product of global_grid(res, world)
         peak, peak_src = load_peaks()
         bpc = bytes_per_cell(prec)
         mv_ms = prof.get("msMatvecAvg", 0.0)
@@ -212,7 +216,7 @@ def run_ours(args):
                 "kernel_gbs": {"matvec_dot": achieved,
                                "axpy2_norm": (bpc["axpy"] * cells_gpu / (prof["msAxpyAvg"] * 1e-3) / 1e9) if prof.get("msAxpyAvg") else None,
                                "update_search": (bpc["update"] * cells_gpu / (prof["msUpdateAvg"] * 1e-3) / 1e9) if prof.get("msUpdateAvg") else None},
-                "roofline": {"bound": "hbm", "kernel": "k_matvec_dot", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "k_matvec_zmarch (the z-marching instantiation of the matvec+dot kernel)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": runner.ncu_traffic(), "peak_source": peak_src,
                              "algorithmic_bytes_per_cell": bpc["matvec"]},
                 "e2e": {"value": cells * iters / (e2e_ms * 1e-3) / 1e9, "unit": "Gcell-iter/s", "ms_per_step": e2e_ms,

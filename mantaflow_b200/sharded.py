@@ -15,6 +15,18 @@ from ._lib import check
 from .grid import Solver
 
 
+def global_grid(res, n):
+    """res^3 cells per GPU, as cubic as possible: N=1 res^3, N=2 res x res x 2res, N=4 res x 2res x 2res, N=8 (2res)^3
+    (res=512, N=8 is the 1024^3 configuration); z is the sharded axis."""
+    dims = [res, res, res]
+    f, axis = n, 2
+    while f > 1:
+        dims[axis] *= 2
+        f //= 2
+        axis = (axis - 1) % 3
+    return tuple(dims)
+
+
 def slab(sz, rank, world):
     """global planes [k0,k1) owned by `rank` -- the same rule as mp_dist_slab"""
     base, rem = divmod(sz, world)
@@ -84,7 +96,7 @@ class ShardedSolver(Solver):
 
 
 class ShardedBench:
-    """bench.py's N>1 runner: 512^3 cells per GPU, global grid res x res x (res*N), PcNone."""
+    """bench.py's N>1 runner: res^3 cells per GPU, global grid bench.global_grid(res, N) (1024^3 at res=512, N=8), PcNone."""
 
     def __init__(self, args, rank, world, device, dist):
         import mantaflow_b200 as mf
@@ -94,10 +106,10 @@ class ShardedBench:
         if args.pc != 0:
             raise SystemExit("bench.py: only PcNone is sharded across GPUs in this round")
         uid = exchange_unique_id(dist, rank)
-        gsz = res * world
-        self.s = ShardedSolver((res, res, gsz), rank, world, uid, prec=prec, device=device)
+        gsx, gsy, gsz = global_grid(res, world)
+        self.s = ShardedSolver((gsx, gsy, gsz), rank, world, uid, prec=prec, device=device)
         self.s.setProfiling(16)
-        flags, vel = scenes.smoke_plume((res, res, gsz), prec, zrange=(self.s.k0 - 1, self.s.k1 + 1))
+        flags, vel = scenes.smoke_plume((gsx, gsy, gsz), prec, zrange=(self.s.k0 - 1, self.s.k1 + 1))
         self.F, self.V0, self.V, self.P = mf.FlagGrid(self.s, flags), mf.MACGrid(self.s, vel), mf.MACGrid(self.s), mf.RealGrid(self.s)
         self.F.dev(); self.V0.dev()
         self.kw = dict(cgAccuracy=1e-4, cgMaxIterFac=99, preconditioner=0)
