@@ -212,8 +212,9 @@ int mp_dist_slab(int sz_global, int rank, int world, int* k0, int* k1);
 /* switch the context to slab mode for a global grid of sz_global planes: from now on every 3-D grid of the context
  * holds the rank's owned planes [k0,k1) plus one ghost plane on each side (local sz = k1-k0+2, local plane kl is global
  * plane k0-1+kl; ghost planes outside the domain are ignored).  Inputs (flags, vel, phi ...) are uploaded WITH their ghost
- * planes; outputs are valid on owned planes (and on ghosts after mp_dist_exchange_halo).  PcNone is sharded in this
- * round; PcMIC / PcMG* return MP_ERR_UNSUPPORTED in slab mode. */
+ * planes; outputs are valid on owned planes (and on ghosts after mp_dist_exchange_halo).  PcNone runs the reference's
+ * algorithm unchanged (bit-identical results in the float build).  PcMIC / PcMG* are applied block-Jacobi over the slabs
+ * (each rank factorises / coarsens its own slab; same solution within the solver tolerance, more iterations). */
 int mp_dist_set_domain(mp_context* ctx, int sz_global);
 /* refresh the two ghost planes of a slab grid from the neighbouring ranks (NCCL send/recv on the context stream) */
 int mp_dist_exchange_halo(mp_context* ctx, mp_grid* g);

@@ -419,8 +419,10 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	if (!cg->flagsChecked) { MP_TRY(mp_check_flags_interior(ctx, cg->flags)); cg->flagsChecked = true; }
 	if (cg->pcMethod == MP_CG_PC_MICP && !d.is3D) MP_FAIL(MP_ERR_INVALID, "mICP only supports 3D grids so far");   // :222
 	if (cg->pcMethod == MP_CG_PC_ICP) MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: PC_ICP is not implemented on the device");
-	if (d.world > 1 && cg->pcMethod != MP_CG_PC_NONE)
-		MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: only PcNone is sharded across GPUs in this round (the MIC sweeps and the MG hierarchy are single-GPU)");
+	// Slab mode with a preconditioner: block-Jacobi over the slabs.  MIC(0) / GridMg are built and applied on
+	// this rank's slab only -- the ghost planes are the local grid's outer layer (A0 == 0 there, so they are non-fluid for the
+	// MIC sweeps and inactive vertices for GridMg), i.e. the preconditioner is the block diagonal of the global one.  It is
+	// still symmetric positive definite, CG converges to the same solution; iteration counts differ and are reported.
 	cg->inited = true; cg->iterations = 0; cg->finished = false; cg->diverged = false; cg->resNorm = 1e20;
 	const bool none = cg->pcMethod == MP_CG_PC_NONE;
 	const IndexInt nOwn = d.i1 - d.i0;
@@ -442,10 +444,11 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 		MP_TRY(cgApplyPrecond(cg, nullptr));
 		MP_TRY(mp_grid_copy_from(cg->search, cg->tmp));                     // mSearch.copyFrom(mTmp) :232
 		DISPATCH_RV(cg->dst, {
-			const unsigned int blocks = streamBlocks(ctx, d.n / V);
-			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(d.n, (const Real*)cg->tmp->d, (const Real*)cg->residual->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 4, 1, nullptr);
+			const unsigned int blocks = streamBlocks(ctx, nOwn / V);
+			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, (const Real*)cg->tmp->d + d.i0, (const Real*)cg->residual->d + d.i0, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 4, 1, dl);
 			MP_CHECK_LAUNCH(ctx);
 		});
+		if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 3, 0));
 	}
 	if (d.world > 1) MP_TRY(cgHalo(cg, cg->search));  // the first matvec reads the neighbours' planes of s
 	return MP_OK;
@@ -477,15 +480,18 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 			MP_CHECK_LAUNCH(ctx);
 			if (dl) MP_TRY(cgHalo(cg, cg->search));
 		} else {
-			k_axpy2_norm<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(nOwn, x, s, r, t, sc, ctx->partials, ctx->tickets + 5, nullptr);
+			k_axpy2_norm<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(nOwn, x, s, r, t, sc, ctx->partials, ctx->tickets + 5, dl);
 			MP_CHECK_LAUNCH(ctx);
+			if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 1, 1));
 			PROF(2);
 			MP_TRY(cgApplyPrecond(cg, &sc->done));
-			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, t, r, sc, ctx->partials, ctx->tickets + 4, 0, nullptr);
+			k_dot_zr<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, t, r, sc, ctx->partials, ctx->tickets + 4, 0, dl);
 			MP_CHECK_LAUNCH(ctx);
+			if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 2, 0));
 			PROF(3);
 			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, s, t, sc);
 			MP_CHECK_LAUNCH(ctx);
+			if (dl) MP_TRY(cgHalo(cg, cg->search));
 		}
 	});
 	PROF(4);

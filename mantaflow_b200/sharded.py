@@ -103,8 +103,6 @@ class ShardedBench:
         from . import scenes
         self.mf, self.args, self.rank, self.world = mf, args, rank, world
         res, prec = args.res, args.prec
-        if args.pc != 0:
-            raise SystemExit("bench.py: only PcNone is sharded across GPUs in this round")
         uid = exchange_unique_id(dist, rank)
         gsx, gsy, gsz = global_grid(res, world)
         self.s = ShardedSolver((gsx, gsy, gsz), rank, world, uid, prec=prec, device=device)
@@ -112,7 +110,7 @@ class ShardedBench:
         flags, vel = scenes.smoke_plume((gsx, gsy, gsz), prec, zrange=(self.s.k0 - 1, self.s.k1 + 1))
         self.F, self.V0, self.V, self.P = mf.FlagGrid(self.s, flags), mf.MACGrid(self.s, vel), mf.MACGrid(self.s), mf.RealGrid(self.s)
         self.F.dev(); self.V0.dev()
-        self.kw = dict(cgAccuracy=1e-4, cgMaxIterFac=99, preconditioner=0)
+        self.kw = dict(cgAccuracy=1e-4, cgMaxIterFac=99, preconditioner=args.pc, zeroPressureFixing=(args.pc >= 2))
         self.last_info = {}
         self.h_flags, self.h_vel0 = flags, vel
         self.h_vel, self.h_p = vel.copy(), np.zeros(flags.shape, vel.dtype)

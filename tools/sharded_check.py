@@ -53,12 +53,23 @@ for name, prec, extra in cases:
         good = abs(info["iterations"] - it_o) <= 1 and e_p <= (1e-4 if prec == 4 else 1e-10) and e_v <= (1e-4 if prec == 4 else 1e-10)
         print("sharded_check %-16s f%d world=%d iterations %d (oracle %d) relL2 p %.2e vel %.2e fixed %d %s" % (name, prec * 8, world, info["iterations"], it_o, e_p, e_v, info["fixedCell"], "OK" if good else "FAIL"), flush=True)
         ok = ok and good
-    # unsupported preconditioners must say so
-    try:
-        mf.solvePressure(vel=V, pressure=P, flags=F, preconditioner=1)
-        ok = False
-    except mf.MantaError as e:
-        assert "sharded" in str(e)
+    # preconditioned solves: block-Jacobi MIC / GridMg over the slabs (different operator than the global preconditioner,
+    # same solution within the solver tolerance; iteration counts are reported, not asserted)
+    if name in ("smoke_pin", "liquid"):
+        for pc in (1, 2):
+            fixp = pc >= 2 or bool(extra.get("zeroPressureFixing"))
+            V.copyFromArray(sharded.local_slab(vel, rank, world))
+            mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=fixp)
+            info = mf.lastSolveInfo()
+            p_all, v_all = gather(P.numpy()), gather(V.numpy())
+            if rank == 0:
+                v_o = vel.copy()
+                p_o, it_o, rn_o = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=fixp)
+                e_p, e_v = rel(p_all, p_o), rel(v_all, v_o)
+                good = info["resNorm"] < acc and e_v <= 2e-3 and e_p <= 2e-3
+                print("sharded_check %-16s f%d world=%d %s block-Jacobi: iterations %d (global preconditioner %d) resNorm %.2e relL2 p %.2e vel %.2e %s"
+                      % (name, prec * 8, world, {1: "PcMIC", 2: "PcMGDynamic"}[pc], info["iterations"], it_o, info["resNorm"], e_p, e_v, "OK" if good else "FAIL"), flush=True)
+                ok = ok and good
     s.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, src=0)
