@@ -36,7 +36,7 @@ class SolveInfo(C.Structure):
                 ("mgLevels", C.c_int), ("msRhs", C.c_float), ("msMatrix", C.c_float), ("msSolve", C.c_float),
                 ("msCorrect", C.c_float), ("msTotal", C.c_float), ("msH2D", C.c_float), ("msD2H", C.c_float),
                 ("msMatvecAvg", C.c_float), ("msAxpyAvg", C.c_float), ("msUpdateAvg", C.c_float), ("msPrecondAvg", C.c_float),
-                ("profSamples", C.c_int)]
+                ("profSamples", C.c_int), ("matvecKernel", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -184,6 +184,94 @@ __global__ void __launch_bounds__(256) k_matvec_zmarch(Dims d, int nvx, int chun
 	}
 }
 
+// ---------------------------------------------------------------- coupling-mask fast path
+// Without face fractions every off-diagonal of the pressure matrix is exactly 0 or -1 (MakeLaplaceMatrix
+// conjugategrad.h:169-171; fixPressure only zeroes entries, pressure.cpp:241-244), so Ai/Aj/Ak carry one bit of
+// information per face.  k_build_cmask verifies that on the actual arrays and packs, per cell, bit0 = fluid row and
+// bits 1..6 = coupling to -x,+x,-y,+y,-z,+z present.  k_matvec_zmarch_masked then streams cmask, A0 and s only:
+// 4+3w B/cell (16 / 28) instead of 4+6w (28 / 52).  A product s_nb * (-1) is exactly -s_nb and s_nb * 0 is a zero, so
+// the result equals ApplyMatrix's value for value (signs of exact zeros aside).  Any other off-diagonal value (face
+// fractions) makes the mask invalid and the general kernel is used.
+template <typename Real>
+__global__ void __launch_bounds__(256) k_build_cmask(Dims d, const int* __restrict__ flags, const Real* __restrict__ Ai, const Real* __restrict__ Aj,
+	const Real* __restrict__ Ak, int* __restrict__ cmask, int* bad)
+{
+	const IndexInt idx = d.i0 + (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.i1) return;
+	int m = 0;
+	if (flags[idx] & TypeFluid) {
+		m = 1;
+		const Real c[6] = { Ai[idx - 1], Ai[idx], Aj[idx - d.Y], Aj[idx], d.is3D ? Ak[idx - d.Z] : (Real)0, d.is3D ? Ak[idx] : (Real)0 };
+		#pragma unroll
+		for (int q = 0; q < 6; q++) {
+			if (c[q] == (Real)-1) m |= 2 << q;
+			else if (c[q] != (Real)0) *bad = 1;
+		}
+	}
+	cmask[idx] = m;
+}
+
+template <typename Real, int V>
+__global__ void __launch_bounds__(256) k_matvec_zmarch_masked(Dims d, int nvx, int chunk, const int* __restrict__ cmask, Real* __restrict__ dst, const Real* __restrict__ src,
+	const Real* __restrict__ A0, CgScal<Real>* sc, double* partials, unsigned int* ticket, int finalize, double* distLocal)
+{
+	if (sc && sc->done) return;
+	const IndexInt Y = d.Y, Z = d.Z;
+	const int vx = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+	const int k0 = d.kb + blockIdx.z * chunk, k1 = min(d.ke, k0 + chunk);
+	double acc = 0.0;
+	if (vx < nvx && j < d.sy && k0 < k1) {
+		IndexInt idx = (IndexInt)vx * V + Y * j + Z * k0;
+		VecT<Real, V> sm, s0, sp;
+		#pragma unroll
+		for (int q = 0; q < V; q++) sm.v[q] = (Real)0;
+		if (k0 > 0) sm = ldv<Real, V>(src + idx - Z);
+		s0 = ldv<Real, V>(src + idx);
+		for (int k = k0; k < k1; k++, idx += Z) {
+			const VecT<int, V> f = ldv<int, V>(cmask + idx);
+			if (k + 1 < d.sz) sp = ldv<Real, V>(src + idx + Z);
+			int any = 0;
+			#pragma unroll
+			for (int q = 0; q < V; q++) any |= f.v[q];
+			VecT<Real, V> out = s0;
+			if (any & 1) {
+				const VecT<Real, V> a0 = ldv<Real, V>(A0 + idx), sym = ldv<Real, V>(src + idx - Y), syp = ldv<Real, V>(src + idx + Y);
+				Real sxm0 = 0, sxpL = 0;
+				if (f.v[0] & 1) sxm0 = src[idx - 1];
+				if (f.v[V - 1] & 1) sxpL = src[idx + V];
+				#pragma unroll
+				for (int q = 0; q < V; q++) {
+					const int m = f.v[q];
+					if (m & 1) {
+						const Real xm = (q == 0) ? sxm0 : s0.v[q - 1 < 0 ? 0 : q - 1];
+						const Real xp = (q == V - 1) ? sxpL : s0.v[q + 1 > V - 1 ? V - 1 : q + 1];
+						// same left-to-right order as ApplyMatrix; a present coupling contributes s_nb * (-1) = -s_nb
+						Real t = s0.v[q] * a0.v[q];
+						t = t + ((m & 2) ? -xm : (Real)0);
+						t = t + ((m & 4) ? -xp : (Real)0);
+						t = t + ((m & 8) ? -sym.v[q] : (Real)0);
+						t = t + ((m & 16) ? -syp.v[q] : (Real)0);
+						t = t + ((m & 32) ? -sm.v[q] : (Real)0);
+						t = t + ((m & 64) ? -sp.v[q] : (Real)0);
+						out.v[q] = t;
+					}
+				}
+			}
+			stv<Real, V>(dst + idx, out);
+			#pragma unroll
+			for (int q = 0; q < V; q++) acc += (double)(out.v[q] * s0.v[q]);
+			sm = s0; s0 = sp;
+		}
+	}
+	if (!finalize) return;
+	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
+	const unsigned int tid = threadIdx.y * 32 + threadIdx.x;
+	const unsigned int blockLinear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z), numBlocks = gridDim.x * gridDim.y * gridDim.z;
+	if (blockReduceFinalL<1>(v, isMax, partials, ticket, fin, tid, 256, blockLinear, numBlocks) && tid == 0) {
+		if (distLocal) distLocal[0] = fin[0]; else cgFinA<Real>(sc, fin[0]);
+	}
+}
+
 // ---------------------------------------------------------------- k_axpy2_norm
 // gridScaledAdd x2 (conjugategrad.cpp:254-255) + residual norm (:267-271) [+ for PcNone z==r: sigmaNew = r.r, :279]
 // MODE 0: PcNone (z = r, finalises beta/sigma here), MODE 1: preconditioned (only the norm / stop test here)
@@ -309,7 +397,7 @@ static int cgCombine(mp_context* ctx, const mp_grid* g, void* sc, int stage, int
 }
 
 int mp_launch_matvec(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const mp_grid* src,
-	const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, void* sc, int finalize)
+	const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, void* sc, int finalize, const mp_grid* cmask = nullptr)
 {
 	const Dims d = dimsOf(flags);
 	double* dl = (sc && finalize) ? distLocalOf(ctx, d) : nullptr;
@@ -323,16 +411,28 @@ int mp_launch_matvec(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const 
 		int chunk = (planes + nchunk - 1) / nchunk; if (chunk < 16) chunk = 16; if (chunk > planes) chunk = planes;
 		nchunk = (planes + chunk - 1) / chunk;
 		const dim3 grid((nvx + 31) / 32, (d.sy + 7) / 8, nchunk), block(32, 8, 1);
+		if (cmask && (long long)grid.x * grid.y * grid.z <= kMaxPartials) {
+			if (dst->prec == 4) k_matvec_zmarch_masked<float, 4><<<grid, block, 0, ctx->stream>>>(d, nvx, chunk, (const int*)cmask->d, (float*)dst->d, (const float*)src->d,
+				(const float*)A0->d, (CgScal<float>*)sc, ctx->partials, ctx->tickets + 2, finalize, dl);
+			else k_matvec_zmarch_masked<double, 2><<<grid, block, 0, ctx->stream>>>(d, nvx, chunk, (const int*)cmask->d, (double*)dst->d, (const double*)src->d,
+				(const double*)A0->d, (CgScal<double>*)sc, ctx->partials, ctx->tickets + 2, finalize, dl);
+			MP_CHECK_LAUNCH(ctx);
+			ctx->lastMatvecKernel = 2;
+			if (dl) MP_TRY(cgCombine(ctx, dst, sc, 0, 0));
+			return MP_OK;
+		}
 		if ((long long)grid.x * grid.y * grid.z <= kMaxPartials) {
 			if (dst->prec == 4) k_matvec_zmarch<float, 4><<<grid, block, 0, ctx->stream>>>(d, nvx, chunk, (const int*)flags->d, (float*)dst->d, (const float*)src->d,
 				(const float*)A0->d, (const float*)Ai->d, (const float*)Aj->d, (const float*)Ak->d, (CgScal<float>*)sc, ctx->partials, ctx->tickets + 2, finalize, dl);
 			else k_matvec_zmarch<double, 2><<<grid, block, 0, ctx->stream>>>(d, nvx, chunk, (const int*)flags->d, (double*)dst->d, (const double*)src->d,
 				(const double*)A0->d, (const double*)Ai->d, (const double*)Aj->d, (const double*)Ak->d, (CgScal<double>*)sc, ctx->partials, ctx->tickets + 2, finalize, dl);
 			MP_CHECK_LAUNCH(ctx);
+			ctx->lastMatvecKernel = 1;
 			if (dl) MP_TRY(cgCombine(ctx, dst, sc, 0, 0));
 			return MP_OK;
 		}
 	}
+	ctx->lastMatvecKernel = 0;
 	DISPATCH_RV(dst, {
 		const unsigned int blocks = streamBlocks(ctx, (d.i1 - d.i0) / V);
 		if (d.is3D) k_matvec_dot<Real, V, true><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (Real*)dst->d, (const Real*)src->d,
@@ -372,6 +472,7 @@ struct mp_cg {
 	cudaEvent_t pollEv[2];
 	int iterations; double resNorm, sigma; bool diverged, finished;
 	bool flagsChecked;
+	mp_grid* cmask;               // coupling mask of the fast matvec path, or NULL (general kernel)
 };
 
 template <typename Real>
@@ -428,6 +529,22 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	const IndexInt nOwn = d.i1 - d.i0;
 	double* dl = distLocalOf(ctx, d);
 	if (d.world > 1) MP_TRY(cgHalo(cg, cg->Ak));      // Ak[idx-Z] of the first owned plane lives on the lower neighbour
+	{	// coupling-mask fast path of the matvec (3-D, vector-aligned rows, every off-diagonal in {0,-1})
+		static const int useMask = getenv("MP_MATVEC_MASK") ? atoi(getenv("MP_MATVEC_MASK")) : 1;
+		if (cg->cmask) { mp_grid_destroy(cg->cmask); cg->cmask = nullptr; }
+		if (useMask && d.is3D && vecWidth(cg->dst) > 1) {
+			MP_TRY(mp_grid_create(ctx, MP_GRID_FLAGS, 4, cg->flags->sx, cg->flags->sy, cg->flags->sz, &cg->cmask));
+			int* bad = (int*)(ctx->dScal + 20);
+			MP_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+			const unsigned int blocks = gridFor(d.i1 - d.i0, 256);
+			if (cg->dst->prec == 4) k_build_cmask<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)cg->flags->d, (const float*)cg->Ai->d, (const float*)cg->Aj->d, (const float*)cg->Ak->d, (int*)cg->cmask->d, bad);
+			else                    k_build_cmask<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)cg->flags->d, (const double*)cg->Ai->d, (const double*)cg->Aj->d, (const double*)cg->Ak->d, (int*)cg->cmask->d, bad);
+			MP_CHECK_LAUNCH(ctx);
+			MP_CUDA(cudaMemcpyAsync(ctx->hScal + 20, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+			MP_CUDA(cudaStreamSynchronize(ctx->stream));
+			if (*(int*)(ctx->hScal + 20)) { mp_grid_destroy(cg->cmask); cg->cmask = nullptr; }     // face fractions: general kernel
+		}
+	}
 	DISPATCH_RV(cg->dst, {
 		k_scal_reset<Real><<<1, 1, 0, ctx->stream>>>((CgScal<Real>*)cg->dSc, (Real)cg->accuracy, cg->useL2 ? 1 : 0);
 		MP_CHECK_LAUNCH(ctx);
@@ -465,7 +582,7 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 	if (ctx->profPeriod > 0 && iterIndex >= 0 && iterIndex % ctx->profPeriod == 0 && ctx->profCount < 128) pe = &ctx->profEv[5 * ctx->profCount++];
 	#define PROF(k) do { if (pe) MP_CUDA(cudaEventRecord(pe[k], ctx->stream)); } while (0)
 	PROF(0);
-	MP_TRY(mp_launch_matvec(ctx, cg->flags, cg->tmp, cg->search, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->dSc, 1));
+	MP_TRY(mp_launch_matvec(ctx, cg->flags, cg->tmp, cg->search, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->dSc, 1, cg->cmask));
 	PROF(1);
 	DISPATCH_RV(cg->dst, {
 		const unsigned int blocks = streamBlocks(ctx, nOwn / V);
@@ -558,7 +675,7 @@ int mp_cg_create(mp_context* ctx, mp_grid* dst, mp_grid* rhs, mp_grid* residual,
 	cg->pcMethod = MP_CG_PC_NONE; cg->pcA0 = nullptr; cg->mg = nullptr;
 	cg->inited = false; cg->useL2 = true;            // GridCgInterface() : mUseL2Norm(true), conjugategrad.h:31
 	cg->accuracy = 1e-8;                             // mAccuracy(VECTOR_EPSILON) conjugategrad.cpp:206, vectorbase.h
-	cg->iterations = 0; cg->resNorm = 1e20; cg->sigma = 0; cg->diverged = false; cg->finished = false; cg->flagsChecked = false;
+	cg->iterations = 0; cg->resNorm = 1e20; cg->sigma = 0; cg->diverged = false; cg->finished = false; cg->flagsChecked = false; cg->cmask = nullptr;
 	MP_CUDA(cudaMalloc(&cg->dSc, 256));
 	MP_CUDA(cudaHostAlloc((void**)&cg->hSc, sizeof(CgScalHost) * 2, cudaHostAllocMapped));
 	memset(cg->hSc, 0, sizeof(CgScalHost) * 2);
@@ -571,6 +688,7 @@ int mp_cg_destroy(mp_cg* cg) {
 	cudaSetDevice(cg->ctx->device);
 	cudaStreamSynchronize(cg->ctx->stream);
 	cudaFree(cg->dSc); cudaFreeHost(cg->hSc); cudaEventDestroy(cg->pollEv[0]); cudaEventDestroy(cg->pollEv[1]);
+	if (cg->cmask) mp_grid_destroy(cg->cmask);
 	delete cg; return MP_OK;
 }
 int mp_cg_set_accuracy(mp_cg* cg, double accuracy) { cg->accuracy = accuracy; return MP_OK; }

@@ -137,6 +137,7 @@ int mp_solve_pressure_system(mp_context* ctx, mp_grid* rhs, mp_grid* vel, mp_gri
 			info->msMatvecAvg = ctx->profMs[0]; info->msAxpyAvg = ctx->profMs[1]; info->msPrecondAvg = ctx->profMs[2]; info->msUpdateAvg = ctx->profMs[3];
 			info->profSamples = ctx->profCount;
 		}
+		info->matvecKernel = ctx->lastMatvecKernel;
 	}
 	if (pmg && preconditioner == MP_PC_MG_DYNAMIC) mp_release_mg(ctx);            // :451
 	return rc;

@@ -142,5 +142,5 @@ class ShardedBench:
         bo = (self.h_vel.nbytes + self.h_p.nbytes) * self.world
         return float(np.mean(ts)), bi, bo
 
-    def ncu_traffic(self):
+    def ncu_traffic(self, kernel):
         return None
