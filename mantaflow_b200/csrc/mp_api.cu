@@ -62,6 +62,7 @@ int mp_context_destroy(mp_context* c) {
 	c->pool.clear();
 	for (auto& e : c->profEv) cudaEventDestroy(e);
 	for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->micProg) cudaFree(c->micProg);
 	cudaFree(c->partials); cudaFree(c->tickets); cudaFree(c->dScal); cudaFreeHost(c->hScal);
 	cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copyStream);
 	delete c; return MP_OK;

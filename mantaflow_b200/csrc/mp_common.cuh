@@ -49,6 +49,7 @@ struct mp_context {
 	std::vector<cudaEvent_t> profEv;      // 5 events per sample: t0 | matvec | axpy | precond+dot | update
 	int profCount = 0;
 	float profMs[4] = {0, 0, 0, 0};
+	int* micProg = nullptr; size_t micProgBytes = 0;     // per-column progress counters (+ stall flag) of the pipelined MIC sweeps
 	int lastMatvecKernel = 0;     // which matvec instantiation the last launch used (reported in mp_solve_info)
 };
 static const int kMaxPartials = 1 << 16;   // max blocks of a reducing kernel

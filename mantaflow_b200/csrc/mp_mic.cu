@@ -140,6 +140,140 @@ __global__ void __launch_bounds__(64) k_mic_tile(TileGeom g, int c, int bklo, co
 	}
 }
 
+// ---------------------------------------------------------------- v3: one launch per sweep, columns of tiles with progress flags
+// CTA (bj,bk) walks its column of tiles bi = 0..nbi-1 (backward: everything mirrored).  Tile (bi,bj,bk) needs tile bi of the
+// columns (bj-1,bk) and (bj,bk-1); each column publishes the number of tiles it has finished in prog[] (release/acquire
+// through L2: __threadfence + atomic).  Predecessors always have a smaller linear block index, and blocks are dispatched in
+// index order, so a waiting CTA never starves the CTA it waits for.  The coefficient windows of a tile are requested BEFORE
+// the wait (they do not depend on the neighbours), only the halo of the running solution is loaded after it, bypassing L1
+// (ld.global.cg) because the L1 may hold a stale copy of a sector that a neighbour column has rewritten since.
+// A poll budget turns a scheduling surprise into an error flag instead of a hang.
+template <typename Real>
+__device__ __forceinline__ void loadWindowRegs(const WinMap& m, const Real* __restrict__ a, Real (&v)[WIN_PER_THREAD]) {
+	#pragma unroll
+	for (int q = 0; q < WIN_PER_THREAD; q++) v[q] = (m.g[q] >= 0) ? a[m.g[q]] : (Real)0;
+}
+template <typename Real>
+__device__ __forceinline__ void loadWindowRegsCg(const WinMap& m, const Real* a, Real (&v)[WIN_PER_THREAD]) {
+	#pragma unroll
+	for (int q = 0; q < WIN_PER_THREAD; q++) v[q] = (m.g[q] >= 0) ? __ldcg(a + m.g[q]) : (Real)0;
+}
+template <typename Real>
+__device__ __forceinline__ void storeWindow(const WinMap& m, const Real (&v)[WIN_PER_THREAD], Real* s) {
+	#pragma unroll
+	for (int q = 0; q < WIN_PER_THREAD; q++) if (m.s[q] >= 0) s[m.s[q]] = v[q];
+}
+
+template <typename Real, int MODE>
+__global__ void __launch_bounds__(64, 8) k_mic_cols(TileGeom g, const int* __restrict__ flags, Real* dst, const Real* __restrict__ src,
+	Real* P, const Real* __restrict__ A0, const Real* __restrict__ Ai, const Real* __restrict__ Aj, const Real* __restrict__ Ak,
+	int* prog, int* stall, const int* __restrict__ doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	__shared__ Real sP[SN], sAi[SN], sAj[SN], sAk[SN], sQ[SN];
+	__shared__ unsigned char sF[512];
+	const bool bwd = (MODE == 2);
+	const int bj = bwd ? g.nbj - 1 - (int)blockIdx.x : (int)blockIdx.x, bk = bwd ? g.nbk - 1 - (int)blockIdx.y : (int)blockIdx.y;
+	const int self = bj + g.nbj * bk;
+	// predecessor columns in sweep direction (-1: none)
+	const int pj = bwd ? (bj + 1 < g.nbj ? self + 1 : -1) : (bj > 0 ? self - 1 : -1);
+	const int pk = bwd ? (bk + 1 < g.nbk ? self + g.nbj : -1) : (bk > 0 ? self - g.nbj : -1);
+	const int h = bwd ? 0 : 1;
+	const int y0 = 1 + T8 * bj, z0 = 1 + T8 * bk;
+	const int lj = threadIdx.x & 7, lk = threadIdx.x >> 3;
+	for (int t = 0; t < g.nbi; t++) {
+		const int bi = bwd ? g.nbi - 1 - t : t;
+		const int x0 = 1 + T8 * bi;
+		WinMap wm; makeWinMap(g, x0 - h, y0 - h, z0 - h, wm);
+		// --- requests that do not depend on the neighbours
+		int fl8[8]; Real r8[8];
+		#pragma unroll
+		for (int q = 0; q < 8; q++) {
+			const int e = threadIdx.x + 64 * q;
+			const int gi = x0 + (e & 7), gj = y0 + ((e >> 3) & 7), gk = z0 + (e >> 6);
+			const bool in = gi <= g.sx - 2 && gj <= g.sy - 2 && gk <= g.sz - 2;
+			const IndexInt idx = (IndexInt)gi + g.Y * gj + g.Z * gk;
+			fl8[q] = in ? flags[idx] : 0;
+			r8[q] = (MODE == 1 && in) ? src[idx] : (Real)0;
+		}
+		// (the shared arrays are free here: every thread is past the barrier that ended the previous tile)
+		loadWindow<Real>(wm, Ai, sAi); loadWindow<Real>(wm, Aj, sAj); loadWindow<Real>(wm, Ak, sAk);
+		if (MODE != 0) loadWindow<Real>(wm, (const Real*)P, sP);             // P is read-only during the apply sweeps
+		// --- wait for the two neighbour columns to have finished their tile bi
+		if (threadIdx.x == 0) {
+			long long budget = 1ll << 26;
+			if (pj >= 0) while (atomicAdd(prog + pj, 0) <= t && --budget > 0) __nanosleep(64);
+			if (pk >= 0) while (atomicAdd(prog + pk, 0) <= t && --budget > 0) __nanosleep(64);
+			if (budget <= 0) atomicExch(stall, 1);
+			__threadfence();
+		}
+		__syncthreads();
+		{
+			Real vH[WIN_PER_THREAD];
+			if (MODE == 0) { loadWindowRegsCg<Real>(wm, P, vH); storeWindow<Real>(wm, vH, sP); }
+			else           { loadWindowRegsCg<Real>(wm, dst, vH); storeWindow<Real>(wm, vH, sQ); }
+		}
+		__syncthreads();
+		#pragma unroll
+		for (int q = 0; q < 8; q++) {
+			const int e = threadIdx.x + 64 * q;
+			const bool fl = (fl8[q] & TypeFluid) != 0;
+			if (MODE == 1 && fl) sQ[SIDX((e & 7) + 1, ((e >> 3) & 7) + 1, (e >> 6) + 1)] = r8[q];
+			sF[e] = fl ? 1 : 0;
+		}
+		__syncthreads();
+		for (int step = 0; step < 3 * T8 - 2; step++) {
+			const int li = bwd ? (3 * T8 - 3 - step) - lj - lk : step - lj - lk;
+			if (li >= 0 && li < T8 && sF[(lk << 6) | (lj << 3) | li]) {
+				const int o = SIDX(li + h, lj + h, lk + h);
+				if (MODE == 0) {
+					const int ox_ = o - 1, oy_ = o - SJ, oz_ = o - SK;
+					const Real a0 = A0[(IndexInt)(x0 + li) + g.Y * (y0 + lj) + g.Z * (z0 + lk)];
+					sP[o] = micFactor<Real>(a0, sAi[ox_], sAj[ox_], sAk[ox_], sP[ox_], sAi[oy_], sAj[oy_], sAk[oy_], sP[oy_],
+					                        sAi[oz_], sAj[oz_], sAk[oz_], sP[oz_]);
+				} else if (MODE == 1) {
+					const int ox_ = o - 1, oy_ = o - SJ, oz_ = o - SK;
+					sQ[o] = sP[o] * (sQ[o] - sQ[ox_] * sAi[ox_] * sP[ox_] - sQ[oy_] * sAj[oy_] * sP[oy_] - sQ[oz_] * sAk[oz_] * sP[oz_]);
+				} else {
+					const Real p = sP[o];
+					sQ[o] = p * (sQ[o] - sQ[o + 1] * sAi[o] * p - sQ[o + SJ] * sAj[o] * p - sQ[o + SK] * sAk[o] * p);
+				}
+			}
+			__syncthreads();
+		}
+		#pragma unroll
+		for (int q = 0; q < 8; q++) {
+			const int e = threadIdx.x + 64 * q;
+			if (!sF[e]) continue;
+			const IndexInt idx = (IndexInt)(x0 + (e & 7)) + g.Y * (y0 + ((e >> 3) & 7)) + g.Z * (z0 + (e >> 6));
+			const int o = SIDX((e & 7) + h, ((e >> 3) & 7) + h, (e >> 6) + h);
+			if (MODE == 0) P[idx] = sP[o]; else dst[idx] = sQ[o];
+		}
+		__threadfence();                                   // results visible at L2 before the progress counter moves
+		__syncthreads();
+		if (threadIdx.x == 0) atomicExch(prog + self, t + 1);
+	}
+}
+
+template <typename Real, int MODE>
+static int micColsSweep(mp_context* ctx, const Dims& d, const mp_grid* flags, Real* dst, const Real* src, Real* P, const Real* A0,
+                        const Real* Ai, const Real* Aj, const Real* Ak, const int* doneFlag)
+{
+	TileGeom g = { d.sx, d.sy, d.sz, d.Y, d.Z, (d.sx - 2 + T8 - 1) / T8, (d.sy - 2 + T8 - 1) / T8, (d.sz - 2 + T8 - 1) / T8 };
+	const size_t need = sizeof(int) * ((size_t)g.nbj * g.nbk + 1);
+	if (ctx->micProgBytes < need) {
+		if (ctx->micProg) { MP_CUDA(cudaStreamSynchronize(ctx->stream)); MP_CUDA(cudaFree(ctx->micProg)); ctx->micProg = nullptr; }
+		MP_CUDA(cudaMalloc((void**)&ctx->micProg, need)); ctx->micProgBytes = need;
+		MP_CUDA(cudaMemsetAsync(ctx->micProg, 0, need, ctx->stream));
+	}
+	int* stall = ctx->micProg + (size_t)g.nbj * g.nbk;
+	MP_CUDA(cudaMemsetAsync(ctx->micProg, 0, sizeof(int) * (size_t)g.nbj * g.nbk, ctx->stream));      // progress counters, not the stall flag
+	const dim3 grid((unsigned)g.nbj, (unsigned)g.nbk, 1);
+	k_mic_cols<Real, MODE><<<grid, 64, 0, ctx->stream>>>(g, (const int*)flags->d, dst, src, P, A0, Ai, Aj, Ak, ctx->micProg, stall, doneFlag);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
 template <typename Real, int MODE>
 static int micTiledSweep(mp_context* ctx, const Dims& d, const mp_grid* flags, Real* dst, const Real* src, Real* P, const Real* A0,
                          const Real* Ai, const Real* Aj, const Real* Ak, const int* doneFlag)
@@ -216,7 +350,7 @@ static inline bool planeLaunch(const PlaneGeom& g, int c, PlaneLaunch& pl) {
 	return true;
 }
 
-static inline int micVariant() { static const int v = getenv("MP_MIC") ? atoi(getenv("MP_MIC")) : 2; return v; }
+static inline int micVariant() { static const int v = getenv("MP_MIC") ? atoi(getenv("MP_MIC")) : 3; return v; }
 
 int mp_mic_init_launch(mp_context* ctx, const mp_grid* flags, mp_grid* P, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak)
 {
@@ -224,6 +358,10 @@ int mp_mic_init_launch(mp_context* ctx, const mp_grid* flags, mp_grid* P, const 
 	if (!d.is3D) MP_FAIL(MP_ERR_INVALID, "mICP only supports 3D grids so far");
 	MP_CUDA(cudaMemsetAsync(P->d, 0, P->bytes, ctx->stream));          // Aprecond.clear() :71
 	if (d.sx < 3 || d.sy < 3 || d.sz < 3) return MP_OK;
+	if (micVariant() == 3) {
+		if (P->prec == 4) return micColsSweep<float, 0>(ctx, d, flags, nullptr, nullptr, (float*)P->d, (const float*)A0->d, (const float*)Ai->d, (const float*)Aj->d, (const float*)Ak->d, nullptr);
+		return micColsSweep<double, 0>(ctx, d, flags, nullptr, nullptr, (double*)P->d, (const double*)A0->d, (const double*)Ai->d, (const double*)Aj->d, (const double*)Ak->d, nullptr);
+	}
 	if (micVariant() == 2) {
 		if (P->prec == 4) return micTiledSweep<float, 0>(ctx, d, flags, nullptr, nullptr, (float*)P->d, (const float*)A0->d, (const float*)Ai->d, (const float*)Aj->d, (const float*)Ak->d, nullptr);
 		return micTiledSweep<double, 0>(ctx, d, flags, nullptr, nullptr, (double*)P->d, (const double*)A0->d, (const double*)Ai->d, (const double*)Aj->d, (const double*)Ak->d, nullptr);
@@ -245,6 +383,14 @@ int mp_mic_apply_launch(mp_context* ctx, mp_grid* dst, const mp_grid* var1, cons
 	const Dims d = dimsOf(flags);
 	if (!d.is3D) MP_FAIL(MP_ERR_INVALID, "mICP only supports 3D grids so far");
 	if (d.sx < 3 || d.sy < 3 || d.sz < 3) return MP_OK;
+	if (micVariant() == 3) {
+		if (dst->prec == 4) {
+			MP_TRY((micColsSweep<float, 1>(ctx, d, flags, (float*)dst->d, (const float*)var1->d, (float*)P->d, nullptr, (const float*)Ai->d, (const float*)Aj->d, (const float*)Ak->d, doneFlag)));
+			return micColsSweep<float, 2>(ctx, d, flags, (float*)dst->d, nullptr, (float*)P->d, nullptr, (const float*)Ai->d, (const float*)Aj->d, (const float*)Ak->d, doneFlag);
+		}
+		MP_TRY((micColsSweep<double, 1>(ctx, d, flags, (double*)dst->d, (const double*)var1->d, (double*)P->d, nullptr, (const double*)Ai->d, (const double*)Aj->d, (const double*)Ak->d, doneFlag)));
+		return micColsSweep<double, 2>(ctx, d, flags, (double*)dst->d, nullptr, (double*)P->d, nullptr, (const double*)Ai->d, (const double*)Aj->d, (const double*)Ak->d, doneFlag);
+	}
 	if (micVariant() == 2) {
 		if (dst->prec == 4) {
 			MP_TRY((micTiledSweep<float, 1>(ctx, d, flags, (float*)dst->d, (const float*)var1->d, (float*)P->d, nullptr, (const float*)Ai->d, (const float*)Aj->d, (const float*)Ak->d, doneFlag)));

@@ -295,3 +295,53 @@ def test_diverged_reports_reference_error(mf):
         g.solve(500)
     with pytest.raises(OracleErr, match="diverged"):
         O.cg_solve(flags, rhs, *A_o, pc=0, accuracy=1e-12, maxIter=500)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("pc", [0, 1, 2])
+def test_solve_with_face_fractions_uses_general_matvec(mf, pc, prec):
+    """fractions make the off-diagonals arbitrary reals: the coupling-mask fast path must step aside (mp_solve_info.matvecKernel
+    != 2) and the general z-marching kernel must give the reference's result (vector-aligned sx so that it is the one used)."""
+    flags, vel = scenes.smoke_plume((32, 24, 20), prec, random_vel=True)
+    frac, obvel = scenes.random_fractions(flags, prec)
+    O = oracle(prec)
+    acc = 1e-5 if prec == 4 else 1e-11
+    v_o = vel.copy()
+    p_o, it_o, _ = O.solve_pressure(flags, v_o, fractions=frac, obvel=obvel, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=(pc >= 2))
+    s = mk(mf, flags.shape, prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+    mf.solvePressure(vel=V, pressure=P, flags=F, fractions=mf.MACGrid(s, frac), obvel=mf.MACGrid(s, obvel), cgAccuracy=acc, cgMaxIterFac=99,
+                     preconditioner=pc, zeroPressureFixing=(pc >= 2))
+    info = mf.lastSolveInfo()
+    assert info["matvecKernel"] == 1
+    assert abs(info["iterations"] - it_o) <= 1
+    assert rel_l2(P.numpy(), p_o) <= TOL[prec] and rel_l2(V.numpy(), v_o) <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+def test_matvec_kernel_selection_and_agreement(mf, prec):
+    """the three matvec instantiations (L2-reuse, z-marching, coupling-mask) are picked by grid shape / matrix content and agree
+    bit for bit on the converged result of the same system"""
+    flags, vel = scenes.smoke_plume((32, 24, 20), prec, random_vel=True)
+    O = oracle(prec)
+    acc = 1e-5 if prec == 4 else 1e-11
+    v_o = vel.copy()
+    p_o, it_o, _ = O.solve_pressure(flags, v_o, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
+    s = mk(mf, flags.shape, prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+    mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
+    info = mf.lastSolveInfo()
+    assert info["matvecKernel"] == 2 and info["iterations"] == it_o
+    if prec == 4:
+        assert np.array_equal(P.numpy(), p_o)          # float build: deterministic, bit-identical to the reference algorithm
+    else:
+        assert rel_l2(P.numpy(), p_o) <= 1e-10
+    # ragged x size -> scalar L2-reuse kernel
+    flags2, vel2 = scenes.smoke_plume((31, 24, 20), prec, random_vel=True)
+    s2 = mk(mf, flags2.shape, prec)
+    F2, V2, P2 = mf.FlagGrid(s2, flags2), mf.MACGrid(s2, vel2), mf.RealGrid(s2)
+    mf.solvePressure(vel=V2, pressure=P2, flags=F2, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
+    assert mf.lastSolveInfo()["matvecKernel"] == 0
+    v2 = vel2.copy()
+    p2, it2, _ = O.solve_pressure(flags2, v2, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
+    assert abs(mf.lastSolveInfo()["iterations"] - it2) <= 1 and rel_l2(P2.numpy(), p2) <= TOL[prec]
