@@ -60,6 +60,21 @@ __host__ __device__ __forceinline__ void vecIdx(const LvlGeom& g, int v, int& x,
 __host__ __device__ __forceinline__ int linIdx(const LvlGeom& g, int x, int y, int z) { return x + g.sx * (y + g.sy * z); }
 __host__ __device__ __forceinline__ bool inGrid(const LvlGeom& g, int x, int y, int z) { return x >= 0 && y >= 0 && z >= 0 && x < g.sx && y < g.sy && z < g.sz; }
 
+// V-cycle kernels are launched on a 3-D grid (x along threadIdx/blockIdx.x, y = blockIdx.y, z = blockIdx.z) so that no thread
+// spends its time on integer divisions to recover (x,y,z) from a linear index
+__device__ __forceinline__ bool cell3(int nx, int& x, int& y, int& z) { x = blockIdx.x * blockDim.x + threadIdx.x; y = blockIdx.y; z = blockIdx.z; return x < nx; }
+static inline dim3 grid3(int nx, int ny, int nz, int block) { return dim3((unsigned)((nx + block - 1) / block), (unsigned)ny, (unsigned)nz); }
+
+// restriction / interpolation weight 1 / 2^(#odd coordinates) (multigrid.cpp:306-307,:623,:646,:921,:951): exact powers of two,
+// built without a division
+template <typename Real> __device__ __forceinline__ Real pow2weight(int nOdd) {
+	Real w = (Real)1;
+	if (nOdd >= 1) w = (Real)0.5;
+	if (nOdd >= 2) w = (Real)0.25;
+	if (nOdd >= 3) w = (Real)0.125;
+	return w;
+}
+
 // ---------------------------------------------------------------- setA: level 0
 template <typename Real>
 __global__ void __launch_bounds__(256) k_mg_copy_activate(LvlGeom g, int is3D, Real trivialScale, const Real* __restrict__ A0, const Real* __restrict__ Ai,
@@ -104,8 +119,9 @@ __global__ void __launch_bounds__(256) k_mg_select(LvlGeom gf, LvlGeom gc, const
 		const int i = linIdx(gc, ix, iy, iz);
 		if (tc[i] == vtFree) { nfree++; last = i; }
 	}
-	if (mode == 0) { if (nfree == 1) { tc[last] = vtZero; flagsOut[0] = 1; } }
-	else if (nfree >= 2) flagsOut[1] = 1;
+	(void)mode;
+	if (nfree == 1) { tc[last] = vtZero; flagsOut[0] = 1; }       // changed
+	else if (nfree >= 2) flagsOut[1] = 1;                         // still undecided (final only in a sweep without changes)
 }
 __global__ void __launch_bounds__(256) k_mg_activate_coarse(signed char* t, int n) {   // knActivateCoarseVertices :507-516
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,7 +242,7 @@ __global__ void __launch_bounds__(128) k_mg_galerkin1_v2(LvlGeom gf, LvlGeom gc,
 		if (!inGrid(gf, Ux, Uy, Uz)) continue;
 		const int u = linIdx(gf, Ux, Uy, Uz);
 		if (tf[u] == vtInactive) continue;
-		const Real rw = (Real)1 / (Real)(1 << ((ux % 2) + (uy % 2) + (uz % 2)));
+		const Real rw = pow2weight<Real>((ux & 1) + (uy & 1) + (uz & 1));
 		for (int i = 0; i < nW; i++) {
 			const int wx = ux + p7[i][0], wy = uy + p7[i][1], wz = uz + p7[i][2];
 			const int Wx = Ux + p7[i][0], Wy = Uy + p7[i][1], Wz = Uz + p7[i][2];
@@ -235,7 +251,7 @@ __global__ void __launch_bounds__(128) k_mg_galerkin1_v2(LvlGeom gf, LvlGeom gc,
 			if (tf[w] == vtInactive) continue;
 			const int sf = (i + 1) / 2;
 			const Real a = Af[(size_t)sf * gf.n + ((i % 2 == 0) ? u : w)];
-			const Real iw = (Real)1 / (Real)(1 << ((wx % 2) + (wy % 2) + (wz % 2)));
+			const Real iw = pow2weight<Real>((wx & 1) + (wy & 1) + (wz & 1));
 			const Real contrib = rw * a * iw;
 			for (int nz = wz / 2; nz <= (wz + 1) / 2; nz++) for (int ny = wy / 2; ny <= (wy + 1) / 2; ny++) for (int nx = wx / 2; nx <= (wx + 1) / 2; nx++) {
 				const int sN = nx + 3 * ny + 9 * nz;
@@ -279,14 +295,14 @@ __global__ void __launch_bounds__(256) k_mg_galerkinN(LvlGeom gf, LvlGeom gc, in
 			bool ok = true;
 			for (int d = 0; d < 3; d++) { const int lo = (U[d] - 1) / 2, hi = min(cs[d] - 1, (U[d] + 2) / 2); if (N[d] < lo || N[d] > hi) ok = false; }
 			if (!ok) continue;
-			const Real rw = (Real)1 / (Real)(1 << ((Ux % 2) + (Uy % 2) + (Uz % 2)));
+			const Real rw = pow2weight<Real>((Ux & 1) + (Uy & 1) + (Uz & 1));
 			int w0[3], w1[3];
 			for (int d = 0; d < 3; d++) { w0[d] = max(0, max(U[d] - 1, N[d] * 2 - 1)); w1[d] = min(fs[d] - 1, min(U[d] + 1, N[d] * 2 + 1)); }
 			for (int Wz = w0[2]; Wz <= w1[2]; Wz++) for (int Wy = w0[1]; Wy <= w1[1]; Wy++) for (int Wx = w0[0]; Wx <= w1[0]; Wx++) {
 				const int w = linIdx(gf, Wx, Wy, Wz);
 				if (tf[w] == vtInactive) continue;
 				const int sf = (Wx - Ux + 1) + 3 * (Wy - Uy + 1) + 9 * (Wz - Uz + smaxz);
-				const Real iw = (Real)1 / (Real)(1 << ((Wx % 2) + (Wy % 2) + (Wz % 2)));
+				const Real iw = pow2weight<Real>((Wx & 1) + (Wy & 1) + (Wz & 1));
 				const Real a = (sf < S) ? Af[(size_t)(S - 1 - sf) * gf.n + w] : Af[(size_t)(sf - S + 1) * gf.n + u];
 				acc += rw * a * iw;
 			}
@@ -309,14 +325,12 @@ __global__ void __launch_bounds__(256) k_mg_set_rhs(int n, Real trivialScale, co
 
 // level-0 colour sweep: colour = (x+y+z) parity ({a0,a3,a5,a6} / {a1,a2,a4,a7}, :721); thread = (x pair, y, z)
 template <typename Real, bool ZEROX>
-__global__ void __launch_bounds__(256) k_mg_smooth0(LvlGeom g, int is3D, int color, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
+__global__ void __launch_bounds__(128) k_mg_smooth0(LvlGeom g, int is3D, int color, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
 	const signed char* __restrict__ type, Real* __restrict__ x, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
-	const int hx = (g.sx + 1) >> 1;
-	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= (long long)hx * g.sy * g.sz) return;
-	const int m = (int)(t % hx); const long long t2 = t / hx; const int j = (int)(t2 % g.sy), k = (int)(t2 / g.sy);
+	int m, j, k;
+	if (!cell3((g.sx + 1) >> 1, m, j, k)) return;
 	const int i = 2 * m + ((j + k + color) & 1);
 	if (i >= g.sx) return;
 	const int v = linIdx(g, i, j, k);
@@ -339,15 +353,15 @@ __global__ void __launch_bounds__(256) k_mg_smooth0(LvlGeom g, int is3D, int col
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(256) k_mg_residual0(LvlGeom g, int is3D, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
+__global__ void __launch_bounds__(128) k_mg_residual0(LvlGeom g, int is3D, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
 	const signed char* __restrict__ type, const Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
-	const int v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= g.n) return;
+	int i, j, k;
+	if (!cell3(g.sx, i, j, k)) return;
+	const int v = linIdx(g, i, j, k);
 	const signed char ty = type[v];
 	if (ty == vtInactive) return;
-	int i, j, k; vecIdx(g, v, i, j, k);
 	const size_t n = (size_t)g.n; const int Y = g.sx, Z = g.sx * g.sy;
 	Real sum = b[v];
 	if (bscale != (Real)0 && ty == vtActiveTrivial) sum *= bscale;
@@ -364,21 +378,32 @@ __global__ void __launch_bounds__(256) k_mg_residual0(LvlGeom g, int is3D, const
 }
 
 // 27-point (9-point in 2-D) stencil application shared by smoother / residual / coarse CG on levels > 0
-template <typename Real, typename VecT, bool SKIPCENTER>
-__device__ __forceinline__ VecT stencilSub(const LvlGeom& g, int is3D, int S, const Real* __restrict__ A, const signed char* __restrict__ type,
+template <typename Real, typename VecT, bool SKIPCENTER, bool IS3D>
+__device__ __forceinline__ VecT stencilSubT(const LvlGeom& g, const Real* __restrict__ A, const signed char* __restrict__ type,
 	const VecT* __restrict__ x, int v, int vx, int vy, int vz, VecT sum)
 {
-	int s = 0;
-	for (int dz = is3D ? -1 : 0; dz <= (is3D ? 1 : 0); dz++) for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++, s++) {
+	constexpr int S = IS3D ? 14 : 5;
+	// interior vertices (the bulk) need no bounds tests; the loops are fully unrolled (compile-time stencil)
+	const bool interior = vx > 0 && vy > 0 && vx < g.sx - 1 && vy < g.sy - 1 && (!IS3D || (vz > 0 && vz < g.sz - 1));
+	#pragma unroll
+	for (int s = 0; s < (IS3D ? 27 : 9); s++) {
 		if (SKIPCENTER && s == S - 1) continue;
-		const int nx = vx + dx, ny = vy + dy, nz = vz + dz;
-		if (!inGrid(g, nx, ny, nz)) continue;
-		const int nb = linIdx(g, nx, ny, nz);
+		const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = IS3D ? s / 9 - 1 : 0;
+		if (!interior && !inGrid(g, vx + dx, vy + dy, vz + dz)) continue;
+		const int nb = v + dx + g.sx * (dy + g.sy * dz);
 		if (type[nb] == vtInactive) continue;
 		if (s < S) sum -= A[(size_t)(S - 1 - s) * g.n + nb] * x[nb];
 		else       sum -= A[(size_t)(s - S + 1) * g.n + v] * x[nb];
 	}
 	return sum;
+}
+template <typename Real, typename VecT, bool SKIPCENTER>
+__device__ __forceinline__ VecT stencilSub(const LvlGeom& g, int is3D, int S, const Real* __restrict__ A, const signed char* __restrict__ type,
+	const VecT* __restrict__ x, int v, int vx, int vy, int vz, VecT sum)
+{
+	(void)S;
+	return is3D ? stencilSubT<Real, VecT, SKIPCENTER, true>(g, A, type, x, v, vx, vy, vz, sum)
+	            : stencilSubT<Real, VecT, SKIPCENTER, false>(g, A, type, x, v, vx, vy, vz, sum);
 }
 
 // levels > 0: colour = offset inside 2x2x2 blocks (:722); thread = block
@@ -387,10 +412,9 @@ __global__ void __launch_bounds__(128) k_mg_smoothN(LvlGeom g, int is3D, int S, 
 	const signed char* __restrict__ type, Real* __restrict__ x, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
-	const int bx = (g.sx + 1) >> 1, by = (g.sy + 1) >> 1, bz = (g.sz + 1) >> 1;
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= bx * by * bz) return;
-	const int vx = 2 * (t % bx) + ox, vy = 2 * ((t / bx) % by) + oy, vz = 2 * (t / (bx * by)) + oz;
+	int tx, ty_, tz;
+	if (!cell3((g.sx + 1) >> 1, tx, ty_, tz)) return;
+	const int vx = 2 * tx + ox, vy = 2 * ty_ + oy, vz = 2 * tz + oz;
 	if (!inGrid(g, vx, vy, vz)) return;
 	const int v = linIdx(g, vx, vy, vz);
 	if (type[v] == vtInactive) return;
@@ -403,9 +427,10 @@ __global__ void __launch_bounds__(128) k_mg_residualN(LvlGeom g, int is3D, int S
 	const signed char* __restrict__ type, const Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
-	const int v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= g.n || type[v] == vtInactive) return;
-	int vx, vy, vz; vecIdx(g, v, vx, vy, vz);
+	int vx, vy, vz;
+	if (!cell3(g.sx, vx, vy, vz)) return;
+	const int v = linIdx(g, vx, vy, vz);
+	if (type[v] == vtInactive) return;
 	r[v] = stencilSub<Real, Real, false>(g, is3D, S, A, type, x, v, vx, vy, vz, b[v]);
 }
 
@@ -415,18 +440,18 @@ __global__ void __launch_bounds__(128) k_mg_restrict(LvlGeom gf, LvlGeom gc, con
 	const Real* __restrict__ src, Real* __restrict__ dst, Real* __restrict__ xc, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
-	const int v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= gc.n) return;
+	int vx, vy, vz;
+	if (!cell3(gc.sx, vx, vy, vz)) return;
+	const int v = linIdx(gc, vx, vy, vz);
 	xc[v] = (Real)0;
 	if (tc[v] == vtInactive) return;
-	int vx, vy, vz; vecIdx(gc, v, vx, vy, vz);
 	Real sum = 0;
 	for (int rz = max(0, vz * 2 - 1); rz <= min(gf.sz - 1, vz * 2 + 1); rz++)
 	for (int ry = max(0, vy * 2 - 1); ry <= min(gf.sy - 1, vy * 2 + 1); ry++)
 	for (int rx = max(0, vx * 2 - 1); rx <= min(gf.sx - 1, vx * 2 + 1); rx++) {
 		const int r = linIdx(gf, rx, ry, rz);
 		if (tf[r] == vtInactive) continue;
-		const Real rw = (Real)1 / (Real)(1 << ((rx % 2) + (ry % 2) + (rz % 2)));
+		const Real rw = pow2weight<Real>((rx & 1) + (ry & 1) + (rz & 1));
 		sum += rw * src[r];
 	}
 	dst[v] = sum;
@@ -434,22 +459,26 @@ __global__ void __launch_bounds__(128) k_mg_restrict(LvlGeom gf, LvlGeom gc, con
 
 // knInterpolate :934-954 into r_l, then x_l += r_l (knAddAssign :445-446, over ALL vertices: inactive ones add their stale r)
 template <typename Real>
-__global__ void __launch_bounds__(256) k_mg_interp_add(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+__global__ void __launch_bounds__(128) k_mg_interp_add(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
 	const Real* __restrict__ xc, Real* __restrict__ rf, Real* __restrict__ xf, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
-	const int v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= gf.n) return;
+	int x, y, z;
+	if (!cell3(gf.sx, x, y, z)) return;
+	const int v = linIdx(gf, x, y, z);
 	// inactive vertices: the reference adds their r entry, which is never written and stays 0 -> nothing to do;
 	// the interpolated value itself (mr[l] in the reference) is a temporary and is not stored
 	if (tf[v] == vtInactive) return;
-	int x, y, z; vecIdx(gf, v, x, y, z);
+	// parents (x>>1 .. (x+1)>>1) x (y..) x (z..), summed in the reference's order (x fastest); y/z parity is warp-uniform
+	const int px = x & 1, py = y & 1, pz = z & 1;
+	const int base = linIdx(gc, x >> 1, y >> 1, z >> 1);
 	Real sum = 0;
-	for (int iz = z / 2; iz <= (z + 1) / 2; iz++) for (int iy = y / 2; iy <= (y + 1) / 2; iy++) for (int ix = x / 2; ix <= (x + 1) / 2; ix++) {
-		const int i = linIdx(gc, ix, iy, iz);
-		if (tc[i] != vtInactive) sum += xc[i];
+	for (int dz = 0; dz <= pz; dz++) for (int dy = 0; dy <= py; dy++) {
+		const int i0 = base + dy * gc.sx + dz * gc.sx * gc.sy;
+		if (tc[i0] != vtInactive) sum += xc[i0];
+		if (px && tc[i0 + 1] != vtInactive) sum += xc[i0 + 1];
 	}
-	const Real iw = (Real)1 / (Real)(1 << ((x % 2) + (y % 2) + (z % 2)));
+	const Real iw = pow2weight<Real>(px + py + pz);
 	xf[v] += iw * sum;
 }
 
@@ -560,18 +589,14 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 	for (int l = 1; l < m->nlev; l++) {
 		const LvlGeom gf = m->geom[l - 1], gc = m->geom[l];
 		k_mg_fill_type<<<nb(gc.n, 256), 256, 0, st>>>(m->type[l], gc.n, vtFree); MP_CHECK_LAUNCH(ctx);
-		// phase-1 closure to its fixed point (a handful of sweeps for bulk domains)
-		for (int sweep = 0; sweep < gf.sx + gf.sy + gf.sz + 8; sweep += 2) {
-			MP_CUDA(cudaMemsetAsync(m->dFlags, 0, sizeof(int), st));
-			for (int q = 0; q < 2; q++) { k_mg_select<<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, 0); MP_CHECK_LAUNCH(ctx); }
-			MP_CUDA(cudaMemcpyAsync(m->hFlags, m->dFlags, sizeof(int), cudaMemcpyDeviceToHost, st));
+		// phase-1 closure to its fixed point: sweep until a sweep changes nothing; that sweep's "undecided" flag is then final
+		for (int sweep = 0; sweep < gf.sx + gf.sy + gf.sz + 8; sweep++) {
+			MP_CUDA(cudaMemsetAsync(m->dFlags, 0, 2 * sizeof(int), st));
+			k_mg_select<<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, 0); MP_CHECK_LAUNCH(ctx);
+			MP_CUDA(cudaMemcpyAsync(m->hFlags, m->dFlags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
 			MP_CUDA(cudaStreamSynchronize(st));
 			if (!m->hFlags[0]) break;
 		}
-		MP_CUDA(cudaMemsetAsync(m->dFlags + 1, 0, sizeof(int), st));
-		k_mg_select<<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, 1); MP_CHECK_LAUNCH(ctx);
-		MP_CUDA(cudaMemcpyAsync(m->hFlags, m->dFlags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-		MP_CUDA(cudaStreamSynchronize(st));
 		if (m->hFlags[1]) {
 			// order-dependent phase needed: redo this level with the exact serial algorithm
 			std::vector<signed char> tf(gf.n), tc(gc.n);
@@ -603,20 +628,22 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	const LvlGeom g = m->geom[l];
 	if (l == 0) {
-		const long long work = (long long)((g.sx + 1) / 2) * g.sy * g.sz;
+		const dim3 gr = grid3((g.sx + 1) / 2, g.sy, g.sz, 128);
 		for (int c = 0; c < 2; c++) {
 			const int color = reversed ? 1 - c : c;
 			// with x == 0 on entry the first colour reduces to x = b / A0 (same arithmetic: the skipped products are exact zeros)
-			if (zeroX && c == 0) k_mg_smooth0<Real, true><<<nb(work, 256), 256, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, doneFlag);
-			else                 k_mg_smooth0<Real, false><<<nb(work, 256), 256, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, doneFlag);
+			if (zeroX && c == 0) k_mg_smooth0<Real, true><<<gr, 128, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, doneFlag);
+			else                 k_mg_smooth0<Real, false><<<gr, 128, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, doneFlag);
 			MP_CHECK_LAUNCH(ctx);
 		}
 	} else {
 		const int ncol = m->is3D ? 8 : 4;
-		const int blocks = ((g.sx + 1) / 2) * ((g.sy + 1) / 2) * ((g.sz + 1) / 2);
+		const int hbx = (g.sx + 1) / 2;
+		const int bsz = hbx >= 96 ? 128 : (hbx >= 48 ? 64 : 32);
+		const dim3 gr = grid3(hbx, (g.sy + 1) / 2, (g.sz + 1) / 2, bsz);
 		for (int c = 0; c < ncol; c++) {
 			const int color = reversed ? ncol - 1 - c : c;
-			k_mg_smoothN<Real><<<nb(blocks, 128), 128, 0, st>>>(g, m->is3D, m->stencil, color & 1, (color >> 1) & 1, (color >> 2) & 1,
+			k_mg_smoothN<Real><<<gr, bsz, 0, st>>>(g, m->is3D, m->stencil, color & 1, (color >> 1) & 1, (color >> 2) & 1,
 				(const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], doneFlag);
 			MP_CHECK_LAUNCH(ctx);
 		}
@@ -629,8 +656,8 @@ static int mgResidual(mp_mg* m, int l, const int* doneFlag, const L0<Real>& l0)
 {
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	const LvlGeom g = m->geom[l];
-	if (l == 0) k_mg_residual0<Real><<<nb(g.n, 256), 256, 0, st>>>(g, m->is3D, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], (const Real*)l0.x, (Real*)m->r[0], doneFlag);
-	else        k_mg_residualN<Real><<<nb(g.n, 128), 128, 0, st>>>(g, m->is3D, m->stencil, (const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (const Real*)m->x[l], (Real*)m->r[l], doneFlag);
+	if (l == 0) k_mg_residual0<Real><<<grid3(g.sx, g.sy, g.sz, 128), 128, 0, st>>>(g, m->is3D, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], (const Real*)l0.x, (Real*)m->r[0], doneFlag);
+	else        k_mg_residualN<Real><<<grid3(g.sx, g.sy, g.sz, g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32)), g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32), 0, st>>>(g, m->is3D, m->stencil, (const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (const Real*)m->x[l], (Real*)m->r[l], doneFlag);
 	MP_CHECK_LAUNCH(ctx);
 	return MP_OK;
 }
@@ -650,7 +677,7 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 		for (int i = 0; i < m->numPre; i++) MP_TRY((mgSmooth<Real>(m, l, false, l == 0 && i == 0 && !xInit, doneFlag, l0)));
 		MP_TRY((mgResidual<Real>(m, l, doneFlag, l0)));
 		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
-		k_mg_restrict<Real><<<nb(gc.n, 128), 128, 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->r[l], (Real*)m->b[l + 1], (Real*)m->x[l + 1], doneFlag);
+		k_mg_restrict<Real><<<grid3(gc.sx, gc.sy, gc.sz, gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32)), gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32), 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->r[l], (Real*)m->b[l + 1], (Real*)m->x[l + 1], doneFlag);
 		MP_CHECK_LAUNCH(ctx);
 	}
 	{
@@ -662,7 +689,7 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 	}
 	for (int l = maxLevel - 1; l >= 0; l--) {
 		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
-		k_mg_interp_add<Real><<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], l == 0 ? l0.x : (Real*)m->x[l], doneFlag);
+		k_mg_interp_add<Real><<<grid3(gf.sx, gf.sy, gf.sz, gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32)), gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32), 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], l == 0 ? l0.x : (Real*)m->x[l], doneFlag);
 		MP_CHECK_LAUNCH(ctx);
 		for (int i = 0; i < m->numPost; i++) MP_TRY((mgSmooth<Real>(m, l, true, false, doneFlag, l0)));
 	}
