@@ -345,3 +345,56 @@ def test_matvec_kernel_selection_and_agreement(mf, prec):
     v2 = vel2.copy()
     p2, it2, _ = O.solve_pressure(flags2, v2, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
     assert abs(mf.lastSolveInfo()["iterations"] - it2) <= 1 and rel_l2(P2.numpy(), p2) <= TOL[prec]
+
+
+def random_domain(shape, prec, seed, liquid=False, outflow=False):
+    """random obstacles (and, for liquids, a random free surface / outflow cells) inside a closed box; no fluid on the outer layer"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sz, sy, sx = shape
+    real = np.float32 if prec == 4 else np.float64
+    flags = scenes.closed_box_flags(sx, sy, sz)
+    inner = flags == 1
+    obst = rng.random(shape) < 0.12
+    flags[inner & obst] = 2
+    phi = None
+    if liquid:
+        phi = (rng.random(shape) * 2.0 - 0.9 + 0.08 * (np.arange(sy).reshape(1, sy, 1) - sy / 2)).astype(real)
+        fl = (flags & (2 | 16)) == 0
+        flags[fl] = np.where(phi[fl] <= 0, 1, 4).astype(np.int32)
+        if outflow:
+            em = (flags == 4) & (rng.random(shape) < 0.2)
+            flags[em] = 4 | 16
+    vel = (rng.random(shape + (3,)) - 0.5).astype(real)
+    if sz == 1:
+        vel[..., 2] = 0
+    scenes.set_wall_bcs(flags, vel)
+    return flags, vel, phi
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("kind", ["smoke", "liquid", "liquid_outflow", "smoke2d", "liquid2d"])
+def test_random_domains_all_preconditioners(mf, kind, prec, seed):
+    """randomised flags / level sets / velocities: every preconditioner against the oracle with the same settings"""
+    shape = {"smoke": (18, 21, 24), "liquid": (17, 20, 28), "liquid_outflow": (16, 18, 20), "smoke2d": (1, 30, 36), "liquid2d": (1, 28, 32)}[kind]
+    flags, vel, phi = random_domain(shape, prec, seed * 7 + len(kind), liquid="liquid" in kind, outflow="outflow" in kind)
+    O = oracle(prec)
+    s = mk(mf, flags.shape, prec)
+    F = mf.FlagGrid(s, flags)
+    PH = mf.RealGrid(s, phi) if phi is not None else None
+    acc = 1e-5 if prec == 4 else 1e-11
+    for pc in (0, 1, 2, 3):
+        fix = pc >= 2
+        v_o = vel.copy()
+        p_o, it_o, rn_o = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=fix,
+                                           enforceCompatibility=(seed == 2 and phi is None), solver_key=900 + seed)
+        V, P, RR = mf.MACGrid(s, vel), mf.RealGrid(s), mf.RealGrid(s)
+        mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=fix,
+                         enforceCompatibility=(seed == 2 and phi is None), retRhs=RR)
+        info = mf.lastSolveInfo()
+        assert abs(info["iterations"] - it_o) <= 1, (kind, pc, info["iterations"], it_o)
+        scale = max(1.0, float(np.abs(p_o).max()))
+        assert np.abs(P.numpy().astype(np.float64) - p_o).max() <= (2e-4 if prec == 4 else 1e-9) * scale, (kind, pc)
+        assert np.abs(V.numpy().astype(np.float64) - v_o).max() <= (2e-4 if prec == 4 else 1e-9) * scale, (kind, pc)
+    O.release_solver(900 + seed)
+    mf.releaseMG(s)
