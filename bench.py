@@ -79,6 +79,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores for the reference's OpenMP build (torchrun exports OMP_NUM_THREADS=1 to its workers, which must not
+    silently serialise the CPU arm); MP_CPU_THREADS overrides.  Must run before the oracle library is loaded."""
+    n = int(os.environ.get("MP_CPU_THREADS", 0)) or len(os.sched_getaffinity(0)) or os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
 def make_scene(res, prec, n_slabs=1):
     from mantaflow_b200 import scenes
     sx = sy = res
@@ -103,8 +111,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle.oracle_api import Oracle, available
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = host_threads()
     kind = "reference" if available("reference", args.prec) else "port"
     O = Oracle(kind, args.prec)
     flags, vel = make_scene(args.res, args.prec)
@@ -304,8 +311,7 @@ class SingleBench:
 
 def cpu_baseline(args):
     from oracle.oracle_api import Oracle, available
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = host_threads()
     kind = "reference" if available("reference", args.prec) else "port"
     O = Oracle(kind, args.prec)
     res = args.cpu_res or args.res
