@@ -125,11 +125,12 @@ def run_reference(args):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = cells * its / (ms * 1e-3) / 1e9
-    sample = "%d^3 %s, GridCg capped at %d iterations per step (full solve needs ~%d)" % (args.res, PC_NAMES[args.pc], cap, 3.2 * args.res)
+    sample = "one %d^3 block of the workload (the per-GPU share), %s, rhs+matrix+GridCg capped at %d iterations+correctVelocity per step (a full %d^3 solve needs ~%d iterations)" % (
+        args.res, PC_NAMES[args.pc], cap, args.res, 3.2 * args.res)
     line = {"impl": "reference", "metric": "pressure-solve CG throughput (cells x iterations / s)", "value": value, "unit": "Gcell-iter/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.prec == 4 else "f64", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, args.gpus),
             "cg_iter_per_s": its / (ms * 1e-3),
             "cpu_baseline": {"value": value, "unit": "Gcell-iter/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Gcell-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -194,6 +194,13 @@ int mp_solve_pressure(mp_context* ctx, mp_grid* vel, mp_grid* pressure, const mp
                       const mp_grid* phi, const mp_grid* perCellCorr, const mp_grid* fractions, const mp_grid* obvel,
                       const mp_grid* curv, mp_grid* retRhs, const mp_pressure_params* params, mp_solve_info* info);
 
+/* ---- another GridCg caller on the same device solver ----
+ * cgSolveDiffusion conjugategrad.cpp:350-423: implicit diffusion (I + alpha*L) u = u_old of a Real grid or, component by
+ * component, of a Vec3 / MAC grid; plain CG, GridCg's default L2 stop test, maxIter = (int)(cgMaxIterFac*maxDim) (x4 in 2-D).
+ * info (optional) reports the iterations / residual of the last component solved. */
+int mp_cg_solve_diffusion(mp_context* ctx, const mp_grid* flags, mp_grid* grid, double alpha, double cgMaxIterFac, double cgAccuracy,
+                          mp_solve_info* info);
+
 /* ---- the plugin with HOST buffers (what pressure.cpp calls when grids have no device mirror yet):
  * uploads flags/vel(/phi...), runs mp_solve_pressure, downloads vel/pressure(/retRhs).  Optional
  * pointers may be NULL.  Buffers may be pageable or pinned (mp_host_alloc). ---- */

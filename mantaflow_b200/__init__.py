@@ -13,6 +13,6 @@ from .grid import (FlagEmpty, FlagFluid, FlagGrid, FlagInflow, FlagObstacle, Fla
                    LevelsetGrid, MACGrid, RealGrid, Solver)
 from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, releaseMG, solvePressure, solvePressureHost,
                        solvePressureSystem)
-from .cg import GridCg, GridMg
+from .cg import GridCg, GridMg, cgSolveDiffusion
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -83,6 +83,16 @@ def GridDotProduct(a, b):
     return out.value
 
 
+def cgSolveDiffusion(flags, grid, alpha=0.25, cgMaxIterFac=1.0, cgAccuracy=1e-4):
+    """conjugategrad.cpp:350-423 (PYTHON() plugin): implicit diffusion of a Real or Vec3/MAC grid on the device GridCg"""
+    from ._lib import SolveInfo
+    s = flags.parent
+    info = SolveInfo()
+    check(s.lib.mp_cg_solve_diffusion(s._ctx, flags.dev(), grid.dev(), C.c_double(alpha), C.c_double(cgMaxIterFac), C.c_double(cgAccuracy), C.byref(info)))
+    grid.markDeviceWritten()
+    return info.as_dict()
+
+
 class GridMg:
     """multigrid.h:31-137"""
 

@@ -674,7 +674,7 @@ int mp_cg_create(mp_context* ctx, mp_grid* dst, mp_grid* rhs, mp_grid* residual,
 	cg->A0 = A0; cg->Ai = Ai; cg->Aj = Aj; cg->Ak = Ak;
 	cg->pcMethod = MP_CG_PC_NONE; cg->pcA0 = nullptr; cg->mg = nullptr;
 	cg->inited = false; cg->useL2 = true;            // GridCgInterface() : mUseL2Norm(true), conjugategrad.h:31
-	cg->accuracy = 1e-8;                             // mAccuracy(VECTOR_EPSILON) conjugategrad.cpp:206, vectorbase.h
+	cg->accuracy = dst->prec == 4 ? (double)1e-6f : 1e-10;   // mAccuracy(VECTOR_EPSILON) conjugategrad.cpp:206, vectorbase.h:52,:55
 	cg->iterations = 0; cg->resNorm = 1e20; cg->sigma = 0; cg->diverged = false; cg->finished = false; cg->flagsChecked = false; cg->cmask = nullptr;
 	MP_CUDA(cudaMalloc(&cg->dSc, 256));
 	MP_CUDA(cudaHostAlloc((void**)&cg->hSc, sizeof(CgScalHost) * 2, cudaHostAllocMapped));

@@ -17,6 +17,30 @@ __global__ void __launch_bounds__(256) k_add_mean_corr(Real* __restrict__ rhs, I
 	for (IndexInt i = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IndexInt)gridDim.x * blockDim.x) rhs[i] += corr;
 }
 
+// cgSolveDiffusion matrix, conjugategrad.cpp:360-375: MakeLaplaceMatrix on an all-fluid dummy FlagGrid (interior cells get
+// A0 = 2*dim, Ai = Aj = Ak = -1), then obstacle rows -> identity, all other rows -> I + alpha * L
+template <typename Real>
+__global__ void __launch_bounds__(256) k_diffusion_matrix(Dims d, const int* __restrict__ flags, Real alpha, Real* __restrict__ A0, Real* __restrict__ Ai,
+	Real* __restrict__ Aj, Real* __restrict__ Ak)
+{
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n) return;
+	const int i = (int)(idx % d.sx); const IndexInt t = idx / d.sx; const int j = (int)(t % d.sy), k = (int)(t / d.sy);
+	const bool interior = i >= 1 && i < d.sx - 1 && j >= 1 && j < d.sy - 1 && (!d.is3D || (k >= 1 && k < d.sz - 1));
+	Real a0 = 0, ai = 0, aj = 0, ak = 0;
+	if (interior) { a0 = d.is3D ? (Real)6 : (Real)4; ai = (Real)-1; aj = (Real)-1; if (d.is3D) ak = (Real)-1; }
+	if (flags[idx] & TypeObstacle) { ai = aj = ak = (Real)0.0; a0 = (Real)1.0; }
+	else { ai *= alpha; aj *= alpha; ak *= alpha; a0 *= alpha; a0 = (Real)((double)a0 + 1.); }
+	A0[idx] = a0; Ai[idx] = ai; Aj[idx] = aj; Ak[idx] = ak;
+}
+// knGetComponent / knSetComponent grid.cpp:676-685
+template <typename Real>
+__global__ void __launch_bounds__(256) k_component(IndexInt n, Real* __restrict__ vec, Real* __restrict__ comp, int c, int set) {
+	for (IndexInt i = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IndexInt)gridDim.x * blockDim.x) {
+		if (set) vec[3 * i + c] = comp[i]; else comp[i] = vec[3 * i + c];
+	}
+}
+
 struct GridHolder {   // RAII for the temp grids of one call (the reference takes them from the FluidSolver pool, pressure.cpp:331-338)
 	std::vector<mp_grid*> gs;
 	~GridHolder() { for (mp_grid* g : gs) mp_grid_destroy(g); }
@@ -167,6 +191,57 @@ int mp_solve_pressure(mp_context* ctx, mp_grid* vel, mp_grid* pressure, const mp
 		cudaEventElapsedTime(&info->msCorrect, ctx->ev[3], ctx->ev[4]);
 		cudaEventElapsedTime(&info->msTotal, ctx->ev[0], ctx->ev[4]);
 	}
+	return MP_OK;
+}
+
+int mp_cg_solve_diffusion(mp_context* ctx, const mp_grid* flags, mp_grid* grid, double alpha, double cgMaxIterFac, double cgAccuracy, mp_solve_info* info)
+{
+	if (!ctx || !flags || !grid) MP_FAIL(MP_ERR_INVALID, "mp_cg_solve_diffusion: NULL argument");
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "mp_cg_solve_diffusion: flags is not a FlagGrid");
+	if (grid->kind != MP_GRID_REAL && grid->kind != MP_GRID_MAC)
+		MP_FAIL(MP_ERR_INVALID, "cgSolveDiffusion: Grid Type is not supported (only Real, Vec3, MAC, or Levelset)");       // conjugategrad.cpp:419
+	if (grid->sx != flags->sx || grid->sy != flags->sy || grid->sz != flags->sz) MP_FAIL(MP_ERR_INVALID, "mp_cg_solve_diffusion: grid and flags differ in size");
+	if (ctx->dist && ctx->dist->active) MP_FAIL(MP_ERR_UNSUPPORTED, "mp_cg_solve_diffusion: not sharded across GPUs");
+	MP_CUDA(cudaSetDevice(ctx->device));
+	const int prec = grid->prec;
+	const Dims d = dimsOf(flags);
+	GridHolder tmp;
+	mp_grid *rhs, *residual, *search, *t, *A0, *Ai, *Aj, *Ak, *u = nullptr;
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &rhs)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &residual));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &search)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &t));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &A0)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &Ai));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &Aj)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &Ak));
+	const unsigned int blocks = gridFor(d.n, 256);
+	if (prec == 4) k_diffusion_matrix<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float)alpha, (float*)A0->d, (float*)Ai->d, (float*)Aj->d, (float*)Ak->d);
+	else           k_diffusion_matrix<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, alpha, (double*)A0->d, (double*)Ai->d, (double*)Aj->d, (double*)Ak->d);
+	MP_CHECK_LAUNCH(ctx);
+	const int maxDim = std::max(flags->sx, std::max(flags->sy, flags->sz));
+	const int maxIter = (prec == 4 ? (int)((float)cgMaxIterFac * (float)maxDim) : (int)(cgMaxIterFac * (double)maxDim)) * (d.is3D ? 1 : 4);   // :379
+	const bool isVec = grid->kind == MP_GRID_MAC;
+	if (isVec) MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &u)); else u = grid;
+	mp_cg* cg = nullptr;
+	MP_TRY(mp_cg_create(ctx, u, rhs, residual, search, flags, t, A0, Ai, Aj, Ak, &cg));           // no preconditioner, L2 norm: GridCg defaults
+	struct CgGuard { mp_cg* c; ~CgGuard() { mp_cg_destroy(c); } } guard{ cg };
+	mp_cg_set_accuracy(cg, prec == 4 ? (double)(float)cgAccuracy : cgAccuracy);
+	const int ncomp = isVec ? (d.is3D ? 3 : 2) : 1;
+	const unsigned int cb = gridFor(d.n, 256 * 4);
+	for (int c = 0; c < ncomp; c++) {
+		if (isVec) {
+			if (prec == 4) k_component<float><<<cb, 256, 0, ctx->stream>>>(d.n, (float*)grid->d, (float*)u->d, c, 0);
+			else           k_component<double><<<cb, 256, 0, ctx->stream>>>(d.n, (double*)grid->d, (double*)u->d, c, 0);
+			MP_CHECK_LAUNCH(ctx);
+			mp_cg_force_reinit(cg);
+		}
+		MP_TRY(mp_grid_copy_from(rhs, u));                                                     // rhs.copyFrom(u) :383,:412
+		MP_TRY(mp_cg_run(cg, maxIter));
+		if (isVec) {
+			if (prec == 4) k_component<float><<<cb, 256, 0, ctx->stream>>>(d.n, (float*)grid->d, (float*)u->d, c, 1);
+			else           k_component<double><<<cb, 256, 0, ctx->stream>>>(d.n, (double*)grid->d, (double*)u->d, c, 1);
+			MP_CHECK_LAUNCH(ctx);
+		}
+	}
+	if (info) { memset(info, 0, sizeof *info); info->fixedCell = -1; mp_cg_get(cg, &info->iterations, &info->resNorm, nullptr); info->maxIter = maxIter; info->matvecKernel = ctx->lastMatvecKernel; }
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MP_OK;
 }
 

@@ -941,6 +941,37 @@ int mfo_cg_solve(int sx, int sy, int sz, const int* flags, const Real* rhs, Real
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * cgSolveDiffusion conjugategrad.cpp:350-423 (another GridCg caller).  ncomp 1: Real grid, 3: Vec3/MAC grid
+ * (each component solved separately through getComponent/setComponent, grid.cpp:676-685).            */
+int mfo_cg_solve_diffusion(int sx, int sy, int sz, const int* flags, Real* data, int ncomp, double alpha_, double cgMaxIterFac, double cgAccuracy)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	const Real alpha = (Real)alpha_;
+	Real *A0 = (Real*)calloc((size_t)n, sizeof(Real)), *Ai = (Real*)calloc((size_t)n, sizeof(Real)), *Aj = (Real*)calloc((size_t)n, sizeof(Real)), *Ak = (Real*)calloc((size_t)n, sizeof(Real));
+	int* dummy = (int*)malloc(sizeof(int) * (size_t)n);
+	for (IndexInt q = 0; q < n; q++) dummy[q] = TypeFluid;                      /* flagsDummy.setConst(TypeFluid) :361 */
+	mfo_make_matrix(sx, sy, sz, dummy, 0, 0, 0., A0, Ai, Aj, Ak);
+	free(dummy);
+	for (IndexInt q = 0; q < n; q++) {                                          /* :364-375 */
+		if (flags[q] & TypeObstacle) { Ai[q] = Aj[q] = Ak[q] = 0.0; A0[q] = 1.0; }
+		else { Ai[q] *= alpha; Aj[q] *= alpha; Ak[q] *= alpha; A0[q] *= alpha; A0[q] += 1.; }
+	}
+	const int maxDim = sx > sy ? (sx > sz ? sx : sz) : (sy > sz ? sy : sz);
+	const int maxIter = (int)((Real)cgMaxIterFac * maxDim) * (IS3D ? 1 : 4);
+	Real* u = (Real*)malloc(sizeof(Real) * (size_t)n); Real* rhs = (Real*)malloc(sizeof(Real) * (size_t)n);
+	int rc = 0;
+	for (int c = 0; c < (ncomp == 1 ? 1 : (IS3D ? 3 : 2)) && rc == 0; c++) {
+		for (IndexInt q = 0; q < n; q++) rhs[q] = data[(size_t)q * ncomp + c];
+		/* GridCg defaults: no preconditioner, L2 norm (sum r^2 un-square-rooted) -- cgSolveDiffusion never calls setUseL2Norm */
+		rc = cg_run(sx, sy, sz, flags, rhs, u, A0, Ai, Aj, Ak, 0, (Real)cgAccuracy, 1, maxIter, 0, 0, 0);
+		for (IndexInt q = 0; q < n; q++) data[(size_t)q * ncomp + c] = u[q];
+	}
+	free(u); free(rhs); free(A0); free(Ai); free(Aj); free(Ak);
+	return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * correctVelocity plugin/pressure.cpp:455-476: knCorrectVelocity :87-109,
  * knCorrectVelocityGhostFluid :154-187, knReplaceClampedGhostFluidVels :198-214                 */
 int mfo_correct_velocity(int sx, int sy, int sz, const int* flags, Real* vel, const Real* pressure,

@@ -149,6 +149,14 @@ class Oracle:
         out = (pressure, it.value, rn.value)
         return out + (rr,) if retRhs else out
 
+    def cg_solve_diffusion(self, flags, grid, alpha=0.25, cgMaxIterFac=1.0, cgAccuracy=1e-4):
+        """conjugategrad.cpp:350-423; grid ([Z,Y,X] or [Z,Y,X,3]) is diffused in place"""
+        assert grid.dtype == self.real and grid.flags.c_contiguous
+        ncomp = 1 if grid.ndim == 3 else 3
+        self._chk(self._f("cg_solve_diffusion")(*self.dims(flags), _p(flags), _p(grid), C.c_int(ncomp), C.c_double(alpha),
+                                                C.c_double(cgMaxIterFac), C.c_double(cgAccuracy)))
+        return grid
+
     def release_solver(self, key):
         self._chk(self._f("release_solver")(C.c_longlong(key)))
 

@@ -59,6 +59,7 @@ int writeObjectsVDB(const std::string&, std::vector<PbClass*>*, float, bool, int
 int readObjectsVDB (const std::string&, std::vector<PbClass*>*, float) { return 0; }
 Real LevelsetGrid::invalidTimeValue() { return -1000; }   // levelset.cpp:103 -> fastmarch.h:134
 void setWallBcs(const FlagGrid& flags, MACGrid& vel, const MACGrid* obvel, const MACGrid* fractions, const Grid<Real>* phiObs, int boundaryWidth);
+void cgSolveDiffusion(const FlagGrid& flags, GridBase& grid, Real alpha, Real cgMaxIterFac, Real cgAccuracy);
 void InitPreconditionModifiedIncompCholesky2(const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
 void ApplyPreconditionModifiedIncompCholesky2(Grid<Real>& dst, Grid<Real>& Var1, const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
 }
@@ -251,6 +252,16 @@ int ref_solve_pressure(long long solver_key, int sx, int sy, int sz, const int* 
 		if (iterations) *iterations = it; if (resNorm) *resNorm = rn;
 	}
 	if (!solver_key) { releaseMG(s); delete s; }
+  CATCH }
+
+// cgSolveDiffusion conjugategrad.cpp:350-423 (another GridCg caller).  ncomp 1: Grid<Real>, 3: Grid<Vec3>
+int ref_cg_solve_diffusion(int sx, int sy, int sz, const int* flags, Real* data, int ncomp, double alpha, double cgMaxIterFac, double cgAccuracy)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags);
+	  if (ncomp == 1) { Grid<Real> G(s, data); cgSolveDiffusion(F, G, (Real)alpha, (Real)cgMaxIterFac, (Real)cgAccuracy); }
+	  else            { Grid<Vec3> G(s, (Vec3*)data); cgSolveDiffusion(F, G, (Real)alpha, (Real)cgMaxIterFac, (Real)cgAccuracy); } }
+	delete s;
   CATCH }
 
 // ---------------- GridMg probes (hierarchy + V-cycle) ----------------

@@ -107,6 +107,13 @@ class CudaImpl:
         out = (P.numpy().copy(), info["iterations"], info["resNorm"])
         return out + (RR.numpy().copy(),) if retRhs else out
 
+    def cg_solve_diffusion(self, flags, grid, alpha=0.25, cgMaxIterFac=1.0, cgAccuracy=1e-4):
+        s = self._solver(flags)
+        G = (mf.RealGrid if grid.ndim == 3 else mf.MACGrid)(s, grid)
+        mf.cgSolveDiffusion(mf.FlagGrid(s, flags), G, alpha=alpha, cgMaxIterFac=cgMaxIterFac, cgAccuracy=cgAccuracy)
+        grid[...] = G.numpy()
+        return grid
+
     def release_solver(self, key):
         for k, s in list(self._solvers.items()):
             if k[3] == key:

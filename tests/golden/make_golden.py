@@ -90,6 +90,9 @@ def kernels_fixture(R, name, prec):
         v = vel.copy()
         p, it, rn = R.solve_pressure(flags, v, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=1)
         out.update(plugin_mic_p=p, plugin_mic_vel=v, plugin_mic_it=it, plugin_mic_res=rn)
+    # cgSolveDiffusion (conjugategrad.cpp:350-423): Real grid with explicit parameters, Vec3 grid with the defaults
+    out["diff_real"] = R.cg_solve_diffusion(flags, src.copy(), alpha=0.7, cgMaxIterFac=2.0, cgAccuracy=1e-7)
+    out["diff_vec"] = R.cg_solve_diffusion(flags, vel.copy())
     return out
 
 

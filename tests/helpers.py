@@ -92,6 +92,14 @@ def check_kernels_against_golden(I, g, prec, exact_reductions):
         assert rel_l2(p, g["plugin_mic_p"]) <= tol and rel_l2(v, g["plugin_mic_vel"]) <= tol
 
 
+def check_diffusion_against_golden(I, g, prec):
+    tol = 1e-5 if prec == 4 else 1e-12
+    d = I.cg_solve_diffusion(g["flags"], g["src"].copy(), alpha=0.7, cgMaxIterFac=2.0, cgAccuracy=1e-7)
+    assert np.abs(d.astype(np.float64) - g["diff_real"]).max() <= tol
+    v = I.cg_solve_diffusion(g["flags"], g["vel"].copy())
+    assert np.abs(v.astype(np.float64) - g["diff_vec"]).max() <= tol
+
+
 def check_psolve52(I, thr=1e-4):
     """tools/tests/test_0100_psolve.py and test_0110_mgsolve.py: max abs per-cell difference (gridMaxDiff, grid.cpp:400-430)
     against the reference's result below the float-build threshold 1e-4 (test_0100_psolve.py:40-41,:54-55)."""

@@ -4,7 +4,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from helpers import KERNEL_FIXTURES, check_kernels_against_golden, check_psolve52, load_golden  # noqa: E402
+from helpers import KERNEL_FIXTURES, check_diffusion_against_golden, check_kernels_against_golden, check_psolve52, load_golden  # noqa: E402
 
 
 @pytest.mark.parametrize("prec", [4, 8])
@@ -12,6 +12,7 @@ from helpers import KERNEL_FIXTURES, check_kernels_against_golden, check_psolve5
 def test_cuda_reproduces_reference_golden(name, prec):
     from cuda_impl import CudaImpl
     check_kernels_against_golden(CudaImpl(prec), load_golden(name, prec), prec, exact_reductions=False)
+    check_diffusion_against_golden(CudaImpl(prec), load_golden(name, prec), prec)
 
 
 def test_cuda_reproduces_test_0100_and_0110():

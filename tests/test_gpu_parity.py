@@ -403,3 +403,27 @@ def test_random_domains_all_preconditioners(mf, kind, prec, seed):
         assert np.abs(V.numpy().astype(np.float64) - v_o).max() <= (2e-4 if prec == 4 else 1e-9) * scale, (kind, pc)
     O.release_solver(900 + seed)
     mf.releaseMG(s)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("shape", [(16, 18, 20), (1, 20, 24), (12, 14, 19)])
+def test_cg_solve_diffusion(mf, shape, prec):
+    """cgSolveDiffusion (conjugategrad.cpp:350-423), the next GridCg caller: Real and Vec3 grids"""
+    sz, sy, sx = shape
+    flags, vel = scenes.smoke_plume((sx, sy, sz), prec, random_vel=True)
+    O = oracle(prec)
+    rng = np.random.Generator(np.random.PCG64(12))
+    dens = rng.random(flags.shape).astype(vel.dtype)
+    s = mk(mf, flags.shape, prec)
+    F = mf.FlagGrid(s, flags)
+    D = mf.RealGrid(s, dens)
+    info = mf.cgSolveDiffusion(F, D, alpha=0.7, cgMaxIterFac=2.0, cgAccuracy=1e-7)
+    d_o = O.cg_solve_diffusion(flags, dens.copy(), alpha=0.7, cgMaxIterFac=2.0, cgAccuracy=1e-7)
+    assert info["iterations"] >= 2 and info["matvecKernel"] != 2          # off-diagonals are -alpha: not maskable
+    assert np.abs(D.numpy().astype(np.float64) - d_o).max() <= (1e-5 if prec == 4 else 1e-12)
+    V = mf.MACGrid(s, vel)
+    mf.cgSolveDiffusion(F, V)                                              # defaults alpha 0.25, fac 1.0, acc 1e-4
+    v_o = O.cg_solve_diffusion(flags, vel.copy())
+    assert np.abs(V.numpy().astype(np.float64) - v_o).max() <= (1e-5 if prec == 4 else 1e-12)
+    with pytest.raises(mf.MantaError, match="not supported"):
+        mf.cgSolveDiffusion(F, F)
