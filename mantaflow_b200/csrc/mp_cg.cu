@@ -324,17 +324,37 @@ __global__ void __launch_bounds__(256) k_dot_zr(IndexInt n, const Real* __restri
 }
 
 // UpdateSearchVec conjugategrad.cpp:193-196: s = z + beta s
+// Slab mode with peer memory: the threads that produce the first / last owned plane also store it into the neighbours'
+// receive buffers (NVLink peer stores); the last block to finish publishes the planes with a system-scope release flag.
 template <typename Real, int V>
-__global__ void __launch_bounds__(256) k_update_search(IndexInt n, Real* __restrict__ s, const Real* __restrict__ z, const CgScal<Real>* sc)
+__global__ void __launch_bounds__(256) k_update_search(IndexInt n, Real* __restrict__ s, const Real* __restrict__ z, const CgScal<Real>* sc,
+	HaloOut ho, IndexInt plane)
 {
 	if (sc->done) return;
 	const Real beta = sc->beta;
 	const IndexInt nv = n / V;
+	Real* const outLo = (Real*)ho.lo; Real* const outHi = (Real*)ho.hi;
 	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
 		VecT<Real, V> sv = ldv<Real, V>(s + vi * V); const VecT<Real, V> zv = ldv<Real, V>(z + vi * V);
 		#pragma unroll
 		for (int q = 0; q < V; q++) sv.v[q] = zv.v[q] + beta * sv.v[q];
 		stv<Real, V>(s + vi * V, sv);
+		const IndexInt idx = vi * V;
+		if (outLo && idx < plane) stv<Real, V>(outLo + idx, sv);
+		if (outHi && idx >= n - plane) stv<Real, V>(outHi + (idx - (n - plane)), sv);
+	}
+	if (ho.ticket) {
+		__threadfence_system();
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			const unsigned int t = atomicAdd(ho.ticket, 1u);
+			if (t == gridDim.x - 1) {
+				*ho.ticket = 0;
+				__threadfence_system();
+				if (ho.flagLo) st_release_sys(ho.flagLo, ho.seq);
+				if (ho.flagHi) st_release_sys(ho.flagHi, ho.seq);
+			}
+		}
 	}
 }
 
@@ -389,7 +409,8 @@ static inline double* distLocalOf(mp_context* ctx, const Dims& d) { return d.wor
 
 // slab mode: all-gather the ranks' partials and apply the scalar update of `stage` (0 alpha, 1 norm/beta, 2 z.r, 3 init sigma)
 static int cgCombine(mp_context* ctx, const mp_grid* g, void* sc, int stage, int mode) {
-	MP_TRY(mp_dist_allgather(ctx, 2));
+	if (ctx->dist->p2p) MP_TRY(mp_dist_p2p_scalars(ctx));      // peer stores + flags instead of an NCCL all-gather
+	else MP_TRY(mp_dist_allgather(ctx, 2));
 	if (g->prec == 4) k_cg_combine<float><<<1, 1, 0, ctx->stream>>>(ctx->dist->dGather, ctx->dist->world, (CgScal<float>*)sc, stage, mode);
 	else              k_cg_combine<double><<<1, 1, 0, ctx->stream>>>(ctx->dist->dGather, ctx->dist->world, (CgScal<double>*)sc, stage, mode);
 	MP_CHECK_LAUNCH(ctx);
@@ -528,6 +549,7 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	const bool none = cg->pcMethod == MP_CG_PC_NONE;
 	const IndexInt nOwn = d.i1 - d.i0;
 	double* dl = distLocalOf(ctx, d);
+	if (d.world > 1) MP_TRY(mp_dist_p2p_prepare(ctx, 4 * (((size_t)d.sx * d.sy * cg->dst->prec + 15) / 16 * 16)));   // collective; no-op once built
 	if (d.world > 1) MP_TRY(cgHalo(cg, cg->Ak));      // Ak[idx-Z] of the first owned plane lives on the lower neighbour
 	{	// coupling-mask fast path of the matvec (3-D, vector-aligned rows, every off-diagonal in {0,-1})
 		static const int useMask = getenv("MP_MATVEC_MASK") ? atoi(getenv("MP_MATVEC_MASK")) : 1;
@@ -577,6 +599,8 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 	const bool none = cg->pcMethod == MP_CG_PC_NONE;
 	const IndexInt nOwn = d.i1 - d.i0;
 	double* dl = distLocalOf(ctx, d);
+	const size_t planeBytes = (size_t)d.sx * d.sy * cg->dst->prec;
+	const bool p2pHalo = dl && ctx->dist->p2p && planeBytes % 16 == 0;
 	// sampled kernel timing: 5 events around the 4 stages of this iteration
 	cudaEvent_t* pe = nullptr;
 	if (ctx->profPeriod > 0 && iterIndex >= 0 && iterIndex % ctx->profPeriod == 0 && ctx->profCount < 128) pe = &ctx->profEv[5 * ctx->profCount++];
@@ -593,9 +617,12 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 			MP_CHECK_LAUNCH(ctx);
 			if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 1, 0));
 			PROF(2); PROF(3);
-			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, s, r, sc);
+			HaloOut ho;
+			if (p2pHalo) MP_TRY(mp_dist_p2p_halo_out(ctx, planeBytes, &ho));
+			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, s, r, sc, ho, (IndexInt)d.sx * d.sy);
 			MP_CHECK_LAUNCH(ctx);
-			if (dl) MP_TRY(cgHalo(cg, cg->search));
+			if (p2pHalo) MP_TRY(mp_dist_p2p_halo_in(ctx, cg->search->d, planeBytes, cg->search->sz, &sc->done));
+			else if (dl) MP_TRY(cgHalo(cg, cg->search));
 		} else {
 			k_axpy2_norm<Real, V, 1><<<blocks, 256, 0, ctx->stream>>>(nOwn, x, s, r, t, sc, ctx->partials, ctx->tickets + 5, dl);
 			MP_CHECK_LAUNCH(ctx);
@@ -606,9 +633,12 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 			MP_CHECK_LAUNCH(ctx);
 			if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 2, 0));
 			PROF(3);
-			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, s, t, sc);
+			HaloOut ho;
+			if (p2pHalo) MP_TRY(mp_dist_p2p_halo_out(ctx, planeBytes, &ho));
+			k_update_search<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, s, t, sc, ho, (IndexInt)d.sx * d.sy);
 			MP_CHECK_LAUNCH(ctx);
-			if (dl) MP_TRY(cgHalo(cg, cg->search));
+			if (p2pHalo) MP_TRY(mp_dist_p2p_halo_in(ctx, cg->search->d, planeBytes, cg->search->sz, &sc->done));
+			else if (dl) MP_TRY(cgHalo(cg, cg->search));
 		}
 	});
 	PROF(4);
@@ -644,6 +674,7 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 	}
 	for (int q = 0; q < 2; q++) if (pending[q]) { MP_TRY(cgPollWait(cg, q)); pending[q] = false; }
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));      // the state after everything that was enqueued
+	MP_TRY(mp_dist_p2p_check(ctx));
 	if (ctx->profPeriod > 0) {
 		// only samples of iterations that really ran (before `done`) count
 		int used = 0; double acc[4] = {0, 0, 0, 0};

@@ -77,7 +77,24 @@ struct DistState {
 	int gsz = 0, k0 = 0, k1 = 0;
 	double* dGather = nullptr;   // world * 8 doubles: all-gathered partial results
 	double* dLocal = nullptr;    // 8 doubles: this rank's partial results
+	// ---- peer-memory path of the per-iteration exchanges (NVLink P2P through CUDA IPC), see mp_dist.cu ----
+	// arena layout (identical on every rank): [0,4K) halo flags | [4K,64K) scalar gather slots | [64K, ...) search vector slab
+	bool p2p = false;
+	char* arena = nullptr; size_t arenaBytes = 0; size_t searchBytes = 0;
+	std::vector<char*> peer;     // peers' arenas mapped into this process (peer[rank] == arena)
+	unsigned int haloSeq = 0, scalSeq = 0;
 };
+static const size_t kArenaFlags = 0, kArenaGather = 4096, kArenaSearch = 65536;
+// what the kernel producing the new search vector needs to push its boundary planes to the neighbours (all null: no push)
+struct HaloOut {
+	char* lo = nullptr; char* hi = nullptr;                     // lower / upper neighbour's receive buffer of this parity
+	unsigned int* flagLo = nullptr; unsigned int* flagHi = nullptr;
+	unsigned int* ticket = nullptr; unsigned int seq = 0;
+};
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) { unsigned int v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long globalTimerNs() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+static const int kGatherStride = 8;          // doubles per rank per slot
 
 struct Dims {
 	int sx, sy, sz;
@@ -101,6 +118,11 @@ static inline Dims dimsOf(const mp_grid* g) {
 int mp_dist_check_grid(const mp_grid* g);                                  // slab grids must have sz == k1-k0+2
 int mp_dist_halo(mp_context* ctx, void* base, size_t planeBytes, int szLocal);   // exchange the two ghost planes (no-op when world == 1)
 int mp_dist_allgather(mp_context* ctx, int nvals);
+int mp_dist_p2p_prepare(mp_context* ctx, size_t searchBytes);                  // collective: (re)build the arena, exchange IPC handles
+int mp_dist_p2p_scalars(mp_context* ctx);                                      // dLocal -> every peer's gather slot + flag; returns the slot parity via ds->scalSeq
+int mp_dist_p2p_halo_out(mp_context* ctx, size_t planeBytes, HaloOut* ho);        // next sequence number + the neighbours' receive buffers
+int mp_dist_p2p_halo_in(mp_context* ctx, void* base, size_t planeBytes, int szLocal, const int* done);   // wait for the neighbours, fill the ghost planes
+int mp_dist_p2p_check(mp_context* ctx);                                        // after a sync: did any wait time out?
 int mp_dist_sum(mp_context* ctx, double* deviceVals, int n);                   // in-place global sum of n <= 8 doubles (no-op when world == 1)                         // dLocal[0..nvals) of every rank -> dGather[rank*8 + q]
 
 int mp_check_same(const mp_grid* ref, const mp_grid* g, int kind, const char* name, bool optional);

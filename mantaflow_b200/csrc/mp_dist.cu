@@ -12,6 +12,8 @@
 #include "mp_common.cuh"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <algorithm>
+#include <cstdlib>
 
 namespace {
 struct NcclApi {
@@ -73,6 +75,161 @@ int mp_dist_allgather(mp_context* ctx, int nvals) {
 	DistState* ds = ctx->dist;
 	(void)nvals;
 	MP_NCCL(g_nccl.AllGather(ds->dLocal, ds->dGather, 8, ncclDouble, (ncclComm_t)ds->comm, ctx->stream));
+	return MP_OK;
+}
+
+// ================================================================ peer-memory path (NVLink P2P over CUDA IPC)
+// The per-iteration exchanges of the CG loop do not go through NCCL: every rank exports one arena (cudaIpcGetMemHandle),
+// maps its peers' arenas, and
+//   * k_update_search writes its first / last owned plane of the new search vector straight into the neighbours' ghost
+//     planes (peer stores over NVLink) and, once all its blocks are done, bumps a flag in their arenas;
+//   * the ranks' partial reductions are scattered into every peer's gather slots with a flag per source rank, and
+//     k_cg_combine_p2p spins on the flags before combining in rank order (slots are double-buffered by sequence parity).
+// NCCL stays for the once-per-solve exchanges and for carrying the IPC handles.
+struct PeerPtrs { char* p[16]; };
+
+// one thread per peer: my partials -> peer's slot [parity][myRank], then the flag (release at system scope)
+__global__ void k_p2p_scatter(PeerPtrs peers, int world, int rank, const double* __restrict__ local, unsigned int seq) {
+	const int r = threadIdx.x;
+	if (r >= world) return;
+	char* base = peers.p[r] + kArenaGather;
+	double* slot = (double*)base + ((seq & 1u) * 16 + rank) * kGatherStride;
+	unsigned int* flag = (unsigned int*)(base + 2 * 16 * kGatherStride * sizeof(double)) + (seq & 1u) * 16 + rank;
+	slot[0] = local[0]; slot[1] = local[1]; slot[2] = local[2]; slot[3] = local[3];
+	__threadfence_system();
+	st_release_sys(flag, seq);
+}
+static const unsigned long long kWaitNs = 30ull * 1000000000ull;   // a peer that is 30 s late is gone: flag the stall instead of hanging the GPU
+__device__ __forceinline__ bool waitFlag(const unsigned int* flag, unsigned int seq) {
+	if ((int)(ld_acquire_sys(flag) - seq) >= 0) return true;
+	const unsigned long long t0 = globalTimerNs();
+	while ((int)(ld_acquire_sys(flag) - seq) < 0) { if (globalTimerNs() - t0 > kWaitNs) return false; }
+	return true;
+}
+// gather my own slots (all ranks) into dGather[r*8+q] once every flag has arrived
+__global__ void k_p2p_collect(char* arena, int world, unsigned int seq, double* __restrict__ gathered, int* stall) {
+	const int r = threadIdx.x;
+	if (r >= world) return;
+	char* base = arena + kArenaGather;
+	const unsigned int* flag = (const unsigned int*)(base + 2 * 16 * kGatherStride * sizeof(double)) + (seq & 1u) * 16 + r;
+	if (!waitFlag(flag, seq)) atomicExch(stall, 1);
+	const double* slot = (const double*)base + ((seq & 1u) * 16 + r) * kGatherStride;
+	for (int q = 0; q < 4; q++) gathered[8 * r + q] = __ldcv(slot + q);
+}
+// every block waits for the neighbours' flags, then the grid copies the two received planes into the ghost planes
+__global__ void __launch_bounds__(256) k_p2p_halo_in(char* arena, const uint4* __restrict__ recvLo, const uint4* __restrict__ recvHi,
+	uint4* __restrict__ ghostLo, uint4* __restrict__ ghostHi, size_t nvec, unsigned int seq, const int* done, int* stall)
+{
+	if (done && *done) return;
+	if (threadIdx.x == 0) {
+		const unsigned int* f = (const unsigned int*)(arena + kArenaFlags);
+		bool o = true;
+		if (recvLo) o = waitFlag(f + 0, seq) && o;
+		if (recvHi) o = waitFlag(f + 1, seq) && o;
+		if (!o) atomicExch(stall, 1);
+	}
+	__syncthreads();
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+		if (recvLo) ghostLo[i] = __ldcv(recvLo + i);
+		if (recvHi) ghostHi[i] = __ldcv(recvHi + i);
+	}
+}
+
+int mp_dist_p2p_prepare(mp_context* ctx, size_t searchBytes) {
+	DistState* ds = ctx->dist;
+	static const int enable = getenv("MP_P2P") ? atoi(getenv("MP_P2P")) : 1;
+	if (!ds || !ds->active || ds->world == 1 || ds->world > 16 || !enable) { if (ds) ds->p2p = false; return MP_OK; }
+	if (ds->arena && ds->searchBytes >= searchBytes) { ds->p2p = true; return MP_OK; }
+	// (re)build: every rank takes this branch in the same call because all slabs change size together
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	for (int r = 0; r < (int)ds->peer.size(); r++) if (ds->peer[r] && r != ds->rank) cudaIpcCloseMemHandle(ds->peer[r]);
+	ds->peer.clear();
+	if (ds->arena) { MP_CUDA(cudaFree(ds->arena)); ds->arena = nullptr; }
+	// all ranks allocate the same size: the largest slab's search vector (slabs differ by at most one plane)
+	size_t maxBytes = searchBytes;
+	{
+		double* tmp = ds->dLocal; const double mine = (double)searchBytes;
+		MP_CUDA(cudaMemcpyAsync(tmp, &mine, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		MP_TRY(mp_dist_allgather(ctx, 1));
+		std::vector<double> all(8 * ds->world);
+		MP_CUDA(cudaMemcpyAsync(all.data(), ds->dGather, sizeof(double) * 8 * ds->world, cudaMemcpyDeviceToHost, ctx->stream));
+		MP_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (int r = 0; r < ds->world; r++) maxBytes = std::max(maxBytes, (size_t)all[8 * r]);
+	}
+	ds->searchBytes = maxBytes; ds->arenaBytes = kArenaSearch + maxBytes + 512;
+	MP_CUDA(cudaMalloc((void**)&ds->arena, ds->arenaBytes));
+	MP_CUDA(cudaMemset(ds->arena, 0, ds->arenaBytes));
+	cudaIpcMemHandle_t h; MP_CUDA(cudaIpcGetMemHandle(&h, ds->arena));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+	char *dH = nullptr, *dAll = nullptr;
+	MP_CUDA(cudaMalloc((void**)&dH, 64)); MP_CUDA(cudaMalloc((void**)&dAll, 64 * ds->world));
+	MP_CUDA(cudaMemcpy(dH, &h, 64, cudaMemcpyHostToDevice));
+	MP_NCCL(g_nccl.AllGather(dH, dAll, 64, ncclChar, (ncclComm_t)ds->comm, ctx->stream));
+	std::vector<cudaIpcMemHandle_t> hs(ds->world);
+	MP_CUDA(cudaMemcpyAsync(hs.data(), dAll, 64 * ds->world, cudaMemcpyDeviceToHost, ctx->stream));
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	cudaFree(dH); cudaFree(dAll);
+	ds->peer.assign(ds->world, nullptr);
+	for (int r = 0; r < ds->world; r++) {
+		if (r == ds->rank) { ds->peer[r] = ds->arena; continue; }
+		void* p = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) { cudaGetLastError(); ds->p2p = false; mp_set_error("cudaIpcOpenMemHandle failed (%s): falling back to NCCL", cudaGetErrorString(e)); return MP_OK; }
+		ds->peer[r] = (char*)p;
+	}
+	ds->haloSeq = 0; ds->scalSeq = 0;
+	// nobody may write into a peer's arena before that peer has finished clearing it
+	MP_TRY(mp_dist_allgather(ctx, 1));
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	ds->p2p = true;
+	return MP_OK;
+}
+
+int mp_dist_p2p_scalars(mp_context* ctx) {
+	DistState* ds = ctx->dist;
+	PeerPtrs pp; for (int r = 0; r < 16; r++) pp.p[r] = r < ds->world ? ds->peer[r] : nullptr;
+	const unsigned int seq = ++ds->scalSeq;
+	k_p2p_scatter<<<1, 32, 0, ctx->stream>>>(pp, ds->world, ds->rank, ds->dLocal, seq); MP_CHECK_LAUNCH(ctx);
+	k_p2p_collect<<<1, 32, 0, ctx->stream>>>(ds->arena, ds->world, seq, ds->dGather, (int*)(ds->arena + kArenaFlags) + 8); MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+static inline size_t recvOffset(const DistState* ds, unsigned int seq, int side) { return kArenaSearch + ((seq & 1u) * 2 + side) * (ds->searchBytes / 4); }
+
+int mp_dist_p2p_halo_out(mp_context* ctx, size_t planeBytes, HaloOut* ho) {
+	DistState* ds = ctx->dist;
+	*ho = HaloOut();
+	if (!ds || !ds->p2p) return MP_OK;
+	if (4 * planeBytes > ds->searchBytes) MP_FAIL(MP_ERR_INVALID, "mp_dist: peer arena smaller than the halo planes");
+	const unsigned int seq = ++ds->haloSeq;
+	ho->seq = seq; ho->ticket = ctx->tickets + 7;
+	if (ds->rank > 0)             { ho->lo = ds->peer[ds->rank - 1] + recvOffset(ds, seq, 1); ho->flagLo = (unsigned int*)(ds->peer[ds->rank - 1] + kArenaFlags) + 1; }
+	if (ds->rank < ds->world - 1) { ho->hi = ds->peer[ds->rank + 1] + recvOffset(ds, seq, 0); ho->flagHi = (unsigned int*)(ds->peer[ds->rank + 1] + kArenaFlags) + 0; }
+	return MP_OK;
+}
+
+int mp_dist_p2p_halo_in(mp_context* ctx, void* base, size_t planeBytes, int szLocal, const int* done) {
+	DistState* ds = ctx->dist;
+	const unsigned int seq = ds->haloSeq;
+	char* b = (char*)base;
+	if (planeBytes % 16) MP_FAIL(MP_ERR_INVALID, "mp_dist: halo plane is not a multiple of 16 bytes");
+	const bool lo = ds->rank > 0, hi = ds->rank < ds->world - 1;
+	const size_t nvec = planeBytes / 16;
+	unsigned int blocks = (unsigned int)std::min<size_t>((nvec + 255) / 256, 64);
+	k_p2p_halo_in<<<blocks, 256, 0, ctx->stream>>>(ds->arena, lo ? (const uint4*)(ds->arena + recvOffset(ds, seq, 0)) : nullptr,
+		hi ? (const uint4*)(ds->arena + recvOffset(ds, seq, 1)) : nullptr, (uint4*)b, (uint4*)(b + planeBytes * (size_t)(szLocal - 1)), nvec, seq, done,
+		(int*)(ds->arena + kArenaFlags) + 8);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+int mp_dist_p2p_check(mp_context* ctx) {
+	DistState* ds = ctx->dist;
+	if (!ds || !ds->p2p) return MP_OK;
+	int stall = 0;
+	MP_CUDA(cudaMemcpyAsync(&stall, ds->arena + kArenaFlags + 8 * sizeof(int), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (stall) MP_FAIL(MP_ERR_COMM, "mp_dist: a peer-memory wait timed out (a neighbouring rank stopped making progress)");
 	return MP_OK;
 }
 
@@ -142,6 +299,8 @@ int mp_dist_shutdown(mp_context* ctx) {
 	DistState* ds = ctx->dist;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	for (int r = 0; r < (int)ds->peer.size(); r++) if (ds->peer[r] && r != ds->rank) cudaIpcCloseMemHandle(ds->peer[r]);
+	if (ds->arena) cudaFree(ds->arena);
 	if (ds->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ds->comm);
 	cudaFree(ds->dGather); cudaFree(ds->dLocal);
 	delete ds; ctx->dist = nullptr;
