@@ -2,6 +2,7 @@
 // Reference: Grid<T> grid.cpp:47-96,:205-210; FluidSolver::GridStorage fluidsolver.cpp:33-50;
 // GridDotProduct conjugategrad.cpp:175-178; getMaxAbs grid.cpp:319-323; GridSumSqr commonkernels.h:32-35.
 #include "mp_common.cuh"
+#include <cstdlib>
 #include <cstdarg>
 
 static thread_local char g_err[1024] = "";
@@ -63,6 +64,10 @@ int mp_context_destroy(mp_context* c) {
 	for (auto& e : c->profEv) cudaEventDestroy(e);
 	for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->micProg) cudaFree(c->micProg);
+	if (c->micMask) cudaFree(c->micMask);
+	if (c->micOrder) cudaFree(c->micOrder);
+	if (c->micStall) cudaFree(c->micStall);
+	if (c->micMail) cudaFree(c->micMail);
 	cudaFree(c->partials); cudaFree(c->tickets); cudaFree(c->dScal); cudaFreeHost(c->hScal);
 	cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copyStream);
 	delete c; return MP_OK;

@@ -518,6 +518,7 @@ static int cgPollWait(mp_cg* cg, int slot) {
 }
 
 int mp_mic_init_launch(mp_context* ctx, const mp_grid* flags, mp_grid* P, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
+int mp_mic_check_stall(mp_context* ctx);
 int mp_mic_apply_launch(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* flags, const mp_grid* P,
                         const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, const int* doneFlag);
 int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, double accuracy);
@@ -675,6 +676,7 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 	for (int q = 0; q < 2; q++) if (pending[q]) { MP_TRY(cgPollWait(cg, q)); pending[q] = false; }
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));      // the state after everything that was enqueued
 	MP_TRY(mp_dist_p2p_check(ctx));
+	if (cg->pcMethod == MP_CG_PC_MICP) MP_TRY(mp_mic_check_stall(ctx));
 	if (ctx->profPeriod > 0) {
 		// only samples of iterations that really ran (before `done`) count
 		int used = 0; double acc[4] = {0, 0, 0, 0};

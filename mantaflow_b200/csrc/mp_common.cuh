@@ -49,6 +49,10 @@ struct mp_context {
 	std::vector<cudaEvent_t> profEv;      // 5 events per sample: t0 | matvec | axpy | precond+dot | update
 	int profCount = 0;
 	float profMs[4] = {0, 0, 0, 0};
+	unsigned char* micMask = nullptr; size_t micMaskBytes = 0; const void* micMaskFor = nullptr; int micMaskPrec = 0;   // per-chunk fluid bits of the MIC warp sweeps
+	void* micMail = nullptr; size_t micMailBytes = 0; unsigned int micTag = 0;   // edge-row mailboxes of the warp sweeps + sweep sequence number
+	int* micStall = nullptr;                              // raised by a MIC sweep whose dependency wait ran out of budget
+	int* micOrder = nullptr; int micOrderCount = 0;       // dispatch order of the warp columns
 	int* micProg = nullptr; size_t micProgBytes = 0;     // per-column progress counters (+ stall flag) of the pipelined MIC sweeps
 	int lastMatvecKernel = 0;     // which matvec instantiation the last launch used (reported in mp_solve_info)
 };

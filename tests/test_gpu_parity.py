@@ -46,6 +46,9 @@ SCENES = {
     "smoke2d": lambda prec: scenes.smoke_plume((40, 36, 1), prec, random_vel=True) + (None,),
     "liquid2d": lambda prec: scenes.liquid_basin((33, 30, 1), prec),
 }
+# rows that are whole 32-byte chunks (the vector path of the MIC warp sweeps), several warp columns in y and z
+MIC_SCENES = dict(SCENES, smoke_vec=lambda prec: scenes.smoke_plume((40, 21, 13), prec, random_vel=True) + (None,),
+                  liquid_vec=lambda prec: scenes.liquid_basin((48, 20, 18), prec))
 
 
 @pytest.mark.parametrize("prec", [4, 8])
@@ -140,11 +143,14 @@ def test_apply_matrix_bit_exact(mf, scene, prec):
     assert abs(cg.GridDotProduct(D, S) - float(np.sum((D.numpy() * src).astype(np.float64)))) < 1e-6 * flags.size
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])   # MP_MIC: cell hyperplanes, tile hyperplanes, tile columns, warp columns
 @pytest.mark.parametrize("prec", [4, 8])
-@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28"])
-def test_mic_bit_exact(mf, scene, prec):
+@pytest.mark.parametrize("scene", ["smoke24", "smoke_ragged", "liquid28", "smoke_vec", "liquid_vec"])
+def test_mic_bit_exact(mf, scene, prec, variant, monkeypatch):
+    """every schedule of the MIC(0) sweeps reproduces the serial factor and solution bit for bit"""
     from mantaflow_b200 import cg
-    flags, vel, phi = SCENES[scene](prec)
+    monkeypatch.setenv("MP_MIC", str(variant))
+    flags, vel, phi = MIC_SCENES[scene](prec)
     O = oracle(prec)
     A_o = O.make_matrix(flags, phi=phi)
     P_o = O.mic_init(flags, *A_o)
@@ -209,6 +215,30 @@ def test_gridcg_iterate_stepwise(mf):
         assert n < 3000
     assert abs(g.getIterations() - it_o) <= 1
     assert rel_l2(x.numpy(), x_o) <= 1e-4
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("scene", ["smoke_vec", "liquid_vec", "smoke_ragged"])
+def test_solve_pressure_pcmic_warp_columns(mf, scene, prec, monkeypatch):
+    """the whole PcMIC solve on the schedule large grids get by default (MP_MIC=4): same iteration count, float bit-identical"""
+    monkeypatch.setenv("MP_MIC", "4")
+    flags, vel, phi = MIC_SCENES[scene](prec)
+    O = oracle(prec)
+    acc = 1e-5 if prec == 4 else 1e-11
+    v_o = vel.copy()
+    p_o, it_o, rn_o = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=1)
+    s = mk(mf, flags.shape, prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+    PH = mf.RealGrid(s, phi) if phi is not None else None
+    for _ in range(2):      # twice: the mailboxes of the first solve are still around, only the sequence tags tell them apart
+        V.copyFromArray(vel)
+        mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=1)
+        info = mf.lastSolveInfo()
+        assert abs(info["iterations"] - it_o) <= 1, (info["iterations"], it_o)
+        assert rel_l2(P.numpy(), p_o) <= TOL[prec]
+        assert rel_l2(V.numpy(), v_o) <= TOL[prec]
+        if prec == 4:
+            assert np.array_equal(P.numpy(), p_o.astype(np.float32))
 
 
 @pytest.mark.parametrize("prec", [4, 8])
