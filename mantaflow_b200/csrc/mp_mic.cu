@@ -7,14 +7,15 @@
 // here (operation order, -fmad=false, IEEE div/sqrt, the double-precision "+ 0." promotion of :85-89) is the reference's,
 // hence Aprecond and z are BIT-IDENTICAL to the serial sweeps and PcMIC keeps the reference's iteration counts.
 //
-// v2 schedule (default): two-level wavefront.  The interior is cut into 8x8x8 tiles; tile (bi,bj,bk) depends on its three
-// minus-neighbours, so all tiles of a tile-hyperplane bi+bj+bk = c run in one launch ((sx+sy+sz-6)/8 launches per sweep,
-// 190 at 512^3, instead of sx+sy+sz-8 = 1528 cell-planes).  Inside a tile one CTA of 64 threads walks the 22 local
-// hyperplanes li+lj+lk out of shared memory (thread = (lj,lk) line, skewed march along x, one __syncthreads per step;
-// padded so that a warp's 32 accesses fall into 32 different banks).  Halo faces come from the already finished
-// neighbour tiles through global memory.
-// v1 (MP_MIC=1): one launch per cell hyperplane, kept for A/B timing.
-// Both are dependency-/latency-bound rather than bandwidth-bound; DESIGN.md gives stage counts.
+// Schedules (MP_MIC forces one; all are tested bit for bit against the serial sweep):
+//  v1  one launch per cell hyperplane (kept for A/B timing);
+//  v2  two-level wavefront: 8x8x8 tiles, all tiles of a tile-hyperplane in one launch ((sx+sy+sz-6)/8 launches per sweep); inside a
+//      tile one CTA of 64 threads walks the 22 local hyperplanes out of padded, bank-conflict-free shared memory;
+//  v3  ONE launch per sweep: CTA (bj,bk) walks its column of tiles and waits on progress counters of its predecessor columns
+//      (the factor always uses this one; the sweeps on grids below ~100 MB);
+//  v4  one WARP per 8x4 column of rows, cell-level wavefront by warp shuffles, cp.async ring, tagged mailboxes between columns
+//      (the sweeps on large grids).
+// All are dependency-/latency-bound rather than bandwidth-bound; DESIGN.md section 5 has the chain analysis.
 #include "mp_common.cuh"
 #include <cstdlib>
 #include <vector>
