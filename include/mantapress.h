@@ -201,6 +201,19 @@ int mp_solve_pressure(mp_context* ctx, mp_grid* vel, mp_grid* pressure, const mp
 int mp_cg_solve_diffusion(mp_context* ctx, const mp_grid* flags, mp_grid* grid, double alpha, double cgMaxIterFac, double cgAccuracy,
                           mp_solve_info* info);
 
+/* ---- the steps either side of the projection, so that a whole smoke step keeps its fields in HBM ----
+ * setWallBcs          plugin/extforces.cpp:186-218, :307-316  (KnSetWallBcs; phiObs + fractions = the second-order variant: MP_ERR_UNSUPPORTED)
+ * addGravity          plugin/extforces.cpp:45-65              (scale != 0: divided by the grid's dx = 1/max(size))
+ * addBuoyancy         plugin/extforces.cpp:75-90
+ * advectSemiLagrange  plugin/advection.cpp:442-461            (grid: Real or MAC; order 1 | 2 (MacCormack), clampMode 1 | 2, convective outflow
+ *                     boundary for MAC grids; orderSpace / orderTrace other than 1: MP_ERR_UNSUPPORTED).  dt = FluidSolver::getDt().
+ * Results are bit-identical to the reference's in both precisions. */
+int mp_set_wall_bcs(mp_context* ctx, const mp_grid* flags, mp_grid* vel, const mp_grid* obvel, const mp_grid* fractions, const mp_grid* phiObs, int boundaryWidth);
+int mp_add_gravity(mp_context* ctx, const mp_grid* flags, mp_grid* vel, double gx, double gy, double gz, const mp_grid* exclude, int scale, double dt);
+int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* density, mp_grid* vel, double gx, double gy, double gz, double coefficient, int scale, double dt);
+int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
+                            int clampMode, int orderTrace, double dt);
+
 /* ---- the plugin with HOST buffers (what pressure.cpp calls when grids have no device mirror yet):
  * uploads flags/vel(/phi...), runs mp_solve_pressure, downloads vel/pressure(/retRhs).  Optional
  * pointers may be NULL.  Buffers may be pageable or pinned (mp_host_alloc). ---- */

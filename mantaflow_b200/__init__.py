@@ -14,5 +14,6 @@ from .grid import (FlagEmpty, FlagFluid, FlagGrid, FlagInflow, FlagObstacle, Fla
 from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, releaseMG, solvePressure, solvePressureHost,
                        solvePressureSystem)
 from .cg import GridCg, GridMg, cgSolveDiffusion
+from .step import addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, setWallBcs
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,452 @@
+// The steps either side of the pressure projection, so that a whole smoke step keeps its fields in HBM:
+//   setWallBcs          plugin/extforces.cpp:186-218, :307-316   (KnSetWallBcs; the phiObs / fractions variant is not built)
+//   addGravity          plugin/extforces.cpp:45-65               (KnApplyForce, additive)
+//   addBuoyancy         plugin/extforces.cpp:75-90               (KnAddBuoyancy)
+//   advectSemiLagrange  plugin/advection.cpp:25-58, :81-316, :323-461 (semi-Lagrange + MacCormack for Real and MAC grids,
+//                       orderSpace 1 / orderTrace 1, clamp modes 1 and 2, convective outflow boundary)
+// One thread per cell, gathers only, every cell written by exactly one thread: any order of execution gives the serial result.
+// The per-cell arithmetic keeps the reference's evaluation (double literals promote, results narrow on assignment; -fmad=false),
+// so the fields are BIT-IDENTICAL to the reference's in both precisions (tests/test_gpu_step.py).
+#include "mp_common.cuh"
+#include <cfloat>
+
+namespace {
+
+template <typename Real> struct V3 { Real x, y, z; };
+
+__device__ __forceinline__ bool interior(const Dims& d, IndexInt idx, int& i, int& j, int& k) {   // the cells of a KERNEL(bnd=1)
+	i = (int)(idx % d.sx); j = (int)((idx / d.sx) % d.sy); k = (int)(idx / ((IndexInt)d.sx * d.sy));
+	return i >= 1 && i <= d.sx - 2 && j >= 1 && j <= d.sy - 2 && (!d.is3D || (k >= 1 && k <= d.sz - 2));
+}
+
+// ---------------------------------------------------------------- setWallBcs / forces
+template <typename Real>
+__global__ void __launch_bounds__(256) k_set_wall_bcs(Dims d, const int* __restrict__ flags, Real* vel, const Real* __restrict__ obvel) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n) return;
+	const int i = (int)(idx % d.sx), j = (int)((idx / d.sx) % d.sy), k = (int)(idx / ((IndexInt)d.sx * d.sy));
+	const int fl = flags[idx];
+	const bool curFluid = fl & TypeFluid, curObs = fl & TypeObstacle;
+	if (!curFluid && !curObs) return;
+	Real* v = vel + 3 * idx;
+	Real bx = 0, by = 0, bz = 0;
+	if (obvel) { bx = obvel[3 * idx]; by = obvel[3 * idx + 1]; if (d.is3D) bz = obvel[3 * idx + 2]; }
+	Real vx = v[0], vy = v[1], vz = v[2];
+	if (i > 0 && (flags[idx - d.X] & TypeObstacle)) vx = bx;
+	if (i > 0 && curObs && (flags[idx - d.X] & TypeFluid)) vx = bx;
+	if (j > 0 && (flags[idx - d.Y] & TypeObstacle)) vy = by;
+	if (j > 0 && curObs && (flags[idx - d.Y] & TypeFluid)) vy = by;
+	if (!d.is3D) vz = 0;
+	else {
+		if (k > 0 && (flags[idx - d.Z] & TypeObstacle)) vz = bz;
+		if (k > 0 && curObs && (flags[idx - d.Z] & TypeFluid)) vz = bz;
+	}
+	if (curFluid) {
+		if ((i > 0 && (flags[idx - d.X] & TypeStick)) || (i < d.sx - 1 && (flags[idx + d.X] & TypeStick))) vy = vz = 0;
+		if ((j > 0 && (flags[idx - d.Y] & TypeStick)) || (j < d.sy - 1 && (flags[idx + d.Y] & TypeStick))) vx = vz = 0;
+		if (d.is3D && ((k > 0 && (flags[idx - d.Z] & TypeStick)) || (k < d.sz - 1 && (flags[idx + d.Z] & TypeStick)))) vx = vy = 0;
+	}
+	v[0] = vx; v[1] = vy; v[2] = vz;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_apply_force(Dims d, const int* __restrict__ flags, Real* vel, Real fx, Real fy, Real fz, const Real* __restrict__ exclude) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	int i, j, k;
+	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+	const bool curFluid = flags[idx] & TypeFluid, curEmpty = flags[idx] & TypeEmpty;
+	if (!curFluid && !curEmpty) return;
+	if (exclude && (exclude[idx] < 0.)) return;
+	Real* v = vel + 3 * idx;
+	if ((flags[idx - d.X] & TypeFluid) || (curFluid && (flags[idx - d.X] & TypeEmpty))) v[0] = v[0] + fx;
+	if ((flags[idx - d.Y] & TypeFluid) || (curFluid && (flags[idx - d.Y] & TypeEmpty))) v[1] = v[1] + fy;
+	if (d.is3D && ((flags[idx - d.Z] & TypeFluid) || (curFluid && (flags[idx - d.Z] & TypeEmpty)))) v[2] = v[2] + fz;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_add_buoyancy(Dims d, const int* __restrict__ flags, const Real* __restrict__ factor, Real* vel, Real sx_, Real sy_, Real sz_) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	int i, j, k;
+	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+	if (!(flags[idx] & TypeFluid)) return;
+	Real* v = vel + 3 * idx;
+	const Real f0 = factor[idx];
+	if (flags[idx - d.X] & TypeFluid) v[0] = (Real)((double)v[0] + (0.5 * (double)sx_) * (double)(f0 + factor[idx - d.X]));
+	if (flags[idx - d.Y] & TypeFluid) v[1] = (Real)((double)v[1] + (0.5 * (double)sy_) * (double)(f0 + factor[idx - d.Y]));
+	if (d.is3D && (flags[idx - d.Z] & TypeFluid)) v[2] = (Real)((double)v[2] + (0.5 * (double)sz_) * (double)(f0 + factor[idx - d.Z]));
+}
+
+// ---------------------------------------------------------------- interpolation (util/interpol.h:50-91) and MAC accessors (grid.h:424-466)
+// STRIDE 1: Grid<Real>; STRIDE 3: one component of a Vec3 grid (a points at that component of cell 0)
+template <typename Real, int STRIDE>
+__device__ __forceinline__ Real interpol(const Dims& d, const Real* __restrict__ a, Real posx, Real posy, Real posz) {
+	const Real px = posx - 0.5f, py = posy - 0.5f, pz = posz - 0.5f;
+	int xi = (int)px, yi = (int)py, zi = (int)pz;
+	Real s1 = px - (Real)xi, s0 = (Real)(1. - s1);
+	Real t1 = py - (Real)yi, t0 = (Real)(1. - t1);
+	Real f1 = pz - (Real)zi, f0 = (Real)(1. - f1);
+	if (px < 0.) { xi = 0; s0 = 1.0; s1 = 0.0; }
+	if (py < 0.) { yi = 0; t0 = 1.0; t1 = 0.0; }
+	if (pz < 0.) { zi = 0; f0 = 1.0; f1 = 0.0; }
+	if (xi >= d.sx - 1) { xi = d.sx - 2; s0 = 0.0; s1 = 1.0; }
+	if (yi >= d.sy - 1) { yi = d.sy - 2; t0 = 0.0; t1 = 1.0; }
+	if (d.sz > 1) { if (zi >= d.sz - 1) { zi = d.sz - 2; f0 = 0.0; f1 = 1.0; } }
+	const IndexInt X = STRIDE, Y = d.Y * STRIDE, Z = d.Z * STRIDE;
+	const Real* p = a + ((IndexInt)xi + d.Y * yi + d.Z * zi) * STRIDE;
+	return ((p[0] * t0 + p[Y] * t1) * s0 + (p[X] * t0 + p[X + Y] * t1) * s1) * f0
+	     + ((p[Z] * t0 + p[Y + Z] * t1) * s0 + (p[X + Z] * t0 + p[X + Y + Z] * t1) * s1) * f1;
+}
+template <typename Real>
+__device__ __forceinline__ V3<Real> macCentered(const Dims& d, const Real* __restrict__ v, IndexInt idx) {
+	V3<Real> o;
+	o.x = (Real)(0.5 * (double)(v[3 * idx] + v[3 * (idx + 1)]));
+	o.y = (Real)(0.5 * (double)(v[3 * idx + 1] + v[3 * (idx + d.Y) + 1]));
+	o.z = 0;
+	if (d.is3D) o.z = (Real)(0.5 * (double)(v[3 * idx + 2] + v[3 * (idx + d.Z) + 2]));
+	return o;
+}
+#define VC(o, c) v[3 * (idx + (o)) + (c)]
+template <typename Real, int C>
+__device__ __forceinline__ V3<Real> macAt(const Dims& d, const Real* __restrict__ v, IndexInt idx) {   // getAtMACX / Y / Z
+	const IndexInt Y = d.Y, Z = d.Z;
+	V3<Real> o;
+	if (C == 0) {
+		o.x = VC(0, 0);
+		o.y = (Real)(0.25 * (double)(VC(0, 1) + VC(-1, 1) + VC(Y, 1) + VC(Y - 1, 1)));
+		o.z = 0;
+		if (d.is3D) o.z = (Real)(0.25 * (double)(VC(0, 2) + VC(-1, 2) + VC(Z, 2) + VC(Z - 1, 2)));
+	} else if (C == 1) {
+		o.x = (Real)(0.25 * (double)(VC(0, 0) + VC(-Y, 0) + VC(1, 0) + VC(1 - Y, 0)));
+		o.y = VC(0, 1);
+		o.z = 0;
+		if (d.is3D) o.z = (Real)(0.25 * (double)(VC(0, 2) + VC(-Y, 2) + VC(Z, 2) + VC(Z - Y, 2)));
+	} else {
+		o.x = (Real)(0.25 * (double)(VC(0, 0) + VC(-Z, 0) + VC(1, 0) + VC(1 - Z, 0)));
+		o.y = (Real)(0.25 * (double)(VC(0, 1) + VC(-Z, 1) + VC(Y, 1) + VC(Y - Z, 1)));
+		o.z = VC(0, 2);
+	}
+	return o;
+}
+#undef VC
+
+// ---------------------------------------------------------------- SemiLagrange / SemiLagrangeMAC (advection.cpp:25-58, orderTrace 1)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_semi_lagrange(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	int i, j, k;
+	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+	const V3<Real> c = macCentered<Real>(d, vel, idx);
+	dst[idx] = interpol<Real, 1>(d, src, (i + 0.5f) - c.x * dt, (j + 0.5f) - c.y * dt, (k + 0.5f) - c.z * dt);
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) k_semi_lagrange_mac(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	int i, j, k;
+	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+	const V3<Real> mx = macAt<Real, 0>(d, vel, idx), my = macAt<Real, 1>(d, vel, idx), mz = macAt<Real, 2>(d, vel, idx);
+	dst[3 * idx + 0] = interpol<Real, 3>(d, src + 0, (i + 0.5f) - mx.x * dt, (j + 0.5f) - mx.y * dt, (k + 0.5f) - mx.z * dt);
+	dst[3 * idx + 1] = interpol<Real, 3>(d, src + 1, (i + 0.5f) - my.x * dt, (j + 0.5f) - my.y * dt, (k + 0.5f) - my.z * dt);
+	dst[3 * idx + 2] = interpol<Real, 3>(d, src + 2, (i + 0.5f) - mz.x * dt, (j + 0.5f) - mz.y * dt, (k + 0.5f) - mz.z * dt);
+}
+
+// ---------------------------------------------------------------- MacCormack (advection.cpp:81-117 correct, :141-287 clamp)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mc_correct(Dims d, const int* __restrict__ flags, Real* __restrict__ dst, const Real* __restrict__ old,
+	const Real* __restrict__ fwd, const Real* __restrict__ bwd, Real strength) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n) return;
+	Real v = fwd[idx];
+	if (flags[idx] & TypeFluid) v = (Real)((double)v + ((double)strength * 0.5) * (double)(old[idx] - bwd[idx]));
+	dst[idx] = v;
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mc_correct_mac(Dims d, const int* __restrict__ flags, Real* __restrict__ dst, const Real* __restrict__ old,
+	const Real* __restrict__ fwd, const Real* __restrict__ bwd, Real strength) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n) return;
+	const int i = (int)(idx % d.sx), j = (int)((idx / d.sx) % d.sy), k = (int)(idx / ((IndexInt)d.sx * d.sy));
+	bool skip[3] = { false, false, false };
+	if (!(flags[idx] & TypeFluid)) skip[0] = skip[1] = skip[2] = true;
+	if (i > 0 && !(flags[idx - d.X] & TypeFluid)) skip[0] = true;
+	if (j > 0 && !(flags[idx - d.Y] & TypeFluid)) skip[1] = true;
+	if (k > 0 && !(flags[idx - d.Z] & TypeFluid)) skip[2] = true;
+	#pragma unroll
+	for (int c = 0; c < 3; c++) {
+		const IndexInt q = 3 * idx + c;
+		dst[q] = skip[c] ? fwd[q] : (Real)((double)fwd[q] + ((double)strength * 0.5) * (double)(old[q] - bwd[q]));
+	}
+}
+
+template <typename Real> __device__ __forceinline__ Real realMax();
+template <> __device__ __forceinline__ float realMax<float>() { return FLT_MAX; }
+template <> __device__ __forceinline__ double realMax<double>() { return DBL_MAX; }
+__device__ __forceinline__ int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ bool checkFlag(const int* flags, IndexInt q) { return flags[q] & (TypeFluid | TypeEmpty); }
+
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mc_clamp(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* dst, const Real* __restrict__ orig,
+	const Real* __restrict__ fwd, Real dt, int clampMode) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	int i, j, k;
+	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+	const V3<Real> c = macCentered<Real>(d, vel, idx);
+	const Real v[3] = { c.x * dt, c.y * dt, c.z * dt }, pos[3] = { (Real)i, (Real)j, (Real)k };
+	Real dval = dst[idx];
+	const Real f = fwd[idx];
+	{	// doClampComponent :141-186
+		Real minv = realMax<Real>(), maxv = -realMax<Real>();
+		bool haveFl = false;
+		const int numPos = clampMode == 1 ? 2 : 1;
+		for (int l = 0; l < numPos; l++) {
+			int cp[3];
+			#pragma unroll
+			for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
+			const int i0 = iclamp(cp[0], 0, d.sx - 2), j0 = iclamp(cp[1], 0, d.sy - 2), k0 = iclamp(cp[2], 0, d.is3D ? d.sz - 2 : 1);
+			const int k1 = d.is3D ? k0 + 1 : k0;
+			for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
+				const IndexInt q = (IndexInt)(i0 + a) + d.Y * (j0 + b) + d.Z * (cc ? k1 : k0);
+				if (checkFlag(flags, q)) { const Real o = orig[q]; if (o < minv) minv = o; if (o > maxv) maxv = o; haveFl = true; }
+			}
+		}
+		if (!haveFl) dval = f;
+		else if (clampMode == 1) dval = dval < minv ? minv : (dval > maxv ? maxv : dval);
+		else if (dval < minv || dval > maxv) dval = f;
+	}
+	if (clampMode == 1) {   // lookups that leave the grid or end in an obstacle fall back to first order (:252-264)
+		int pf[3], pb[3];
+		#pragma unroll
+		for (int a = 0; a < 3; a++) { pf[a] = (int)((pos[a] + (Real)0.5) - v[a]); pb[a] = (int)((pos[a] + (Real)0.5) + v[a]); }
+		const int ux = d.sx - 1, uy = d.sy - 1, uz = d.sz - 1;
+		bool bad = pf[0] < 0 || pf[1] < 0 || pf[2] < 0 || pb[0] < 0 || pb[1] < 0 || pb[2] < 0 ||
+		           pf[0] > ux || pf[1] > uy || ((pf[2] > uz) && d.is3D) || pb[0] > ux || pb[1] > uy || ((pb[2] > uz) && d.is3D);
+		if (!bad) bad = (flags[(IndexInt)pf[0] + d.Y * pf[1] + d.Z * pf[2]] & TypeObstacle) || (flags[(IndexInt)pb[0] + d.Y * pb[1] + d.Z * pb[2]] & TypeObstacle);
+		if (bad) dval = f;
+	}
+	dst[idx] = dval;
+}
+
+template <typename Real, int C>     // doClampComponentMAC<c> :191-235
+__device__ __forceinline__ Real clampComponentMAC(const Dims& d, const int* __restrict__ flags, Real dst, const Real* __restrict__ orig, Real fwd,
+	int i, int j, int k, IndexInt idx, V3<Real> vel, int clampMode) {
+	Real minv = realMax<Real>(), maxv = -realMax<Real>();
+	const Real pos[3] = { (Real)i, (Real)j, (Real)k }, v[3] = { vel.x, vel.y, vel.z };
+	if (clampMode == 2) {
+		const IndexInt nb = idx - (C == 0 ? d.X : (C == 1 ? d.Y : d.Z));
+		if (!(checkFlag(flags, idx) && checkFlag(flags, nb))) return fwd;
+	}
+	const int numPos = clampMode == 1 ? 2 : 1;
+	for (int l = 0; l < numPos; l++) {
+		int cp[3];
+		#pragma unroll
+		for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
+		const int i0 = iclamp(cp[0], 0, d.sx - 2), j0 = iclamp(cp[1], 0, d.sy - 2), k0 = iclamp(cp[2], 0, d.is3D ? d.sz - 2 : 0);
+		const int k1 = d.is3D ? k0 + 1 : k0;
+		for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
+			const Real o = orig[3 * ((IndexInt)(i0 + a) + d.Y * (j0 + b) + d.Z * (cc ? k1 : k0)) + C];
+			if (o < minv) minv = o;
+			if (o > maxv) maxv = o;
+		}
+	}
+	if (clampMode == 1) return dst < minv ? minv : (dst > maxv ? maxv : dst);
+	if (dst < minv || dst > maxv) dst = fwd;
+	return dst;
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mc_clamp_mac(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* dst, const Real* __restrict__ orig,
+	const Real* __restrict__ fwd, Real dt, int clampMode) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	int i, j, k;
+	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+	V3<Real> m = macAt<Real, 0>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
+	dst[3 * idx] = clampComponentMAC<Real, 0>(d, flags, dst[3 * idx], orig, fwd[3 * idx], i, j, k, idx, m, clampMode);
+	m = macAt<Real, 1>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
+	dst[3 * idx + 1] = clampComponentMAC<Real, 1>(d, flags, dst[3 * idx + 1], orig, fwd[3 * idx + 1], i, j, k, idx, m, clampMode);
+	if (d.is3D) {
+		m = macAt<Real, 2>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
+		dst[3 * idx + 2] = clampComponentMAC<Real, 2>(d, flags, dst[3 * idx + 2], orig, fwd[3 * idx + 2], i, j, k, idx, m, clampMode);
+	}
+}
+
+// ---------------------------------------------------------------- convective outflow boundary (advection.cpp:323-392)
+// writes the extrapolated velocity of the outflow cells into velDst (zero elsewhere); k_outflow_copy then moves it into vel
+template <typename Real>
+__global__ void __launch_bounds__(128) k_outflow_extrapolate(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ velDst,
+	const Real* __restrict__ velPrev, Real timeStep) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n || !(flags[idx] & TypeOutflow)) return;
+	const int i = (int)(idx % d.sx), j = (int)((idx / d.sx) % d.sy), k = (int)(idx / ((IndexInt)d.sx * d.sy));
+	Real avg[3] = { 0, 0, 0 }; int count = 0;
+	const int nmax = d.is3D ? 1 : 0;
+	for (int nn = -nmax; nn <= nmax; nn++) for (int m = -1; m <= 1; m++) for (int l = -1; l <= 1; l++) {
+		const int a = i + l, b = j + m, c = k + nn;
+		if (a < 0 || b < 0 || c < 0 || a >= d.sx || b >= d.sy || c >= d.sz) continue;
+		const IndexInt q = (IndexInt)a + d.Y * b + d.Z * c;
+		if (flags[q] & (TypeFluid | TypeOutflow)) { avg[0] += vel[3 * q]; avg[1] += vel[3 * q + 1]; avg[2] += vel[3 * q + 2]; count++; }
+	}
+	if (count > 0) { avg[0] = avg[0] / (Real)count; avg[1] = avg[1] / (Real)count; avg[2] = avg[2] / (Real)count; }
+	const int cur[3] = { i, j, k }, size[3] = { d.sx, d.sy, d.sz };
+	const IndexInt stride[3] = { d.X, d.Y, d.Z };
+	const Real v0 = vel[3 * idx], v1 = vel[3 * idx + 1], v2 = vel[3 * idx + 2];
+	const Real p0 = velPrev[3 * idx], p1 = velPrev[3 * idx + 1], p2 = velPrev[3 * idx + 2];
+	Real o0 = 0, o1 = 0, o2 = 0;
+	int cnt = 0;
+	const int dim = d.is3D ? 3 : 2;
+	for (int c = 0; c < dim; c++) {
+		const Real factor = timeStep * ((Real)1.0 > avg[c] ? (Real)1.0 : avg[c]);
+		int lo = cur[c] - 1, up = cur[c] + 1;
+		for (int dd = 0; dd < 2; dd++) {
+			const bool fromLower = lo >= 0 && lo < size[c] && (flags[idx + (IndexInt)(lo - cur[c]) * stride[c]] & TypeFluid);
+			const bool fromUpper = up >= 0 && up < size[c] && (flags[idx + (IndexInt)(up - cur[c]) * stride[c]] & TypeFluid);
+			if (fromLower || fromUpper) {
+				if (fromLower) { const IndexInt q = idx - stride[c];      // the value is always taken from the DIRECT neighbour (:367 uses `low`, not `flLow`)
+					o0 += ((v0 - p0) / factor) + vel[3 * q]; o1 += ((v1 - p1) / factor) + vel[3 * q + 1]; o2 += ((v2 - p2) / factor) + vel[3 * q + 2]; cnt++; }
+				if (fromUpper) { const IndexInt q = idx + stride[c];
+					o0 += ((v0 - p0) / factor) + vel[3 * q]; o1 += ((v1 - p1) / factor) + vel[3 * q + 1]; o2 += ((v2 - p2) / factor) + vel[3 * q + 2]; cnt++; }
+				break;
+			}
+			lo--; up++;
+		}
+	}
+	if (cnt > 0) { o0 /= (Real)cnt; o1 /= (Real)cnt; o2 /= (Real)cnt; }
+	velDst[3 * idx] = o0; velDst[3 * idx + 1] = o1; velDst[3 * idx + 2] = o2;
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) k_outflow_copy(Dims d, const int* __restrict__ flags, const Real* __restrict__ velDst, Real* __restrict__ vel) {
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n || !(flags[idx] & TypeOutflow)) return;
+	vel[3 * idx] = velDst[3 * idx]; vel[3 * idx + 1] = velDst[3 * idx + 1]; vel[3 * idx + 2] = velDst[3 * idx + 2];
+}
+
+struct Tmp {      // scratch grid of the context's pool, released on scope exit
+	mp_grid* g = nullptr;
+	~Tmp() { if (g) mp_grid_destroy(g); }
+};
+
+template <typename Real>
+int applyOutflowBC(mp_context* ctx, const Dims& d, const mp_grid* flags, mp_grid* vel, const mp_grid* velPrev, double dt) {
+	Tmp t; MP_TRY(mp_grid_create(ctx, MP_GRID_MAC, vel->prec, vel->sx, vel->sy, vel->sz, &t.g));     // zero-initialised, like the reference's velDst
+	const double ts = 1.0 > dt * 4 ? 1.0 : dt * 4;
+	k_outflow_extrapolate<Real><<<gridFor(d.n, 128), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (const Real*)vel->d, (Real*)t.g->d, (const Real*)velPrev->d, (Real)ts); MP_CHECK_LAUNCH(ctx);
+	k_outflow_copy<Real><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (const Real*)t.g->d, (Real*)vel->d); MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+// result grid `neu` becomes the content of `grid` (the reference swaps the data pointers, grid.cpp:99-110)
+int adopt(mp_context* ctx, mp_grid* grid, mp_grid* neu) {
+	if (grid->owns && neu->owns) { void* p = grid->d; grid->d = neu->d; neu->d = p; return MP_OK; }
+	MP_CUDA(cudaMemcpyAsync(grid->d, neu->d, grid->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	return MP_OK;
+}
+
+template <typename Real>
+int advect(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int clampMode, double dt_) {
+	const Dims d = dimsOf(flags);
+	const bool mac = grid->kind == MP_GRID_MAC;
+	const Real dt = (Real)dt_;
+	const unsigned int blocks = gridFor(d.n, 256);
+	const int* F = (const int*)flags->d; const Real* V = (const Real*)vel->d;
+	Tmp fwd; MP_TRY(mp_grid_create(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &fwd.g));     // zero: the outer layer of the result stays 0
+	if (mac) k_semi_lagrange_mac<Real><<<blocks, 256, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	else     k_semi_lagrange<Real><<<blocks, 256, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	MP_CHECK_LAUNCH(ctx);
+	if (order == 1) {
+		if (mac) MP_TRY(applyOutflowBC<Real>(ctx, d, flags, fwd.g, grid, (double)dt));
+		return adopt(ctx, grid, fwd.g);
+	}
+	Tmp bwd, neu;
+	MP_TRY(mp_grid_create(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &bwd.g));
+	MP_TRY(mp_grid_create(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &neu.g));
+	if (mac) {
+		k_semi_lagrange_mac<Real><<<blocks, 256, 0, ctx->stream>>>(d, V, (Real*)bwd.g->d, (const Real*)fwd.g->d, -dt); MP_CHECK_LAUNCH(ctx);
+		k_mc_correct_mac<Real><<<blocks, 256, 0, ctx->stream>>>(d, F, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, (const Real*)bwd.g->d, (Real)strength); MP_CHECK_LAUNCH(ctx);
+		k_mc_clamp_mac<Real><<<blocks, 256, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, clampMode); MP_CHECK_LAUNCH(ctx);
+		MP_TRY(applyOutflowBC<Real>(ctx, d, flags, neu.g, grid, (double)dt));
+	} else {
+		k_semi_lagrange<Real><<<blocks, 256, 0, ctx->stream>>>(d, V, (Real*)bwd.g->d, (const Real*)fwd.g->d, -dt); MP_CHECK_LAUNCH(ctx);
+		k_mc_correct<Real><<<blocks, 256, 0, ctx->stream>>>(d, F, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, (const Real*)bwd.g->d, (Real)strength); MP_CHECK_LAUNCH(ctx);
+		k_mc_clamp<Real><<<blocks, 256, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, clampMode); MP_CHECK_LAUNCH(ctx);
+	}
+	return adopt(ctx, grid, neu.g);
+}
+
+int checkStep(const char* who, mp_context* ctx, const mp_grid* flags, const mp_grid* vel) {
+	if (!ctx || !flags || !vel) MP_FAIL(MP_ERR_INVALID, "%s: NULL argument", who);
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "%s: flags is not a FlagGrid", who);
+	MP_TRY(mp_check_same(flags, vel, MP_GRID_MAC, "vel", false));
+	if (ctx->dist && ctx->dist->active) MP_FAIL(MP_ERR_UNSUPPORTED, "%s: not available on z-slab sharded grids yet", who);
+	MP_CUDA(cudaSetDevice(ctx->device));
+	return MP_OK;
+}
+static inline int imax3(int a, int b, int c) { const int m = a > b ? a : b; return m > c ? m : c; }
+
+}  // namespace
+
+extern "C" {
+
+int mp_set_wall_bcs(mp_context* ctx, const mp_grid* flags, mp_grid* vel, const mp_grid* obvel, const mp_grid* fractions, const mp_grid* phiObs, int boundaryWidth)
+{
+	MP_TRY(checkStep("mp_set_wall_bcs", ctx, flags, vel));
+	(void)boundaryWidth;
+	if (phiObs && fractions) MP_FAIL(MP_ERR_UNSUPPORTED, "setWallBcs: the second-order variant (phiObs + fractions, KnSetWallBcsFrac) is not built");
+	if (obvel) MP_TRY(mp_check_same(vel, obvel, MP_GRID_MAC, "obvel", false));
+	const Dims d = dimsOf(flags);
+	if (vel->prec == 4) k_set_wall_bcs<float><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, obvel ? (const float*)obvel->d : nullptr);
+	else                k_set_wall_bcs<double><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, obvel ? (const double*)obvel->d : nullptr);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+int mp_add_gravity(mp_context* ctx, const mp_grid* flags, mp_grid* vel, double gx, double gy, double gz, const mp_grid* exclude, int scale, double dt)
+{
+	MP_TRY(checkStep("mp_add_gravity", ctx, flags, vel));
+	if (exclude) MP_TRY(mp_check_same(flags, exclude, MP_GRID_REAL, "exclude", false));
+	const Dims d = dimsOf(flags);
+	const double g[3] = { gx, gy, gz };
+	if (vel->prec == 4) {
+		const float gridScale = scale ? (float)(float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; float f[3];
+		for (int c = 0; c < 3; c++) f[c] = ((float)g[c] * (float)dt) / gridScale;
+		k_apply_force<float><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, f[0], f[1], f[2], exclude ? (const float*)exclude->d : nullptr);
+	} else {
+		const float gridScale = scale ? (float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; double f[3];
+		for (int c = 0; c < 3; c++) f[c] = (g[c] * dt) / gridScale;
+		k_apply_force<double><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, f[0], f[1], f[2], exclude ? (const double*)exclude->d : nullptr);
+	}
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* density, mp_grid* vel, double gx, double gy, double gz, double coefficient, int scale, double dt)
+{
+	MP_TRY(checkStep("mp_add_buoyancy", ctx, flags, vel));
+	if (!density) MP_FAIL(MP_ERR_INVALID, "mp_add_buoyancy: NULL density");
+	MP_TRY(mp_check_same(flags, density, MP_GRID_REAL, "density", false));
+	const Dims d = dimsOf(flags);
+	const double g[3] = { gx, gy, gz };
+	if (vel->prec == 4) {
+		const float gridScale = scale ? (float)(float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; float f[3];
+		for (int c = 0; c < 3; c++) f[c] = (((-(float)g[c]) * (float)dt) / gridScale) * (float)coefficient;
+		k_add_buoyancy<float><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (const float*)density->d, (float*)vel->d, f[0], f[1], f[2]);
+	} else {
+		const float gridScale = scale ? (float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; double f[3];
+		for (int c = 0; c < 3; c++) f[c] = (((-g[c]) * dt) / gridScale) * coefficient;
+		k_add_buoyancy<double><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (const double*)density->d, (double*)vel->d, f[0], f[1], f[2]);
+	}
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
+int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
+                            int clampMode, int orderTrace, double dt)
+{
+	MP_TRY(checkStep("mp_advect_semi_lagrange", ctx, flags, vel));
+	if (!grid) MP_FAIL(MP_ERR_INVALID, "mp_advect_semi_lagrange: NULL grid");
+	if (order != 1 && order != 2) MP_FAIL(MP_ERR_INVALID, "AdvectSemiLagrange: Only order 1 (regular SL) and 2 (MacCormack) supported");
+	if (orderSpace != 1 || orderTrace != 1) MP_FAIL(MP_ERR_UNSUPPORTED, "advectSemiLagrange: orderSpace %d / orderTrace %d are not built (only 1 / 1, the defaults)", orderSpace, orderTrace);
+	if (grid->kind != MP_GRID_REAL && grid->kind != MP_GRID_MAC) MP_FAIL(MP_ERR_INVALID, "AdvectSemiLagrange: Grid Type is not supported (only Real, MAC, Levelset)");
+	MP_TRY(mp_check_same(flags, grid, grid->kind, "grid", false));
+	if (flags->sx < 3 || flags->sy < 3 || (flags->sz > 1 && flags->sz < 3)) return MP_OK;       // no interior cells
+	if (grid->prec == 4) return advect<float>(ctx, flags, vel, grid, order, strength, clampMode, dt);
+	return advect<double>(ctx, flags, vel, grid, order, strength, clampMode, dt);
+}
+
+}

@@ -1091,3 +1091,355 @@ int mfo_solve_pressure(long long solver_key, int sx, int sy, int sz, const int* 
 	free(rhs); free(A0); free(Ai); free(Aj); free(Ak);
 	return rc;
 }
+
+/* =============================================================================================
+ * The steps either side of the projection: wall boundary conditions with obstacle velocity,
+ * gravity / buoyancy, semi-Lagrangian and MacCormack advection.  Same mixed float/double evaluation as the
+ * reference (double literals promote, results narrow on assignment).
+ * ============================================================================================= */
+
+/* setWallBcs with obvel: plugin/extforces.cpp:186-218 */
+int mfo_set_wall_bcs_obvel(int sx, int sy, int sz, const int* flags, Real* vel, const Real* obvel)
+{
+	STRIDES
+	if (!obvel) return mfo_set_wall_bcs(sx, sy, sz, flags, vel);
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		const int curFluid = flags[idx] & TypeFluid, curObs = flags[idx] & TypeObstacle;
+		if (!curFluid && !curObs) continue;
+		Real* v = vel + 3 * idx;
+		const Real bx = obvel[3 * idx], by = obvel[3 * idx + 1], bz = IS3D ? obvel[3 * idx + 2] : (Real)0;
+		if (i > 0 && (flags[idx - X] & TypeObstacle)) v[0] = bx;
+		if (i > 0 && curObs && (flags[idx - X] & TypeFluid)) v[0] = bx;
+		if (j > 0 && (flags[idx - Y] & TypeObstacle)) v[1] = by;
+		if (j > 0 && curObs && (flags[idx - Y] & TypeFluid)) v[1] = by;
+		if (!IS3D) { v[2] = 0; } else {
+			if (k > 0 && (flags[idx - Z] & TypeObstacle)) v[2] = bz;
+			if (k > 0 && curObs && (flags[idx - Z] & TypeFluid)) v[2] = bz;
+		}
+		if (curFluid) {
+			if ((i > 0 && (flags[idx - X] & TypeStick)) || (i < sx - 1 && (flags[idx + X] & TypeStick))) v[1] = v[2] = 0;
+			if ((j > 0 && (flags[idx - Y] & TypeStick)) || (j < sy - 1 && (flags[idx + Y] & TypeStick))) v[0] = v[2] = 0;
+			if (IS3D && ((k > 0 && (flags[idx - Z] & TypeStick)) || (k < sz - 1 && (flags[idx + Z] & TypeStick)))) v[0] = v[1] = 0;
+		}
+	}
+	return 0;
+}
+
+/* interior loop of a KERNEL(bnd=1): 2-D grids run k = 0 only */
+#define FOR_BND1 const int k0_ = IS3D ? 1 : 0, k1_ = IS3D ? sz - 1 : 1; \
+	for (int k = k0_; k < k1_; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++)
+
+static inline int imax3(int a, int b, int c) { int m = a > b ? a : b; return m > c ? m : c; }
+
+/* addGravity: extforces.cpp:61-65 (force vector), KnApplyForce :45-58 with additive = true */
+int mfo_add_gravity(int sx, int sy, int sz, const int* flags, Real* vel, double gx, double gy, double gz, const Real* exclude, int scale, double dt_)
+{
+	STRIDES
+	const Real dt = (Real)dt_, dx = (Real)(1.0 / imax3(sx, sy, sz));       /* grid.cpp:56 mDx */
+	const float gridScale = scale ? (float)dx : 1;
+	const Real g[3] = { (Real)gx, (Real)gy, (Real)gz };
+	Real f[3];
+	for (int c = 0; c < 3; c++) f[c] = (g[c] * dt) / gridScale;
+	FOR_BND1 {
+		const IndexInt idx = IDX(i, j, k);
+		const int curFluid = flags[idx] & TypeFluid, curEmpty = flags[idx] & TypeEmpty;
+		if (!curFluid && !curEmpty) continue;
+		if (exclude && (exclude[idx] < 0.)) continue;
+		Real* v = vel + 3 * idx;
+		if ((flags[idx - X] & TypeFluid) || (curFluid && (flags[idx - X] & TypeEmpty))) v[0] = v[0] + f[0];
+		if ((flags[idx - Y] & TypeFluid) || (curFluid && (flags[idx - Y] & TypeEmpty))) v[1] = v[1] + f[1];
+		if (IS3D && ((flags[idx - Z] & TypeFluid) || (curFluid && (flags[idx - Z] & TypeEmpty)))) v[2] = v[2] + f[2];
+	}
+	return 0;
+}
+
+/* addBuoyancy: extforces.cpp:86-90, KnAddBuoyancy :75-83 */
+int mfo_add_buoyancy(int sx, int sy, int sz, const int* flags, const Real* density, Real* vel, double gx, double gy, double gz,
+                     double coefficient, int scale, double dt_)
+{
+	STRIDES
+	const Real dt = (Real)dt_, dx = (Real)(1.0 / imax3(sx, sy, sz)), coef = (Real)coefficient;
+	const float gridScale = scale ? (float)dx : 1;
+	const Real g[3] = { (Real)gx, (Real)gy, (Real)gz };
+	Real f[3];
+	for (int c = 0; c < 3; c++) f[c] = (((-g[c]) * dt) / gridScale) * coef;
+	FOR_BND1 {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		Real* v = vel + 3 * idx;
+		if (flags[idx - X] & TypeFluid) v[0] = (Real)((double)v[0] + (0.5 * (double)f[0]) * (double)(density[idx] + density[idx - X]));
+		if (flags[idx - Y] & TypeFluid) v[1] = (Real)((double)v[1] + (0.5 * (double)f[1]) * (double)(density[idx] + density[idx - Y]));
+		if (IS3D && (flags[idx - Z] & TypeFluid)) v[2] = (Real)((double)v[2] + (0.5 * (double)f[2]) * (double)(density[idx] + density[idx - Z]));
+	}
+	return 0;
+}
+
+/* ---- interpolation: util/interpol.h:50-91 (BUILD_INDEX, interpol, interpolComponent) */
+typedef struct { IndexInt idx; Real s0, s1, t0, t1, f0, f1; } Interp;
+static inline Interp build_index(int sx, int sy, int sz, const Real pos[3])
+{
+	const IndexInt SZ = (sz > 1) ? (IndexInt)sx * sy : 0;
+	Interp o;
+	const Real px = pos[0] - 0.5f, py = pos[1] - 0.5f, pz = pos[2] - 0.5f;
+	int xi = (int)px, yi = (int)py, zi = (int)pz;
+	o.s1 = px - (Real)xi; o.s0 = (Real)(1. - o.s1);
+	o.t1 = py - (Real)yi; o.t0 = (Real)(1. - o.t1);
+	o.f1 = pz - (Real)zi; o.f0 = (Real)(1. - o.f1);
+	if (px < 0.) { xi = 0; o.s0 = 1.0; o.s1 = 0.0; }
+	if (py < 0.) { yi = 0; o.t0 = 1.0; o.t1 = 0.0; }
+	if (pz < 0.) { zi = 0; o.f0 = 1.0; o.f1 = 0.0; }
+	if (xi >= sx - 1) { xi = sx - 2; o.s0 = 0.0; o.s1 = 1.0; }
+	if (yi >= sy - 1) { yi = sy - 2; o.t0 = 0.0; o.t1 = 1.0; }
+	if (sz > 1) { if (zi >= sz - 1) { zi = sz - 2; o.f0 = 0.0; o.f1 = 1.0; } }
+	o.idx = (IndexInt)xi + (IndexInt)sx * yi + SZ * zi;
+	return o;
+}
+/* stride = 1 for Grid<Real>, 3 (+ component offset in d) for one component of a Vec3 grid */
+static inline Real interpol_s(const Real* d, int stride, int sx, int sy, int sz, const Real pos[3])
+{
+	const IndexInt X = stride, Y = (IndexInt)sx * stride, Z = (sz > 1) ? (IndexInt)sx * sy * stride : 0;
+	const Interp q = build_index(sx, sy, sz, pos);
+	const Real* p = d + q.idx * stride;
+	return ((p[0] * q.t0 + p[Y] * q.t1) * q.s0 + (p[X] * q.t0 + p[X + Y] * q.t1) * q.s1) * q.f0
+	     + ((p[Z] * q.t0 + p[Y + Z] * q.t1) * q.s0 + (p[X + Z] * q.t0 + p[X + Y + Z] * q.t1) * q.s1) * q.f1;
+}
+
+/* ---- MAC accessors: grid.h:424-466 */
+static inline void mac_centered(const Real* v, int sx, int sy, int sz, IndexInt idx, Real out[3])
+{
+	const IndexInt Y = sx, Z = (sz > 1) ? (IndexInt)sx * sy : 0;
+	out[0] = (Real)(0.5 * (double)(v[3 * idx] + v[3 * (idx + 1)]));
+	out[1] = (Real)(0.5 * (double)(v[3 * idx + 1] + v[3 * (idx + Y) + 1]));
+	out[2] = 0;
+	if (sz > 1) out[2] = (Real)(0.5 * (double)(v[3 * idx + 2] + v[3 * (idx + Z) + 2]));
+}
+static inline void mac_at(const Real* v, int sx, int sy, int sz, IndexInt idx, int c, Real out[3])
+{
+	const IndexInt Y = sx, Z = (sz > 1) ? (IndexInt)sx * sy : 0;
+#define Vc(o, cc) v[3 * (idx + (o)) + (cc)]
+	if (c == 0) {
+		out[0] = Vc(0, 0);
+		out[1] = (Real)(0.25 * (double)(Vc(0, 1) + Vc(-1, 1) + Vc(Y, 1) + Vc(Y - 1, 1)));
+		out[2] = 0;
+		if (sz > 1) out[2] = (Real)(0.25 * (double)(Vc(0, 2) + Vc(-1, 2) + Vc(Z, 2) + Vc(Z - 1, 2)));
+	} else if (c == 1) {
+		out[0] = (Real)(0.25 * (double)(Vc(0, 0) + Vc(-Y, 0) + Vc(1, 0) + Vc(1 - Y, 0)));
+		out[1] = Vc(0, 1);
+		out[2] = 0;
+		if (sz > 1) out[2] = (Real)(0.25 * (double)(Vc(0, 2) + Vc(-Y, 2) + Vc(Z, 2) + Vc(Z - Y, 2)));
+	} else {
+		out[0] = (Real)(0.25 * (double)(Vc(0, 0) + Vc(-Z, 0) + Vc(1, 0) + Vc(1 - Z, 0)));
+		out[1] = (Real)(0.25 * (double)(Vc(0, 1) + Vc(-Z, 1) + Vc(Y, 1) + Vc(Y - Z, 1)));
+		out[2] = Vc(0, 2);
+	}
+#undef Vc
+}
+
+/* SemiLagrange (advection.cpp:25-41, orderTrace 1) and SemiLagrangeMAC (:44-58): dst interior only, rest stays as it was */
+static void semi_lagrange_real(int sx, int sy, int sz, const Real* vel, Real* dst, const Real* src, Real dt)
+{
+	STRIDES
+	FOR_BND1 {
+		const IndexInt idx = IDX(i, j, k);
+		Real c[3]; mac_centered(vel, sx, sy, sz, idx, c);
+		const Real pos[3] = { (i + 0.5f) - c[0] * dt, (j + 0.5f) - c[1] * dt, (k + 0.5f) - c[2] * dt };
+		dst[idx] = interpol_s(src, 1, sx, sy, sz, pos);
+	}
+}
+static void semi_lagrange_mac(int sx, int sy, int sz, const Real* vel, Real* dst, const Real* src, Real dt)
+{
+	STRIDES
+	FOR_BND1 {
+		const IndexInt idx = IDX(i, j, k);
+		for (int c = 0; c < 3; c++) {
+			Real m[3]; mac_at(vel, sx, sy, sz, idx, c, m);      /* getAtMACZ is evaluated in 2-D too (:53); its z stride is 0 there */
+			const Real pos[3] = { (i + 0.5f) - m[0] * dt, (j + 0.5f) - m[1] * dt, (k + 0.5f) - m[2] * dt };
+			dst[3 * idx + c] = interpol_s(src + c, 3, sx, sy, sz, pos);
+		}
+	}
+}
+
+static inline int check_flag(const int* flags, IndexInt idx) { return flags[idx] & (TypeFluid | TypeEmpty); }
+static inline int iclamp(int v, int lo, int hi) { if (v < lo) return lo; if (v > hi) return hi; return v; }
+#define REAL_MAX_ (sizeof(Real) == 4 ? (Real)3.402823466e+38F : (Real)1.7976931348623157e+308)
+
+/* doClampComponent: advection.cpp:141-186 */
+static Real clamp_component(int sx, int sy, int sz, const int* flags, Real dst, const Real* orig, Real fwd, const Real pos[3], const Real vel[3], int clampMode)
+{
+	STRIDES
+	Real minv = REAL_MAX_, maxv = -REAL_MAX_;
+	int haveFl = 0;
+	const int numPos = clampMode == 1 ? 2 : 1;
+	for (int l = 0; l < numPos; l++) {
+		int cp[3];
+		for (int c = 0; c < 3; c++) cp[c] = (int)(l == 0 ? pos[c] - vel[c] : pos[c] + vel[c]);
+		const int i0 = iclamp(cp[0], 0, sx - 2), j0 = iclamp(cp[1], 0, sy - 2), k0 = iclamp(cp[2], 0, IS3D ? sz - 2 : 1);
+		const int i1 = i0 + 1, j1 = j0 + 1, k1 = IS3D ? k0 + 1 : k0;
+		const int ii[2] = { i0, i1 }, jj[2] = { j0, j1 }, kk[2] = { k0, k1 };
+		for (int c = 0; c < (IS3D ? 2 : 1); c++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
+			const IndexInt q = IDX(ii[a], jj[b], kk[c]);
+			if (check_flag(flags, q)) { if (orig[q] < minv) minv = orig[q]; if (orig[q] > maxv) maxv = orig[q]; haveFl = 1; }
+		}
+	}
+	if (!haveFl) return fwd;
+	if (clampMode == 1) { if (dst < minv) return minv; if (dst > maxv) return maxv; return dst; }
+	if (dst < minv || dst > maxv) dst = fwd;
+	return dst;
+}
+/* doClampComponentMAC<c>: advection.cpp:191-235 */
+static Real clamp_component_mac(int sx, int sy, int sz, const int* flags, int c, Real dst, const Real* orig, Real fwd, int i, int j, int k, const Real vel[3], int clampMode)
+{
+	STRIDES
+	Real minv = REAL_MAX_, maxv = -REAL_MAX_;
+	const Real pos[3] = { (Real)i, (Real)j, (Real)k };
+	const int numPos = clampMode == 1 ? 2 : 1;
+	if (clampMode == 2) {
+		int nb[3] = { i, j, k }; nb[c] -= 1;
+		if (!(check_flag(flags, IDX(i, j, k)) && check_flag(flags, IDX(nb[0], nb[1], nb[2])))) return fwd;
+	}
+	for (int l = 0; l < numPos; l++) {
+		int cp[3];
+		for (int d = 0; d < 3; d++) cp[d] = (int)(l == 0 ? pos[d] - vel[d] : pos[d] + vel[d]);
+		const int i0 = iclamp(cp[0], 0, sx - 2), j0 = iclamp(cp[1], 0, sy - 2), k0 = iclamp(cp[2], 0, IS3D ? sz - 2 : 0);
+		const int i1 = i0 + 1, j1 = j0 + 1, k1 = IS3D ? k0 + 1 : k0;
+		const int ii[2] = { i0, i1 }, jj[2] = { j0, j1 }, kk[2] = { k0, k1 };
+		for (int cc = 0; cc < (IS3D ? 2 : 1); cc++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
+			const Real o = orig[3 * IDX(ii[a], jj[b], kk[cc]) + c];
+			if (o < minv) minv = o;
+			if (o > maxv) maxv = o;
+		}
+	}
+	if (clampMode == 1) { if (dst < minv) return minv; if (dst > maxv) return maxv; return dst; }
+	if (dst < minv || dst > maxv) dst = fwd;
+	return dst;
+}
+
+/* applyOutflowBC: advection.cpp:323-392 (getBulkVel, extrapolateVelConvectiveBC, copyChangedVels) */
+static void apply_outflow_bc(int sx, int sy, int sz, const int* flags, Real* vel, const Real* velPrev, double dt)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	const double ts_d = 1.0 > dt * 4 ? 1.0 : dt * 4;
+	const Real timeStep = (Real)ts_d;
+	Real* velDst = (Real*)calloc((size_t)n * 3, sizeof(Real));
+	const int dim = IS3D ? 3 : 2, nmax = IS3D ? 1 : 0;
+	const int size[3] = { sx, sy, sz };
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeOutflow)) continue;
+		Real avg[3] = { 0, 0, 0 }; int count = 0;
+		for (int nn = -nmax; nn <= nmax; nn++) for (int m = -1; m <= 1; m++) for (int l = -1; l <= 1; l++) {
+			const int a = i + l, b = j + m, c = k + nn;
+			if (a < 0 || b < 0 || c < 0 || a >= sx || b >= sy || c >= sz) continue;
+			const IndexInt q = IDX(a, b, c);
+			if (flags[q] & (TypeFluid | TypeOutflow)) { for (int d = 0; d < 3; d++) avg[d] += vel[3 * q + d]; count++; }
+		}
+		if (count > 0) for (int d = 0; d < 3; d++) avg[d] = avg[d] / (Real)count;
+		const int cur[3] = { i, j, k };
+		int cnt = 0;
+		Real* vd = velDst + 3 * idx;
+		for (int c = 0; c < dim; c++) {
+			int low[3] = { i, j, k }, up[3] = { i, j, k }, flLow[3] = { i, j, k }, flUp[3] = { i, j, k };
+			const Real factor = timeStep * ((Real)1.0 > avg[c] ? (Real)1.0 : avg[c]);
+			low[c] = flLow[c] = cur[c] - 1;
+			up[c] = flUp[c] = cur[c] + 1;
+			for (int d = 0; d < 2; d++) {
+				const int inLo = flLow[c] >= 0 && flLow[c] < size[c], inUp = flUp[c] >= 0 && flUp[c] < size[c];
+				const int fromLower = inLo && (flags[IDX(flLow[0], flLow[1], flLow[2])] & TypeFluid);
+				const int fromUpper = inUp && (flags[IDX(flUp[0], flUp[1], flUp[2])] & TypeFluid);
+				if (fromLower || fromUpper) {
+					if (fromLower) { const IndexInt q = IDX(low[0], low[1], low[2]);
+						for (int e = 0; e < 3; e++) vd[e] += ((vel[3 * idx + e] - velPrev[3 * idx + e]) / factor) + vel[3 * q + e];
+						cnt++; }
+					if (fromUpper) { const IndexInt q = IDX(up[0], up[1], up[2]);
+						for (int e = 0; e < 3; e++) vd[e] += ((vel[3 * idx + e] - velPrev[3 * idx + e]) / factor) + vel[3 * q + e];
+						cnt++; }
+					break;
+				}
+				flLow[c]--; flUp[c]++;
+			}
+		}
+		if (cnt > 0) for (int e = 0; e < 3; e++) vd[e] /= (Real)cnt;
+	}
+	for (IndexInt idx = 0; idx < n; idx++) if (flags[idx] & TypeOutflow) for (int e = 0; e < 3; e++) vel[3 * idx + e] = velDst[3 * idx + e];
+	free(velDst);
+}
+
+/* advectSemiLagrange: advection.cpp:442-461, fnAdvectSemiLagrange :289-316 (Real) and :404-434 (MAC).
+ * kind 0: Grid<Real> (density, level set), 1: MACGrid.  orderSpace 1 and orderTrace 1 only (the defaults). */
+int mfo_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Real* vel, Real* grid, int kind,
+                             int order, double strength_, int orderSpace, int clampMode, int orderTrace, double dt_)
+{
+	STRIDES
+	if (order != 1 && order != 2) { snprintf(g_err, sizeof g_err, "AdvectSemiLagrange: Only order 1 (regular SL) and 2 (MacCormack) supported"); return 1; }
+	if (orderSpace != 1 || orderTrace != 1) { snprintf(g_err, sizeof g_err, "oracle: only orderSpace 1 / orderTrace 1 are restated"); return 1; }
+	if (kind != 0 && kind != 1) { snprintf(g_err, sizeof g_err, "oracle: grid kind %d not restated", kind); return 1; }
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	const int nc = kind == 0 ? 1 : 3;
+	const Real dt = (Real)dt_, strength = (Real)strength_;
+	Real* fwd = (Real*)calloc((size_t)n * nc, sizeof(Real));
+	if (kind == 0) semi_lagrange_real(sx, sy, sz, vel, fwd, grid, dt); else semi_lagrange_mac(sx, sy, sz, vel, fwd, grid, dt);
+	if (order == 1) {
+		if (kind == 1) apply_outflow_bc(sx, sy, sz, flags, fwd, grid, (double)dt);
+		memcpy(grid, fwd, sizeof(Real) * (size_t)n * nc);
+		free(fwd);
+		return 0;
+	}
+	Real* bwd = (Real*)calloc((size_t)n * nc, sizeof(Real));
+	Real* neu = (Real*)calloc((size_t)n * nc, sizeof(Real));
+	if (kind == 0) semi_lagrange_real(sx, sy, sz, vel, bwd, fwd, -dt); else semi_lagrange_mac(sx, sy, sz, vel, bwd, fwd, -dt);
+	const double half = (double)strength * 0.5;
+	if (kind == 0) {
+		/* MacCormackCorrect :81-91 (all cells) */
+		for (IndexInt idx = 0; idx < n; idx++) {
+			neu[idx] = fwd[idx];
+			if (flags[idx] & TypeFluid) neu[idx] = (Real)((double)neu[idx] + half * (double)(grid[idx] - bwd[idx]));
+		}
+		/* MacCormackClamp :241-267 */
+		FOR_BND1 {
+			const IndexInt idx = IDX(i, j, k);
+			Real c[3]; mac_centered(vel, sx, sy, sz, idx, c);
+			const Real v[3] = { c[0] * dt, c[1] * dt, c[2] * dt };
+			const Real pos[3] = { (Real)i, (Real)j, (Real)k };
+			Real dval = clamp_component(sx, sy, sz, flags, neu[idx], grid, fwd[idx], pos, v, clampMode);
+			if (clampMode == 1) {
+				int pf[3], pb[3];
+				for (int d = 0; d < 3; d++) { pf[d] = (int)((pos[d] + (Real)0.5) - v[d]); pb[d] = (int)((pos[d] + (Real)0.5) + v[d]); }
+				const int ux = sx - 1, uy = sy - 1, uz = sz - 1;
+				int bad = pf[0] < 0 || pf[1] < 0 || pf[2] < 0 || pb[0] < 0 || pb[1] < 0 || pb[2] < 0 ||
+				          pf[0] > ux || pf[1] > uy || ((pf[2] > uz) && IS3D) || pb[0] > ux || pb[1] > uy || ((pb[2] > uz) && IS3D);
+				if (!bad) bad = (flags[IDX(pf[0], pf[1], pf[2])] & TypeObstacle) || (flags[IDX(pb[0], pb[1], pb[2])] & TypeObstacle);
+				if (bad) dval = fwd[idx];
+			}
+			neu[idx] = dval;
+		}
+	} else {
+		/* MacCormackCorrectMAC :94-117 (all cells, isMAC) */
+		for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+			const IndexInt idx = IDX(i, j, k);
+			int skip[3] = { 0, 0, 0 };
+			if (!(flags[idx] & TypeFluid)) skip[0] = skip[1] = skip[2] = 1;
+			if (i > 0 && !(flags[idx - X] & TypeFluid)) skip[0] = 1;
+			if (j > 0 && !(flags[idx - Y] & TypeFluid)) skip[1] = 1;
+			if (k > 0 && !(flags[idx - Z] & TypeFluid)) skip[2] = 1;
+			for (int c = 0; c < 3; c++) {
+				const IndexInt q = 3 * idx + c;
+				neu[q] = skip[c] ? fwd[q] : (Real)((double)fwd[q] + half * (double)(grid[q] - bwd[q]));
+			}
+		}
+		/* MacCormackClampMAC :270-287 */
+		FOR_BND1 {
+			const IndexInt idx = IDX(i, j, k);
+			for (int c = 0; c < (IS3D ? 3 : 2); c++) {
+				Real m[3]; mac_at(vel, sx, sy, sz, idx, c, m);
+				const Real v[3] = { m[0] * dt, m[1] * dt, m[2] * dt };
+				neu[3 * idx + c] = clamp_component_mac(sx, sy, sz, flags, c, neu[3 * idx + c], grid, fwd[3 * idx + c], i, j, k, v, clampMode);
+			}
+		}
+		apply_outflow_bc(sx, sy, sz, flags, neu, grid, (double)dt);
+	}
+	memcpy(grid, neu, sizeof(Real) * (size_t)n * nc);
+	free(fwd); free(bwd); free(neu);
+	return 0;
+}

@@ -77,6 +77,32 @@ class Oracle:
         self._chk(self._f("set_wall_bcs")(*self.dims(flags), _p(flags), _p(vel)))
         return vel
 
+    # -- the steps either side of the projection: arrays are updated in place and returned --
+    def set_wall_bcs_obvel(self, flags, vel, obvel=None):
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        self._chk(self._f("set_wall_bcs_obvel")(*self.dims(flags), _p(flags), _p(vel), _p(self._r(obvel))))
+        return vel
+
+    def add_gravity(self, flags, vel, gravity, exclude=None, scale=True, dt=1.0):
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        self._chk(self._f("add_gravity")(*self.dims(flags), _p(flags), _p(vel), *[C.c_double(float(g)) for g in gravity],
+                                         _p(self._r(exclude)), C.c_int(int(scale)), C.c_double(dt)))
+        return vel
+
+    def add_buoyancy(self, flags, density, vel, gravity, coefficient=1.0, scale=True, dt=1.0):
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        self._chk(self._f("add_buoyancy")(*self.dims(flags), _p(flags), _p(self._r(density)), _p(vel), *[C.c_double(float(g)) for g in gravity],
+                                          C.c_double(coefficient), C.c_int(int(scale)), C.c_double(dt)))
+        return vel
+
+    def advect_semi_lagrange(self, flags, vel, grid, order=1, strength=1.0, orderSpace=1, clampMode=2, orderTrace=1, dt=1.0):
+        """grid: (sz,sy,sx) Real grid or (sz,sy,sx,3) MAC grid, advected in place"""
+        assert grid.dtype == self.real and grid.flags.c_contiguous
+        kind = 1 if grid.ndim == 4 else 0
+        self._chk(self._f("advect_semi_lagrange")(*self.dims(flags), _p(flags), _p(self._r(vel)), _p(grid), C.c_int(kind), C.c_int(order),
+                                                  C.c_double(strength), C.c_int(orderSpace), C.c_int(clampMode), C.c_int(orderTrace), C.c_double(dt)))
+        return grid
+
     def compute_rhs(self, flags, vel, phi=None, perCellCorr=None, fractions=None, obvel=None, curv=None,
                     gfClamp=1e-4, surfTens=0.0, enforceCompatibility=False):
         vel, phi, perCellCorr, fractions, obvel, curv = map(self._r, (vel, phi, perCellCorr, fractions, obvel, curv))

@@ -13,6 +13,8 @@
 //   correctVelocity         plugin/pressure.cpp:455-476
 //   solvePressure           plugin/pressure.cpp:480-521
 //   setWallBcs              plugin/extforces.cpp:307-316
+//   addGravity, addBuoyancy plugin/extforces.cpp:61-90
+//   advectSemiLagrange      plugin/advection.cpp:442-461
 // Nothing of the reference is copied: its sources are compiled where they lie.
 //
 // The signatures are shared with oracle/mf_oracle.c (the restatement) so the same
@@ -60,6 +62,9 @@ int readObjectsVDB (const std::string&, std::vector<PbClass*>*, float) { return 
 Real LevelsetGrid::invalidTimeValue() { return -1000; }   // levelset.cpp:103 -> fastmarch.h:134
 void setWallBcs(const FlagGrid& flags, MACGrid& vel, const MACGrid* obvel, const MACGrid* fractions, const Grid<Real>* phiObs, int boundaryWidth);
 void cgSolveDiffusion(const FlagGrid& flags, GridBase& grid, Real alpha, Real cgMaxIterFac, Real cgAccuracy);
+void addGravity(const FlagGrid& flags, MACGrid& vel, Vec3 gravity, const Grid<Real>* exclude, bool scale);
+void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGrid& vel, Vec3 gravity, Real coefficient, bool scale);
+void advectSemiLagrange(const FlagGrid* flags, const MACGrid* vel, GridBase* grid, int order, Real strength, int orderSpace, bool openBounds, int boundaryWidth, int clampMode, int orderTrace);
 void InitPreconditionModifiedIncompCholesky2(const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
 void ApplyPreconditionModifiedIncompCholesky2(Grid<Real>& dst, Grid<Real>& Var1, const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
 }
@@ -94,6 +99,51 @@ int ref_set_wall_bcs(int sx, int sy, int sz, const int* flags, Real* vel)
 	FluidSolver* s = mkSolver(sx, sy, sz);
 	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
 	  setWallBcs(F, V, 0, 0, 0, 0); }
+	delete s;
+  CATCH }
+
+int ref_set_wall_bcs_obvel(int sx, int sy, int sz, const int* flags, Real* vel, const Real* obvel)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
+	  MACGrid* Ov = obvel ? new MACGrid(s, (Vec3*)obvel) : 0;
+	  setWallBcs(F, V, Ov, 0, 0, 0);
+	  delete Ov; }
+	delete s;
+  CATCH }
+
+int ref_add_gravity(int sx, int sy, int sz, const int* flags, Real* vel, double gx, double gy, double gz, const Real* exclude, int scale, double dt)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz); s->mDt = (Real)dt;
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
+	  Grid<Real>* E = exclude ? new Grid<Real>(s, (Real*)exclude) : 0;
+	  addGravity(F, V, Vec3((Real)gx, (Real)gy, (Real)gz), E, scale != 0);
+	  delete E; }
+	delete s;
+  CATCH }
+
+int ref_add_buoyancy(int sx, int sy, int sz, const int* flags, const Real* density, Real* vel, double gx, double gy, double gz, double coefficient, int scale, double dt)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz); s->mDt = (Real)dt;
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel); Grid<Real> D(s, (Real*)density);
+	  addBuoyancy(F, D, V, Vec3((Real)gx, (Real)gy, (Real)gz), (Real)coefficient, scale != 0); }
+	delete s;
+  CATCH }
+
+// kind 0: Grid<Real>, 1: MACGrid.  The plugin swaps its result in, which the reference forbids for external data: work on solver-owned copies.
+int ref_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Real* vel, Real* grid, int kind,
+	int order, double strength, int orderSpace, int clampMode, int orderTrace, double dt)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz); s->mDt = (Real)dt;
+	const size_t n = (size_t)sx * sy * sz;
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
+	  if (kind == 0) { Grid<Real> G(s); memcpy(&G[0], grid, n * sizeof(Real));
+	    advectSemiLagrange(&F, &V, &G, order, (Real)strength, orderSpace, false, -1, clampMode, orderTrace);
+	    memcpy(grid, &G[0], n * sizeof(Real)); }
+	  else { MACGrid G(s); memcpy(&G[0], grid, n * sizeof(Vec3));
+	    MACGrid Vc(s); memcpy(&Vc[0], vel, n * sizeof(Vec3));      // self-advection passes the same grid as vel and grid: keep that aliasing out of the harness
+	    advectSemiLagrange(&F, &Vc, &G, order, (Real)strength, orderSpace, false, -1, clampMode, orderTrace);
+	    memcpy(grid, &G[0], n * sizeof(Vec3)); } }
 	delete s;
   CATCH }
 

@@ -114,6 +114,36 @@ class CudaImpl:
         grid[...] = G.numpy()
         return grid
 
+    # the steps either side of the projection: same signatures as oracle_api.Oracle, arrays updated in place
+    def set_wall_bcs_obvel(self, flags, vel, obvel=None):
+        s = self._solver(flags)
+        V = mf.MACGrid(s, vel)
+        mf.setWallBcs(mf.FlagGrid(s, flags), V, obvel=self._g(s, mf.MACGrid, obvel))
+        vel[...] = V.numpy()
+        return vel
+
+    def add_gravity(self, flags, vel, gravity, exclude=None, scale=True, dt=1.0):
+        s = self._solver(flags); s.timestep = dt
+        V = mf.MACGrid(s, vel)
+        mf.addGravity(mf.FlagGrid(s, flags), V, gravity, exclude=self._g(s, mf.RealGrid, exclude), scale=scale)
+        vel[...] = V.numpy()
+        return vel
+
+    def add_buoyancy(self, flags, density, vel, gravity, coefficient=1.0, scale=True, dt=1.0):
+        s = self._solver(flags); s.timestep = dt
+        V = mf.MACGrid(s, vel)
+        mf.addBuoyancy(mf.FlagGrid(s, flags), mf.RealGrid(s, density), V, gravity, coefficient=coefficient, scale=scale)
+        vel[...] = V.numpy()
+        return vel
+
+    def advect_semi_lagrange(self, flags, vel, grid, order=1, strength=1.0, orderSpace=1, clampMode=2, orderTrace=1, dt=1.0):
+        s = self._solver(flags); s.timestep = dt
+        V = mf.MACGrid(s, vel)
+        G = V if grid is vel else (mf.RealGrid if grid.ndim == 3 else mf.MACGrid)(s, grid)      # self-advection: one grid, as in the scenes
+        mf.advectSemiLagrange(mf.FlagGrid(s, flags), V, G, order=order, strength=strength, orderSpace=orderSpace, clampMode=clampMode, orderTrace=orderTrace)
+        grid[...] = G.numpy()
+        return grid
+
     def release_solver(self, key):
         for k, s in list(self._solvers.items()):
             if k[3] == key:

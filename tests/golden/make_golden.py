@@ -9,6 +9,8 @@ Fixtures
   kernels_<scene>_f{32,64}.npz : per-kernel outputs (rhs, A0..Ak, pinned system, ApplyMatrix, MIC factor + sweeps,
                                  GridMg vertex types / operators / V-cycle, GridCg runs for PC_None/mICP/MGP,
                                  correctVelocity, the solvePressure plugin with PcMIC / PcMGDynamic)
+  step_<scene>_f{32,64}.npz    : setWallBcs (with obvel), addGravity, addBuoyancy, advectSemiLagrange (Real / MAC, order 1 / 2, both clamp
+                                 modes, outflow cells) on seeded random boxes; plume{3d,2d}_f32.npz: six steps of the simpleplume main loop
   psolve52_f32.npz             : the scenario of tools/tests/test_0100_psolve.py and test_0110_mgsolve.py (52^3 closed box,
                                  box velocity source, solves with PcMIC / PcMGDynamic / PcMGStatic), float build
 """
@@ -141,7 +143,33 @@ def psolve52(R, prec=4):
     return out
 
 
+def step_fixtures():
+    """step_<scene>_f{32,64}.npz: setWallBcs / addGravity / addBuoyancy / advectSemiLagrange outputs of the reference on the seeded
+    scenes of tests/helpers.py; plume_f32.npz: six steps of the simpleplume main loop (advect density + velocity with MacCormack,
+    setWallBcs, addBuoyancy, solvePressure PcMIC) run by the reference."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import helpers
+    for prec in (4, 8):
+        R = Oracle("reference", prec)
+        for name in helpers.STEP_SCENES:
+            flags, vel, dens, obvel = helpers.step_scene(name, prec)
+            fx = dict(flags=flags, vel=vel)
+            for case in helpers.STEP_CASES:
+                fx[case] = helpers.run_step_case(R, case, flags, vel, dens, obvel)
+            path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, **fx)
+            print("%-34s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+    for shape, tag in (((24, 36, 24), "3d"), ((1, 48, 32), "2d")):
+        dens, vel, p, its = helpers.run_plume_steps(Oracle("reference", 4), shape, 4, steps=6)
+        path = os.path.join(HERE, "plume%s_f32.npz" % tag)
+        np.savez_compressed(path, density=dens, vel=vel, pressure=p, iterations=np.array(its))
+        print("%-34s %7.1f KiB  its %s  max density %.3f" % (os.path.basename(path), os.path.getsize(path) / 1024, its, float(dens.max())))
+
+
 def main():
+    if "--only-step" in sys.argv:
+        return step_fixtures()
+    step_fixtures()
     for prec in (4, 8):
         R = Oracle("reference", prec)
         for name in KERNEL_SCENES:

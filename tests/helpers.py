@@ -13,7 +13,9 @@ KERNEL_FIXTURES = ["smoke16", "liquid14", "smoke2d"]
 
 
 def load_golden(name, prec):
-    return dict(np.load(os.path.join(GOLDEN, "kernels_%s_f%d.npz" % (name, prec * 8))))
+    """kernels_<name>_f<bits>.npz, or <name>_f<bits>.npz for the step_* / plume* fixtures"""
+    stem = name if name.startswith(("step_", "plume")) else "kernels_" + name
+    return dict(np.load(os.path.join(GOLDEN, "%s_f%d.npz" % (stem, prec * 8))))
 
 
 def rel_l2(a, b):
@@ -130,3 +132,99 @@ def check_psolve52(I, thr=1e-4):
     p, it, _ = I.solve_pressure(flags, v, zeroPressureFixing=True, preconditioner=3, solver_key=key, **kw)
     assert md(p, g["t0110_p2"]) <= thr * 10 and md(v, g["t0110_v2"]) <= thr * 10 and abs(it - int(g["t0110_it3"])) <= 1
     I.release_solver(key)
+
+
+# ---------------------------------------------------------------- the steps either side of the projection
+STEP_SCENES = {"box3d": (16, 18, 20), "box2d": (1, 24, 30), "ragged3d": (13, 17, 22)}      # (sz, sy, sx)
+STEP_CASES = ["wall_obvel", "wall", "gravity_excl", "gravity_noscale", "buoyancy", "adv_real_o1", "adv_real_o2_c2", "adv_real_o2_c1",
+              "adv_mac_o1", "adv_mac_o2_c2", "adv_mac_o2_c1", "adv_self_o2"]
+
+
+def step_scene(name, prec):
+    """closed box with random obstacle / empty cells, an outflow band below the top wall, random velocity / density / obstacle velocity"""
+    from mantaflow_b200 import scenes
+    shape = STEP_SCENES[name]
+    sz, sy, sx = shape
+    real = np.float32 if prec == 4 else np.float64
+    rng = np.random.default_rng(5 + sx)
+    flags = scenes.closed_box_flags(sx, sy, sz)
+    inner = (slice(1, -1) if sz > 1 else slice(None), slice(1, -1), slice(1, -1))
+    r = rng.random(flags[inner].shape)
+    f = flags[inner]
+    f[r < 0.08] = 2            # obstacle
+    f[(r > 0.08) & (r < 0.14)] = 4   # empty
+    flags[inner] = f
+    flags[(slice(1, -1) if sz > 1 else slice(None)), sy - 2, 1:-1] = 16 | 4      # outflow | empty
+    vel = (rng.random(shape + (3,)) * 3 - 1.5).astype(real)
+    if sz == 1:
+        vel[..., 2] = 0
+    dens = rng.random(shape).astype(real)
+    obvel = (rng.random(shape + (3,)) - 0.5).astype(real)
+    return flags, vel, dens, obvel
+
+
+def run_step_case(I, case, flags, vel, dens, obvel):
+    real = vel.dtype
+    if case == "wall_obvel":
+        return I.set_wall_bcs_obvel(flags, vel.copy(), obvel)
+    if case == "wall":
+        return I.set_wall_bcs_obvel(flags, vel.copy(), None)
+    if case == "gravity_excl":
+        return I.add_gravity(flags, vel.copy(), (0.1, -0.3, 0.2), exclude=(dens - 0.3).astype(real), scale=True, dt=0.7)
+    if case == "gravity_noscale":
+        return I.add_gravity(flags, vel.copy(), (0.1, -0.3, 0.2), scale=False, dt=0.7)
+    if case == "buoyancy":
+        return I.add_buoyancy(flags, dens, vel.copy(), (0, -6e-4, 1e-4), coefficient=1.3, scale=True, dt=0.9)
+    if case == "adv_real_o1":
+        return I.advect_semi_lagrange(flags, vel, dens.copy(), order=1, dt=0.8)
+    if case == "adv_real_o2_c2":
+        return I.advect_semi_lagrange(flags, vel, dens.copy(), order=2, clampMode=2, dt=0.8)
+    if case == "adv_real_o2_c1":
+        return I.advect_semi_lagrange(flags, vel, dens.copy(), order=2, clampMode=1, strength=0.8, dt=0.8)
+    if case == "adv_mac_o1":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=1, dt=0.8)
+    if case == "adv_mac_o2_c2":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=2, clampMode=2, dt=0.8)
+    if case == "adv_mac_o2_c1":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=2, clampMode=1, dt=1.7)
+    if case == "adv_self_o2":      # advectSemiLagrange(vel=vel, grid=vel): the grid advects itself
+        v = vel.copy()
+        return I.advect_semi_lagrange(flags, v, v, order=2, dt=0.8)
+    raise KeyError(case)
+
+
+def check_step_against_golden(I, name, prec):
+    """every step plugin bit for bit against the reference's output on the same seeded inputs"""
+    g = load_golden("step_" + name, prec)
+    flags, vel, dens, obvel = step_scene(name, prec)
+    assert np.array_equal(flags, g["flags"]) and np.array_equal(vel, g["vel"])
+    for case in STEP_CASES:
+        out = run_step_case(I, case, flags, vel, dens, obvel)
+        assert np.array_equal(out, g[case]), (name, prec, case, float(np.abs(out.astype(np.float64) - g[case]).max()))
+
+
+def plume_scene(shape, prec):
+    """simpleplume-like: closed box, density source blob near the floor"""
+    from mantaflow_b200 import scenes
+    sz, sy, sx = shape
+    real = np.float32 if prec == 4 else np.float64
+    flags = scenes.closed_box_flags(sx, sy, sz)
+    k, j, i = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
+    src = ((i + 0.5 - 0.5 * sx) ** 2 + ((k + 0.5 - 0.5 * sz) ** 2 if sz > 1 else 0) <= (0.14 * sx) ** 2) & (j >= 0.08 * sy) & (j <= 0.14 * sy) & (flags == 1)
+    return flags, src, real
+
+
+def run_plume_steps(I, shape, prec, steps, pc=1):
+    """the main loop of scenes/simpleplume.py:48-60 with a constant density source instead of the noise inflow"""
+    flags, src, real = plume_scene(shape, prec)
+    vel = np.zeros(shape + (3,), real); dens = np.zeros(shape, real); p = np.zeros(shape, real)
+    its = []
+    for _ in range(steps):
+        dens[src] = 1
+        I.advect_semi_lagrange(flags, vel, dens, order=2)
+        I.advect_semi_lagrange(flags, vel, vel, order=2, strength=1.0)
+        I.set_wall_bcs_obvel(flags, vel, None)
+        I.add_buoyancy(flags, dens, vel, (0, -6e-4, 0))
+        p, it, _ = I.solve_pressure(flags, vel, preconditioner=pc, zeroPressureFixing=(pc >= 2))
+        its.append(it)
+    return dens, vel, p, its
