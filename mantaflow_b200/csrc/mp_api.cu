@@ -83,7 +83,7 @@ int mp_context_set_profiling(mp_context* c, int period) {
 	return MP_OK;
 }
 
-int mp_grid_create(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, mp_grid** out) {
+static int gridCreate(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, mp_grid** out, bool clear) {
 	if (!ctx || !out) MP_FAIL(MP_ERR_INVALID, "mp_grid_create: NULL argument");
 	if (kind != MP_GRID_REAL && kind != MP_GRID_FLAGS && kind != MP_GRID_MAC) MP_FAIL(MP_ERR_INVALID, "mp_grid_create: bad kind %d", kind);
 	if (kind != MP_GRID_FLAGS && prec != 4 && prec != 8) MP_FAIL(MP_ERR_INVALID, "mp_grid_create: prec must be 4 or 8, got %d", prec);
@@ -105,9 +105,12 @@ int mp_grid_create(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, 
 		}
 		if (e != cudaSuccess) { const size_t b = g->bytes; delete g; cudaGetLastError(); mp_set_error("mp_grid_create: cudaMalloc(%zu) failed: %s", b, cudaGetErrorString(e)); return MP_ERR_CUDA; }
 	}
-	MP_CUDA(cudaMemsetAsync(g->d, 0, g->bytes + 256, ctx->stream));     // Grid<T>(parent) clears, grid.cpp:57
+	if (clear) MP_CUDA(cudaMemsetAsync(g->d, 0, g->bytes + 256, ctx->stream));     // Grid<T>(parent) clears, grid.cpp:57
 	*out = g; return MP_OK;
 }
+int mp_grid_create(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, mp_grid** out) { return gridCreate(ctx, kind, prec, sx, sy, sz, out, true); }
+// internal: scratch grid whose every cell the caller writes before reading (no clear pass)
+int mp_grid_create_scratch(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, mp_grid** out) { return gridCreate(ctx, kind, prec, sx, sy, sz, out, false); }
 int mp_grid_destroy(mp_grid* g) {
 	if (!g) return MP_OK;
 	cudaSetDevice(g->ctx->device);

@@ -14,17 +14,22 @@ namespace {
 
 template <typename Real> struct V3 { Real x, y, z; };
 
-__device__ __forceinline__ bool interior(const Dims& d, IndexInt idx, int& i, int& j, int& k) {   // the cells of a KERNEL(bnd=1)
-	i = (int)(idx % d.sx); j = (int)((idx / d.sx) % d.sy); k = (int)(idx / ((IndexInt)d.sx * d.sy));
+// launch: x over i (128 threads), blockIdx.y = j, blockIdx.z = k -- no 64-bit division per cell
+__device__ __forceinline__ bool cellOf(const Dims& d, int& i, int& j, int& k, IndexInt& idx) {
+	i = blockIdx.x * blockDim.x + threadIdx.x; j = blockIdx.y; k = blockIdx.z;
+	idx = (IndexInt)i + d.Y * j + (IndexInt)d.sx * d.sy * k;
+	return i < d.sx;
+}
+__device__ __forceinline__ bool isInterior(const Dims& d, int i, int j, int k) {   // the cells of a KERNEL(bnd=1)
 	return i >= 1 && i <= d.sx - 2 && j >= 1 && j <= d.sy - 2 && (!d.is3D || (k >= 1 && k <= d.sz - 2));
 }
+static inline dim3 cellGrid(const Dims& d) { return dim3((unsigned)((d.sx + 127) / 128), (unsigned)d.sy, (unsigned)d.sz); }
 
 // ---------------------------------------------------------------- setWallBcs / forces
 template <typename Real>
-__global__ void __launch_bounds__(256) k_set_wall_bcs(Dims d, const int* __restrict__ flags, Real* vel, const Real* __restrict__ obvel) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= d.n) return;
-	const int i = (int)(idx % d.sx), j = (int)((idx / d.sx) % d.sy), k = (int)(idx / ((IndexInt)d.sx * d.sy));
+__global__ void __launch_bounds__(128) k_set_wall_bcs(Dims d, const int* __restrict__ flags, Real* vel, const Real* __restrict__ obvel) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx)) return;
 	const int fl = flags[idx];
 	const bool curFluid = fl & TypeFluid, curObs = fl & TypeObstacle;
 	if (!curFluid && !curObs) return;
@@ -46,14 +51,13 @@ __global__ void __launch_bounds__(256) k_set_wall_bcs(Dims d, const int* __restr
 		if ((j > 0 && (flags[idx - d.Y] & TypeStick)) || (j < d.sy - 1 && (flags[idx + d.Y] & TypeStick))) vx = vz = 0;
 		if (d.is3D && ((k > 0 && (flags[idx - d.Z] & TypeStick)) || (k < d.sz - 1 && (flags[idx + d.Z] & TypeStick)))) vx = vy = 0;
 	}
-	v[0] = vx; v[1] = vy; v[2] = vz;
+	if (vx != v[0] || vy != v[1] || vz != v[2] || (vx != vx) || (vy != vy) || (vz != vz)) { v[0] = vx; v[1] = vy; v[2] = vz; }     // most cells stay as they are: read-only for them
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(256) k_apply_force(Dims d, const int* __restrict__ flags, Real* vel, Real fx, Real fy, Real fz, const Real* __restrict__ exclude) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	int i, j, k;
-	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+__global__ void __launch_bounds__(128) k_apply_force(Dims d, const int* __restrict__ flags, Real* vel, Real fx, Real fy, Real fz, const Real* __restrict__ exclude) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx) || !isInterior(d, i, j, k)) return;
 	const bool curFluid = flags[idx] & TypeFluid, curEmpty = flags[idx] & TypeEmpty;
 	if (!curFluid && !curEmpty) return;
 	if (exclude && (exclude[idx] < 0.)) return;
@@ -64,10 +68,9 @@ __global__ void __launch_bounds__(256) k_apply_force(Dims d, const int* __restri
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(256) k_add_buoyancy(Dims d, const int* __restrict__ flags, const Real* __restrict__ factor, Real* vel, Real sx_, Real sy_, Real sz_) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	int i, j, k;
-	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+__global__ void __launch_bounds__(128) k_add_buoyancy(Dims d, const int* __restrict__ flags, const Real* __restrict__ factor, Real* vel, Real sx_, Real sy_, Real sz_) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx) || !isInterior(d, i, j, k)) return;
 	if (!(flags[idx] & TypeFluid)) return;
 	Real* v = vel + 3 * idx;
 	const Real f0 = factor[idx];
@@ -130,97 +133,88 @@ __device__ __forceinline__ V3<Real> macAt(const Dims& d, const Real* __restrict_
 #undef VC
 
 // ---------------------------------------------------------------- SemiLagrange / SemiLagrangeMAC (advection.cpp:25-58, orderTrace 1)
+// Pass 1 of an advection: dst = src traced back along vel in the interior, 0 on the outer layer (the reference's fresh grid).
 template <typename Real>
-__global__ void __launch_bounds__(256) k_semi_lagrange(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	int i, j, k;
-	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+__device__ __forceinline__ Real slReal(const Dims& d, const Real* __restrict__ vel, const Real* __restrict__ src, Real dt, int i, int j, int k, IndexInt idx) {
 	const V3<Real> c = macCentered<Real>(d, vel, idx);
-	dst[idx] = interpol<Real, 1>(d, src, (i + 0.5f) - c.x * dt, (j + 0.5f) - c.y * dt, (k + 0.5f) - c.z * dt);
+	return interpol<Real, 1>(d, src, (i + 0.5f) - c.x * dt, (j + 0.5f) - c.y * dt, (k + 0.5f) - c.z * dt);
 }
 template <typename Real>
-__global__ void __launch_bounds__(256) k_semi_lagrange_mac(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	int i, j, k;
-	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
+__device__ __forceinline__ V3<Real> slMAC(const Dims& d, const Real* __restrict__ vel, const Real* __restrict__ src, Real dt, int i, int j, int k, IndexInt idx) {
 	const V3<Real> mx = macAt<Real, 0>(d, vel, idx), my = macAt<Real, 1>(d, vel, idx), mz = macAt<Real, 2>(d, vel, idx);
-	dst[3 * idx + 0] = interpol<Real, 3>(d, src + 0, (i + 0.5f) - mx.x * dt, (j + 0.5f) - mx.y * dt, (k + 0.5f) - mx.z * dt);
-	dst[3 * idx + 1] = interpol<Real, 3>(d, src + 1, (i + 0.5f) - my.x * dt, (j + 0.5f) - my.y * dt, (k + 0.5f) - my.z * dt);
-	dst[3 * idx + 2] = interpol<Real, 3>(d, src + 2, (i + 0.5f) - mz.x * dt, (j + 0.5f) - mz.y * dt, (k + 0.5f) - mz.z * dt);
+	V3<Real> o;
+	o.x = interpol<Real, 3>(d, src + 0, (i + 0.5f) - mx.x * dt, (j + 0.5f) - mx.y * dt, (k + 0.5f) - mx.z * dt);
+	o.y = interpol<Real, 3>(d, src + 1, (i + 0.5f) - my.x * dt, (j + 0.5f) - my.y * dt, (k + 0.5f) - my.z * dt);
+	o.z = interpol<Real, 3>(d, src + 2, (i + 0.5f) - mz.x * dt, (j + 0.5f) - mz.y * dt, (k + 0.5f) - mz.z * dt);
+	return o;
+}
+template <typename Real>
+__global__ void __launch_bounds__(128) k_semi_lagrange(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx)) return;
+	dst[idx] = isInterior(d, i, j, k) ? slReal<Real>(d, vel, src, dt, i, j, k, idx) : (Real)0;
+}
+template <typename Real>
+__global__ void __launch_bounds__(128) k_semi_lagrange_mac(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx)) return;
+	V3<Real> o; o.x = o.y = o.z = 0;
+	if (isInterior(d, i, j, k)) o = slMAC<Real>(d, vel, src, dt, i, j, k, idx);
+	dst[3 * idx] = o.x; dst[3 * idx + 1] = o.y; dst[3 * idx + 2] = o.z;
 }
 
 // ---------------------------------------------------------------- MacCormack (advection.cpp:81-117 correct, :141-287 clamp)
-template <typename Real>
-__global__ void __launch_bounds__(256) k_mc_correct(Dims d, const int* __restrict__ flags, Real* __restrict__ dst, const Real* __restrict__ old,
-	const Real* __restrict__ fwd, const Real* __restrict__ bwd, Real strength) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= d.n) return;
-	Real v = fwd[idx];
-	if (flags[idx] & TypeFluid) v = (Real)((double)v + ((double)strength * 0.5) * (double)(old[idx] - bwd[idx]));
-	dst[idx] = v;
-}
-template <typename Real>
-__global__ void __launch_bounds__(256) k_mc_correct_mac(Dims d, const int* __restrict__ flags, Real* __restrict__ dst, const Real* __restrict__ old,
-	const Real* __restrict__ fwd, const Real* __restrict__ bwd, Real strength) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= d.n) return;
-	const int i = (int)(idx % d.sx), j = (int)((idx / d.sx) % d.sy), k = (int)(idx / ((IndexInt)d.sx * d.sy));
-	bool skip[3] = { false, false, false };
-	if (!(flags[idx] & TypeFluid)) skip[0] = skip[1] = skip[2] = true;
-	if (i > 0 && !(flags[idx - d.X] & TypeFluid)) skip[0] = true;
-	if (j > 0 && !(flags[idx - d.Y] & TypeFluid)) skip[1] = true;
-	if (k > 0 && !(flags[idx - d.Z] & TypeFluid)) skip[2] = true;
-	#pragma unroll
-	for (int c = 0; c < 3; c++) {
-		const IndexInt q = 3 * idx + c;
-		dst[q] = skip[c] ? fwd[q] : (Real)((double)fwd[q] + ((double)strength * 0.5) * (double)(old[q] - bwd[q]));
-	}
-}
-
 template <typename Real> __device__ __forceinline__ Real realMax();
 template <> __device__ __forceinline__ float realMax<float>() { return FLT_MAX; }
 template <> __device__ __forceinline__ double realMax<double>() { return DBL_MAX; }
 __device__ __forceinline__ int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ bool checkFlag(const int* flags, IndexInt q) { return flags[q] & (TypeFluid | TypeEmpty); }
 
+// Pass 2 of a MacCormack advection of a Real grid: the reference's backward trace (SemiLagrange with -dt on fwd), MacCormackCorrect and
+// MacCormackClamp only ever combine values of ONE cell (plus read-only neighbourhoods of fwd / orig), so they are one kernel here:
+// three full-grid round trips of bwd and the corrected grid never reach HBM.
 template <typename Real>
-__global__ void __launch_bounds__(256) k_mc_clamp(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* dst, const Real* __restrict__ orig,
-	const Real* __restrict__ fwd, Real dt, int clampMode) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	int i, j, k;
-	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
-	const V3<Real> c = macCentered<Real>(d, vel, idx);
-	const Real v[3] = { c.x * dt, c.y * dt, c.z * dt }, pos[3] = { (Real)i, (Real)j, (Real)k };
-	Real dval = dst[idx];
+__global__ void __launch_bounds__(128) k_mc_rest(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
+	const Real* __restrict__ fwd, Real dt, Real strength, int clampMode) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx)) return;
+	const bool in = isInterior(d, i, j, k);
 	const Real f = fwd[idx];
-	{	// doClampComponent :141-186
-		Real minv = realMax<Real>(), maxv = -realMax<Real>();
-		bool haveFl = false;
-		const int numPos = clampMode == 1 ? 2 : 1;
-		for (int l = 0; l < numPos; l++) {
-			int cp[3];
-			#pragma unroll
-			for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
-			const int i0 = iclamp(cp[0], 0, d.sx - 2), j0 = iclamp(cp[1], 0, d.sy - 2), k0 = iclamp(cp[2], 0, d.is3D ? d.sz - 2 : 1);
-			const int k1 = d.is3D ? k0 + 1 : k0;
-			for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
-				const IndexInt q = (IndexInt)(i0 + a) + d.Y * (j0 + b) + d.Z * (cc ? k1 : k0);
-				if (checkFlag(flags, q)) { const Real o = orig[q]; if (o < minv) minv = o; if (o > maxv) maxv = o; haveFl = true; }
+	const Real bwd = in ? slReal<Real>(d, vel, fwd, -dt, i, j, k, idx) : (Real)0;
+	Real dval = f;                                                   // MacCormackCorrect :81-91 (all cells)
+	if (flags[idx] & TypeFluid) dval = (Real)((double)dval + ((double)strength * 0.5) * (double)(orig[idx] - bwd));
+	if (in) {                                                        // MacCormackClamp :241-267
+		const V3<Real> c = macCentered<Real>(d, vel, idx);
+		const Real v[3] = { c.x * dt, c.y * dt, c.z * dt }, pos[3] = { (Real)i, (Real)j, (Real)k };
+		{	// doClampComponent :141-186
+			Real minv = realMax<Real>(), maxv = -realMax<Real>();
+			bool haveFl = false;
+			const int numPos = clampMode == 1 ? 2 : 1;
+			for (int l = 0; l < numPos; l++) {
+				int cp[3];
+				#pragma unroll
+				for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
+				const int i0 = iclamp(cp[0], 0, d.sx - 2), j0 = iclamp(cp[1], 0, d.sy - 2), k0 = iclamp(cp[2], 0, d.is3D ? d.sz - 2 : 1);
+				const int k1 = d.is3D ? k0 + 1 : k0;
+				for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
+					const IndexInt q = (IndexInt)(i0 + a) + d.Y * (j0 + b) + d.Z * (cc ? k1 : k0);
+					if (checkFlag(flags, q)) { const Real o = orig[q]; if (o < minv) minv = o; if (o > maxv) maxv = o; haveFl = true; }
+				}
 			}
+			if (!haveFl) dval = f;
+			else if (clampMode == 1) dval = dval < minv ? minv : (dval > maxv ? maxv : dval);
+			else if (dval < minv || dval > maxv) dval = f;
 		}
-		if (!haveFl) dval = f;
-		else if (clampMode == 1) dval = dval < minv ? minv : (dval > maxv ? maxv : dval);
-		else if (dval < minv || dval > maxv) dval = f;
-	}
-	if (clampMode == 1) {   // lookups that leave the grid or end in an obstacle fall back to first order (:252-264)
-		int pf[3], pb[3];
-		#pragma unroll
-		for (int a = 0; a < 3; a++) { pf[a] = (int)((pos[a] + (Real)0.5) - v[a]); pb[a] = (int)((pos[a] + (Real)0.5) + v[a]); }
-		const int ux = d.sx - 1, uy = d.sy - 1, uz = d.sz - 1;
-		bool bad = pf[0] < 0 || pf[1] < 0 || pf[2] < 0 || pb[0] < 0 || pb[1] < 0 || pb[2] < 0 ||
-		           pf[0] > ux || pf[1] > uy || ((pf[2] > uz) && d.is3D) || pb[0] > ux || pb[1] > uy || ((pb[2] > uz) && d.is3D);
-		if (!bad) bad = (flags[(IndexInt)pf[0] + d.Y * pf[1] + d.Z * pf[2]] & TypeObstacle) || (flags[(IndexInt)pb[0] + d.Y * pb[1] + d.Z * pb[2]] & TypeObstacle);
-		if (bad) dval = f;
+		if (clampMode == 1) {   // lookups that leave the grid or end in an obstacle fall back to first order (:252-264)
+			int pf[3], pb[3];
+			#pragma unroll
+			for (int a = 0; a < 3; a++) { pf[a] = (int)((pos[a] + (Real)0.5) - v[a]); pb[a] = (int)((pos[a] + (Real)0.5) + v[a]); }
+			const int ux = d.sx - 1, uy = d.sy - 1, uz = d.sz - 1;
+			bool bad = pf[0] < 0 || pf[1] < 0 || pf[2] < 0 || pb[0] < 0 || pb[1] < 0 || pb[2] < 0 ||
+			           pf[0] > ux || pf[1] > uy || ((pf[2] > uz) && d.is3D) || pb[0] > ux || pb[1] > uy || ((pb[2] > uz) && d.is3D);
+			if (!bad) bad = (flags[(IndexInt)pf[0] + d.Y * pf[1] + d.Z * pf[2]] & TypeObstacle) || (flags[(IndexInt)pb[0] + d.Y * pb[1] + d.Z * pb[2]] & TypeObstacle);
+			if (bad) dval = f;
+		}
 	}
 	dst[idx] = dval;
 }
@@ -251,30 +245,49 @@ __device__ __forceinline__ Real clampComponentMAC(const Dims& d, const int* __re
 	if (dst < minv || dst > maxv) dst = fwd;
 	return dst;
 }
+// Pass 2 for a MAC grid: backward trace + MacCormackCorrectMAC (:94-117, all cells) + MacCormackClampMAC (:270-287, interior);
+// *anyOutflow is raised when the flags hold an outflow cell, so that the boundary pass can be skipped otherwise
 template <typename Real>
-__global__ void __launch_bounds__(256) k_mc_clamp_mac(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* dst, const Real* __restrict__ orig,
-	const Real* __restrict__ fwd, Real dt, int clampMode) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	int i, j, k;
-	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
-	V3<Real> m = macAt<Real, 0>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
-	dst[3 * idx] = clampComponentMAC<Real, 0>(d, flags, dst[3 * idx], orig, fwd[3 * idx], i, j, k, idx, m, clampMode);
-	m = macAt<Real, 1>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
-	dst[3 * idx + 1] = clampComponentMAC<Real, 1>(d, flags, dst[3 * idx + 1], orig, fwd[3 * idx + 1], i, j, k, idx, m, clampMode);
-	if (d.is3D) {
-		m = macAt<Real, 2>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
-		dst[3 * idx + 2] = clampComponentMAC<Real, 2>(d, flags, dst[3 * idx + 2], orig, fwd[3 * idx + 2], i, j, k, idx, m, clampMode);
+__global__ void __launch_bounds__(128) k_mc_rest_mac(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
+	const Real* __restrict__ fwd, Real dt, Real strength, int clampMode, int* anyOutflow) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx)) return;
+	const bool in = isInterior(d, i, j, k);
+	const int fl = flags[idx];
+	if (fl & TypeOutflow) *anyOutflow = 1;
+	const Real f[3] = { fwd[3 * idx], fwd[3 * idx + 1], fwd[3 * idx + 2] };
+	V3<Real> bw; bw.x = bw.y = bw.z = 0;
+	if (in) bw = slMAC<Real>(d, vel, fwd, -dt, i, j, k, idx);
+	const Real b[3] = { bw.x, bw.y, bw.z };
+	bool skip[3] = { false, false, false };
+	if (!(fl & TypeFluid)) skip[0] = skip[1] = skip[2] = true;
+	if (i > 0 && !(flags[idx - d.X] & TypeFluid)) skip[0] = true;
+	if (j > 0 && !(flags[idx - d.Y] & TypeFluid)) skip[1] = true;
+	if (k > 0 && !(flags[idx - d.Z] & TypeFluid)) skip[2] = true;
+	Real o[3];
+	#pragma unroll
+	for (int c = 0; c < 3; c++) o[c] = skip[c] ? f[c] : (Real)((double)f[c] + ((double)strength * 0.5) * (double)(orig[3 * idx + c] - b[c]));
+	if (in) {
+		V3<Real> m = macAt<Real, 0>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
+		o[0] = clampComponentMAC<Real, 0>(d, flags, o[0], orig, f[0], i, j, k, idx, m, clampMode);
+		m = macAt<Real, 1>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
+		o[1] = clampComponentMAC<Real, 1>(d, flags, o[1], orig, f[1], i, j, k, idx, m, clampMode);
+		if (d.is3D) {
+			m = macAt<Real, 2>(d, vel, idx); m.x = m.x * dt; m.y = m.y * dt; m.z = m.z * dt;
+			o[2] = clampComponentMAC<Real, 2>(d, flags, o[2], orig, f[2], i, j, k, idx, m, clampMode);
+		}
 	}
+	dst[3 * idx] = o[0]; dst[3 * idx + 1] = o[1]; dst[3 * idx + 2] = o[2];
 }
 
 // ---------------------------------------------------------------- convective outflow boundary (advection.cpp:323-392)
 // writes the extrapolated velocity of the outflow cells into velDst (zero elsewhere); k_outflow_copy then moves it into vel
 template <typename Real>
 __global__ void __launch_bounds__(128) k_outflow_extrapolate(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ velDst,
-	const Real* __restrict__ velPrev, Real timeStep) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= d.n || !(flags[idx] & TypeOutflow)) return;
-	const int i = (int)(idx % d.sx), j = (int)((idx / d.sx) % d.sy), k = (int)(idx / ((IndexInt)d.sx * d.sy));
+	const Real* __restrict__ velPrev, Real timeStep, const int* __restrict__ anyOutflow) {
+	if (anyOutflow && !*anyOutflow) return;
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx) || !(flags[idx] & TypeOutflow)) return;
 	Real avg[3] = { 0, 0, 0 }; int count = 0;
 	const int nmax = d.is3D ? 1 : 0;
 	for (int nn = -nmax; nn <= nmax; nn++) for (int m = -1; m <= 1; m++) for (int l = -1; l <= 1; l++) {
@@ -311,9 +324,10 @@ __global__ void __launch_bounds__(128) k_outflow_extrapolate(Dims d, const int* 
 	velDst[3 * idx] = o0; velDst[3 * idx + 1] = o1; velDst[3 * idx + 2] = o2;
 }
 template <typename Real>
-__global__ void __launch_bounds__(256) k_outflow_copy(Dims d, const int* __restrict__ flags, const Real* __restrict__ velDst, Real* __restrict__ vel) {
-	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= d.n || !(flags[idx] & TypeOutflow)) return;
+__global__ void __launch_bounds__(128) k_outflow_copy(Dims d, const int* __restrict__ flags, const Real* __restrict__ velDst, Real* __restrict__ vel, const int* __restrict__ anyOutflow) {
+	if (anyOutflow && !*anyOutflow) return;
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx) || !(flags[idx] & TypeOutflow)) return;
 	vel[3 * idx] = velDst[3 * idx]; vel[3 * idx + 1] = velDst[3 * idx + 1]; vel[3 * idx + 2] = velDst[3 * idx + 2];
 }
 
@@ -323,11 +337,11 @@ struct Tmp {      // scratch grid of the context's pool, released on scope exit
 };
 
 template <typename Real>
-int applyOutflowBC(mp_context* ctx, const Dims& d, const mp_grid* flags, mp_grid* vel, const mp_grid* velPrev, double dt) {
-	Tmp t; MP_TRY(mp_grid_create(ctx, MP_GRID_MAC, vel->prec, vel->sx, vel->sy, vel->sz, &t.g));     // zero-initialised, like the reference's velDst
+int applyOutflowBC(mp_context* ctx, const Dims& d, const mp_grid* flags, mp_grid* vel, const mp_grid* velPrev, double dt, const int* anyOutflow) {
+	Tmp t; MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_MAC, vel->prec, vel->sx, vel->sy, vel->sz, &t.g));     // only its outflow cells are written and read
 	const double ts = 1.0 > dt * 4 ? 1.0 : dt * 4;
-	k_outflow_extrapolate<Real><<<gridFor(d.n, 128), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (const Real*)vel->d, (Real*)t.g->d, (const Real*)velPrev->d, (Real)ts); MP_CHECK_LAUNCH(ctx);
-	k_outflow_copy<Real><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (const Real*)t.g->d, (Real*)vel->d); MP_CHECK_LAUNCH(ctx);
+	k_outflow_extrapolate<Real><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (const Real*)vel->d, (Real*)t.g->d, (const Real*)velPrev->d, (Real)ts, anyOutflow); MP_CHECK_LAUNCH(ctx);
+	k_outflow_copy<Real><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (const Real*)t.g->d, (Real*)vel->d, anyOutflow); MP_CHECK_LAUNCH(ctx);
 	return MP_OK;
 }
 
@@ -338,33 +352,31 @@ int adopt(mp_context* ctx, mp_grid* grid, mp_grid* neu) {
 	return MP_OK;
 }
 
+// Two passes per advection: (1) the forward trace, (2, MacCormack only) backward trace + correction + clamping; the reference's
+// four kernels and three temporaries (fwd, bwd, newGrid) become two kernels and two temporaries, every cell written exactly once.
 template <typename Real>
 int advect(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int clampMode, double dt_) {
 	const Dims d = dimsOf(flags);
 	const bool mac = grid->kind == MP_GRID_MAC;
 	const Real dt = (Real)dt_;
-	const unsigned int blocks = gridFor(d.n, 256);
+	const dim3 cg = cellGrid(d);
 	const int* F = (const int*)flags->d; const Real* V = (const Real*)vel->d;
-	Tmp fwd; MP_TRY(mp_grid_create(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &fwd.g));     // zero: the outer layer of the result stays 0
-	if (mac) k_semi_lagrange_mac<Real><<<blocks, 256, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
-	else     k_semi_lagrange<Real><<<blocks, 256, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	Tmp fwd; MP_TRY(mp_grid_create_scratch(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &fwd.g));
+	if (mac) k_semi_lagrange_mac<Real><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	else     k_semi_lagrange<Real><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
 	MP_CHECK_LAUNCH(ctx);
 	if (order == 1) {
-		if (mac) MP_TRY(applyOutflowBC<Real>(ctx, d, flags, fwd.g, grid, (double)dt));
+		if (mac) MP_TRY(applyOutflowBC<Real>(ctx, d, flags, fwd.g, grid, (double)dt, nullptr));
 		return adopt(ctx, grid, fwd.g);
 	}
-	Tmp bwd, neu;
-	MP_TRY(mp_grid_create(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &bwd.g));
-	MP_TRY(mp_grid_create(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &neu.g));
+	Tmp neu; MP_TRY(mp_grid_create_scratch(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &neu.g));
 	if (mac) {
-		k_semi_lagrange_mac<Real><<<blocks, 256, 0, ctx->stream>>>(d, V, (Real*)bwd.g->d, (const Real*)fwd.g->d, -dt); MP_CHECK_LAUNCH(ctx);
-		k_mc_correct_mac<Real><<<blocks, 256, 0, ctx->stream>>>(d, F, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, (const Real*)bwd.g->d, (Real)strength); MP_CHECK_LAUNCH(ctx);
-		k_mc_clamp_mac<Real><<<blocks, 256, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, clampMode); MP_CHECK_LAUNCH(ctx);
-		MP_TRY(applyOutflowBC<Real>(ctx, d, flags, neu.g, grid, (double)dt));
+		int* any = (int*)(ctx->dScal + 24);
+		MP_CUDA(cudaMemsetAsync(any, 0, sizeof(int), ctx->stream));
+		k_mc_rest_mac<Real><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode, any); MP_CHECK_LAUNCH(ctx);
+		MP_TRY(applyOutflowBC<Real>(ctx, d, flags, neu.g, grid, (double)dt, any));
 	} else {
-		k_semi_lagrange<Real><<<blocks, 256, 0, ctx->stream>>>(d, V, (Real*)bwd.g->d, (const Real*)fwd.g->d, -dt); MP_CHECK_LAUNCH(ctx);
-		k_mc_correct<Real><<<blocks, 256, 0, ctx->stream>>>(d, F, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, (const Real*)bwd.g->d, (Real)strength); MP_CHECK_LAUNCH(ctx);
-		k_mc_clamp<Real><<<blocks, 256, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, clampMode); MP_CHECK_LAUNCH(ctx);
+		k_mc_rest<Real><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode); MP_CHECK_LAUNCH(ctx);
 	}
 	return adopt(ctx, grid, neu.g);
 }
@@ -390,8 +402,8 @@ int mp_set_wall_bcs(mp_context* ctx, const mp_grid* flags, mp_grid* vel, const m
 	if (phiObs && fractions) MP_FAIL(MP_ERR_UNSUPPORTED, "setWallBcs: the second-order variant (phiObs + fractions, KnSetWallBcsFrac) is not built");
 	if (obvel) MP_TRY(mp_check_same(vel, obvel, MP_GRID_MAC, "obvel", false));
 	const Dims d = dimsOf(flags);
-	if (vel->prec == 4) k_set_wall_bcs<float><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, obvel ? (const float*)obvel->d : nullptr);
-	else                k_set_wall_bcs<double><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, obvel ? (const double*)obvel->d : nullptr);
+	if (vel->prec == 4) k_set_wall_bcs<float><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, obvel ? (const float*)obvel->d : nullptr);
+	else                k_set_wall_bcs<double><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, obvel ? (const double*)obvel->d : nullptr);
 	MP_CHECK_LAUNCH(ctx);
 	return MP_OK;
 }
@@ -405,11 +417,11 @@ int mp_add_gravity(mp_context* ctx, const mp_grid* flags, mp_grid* vel, double g
 	if (vel->prec == 4) {
 		const float gridScale = scale ? (float)(float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; float f[3];
 		for (int c = 0; c < 3; c++) f[c] = ((float)g[c] * (float)dt) / gridScale;
-		k_apply_force<float><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, f[0], f[1], f[2], exclude ? (const float*)exclude->d : nullptr);
+		k_apply_force<float><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, f[0], f[1], f[2], exclude ? (const float*)exclude->d : nullptr);
 	} else {
 		const float gridScale = scale ? (float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; double f[3];
 		for (int c = 0; c < 3; c++) f[c] = (g[c] * dt) / gridScale;
-		k_apply_force<double><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, f[0], f[1], f[2], exclude ? (const double*)exclude->d : nullptr);
+		k_apply_force<double><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, f[0], f[1], f[2], exclude ? (const double*)exclude->d : nullptr);
 	}
 	MP_CHECK_LAUNCH(ctx);
 	return MP_OK;
@@ -425,11 +437,11 @@ int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* densit
 	if (vel->prec == 4) {
 		const float gridScale = scale ? (float)(float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; float f[3];
 		for (int c = 0; c < 3; c++) f[c] = (((-(float)g[c]) * (float)dt) / gridScale) * (float)coefficient;
-		k_add_buoyancy<float><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (const float*)density->d, (float*)vel->d, f[0], f[1], f[2]);
+		k_add_buoyancy<float><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (const float*)density->d, (float*)vel->d, f[0], f[1], f[2]);
 	} else {
 		const float gridScale = scale ? (float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; double f[3];
 		for (int c = 0; c < 3; c++) f[c] = (((-g[c]) * dt) / gridScale) * coefficient;
-		k_add_buoyancy<double><<<gridFor(d.n, 256), 256, 0, ctx->stream>>>(d, (const int*)flags->d, (const double*)density->d, (double*)vel->d, f[0], f[1], f[2]);
+		k_add_buoyancy<double><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (const double*)density->d, (double*)vel->d, f[0], f[1], f[2]);
 	}
 	MP_CHECK_LAUNCH(ctx);
 	return MP_OK;
