@@ -201,6 +201,11 @@ int mp_solve_pressure(mp_context* ctx, mp_grid* vel, mp_grid* pressure, const mp
 int mp_cg_solve_diffusion(mp_context* ctx, const mp_grid* flags, mp_grid* grid, double alpha, double cgMaxIterFac, double cgAccuracy,
                           mp_solve_info* info);
 
+/* cgSolveWE plugin/waves.cpp:86-147: one implicit (optionally Crank-Nicolson) step of the wave equation; afterwards utm1 holds the old ut and
+ * ut the new solution (= out), as the plugin leaves them.  dt = FluidSolver::getDt(). */
+int mp_cg_solve_we(mp_context* ctx, const mp_grid* flags, mp_grid* ut, mp_grid* utm1, mp_grid* out, int crankNic, double cSqr, double cgMaxIterFac,
+                   double cgAccuracy, double dt, mp_solve_info* info);
+
 /* ---- the steps either side of the projection, so that a whole smoke step keeps its fields in HBM ----
  * setWallBcs          plugin/extforces.cpp:186-218, :307-316  (KnSetWallBcs; phiObs + fractions = the second-order variant: MP_ERR_UNSUPPORTED)
  * addGravity          plugin/extforces.cpp:45-65              (scale != 0: divided by the grid's dx = 1/max(size))

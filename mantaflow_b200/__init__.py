@@ -13,7 +13,7 @@ from .grid import (FlagEmpty, FlagFluid, FlagGrid, FlagInflow, FlagObstacle, Fla
                    LevelsetGrid, MACGrid, RealGrid, Solver)
 from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, releaseMG, solvePressure, solvePressureHost,
                        solvePressureSystem)
-from .cg import GridCg, GridMg, cgSolveDiffusion
+from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE
 from .step import addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, setWallBcs
 
 __all__ = [n for n in dir() if not n.startswith("_")]

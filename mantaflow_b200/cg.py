@@ -93,6 +93,18 @@ def cgSolveDiffusion(flags, grid, alpha=0.25, cgMaxIterFac=1.0, cgAccuracy=1e-4)
     return info.as_dict()
 
 
+def cgSolveWE(flags, ut, utm1, out, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5):
+    """plugin/waves.cpp:86-147 (PYTHON() plugin): implicit wave-equation step on the device GridCg; utm1 <- ut, ut <- out"""
+    from ._lib import SolveInfo
+    s = flags.parent
+    info = SolveInfo()
+    check(s.lib.mp_cg_solve_we(s._ctx, flags.dev(), ut.dev(), utm1.dev(), out.dev(), C.c_int(int(bool(crankNic))), C.c_double(cSqr),
+                               C.c_double(cgMaxIterFac), C.c_double(cgAccuracy), C.c_double(s.timestep), C.byref(info)))
+    for g in (ut, utm1, out):
+        g.markDeviceWritten()
+    return info.as_dict()
+
+
 class GridMg:
     """multigrid.h:31-137"""
 

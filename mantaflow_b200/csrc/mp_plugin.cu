@@ -33,6 +33,25 @@ __global__ void __launch_bounds__(256) k_diffusion_matrix(Dims d, const int* __r
 	else { ai *= alpha; aj *= alpha; ak *= alpha; a0 *= alpha; a0 = (Real)((double)a0 + 1.); }
 	A0[idx] = a0; Ai[idx] = ai; Aj[idx] = aj; Ak[idx] = ak;
 }
+// cgSolveWE waves.cpp:112-118: A *= s, A0 += 1 on every cell;  MakeRhsWE :72-80 on the interior (the stencil of the Crank-Nicolson term is
+// the reference's: x and y neighbours only, also in 3-D)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_we_setup(Dims d, Real s, Real* __restrict__ A0, Real* __restrict__ Ai, Real* __restrict__ Aj, Real* __restrict__ Ak,
+	Real* __restrict__ rhs, const Real* __restrict__ ut, const Real* __restrict__ utm1, int crankNic)
+{
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n) return;
+	const int i = (int)(idx % d.sx); const IndexInt t = idx / d.sx; const int j = (int)(t % d.sy), k = (int)(t / d.sy);
+	Ai[idx] = Ai[idx] * s; Aj[idx] = Aj[idx] * s; Ak[idx] = Ak[idx] * s;
+	A0[idx] = (Real)((double)(A0[idx] * s) + 1.);
+	const bool interior = i >= 1 && i < d.sx - 1 && j >= 1 && j < d.sy - 1 && (!d.is3D || (k >= 1 && k < d.sz - 1));
+	Real r = 0;
+	if (interior) {
+		r = (Real)(2. * (double)ut[idx] - (double)utm1[idx]);
+		if (crankNic) r = (Real)((double)r + (double)s * (-4. * (double)ut[idx] + 1. * (double)ut[idx - d.X] + 1. * (double)ut[idx + d.X] + 1. * (double)ut[idx - d.Y] + 1. * (double)ut[idx + d.Y]));
+	}
+	rhs[idx] = r;
+}
 // knGetComponent / knSetComponent grid.cpp:676-685
 template <typename Real>
 __global__ void __launch_bounds__(256) k_component(IndexInt n, Real* __restrict__ vec, Real* __restrict__ comp, int c, int set) {
@@ -241,6 +260,51 @@ int mp_cg_solve_diffusion(mp_context* ctx, const mp_grid* flags, mp_grid* grid, 
 		}
 	}
 	if (info) { memset(info, 0, sizeof *info); info->fixedCell = -1; mp_cg_get(cg, &info->iterations, &info->resNorm, nullptr); info->maxIter = maxIter; info->matvecKernel = ctx->lastMatvecKernel; }
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MP_OK;
+}
+
+// cgSolveWE plugin/waves.cpp:86-147: one implicit step of the wave equation on the device GridCg (no preconditioner, GridCg's default stop test)
+int mp_cg_solve_we(mp_context* ctx, const mp_grid* flags, mp_grid* ut, mp_grid* utm1, mp_grid* out, int crankNic, double cSqr, double cgMaxIterFac,
+                   double cgAccuracy, double dt, mp_solve_info* info)
+{
+	if (!ctx || !flags || !ut || !utm1 || !out) MP_FAIL(MP_ERR_INVALID, "mp_cg_solve_we: NULL argument");
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "mp_cg_solve_we: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, ut, MP_GRID_REAL, "ut", false)); MP_TRY(mp_check_same(ut, utm1, MP_GRID_REAL, "utm1", false)); MP_TRY(mp_check_same(ut, out, MP_GRID_REAL, "out", false));
+	if (ut == utm1 || ut == out || utm1 == out) MP_FAIL(MP_ERR_INVALID, "mp_cg_solve_we: ut, utm1 and out must be three grids");
+	if (ctx->dist && ctx->dist->active) MP_FAIL(MP_ERR_UNSUPPORTED, "mp_cg_solve_we: not sharded across GPUs");
+	MP_CUDA(cudaSetDevice(ctx->device));
+	const int prec = ut->prec;
+	const Dims d = dimsOf(flags);
+	GridHolder tmp;
+	mp_grid *rhs, *residual, *search, *t, *A0, *Ai, *Aj, *Ak;
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &rhs)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &residual));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &search)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &t));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &A0)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &Ai));
+	MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &Aj)); MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, &Ak));
+	MP_CUDA(cudaMemsetAsync(out->d, 0, out->bytes, ctx->stream));                                   // out.clear() :106
+	MP_TRY(mp_make_laplace_matrix(ctx, flags, A0, Ai, Aj, Ak, nullptr));
+	const unsigned int blocks = gridFor(d.n, 256);
+	if (prec == 4) {
+		const float fdt = (float)dt, s = (float)((double)(fdt * fdt * (float)cSqr) * 0.5);           // :111
+		k_we_setup<float><<<blocks, 256, 0, ctx->stream>>>(d, s, (float*)A0->d, (float*)Ai->d, (float*)Aj->d, (float*)Ak->d, (float*)rhs->d, (const float*)ut->d, (const float*)utm1->d, crankNic);
+	} else {
+		const double s = (dt * dt * cSqr) * 0.5;
+		k_we_setup<double><<<blocks, 256, 0, ctx->stream>>>(d, s, (double*)A0->d, (double*)Ai->d, (double*)Aj->d, (double*)Ak->d, (double*)rhs->d, (const double*)ut->d, (const double*)utm1->d, crankNic);
+	}
+	MP_CHECK_LAUNCH(ctx);
+	const int maxDim = std::max(flags->sx, std::max(flags->sy, flags->sz));
+	const int maxIter = (prec == 4 ? (int)((float)cgMaxIterFac * (float)maxDim) : (int)(cgMaxIterFac * (double)maxDim)) * (d.is3D ? 1 : 4);   // :129
+	mp_cg* cg = nullptr;
+	MP_TRY(mp_cg_create(ctx, out, rhs, residual, search, flags, t, A0, Ai, Aj, Ak, &cg));
+	struct CgGuard { mp_cg* c; ~CgGuard() { mp_cg_destroy(c); } } guard{ cg };
+	mp_cg_set_accuracy(cg, prec == 4 ? (double)(float)cgAccuracy : cgAccuracy);
+	MP_TRY(mp_cg_run(cg, maxIter));
+	if (info) { memset(info, 0, sizeof *info); info->fixedCell = -1; mp_cg_get(cg, &info->iterations, &info->resNorm, nullptr); info->maxIter = maxIter; info->matvecKernel = ctx->lastMatvecKernel; }
+	// utm1.swap(ut); ut.copyFrom(out) :145-146
+	if (ut->owns && utm1->owns) { void* p = ut->d; ut->d = utm1->d; utm1->d = p; }
+	else MP_CUDA(cudaMemcpyAsync(utm1->d, ut->d, ut->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	MP_CUDA(cudaMemcpyAsync(ut->d, out->d, ut->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MP_OK;
 }

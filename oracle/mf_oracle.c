@@ -1443,3 +1443,31 @@ int mfo_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Rea
 	free(fwd); free(bwd); free(neu);
 	return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * cgSolveWE plugin/waves.cpp:86-147 (implicit wave equation step, another GridCg caller);
+ * MakeRhsWE :72-80.  ut / utm1 / out are updated as the plugin leaves them: utm1 <- old ut, ut <- out.        */
+int mfo_cg_solve_we(int sx, int sy, int sz, const int* flags, Real* ut, Real* utm1, Real* out, int crankNic, double cSqr_, double cgMaxIterFac,
+                    double cgAccuracy, double dt_)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	const Real dt = (Real)dt_, cSqr = (Real)cSqr_;
+	const Real s = (Real)((double)(dt * dt * cSqr) * 0.5);                         /* :111 */
+	Real *A0 = (Real*)calloc((size_t)n, sizeof(Real)), *Ai = (Real*)calloc((size_t)n, sizeof(Real)), *Aj = (Real*)calloc((size_t)n, sizeof(Real)), *Ak = (Real*)calloc((size_t)n, sizeof(Real));
+	Real* rhs = (Real*)calloc((size_t)n, sizeof(Real));
+	memset(out, 0, sizeof(Real) * (size_t)n);                                      /* out.clear() :106 */
+	mfo_make_matrix(sx, sy, sz, flags, 0, 0, 0., A0, Ai, Aj, Ak);
+	for (IndexInt q = 0; q < n; q++) { Ai[q] *= s; Aj[q] *= s; Ak[q] *= s; A0[q] *= s; A0[q] = (Real)((double)A0[q] + 1.); }      /* :112-118 */
+	FOR_BND1 {
+		const IndexInt idx = IDX(i, j, k);
+		rhs[idx] = (Real)(2. * (double)ut[idx] - (double)utm1[idx]);
+		if (crankNic) rhs[idx] = (Real)((double)rhs[idx] + (double)s * (-4. * (double)ut[idx] + 1. * (double)ut[idx - X] + 1. * (double)ut[idx + X] + 1. * (double)ut[idx - Y] + 1. * (double)ut[idx + Y]));
+	}
+	const int maxDim = sx > sy ? (sx > sz ? sx : sz) : (sy > sz ? sy : sz);
+	const int maxIter = (int)((Real)cgMaxIterFac * maxDim) * (IS3D ? 1 : 4);
+	const int rc = cg_run(sx, sy, sz, flags, rhs, out, A0, Ai, Aj, Ak, 0, (Real)cgAccuracy, 1, maxIter, 0, 0, 0);    /* GridCg defaults: no preconditioner, L2 stop test */
+	for (IndexInt q = 0; q < n; q++) { utm1[q] = ut[q]; ut[q] = out[q]; }           /* utm1.swap(ut); ut.copyFrom(out) :145-146 */
+	free(A0); free(Ai); free(Aj); free(Ak); free(rhs);
+	return rc;
+}

@@ -103,6 +103,14 @@ class Oracle:
                                                   C.c_double(strength), C.c_int(orderSpace), C.c_int(clampMode), C.c_int(orderTrace), C.c_double(dt)))
         return grid
 
+    def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
+        """plugin/waves.cpp:86 cgSolveWE; ut / utm1 are advanced in place, returns `out`"""
+        assert ut.dtype == self.real and utm1.dtype == self.real and ut.flags.c_contiguous and utm1.flags.c_contiguous
+        out = np.zeros(flags.shape, self.real)
+        self._chk(self._f("cg_solve_we")(*self.dims(flags), _p(flags), _p(ut), _p(utm1), _p(out), C.c_int(int(crankNic)), C.c_double(cSqr),
+                                         C.c_double(cgMaxIterFac), C.c_double(cgAccuracy), C.c_double(dt)))
+        return out
+
     def compute_rhs(self, flags, vel, phi=None, perCellCorr=None, fractions=None, obvel=None, curv=None,
                     gfClamp=1e-4, surfTens=0.0, enforceCompatibility=False):
         vel, phi, perCellCorr, fractions, obvel, curv = map(self._r, (vel, phi, perCellCorr, fractions, obvel, curv))

@@ -15,6 +15,7 @@
 //   setWallBcs              plugin/extforces.cpp:307-316
 //   addGravity, addBuoyancy plugin/extforces.cpp:61-90
 //   advectSemiLagrange      plugin/advection.cpp:442-461
+//   cgSolveWE               plugin/waves.cpp:86-147
 // Nothing of the reference is copied: its sources are compiled where they lie.
 //
 // The signatures are shared with oracle/mf_oracle.c (the restatement) so the same
@@ -62,6 +63,7 @@ int readObjectsVDB (const std::string&, std::vector<PbClass*>*, float) { return 
 Real LevelsetGrid::invalidTimeValue() { return -1000; }   // levelset.cpp:103 -> fastmarch.h:134
 void setWallBcs(const FlagGrid& flags, MACGrid& vel, const MACGrid* obvel, const MACGrid* fractions, const Grid<Real>* phiObs, int boundaryWidth);
 void cgSolveDiffusion(const FlagGrid& flags, GridBase& grid, Real alpha, Real cgMaxIterFac, Real cgAccuracy);
+void cgSolveWE(const FlagGrid& flags, Grid<Real>& ut, Grid<Real>& utm1, Grid<Real>& out, bool crankNic, Real cSqr, Real cgMaxIterFac, Real cgAccuracy);
 void addGravity(const FlagGrid& flags, MACGrid& vel, Vec3 gravity, const Grid<Real>* exclude, bool scale);
 void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGrid& vel, Vec3 gravity, Real coefficient, bool scale);
 void advectSemiLagrange(const FlagGrid* flags, const MACGrid* vel, GridBase* grid, int order, Real strength, int orderSpace, bool openBounds, int boundaryWidth, int clampMode, int orderTrace);
@@ -144,6 +146,18 @@ int ref_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Rea
 	    MACGrid Vc(s); memcpy(&Vc[0], vel, n * sizeof(Vec3));      // self-advection passes the same grid as vel and grid: keep that aliasing out of the harness
 	    advectSemiLagrange(&F, &Vc, &G, order, (Real)strength, orderSpace, false, -1, clampMode, orderTrace);
 	    memcpy(grid, &G[0], n * sizeof(Vec3)); } }
+	delete s;
+  CATCH }
+
+// ut / utm1 are swapped by the plugin (not allowed for external data): solver-owned copies, results copied back
+int ref_cg_solve_we(int sx, int sy, int sz, const int* flags, Real* ut, Real* utm1, Real* out, int crankNic, double cSqr, double cgMaxIterFac, double cgAccuracy, double dt)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz); s->mDt = (Real)dt;
+	const size_t n = (size_t)sx * sy * sz;
+	{ FlagGrid F(s, (int*)flags); Grid<Real> U(s), Um(s), O(s);
+	  memcpy(&U[0], ut, n * sizeof(Real)); memcpy(&Um[0], utm1, n * sizeof(Real)); memcpy(&O[0], out, n * sizeof(Real));
+	  cgSolveWE(F, U, Um, O, crankNic != 0, (Real)cSqr, (Real)cgMaxIterFac, (Real)cgAccuracy);
+	  memcpy(ut, &U[0], n * sizeof(Real)); memcpy(utm1, &Um[0], n * sizeof(Real)); memcpy(out, &O[0], n * sizeof(Real)); }
 	delete s;
   CATCH }
 

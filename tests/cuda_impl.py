@@ -144,6 +144,13 @@ class CudaImpl:
         grid[...] = G.numpy()
         return grid
 
+    def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
+        s = self._solver(flags); s.timestep = dt
+        U, Um, O = mf.RealGrid(s, ut), mf.RealGrid(s, utm1), mf.RealGrid(s)
+        mf.cgSolveWE(mf.FlagGrid(s, flags), U, Um, O, crankNic=crankNic, cSqr=cSqr, cgMaxIterFac=cgMaxIterFac, cgAccuracy=cgAccuracy)
+        ut[...] = U.numpy(); utm1[...] = Um.numpy()
+        return O.numpy().copy()
+
     def release_solver(self, key):
         for k, s in list(self._solvers.items()):
             if k[3] == key:

@@ -159,6 +159,14 @@ def step_fixtures():
             path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
             np.savez_compressed(path, **fx)
             print("%-34s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+        for name in helpers.WE_SCENES:       # cgSolveWE: three implicit wave steps, plain and Crank-Nicolson
+            fx = {}
+            for cn in (False, True):
+                for a, key in zip(helpers.run_wave_steps(R, name, prec, cn), ("ut", "utm1", "out")):
+                    fx["%s_cn%d" % (key, int(cn))] = a
+            path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, **fx)
+            print("%-34s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024))
     for shape, tag in (((24, 36, 24), "3d"), ((1, 48, 32), "2d")):
         dens, vel, p, its = helpers.run_plume_steps(Oracle("reference", 4), shape, 4, steps=6)
         path = os.path.join(HERE, "plume%s_f32.npz" % tag)

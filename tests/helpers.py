@@ -228,3 +228,28 @@ def run_plume_steps(I, shape, prec, steps, pc=1):
         p, it, _ = I.solve_pressure(flags, vel, preconditioner=pc, zeroPressureFixing=(pc >= 2))
         its.append(it)
     return dens, vel, p, its
+
+
+# ---------------------------------------------------------------- cgSolveWE (plugin/waves.cpp:86-147)
+WE_SCENES = {"we2d": (1, 40, 36), "we3d": (14, 18, 20)}
+
+
+def run_wave_steps(I, name, prec, crankNic, steps=3):
+    from mantaflow_b200 import scenes
+    sz, sy, sx = shape = WE_SCENES[name]
+    real = np.float32 if prec == 4 else np.float64
+    flags = scenes.closed_box_flags(sx, sy, sz)
+    rng = np.random.default_rng(3)
+    ut, utm1 = rng.random(shape).astype(real), rng.random(shape).astype(real)
+    out = None
+    for _ in range(steps):
+        out = I.cg_solve_we(flags, ut, utm1, crankNic=crankNic, cSqr=0.3, dt=0.9)
+    return ut, utm1, out
+
+
+def check_waves_against_golden(I, name, prec, tol):
+    g = load_golden("step_" + name, prec)
+    for cn in (False, True):
+        for a, key in zip(run_wave_steps(I, name, prec, cn), ("ut", "utm1", "out")):
+            ref = g["%s_cn%d" % (key, int(cn))]
+            assert np.abs(a.astype(np.float64) - ref).max() <= tol, (name, prec, cn, key)

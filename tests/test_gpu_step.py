@@ -6,7 +6,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from helpers import STEP_CASES, STEP_SCENES, check_step_against_golden, load_golden, run_plume_steps, run_step_case, step_scene  # noqa: E402
+from helpers import (STEP_CASES, STEP_SCENES, WE_SCENES, check_step_against_golden, check_waves_against_golden, load_golden,  # noqa: E402
+                     run_plume_steps, run_step_case, step_scene)
 
 
 @pytest.fixture(scope="module")
@@ -82,3 +83,11 @@ def test_unsupported_variants_fail_loudly(mf):
         mf.advectSemiLagrange(F, V, D, orderTrace=2)
     with pytest.raises(mf.MantaError):
         mf.setWallBcs(F, V, fractions=mf.MACGrid(s), phiObs=mf.RealGrid(s))
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(WE_SCENES))
+def test_cuda_reproduces_wave_equation_golden(name, prec):
+    """cgSolveWE on the device GridCg: float bit-identical to the reference, double within the reduction order"""
+    from cuda_impl import CudaImpl
+    check_waves_against_golden(CudaImpl(prec), name, prec, tol=0.0 if prec == 4 else 1e-12)

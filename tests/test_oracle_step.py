@@ -4,7 +4,8 @@ oracle/_ref is built."""
 import numpy as np
 import pytest
 
-from helpers import STEP_CASES, STEP_SCENES, check_step_against_golden, load_golden, run_plume_steps, run_step_case, step_scene
+from helpers import (STEP_CASES, STEP_SCENES, WE_SCENES, check_step_against_golden, check_waves_against_golden, load_golden, run_plume_steps,
+                     run_step_case, step_scene)
 
 
 @pytest.mark.parametrize("prec", [4, 8])
@@ -38,3 +39,10 @@ def test_unsupported_orders_are_errors(port32):
         port32.advect_semi_lagrange(flags, vel, dens.copy(), order=3)
     with pytest.raises(OracleError):
         port32.advect_semi_lagrange(flags, vel, dens.copy(), order=1, orderSpace=2)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(WE_SCENES))
+def test_port_reproduces_wave_equation_golden(name, prec, port32, port64):
+    """cgSolveWE: float bit-identical (double accumulators of float products), double up to the reduction order"""
+    check_waves_against_golden(port32 if prec == 4 else port64, name, prec, tol=0.0 if prec == 4 else 1e-13)
