@@ -219,6 +219,15 @@ int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* densit
 int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
                             int clampMode, int orderTrace, double dt);
 
+/* ---- PD_fluid_guiding plugin/fluidguiding.cpp:294-353: primal-dual guiding of vel towards velT with per-cell weight;
+ * up to maxIters solvePressure calls on device-resident copies, separable Gaussian blurs of radius blurRadius, stop test as in the reference.
+ * vel receives the guided, divergence-free field; *iterations = the loop index at exit (what the reference prints).  The optional grids and
+ * the solver settings are passed to every inner solvePressure as the plugin does (precondition = true, enforceCompatibility = useL2Norm = false). */
+int mp_pd_fluid_guiding(mp_context* ctx, mp_grid* vel, const mp_grid* velT, mp_grid* pressure, const mp_grid* flags, const mp_grid* weight,
+                        int blurRadius, double theta, double tau, double sigma, double epsRel, double epsAbs, int maxIters,
+                        const mp_grid* phi, const mp_grid* perCellCorr, const mp_grid* fractions, const mp_grid* obvel, double gfClamp, double cgMaxIterFac,
+                        double cgAccuracy, int preconditioner, int zeroPressureFixing, const mp_grid* curv, double surfTens, int* iterations);
+
 /* ---- the plugin with HOST buffers (what pressure.cpp calls when grids have no device mirror yet):
  * uploads flags/vel(/phi...), runs mp_solve_pressure, downloads vel/pressure(/retRhs).  Optional
  * pointers may be NULL.  Buffers may be pageable or pinned (mp_host_alloc). ---- */

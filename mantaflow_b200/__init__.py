@@ -14,6 +14,7 @@ from .grid import (FlagEmpty, FlagFluid, FlagGrid, FlagInflow, FlagObstacle, Fla
 from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, releaseMG, solvePressure, solvePressureHost,
                        solvePressureSystem)
 from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE
-from .step import addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, setWallBcs
+from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, lastGuidingIterations, releaseBlurPrecomp,
+                   setWallBcs)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

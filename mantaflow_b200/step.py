@@ -5,6 +5,7 @@ defaults as the reference, so the main loop of scenes/simpleplume.py runs with e
     addGravity          plugin/extforces.cpp:61-65      addGravityNoScale :67-69
     addBuoyancy         plugin/extforces.cpp:86-90
     advectSemiLagrange  plugin/advection.cpp:442-461
+    PD_fluid_guiding    plugin/fluidguiding.cpp:294-353  (+ getSpiralVelocity :171-192, setGradientYWeight :195-207 for its scenes)
 """
 import ctypes as C
 
@@ -54,3 +55,29 @@ def advectSemiLagrange(flags, vel, grid, order=1, strength=1.0, orderSpace=1, op
     check(s.lib.mp_advect_semi_lagrange(s._ctx, flags.dev(), vel.dev(), grid.dev(), C.c_int(order), C.c_double(strength), C.c_int(orderSpace),
                                         C.c_int(clampMode), C.c_int(orderTrace), C.c_double(s.timestep)))
     grid.markDeviceWritten()
+
+
+_last_guiding = {"iterations": -1}
+
+
+def PD_fluid_guiding(vel, velT, pressure, flags, weight, blurRadius=5, theta=1.0, tau=1.0, sigma=1.0, epsRel=1e-3, epsAbs=1e-3, maxIters=200,
+                     phi=None, perCellCorr=None, fractions=None, obvel=None, gfClamp=1e-04, cgMaxIterFac=1.5, cgAccuracy=1e-3,
+                     preconditioner=1, zeroPressureFixing=False, curv=None, surfTens=0.):
+    """primal-dual fluid guiding around solvePressure, every temporary on the device; the loop count the reference prints is kept in
+    lastGuidingIterations()"""
+    s = flags.parent
+    it = C.c_int(-1)
+    check(s.lib.mp_pd_fluid_guiding(s._ctx, vel.dev(), velT.dev(), pressure.dev(), flags.dev(), weight.dev(), C.c_int(blurRadius), C.c_double(theta),
+                                    C.c_double(tau), C.c_double(sigma), C.c_double(epsRel), C.c_double(epsAbs), C.c_int(maxIters), _d(phi), _d(perCellCorr),
+                                    _d(fractions), _d(obvel), C.c_double(gfClamp), C.c_double(cgMaxIterFac), C.c_double(cgAccuracy), C.c_int(preconditioner),
+                                    C.c_int(int(bool(zeroPressureFixing))), _d(curv), C.c_double(surfTens), C.byref(it)))
+    vel.markDeviceWritten(); pressure.markDeviceWritten()
+    _last_guiding["iterations"] = it.value
+
+
+def lastGuidingIterations():
+    return _last_guiding["iterations"]
+
+
+def releaseBlurPrecomp():
+    """fluidguiding.cpp:356-360: the reference caches one blur kernel in globals; here it is rebuilt per call, nothing to release"""

@@ -1471,3 +1471,135 @@ int mfo_cg_solve_we(int sx, int sy, int sz, const int* flags, Real* ut, Real* ut
 	free(A0); free(Ai); free(Aj); free(Ak); free(rhs);
 	return rc;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * PD_fluid_guiding plugin/fluidguiding.cpp:294-353: primal-dual guiding loop around solvePressure.
+ * Helpers: get1DGaussianBlurKernel :30-45 (through the sparse Matrix class util/rcmatrix.h: increments <= VECTOR_EPSILON are dropped,
+ * :186-187), apply1DKernelDirX/Y/Z :49-82, applySeparableKernel2D/3D :85-130, getRNorm :140-145, getEpsDual :165-168,
+ * applyApproxInvM :229-239, precomputeQ :243-250, precomputeInvA :254-264, prox_f :267-272.
+ * MACGrid algebra (grid.h:478-486 via grid.cpp add/sub/mult/multConst/addScaled) is componentwise in Real.                       */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846   /* math.h value (hidden by -std=c11) */
+#endif
+#if MF_REAL_IS_DOUBLE
+#define R_EXP exp
+#define VEC_EPS 1e-10
+#else
+#define R_EXP expf
+#define VEC_EPS 1e-6f
+#endif
+static void pd_blur_kernel(int n, Real* G)
+{
+	const int sigma = n;
+	Real sumG = 0;
+	for (int j = 0; j < n; j++) {
+		Real xv = (Real)(-(n - 1) * 0.5), yv = (Real)(j - (n - 1) * 0.5);
+		if (!(R_FABS(xv) > VEC_EPS)) xv = 0;
+		if (!(R_FABS(yv) > VEC_EPS)) yv = 0;
+		Real g = (Real)(1 / (2 * M_PI * sigma * sigma) * R_EXP(-(xv * xv + yv * yv) / (2 * sigma * sigma)));
+		if (!(R_FABS(g) > VEC_EPS)) g = 0;
+		G[j] = g;
+		sumG += G[j];
+	}
+	const double k = 1.0 / sumG;
+	for (int j = 0; j < n; j++) { Real v = (Real)(G[j] * k); if (!(R_FABS(v) > VEC_EPS)) v = 0; G[j] = v; }
+}
+static void pd_conv1d(int sx, int sy, int sz, int dir, const Real* in, Real* out, const Real* kernel, int kn)
+{
+	STRIDES
+	const int size[3] = { sx, sy, sz }, kCentre = kn / 2;
+	const IndexInt stride[3] = { X, Y, Z };
+	#pragma omp parallel for schedule(static)
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		const int pos[3] = { i, j, k };
+		Real acc[3] = { 0, 0, 0 };
+		for (int m = 0, ind = kn - 1, q = pos[dir] - kCentre; m < kn; m++, ind--, q++) {
+			if (q < 0) continue;
+			else if (q >= size[dir]) break;
+			const Real* v = in + 3 * (idx + (IndexInt)(q - pos[dir]) * stride[dir]);
+			for (int c = 0; c < 3; c++) acc[c] += v[c] * kernel[ind];
+		}
+		for (int c = 0; c < 3; c++) out[3 * idx + c] = acc[c];
+	}
+}
+static void pd_blur(int sx, int sy, int sz, const int* flags, Real* grid, const Real* kernel, int kn, Real* t1, Real* t2)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	Real* orig = (Real*)malloc(sizeof(Real) * 3 * (size_t)n);
+	memcpy(orig, grid, sizeof(Real) * 3 * (size_t)n);
+	pd_conv1d(sx, sy, sz, 0, grid, t1, kernel, kn);
+	pd_conv1d(sx, sy, sz, 1, t1, t2, kernel, kn);
+	if (IS3D) { pd_conv1d(sx, sy, sz, 2, t2, t1, kernel, kn); memcpy(grid, t1, sizeof(Real) * 3 * (size_t)n); }
+	else memcpy(grid, t2, sizeof(Real) * 3 * (size_t)n);
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		if ((i > 0 && (flags[idx - X] & TypeObstacle)) || (j > 0 && (flags[idx - Y] & TypeObstacle)) || (IS3D && k > 0 && (flags[idx - Z] & TypeObstacle)) || (flags[idx] & TypeObstacle))
+			for (int c = 0; c < 3; c++) grid[3 * idx + c] = orig[3 * idx + c];
+	}
+	free(orig);
+}
+static Real pd_max_abs(const Real* v, IndexInt n)      /* Grid<Vec3>::getMaxAbs grid.cpp:330-332, CompMaxVec :198-203 */
+{
+	Real m = -REAL_MAX_;
+	for (IndexInt q = 0; q < n; q++) { const Real s = v[3 * q] * v[3 * q] + v[3 * q + 1] * v[3 * q + 1] + v[3 * q + 2] * v[3 * q + 2]; if (s > m) m = s; }
+	return R_SQRT(m);
+}
+int mfo_pd_fluid_guiding(int sx, int sy, int sz, const int* flags, Real* vel, const Real* velT, Real* pressure, const Real* weight,
+	int blurRadius, double theta_, double tau_, double sigma_, double epsRel_, double epsAbs_, int maxIters,
+	double cgMaxIterFac, double cgAccuracy, int preconditioner, int zeroPressureFixing, int* iterations)
+{
+	const IndexInt n = (IndexInt)sx * sy * sz; const size_t n3 = 3 * (size_t)n;
+	const Real theta = (Real)theta_, tau = (Real)tau_, sigma = (Real)sigma_, epsRel = (Real)epsRel_, epsAbs = (Real)epsAbs_;
+	const int kn = 2 * blurRadius + 1;
+	Real* G = (Real*)calloc((size_t)kn, sizeof(Real)); pd_blur_kernel(kn, G);
+	Real *velC = (Real*)malloc(n3 * sizeof(Real)), *x = (Real*)calloc(n3, sizeof(Real)), *y = (Real*)calloc(n3, sizeof(Real)), *z = (Real*)calloc(n3, sizeof(Real));
+	Real *x0 = (Real*)calloc(n3, sizeof(Real)), *z0 = (Real*)calloc(n3, sizeof(Real)), *Q = (Real*)malloc(n3 * sizeof(Real)), *invA = (Real*)malloc(n3 * sizeof(Real));
+	Real *vn = (Real*)malloc(n3 * sizeof(Real)), *t1 = (Real*)malloc(n3 * sizeof(Real)), *t2 = (Real*)malloc(n3 * sizeof(Real));
+	memcpy(velC, vel, n3 * sizeof(Real));
+	/* precomputeQ */
+	for (size_t q = 0; q < n3; q++) Q[q] = velT[q] - velC[q];
+	pd_blur(sx, sy, sz, flags, Q, G, kn, t1, t2); pd_blur(sx, sy, sz, flags, Q, G, kn, t1, t2);
+	for (size_t q = 0; q < n3; q++) { Q[q] = Q[q] * (Real)2.0; Q[q] = Q[q] + (-sigma) * velC[q]; }
+	/* precomputeInvA */
+	for (IndexInt q = 0; q < n; q++) {
+		Real val = 2 * weight[q] * weight[q] + sigma;
+		if (val < 0.01) val = (Real)0.01;
+		const Real inv = (Real)(1.0 / val);
+		invA[3 * q] = invA[3 * q + 1] = invA[3 * q + 2] = inv;
+	}
+	const Real invSigma = (Real)(1.0 / sigma);
+	int iter = 0, rc = 0;
+	for (iter = 0; iter < maxIters; iter++) {
+		/* x-update */
+		for (size_t q = 0; q < n3; q++) { x0[q] = x[q]; x[q] = x[q] * invSigma; x[q] = x[q] + y[q]; }
+		/* prox_f(x) */
+		for (size_t q = 0; q < n3; q++) { x[q] = x[q] * sigma; x[q] = x[q] + Q[q]; }
+		/*   applyApproxInvM(x) */
+		for (size_t q = 0; q < n3; q++) vn[q] = x[q] * invA[q];
+		pd_blur(sx, sy, sz, flags, vn, G, kn, t1, t2); pd_blur(sx, sy, sz, flags, vn, G, kn, t1, t2);
+		for (size_t q = 0; q < n3; q++) { vn[q] = vn[q] * (Real)2.0; vn[q] = vn[q] * invA[q]; x[q] = x[q] * invA[q]; x[q] = x[q] - vn[q]; }
+		for (size_t q = 0; q < n3; q++) x[q] = x[q] + velC[q];
+		for (size_t q = 0; q < n3; q++) { x[q] = x[q] * (-sigma); x[q] = x[q] + sigma * y[q]; x[q] = x[q] + x0[q]; }
+		/* z-update */
+		for (size_t q = 0; q < n3; q++) { z0[q] = z[q]; z[q] = z[q] + (-tau) * x[q]; }
+		rc = mfo_solve_pressure(0, sx, sy, sz, flags, z, pressure, 0, 0, 0, 0, 0, 0, cgAccuracy, 1e-04, cgMaxIterFac, 1, preconditioner, 0, 0, zeroPressureFixing, 0., 0, 0);
+		if (rc) break;
+		/* y-update */
+		for (size_t q = 0; q < n3; q++) { y[q] = z[q]; y[q] = y[q] - z0[q]; y[q] = y[q] * theta; y[q] = y[q] + z[q]; }
+		/* stopping criterion: getRNorm(z, z0) < getEpsDual(epsAbs, epsRel, z) */
+		int stop = 0;
+		if (iter > 0) {
+			for (size_t q = 0; q < n3; q++) t1[q] = z[q] - z0[q];
+			const Real rnorm = pd_max_abs(t1, n);
+			const Real epsDual = (Real)(sqrt(sz > 1 ? 3.0 : 2.0) * (double)epsAbs + (double)(epsRel * pd_max_abs(z, n)));
+			stop = rnorm < epsDual;
+		}
+		if (stop || (iter == maxIters - 1)) break;
+	}
+	memcpy(vel, z, n3 * sizeof(Real));
+	if (iterations) *iterations = iter;
+	free(G); free(velC); free(x); free(y); free(z); free(x0); free(z0); free(Q); free(invA); free(vn); free(t1); free(t2);
+	return rc;
+}

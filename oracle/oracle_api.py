@@ -111,6 +111,18 @@ class Oracle:
                                          C.c_double(cgMaxIterFac), C.c_double(cgAccuracy), C.c_double(dt)))
         return out
 
+    def pd_fluid_guiding(self, flags, vel, velT, weight, blurRadius=5, theta=1.0, tau=1.0, sigma=1.0, epsRel=1e-3, epsAbs=1e-3, maxIters=200,
+                         cgMaxIterFac=1.5, cgAccuracy=1e-3, preconditioner=1, zeroPressureFixing=False):
+        """plugin/fluidguiding.cpp:294 PD_fluid_guiding; vel is replaced by the guided, divergence-free field; returns (pressure, iterations)"""
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        p = np.zeros(flags.shape, self.real)
+        it = C.c_int(0)
+        self._chk(self._f("pd_fluid_guiding")(*self.dims(flags), _p(flags), _p(vel), _p(self._r(velT)), _p(p), _p(self._r(weight)), C.c_int(blurRadius),
+                                              C.c_double(theta), C.c_double(tau), C.c_double(sigma), C.c_double(epsRel), C.c_double(epsAbs), C.c_int(maxIters),
+                                              C.c_double(cgMaxIterFac), C.c_double(cgAccuracy), C.c_int(preconditioner), C.c_int(int(zeroPressureFixing)),
+                                              C.byref(it)))
+        return p, it.value
+
     def compute_rhs(self, flags, vel, phi=None, perCellCorr=None, fractions=None, obvel=None, curv=None,
                     gfClamp=1e-4, surfTens=0.0, enforceCompatibility=False):
         vel, phi, perCellCorr, fractions, obvel, curv = map(self._r, (vel, phi, perCellCorr, fractions, obvel, curv))

@@ -16,6 +16,7 @@
 //   addGravity, addBuoyancy plugin/extforces.cpp:61-90
 //   advectSemiLagrange      plugin/advection.cpp:442-461
 //   cgSolveWE               plugin/waves.cpp:86-147
+//   PD_fluid_guiding        plugin/fluidguiding.cpp:294-353
 // Nothing of the reference is copied: its sources are compiled where they lie.
 //
 // The signatures are shared with oracle/mf_oracle.c (the restatement) so the same
@@ -64,6 +65,10 @@ Real LevelsetGrid::invalidTimeValue() { return -1000; }   // levelset.cpp:103 ->
 void setWallBcs(const FlagGrid& flags, MACGrid& vel, const MACGrid* obvel, const MACGrid* fractions, const Grid<Real>* phiObs, int boundaryWidth);
 void cgSolveDiffusion(const FlagGrid& flags, GridBase& grid, Real alpha, Real cgMaxIterFac, Real cgAccuracy);
 void cgSolveWE(const FlagGrid& flags, Grid<Real>& ut, Grid<Real>& utm1, Grid<Real>& out, bool crankNic, Real cSqr, Real cgMaxIterFac, Real cgAccuracy);
+void PD_fluid_guiding(MACGrid& vel, MACGrid& velT, Grid<Real>& pressure, FlagGrid& flags, Grid<Real>& weight, int blurRadius, Real theta, Real tau, Real sigma,
+	Real epsRel, Real epsAbs, int maxIters, Grid<Real>* phi, Grid<Real>* perCellCorr, MACGrid* fractions, MACGrid* obvel, Real gfClamp, Real cgMaxIterFac,
+	Real cgAccuracy, int preconditioner, bool zeroPressureFixing, const Grid<Real>* curv, const Real surfTens);
+void releaseBlurPrecomp();
 void addGravity(const FlagGrid& flags, MACGrid& vel, Vec3 gravity, const Grid<Real>* exclude, bool scale);
 void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGrid& vel, Vec3 gravity, Real coefficient, bool scale);
 void advectSemiLagrange(const FlagGrid* flags, const MACGrid* vel, GridBase* grid, int order, Real strength, int orderSpace, bool openBounds, int boundaryWidth, int clampMode, int orderTrace);
@@ -146,6 +151,30 @@ int ref_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Rea
 	    MACGrid Vc(s); memcpy(&Vc[0], vel, n * sizeof(Vec3));      // self-advection passes the same grid as vel and grid: keep that aliasing out of the harness
 	    advectSemiLagrange(&F, &Vc, &G, order, (Real)strength, orderSpace, false, -1, clampMode, orderTrace);
 	    memcpy(grid, &G[0], n * sizeof(Vec3)); } }
+	delete s;
+  CATCH }
+
+int ref_pd_fluid_guiding(int sx, int sy, int sz, const int* flags, Real* vel, const Real* velT, Real* pressure, const Real* weight,
+	int blurRadius, double theta, double tau, double sigma, double epsRel, double epsAbs, int maxIters,
+	double cgMaxIterFac, double cgAccuracy, int preconditioner, int zeroPressureFixing, int* iterations)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	std::string log;
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel); MACGrid VT(s, (Vec3*)velT); Grid<Real> P(s, pressure); Grid<Real> W(s, (Real*)weight);
+	  int oldLevel = gDebugLevel; gDebugLevel = 1;
+	  try {
+		CoutCapture cap;
+		try {
+			PD_fluid_guiding(V, VT, P, F, W, blurRadius, (Real)theta, (Real)tau, (Real)sigma, (Real)epsRel, (Real)epsAbs, maxIters, 0, 0, 0, 0, (Real)1e-04,
+				(Real)cgMaxIterFac, (Real)cgAccuracy, preconditioner, zeroPressureFixing != 0, 0, (Real)0.);
+		} catch (...) { log = cap.ss.str(); throw; }
+		log = cap.ss.str();
+	  } catch (...) { gDebugLevel = oldLevel; releaseBlurPrecomp(); releaseMG(s); throw; }
+	  gDebugLevel = oldLevel; }
+	releaseBlurPrecomp();              // the plugin keeps its blur kernel in globals (fluidguiding.cpp:22-24)
+	releaseMG(s);
+	size_t p = log.rfind("PD_fluid_guiding iterations:");      // :350
+	if (iterations) *iterations = (p != std::string::npos) ? atoi(log.c_str() + p + 28) : -1;
 	delete s;
   CATCH }
 

@@ -151,6 +151,17 @@ class CudaImpl:
         ut[...] = U.numpy(); utm1[...] = Um.numpy()
         return O.numpy().copy()
 
+    def pd_fluid_guiding(self, flags, vel, velT, weight, blurRadius=5, theta=1.0, tau=1.0, sigma=1.0, epsRel=1e-3, epsAbs=1e-3, maxIters=200,
+                         cgMaxIterFac=1.5, cgAccuracy=1e-3, preconditioner=1, zeroPressureFixing=False):
+        s = self._solver(flags)
+        V, P = mf.MACGrid(s, vel), mf.RealGrid(s)
+        mf.PD_fluid_guiding(V, mf.MACGrid(s, velT), P, mf.FlagGrid(s, flags), mf.RealGrid(s, weight), blurRadius=blurRadius, theta=theta, tau=tau, sigma=sigma,
+                            epsRel=epsRel, epsAbs=epsAbs, maxIters=maxIters, cgMaxIterFac=cgMaxIterFac, cgAccuracy=cgAccuracy, preconditioner=preconditioner,
+                            zeroPressureFixing=zeroPressureFixing)
+        mf.releaseMG(s)
+        vel[...] = V.numpy()
+        return P.numpy().copy(), mf.lastGuidingIterations()
+
     def release_solver(self, key):
         for k, s in list(self._solvers.items()):
             if k[3] == key:

@@ -167,6 +167,11 @@ def step_fixtures():
             path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
             np.savez_compressed(path, **fx)
             print("%-34s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+        for name in helpers.GUIDING_SCENES:  # PD_fluid_guiding: the whole primal-dual loop incl. its multigrid solves
+            v, p, it = helpers.run_guiding(R, name, prec)
+            path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, vel=v, pressure=p, iterations=np.array(it))
+            print("%-34s %7.1f KiB  %d PD iterations" % (os.path.basename(path), os.path.getsize(path) / 1024, it))
     for shape, tag in (((24, 36, 24), "3d"), ((1, 48, 32), "2d")):
         dens, vel, p, its = helpers.run_plume_steps(Oracle("reference", 4), shape, 4, steps=6)
         path = os.path.join(HERE, "plume%s_f32.npz" % tag)

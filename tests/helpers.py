@@ -253,3 +253,49 @@ def check_waves_against_golden(I, name, prec, tol):
         for a, key in zip(run_wave_steps(I, name, prec, cn), ("ut", "utm1", "out")):
             ref = g["%s_cn%d" % (key, int(cn))]
             assert np.abs(a.astype(np.float64) - ref).max() <= tol, (name, prec, cn, key)
+
+
+# ---------------------------------------------------------------- PD_fluid_guiding (plugin/fluidguiding.cpp:294-353)
+GUIDING_SCENES = {"guide2d": ((1, 40, 36), 3), "guide3d": ((14, 18, 20), 2)}      # shape, preconditioner (the scenes use the multigrid ones)
+
+
+def guiding_scene(name, prec):
+    """closed box with an obstacle block, small random velocity, the spiral target field of getSpiralVelocity (fluidguiding.cpp:171-192,
+    strength 0.5) and the two-band weight of scenes/guiding_2d.py:55-56"""
+    from mantaflow_b200 import scenes
+    shape, pc = GUIDING_SCENES[name]
+    sz, sy, sx = shape
+    real = np.float32 if prec == 4 else np.float64
+    flags = scenes.closed_box_flags(sx, sy, sz)
+    if sz > 1:
+        flags[5:8, 6:9, 7:11] = 2
+    else:
+        flags[0, 10:14, 12:16] = 2
+    rng = np.random.default_rng(3)
+    vel = ((rng.random(shape + (3,)) - 0.5) * 0.2).astype(real)
+    if sz == 1:
+        vel[..., 2] = 0
+    scenes.set_wall_bcs(flags, vel)
+    velT = np.zeros(shape + (3,), real)
+    j, i = np.meshgrid(np.arange(sy), np.arange(sx), indexing="ij")
+    dx = real(0.5 * (sx - 1)) - i.astype(real); dy = real(0.5 * (sy - 1)) - j.astype(real)
+    h = np.sqrt(dx * dx + dy * dy)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        velT[:, :, :, 0] = np.where(h > 0, dy / h, 0)[None]; velT[:, :, :, 1] = np.where(h > 0, -dx / h, 0)[None]
+    velT *= real(0.5)
+    w = np.ones(shape, real); w[:, sy // 2:, :] = 5
+    return flags, vel, velT, w, pc
+
+
+def run_guiding(I, name, prec):
+    flags, vel, velT, w, pc = guiding_scene(name, prec)
+    v = vel.copy()
+    p, it = I.pd_fluid_guiding(flags, v, velT, w, blurRadius=2, sigma=0.99, maxIters=40, cgAccuracy=1e-4, preconditioner=pc, zeroPressureFixing=True)
+    return v, p, it
+
+
+def check_guiding_against_golden(I, name, prec, tol):
+    g = load_golden("step_" + name, prec)
+    v, p, it = run_guiding(I, name, prec)
+    assert it == int(g["iterations"]), (it, int(g["iterations"]))
+    assert np.abs(v.astype(np.float64) - g["vel"]).max() <= tol and np.abs(p.astype(np.float64) - g["pressure"]).max() <= tol * 10

@@ -6,7 +6,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-from helpers import (STEP_CASES, STEP_SCENES, WE_SCENES, check_step_against_golden, check_waves_against_golden, load_golden,  # noqa: E402
+from helpers import (GUIDING_SCENES, STEP_CASES, STEP_SCENES, WE_SCENES, check_guiding_against_golden, check_step_against_golden,  # noqa: E402
+                     check_waves_against_golden, load_golden,
                      run_plume_steps, run_step_case, step_scene)
 
 
@@ -91,3 +92,11 @@ def test_cuda_reproduces_wave_equation_golden(name, prec):
     """cgSolveWE on the device GridCg: float bit-identical to the reference, double within the reduction order"""
     from cuda_impl import CudaImpl
     check_waves_against_golden(CudaImpl(prec), name, prec, tol=0.0 if prec == 4 else 1e-12)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(GUIDING_SCENES))
+def test_cuda_reproduces_fluid_guiding_golden(name, prec):
+    """PD_fluid_guiding on the device: same loop count, float within the multigrid solves' tolerance of the reference"""
+    from cuda_impl import CudaImpl
+    check_guiding_against_golden(CudaImpl(prec), name, prec, tol=2e-5 if prec == 4 else 1e-9)

@@ -4,7 +4,7 @@ oracle/_ref is built."""
 import numpy as np
 import pytest
 
-from helpers import (STEP_CASES, STEP_SCENES, WE_SCENES, check_step_against_golden, check_waves_against_golden, load_golden, run_plume_steps,
+from helpers import (GUIDING_SCENES, STEP_CASES, STEP_SCENES, WE_SCENES, check_guiding_against_golden, check_step_against_golden, check_waves_against_golden, load_golden, run_plume_steps,
                      run_step_case, step_scene)
 
 
@@ -46,3 +46,10 @@ def test_unsupported_orders_are_errors(port32):
 def test_port_reproduces_wave_equation_golden(name, prec, port32, port64):
     """cgSolveWE: float bit-identical (double accumulators of float products), double up to the reduction order"""
     check_waves_against_golden(port32 if prec == 4 else port64, name, prec, tol=0.0 if prec == 4 else 1e-13)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(GUIDING_SCENES))
+def test_port_reproduces_fluid_guiding_golden(name, prec, port32, port64):
+    """PD_fluid_guiding: ~22 primal-dual iterations, each with blurs and a multigrid solve; float bit-identical"""
+    check_guiding_against_golden(port32 if prec == 4 else port64, name, prec, tol=0.0 if prec == 4 else 1e-11)
