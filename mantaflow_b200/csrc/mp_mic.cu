@@ -609,17 +609,22 @@ static int micWarpSweep(mp_context* ctx, const Dims& d, Real* dst, const Real* s
 	uint4* mailY = (uint4*)ctx->micMail; uint4* mailZ = mailY + (size_t)g.nJ * g.sz * g.nch * 4;
 	MP_TRY(micStallFlag(ctx)); int* stall = ctx->micStall;
 	if (++ctx->micTag == 0) ctx->micTag = 1;         // mailboxes are zero-initialised: 0 is never a valid tag
-	const unsigned int grid = (unsigned)(g.nJ * g.nK); const size_t smem = (size_t)S * MW_SLOT_BYTES;
+	// shared memory doubles as the occupancy knob: the sweep is a chain of dependent rounds, and a warp that shares its scheduler
+	// with others runs its rounds slower -- MP_MIC_WARPS_PER_SM caps the resident warps per SM by padding the allocation
+	static const int capWarps = getenv("MP_MIC_WARPS_PER_SM") ? atoi(getenv("MP_MIC_WARPS_PER_SM")) : 0;
+	size_t smem = (size_t)S * MW_SLOT_BYTES;
+	if (capWarps > 0) { const size_t want = (size_t)(227 * 1024) / capWarps - 1024; if (want > smem) smem = want; }
+	const unsigned int grid = (unsigned)(g.nJ * g.nK);
 	static bool attr = false;
 	if (!attr) {
-		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<float, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * MW_SLOT_BYTES));
-		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<float, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * MW_SLOT_BYTES));
-		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<float, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * MW_SLOT_BYTES));
-		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<float, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * MW_SLOT_BYTES));
-		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<double, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * MW_SLOT_BYTES));
-		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<double, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * MW_SLOT_BYTES));
-		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<double, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * MW_SLOT_BYTES));
-		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<double, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * MW_SLOT_BYTES));
+		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<float, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<float, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<float, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<float, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<double, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<double, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<double, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		MP_CUDA(cudaFuncSetAttribute(k_mic_warp<double, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		attr = true;
 	}
 	if (vec) k_mic_warp<Real, MODE, true><<<grid, 32, smem, ctx->stream>>>(g, ctx->micMask, dst, src, P, Ai, Aj, Ak, mailY, mailZ, ctx->micTag, stall, doneFlag, ctx->micOrder);
