@@ -2,6 +2,9 @@
 // Reference: Grid<T> grid.cpp:47-96,:205-210; FluidSolver::GridStorage fluidsolver.cpp:33-50;
 // GridDotProduct conjugategrad.cpp:175-178; getMaxAbs grid.cpp:319-323; GridSumSqr commonkernels.h:32-35.
 #include "mp_common.cuh"
+#include <thread>
+#include <vector>
+#include <cstring>
 #include <cstdlib>
 #include <cstdarg>
 
@@ -68,6 +71,7 @@ int mp_context_destroy(mp_context* c) {
 	if (c->micOrder) cudaFree(c->micOrder);
 	if (c->micStall) cudaFree(c->micStall);
 	if (c->micMail) cudaFree(c->micMail);
+	for (int b = 0; b < 2; b++) if (c->stagePin[b]) { cudaFreeHost(c->stagePin[b]); cudaEventDestroy(c->stageEv[b]); }
 	cudaFree(c->partials); cudaFree(c->tickets); cudaFree(c->dScal); cudaFreeHost(c->hScal);
 	cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copyStream);
 	delete c; return MP_OK;
@@ -122,21 +126,76 @@ int mp_grid_destroy(mp_grid* g) {
 	}
 	delete g; return MP_OK;
 }
+// Host <-> device copies.  Pinned (cudaHostAlloc'ed / registered) host memory goes to the DMA engine directly.  Pageable memory -- what
+// the reference's Grid<T>::mData is (new T[], fluidsolver.cpp:37) -- would be staged by the driver through one bounce buffer at ~10 GB/s;
+// here it is pipelined through two pinned 32 MiB buffers filled / drained by a few host threads, so that the CPU copy of one chunk
+// overlaps the DMA of the other.
+static bool hostIsPinned(const void* p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+}
+static void parallelCopy(void* dst, const void* src, size_t bytes, int nthreads) {
+	if (bytes < ((size_t)4 << 20) || nthreads <= 1) { memcpy(dst, src, bytes); return; }
+	std::vector<std::thread> th;
+	const size_t per = ((bytes / nthreads) + 4095) & ~(size_t)4095;
+	for (int t = 0; t < nthreads; t++) {
+		const size_t off = (size_t)t * per;
+		if (off >= bytes) break;
+		const size_t len = off + per > bytes ? bytes - off : per;
+		th.emplace_back([=]() { memcpy((char*)dst + off, (const char*)src + off, len); });
+	}
+	for (auto& t : th) t.join();
+}
+static int stagerInit(mp_context* ctx) {
+	if (ctx->stagePin[0]) return MP_OK;
+	for (int b = 0; b < 2; b++) { MP_CUDA(cudaHostAlloc(&ctx->stagePin[b], kStageBytes, cudaHostAllocDefault)); MP_CUDA(cudaEventCreateWithFlags(&ctx->stageEv[b], cudaEventDisableTiming)); }
+	const unsigned hc = std::thread::hardware_concurrency();
+	ctx->stageThreads = getenv("MP_COPY_THREADS") ? atoi(getenv("MP_COPY_THREADS")) : (int)(hc >= 16 ? 8 : (hc >= 4 ? hc / 2 : 1));
+	return MP_OK;
+}
+static int stagedUpload(mp_context* ctx, void* dev, const void* host, size_t bytes) {
+	MP_TRY(stagerInit(ctx));
+	int b = 0;
+	for (size_t off = 0; off < bytes; off += kStageBytes, b ^= 1) {
+		const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+		MP_CUDA(cudaEventSynchronize(ctx->stageEv[b]));                    // the DMA that last read this buffer is done
+		parallelCopy(ctx->stagePin[b], (const char*)host + off, len, ctx->stageThreads);
+		MP_CUDA(cudaMemcpyAsync((char*)dev + off, ctx->stagePin[b], len, cudaMemcpyHostToDevice, ctx->stream));
+		MP_CUDA(cudaEventRecord(ctx->stageEv[b], ctx->stream));
+	}
+	return MP_OK;
+}
+static int stagedDownload(mp_context* ctx, void* host, const void* dev, size_t bytes) {       // returns with the host copy complete
+	MP_TRY(stagerInit(ctx));
+	int b = 0; size_t prevOff = 0, prevLen = 0; bool havePrev = false;
+	for (size_t off = 0; off < bytes; off += kStageBytes, b ^= 1) {
+		const size_t len = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+		MP_CUDA(cudaMemcpyAsync(ctx->stagePin[b], (const char*)dev + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+		MP_CUDA(cudaEventRecord(ctx->stageEv[b], ctx->stream));
+		if (havePrev) { MP_CUDA(cudaEventSynchronize(ctx->stageEv[b ^ 1])); parallelCopy((char*)host + prevOff, ctx->stagePin[b ^ 1], prevLen, ctx->stageThreads); }
+		prevOff = off; prevLen = len; havePrev = true;
+	}
+	if (havePrev) { MP_CUDA(cudaEventSynchronize(ctx->stageEv[b ^ 1])); parallelCopy((char*)host + prevOff, ctx->stagePin[b ^ 1], prevLen, ctx->stageThreads); }
+	return MP_OK;
+}
+int mp_grid_upload_async(mp_grid* g, const void* host) {
+	if (hostIsPinned(host) || g->bytes < ((size_t)1 << 20)) { MP_CUDA(cudaMemcpyAsync(g->d, host, g->bytes, cudaMemcpyHostToDevice, g->ctx->stream)); return MP_OK; }
+	return stagedUpload(g->ctx, g->d, host, g->bytes);
+}
+int mp_grid_download_async(const mp_grid* g, void* host) {
+	if (hostIsPinned(host) || g->bytes < ((size_t)1 << 20)) { MP_CUDA(cudaMemcpyAsync(host, g->d, g->bytes, cudaMemcpyDeviceToHost, g->ctx->stream)); return MP_OK; }
+	return stagedDownload(g->ctx, host, g->d, g->bytes);
+}
 int mp_grid_upload(mp_grid* g, const void* host) {
 	MP_CUDA(cudaSetDevice(g->ctx->device));
-	MP_CUDA(cudaMemcpyAsync(g->d, host, g->bytes, cudaMemcpyHostToDevice, g->ctx->stream));
+	MP_TRY(mp_grid_upload_async(g, host));
 	MP_CUDA(cudaStreamSynchronize(g->ctx->stream)); return MP_OK;
 }
 int mp_grid_download(const mp_grid* g, void* host) {
 	MP_CUDA(cudaSetDevice(g->ctx->device));
-	MP_CUDA(cudaMemcpyAsync(host, g->d, g->bytes, cudaMemcpyDeviceToHost, g->ctx->stream));
+	MP_TRY(mp_grid_download_async(g, host));
 	MP_CUDA(cudaStreamSynchronize(g->ctx->stream)); return MP_OK;
-}
-int mp_grid_upload_async(mp_grid* g, const void* host) {
-	MP_CUDA(cudaMemcpyAsync(g->d, host, g->bytes, cudaMemcpyHostToDevice, g->ctx->stream)); return MP_OK;
-}
-int mp_grid_download_async(const mp_grid* g, void* host) {
-	MP_CUDA(cudaMemcpyAsync(host, g->d, g->bytes, cudaMemcpyDeviceToHost, g->ctx->stream)); return MP_OK;
 }
 int mp_grid_clear(mp_grid* g) { MP_CUDA(cudaMemsetAsync(g->d, 0, g->bytes, g->ctx->stream)); return MP_OK; }
 int mp_grid_copy_from(mp_grid* dst, const mp_grid* src) {

@@ -51,6 +51,7 @@ struct mp_context {
 	float profMs[4] = {0, 0, 0, 0};
 	unsigned char* micMask = nullptr; size_t micMaskBytes = 0; const void* micMaskFor = nullptr; int micMaskPrec = 0;   // per-chunk fluid bits of the MIC warp sweeps
 	void* micMail = nullptr; size_t micMailBytes = 0; unsigned int micTag = 0;   // edge-row mailboxes of the warp sweeps + sweep sequence number
+	void* stagePin[2] = { nullptr, nullptr }; cudaEvent_t stageEv[2]; int stageThreads = 1;     // pinned bounce buffers of the pageable-memory copies
 	int* micStall = nullptr;                              // raised by a MIC sweep whose dependency wait ran out of budget
 	int* micOrder = nullptr; int micOrderCount = 0;       // dispatch order of the warp columns
 	int* micProg = nullptr; size_t micProgBytes = 0;     // per-column progress counters (+ stall flag) of the pipelined MIC sweeps
@@ -88,6 +89,7 @@ struct DistState {
 	std::vector<char*> peer;     // peers' arenas mapped into this process (peer[rank] == arena)
 	unsigned int haloSeq = 0, scalSeq = 0;
 };
+static const size_t kStageBytes = (size_t)32 << 20;
 static const size_t kArenaFlags = 0, kArenaGather = 4096, kArenaSearch = 65536;
 // what the kernel producing the new search vector needs to push its boundary planes to the neighbours (all null: no push)
 struct HaloOut {
