@@ -129,7 +129,8 @@ int mp_grid_destroy(mp_grid* g) {
 // Host <-> device copies.  Pinned (cudaHostAlloc'ed / registered) host memory goes to the DMA engine directly.  Pageable memory -- what
 // the reference's Grid<T>::mData is (new T[], fluidsolver.cpp:37) -- would be staged by the driver through one bounce buffer at ~10 GB/s;
 // here it is pipelined through two pinned 32 MiB buffers filled / drained by a few host threads, so that the CPU copy of one chunk
-// overlaps the DMA of the other.
+// overlaps the DMA of the other.  Small grids (< 16 MiB) keep the plain copy: the bounce buffers would cost more than they save.
+static const size_t kStageMinBytes = (size_t)16 << 20;
 static bool hostIsPinned(const void* p) {
 	cudaPointerAttributes a;
 	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -180,11 +181,11 @@ static int stagedDownload(mp_context* ctx, void* host, const void* dev, size_t b
 	return MP_OK;
 }
 int mp_grid_upload_async(mp_grid* g, const void* host) {
-	if (hostIsPinned(host) || g->bytes < ((size_t)1 << 20)) { MP_CUDA(cudaMemcpyAsync(g->d, host, g->bytes, cudaMemcpyHostToDevice, g->ctx->stream)); return MP_OK; }
+	if (g->bytes < kStageMinBytes || hostIsPinned(host)) { MP_CUDA(cudaMemcpyAsync(g->d, host, g->bytes, cudaMemcpyHostToDevice, g->ctx->stream)); return MP_OK; }
 	return stagedUpload(g->ctx, g->d, host, g->bytes);
 }
 int mp_grid_download_async(const mp_grid* g, void* host) {
-	if (hostIsPinned(host) || g->bytes < ((size_t)1 << 20)) { MP_CUDA(cudaMemcpyAsync(host, g->d, g->bytes, cudaMemcpyDeviceToHost, g->ctx->stream)); return MP_OK; }
+	if (g->bytes < kStageMinBytes || hostIsPinned(host)) { MP_CUDA(cudaMemcpyAsync(host, g->d, g->bytes, cudaMemcpyDeviceToHost, g->ctx->stream)); return MP_OK; }
 	return stagedDownload(g->ctx, host, g->d, g->bytes);
 }
 int mp_grid_upload(mp_grid* g, const void* host) {
