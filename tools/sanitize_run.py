@@ -48,5 +48,6 @@ for prec in (4, 8):
             helpers.run_step_case(I, case, flags, vel, dens, obvel)
         print("step plugins", prec, name, flush=True)
     helpers.run_wave_steps(I, "we3d", prec, True, steps=1)
+    helpers.run_guiding(I, "guide3d", prec)
     helpers.run_plume_steps(I, (12, 18, 12), prec, steps=2)
 print("sanitize_run done")
