@@ -212,13 +212,21 @@ def run_ours(args):
         peak, peak_src = load_peaks()
         bpc = bytes_per_cell(prec)
         mvk = prof.get("matvecKernel", 1)
-        mv_name = {0: "k_matvec_dot", 1: "k_matvec_zmarch", 2: "k_matvec_zmarch_masked"}[mvk]
+        mv_name = {0: "k_matvec_dot", 1: "k_matvec_zmarch", 2: "k_matvec_zmarch_masked", 3: "k_matvec_fused"}[mvk]
         if mvk == 2:
             bpc["matvec"] = 4 + 3 * prec          # coupling-mask fast path: cmask 4 + A0 w + s w + t w
+        ax_name, up_name = "k_axpy2_norm", "k_update_search"
+        if mvk == 3:                              # fused PcNone iteration: R r, s_old, x, cmask, A0; W s, t, x  |  R r, t; W r
+            bpc["matvec"] = 4 + 7 * prec
+            bpc["axpy"] = 3 * prec
+            bpc["update"] = 0
+            ax_name, up_name = "k_axpy1_norm", None
         mv_ms = prof.get("msMatvecAvg", 0.0)
         cells_gpu = res ** 3
         kt = {"matvec": mv_ms, "axpy": prof.get("msAxpyAvg") or 0.0, "update": prof.get("msUpdateAvg") or 0.0}
-        kn = {"matvec": mv_name, "axpy": "k_axpy2_norm", "update": "k_update_search"}
+        kn = {"matvec": mv_name, "axpy": ax_name, "update": up_name}
+        if up_name is None:                       # the search-vector update rides on the matvec: two kernels per iteration
+            del kt["update"], kn["update"]
         gbs = {k: (bpc[k] * cells_gpu / (kt[k] * 1e-3) / 1e9) if kt[k] > 0 else None for k in kt}
         dom = max(kt, key=lambda k: kt[k])        # the kernel with the largest share of the timed solve
         achieved = gbs[dom]
@@ -227,8 +235,8 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f32" if prec == 4 else "f64", "data": "synthetic", "config": workload_config(args, world),
                 "solve_ms": dev_ms, "wall_ms_per_step": wall_ms, "iterations": iters, "cg_iter_per_s": iters / (dev_ms * 1e-3),
                 "stage_ms": {k: prof.get(k) for k in ("msRhs", "msMatrix", "msSolve", "msCorrect")},
-                "kernel_ms": {mv_name: mv_ms, "axpy2_norm": prof.get("msAxpyAvg"), "update_search": prof.get("msUpdateAvg"),
-                              "precond": prof.get("msPrecondAvg"), "samples": prof.get("profSamples")},
+                "kernel_ms": dict([(mv_name, mv_ms), (ax_name, prof.get("msAxpyAvg"))] + ([(up_name, prof.get("msUpdateAvg"))] if up_name else []) +
+                                  [("precond", prof.get("msPrecondAvg")), ("samples", prof.get("profSamples"))]),
                 "kernel_gbs": {kn[k]: gbs[k] for k in kt},
                 "kernel_frac_of_peak": {kn[k]: (gbs[k] / peak if gbs[k] else None) for k in kt},
                 "kernel_bytes_per_cell": {kn[k]: bpc[k] for k in kt},

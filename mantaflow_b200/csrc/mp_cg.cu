@@ -28,6 +28,7 @@ template <typename Real> __device__ __forceinline__ void cgFinA(CgScal<Real>* sc
 	if (fabs((double)dp) > 0.) alpha = sc->sigma / dp;
 	sc->alpha = alpha; sc->dp = dp;
 	sc->iterations += 1;
+	sc->xPending = 1;
 }
 template <typename Real> __device__ __forceinline__ void cgFinB(CgScal<Real>* sc, double nrm, double rr, int mode) {
 	const Real resNorm = (Real)nrm;
@@ -275,6 +276,158 @@ __global__ void __launch_bounds__(256) k_matvec_zmarch_masked(Dims d, int nvx, i
 // ---------------------------------------------------------------- k_axpy2_norm
 // gridScaledAdd x2 (conjugategrad.cpp:254-255) + residual norm (:267-271) [+ for PcNone z==r: sigmaNew = r.r, :279]
 // MODE 0: PcNone (z = r, finalises beta/sigma here), MODE 1: preconditioned (only the norm / stop test here)
+// ================================================================ fused PcNone iteration (coupling-mask matrices, 3-D, vector rows)
+// Two kernels per iteration instead of three, 44 instead of 52 B/cell (float): the search-vector update of iteration k-1 and its
+// x-update ride on the matvec of iteration k, which reads r and the old search vector anyway:
+//   k_matvec_fused   s = r + beta s_old  (UpdateSearchVec :193-196, recomputed for the stencil neighbours: same inputs, same bits),
+//                    x += alpha_prev s_old (gridScaledAdd :257), t = A s, dp = t.s -> alpha      (R r,s_old,x,cmask,A0  W s,t,x : 4+7w)
+//   k_axpy1_norm     r -= alpha t, |r| (or sum r^2), r.r -> beta                                  (R r,t  W r : 3w)
+// s ping-pongs between the caller's search grid and one more grid (no thread reads what another writes in the same launch);
+// iteration k (0-based) writes buffer (k even ? B : A).  After the loop k_flush_x applies the last pending x-update.
+template <typename Real, int V>
+__global__ void __launch_bounds__(256) k_matvec_fused(Dims d, int nvx, int chunk, const int* __restrict__ cmask, Real* __restrict__ dst,
+	const Real* __restrict__ sOld, Real* __restrict__ sNew, const Real* __restrict__ r, Real* __restrict__ x,
+	const Real* __restrict__ A0, CgScal<Real>* sc, double* partials, unsigned int* ticket, double* distLocal)
+{
+	if (sc->done) return;
+	// (a shared-memory tile of the new vector with one barrier per plane was measured slower than re-forming the +-y / +-x neighbours
+	//  from r and s_old through L1: 0.98 vs 0.87 ms at 512^3)
+	const Real beta = sc->beta, alphaP = sc->xPending ? sc->alpha : (Real)0;
+	const IndexInt Y = d.Y, Z = d.Z;
+	const int vx = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+	const int k0 = d.kb + blockIdx.z * chunk, k1 = min(d.ke, k0 + chunk);
+	double acc = 0.0;
+	#define SNEW(off) snewOf(ldv<Real, V>(r + (off)), ldv<Real, V>(sOld + (off)), beta)
+	auto snewOf = [](const VecT<Real, V>& rv, const VecT<Real, V>& sv, Real b) { VecT<Real, V> o;
+		#pragma unroll
+		for (int q = 0; q < V; q++) o.v[q] = rv.v[q] + b * sv.v[q];
+		return o; };
+	if (vx < nvx && j < d.sy && k0 < k1) {
+		IndexInt idx = (IndexInt)vx * V + Y * j + Z * k0;
+		VecT<Real, V> sm, s0, sp, so0, sop;      // new search vector at k-1, k, k+1; old one at k, k+1 (for the x-update)
+		#pragma unroll
+		for (int q = 0; q < V; q++) { sm.v[q] = (Real)0; sp.v[q] = (Real)0; sop.v[q] = (Real)0; }
+		if (k0 > 0) {
+			sm = SNEW(idx - Z);
+			if (d.world > 1 && k0 == d.kb) stv<Real, V>(sNew + idx - Z, sm);       // slab mode: the lower ghost plane of the new vector
+		}
+		so0 = ldv<Real, V>(sOld + idx);
+		{ const VecT<Real, V> rv = ldv<Real, V>(r + idx);
+			#pragma unroll
+			for (int q = 0; q < V; q++) s0.v[q] = rv.v[q] + beta * so0.v[q]; }
+		for (int k = k0; k < k1; k++, idx += Z) {
+			const VecT<int, V> f = ldv<int, V>(cmask + idx);
+			if (k + 1 < d.sz) {
+				sop = ldv<Real, V>(sOld + idx + Z);
+				const VecT<Real, V> rv = ldv<Real, V>(r + idx + Z);
+				#pragma unroll
+				for (int q = 0; q < V; q++) sp.v[q] = rv.v[q] + beta * sop.v[q];
+			}
+			VecT<Real, V> xv = ldv<Real, V>(x + idx);
+			#pragma unroll
+			for (int q = 0; q < V; q++) xv.v[q] += alphaP * so0.v[q];
+			stv<Real, V>(x + idx, xv);
+			int any = 0;
+			#pragma unroll
+			for (int q = 0; q < V; q++) any |= f.v[q];
+			VecT<Real, V> out = s0;
+			if (any & 1) {
+				const VecT<Real, V> a0 = ldv<Real, V>(A0 + idx), sym = SNEW(idx - Y), syp = SNEW(idx + Y);
+				Real sxm0 = 0, sxpL = 0;
+				if (f.v[0] & 1) sxm0 = r[idx - 1] + beta * sOld[idx - 1];
+				if (f.v[V - 1] & 1) sxpL = r[idx + V] + beta * sOld[idx + V];
+				#pragma unroll
+				for (int q = 0; q < V; q++) {
+					const int m = f.v[q];
+					if (m & 1) {
+						const Real xm = (q == 0) ? sxm0 : s0.v[q - 1 < 0 ? 0 : q - 1];
+						const Real xp = (q == V - 1) ? sxpL : s0.v[q + 1 > V - 1 ? V - 1 : q + 1];
+						Real t = s0.v[q] * a0.v[q];
+						t = t + ((m & 2) ? -xm : (Real)0);
+						t = t + ((m & 4) ? -xp : (Real)0);
+						t = t + ((m & 8) ? -sym.v[q] : (Real)0);
+						t = t + ((m & 16) ? -syp.v[q] : (Real)0);
+						t = t + ((m & 32) ? -sm.v[q] : (Real)0);
+						t = t + ((m & 64) ? -sp.v[q] : (Real)0);
+						out.v[q] = t;
+					}
+				}
+			}
+			stv<Real, V>(dst + idx, out);
+			stv<Real, V>(sNew + idx, s0);
+			#pragma unroll
+			for (int q = 0; q < V; q++) acc += (double)(out.v[q] * s0.v[q]);
+			sm = s0; s0 = sp; so0 = sop;
+		}
+		if (d.world > 1 && k1 == d.ke && k1 < d.sz) stv<Real, V>(sNew + idx, s0);      // slab mode: the upper ghost plane (idx is at plane k1 now)
+	}
+	#undef SNEW
+	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
+	const unsigned int tid = threadIdx.y * 32 + threadIdx.x;
+	const unsigned int blockLinear = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z), numBlocks = gridDim.x * gridDim.y * gridDim.z;
+	if (blockReduceFinalL<1>(v, isMax, partials, ticket, fin, tid, 256, blockLinear, numBlocks) && tid == 0) {
+		if (distLocal) distLocal[0] = fin[0]; else cgFinA<Real>(sc, fin[0]);
+	}
+}
+
+// r -= alpha t with the residual norms of the stop test and r.r (the next sigma); in slab mode it also hands the first / last owned plane
+// of the new residual to the neighbours (see k_update_search)
+template <typename Real, int V>
+__global__ void __launch_bounds__(256) k_axpy1_norm(IndexInt n, Real* __restrict__ r, const Real* __restrict__ t,
+	CgScal<Real>* sc, double* partials, unsigned int* ticket, double* distLocal, HaloOut ho, IndexInt plane)
+{
+	if (sc->done) return;
+	const Real nalpha = -sc->alpha;
+	const bool useL2 = sc->useL2 != 0;
+	const IndexInt nv = n / V;
+	Real* const outLo = (Real*)ho.lo; Real* const outHi = (Real*)ho.hi;
+	double nrm = useL2 ? 0.0 : -1.0, rr = 0.0;
+	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
+		const IndexInt idx = vi * V;
+		VecT<Real, V> rv = ldv<Real, V>(r + idx);
+		const VecT<Real, V> tv = ldv<Real, V>(t + idx);
+		#pragma unroll
+		for (int q = 0; q < V; q++) {
+			rv.v[q] += nalpha * tv.v[q];
+			const double rd = (double)rv.v[q];
+			if (useL2) nrm += rd * rd; else nrm = fmax(nrm, fabs(rd));
+			rr += (double)(rv.v[q] * rv.v[q]);
+		}
+		stv<Real, V>(r + idx, rv);
+		if (outLo && idx < plane) stv<Real, V>(outLo + idx, rv);
+		if (outHi && idx >= n - plane) stv<Real, V>(outHi + (idx - (n - plane)), rv);
+	}
+	if (ho.ticket) __threadfence_system();
+	double v[2] = { nrm, rr }; const bool isMax[2] = { !useL2, false }; double fin[2];
+	if (blockReduceFinal<2>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) {
+		if (distLocal) { distLocal[0] = fin[0]; distLocal[1] = fin[1]; } else cgFinB<Real>(sc, fin[0], fin[1], 0);
+		if (ho.ticket) {      // this thread runs after every block has finished (and fenced) its stores
+			__threadfence_system();
+			if (ho.flagLo) st_release_sys(ho.flagLo, ho.seq);
+			if (ho.flagHi) st_release_sys(ho.flagHi, ho.seq);
+		}
+	}
+}
+
+// after the loop: the x-update of the last executed iteration.  That iteration (index iterations-1) wrote its search vector to
+// buffer B when its index is even, to A when odd.
+template <typename Real, int V>
+__global__ void __launch_bounds__(256) k_flush_x(IndexInt n, Real* __restrict__ x, const Real* __restrict__ sA, const Real* __restrict__ sB, CgScal<Real>* sc, unsigned int* ticket)
+{
+	if (!sc->xPending) return;
+	const Real alpha = sc->alpha;
+	const Real* s = (sc->iterations & 1) ? sB : sA;
+	const IndexInt nv = n / V;
+	for (IndexInt vi = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; vi < nv; vi += (IndexInt)gridDim.x * blockDim.x) {
+		VecT<Real, V> xv = ldv<Real, V>(x + vi * V); const VecT<Real, V> sv = ldv<Real, V>(s + vi * V);
+		#pragma unroll
+		for (int q = 0; q < V; q++) xv.v[q] += alpha * sv.v[q];
+		stv<Real, V>(x + vi * V, xv);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) { __threadfence(); if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0; sc->xPending = 0; } }     // the last block clears the flag
+}
+
 template <typename Real, int V, int MODE>
 __global__ void __launch_bounds__(256) k_axpy2_norm(IndexInt n, Real* __restrict__ x, const Real* __restrict__ s, Real* __restrict__ r, const Real* __restrict__ t,
 	CgScal<Real>* sc, double* partials, unsigned int* ticket, double* distLocal)
@@ -387,7 +540,7 @@ __global__ void __launch_bounds__(256) k_cg_init(IndexInt n, Real* __restrict__ 
 template <typename Real>
 __global__ void k_scal_reset(CgScal<Real>* sc, Real accuracy, int useL2) {
 	sc->sigma = (Real)0; sc->alpha = (Real)0; sc->beta = (Real)0; sc->dp = (Real)0; sc->resNorm = (Real)1e20; sc->accuracy = accuracy;
-	sc->iterations = 0; sc->done = 0; sc->diverged = 0; sc->useL2 = useL2;
+	sc->iterations = 0; sc->done = 0; sc->diverged = 0; sc->useL2 = useL2; sc->xPending = 0;
 }
 
 // ================================================================ launch helpers
@@ -494,6 +647,9 @@ struct mp_cg {
 	int iterations; double resNorm, sigma; bool diverged, finished;
 	bool flagsChecked;
 	mp_grid* cmask;               // coupling mask of the fast matvec path, or NULL (general kernel)
+	bool fused;                   // PcNone on a masked matrix: two fused kernels per iteration, search vector ping-pongs between search / search2
+	mp_grid* search2; long long fusedEnq;
+	int fusedNvx, fusedChunk; dim3 fusedGrid;
 };
 
 template <typename Real>
@@ -568,6 +724,22 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 			if (*(int*)(ctx->hScal + 20)) { mp_grid_destroy(cg->cmask); cg->cmask = nullptr; }     // face fractions: general kernel
 		}
 	}
+	{	// fused PcNone loop: same launch geometry as the masked z-marching matvec
+		const int useFused = getenv("MP_CG_FUSED") ? atoi(getenv("MP_CG_FUSED")) : 1;     // read per solve: the parity tests run both loops in one process
+		cg->fused = false; cg->fusedEnq = 0;
+		if (useFused && none && cg->cmask) {
+			const int Vw = vecWidth(cg->dst), nvx = d.sx / Vw, planes = d.ke - d.kb;
+			const int tiles = ((nvx + 31) / 32) * ((d.sy + 7) / 8);
+			int nchunk = (4 * 3 * ctx->smCount + tiles - 1) / tiles; if (nchunk < 1) nchunk = 1;
+			int chunk = (planes + nchunk - 1) / nchunk; if (chunk < 16) chunk = 16; if (chunk > planes) chunk = planes;
+			nchunk = (planes + chunk - 1) / chunk;
+			const dim3 grid((nvx + 31) / 32, (d.sy + 7) / 8, nchunk);
+			if ((long long)grid.x * grid.y * grid.z <= kMaxPartials) {
+				cg->fused = true; cg->fusedNvx = nvx; cg->fusedChunk = chunk; cg->fusedGrid = grid;
+				if (!cg->search2) MP_TRY(mp_grid_create(ctx, MP_GRID_REAL, cg->dst->prec, cg->dst->sx, cg->dst->sy, cg->dst->sz, &cg->search2));
+			}
+		}
+	}
 	DISPATCH_RV(cg->dst, {
 		k_scal_reset<Real><<<1, 1, 0, ctx->stream>>>((CgScal<Real>*)cg->dSc, (Real)cg->accuracy, cg->useL2 ? 1 : 0);
 		MP_CHECK_LAUNCH(ctx);
@@ -591,6 +763,7 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 		if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 3, 0));
 	}
 	if (d.world > 1) MP_TRY(cgHalo(cg, cg->search));  // the first matvec reads the neighbours' planes of s
+	if (d.world > 1 && cg->fused) MP_TRY(cgHalo(cg, cg->residual));   // ... and, fused, forms s = r + beta s_old on them
 	return MP_OK;
 }
 
@@ -607,6 +780,31 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 	if (ctx->profPeriod > 0 && iterIndex >= 0 && iterIndex % ctx->profPeriod == 0 && ctx->profCount < 128) pe = &ctx->profEv[5 * ctx->profCount++];
 	#define PROF(k) do { if (pe) MP_CUDA(cudaEventRecord(pe[k], ctx->stream)); } while (0)
 	PROF(0);
+	if (cg->fused) {
+		const bool even = (cg->fusedEnq & 1) == 0; cg->fusedEnq++;
+		mp_grid* sOld = even ? cg->search : cg->search2; mp_grid* sNew = even ? cg->search2 : cg->search;
+		const dim3 block(32, 8, 1);
+		HaloOut ho;
+		if (p2pHalo) MP_TRY(mp_dist_p2p_halo_out(ctx, planeBytes, &ho));
+		DISPATCH_RV(cg->dst, {
+			CgScal<Real>* sc = (CgScal<Real>*)cg->dSc;
+			k_matvec_fused<Real, V><<<cg->fusedGrid, block, 0, ctx->stream>>>(d, cg->fusedNvx, cg->fusedChunk, (const int*)cg->cmask->d, (Real*)cg->tmp->d,
+				(const Real*)sOld->d, (Real*)sNew->d, (const Real*)cg->residual->d, (Real*)cg->dst->d, (const Real*)cg->A0->d, sc, ctx->partials, ctx->tickets + 2, dl);
+			MP_CHECK_LAUNCH(ctx);
+			ctx->lastMatvecKernel = 3;
+			if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 0, 0));
+			PROF(1);
+			const unsigned int blocks = streamBlocks(ctx, nOwn / V);
+			k_axpy1_norm<Real, V><<<blocks, 256, 0, ctx->stream>>>(nOwn, (Real*)cg->residual->d + d.i0, (const Real*)cg->tmp->d + d.i0, sc, ctx->partials, ctx->tickets + 5, dl,
+				ho, (IndexInt)d.sx * d.sy);
+			MP_CHECK_LAUNCH(ctx);
+			if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 1, 0));
+			if (p2pHalo) MP_TRY(mp_dist_p2p_halo_in(ctx, cg->residual->d, planeBytes, cg->residual->sz, &sc->done));
+			else if (dl) MP_TRY(cgHalo(cg, cg->residual));
+		});
+		PROF(2); PROF(3); PROF(4);
+		return MP_OK;
+	}
 	MP_TRY(mp_launch_matvec(ctx, cg->flags, cg->tmp, cg->search, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->dSc, 1, cg->cmask));
 	PROF(1);
 	DISPATCH_RV(cg->dst, {
@@ -674,6 +872,15 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 		slot = other;
 	}
 	for (int q = 0; q < 2; q++) if (pending[q]) { MP_TRY(cgPollWait(cg, q)); pending[q] = false; }
+	if (cg->fused) {      // the x-update of the last executed iteration is still pending
+		const Dims d = dimsOf(cg->flags);
+		const IndexInt nOwn = d.i1 - d.i0;
+		DISPATCH_RV(cg->dst, {
+			k_flush_x<Real, V><<<streamBlocks(ctx, nOwn / V), 256, 0, ctx->stream>>>(nOwn, (Real*)cg->dst->d + d.i0, (const Real*)cg->search->d + d.i0,
+				(const Real*)cg->search2->d + d.i0, (CgScal<Real>*)cg->dSc, ctx->tickets + 8);
+			MP_CHECK_LAUNCH(ctx);
+		});
+	}
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));      // the state after everything that was enqueued
 	MP_TRY(mp_dist_p2p_check(ctx));
 	if (cg->pcMethod == MP_CG_PC_MICP) MP_TRY(mp_mic_check_stall(ctx));
@@ -708,7 +915,7 @@ int mp_cg_create(mp_context* ctx, mp_grid* dst, mp_grid* rhs, mp_grid* residual,
 	cg->pcMethod = MP_CG_PC_NONE; cg->pcA0 = nullptr; cg->mg = nullptr;
 	cg->inited = false; cg->useL2 = true;            // GridCgInterface() : mUseL2Norm(true), conjugategrad.h:31
 	cg->accuracy = dst->prec == 4 ? (double)1e-6f : 1e-10;   // mAccuracy(VECTOR_EPSILON) conjugategrad.cpp:206, vectorbase.h:52,:55
-	cg->iterations = 0; cg->resNorm = 1e20; cg->sigma = 0; cg->diverged = false; cg->finished = false; cg->flagsChecked = false; cg->cmask = nullptr;
+	cg->iterations = 0; cg->resNorm = 1e20; cg->sigma = 0; cg->diverged = false; cg->finished = false; cg->flagsChecked = false; cg->cmask = nullptr; cg->fused = false; cg->search2 = nullptr; cg->fusedEnq = 0;
 	MP_CUDA(cudaMalloc(&cg->dSc, 256));
 	MP_CUDA(cudaHostAlloc((void**)&cg->hSc, sizeof(CgScalHost) * 2, cudaHostAllocMapped));
 	memset(cg->hSc, 0, sizeof(CgScalHost) * 2);
@@ -722,6 +929,7 @@ int mp_cg_destroy(mp_cg* cg) {
 	cudaStreamSynchronize(cg->ctx->stream);
 	cudaFree(cg->dSc); cudaFreeHost(cg->hSc); cudaEventDestroy(cg->pollEv[0]); cudaEventDestroy(cg->pollEv[1]);
 	if (cg->cmask) mp_grid_destroy(cg->cmask);
+	if (cg->search2) mp_grid_destroy(cg->search2);
 	delete cg; return MP_OK;
 }
 int mp_cg_set_accuracy(mp_cg* cg, double accuracy) { cg->accuracy = accuracy; return MP_OK; }

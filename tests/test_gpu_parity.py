@@ -349,7 +349,7 @@ def test_solve_with_face_fractions_uses_general_matvec(mf, pc, prec):
 
 
 @pytest.mark.parametrize("prec", [4, 8])
-def test_matvec_kernel_selection_and_agreement(mf, prec):
+def test_matvec_kernel_selection_and_agreement(mf, prec, monkeypatch):
     """the three matvec instantiations (L2-reuse, z-marching, coupling-mask) are picked by grid shape / matrix content and agree
     bit for bit on the converged result of the same system"""
     flags, vel = scenes.smoke_plume((32, 24, 20), prec, random_vel=True)
@@ -361,7 +361,14 @@ def test_matvec_kernel_selection_and_agreement(mf, prec):
     F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
     mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
     info = mf.lastSolveInfo()
-    assert info["matvecKernel"] == 2 and info["iterations"] == it_o
+    assert info["matvecKernel"] == 3 and info["iterations"] == it_o      # PcNone on a 0/-1 matrix: the fused two-kernel iteration
+    p_fused = P.numpy().copy()
+    monkeypatch.setenv("MP_CG_FUSED", "0")                                # the three-kernel loop with the coupling-mask matvec
+    V.copyFromArray(vel)
+    mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
+    monkeypatch.delenv("MP_CG_FUSED")
+    info = mf.lastSolveInfo()
+    assert info["matvecKernel"] == 2 and info["iterations"] == it_o and np.array_equal(P.numpy(), p_fused)
     if prec == 4:
         assert np.array_equal(P.numpy(), p_o)          # float build: deterministic, bit-identical to the reference algorithm
     else:
