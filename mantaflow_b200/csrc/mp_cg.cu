@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) k_matvec_zmarch_masked(Dims d, int nvx, i
 // s ping-pongs between the caller's search grid and one more grid (no thread reads what another writes in the same launch);
 // iteration k (0-based) writes buffer (k even ? B : A).  After the loop k_flush_x applies the last pending x-update.
 template <typename Real, int V>
-__global__ void __launch_bounds__(256) k_matvec_fused(Dims d, int nvx, int chunk, const int* __restrict__ cmask, Real* __restrict__ dst,
+__global__ void __launch_bounds__(256, 5) k_matvec_fused(Dims d, int nvx, int chunk, const int* __restrict__ cmask, Real* __restrict__ dst,
 	const Real* __restrict__ sOld, Real* __restrict__ sNew, const Real* __restrict__ r, Real* __restrict__ x,
 	const Real* __restrict__ A0, CgScal<Real>* sc, double* partials, unsigned int* ticket, double* distLocal)
 {
