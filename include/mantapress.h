@@ -79,7 +79,7 @@ typedef struct mp_solve_info {
 	/* per-kernel averages over sampled launches of the CG loop (mp_context_set_profiling), 0 when off */
 	float     msMatvecAvg, msAxpyAvg, msUpdateAvg, msPrecondAvg;
 	int       profSamples;
-	int       matvecKernel;       /* 0 k_matvec_dot (L2 reuse), 1 k_matvec_zmarch (4+6w B/cell), 2 k_matvec_zmarch_masked (4+3w B/cell) */
+	int       matvecKernel;       /* 0 k_matvec_dot (L2 reuse), 1 k_matvec_zmarch (4+6w B/cell), 2 k_matvec_zmarch_masked (4+3w), 3 k_matvec_fused (PcNone loop, 4+7w incl. the s and x updates) */
 } mp_solve_info;
 
 /* ---- library / errors ---- */

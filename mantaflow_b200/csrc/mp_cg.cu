@@ -6,6 +6,8 @@
 //                                                                             (R x,s,r,t W x,r : 6w B/cell)
 //   [preconditioner z = M^-1 r : MIC sweeps (mp_mic.cu) or a GridMg V-cycle (mp_mg.cu), then k_dot_zr -> beta]
 //   k_update_search s = z + beta s                                            (R z,s W s : 3w B/cell)
+// PcNone on a matrix whose off-diagonals are all 0 / -1 (every case without face fractions) runs two kernels instead:
+//   k_matvec_fused  s = r + beta s_old, x += alpha_prev s_old, t = A s, dp = t.s  ->  k_axpy1_norm  r -= alpha t, norms   (44 B/cell float)
 // All scalars (sigma, alpha, beta, dp, resNorm are `Real`, accumulators double, conjugategrad.h:108-113,
 // conjugategrad.cpp:250-252,279-280) live on the device; the host only polls a pinned copy every few
 // iterations, so the loop of solvePressureSystem (pressure.cpp:436-439) never stalls the stream.
