@@ -26,59 +26,97 @@ __device__ __forceinline__ bool isInterior(const Dims& d, int i, int j, int k) {
 static inline dim3 cellGrid(const Dims& d) { return dim3((unsigned)((d.sx + 127) / 128), (unsigned)d.sy, (unsigned)d.sz); }
 
 // ---------------------------------------------------------------- setWallBcs / forces
-template <typename Real>
-__global__ void __launch_bounds__(128) k_set_wall_bcs(Dims d, const int* __restrict__ flags, Real* vel, const Real* __restrict__ obvel) {
-	int i, j, k; IndexInt idx;
-	if (!cellOf(d, i, j, k, idx)) return;
-	const int fl = flags[idx];
-	const bool curFluid = fl & TypeFluid, curObs = fl & TypeObstacle;
-	if (!curFluid && !curObs) return;
-	Real* v = vel + 3 * idx;
-	Real bx = 0, by = 0, bz = 0;
-	if (obvel) { bx = obvel[3 * idx]; by = obvel[3 * idx + 1]; if (d.is3D) bz = obvel[3 * idx + 2]; }
-	Real vx = v[0], vy = v[1], vz = v[2];
-	if (i > 0 && (flags[idx - d.X] & TypeObstacle)) vx = bx;
-	if (i > 0 && curObs && (flags[idx - d.X] & TypeFluid)) vx = bx;
-	if (j > 0 && (flags[idx - d.Y] & TypeObstacle)) vy = by;
-	if (j > 0 && curObs && (flags[idx - d.Y] & TypeFluid)) vy = by;
-	if (!d.is3D) vz = 0;
+// The three one-pass plugins share one kernel shell: a thread owns V consecutive cells of a row (V = 4 float / 2 double when sx % V == 0,
+// i.e. three 16-byte accesses to the AoS velocity instead of 3V strided ones; V = 1 otherwise), applies the per-cell operation and writes
+// the vectors back only if a cell changed.
+template <typename Real, int V> struct alignas(sizeof(Real) * V) VecS { Real v[V]; };
+
+template <typename Real> struct WallBcsOp {          // KnSetWallBcs extforces.cpp:186-218
+	const int* flags; const Real* obvel;
+	__device__ __forceinline__ bool operator()(const Dims& d, int i, int j, int k, IndexInt idx, Real& vx, Real& vy, Real& vz) const {
+		const int fl = flags[idx];
+		const bool curFluid = fl & TypeFluid, curObs = fl & TypeObstacle;
+		if (!curFluid && !curObs) return false;
+		Real bx = 0, by = 0, bz = 0;
+		if (obvel) { bx = obvel[3 * idx]; by = obvel[3 * idx + 1]; if (d.is3D) bz = obvel[3 * idx + 2]; }
+		const Real ox = vx, oy = vy, oz = vz;
+		if (i > 0 && (flags[idx - d.X] & TypeObstacle)) vx = bx;
+		if (i > 0 && curObs && (flags[idx - d.X] & TypeFluid)) vx = bx;
+		if (j > 0 && (flags[idx - d.Y] & TypeObstacle)) vy = by;
+		if (j > 0 && curObs && (flags[idx - d.Y] & TypeFluid)) vy = by;
+		if (!d.is3D) vz = 0;
+		else {
+			if (k > 0 && (flags[idx - d.Z] & TypeObstacle)) vz = bz;
+			if (k > 0 && curObs && (flags[idx - d.Z] & TypeFluid)) vz = bz;
+		}
+		if (curFluid) {
+			if ((i > 0 && (flags[idx - d.X] & TypeStick)) || (i < d.sx - 1 && (flags[idx + d.X] & TypeStick))) vy = vz = 0;
+			if ((j > 0 && (flags[idx - d.Y] & TypeStick)) || (j < d.sy - 1 && (flags[idx + d.Y] & TypeStick))) vx = vz = 0;
+			if (d.is3D && ((k > 0 && (flags[idx - d.Z] & TypeStick)) || (k < d.sz - 1 && (flags[idx + d.Z] & TypeStick)))) vx = vy = 0;
+		}
+		return !(vx == ox && vy == oy && vz == oz);      // (NaN compares unequal: rewritten, harmless)
+	}
+};
+template <typename Real> struct ApplyForceOp {       // KnApplyForce extforces.cpp:45-58, additive
+	const int* flags; const Real* exclude; Real fx, fy, fz;
+	__device__ __forceinline__ bool operator()(const Dims& d, int i, int j, int k, IndexInt idx, Real& vx, Real& vy, Real& vz) const {
+		if (!isInterior(d, i, j, k)) return false;
+		const bool curFluid = flags[idx] & TypeFluid, curEmpty = flags[idx] & TypeEmpty;
+		if (!curFluid && !curEmpty) return false;
+		if (exclude && (exclude[idx] < 0.)) return false;
+		if ((flags[idx - d.X] & TypeFluid) || (curFluid && (flags[idx - d.X] & TypeEmpty))) vx = vx + fx;
+		if ((flags[idx - d.Y] & TypeFluid) || (curFluid && (flags[idx - d.Y] & TypeEmpty))) vy = vy + fy;
+		if (d.is3D && ((flags[idx - d.Z] & TypeFluid) || (curFluid && (flags[idx - d.Z] & TypeEmpty)))) vz = vz + fz;
+		return true;
+	}
+};
+template <typename Real> struct BuoyancyOp {         // KnAddBuoyancy extforces.cpp:75-83
+	const int* flags; const Real* factor; Real sx_, sy_, sz_;
+	__device__ __forceinline__ bool operator()(const Dims& d, int i, int j, int k, IndexInt idx, Real& vx, Real& vy, Real& vz) const {
+		if (!isInterior(d, i, j, k)) return false;
+		if (!(flags[idx] & TypeFluid)) return false;
+		const Real f0 = factor[idx];
+		if (flags[idx - d.X] & TypeFluid) vx = (Real)((double)vx + (0.5 * (double)sx_) * (double)(f0 + factor[idx - d.X]));
+		if (flags[idx - d.Y] & TypeFluid) vy = (Real)((double)vy + (0.5 * (double)sy_) * (double)(f0 + factor[idx - d.Y]));
+		if (d.is3D && (flags[idx - d.Z] & TypeFluid)) vz = (Real)((double)vz + (0.5 * (double)sz_) * (double)(f0 + factor[idx - d.Z]));
+		return true;
+	}
+};
+template <typename Real, int V, typename Op>
+__global__ void __launch_bounds__(128) k_cells(Dims d, Real* vel, Op op) {
+	const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * V, j = blockIdx.y, k = blockIdx.z;
+	if (i0 >= d.sx) return;
+	const IndexInt idx0 = (IndexInt)i0 + d.Y * j + (IndexInt)d.sx * d.sy * k;
+	Real* p = vel + 3 * idx0;
+	Real v[3 * V];
+	if (V == 1) { v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; }
 	else {
-		if (k > 0 && (flags[idx - d.Z] & TypeObstacle)) vz = bz;
-		if (k > 0 && curObs && (flags[idx - d.Z] & TypeFluid)) vz = bz;
+		#pragma unroll
+		for (int q = 0; q < 3; q++) { const VecS<Real, V> t = ((const VecS<Real, V>*)p)[q];
+			#pragma unroll
+			for (int e = 0; e < V; e++) v[q * V + e] = t.v[e]; }
 	}
-	if (curFluid) {
-		if ((i > 0 && (flags[idx - d.X] & TypeStick)) || (i < d.sx - 1 && (flags[idx + d.X] & TypeStick))) vy = vz = 0;
-		if ((j > 0 && (flags[idx - d.Y] & TypeStick)) || (j < d.sy - 1 && (flags[idx + d.Y] & TypeStick))) vx = vz = 0;
-		if (d.is3D && ((k > 0 && (flags[idx - d.Z] & TypeStick)) || (k < d.sz - 1 && (flags[idx + d.Z] & TypeStick)))) vx = vy = 0;
+	bool changed = false;
+	#pragma unroll
+	for (int c = 0; c < V; c++) changed |= op(d, i0 + c, j, k, idx0 + c, v[3 * c], v[3 * c + 1], v[3 * c + 2]);
+	if (!changed) return;
+	if (V == 1) { p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; }
+	else {
+		#pragma unroll
+		for (int q = 0; q < 3; q++) { VecS<Real, V> t;
+			#pragma unroll
+			for (int e = 0; e < V; e++) t.v[e] = v[q * V + e];
+			((VecS<Real, V>*)p)[q] = t; }
 	}
-	if (vx != v[0] || vy != v[1] || vz != v[2] || (vx != vx) || (vy != vy) || (vz != vz)) { v[0] = vx; v[1] = vy; v[2] = vz; }     // most cells stay as they are: read-only for them
 }
-
-template <typename Real>
-__global__ void __launch_bounds__(128) k_apply_force(Dims d, const int* __restrict__ flags, Real* vel, Real fx, Real fy, Real fz, const Real* __restrict__ exclude) {
-	int i, j, k; IndexInt idx;
-	if (!cellOf(d, i, j, k, idx) || !isInterior(d, i, j, k)) return;
-	const bool curFluid = flags[idx] & TypeFluid, curEmpty = flags[idx] & TypeEmpty;
-	if (!curFluid && !curEmpty) return;
-	if (exclude && (exclude[idx] < 0.)) return;
-	Real* v = vel + 3 * idx;
-	if ((flags[idx - d.X] & TypeFluid) || (curFluid && (flags[idx - d.X] & TypeEmpty))) v[0] = v[0] + fx;
-	if ((flags[idx - d.Y] & TypeFluid) || (curFluid && (flags[idx - d.Y] & TypeEmpty))) v[1] = v[1] + fy;
-	if (d.is3D && ((flags[idx - d.Z] & TypeFluid) || (curFluid && (flags[idx - d.Z] & TypeEmpty)))) v[2] = v[2] + fz;
+template <typename Real, typename Op>
+int launchCells(mp_context* ctx, const Dims& d, Real* vel, const Op& op) {
+	constexpr int VV = 16 / (int)sizeof(Real);
+	if (d.sx % VV == 0) k_cells<Real, VV, Op><<<dim3((unsigned)((d.sx / VV + 127) / 128), (unsigned)d.sy, (unsigned)d.sz), 128, 0, ctx->stream>>>(d, vel, op);
+	else                k_cells<Real, 1, Op><<<cellGrid(d), 128, 0, ctx->stream>>>(d, vel, op);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
 }
-
-template <typename Real>
-__global__ void __launch_bounds__(128) k_add_buoyancy(Dims d, const int* __restrict__ flags, const Real* __restrict__ factor, Real* vel, Real sx_, Real sy_, Real sz_) {
-	int i, j, k; IndexInt idx;
-	if (!cellOf(d, i, j, k, idx) || !isInterior(d, i, j, k)) return;
-	if (!(flags[idx] & TypeFluid)) return;
-	Real* v = vel + 3 * idx;
-	const Real f0 = factor[idx];
-	if (flags[idx - d.X] & TypeFluid) v[0] = (Real)((double)v[0] + (0.5 * (double)sx_) * (double)(f0 + factor[idx - d.X]));
-	if (flags[idx - d.Y] & TypeFluid) v[1] = (Real)((double)v[1] + (0.5 * (double)sy_) * (double)(f0 + factor[idx - d.Y]));
-	if (d.is3D && (flags[idx - d.Z] & TypeFluid)) v[2] = (Real)((double)v[2] + (0.5 * (double)sz_) * (double)(f0 + factor[idx - d.Z]));
-}
-
 // ---------------------------------------------------------------- interpolation (util/interpol.h:50-91) and MAC accessors (grid.h:424-466)
 // STRIDE 1: Grid<Real>; STRIDE 3: one component of a Vec3 grid (a points at that component of cell 0)
 template <typename Real, int STRIDE>
@@ -402,10 +440,9 @@ int mp_set_wall_bcs(mp_context* ctx, const mp_grid* flags, mp_grid* vel, const m
 	if (phiObs && fractions) MP_FAIL(MP_ERR_UNSUPPORTED, "setWallBcs: the second-order variant (phiObs + fractions, KnSetWallBcsFrac) is not built");
 	if (obvel) MP_TRY(mp_check_same(vel, obvel, MP_GRID_MAC, "obvel", false));
 	const Dims d = dimsOf(flags);
-	if (vel->prec == 4) k_set_wall_bcs<float><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, obvel ? (const float*)obvel->d : nullptr);
-	else                k_set_wall_bcs<double><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, obvel ? (const double*)obvel->d : nullptr);
-	MP_CHECK_LAUNCH(ctx);
-	return MP_OK;
+	if (vel->prec == 4) { WallBcsOp<float> op = { (const int*)flags->d, obvel ? (const float*)obvel->d : nullptr }; return launchCells<float>(ctx, d, (float*)vel->d, op); }
+	WallBcsOp<double> op = { (const int*)flags->d, obvel ? (const double*)obvel->d : nullptr };
+	return launchCells<double>(ctx, d, (double*)vel->d, op);
 }
 
 int mp_add_gravity(mp_context* ctx, const mp_grid* flags, mp_grid* vel, double gx, double gy, double gz, const mp_grid* exclude, int scale, double dt)
@@ -417,14 +454,14 @@ int mp_add_gravity(mp_context* ctx, const mp_grid* flags, mp_grid* vel, double g
 	if (vel->prec == 4) {
 		const float gridScale = scale ? (float)(float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; float f[3];
 		for (int c = 0; c < 3; c++) f[c] = ((float)g[c] * (float)dt) / gridScale;
-		k_apply_force<float><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, f[0], f[1], f[2], exclude ? (const float*)exclude->d : nullptr);
+		ApplyForceOp<float> op = { (const int*)flags->d, exclude ? (const float*)exclude->d : nullptr, f[0], f[1], f[2] };
+		return launchCells<float>(ctx, d, (float*)vel->d, op);
 	} else {
 		const float gridScale = scale ? (float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; double f[3];
 		for (int c = 0; c < 3; c++) f[c] = (g[c] * dt) / gridScale;
-		k_apply_force<double><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, f[0], f[1], f[2], exclude ? (const double*)exclude->d : nullptr);
+		ApplyForceOp<double> op = { (const int*)flags->d, exclude ? (const double*)exclude->d : nullptr, f[0], f[1], f[2] };
+		return launchCells<double>(ctx, d, (double*)vel->d, op);
 	}
-	MP_CHECK_LAUNCH(ctx);
-	return MP_OK;
 }
 
 int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* density, mp_grid* vel, double gx, double gy, double gz, double coefficient, int scale, double dt)
@@ -437,14 +474,14 @@ int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* densit
 	if (vel->prec == 4) {
 		const float gridScale = scale ? (float)(float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; float f[3];
 		for (int c = 0; c < 3; c++) f[c] = (((-(float)g[c]) * (float)dt) / gridScale) * (float)coefficient;
-		k_add_buoyancy<float><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (const float*)density->d, (float*)vel->d, f[0], f[1], f[2]);
+		BuoyancyOp<float> op = { (const int*)flags->d, (const float*)density->d, f[0], f[1], f[2] };
+		return launchCells<float>(ctx, d, (float*)vel->d, op);
 	} else {
 		const float gridScale = scale ? (float)(1.0 / imax3(d.sx, d.sy, d.sz)) : 1.f; double f[3];
 		for (int c = 0; c < 3; c++) f[c] = (((-g[c]) * dt) / gridScale) * coefficient;
-		k_add_buoyancy<double><<<cellGrid(d), 128, 0, ctx->stream>>>(d, (const int*)flags->d, (const double*)density->d, (double*)vel->d, f[0], f[1], f[2]);
+		BuoyancyOp<double> op = { (const int*)flags->d, (const double*)density->d, f[0], f[1], f[2] };
+		return launchCells<double>(ctx, d, (double*)vel->d, op);
 	}
-	MP_CHECK_LAUNCH(ctx);
-	return MP_OK;
 }
 
 int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
