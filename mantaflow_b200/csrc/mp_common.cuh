@@ -84,7 +84,7 @@ struct DistState {
 	double* dLocal = nullptr;    // 8 doubles: this rank's partial results
 	// ---- peer-memory path of the per-iteration exchanges (NVLink P2P through CUDA IPC), see mp_dist.cu ----
 	// arena layout (identical on every rank): [0,4K) halo flags | [4K,64K) scalar gather slots | [64K, ...) search vector slab
-	bool p2p = false;
+	bool p2p = false, p2pUnavailable = false;     // unavailable: some rank could not map a peer's arena -> every rank stays on NCCL
 	char* arena = nullptr; size_t arenaBytes = 0; size_t searchBytes = 0;
 	std::vector<char*> peer;     // peers' arenas mapped into this process (peer[rank] == arena)
 	unsigned int haloSeq = 0, scalSeq = 0;

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_p2p_halo_in(char* arena, const uint4* _
 int mp_dist_p2p_prepare(mp_context* ctx, size_t searchBytes) {
 	DistState* ds = ctx->dist;
 	static const int enable = getenv("MP_P2P") ? atoi(getenv("MP_P2P")) : 1;
-	if (!ds || !ds->active || ds->world == 1 || ds->world > 16 || !enable) { if (ds) ds->p2p = false; return MP_OK; }
+	if (!ds || !ds->active || ds->world == 1 || ds->world > 16 || !enable || ds->p2pUnavailable) { if (ds) ds->p2p = false; return MP_OK; }
 	if (ds->arena && ds->searchBytes >= searchBytes) { ds->p2p = true; return MP_OK; }
 	// (re)build: every rank takes this branch in the same call because all slabs change size together
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -170,17 +170,34 @@ int mp_dist_p2p_prepare(mp_context* ctx, size_t searchBytes) {
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));
 	cudaFree(dH); cudaFree(dAll);
 	ds->peer.assign(ds->world, nullptr);
+	bool okLocal = true;
 	for (int r = 0; r < ds->world; r++) {
 		if (r == ds->rank) { ds->peer[r] = ds->arena; continue; }
 		void* p = nullptr;
 		cudaError_t e = cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess);
-		if (e != cudaSuccess) { cudaGetLastError(); ds->p2p = false; mp_set_error("cudaIpcOpenMemHandle failed (%s): falling back to NCCL", cudaGetErrorString(e)); return MP_OK; }
+		if (e != cudaSuccess) { cudaGetLastError(); okLocal = false; continue; }     // (no peer access / separate IPC namespace)
 		ds->peer[r] = (char*)p;
 	}
+	if (getenv("MP_P2P_FAIL_RANK") && atoi(getenv("MP_P2P_FAIL_RANK")) == ds->rank) okLocal = false;      // test hook: pretend this rank could not map its peers
 	ds->haloSeq = 0; ds->scalSeq = 0;
-	// nobody may write into a peer's arena before that peer has finished clearing it
-	MP_TRY(mp_dist_allgather(ctx, 1));
-	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	// One all-gather does two jobs: nobody may write into a peer's arena before that peer has finished clearing it, and the ranks
+	// agree on the outcome -- if ANY rank could not map a peer, ALL of them keep the NCCL exchanges (a mixed choice would deadlock).
+	{
+		const double mine = okLocal ? 1.0 : 0.0;
+		MP_CUDA(cudaMemcpyAsync(ds->dLocal, &mine, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		MP_TRY(mp_dist_allgather(ctx, 1));
+		std::vector<double> all(8 * ds->world);
+		MP_CUDA(cudaMemcpyAsync(all.data(), ds->dGather, sizeof(double) * 8 * ds->world, cudaMemcpyDeviceToHost, ctx->stream));
+		MP_CUDA(cudaStreamSynchronize(ctx->stream));
+		bool allOk = true;
+		for (int r = 0; r < ds->world; r++) allOk = allOk && all[8 * r] > 0.5;
+		if (!allOk) {
+			for (int r = 0; r < ds->world; r++) if (ds->peer[r] && r != ds->rank) cudaIpcCloseMemHandle(ds->peer[r]);
+			ds->peer.clear();
+			ds->p2p = false; ds->p2pUnavailable = true;
+			return MP_OK;
+		}
+	}
 	ds->p2p = true;
 	return MP_OK;
 }
