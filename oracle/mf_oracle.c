@@ -1603,3 +1603,177 @@ int mfo_pd_fluid_guiding(int sx, int sy, int sz, const int* flags, Real* vel, co
 	free(G); free(velC); free(x); free(y); free(z); free(x0); free(z0); free(Q); free(invA); free(vn); free(t1); free(t2);
 	return rc;
 }
+
+/* =============================================================================================
+ * Liquid neighbours (first slice): the functions that make the level-set free-surface loop of
+ * scenes/freesurface.py:54-84 (useMarching = False) device-resident around solvePressure(phi=...).            */
+
+static const int NB6[6][3] = { { 1, 0, 0 }, { -1, 0, 0 }, { 0, 1, 0 }, { 0, -1, 0 }, { 0, 0, 1 }, { 0, 0, -1 } };   /* fastmarch.cpp:233-236, :433-436 */
+
+/* FlagGrid::updateFromLevelset grid.cpp:844-854; invalidTimeValue = -1000 (levelset.cpp:103 -> fastmarch.h:134) */
+int mfo_update_from_levelset(int sx, int sy, int sz, int* flags, const Real* phi)
+{
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	for (IndexInt idx = 0; idx < n; idx++) {
+		if ((flags[idx] & TypeObstacle) || (flags[idx] & TypeOutflow)) continue;
+		const Real p = phi[idx];
+		if (p <= (Real)-1000) continue;
+		flags[idx] &= ~(TypeEmpty | TypeFluid);
+		flags[idx] |= (p <= 0) ? TypeFluid : TypeEmpty;
+	}
+	return 0;
+}
+
+/* Grid<T>::setBound grid.cpp:591-593, knSetBoundary :585-589 (ncomp 1: Grid<Real>, 3: Grid<Vec3>; the same value in every component) */
+int mfo_set_bound(int sx, int sy, int sz, Real* grid, int ncomp, double value, int w)
+{
+	STRIDES
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const int bnd = (i <= w || i >= sx - 1 - w || j <= w || j >= sy - 1 - w || (IS3D && (k <= w || k >= sz - 1 - w)));
+		if (bnd) for (int c = 0; c < ncomp; c++) grid[ncomp * IDX(i, j, k) + c] = (Real)value;
+	}
+	return 0;
+}
+
+/* normalize util/vectorbase.h:415-429 (the comparisons against 1. and the reciprocal are double expressions) */
+static Real normalize3(Real v[3])
+{
+	Real norm;
+	const Real l = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+#if MF_REAL_IS_DOUBLE
+	const double eps2 = 1e-10 * 1e-10;            /* VECTOR_EPSILON vectorbase.h:55 */
+#else
+	const float eps2 = 1e-6f * 1e-6f;             /* vectorbase.h:52 */
+#endif
+	if (fabs((double)l - 1.) < eps2) norm = 1.;
+	else if (l > eps2) {
+		norm = R_SQRT(l);
+		const Real s = (Real)(1. / (double)norm);
+		v[0] *= s; v[1] *= s; v[2] *= s;
+	} else { v[0] = v[1] = v[2] = 0; norm = 0.; }
+	return norm;
+}
+
+/* extrapolateMACSimple fastmarch.cpp:337-375: knExtrapolateMACSimple :231-258, knUnprojectNormalComp :319-331 (getNormal :302-318),
+ * knExtrapolateIntoBnd :260-299 */
+int mfo_extrapolate_mac_simple(int sx, int sy, int sz, const int* flags, Real* vel, int distance, const Real* phiObs, int intoObs)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	const int dim = IS3D ? 3 : 2;
+	if (sx < 3 || sy < 3 || (IS3D && sz < 3)) { snprintf(g_err, sizeof g_err, "extrapolateMACSimple: grid without interior cells"); return 1; }
+	int* tmp = (int*)malloc(sizeof(int) * (size_t)n);
+	for (int c = 0; c < dim; c++) {
+		const IndexInt dir = c == 0 ? X : (c == 1 ? Y : Z);
+		memset(tmp, 0, sizeof(int) * (size_t)n);
+		{ FOR_BND1 {
+			const IndexInt p = IDX(i, j, k);
+			int mark = 0;
+			if (!intoObs) { if ((flags[p] & TypeFluid) || (flags[p - dir] & TypeFluid)) mark = 1; }
+			else { if (((flags[p] & TypeFluid) || (flags[p - dir] & TypeFluid)) && !(flags[p] & TypeObstacle) && !(flags[p - dir] & TypeObstacle)) mark = 1; }
+			if (mark) tmp[p] = 1;
+		} }
+		for (int d = 1; d < 1 + distance; d++) {
+			FOR_BND1 {
+				const IndexInt p = IDX(i, j, k);
+				if (tmp[p] != 0) continue;
+				int nbs = 0; Real avgVel = 0.;
+				for (int q = 0; q < 2 * dim; q++) {
+					const IndexInt pn = IDX(i + NB6[q][0], j + NB6[q][1], k + NB6[q][2]);
+					if (tmp[pn] == d) { avgVel += vel[3 * pn + c]; nbs++; }
+				}
+				if (nbs > 0) { tmp[p] = d + 1; vel[3 * p + c] = avgVel / nbs; }
+			}
+		}
+	}
+	free(tmp);
+	if (phiObs) {
+		const Real maxDist = (Real)distance;
+		FOR_BND1 {
+			const IndexInt p = IDX(i, j, k);
+			if (phiObs[p] > 0. || phiObs[p] < -maxDist) continue;
+			Real nrm[3] = { phiObs[p + X] - phiObs[p - X], phiObs[p + Y] - phiObs[p - Y], phiObs[p + Z] - phiObs[p - Z] };   /* 2-D: Z == 0 -> 0 */
+			Real* v = vel + 3 * p;
+			if (nrm[0] * v[0] + nrm[1] * v[1] + nrm[2] * v[2] < 0.) {
+				normalize3(nrm);
+				const Real l = nrm[0] * v[0] + nrm[1] * v[1] + nrm[2] * v[2];
+				v[0] -= nrm[0] * l; v[1] -= nrm[1] * l; v[2] -= nrm[2] * l;
+			}
+		}
+	}
+	Real* velTmp = (Real*)malloc(sizeof(Real) * 3 * (size_t)n);
+	memcpy(velTmp, vel, sizeof(Real) * 3 * (size_t)n);
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt p = IDX(i, j, k);
+		int c = 0;
+		Real v[3] = { 0, 0, 0 };
+		const int isObs = flags[p] & TypeObstacle;
+		if (i == 0)           { memcpy(v, velTmp + 3 * (p + X), sizeof v); if (isObs && v[0] < 0.) v[0] = 0.; c++; }
+		else if (i == sx - 1) { memcpy(v, velTmp + 3 * (p - X), sizeof v); if (isObs && v[0] > 0.) v[0] = 0.; c++; }
+		if (j == 0)           { memcpy(v, velTmp + 3 * (p + Y), sizeof v); if (isObs && v[1] < 0.) v[1] = 0.; c++; }
+		else if (j == sy - 1) { memcpy(v, velTmp + 3 * (p - Y), sizeof v); if (isObs && v[1] > 0.) v[1] = 0.; c++; }
+		if (IS3D) {
+			if (k == 0)           { memcpy(v, velTmp + 3 * (p + Z), sizeof v); if (isObs && v[2] < 0.) v[2] = 0.; c++; }
+			else if (k == sz - 1) { memcpy(v, velTmp + 3 * (p - Z), sizeof v); if (isObs && v[2] > 0.) v[2] = 0.; c++; }
+		}
+		if (c > 0) { vel[3 * p] = v[0] / (Real)c; vel[3 * p + 1] = v[1] / (Real)c; vel[3 * p + 2] = v[2] / (Real)c; }
+	}
+	free(velTmp);
+	return 0;
+}
+
+/* marks of extrapolateLsSimple / extrapolateVec3Simple fastmarch.cpp:475-498, :516-536: 1 on the chosen side of phi, 2 on the first layer next to it */
+static int* ls_marks(int sx, int sy, int sz, const Real* phi, int inside)
+{
+	STRIDES
+	const int dim = IS3D ? 3 : 2;
+	int* tmp = (int*)calloc((size_t)sx * sy * sz, sizeof(int));
+	{ FOR_BND1 { const IndexInt p = IDX(i, j, k); if (!inside ? (phi[p] < 0.) : (phi[p] > 0.)) tmp[p] = 1; } }
+	{ FOR_BND1 {
+		const IndexInt p = IDX(i, j, k);
+		if (tmp[p]) continue;
+		for (int q = 0; q < 2 * dim; q++) if (tmp[IDX(i + NB6[q][0], j + NB6[q][1], k + NB6[q][2])] == 1) { tmp[p] = 2; break; }
+	} }
+	return tmp;
+}
+
+/* knExtrapolateLsSimple<S> fastmarch.cpp:439-460 for d = 2 .. distance, then knSetRemaining :463-467 */
+static void ls_extrapolate(int sx, int sy, int sz, Real* val, int ncomp, int* tmp, int distance, Real direction, Real remaining)
+{
+	STRIDES
+	const int dim = IS3D ? 3 : 2;
+	for (int d = 2; d < 1 + distance; d++) {
+		FOR_BND1 {
+			const IndexInt p = IDX(i, j, k);
+			if (tmp[p] != 0) continue;
+			int nbs = 0; Real avg[3] = { 0, 0, 0 };
+			for (int q = 0; q < 2 * dim; q++) {
+				const IndexInt pn = IDX(i + NB6[q][0], j + NB6[q][1], k + NB6[q][2]);
+				if (tmp[pn] == d) { for (int c = 0; c < ncomp; c++) avg[c] += val[ncomp * pn + c]; nbs++; }
+			}
+			if (nbs > 0) { tmp[p] = d + 1; for (int c = 0; c < ncomp; c++) val[ncomp * p + c] = avg[c] / nbs + direction; }
+		}
+	}
+	{ FOR_BND1 { const IndexInt p = IDX(i, j, k); if (tmp[p] == 0) for (int c = 0; c < ncomp; c++) val[ncomp * p + c] = remaining; } }
+}
+
+/* extrapolateLsSimple fastmarch.cpp:470-507 */
+int mfo_extrapolate_ls_simple(int sx, int sy, int sz, Real* phi, int distance, int inside)
+{
+	if (sx < 3 || sy < 3 || (IS3D && sz < 3)) { snprintf(g_err, sizeof g_err, "extrapolateLsSimple: grid without interior cells"); return 1; }
+	const Real direction = inside ? -1. : 1.;
+	int* tmp = ls_marks(sx, sy, sz, phi, inside);
+	ls_extrapolate(sx, sy, sz, phi, 1, tmp, distance, direction, (Real)(direction * (distance + 2)));
+	free(tmp);
+	return 0;
+}
+
+/* extrapolateVec3Simple fastmarch.cpp:510-542 */
+int mfo_extrapolate_vec3_simple(int sx, int sy, int sz, Real* vel, const Real* phi, int distance, int inside)
+{
+	if (sx < 3 || sy < 3 || (IS3D && sz < 3)) { snprintf(g_err, sizeof g_err, "extrapolateVec3Simple: grid without interior cells"); return 1; }
+	int* tmp = ls_marks(sx, sy, sz, phi, inside);
+	ls_extrapolate(sx, sy, sz, vel, 3, tmp, distance, (Real)0, (Real)0);
+	free(tmp);
+	return 0;
+}

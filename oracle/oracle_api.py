@@ -203,6 +203,38 @@ class Oracle:
                                                 C.c_double(cgMaxIterFac), C.c_double(cgAccuracy)))
         return grid
 
+    # -- liquid neighbours: arrays are updated in place and returned --
+    def extrapolate_mac_simple(self, flags, vel, distance=4, phiObs=None, intoObs=False):
+        """fastmarch.cpp:337-375"""
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        self._chk(self._f("extrapolate_mac_simple")(*self.dims(flags), _p(flags), _p(vel), C.c_int(distance), _p(self._r(phiObs)), C.c_int(int(intoObs))))
+        return vel
+
+    def extrapolate_ls_simple(self, phi, distance=4, inside=False):
+        """fastmarch.cpp:470-507"""
+        assert phi.dtype == self.real and phi.flags.c_contiguous
+        self._chk(self._f("extrapolate_ls_simple")(*self.dims(phi), _p(phi), C.c_int(distance), C.c_int(int(inside))))
+        return phi
+
+    def extrapolate_vec3_simple(self, vel, phi, distance=4, inside=False):
+        """fastmarch.cpp:510-542"""
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        self._chk(self._f("extrapolate_vec3_simple")(*self.dims(phi), _p(vel), _p(self._r(phi)), C.c_int(distance), C.c_int(int(inside))))
+        return vel
+
+    def update_from_levelset(self, flags, phi):
+        """FlagGrid::updateFromLevelset grid.cpp:844-854"""
+        assert flags.dtype == np.int32 and flags.flags.c_contiguous
+        self._chk(self._f("update_from_levelset")(*self.dims(flags), _p(flags), _p(self._r(phi))))
+        return flags
+
+    def set_bound(self, grid, value, boundaryWidth=1):
+        """Grid<T>::setBound grid.cpp:591-593 ([Z,Y,X] or [Z,Y,X,3]; the same value in every component)"""
+        assert grid.dtype == self.real and grid.flags.c_contiguous
+        ncomp = 1 if grid.ndim == 3 else 3
+        self._chk(self._f("set_bound")(*self.dims(grid[..., 0] if ncomp == 3 else grid), _p(grid), C.c_int(ncomp), C.c_double(value), C.c_int(boundaryWidth)))
+        return grid
+
     def release_solver(self, key):
         self._chk(self._f("release_solver")(C.c_longlong(key)))
 

@@ -17,6 +17,8 @@
 //   advectSemiLagrange      plugin/advection.cpp:442-461
 //   cgSolveWE               plugin/waves.cpp:86-147
 //   PD_fluid_guiding        plugin/fluidguiding.cpp:294-353
+//   extrapolateMACSimple, extrapolateLsSimple, extrapolateVec3Simple   fastmarch.cpp:337-375, :470-542
+//   FlagGrid::updateFromLevelset, Grid<T>::setBound                    grid.cpp:844-854, :591-593
 // Nothing of the reference is copied: its sources are compiled where they lie.
 //
 // The signatures are shared with oracle/mf_oracle.c (the restatement) so the same
@@ -69,6 +71,9 @@ void PD_fluid_guiding(MACGrid& vel, MACGrid& velT, Grid<Real>& pressure, FlagGri
 	Real epsRel, Real epsAbs, int maxIters, Grid<Real>* phi, Grid<Real>* perCellCorr, MACGrid* fractions, MACGrid* obvel, Real gfClamp, Real cgMaxIterFac,
 	Real cgAccuracy, int preconditioner, bool zeroPressureFixing, const Grid<Real>* curv, const Real surfTens);
 void releaseBlurPrecomp();
+void extrapolateMACSimple(FlagGrid& flags, MACGrid& vel, int distance, LevelsetGrid* phiObs, bool intoObs);
+void extrapolateLsSimple(Grid<Real>& phi, int distance, bool inside);
+void extrapolateVec3Simple(Grid<Vec3>& vel, Grid<Real>& phi, int distance, bool inside);
 void addGravity(const FlagGrid& flags, MACGrid& vel, Vec3 gravity, const Grid<Real>* exclude, bool scale);
 void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGrid& vel, Vec3 gravity, Real coefficient, bool scale);
 void advectSemiLagrange(const FlagGrid* flags, const MACGrid* vel, GridBase* grid, int order, Real strength, int orderSpace, bool openBounds, int boundaryWidth, int clampMode, int orderTrace);
@@ -134,6 +139,47 @@ int ref_add_buoyancy(int sx, int sy, int sz, const int* flags, const Real* densi
 	FluidSolver* s = mkSolver(sx, sy, sz); s->mDt = (Real)dt;
 	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel); Grid<Real> D(s, (Real*)density);
 	  addBuoyancy(F, D, V, Vec3((Real)gx, (Real)gy, (Real)gz), (Real)coefficient, scale != 0); }
+	delete s;
+  CATCH }
+
+// LevelsetGrid adds no data members to Grid<Real> (levelset.h:25-60) and its constructors live in levelset.cpp, which drags in the mesh
+// code; the plugins below only use the Grid<Real> interface of their level-set arguments, so a Grid<Real> over the caller's array stands in.
+int ref_extrapolate_mac_simple(int sx, int sy, int sz, const int* flags, Real* vel, int distance, const Real* phiObs, int intoObs)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
+	  Grid<Real>* P = phiObs ? new Grid<Real>(s, (Real*)phiObs) : 0;
+	  extrapolateMACSimple(F, V, distance, reinterpret_cast<LevelsetGrid*>(P), intoObs != 0);
+	  delete P; }
+	delete s;
+  CATCH }
+
+int ref_extrapolate_ls_simple(int sx, int sy, int sz, Real* phi, int distance, int inside)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ Grid<Real> P(s, phi); extrapolateLsSimple(P, distance, inside != 0); }
+	delete s;
+  CATCH }
+
+int ref_extrapolate_vec3_simple(int sx, int sy, int sz, Real* vel, const Real* phi, int distance, int inside)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ Grid<Vec3> V(s, (Vec3*)vel); Grid<Real> P(s, (Real*)phi); extrapolateVec3Simple(V, P, distance, inside != 0); }
+	delete s;
+  CATCH }
+
+int ref_update_from_levelset(int sx, int sy, int sz, int* flags, const Real* phi)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, flags); Grid<Real> P(s, (Real*)phi); F.updateFromLevelset(*reinterpret_cast<LevelsetGrid*>(&P)); }
+	delete s;
+  CATCH }
+
+int ref_set_bound(int sx, int sy, int sz, Real* grid, int ncomp, double value, int boundaryWidth)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	if (ncomp == 1) { Grid<Real> G(s, grid); G.setBound((Real)value, boundaryWidth); }
+	else { Grid<Vec3> G(s, (Vec3*)grid); G.setBound(Vec3((Real)value), boundaryWidth); }
 	delete s;
   CATCH }
 
