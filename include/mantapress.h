@@ -219,6 +219,21 @@ int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* densit
 int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
                             int clampMode, int orderTrace, double dt);
 
+/* ---- liquid neighbours (first slice): with them the level-set free-surface loop of scenes/freesurface.py:54-84
+ * (extrapolateLsSimple x2, extrapolateMACSimple, advect phi, phi.setBound, flags.updateFromLevelset, advect vel, addGravity, setWallBcs,
+ * solvePressure with phi) keeps every field in HBM.
+ * extrapolateMACSimple          fastmarch.cpp:337-375  (distance <= 250; phiObs may be NULL)
+ * extrapolateLsSimple           fastmarch.cpp:470-507
+ * extrapolateVec3Simple         fastmarch.cpp:510-542  (vel: a Vec3 grid, same storage as MP_GRID_MAC)
+ * FlagGrid::updateFromLevelset  grid.cpp:844-854
+ * Grid<T>::setBound             grid.cpp:585-593       (value = vx for Real / flag grids, (vx,vy,vz) for Vec3 grids)
+ * Results are bit-identical to the reference's in both precisions. */
+int mp_extrapolate_mac_simple(mp_context* ctx, const mp_grid* flags, mp_grid* vel, int distance, const mp_grid* phiObs, int intoObs);
+int mp_extrapolate_ls_simple(mp_context* ctx, mp_grid* phi, int distance, int inside);
+int mp_extrapolate_vec3_simple(mp_context* ctx, mp_grid* vel, const mp_grid* phi, int distance, int inside);
+int mp_flags_update_from_levelset(mp_context* ctx, mp_grid* flags, const mp_grid* levelset);
+int mp_grid_set_bound(mp_context* ctx, mp_grid* g, double vx, double vy, double vz, int boundaryWidth);
+
 /* ---- PD_fluid_guiding plugin/fluidguiding.cpp:294-353: primal-dual guiding of vel towards velT with per-cell weight;
  * up to maxIters solvePressure calls on device-resident copies, separable Gaussian blurs of radius blurRadius, stop test as in the reference.
  * vel receives the guided, divergence-free field; *iterations = the loop index at exit (what the reference prints).  The optional grids and

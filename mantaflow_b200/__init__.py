@@ -10,11 +10,11 @@ Importing the package does not need a GPU; creating a Solver does (there is no C
 from ._lib import (MantaError, PcMGDynamic, PcMGStatic, PcMIC, PcNone, PressureParams, SolveInfo, declared_symbols,
                    device_count, load)
 from .grid import (FlagEmpty, FlagFluid, FlagGrid, FlagInflow, FlagObstacle, FlagOpen, FlagOutflow, FlagStick,
-                   LevelsetGrid, MACGrid, RealGrid, Solver)
+                   LevelsetGrid, MACGrid, RealGrid, Solver, VecGrid)
 from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, releaseMG, solvePressure, solvePressureHost,
                        solvePressureSystem)
 from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE
-from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, lastGuidingIterations, releaseBlurPrecomp,
-                   setWallBcs)
+from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, extrapolateLsSimple, extrapolateMACSimple,
+                   extrapolateVec3Simple, lastGuidingIterations, releaseBlurPrecomp, setWallBcs)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

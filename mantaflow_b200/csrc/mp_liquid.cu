@@ -1,0 +1,125 @@
+// Liquid neighbours of the pressure projection on the device (first slice).  The per-cell operations and the pass
+// sequences are in mp_liquid_cells.cuh (shared with the host emulation the CPU tests run); this file is the CUDA executor -- one
+// thread per cell, x over i (128 threads), blockIdx.y = j, blockIdx.z = k, like mp_step.cu -- and the C-ABI entry points.
+// Every pass is a streaming sweep: 4 B/cell of marks plus the few values that change; nothing returns to the host.
+#include "mp_liquid_cells.cuh"
+
+namespace {
+
+template <typename F>
+__global__ void __launch_bounds__(128) k_liquid_cells(Dims d, F f) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+	if (i >= d.sx) return;
+	f(d, i, j, k, (IndexInt)i + d.Y * j + (IndexInt)d.sx * d.sy * k);
+}
+
+struct CudaExec {
+	mp_context* ctx;
+	template <typename F> int cells(const Dims& d, const F& f) {
+		k_liquid_cells<F><<<dim3((unsigned)((d.sx + 127) / 128), (unsigned)d.sy, (unsigned)d.sz), 128, 0, ctx->stream>>>(d, f);
+		MP_CHECK_LAUNCH(ctx);
+		return MP_OK;
+	}
+};
+
+struct Tmp {      // scratch grid of the context's pool, released on scope exit
+	mp_grid* g = nullptr;
+	~Tmp() { if (g) mp_grid_destroy(g); }
+};
+
+int checkLiquid(const char* who, mp_context* ctx, const mp_grid* g) {
+	if (!ctx || !g) MP_FAIL(MP_ERR_INVALID, "%s: NULL argument", who);
+	if (ctx->dist && ctx->dist->active) MP_FAIL(MP_ERR_UNSUPPORTED, "%s: not available on z-slab sharded grids yet", who);
+	if (g->sy > 65535 || g->sz > 65535) MP_FAIL(MP_ERR_UNSUPPORTED, "%s: grids beyond 65535 cells in y or z are not supported", who);
+	MP_CUDA(cudaSetDevice(ctx->device));
+	return MP_OK;
+}
+bool noInterior(const mp_grid* g) { return g->sx < 3 || g->sy < 3 || (g->sz > 1 && g->sz < 3); }
+
+template <typename Real>
+int macSimple(mp_context* ctx, const mp_grid* flags, mp_grid* vel, int distance, const mp_grid* phiObs, int intoObs) {
+	Tmp tmp, stage;
+	MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_FLAGS, vel->prec, vel->sx, vel->sy, vel->sz, &tmp.g));      // every cell written by MacMark
+	MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_MAC, vel->prec, vel->sx, vel->sy, vel->sz, &stage.g));       // only its outer layer is written and read
+	CudaExec ex = { ctx };
+	return liquid::extrapolateMacSimple<Real>(ex, dimsOf(flags), (const int*)flags->d, (Real*)vel->d, distance, phiObs ? (const Real*)phiObs->d : nullptr,
+	                                          intoObs != 0, (int*)tmp.g->d, (Real*)stage.g->d);
+}
+
+template <typename Real>
+int lsSimple(mp_context* ctx, mp_grid* val, const mp_grid* phi, int distance, int inside, bool vec3) {
+	Tmp tmp;
+	MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_FLAGS, val->prec, val->sx, val->sy, val->sz, &tmp.g));
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(val);
+	if (vec3) return liquid::extrapolateLs<Real, 3>(ex, d, (Real*)val->d, (const Real*)phi->d, distance, inside != 0, (Real)0, (Real)0, (int*)tmp.g->d);
+	const Real direction = inside ? (Real)-1. : (Real)1.;
+	return liquid::extrapolateLs<Real, 1>(ex, d, (Real*)val->d, (const Real*)phi->d, distance, inside != 0, direction, (Real)(direction * (distance + 2)), (int*)tmp.g->d);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mp_extrapolate_mac_simple(mp_context* ctx, const mp_grid* flags, mp_grid* vel, int distance, const mp_grid* phiObs, int intoObs)
+{
+	MP_TRY(checkLiquid("mp_extrapolate_mac_simple", ctx, flags));
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "extrapolateMACSimple: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, vel, MP_GRID_MAC, "vel", false));
+	if (phiObs) MP_TRY(mp_check_same(flags, phiObs, MP_GRID_REAL, "phiObs", false));
+	if (phiObs && phiObs->prec != vel->prec) MP_FAIL(MP_ERR_INVALID, "extrapolateMACSimple: phiObs and vel differ in precision");
+	if (distance > 250) MP_FAIL(MP_ERR_UNSUPPORTED, "extrapolateMACSimple: distance %d > 250 is not supported (marks are bytes)", distance);
+	if (noInterior(flags)) MP_FAIL(MP_ERR_INVALID, "extrapolateMACSimple: grid without interior cells");
+	if (vel->prec == 4) return macSimple<float>(ctx, flags, vel, distance, phiObs, intoObs);
+	return macSimple<double>(ctx, flags, vel, distance, phiObs, intoObs);
+}
+
+int mp_extrapolate_ls_simple(mp_context* ctx, mp_grid* phi, int distance, int inside)
+{
+	MP_TRY(checkLiquid("mp_extrapolate_ls_simple", ctx, phi));
+	if (phi->kind != MP_GRID_REAL) MP_FAIL(MP_ERR_INVALID, "extrapolateLsSimple: phi is not a real grid");
+	if (noInterior(phi)) MP_FAIL(MP_ERR_INVALID, "extrapolateLsSimple: grid without interior cells");
+	if (phi->prec == 4) return lsSimple<float>(ctx, phi, phi, distance, inside, false);
+	return lsSimple<double>(ctx, phi, phi, distance, inside, false);
+}
+
+int mp_extrapolate_vec3_simple(mp_context* ctx, mp_grid* vel, const mp_grid* phi, int distance, int inside)
+{
+	MP_TRY(checkLiquid("mp_extrapolate_vec3_simple", ctx, vel));
+	if (!phi) MP_FAIL(MP_ERR_INVALID, "mp_extrapolate_vec3_simple: NULL phi");
+	if (vel->kind != MP_GRID_MAC) MP_FAIL(MP_ERR_INVALID, "extrapolateVec3Simple: vel is not a Vec3 grid");
+	if (phi->kind != MP_GRID_REAL || phi->sx != vel->sx || phi->sy != vel->sy || phi->sz != vel->sz || phi->prec != vel->prec)
+		MP_FAIL(MP_ERR_INVALID, "extrapolateVec3Simple: phi does not match vel (kind, size or precision)");
+	if (noInterior(vel)) MP_FAIL(MP_ERR_INVALID, "extrapolateVec3Simple: grid without interior cells");
+	if (vel->prec == 4) return lsSimple<float>(ctx, vel, phi, distance, inside, true);
+	return lsSimple<double>(ctx, vel, phi, distance, inside, true);
+}
+
+int mp_flags_update_from_levelset(mp_context* ctx, mp_grid* flags, const mp_grid* levelset)
+{
+	MP_TRY(checkLiquid("mp_flags_update_from_levelset", ctx, flags));
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "updateFromLevelset: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, levelset, MP_GRID_REAL, "levelset", false));
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(flags);
+	if (levelset->prec == 4) { liquid::UpdateFromLevelset<float> op = { (int*)flags->d, (const float*)levelset->d }; return ex.cells(d, op); }
+	liquid::UpdateFromLevelset<double> op = { (int*)flags->d, (const double*)levelset->d };
+	return ex.cells(d, op);
+}
+
+int mp_grid_set_bound(mp_context* ctx, mp_grid* g, double vx, double vy, double vz, int boundaryWidth)
+{
+	MP_TRY(checkLiquid("mp_grid_set_bound", ctx, g));
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(g);
+	if (g->kind == MP_GRID_FLAGS) { liquid::SetBound<int, 1> op = { (int*)g->d, { (int)vx }, boundaryWidth }; return ex.cells(d, op); }
+	if (g->kind == MP_GRID_REAL) {
+		if (g->prec == 4) { liquid::SetBound<float, 1> op = { (float*)g->d, { (float)vx }, boundaryWidth }; return ex.cells(d, op); }
+		liquid::SetBound<double, 1> op = { (double*)g->d, { vx }, boundaryWidth }; return ex.cells(d, op);
+	}
+	if (g->prec == 4) { liquid::SetBound<float, 3> op = { (float*)g->d, { (float)vx, (float)vy, (float)vz }, boundaryWidth }; return ex.cells(d, op); }
+	liquid::SetBound<double, 3> op = { (double*)g->d, { vx, vy, vz }, boundaryWidth };
+	return ex.cells(d, op);
+}
+
+}

@@ -1,0 +1,229 @@
+// Liquid neighbours of the pressure projection (first slice): the plugins that make the level-set free-surface loop of
+// scenes/freesurface.py:54-84 device-resident around solvePressure(phi=...):
+//   extrapolateMACSimple   fastmarch.cpp:337-375  (knExtrapolateMACSimple :231-258, knUnprojectNormalComp :319-331, knExtrapolateIntoBnd :260-299)
+//   extrapolateLsSimple    fastmarch.cpp:470-507  (knExtrapolateLsSimple :439-460, knSetRemaining :463-467)
+//   extrapolateVec3Simple  fastmarch.cpp:510-542
+//   FlagGrid::updateFromLevelset  grid.cpp:844-854
+//   Grid<T>::setBound             grid.cpp:585-593
+//
+// This header holds the per-cell operations and the pass sequences, written against an executor `Exec` with one member
+//     template <class F> int cells(const Dims& d, const F& f);     // run f(d, i, j, k, idx) once for every cell, in any order
+// mp_liquid.cu instantiates it with the CUDA launcher (one thread per cell).  tests/emul/liquid_emul.cpp instantiates the SAME code with a
+// host loop, so that the build container (which has no GPU) can check cell arithmetic and pass structure against the reference; that
+// shim is test infrastructure and is never part of libmantapress.so.
+//
+// Why any execution order gives the serial result: a pass `d` only reads marks equal to d and values of cells carrying that mark, and
+// only writes cells whose mark is 0 (new mark d+1) -- the sets read and written by one pass are disjoint.
+#pragma once
+#include <cmath>
+#include "mp_common.cuh"
+
+#ifdef __CUDACC__
+#define MP_HD __host__ __device__ __forceinline__
+#else
+#define MP_HD inline
+#endif
+
+namespace liquid {
+
+MP_HD bool interiorCell(const Dims& d, int i, int j, int k) {      // the cells of a KERNEL(bnd=1) / FOR_IJK_BND(g, 1)
+	return i >= 1 && i <= d.sx - 2 && j >= 1 && j <= d.sy - 2 && (!d.is3D || (k >= 1 && k <= d.sz - 2));
+}
+MP_HD int outerFaces(const Dims& d, int i, int j, int k) {           // on how many outer faces of the domain the cell lies (per axis at most one)
+	return (i == 0 || i == d.sx - 1 ? 1 : 0) + (j == 0 || j == d.sy - 1 ? 1 : 0) + (d.is3D && (k == 0 || k == d.sz - 1) ? 1 : 0);
+}
+// neighbour q of fastmarch.cpp:233-236: +x -x +y -y +z -z
+MP_HD IndexInt nbOffset(const Dims& d, int q) {
+	const IndexInt o = (q >> 1) == 0 ? d.X : ((q >> 1) == 1 ? d.Y : d.Z);
+	return (q & 1) ? -o : o;
+}
+MP_HD bool nbInterior(const Dims& d, int q, int i, int j, int k) {
+	const int s = (q & 1) ? -1 : 1;
+	return interiorCell(d, i + ((q >> 1) == 0 ? s : 0), j + ((q >> 1) == 1 ? s : 0), k + ((q >> 1) == 2 ? s : 0));
+}
+
+// ---------------------------------------------------------------- extrapolateMACSimple
+// The reference runs the three velocity components one after the other with one Grid<int> of marks each; they are independent, so
+// here byte c of ONE int per cell carries the mark of component c and a pass advances all components at once (distance <= 250).
+template <typename Real> struct MacMark {                // fastmarch.cpp:346-358
+	const int* flags; int* tmp; int intoObs;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		int w = 0;
+		if (interiorCell(d, i, j, k)) {
+			const int f = flags[idx];
+			const int dim = d.is3D ? 3 : 2;
+			for (int c = 0; c < dim; c++) {
+				const int fn = flags[idx - (c == 0 ? d.X : (c == 1 ? d.Y : d.Z))];
+				bool mark = (f & TypeFluid) || (fn & TypeFluid);
+				if (intoObs) mark = mark && !(f & TypeObstacle) && !(fn & TypeObstacle);
+				if (mark) w |= 1 << (8 * c);
+			}
+		}
+		tmp[idx] = w;
+	}
+};
+template <typename Real> struct MacExtrapolate {         // knExtrapolateMACSimple fastmarch.cpp:231-258, pass d for every component
+	Real* vel; int* tmp; int pass;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (!interiorCell(d, i, j, k)) return;
+		const int dim = d.is3D ? 3 : 2;
+		const int t = tmp[idx];
+		bool open = false;
+		for (int c = 0; c < dim; c++) open = open || (((t >> (8 * c)) & 255) == 0);
+		if (!open) return;
+		// a neighbour's word may be rewritten by its own thread meanwhile: its changing bytes go from 0 to pass+1, never through `pass`
+		int tn[6];
+		for (int q = 0; q < 2 * dim; q++) tn[q] = tmp[idx + nbOffset(d, q)];
+		int tNew = t;
+		for (int c = 0; c < dim; c++) {
+			if (((t >> (8 * c)) & 255) != 0) continue;
+			int nbs = 0; Real avgVel = 0;
+			for (int q = 0; q < 2 * dim; q++)
+				if (((tn[q] >> (8 * c)) & 255) == pass) { avgVel += vel[3 * (idx + nbOffset(d, q)) + c]; nbs++; }
+			if (nbs > 0) { tNew |= (pass + 1) << (8 * c); vel[3 * idx + c] = avgVel / (Real)nbs; }
+		}
+		if (tNew != t) tmp[idx] = tNew;
+	}
+};
+// normalize util/vectorbase.h:415-429: the comparison against 1. and the reciprocal are double expressions
+template <typename Real> MP_HD void normalize3(Real& x, Real& y, Real& z) {
+	const Real l = x * x + y * y + z * z;
+	const Real eps2 = sizeof(Real) == 4 ? (Real)(1e-6f * 1e-6f) : (Real)(1e-10 * 1e-10);      // VECTOR_EPSILON^2 vectorbase.h:52,:55
+	const double dl = (double)l - 1.;
+	if ((dl < 0 ? -dl : dl) < (double)eps2) return;
+	if (l > eps2) {
+		const Real norm = sizeof(Real) == 4 ? (Real)sqrtf((float)l) : (Real)sqrt((double)l);
+		const Real s = (Real)(1. / (double)norm);
+		x *= s; y *= s; z *= s;
+	} else { x = 0; y = 0; z = 0; }
+}
+template <typename Real> struct UnprojectNormal {        // knUnprojectNormalComp fastmarch.cpp:319-331 with getNormal :302-318
+	Real* vel; const Real* phi; Real maxDist;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (!interiorCell(d, i, j, k)) return;
+		const Real ph = phi[idx];
+		if (ph > 0. || ph < -maxDist) return;
+		Real nx = phi[idx + d.X] - phi[idx - d.X], ny = phi[idx + d.Y] - phi[idx - d.Y], nz = phi[idx + d.Z] - phi[idx - d.Z];   // 2-D: Z == 0
+		const Real vx = vel[3 * idx], vy = vel[3 * idx + 1], vz = vel[3 * idx + 2];
+		if (nx * vx + ny * vy + nz * vz < 0.) {
+			normalize3<Real>(nx, ny, nz);
+			const Real l = nx * vx + ny * vy + nz * vz;
+			vel[3 * idx] = vx - nx * l; vel[3 * idx + 1] = vy - ny * l; vel[3 * idx + 2] = vz - nz * l;
+		}
+	}
+};
+// knExtrapolateIntoBnd fastmarch.cpp:260-299 reads a copy of the whole velocity grid; only the cells of the outer layer are written
+// and they read cells one step inwards, so the new values are first collected in `stage` (outer-layer entries only) and then moved.
+template <typename Real> struct IntoBndStage {
+	const int* flags; const Real* vel; Real* stage;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (outerFaces(d, i, j, k) == 0) return;
+		int c = 0;
+		Real v0 = 0, v1 = 0, v2 = 0;
+		const bool isObs = flags[idx] & TypeObstacle;
+		#define MP_TAKE(off) { const Real* s_ = vel + 3 * (idx + (off)); v0 = s_[0]; v1 = s_[1]; v2 = s_[2]; }
+		if (i == 0)              { MP_TAKE(d.X)  if (isObs && v0 < 0.) v0 = 0; c++; }
+		else if (i == d.sx - 1)  { MP_TAKE(-d.X) if (isObs && v0 > 0.) v0 = 0; c++; }
+		if (j == 0)              { MP_TAKE(d.Y)  if (isObs && v1 < 0.) v1 = 0; c++; }
+		else if (j == d.sy - 1)  { MP_TAKE(-d.Y) if (isObs && v1 > 0.) v1 = 0; c++; }
+		if (d.is3D) {
+			if (k == 0)              { MP_TAKE(d.Z)  if (isObs && v2 < 0.) v2 = 0; c++; }
+			else if (k == d.sz - 1)  { MP_TAKE(-d.Z) if (isObs && v2 > 0.) v2 = 0; c++; }
+		}
+		#undef MP_TAKE
+		stage[3 * idx] = v0 / (Real)c; stage[3 * idx + 1] = v1 / (Real)c; stage[3 * idx + 2] = v2 / (Real)c;
+	}
+};
+template <typename Real> struct IntoBndCopy {
+	const Real* stage; Real* vel;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (outerFaces(d, i, j, k) == 0) return;
+		vel[3 * idx] = stage[3 * idx]; vel[3 * idx + 1] = stage[3 * idx + 1]; vel[3 * idx + 2] = stage[3 * idx + 2];
+	}
+};
+
+// tmp: one int per cell; stage: 3 Reals per cell (only outer-layer entries are touched)
+template <typename Real, typename Exec>
+int extrapolateMacSimple(Exec& ex, const Dims& d, const int* flags, Real* vel, int distance, const Real* phiObs, bool intoObs, int* tmp, Real* stage) {
+	{ MacMark<Real> op = { flags, tmp, intoObs ? 1 : 0 }; MP_TRY(ex.cells(d, op)); }
+	for (int pass = 1; pass < 1 + distance; pass++) { MacExtrapolate<Real> op = { vel, tmp, pass }; MP_TRY(ex.cells(d, op)); }
+	if (phiObs) { UnprojectNormal<Real> op = { vel, phiObs, (Real)distance }; MP_TRY(ex.cells(d, op)); }
+	{ IntoBndStage<Real> op = { flags, vel, stage }; MP_TRY(ex.cells(d, op)); }
+	{ IntoBndCopy<Real> op = { stage, vel }; MP_TRY(ex.cells(d, op)); }
+	return MP_OK;
+}
+
+// ---------------------------------------------------------------- extrapolateLsSimple / extrapolateVec3Simple
+template <typename Real> struct LsMark {                 // fastmarch.cpp:475-498: 1 on the chosen side of phi, 2 on the first layer next to it, 0 elsewhere
+	const Real* phi; int* tmp; int inside;
+	MP_HD bool on(Real p) const { return inside ? (p > 0.) : (p < 0.); }
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		int m = 0;
+		if (interiorCell(d, i, j, k)) {
+			if (on(phi[idx])) m = 1;
+			else {
+				const int dim = d.is3D ? 3 : 2;
+				for (int q = 0; q < 2 * dim; q++)
+					if (nbInterior(d, q, i, j, k) && on(phi[idx + nbOffset(d, q)])) { m = 2; break; }
+			}
+		}
+		tmp[idx] = m;
+	}
+};
+// knExtrapolateLsSimple<S> fastmarch.cpp:439-460 (NC = 1: Real, 3: Vec3).  `last`: this is the final pass, so cells that stay unmarked
+// get knSetRemaining's value (:463-467) right away -- nobody reads the value of an unmarked cell during the pass.
+template <typename Real, int NC> struct LsExtrapolate {
+	Real* val; int* tmp; int pass; Real direction; int last; Real remaining;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (!interiorCell(d, i, j, k)) return;
+		if (tmp[idx] != 0) return;
+		const int dim = d.is3D ? 3 : 2;
+		int nbs = 0;
+		Real avg[NC];
+		for (int c = 0; c < NC; c++) avg[c] = 0;
+		for (int q = 0; q < 2 * dim; q++) {
+			const IndexInt nb = idx + nbOffset(d, q);
+			if (tmp[nb] == pass) { for (int c = 0; c < NC; c++) avg[c] += val[NC * nb + c]; nbs++; }
+		}
+		if (nbs > 0) { tmp[idx] = pass + 1; for (int c = 0; c < NC; c++) val[NC * idx + c] = avg[c] / (Real)nbs + direction; }
+		else if (last) for (int c = 0; c < NC; c++) val[NC * idx + c] = remaining;
+	}
+};
+template <typename Real, int NC> struct LsRemaining {    // knSetRemaining fastmarch.cpp:463-467 when there was no pass to ride on
+	Real* val; const int* tmp; Real remaining;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (!interiorCell(d, i, j, k) || tmp[idx] != 0) return;
+		for (int c = 0; c < NC; c++) val[NC * idx + c] = remaining;
+	}
+};
+template <typename Real, int NC, typename Exec>
+int extrapolateLs(Exec& ex, const Dims& d, Real* val, const Real* phi, int distance, bool inside, Real direction, Real remaining, int* tmp) {
+	{ LsMark<Real> op = { phi, tmp, inside ? 1 : 0 }; MP_TRY(ex.cells(d, op)); }
+	if (distance < 2) { LsRemaining<Real, NC> op = { val, tmp, remaining }; return ex.cells(d, op); }
+	for (int pass = 2; pass < 1 + distance; pass++) {
+		LsExtrapolate<Real, NC> op = { val, tmp, pass, direction, pass == distance ? 1 : 0, remaining };
+		MP_TRY(ex.cells(d, op));
+	}
+	return MP_OK;
+}
+
+// ---------------------------------------------------------------- FlagGrid::updateFromLevelset, Grid<T>::setBound
+template <typename Real> struct UpdateFromLevelset {     // grid.cpp:844-854; invalidTimeValue = -1000 (levelset.cpp:103 -> fastmarch.h:134)
+	int* flags; const Real* phi;
+	MP_HD void operator()(const Dims&, int, int, int, IndexInt idx) const {
+		const int f = flags[idx];
+		if ((f & TypeObstacle) || (f & TypeOutflow)) return;
+		const Real p = phi[idx];
+		if (p <= (Real)-1000) return;
+		flags[idx] = (f & ~(TypeEmpty | TypeFluid)) | ((p <= 0) ? TypeFluid : TypeEmpty);
+	}
+};
+template <typename T, int NC> struct SetBound {          // knSetBoundary grid.cpp:585-589
+	T* g; T value[NC]; int w;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		const bool bnd = i <= w || i >= d.sx - 1 - w || j <= w || j >= d.sy - 1 - w || (d.is3D && (k <= w || k >= d.sz - 1 - w));
+		if (bnd) for (int c = 0; c < NC; c++) g[NC * idx + c] = value[c];
+	}
+};
+
+}  // namespace liquid

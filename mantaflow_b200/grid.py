@@ -3,8 +3,8 @@
 reference layout ([Z,Y,X] / [Z,Y,X,3], the convention of plugin/numpyconvert.cpp:145-183) AND an mp_grid in HBM.
 Two dirty bits keep them coherent lazily, so a sequence of pressure plugins never leaves the device.
 
-Only what the pressure path and its callers need is here; scene construction helpers (initDomain, fillGrid,
-updateFromLevelset, setConst) are the simple host loops of grid.cpp:732-861."""
+Only what the pressure path and its callers need is here; scene construction helpers (initDomain, fillGrid, setConst) are
+the simple host loops of grid.cpp:732-861; updateFromLevelset and setBound, which liquid scenes call every step, run on the device."""
 import ctypes as C
 import numpy as np
 
@@ -128,6 +128,15 @@ class _GridBase:
     def copyFrom(self, other):
         self.copyFromArray(other.numpy())
 
+    def setBound(self, value, boundaryWidth=1):
+        """Grid<T>::setBound grid.cpp:585-593, on the device (Vec3 grids take a 3-tuple or one value for every component)"""
+        try:
+            vx, vy, vz = (float(c) for c in value)
+        except TypeError:
+            vx = vy = vz = float(value)
+        check(self.parent.lib.mp_grid_set_bound(self.parent._ctx, self.dev(), C.c_double(vx), C.c_double(vy), C.c_double(vz), C.c_int(int(boundaryWidth))))
+        self.markDeviceWritten()
+
     def close(self):
         if getattr(self, "_dev", None) is not None and self._dev and self.parent._ctx:
             self.parent.lib.mp_grid_destroy(self._dev)
@@ -157,6 +166,10 @@ class LevelsetGrid(RealGrid):
 class MACGrid(_GridBase):
     """MACGrid (grid.h:243-281), AoS Vec3"""
     KIND = MP_GRID_MAC
+
+
+class VecGrid(MACGrid):
+    """Grid<Vec3> (cell-centred vectors): the same AoS storage as a MACGrid"""
 
 
 class FlagGrid(_GridBase):
@@ -196,8 +209,6 @@ class FlagGrid(_GridBase):
         f[m] = (f[m] & ~(FlagEmpty | FlagFluid)) | type
 
     def updateFromLevelset(self, levelset):
-        """grid.cpp:844-854 (invalidTimeValue = -1000, fastmarch.h:134)"""
-        f = self.numpy(writable=True)
-        phi = levelset.numpy()
-        m = ((f & (FlagObstacle | FlagOutflow)) == 0) & (phi > -1000)
-        f[m] = (f[m] & ~(FlagEmpty | FlagFluid)) | np.where(phi[m] <= 0, FlagFluid, FlagEmpty).astype(np.int32)
+        """grid.cpp:844-854 (invalidTimeValue = -1000, fastmarch.h:134), on the device: neither grid returns to the host"""
+        check(self.parent.lib.mp_flags_update_from_levelset(self.parent._ctx, self.dev(), levelset.dev()))
+        self.markDeviceWritten()

@@ -6,6 +6,11 @@ defaults as the reference, so the main loop of scenes/simpleplume.py runs with e
     addBuoyancy         plugin/extforces.cpp:86-90
     advectSemiLagrange  plugin/advection.cpp:442-461
     PD_fluid_guiding    plugin/fluidguiding.cpp:294-353  (+ getSpiralVelocity :171-192, setGradientYWeight :195-207 for its scenes)
+
+and the liquid neighbours (first slice) with which the level-set loop of scenes/freesurface.py:54-84 does the same:
+
+    extrapolateMACSimple   fastmarch.cpp:337-375      extrapolateLsSimple :470-507      extrapolateVec3Simple :510-542
+    (FlagGrid.updateFromLevelset and Grid.setBound are methods of the grid classes, grid.py)
 """
 import ctypes as C
 
@@ -55,6 +60,24 @@ def advectSemiLagrange(flags, vel, grid, order=1, strength=1.0, orderSpace=1, op
     check(s.lib.mp_advect_semi_lagrange(s._ctx, flags.dev(), vel.dev(), grid.dev(), C.c_int(order), C.c_double(strength), C.c_int(orderSpace),
                                         C.c_int(clampMode), C.c_int(orderTrace), C.c_double(s.timestep)))
     grid.markDeviceWritten()
+
+
+def extrapolateMACSimple(flags, vel, distance=4, phiObs=None, intoObs=False):
+    s = flags.parent
+    check(s.lib.mp_extrapolate_mac_simple(s._ctx, flags.dev(), vel.dev(), C.c_int(int(distance)), _d(phiObs), C.c_int(int(bool(intoObs)))))
+    vel.markDeviceWritten()
+
+
+def extrapolateLsSimple(phi, distance=4, inside=False):
+    s = phi.parent
+    check(s.lib.mp_extrapolate_ls_simple(s._ctx, phi.dev(), C.c_int(int(distance)), C.c_int(int(bool(inside)))))
+    phi.markDeviceWritten()
+
+
+def extrapolateVec3Simple(vel, phi, distance=4, inside=False):
+    s = vel.parent
+    check(s.lib.mp_extrapolate_vec3_simple(s._ctx, vel.dev(), phi.dev(), C.c_int(int(distance)), C.c_int(int(bool(inside)))))
+    vel.markDeviceWritten()
 
 
 _last_guiding = {"iterations": -1}

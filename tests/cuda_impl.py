@@ -144,6 +144,42 @@ class CudaImpl:
         grid[...] = G.numpy()
         return grid
 
+    # -- liquid neighbours --
+    def extrapolate_mac_simple(self, flags, vel, distance=4, phiObs=None, intoObs=False):
+        s = self._solver(flags)
+        V = mf.MACGrid(s, vel)
+        mf.extrapolateMACSimple(mf.FlagGrid(s, flags), V, distance=distance, phiObs=self._g(s, mf.LevelsetGrid, phiObs), intoObs=intoObs)
+        vel[...] = V.numpy()
+        return vel
+
+    def extrapolate_ls_simple(self, phi, distance=4, inside=False):
+        s = self._solver(phi)
+        P = mf.LevelsetGrid(s, phi)
+        mf.extrapolateLsSimple(P, distance=distance, inside=inside)
+        phi[...] = P.numpy()
+        return phi
+
+    def extrapolate_vec3_simple(self, vel, phi, distance=4, inside=False):
+        s = self._solver(phi)
+        V = mf.VecGrid(s, vel)
+        mf.extrapolateVec3Simple(V, mf.LevelsetGrid(s, phi), distance=distance, inside=inside)
+        vel[...] = V.numpy()
+        return vel
+
+    def update_from_levelset(self, flags, phi):
+        s = self._solver(flags)
+        F = mf.FlagGrid(s, flags)
+        F.updateFromLevelset(mf.LevelsetGrid(s, phi))
+        flags[...] = F.numpy()
+        return flags
+
+    def set_bound(self, grid, value, boundaryWidth=1):
+        s = self._solver(grid[..., 0] if grid.ndim == 4 else grid)
+        G = (mf.RealGrid if grid.ndim == 3 else mf.VecGrid)(s, grid)
+        G.setBound(value, boundaryWidth)
+        grid[...] = G.numpy()
+        return grid
+
     def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
         s = self._solver(flags); s.timestep = dt
         U, Um, O = mf.RealGrid(s, ut), mf.RealGrid(s, utm1), mf.RealGrid(s)

@@ -1,0 +1,89 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into libmantapress.so and never used by the product path.
+//
+// Host emulation of the liquid-neighbour kernels: instantiates the per-cell operations and pass sequences of
+// mantaflow_b200/csrc/mp_liquid_cells.cuh (the code the CUDA kernels of mp_liquid.cu run, one thread per cell) with an executor that
+// walks the cells in a host loop.  The build container has no GPU; this lets `pytest -m "not gpu"` check the arithmetic and the pass
+// structure of those kernels against the unmodified reference.  `order` selects the walk (0 lexicographic, 1 reverse, 2 a strided
+// permutation): the passes are written so that any order gives the same result, which the tests assert.
+// Built by tests/test_liquid_emulation.py:  g++ -O2 -ffp-contract=off -I/usr/local/cuda/include -shared -fPIC
+#include "../../mantaflow_b200/csrc/mp_liquid_cells.cuh"
+#include <cstdarg>
+#include <cstdlib>
+
+void mp_set_error(const char*, ...) {}
+
+namespace {
+struct HostExec {
+	int order;
+	static IndexInt gcd(IndexInt a, IndexInt b) { while (b) { const IndexInt t = a % b; a = b; b = t; } return a; }
+	template <typename F> int cells(const Dims& d, const F& f) {
+		const IndexInt n = d.n;
+		IndexInt stride = 1;
+		if (order == 2) { stride = 7919; while (gcd(stride, n) != 1) stride += 2; }       // a stride coprime to n visits every cell exactly once
+		for (IndexInt t = 0; t < n; t++) {
+			IndexInt idx = t;
+			if (order == 1) idx = n - 1 - t;
+			else if (order == 2) idx = (t * stride) % n;
+			const int i = (int)(idx % d.sx), j = (int)((idx / d.sx) % d.sy), k = (int)(idx / ((IndexInt)d.sx * d.sy));
+			f(d, i, j, k, idx);
+		}
+		return MP_OK;
+	}
+};
+Dims mkDims(int sx, int sy, int sz) {
+	mp_grid g; g.ctx = nullptr; g.kind = MP_GRID_REAL; g.prec = 4; g.sx = sx; g.sy = sy; g.sz = sz; g.n = (IndexInt)sx * sy * sz; g.bytes = 0; g.d = nullptr; g.owns = false;
+	return dimsOf(&g);
+}
+template <typename Real> int macSimple(int order, int sx, int sy, int sz, const int* flags, Real* vel, int distance, const Real* phiObs, int intoObs) {
+	const Dims d = mkDims(sx, sy, sz);
+	int* tmp = (int*)malloc(sizeof(int) * (size_t)d.n);
+	Real* stage = (Real*)malloc(sizeof(Real) * 3 * (size_t)d.n);
+	for (IndexInt q = 0; q < d.n; q++) tmp[q] = 0x5a5a5a5a;          // scratch grids come uninitialised from the pool
+	for (IndexInt q = 0; q < 3 * d.n; q++) stage[q] = (Real)1e30;
+	HostExec ex = { order };
+	const int rc = liquid::extrapolateMacSimple<Real>(ex, d, flags, vel, distance, phiObs, intoObs != 0, tmp, stage);
+	free(tmp); free(stage);
+	return rc;
+}
+template <typename Real> int lsSimple(int order, int sx, int sy, int sz, Real* val, const Real* phi, int distance, int inside, bool vec3) {
+	const Dims d = mkDims(sx, sy, sz);
+	int* tmp = (int*)malloc(sizeof(int) * (size_t)d.n);
+	for (IndexInt q = 0; q < d.n; q++) tmp[q] = 0x5a5a5a5a;
+	HostExec ex = { order };
+	int rc;
+	if (vec3) rc = liquid::extrapolateLs<Real, 3>(ex, d, val, phi, distance, inside != 0, (Real)0, (Real)0, tmp);
+	else { const Real direction = inside ? (Real)-1. : (Real)1.;
+	       rc = liquid::extrapolateLs<Real, 1>(ex, d, val, phi, distance, inside != 0, direction, (Real)(direction * (distance + 2)), tmp); }
+	free(tmp);
+	return rc;
+}
+}  // namespace
+
+extern "C" {
+int emu_extrapolate_mac_simple(int prec, int order, int sx, int sy, int sz, const int* flags, void* vel, int distance, const void* phiObs, int intoObs) {
+	return prec == 4 ? macSimple<float>(order, sx, sy, sz, flags, (float*)vel, distance, (const float*)phiObs, intoObs)
+	                 : macSimple<double>(order, sx, sy, sz, flags, (double*)vel, distance, (const double*)phiObs, intoObs);
+}
+int emu_extrapolate_ls_simple(int prec, int order, int sx, int sy, int sz, void* phi, int distance, int inside) {
+	return prec == 4 ? lsSimple<float>(order, sx, sy, sz, (float*)phi, (const float*)phi, distance, inside, false)
+	                 : lsSimple<double>(order, sx, sy, sz, (double*)phi, (const double*)phi, distance, inside, false);
+}
+int emu_extrapolate_vec3_simple(int prec, int order, int sx, int sy, int sz, void* vel, const void* phi, int distance, int inside) {
+	return prec == 4 ? lsSimple<float>(order, sx, sy, sz, (float*)vel, (const float*)phi, distance, inside, true)
+	                 : lsSimple<double>(order, sx, sy, sz, (double*)vel, (const double*)phi, distance, inside, true);
+}
+int emu_update_from_levelset(int prec, int order, int sx, int sy, int sz, int* flags, const void* phi) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	if (prec == 4) { liquid::UpdateFromLevelset<float> op = { flags, (const float*)phi }; return ex.cells(d, op); }
+	liquid::UpdateFromLevelset<double> op = { flags, (const double*)phi }; return ex.cells(d, op);
+}
+int emu_set_bound(int prec, int order, int sx, int sy, int sz, void* grid, int ncomp, double value, int w) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	if (prec == 4) {
+		if (ncomp == 1) { liquid::SetBound<float, 1> op = { (float*)grid, { (float)value }, w }; return ex.cells(d, op); }
+		liquid::SetBound<float, 3> op = { (float*)grid, { (float)value, (float)value, (float)value }, w }; return ex.cells(d, op);
+	}
+	if (ncomp == 1) { liquid::SetBound<double, 1> op = { (double*)grid, { value }, w }; return ex.cells(d, op); }
+	liquid::SetBound<double, 3> op = { (double*)grid, { value, value, value }, w }; return ex.cells(d, op);
+}
+}

@@ -10,7 +10,8 @@ Fixtures
                                  GridMg vertex types / operators / V-cycle, GridCg runs for PC_None/mICP/MGP,
                                  correctVelocity, the solvePressure plugin with PcMIC / PcMGDynamic)
   step_<scene>_f{32,64}.npz    : setWallBcs (with obvel), addGravity, addBuoyancy, advectSemiLagrange (Real / MAC, order 1 / 2, both clamp
-                                 modes, outflow cells) on seeded random boxes; plume{3d,2d}_f32.npz: six steps of the simpleplume main loop
+                                 modes, outflow cells) on seeded random boxes; plume{3d,2d}_f32.npz: six steps of the simpleplume main loop;
+                                 step_liq*: the extrapolation plugins, updateFromLevelset, setBound; step_fs*: six steps of the free-surface loop
   psolve52_f32.npz             : the scenario of tools/tests/test_0100_psolve.py and test_0110_mgsolve.py (52^3 closed box,
                                  box velocity source, solves with PcMIC / PcMGDynamic / PcMGStatic), float build
 """
@@ -179,10 +180,36 @@ def step_fixtures():
         print("%-34s %7.1f KiB  its %s  max density %.3f" % (os.path.basename(path), os.path.getsize(path) / 1024, its, float(dens.max())))
 
 
+def liquid_fixtures():
+    """step_liq*_f{32,64}.npz: the reference's extrapolateMACSimple / extrapolateLsSimple / extrapolateVec3Simple, FlagGrid::updateFromLevelset and
+    Grid::setBound on the seeded scenes of tests/helpers.py; step_fs*: six steps of the free-surface loop of scenes/freesurface.py:54-84."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import helpers
+    for prec in (4, 8):
+        R = Oracle("reference", prec)
+        for name in helpers.LIQUID_SCENES:   # extrapolateMACSimple / LsSimple / Vec3Simple, updateFromLevelset, setBound
+            flags, vel, phi, phiObs = helpers.liquid_scene(name, prec)
+            fx = dict(flags=flags, vel=vel, phi=phi)
+            for case in helpers.LIQUID_CASES:
+                fx[case] = helpers.run_liquid_case(R, case, flags, vel, phi, phiObs)
+            path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, **fx)
+            print("%-34s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+        for name in helpers.FREESURFACE_SCENES:   # six steps of the level-set free-surface loop (scenes/freesurface.py:54-84)
+            flags, phi, vel, p, its = helpers.run_freesurface_steps(R, name, prec, steps=6)
+            path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, flags=flags, phi=phi, vel=vel, pressure=p, iterations=np.array(its))
+            print("%-34s %7.1f KiB  its %s  fluid cells %d" % (os.path.basename(path), os.path.getsize(path) / 1024, its, int((flags & 1).sum())))
+
+
 def main():
+    if "--only-liquid" in sys.argv:
+        return liquid_fixtures()
     if "--only-step" in sys.argv:
-        return step_fixtures()
+        step_fixtures()
+        return liquid_fixtures()
     step_fixtures()
+    liquid_fixtures()
     for prec in (4, 8):
         R = Oracle("reference", prec)
         for name in KERNEL_SCENES:

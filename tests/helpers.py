@@ -299,3 +299,106 @@ def check_guiding_against_golden(I, name, prec, tol):
     v, p, it = run_guiding(I, name, prec)
     assert it == int(g["iterations"]), (it, int(g["iterations"]))
     assert np.abs(v.astype(np.float64) - g["vel"]).max() <= tol and np.abs(p.astype(np.float64) - g["pressure"]).max() <= tol * 10
+
+
+# ---------------------------------------------------------------- liquid neighbours: fastmarch.cpp:337-542, grid.cpp:585-593,:844-854
+LIQUID_SCENES = {"liq3d": (12, 16, 14), "liq2d": (1, 28, 24), "liqragged": (11, 13, 9)}      # (sz, sy, sx)
+LIQUID_CASES = ["mac_d4", "mac_d3_into", "mac_d5_phiobs", "mac_d0", "ls_out_d4", "ls_in_d5", "ls_out_d1", "ls_in_d2", "v3_out_d4", "v3_in_d2",
+                "v3_out_d1", "from_levelset", "bound_real_w0", "bound_real_w2", "bound_vec_w1"]
+
+
+def liquid_scene(name, prec):
+    """basin + drop level set with noise, flags from it plus random obstacle cells, random velocity, a random obstacle level set"""
+    from mantaflow_b200 import scenes
+    sz, sy, sx = shape = LIQUID_SCENES[name]
+    real = np.float32 if prec == 4 else np.float64
+    flags, _, phi = scenes.liquid_basin((sx, sy, sz), prec)
+    rng = np.random.default_rng(11 + sx)
+    inner = np.zeros(shape, bool)
+    inner[(slice(1, -1) if sz > 1 else slice(None)), 1:-1, 1:-1] = True
+    flags[inner & (rng.random(shape) < 0.06)] = 2
+    vel = (rng.random(shape + (3,)) - 0.5).astype(real)
+    if sz == 1:
+        vel[..., 2] = 0
+    phi = (phi + (rng.random(shape) - 0.5).astype(real)).astype(real)
+    phi[rng.random(shape) < 0.03] = -2000          # below invalidTimeValue: updateFromLevelset leaves those cells alone
+    phiObs = (rng.random(shape) * 6 - 4).astype(real)
+    return flags, vel, phi, phiObs
+
+
+def run_liquid_case(I, case, flags, vel, phi, phiObs):
+    if case == "mac_d4":
+        return I.extrapolate_mac_simple(flags, vel.copy(), distance=4)
+    if case == "mac_d3_into":
+        return I.extrapolate_mac_simple(flags, vel.copy(), distance=3, intoObs=True)
+    if case == "mac_d5_phiobs":
+        return I.extrapolate_mac_simple(flags, vel.copy(), distance=5, phiObs=phiObs)
+    if case == "mac_d0":
+        return I.extrapolate_mac_simple(flags, vel.copy(), distance=0)
+    if case.startswith("ls_"):
+        return I.extrapolate_ls_simple(phi.copy(), distance=int(case[-1]), inside="_in_" in case)
+    if case.startswith("v3_"):
+        return I.extrapolate_vec3_simple(vel.copy(), phi, distance=int(case[-1]), inside="_in_" in case)
+    if case == "from_levelset":
+        return I.update_from_levelset(flags.copy(), phi)
+    if case == "bound_real_w0":
+        return I.set_bound(phi.copy(), 0.5, 0)
+    if case == "bound_real_w2":
+        return I.set_bound(phi.copy(), -3.0, 2)
+    if case == "bound_vec_w1":
+        return I.set_bound(vel.copy(), 0.25, 1)
+    raise KeyError(case)
+
+
+def check_liquid_against_golden(I, name, prec):
+    g = load_golden("step_" + name, prec)
+    flags, vel, phi, phiObs = liquid_scene(name, prec)
+    assert np.array_equal(flags, g["flags"]) and np.array_equal(vel, g["vel"]) and np.array_equal(phi, g["phi"])
+    for case in LIQUID_CASES:
+        out = run_liquid_case(I, case, flags, vel, phi, phiObs)
+        assert np.array_equal(out, g[case]), (name, prec, case, float(np.abs(out.astype(np.float64) - g[case]).max()))
+
+
+FREESURFACE_SCENES = {"fs3d": ((20, 24, 20), 1), "fs2d": ((1, 40, 36), 2)}       # shape, preconditioner (mICP only supports 3-D, conjugategrad.cpp:222)
+
+
+def run_freesurface_steps(I, name, prec, steps):
+    """the main loop of scenes/freesurface.py:54-84 with useMarching = False, ghostFluid = True, doOpen = False: two-cell walls (bWidth 1),
+    basin + drop, every plugin of the loop through the implementation under test.  The solver tolerance is tighter than the scene's 5e-4
+    (and the iteration cap wider) so that implementations whose iteration counts differ by one still agree to ~1e-5."""
+    from mantaflow_b200 import scenes
+    shape, pc = FREESURFACE_SCENES[name]
+    sz, sy, sx = shape
+    real = np.float32 if prec == 4 else np.float64
+    flags = scenes.closed_box_flags(sx, sy, sz, boundaryWidth=1)
+    k, j, i = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
+    basin = (j + 0.5) - 0.2 * sy
+    drop = np.sqrt((i + 0.5 - 0.5 * sx) ** 2 + (j + 0.5 - 0.5 * sy) ** 2 + ((k + 0.5 - 0.5 * sz) ** 2 if sz > 1 else 0)) - 0.125 * sx
+    phi = np.ascontiguousarray(np.minimum(basin, drop).astype(real))
+    I.update_from_levelset(flags, phi)
+    vel = np.zeros(shape + (3,), real); p = np.zeros(shape, real)
+    its = []
+    for _ in range(steps):
+        I.extrapolate_ls_simple(phi, distance=5, inside=False)
+        I.extrapolate_ls_simple(phi, distance=5, inside=True)
+        I.extrapolate_mac_simple(flags, vel, distance=5)
+        I.advect_semi_lagrange(flags, vel, phi, order=2, clampMode=2)
+        I.set_bound(phi, 1.0, 1)
+        I.update_from_levelset(flags, phi)
+        I.advect_semi_lagrange(flags, vel, vel, order=2)
+        I.add_gravity(flags, vel, (0, -0.025, 0))
+        I.set_wall_bcs_obvel(flags, vel, None)
+        p, it, _ = I.solve_pressure(flags, vel, phi=phi, cgMaxIterFac=5, cgAccuracy=1e-5 if prec == 4 else 1e-10, preconditioner=pc)
+        its.append(it)
+    return flags, phi, vel, p, its
+
+
+def check_freesurface_against_golden(I, name, prec, tol):
+    """six steps of the free-surface loop: identical flags, iteration counts within one, fields within tol (0: bit-identical)"""
+    g = load_golden("step_" + name, prec)
+    flags, phi, vel, p, its = run_freesurface_steps(I, name, prec, steps=6)
+    assert np.array_equal(flags, g["flags"]), "fluid / empty cells differ after six steps"
+    assert all(abs(a - int(b)) <= 1 for a, b in zip(its, g["iterations"])), (its, g["iterations"])
+    for a, key, f in ((phi, "phi", 1), (vel, "vel", 1), (p, "pressure", 10)):
+        err = float(np.abs(a.astype(np.float64) - g[key]).max())
+        assert err <= tol * f, (name, prec, key, err)

@@ -1,0 +1,103 @@
+"""GPU: the liquid neighbours of the projection on the device (first slice) -- extrapolateMACSimple, extrapolateLsSimple,
+extrapolateVec3Simple, FlagGrid.updateFromLevelset, Grid.setBound -- bit for bit against the reference's golden vectors and against the
+oracle on larger grids, and six steps of the level-set free-surface loop of scenes/freesurface.py:54-84 with every field resident on
+the device."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import helpers  # noqa: E402
+from helpers import (FREESURFACE_SCENES, LIQUID_CASES, LIQUID_SCENES, check_freesurface_against_golden, check_liquid_against_golden,  # noqa: E402
+                     liquid_scene, load_golden, run_liquid_case)
+
+
+@pytest.fixture(scope="module")
+def mf():
+    import mantaflow_b200 as m
+    if m.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests need a B200")
+    return m
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(LIQUID_SCENES))
+def test_cuda_reproduces_liquid_golden(name, prec):
+    from cuda_impl import CudaImpl
+    check_liquid_against_golden(CudaImpl(prec), name, prec)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("shape", [(34, 44, 150), (1, 70, 260)])
+def test_cuda_equals_oracle_on_larger_scenes(shape, prec):
+    """rows longer than one thread block (128 cells) and many blocks in y / z"""
+    from cuda_impl import CudaImpl
+    from oracle.oracle_api import Oracle
+    helpers.LIQUID_SCENES["large"] = shape
+    try:
+        flags, vel, phi, phiObs = liquid_scene("large", prec)
+    finally:
+        del helpers.LIQUID_SCENES["large"]
+    O, I = Oracle("port", prec), CudaImpl(prec)
+    for case in LIQUID_CASES:
+        assert np.array_equal(run_liquid_case(I, case, flags, vel, phi, phiObs), run_liquid_case(O, case, flags, vel, phi, phiObs)), case
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(FREESURFACE_SCENES))
+def test_freesurface_steps_match_the_reference(name, prec):
+    """scenes/freesurface.py:54-84 through the adapter: identical fluid / empty cells after six steps, fields within the solver tolerance"""
+    from cuda_impl import CudaImpl
+    check_freesurface_against_golden(CudaImpl(prec), name, prec, tol=1e-4 if prec == 4 else 1e-8)
+
+
+def test_freesurface_steps_device_resident(mf):
+    """the same loop written like the scene: grids are created once and stay on the device until the end"""
+    shape, pc = FREESURFACE_SCENES["fs3d"]
+    sz, sy, sx = shape
+    g = load_golden("step_fs3d", 4)
+    from mantaflow_b200 import scenes
+    k, j, i = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
+    basin = (j + 0.5) - 0.2 * sy
+    drop = np.sqrt((i + 0.5 - 0.5 * sx) ** 2 + (j + 0.5 - 0.5 * sy) ** 2 + (k + 0.5 - 0.5 * sz) ** 2) - 0.125 * sx
+    s = mf.Solver(gridSize=(sx, sy, sz), dim=3, prec=4)
+    flags = mf.FlagGrid(s, scenes.closed_box_flags(sx, sy, sz, boundaryWidth=1))
+    phi = mf.LevelsetGrid(s, np.minimum(basin, drop).astype(np.float32))
+    vel, pressure = s.create(mf.MACGrid), s.create(mf.RealGrid)
+    flags.updateFromLevelset(phi)
+    launches0 = s.kernelLaunches()
+    for _ in range(6):
+        mf.extrapolateLsSimple(phi=phi, distance=5, inside=False)
+        mf.extrapolateLsSimple(phi=phi, distance=5, inside=True)
+        mf.extrapolateMACSimple(flags=flags, vel=vel, distance=5)
+        mf.advectSemiLagrange(flags=flags, vel=vel, grid=phi, order=2, clampMode=2)
+        phi.setBound(1, 1.)
+        flags.updateFromLevelset(phi)
+        mf.advectSemiLagrange(flags=flags, vel=vel, grid=vel, order=2)
+        mf.addGravity(flags=flags, vel=vel, gravity=(0, -0.025, 0))
+        mf.setWallBcs(flags=flags, vel=vel)
+        mf.solvePressure(flags=flags, vel=vel, pressure=pressure, cgMaxIterFac=5, cgAccuracy=1e-5, phi=phi)
+    assert s.kernelLaunches() > launches0
+    assert not (flags._hostDirty or phi._hostDirty or vel._hostDirty), "a grid went back to the host inside the loop"
+    assert np.array_equal(flags.numpy(), g["flags"])
+    for a, key, tol in ((phi, "phi", 1e-4), (vel, "vel", 1e-4), (pressure, "pressure", 1e-3)):
+        assert float(np.abs(a.numpy().astype(np.float64) - g[key]).max()) <= tol, key
+
+
+def test_invalid_arguments_fail_loudly(mf):
+    flags_h, vel_h, phi_h, _ = liquid_scene("liq2d", 4)
+    s = mf.Solver(gridSize=(24, 28, 1), dim=2, prec=4)
+    F, V, P = mf.FlagGrid(s, flags_h), mf.MACGrid(s, vel_h), mf.LevelsetGrid(s, phi_h)
+    with pytest.raises(mf.MantaError):
+        mf.extrapolateMACSimple(F, V, distance=251)
+    with pytest.raises(mf.MantaError):
+        mf.extrapolateMACSimple(V, V)                 # flags is not a FlagGrid
+    with pytest.raises(mf.MantaError):
+        mf.extrapolateLsSimple(V)                     # not a real grid
+    with pytest.raises(mf.MantaError):
+        mf.extrapolateVec3Simple(P, P)                # not a Vec3 grid
+    with pytest.raises(mf.MantaError):
+        F.updateFromLevelset(V)                       # not a level set
+    t = mf.Solver(gridSize=(2, 28, 1), dim=2, prec=4)
+    with pytest.raises(mf.MantaError):
+        mf.extrapolateLsSimple(mf.LevelsetGrid(t))    # no interior cells
