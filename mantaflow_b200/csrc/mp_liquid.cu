@@ -1,22 +1,21 @@
 // Liquid neighbours of the pressure projection on the device (first slice).  The per-cell operations and the pass
-// sequences are in mp_liquid_cells.cuh (shared with the host emulation the CPU tests run); this file is the CUDA executor -- one
-// thread per cell, x over i (128 threads), blockIdx.y = j, blockIdx.z = k, like mp_step.cu -- and the C-ABI entry points.
+// sequences are in mp_liquid_cells.cuh (shared with the host emulation the CPU tests run); this file is the CUDA executor (launch geometry:
+// liquid::threadCells, 128 threads x 4 x 4 cells per block) and the C-ABI entry points.
 // Every pass is a streaming sweep: 4 B/cell of marks plus the few values that change; nothing returns to the host.
 #include "mp_liquid_cells.cuh"
 
 namespace {
 
 template <typename F>
-__global__ void __launch_bounds__(128) k_liquid_cells(Dims d, F f) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
-	if (i >= d.sx) return;
-	f(d, i, j, k, (IndexInt)i + d.Y * j + (IndexInt)d.sx * d.sy * k);
+__global__ void __launch_bounds__(liquid::kThreads, 4) k_liquid_cells(Dims d, F f) {
+	liquid::threadCells(d, f, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);
 }
 
 struct CudaExec {
 	mp_context* ctx;
 	template <typename F> int cells(const Dims& d, const F& f) {
-		k_liquid_cells<F><<<dim3((unsigned)((d.sx + 127) / 128), (unsigned)d.sy, (unsigned)d.sz), 128, 0, ctx->stream>>>(d, f);
+		const liquid::LaunchGeom g = liquid::launchGeomOf(d);
+		k_liquid_cells<F><<<dim3(g.gx, g.gy, g.gz), liquid::kThreads, 0, ctx->stream>>>(d, f);
 		MP_CHECK_LAUNCH(ctx);
 		return MP_OK;
 	}

@@ -8,7 +8,7 @@
 //
 // This header holds the per-cell operations and the pass sequences, written against an executor `Exec` with one member
 //     template <class F> int cells(const Dims& d, const F& f);     // run f(d, i, j, k, idx) once for every cell, in any order
-// mp_liquid.cu instantiates it with the CUDA launcher (one thread per cell).  tests/emul/liquid_emul.cpp instantiates the SAME code with a
+// mp_liquid.cu instantiates it with the CUDA launcher (threadCells below: a few cells per thread).  tests/emul/liquid_emul.cpp instantiates the SAME code with a
 // host loop, so that the build container (which has no GPU) can check cell arithmetic and pass structure against the reference; that
 // shim is test infrastructure and is never part of libmantapress.so.
 //
@@ -25,6 +25,54 @@
 #endif
 
 namespace liquid {
+
+// Launch geometry of the CUDA executor.  One cell per thread makes these passes block-scheduling bound (a million 128-thread blocks of
+// a few instructions each at 512^3: 0.55 ms for a pass that touches nothing), so a block of kThreads threads covers kRows rows of up
+// to kThreads * kCols cells: thread tx owns the cells i = (bx * kCols + c) * kThreads + tx, c < kCols, of rows by * kRows + r, r < kRows
+// -- consecutive lanes stay on consecutive cells.  The host emulation walks the same function (order 3), so the cover is checked.
+static const int kThreads = 128, kCols = 4, kRows = 4;
+struct LaunchGeom { unsigned gx, gy, gz; };
+inline LaunchGeom launchGeomOf(const Dims& d) {
+	LaunchGeom g;
+	g.gx = (unsigned)((d.sx + kThreads * kCols - 1) / (kThreads * kCols)); g.gy = (unsigned)((d.sy + kRows - 1) / kRows); g.gz = (unsigned)d.sz;
+	return g;
+}
+// Functors with kSplit == true separate their reads from their writes: State load(...) only reads, apply(..., State) computes and
+// writes.  A thread first loads for all its kCols cells of a row and then applies -- the loads of several cells are in flight together
+// instead of one dependent round trip after the other (the passes are latency bound otherwise: 1 ms per pass at 512^3).  Any order of
+// loads and applies of different cells is as good as any other (see the note on execution order above).
+template <typename F> MP_HD void threadCells(const Dims& d, const F& f, int bx, int by, int bz, int tx) {
+	const IndexInt plane = (IndexInt)d.sx * d.sy * bz;
+	for (int r = 0; r < kRows; r++) {
+		const int j = by * kRows + r;
+		if (j >= d.sy) break;
+		const IndexInt row = d.Y * j + plane;
+		if constexpr (F::kSplit) {
+			typename F::State st[kCols];
+			#pragma unroll
+			for (int c = 0; c < kCols; c++) {
+				const int i = (bx * kCols + c) * kThreads + tx;
+				if (i < d.sx) st[c] = f.load(d, i, j, bz, (IndexInt)i + row);
+			}
+			#pragma unroll
+			for (int c = 0; c < kCols; c++) {
+				const int i = (bx * kCols + c) * kThreads + tx;
+				if (i < d.sx) f.apply(d, i, j, bz, (IndexInt)i + row, st[c]);
+			}
+		} else {
+			for (int c = 0; c < kCols; c++) {
+				const int i = (bx * kCols + c) * kThreads + tx;
+				if (i >= d.sx) break;
+				f(d, i, j, bz, (IndexInt)i + row);
+			}
+		}
+	}
+}
+// what a cell-by-cell executor (the host emulation's plain walks) calls
+template <typename F> MP_HD void oneCell(const Dims& d, const F& f, int i, int j, int k, IndexInt idx) {
+	if constexpr (F::kSplit) f.apply(d, i, j, k, idx, f.load(d, i, j, k, idx));
+	else f(d, i, j, k, idx);
+}
 
 MP_HD bool interiorCell(const Dims& d, int i, int j, int k) {      // the cells of a KERNEL(bnd=1) / FOR_IJK_BND(g, 1)
 	return i >= 1 && i <= d.sx - 2 && j >= 1 && j <= d.sy - 2 && (!d.is3D || (k >= 1 && k <= d.sz - 2));
@@ -45,7 +93,8 @@ MP_HD bool nbInterior(const Dims& d, int q, int i, int j, int k) {
 // ---------------------------------------------------------------- extrapolateMACSimple
 // The reference runs the three velocity components one after the other with one Grid<int> of marks each; they are independent, so
 // here byte c of ONE int per cell carries the mark of component c and a pass advances all components at once (distance <= 250).
-template <typename Real> struct MacMark {                // fastmarch.cpp:346-358
+template <typename Real> struct MacMark {
+	static const bool kSplit = false;                // fastmarch.cpp:346-358
 	const int* flags; int* tmp; int intoObs;
 	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		int w = 0;
@@ -63,23 +112,29 @@ template <typename Real> struct MacMark {                // fastmarch.cpp:346-35
 	}
 };
 template <typename Real> struct MacExtrapolate {         // knExtrapolateMACSimple fastmarch.cpp:231-258, pass d for every component
+	static const bool kSplit = true;
 	Real* vel; int* tmp; int pass;
-	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
-		if (!interiorCell(d, i, j, k)) return;
+	struct State { int t, tn[6]; bool interior; };
+	// a neighbour's word may be rewritten by its own thread meanwhile: its changing bytes go from 0 to pass+1, never through `pass`
+	MP_HD State load(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		State s;
+		s.interior = interiorCell(d, i, j, k);
+		if (!s.interior) return s;
+		s.t = tmp[idx];
+		s.tn[0] = tmp[idx + d.X]; s.tn[1] = tmp[idx - d.X]; s.tn[2] = tmp[idx + d.Y]; s.tn[3] = tmp[idx - d.Y];
+		s.tn[4] = tmp[idx + d.Z]; s.tn[5] = tmp[idx - d.Z];            // 2-D: Z == 0, the cell itself; not used
+		return s;
+	}
+	MP_HD void apply(const Dims& d, int, int, int, IndexInt idx, const State& s) const {
+		if (!s.interior) return;
 		const int dim = d.is3D ? 3 : 2;
-		const int t = tmp[idx];
-		bool open = false;
-		for (int c = 0; c < dim; c++) open = open || (((t >> (8 * c)) & 255) == 0);
-		if (!open) return;
-		// a neighbour's word may be rewritten by its own thread meanwhile: its changing bytes go from 0 to pass+1, never through `pass`
-		int tn[6];
-		for (int q = 0; q < 2 * dim; q++) tn[q] = tmp[idx + nbOffset(d, q)];
+		const int t = s.t;
 		int tNew = t;
 		for (int c = 0; c < dim; c++) {
 			if (((t >> (8 * c)) & 255) != 0) continue;
 			int nbs = 0; Real avgVel = 0;
 			for (int q = 0; q < 2 * dim; q++)
-				if (((tn[q] >> (8 * c)) & 255) == pass) { avgVel += vel[3 * (idx + nbOffset(d, q)) + c]; nbs++; }
+				if (((s.tn[q] >> (8 * c)) & 255) == pass) { avgVel += vel[3 * (idx + nbOffset(d, q)) + c]; nbs++; }
 			if (nbs > 0) { tNew |= (pass + 1) << (8 * c); vel[3 * idx + c] = avgVel / (Real)nbs; }
 		}
 		if (tNew != t) tmp[idx] = tNew;
@@ -97,7 +152,8 @@ template <typename Real> MP_HD void normalize3(Real& x, Real& y, Real& z) {
 		x *= s; y *= s; z *= s;
 	} else { x = 0; y = 0; z = 0; }
 }
-template <typename Real> struct UnprojectNormal {        // knUnprojectNormalComp fastmarch.cpp:319-331 with getNormal :302-318
+template <typename Real> struct UnprojectNormal {
+	static const bool kSplit = false;        // knUnprojectNormalComp fastmarch.cpp:319-331 with getNormal :302-318
 	Real* vel; const Real* phi; Real maxDist;
 	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		if (!interiorCell(d, i, j, k)) return;
@@ -115,6 +171,7 @@ template <typename Real> struct UnprojectNormal {        // knUnprojectNormalCom
 // knExtrapolateIntoBnd fastmarch.cpp:260-299 reads a copy of the whole velocity grid; only the cells of the outer layer are written
 // and they read cells one step inwards, so the new values are first collected in `stage` (outer-layer entries only) and then moved.
 template <typename Real> struct IntoBndStage {
+	static const bool kSplit = false;
 	const int* flags; const Real* vel; Real* stage;
 	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		if (outerFaces(d, i, j, k) == 0) return;
@@ -135,6 +192,7 @@ template <typename Real> struct IntoBndStage {
 	}
 };
 template <typename Real> struct IntoBndCopy {
+	static const bool kSplit = false;
 	const Real* stage; Real* vel;
 	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		if (outerFaces(d, i, j, k) == 0) return;
@@ -155,16 +213,27 @@ int extrapolateMacSimple(Exec& ex, const Dims& d, const int* flags, Real* vel, i
 
 // ---------------------------------------------------------------- extrapolateLsSimple / extrapolateVec3Simple
 template <typename Real> struct LsMark {                 // fastmarch.cpp:475-498: 1 on the chosen side of phi, 2 on the first layer next to it, 0 elsewhere
+	static const bool kSplit = true;
 	const Real* phi; int* tmp; int inside;
+	struct State { Real p, pn[6]; bool interior; };
 	MP_HD bool on(Real p) const { return inside ? (p > 0.) : (p < 0.); }
-	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+	MP_HD State load(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		State s;
+		s.interior = interiorCell(d, i, j, k);
+		if (!s.interior) return s;
+		s.p = phi[idx];
+		s.pn[0] = phi[idx + d.X]; s.pn[1] = phi[idx - d.X]; s.pn[2] = phi[idx + d.Y]; s.pn[3] = phi[idx - d.Y];
+		s.pn[4] = phi[idx + d.Z]; s.pn[5] = phi[idx - d.Z];
+		return s;
+	}
+	MP_HD void apply(const Dims& d, int i, int j, int k, IndexInt idx, const State& s) const {
 		int m = 0;
-		if (interiorCell(d, i, j, k)) {
-			if (on(phi[idx])) m = 1;
+		if (s.interior) {
+			if (on(s.p)) m = 1;
 			else {
 				const int dim = d.is3D ? 3 : 2;
 				for (int q = 0; q < 2 * dim; q++)
-					if (nbInterior(d, q, i, j, k) && on(phi[idx + nbOffset(d, q)])) { m = 2; break; }
+					if (nbInterior(d, q, i, j, k) && on(s.pn[q])) { m = 2; break; }      // cells of the outer layer carry no mark
 			}
 		}
 		tmp[idx] = m;
@@ -173,23 +242,36 @@ template <typename Real> struct LsMark {                 // fastmarch.cpp:475-49
 // knExtrapolateLsSimple<S> fastmarch.cpp:439-460 (NC = 1: Real, 3: Vec3).  `last`: this is the final pass, so cells that stay unmarked
 // get knSetRemaining's value (:463-467) right away -- nobody reads the value of an unmarked cell during the pass.
 template <typename Real, int NC> struct LsExtrapolate {
+	static const bool kSplit = true;
 	Real* val; int* tmp; int pass; Real direction; int last; Real remaining;
-	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
-		if (!interiorCell(d, i, j, k)) return;
-		if (tmp[idx] != 0) return;
+	struct State { int t, tn[6]; bool interior; };
+	MP_HD State load(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		State s;
+		s.interior = interiorCell(d, i, j, k);
+		if (!s.interior) return s;
+		s.t = tmp[idx];
+		s.tn[0] = tmp[idx + d.X]; s.tn[1] = tmp[idx - d.X]; s.tn[2] = tmp[idx + d.Y]; s.tn[3] = tmp[idx - d.Y];
+		s.tn[4] = tmp[idx + d.Z]; s.tn[5] = tmp[idx - d.Z];
+		return s;
+	}
+	MP_HD void apply(const Dims& d, int, int, int, IndexInt idx, const State& s) const {
+		if (!s.interior || s.t != 0) return;
 		const int dim = d.is3D ? 3 : 2;
 		int nbs = 0;
 		Real avg[NC];
 		for (int c = 0; c < NC; c++) avg[c] = 0;
 		for (int q = 0; q < 2 * dim; q++) {
+			if (s.tn[q] != pass) continue;
 			const IndexInt nb = idx + nbOffset(d, q);
-			if (tmp[nb] == pass) { for (int c = 0; c < NC; c++) avg[c] += val[NC * nb + c]; nbs++; }
+			for (int c = 0; c < NC; c++) avg[c] += val[NC * nb + c];
+			nbs++;
 		}
 		if (nbs > 0) { tmp[idx] = pass + 1; for (int c = 0; c < NC; c++) val[NC * idx + c] = avg[c] / (Real)nbs + direction; }
 		else if (last) for (int c = 0; c < NC; c++) val[NC * idx + c] = remaining;
 	}
 };
-template <typename Real, int NC> struct LsRemaining {    // knSetRemaining fastmarch.cpp:463-467 when there was no pass to ride on
+template <typename Real, int NC> struct LsRemaining {
+	static const bool kSplit = false;    // knSetRemaining fastmarch.cpp:463-467 when there was no pass to ride on
 	Real* val; const int* tmp; Real remaining;
 	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		if (!interiorCell(d, i, j, k) || tmp[idx] != 0) return;
@@ -208,7 +290,8 @@ int extrapolateLs(Exec& ex, const Dims& d, Real* val, const Real* phi, int dista
 }
 
 // ---------------------------------------------------------------- FlagGrid::updateFromLevelset, Grid<T>::setBound
-template <typename Real> struct UpdateFromLevelset {     // grid.cpp:844-854; invalidTimeValue = -1000 (levelset.cpp:103 -> fastmarch.h:134)
+template <typename Real> struct UpdateFromLevelset {
+	static const bool kSplit = false;     // grid.cpp:844-854; invalidTimeValue = -1000 (levelset.cpp:103 -> fastmarch.h:134)
 	int* flags; const Real* phi;
 	MP_HD void operator()(const Dims&, int, int, int, IndexInt idx) const {
 		const int f = flags[idx];
@@ -218,7 +301,8 @@ template <typename Real> struct UpdateFromLevelset {     // grid.cpp:844-854; in
 		flags[idx] = (f & ~(TypeEmpty | TypeFluid)) | ((p <= 0) ? TypeFluid : TypeEmpty);
 	}
 };
-template <typename T, int NC> struct SetBound {          // knSetBoundary grid.cpp:585-589
+template <typename T, int NC> struct SetBound {
+	static const bool kSplit = false;          // knSetBoundary grid.cpp:585-589
 	T* g; T value[NC]; int w;
 	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		const bool bnd = i <= w || i >= d.sx - 1 - w || j <= w || j >= d.sy - 1 - w || (d.is3D && (k <= w || k >= d.sz - 1 - w));

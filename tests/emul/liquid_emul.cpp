@@ -4,7 +4,7 @@
 // mantaflow_b200/csrc/mp_liquid_cells.cuh (the code the CUDA kernels of mp_liquid.cu run, one thread per cell) with an executor that
 // walks the cells in a host loop.  The build container has no GPU; this lets `pytest -m "not gpu"` check the arithmetic and the pass
 // structure of those kernels against the unmodified reference.  `order` selects the walk (0 lexicographic, 1 reverse, 2 a strided
-// permutation): the passes are written so that any order gives the same result, which the tests assert.
+// permutation, 3 the block / thread geometry of the CUDA launch): the passes are written so that any order gives the same result, which the tests assert.
 // Built by tests/test_liquid_emulation.py:  g++ -O2 -ffp-contract=off -I/usr/local/cuda/include -shared -fPIC
 #include "../../mantaflow_b200/csrc/mp_liquid_cells.cuh"
 #include <cstdarg>
@@ -17,6 +17,12 @@ struct HostExec {
 	int order;
 	static IndexInt gcd(IndexInt a, IndexInt b) { while (b) { const IndexInt t = a % b; a = b; b = t; } return a; }
 	template <typename F> int cells(const Dims& d, const F& f) {
+		if (order == 3) {      // the CUDA launch: every thread of every block of liquid::launchGeomOf(d), through the kernel's own cell mapping
+			const liquid::LaunchGeom g = liquid::launchGeomOf(d);
+			for (unsigned bz = 0; bz < g.gz; bz++) for (unsigned by = 0; by < g.gy; by++) for (unsigned bx = 0; bx < g.gx; bx++)
+				for (int tx = liquid::kThreads - 1; tx >= 0; tx--) liquid::threadCells(d, f, (int)bx, (int)by, (int)bz, tx);
+			return MP_OK;
+		}
 		const IndexInt n = d.n;
 		IndexInt stride = 1;
 		if (order == 2) { stride = 7919; while (gcd(stride, n) != 1) stride += 2; }       // a stride coprime to n visits every cell exactly once
@@ -25,7 +31,7 @@ struct HostExec {
 			if (order == 1) idx = n - 1 - t;
 			else if (order == 2) idx = (t * stride) % n;
 			const int i = (int)(idx % d.sx), j = (int)((idx / d.sx) % d.sy), k = (int)(idx / ((IndexInt)d.sx * d.sy));
-			f(d, i, j, k, idx);
+			liquid::oneCell(d, f, i, j, k, idx);
 		}
 		return MP_OK;
 	}

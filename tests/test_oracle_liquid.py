@@ -97,9 +97,24 @@ def emul_lib():
     return C.CDLL(out)
 
 
-@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
 @pytest.mark.parametrize("prec", [4, 8])
 @pytest.mark.parametrize("name", list(LIQUID_SCENES))
 def test_kernel_emulation_reproduces_liquid_golden(name, prec, order, emul_lib):
-    """the code the CUDA kernels run, cell by cell on the host, in three different cell orders: bit-identical to the reference"""
+    """the code the CUDA kernels run, cell by cell on the host, in four different cell orders (3 = block by block, thread by thread as the CUDA launch maps them): bit-identical to the reference"""
     check_liquid_against_golden(Emulation(emul_lib, prec, order), name, prec)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("shape", [(5, 7, 1100), (1, 9, 530)])
+def test_kernel_emulation_launch_geometry_on_wide_rows(shape, prec, emul_lib, port32, port64):
+    """rows wider than one block's 4 x 128 cells and row counts that are no multiple of 4: the CUDA launch's cell mapping covers every cell"""
+    import helpers
+    helpers.LIQUID_SCENES["wide"] = shape
+    try:
+        flags, vel, phi, phiObs = liquid_scene("wide", prec)
+    finally:
+        del helpers.LIQUID_SCENES["wide"]
+    O, E = (port32 if prec == 4 else port64), Emulation(emul_lib, prec, 3)
+    for case in LIQUID_CASES:
+        assert np.array_equal(run_liquid_case(E, case, flags, vel, phi, phiObs), run_liquid_case(O, case, flags, vel, phi, phiObs)), case
