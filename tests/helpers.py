@@ -402,3 +402,60 @@ def check_freesurface_against_golden(I, name, prec, tol):
     for a, key, f in ((phi, "phi", 1), (vel, "vel", 1), (p, "pressure", 10)):
         err = float(np.abs(a.astype(np.float64) - g[key]).max())
         assert err <= tol * f, (name, prec, key, err)
+
+
+# ---------------------------------------------------------------- size-independent properties of the projection (checked at BASELINE's full sizes on the GPU)
+def check_projection_properties(I, res, prec, preconditioners, accuracy=1e-4, random_vel=True, seed=5):
+    """What must hold at ANY grid size, with no second implementation at hand (the reference cannot run 512^3 inside a test):
+    (1) ApplyMatrix is linear and symmetric (x.Ay == y.Ax), identity rows included;
+    (2) the right-hand side of a closed box is compatible: sum(rhs) ~ 0, and the device reduction agrees with the grid it reduced;
+    (3) after solvePressure the divergence of every fluid cell is below the solver's max-norm tolerance (the residual of the last
+        iterate IS the divergence after correctVelocity), for every preconditioner; a closed box is singular, so with a pinned cell the
+        pinned row alone may carry the sum of all other residuals;
+    (4) projecting an already projected field changes it by no more than the tolerance allows (idempotence).
+    Returns {preconditioner: iterations}."""
+    from mantaflow_b200 import scenes
+    real = np.float32 if prec == 4 else np.float64
+    eps = 1.2e-7 if prec == 4 else 2.3e-16
+    flags, vel = scenes.smoke_plume(res, prec, random_vel=random_vel)
+    shape = flags.shape
+    fluid = (flags & 1) != 0
+    rng = np.random.default_rng(seed)
+    dot = lambda a, b: float(np.dot(a.ravel().astype(np.float64), b.ravel().astype(np.float64)))
+    # (1)
+    A = I.make_matrix(flags)
+    x = (rng.random(shape) - 0.5).astype(real); y = (rng.random(shape) - 0.5).astype(real)
+    Ax, Ay = I.apply_matrix(flags, x, *A), I.apply_matrix(flags, y, *A)
+    a = real(0.375)                                   # exactly representable: a*x carries no rounding of its own
+    Axy = I.apply_matrix(flags, (a * x + y).astype(real), *A)
+    lin = float(np.abs(Axy.astype(np.float64) - (float(a) * Ax.astype(np.float64) + Ay.astype(np.float64))).max())
+    assert lin <= 64 * eps * 12, ("ApplyMatrix not linear", lin)             # |A| rows sum to <= 12, |x| <= 1
+    sxy, syx = dot(x, Ay), dot(y, Ax)
+    assert abs(sxy - syx) <= 1e3 * eps * (np.sqrt(dot(x, x) * dot(Ay, Ay)) + 1), ("ApplyMatrix not symmetric", sxy, syx)
+    assert np.array_equal(Ax[~fluid], x[~fluid]), "non-fluid rows are not the identity"
+    del Ax, Ay, Axy, x, y, A
+    # (2)
+    rhs, s, cnt = I.compute_rhs(flags, vel)
+    assert cnt == int(fluid.sum())
+    absum = float(np.abs(rhs.astype(np.float64)).sum())
+    assert abs(s) <= 1e-5 * absum + 1e-6, ("closed box, wall conditions set: the fluxes must cancel", s, absum)
+    assert abs(float(rhs.astype(np.float64).sum()) - s) <= 1e-6 * absum + 1e-9, "the reduction disagrees with the grid it reduced"
+    its = {}
+    for pc in preconditioners:
+        # (3)
+        v = vel.copy()
+        p, it, rn = I.solve_pressure(flags, v, cgAccuracy=accuracy, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=(pc >= 2))
+        its[pc] = it
+        assert np.isfinite(p).all() and rn <= accuracy, (pc, it, rn)
+        div, _, _ = I.compute_rhs(flags, v)
+        d = np.abs(div[fluid].astype(np.float64))
+        over = int((d > 2 * accuracy).sum())
+        assert over <= (1 if pc >= 2 else 0), ("divergence above the solver tolerance after the projection", pc, over, float(d.max()))
+        assert np.array_equal(div[~fluid], np.zeros_like(div[~fluid]))
+        # (4)
+        v2 = v.copy()
+        p2, it2, _ = I.solve_pressure(flags, v2, cgAccuracy=accuracy, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=(pc >= 2))
+        assert it2 <= max(2, it // 4), ("a projected field needed a full solve again", pc, it, it2)
+        d2 = np.abs(I.compute_rhs(flags, v2)[0][fluid].astype(np.float64))
+        assert int((d2 > 2 * accuracy).sum()) <= (1 if pc >= 2 else 0), ("second projection", pc, float(d2.max()))
+    return its
