@@ -128,6 +128,16 @@ class _GridBase:
     def copyFrom(self, other):
         self.copyFromArray(other.numpy())
 
+    def save(self, name):
+        """Grid<T>::save grid.cpp:134-156 (.uni, .raw, .npz) from the device-resident grid"""
+        from . import fileio
+        return fileio.save(self, name)
+
+    def load(self, name):
+        """Grid<T>::load grid.cpp:112-132"""
+        from . import fileio
+        return fileio.load(self, name)
+
     def setBound(self, value, boundaryWidth=1):
         """Grid<T>::setBound grid.cpp:585-593, on the device (Vec3 grids take a 3-tuple or one value for every component)"""
         try:

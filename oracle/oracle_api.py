@@ -235,6 +235,15 @@ class Oracle:
         self._chk(self._f("set_bound")(*self.dims(grid[..., 0] if ncomp == 3 else grid), _p(grid), C.c_int(ncomp), C.c_double(value), C.c_int(boundaryWidth)))
         return grid
 
+    def grid_file(self, name, array, kind, load=False):
+        """Grid<T>::save / load of the unmodified reference (grid.cpp:113-156; reference build only).
+        kind: "real" | "mac" | "flags" | "levelset" | "vec3"; `array` is written to / filled from the file `name`."""
+        assert self.kind == "reference", "file I/O is the reference's own code (fileio/iogrids.cpp); the restatement has none"
+        k = {"real": 0, "mac": 1, "flags": 2, "levelset": 3, "vec3": 4}[kind]
+        assert array.flags.c_contiguous and array.dtype == (np.int32 if kind == "flags" else self.real)
+        self._chk(self._f("grid_file")(*self.dims(array[..., 0] if array.ndim == 4 else array), C.c_int(k), _p(array), name.encode(), C.c_int(int(load))))
+        return array
+
     def release_solver(self, key):
         self._chk(self._f("release_solver")(C.c_longlong(key)))
 

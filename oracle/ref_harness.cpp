@@ -19,6 +19,7 @@
 //   PD_fluid_guiding        plugin/fluidguiding.cpp:294-353
 //   extrapolateMACSimple, extrapolateLsSimple, extrapolateVec3Simple   fastmarch.cpp:337-375, :470-542
 //   FlagGrid::updateFromLevelset, Grid<T>::setBound                    grid.cpp:844-854, :591-593
+//   Grid<T>::save / load (.uni, .raw, .npz)                            grid.cpp:113-156, fileio/iogrids.cpp
 // Nothing of the reference is copied: its sources are compiled where they lie.
 //
 // The signatures are shared with oracle/mf_oracle.c (the restatement) so the same
@@ -44,23 +45,7 @@
 #include "levelset.h"
 
 namespace Manta {
-// --- link stubs for I/O entry points referenced by grid.cpp but irrelevant here ---
-template<class T> int writeGridUni  (const std::string&, Grid<T>*) { return 0; }
-template<class T> int writeGridVol  (const std::string&, Grid<T>*) { return 0; }
-template<class T> int writeGridTxt  (const std::string&, Grid<T>*) { return 0; }
-template<class T> int writeGridRaw  (const std::string&, Grid<T>*) { return 0; }
-template<class T> int writeGridNumpy(const std::string&, Grid<T>*) { return 0; }
-template<class T> int readGridUni   (const std::string&, Grid<T>*) { return 0; }
-template<class T> int readGridVol   (const std::string&, Grid<T>*) { return 0; }
-template<class T> int readGridRaw   (const std::string&, Grid<T>*) { return 0; }
-template<class T> int readGridNumpy (const std::string&, Grid<T>*) { return 0; }
-#define INST(T) \
- template int writeGridUni<T>(const std::string&, Grid<T>*);  template int writeGridVol<T>(const std::string&, Grid<T>*); \
- template int writeGridTxt<T>(const std::string&, Grid<T>*);  template int writeGridRaw<T>(const std::string&, Grid<T>*); \
- template int writeGridNumpy<T>(const std::string&, Grid<T>*); template int readGridUni<T>(const std::string&, Grid<T>*); \
- template int readGridVol<T>(const std::string&, Grid<T>*);   template int readGridRaw<T>(const std::string&, Grid<T>*); \
- template int readGridNumpy<T>(const std::string&, Grid<T>*);
-INST(int) INST(Real) INST(Vec3)
+// --- link stubs for the OpenVDB entry points referenced by grid.cpp (the .uni / .raw / .npz readers and writers are the reference's own, fileio/iogrids.cpp) ---
 int writeObjectsVDB(const std::string&, std::vector<PbClass*>*, float, bool, int, bool) { return 0; }
 int readObjectsVDB (const std::string&, std::vector<PbClass*>*, float) { return 0; }
 Real LevelsetGrid::invalidTimeValue() { return -1000; }   // levelset.cpp:103 -> fastmarch.h:134
@@ -98,6 +83,11 @@ static FluidSolver* mkSolver(int sx, int sy, int sz) {
 
 #define TRY try {
 #define CATCH } catch (std::exception& e) { gLastError = e.what(); return 1; } return 0;
+
+template <class G> static int saveLoad(G& g, const char* name, int load) { return load ? g.load(name) : g.save(name); }
+struct LsTypedGrid : public Grid<Real> {      // the grid type a LevelsetGrid carries (levelset.cpp:91-101); its constructors live in levelset.cpp, which is not built here
+	LsTypedGrid(FluidSolver* s, Real* d) : Grid<Real>(s, d) { mType = (GridType)(TypeLevelset | TypeReal); }
+};
 
 extern "C" {
 
@@ -181,6 +171,20 @@ int ref_set_bound(int sx, int sy, int sz, Real* grid, int ncomp, double value, i
 	if (ncomp == 1) { Grid<Real> G(s, grid); G.setBound((Real)value, boundaryWidth); }
 	else { Grid<Vec3> G(s, (Vec3*)grid); G.setBound(Vec3((Real)value), boundaryWidth); }
 	delete s;
+  CATCH }
+
+// kind 0: Grid<Real>, 1: MACGrid, 2: FlagGrid, 3: LevelsetGrid-typed Grid<Real>, 4: Grid<Vec3>.  Grid<T>::save / load grid.cpp:113-156.
+int ref_grid_file(int sx, int sy, int sz, int kind, void* data, const char* name, int load)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	int ok = 0;
+	if (kind == 0) { Grid<Real> G(s, (Real*)data); ok = saveLoad(G, name, load); }
+	else if (kind == 1) { MACGrid G(s, (Vec3*)data); ok = saveLoad(G, name, load); }
+	else if (kind == 2) { FlagGrid G(s, (int*)data); ok = saveLoad(G, name, load); }
+	else if (kind == 3) { LsTypedGrid G(s, (Real*)data); ok = saveLoad(G, name, load); }
+	else { Grid<Vec3> G(s, (Vec3*)data); ok = saveLoad(G, name, load); }
+	delete s;
+	if (!ok) { gLastError = std::string("Grid::") + (load ? "load" : "save") + " returned 0 for " + name; return 1; }
   CATCH }
 
 // kind 0: Grid<Real>, 1: MACGrid.  The plugin swaps its result in, which the reference forbids for external data: work on solver-owned copies.

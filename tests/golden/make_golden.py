@@ -202,7 +202,24 @@ def liquid_fixtures():
             print("%-34s %7.1f KiB  its %s  fluid cells %d" % (os.path.basename(path), os.path.getsize(path) / 1024, its, int((flags & 1).sum())))
 
 
+def io_fixtures():
+    """tests/golden/io/ref_<kind>_<2d|3d>_f{32,64}.uni: grid files written by the unmodified reference's Grid<T>::save (fileio/iogrids.cpp)
+    from the seeded arrays of tests/test_fileio.py::sample"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_fileio as T
+    os.makedirs(os.path.join(HERE, "io"), exist_ok=True)
+    for prec in (4, 8):
+        R = Oracle("reference", prec)
+        for kind in T.KINDS:
+            for tag in T.SHAPES:
+                path = os.path.join(HERE, "io", "ref_%s_%s_f%d.uni" % (kind, tag, prec * 8))
+                R.grid_file(path, T.sample(kind, tag, prec), kind, load=False)
+                print("%-34s %6d B" % (os.path.basename(path), os.path.getsize(path)))
+
+
 def main():
+    if "--only-io" in sys.argv:
+        return io_fixtures()
     if "--only-liquid" in sys.argv:
         return liquid_fixtures()
     if "--only-step" in sys.argv:
@@ -210,6 +227,7 @@ def main():
         return liquid_fixtures()
     step_fixtures()
     liquid_fixtures()
+    io_fixtures()
     for prec in (4, 8):
         R = Oracle("reference", prec)
         for name in KERNEL_SCENES:

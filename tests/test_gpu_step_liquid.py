@@ -101,3 +101,28 @@ def test_invalid_arguments_fail_loudly(mf):
     t = mf.Solver(gridSize=(2, 28, 1), dim=2, prec=4)
     with pytest.raises(mf.MantaError):
         mf.extrapolateLsSimple(mf.LevelsetGrid(t))    # no interior cells
+
+
+@pytest.mark.parametrize("ext", [".uni", ".raw", ".npz"])
+def test_grid_save_load_from_device_mirror(mf, ext, tmp_path):
+    """Grid.save writes what the DEVICE holds (the host copy is stale after a device plugin), Grid.load reaches the device with the next plugin"""
+    flags_h, vel_h, phi_h, _ = liquid_scene("liq3d", 4)
+    sz, sy, sx = flags_h.shape
+    s = mf.Solver(gridSize=(sx, sy, sz), dim=3, prec=4)
+    P, V, F = mf.LevelsetGrid(s, phi_h), mf.MACGrid(s, vel_h), mf.FlagGrid(s, flags_h)
+    P.setBound(0.5, 1); F.updateFromLevelset(P); mf.extrapolateMACSimple(F, V, distance=3)      # device copies are now the newer ones
+    names = [str(tmp_path / (n + ext)) for n in ("phi", "vel", "flags")]
+    for g, n in zip((P, V, F), names):
+        assert g._devDirty and g.save(n) == 1
+    P2, V2, F2 = mf.LevelsetGrid(s), mf.MACGrid(s), mf.FlagGrid(s)
+    for g, n in zip((P2, V2, F2), names):
+        assert g.load(n) == 1 and g._hostDirty
+    assert np.array_equal(P2.numpy(), P.numpy()) and np.array_equal(V2.numpy(), V.numpy()) and np.array_equal(F2.numpy(), F.numpy())
+    assert np.array_equal(P.numpy()[0], np.full((sy, sx), 0.5, np.float32))
+    mf.extrapolateLsSimple(P2, distance=3); mf.extrapolateLsSimple(P, distance=3)               # the loaded grid is uploaded by its first plugin
+    assert np.array_equal(P2.numpy(), P.numpy())
+    R = mf.RealGrid(s)
+    if ext == ".uni":
+        assert R.load(names[0]) == 1                  # real <-> levelset are interchangeable (unifyGridType)
+        with pytest.raises(mf.MantaError):
+            R.load(names[2])                          # a flag grid is not
