@@ -233,6 +233,10 @@ int mp_extrapolate_ls_simple(mp_context* ctx, mp_grid* phi, int distance, int in
 int mp_extrapolate_vec3_simple(mp_context* ctx, mp_grid* vel, const mp_grid* phi, int distance, int inside);
 int mp_flags_update_from_levelset(mp_context* ctx, mp_grid* flags, const mp_grid* levelset);
 int mp_grid_set_bound(mp_context* ctx, mp_grid* g, double vx, double vy, double vz, int boundaryWidth);
+/* getLaplacian / getCurvature plugin/flip.cpp:710-716 (LaplaceOp, CurvatureOp commonkernels.h:75-101): the `curv` input of the surface-tension
+ * variant of solvePressure.  Cells of the outer layer keep their content (KERNEL(bnd=1)); result and input must be different grids. */
+int mp_get_laplacian(mp_context* ctx, mp_grid* laplacian, const mp_grid* grid);
+int mp_get_curvature(mp_context* ctx, mp_grid* curv, const mp_grid* grid, double h);
 
 /* ---- PD_fluid_guiding plugin/fluidguiding.cpp:294-353: primal-dual guiding of vel towards velT with per-cell weight;
  * up to maxIters solvePressure calls on device-resident copies, separable Gaussian blurs of radius blurRadius, stop test as in the reference.

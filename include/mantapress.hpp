@@ -8,6 +8,7 @@
 //     setWallBcs, addGravity, addGravityNoScale, addBuoyancy          plugin/extforces.cpp:61-90,:307-316
 //     advectSemiLagrange                                              plugin/advection.cpp:442-461
 //     extrapolateMACSimple, extrapolateLsSimple, extrapolateVec3Simple fastmarch.cpp:337-375,:470-542
+//     getLaplacian, getCurvature                                      plugin/flip.cpp:710-716
 //     cgSolveDiffusion, cgSolveWE                                     conjugategrad.cpp:350, plugin/waves.cpp:86
 // so that C++ callers of these plugins (e.g. plugin/fluidguiding.cpp:276-335) and tests written against the reference's headers compile
 // against this header unchanged.  Every grid owns a host array in the reference layout (grid.h:70) AND an mp_grid in HBM; two dirty
@@ -288,6 +289,14 @@ inline void extrapolateVec3Simple(Grid<Vec3>& vel, Grid<Real>& phi, int distance
 	vel.markDeviceWritten();
 }
 
+inline void getLaplacian(Grid<Real>& laplacian, const Grid<Real>& grid) {            // plugin/flip.cpp:710-712
+	mpCheck(mp_get_laplacian(grid.getParent()->ctx(), laplacian.dev(), grid.dev()));
+	laplacian.markDeviceWritten();
+}
+inline void getCurvature(Grid<Real>& curv, const Grid<Real>& grid, const Real h = 1.0) {   // plugin/flip.cpp:714-716
+	mpCheck(mp_get_curvature(grid.getParent()->ctx(), curv.dev(), grid.dev(), h));
+	curv.markDeviceWritten();
+}
 
 // ---- the other GridCg callers ----
 template <class G>          // G: Grid<Real> or a Vec3 / MAC grid (the reference takes a GridBase&, conjugategrad.cpp:350-351)

@@ -106,6 +106,25 @@ int mp_flags_update_from_levelset(mp_context* ctx, mp_grid* flags, const mp_grid
 	return ex.cells(d, op);
 }
 
+static int stencilOp(const char* who, mp_context* ctx, mp_grid* out, const mp_grid* grid, double h, bool curvature)
+{
+	MP_TRY(checkLiquid(who, ctx, out));
+	if (out->kind != MP_GRID_REAL) MP_FAIL(MP_ERR_INVALID, "%s: the result is not a real grid", who);
+	MP_TRY(mp_check_same(out, grid, MP_GRID_REAL, "grid", false));
+	if (out == grid || out->d == grid->d) MP_FAIL(MP_ERR_INVALID, "%s: result and input must be different grids", who);
+	if (noInterior(out)) return MP_OK;
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(out);
+	if (out->prec == 4) {
+		if (curvature) { liquid::CurvatureCell<float> op = { (float*)out->d, (const float*)grid->d, (float)h }; return ex.cells(d, op); }
+		liquid::LaplaceCell<float> op = { (float*)out->d, (const float*)grid->d }; return ex.cells(d, op);
+	}
+	if (curvature) { liquid::CurvatureCell<double> op = { (double*)out->d, (const double*)grid->d, h }; return ex.cells(d, op); }
+	liquid::LaplaceCell<double> op = { (double*)out->d, (const double*)grid->d }; return ex.cells(d, op);
+}
+int mp_get_laplacian(mp_context* ctx, mp_grid* laplacian, const mp_grid* grid) { return stencilOp("mp_get_laplacian", ctx, laplacian, grid, 1.0, false); }
+int mp_get_curvature(mp_context* ctx, mp_grid* curv, const mp_grid* grid, double h) { return stencilOp("mp_get_curvature", ctx, curv, grid, h, true); }
+
 int mp_grid_set_bound(mp_context* ctx, mp_grid* g, double vx, double vy, double vz, int boundaryWidth)
 {
 	MP_TRY(checkLiquid("mp_grid_set_bound", ctx, g));

@@ -310,4 +310,47 @@ template <typename T, int NC> struct SetBound {
 	}
 };
 
+// ---------------------------------------------------------------- getLaplacian / getCurvature (surface tension helpers of solvePressure's `curv` argument)
+// LaplaceOp commonkernels.h:75-80, CurvatureOp :83-101, wrapped by plugin/flip.cpp:710-716.  The reference's double literals promote every
+// product to double and every named Real narrows; the same evaluation here.  Cells of the outer layer are left alone (KERNEL(bnd=1)).
+template <typename Real> struct LaplaceCell {
+	static const bool kSplit = false;
+	Real* laplace; const Real* grid;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt p) const {
+		if (!interiorCell(d, i, j, k)) return;
+		Real l = (Real)(((double)grid[p + d.X] - 2.0 * (double)grid[p]) + (double)grid[p - d.X]);
+		l = (Real)((double)l + (((double)grid[p + d.Y] - 2.0 * (double)grid[p]) + (double)grid[p - d.Y]));
+		if (d.is3D) l = (Real)((double)l + (((double)grid[p + d.Z] - 2.0 * (double)grid[p]) + (double)grid[p - d.Z]));
+		laplace[p] = l;
+	}
+};
+template <typename Real> struct CurvatureCell {
+	static const bool kSplit = false;
+	Real* curv; const Real* grid; Real h;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt p) const {
+		if (!interiorCell(d, i, j, k)) return;
+		const IndexInt X = d.X, Y = d.Y, Z = d.Z;
+		const Real over_h = (Real)(1.0 / (double)h);
+		const double oh = (double)over_h, g2 = 2.0 * (double)grid[p];
+		const Real x = (Real)((0.5 * (double)(grid[p + X] - grid[p - X])) * oh);
+		const Real y = (Real)((0.5 * (double)(grid[p + Y] - grid[p - Y])) * oh);
+		const Real xx = (Real)(((((double)grid[p + X] - g2) + (double)grid[p - X]) * oh) * oh);
+		const Real yy = (Real)(((((double)grid[p + Y] - g2) + (double)grid[p - Y]) * oh) * oh);
+		const Real xy = (Real)(((0.25 * (double)(((grid[p + X + Y] + grid[p - X - Y]) - grid[p - X + Y]) - grid[p + X - Y])) * oh) * oh);
+		Real c = (Real)(((double)(x * x * yy + y * y * xx)) - (2.0 * (double)x) * (double)y * (double)xy);
+		Real denom = x * x + y * y;
+		if (d.is3D) {
+			const Real z = (Real)((0.5 * (double)(grid[p + Z] - grid[p - Z])) * oh);
+			const Real zz = (Real)(((((double)grid[p + Z] - g2) + (double)grid[p - Z]) * oh) * oh);
+			const Real xz = (Real)(((0.25 * (double)(((grid[p + X + Z] + grid[p - X - Z]) - grid[p - X + Z]) - grid[p + X - Z])) * oh) * oh);
+			const Real yz = (Real)(((0.25 * (double)(((grid[p + Y + Z] + grid[p - Y - Z]) - grid[p + Y - Z]) - grid[p - Y + Z])) * oh) * oh);
+			c = (Real)((double)c + ((double)(x * x * zz + z * z * xx + y * y * zz + z * z * yy) - 2.0 * (double)(x * z * xz + y * z * yz)));
+			denom += z * z;
+		}
+		const Real eps = sizeof(Real) == 4 ? (Real)1e-6f : (Real)1e-10;           // VECTOR_EPSILON vectorbase.h:52,:55
+		const Real dmax = denom > eps ? denom : eps;
+		curv[p] = (Real)((double)c / pow((double)dmax, 1.5));                     // the one operation that is not correctly rounded on either side: last-bit differences possible
+	}
+};
+
 }  // namespace liquid

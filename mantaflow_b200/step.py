@@ -10,6 +10,7 @@ defaults as the reference, so the main loop of scenes/simpleplume.py runs with e
 and the liquid neighbours (first slice) with which the level-set loop of scenes/freesurface.py:54-84 does the same:
 
     extrapolateMACSimple   fastmarch.cpp:337-375      extrapolateLsSimple :470-507      extrapolateVec3Simple :510-542
+    getLaplacian, getCurvature   plugin/flip.cpp:710-716
     (FlagGrid.updateFromLevelset and Grid.setBound are methods of the grid classes, grid.py)
 """
 import ctypes as C
@@ -78,6 +79,20 @@ def extrapolateVec3Simple(vel, phi, distance=4, inside=False):
     s = vel.parent
     check(s.lib.mp_extrapolate_vec3_simple(s._ctx, vel.dev(), phi.dev(), C.c_int(int(distance)), C.c_int(int(bool(inside)))))
     vel.markDeviceWritten()
+
+
+def getLaplacian(laplacian, grid):
+    """plugin/flip.cpp:710-712"""
+    s = grid.parent
+    check(s.lib.mp_get_laplacian(s._ctx, laplacian.dev(), grid.dev()))
+    laplacian.markDeviceWritten()
+
+
+def getCurvature(curv, grid, h=1.0):
+    """plugin/flip.cpp:714-716: the `curv` argument of solvePressure's surface-tension variant"""
+    s = grid.parent
+    check(s.lib.mp_get_curvature(s._ctx, curv.dev(), grid.dev(), C.c_double(h)))
+    curv.markDeviceWritten()
 
 
 _last_guiding = {"iterations": -1}

@@ -1777,3 +1777,49 @@ int mfo_extrapolate_vec3_simple(int sx, int sy, int sz, Real* vel, const Real* p
 	free(tmp);
 	return 0;
 }
+
+/* getLaplacian plugin/flip.cpp:710-712 -> LaplaceOp commonkernels.h:75-80; getCurvature flip.cpp:714-716 -> CurvatureOp commonkernels.h:83-101.
+ * The double literals promote every product to double; each named Real narrows. */
+int mfo_get_laplacian(int sx, int sy, int sz, Real* laplace, const Real* grid)
+{
+	STRIDES
+	FOR_BND1 {
+		const IndexInt p = IDX(i, j, k);
+		laplace[p] = (Real)(((double)grid[p + X] - 2.0 * (double)grid[p]) + (double)grid[p - X]);
+		laplace[p] = (Real)((double)laplace[p] + (((double)grid[p + Y] - 2.0 * (double)grid[p]) + (double)grid[p - Y]));
+		if (IS3D) laplace[p] = (Real)((double)laplace[p] + (((double)grid[p + Z] - 2.0 * (double)grid[p]) + (double)grid[p - Z]));
+	}
+	return 0;
+}
+int mfo_get_curvature(int sx, int sy, int sz, Real* curv, const Real* grid, double h_)
+{
+	STRIDES
+	const Real h = (Real)h_;
+	FOR_BND1 {
+		const IndexInt p = IDX(i, j, k);
+		const Real over_h = (Real)(1.0 / (double)h);
+		const double oh = (double)over_h, g2 = 2.0 * (double)grid[p];
+		const Real x = (Real)((0.5 * (double)(grid[p + X] - grid[p - X])) * oh);
+		const Real y = (Real)((0.5 * (double)(grid[p + Y] - grid[p - Y])) * oh);
+		const Real xx = (Real)(((((double)grid[p + X] - g2) + (double)grid[p - X]) * oh) * oh);
+		const Real yy = (Real)(((((double)grid[p + Y] - g2) + (double)grid[p - Y]) * oh) * oh);
+		const Real xy = (Real)(((0.25 * (double)(((grid[p + X + Y] + grid[p - X - Y]) - grid[p - X + Y]) - grid[p + X - Y])) * oh) * oh);
+		Real c = (Real)(((double)(x * x * yy + y * y * xx)) - (2.0 * (double)x) * (double)y * (double)xy);
+		Real denom = x * x + y * y;
+		if (IS3D) {
+			const Real z = (Real)((0.5 * (double)(grid[p + Z] - grid[p - Z])) * oh);
+			const Real zz = (Real)(((((double)grid[p + Z] - g2) + (double)grid[p - Z]) * oh) * oh);
+			const Real xz = (Real)(((0.25 * (double)(((grid[p + X + Z] + grid[p - X - Z]) - grid[p - X + Z]) - grid[p + X - Z])) * oh) * oh);
+			const Real yz = (Real)(((0.25 * (double)(((grid[p + Y + Z] + grid[p - Y - Z]) - grid[p + Y - Z]) - grid[p - Y + Z])) * oh) * oh);
+			c = (Real)((double)c + ((double)(x * x * zz + z * z * xx + y * y * zz + z * z * yy) - 2.0 * (double)(x * z * xz + y * z * yz)));
+			denom += z * z;
+		}
+#if MF_REAL_IS_DOUBLE
+		const Real dmax = denom > 1e-10 ? denom : 1e-10;
+#else
+		const Real dmax = denom > 1e-6f ? denom : 1e-6f;
+#endif
+		curv[p] = (Real)((double)c / pow((double)dmax, 1.5));
+	}
+	return 0;
+}

@@ -235,6 +235,18 @@ class Oracle:
         self._chk(self._f("set_bound")(*self.dims(grid[..., 0] if ncomp == 3 else grid), _p(grid), C.c_int(ncomp), C.c_double(value), C.c_int(boundaryWidth)))
         return grid
 
+    def get_laplacian(self, grid):
+        """plugin/flip.cpp:710-712; returns the Laplacian (outer layer 0)"""
+        out = np.zeros(grid.shape, self.real)
+        self._chk(self._f("get_laplacian")(*self.dims(grid), _p(out), _p(self._r(grid))))
+        return out
+
+    def get_curvature(self, grid, h=1.0):
+        """plugin/flip.cpp:714-716; returns the curvature (outer layer 0)"""
+        out = np.zeros(grid.shape, self.real)
+        self._chk(self._f("get_curvature")(*self.dims(grid), _p(out), _p(self._r(grid)), C.c_double(h)))
+        return out
+
     def grid_file(self, name, array, kind, load=False):
         """Grid<T>::save / load of the unmodified reference (grid.cpp:113-156; reference build only).
         kind: "real" | "mac" | "flags" | "levelset" | "vec3"; `array` is written to / filled from the file `name`."""

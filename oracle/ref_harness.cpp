@@ -19,6 +19,7 @@
 //   PD_fluid_guiding        plugin/fluidguiding.cpp:294-353
 //   extrapolateMACSimple, extrapolateLsSimple, extrapolateVec3Simple   fastmarch.cpp:337-375, :470-542
 //   FlagGrid::updateFromLevelset, Grid<T>::setBound                    grid.cpp:844-854, :591-593
+//   LaplaceOp, CurvatureOp (getLaplacian / getCurvature)               commonkernels.h:75-101, plugin/flip.cpp:710-716
 //   Grid<T>::save / load (.uni, .raw, .npz)                            grid.cpp:113-156, fileio/iogrids.cpp
 // Nothing of the reference is copied: its sources are compiled where they lie.
 //
@@ -170,6 +171,20 @@ int ref_set_bound(int sx, int sy, int sz, Real* grid, int ncomp, double value, i
 	FluidSolver* s = mkSolver(sx, sy, sz);
 	if (ncomp == 1) { Grid<Real> G(s, grid); G.setBound((Real)value, boundaryWidth); }
 	else { Grid<Vec3> G(s, (Vec3*)grid); G.setBound(Vec3((Real)value), boundaryWidth); }
+	delete s;
+  CATCH }
+
+// getLaplacian / getCurvature plugin/flip.cpp:710-716 are one-line wrappers of these two kernels (commonkernels.h:75-101)
+int ref_get_laplacian(int sx, int sy, int sz, Real* laplace, const Real* grid)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ Grid<Real> L(s, laplace); Grid<Real> G(s, (Real*)grid); LaplaceOp(L, G); }
+	delete s;
+  CATCH }
+int ref_get_curvature(int sx, int sy, int sz, Real* curv, const Real* grid, double h)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ Grid<Real> C(s, curv); Grid<Real> G(s, (Real*)grid); CurvatureOp(C, G, (Real)h); }
 	delete s;
   CATCH }
 

@@ -180,6 +180,18 @@ class CudaImpl:
         grid[...] = G.numpy()
         return grid
 
+    def get_laplacian(self, grid):
+        s = self._solver(grid)
+        L = mf.RealGrid(s)
+        mf.getLaplacian(L, mf.RealGrid(s, grid))
+        return L.numpy().copy()
+
+    def get_curvature(self, grid, h=1.0):
+        s = self._solver(grid)
+        Cv = mf.RealGrid(s)
+        mf.getCurvature(Cv, mf.RealGrid(s, grid), h)
+        return Cv.numpy().copy()
+
     def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
         s = self._solver(flags); s.timestep = dt
         U, Um, O = mf.RealGrid(s, ut), mf.RealGrid(s, utm1), mf.RealGrid(s)

@@ -83,6 +83,15 @@ int emu_update_from_levelset(int prec, int order, int sx, int sy, int sz, int* f
 	if (prec == 4) { liquid::UpdateFromLevelset<float> op = { flags, (const float*)phi }; return ex.cells(d, op); }
 	liquid::UpdateFromLevelset<double> op = { flags, (const double*)phi }; return ex.cells(d, op);
 }
+int emu_stencil(int prec, int order, int sx, int sy, int sz, void* out, const void* grid, double h, int curvature) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	if (prec == 4) {
+		if (curvature) { liquid::CurvatureCell<float> op = { (float*)out, (const float*)grid, (float)h }; return ex.cells(d, op); }
+		liquid::LaplaceCell<float> op = { (float*)out, (const float*)grid }; return ex.cells(d, op);
+	}
+	if (curvature) { liquid::CurvatureCell<double> op = { (double*)out, (const double*)grid, h }; return ex.cells(d, op); }
+	liquid::LaplaceCell<double> op = { (double*)out, (const double*)grid }; return ex.cells(d, op);
+}
 int emu_set_bound(int prec, int order, int sx, int sy, int sz, void* grid, int ncomp, double value, int w) {
 	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
 	if (prec == 4) {

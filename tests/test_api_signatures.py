@@ -19,6 +19,7 @@ PLUGINS = {     # plugin -> reference file
     "advectSemiLagrange": "plugin/advection.cpp", "cgSolveDiffusion": "conjugategrad.cpp", "cgSolveWE": "plugin/waves.cpp",
     "PD_fluid_guiding": "plugin/fluidguiding.cpp",
     "extrapolateMACSimple": "fastmarch.cpp", "extrapolateLsSimple": "fastmarch.cpp", "extrapolateVec3Simple": "fastmarch.cpp",
+    "getLaplacian": "plugin/flip.cpp", "getCurvature": "plugin/flip.cpp",
 }
 
 

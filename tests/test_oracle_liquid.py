@@ -77,6 +77,16 @@ class Emulation:
         assert self.lib.emu_update_from_levelset(*self._head(flags), self._p(flags), self._p(phi)) == 0
         return flags
 
+    def get_laplacian(self, grid):
+        out = np.zeros_like(grid)
+        assert self.lib.emu_stencil(*self._head(grid), self._p(out), self._p(grid), C.c_double(1.0), C.c_int(0)) == 0
+        return out
+
+    def get_curvature(self, grid, h=1.0):
+        out = np.zeros_like(grid)
+        assert self.lib.emu_stencil(*self._head(grid), self._p(out), self._p(grid), C.c_double(h), C.c_int(1)) == 0
+        return out
+
     def set_bound(self, grid, value, boundaryWidth=1):
         assert self.lib.emu_set_bound(*self._head(grid), self._p(grid), C.c_int(1 if grid.ndim == 3 else 3), C.c_double(value), C.c_int(boundaryWidth)) == 0
         return grid
