@@ -42,7 +42,7 @@ def test_cuda_equals_oracle_on_larger_scenes(shape, prec):
     for case in LIQUID_CASES:
         a, b = run_liquid_case(I, case, flags, vel, phi, phiObs), run_liquid_case(O, case, flags, vel, phi, phiObs)
         if case in helpers.LIQUID_ULP_CASES:          # pow() in double: last-bit differences between libm and the device
-            assert np.allclose(a, b, rtol=3e-7 if prec == 4 else 1e-15, atol=0), case
+            assert np.allclose(a, b, rtol=3e-7 if prec == 4 else 4e-15, atol=0), case
         else:
             assert np.array_equal(a, b), case
 
