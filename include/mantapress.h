@@ -207,7 +207,7 @@ int mp_cg_solve_we(mp_context* ctx, const mp_grid* flags, mp_grid* ut, mp_grid* 
                    double cgAccuracy, double dt, mp_solve_info* info);
 
 /* ---- the steps either side of the projection, so that a whole smoke step keeps its fields in HBM ----
- * setWallBcs          plugin/extforces.cpp:186-218, :307-316  (KnSetWallBcs; phiObs + fractions = the second-order variant: MP_ERR_UNSUPPORTED)
+ * setWallBcs          plugin/extforces.cpp:186-218, :307-316  (KnSetWallBcs; with phiObs AND fractions the second-order variant KnSetWallBcsFrac :220-303)
  * addGravity          plugin/extforces.cpp:45-65              (scale != 0: divided by the grid's dx = 1/max(size))
  * addBuoyancy         plugin/extforces.cpp:75-90
  * advectSemiLagrange  plugin/advection.cpp:442-461            (grid: Real or MAC; order 1 | 2 (MacCormack), clampMode 1 | 2, convective outflow

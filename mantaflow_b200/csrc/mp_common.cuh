@@ -133,7 +133,8 @@ int mp_dist_sum(mp_context* ctx, double* deviceVals, int n);                   /
 
 int mp_check_same(const mp_grid* ref, const mp_grid* g, int kind, const char* name, bool optional);
 extern "C" int mp_grid_create_scratch(mp_context* ctx, int kind, int prec, int sx, int sy, int sz, mp_grid** out);   // no clear pass: the caller writes every cell
-int mp_check_flags_interior(mp_context* ctx, const mp_grid* flags);   // fluid cells must not touch the outer layer
+int mp_check_flags_interior(mp_context* ctx, const mp_grid* flags);
+int mp_set_wall_bcs_frac_impl(mp_context* ctx, const mp_grid* flags, mp_grid* vel, const mp_grid* phiObs);   // KnSetWallBcsFrac (mp_liquid.cu)   // fluid cells must not touch the outer layer
 
 template <typename T> static inline T* dptr(const mp_grid* g) { return g ? (T*)g->d : (T*)nullptr; }
 

@@ -58,6 +58,22 @@ int lsSimple(mp_context* ctx, mp_grid* val, const mp_grid* phi, int distance, in
 
 }  // namespace
 
+// setWallBcs(fractions, phiObs): called by mp_set_wall_bcs (mp_step.cu); the result grid is swapped in like MACGrid::swap (extforces.cpp:313)
+int mp_set_wall_bcs_frac_impl(mp_context* ctx, const mp_grid* flags, mp_grid* vel, const mp_grid* phiObs)
+{
+	MP_TRY(checkLiquid("mp_set_wall_bcs", ctx, flags));
+	MP_TRY(mp_check_same(flags, phiObs, MP_GRID_REAL, "phiObs", false));
+	if (phiObs->prec != vel->prec) MP_FAIL(MP_ERR_INVALID, "setWallBcs: phiObs and vel differ in precision");
+	Tmp tgt; MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_MAC, vel->prec, vel->sx, vel->sy, vel->sz, &tgt.g));      // every cell is written
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(flags);
+	if (vel->prec == 4) { liquid::WallBcsFrac<float> op = { (const int*)flags->d, (const float*)vel->d, (float*)tgt.g->d, (const float*)phiObs->d }; MP_TRY(ex.cells(d, op)); }
+	else { liquid::WallBcsFrac<double> op = { (const int*)flags->d, (const double*)vel->d, (double*)tgt.g->d, (const double*)phiObs->d }; MP_TRY(ex.cells(d, op)); }
+	if (vel->owns && tgt.g->owns) { void* q = vel->d; vel->d = tgt.g->d; tgt.g->d = q; return MP_OK; }
+	MP_CUDA(cudaMemcpyAsync(vel->d, tgt.g->d, vel->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	return MP_OK;
+}
+
 extern "C" {
 
 int mp_extrapolate_mac_simple(mp_context* ctx, const mp_grid* flags, mp_grid* vel, int distance, const mp_grid* phiObs, int intoObs)

@@ -310,6 +310,63 @@ template <typename T, int NC> struct SetBound {
 	}
 };
 
+// ---------------------------------------------------------------- setWallBcs, second-order variant
+// KnSetWallBcsFrac plugin/extforces.cpp:220-303 (taken by setWallBcs when fractions AND phiObs are given, :307-316): on faces next to an
+// obstacle the velocity component along the obstacle normal (gradient of phiObs at the face) is removed.  Writes a fresh grid (every cell).
+template <typename Real> MP_HD Real halfSum(Real a, Real b) { return (Real)((double)(a + b) * .5); }
+template <typename Real> MP_HD void macAtFace(const Dims& d, const Real* v, IndexInt idx, int c, Real& ox, Real& oy, Real& oz) {      // MACGrid::getAtMACX/Y/Z grid.h:437-470
+	const IndexInt Y = d.Y, Z = d.Z;
+	#define MP_VC(o, cc) v[3 * (idx + (o)) + (cc)]
+	if (c == 0) {
+		ox = MP_VC(0, 0);
+		oy = (Real)(0.25 * (double)(MP_VC(0, 1) + MP_VC(-1, 1) + MP_VC(Y, 1) + MP_VC(Y - 1, 1)));
+		oz = 0;
+		if (d.is3D) oz = (Real)(0.25 * (double)(MP_VC(0, 2) + MP_VC(-1, 2) + MP_VC(Z, 2) + MP_VC(Z - 1, 2)));
+	} else if (c == 1) {
+		ox = (Real)(0.25 * (double)(MP_VC(0, 0) + MP_VC(-Y, 0) + MP_VC(1, 0) + MP_VC(1 - Y, 0)));
+		oy = MP_VC(0, 1);
+		oz = 0;
+		if (d.is3D) oz = (Real)(0.25 * (double)(MP_VC(0, 2) + MP_VC(-Y, 2) + MP_VC(Z, 2) + MP_VC(Z - Y, 2)));
+	} else {
+		ox = (Real)(0.25 * (double)(MP_VC(0, 0) + MP_VC(-Z, 0) + MP_VC(1, 0) + MP_VC(1 - Z, 0)));
+		oy = (Real)(0.25 * (double)(MP_VC(0, 1) + MP_VC(-Z, 1) + MP_VC(Y, 1) + MP_VC(Y - Z, 1)));
+		oz = MP_VC(0, 2);
+	}
+	#undef MP_VC
+}
+template <typename Real> struct WallBcsFrac {
+	static const bool kSplit = false;
+	const int* flags; const Real* vel; Real* tgt; const Real* phiObs;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt p) const {
+		Real out[3] = { vel[3 * p], vel[3 * p + 1], vel[3 * p + 2] };
+		const int f = flags[p];
+		const bool curFluid = f & TypeFluid, curObs = f & TypeObstacle;
+		if ((curFluid || curObs) && interiorCell(d, i, j, k)) {
+			const int dim = d.is3D ? 3 : 2;
+			const IndexInt S[3] = { d.X, d.Y, d.Z };
+			for (int c = 0; c < dim; c++) {
+				if (!(curObs || (flags[p - S[c]] & TypeObstacle))) continue;
+				Real dphi[3] = { 0, 0, 0 };
+				const Real tmp1 = halfSum<Real>(phiObs[p], phiObs[p - S[c]]);
+				for (int a = 0; a < dim; a++) {
+					if (a == c) { dphi[a] = phiObs[p] - phiObs[p - S[c]]; continue; }
+					Real tmp2 = halfSum<Real>(phiObs[p + S[a]], phiObs[p + S[a] - S[c]]);
+					const Real phi1 = halfSum<Real>(tmp1, tmp2);
+					tmp2 = halfSum<Real>(phiObs[p - S[a]], phiObs[p - S[a] - S[c]]);
+					const Real phi2 = halfSum<Real>(tmp1, tmp2);
+					dphi[a] = phi1 - phi2;
+				}
+				normalize3<Real>(dphi[0], dphi[1], dphi[2]);
+				Real vx, vy, vz;
+				macAtFace<Real>(d, vel, p, c, vx, vy, vz);
+				const Real vm = c == 0 ? vx : (c == 1 ? vy : vz);
+				out[c] = vm - (dphi[0] * vx + dphi[1] * vy + dphi[2] * vz) * dphi[c];
+			}
+		}
+		tgt[3 * p] = out[0]; tgt[3 * p + 1] = out[1]; tgt[3 * p + 2] = out[2];
+	}
+};
+
 // ---------------------------------------------------------------- getLaplacian / getCurvature (surface tension helpers of solvePressure's `curv` argument)
 // LaplaceOp commonkernels.h:75-80, CurvatureOp :83-101, wrapped by plugin/flip.cpp:710-716.  The reference's double literals promote every
 // product to double and every named Real narrows; the same evaluation here.  Cells of the outer layer are left alone (KERNEL(bnd=1)).

@@ -1,5 +1,5 @@
 // The steps either side of the pressure projection, so that a whole smoke step keeps its fields in HBM:
-//   setWallBcs          plugin/extforces.cpp:186-218, :307-316   (KnSetWallBcs; the phiObs / fractions variant is not built)
+//   setWallBcs          plugin/extforces.cpp:186-218, :307-316   (KnSetWallBcs; the phiObs + fractions variant KnSetWallBcsFrac is in mp_liquid.cu)
 //   addGravity          plugin/extforces.cpp:45-65               (KnApplyForce, additive)
 //   addBuoyancy         plugin/extforces.cpp:75-90               (KnAddBuoyancy)
 //   advectSemiLagrange  plugin/advection.cpp:25-58, :81-316, :323-461 (semi-Lagrange + MacCormack for Real and MAC grids,
@@ -437,7 +437,10 @@ int mp_set_wall_bcs(mp_context* ctx, const mp_grid* flags, mp_grid* vel, const m
 {
 	MP_TRY(checkStep("mp_set_wall_bcs", ctx, flags, vel));
 	(void)boundaryWidth;
-	if (phiObs && fractions) MP_FAIL(MP_ERR_UNSUPPORTED, "setWallBcs: the second-order variant (phiObs + fractions, KnSetWallBcsFrac) is not built");
+	if (phiObs && fractions) {       // the second-order variant KnSetWallBcsFrac (extforces.cpp:220-303); it reads neither fractions nor obvel
+		MP_TRY(mp_check_same(vel, fractions, MP_GRID_MAC, "fractions", false));
+		return mp_set_wall_bcs_frac_impl(ctx, flags, vel, phiObs);
+	}
 	if (obvel) MP_TRY(mp_check_same(vel, obvel, MP_GRID_MAC, "obvel", false));
 	const Dims d = dimsOf(flags);
 	if (vel->prec == 4) { WallBcsOp<float> op = { (const int*)flags->d, obvel ? (const float*)obvel->d : nullptr }; return launchCells<float>(ctx, d, (float*)vel->d, op); }

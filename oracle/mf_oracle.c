@@ -1823,3 +1823,41 @@ int mfo_get_curvature(int sx, int sy, int sz, Real* curv, const Real* grid, doub
 	}
 	return 0;
 }
+
+/* setWallBcs with fractions + phiObs: plugin/extforces.cpp:307-316 -> KnSetWallBcsFrac :220-303 (second-order obstacle boundaries; the
+ * kernel writes a fresh grid that is then swapped in).  mac_at = MACGrid::getAtMACX/Y/Z grid.h:437-470, normalize3 as above. */
+static inline Real half_sum(Real a, Real b) { return (Real)((double)(a + b) * .5); }
+int mfo_set_wall_bcs_frac(int sx, int sy, int sz, const int* flags, Real* vel, const Real* phiObs)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	Real* tgt = (Real*)malloc(sizeof(Real) * 3 * (size_t)n);
+	memcpy(tgt, vel, sizeof(Real) * 3 * (size_t)n);                  /* velTarget(i,j,k) = vel(i,j,k) for every cell */
+	const IndexInt S[3] = { X, Y, Z };
+	FOR_BND1 {
+		const IndexInt p = IDX(i, j, k);
+		const int curFluid = flags[p] & TypeFluid, curObs = flags[p] & TypeObstacle;
+		if (!curFluid && !curObs) continue;
+		const int dim = IS3D ? 3 : 2;
+		for (int c = 0; c < dim; c++) {
+			if (!(curObs || (flags[p - S[c]] & TypeObstacle))) continue;
+			Real dphi[3] = { 0, 0, 0 };
+			const Real tmp1 = half_sum(phiObs[p], phiObs[p - S[c]]);
+			for (int a = 0; a < dim; a++) {
+				if (a == c) { dphi[a] = phiObs[p] - phiObs[p - S[c]]; continue; }
+				Real tmp2 = half_sum(phiObs[p + S[a]], phiObs[p + S[a] - S[c]]);
+				const Real phi1 = half_sum(tmp1, tmp2);
+				tmp2 = half_sum(phiObs[p - S[a]], phiObs[p - S[a] - S[c]]);
+				const Real phi2 = half_sum(tmp1, tmp2);
+				dphi[a] = phi1 - phi2;
+			}
+			normalize3(dphi);
+			Real vm[3];
+			mac_at(vel, sx, sy, sz, p, c, vm);
+			tgt[3 * p + c] = vm[c] - (dphi[0] * vm[0] + dphi[1] * vm[1] + dphi[2] * vm[2]) * dphi[c];
+		}
+	}
+	memcpy(vel, tgt, sizeof(Real) * 3 * (size_t)n);
+	free(tgt);
+	return 0;
+}

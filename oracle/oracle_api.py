@@ -83,6 +83,12 @@ class Oracle:
         self._chk(self._f("set_wall_bcs_obvel")(*self.dims(flags), _p(flags), _p(vel), _p(self._r(obvel))))
         return vel
 
+    def set_wall_bcs_frac(self, flags, vel, phiObs):
+        """setWallBcs(flags, vel, fractions=..., phiObs=...): the second-order variant, plugin/extforces.cpp:220-303,:307-316"""
+        assert vel.dtype == self.real and vel.flags.c_contiguous
+        self._chk(self._f("set_wall_bcs_frac")(*self.dims(flags), _p(flags), _p(vel), _p(self._r(phiObs))))
+        return vel
+
     def add_gravity(self, flags, vel, gravity, exclude=None, scale=True, dt=1.0):
         assert vel.dtype == self.real and vel.flags.c_contiguous
         self._chk(self._f("add_gravity")(*self.dims(flags), _p(flags), _p(vel), *[C.c_double(float(g)) for g in gravity],

@@ -115,6 +115,18 @@ int ref_set_wall_bcs_obvel(int sx, int sy, int sz, const int* flags, Real* vel, 
 	delete s;
   CATCH }
 
+// the second-order variant (KnSetWallBcsFrac extforces.cpp:220-303) is taken when both fractions and phiObs are given; it never reads the fractions
+int ref_set_wall_bcs_frac(int sx, int sy, int sz, const int* flags, Real* vel, const Real* phiObs)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	const size_t n = (size_t)sx * sy * sz;
+	{ FlagGrid F(s, (int*)flags); Grid<Real> P(s, (Real*)phiObs); MACGrid Fr(s);
+	  MACGrid V(s); memcpy(&V[0], vel, n * sizeof(Vec3));            // the plugin swaps its result in: work on a solver-owned copy
+	  setWallBcs(F, V, 0, &Fr, &P, 0);
+	  memcpy(vel, &V[0], n * sizeof(Vec3)); }
+	delete s;
+  CATCH }
+
 int ref_add_gravity(int sx, int sy, int sz, const int* flags, Real* vel, double gx, double gy, double gz, const Real* exclude, int scale, double dt)
 { TRY
 	FluidSolver* s = mkSolver(sx, sy, sz); s->mDt = (Real)dt;

@@ -180,6 +180,13 @@ class CudaImpl:
         grid[...] = G.numpy()
         return grid
 
+    def set_wall_bcs_frac(self, flags, vel, phiObs):
+        s = self._solver(flags)
+        V = mf.MACGrid(s, vel)
+        mf.setWallBcs(mf.FlagGrid(s, flags), V, fractions=mf.MACGrid(s), phiObs=mf.RealGrid(s, phiObs))
+        vel[...] = V.numpy()
+        return vel
+
     def get_laplacian(self, grid):
         s = self._solver(grid)
         L = mf.RealGrid(s)

@@ -83,6 +83,16 @@ int emu_update_from_levelset(int prec, int order, int sx, int sy, int sz, int* f
 	if (prec == 4) { liquid::UpdateFromLevelset<float> op = { flags, (const float*)phi }; return ex.cells(d, op); }
 	liquid::UpdateFromLevelset<double> op = { flags, (const double*)phi }; return ex.cells(d, op);
 }
+int emu_set_wall_bcs_frac(int prec, int order, int sx, int sy, int sz, const int* flags, void* vel, const void* phiObs) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	const size_t bytes = (size_t)prec * 3 * (size_t)d.n;
+	void* tgt = malloc(bytes); memset(tgt, 0x5a, bytes);
+	int rc;
+	if (prec == 4) { liquid::WallBcsFrac<float> op = { flags, (const float*)vel, (float*)tgt, (const float*)phiObs }; rc = ex.cells(d, op); }
+	else { liquid::WallBcsFrac<double> op = { flags, (const double*)vel, (double*)tgt, (const double*)phiObs }; rc = ex.cells(d, op); }
+	memcpy(vel, tgt, bytes); free(tgt);
+	return rc;
+}
 int emu_stencil(int prec, int order, int sx, int sy, int sz, void* out, const void* grid, double h, int curvature) {
 	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
 	if (prec == 4) {

@@ -82,8 +82,6 @@ def test_unsupported_variants_fail_loudly(mf):
         mf.advectSemiLagrange(F, V, D, orderSpace=2)
     with pytest.raises(mf.MantaError):
         mf.advectSemiLagrange(F, V, D, orderTrace=2)
-    with pytest.raises(mf.MantaError):
-        mf.setWallBcs(F, V, fractions=mf.MACGrid(s), phiObs=mf.RealGrid(s))
 
 
 @pytest.mark.parametrize("prec", [4, 8])

@@ -77,6 +77,10 @@ class Emulation:
         assert self.lib.emu_update_from_levelset(*self._head(flags), self._p(flags), self._p(phi)) == 0
         return flags
 
+    def set_wall_bcs_frac(self, flags, vel, phiObs):
+        assert self.lib.emu_set_wall_bcs_frac(*self._head(flags), self._p(flags), self._p(vel), self._p(phiObs)) == 0
+        return vel
+
     def get_laplacian(self, grid):
         out = np.zeros_like(grid)
         assert self.lib.emu_stencil(*self._head(grid), self._p(out), self._p(grid), C.c_double(1.0), C.c_int(0)) == 0
