@@ -223,12 +223,14 @@ int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid
  * (extrapolateLsSimple x2, extrapolateMACSimple, advect phi, phi.setBound, flags.updateFromLevelset, advect vel, addGravity, setWallBcs,
  * solvePressure with phi) keeps every field in HBM.
  * extrapolateMACSimple          fastmarch.cpp:337-375  (distance <= 250; phiObs may be NULL)
+ * extrapolateMACFromWeight      fastmarch.cpp:410-432  (weight: a Vec3 grid whose positive entries mark initialised faces; it is destroyed)
  * extrapolateLsSimple           fastmarch.cpp:470-507
  * extrapolateVec3Simple         fastmarch.cpp:510-542  (vel: a Vec3 grid, same storage as MP_GRID_MAC)
  * FlagGrid::updateFromLevelset  grid.cpp:844-854
  * Grid<T>::setBound             grid.cpp:585-593       (value = vx for Real / flag grids, (vx,vy,vz) for Vec3 grids)
  * Results are bit-identical to the reference's in both precisions. */
 int mp_extrapolate_mac_simple(mp_context* ctx, const mp_grid* flags, mp_grid* vel, int distance, const mp_grid* phiObs, int intoObs);
+int mp_extrapolate_mac_from_weight(mp_context* ctx, mp_grid* vel, mp_grid* weight, int distance);
 int mp_extrapolate_ls_simple(mp_context* ctx, mp_grid* phi, int distance, int inside);
 int mp_extrapolate_vec3_simple(mp_context* ctx, mp_grid* vel, const mp_grid* phi, int distance, int inside);
 int mp_flags_update_from_levelset(mp_context* ctx, mp_grid* flags, const mp_grid* levelset);

@@ -280,6 +280,10 @@ inline void extrapolateMACSimple(FlagGrid& flags, MACGrid& vel, int distance = 4
 	mpCheck(mp_extrapolate_mac_simple(flags.getParent()->ctx(), flags.dev(), vel.dev(), distance, detail::dv(phiObs), intoObs));
 	vel.markDeviceWritten();
 }
+inline void extrapolateMACFromWeight(MACGrid& vel, Grid<Vec3>& weight, int distance = 2) {      // fastmarch.cpp:410
+	mpCheck(mp_extrapolate_mac_from_weight(vel.getParent()->ctx(), vel.dev(), weight.dev(), distance));
+	vel.markDeviceWritten(); weight.markDeviceWritten();
+}
 inline void extrapolateLsSimple(Grid<Real>& phi, int distance = 4, bool inside = false) {
 	mpCheck(mp_extrapolate_ls_simple(phi.getParent()->ctx(), phi.dev(), distance, inside));
 	phi.markDeviceWritten();

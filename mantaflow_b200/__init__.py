@@ -14,7 +14,7 @@ from .grid import (FlagEmpty, FlagFluid, FlagGrid, FlagInflow, FlagObstacle, Fla
 from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, releaseMG, solvePressure, solvePressureHost,
                        solvePressureSystem)
 from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE
-from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, extrapolateLsSimple, extrapolateMACSimple,
+from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, extrapolateLsSimple, extrapolateMACFromWeight, extrapolateMACSimple,
                    extrapolateVec3Simple, getCurvature, getLaplacian, lastGuidingIterations, releaseBlurPrecomp, setWallBcs)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

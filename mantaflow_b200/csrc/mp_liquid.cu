@@ -89,6 +89,18 @@ int mp_extrapolate_mac_simple(mp_context* ctx, const mp_grid* flags, mp_grid* ve
 	return macSimple<double>(ctx, flags, vel, distance, phiObs, intoObs);
 }
 
+int mp_extrapolate_mac_from_weight(mp_context* ctx, mp_grid* vel, mp_grid* weight, int distance)
+{
+	MP_TRY(checkLiquid("mp_extrapolate_mac_from_weight", ctx, vel));
+	if (vel->kind != MP_GRID_MAC) MP_FAIL(MP_ERR_INVALID, "extrapolateMACFromWeight: vel is not a MAC grid");
+	MP_TRY(mp_check_same(vel, weight, MP_GRID_MAC, "weight", false));
+	if (vel == weight || vel->d == weight->d) MP_FAIL(MP_ERR_INVALID, "extrapolateMACFromWeight: vel and weight must be different grids");
+	if (noInterior(vel)) MP_FAIL(MP_ERR_INVALID, "extrapolateMACFromWeight: grid without interior cells");
+	CudaExec ex = { ctx };
+	if (vel->prec == 4) return liquid::extrapolateMacFromWeight<float>(ex, dimsOf(vel), (float*)vel->d, (float*)weight->d, distance);
+	return liquid::extrapolateMacFromWeight<double>(ex, dimsOf(vel), (double*)vel->d, (double*)weight->d, distance);
+}
+
 int mp_extrapolate_ls_simple(mp_context* ctx, mp_grid* phi, int distance, int inside)
 {
 	MP_TRY(checkLiquid("mp_extrapolate_ls_simple", ctx, phi));

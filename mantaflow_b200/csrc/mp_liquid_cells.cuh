@@ -200,6 +200,41 @@ template <typename Real> struct IntoBndCopy {
 	}
 };
 
+// extrapolateMACFromWeight fastmarch.cpp:410-432: the marks live in a Vec3 weight grid (what mapPartsToMAC leaves behind).  Components are
+// independent, so one reset pass and `distance` extrapolation passes serve all three (the reference runs them one component after the other).
+template <typename Real> struct WeightReset {            // fastmarch.cpp:419-422
+	static const bool kSplit = false;
+	Real* weight;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (!interiorCell(d, i, j, k)) return;
+		const int dim = d.is3D ? 3 : 2;
+		for (int c = 0; c < dim; c++) if (weight[3 * idx + c] > 0.) weight[3 * idx + c] = 1.0;
+	}
+};
+template <typename Real> struct WeightExtrapolate {      // knExtrapolateMACFromWeight fastmarch.cpp:378-403
+	static const bool kSplit = false;
+	Real* vel; Real* weight; int pass;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (!interiorCell(d, i, j, k)) return;
+		const int dim = d.is3D ? 3 : 2;
+		for (int c = 0; c < dim; c++) {
+			if (weight[3 * idx + c] != 0) continue;
+			int nbs = 0; Real avgVel = 0;
+			for (int q = 0; q < 2 * dim; q++) {
+				const IndexInt nb = idx + nbOffset(d, q);
+				if (weight[3 * nb + c] == (Real)pass) { avgVel += vel[3 * nb + c]; nbs++; }     // a neighbour being marked right now goes 0 -> pass+1, never through `pass`
+			}
+			if (nbs > 0) { weight[3 * idx + c] = (Real)(pass + 1); vel[3 * idx + c] = avgVel / (Real)nbs; }
+		}
+	}
+};
+template <typename Real, typename Exec>
+int extrapolateMacFromWeight(Exec& ex, const Dims& d, Real* vel, Real* weight, int distance) {
+	{ WeightReset<Real> op = { weight }; MP_TRY(ex.cells(d, op)); }
+	for (int pass = 1; pass < 1 + distance; pass++) { WeightExtrapolate<Real> op = { vel, weight, pass }; MP_TRY(ex.cells(d, op)); }
+	return MP_OK;
+}
+
 // tmp: one int per cell; stage: 3 Reals per cell (only outer-layer entries are touched)
 template <typename Real, typename Exec>
 int extrapolateMacSimple(Exec& ex, const Dims& d, const int* flags, Real* vel, int distance, const Real* phiObs, bool intoObs, int* tmp, Real* stage) {

@@ -10,6 +10,7 @@ defaults as the reference, so the main loop of scenes/simpleplume.py runs with e
 and the liquid neighbours (first slice) with which the level-set loop of scenes/freesurface.py:54-84 does the same:
 
     extrapolateMACSimple   fastmarch.cpp:337-375      extrapolateLsSimple :470-507      extrapolateVec3Simple :510-542
+    extrapolateMACFromWeight :410-432
     getLaplacian, getCurvature   plugin/flip.cpp:710-716
     (FlagGrid.updateFromLevelset and Grid.setBound are methods of the grid classes, grid.py)
 """
@@ -67,6 +68,12 @@ def extrapolateMACSimple(flags, vel, distance=4, phiObs=None, intoObs=False):
     s = flags.parent
     check(s.lib.mp_extrapolate_mac_simple(s._ctx, flags.dev(), vel.dev(), C.c_int(int(distance)), _d(phiObs), C.c_int(int(bool(intoObs)))))
     vel.markDeviceWritten()
+
+
+def extrapolateMACFromWeight(vel, weight, distance=2):
+    s = vel.parent
+    check(s.lib.mp_extrapolate_mac_from_weight(s._ctx, vel.dev(), weight.dev(), C.c_int(int(distance))))
+    vel.markDeviceWritten(); weight.markDeviceWritten()
 
 
 def extrapolateLsSimple(phi, distance=4, inside=False):

@@ -1861,3 +1861,28 @@ int mfo_set_wall_bcs_frac(int sx, int sy, int sz, const int* flags, Real* vel, c
 	free(tgt);
 	return 0;
 }
+
+/* extrapolateMACFromWeight fastmarch.cpp:410-432 (knExtrapolateMACFromWeight :378-403): like extrapolateMACSimple, but the marks live in a
+ * Vec3 weight grid (what mapPartsToMAC leaves behind): > 0 becomes 1 = initialised, pass d turns reached cells into d+1.  The weight grid is destroyed. */
+int mfo_extrapolate_mac_from_weight(int sx, int sy, int sz, Real* vel, Real* weight, int distance)
+{
+	STRIDES
+	const int dim = IS3D ? 3 : 2;
+	if (sx < 3 || sy < 3 || (IS3D && sz < 3)) { snprintf(g_err, sizeof g_err, "extrapolateMACFromWeight: grid without interior cells"); return 1; }
+	for (int c = 0; c < dim; c++) {
+		{ FOR_BND1 { const IndexInt p = IDX(i, j, k); if (weight[3 * p + c] > 0.) weight[3 * p + c] = 1.0; } }
+		for (int d = 1; d < 1 + distance; d++) {
+			FOR_BND1 {
+				const IndexInt p = IDX(i, j, k);
+				if (weight[3 * p + c] != 0) continue;
+				int nbs = 0; Real avgVel = 0.;
+				for (int q = 0; q < 2 * dim; q++) {
+					const IndexInt pn = IDX(i + NB6[q][0], j + NB6[q][1], k + NB6[q][2]);
+					if (weight[3 * pn + c] == d) { avgVel += vel[3 * pn + c]; nbs++; }
+				}
+				if (nbs > 0) { weight[3 * p + c] = d + 1; vel[3 * p + c] = avgVel / nbs; }
+			}
+		}
+	}
+	return 0;
+}

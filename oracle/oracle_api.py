@@ -216,6 +216,12 @@ class Oracle:
         self._chk(self._f("extrapolate_mac_simple")(*self.dims(flags), _p(flags), _p(vel), C.c_int(distance), _p(self._r(phiObs)), C.c_int(int(intoObs))))
         return vel
 
+    def extrapolate_mac_from_weight(self, vel, weight, distance=2):
+        """fastmarch.cpp:410-432; vel and weight are both updated in place (the weight grid ends up holding the marks), vel is returned"""
+        assert vel.dtype == self.real and weight.dtype == self.real and vel.flags.c_contiguous and weight.flags.c_contiguous
+        self._chk(self._f("extrapolate_mac_from_weight")(*self.dims(vel[..., 0]), _p(vel), _p(weight), C.c_int(distance)))
+        return vel
+
     def extrapolate_ls_simple(self, phi, distance=4, inside=False):
         """fastmarch.cpp:470-507"""
         assert phi.dtype == self.real and phi.flags.c_contiguous

@@ -59,6 +59,7 @@ void PD_fluid_guiding(MACGrid& vel, MACGrid& velT, Grid<Real>& pressure, FlagGri
 void releaseBlurPrecomp();
 void extrapolateMACSimple(FlagGrid& flags, MACGrid& vel, int distance, LevelsetGrid* phiObs, bool intoObs);
 void extrapolateLsSimple(Grid<Real>& phi, int distance, bool inside);
+void extrapolateMACFromWeight(MACGrid& vel, Grid<Vec3>& weight, int distance);
 void extrapolateVec3Simple(Grid<Vec3>& vel, Grid<Real>& phi, int distance, bool inside);
 void addGravity(const FlagGrid& flags, MACGrid& vel, Vec3 gravity, const Grid<Real>* exclude, bool scale);
 void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGrid& vel, Vec3 gravity, Real coefficient, bool scale);
@@ -154,6 +155,13 @@ int ref_extrapolate_mac_simple(int sx, int sy, int sz, const int* flags, Real* v
 	  Grid<Real>* P = phiObs ? new Grid<Real>(s, (Real*)phiObs) : 0;
 	  extrapolateMACSimple(F, V, distance, reinterpret_cast<LevelsetGrid*>(P), intoObs != 0);
 	  delete P; }
+	delete s;
+  CATCH }
+
+int ref_extrapolate_mac_from_weight(int sx, int sy, int sz, Real* vel, Real* weight, int distance)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ MACGrid V(s, (Vec3*)vel); Grid<Vec3> W(s, (Vec3*)weight); extrapolateMACFromWeight(V, W, distance); }
 	delete s;
   CATCH }
 

@@ -152,6 +152,13 @@ class CudaImpl:
         vel[...] = V.numpy()
         return vel
 
+    def extrapolate_mac_from_weight(self, vel, weight, distance=2):
+        s = self._solver(vel[..., 0])
+        V, W = mf.MACGrid(s, vel), mf.VecGrid(s, weight)
+        mf.extrapolateMACFromWeight(V, W, distance=distance)
+        vel[...] = V.numpy(); weight[...] = W.numpy()
+        return vel
+
     def extrapolate_ls_simple(self, phi, distance=4, inside=False):
         s = self._solver(phi)
         P = mf.LevelsetGrid(s, phi)

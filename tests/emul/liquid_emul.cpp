@@ -70,6 +70,11 @@ int emu_extrapolate_mac_simple(int prec, int order, int sx, int sy, int sz, cons
 	return prec == 4 ? macSimple<float>(order, sx, sy, sz, flags, (float*)vel, distance, (const float*)phiObs, intoObs)
 	                 : macSimple<double>(order, sx, sy, sz, flags, (double*)vel, distance, (const double*)phiObs, intoObs);
 }
+int emu_extrapolate_mac_from_weight(int prec, int order, int sx, int sy, int sz, void* vel, void* weight, int distance) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	return prec == 4 ? liquid::extrapolateMacFromWeight<float>(ex, d, (float*)vel, (float*)weight, distance)
+	                 : liquid::extrapolateMacFromWeight<double>(ex, d, (double*)vel, (double*)weight, distance);
+}
 int emu_extrapolate_ls_simple(int prec, int order, int sx, int sy, int sz, void* phi, int distance, int inside) {
 	return prec == 4 ? lsSimple<float>(order, sx, sy, sz, (float*)phi, (const float*)phi, distance, inside, false)
 	                 : lsSimple<double>(order, sx, sy, sz, (double*)phi, (const double*)phi, distance, inside, false);

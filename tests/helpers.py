@@ -304,7 +304,7 @@ def check_guiding_against_golden(I, name, prec, tol):
 # ---------------------------------------------------------------- liquid neighbours: fastmarch.cpp:337-542, grid.cpp:585-593,:844-854
 LIQUID_SCENES = {"liq3d": (12, 16, 14), "liq2d": (1, 28, 24), "liqragged": (11, 13, 9)}      # (sz, sy, sx)
 LIQUID_CASES = ["mac_d4", "mac_d3_into", "mac_d5_phiobs", "mac_d0", "ls_out_d4", "ls_in_d5", "ls_out_d1", "ls_in_d2", "v3_out_d4", "v3_in_d2",
-                "v3_out_d1", "from_levelset", "bound_real_w0", "bound_real_w2", "bound_vec_w1", "laplacian", "curvature_h1", "curvature_h07", "wall_frac"]
+                "v3_out_d1", "from_levelset", "bound_real_w0", "bound_real_w2", "bound_vec_w1", "laplacian", "curvature_h1", "curvature_h07", "wall_frac", "macw_d2", "macw_d4", "macw_marks_d4"]
 LIQUID_ULP_CASES = ("curvature_h1", "curvature_h07")      # end in a double pow(), which neither libm nor the device rounds correctly: last bit may differ
 
 
@@ -348,6 +348,10 @@ def run_liquid_case(I, case, flags, vel, phi, phiObs):
         return I.set_bound(phi.copy(), -3.0, 2)
     if case == "bound_vec_w1":
         return I.set_bound(vel.copy(), 0.25, 1)
+    if case.startswith("macw"):          # weights as mapPartsToMAC leaves them: positive where a face got a contribution
+        w = np.where(np.repeat((phi < 0)[..., None], 3, axis=3), np.abs(vel) + 0.1, 0).astype(vel.dtype)
+        v = I.extrapolate_mac_from_weight(vel.copy(), w, distance=int(case[-1]))
+        return w if "marks" in case else v
     if case == "wall_frac":
         return I.set_wall_bcs_frac(flags, vel.copy(), phiObs)
     if case == "laplacian":

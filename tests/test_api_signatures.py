@@ -18,7 +18,7 @@ PLUGINS = {     # plugin -> reference file
     "setWallBcs": "plugin/extforces.cpp", "addGravity": "plugin/extforces.cpp", "addGravityNoScale": "plugin/extforces.cpp", "addBuoyancy": "plugin/extforces.cpp",
     "advectSemiLagrange": "plugin/advection.cpp", "cgSolveDiffusion": "conjugategrad.cpp", "cgSolveWE": "plugin/waves.cpp",
     "PD_fluid_guiding": "plugin/fluidguiding.cpp",
-    "extrapolateMACSimple": "fastmarch.cpp", "extrapolateLsSimple": "fastmarch.cpp", "extrapolateVec3Simple": "fastmarch.cpp",
+    "extrapolateMACSimple": "fastmarch.cpp", "extrapolateLsSimple": "fastmarch.cpp", "extrapolateVec3Simple": "fastmarch.cpp", "extrapolateMACFromWeight": "fastmarch.cpp",
     "getLaplacian": "plugin/flip.cpp", "getCurvature": "plugin/flip.cpp",
 }
 

@@ -65,6 +65,10 @@ class Emulation:
         assert self.lib.emu_extrapolate_mac_simple(*self._head(flags), self._p(flags), self._p(vel), C.c_int(distance), self._p(phiObs), C.c_int(int(intoObs))) == 0
         return vel
 
+    def extrapolate_mac_from_weight(self, vel, weight, distance=2):
+        assert self.lib.emu_extrapolate_mac_from_weight(*self._head(vel), self._p(vel), self._p(weight), C.c_int(distance)) == 0
+        return vel
+
     def extrapolate_ls_simple(self, phi, distance=4, inside=False):
         assert self.lib.emu_extrapolate_ls_simple(*self._head(phi), self._p(phi), C.c_int(distance), C.c_int(int(inside))) == 0
         return phi
