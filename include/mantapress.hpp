@@ -268,6 +268,7 @@ template <class G>          // G: Grid<Real> (incl. LevelsetGrid) or MACGrid -- 
 inline void advectSemiLagrange(const FlagGrid* flags, const MACGrid* vel, G* grid, int order = 1, Real strength = 1.0, int orderSpace = 1, bool openBounds = false,
 	int boundaryWidth = -1, int clampMode = 2, int orderTrace = 1)
 {
+	static_assert(!std::is_same<G, Grid<Vec3> >::value, "advectSemiLagrange: plain Grid<Vec3> advection is not built (only Grid<Real>, LevelsetGrid, MACGrid)");
 	(void)openBounds; (void)boundaryWidth;             // deprecated in the reference, no effect (advection.cpp:446)
 	if (order != 1 && order != 2) throw Error(MP_ERR_INVALID, "AdvectSemiLagrange: Only order 1 (regular SL) and 2 (MacCormack) supported");
 	mpCheck(mp_advect_semi_lagrange(flags->getParent()->ctx(), flags->dev(), vel->dev(), grid->dev(), order, strength, orderSpace, clampMode, orderTrace,
