@@ -49,7 +49,6 @@ namespace Manta {
 // --- link stubs for the OpenVDB entry points referenced by grid.cpp (the .uni / .raw / .npz readers and writers are the reference's own, fileio/iogrids.cpp) ---
 int writeObjectsVDB(const std::string&, std::vector<PbClass*>*, float, bool, int, bool) { return 0; }
 int readObjectsVDB (const std::string&, std::vector<PbClass*>*, float) { return 0; }
-Real LevelsetGrid::invalidTimeValue() { return -1000; }   // levelset.cpp:103 -> fastmarch.h:134
 void setWallBcs(const FlagGrid& flags, MACGrid& vel, const MACGrid* obvel, const MACGrid* fractions, const Grid<Real>* phiObs, int boundaryWidth);
 void cgSolveDiffusion(const FlagGrid& flags, GridBase& grid, Real alpha, Real cgMaxIterFac, Real cgAccuracy);
 void cgSolveWE(const FlagGrid& flags, Grid<Real>& ut, Grid<Real>& utm1, Grid<Real>& out, bool crankNic, Real cSqr, Real cgMaxIterFac, Real cgAccuracy);
@@ -87,9 +86,6 @@ static FluidSolver* mkSolver(int sx, int sy, int sz) {
 #define CATCH } catch (std::exception& e) { gLastError = e.what(); return 1; } return 0;
 
 template <class G> static int saveLoad(G& g, const char* name, int load) { return load ? g.load(name) : g.save(name); }
-struct LsTypedGrid : public Grid<Real> {      // the grid type a LevelsetGrid carries (levelset.cpp:91-101); its constructors live in levelset.cpp, which is not built here
-	LsTypedGrid(FluidSolver* s, Real* d) : Grid<Real>(s, d) { mType = (GridType)(TypeLevelset | TypeReal); }
-};
 
 extern "C" {
 
@@ -146,14 +142,12 @@ int ref_add_buoyancy(int sx, int sy, int sz, const int* flags, const Real* densi
 	delete s;
   CATCH }
 
-// LevelsetGrid adds no data members to Grid<Real> (levelset.h:25-60) and its constructors live in levelset.cpp, which drags in the mesh
-// code; the plugins below only use the Grid<Real> interface of their level-set arguments, so a Grid<Real> over the caller's array stands in.
 int ref_extrapolate_mac_simple(int sx, int sy, int sz, const int* flags, Real* vel, int distance, const Real* phiObs, int intoObs)
 { TRY
 	FluidSolver* s = mkSolver(sx, sy, sz);
 	{ FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
-	  Grid<Real>* P = phiObs ? new Grid<Real>(s, (Real*)phiObs) : 0;
-	  extrapolateMACSimple(F, V, distance, reinterpret_cast<LevelsetGrid*>(P), intoObs != 0);
+	  LevelsetGrid* P = phiObs ? new LevelsetGrid(s, (Real*)phiObs) : 0;
+	  extrapolateMACSimple(F, V, distance, P, intoObs != 0);
 	  delete P; }
 	delete s;
   CATCH }
@@ -182,7 +176,7 @@ int ref_extrapolate_vec3_simple(int sx, int sy, int sz, Real* vel, const Real* p
 int ref_update_from_levelset(int sx, int sy, int sz, int* flags, const Real* phi)
 { TRY
 	FluidSolver* s = mkSolver(sx, sy, sz);
-	{ FlagGrid F(s, flags); Grid<Real> P(s, (Real*)phi); F.updateFromLevelset(*reinterpret_cast<LevelsetGrid*>(&P)); }
+	{ FlagGrid F(s, flags); LevelsetGrid P(s, (Real*)phi); F.updateFromLevelset(P); }
 	delete s;
   CATCH }
 
@@ -216,7 +210,7 @@ int ref_grid_file(int sx, int sy, int sz, int kind, void* data, const char* name
 	if (kind == 0) { Grid<Real> G(s, (Real*)data); ok = saveLoad(G, name, load); }
 	else if (kind == 1) { MACGrid G(s, (Vec3*)data); ok = saveLoad(G, name, load); }
 	else if (kind == 2) { FlagGrid G(s, (int*)data); ok = saveLoad(G, name, load); }
-	else if (kind == 3) { LsTypedGrid G(s, (Real*)data); ok = saveLoad(G, name, load); }
+	else if (kind == 3) { LevelsetGrid G(s, (Real*)data); ok = saveLoad(G, name, load); }
 	else { Grid<Vec3> G(s, (Vec3*)data); ok = saveLoad(G, name, load); }
 	delete s;
 	if (!ok) { gLastError = std::string("Grid::") + (load ? "load" : "save") + " returned 0 for " + name; return 1; }
