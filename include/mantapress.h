@@ -235,6 +235,11 @@ int mp_extrapolate_ls_simple(mp_context* ctx, mp_grid* phi, int distance, int in
 int mp_extrapolate_vec3_simple(mp_context* ctx, mp_grid* vel, const mp_grid* phi, int distance, int inside);
 int mp_flags_update_from_levelset(mp_context* ctx, mp_grid* flags, const mp_grid* levelset);
 int mp_grid_set_bound(mp_context* ctx, mp_grid* g, double vx, double vy, double vz, int boundaryWidth);
+/* updateFractions / setObstacleFlags plugin/initplugins.cpp:437-440,:473-475: the producers of the `fractions` argument of solvePressure and
+ * setWallBcs (second-order obstacle boundaries from an obstacle level set).  updateFractions gives the result of the reference's serial loop
+ * (its OpenMP build races on the max-side walls for boundaryWidth > 0); setObstacleFlags needs boundaryWidth >= 1. Optional grids may be NULL. */
+int mp_update_fractions(mp_context* ctx, const mp_grid* flags, const mp_grid* phiObs, mp_grid* fractions, int boundaryWidth, double fracThreshold);
+int mp_set_obstacle_flags(mp_context* ctx, mp_grid* flags, const mp_grid* phiObs, const mp_grid* fractions, const mp_grid* phiOut, const mp_grid* phiIn, int boundaryWidth);
 /* getLaplacian / getCurvature plugin/flip.cpp:710-716 (LaplaceOp, CurvatureOp commonkernels.h:75-101): the `curv` input of the surface-tension
  * variant of solvePressure.  Cells of the outer layer keep their content (KERNEL(bnd=1)); result and input must be different grids. */
 int mp_get_laplacian(mp_context* ctx, mp_grid* laplacian, const mp_grid* grid);

@@ -9,6 +9,7 @@
 //     advectSemiLagrange                                              plugin/advection.cpp:442-461
 //     extrapolateMACSimple, extrapolateLsSimple, extrapolateVec3Simple fastmarch.cpp:337-375,:470-542
 //     getLaplacian, getCurvature                                      plugin/flip.cpp:710-716
+//     updateFractions, setObstacleFlags                               plugin/initplugins.cpp:437-440,:473-475
 //     cgSolveDiffusion, cgSolveWE                                     conjugategrad.cpp:350, plugin/waves.cpp:86
 // so that C++ callers of these plugins (e.g. plugin/fluidguiding.cpp:276-335) and tests written against the reference's headers compile
 // against this header unchanged.  Every grid owns a host array in the reference layout (grid.h:70) AND an mp_grid in HBM; two dirty
@@ -294,6 +295,15 @@ inline void extrapolateVec3Simple(Grid<Vec3>& vel, Grid<Real>& phi, int distance
 	vel.markDeviceWritten();
 }
 
+inline void updateFractions(const FlagGrid& flags, const Grid<Real>& phiObs, MACGrid& fractions, const int& boundaryWidth = 0, const Real fracThreshold = 0.01) {   // initplugins.cpp:437
+	mpCheck(mp_update_fractions(flags.getParent()->ctx(), flags.dev(), phiObs.dev(), fractions.dev(), boundaryWidth, fracThreshold));
+	fractions.markDeviceWritten();
+}
+inline void setObstacleFlags(FlagGrid& flags, const Grid<Real>& phiObs, const MACGrid* fractions = NULL, const Grid<Real>* phiOut = NULL, const Grid<Real>* phiIn = NULL,
+	int boundaryWidth = 1) {                                                                                                                                          // initplugins.cpp:473
+	mpCheck(mp_set_obstacle_flags(flags.getParent()->ctx(), flags.dev(), phiObs.dev(), detail::dv(fractions), detail::dv(phiOut), detail::dv(phiIn), boundaryWidth));
+	flags.markDeviceWritten();
+}
 inline void getLaplacian(Grid<Real>& laplacian, const Grid<Real>& grid) {            // plugin/flip.cpp:710-712
 	mpCheck(mp_get_laplacian(grid.getParent()->ctx(), laplacian.dev(), grid.dev()));
 	laplacian.markDeviceWritten();

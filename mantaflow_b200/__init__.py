@@ -15,6 +15,6 @@ from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, relea
                        solvePressureSystem)
 from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE
 from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, extrapolateLsSimple, extrapolateMACFromWeight, extrapolateMACSimple,
-                   extrapolateVec3Simple, getCurvature, getLaplacian, lastGuidingIterations, releaseBlurPrecomp, setWallBcs)
+                   extrapolateVec3Simple, getCurvature, getLaplacian, lastGuidingIterations, releaseBlurPrecomp, setObstacleFlags, setWallBcs, updateFractions)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

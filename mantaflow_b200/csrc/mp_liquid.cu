@@ -134,6 +134,40 @@ int mp_flags_update_from_levelset(mp_context* ctx, mp_grid* flags, const mp_grid
 	return ex.cells(d, op);
 }
 
+int mp_update_fractions(mp_context* ctx, const mp_grid* flags, const mp_grid* phiObs, mp_grid* fractions, int boundaryWidth, double fracThreshold)
+{
+	MP_TRY(checkLiquid("mp_update_fractions", ctx, flags));
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "updateFractions: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, phiObs, MP_GRID_REAL, "phiObs", false));
+	MP_TRY(mp_check_same(flags, fractions, MP_GRID_MAC, "fractions", false));
+	if (phiObs->prec != fractions->prec) MP_FAIL(MP_ERR_INVALID, "updateFractions: phiObs and fractions differ in precision");
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(flags);
+	if (fractions->prec == 4) { liquid::UpdateFractions<float> op = { (const int*)flags->d, (const float*)phiObs->d, (float*)fractions->d, boundaryWidth, (float)fracThreshold }; return ex.cells(d, op); }
+	liquid::UpdateFractions<double> op = { (const int*)flags->d, (const double*)phiObs->d, (double*)fractions->d, boundaryWidth, fracThreshold };
+	return ex.cells(d, op);
+}
+
+int mp_set_obstacle_flags(mp_context* ctx, mp_grid* flags, const mp_grid* phiObs, const mp_grid* fractions, const mp_grid* phiOut, const mp_grid* phiIn, int boundaryWidth)
+{
+	MP_TRY(checkLiquid("mp_set_obstacle_flags", ctx, flags));
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "setObstacleFlags: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, phiObs, MP_GRID_REAL, "phiObs", false));
+	MP_TRY(mp_check_same(flags, fractions, MP_GRID_MAC, "fractions", true));
+	MP_TRY(mp_check_same(flags, phiOut, MP_GRID_REAL, "phiOut", true));
+	MP_TRY(mp_check_same(flags, phiIn, MP_GRID_REAL, "phiIn", true));
+	const int prec = phiObs->prec;
+	if ((fractions && fractions->prec != prec) || (phiOut && phiOut->prec != prec) || (phiIn && phiIn->prec != prec)) MP_FAIL(MP_ERR_INVALID, "setObstacleFlags: grids differ in precision");
+	if (boundaryWidth < 1) MP_FAIL(MP_ERR_INVALID, "setObstacleFlags: boundaryWidth must be >= 1 (the kernel reads the +x / +y / +z neighbour of every cell it visits)");
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(flags);
+	if (prec == 4) { liquid::SetObstacleFlags<float> op = { (int*)flags->d, (const float*)phiObs->d, fractions ? (const float*)fractions->d : nullptr, phiOut ? (const float*)phiOut->d : nullptr,
+	                                                        phiIn ? (const float*)phiIn->d : nullptr, boundaryWidth }; return ex.cells(d, op); }
+	liquid::SetObstacleFlags<double> op = { (int*)flags->d, (const double*)phiObs->d, fractions ? (const double*)fractions->d : nullptr, phiOut ? (const double*)phiOut->d : nullptr,
+	                                        phiIn ? (const double*)phiIn->d : nullptr, boundaryWidth };
+	return ex.cells(d, op);
+}
+
 static int stencilOp(const char* who, mp_context* ctx, mp_grid* out, const mp_grid* grid, double h, bool curvature)
 {
 	MP_TRY(checkLiquid(who, ctx, out));

@@ -402,6 +402,67 @@ template <typename Real> struct WallBcsFrac {
 	}
 };
 
+// ---------------------------------------------------------------- updateFractions / setObstacleFlags
+// plugin/initplugins.cpp:437-440 (KnUpdateFractions :371-434, calcFraction :356-369) and :473-475 (KnUpdateFlagsObs :443-470): the producers of
+// the `fractions` argument of solvePressure / setWallBcs.  The reference's kernel also writes the +x / +y / +z NEIGHBOUR of a cell next to an
+// open / inflow / outflow wall; in the serial order of its loop such a write only survives when the neighbour lies on the outer layer (an
+// interior neighbour recomputes its own entry afterwards), so here every cell GATHERS: interior cells compute their own entry and the min-side
+// overrides, outer-layer cells take the max-side override of their inner neighbour.  The max-z test reads j, as the reference does (:423).
+template <typename Real> MP_HD Real calcFraction(Real phi1, Real phi2, Real fracThreshold) {
+	if (phi1 > 0. && phi2 > 0.) return 1.;
+	if (phi1 < 0. && phi2 < 0.) return 0.;
+	if (phi2 < phi1) { const Real t = phi1; phi1 = phi2; phi2 = t; }
+	const Real denom = phi1 - phi2;
+	if (denom > -1e-04) return 0.5;
+	Real frac = (Real)(1. - (double)(phi1 / denom));
+	if (frac < fracThreshold) frac = 0.;
+	return (Real)1 < frac ? (Real)1 : frac;           // std::min(Real(1), frac)
+}
+MP_HD bool openKind(int f) { return (f & TypeInflow) || (f & TypeOutflow) || (f & TypeOpen); }
+template <typename Real> struct UpdateFractions {
+	static const bool kSplit = false;
+	const int* flags; const Real* phiObs; Real* fractions; int w; Real fracThreshold;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt q) const {
+		Real fx = 0, fy = 0, fz = 0;
+		bool one = false;
+		if (interiorCell(d, i, j, k)) {
+			const Real ph = phiObs[q];
+			fx = calcFraction<Real>(ph, phiObs[q - d.X], fracThreshold);
+			fy = calcFraction<Real>(ph, phiObs[q - d.Y], fracThreshold);
+			if (d.is3D) fz = calcFraction<Real>(ph, phiObs[q - d.Z], fracThreshold);
+			if (!(ph < 0.)) {
+				if (i <= w + 1 && openKind(flags[q - d.X])) one = true;
+				if (j <= w + 1 && openKind(flags[q - d.Y])) one = true;
+				if (d.is3D && k <= w + 1 && openKind(flags[q - d.Z])) one = true;
+			}
+		} else if (openKind(flags[q])) {
+			// the inner neighbour p = q - X / Y / Z of an outer-layer cell, if it is an interior cell outside the obstacle and close enough to its max wall
+			if (i == d.sx - 1 && interiorCell(d, i - 1, j, k) && !(phiObs[q - d.X] < 0.) && i - 1 >= d.sx - w - 2) one = true;
+			if (j == d.sy - 1 && interiorCell(d, i, j - 1, k) && !(phiObs[q - d.Y] < 0.) && j - 1 >= d.sy - w - 2) one = true;
+			if (d.is3D && k == d.sz - 1 && interiorCell(d, i, j, k - 1) && !(phiObs[q - d.Z] < 0.) && j >= d.sz - w - 2) one = true;
+		}
+		if (one) { fx = 1; fy = 1; if (d.is3D) fz = 1; }
+		fractions[3 * q] = fx; fractions[3 * q + 1] = fy; fractions[3 * q + 2] = fz;
+	}
+};
+template <typename Real> struct SetObstacleFlags {       // KnUpdateFlagsObs, KERNEL(bnd = boundaryWidth >= 1)
+	static const bool kSplit = false;
+	int* flags; const Real* phiObs; const Real* fractions; const Real* phiOut; const Real* phiIn; int bw;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt p) const {
+		if (i < bw || i >= d.sx - bw || j < bw || j >= d.sy - bw || (d.is3D && (k < bw || k >= d.sz - bw))) return;
+		bool isObs = false;
+		if (fractions) {
+			Real f = 0;
+			f += fractions[3 * p]; f += fractions[3 * (p + d.X)];
+			f += fractions[3 * p + 1]; f += fractions[3 * (p + d.Y) + 1];
+			if (d.is3D) { f += fractions[3 * p + 2]; f += fractions[3 * (p + d.Z) + 2]; }
+			if (f == 0.) isObs = true;
+		} else if (phiObs[p] < 0.) isObs = true;
+		const bool isOutflow = phiOut && phiOut[p] < 0., isInflow = phiIn && phiIn[p] < 0.;
+		flags[p] = isObs ? TypeObstacle : (isInflow ? (TypeFluid | TypeInflow) : (isOutflow ? (TypeEmpty | TypeOutflow) : TypeEmpty));
+	}
+};
+
 // ---------------------------------------------------------------- getLaplacian / getCurvature (surface tension helpers of solvePressure's `curv` argument)
 // LaplaceOp commonkernels.h:75-80, CurvatureOp :83-101, wrapped by plugin/flip.cpp:710-716.  The reference's double literals promote every
 // product to double and every named Real narrows; the same evaluation here.  Cells of the outer layer are left alone (KERNEL(bnd=1)).

@@ -12,6 +12,7 @@ and the liquid neighbours (first slice) with which the level-s
     extrapolateMACSimple   fastmarch.cpp:337-375      extrapolateLsSimple :470-507      extrapolateVec3Simple :510-542
     extrapolateMACFromWeight :410-432
     getLaplacian, getCurvature   plugin/flip.cpp:710-716
+    updateFractions, setObstacleFlags   plugin/initplugins.cpp:437-440,:473-475
     (FlagGrid.updateFromLevelset and Grid.setBound are methods of the grid classes, grid.py)
 """
 import ctypes as C
@@ -89,6 +90,20 @@ def extrapolateVec3Simple(vel, phi, distance=4, inside=False):
     s = vel.parent
     check(s.lib.mp_extrapolate_vec3_simple(s._ctx, vel.dev(), phi.dev(), C.c_int(int(distance)), C.c_int(int(bool(inside)))))
     vel.markDeviceWritten()
+
+
+def updateFractions(flags, phiObs, fractions, boundaryWidth=0, fracThreshold=0.01):
+    """plugin/initplugins.cpp:437-440"""
+    s = flags.parent
+    check(s.lib.mp_update_fractions(s._ctx, flags.dev(), phiObs.dev(), fractions.dev(), C.c_int(int(boundaryWidth)), C.c_double(fracThreshold)))
+    fractions.markDeviceWritten()
+
+
+def setObstacleFlags(flags, phiObs, fractions=None, phiOut=None, phiIn=None, boundaryWidth=1):
+    """plugin/initplugins.cpp:473-475"""
+    s = flags.parent
+    check(s.lib.mp_set_obstacle_flags(s._ctx, flags.dev(), phiObs.dev(), _d(fractions), _d(phiOut), _d(phiIn), C.c_int(int(boundaryWidth))))
+    flags.markDeviceWritten()
 
 
 def getLaplacian(laplacian, grid):

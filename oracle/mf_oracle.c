@@ -1886,3 +1886,69 @@ int mfo_extrapolate_mac_from_weight(int sx, int sy, int sz, Real* vel, Real* wei
 	}
 	return 0;
 }
+
+/* updateFractions plugin/initplugins.cpp:437-440 (KnUpdateFractions :371-434, calcFraction :356-369) and setObstacleFlags :473-475
+ * (KnUpdateFlagsObs :443-470): the producers of the `fractions` argument of solvePressure / setWallBcs (second-order obstacle boundaries).
+ * KnUpdateFractions writes neighbour cells on the max sides; this is the SERIAL order of the loop (with OpenMP the reference races there
+ * for boundaryWidth > 0).  The max-z test reads j, as the reference does (:423). */
+static inline Real calc_fraction(Real phi1, Real phi2, Real fracThreshold)
+{
+	if (phi1 > 0. && phi2 > 0.) return 1.;
+	if (phi1 < 0. && phi2 < 0.) return 0.;
+	if (phi2 < phi1) { Real t = phi1; phi1 = phi2; phi2 = t; }
+	const Real denom = phi1 - phi2;
+	if (denom > -1e-04) return 0.5;
+	Real frac = (Real)(1. - (double)(phi1 / denom));
+	if (frac < fracThreshold) frac = 0.;
+	return rmin((Real)1, frac);
+}
+static inline int is_open_kind(int f) { return (f & TypeInflow) || (f & TypeOutflow) || (f & TypeOpen); }
+int mfo_update_fractions(int sx, int sy, int sz, const int* flags, const Real* phiObs, Real* fractions, int boundaryWidth, double fracThreshold_)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	const Real thr = (Real)fracThreshold_;
+	const int w = boundaryWidth;
+	for (IndexInt q = 0; q < 3 * n; q++) fractions[q] = 0;
+	FOR_BND1 {
+		const IndexInt p = IDX(i, j, k);
+		Real* f = fractions + 3 * p;
+		f[0] = calc_fraction(phiObs[p], phiObs[p - X], thr);
+		f[1] = calc_fraction(phiObs[p], phiObs[p - Y], thr);
+		if (IS3D) f[2] = calc_fraction(phiObs[p], phiObs[p - Z], thr);
+		if (phiObs[p] < 0.) continue;
+#define SET1(cell) { Real* g_ = fractions + 3 * (cell); g_[0] = g_[1] = 1.; if (IS3D) g_[2] = 1.; }
+		if (i <= w + 1 && is_open_kind(flags[p - X])) SET1(p)
+		if (i >= sx - w - 2 && is_open_kind(flags[p + X])) SET1(p + X)
+		if (j <= w + 1 && is_open_kind(flags[p - Y])) SET1(p)
+		if (j >= sy - w - 2 && is_open_kind(flags[p + Y])) SET1(p + Y)
+		if (IS3D) {
+			if (k <= w + 1 && is_open_kind(flags[p - Z])) SET1(p)
+			if (j >= sz - w - 2 && is_open_kind(flags[p + Z])) SET1(p + Z)
+		}
+#undef SET1
+	}
+	return 0;
+}
+int mfo_set_obstacle_flags(int sx, int sy, int sz, int* flags, const Real* phiObs, const Real* fractions, const Real* phiOut, const Real* phiIn, int bw)
+{
+	STRIDES
+	const int k0 = IS3D ? bw : 0, k1 = IS3D ? sz - bw : 1;
+	for (int k = k0; k < k1; k++) for (int j = bw; j < sy - bw; j++) for (int i = bw; i < sx - bw; i++) {
+		const IndexInt p = IDX(i, j, k);
+		int isObs = 0;
+		if (fractions) {
+			Real f = 0.;
+			f += fractions[3 * p]; f += fractions[3 * (p + X)];
+			f += fractions[3 * p + 1]; f += fractions[3 * (p + Y) + 1];
+			if (IS3D) { f += fractions[3 * p + 2]; f += fractions[3 * (p + Z) + 2]; }
+			if (f == 0.) isObs = 1;
+		} else if (phiObs[p] < 0.) isObs = 1;
+		const int isOutflow = phiOut && phiOut[p] < 0., isInflow = phiIn && phiIn[p] < 0.;
+		if (isObs) flags[p] = TypeObstacle;
+		else if (isInflow) flags[p] = TypeFluid | TypeInflow;
+		else if (isOutflow) flags[p] = TypeEmpty | TypeOutflow;
+		else flags[p] = TypeEmpty;
+	}
+	return 0;
+}

@@ -216,6 +216,19 @@ class Oracle:
         self._chk(self._f("extrapolate_mac_simple")(*self.dims(flags), _p(flags), _p(vel), C.c_int(distance), _p(self._r(phiObs)), C.c_int(int(intoObs))))
         return vel
 
+    def update_fractions(self, flags, phiObs, boundaryWidth=0, fracThreshold=0.01):
+        """plugin/initplugins.cpp:437-440; returns the fractions grid [Z,Y,X,3]"""
+        fr = np.zeros(flags.shape + (3,), self.real)
+        self._chk(self._f("update_fractions")(*self.dims(flags), _p(flags), _p(self._r(phiObs)), _p(fr), C.c_int(boundaryWidth), C.c_double(fracThreshold)))
+        return fr
+
+    def set_obstacle_flags(self, flags, phiObs, fractions=None, phiOut=None, phiIn=None, boundaryWidth=1):
+        """plugin/initplugins.cpp:473-475; flags are updated in place and returned"""
+        assert flags.dtype == np.int32 and flags.flags.c_contiguous
+        self._chk(self._f("set_obstacle_flags")(*self.dims(flags), _p(flags), _p(self._r(phiObs)), _p(self._r(fractions)), _p(self._r(phiOut)), _p(self._r(phiIn)),
+                                                C.c_int(boundaryWidth)))
+        return flags
+
     def extrapolate_mac_from_weight(self, vel, weight, distance=2):
         """fastmarch.cpp:410-432; vel and weight are both updated in place (the weight grid ends up holding the marks), vel is returned"""
         assert vel.dtype == self.real and weight.dtype == self.real and vel.flags.c_contiguous and weight.flags.c_contiguous

@@ -19,6 +19,7 @@
 //   PD_fluid_guiding        plugin/fluidguiding.cpp:294-353
 //   extrapolateMACSimple, extrapolateLsSimple, extrapolateVec3Simple   fastmarch.cpp:337-375, :470-542
 //   FlagGrid::updateFromLevelset, Grid<T>::setBound                    grid.cpp:844-854, :591-593
+//   updateFractions, setObstacleFlags                                  plugin/initplugins.cpp:437-440,:473-475
 //   LaplaceOp, CurvatureOp (getLaplacian / getCurvature)               commonkernels.h:75-101, plugin/flip.cpp:710-716
 //   Grid<T>::save / load (.uni, .raw, .npz)                            grid.cpp:113-156, fileio/iogrids.cpp
 // Nothing of the reference is copied: its sources are compiled where they lie.
@@ -34,6 +35,7 @@
 #include <cstdio>
 #include <cmath>
 #include <algorithm>
+#include <omp.h>
 
 #define private public      // dump GridMg internals (levels, types, operators) for parity tests
 #include "multigrid.h"
@@ -59,6 +61,8 @@ void releaseBlurPrecomp();
 void extrapolateMACSimple(FlagGrid& flags, MACGrid& vel, int distance, LevelsetGrid* phiObs, bool intoObs);
 void extrapolateLsSimple(Grid<Real>& phi, int distance, bool inside);
 void extrapolateMACFromWeight(MACGrid& vel, Grid<Vec3>& weight, int distance);
+void updateFractions(const FlagGrid& flags, const Grid<Real>& phiObs, MACGrid& fractions, const int& boundaryWidth, const Real fracThreshold);
+void setObstacleFlags(FlagGrid& flags, const Grid<Real>& phiObs, const MACGrid* fractions, const Grid<Real>* phiOut, const Grid<Real>* phiIn, int boundaryWidth);
 void extrapolateVec3Simple(Grid<Vec3>& vel, Grid<Real>& phi, int distance, bool inside);
 void addGravity(const FlagGrid& flags, MACGrid& vel, Vec3 gravity, const Grid<Real>* exclude, bool scale);
 void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGrid& vel, Vec3 gravity, Real coefficient, bool scale);
@@ -149,6 +153,28 @@ int ref_extrapolate_mac_simple(int sx, int sy, int sz, const int* flags, Real* v
 	  LevelsetGrid* P = phiObs ? new LevelsetGrid(s, (Real*)phiObs) : 0;
 	  extrapolateMACSimple(F, V, distance, P, intoObs != 0);
 	  delete P; }
+	delete s;
+  CATCH }
+
+// updateFractions / setObstacleFlags plugin/initplugins.cpp:437-440,:473-475.  The kernel of updateFractions writes neighbour cells on the
+// max sides; single-threaded here so that the result is the serial loop's also for boundaryWidth > 0.
+int ref_update_fractions(int sx, int sy, int sz, const int* flags, const Real* phiObs, Real* fractions, int boundaryWidth, double fracThreshold)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	const int nt = omp_get_max_threads(); omp_set_num_threads(1);
+	try { FlagGrid F(s, (int*)flags); Grid<Real> P(s, (Real*)phiObs); MACGrid Fr(s, (Vec3*)fractions); updateFractions(F, P, Fr, boundaryWidth, (Real)fracThreshold); }
+	catch (...) { omp_set_num_threads(nt); delete s; throw; }
+	omp_set_num_threads(nt);
+	delete s;
+  CATCH }
+int ref_set_obstacle_flags(int sx, int sy, int sz, int* flags, const Real* phiObs, const Real* fractions, const Real* phiOut, const Real* phiIn, int boundaryWidth)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, flags); Grid<Real> P(s, (Real*)phiObs);
+	  MACGrid* Fr = fractions ? new MACGrid(s, (Vec3*)fractions) : 0;
+	  Grid<Real>* Po = phiOut ? new Grid<Real>(s, (Real*)phiOut) : 0; Grid<Real>* Pi = phiIn ? new Grid<Real>(s, (Real*)phiIn) : 0;
+	  setObstacleFlags(F, P, Fr, Po, Pi, boundaryWidth);
+	  delete Fr; delete Po; delete Pi; }
 	delete s;
   CATCH }
 

@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
 		// take the address of every plugin so that a missing C-ABI symbol is a link error of this test
 		void* p[] = { (void*)&computePressureRhs, (void*)&solvePressureSystem, (void*)&correctVelocity, (void*)&solvePressure, (void*)&releaseMG, (void*)&setWallBcs,
 		              (void*)&addGravity, (void*)&addGravityNoScale, (void*)&addBuoyancy, (void*)&advectSemiLagrange<Grid<Real> >, (void*)&advectSemiLagrange<MACGrid>,
-		              (void*)&extrapolateMACSimple, (void*)&extrapolateLsSimple, (void*)&extrapolateVec3Simple, (void*)&extrapolateMACFromWeight, (void*)&getLaplacian, (void*)&getCurvature, (void*)&cgSolveDiffusion<Grid<Real> >, (void*)&cgSolveWE };
+		              (void*)&extrapolateMACSimple, (void*)&extrapolateLsSimple, (void*)&extrapolateVec3Simple, (void*)&extrapolateMACFromWeight, (void*)&updateFractions, (void*)&setObstacleFlags, (void*)&getLaplacian, (void*)&getCurvature, (void*)&cgSolveDiffusion<Grid<Real> >, (void*)&cgSolveWE };
 		std::printf("OK: %d plugins link\n", (int)(sizeof p / sizeof p[0]));
 		return 0;
 	}

@@ -194,6 +194,20 @@ class CudaImpl:
         vel[...] = V.numpy()
         return vel
 
+    def update_fractions(self, flags, phiObs, boundaryWidth=0, fracThreshold=0.01):
+        s = self._solver(flags)
+        Fr = mf.MACGrid(s, np.full(flags.shape + (3,), 7.0, self.real))         # every entry is written
+        mf.updateFractions(mf.FlagGrid(s, flags), mf.RealGrid(s, phiObs), Fr, boundaryWidth=boundaryWidth, fracThreshold=fracThreshold)
+        return Fr.numpy().copy()
+
+    def set_obstacle_flags(self, flags, phiObs, fractions=None, phiOut=None, phiIn=None, boundaryWidth=1):
+        s = self._solver(flags)
+        F = mf.FlagGrid(s, flags)
+        mf.setObstacleFlags(F, mf.RealGrid(s, phiObs), fractions=self._g(s, mf.MACGrid, fractions), phiOut=self._g(s, mf.RealGrid, phiOut),
+                            phiIn=self._g(s, mf.RealGrid, phiIn), boundaryWidth=boundaryWidth)
+        flags[...] = F.numpy()
+        return flags
+
     def get_laplacian(self, grid):
         s = self._solver(grid)
         L = mf.RealGrid(s)

@@ -98,6 +98,16 @@ int emu_set_wall_bcs_frac(int prec, int order, int sx, int sy, int sz, const int
 	memcpy(vel, tgt, bytes); free(tgt);
 	return rc;
 }
+int emu_update_fractions(int prec, int order, int sx, int sy, int sz, const int* flags, const void* phiObs, void* fractions, int w, double thr) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	if (prec == 4) { liquid::UpdateFractions<float> op = { flags, (const float*)phiObs, (float*)fractions, w, (float)thr }; return ex.cells(d, op); }
+	liquid::UpdateFractions<double> op = { flags, (const double*)phiObs, (double*)fractions, w, thr }; return ex.cells(d, op);
+}
+int emu_set_obstacle_flags(int prec, int order, int sx, int sy, int sz, int* flags, const void* phiObs, const void* fractions, const void* phiOut, const void* phiIn, int bw) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	if (prec == 4) { liquid::SetObstacleFlags<float> op = { flags, (const float*)phiObs, (const float*)fractions, (const float*)phiOut, (const float*)phiIn, bw }; return ex.cells(d, op); }
+	liquid::SetObstacleFlags<double> op = { flags, (const double*)phiObs, (const double*)fractions, (const double*)phiOut, (const double*)phiIn, bw }; return ex.cells(d, op);
+}
 int emu_stencil(int prec, int order, int sx, int sy, int sz, void* out, const void* grid, double h, int curvature) {
 	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
 	if (prec == 4) {

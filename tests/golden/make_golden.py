@@ -11,7 +11,7 @@ Fixtures
                                  correctVelocity, the solvePressure plugin with PcMIC / PcMGDynamic)
   step_<scene>_f{32,64}.npz    : setWallBcs (with obvel), addGravity, addBuoyancy, advectSemiLagrange (Real / MAC, order 1 / 2, both clamp
                                  modes, outflow cells) on seeded random boxes; plume{3d,2d}_f32.npz: six steps of the simpleplume main loop;
-                                 step_liq*: the extrapolation plugins, updateFromLevelset, setBound; step_fs*: six steps of the free-surface loop
+                                 step_liq*: the extrapolation plugins, updateFromLevelset, setBound; step_fs*: six steps of the free-surface loop; step_sob*: the scenario of test_1040_secOrderBnd.py
   psolve52_f32.npz             : the scenario of tools/tests/test_0100_psolve.py and test_0110_mgsolve.py (52^3 closed box,
                                  box velocity source, solves with PcMIC / PcMGDynamic / PcMGStatic), float build
 """
@@ -182,7 +182,7 @@ def step_fixtures():
 
 def liquid_fixtures():
     """step_liq*_f{32,64}.npz: the reference's extrapolateMACSimple / extrapolateLsSimple / extrapolateVec3Simple, FlagGrid::updateFromLevelset and
-    Grid::setBound on the seeded scenes of tests/helpers.py; step_fs*: six steps of the free-surface loop of scenes/freesurface.py:54-84."""
+    Grid::setBound on the seeded scenes of tests/helpers.py; step_fs*: six steps of the free-surface loop; step_sob*: the scenario of test_1040_secOrderBnd.py of scenes/freesurface.py:54-84."""
     sys.path.insert(0, os.path.dirname(HERE))
     import helpers
     for prec in (4, 8):
@@ -195,6 +195,11 @@ def liquid_fixtures():
             path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
             np.savez_compressed(path, **fx)
             print("%-34s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+        for name in helpers.SECORDER_SCENES:      # the scenario of tools/tests/test_1040_secOrderBnd.py (fill fractions, second-order wall conditions)
+            flags, fractions, dens, vel, p, its = helpers.run_sec_order_bnd(R, name, prec)
+            path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, flags=flags, fractions=fractions, density=dens, vel=vel, pressure=p, iterations=np.array(its))
+            print("%-34s %7.1f KiB  its %s  fluid cells %d" % (os.path.basename(path), os.path.getsize(path) / 1024, its, int((flags & 1).sum())))
         for name in helpers.FREESURFACE_SCENES:   # six steps of the level-set free-surface loop (scenes/freesurface.py:54-84)
             flags, phi, vel, p, its = helpers.run_freesurface_steps(R, name, prec, steps=6)
             path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))

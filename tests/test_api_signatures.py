@@ -20,6 +20,7 @@ PLUGINS = {     # plugin -> reference file
     "PD_fluid_guiding": "plugin/fluidguiding.cpp",
     "extrapolateMACSimple": "fastmarch.cpp", "extrapolateLsSimple": "fastmarch.cpp", "extrapolateVec3Simple": "fastmarch.cpp", "extrapolateMACFromWeight": "fastmarch.cpp",
     "getLaplacian": "plugin/flip.cpp", "getCurvature": "plugin/flip.cpp",
+    "updateFractions": "plugin/initplugins.cpp", "setObstacleFlags": "plugin/initplugins.cpp",
 }
 
 

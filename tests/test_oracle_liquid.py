@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import (FREESURFACE_SCENES, LIQUID_CASES, LIQUID_SCENES, check_freesurface_against_golden, check_liquid_against_golden, liquid_scene,
+from helpers import (SECORDER_SCENES, check_sec_order_bnd_against_golden, FREESURFACE_SCENES, LIQUID_CASES, LIQUID_SCENES, check_freesurface_against_golden, check_liquid_against_golden, liquid_scene,
                      run_liquid_case)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -33,6 +33,15 @@ def test_port_reproduces_freesurface_steps(name, prec, port32, port64):
     agree up to the reduction order"""
     tol = {("fs3d", 4): 0.0, ("fs2d", 4): 1e-3, ("fs3d", 8): 1e-11, ("fs2d", 8): 1e-10}[(name, prec)]
     check_freesurface_against_golden(port32 if prec == 4 else port64, name, prec, tol)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(SECORDER_SCENES))
+def test_port_reproduces_second_order_boundary_scenario(name, prec, port32, port64):
+    """tools/tests/test_1040_secOrderBnd.py: updateFractions, setObstacleFlags, setWallBcs(fractions, phiObs), extrapolateMACSimple and the
+    projection with fractions; float 3-D (PcMIC) bit-identical, the rest up to the reduction order"""
+    tol = {("sob3d", 4): 0.0, ("sob2d", 4): 1e-4, ("sob3d", 8): 1e-10, ("sob2d", 8): 1e-10}[(name, prec)]
+    check_sec_order_bnd_against_golden(port32 if prec == 4 else port64, name, prec, tol)
 
 
 @pytest.mark.parametrize("prec", [4, 8])
@@ -84,6 +93,15 @@ class Emulation:
     def set_wall_bcs_frac(self, flags, vel, phiObs):
         assert self.lib.emu_set_wall_bcs_frac(*self._head(flags), self._p(flags), self._p(vel), self._p(phiObs)) == 0
         return vel
+
+    def update_fractions(self, flags, phiObs, boundaryWidth=0, fracThreshold=0.01):
+        fr = np.full(flags.shape + (3,), 7.0, self.real)       # every entry is written
+        assert self.lib.emu_update_fractions(*self._head(flags), self._p(flags), self._p(phiObs), self._p(fr), C.c_int(boundaryWidth), C.c_double(fracThreshold)) == 0
+        return fr
+
+    def set_obstacle_flags(self, flags, phiObs, fractions=None, phiOut=None, phiIn=None, boundaryWidth=1):
+        assert self.lib.emu_set_obstacle_flags(*self._head(flags), self._p(flags), self._p(phiObs), self._p(fractions), self._p(phiOut), self._p(phiIn), C.c_int(boundaryWidth)) == 0
+        return flags
 
     def get_laplacian(self, grid):
         out = np.zeros_like(grid)
