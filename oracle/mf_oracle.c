@@ -1952,3 +1952,221 @@ int mfo_set_obstacle_flags(int sx, int sy, int sz, int* flags, const Real* phiOb
 	}
 	return 0;
 }
+
+/* =============================================================================================
+ * FLIP particle <-> grid plugins (mapPartsToMAC, gridParticleIndex + unionParticleLevelset are 8.7 % + 13.5 % of a
+ * benchmark_dam step; markFluidCells, mapMACToParts, flipVelocityUpdate sit beside them in the loop, scenes/benchmark_dam.py:100-125).
+ * Restated here ahead of the device versions ("the oracle first").  Particles are plain arrays: pos [N][3], pflag [N]
+ * (BasicParticleData particle.h:182-191, active = !(flag & PDELETE)), optional ptype [N], velocities [N][3].                        */
+enum { PDELETE = 1 << 10 };                                  /* particle.h:41 */
+#define P_SKIP(idx) ((pflag[idx] & PDELETE) || (ptype && (ptype[idx] & exclude)))
+static inline int in_bounds0(int sx, int sy, int sz, int x, int y, int z)     /* GridBase::isInBounds(p, 0) grid.h */
+{ return x >= 0 && y >= 0 && x < sx && y < sy && (sz > 1 ? (z >= 0 && z < sz) : z == 0); }
+
+/* markFluidCells plugin/flip.cpp:158-177 (knClearFluidFlags :137-141, knSetNbObstacle :142-157) */
+int mfo_mark_fluid_cells(int sx, int sy, int sz, int* flags, long long np, const Real* pos, const int* pflag, const Real* phiObs, const int* ptype, int exclude)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	for (IndexInt q = 0; q < n; q++) if (flags[q] & TypeFluid) flags[q] = (flags[q] | TypeEmpty) & ~TypeFluid;
+	for (long long idx = 0; idx < np; idx++) {
+		if (P_SKIP(idx)) continue;
+		const int x = (int)pos[3 * idx], y = (int)pos[3 * idx + 1], z = (int)pos[3 * idx + 2];
+		if (!in_bounds0(sx, sy, sz, x, y, z)) continue;
+		const IndexInt p = IDX(x, y, z);
+		if (flags[p] & TypeEmpty) flags[p] = (flags[p] | TypeFluid) & ~TypeEmpty;
+	}
+	if (phiObs) {
+		int* tmp = (int*)malloc(sizeof(int) * (size_t)n);
+		memcpy(tmp, flags, sizeof(int) * (size_t)n);
+		FOR_BND1 {
+			const IndexInt p = IDX(i, j, k);
+			if (phiObs[p] > 0.) continue;
+			if (!(flags[p] & TypeEmpty)) continue;
+			int set = 0;
+			if ((flags[p - X] & TypeFluid) && (phiObs[p + X] <= 0.)) set = 1;
+			if ((flags[p + X] & TypeFluid) && (phiObs[p - X] <= 0.)) set = 1;
+			if ((flags[p - Y] & TypeFluid) && (phiObs[p + Y] <= 0.)) set = 1;
+			if ((flags[p + Y] & TypeFluid) && (phiObs[p - Y] <= 0.)) set = 1;
+			if (IS3D) {
+				if ((flags[p - Z] & TypeFluid) && (phiObs[p + Z] <= 0.)) set = 1;
+				if ((flags[p + Z] & TypeFluid) && (phiObs[p - Z] <= 0.)) set = 1;
+			}
+			if (set) tmp[p] = (flags[p] | TypeFluid) & ~TypeEmpty;
+		}
+		memcpy(flags, tmp, sizeof(int) * (size_t)n);
+		free(tmp);
+	}
+	return 0;
+}
+
+/* gridParticleIndex plugin/flip.cpp:260-306: index[cell] = first slot of the cell in indexSys, indexSys[slot] = particle (cells in grid
+ * order, particles of a cell in ascending order); returns the number of indexed particles in *count */
+int mfo_grid_particle_index(int sx, int sy, int sz, long long np, const Real* pos, const int* pflag, int* index, int* indexSys, long long* count)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	int* counter = (int*)calloc((size_t)n, sizeof(int));
+	memset(index, 0, sizeof(int) * (size_t)n);
+	for (long long idx = 0; idx < np; idx++) {
+		if (pflag[idx] & PDELETE) continue;
+		const int x = (int)pos[3 * idx], y = (int)pos[3 * idx + 1], z = (int)pos[3 * idx + 2];
+		if (!in_bounds0(sx, sy, sz, x, y, z)) continue;
+		index[IDX(x, y, z)]++;
+	}
+	IndexInt run = 0;
+	for (IndexInt q = 0; q < n; q++) { const int num = index[q]; index[q] = (int)run; run += num; }
+	for (long long idx = 0; idx < np; idx++) {
+		if (pflag[idx] & PDELETE) continue;
+		const int x = (int)pos[3 * idx], y = (int)pos[3 * idx + 1], z = (int)pos[3 * idx + 2];
+		if (!in_bounds0(sx, sy, sz, x, y, z)) continue;
+		const IndexInt p = IDX(x, y, z);
+		indexSys[index[p] + counter[p]] = (int)idx;
+		counter[p]++;
+	}
+	free(counter);
+	*count = run;
+	return 0;
+}
+
+/* unionParticleLevelset plugin/flip.cpp:340-350 (ComputeUnionLevelsetPindex :308-338, calculateRadiusFactor :186-188), then phi.setBound(0.5, 0) */
+int mfo_union_particle_levelset(int sx, int sy, int sz, long long np, const Real* pos, const int* index, const int* indexSys, long long count,
+                                Real* phi, double radiusFactor_, const int* ptype, int exclude)
+{
+	STRIDES
+	(void)np;
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	const Real radiusFactor = (Real)radiusFactor_;
+	const Real radius = (Real)(0.5 * (double)(Real)((IS3D ? sqrt(3.) : sqrt(2.)) * ((double)radiusFactor + .01)));
+	const int r = (int)radius + 1, rZ = IS3D ? r : 0;
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const Real gx = (Real)i + (Real)0.5, gy = (Real)j + (Real)0.5, gz = (Real)k + (Real)0.5;
+		Real phiv = (Real)((double)radius * 1.0);
+		for (int zj = k - rZ; zj <= k + rZ; zj++) for (int yj = j - r; yj <= j + r; yj++) for (int xj = i - r; xj <= i + r; xj++) {
+			if (!in_bounds0(sx, sy, sz, xj, yj, zj)) continue;
+			const IndexInt c = IDX(xj, yj, zj);
+			const IndexInt pStart = index[c], pEnd = (c + 1 < n) ? index[c + 1] : count;
+			for (IndexInt p = pStart; p < pEnd; p++) {
+				const int psrc = indexSys[p];
+				if (ptype && (ptype[psrc] & exclude)) continue;
+				const Real dx = gx - pos[3 * psrc], dy = gy - pos[3 * psrc + 1], dz = gz - pos[3 * psrc + 2];
+				const Real l = dx * dx + dy * dy + dz * dz;
+				const Real nrm = l <= (Real)(MF_REAL_IS_DOUBLE ? 1e-10 * 1e-10 : 1e-6f * 1e-6f) ? (Real)0 : ((double)fabs((double)l - 1.) < (double)(Real)(MF_REAL_IS_DOUBLE ? 1e-10 * 1e-10 : 1e-6f * 1e-6f) ? (Real)1 : R_SQRT(l));
+				const Real v = (Real)fabs((double)nrm) - radius;
+				phiv = rmin(phiv, v);
+			}
+		}
+		phi[IDX(i, j, k)] = phiv;
+	}
+	return mfo_set_bound(sx, sy, sz, phi, 1, 0.5, 0);
+}
+
+/* BUILD_INDEX / BUILD_INDEX_SHIFT util/interpol.h:50-66,:112-125 */
+typedef struct { int xi, yi, zi, sxi, syi, szi; Real s0, s1, t0, t1, f0, f1, ss0, ss1, st0, st1, sf0, sf1; } MacIdx;
+static inline MacIdx build_index_shift(int sx, int sy, int sz, const Real* pos)
+{
+	MacIdx m;
+	const Real px = pos[0] - 0.5f, py = pos[1] - 0.5f, pz = pos[2] - 0.5f;
+	m.xi = (int)px; m.yi = (int)py; m.zi = (int)pz;
+	m.s1 = px - (Real)m.xi; m.s0 = (Real)(1. - m.s1); m.t1 = py - (Real)m.yi; m.t0 = (Real)(1. - m.t1); m.f1 = pz - (Real)m.zi; m.f0 = (Real)(1. - m.f1);
+	if (px < 0.) { m.xi = 0; m.s0 = 1.0; m.s1 = 0.0; }
+	if (py < 0.) { m.yi = 0; m.t0 = 1.0; m.t1 = 0.0; }
+	if (pz < 0.) { m.zi = 0; m.f0 = 1.0; m.f1 = 0.0; }
+	if (m.xi >= sx - 1) { m.xi = sx - 2; m.s0 = 0.0; m.s1 = 1.0; }
+	if (m.yi >= sy - 1) { m.yi = sy - 2; m.t0 = 0.0; m.t1 = 1.0; }
+	if (sz > 1) { if (m.zi >= sz - 1) { m.zi = sz - 2; m.f0 = 0.0; m.f1 = 1.0; } }
+	m.sxi = (int)pos[0]; m.syi = (int)pos[1]; m.szi = (int)pos[2];
+	m.ss1 = pos[0] - (Real)m.sxi; m.ss0 = (Real)(1. - m.ss1); m.st1 = pos[1] - (Real)m.syi; m.st0 = (Real)(1. - m.st1); m.sf1 = pos[2] - (Real)m.szi; m.sf0 = (Real)(1. - m.sf1);
+	if (pos[0] < 0) { m.sxi = 0; m.ss0 = 1.0; m.ss1 = 0.0; }
+	if (pos[1] < 0) { m.syi = 0; m.st0 = 1.0; m.st1 = 0.0; }
+	if (pos[2] < 0) { m.szi = 0; m.sf0 = 1.0; m.sf1 = 0.0; }
+	if (m.sxi >= sx - 1) { m.sxi = sx - 2; m.ss0 = 0.0; m.ss1 = 1.0; }
+	if (m.syi >= sy - 1) { m.syi = sy - 2; m.st0 = 0.0; m.st1 = 1.0; }
+	if (sz > 1) { if (m.szi >= sz - 1) { m.szi = sz - 2; m.sf0 = 0.0; m.sf1 = 1.0; } }
+	return m;
+}
+/* interpolMAC util/interpol.h:127-157 */
+static void interpol_mac(int sx, int sy, int sz, const Real* data, const Real* pos, Real out[3])
+{
+	const MacIdx m = build_index_shift(sx, sy, sz, pos);
+	const IndexInt X = 1, Y = sx, Z = (sz > 1) ? (IndexInt)sx * sy : 0;
+#define RF(o, c) ref[3 * (o) + (c)]
+	{ const Real* ref = data + 3 * (((IndexInt)m.zi * sy + m.yi) * sx + m.sxi);
+	  out[0] = m.f0 * ((RF(0, 0) * m.t0 + RF(Y, 0) * m.t1) * m.ss0 + (RF(X, 0) * m.t0 + RF(X + Y, 0) * m.t1) * m.ss1) +
+	           m.f1 * ((RF(Z, 0) * m.t0 + RF(Z + Y, 0) * m.t1) * m.ss0 + (RF(X + Z, 0) * m.t0 + RF(X + Y + Z, 0) * m.t1) * m.ss1); }
+	{ const Real* ref = data + 3 * (((IndexInt)m.zi * sy + m.syi) * sx + m.xi);
+	  out[1] = m.f0 * ((RF(0, 1) * m.st0 + RF(Y, 1) * m.st1) * m.s0 + (RF(X, 1) * m.st0 + RF(X + Y, 1) * m.st1) * m.s1) +
+	           m.f1 * ((RF(Z, 1) * m.st0 + RF(Z + Y, 1) * m.st1) * m.s0 + (RF(X + Z, 1) * m.st0 + RF(X + Y + Z, 1) * m.st1) * m.s1); }
+	{ const Real* ref = data + 3 * (((IndexInt)m.szi * sy + m.yi) * sx + m.xi);
+	  out[2] = m.sf0 * ((RF(0, 2) * m.t0 + RF(Y, 2) * m.t1) * m.s0 + (RF(X, 2) * m.t0 + RF(X + Y, 2) * m.t1) * m.s1) +
+	           m.sf1 * ((RF(Z, 2) * m.t0 + RF(Z + Y, 2) * m.t1) * m.s0 + (RF(X + Z, 2) * m.t0 + RF(X + Y + Z, 2) * m.t1) * m.s1); }
+#undef RF
+}
+/* one component of setInterpolMAC util/interpol.h:159-203: weights and the order of the sixteen updates as in the reference */
+static void scatter8(Real* ref, Real* sum, int c, IndexInt X, IndexInt Y, IndexInt Z, Real a0, Real a1, Real b0, Real b1, Real c0, Real c1, Real v, int zFirst)
+{	/* a: weights along x, b: along y, c: along z */
+	const Real s0f0 = a0 * c0, s1f0 = a1 * c0, s0f1 = a0 * c1, s1f1 = a1 * c1;
+	const Real w0 = b0 * s0f0, wx = b0 * s1f0, wy = b1 * s0f0, wxy = b1 * s1f0, wz = b0 * s0f1, wxz = b0 * s1f1, wyz = b1 * s0f1, wxyz = b1 * s1f1;
+#define S_(o) sum[3 * (o) + c]
+#define R_(o) ref[3 * (o) + c]
+	if (zFirst) {
+		S_(Z) += wz; S_(X + Z) += wxz; S_(Y + Z) += wyz; S_(X + Y + Z) += wxyz;
+		R_(Z) += wz * v; R_(X + Z) += wxz * v; R_(Y + Z) += wyz * v; R_(X + Y + Z) += wxyz * v;
+		S_(0) += w0; S_(X) += wx; S_(Y) += wy; S_(X + Y) += wxy;
+		R_(0) += w0 * v; R_(X) += wx * v; R_(Y) += wy * v; R_(X + Y) += wxy * v;
+	} else {
+		S_(0) += w0; S_(X) += wx; S_(Y) += wy; S_(X + Y) += wxy;
+		S_(Z) += wz; S_(X + Z) += wxz; S_(Y + Z) += wyz; S_(X + Y + Z) += wxyz;
+		R_(0) += w0 * v; R_(X) += wx * v; R_(Y) += wy * v; R_(X + Y) += wxy * v;
+		R_(Z) += wz * v; R_(X + Z) += wxz * v; R_(Y + Z) += wyz * v; R_(X + Y + Z) += wxyz * v;
+	}
+#undef S_
+#undef R_
+}
+/* mapPartsToMAC plugin/flip.cpp:573-595 (knMapLinearVec3ToMACGrid :562-569 is a serial kernel: contributions are added in particle order),
+ * weight->stomp(VECTOR_EPSILON) grid.cpp:224-226, vel.safeDivide(weight) general.h:148-151; weight (optional, may be NULL) receives the weights */
+int mfo_map_parts_to_mac(int sx, int sy, int sz, Real* vel, Real* velOld, long long np, const Real* pos, const int* pflag, const Real* pvel,
+                         Real* weight, const int* ptype, int exclude)
+{
+	const IndexInt n = (IndexInt)sx * sy * sz, X = 1, Y = sx, Z = (sz > 1) ? (IndexInt)sx * sy : 0;
+	Real* w = weight ? weight : (Real*)malloc(sizeof(Real) * 3 * (size_t)n);
+	memset(w, 0, sizeof(Real) * 3 * (size_t)n);
+	memset(vel, 0, sizeof(Real) * 3 * (size_t)n);
+	for (long long idx = 0; idx < np; idx++) {
+		if (P_SKIP(idx)) continue;
+		const MacIdx m = build_index_shift(sx, sy, sz, pos + 3 * idx);
+		const Real* v = pvel + 3 * idx;
+		{ const IndexInt q = ((IndexInt)m.zi * sy + m.yi) * sx + m.sxi;  scatter8(vel + 3 * q, w + 3 * q, 0, X, Y, Z, m.ss0, m.ss1, m.t0, m.t1, m.f0, m.f1, v[0], 1); }
+		{ const IndexInt q = ((IndexInt)m.zi * sy + m.syi) * sx + m.xi;  scatter8(vel + 3 * q, w + 3 * q, 1, X, Y, Z, m.s0, m.s1, m.st0, m.st1, m.f0, m.f1, v[1], 1); }
+		{ const IndexInt q = ((IndexInt)m.szi * sy + m.yi) * sx + m.xi;  scatter8(vel + 3 * q, w + 3 * q, 2, X, Y, Z, m.s0, m.s1, m.t0, m.t1, m.sf0, m.sf1, v[2], 0); }
+	}
+#if MF_REAL_IS_DOUBLE
+	const Real eps = 1e-10;
+#else
+	const Real eps = 1e-6f;
+#endif
+	for (IndexInt q = 0; q < 3 * n; q++) { if (w[q] < eps) w[q] = 0; vel[q] = w[q] ? (vel[q] / w[q]) : vel[q]; }
+	memcpy(velOld, vel, sizeof(Real) * 3 * (size_t)n);
+	if (!weight) free(w);
+	return 0;
+}
+
+/* mapMACToParts plugin/flip.cpp:651-656 (flipRatio < 0) and flipVelocityUpdate :669-677 */
+int mfo_flip_velocity_update(int sx, int sy, int sz, const Real* vel, const Real* velOld, long long np, const Real* pos, const int* pflag, Real* pvel,
+                             double flipRatio_, const int* ptype, int exclude)
+{
+	const Real flipRatio = (Real)flipRatio_;
+	for (long long idx = 0; idx < np; idx++) {
+		if (P_SKIP(idx)) continue;
+		Real v[3];
+		interpol_mac(sx, sy, sz, vel, pos + 3 * idx, v);
+		if (flipRatio_ < 0) { for (int c = 0; c < 3; c++) pvel[3 * idx + c] = v[c]; continue; }
+		Real o[3];
+		interpol_mac(sx, sy, sz, velOld, pos + 3 * idx, o);
+		for (int c = 0; c < 3; c++) {
+			const Real delta = v[c] - o[c];
+			pvel[3 * idx + c] = (Real)((double)(flipRatio * (pvel[3 * idx + c] + delta)) + (double)(Real)((1.0 - (double)flipRatio) * (double)v[c]));
+		}
+	}
+	return 0;
+}

@@ -272,6 +272,46 @@ class Oracle:
         self._chk(self._f("get_curvature")(*self.dims(grid), _p(out), _p(self._r(grid)), C.c_double(h)))
         return out
 
+    # -- FLIP particle <-> grid plugins (plugin/flip.cpp); particles are arrays: pos [N,3], pflag [N] int32, optional ptype [N] int32, pvel [N,3] --
+    def _parts(self, pos, pflag, ptype=None):
+        assert pos.dtype == self.real and pos.flags.c_contiguous and pflag.dtype == np.int32
+        return C.c_longlong(len(pos)), _p(pos), _p(pflag), (None if ptype is None else _p(np.ascontiguousarray(ptype, np.int32)))
+
+    def mark_fluid_cells(self, flags, pos, pflag, phiObs=None, ptype=None, exclude=0):
+        """plugin/flip.cpp:158-177; flags updated in place and returned"""
+        n, pp, pf, pt = self._parts(pos, pflag, ptype)
+        self._chk(self._f("mark_fluid_cells")(*self.dims(flags), _p(flags), n, pp, pf, _p(self._r(phiObs)), pt, C.c_int(exclude)))
+        return flags
+
+    def grid_particle_index(self, shape, pos, pflag):
+        """plugin/flip.cpp:260-306; returns (index [Z,Y,X] int32, indexSys [count] int32)"""
+        index = np.zeros(shape, np.int32); isys = np.zeros(len(pos), np.int32); cnt = C.c_longlong(0)
+        n, pp, pf, _ = self._parts(pos, pflag)
+        self._chk(self._f("grid_particle_index")(*self.dims(index), n, pp, pf, _p(index), _p(isys), C.byref(cnt)))
+        return index, isys[:cnt.value].copy()
+
+    def union_particle_levelset(self, pos, index, indexSys, radiusFactor=1.0, ptype=None, exclude=0):
+        """plugin/flip.cpp:340-350; returns phi"""
+        phi = np.zeros(index.shape, self.real)
+        pt = None if ptype is None else _p(np.ascontiguousarray(ptype, np.int32))
+        self._chk(self._f("union_particle_levelset")(*self.dims(index), C.c_longlong(len(pos)), _p(pos), _p(index), _p(indexSys), C.c_longlong(len(indexSys)), _p(phi),
+                                                     C.c_double(radiusFactor), pt, C.c_int(exclude)))
+        return phi
+
+    def map_parts_to_mac(self, shape, pos, pflag, pvel, want_weight=False, ptype=None, exclude=0):
+        """plugin/flip.cpp:573-595; returns (vel, velOld[, weight])"""
+        vel = np.zeros(tuple(shape) + (3,), self.real); velOld = np.zeros_like(vel); w = np.zeros_like(vel) if want_weight else None
+        n, pp, pf, pt = self._parts(pos, pflag, ptype)
+        self._chk(self._f("map_parts_to_mac")(*self.dims(vel[..., 0]), _p(vel), _p(velOld), n, pp, pf, _p(self._r(pvel)), _p(w), pt, C.c_int(exclude)))
+        return (vel, velOld, w) if want_weight else (vel, velOld)
+
+    def flip_velocity_update(self, vel, velOld, pos, pflag, pvel, flipRatio, ptype=None, exclude=0):
+        """flipVelocityUpdate plugin/flip.cpp:669-677; flipRatio < 0: mapMACToParts :651-656 (pure PIC).  pvel updated in place and returned"""
+        assert pvel.dtype == self.real and pvel.flags.c_contiguous
+        n, pp, pf, pt = self._parts(pos, pflag, ptype)
+        self._chk(self._f("flip_velocity_update")(*self.dims(vel[..., 0]), _p(self._r(vel)), _p(self._r(velOld)), n, pp, pf, _p(pvel), C.c_double(flipRatio), pt, C.c_int(exclude)))
+        return pvel
+
     def grid_file(self, name, array, kind, load=False):
         """Grid<T>::save / load of the unmodified reference (grid.cpp:113-156; reference build only).
         kind: "real" | "mac" | "flags" | "levelset" | "vec3"; `array` is written to / filled from the file `name`."""

@@ -20,6 +20,7 @@
 //   extrapolateMACSimple, extrapolateLsSimple, extrapolateVec3Simple   fastmarch.cpp:337-375, :470-542
 //   FlagGrid::updateFromLevelset, Grid<T>::setBound                    grid.cpp:844-854, :591-593
 //   updateFractions, setObstacleFlags                                  plugin/initplugins.cpp:437-440,:473-475
+//   markFluidCells, gridParticleIndex, unionParticleLevelset, mapPartsToMAC, mapMACToParts, flipVelocityUpdate   plugin/flip.cpp:158-177,:260-350,:562-595,:643-677
 //   LaplaceOp, CurvatureOp (getLaplacian / getCurvature)               commonkernels.h:75-101, plugin/flip.cpp:710-716
 //   Grid<T>::save / load (.uni, .raw, .npz)                            grid.cpp:113-156, fileio/iogrids.cpp
 // Nothing of the reference is copied: its sources are compiled where they lie.
@@ -46,6 +47,7 @@
 #include "plugin/pressure.cpp"
 #include "commonkernels.h"
 #include "levelset.h"
+#include "particle.h"
 
 namespace Manta {
 // --- link stubs for the OpenVDB entry points referenced by grid.cpp (the .uni / .raw / .npz readers and writers are the reference's own, fileio/iogrids.cpp) ---
@@ -61,6 +63,15 @@ void releaseBlurPrecomp();
 void extrapolateMACSimple(FlagGrid& flags, MACGrid& vel, int distance, LevelsetGrid* phiObs, bool intoObs);
 void extrapolateLsSimple(Grid<Real>& phi, int distance, bool inside);
 void extrapolateMACFromWeight(MACGrid& vel, Grid<Vec3>& weight, int distance);
+void markFluidCells(const BasicParticleSystem& parts, FlagGrid& flags, const Grid<Real>* phiObs, const ParticleDataImpl<int>* ptype, const int exclude);
+void gridParticleIndex(const BasicParticleSystem& parts, ParticleIndexSystem& indexSys, const FlagGrid& flags, Grid<int>& index, Grid<int>* counter);
+void unionParticleLevelset(const BasicParticleSystem& parts, const ParticleIndexSystem& indexSys, const FlagGrid& flags, const Grid<int>& index, LevelsetGrid& phi,
+	const Real radiusFactor, const ParticleDataImpl<int>* ptype, const int exclude);
+void mapPartsToMAC(const FlagGrid& flags, MACGrid& vel, MACGrid& velOld, const BasicParticleSystem& parts, const ParticleDataImpl<Vec3>& partVel, Grid<Vec3>* weight,
+	const ParticleDataImpl<int>* ptype, const int exclude);
+void mapMACToParts(const FlagGrid& flags, const MACGrid& vel, const BasicParticleSystem& parts, ParticleDataImpl<Vec3>& partVel, const ParticleDataImpl<int>* ptype, const int exclude);
+void flipVelocityUpdate(const FlagGrid& flags, const MACGrid& vel, const MACGrid& velOld, const BasicParticleSystem& parts, ParticleDataImpl<Vec3>& partVel, const Real flipRatio,
+	const ParticleDataImpl<int>* ptype, const int exclude);
 void updateFractions(const FlagGrid& flags, const Grid<Real>& phiObs, MACGrid& fractions, const int& boundaryWidth, const Real fracThreshold);
 void setObstacleFlags(FlagGrid& flags, const Grid<Real>& phiObs, const MACGrid* fractions, const Grid<Real>* phiOut, const Grid<Real>* phiIn, int boundaryWidth);
 void extrapolateVec3Simple(Grid<Vec3>& vel, Grid<Real>& phi, int distance, bool inside);
@@ -175,6 +186,73 @@ int ref_set_obstacle_flags(int sx, int sy, int sz, int* flags, const Real* phiOb
 	  Grid<Real>* Po = phiOut ? new Grid<Real>(s, (Real*)phiOut) : 0; Grid<Real>* Pi = phiIn ? new Grid<Real>(s, (Real*)phiIn) : 0;
 	  setObstacleFlags(F, P, Fr, Po, Pi, boundaryWidth);
 	  delete Fr; delete Po; delete Pi; }
+	delete s;
+  CATCH }
+
+// ---- FLIP particle <-> grid plugins (plugin/flip.cpp): the caller's arrays are copied into the reference's own particle system
+struct RefParts {
+	BasicParticleSystem pp; ParticleDataImpl<int>* pt; ParticleDataImpl<Vec3>* pv;
+	RefParts(FluidSolver* s, long long np, const Real* pos, const int* pflag, const int* ptype, const Real* pvel) : pp(s), pt(0), pv(0) {
+		pp.resizeAll(np);
+		for (long long q = 0; q < np; q++) { pp[q].pos = Vec3(pos[3 * q], pos[3 * q + 1], pos[3 * q + 2]); pp[q].flag = pflag[q]; }
+		if (ptype) { pt = new ParticleDataImpl<int>(s); pp.registerPdata(pt); pt->resize(np); for (long long q = 0; q < np; q++) (*pt)[q] = ptype[q]; }
+		if (pvel) { pv = new ParticleDataImpl<Vec3>(s); pp.registerPdata(pv); pv->resize(np); for (long long q = 0; q < np; q++) (*pv)[q] = Vec3(pvel[3 * q], pvel[3 * q + 1], pvel[3 * q + 2]); }
+	}
+	~RefParts() { delete pt; delete pv; }
+};
+int ref_mark_fluid_cells(int sx, int sy, int sz, int* flags, long long np, const Real* pos, const int* pflag, const Real* phiObs, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	const size_t n = (size_t)sx * sy * sz;
+	{ RefParts P(s, np, pos, pflag, ptype, 0);
+	  FlagGrid F(s); memcpy(&F[0], flags, n * sizeof(int));            // the plugin swaps a copy in when phiObs is given: solver-owned storage
+	  Grid<Real>* Po = phiObs ? new Grid<Real>(s, (Real*)phiObs) : 0;
+	  markFluidCells(P.pp, F, Po, P.pt, exclude);
+	  memcpy(flags, &F[0], n * sizeof(int)); delete Po; }
+	delete s;
+  CATCH }
+int ref_grid_particle_index(int sx, int sy, int sz, long long np, const Real* pos, const int* pflag, int* index, int* indexSys, long long* count)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ RefParts P(s, np, pos, pflag, 0, 0);
+	  FlagGrid F(s); Grid<int> I(s, index); ParticleIndexSystem IS(s);
+	  gridParticleIndex(P.pp, IS, F, I, 0);
+	  *count = IS.size();
+	  for (IndexInt q = 0; q < IS.size(); q++) indexSys[q] = (int)IS[q].sourceIndex; }
+	delete s;
+  CATCH }
+int ref_union_particle_levelset(int sx, int sy, int sz, long long np, const Real* pos, const int* index, const int* indexSys, long long count,
+                                Real* phi, double radiusFactor, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ std::vector<int> active(np, 0);
+	  RefParts P(s, np, pos, active.data(), ptype, 0);
+	  FlagGrid F(s); Grid<int> I(s, (int*)index); ParticleIndexSystem IS(s); IS.resizeAll(count);
+	  for (long long q = 0; q < count; q++) IS[q].sourceIndex = indexSys[q];
+	  LevelsetGrid Ph(s, phi);
+	  unionParticleLevelset(P.pp, IS, F, I, Ph, (Real)radiusFactor, P.pt, exclude); }
+	delete s;
+  CATCH }
+int ref_map_parts_to_mac(int sx, int sy, int sz, Real* vel, Real* velOld, long long np, const Real* pos, const int* pflag, const Real* pvel,
+                         Real* weight, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ RefParts P(s, np, pos, pflag, ptype, pvel);
+	  FlagGrid F(s); MACGrid V(s, (Vec3*)vel), Vo(s, (Vec3*)velOld);
+	  Grid<Vec3>* W = weight ? new Grid<Vec3>(s, (Vec3*)weight) : 0;
+	  mapPartsToMAC(F, V, Vo, P.pp, *P.pv, W, P.pt, exclude);
+	  delete W; }
+	delete s;
+  CATCH }
+int ref_flip_velocity_update(int sx, int sy, int sz, const Real* vel, const Real* velOld, long long np, const Real* pos, const int* pflag, Real* pvel,
+                             double flipRatio, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ RefParts P(s, np, pos, pflag, ptype, pvel);
+	  FlagGrid F(s); MACGrid V(s, (Vec3*)vel), Vo(s, (Vec3*)velOld);
+	  if (flipRatio < 0) mapMACToParts(F, V, P.pp, *P.pv, P.pt, exclude);
+	  else flipVelocityUpdate(F, V, Vo, P.pp, *P.pv, (Real)flipRatio, P.pt, exclude);
+	  for (long long q = 0; q < np; q++) { pvel[3 * q] = (*P.pv)[q].x; pvel[3 * q + 1] = (*P.pv)[q].y; pvel[3 * q + 2] = (*P.pv)[q].z; } }
 	delete s;
   CATCH }
 

@@ -207,6 +207,20 @@ def liquid_fixtures():
             print("%-34s %7.1f KiB  its %s  fluid cells %d" % (os.path.basename(path), os.path.getsize(path) / 1024, its, int((flags & 1).sum())))
 
 
+def flip_fixtures():
+    """step_flip*_f{32,64}.npz: the reference's markFluidCells, gridParticleIndex, unionParticleLevelset, mapPartsToMAC, mapMACToParts and
+    flipVelocityUpdate (plugin/flip.cpp) on the seeded particle scenes of tests/helpers.py"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import helpers
+    for prec in (4, 8):
+        R = Oracle("reference", prec)
+        for name in helpers.FLIP_SCENES:
+            fx = helpers.run_flip_plugins(R, name, prec)
+            path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, **fx)
+            print("%-34s %7.1f KiB  %d indexed particles, %d fluid cells" % (os.path.basename(path), os.path.getsize(path) / 1024, len(fx["index_sys"]), int((fx["mark"] & 1).sum())))
+
+
 def io_fixtures():
     """tests/golden/io/ref_<kind>_<2d|3d>_f{32,64}.uni: grid files written by the unmodified reference's Grid<T>::save (fileio/iogrids.cpp)
     from the seeded arrays of tests/test_fileio.py::sample"""
@@ -225,6 +239,8 @@ def io_fixtures():
 def main():
     if "--only-io" in sys.argv:
         return io_fixtures()
+    if "--only-flip" in sys.argv:
+        return flip_fixtures()
     if "--only-liquid" in sys.argv:
         return liquid_fixtures()
     if "--only-step" in sys.argv:
@@ -232,6 +248,7 @@ def main():
         return liquid_fixtures()
     step_fixtures()
     liquid_fixtures()
+    flip_fixtures()
     io_fixtures()
     for prec in (4, 8):
         R = Oracle("reference", prec)

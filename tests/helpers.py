@@ -547,3 +547,57 @@ def check_sec_order_bnd_against_golden(I, name, prec, tol):
     for a, key, f in ((dens, "density", 1), (vel, "vel", 1), (p, "pressure", 10)):
         err = float(np.abs(a.astype(np.float64) - g[key]).max())
         assert err <= tol * f, (name, prec, key, err)
+
+
+# ---------------------------------------------------------------- FLIP particle <-> grid plugins (plugin/flip.cpp), oracle side (the device versions come next)
+FLIP_SCENES = {"flip3d": (10, 14, 12), "flip2d": (1, 20, 18)}
+
+
+def flip_scene(name, prec):
+    """particles sampled in a basin + drop (about 4 per liquid cell in 2-D, 6 in 3-D), some outside the domain, some deleted, a few typed
+    as FlagEmpty (excluded); random particle velocities; an obstacle level set"""
+    from mantaflow_b200 import scenes
+    sz, sy, sx = shape = FLIP_SCENES[name]
+    real = np.float32 if prec == 4 else np.float64
+    flags, _, phi = scenes.liquid_basin((sx, sy, sz), prec)
+    rng = np.random.default_rng(23 + sx)
+    k, j, i = np.nonzero(phi < 0)
+    per = 6 if sz > 1 else 4
+    base = np.repeat(np.stack([i, j, k], 1), per, 0).astype(np.float64)
+    pos = base + rng.random(base.shape)
+    if sz == 1:
+        pos[:, 2] = 0.5
+    pos[rng.random(len(pos)) < 0.01] += np.array([sx, 0, 0])            # left the domain
+    pos[rng.random(len(pos)) < 0.01] *= -1
+    pos = np.ascontiguousarray(pos.astype(real))
+    pflag = np.zeros(len(pos), np.int32)
+    pflag[rng.random(len(pos)) < 0.03] |= 1 << 10                       # PDELETE
+    pflag[rng.random(len(pos)) < 0.05] |= 1                             # PNEW: still active
+    ptype = np.where(rng.random(len(pos)) < 0.1, 4, 1).astype(np.int32)  # FlagEmpty-typed particles are excluded by the scenes
+    pvel = (rng.random(pos.shape) * 2 - 1).astype(real)
+    if sz == 1:
+        pvel[:, 2] = 0
+    phiObs = (rng.random(shape) * 6 - 2).astype(real)
+    return flags, pos, pflag, ptype, pvel, phiObs
+
+
+def run_flip_plugins(I, name, prec):
+    """every plugin once, on the outputs of the previous ones where the scene chains them (scenes/benchmark_dam.py:100-125)"""
+    flags, pos, pflag, ptype, pvel, phiObs = flip_scene(name, prec)
+    shape = flags.shape
+    out = {}
+    out["mark"] = I.mark_fluid_cells(flags.copy(), pos, pflag, ptype=ptype, exclude=4)
+    out["mark_phiobs"] = I.mark_fluid_cells(flags.copy(), pos, pflag, phiObs=phiObs)
+    index, isys = I.grid_particle_index(shape, pos, pflag)
+    out["index"], out["index_sys"] = index, isys
+    out["union"] = I.union_particle_levelset(pos, index, isys, radiusFactor=1.0)
+    out["union_excl"] = I.union_particle_levelset(pos, index, isys, radiusFactor=1.5, ptype=ptype, exclude=4)
+    vel, velOld, w = I.map_parts_to_mac(shape, pos, pflag, pvel, want_weight=True, ptype=ptype, exclude=4)
+    out["map_vel"], out["map_weight"] = vel, w
+    assert np.array_equal(vel, velOld)
+    out["map_vel_noweight"] = I.map_parts_to_mac(shape, pos, pflag, pvel)[0]
+    rng = np.random.default_rng(5)
+    vnew = (vel + (rng.random(vel.shape) - 0.5).astype(vel.dtype) * 0.1).astype(vel.dtype)
+    out["pic"] = I.flip_velocity_update(vnew, vel, pos, pflag, pvel.copy(), -1.0, ptype=ptype, exclude=4)
+    out["flip"] = I.flip_velocity_update(vnew, vel, pos, pflag, pvel.copy(), 0.97, ptype=ptype, exclude=4)
+    return out
