@@ -245,6 +245,30 @@ int mp_set_obstacle_flags(mp_context* ctx, mp_grid* flags, const mp_grid* phiObs
 int mp_get_laplacian(mp_context* ctx, mp_grid* laplacian, const mp_grid* grid);
 int mp_get_curvature(mp_context* ctx, mp_grid* curv, const mp_grid* grid, double h);
 
+/* ---- FLIP particle <-> grid plugins (second slice; the loop of scenes/benchmark_dam.py:100-125 / flip02_surface.py).
+ * A particle system is a set of device arrays, each created with mp_grid_create(ctx, kind, prec, capacity, 1, 1):
+ *   pos      MP_GRID_MAC    BasicParticleData::pos   particle.h:182-191        pflag    MP_GRID_FLAGS  BasicParticleData::flag (PDELETE = 1 << 10)
+ *   partVel  MP_GRID_MAC    ParticleDataImpl<Vec3>   particle.h:392            ptype    MP_GRID_FLAGS  ParticleDataImpl<int> (optional, may be NULL)
+ *   indexSys MP_GRID_FLAGS  ParticleIndexSystem      particle.h:276 (sourceIndex of every slot)
+ * np = particles in use (<= capacity).  `flags` arguments that the reference only takes for the grid size may be NULL.
+ * markFluidCells         plugin/flip.cpp:158-177
+ * gridParticleIndex      plugin/flip.cpp:260-306  (*count = indexed particles = indexSys.size(); one stream synchronisation)
+ * unionParticleLevelset  plugin/flip.cpp:340-350  (count = what gridParticleIndex returned)
+ * mapPartsToMAC          plugin/flip.cpp:573-595  (weight may be NULL; faces sum in particle order like the reference's serial kernel)
+ * mapMACToParts          plugin/flip.cpp:651-656
+ * flipVelocityUpdate     plugin/flip.cpp:669-677
+ * Results are bit-identical to the reference's in both precisions and independent of the launch geometry (no floating-point atomics). */
+int mp_mark_fluid_cells(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* flags, const mp_grid* phiObs, const mp_grid* ptype, int exclude);
+int mp_grid_particle_index(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* indexSys, const mp_grid* flags, mp_grid* index, long long* count);
+int mp_union_particle_levelset(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* indexSys, long long count, const mp_grid* flags, const mp_grid* index,
+                               mp_grid* phi, double radiusFactor, const mp_grid* ptype, int exclude);
+int mp_map_parts_to_mac(mp_context* ctx, const mp_grid* flags, mp_grid* vel, mp_grid* velOld, long long np, const mp_grid* pos, const mp_grid* pflag, const mp_grid* partVel,
+                        mp_grid* weight, const mp_grid* ptype, int exclude);
+int mp_map_mac_to_parts(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* partVel,
+                        const mp_grid* ptype, int exclude);
+int mp_flip_velocity_update(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, const mp_grid* velOld, long long np, const mp_grid* pos, const mp_grid* pflag,
+                            mp_grid* partVel, double flipRatio, const mp_grid* ptype, int exclude);
+
 /* ---- PD_fluid_guiding plugin/fluidguiding.cpp:294-353: primal-dual guiding of vel towards velT with per-cell weight;
  * up to maxIters solvePressure calls on device-resident copies, separable Gaussian blurs of radius blurRadius, stop test as in the reference.
  * vel receives the guided, divergence-free field; *iterations = the loop index at exit (what the reference prints).  The optional grids and

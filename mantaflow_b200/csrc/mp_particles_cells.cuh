@@ -1,0 +1,314 @@
+// FLIP particle <-> grid plugins on the device (second slice; scenes/benchmark_dam.py:100-125):
+//   markFluidCells         plugin/flip.cpp:158-177  (knClearFluidFlags :137-141, knSetNbObstacle :142-157)
+//   gridParticleIndex      plugin/flip.cpp:260-306
+//   unionParticleLevelset  plugin/flip.cpp:340-350  (ComputeUnionLevelsetPindex :308-338) + phi.setBound(0.5, 0)
+//   mapPartsToMAC          plugin/flip.cpp:573-595  (knMapLinearVec3ToMACGrid :562-569, setInterpolMAC util/interpol.h:159-203)
+//   mapMACToParts          plugin/flip.cpp:651-656, flipVelocityUpdate :669-677 (interpolMAC util/interpol.h:127-157)
+//
+// Particles are device arrays: pos [N][3] Real, pflag [N] int (BasicParticleData particle.h:182-191; active = !(flag & PDELETE)),
+// per-particle data (ParticleDataImpl<Vec3|int>) [N][3] Real / [N] int.
+//
+// As in mp_liquid_cells.cuh, the per-cell / per-particle operations and the pass sequences are written against an executor `Exec`:
+//     template <class F> int cells(const Dims& d, const F& f);            // f(d, i, j, k, idx) once per cell, any order
+//     template <class F> int parts(IndexInt np, const F& f);              // f(idx) once per particle, any order
+//     int zero(void* p, size_t bytes);
+//     int exclusiveScan(int* data, IndexInt n, IndexInt* total);          // in place; *total = sum (on the host)
+//     int sortPairs(int* keys, int* keysTmp, int* vals, int* valsOut, IndexInt n, int keyBits);   // STABLE sort by key; keys may be clobbered
+// mp_particles.cu instantiates it with CUDA launches (+ cub for the scan and the radix sort); tests/emul/liquid_emul.cpp with host loops.
+//
+// Determinism.  The reference's scatter kernels are serial (knMapLinearVec3ToMACGrid is a `KERNEL(pts, single)`): a face sums its
+// contributions in particle order.  Floating-point atomics would give a different, run-dependent sum.  Here the scatter is turned into
+// a gather: particles are bucketed by cell (integer atomics for the counts, a scan, a stable radix sort -- all order independent), and a
+// face walks the particles of the 3 x 3 (x 3) cells around it in ASCENDING PARTICLE ORDER (a k-way merge of the cells' ascending lists),
+// adding the same products in the same order as the reference -> bit-identical grids, independent of the launch geometry.
+#pragma once
+#include "mp_liquid_cells.cuh"
+
+namespace parts {
+
+enum : int { PDELETE = 1 << 10 };      // particle.h:41
+
+MP_HD int atomicIncr(int* p) {
+#ifdef __CUDA_ARCH__
+	return atomicAdd(p, 1);
+#else
+	return (*p)++;
+#endif
+}
+MP_HD bool inBounds0(const Dims& d, int x, int y, int z) {      // GridBase::isInBounds(p, 0)
+	return x >= 0 && y >= 0 && x < d.sx && y < d.sy && (d.is3D ? (z >= 0 && z < d.sz) : z == 0);
+}
+template <typename Real> struct PSet {       // the particles a plugin visits: active and not of an excluded type
+	const Real* pos; const int* pflag; const int* ptype; int exclude;
+	MP_HD bool skip(IndexInt idx) const { return (pflag[idx] & PDELETE) || (ptype && (ptype[idx] & exclude)); }
+};
+
+// ---------------------------------------------------------------- markFluidCells
+struct ClearFluid {
+	static const bool kSplit = false;         // knClearFluidFlags flip.cpp:137-141
+	int* flags;
+	MP_HD void operator()(const Dims&, int, int, int, IndexInt idx) const {
+		const int f = flags[idx];
+		if (f & TypeFluid) flags[idx] = (f | TypeEmpty) & ~TypeFluid;
+	}
+};
+// flip.cpp:165-172.  Several particles of one cell race on the same word, but all of them store the same value (the cell's flag with
+// Fluid set and Empty cleared), and a particle that reads the already converted flag stores nothing.
+template <typename Real> struct MarkFluid {
+	Dims d; int* flags; PSet<Real> ps;
+	MP_HD void operator()(IndexInt idx) const {
+		if (ps.skip(idx)) return;
+		const int x = (int)ps.pos[3 * idx], y = (int)ps.pos[3 * idx + 1], z = (int)ps.pos[3 * idx + 2];
+		if (!inBounds0(d, x, y, z)) return;
+		const IndexInt p = (IndexInt)x + d.Y * y + d.Z * z;
+		const int f = flags[p];
+		if (f & TypeEmpty) flags[p] = (f | TypeFluid) & ~TypeEmpty;
+	}
+};
+// knSetNbObstacle flip.cpp:142-157: reads `flags`, writes every cell of `out` (the caller swaps the two)
+template <typename Real> struct SetNbObstacle {
+	static const bool kSplit = false;
+	const int* flags; int* out; const Real* phiObs;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt p) const {
+		const int f = flags[p];
+		int r = f;
+		if (liquid::interiorCell(d, i, j, k) && !(phiObs[p] > 0.) && (f & TypeEmpty)) {
+			const IndexInt X = 1, Y = d.Y, Z = d.Z;
+			bool set = false;
+			if ((flags[p - X] & TypeFluid) && (phiObs[p + X] <= 0.)) set = true;
+			if ((flags[p + X] & TypeFluid) && (phiObs[p - X] <= 0.)) set = true;
+			if ((flags[p - Y] & TypeFluid) && (phiObs[p + Y] <= 0.)) set = true;
+			if ((flags[p + Y] & TypeFluid) && (phiObs[p - Y] <= 0.)) set = true;
+			if (d.is3D) {
+				if ((flags[p - Z] & TypeFluid) && (phiObs[p + Z] <= 0.)) set = true;
+				if ((flags[p + Z] & TypeFluid) && (phiObs[p - Z] <= 0.)) set = true;
+			}
+			if (set) r = (f | TypeFluid) & ~TypeEmpty;
+		}
+		out[p] = r;
+	}
+};
+// `tmp`: scratch FlagGrid (only used with phiObs); *swapped is set when the result is in tmp (the caller exchanges the buffers)
+template <typename Real, typename Exec>
+int markFluidCells(Exec& ex, const Dims& d, int* flags, IndexInt np, const PSet<Real>& ps, const Real* phiObs, int* tmp, bool* swapped) {
+	*swapped = false;
+	ClearFluid cf = { flags }; MP_TRY(ex.cells(d, cf));
+	if (np > 0) { MarkFluid<Real> mf = { d, flags, ps }; MP_TRY(ex.parts(np, mf)); }
+	if (phiObs) { SetNbObstacle<Real> nb = { flags, tmp, phiObs }; MP_TRY(ex.cells(d, nb)); *swapped = true; }
+	return MP_OK;
+}
+
+// ---------------------------------------------------------------- bucketing particles by cell
+// key[idx] = cell of the particle (or the sentinel d.n for particles that are left out), val[idx] = idx, count[cell]++.
+// clampToGrid == false: gridParticleIndex (flip.cpp:275-283: deleted and out-of-bounds particles are left out, ptype is not looked at);
+// clampToGrid == true : the private buckets of mapPartsToMAC (skipped particles are left out, positions outside are clamped, as
+// BUILD_INDEX clamps them).
+template <typename Real> struct KeyCount {
+	Dims d; PSet<Real> ps; int* key; int* val; int* count; bool clampToGrid;
+	MP_HD void operator()(IndexInt idx) const {
+		val[idx] = (int)idx;
+		int k = (int)d.n;
+		if (!clampToGrid) {
+			if (!(ps.pflag[idx] & PDELETE)) {
+				const int x = (int)ps.pos[3 * idx], y = (int)ps.pos[3 * idx + 1], z = (int)ps.pos[3 * idx + 2];
+				if (inBounds0(d, x, y, z)) k = (int)((IndexInt)x + d.Y * y + d.Z * z);
+			}
+		} else if (!ps.skip(idx)) {
+			k = (int)cellClamped(d, ps.pos + 3 * idx);
+		}
+		key[idx] = k;
+		if (k < (int)d.n) atomicIncr(count + k);
+	}
+	// the bucket of a particle for the gather of mapPartsToMAC: int(pos) per axis, clamped into the grid.  Every face the particle
+	// contributes to lies in the 3 x 3 (x 3) cells around this one (see MapPartsGather).
+	static MP_HD int clampAxis(Real p, int s) {
+		if (!(p > (Real)0)) return 0;                  // negative or NaN
+		if (!(p < (Real)s)) return s - 1;
+		return (int)p;
+	}
+	static MP_HD IndexInt cellClamped(const Dims& d, const Real* pos) {
+		const int x = clampAxis(pos[0], d.sx), y = clampAxis(pos[1], d.sy), z = d.is3D ? clampAxis(pos[2], d.sz) : 0;
+		return (IndexInt)x + d.Y * y + d.Z * z;
+	}
+};
+MP_HD int bitsFor(IndexInt maxKey) { int b = 1; while (((IndexInt)1 << b) <= maxKey) b++; return b; }
+
+// count -> index (first slot of each cell), sorted particle ids -> sorted.  key/keyTmp/val: scratch int[np]; sorted: int[np].
+template <typename Real, typename Exec>
+int bucketParticles(Exec& ex, const Dims& d, IndexInt np, const PSet<Real>& ps, bool clampToGrid, int* index, int* key, int* keyTmp, int* val, int* sorted, IndexInt* count) {
+	MP_TRY(ex.zero(index, sizeof(int) * (size_t)d.n));
+	*count = 0;
+	if (np <= 0) return MP_OK;
+	KeyCount<Real> kc = { d, ps, key, val, index, clampToGrid };
+	MP_TRY(ex.parts(np, kc));
+	MP_TRY(ex.exclusiveScan(index, d.n, count));
+	MP_TRY(ex.sortPairs(key, keyTmp, val, sorted, np, bitsFor(d.n)));
+	return MP_OK;
+}
+
+// ---------------------------------------------------------------- unionParticleLevelset
+// ComputeUnionLevelsetPindex flip.cpp:308-338 (a gather already in the reference: min over the particles of the cells within `r`),
+// fused with the setBound(0.5, 0) that follows it (flip.cpp:349).
+template <typename Real> struct UnionLevelset {
+	static const bool kSplit = false;
+	const Real* pos; const int* index; const int* indexSys; IndexInt count; Real* phi; Real radius; int r; const int* ptype; int exclude;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		if (i <= 0 || i >= d.sx - 1 || j <= 0 || j >= d.sy - 1 || (d.is3D && (k <= 0 || k >= d.sz - 1))) { phi[idx] = (Real)0.5; return; }
+		const Real gx = (Real)i + (Real)0.5, gy = (Real)j + (Real)0.5, gz = (Real)k + (Real)0.5;      // gridPos, flip.cpp:317
+		const Real eps2 = sizeof(Real) == 8 ? (Real)(1e-10 * 1e-10) : (Real)(1e-6f * 1e-6f);            // VECTOR_EPSILON^2 vectorbase.h:399-411
+		Real phiv = radius;
+		const int rZ = d.is3D ? r : 0;
+		for (int zj = k - rZ; zj <= k + rZ; zj++) for (int yj = j - r; yj <= j + r; yj++) {
+			if (yj < 0 || yj >= d.sy || (d.is3D ? (zj < 0 || zj >= d.sz) : zj != 0)) continue;
+			// the cells of one row are neighbours in the index: one particle range per row
+			const int x0 = i - r < 0 ? 0 : i - r, x1 = i + r >= d.sx ? d.sx - 1 : i + r;
+			const IndexInt c0 = (IndexInt)x0 + d.Y * yj + d.Z * zj, c1 = (IndexInt)x1 + d.Y * yj + d.Z * zj;
+			const IndexInt pStart = index[c0], pEnd = (c1 + 1 < d.n) ? (IndexInt)index[c1 + 1] : count;
+			for (IndexInt p = pStart; p < pEnd; p++) {
+				const int psrc = indexSys[p];
+				if (ptype && (ptype[psrc] & exclude)) continue;
+				const Real dx = gx - pos[3 * psrc], dy = gy - pos[3 * psrc + 1], dz = gz - pos[3 * psrc + 2];
+				const Real l = dx * dx + dy * dy + dz * dz;
+				Real nrm;                                                                        // norm() vectorbase.h:399-404
+				if (l <= eps2) nrm = (Real)0;
+				else if (fabs((double)l - 1.) < (double)eps2) nrm = (Real)1;
+				else nrm = (Real)sqrt(l);
+				const Real v = (Real)fabs((double)nrm) - radius;
+				phiv = phiv < v ? phiv : v;
+			}
+		}
+		phi[idx] = phiv;
+	}
+};
+template <typename Real, typename Exec>
+int unionParticleLevelset(Exec& ex, const Dims& d, const Real* pos, const int* index, const int* indexSys, IndexInt count, Real* phi, double radiusFactor_,
+                          const int* ptype, int exclude) {
+	const Real radiusFactor = (Real)radiusFactor_;
+	const Real radius = (Real)(0.5 * (double)(Real)((d.is3D ? sqrt(3.) : sqrt(2.)) * ((double)radiusFactor + .01)));      // flip.cpp:186-188, :343
+	UnionLevelset<Real> op = { pos, index, indexSys, count, phi, radius, (int)radius + 1, ptype, exclude };
+	return ex.cells(d, op);
+}
+
+// ---------------------------------------------------------------- MAC interpolation weights
+// BUILD_INDEX / BUILD_INDEX_SHIFT util/interpol.h:50-66,:112-125: cell-centred base (xi, yi, zi) with weights s, t, f and the face
+// base (sxi, syi, szi) with weights ss, st, sf; the `1 - w` are double subtractions narrowed on assignment.
+template <typename Real> struct MacWeights {
+	int xi, yi, zi, sxi, syi, szi;
+	Real s[2], t[2], f[2], ss[2], st[2], sf[2];
+	static MP_HD void axis(Real p, int size, bool clampHigh, int& i, Real (&w)[2]) {
+		i = (int)p;
+		w[1] = p - (Real)i; w[0] = (Real)(1. - w[1]);
+		if (p < 0.) { i = 0; w[0] = (Real)1; w[1] = (Real)0; }
+		if (clampHigh && i >= size - 1) { i = size - 2; w[0] = (Real)0; w[1] = (Real)1; }
+	}
+	MP_HD MacWeights(const Dims& d, const Real* pos) {
+		const Real px = pos[0] - (Real)0.5f, py = pos[1] - (Real)0.5f, pz = pos[2] - (Real)0.5f;
+		axis(px, d.sx, true, xi, s); axis(py, d.sy, true, yi, t); axis(pz, d.sz, d.is3D, zi, f);
+		axis(pos[0], d.sx, true, sxi, ss); axis(pos[1], d.sy, true, syi, st); axis(pos[2], d.sz, d.is3D, szi, sf);
+	}
+};
+// interpolMAC util/interpol.h:127-157
+template <typename Real> MP_HD void interpolMAC(const Dims& d, const Real* data, const MacWeights<Real>& m, Real (&out)[3]) {
+	const IndexInt X = 1, Y = d.Y, Z = d.Z;
+	#define MP_RF(o, c) ref[3 * (o) + (c)]
+	{ const Real* ref = data + 3 * (((IndexInt)m.zi * d.sy + m.yi) * d.sx + m.sxi);
+	  out[0] = m.f[0] * ((MP_RF(0, 0) * m.t[0] + MP_RF(Y, 0) * m.t[1]) * m.ss[0] + (MP_RF(X, 0) * m.t[0] + MP_RF(X + Y, 0) * m.t[1]) * m.ss[1]) +
+	           m.f[1] * ((MP_RF(Z, 0) * m.t[0] + MP_RF(Z + Y, 0) * m.t[1]) * m.ss[0] + (MP_RF(X + Z, 0) * m.t[0] + MP_RF(X + Y + Z, 0) * m.t[1]) * m.ss[1]); }
+	{ const Real* ref = data + 3 * (((IndexInt)m.zi * d.sy + m.syi) * d.sx + m.xi);
+	  out[1] = m.f[0] * ((MP_RF(0, 1) * m.st[0] + MP_RF(Y, 1) * m.st[1]) * m.s[0] + (MP_RF(X, 1) * m.st[0] + MP_RF(X + Y, 1) * m.st[1]) * m.s[1]) +
+	           m.f[1] * ((MP_RF(Z, 1) * m.st[0] + MP_RF(Z + Y, 1) * m.st[1]) * m.s[0] + (MP_RF(X + Z, 1) * m.st[0] + MP_RF(X + Y + Z, 1) * m.st[1]) * m.s[1]); }
+	{ const Real* ref = data + 3 * (((IndexInt)m.szi * d.sy + m.yi) * d.sx + m.xi);
+	  out[2] = m.sf[0] * ((MP_RF(0, 2) * m.t[0] + MP_RF(Y, 2) * m.t[1]) * m.s[0] + (MP_RF(X, 2) * m.t[0] + MP_RF(X + Y, 2) * m.t[1]) * m.s[1]) +
+	           m.sf[1] * ((MP_RF(Z, 2) * m.t[0] + MP_RF(Z + Y, 2) * m.t[1]) * m.s[0] + (MP_RF(X + Z, 2) * m.t[0] + MP_RF(X + Y + Z, 2) * m.t[1]) * m.s[1]); }
+	#undef MP_RF
+}
+
+// ---------------------------------------------------------------- mapMACToParts / flipVelocityUpdate
+// knMapLinearMACGridToVec3_PIC flip.cpp:643-649 (flipRatio < 0) and knMapLinearMACGridToVec3_FLIP :659-667: a gather per particle.
+template <typename Real> struct FlipVelocityUpdate {
+	Dims d; const Real* vel; const Real* velOld; PSet<Real> ps; Real* pvel; Real flipRatio; bool pic;
+	MP_HD void operator()(IndexInt idx) const {
+		if (ps.skip(idx)) return;
+		const MacWeights<Real> m(d, ps.pos + 3 * idx);
+		Real v[3];
+		interpolMAC(d, vel, m, v);
+		if (pic) { for (int c = 0; c < 3; c++) pvel[3 * idx + c] = v[c]; return; }
+		Real o[3];
+		interpolMAC(d, velOld, m, o);
+		for (int c = 0; c < 3; c++) {
+			const Real delta = v[c] - o[c];
+			// flipRatio * (v + delta) + (1.0 - flipRatio) * vNew: the second product is a double expression narrowed by the Vec3 operator* (flip.cpp:665)
+			pvel[3 * idx + c] = (Real)((double)(flipRatio * (pvel[3 * idx + c] + delta)) + (double)(Real)((1.0 - (double)flipRatio) * (double)v[c]));
+		}
+	}
+};
+
+// ---------------------------------------------------------------- mapPartsToMAC
+// One thread per cell: its three faces gather from the particles bucketed (clamped) into the 3 x 3 (x 3) cells around it, visited in
+// ascending particle order, which is the order the reference's serial scatter adds them in.  A particle with bucket cell (kx, ky, kz)
+// has its face / centre bases in {k-1, k} per axis and spreads to base + {0, 1}, i.e. to faces within one cell of its bucket.
+// stomp(VECTOR_EPSILON) grid.cpp:224-226, safeDivide general.h:148-151 and velOld.copyFrom(vel) (flip.cpp:590-594) are fused in.
+template <typename Real> struct MapPartsGather {
+	static const bool kSplit = false;
+	const int* start; const int* sorted; IndexInt count; const Real* pos; const Real* pvel; Real* vel; Real* velOld; Real* weight;
+	static MP_HD void add(Real& S, Real& R, Real a, Real b, Real c, Real v) { const Real w = b * (a * c); S += w; R += w * v; }
+	// one component of setInterpolMAC (util/interpol.h:159-203) as seen from face (i, j, k): base (bx, by, bz), weights a (x), b (y), c (z)
+	static MP_HD void comp(const Dims& d, int i, int j, int k, int bx, int by, int bz, const Real (&a)[2], const Real (&b)[2], const Real (&c)[2], Real v, bool zFirst, Real& S, Real& R) {
+		const int di = i - bx, dj = j - by;
+		if (di < 0 || di > 1 || dj < 0 || dj > 1) return;
+		if (d.is3D) {
+			const int dk = k - bz;
+			if (dk < 0 || dk > 1) return;
+			add(S, R, a[di], b[dj], c[dk], v);
+		} else {            // Z stride 0: both z-weights land on the same face, in the order the reference adds them
+			if (bz != 0) return;
+			if (zFirst) { add(S, R, a[di], b[dj], c[1], v); add(S, R, a[di], b[dj], c[0], v); }
+			else        { add(S, R, a[di], b[dj], c[0], v); add(S, R, a[di], b[dj], c[1], v); }
+		}
+	}
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		// segments of the neighbouring rows: the three cells (i-1, i, i+1) of a row are consecutive buckets, but only each cell's own
+		// list is ascending -> one cursor per cell
+		int cur[27], end[27], head[27];
+		int nseg = 0;
+		const int kz0 = d.is3D ? k - 1 : 0, kz1 = d.is3D ? k + 1 : 0;
+		for (int zz = kz0; zz <= kz1; zz++) for (int yy = j - 1; yy <= j + 1; yy++) for (int xx = i - 1; xx <= i + 1; xx++) {
+			if (xx < 0 || xx >= d.sx || yy < 0 || yy >= d.sy || zz < 0 || zz >= d.sz) continue;
+			const IndexInt c = (IndexInt)xx + d.Y * yy + d.Z * zz;
+			const int b = start[c], e = (c + 1 < d.n) ? start[c + 1] : (int)count;
+			if (b < e) { cur[nseg] = b; end[nseg] = e; head[nseg] = sorted[b]; nseg++; }
+		}
+		Real S[3] = { 0, 0, 0 }, R[3] = { 0, 0, 0 };
+		while (nseg > 0) {
+			int best = 0;
+			for (int q = 1; q < nseg; q++) if (head[q] < head[best]) best = q;
+			const int p = head[best];
+			if (++cur[best] < end[best]) head[best] = sorted[cur[best]];
+			else { nseg--; cur[best] = cur[nseg]; end[best] = end[nseg]; head[best] = head[nseg]; }
+			const MacWeights<Real> m(d, pos + 3 * (IndexInt)p);
+			const Real* v = pvel + 3 * (IndexInt)p;
+			comp(d, i, j, k, m.sxi, m.yi, m.zi, m.ss, m.t, m.f, v[0], true, S[0], R[0]);
+			comp(d, i, j, k, m.xi, m.syi, m.zi, m.s, m.st, m.f, v[1], true, S[1], R[1]);
+			comp(d, i, j, k, m.xi, m.yi, m.szi, m.s, m.t, m.sf, v[2], false, S[2], R[2]);
+		}
+		const Real eps = sizeof(Real) == 8 ? (Real)1e-10 : (Real)1e-6f;
+		for (int c = 0; c < 3; c++) {
+			Real w = S[c];
+			if (w < eps) w = 0;
+			const Real r = w ? (R[c] / w) : R[c];
+			vel[3 * idx + c] = r; velOld[3 * idx + c] = r;
+			if (weight) weight[3 * idx + c] = w;
+		}
+	}
+};
+// start: scratch int[d.n]; key / keyTmp / val / sorted: scratch int[np]
+template <typename Real, typename Exec>
+int mapPartsToMAC(Exec& ex, const Dims& d, Real* vel, Real* velOld, IndexInt np, const PSet<Real>& ps, const Real* pvel, Real* weight,
+                  int* start, int* key, int* keyTmp, int* val, int* sorted) {
+	IndexInt count = 0;
+	MP_TRY(bucketParticles<Real>(ex, d, np, ps, true, start, key, keyTmp, val, sorted, &count));
+	MapPartsGather<Real> op = { start, sorted, count, ps.pos, pvel, vel, velOld, weight };
+	return ex.cells(d, op);
+}
+
+}  // namespace parts

@@ -1,11 +1,19 @@
 """CPU (not gpu): the FLIP particle <-> grid plugins (plugin/flip.cpp: markFluidCells, gridParticleIndex, unionParticleLevelset, mapPartsToMAC,
 mapMACToParts, flipVelocityUpdate -- SURVEY 8f-4) restated in the oracle ahead of their device versions: bit for bit the golden vectors of
 the unmodified reference, and the reference itself on another seed."""
+import ctypes as C
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
 import helpers
+from oracle.oracle_api import Oracle
 from helpers import FLIP_SCENES, load_golden, run_flip_plugins
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 
 
 @pytest.mark.parametrize("prec", [4, 8])
@@ -28,3 +36,70 @@ def test_port_equals_reference_on_another_scene(prec, port32, port64, ref32, ref
     a, b = run_flip_plugins(P, "other", prec), run_flip_plugins(R, "other", prec)
     for key in a:
         assert np.array_equal(a[key], b[key]), key
+
+
+# ---------------------------------------------------------------- host emulation of the CUDA kernels (mp_particles_cells.cuh)
+class FlipEmulation(Oracle):
+    """the oracle_api FLIP interface over tests/emul/particles_emul.cpp: the per-cell / per-particle code and the pass sequences the CUDA
+    kernels of mantaflow_b200/csrc/mp_particles.cu run, walked by host loops (the build container has no GPU)"""
+    kind = "emulation"
+
+    def __init__(self, lib, prec, order):
+        self.lib, self.prec, self.order = lib, prec, order
+        self.real = np.float32 if prec == 4 else np.float64
+
+    def _f(self, name, restype=C.c_int):
+        f = getattr(self.lib, "emu_" + name)
+        f.restype = restype
+        return lambda *a: f(C.c_int(self.prec), C.c_int(self.order), *a)
+
+    def _chk(self, rc):
+        assert rc == 0
+
+
+@pytest.fixture(scope="module")
+def parts_emul_lib():
+    src = os.path.join(HERE, "emul", "particles_emul.cpp")
+    out = os.path.join(HERE, "emul", "_build", "libparticles_emul.so")
+    csrc = os.path.join(ROOT, "mantaflow_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("mp_particles_cells.cuh", "mp_liquid_cells.cuh", "mp_common.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+            pytest.skip("cuda_runtime.h not found: the kernel header cannot be compiled for the host emulation")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        # -ffp-contract=off: the kernels are compiled -fmad=false, the reference build has no FMA either
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-w", "-I" + cuda_inc, "-shared", "-fPIC", src, "-o", out])
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(FLIP_SCENES))
+def test_kernel_emulation_reproduces_flip_golden(name, prec, order, parts_emul_lib):
+    """the code the CUDA kernels run, on the host, in four cell / particle orders: bit-identical to the unmodified reference -- including
+    mapPartsToMAC, whose faces gather their particles in ascending particle order (the order of the reference's serial scatter)"""
+    g = load_golden("step_" + name, prec)
+    out = run_flip_plugins(FlipEmulation(parts_emul_lib, prec, order), name, prec)
+    for key in g:
+        assert np.array_equal(out[key], g[key]), (name, prec, order, key)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("shape", [(6, 5, 7), (1, 9, 530)])
+def test_kernel_emulation_equals_port_on_other_scenes(shape, prec, parts_emul_lib, port32, port64, monkeypatch):
+    """another seed, a row wider than one block's 4 x 128 cells, and no particles at all"""
+    monkeypatch.setitem(helpers.FLIP_SCENES, "other", shape)
+    P, E = (port32 if prec == 4 else port64), FlipEmulation(parts_emul_lib, prec, 3)
+    a, b = run_flip_plugins(P, "other", prec), run_flip_plugins(E, "other", prec)
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+    flags, pos, pflag, ptype, pvel, phiObs = helpers.flip_scene("other", prec)
+    none = slice(0, 0)
+    for I in (P, E):
+        index, isys = I.grid_particle_index(flags.shape, pos[none], pflag[none])
+        assert not index.any() and len(isys) == 0
+        assert np.array_equal(I.union_particle_levelset(pos[none], index, isys), P.union_particle_levelset(pos[none], index, isys))
+        vel, velOld = I.map_parts_to_mac(flags.shape, pos[none], pflag[none], pvel[none])
+        assert not vel.any() and not velOld.any()
+        assert np.array_equal(I.mark_fluid_cells(flags.copy(), pos[none], pflag[none]), P.mark_fluid_cells(flags.copy(), pos[none], pflag[none]))
