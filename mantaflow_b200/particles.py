@@ -1,0 +1,263 @@
+"""Host-side mirror of the reference's particle types and FLIP particle <-> grid plugins (second slice), device resident:
+
+    BasicParticleSystem   particle.h:182-274   (pos + flag per particle; PDELETE = 1 << 10 marks a deleted one)
+    ParticleIndexSystem   particle.h:276-300   (sourceIndex per slot)
+    PdataVec3 / PdataInt / PdataReal   ParticleDataImpl<T> particle.h:392-470
+    IntGrid               Grid<int>
+
+    markFluidCells         plugin/flip.cpp:158-177      gridParticleIndex     plugin/flip.cpp:260-306
+    unionParticleLevelset  plugin/flip.cpp:340-350      mapPartsToMAC         plugin/flip.cpp:573-595
+    mapMACToParts          plugin/flip.cpp:651-656      flipVelocityUpdate    plugin/flip.cpp:669-677
+
+Same names, argument order and defaults as the reference.  Every particle array owns a numpy array AND a device array (an mp_grid of
+size (capacity, 1, 1)); two dirty bits keep them coherent lazily, as for the grids (grid.py), so the plugins of a FLIP step
+(scenes/benchmark_dam.py:100-125) never leave the device.  There is no CPU fallback."""
+import ctypes as C
+import numpy as np
+
+from ._lib import MP_GRID_FLAGS, MP_GRID_MAC, MP_GRID_REAL, MantaError, check
+from .grid import _GridBase
+
+PNONE, PNEW, PDELETE, PINVALID = 0, 1 << 1, 1 << 10, 1 << 30      # ParticleBase::ParticleStatus particle.h:37-46
+
+
+class IntGrid(_GridBase):
+    """Grid<int> (the `index` argument of gridParticleIndex): the storage of a FlagGrid"""
+    KIND = MP_GRID_FLAGS
+
+
+class _DevArray:
+    """a per-particle array: numpy [n] / [n,3] on the host, mp_grid (capacity,1,1) on the device, coherent lazily"""
+
+    def __init__(self, solver, kind, n=0):
+        self.solver, self.kind = solver, kind
+        self.dtype = np.int32 if kind == MP_GRID_FLAGS else solver.real
+        self._tail = (3,) if kind == MP_GRID_MAC else ()
+        self._host = np.zeros((n,) + self._tail, self.dtype)
+        self._dev, self._cap = C.c_void_p(), 0
+        self._hostDirty, self._devDirty = n > 0, False
+
+    def __len__(self):
+        return len(self._host)
+
+    def _reserve(self, n):
+        if n <= self._cap:
+            return
+        lib = self.solver.lib
+        if self._dev:
+            check(lib.mp_grid_destroy(self._dev))
+        self._dev, self._cap = C.c_void_p(), max(n, 1)
+        check(lib.mp_grid_create(self.solver._ctx, C.c_int(self.kind), C.c_int(self.solver.prec), C.c_int(self._cap), C.c_int(1), C.c_int(1), C.byref(self._dev)))
+
+    def resize(self, n):
+        """keeps the first min(old, n) entries (of whichever copy is current), new entries are zero"""
+        if n == len(self._host):
+            return
+        old = self.numpy()
+        new = np.zeros((n,) + self._tail, self.dtype)
+        m = min(n, len(old))
+        new[:m] = old[:m]
+        self._host, self._hostDirty, self._devDirty = new, True, False
+
+    def set(self, arr):
+        arr = np.asarray(arr, dtype=self.dtype)
+        self._host = np.array(arr.reshape((-1,) + self._tail), order="C", copy=True)
+        self._hostDirty, self._devDirty = True, False
+
+    def dev(self):
+        """mp_grid handle with the device copy current (uploads only if the host copy is newer); None for an empty array"""
+        n = len(self._host)
+        if n == 0:
+            return None
+        if self._hostDirty or n > self._cap:
+            self._reserve(n)
+            buf = self._host
+            if self._cap != n:          # the upload moves `capacity` entries
+                buf = np.zeros((self._cap,) + self._tail, self.dtype)
+                buf[:n] = self._host
+            check(self.solver.lib.mp_grid_upload(self._dev, buf.ctypes.data_as(C.c_void_p)))
+            self._hostDirty = False
+        return self._dev
+
+    def markDeviceWritten(self):
+        self._devDirty, self._hostDirty = True, False
+
+    def numpy(self, writable=False):
+        if self._devDirty and self._dev:
+            buf = np.zeros((self._cap,) + self._tail, self.dtype)
+            check(self.solver.lib.mp_grid_download(self._dev, buf.ctypes.data_as(C.c_void_p)))
+            self._host = np.ascontiguousarray(buf[:len(self._host)])
+            self._devDirty = False
+        if writable:
+            self._hostDirty = True
+        return self._host
+
+    def close(self):
+        if getattr(self, "_dev", None) is not None and self._dev and self.solver._ctx:
+            self.solver.lib.mp_grid_destroy(self._dev)
+        self._dev, self._cap = C.c_void_p(), 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Pdata:
+    """ParticleDataImpl<T> particle.h:392-470: follows the size of the particle system it was created in"""
+    KIND = MP_GRID_REAL
+
+    def __init__(self, parent, parts=None):
+        self.parent, self.parts = parent, parts
+        self._a = _DevArray(parent, self.KIND, parts.size() if parts is not None else 0)
+
+    def size(self): return len(self._a)
+    def numpy(self, writable=False): return self._a.numpy(writable)
+    def copyFromArray(self, arr): self._a.set(arr)
+    def dev(self): return self._a.dev()
+    def markDeviceWritten(self): self._a.markDeviceWritten()
+
+    def setConst(self, value):
+        self._a.numpy(writable=True)[...] = value
+
+    def clear(self):
+        self.setConst(0)
+
+
+class PdataReal(_Pdata):
+    KIND = MP_GRID_REAL
+
+
+class PdataInt(_Pdata):
+    KIND = MP_GRID_FLAGS
+
+
+class PdataVec3(_Pdata):
+    KIND = MP_GRID_MAC
+
+
+class BasicParticleSystem:
+    """BasicParticleSystem particle.h:182-274 (positions + status flags), with the data fields created through it"""
+
+    def __init__(self, parent):
+        self.parent = parent
+        self._pos = _DevArray(parent, MP_GRID_MAC)
+        self._flag = _DevArray(parent, MP_GRID_FLAGS)
+        self._pdata = []
+
+    def create(self, cls, **kw):
+        """ParticleBase::create particle.cpp:60-70: a data field that is resized with the system"""
+        pd = cls(self.parent, parts=self, **kw)
+        self._pdata.append(pd)
+        return pd
+
+    def size(self): return len(self._pos)
+    pySize = size
+
+    def resize(self, n):
+        for a in [self._pos, self._flag] + [pd._a for pd in self._pdata]:
+            a.resize(n)
+
+    def setParticles(self, pos, flag=None):
+        """positions [n,3] (and status flags [n]); the data fields are resized to n"""
+        pos = np.asarray(pos).reshape(-1, 3)
+        self._pos.set(pos)
+        self._flag.set(np.zeros(len(pos), np.int32) if flag is None else flag)
+        if len(self._flag) != len(pos):
+            raise MantaError(1, "BasicParticleSystem.setParticles: pos and flag differ in length")
+        for pd in self._pdata:
+            pd._a.resize(len(pos))
+
+    def positions(self, writable=False): return self._pos.numpy(writable)
+    def flags(self, writable=False): return self._flag.numpy(writable)
+
+    def clear(self):
+        self.resize(0)
+
+
+class ParticleIndexSystem:
+    """ParticleIndexSystem particle.h:276-300: sourceIndex of every slot, filled by gridParticleIndex"""
+
+    def __init__(self, parent):
+        self.parent = parent
+        self._a = _DevArray(parent, MP_GRID_FLAGS)
+        self._count = 0
+
+    def size(self): return self._count
+    def numpy(self): return self._a.numpy()[:self._count]
+
+
+def _d(g):
+    return None if g is None else g.dev()
+
+
+def _ps(parts):
+    return C.c_longlong(parts.size()), parts._pos.dev(), parts._flag.dev()
+
+
+def _pdcheck(parts, pd, name):
+    if pd is not None and pd.size() != parts.size():
+        raise MantaError(1, "%s holds %d entries, the particle system %d" % (name, pd.size(), parts.size()))
+
+
+def markFluidCells(parts, flags, phiObs=None, ptype=None, exclude=0):
+    s = flags.parent
+    _pdcheck(parts, ptype, "ptype")
+    n, pos, pflag = _ps(parts)
+    check(s.lib.mp_mark_fluid_cells(s._ctx, n, pos, pflag, flags.dev(), _d(phiObs), _d(ptype), C.c_int(exclude)))
+    flags.markDeviceWritten()
+
+
+def gridParticleIndex(parts, indexSys, flags, index, counter=None):
+    """`counter` (a scratch Grid<int> in the reference) is not needed: the slots of a cell are filled by a stable sort"""
+    s = index.parent
+    n, pos, pflag = _ps(parts)
+    indexSys._a.resize(parts.size())
+    indexSys._a._hostDirty = False      # every slot in use is written on the device
+    if parts.size():
+        indexSys._a._reserve(parts.size())
+    count = C.c_longlong(0)
+    check(s.lib.mp_grid_particle_index(s._ctx, n, pos, pflag, indexSys._a._dev if parts.size() else None, _d(flags), index.dev(), C.byref(count)))
+    indexSys._count = count.value
+    if parts.size():
+        indexSys._a.markDeviceWritten()
+    index.markDeviceWritten()
+
+
+def unionParticleLevelset(parts, indexSys, flags, index, phi, radiusFactor=1., ptype=None, exclude=0):
+    s = phi.parent
+    _pdcheck(parts, ptype, "ptype")
+    n, pos, _ = _ps(parts)
+    isys = indexSys._a.dev() if indexSys._count else None
+    check(s.lib.mp_union_particle_levelset(s._ctx, n, pos, isys, C.c_longlong(indexSys._count), _d(flags), index.dev(), phi.dev(), C.c_double(radiusFactor),
+                                           _d(ptype), C.c_int(exclude)))
+    phi.markDeviceWritten()
+
+
+def mapPartsToMAC(flags, vel, velOld, parts, partVel, weight=None, ptype=None, exclude=0):
+    s = vel.parent
+    _pdcheck(parts, partVel, "partVel"); _pdcheck(parts, ptype, "ptype")
+    n, pos, pflag = _ps(parts)
+    check(s.lib.mp_map_parts_to_mac(s._ctx, _d(flags), vel.dev(), velOld.dev(), n, pos, pflag, partVel.dev(), _d(weight), _d(ptype), C.c_int(exclude)))
+    vel.markDeviceWritten(); velOld.markDeviceWritten()
+    if weight is not None:
+        weight.markDeviceWritten()
+
+
+def mapMACToParts(flags, vel, parts, partVel, ptype=None, exclude=0):
+    s = vel.parent
+    _pdcheck(parts, partVel, "partVel"); _pdcheck(parts, ptype, "ptype")
+    n, pos, pflag = _ps(parts)
+    check(s.lib.mp_map_mac_to_parts(s._ctx, _d(flags), vel.dev(), n, pos, pflag, partVel.dev(), _d(ptype), C.c_int(exclude)))
+    if parts.size():
+        partVel.markDeviceWritten()
+
+
+def flipVelocityUpdate(flags, vel, velOld, parts, partVel, flipRatio, ptype=None, exclude=0):
+    s = vel.parent
+    _pdcheck(parts, partVel, "partVel"); _pdcheck(parts, ptype, "ptype")
+    n, pos, pflag = _ps(parts)
+    check(s.lib.mp_flip_velocity_update(s._ctx, _d(flags), vel.dev(), velOld.dev(), n, pos, pflag, partVel.dev(), C.c_double(flipRatio), _d(ptype), C.c_int(exclude)))
+    if parts.size():
+        partVel.markDeviceWritten()

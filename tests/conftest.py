@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+# The driver runs `pytest -x -m gpu`: one failure ends the run.  Files whose current kernels have not run on a B200 yet (the round's GPU
+# minutes were used up before they were written; they are checked through the host emulation only) go last, so that a launch problem in
+# them cannot hide the results of the tests that are known to pass on the device.
+_LAST = ["test_gpu_step_liquid.py", "test_gpu_zzz_flip.py"]
+
+
+def pytest_collection_modifyitems(session, config, items):
+    def rank(item):
+        name = os.path.basename(str(item.fspath))
+        return _LAST.index(name) + 1 if name in _LAST else 0
+    items.sort(key=rank)      # stable: the order inside each group stays
+
+
 def _build_once():
     # the C restatement is cheap to build; the CUDA library and oracle/_ref are built by __graft_entry__.build()
     import subprocess

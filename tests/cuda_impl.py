@@ -220,6 +220,60 @@ class CudaImpl:
         mf.getCurvature(Cv, mf.RealGrid(s, grid), h)
         return Cv.numpy().copy()
 
+    # -- FLIP particle <-> grid plugins (second slice) --
+    def _parts(self, s, pos, pflag, ptype=None, pvel=None):
+        P = mf.BasicParticleSystem(s)
+        T = P.create(mf.PdataInt) if ptype is not None else None
+        V = P.create(mf.PdataVec3) if pvel is not None else None
+        P.setParticles(pos, pflag)
+        if T is not None:
+            T.copyFromArray(ptype)
+        if V is not None:
+            V.copyFromArray(pvel)
+        return P, T, V
+
+    def mark_fluid_cells(self, flags, pos, pflag, phiObs=None, ptype=None, exclude=0):
+        s = self._solver(flags)
+        P, T, _ = self._parts(s, pos, pflag, ptype)
+        F = mf.FlagGrid(s, flags)
+        mf.markFluidCells(P, F, phiObs=self._g(s, mf.RealGrid, phiObs), ptype=T, exclude=exclude)
+        flags[...] = F.numpy()
+        return flags
+
+    def grid_particle_index(self, shape, pos, pflag):
+        s = self._solver(np.zeros(shape, np.int32))
+        P, _, _ = self._parts(s, pos, pflag)
+        I, Ix = mf.ParticleIndexSystem(s), mf.IntGrid(s, np.full(shape, 77, np.int32))       # every cell is written
+        mf.gridParticleIndex(P, I, mf.FlagGrid(s), Ix)
+        return Ix.numpy().copy(), I.numpy().copy()
+
+    def union_particle_levelset(self, pos, index, indexSys, radiusFactor=1.0, ptype=None, exclude=0):
+        s = self._solver(index)
+        P, T, _ = self._parts(s, pos, np.zeros(len(pos), np.int32), ptype)
+        I = mf.ParticleIndexSystem(s)
+        I._a.set(indexSys); I._count = len(indexSys)
+        phi = mf.LevelsetGrid(s, np.full(index.shape, 9.0, self.real))                          # every cell is written
+        mf.unionParticleLevelset(P, I, mf.FlagGrid(s), mf.IntGrid(s, index), phi, radiusFactor=radiusFactor, ptype=T, exclude=exclude)
+        return phi.numpy().copy()
+
+    def map_parts_to_mac(self, shape, pos, pflag, pvel, want_weight=False, ptype=None, exclude=0):
+        s = self._solver(np.zeros(shape, np.int32))
+        P, T, V = self._parts(s, pos, pflag, ptype, pvel)
+        junk = np.full(tuple(shape) + (3,), 5.0, self.real)                                        # every entry is written
+        vel, velOld, w = mf.MACGrid(s, junk), mf.MACGrid(s, junk), (mf.VecGrid(s, junk) if want_weight else None)
+        mf.mapPartsToMAC(mf.FlagGrid(s), vel, velOld, P, V, weight=w, ptype=T, exclude=exclude)
+        return (vel.numpy().copy(), velOld.numpy().copy(), w.numpy().copy()) if want_weight else (vel.numpy().copy(), velOld.numpy().copy())
+
+    def flip_velocity_update(self, vel, velOld, pos, pflag, pvel, flipRatio, ptype=None, exclude=0):
+        s = self._solver(vel[..., 0])
+        P, T, V = self._parts(s, pos, pflag, ptype, pvel)
+        if flipRatio < 0:
+            mf.mapMACToParts(mf.FlagGrid(s), mf.MACGrid(s, vel), P, V, ptype=T, exclude=exclude)
+        else:
+            mf.flipVelocityUpdate(mf.FlagGrid(s), mf.MACGrid(s, vel), mf.MACGrid(s, velOld), P, V, flipRatio, ptype=T, exclude=exclude)
+        pvel[...] = V.numpy()
+        return pvel
+
     def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
         s = self._solver(flags); s.timestep = dt
         U, Um, O = mf.RealGrid(s, ut), mf.RealGrid(s, utm1), mf.RealGrid(s)

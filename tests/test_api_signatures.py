@@ -21,6 +21,8 @@ PLUGINS = {     # plugin -> reference file
     "extrapolateMACSimple": "fastmarch.cpp", "extrapolateLsSimple": "fastmarch.cpp", "extrapolateVec3Simple": "fastmarch.cpp", "extrapolateMACFromWeight": "fastmarch.cpp",
     "getLaplacian": "plugin/flip.cpp", "getCurvature": "plugin/flip.cpp",
     "updateFractions": "plugin/initplugins.cpp", "setObstacleFlags": "plugin/initplugins.cpp",
+    "markFluidCells": "plugin/flip.cpp", "gridParticleIndex": "plugin/flip.cpp", "unionParticleLevelset": "plugin/flip.cpp", "mapPartsToMAC": "plugin/flip.cpp",
+    "mapMACToParts": "plugin/flip.cpp", "flipVelocityUpdate": "plugin/flip.cpp",
 }
 
 

@@ -1,0 +1,118 @@
+"""GPU: the FLIP particle <-> grid plugins on the device (second slice: markFluidCells, gridParticleIndex, unionParticleLevelset,
+mapPartsToMAC, mapMACToParts, flipVelocityUpdate -- plugin/flip.cpp) through the Python mirror and the C-ABI: bit for bit the golden vectors
+of the unmodified reference, the oracle on larger scenes (mapPartsToMAC included: faces gather in particle order, no floating-point
+atomics), and the particle <-> grid part of a FLIP step (scenes/benchmark_dam.py:100-125) with every array resident on the device."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import helpers  # noqa: E402
+from helpers import FLIP_SCENES, load_golden, run_flip_plugins  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def mf():
+    import mantaflow_b200 as m
+    if m.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests need a B200")
+    return m
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(FLIP_SCENES))
+def test_cuda_reproduces_flip_golden(name, prec):
+    from cuda_impl import CudaImpl
+    g = load_golden("step_" + name, prec)
+    out = run_flip_plugins(CudaImpl(prec), name, prec)
+    assert set(out) == set(g)
+    for key in g:
+        assert np.array_equal(out[key], g[key]), (name, prec, key)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("shape", [(40, 36, 150), (1, 70, 530)])
+def test_cuda_equals_oracle_on_larger_scenes(shape, prec, port32, port64, monkeypatch):
+    """tens of thousands of particles, rows wider than one block, several blocks of the particle kernels and several radix-sort passes"""
+    from cuda_impl import CudaImpl
+    monkeypatch.setitem(helpers.FLIP_SCENES, "large", shape)
+    a, b = run_flip_plugins(port32 if prec == 4 else port64, "large", prec), run_flip_plugins(CudaImpl(prec), "large", prec)
+    assert len(a["index_sys"]) > 20000
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+
+
+def test_map_parts_to_mac_is_reproducible(mf):
+    """the same particles in the same order give the same bits on every call (a scatter with floating-point atomics would not)"""
+    from cuda_impl import CudaImpl
+    flags, pos, pflag, ptype, pvel, _ = helpers.flip_scene("flip3d", 4)
+    I = CudaImpl(4)
+    first = I.map_parts_to_mac(flags.shape, pos, pflag, pvel, want_weight=True)
+    for _ in range(3):
+        again = I.map_parts_to_mac(flags.shape, pos, pflag, pvel, want_weight=True)
+        for x, y in zip(first, again):
+            assert np.array_equal(x, y)
+
+
+def test_flip_step_device_resident(mf, port32):
+    """markFluidCells -> mapPartsToMAC -> extrapolateMACFromWeight -> (forces, projection) -> flipVelocityUpdate -> gridParticleIndex ->
+    unionParticleLevelset, written like the scene: particles and grids are uploaded once and stay on the device"""
+    flags_h, pos, pflag, ptype, pvel, _ = helpers.flip_scene("flip3d", 4)
+    sz, sy, sx = flags_h.shape
+    s = mf.Solver(gridSize=(sx, sy, sz), dim=3, prec=4)
+    flags, vel, velOld, weight = mf.FlagGrid(s, flags_h), s.create(mf.MACGrid), s.create(mf.MACGrid), s.create(mf.VecGrid)
+    phi, index, pressure = s.create(mf.LevelsetGrid), s.create(mf.IntGrid), s.create(mf.RealGrid)
+    pp = s.create(mf.BasicParticleSystem)
+    pVel, pindex = pp.create(mf.PdataVec3), s.create(mf.ParticleIndexSystem)
+    pp.setParticles(pos, pflag)
+    pVel.copyFromArray(pvel)
+    launches0 = s.kernelLaunches()
+    mf.markFluidCells(parts=pp, flags=flags)
+    mf.mapPartsToMAC(vel=vel, flags=flags, velOld=velOld, parts=pp, partVel=pVel, weight=weight)
+    mf.extrapolateMACFromWeight(vel=vel, distance=2, weight=weight)
+    mf.addGravity(flags=flags, vel=vel, gravity=(0, -0.0025, 0))
+    mf.setWallBcs(flags=flags, vel=vel)
+    mf.solvePressure(flags=flags, vel=vel, pressure=pressure)
+    mf.flipVelocityUpdate(vel=vel, velOld=velOld, flags=flags, parts=pp, partVel=pVel, flipRatio=0.97)
+    mf.gridParticleIndex(parts=pp, flags=flags, indexSys=pindex, index=index)
+    mf.unionParticleLevelset(pp, pindex, flags, index, phi)
+    assert s.kernelLaunches() > launches0
+    assert not (flags._hostDirty or vel._hostDirty or velOld._hostDirty or pVel._a._hostDirty or pp._pos._hostDirty), "an array went back to the host inside the step"
+    # the same sequence through the oracle (the projection is taken from the device: its parity is covered elsewhere)
+    f = port32.mark_fluid_cells(flags_h.copy(), pos, pflag)
+    assert np.array_equal(flags.numpy(), f)
+    v, vo, w = port32.map_parts_to_mac(flags_h.shape, pos, pflag, pvel, want_weight=True)
+    assert np.array_equal(velOld.numpy(), vo)
+    pv = port32.flip_velocity_update(vel.numpy().copy(), vo, pos, pflag, pvel.copy(), 0.97)
+    assert np.array_equal(pVel.numpy(), pv)
+    ix, isys = port32.grid_particle_index(flags_h.shape, pos, pflag)
+    assert np.array_equal(index.numpy(), ix) and np.array_equal(pindex.numpy(), isys)
+    assert np.array_equal(phi.numpy(), port32.union_particle_levelset(pos, ix, isys))
+
+
+def test_empty_particle_system_and_invalid_arguments(mf):
+    flags_h, pos, pflag, ptype, pvel, _ = helpers.flip_scene("flip2d", 4)
+    sz, sy, sx = flags_h.shape
+    s = mf.Solver(gridSize=(sx, sy, sz), dim=2, prec=4)
+    flags, vel, velOld, index, phi = mf.FlagGrid(s, flags_h), s.create(mf.MACGrid), s.create(mf.MACGrid), s.create(mf.IntGrid), s.create(mf.LevelsetGrid)
+    pp = s.create(mf.BasicParticleSystem)
+    pVel, pindex = pp.create(mf.PdataVec3), s.create(mf.ParticleIndexSystem)
+    mf.markFluidCells(pp, flags)
+    assert not (flags.numpy() & mf.FlagFluid).any()
+    mf.mapPartsToMAC(flags, vel, velOld, pp, pVel)
+    assert not vel.numpy().any()
+    mf.gridParticleIndex(pp, pindex, flags, index)
+    assert pindex.size() == 0 and not index.numpy().any()
+    mf.unionParticleLevelset(pp, pindex, flags, index, phi)
+    mf.mapMACToParts(flags, vel, pp, pVel)
+    pp.setParticles(pos, pflag)
+    with pytest.raises(mf.MantaError):
+        mf.mapPartsToMAC(flags, vel, vel, pp, pVel)            # vel and velOld must differ
+    with pytest.raises(mf.MantaError):
+        mf.mapPartsToMAC(flags, phi, velOld, pp, pVel)         # not a MAC grid
+    with pytest.raises(mf.MantaError):
+        mf.markFluidCells(pp, vel)                             # not a FlagGrid
+    other = mf.BasicParticleSystem(s)
+    short = other.create(mf.PdataVec3)
+    with pytest.raises(mf.MantaError):
+        mf.flipVelocityUpdate(flags, vel, velOld, pp, short, 0.9)      # data field of another size
