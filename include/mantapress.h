@@ -147,6 +147,10 @@ int mp_apply_matrix(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const m
 int mp_mic_init(mp_context* ctx, const mp_grid* flags, mp_grid* Aprecond, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
 int mp_mic_apply(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* flags, const mp_grid* Aprecond,
                  const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
+/* IC(0) "a la Wavelet Turbulence" (PC_ICP): InitPreconditionIncompCholesky conjugategrad.cpp:26-63, ApplyPreconditionIncompCholesky :109-132.
+ * P0..Pk receive the factor (a scaled copy of the matrix, diagonal inverted; bit-identical to the reference's four grids). 3-D only, like the reference. */
+int mp_ic_init(mp_context* ctx, const mp_grid* flags, mp_grid* P0, mp_grid* Pi, mp_grid* Pj, mp_grid* Pk, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
+int mp_ic_apply(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* flags, const mp_grid* P0, const mp_grid* Pi, const mp_grid* Pj, const mp_grid* Pk);
 
 /* ---- GridCg conjugategrad.h:65-114 ---- */
 int mp_cg_create(mp_context* ctx, mp_grid* dst, mp_grid* rhs, mp_grid* residual, mp_grid* search, const mp_grid* flags, mp_grid* tmp,

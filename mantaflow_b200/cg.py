@@ -76,6 +76,21 @@ def ApplyPreconditionModifiedIncompCholesky2(dst, Var1, flags, Aprecond, A0, Ai,
     dst.markDeviceWritten()
 
 
+def InitPreconditionIncompCholesky(flags, A0, Ai, Aj, Ak, orgA0, orgAi, orgAj, orgAk):
+    """IC(0) "a la Wavelet Turbulence" conjugategrad.cpp:26-63: A0..Ak receive the factor of orgA0..orgAk"""
+    s = flags.parent
+    check(s.lib.mp_ic_init(s._ctx, flags.dev(), A0.dev(), Ai.dev(), Aj.dev(), Ak.dev(), orgA0.dev(), orgAi.dev(), orgAj.dev(), orgAk.dev()))
+    for g in (A0, Ai, Aj, Ak):
+        g.markDeviceWritten()
+
+
+def ApplyPreconditionIncompCholesky(dst, Var1, flags, A0, Ai, Aj, Ak, orgA0=None, orgAi=None, orgAj=None, orgAk=None):
+    """conjugategrad.cpp:109-132 (the org* arguments are unused there as well)"""
+    s = flags.parent
+    check(s.lib.mp_ic_apply(s._ctx, dst.dev(), Var1.dev(), flags.dev(), A0.dev(), Ai.dev(), Aj.dev(), Ak.dev()))
+    dst.markDeviceWritten()
+
+
 def GridDotProduct(a, b):
     s = a.parent
     out = C.c_double(0)
@@ -205,6 +220,9 @@ class GridCg:
     def _mark(self):
         for g in self._written:
             g.markDeviceWritten()
+        for g in self._keep:          # the preconditioner grids of PC_ICP / PC_mICP are written by doInit
+            if hasattr(g, "markDeviceWritten"):
+                g.markDeviceWritten()
 
     def iterate(self):
         for g in self._grids:

@@ -641,7 +641,7 @@ struct mp_cg {
 	mp_context* ctx;
 	mp_grid *dst, *rhs, *residual, *search, *tmp, *A0, *Ai, *Aj, *Ak; const mp_grid* flags;
 	int pcMethod;                 // mp_cg_pc_type
-	mp_grid* pcA0; mp_mg* mg;
+	mp_grid* pcA0; mp_grid *pcAi = nullptr, *pcAj = nullptr, *pcAk = nullptr; mp_mg* mg;
 	bool inited; bool useL2; double accuracy;
 	void* dSc;                    // CgScal<Real> on the device
 	CgScalHost* hSc;              // pinned mirror (2 slots for the lagged poll)
@@ -679,6 +679,8 @@ int mp_mic_init_launch(mp_context* ctx, const mp_grid* flags, mp_grid* P, const 
 int mp_mic_check_stall(mp_context* ctx);
 int mp_mic_apply_launch(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* flags, const mp_grid* P,
                         const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, const int* doneFlag);
+int mp_ic_init_launch(mp_context* ctx, const mp_grid* flags, mp_grid* P0, mp_grid* Pi, mp_grid* Pj, mp_grid* Pk, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
+int mp_ic_apply_launch(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* flags, const mp_grid* P0, const mp_grid* Pi, const mp_grid* Pj, const mp_grid* Pk, const int* doneFlag);
 int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, double accuracy);
 int mp_mg_precond_apply(mp_mg* mg, mp_grid* dst, const mp_grid* rhs, const int* doneFlag);
 
@@ -686,7 +688,8 @@ static int cgApplyPrecond(mp_cg* cg, const int* doneFlag) {
 	mp_context* ctx = cg->ctx;
 	if (cg->pcMethod == MP_CG_PC_MICP) return mp_mic_apply_launch(ctx, cg->tmp, cg->residual, cg->flags, cg->pcA0, cg->Ai, cg->Aj, cg->Ak, doneFlag);
 	if (cg->pcMethod == MP_CG_PC_MGP) return mp_mg_precond_apply(cg->mg, cg->tmp, cg->residual, doneFlag);
-	MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: preconditioner %d not implemented on the device (PC_ICP is not reachable from solvePressure)", cg->pcMethod);
+	if (cg->pcMethod == MP_CG_PC_ICP) return mp_ic_apply_launch(ctx, cg->tmp, cg->residual, cg->flags, cg->pcA0, cg->pcAi, cg->pcAj, cg->pcAk, doneFlag);   // :257-258
+	MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: preconditioner %d not implemented on the device", cg->pcMethod);
 }
 
 static int cgHalo(mp_cg* cg, mp_grid* g) {       // one-plane ghost exchange of a Real slab grid (no-op on a single GPU)
@@ -699,7 +702,8 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	MP_TRY(mp_dist_check_grid(cg->flags));
 	if (!cg->flagsChecked) { MP_TRY(mp_check_flags_interior(ctx, cg->flags)); cg->flagsChecked = true; }
 	if (cg->pcMethod == MP_CG_PC_MICP && !d.is3D) MP_FAIL(MP_ERR_INVALID, "mICP only supports 3D grids so far");   // :222
-	if (cg->pcMethod == MP_CG_PC_ICP) MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: PC_ICP is not implemented on the device");
+	if (cg->pcMethod == MP_CG_PC_ICP && !d.is3D) MP_FAIL(MP_ERR_INVALID, "ICP only supports 3D grids so far");    // :218
+	if (cg->pcMethod == MP_CG_PC_ICP && d.world > 1) MP_FAIL(MP_ERR_UNSUPPORTED, "GridCg: PC_ICP is not available on z-slab sharded grids");
 	// Slab mode with a preconditioner: block-Jacobi over the slabs.  MIC(0) / GridMg are built and applied on
 	// this rank's slab only -- the ghost planes are the local grid's outer layer (A0 == 0 there, so they are non-fluid for the
 	// MIC sweeps and inactive vertices for GridMg), i.e. the preconditioner is the block diagonal of the global one.  It is
@@ -754,6 +758,7 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	if (none && dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 3, 0));
 	if (!none) {
 		if (cg->pcMethod == MP_CG_PC_MICP) MP_TRY(mp_mic_init_launch(ctx, cg->flags, cg->pcA0, cg->A0, cg->Ai, cg->Aj, cg->Ak));
+		else if (cg->pcMethod == MP_CG_PC_ICP) MP_TRY(mp_ic_init_launch(ctx, cg->flags, cg->pcA0, cg->pcAi, cg->pcAj, cg->pcAk, cg->A0, cg->Ai, cg->Aj, cg->Ak));   // :219
 		else MP_TRY(mp_mg_precond_init(cg->mg, cg->A0, cg->Ai, cg->Aj, cg->Ak, cg->accuracy));
 		MP_TRY(cgApplyPrecond(cg, nullptr));
 		MP_TRY(mp_grid_copy_from(cg->search, cg->tmp));                     // mSearch.copyFrom(mTmp) :232
@@ -945,9 +950,13 @@ int mp_cg_set_ic_preconditioner(mp_cg* cg, int method, mp_grid* A0, mp_grid* Ai,
 		if (!A0) MP_FAIL(MP_ERR_INVALID, "setICPreconditioner: preconditioner grid A0 is NULL");
 		MP_TRY(mp_check_same(cg->dst, A0, MP_GRID_REAL, "pcA0", false));
 	}
+	if (method == MP_CG_PC_ICP) {       // IC(0) keeps a scaled copy of the whole matrix (":25 needs 4 add. grids")
+		if (!Ai || !Aj || !Ak) MP_FAIL(MP_ERR_INVALID, "setICPreconditioner: PC_ICP needs the four preconditioner grids A0, Ai, Aj, Ak");
+		MP_TRY(mp_check_same(cg->dst, Ai, MP_GRID_REAL, "pcAi", false)); MP_TRY(mp_check_same(cg->dst, Aj, MP_GRID_REAL, "pcAj", false)); MP_TRY(mp_check_same(cg->dst, Ak, MP_GRID_REAL, "pcAk", false));
+	}
 	cg->pcMethod = method;
 	if (method != MP_CG_PC_NONE && cg->dst->sz == 1) cg->pcMethod = MP_CG_PC_NONE;   // "only supported in 3D for now, disabling it" :315-321
-	cg->pcA0 = A0; (void)Ai; (void)Aj; (void)Ak;
+	cg->pcA0 = A0; cg->pcAi = Ai; cg->pcAj = Aj; cg->pcAk = Ak;
 	return MP_OK;
 }
 int mp_cg_set_mg_preconditioner(mp_cg* cg, int method, mp_mg* mg) {

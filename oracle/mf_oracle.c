@@ -874,9 +874,54 @@ int mfo_mg_vcycle(const Real* rhs, Real* dst, double coarsestAccuracy, int pre, 
 	mg_set_rhs(g_mg, rhs); mg_vcycle(g_mg, dst); return 0;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * IC(0) "a la Wavelet Turbulence": InitPreconditionIncompCholesky conjugategrad.cpp:26-63 (serial, k/j/i order; the scatter to the
+ * +x/+y/+z neighbours also lands on non-fluid cells), InvertCheckFluid commonkernels.h:25-29.  P0..Pk receive the factor. */
+static void ic_init(int sx, int sy, int sz, const int* flags, Real* P0, Real* Pi, Real* Pj, Real* Pk, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	memcpy(P0, A0, sizeof(Real) * (size_t)n); memcpy(Pi, Ai, sizeof(Real) * (size_t)n);
+	memcpy(Pj, Aj, sizeof(Real) * (size_t)n); memcpy(Pk, Ak, sizeof(Real) * (size_t)n);
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		P0[idx] = R_SQRT(P0[idx]);
+		const Real invDiagonal = 1.0f / P0[idx];
+		Pi[idx] *= invDiagonal; Pj[idx] *= invDiagonal; Pk[idx] *= invDiagonal;
+		P0[idx + X] -= Pi[idx] * Pi[idx];
+		P0[idx + Y] -= Pj[idx] * Pj[idx];
+		P0[idx + Z] -= Pk[idx] * Pk[idx];
+	}
+	for (IndexInt q = 0; q < n; q++) if ((flags[q] & TypeFluid) && P0[q] > 0) P0[q] = (Real)(1.0 / (double)P0[q]);
+}
+int mfo_ic_init(int sx, int sy, int sz, const int* flags, Real* P0, Real* Pi, Real* Pj, Real* Pk, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{
+	if (sz < 2) { snprintf(g_err, sizeof g_err, "ICP only supports 3D grids so far"); return 1; }
+	ic_init(sx, sy, sz, flags, P0, Pi, Pj, Pk, A0, Ai, Aj, Ak); return 0;
+}
+
+/* ApplyPreconditionIncompCholesky conjugategrad.cpp:109-132 */
+static void ic_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src, const Real* P0, const Real* Pi, const Real* Pj, const Real* Pk)
+{
+	STRIDES
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		dst[idx] = P0[idx] * (src[idx] - dst[idx - X] * Pi[idx - X] - dst[idx - Y] * Pj[idx - Y] - dst[idx - Z] * Pk[idx - Z]);
+	}
+	for (int k = sz - 1; k >= 0; k--) for (int j = sy - 1; j >= 0; j--) for (int i = sx - 1; i >= 0; i--) {
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		dst[idx] = P0[idx] * (dst[idx] - dst[idx + X] * Pi[idx] - dst[idx + Y] * Pj[idx] - dst[idx + Z] * Pk[idx]);
+	}
+}
+int mfo_ic_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src, const Real* P0, const Real* Pi, const Real* Pj, const Real* Pk)
+{ ic_apply(sx, sy, sz, flags, dst, src, P0, Pi, Pj, Pk); return 0; }
+
 /* =============================================================================================
  * GridCg<APPLYMAT>: conjugategrad.cpp:201-307 (doInit :209-235, iterate :237-299)
- * pc: 0 PC_None, 1 PC_mICP, 2 PC_MGP.  `mg` may carry an already-set hierarchy (PcMGStatic).     */
+ * pc: 0 PC_None, 1 PC_mICP, 2 PC_MGP, 3 PC_ICP.  `mg` may carry an already-set hierarchy (PcMGStatic).     */
 static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Real* x,
 	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak,
 	int pc, Real accuracy, int useL2, int maxIter, MgState* mg, int* iterations, double* resNormOut)
@@ -885,9 +930,9 @@ static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Rea
 	Real* residual = (Real*)calloc((size_t)n, sizeof(Real));
 	Real* search = (Real*)calloc((size_t)n, sizeof(Real));
 	Real* tmp = (Real*)calloc((size_t)n, sizeof(Real));
-	Real* P = 0;
+	Real* P = 0; Real* Pc[3] = { 0, 0, 0 };
 	int rc = 0;
-	if (pc == 1 && !IS3D) pc = 0;                              /* setICPreconditioner :315-321 */
+	if ((pc == 1 || pc == 3) && !IS3D) pc = 0;                 /* setICPreconditioner :315-321 */
 	/* doInit */
 	memset(x, 0, sizeof(Real) * (size_t)n);
 	memcpy(residual, rhs, sizeof(Real) * (size_t)n);
@@ -895,6 +940,11 @@ static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Rea
 		P = (Real*)calloc((size_t)n, sizeof(Real));
 		mic_init(sx, sy, sz, flags, P, A0, Ai, Aj, Ak);
 		mic_apply(sx, sy, sz, flags, tmp, residual, P, Ai, Aj, Ak);
+	} else if (pc == 3) {
+		P = (Real*)calloc((size_t)n, sizeof(Real));
+		for (int c = 0; c < 3; c++) Pc[c] = (Real*)calloc((size_t)n, sizeof(Real));
+		ic_init(sx, sy, sz, flags, P, Pc[0], Pc[1], Pc[2], A0, Ai, Aj, Ak);
+		ic_apply(sx, sy, sz, flags, tmp, residual, P, Pc[0], Pc[1], Pc[2]);
 	} else if (pc == 2) {
 		if (!mg->isASet) mg_set_a(mg, A0, Ai, Aj, Ak);         /* InitPreconditionMultigrid :100-106 */
 		mg->coarsestAcc = (Real)(accuracy * 1E-4); mg->numPre = 1; mg->numPost = 1;
@@ -913,6 +963,7 @@ static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Rea
 		scaled_add(x, search, alpha, n);
 		scaled_add(residual, tmp, -alpha, n);
 		if (pc == 1) mic_apply(sx, sy, sz, flags, tmp, residual, P, Ai, Aj, Ak);
+		else if (pc == 3) ic_apply(sx, sy, sz, flags, tmp, residual, P, Pc[0], Pc[1], Pc[2]);
 		else if (pc == 2) { mg_set_rhs(mg, residual); mg_vcycle(mg, tmp); }
 		else memcpy(tmp, residual, sizeof(Real) * (size_t)n);
 		if (useL2) resNorm = (Real)sum_sqr(residual, n); else resNorm = max_abs(residual, n);
@@ -926,7 +977,7 @@ static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Rea
 	}
 	if (iterations) *iterations = its;
 	if (resNormOut) *resNormOut = resNorm;
-	free(residual); free(search); free(tmp); free(P);
+	free(residual); free(search); free(tmp); free(P); free(Pc[0]); free(Pc[1]); free(Pc[2]);
 	return rc;
 }
 

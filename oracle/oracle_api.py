@@ -168,6 +168,18 @@ class Oracle:
         self._chk(self._f("mic_apply")(*self.dims(flags), _p(flags), _p(dst), _p(self._r(src)), _p(P), _p(A0), _p(Ai), _p(Aj), _p(Ak)))
         return dst
 
+    def ic_init(self, flags, A0, Ai, Aj, Ak):
+        """InitPreconditionIncompCholesky conjugategrad.cpp:26-63 (PC_ICP); returns the factor grids (P0, Pi, Pj, Pk)"""
+        P = [np.zeros(flags.shape, self.real) for _ in range(4)]
+        self._chk(self._f("ic_init")(*self.dims(flags), _p(flags), *[_p(a) for a in P], _p(A0), _p(Ai), _p(Aj), _p(Ak)))
+        return P
+
+    def ic_apply(self, flags, src, P0, Pi, Pj, Pk, dst=None):
+        """ApplyPreconditionIncompCholesky conjugategrad.cpp:109-132"""
+        dst = np.zeros(flags.shape, self.real) if dst is None else dst
+        self._chk(self._f("ic_apply")(*self.dims(flags), _p(flags), _p(dst), _p(self._r(src)), _p(P0), _p(Pi), _p(Pj), _p(Pk)))
+        return dst
+
     def cg_solve(self, flags, rhs, A0, Ai, Aj, Ak, pc=0, accuracy=1e-4, useL2=False, maxIter=1000):
         x = np.zeros(flags.shape, self.real)
         it, rn = C.c_int(0), C.c_double(0)

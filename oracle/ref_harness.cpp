@@ -78,6 +78,8 @@ void extrapolateVec3Simple(Grid<Vec3>& vel, Grid<Real>& phi, int distance, bool 
 void addGravity(const FlagGrid& flags, MACGrid& vel, Vec3 gravity, const Grid<Real>* exclude, bool scale);
 void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGrid& vel, Vec3 gravity, Real coefficient, bool scale);
 void advectSemiLagrange(const FlagGrid* flags, const MACGrid* vel, GridBase* grid, int order, Real strength, int orderSpace, bool openBounds, int boundaryWidth, int clampMode, int orderTrace);
+void InitPreconditionIncompCholesky(const FlagGrid& flags, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak, Grid<Real>& orgA0, Grid<Real>& orgAi, Grid<Real>& orgAj, Grid<Real>& orgAk);
+void ApplyPreconditionIncompCholesky(Grid<Real>& dst, Grid<Real>& Var1, const FlagGrid& flags, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak, Grid<Real>& orgA0, Grid<Real>& orgAi, Grid<Real>& orgAj, Grid<Real>& orgAk);
 void InitPreconditionModifiedIncompCholesky2(const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
 void ApplyPreconditionModifiedIncompCholesky2(Grid<Real>& dst, Grid<Real>& Var1, const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
 }
@@ -438,8 +440,25 @@ int ref_mic_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Rea
 	delete s;
   CATCH }
 
+// IC(0) "a la Wavelet Turbulence" conjugategrad.cpp:26-63,:109-132 (PC_ICP, the preconditioner of the VIC Poisson solve)
+int ref_ic_init(int sx, int sy, int sz, const int* flags, Real* P0, Real* Pi, Real* Pj, Real* Pk, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); Grid<Real> p0(s, P0), pi(s, Pi), pj(s, Pj), pk(s, Pk), a0(s, (Real*)A0), ai(s, (Real*)Ai), aj(s, (Real*)Aj), ak(s, (Real*)Ak);
+	  InitPreconditionIncompCholesky(F, p0, pi, pj, pk, a0, ai, aj, ak); }
+	delete s;
+  CATCH }
+
+int ref_ic_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src, const Real* P0, const Real* Pi, const Real* Pj, const Real* Pk)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, (int*)flags); Grid<Real> d(s, dst), sr(s, (Real*)src), p0(s, (Real*)P0), pi(s, (Real*)Pi), pj(s, (Real*)Pj), pk(s, (Real*)Pk);
+	  ApplyPreconditionIncompCholesky(d, sr, F, p0, pi, pj, pk, p0, pi, pj, pk); }      // the org* arguments are unused (:109-132)
+	delete s;
+  CATCH }
+
 // GridCg driven directly (the only unpatched route to PcNone in 3-D).
-// pc: 0 none, 1 mICP, 2 MG (fresh GridMg).  x is overwritten; returns iterations / resNorm.
+// pc: 0 none, 1 mICP, 2 MG (fresh GridMg), 3 ICP.  x is overwritten; returns iterations / resNorm.
 int ref_cg_solve(int sx, int sy, int sz, const int* flags, const Real* rhs, Real* x,
 	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak,
 	int pc, double accuracy, int useL2, int maxIter, int* iterations, double* resNorm)
@@ -457,6 +476,9 @@ int ref_cg_solve(int sx, int sy, int sz, const int* flags, const Real* rhs, Real
 	  if (pc == 1) {
 		pca0 = new Grid<Real>(s); pca1 = new Grid<Real>(s); pca2 = new Grid<Real>(s); pca3 = new Grid<Real>(s);
 		gcg->setICPreconditioner(GridCgInterface::PC_mICP, pca0, pca1, pca2, pca3);
+	  } else if (pc == 3) {
+		pca0 = new Grid<Real>(s); pca1 = new Grid<Real>(s); pca2 = new Grid<Real>(s); pca3 = new Grid<Real>(s);
+		gcg->setICPreconditioner(GridCgInterface::PC_ICP, pca0, pca1, pca2, pca3);
 	  } else if (pc == 2) {
 		mg = new GridMg(Vec3i(sx, sy, sz));
 		gcg->setMGPreconditioner(GridCgInterface::PC_MGP, mg);

@@ -71,6 +71,18 @@ class CudaImpl:
         cg.ApplyPreconditionModifiedIncompCholesky2(D, mf.RealGrid(s, src), mf.FlagGrid(s, flags), mf.RealGrid(s, P), *[mf.RealGrid(s, a) for a in (A0, Ai, Aj, Ak)])
         return D.numpy().copy()
 
+    def ic_init(self, flags, A0, Ai, Aj, Ak):
+        s = self._solver(flags)
+        P = [mf.RealGrid(s, np.full(flags.shape, 3.0, self.real)) for _ in range(4)]      # every cell is written
+        cg.InitPreconditionIncompCholesky(mf.FlagGrid(s, flags), *P, *[mf.RealGrid(s, a) for a in (A0, Ai, Aj, Ak)])
+        return [p.numpy().copy() for p in P]
+
+    def ic_apply(self, flags, src, P0, Pi, Pj, Pk):
+        s = self._solver(flags)
+        D = mf.RealGrid(s)
+        cg.ApplyPreconditionIncompCholesky(D, mf.RealGrid(s, src), mf.FlagGrid(s, flags), *[mf.RealGrid(s, a) for a in (P0, Pi, Pj, Pk)])
+        return D.numpy().copy()
+
     def cg_solve(self, flags, rhs, A0, Ai, Aj, Ak, pc=0, accuracy=1e-4, useL2=False, maxIter=1000):
         s = self._solver(flags)
         F = mf.FlagGrid(s, flags)
@@ -85,6 +97,9 @@ class CudaImpl:
         elif pc == 2:
             keep = cg.GridMg(s)
             g.setMGPreconditioner(cg.GridCg.PC_MGP, keep)
+        elif pc == 3:
+            keep = [mf.RealGrid(s) for _ in range(4)]
+            g.setICPreconditioner(cg.GridCg.PC_ICP, *keep)
         g.solve(maxIter)
         return x.numpy().copy(), g.getIterations(), g.getResNorm()
 

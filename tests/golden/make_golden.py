@@ -221,6 +221,20 @@ def flip_fixtures():
             print("%-34s %7.1f KiB  %d indexed particles, %d fluid cells" % (os.path.basename(path), os.path.getsize(path) / 1024, len(fx["index_sys"]), int((fx["mark"] & 1).sum())))
 
 
+def icp_fixtures():
+    """icp_<scene>_f{32,64}.npz: the reference's IC(0) preconditioner (InitPreconditionIncompCholesky / ApplyPreconditionIncompCholesky,
+    conjugategrad.cpp:26-63,:109-132) and a GridCg solve with PC_ICP on the systems of the 3-D kernels_* fixtures"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import helpers
+    for prec in (4, 8):
+        R = Oracle("reference", prec)
+        for name in helpers.ICP_SCENES:
+            fx = helpers.run_icp(R, helpers.load_golden(name, prec), prec)
+            path = os.path.join(HERE, "icp_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, **fx)
+            print("%-34s %7.1f KiB  PC_ICP %d its" % (os.path.basename(path), os.path.getsize(path) / 1024, int(fx["cg_ic_it"])))
+
+
 def io_fixtures():
     """tests/golden/io/ref_<kind>_<2d|3d>_f{32,64}.uni: grid files written by the unmodified reference's Grid<T>::save (fileio/iogrids.cpp)
     from the seeded arrays of tests/test_fileio.py::sample"""
@@ -241,6 +255,8 @@ def main():
         return io_fixtures()
     if "--only-flip" in sys.argv:
         return flip_fixtures()
+    if "--only-icp" in sys.argv:
+        return icp_fixtures()
     if "--only-liquid" in sys.argv:
         return liquid_fixtures()
     if "--only-step" in sys.argv:
@@ -250,6 +266,7 @@ def main():
     liquid_fixtures()
     flip_fixtures()
     io_fixtures()
+    icp_fixtures()
     for prec in (4, 8):
         R = Oracle("reference", prec)
         for name in KERNEL_SCENES:

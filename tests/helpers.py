@@ -14,7 +14,7 @@ KERNEL_FIXTURES = ["smoke16", "liquid14", "smoke2d"]
 
 def load_golden(name, prec):
     """kernels_<name>_f<bits>.npz, or <name>_f<bits>.npz for the step_* / plume* fixtures"""
-    stem = name if name.startswith(("step_", "plume")) else "kernels_" + name
+    stem = name if name.startswith(("step_", "plume", "icp_")) else "kernels_" + name
     return dict(np.load(os.path.join(GOLDEN, "%s_f%d.npz" % (stem, prec * 8))))
 
 
@@ -601,3 +601,33 @@ def run_flip_plugins(I, name, prec):
     out["pic"] = I.flip_velocity_update(vnew, vel, pos, pflag, pvel.copy(), -1.0, ptype=ptype, exclude=4)
     out["flip"] = I.flip_velocity_update(vnew, vel, pos, pflag, pvel.copy(), 0.97, ptype=ptype, exclude=4)
     return out
+
+
+# ---------------------------------------------------------------- IC(0) preconditioner (PC_ICP, conjugategrad.cpp:26-63,:109-132)
+ICP_SCENES = ["smoke16", "liquid14"]          # the 3-D systems of the kernels_* fixtures (ICP only supports 3-D grids, conjugategrad.cpp:218)
+
+
+def run_icp(I, g, prec):
+    """factor, one application and a GridCg solve with PC_ICP (pc = 3 in the oracle interface) on the system of a kernels_* fixture"""
+    flags, A = g["flags"], [g[n] for n in "A0 Ai Aj Ak".split()]
+    P = I.ic_init(flags, *A)
+    out = {"ic_P%s" % n: p for n, p in zip("0ijk", P)}
+    out["ic_apply"] = I.ic_apply(flags, g["src"], *P)
+    x, it, rn = I.cg_solve(flags, g["rhs"], *A, pc=3, accuracy=1e-5 if prec == 4 else 1e-11, maxIter=4000)
+    out.update(cg_ic_x=x, cg_ic_it=np.array(it), cg_ic_res=np.array(rn))
+    return out
+
+
+def check_icp_against_golden(I, name, prec, exact_reductions):
+    g, k = load_golden("icp_" + name, prec), load_golden(name, prec)
+    out = run_icp(I, k, prec)
+    fluid = (k["flags"] & 1) != 0
+    for n in "0ijk":
+        assert np.array_equal(out["ic_P" + n], g["ic_P" + n]), "IC factor P%s not bit-exact" % n
+    assert np.array_equal(out["ic_apply"][fluid], g["ic_apply"][fluid]), "IC sweeps not bit-exact"
+    assert abs(int(out["cg_ic_it"]) - int(g["cg_ic_it"])) <= 1
+    assert rel_l2(out["cg_ic_x"], g["cg_ic_x"]) <= (1e-4 if prec == 4 else 1e-10)
+    if exact_reductions:
+        assert int(out["cg_ic_it"]) == int(g["cg_ic_it"]) and np.array_equal(out["cg_ic_x"], g["cg_ic_x"])
+    # the fixture is not vacuous: ICP beats the unpreconditioned solve
+    assert int(g["cg_ic_it"]) < int(k["cg_none_it"])

@@ -116,3 +116,27 @@ def test_empty_particle_system_and_invalid_arguments(mf):
     short = other.create(mf.PdataVec3)
     with pytest.raises(mf.MantaError):
         mf.flipVelocityUpdate(flags, vel, velOld, pp, short, 0.9)      # data field of another size
+
+
+# ---------------------------------------------------------------- IC(0) preconditioner PC_ICP (written in the same GPU-less session)
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", helpers.ICP_SCENES)
+def test_cuda_reproduces_icp_golden(name, prec):
+    """InitPreconditionIncompCholesky / ApplyPreconditionIncompCholesky (conjugategrad.cpp:26-63,:109-132) on the device: the four factor grids
+    and the sweeps bit for bit, GridCg with PC_ICP to the iteration"""
+    from cuda_impl import CudaImpl
+    helpers.check_icp_against_golden(CudaImpl(prec), name, prec, exact_reductions=False)
+
+
+def test_gridcg_icp_larger_system(mf, port32):
+    """a 40 x 36 x 44 smoke system: same iteration count (+-1) and solution as the restatement; 2-D grids disable the preconditioner like the reference"""
+    from cuda_impl import CudaImpl
+    from mantaflow_b200 import scenes
+    flags, vel = scenes.smoke_plume((40, 36, 44), 4, random_vel=True)
+    rhs = port32.compute_rhs(flags, vel)[0]
+    A = port32.make_matrix(flags)
+    xo, ito, _ = port32.cg_solve(flags, rhs, *A, pc=3, accuracy=1e-5, maxIter=2000)
+    xc, itc, _ = CudaImpl(4).cg_solve(flags, rhs, *A, pc=3, accuracy=1e-5, maxIter=2000)
+    assert abs(ito - itc) <= 1 and helpers.rel_l2(xc, xo) <= 1e-4
+    xn, itn, _ = port32.cg_solve(flags, rhs, *A, pc=0, accuracy=1e-5, maxIter=2000)
+    assert itc < itn
