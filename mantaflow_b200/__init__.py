@@ -16,7 +16,7 @@ from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, relea
 from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE
 from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, extrapolateLsSimple, extrapolateMACFromWeight, extrapolateMACSimple,
                    extrapolateVec3Simple, getCurvature, getLaplacian, lastGuidingIterations, releaseBlurPrecomp, setObstacleFlags, setWallBcs, updateFractions)
-from .particles import (PDELETE, PNEW, BasicParticleSystem, IntGrid, ParticleIndexSystem, PdataInt, PdataReal, PdataVec3, flipVelocityUpdate, gridParticleIndex, mapMACToParts,
+from .particles import (PDELETE, PNEW, IntEuler, IntRK2, IntRK4, BasicParticleSystem, IntGrid, ParticleIndexSystem, PdataInt, PdataReal, PdataVec3, flipVelocityUpdate, gridParticleIndex, mapMACToParts,
                         mapPartsToMAC, markFluidCells, unionParticleLevelset)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -219,6 +219,29 @@ int mp_map_parts_to_mac(mp_context* ctx, const mp_grid* flags, mp_grid* vel, mp_
 	return mapParts<double>(ctx, vel, velOld, np, pos, pflag, partVel, weight, ptype, exclude);
 }
 
+int mp_parts_advect_in_grid(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, long long np, mp_grid* pos, mp_grid* pflag, double dt, int integrationMode,
+                            int deleteInObstacle, int stopInObstacle, int skipNew, const mp_grid* ptype, int exclude)
+{
+	MP_TRY(checkCtx("mp_parts_advect_in_grid", ctx, flags));
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "advectInGrid: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, vel, MP_GRID_MAC, "vel", false));
+	if (integrationMode < 0 || integrationMode > 2) MP_FAIL(MP_ERR_INVALID, "unknown integration type");      // util/integrator.h:63
+	MP_TRY(checkParts("mp_parts_advect_in_grid", np, pos, pflag, ptype, vel->prec));
+	if (vel->sx < 2 || vel->sy < 2 || (vel->sz > 1 && vel->sz < 2)) MP_FAIL(MP_ERR_INVALID, "advectInGrid: the interpolation needs at least two cells per axis");
+	if (np == 0) return MP_OK;
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(flags);
+	const int* pt = ptype ? (const int*)ptype->d : nullptr;
+	if (vel->prec == 4) {
+		parts::AdvectInGrid<float> op = { d, (const int*)flags->d, (const float*)vel->d, (float*)pos->d, (int*)pflag->d, pt, exclude, (float)dt, integrationMode,
+		                                  deleteInObstacle != 0, stopInObstacle != 0, skipNew != 0 };
+		return ex.parts(np, op);
+	}
+	parts::AdvectInGrid<double> op = { d, (const int*)flags->d, (const double*)vel->d, (double*)pos->d, (int*)pflag->d, pt, exclude, dt, integrationMode,
+	                                   deleteInObstacle != 0, stopInObstacle != 0, skipNew != 0 };
+	return ex.parts(np, op);
+}
+
 int mp_map_mac_to_parts(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* partVel,
                         const mp_grid* ptype, int exclude)
 {

@@ -4,6 +4,7 @@
 //   unionParticleLevelset  plugin/flip.cpp:340-350  (ComputeUnionLevelsetPindex :308-338) + phi.setBound(0.5, 0)
 //   mapPartsToMAC          plugin/flip.cpp:573-595  (knMapLinearVec3ToMACGrid :562-569, setInterpolMAC util/interpol.h:159-203)
 //   mapMACToParts          plugin/flip.cpp:651-656, flipVelocityUpdate :669-677 (interpolMAC util/interpol.h:127-157)
+//   ParticleSystem::advectInGrid  particle.h:512-536 (Euler / RK2 / RK4 through the MAC grid, clamping / deletion in obstacles)
 //
 // Particles are device arrays: pos [N][3] Real, pflag [N] int (BasicParticleData particle.h:182-191; active = !(flag & PDELETE)),
 // per-particle data (ParticleDataImpl<Vec3|int>) [N][3] Real / [N] int.
@@ -240,6 +241,89 @@ template <typename Real> struct FlipVelocityUpdate {
 			// flipRatio * (v + delta) + (1.0 - flipRatio) * vNew: the second product is a double expression narrowed by the Vec3 operator* (flip.cpp:665)
 			pvel[3 * idx + c] = (Real)((double)(flipRatio * (pvel[3 * idx + c] + delta)) + (double)(Real)((1.0 - (double)flipRatio) * (double)v[c]));
 		}
+	}
+};
+
+// ---------------------------------------------------------------- ParticleSystem::advectInGrid
+// particle.h:512-536: GridAdvectKernel :446-467 run 1 / 2 / 4 times by integratePointSet (util/integrator.h:26-68), then KnClampPositions
+// :494-509 (with bisectBacktracePos :480-490) or KnDeleteInObstacle :471-477.  The reference runs each stage over all particles; no stage
+// couples two particles, so one thread takes a particle through all stages (positions and flags are read and written once).
+// Mixed precision as in the reference: `0.5 * u` is a double product narrowed by the Vec3 constructor, `oldp * (1. - s)` likewise.
+enum : int { PNEW = 1 << 0 };              // particle.h:36
+enum : int { IntEuler = 0, IntRK2 = 1, IntRK4 = 2 };      // util/integrator.h:23
+template <typename Real> struct AdvectInGrid {
+	Dims d; const int* flags; const Real* vel; Real* pos; int* pflag; const int* ptype; int exclude;
+	Real dt; int mode; bool deleteInObstacle, stopInObstacle, skipNew;
+	MP_HD bool inBounds(const Real* p, int b) const {                                          // GridBase::isInBounds(Vec3, bnd) grid.h:60,:407-415
+		const int x = (int)p[0], y = (int)p[1], z = (int)p[2];
+		return x >= b && y >= b && x < d.sx - b && y < d.sy - b && (d.is3D ? (z >= b && z < d.sz - b) : z == 0);
+	}
+	MP_HD bool obstacleAt(const Real* p) const {                                               // FlagGrid::isObstacle(const Vec3&) grid.h:313
+		const IndexInt q = (IndexInt)(int)p[0] + d.Y * (int)p[1] + d.Z * (int)p[2];
+		if (q < 0 || q >= d.n) return false;                                                    // the reference reads out of bounds here (bisection from a position outside)
+		return (flags[q] & TypeObstacle) != 0;
+	}
+	MP_HD void velKernel(const Real* x, int& fl, int pt, Real (&u)[3]) const {
+		if ((fl & PDELETE) || (pt & exclude) || (skipNew && (fl & PNEW))) { u[0] = u[1] = u[2] = 0; return; }
+		if (deleteInObstacle || stopInObstacle) {
+			if (!inBounds(x, 1) || obstacleAt(x)) {
+				if (stopInObstacle) u[0] = u[1] = u[2] = 0;          // otherwise u keeps the value of the previous stage (the result vector persists)
+				if (deleteInObstacle) fl |= PDELETE;
+				return;
+			}
+		}
+		const MacWeights<Real> m(d, x);
+		Real v[3];
+		interpolMAC(d, vel, m, v);
+		for (int c = 0; c < 3; c++) u[c] = v[c] * dt;
+	}
+	MP_HD void operator()(IndexInt idx) const {
+		Real x[3] = { pos[3 * idx], pos[3 * idx + 1], pos[3 * idx + 2] };
+		const Real x0[3] = { x[0], x[1], x[2] };
+		int fl = pflag[idx];
+		const int fl0 = fl, pt = ptype ? ptype[idx] : 0;
+		Real u[3] = { 0, 0, 0 }, uTotal[3];
+		velKernel(x, fl, pt, u);
+		if (mode == IntEuler) { for (int c = 0; c < 3; c++) x[c] += u[c]; }
+		else if (mode == IntRK2) {
+			for (int c = 0; c < 3; c++) x[c] = x0[c] + (Real)(0.5 * (double)u[c]);
+			velKernel(x, fl, pt, u);
+			for (int c = 0; c < 3; c++) x[c] = x0[c] + u[c];
+		} else {
+			for (int c = 0; c < 3; c++) { uTotal[c] = u[c]; x[c] = x0[c] + (Real)(0.5 * (double)u[c]); }
+			velKernel(x, fl, pt, u);
+			for (int c = 0; c < 3; c++) { x[c] = x0[c] + (Real)(0.5 * (double)u[c]); uTotal[c] += (Real)(2 * u[c]); }
+			velKernel(x, fl, pt, u);
+			for (int c = 0; c < 3; c++) { x[c] = x0[c] + u[c]; uTotal[c] += (Real)(2 * u[c]); }
+			velKernel(x, fl, pt, u);
+			for (int c = 0; c < 3; c++) x[c] = x0[c] + (Real)(1. / 6.) * (uTotal[c] + u[c]);
+		}
+		if (!deleteInObstacle) {                                     // KnClampPositions
+			if (!(fl & PDELETE)) {
+				if (pt & exclude) { for (int c = 0; c < 3; c++) x[c] = x0[c]; }
+				else {
+					if (!inBounds(x, 0)) {
+						const Real hi[3] = { (Real)d.sx - (Real)1, (Real)d.sy - (Real)1, (Real)d.sz - (Real)1 };
+						for (int c = 0; c < 3; c++) { if (x[c] < (Real)0) x[c] = 0; else if (x[c] > hi[c]) x[c] = hi[c]; }
+					}
+					if (stopInObstacle && obstacleAt(x)) {              // bisectBacktracePos
+						Real s = 0.;
+						for (int i = 1; i < 5; ++i) {
+							const Real ds = (Real)(1. / (double)(Real)(1 << i));
+							const Real sd = s + ds;
+							Real q[3];
+							for (int c = 0; c < 3; c++) q[c] = (Real)((double)x0[c] * (1. - (double)sd)) + x[c] * sd;
+							if (!obstacleAt(q)) s += ds;
+						}
+						for (int c = 0; c < 3; c++) x[c] = (Real)((double)x0[c] * (1. - (double)s)) + x[c] * s;
+					}
+				}
+			}
+		} else if (!(fl & PDELETE)) {                                 // KnDeleteInObstacle
+			if (!inBounds(x, 1) || obstacleAt(x)) fl |= PDELETE;
+		}
+		for (int c = 0; c < 3; c++) pos[3 * idx + c] = x[c];
+		if (fl != fl0) pflag[idx] = fl;
 	}
 };
 

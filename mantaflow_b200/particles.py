@@ -18,7 +18,8 @@ import numpy as np
 from ._lib import MP_GRID_FLAGS, MP_GRID_MAC, MP_GRID_REAL, MantaError, check
 from .grid import _GridBase
 
-PNONE, PNEW, PDELETE, PINVALID = 0, 1 << 1, 1 << 10, 1 << 30      # ParticleBase::ParticleStatus particle.h:37-46
+IntEuler, IntRK2, IntRK4 = 0, 1, 2      # util/integrator.h:23
+PNONE, PNEW, PSPRAY, PBUBBLE, PFOAM, PTRACER, PDELETE, PINVALID = 0, 1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 10, 1 << 30      # ParticleBase::ParticleStatus particle.h:34-43
 
 
 class IntGrid(_GridBase):
@@ -168,6 +169,18 @@ class BasicParticleSystem:
             raise MantaError(1, "BasicParticleSystem.setParticles: pos and flag differ in length")
         for pd in self._pdata:
             pd._a.resize(len(pos))
+
+    def advectInGrid(self, flags, vel, integrationMode, deleteInObstacle=True, stopInObstacle=True, skipNew=False, ptype=None, exclude=0):
+        """ParticleSystem::advectInGrid particle.h:154,:512-536 (IntEuler / IntRK2 / IntRK4), on the device: positions and flags stay there"""
+        s = self.parent
+        _pdcheck(self, ptype, "ptype")
+        if self.size() == 0:
+            return
+        check(s.lib.mp_parts_advect_in_grid(s._ctx, flags.dev(), vel.dev(), C.c_longlong(self.size()), self._pos.dev(), self._flag.dev(), C.c_double(s.timestep),
+                                            C.c_int(int(integrationMode)), C.c_int(int(deleteInObstacle)), C.c_int(int(stopInObstacle)), C.c_int(int(skipNew)),
+                                            None if ptype is None else ptype.dev(), C.c_int(exclude)))
+        self._pos.markDeviceWritten()
+        self._flag.markDeviceWritten()
 
     def positions(self, writable=False): return self._pos.numpy(writable)
     def flags(self, writable=False): return self._flag.numpy(writable)

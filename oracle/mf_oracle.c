@@ -2221,3 +2221,81 @@ int mfo_flip_velocity_update(int sx, int sy, int sz, const Real* vel, const Real
 	}
 	return 0;
 }
+
+/* ParticleSystem<S>::advectInGrid particle.h:512-536 (GridAdvectKernel :446-467, integratePointSet util/integrator.h:26-68, KnClampPositions :494-509
+ * with bisectBacktracePos :480-490, KnDeleteInObstacle :471-477).  mode: 0 IntEuler, 1 IntRK2, 2 IntRK4.  pos and pflag are updated in place.
+ * The velocity kernel leaves u untouched for a particle in an obstacle when stopInObstacle is off (the reference's result vector persists between runs). */
+enum { PNEW_ = 1 << 0 };                                 /* particle.h:36 */
+static inline int is_obstacle_at(int sx, int sy, int sz, const int* flags, const Real* p)   /* FlagGrid::isObstacle(const Vec3&) grid.h:313 */
+{ return flags[(IndexInt)(int)p[0] + (IndexInt)sx * (int)p[1] + (sz > 1 ? (IndexInt)sx * sy * (int)p[2] : 0)] & TypeObstacle; }
+static inline int in_bounds_b(int sx, int sy, int sz, const Real* p, int b)                  /* GridBase::isInBounds(Vec3, bnd) grid.h:60,:407-415 */
+{ const int x = (int)p[0], y = (int)p[1], z = (int)p[2];
+  return x >= b && y >= b && x < sx - b && y < sy - b && (sz > 1 ? (z >= b && z < sz - b) : z == 0); }
+static void advect_vel_kernel(int sx, int sy, int sz, const int* flags, const Real* vel, const Real* pos, int* pflag, int ptype, int exclude, Real dt,
+                              int deleteInObstacle, int stopInObstacle, int skipNew, Real u[3])
+{
+	if ((*pflag & PDELETE) || (ptype & exclude) || (skipNew && (*pflag & PNEW_))) { u[0] = u[1] = u[2] = 0; return; }
+	if (deleteInObstacle || stopInObstacle) {
+		if (!in_bounds_b(sx, sy, sz, pos, 1) || is_obstacle_at(sx, sy, sz, flags, pos)) {
+			if (stopInObstacle) u[0] = u[1] = u[2] = 0;
+			if (deleteInObstacle) *pflag |= PDELETE;
+			return;
+		}
+	}
+	Real v[3];
+	interpol_mac(sx, sy, sz, vel, pos, v);
+	for (int c = 0; c < 3; c++) u[c] = v[c] * dt;
+}
+int mfo_advect_in_grid(int sx, int sy, int sz, const int* flags, const Real* vel, long long np, Real* pos, int* pflag, double dt_, int mode,
+                       int deleteInObstacle, int stopInObstacle, int skipNew, const int* ptype, int exclude)
+{
+	const Real dt = (Real)dt_;
+	if (mode < 0 || mode > 2) { snprintf(g_err, sizeof g_err, "unknown integration type"); return 1; }
+	for (long long idx = 0; idx < np; idx++) {
+		Real* x = pos + 3 * idx;
+		int* fl = pflag + idx;
+		const int pt = ptype ? ptype[idx] : 0;
+		const Real x0[3] = { x[0], x[1], x[2] };
+		Real u[3] = { 0, 0, 0 }, uTotal[3];
+#define RUN_ advect_vel_kernel(sx, sy, sz, flags, vel, x, fl, pt, exclude, dt, deleteInObstacle, stopInObstacle, skipNew, u)
+		RUN_;
+		if (mode == 0) { for (int c = 0; c < 3; c++) x[c] += u[c]; }
+		else if (mode == 1) {
+			for (int c = 0; c < 3; c++) x[c] = x0[c] + (Real)(0.5 * (double)u[c]);
+			RUN_;
+			for (int c = 0; c < 3; c++) x[c] = x0[c] + u[c];
+		} else {
+			for (int c = 0; c < 3; c++) { uTotal[c] = u[c]; x[c] = x0[c] + (Real)(0.5 * (double)u[c]); }
+			RUN_;
+			for (int c = 0; c < 3; c++) { x[c] = x0[c] + (Real)(0.5 * (double)u[c]); uTotal[c] += (Real)(2 * u[c]); }
+			RUN_;
+			for (int c = 0; c < 3; c++) { x[c] = x0[c] + u[c]; uTotal[c] += (Real)(2 * u[c]); }
+			RUN_;
+			for (int c = 0; c < 3; c++) x[c] = x0[c] + (Real)(1. / 6.) * (uTotal[c] + u[c]);
+		}
+#undef RUN_
+		if (!deleteInObstacle) {                                      /* KnClampPositions */
+			if (*fl & PDELETE) continue;
+			if (pt & exclude) { for (int c = 0; c < 3; c++) x[c] = x0[c]; continue; }
+			if (!in_bounds_b(sx, sy, sz, x, 0)) {
+				const Real hi[3] = { (Real)sx - (Real)1, (Real)sy - (Real)1, (Real)sz - (Real)1 };
+				for (int c = 0; c < 3; c++) { if (x[c] < (Real)0) x[c] = 0; else if (x[c] > hi[c]) x[c] = hi[c]; }
+			}
+			if (stopInObstacle && is_obstacle_at(sx, sy, sz, flags, x)) {      /* bisectBacktracePos */
+				Real sacc = 0.;
+				for (int i = 1; i < 5; ++i) {
+					const Real ds = (Real)(1. / (double)(Real)(1 << i));
+					const Real sd = sacc + ds;
+					Real q[3];
+					for (int c = 0; c < 3; c++) q[c] = (Real)((double)x0[c] * (1. - (double)sd)) + x[c] * sd;
+					if (!is_obstacle_at(sx, sy, sz, flags, q)) sacc += ds;
+				}
+				for (int c = 0; c < 3; c++) x[c] = (Real)((double)x0[c] * (1. - (double)sacc)) + x[c] * sacc;
+			}
+		} else {                                                       /* KnDeleteInObstacle */
+			if (*fl & PDELETE) continue;
+			if (!in_bounds_b(sx, sy, sz, x, 1) || is_obstacle_at(sx, sy, sz, flags, x)) *fl |= PDELETE;
+		}
+	}
+	return 0;
+}

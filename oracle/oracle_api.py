@@ -324,6 +324,14 @@ class Oracle:
         self._chk(self._f("flip_velocity_update")(*self.dims(vel[..., 0]), _p(self._r(vel)), _p(self._r(velOld)), n, pp, pf, _p(pvel), C.c_double(flipRatio), pt, C.c_int(exclude)))
         return pvel
 
+    def advect_in_grid(self, flags, vel, pos, pflag, dt, integrationMode=2, deleteInObstacle=True, stopInObstacle=True, skipNew=False, ptype=None, exclude=0):
+        """ParticleSystem::advectInGrid particle.h:512-536 (IntEuler 0, IntRK2 1, IntRK4 2); pos and pflag are updated in place and returned"""
+        assert pos.dtype == self.real and pos.flags.c_contiguous and pflag.dtype == np.int32 and pflag.flags.c_contiguous
+        pt = None if ptype is None else _p(np.ascontiguousarray(ptype, np.int32))
+        self._chk(self._f("advect_in_grid")(*self.dims(flags), _p(flags), _p(self._r(vel)), C.c_longlong(len(pos)), _p(pos), _p(pflag), C.c_double(dt), C.c_int(integrationMode),
+                                            C.c_int(int(deleteInObstacle)), C.c_int(int(stopInObstacle)), C.c_int(int(skipNew)), pt, C.c_int(exclude)))
+        return pos, pflag
+
     def grid_file(self, name, array, kind, load=False):
         """Grid<T>::save / load of the unmodified reference (grid.cpp:113-156; reference build only).
         kind: "real" | "mac" | "flags" | "levelset" | "vec3"; `array` is written to / filled from the file `name`."""

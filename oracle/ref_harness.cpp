@@ -258,6 +258,18 @@ int ref_flip_velocity_update(int sx, int sy, int sz, const Real* vel, const Real
 	delete s;
   CATCH }
 
+// ParticleSystem::advectInGrid particle.h:512-536 through the unmodified class (mode: IntEuler 0, IntRK2 1, IntRK4 2); pos and pflag are updated
+int ref_advect_in_grid(int sx, int sy, int sz, const int* flags, const Real* vel, long long np, Real* pos, int* pflag, double dt, int mode,
+                       int deleteInObstacle, int stopInObstacle, int skipNew, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz); s->mDt = (Real)dt;
+	{ RefParts P(s, np, pos, pflag, ptype, 0);
+	  FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
+	  P.pp.advectInGrid(F, V, mode, deleteInObstacle != 0, stopInObstacle != 0, skipNew != 0, P.pt, exclude);
+	  for (long long q = 0; q < np; q++) { pos[3 * q] = P.pp[q].pos.x; pos[3 * q + 1] = P.pp[q].pos.y; pos[3 * q + 2] = P.pp[q].pos.z; pflag[q] = P.pp[q].flag; } }
+	delete s;
+  CATCH }
+
 int ref_extrapolate_mac_from_weight(int sx, int sy, int sz, Real* vel, Real* weight, int distance)
 { TRY
 	FluidSolver* s = mkSolver(sx, sy, sz);

@@ -289,6 +289,14 @@ class CudaImpl:
         pvel[...] = V.numpy()
         return pvel
 
+    def advect_in_grid(self, flags, vel, pos, pflag, dt, integrationMode=2, deleteInObstacle=True, stopInObstacle=True, skipNew=False, ptype=None, exclude=0):
+        s = self._solver(flags); s.timestep = dt
+        P, T, _ = self._parts(s, pos, pflag, ptype)
+        P.advectInGrid(mf.FlagGrid(s, flags), mf.MACGrid(s, vel), integrationMode, deleteInObstacle=deleteInObstacle, stopInObstacle=stopInObstacle, skipNew=skipNew,
+                       ptype=T, exclude=exclude)
+        pos[...] = P.positions(); pflag[...] = P.flags()
+        return pos, pflag
+
     def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
         s = self._solver(flags); s.timestep = dt
         U, Um, O = mf.RealGrid(s, ut), mf.RealGrid(s, utm1), mf.RealGrid(s)

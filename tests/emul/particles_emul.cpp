@@ -111,9 +111,21 @@ template <typename Real> int flipUpdate(int order, const Dims& d, const Real* ve
 	parts::FlipVelocityUpdate<Real> op = { d, vel, velOld, ps, pvel, (Real)flipRatio, flipRatio < 0 };
 	return ex.parts(np, op);
 }
+template <typename Real> int advect(int order, const Dims& d, const int* flags, const Real* vel, long long np, Real* pos, int* pflag, double dt, int mode, int del, int stop, int skipNew,
+                                    const int* ptype, int exclude) {
+	HostExec ex = { order };
+	parts::AdvectInGrid<Real> op = { d, flags, vel, pos, pflag, ptype, exclude, (Real)dt, mode, del != 0, stop != 0, skipNew != 0 };
+	return ex.parts(np, op);
+}
 }  // namespace
 
 extern "C" {
+int emu_advect_in_grid(int prec, int order, int sx, int sy, int sz, const int* flags, const void* vel, long long np, void* pos, int* pflag, double dt, int mode, int del, int stop,
+                       int skipNew, const int* ptype, int exclude) {
+	const Dims d = mkDims(sx, sy, sz);
+	return prec == 4 ? advect<float>(order, d, flags, (const float*)vel, np, (float*)pos, pflag, dt, mode, del, stop, skipNew, ptype, exclude)
+	                 : advect<double>(order, d, flags, (const double*)vel, np, (double*)pos, pflag, dt, mode, del, stop, skipNew, ptype, exclude);
+}
 // signatures follow the oracle's mfo_* entry points (oracle/mf_oracle.c), with (prec, order) in front
 int emu_mark_fluid_cells(int prec, int order, int sx, int sy, int sz, int* flags, long long np, const void* pos, const int* pflag, const void* phiObs, const int* ptype, int exclude) {
 	const Dims d = mkDims(sx, sy, sz);

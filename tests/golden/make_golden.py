@@ -219,6 +219,10 @@ def flip_fixtures():
             path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
             np.savez_compressed(path, **fx)
             print("%-34s %7.1f KiB  %d indexed particles, %d fluid cells" % (os.path.basename(path), os.path.getsize(path) / 1024, len(fx["index_sys"]), int((fx["mark"] & 1).sum())))
+            fx = helpers.run_advect_cases(R, name, prec)          # ParticleSystem::advectInGrid on the same particles
+            path = os.path.join(HERE, "step_adv_%s_f%d.npz" % (name, prec * 8))
+            np.savez_compressed(path, **fx)
+            print("%-34s %7.1f KiB  %d particles" % (os.path.basename(path), os.path.getsize(path) / 1024, len(fx["rk4_flip_flag"])))
 
 
 def icp_fixtures():

@@ -631,3 +631,40 @@ def check_icp_against_golden(I, name, prec, exact_reductions):
         assert int(out["cg_ic_it"]) == int(g["cg_ic_it"]) and np.array_equal(out["cg_ic_x"], g["cg_ic_x"])
     # the fixture is not vacuous: ICP beats the unpreconditioned solve
     assert int(g["cg_ic_it"]) < int(k["cg_none_it"])
+
+
+# ---------------------------------------------------------------- ParticleSystem::advectInGrid (particle.h:512-536)
+ADVECT_CASES = {   # integrationMode, deleteInObstacle, stopInObstacle, skipNew, use ptype / exclude
+    "rk4_flip": (2, False, True, False, True),        # the call of scenes/benchmark_dam.py:121 / flip02_surface.py
+    "rk4_tracer": (2, True, True, False, False),      # the defaults (tracer particles are deleted in obstacles)
+    "rk2_nostop": (1, False, False, True, False),
+    "euler_delete_nostop": (0, True, False, False, True),
+}
+
+
+def advect_scene(name, prec):
+    """the particles of flip_scene (active ones inside the domain; a few deleted), an obstacle block inside the basin, and a velocity field
+    fast enough (up to 2.5 cells per step) to push particles into the walls and the block"""
+    flags, pos, pflag, ptype, pvel, _ = flip_scene(name, prec)
+    sz, sy, sx = flags.shape
+    real = np.float32 if prec == 4 else np.float64
+    flags = flags.copy()
+    flags[(sz // 3 if sz > 1 else 0):(2 * sz // 3 if sz > 1 else 1), 2:sy // 4, sx // 3:sx // 2] = 2       # obstacle block
+    nd = 3 if sz > 1 else 2
+    inside = np.all((pos[:, :nd] >= 1) & (pos[:, :nd] < np.array([sx - 1, sy - 1, sz - 1])[:nd]), axis=1)
+    pos, pflag, ptype = np.ascontiguousarray(pos[inside]), np.ascontiguousarray(pflag[inside]), np.ascontiguousarray(ptype[inside])
+    rng = np.random.default_rng(77 + sx)
+    vel = ((rng.random(flags.shape + (3,)) - 0.5) * 5).astype(real)
+    if sz == 1:
+        vel[..., 2] = 0
+    return flags, vel, pos, pflag, ptype
+
+
+def run_advect_cases(I, name, prec):
+    flags, vel, pos, pflag, ptype = advect_scene(name, prec)
+    out = {}
+    for case, (mode, dele, stop, skip, typed) in ADVECT_CASES.items():
+        p, f = I.advect_in_grid(flags, vel, pos.copy(), pflag.copy(), 0.8, integrationMode=mode, deleteInObstacle=dele, stopInObstacle=stop, skipNew=skip,
+                                ptype=ptype if typed else None, exclude=4 if typed else 0)
+        out[case + "_pos"], out[case + "_flag"] = p, f
+    return out

@@ -42,6 +42,17 @@ def test_cuda_equals_oracle_on_larger_scenes(shape, prec, port32, port64, monkey
         assert np.array_equal(a[key], b[key]), key
 
 
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(FLIP_SCENES))
+def test_cuda_reproduces_advect_golden(name, prec):
+    """ParticleSystem::advectInGrid (particle.h:512-536) on the device, all integration modes and obstacle policies: positions and flags bit for bit"""
+    from cuda_impl import CudaImpl
+    g = load_golden("step_adv_" + name, prec)
+    out = helpers.run_advect_cases(CudaImpl(prec), name, prec)
+    for key in g:
+        assert np.array_equal(out[key], g[key]), (name, prec, key)
+
+
 def test_map_parts_to_mac_is_reproducible(mf):
     """the same particles in the same order give the same bits on every call (a scatter with floating-point atomics would not)"""
     from cuda_impl import CudaImpl
@@ -55,9 +66,10 @@ def test_map_parts_to_mac_is_reproducible(mf):
 
 
 def test_flip_step_device_resident(mf, port32):
-    """markFluidCells -> mapPartsToMAC -> extrapolateMACFromWeight -> (forces, projection) -> flipVelocityUpdate -> gridParticleIndex ->
+    """markFluidCells -> mapPartsToMAC -> extrapolateMACFromWeight -> (forces, projection) -> flipVelocityUpdate -> advectInGrid -> gridParticleIndex ->
     unionParticleLevelset, written like the scene: particles and grids are uploaded once and stay on the device"""
-    flags_h, pos, pflag, ptype, pvel, _ = helpers.flip_scene("flip3d", 4)
+    flags_h, _, pos, pflag, ptype = helpers.advect_scene("flip3d", 4)          # particles inside the domain, an obstacle block in the basin
+    pvel = (np.random.default_rng(8).random(pos.shape) * 2 - 1).astype(np.float32)
     sz, sy, sx = flags_h.shape
     s = mf.Solver(gridSize=(sx, sy, sz), dim=3, prec=4)
     flags, vel, velOld, weight = mf.FlagGrid(s, flags_h), s.create(mf.MACGrid), s.create(mf.MACGrid), s.create(mf.VecGrid)
@@ -74,6 +86,8 @@ def test_flip_step_device_resident(mf, port32):
     mf.setWallBcs(flags=flags, vel=vel)
     mf.solvePressure(flags=flags, vel=vel, pressure=pressure)
     mf.flipVelocityUpdate(vel=vel, velOld=velOld, flags=flags, parts=pp, partVel=pVel, flipRatio=0.97)
+    velAdv = vel.numpy().copy()
+    pp.advectInGrid(flags=flags, vel=vel, integrationMode=mf.IntRK4, deleteInObstacle=False)
     mf.gridParticleIndex(parts=pp, flags=flags, indexSys=pindex, index=index)
     mf.unionParticleLevelset(pp, pindex, flags, index, phi)
     assert s.kernelLaunches() > launches0
@@ -85,6 +99,8 @@ def test_flip_step_device_resident(mf, port32):
     assert np.array_equal(velOld.numpy(), vo)
     pv = port32.flip_velocity_update(vel.numpy().copy(), vo, pos, pflag, pvel.copy(), 0.97)
     assert np.array_equal(pVel.numpy(), pv)
+    pos, pflag = port32.advect_in_grid(f, velAdv, pos.copy(), pflag.copy(), 1.0, integrationMode=2, deleteInObstacle=False)
+    assert np.array_equal(pp.positions(), pos) and np.array_equal(pp.flags(), pflag)
     ix, isys = port32.grid_particle_index(flags_h.shape, pos, pflag)
     assert np.array_equal(index.numpy(), ix) and np.array_equal(pindex.numpy(), isys)
     assert np.array_equal(phi.numpy(), port32.union_particle_levelset(pos, ix, isys))

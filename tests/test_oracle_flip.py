@@ -103,3 +103,32 @@ def test_kernel_emulation_equals_port_on_other_scenes(shape, prec, parts_emul_li
         vel, velOld = I.map_parts_to_mac(flags.shape, pos[none], pflag[none], pvel[none])
         assert not vel.any() and not velOld.any()
         assert np.array_equal(I.mark_fluid_cells(flags.copy(), pos[none], pflag[none]), P.mark_fluid_cells(flags.copy(), pos[none], pflag[none]))
+
+
+# ---------------------------------------------------------------- ParticleSystem::advectInGrid (particle.h:512-536)
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(FLIP_SCENES))
+def test_port_reproduces_advect_golden(name, prec, port32, port64):
+    """Euler / RK2 / RK4 through the MAC grid with the four combinations of deleteInObstacle / stopInObstacle, skipNew and an excluded type:
+    positions and flags bit for bit"""
+    g = load_golden("step_adv_" + name, prec)
+    out = helpers.run_advect_cases(port32 if prec == 4 else port64, name, prec)
+    assert set(out) == set(g)
+    for key in g:
+        assert np.array_equal(out[key], g[key]), (name, prec, key)
+    # not vacuous: particles are deleted in obstacles, stopped at them (bisection: neither the old nor the integrated position), and moved
+    _, _, pos, pflag, _ = helpers.advect_scene(name, prec)
+    assert ((g["rk4_tracer_flag"] & 1024) != 0).sum() > ((pflag & 1024) != 0).sum() + 20
+    assert (np.abs(g["rk4_flip_pos"] - pos).max(1) > 0.5).sum() > 100
+    assert not np.array_equal(g["rk4_flip_pos"], g["rk2_nostop_pos"])
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(FLIP_SCENES))
+def test_kernel_emulation_reproduces_advect_golden(name, prec, order, parts_emul_lib):
+    """the fused per-particle kernel (all Runge-Kutta stages and the clamping in one pass) on the host"""
+    g = load_golden("step_adv_" + name, prec)
+    out = helpers.run_advect_cases(FlipEmulation(parts_emul_lib, prec, order), name, prec)
+    for key in g:
+        assert np.array_equal(out[key], g[key]), (name, prec, order, key)
