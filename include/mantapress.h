@@ -266,6 +266,11 @@ int mp_get_curvature(mp_context* ctx, mp_grid* curv, const mp_grid* grid, double
  * integrationMode: 0 IntEuler, 1 IntRK2, 2 IntRK4 (util/integrator.h:23); dt = FluidSolver::getDt(). One pass over the particles for all stages. */
 int mp_parts_advect_in_grid(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, long long np, mp_grid* pos, mp_grid* pflag, double dt, int integrationMode,
                             int deleteInObstacle, int stopInObstacle, int skipNew, const mp_grid* ptype, int exclude);
+/* pushOutofObs plugin/flip.cpp:542-545 and ParticleSystem<S>::projectOutOfBnd particle.h:578-590 (`plane`: any of the letters "xXyYzZ"): positions updated in place. */
+int mp_push_out_of_obs(mp_context* ctx, long long np, mp_grid* pos, const mp_grid* pflag, const mp_grid* flags, const mp_grid* phiObs, double shift, double thresh,
+                       const mp_grid* ptype, int exclude);
+int mp_parts_project_out_of_bnd(mp_context* ctx, const mp_grid* flags, long long np, mp_grid* pos, const mp_grid* pflag, double bnd, const char* plane,
+                                const mp_grid* ptype, int exclude);
 int mp_mark_fluid_cells(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* flags, const mp_grid* phiObs, const mp_grid* ptype, int exclude);
 int mp_grid_particle_index(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* indexSys, const mp_grid* flags, mp_grid* index, long long* count);
 int mp_union_particle_levelset(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* indexSys, long long count, const mp_grid* flags, const mp_grid* index,

@@ -242,6 +242,40 @@ int mp_parts_advect_in_grid(mp_context* ctx, const mp_grid* flags, const mp_grid
 	return ex.parts(np, op);
 }
 
+int mp_push_out_of_obs(mp_context* ctx, long long np, mp_grid* pos, const mp_grid* pflag, const mp_grid* flags, const mp_grid* phiObs, double shift, double thresh,
+                       const mp_grid* ptype, int exclude)
+{
+	MP_TRY(checkCtx("mp_push_out_of_obs", ctx, phiObs));
+	if (phiObs->kind != MP_GRID_REAL) MP_FAIL(MP_ERR_INVALID, "pushOutofObs: phiObs is not a real grid");
+	if (flags) MP_TRY(mp_check_same(phiObs, flags, MP_GRID_FLAGS, "flags", false));
+	MP_TRY(checkParts("mp_push_out_of_obs", np, pos, pflag, ptype, phiObs->prec));
+	if (phiObs->sx < 3 || phiObs->sy < 3 || (phiObs->sz > 1 && phiObs->sz < 3)) MP_FAIL(MP_ERR_INVALID, "pushOutofObs: the gradient needs at least three cells per axis");
+	if (np == 0) return MP_OK;
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(phiObs);
+	if (phiObs->prec == 4) { parts::PushOutOfObs<float> op = { d, (float*)pos->d, psetOf<float>(pos, pflag, ptype, exclude), (const float*)phiObs->d, (float)shift, (float)thresh }; return ex.parts(np, op); }
+	parts::PushOutOfObs<double> op = { d, (double*)pos->d, psetOf<double>(pos, pflag, ptype, exclude), (const double*)phiObs->d, shift, thresh };
+	return ex.parts(np, op);
+}
+
+int mp_parts_project_out_of_bnd(mp_context* ctx, const mp_grid* flags, long long np, mp_grid* pos, const mp_grid* pflag, double bnd, const char* plane,
+                                const mp_grid* ptype, int exclude)
+{
+	MP_TRY(checkCtx("mp_parts_project_out_of_bnd", ctx, flags));
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "projectOutOfBnd: flags is not a FlagGrid");
+	if (!plane) MP_FAIL(MP_ERR_INVALID, "mp_parts_project_out_of_bnd: NULL plane");
+	if (!pos && np > 0) MP_FAIL(MP_ERR_INVALID, "mp_parts_project_out_of_bnd: NULL pos");
+	MP_TRY(checkParts("mp_parts_project_out_of_bnd", np, pos, pflag, ptype, pos ? pos->prec : 4));
+	if (np == 0) return MP_OK;
+	int axis = 0;
+	for (const char* c = plane; *c; c++) for (int q = 0; q < 6; q++) if (*c == "xXyYzZ"[q]) axis |= 1 << q;      // particle.h:580-588
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(flags);
+	if (pos->prec == 4) { parts::ProjectOutOfBnd<float> op = { d, (float*)pos->d, psetOf<float>(pos, pflag, ptype, exclude), (float)bnd, axis }; return ex.parts(np, op); }
+	parts::ProjectOutOfBnd<double> op = { d, (double*)pos->d, psetOf<double>(pos, pflag, ptype, exclude), bnd, axis };
+	return ex.parts(np, op);
+}
+
 int mp_map_mac_to_parts(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* partVel,
                         const mp_grid* ptype, int exclude)
 {

@@ -5,6 +5,7 @@
 //   mapPartsToMAC          plugin/flip.cpp:573-595  (knMapLinearVec3ToMACGrid :562-569, setInterpolMAC util/interpol.h:159-203)
 //   mapMACToParts          plugin/flip.cpp:651-656, flipVelocityUpdate :669-677 (interpolMAC util/interpol.h:127-157)
 //   ParticleSystem::advectInGrid  particle.h:512-536 (Euler / RK2 / RK4 through the MAC grid, clamping / deletion in obstacles)
+//   pushOutofObs           plugin/flip.cpp:528-545,  ParticleSystem::projectOutOfBnd  particle.h:565-590
 //
 // Particles are device arrays: pos [N][3] Real, pflag [N] int (BasicParticleData particle.h:182-191; active = !(flag & PDELETE)),
 // per-particle data (ParticleDataImpl<Vec3|int>) [N][3] Real / [N] int.
@@ -324,6 +325,68 @@ template <typename Real> struct AdvectInGrid {
 		}
 		for (int c = 0; c < 3; c++) pos[3 * idx + c] = x[c];
 		if (fl != fl0) pflag[idx] = fl;
+	}
+};
+
+// ---------------------------------------------------------------- pushOutofObs / projectOutOfBnd
+// knPushOutofObs plugin/flip.cpp:528-540: particles whose interpolated obstacle distance is below `thresh` move along the normalised
+// central-difference gradient of the cell they are in (getGradient grid.h:520-537, interpol util/interpol.h:68-78, normalize vectorbase.h:415-429).
+template <typename Real> struct PushOutOfObs {
+	Dims d; Real* pos; PSet<Real> ps; const Real* phiObs; Real shift, thresh;
+	MP_HD void operator()(IndexInt idx) const {
+		if (ps.skip(idx)) return;
+		Real* x = pos + 3 * idx;
+		int i = (int)x[0], j = (int)x[1], k = (int)x[2];
+		if (!(i >= 0 && j >= 0 && k >= 0 && i < d.sx && j < d.sy && k < d.sz)) return;      // GridBase::isInBounds(Vec3i) grid.h:403-405
+		const MacWeights<Real> m(d, x);
+		const IndexInt X = 1, Y = d.Y, Z = d.Z;
+		const Real* p = phiObs + ((IndexInt)m.xi + Y * m.yi + Z * m.zi);
+		const Real v = ((p[0] * m.t[0] + p[Y] * m.t[1]) * m.s[0] + (p[X] * m.t[0] + p[X + Y] * m.t[1]) * m.s[1]) * m.f[0]
+		             + ((p[Z] * m.t[0] + p[Y + Z] * m.t[1]) * m.s[0] + (p[X + Z] * m.t[0] + p[X + Y + Z] * m.t[1]) * m.s[1]) * m.f[1];
+		if (!(v < thresh)) return;
+		if (i > d.sx - 2) i = d.sx - 2;
+		if (j > d.sy - 2) j = d.sy - 2;
+		if (i < 1) i = 1;
+		if (j < 1) j = 1;
+		Real g[3];
+		g[0] = phiObs[(i + 1) + Y * j + Z * k] - phiObs[(i - 1) + Y * j + Z * k];
+		g[1] = phiObs[i + Y * (j + 1) + Z * k] - phiObs[i + Y * (j - 1) + Z * k];
+		g[2] = 0;
+		if (d.is3D) {
+			if (k > d.sz - 2) k = d.sz - 2;
+			if (k < 1) k = 1;
+			g[2] = phiObs[i + Y * j + Z * (k + 1)] - phiObs[i + Y * j + Z * (k - 1)];
+		}
+		// normalize(): the comparison against 1. and the reciprocal are double expressions
+		const Real l = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+		const Real eps = sizeof(Real) == 8 ? (Real)1e-10 : (Real)1e-6f;
+		const Real eps2 = sizeof(Real) == 8 ? (Real)(1e-10 * 1e-10) : (Real)(1e-6f * 1e-6f);
+		Real norm;
+		if (fabs((double)l - 1.) < (double)eps2) norm = (Real)1.;
+		else if (l > eps2) {
+			norm = (Real)sqrt(l);
+			const Real r = (Real)(1. / (double)norm);
+			g[0] *= r; g[1] *= r; g[2] *= r;
+		} else return;                                                                     // norm 0 < VECTOR_EPSILON
+		if (norm < eps) return;
+		const Real a = thresh - v + shift;
+		for (int c = 0; c < 3; c++) x[c] = x[c] + g[c] * a;
+	}
+};
+// KnProjectOutOfBnd particle.h:565-576; axis: bit q <-> the q-th letter of "xXyYzZ"
+template <typename Real> struct ProjectOutOfBnd {
+	Dims d; Real* pos; PSet<Real> ps; Real bnd; int axis;
+	MP_HD void operator()(IndexInt idx) const {
+		if (ps.skip(idx)) return;
+		Real* x = pos + 3 * idx;
+		if (axis & 1) x[0] = x[0] < bnd ? bnd : x[0];                                        // std::max(pos.x, bnd)
+		if (axis & 2) { const Real hi = (Real)d.sx - bnd; x[0] = hi < x[0] ? hi : x[0]; }    // std::min(pos.x, size - bnd)
+		if (axis & 4) x[1] = x[1] < bnd ? bnd : x[1];
+		if (axis & 8) { const Real hi = (Real)d.sy - bnd; x[1] = hi < x[1] ? hi : x[1]; }
+		if (d.is3D) {
+			if (axis & 16) x[2] = x[2] < bnd ? bnd : x[2];
+			if (axis & 32) { const Real hi = (Real)d.sz - bnd; x[2] = hi < x[2] ? hi : x[2]; }
+		}
 	}
 };
 

@@ -8,6 +8,7 @@
     markFluidCells         plugin/flip.cpp:158-177      gridParticleIndex     plugin/flip.cpp:260-306
     unionParticleLevelset  plugin/flip.cpp:340-350      mapPartsToMAC         plugin/flip.cpp:573-595
     mapMACToParts          plugin/flip.cpp:651-656      flipVelocityUpdate    plugin/flip.cpp:669-677
+    pushOutofObs           plugin/flip.cpp:542-545      BasicParticleSystem.advectInGrid / projectOutOfBnd  particle.h:154-158
 
 Same names, argument order and defaults as the reference.  Every particle array owns a numpy array AND a device array (an mp_grid of
 size (capacity, 1, 1)); two dirty bits keep them coherent lazily, as for the grids (grid.py), so the plugins of a FLIP step
@@ -182,6 +183,16 @@ class BasicParticleSystem:
         self._pos.markDeviceWritten()
         self._flag.markDeviceWritten()
 
+    def projectOutOfBnd(self, flags, bnd, plane="xXyYzZ", ptype=None, exclude=0):
+        """ParticleSystem::projectOutOfBnd particle.h:158,:578-590, on the device"""
+        s = self.parent
+        _pdcheck(self, ptype, "ptype")
+        if self.size() == 0:
+            return
+        check(s.lib.mp_parts_project_out_of_bnd(s._ctx, flags.dev(), C.c_longlong(self.size()), self._pos.dev(), self._flag.dev(), C.c_double(bnd), str(plane).encode(),
+                                                None if ptype is None else ptype.dev(), C.c_int(exclude)))
+        self._pos.markDeviceWritten()
+
     def positions(self, writable=False): return self._pos.numpy(writable)
     def flags(self, writable=False): return self._flag.numpy(writable)
 
@@ -246,6 +257,16 @@ def unionParticleLevelset(parts, indexSys, flags, index, phi, radiusFactor=1., p
     check(s.lib.mp_union_particle_levelset(s._ctx, n, pos, isys, C.c_longlong(indexSys._count), _d(flags), index.dev(), phi.dev(), C.c_double(radiusFactor),
                                            _d(ptype), C.c_int(exclude)))
     phi.markDeviceWritten()
+
+
+def pushOutofObs(parts, flags, phiObs, shift=0, thresh=0, ptype=None, exclude=0):
+    s = phiObs.parent
+    _pdcheck(parts, ptype, "ptype")
+    if parts.size() == 0:
+        return
+    n, pos, pflag = _ps(parts)
+    check(s.lib.mp_push_out_of_obs(s._ctx, n, pos, pflag, _d(flags), phiObs.dev(), C.c_double(shift), C.c_double(thresh), _d(ptype), C.c_int(exclude)))
+    parts._pos.markDeviceWritten()
 
 
 def mapPartsToMAC(flags, vel, velOld, parts, partVel, weight=None, ptype=None, exclude=0):

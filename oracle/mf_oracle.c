@@ -2299,3 +2299,60 @@ int mfo_advect_in_grid(int sx, int sy, int sz, const int* flags, const Real* vel
 	}
 	return 0;
 }
+
+/* pushOutofObs plugin/flip.cpp:528-545 (knPushOutofObs; getGradient grid.h:520-537, interpol util/interpol.h:68-78, normalize vectorbase.h:415-429) */
+int mfo_push_out_of_obs(int sx, int sy, int sz, long long np, Real* pos, const int* pflag, const Real* phiObs, double shift_, double thresh_, const int* ptype, int exclude)
+{
+	const Real shift = (Real)shift_, thresh = (Real)thresh_;
+	const IndexInt Y = sx, Z = (sz > 1) ? (IndexInt)sx * sy : 0;
+#if MF_REAL_IS_DOUBLE
+	const Real eps = 1e-10;
+#else
+	const Real eps = 1e-6f;
+#endif
+	for (long long idx = 0; idx < np; idx++) {
+		if (P_SKIP(idx)) continue;
+		Real* x = pos + 3 * idx;
+		int i = (int)x[0], j = (int)x[1], k = (int)x[2];
+		if (!(i >= 0 && j >= 0 && k >= 0 && i < sx && j < sy && k < sz)) continue;          /* GridBase::isInBounds(Vec3i) grid.h:403-405 */
+		const Real v = interpol_s(phiObs, 1, sx, sy, sz, x);
+		if (v < thresh) {
+			if (i > sx - 2) i = sx - 2;
+			if (j > sy - 2) j = sy - 2;
+			if (i < 1) i = 1;
+			if (j < 1) j = 1;
+			Real g[3];
+			g[0] = phiObs[(i + 1) + Y * j + Z * k] - phiObs[(i - 1) + Y * j + Z * k];
+			g[1] = phiObs[i + Y * (j + 1) + Z * k] - phiObs[i + Y * (j - 1) + Z * k];
+			g[2] = 0.;
+			if (sz > 1) {
+				if (k > sz - 2) k = sz - 2;
+				if (k < 1) k = 1;
+				g[2] = phiObs[i + Y * j + Z * (k + 1)] - phiObs[i + Y * j + Z * (k - 1)];
+			}
+			if (normalize3(g) < eps) continue;
+			const Real a = thresh - v + shift;
+			for (int c = 0; c < 3; c++) x[c] = x[c] + g[c] * a;
+		}
+	}
+	return 0;
+}
+
+/* ParticleSystem<S>::projectOutOfBnd particle.h:565-590; axis: bit q set <-> the q-th letter of "xXyYzZ" is in `plane` */
+int mfo_project_out_of_bnd(int sx, int sy, int sz, long long np, Real* pos, const int* pflag, double bnd_, int axis, const int* ptype, int exclude)
+{
+	const Real bnd = (Real)bnd_;
+	for (long long idx = 0; idx < np; idx++) {
+		if (P_SKIP(idx)) continue;
+		Real* x = pos + 3 * idx;
+		if (axis & 1) x[0] = x[0] < bnd ? bnd : x[0];                                       /* std::max(pos.x, bnd) */
+		if (axis & 2) { const Real hi = (Real)sx - bnd; x[0] = hi < x[0] ? hi : x[0]; }     /* std::min(pos.x, size - bnd) */
+		if (axis & 4) x[1] = x[1] < bnd ? bnd : x[1];
+		if (axis & 8) { const Real hi = (Real)sy - bnd; x[1] = hi < x[1] ? hi : x[1]; }
+		if (sz > 1) {
+			if (axis & 16) x[2] = x[2] < bnd ? bnd : x[2];
+			if (axis & 32) { const Real hi = (Real)sz - bnd; x[2] = hi < x[2] ? hi : x[2]; }
+		}
+	}
+	return 0;
+}

@@ -332,6 +332,19 @@ class Oracle:
                                             C.c_int(int(deleteInObstacle)), C.c_int(int(stopInObstacle)), C.c_int(int(skipNew)), pt, C.c_int(exclude)))
         return pos, pflag
 
+    def push_out_of_obs(self, shape, pos, pflag, phiObs, shift=0.0, thresh=0.0, ptype=None, exclude=0):
+        """pushOutofObs plugin/flip.cpp:528-545; pos updated in place and returned"""
+        n, pp, pf, pt = self._parts(pos, pflag, ptype)
+        self._chk(self._f("push_out_of_obs")(*self.dims(np.empty(shape, np.int8)), n, pp, pf, _p(self._r(phiObs)), C.c_double(shift), C.c_double(thresh), pt, C.c_int(exclude)))
+        return pos
+
+    def project_out_of_bnd(self, shape, pos, pflag, bnd, plane="xXyYzZ", ptype=None, exclude=0):
+        """ParticleSystem::projectOutOfBnd particle.h:565-590; pos updated in place and returned"""
+        n, pp, pf, pt = self._parts(pos, pflag, ptype)
+        axis = sum(1 << q for q, ch in enumerate("xXyYzZ") if ch in plane)
+        self._chk(self._f("project_out_of_bnd")(*self.dims(np.empty(shape, np.int8)), n, pp, pf, C.c_double(bnd), C.c_int(axis), pt, C.c_int(exclude)))
+        return pos
+
     def grid_file(self, name, array, kind, load=False):
         """Grid<T>::save / load of the unmodified reference (grid.cpp:113-156; reference build only).
         kind: "real" | "mac" | "flags" | "levelset" | "vec3"; `array` is written to / filled from the file `name`."""

@@ -63,6 +63,7 @@ void releaseBlurPrecomp();
 void extrapolateMACSimple(FlagGrid& flags, MACGrid& vel, int distance, LevelsetGrid* phiObs, bool intoObs);
 void extrapolateLsSimple(Grid<Real>& phi, int distance, bool inside);
 void extrapolateMACFromWeight(MACGrid& vel, Grid<Vec3>& weight, int distance);
+void pushOutofObs(BasicParticleSystem& parts, const FlagGrid& flags, const Grid<Real>& phiObs, const Real shift, const Real thresh, const ParticleDataImpl<int>* ptype, const int exclude);
 void markFluidCells(const BasicParticleSystem& parts, FlagGrid& flags, const Grid<Real>* phiObs, const ParticleDataImpl<int>* ptype, const int exclude);
 void gridParticleIndex(const BasicParticleSystem& parts, ParticleIndexSystem& indexSys, const FlagGrid& flags, Grid<int>& index, Grid<int>* counter);
 void unionParticleLevelset(const BasicParticleSystem& parts, const ParticleIndexSystem& indexSys, const FlagGrid& flags, const Grid<int>& index, LevelsetGrid& phi,
@@ -267,6 +268,26 @@ int ref_advect_in_grid(int sx, int sy, int sz, const int* flags, const Real* vel
 	  FlagGrid F(s, (int*)flags); MACGrid V(s, (Vec3*)vel);
 	  P.pp.advectInGrid(F, V, mode, deleteInObstacle != 0, stopInObstacle != 0, skipNew != 0, P.pt, exclude);
 	  for (long long q = 0; q < np; q++) { pos[3 * q] = P.pp[q].pos.x; pos[3 * q + 1] = P.pp[q].pos.y; pos[3 * q + 2] = P.pp[q].pos.z; pflag[q] = P.pp[q].flag; } }
+	delete s;
+  CATCH }
+
+int ref_push_out_of_obs(int sx, int sy, int sz, long long np, Real* pos, const int* pflag, const Real* phiObs, double shift, double thresh, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ RefParts P(s, np, pos, pflag, ptype, 0);
+	  FlagGrid F(s); Grid<Real> Po(s, (Real*)phiObs);
+	  pushOutofObs(P.pp, F, Po, (Real)shift, (Real)thresh, P.pt, exclude);
+	  for (long long q = 0; q < np; q++) { pos[3 * q] = P.pp[q].pos.x; pos[3 * q + 1] = P.pp[q].pos.y; pos[3 * q + 2] = P.pp[q].pos.z; } }
+	delete s;
+  CATCH }
+int ref_project_out_of_bnd(int sx, int sy, int sz, long long np, Real* pos, const int* pflag, double bnd, int axis, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ RefParts P(s, np, pos, pflag, ptype, 0);
+	  FlagGrid F(s);
+	  std::string plane; for (int q = 0; q < 6; q++) if (axis & (1 << q)) plane += "xXyYzZ"[q];
+	  P.pp.projectOutOfBnd(F, (Real)bnd, plane, P.pt, exclude);
+	  for (long long q = 0; q < np; q++) { pos[3 * q] = P.pp[q].pos.x; pos[3 * q + 1] = P.pp[q].pos.y; pos[3 * q + 2] = P.pp[q].pos.z; } }
 	delete s;
   CATCH }
 

@@ -297,6 +297,20 @@ class CudaImpl:
         pos[...] = P.positions(); pflag[...] = P.flags()
         return pos, pflag
 
+    def push_out_of_obs(self, shape, pos, pflag, phiObs, shift=0.0, thresh=0.0, ptype=None, exclude=0):
+        s = self._solver(np.zeros(shape, np.int32))
+        P, T, _ = self._parts(s, pos, pflag, ptype)
+        mf.pushOutofObs(P, mf.FlagGrid(s), mf.RealGrid(s, phiObs), shift=shift, thresh=thresh, ptype=T, exclude=exclude)
+        pos[...] = P.positions()
+        return pos
+
+    def project_out_of_bnd(self, shape, pos, pflag, bnd, plane="xXyYzZ", ptype=None, exclude=0):
+        s = self._solver(np.zeros(shape, np.int32))
+        P, T, _ = self._parts(s, pos, pflag, ptype)
+        P.projectOutOfBnd(mf.FlagGrid(s), bnd, plane=plane, ptype=T, exclude=exclude)
+        pos[...] = P.positions()
+        return pos
+
     def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
         s = self._solver(flags); s.timestep = dt
         U, Um, O = mf.RealGrid(s, ut), mf.RealGrid(s, utm1), mf.RealGrid(s)

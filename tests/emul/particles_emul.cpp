@@ -120,6 +120,16 @@ template <typename Real> int advect(int order, const Dims& d, const int* flags, 
 }  // namespace
 
 extern "C" {
+int emu_push_out_of_obs(int prec, int order, int sx, int sy, int sz, long long np, void* pos, const int* pflag, const void* phiObs, double shift, double thresh, const int* ptype, int exclude) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	if (prec == 4) { parts::PSet<float> ps = { (const float*)pos, pflag, ptype, exclude }; parts::PushOutOfObs<float> op = { d, (float*)pos, ps, (const float*)phiObs, (float)shift, (float)thresh }; return ex.parts(np, op); }
+	parts::PSet<double> ps = { (const double*)pos, pflag, ptype, exclude }; parts::PushOutOfObs<double> op = { d, (double*)pos, ps, (const double*)phiObs, shift, thresh }; return ex.parts(np, op);
+}
+int emu_project_out_of_bnd(int prec, int order, int sx, int sy, int sz, long long np, void* pos, const int* pflag, double bnd, int axis, const int* ptype, int exclude) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	if (prec == 4) { parts::PSet<float> ps = { (const float*)pos, pflag, ptype, exclude }; parts::ProjectOutOfBnd<float> op = { d, (float*)pos, ps, (float)bnd, axis }; return ex.parts(np, op); }
+	parts::PSet<double> ps = { (const double*)pos, pflag, ptype, exclude }; parts::ProjectOutOfBnd<double> op = { d, (double*)pos, ps, bnd, axis }; return ex.parts(np, op);
+}
 int emu_advect_in_grid(int prec, int order, int sx, int sy, int sz, const int* flags, const void* vel, long long np, void* pos, int* pflag, double dt, int mode, int del, int stop,
                        int skipNew, const int* ptype, int exclude) {
 	const Dims d = mkDims(sx, sy, sz);

@@ -667,4 +667,25 @@ def run_advect_cases(I, name, prec):
         p, f = I.advect_in_grid(flags, vel, pos.copy(), pflag.copy(), 0.8, integrationMode=mode, deleteInObstacle=dele, stopInObstacle=stop, skipNew=skip,
                                 ptype=ptype if typed else None, exclude=4 if typed else 0)
         out[case + "_pos"], out[case + "_flag"] = p, f
+    # pushOutofObs (flip.cpp:528-545) and projectOutOfBnd (particle.h:565-590) on the advected particles, as scenes/benchmark_dam.py:123-124 chains them
+    sz, sy, sx = flags.shape
+    phiObs = obstacle_levelset(flags.shape, prec)
+    moved, mflag = out["rk2_nostop_pos"], out["rk2_nostop_flag"]          # some of these left the domain or sit inside the block
+    out["project"] = I.project_out_of_bnd(flags.shape, moved.copy(), mflag, 1.5, plane="xXyYzZ", ptype=ptype, exclude=4)
+    out["project_xY"] = I.project_out_of_bnd(flags.shape, moved.copy(), mflag, 2.25, plane="xY")
+    out["push"] = I.push_out_of_obs(flags.shape, out["project"].copy(), mflag, phiObs, shift=0.0, thresh=0.5, ptype=ptype, exclude=4)
+    out["push_shift"] = I.push_out_of_obs(flags.shape, moved.copy(), mflag, phiObs, shift=0.25, thresh=0.0)
     return out
+
+
+def obstacle_levelset(shape, prec):
+    """signed distance to the walls of the box (one cell thick) and to a sphere standing where advect_scene puts its obstacle block"""
+    sz, sy, sx = shape
+    k, j, i = np.meshgrid(np.arange(sz), np.arange(sy), np.arange(sx), indexing="ij")
+    x, y, z = i + 0.5, j + 0.5, k + 0.5
+    d = np.minimum(np.minimum(x - 1, sx - 1 - x), np.minimum(y - 1, sy - 1 - y))
+    if sz > 1:
+        d = np.minimum(d, np.minimum(z - 1, sz - 1 - z))
+    cz = 0.5 * sz if sz > 1 else 0.5
+    sphere = np.sqrt((x - 5 * sx / 12.0) ** 2 + (y - (1 + sy / 8.0)) ** 2 + ((z - cz) ** 2 if sz > 1 else 0)) - sx / 8.0
+    return np.ascontiguousarray(np.minimum(d, sphere).astype(np.float32 if prec == 4 else np.float64))

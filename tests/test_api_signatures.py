@@ -22,7 +22,7 @@ PLUGINS = {     # plugin -> reference file
     "getLaplacian": "plugin/flip.cpp", "getCurvature": "plugin/flip.cpp",
     "updateFractions": "plugin/initplugins.cpp", "setObstacleFlags": "plugin/initplugins.cpp",
     "markFluidCells": "plugin/flip.cpp", "gridParticleIndex": "plugin/flip.cpp", "unionParticleLevelset": "plugin/flip.cpp", "mapPartsToMAC": "plugin/flip.cpp",
-    "mapMACToParts": "plugin/flip.cpp", "flipVelocityUpdate": "plugin/flip.cpp",
+    "mapMACToParts": "plugin/flip.cpp", "flipVelocityUpdate": "plugin/flip.cpp", "pushOutofObs": "plugin/flip.cpp",
 }
 
 
