@@ -8,6 +8,7 @@
 //     setWallBcs, addGravity, addGravityNoScale, addBuoyancy          plugin/extforces.cpp:61-90,:307-316
 //     advectSemiLagrange                                              plugin/advection.cpp:442-461
 //     extrapolateMACSimple, extrapolateLsSimple, extrapolateVec3Simple fastmarch.cpp:337-375,:470-542
+//     BasicParticleSystem, ParticleDataImpl<T>, ParticleIndexSystem (particle.h) and the FLIP plugins of plugin/flip.cpp (markFluidCells ... pushOutofObs)
 //     getLaplacian, getCurvature                                      plugin/flip.cpp:710-716
 //     updateFractions, setObstacleFlags                               plugin/initplugins.cpp:437-440,:473-475
 //     cgSolveDiffusion, cgSolveWE                                     conjugategrad.cpp:350, plugin/waves.cpp:86
@@ -186,6 +187,85 @@ public:
 	}
 };
 
+// ---------------------------------------------------------------- particles (particle.h): device-resident arrays, coherent lazily like the grids
+template <class T>
+class DevArray {                                     // one per-particle array: std::vector on the host, an mp_grid of size (capacity, 1, 1) on the device
+public:
+	DevArray(FluidSolver* parent) : mParent(parent), mDev(nullptr), mCap(0), mHostDirty(false), mDevDirty(false) {}
+	~DevArray() { if (mDev) mp_grid_destroy(mDev); }
+	DevArray(const DevArray&) = delete;
+	DevArray& operator=(const DevArray&) = delete;
+	long long size() const { return (long long)mData.size(); }
+	void resize(long long n) { syncToHost(); mData.resize((size_t)n); if (n) mHostDirty = true; }
+	const T& operator[](long long idx) const { syncToHost(); return mData[(size_t)idx]; }
+	T& operator[](long long idx) { syncToHost(); mHostDirty = true; return mData[(size_t)idx]; }
+	mp_grid* dev() const {                             // nullptr for an empty array (the C-ABI accepts it with np == 0)
+		const long long n = size();
+		if (n == 0) return nullptr;
+		if (n > mCap) { reserveDev(n); mHostDirty = true; }
+		if (mHostDirty) {
+			std::vector<T> buf(mData); buf.resize((size_t)mCap);      // the upload moves `capacity` entries
+			mpCheck(mp_grid_upload(mDev, buf.data())); mHostDirty = false;
+		}
+		return mDev;
+	}
+	void reserveDev(long long n) const {
+		if (n <= mCap) return;
+		if (mDev) mpCheck(mp_grid_destroy(mDev));
+		mDev = nullptr; mCap = n;
+		mpCheck(mp_grid_create(mParent->ctx(), GridKind<T>::kind, (int)sizeof(Real), (int)n, 1, 1, &mDev));
+	}
+	void syncToHost() const {
+		if (!mDevDirty || !mDev) return;
+		std::vector<T> buf((size_t)mCap);
+		mpCheck(mp_grid_download(mDev, buf.data()));
+		std::copy(buf.begin(), buf.begin() + (long long)mData.size(), mData.begin()); mDevDirty = false;
+	}
+	void markDeviceWritten() { mDevDirty = true; mHostDirty = false; }
+protected:
+	FluidSolver* mParent; mutable std::vector<T> mData; mutable mp_grid* mDev; mutable long long mCap; mutable bool mHostDirty, mDevDirty;
+};
+template <class T> class ParticleDataImpl : public DevArray<T> {      // particle.h:392-470
+public:
+	ParticleDataImpl(FluidSolver* parent) : DevArray<T>(parent) {}
+};
+enum IntegrationMode { IntEuler = 0, IntRK2, IntRK4 };                 // util/integrator.h:23
+class BasicParticleSystem {                          // particle.h:193-274 (BasicParticleData {Vec3 pos; int flag;} as two arrays)
+public:
+	enum ParticleStatus { PNONE = 0, PNEW = 1 << 0, PSPRAY = 1 << 1, PBUBBLE = 1 << 2, PFOAM = 1 << 3, PTRACER = 1 << 4, PDELETE = 1 << 10, PINVALID = 1 << 30 };   // particle.h:34-43
+	BasicParticleSystem(FluidSolver* parent) : mParent(parent), mPos(parent), mFlag(parent) {}
+	FluidSolver* getParent() const { return mParent; }
+	long long size() const { return mPos.size(); }
+	void resizeAll(long long n) { mPos.resize(n); mFlag.resize(n); }
+	Vec3 getPos(long long idx) const { return mPos[idx]; }
+	void setPos(long long idx, const Vec3& p) { mPos[idx] = p; }
+	int getStatus(long long idx) const { return mFlag[idx]; }
+	void setStatus(long long idx, int f) { mFlag[idx] = f; }
+	bool isActive(long long idx) const { return (mFlag[idx] & PDELETE) == 0; }
+	mp_grid* devPos() const { return mPos.dev(); }
+	mp_grid* devFlag() const { return mFlag.dev(); }
+	void advectInGrid(const FlagGrid& flags, const MACGrid& vel, const int integrationMode, const bool deleteInObstacle = true, const bool stopInObstacle = true,
+	                  const bool skipNew = false, const ParticleDataImpl<int>* ptype = NULL, const int exclude = 0) {                       // particle.h:154
+		if (!size()) return;
+		mpCheck(mp_parts_advect_in_grid(mParent->ctx(), flags.dev(), vel.dev(), size(), devPos(), devFlag(), mParent->getDt(), integrationMode, deleteInObstacle, stopInObstacle,
+		                                skipNew, ptype ? ptype->dev() : nullptr, exclude));
+		mPos.markDeviceWritten(); mFlag.markDeviceWritten();
+	}
+	void projectOutOfBnd(const FlagGrid& flags, const Real bnd, const std::string& plane = "xXyYzZ", const ParticleDataImpl<int>* ptype = NULL, const int exclude = 0) {   // particle.h:158
+		if (!size()) return;
+		mpCheck(mp_parts_project_out_of_bnd(mParent->ctx(), flags.dev(), size(), devPos(), devFlag(), bnd, plane.c_str(), ptype ? ptype->dev() : nullptr, exclude));
+		mPos.markDeviceWritten();
+	}
+	void markPosDeviceWritten() { mPos.markDeviceWritten(); }
+private:
+	FluidSolver* mParent; DevArray<Vec3> mPos; DevArray<int> mFlag;
+};
+class ParticleIndexSystem : public DevArray<int> {   // particle.h:276-300: sourceIndex per slot
+public:
+	ParticleIndexSystem(FluidSolver* parent) : DevArray<int>(parent) {}
+	void setCountOnDevice(long long n) { mData.resize((size_t)n); mHostDirty = false; mDevDirty = n > 0; }
+};
+
 // ---------------------------------------------------------------- plugins
 namespace detail {
 template <class G> inline const mp_grid* dv(const G* g) { return g ? g->dev() : nullptr; }
@@ -325,6 +405,50 @@ inline void cgSolveWE(const FlagGrid& flags, Grid<Real>& ut, Grid<Real>& utm1, G
 	mpCheck(mp_cg_solve_we(flags.getParent()->ctx(), flags.dev(), ut.dev(), utm1.dev(), out.dev(), crankNic, cSqr, cgMaxIterFac, cgAccuracy, flags.getParent()->getDt(),
 	                       &detail::lastInfo()));
 	ut.markDeviceWritten(); utm1.markDeviceWritten(); out.markDeviceWritten();
+}
+
+// ---- FLIP particle <-> grid plugins plugin/flip.cpp (second slice)
+namespace detail { template <class T> inline const mp_grid* dp(const ParticleDataImpl<T>* p) { return p ? p->dev() : nullptr; } }
+inline void markFluidCells(const BasicParticleSystem& parts, FlagGrid& flags, const Grid<Real>* phiObs = NULL, const ParticleDataImpl<int>* ptype = NULL, const int exclude = 0) {   // :158
+	mpCheck(mp_mark_fluid_cells(flags.getParent()->ctx(), parts.size(), parts.devPos(), parts.devFlag(), flags.dev(), detail::dv(phiObs), detail::dp(ptype), exclude));
+	flags.markDeviceWritten();
+}
+inline void gridParticleIndex(const BasicParticleSystem& parts, ParticleIndexSystem& indexSys, const FlagGrid& flags, Grid<int>& index, Grid<int>* counter = NULL) {   // :260
+	(void)counter;                                   // the slots of a cell are filled by a stable sort, no counter grid is needed
+	long long count = 0;
+	if (parts.size()) indexSys.reserveDev(parts.size());
+	indexSys.resize(parts.size());
+	mpCheck(mp_grid_particle_index(index.getParent()->ctx(), parts.size(), parts.devPos(), parts.devFlag(), parts.size() ? indexSys.dev() : nullptr, flags.dev(), index.dev(), &count));
+	indexSys.setCountOnDevice(count); index.markDeviceWritten();
+}
+inline void unionParticleLevelset(const BasicParticleSystem& parts, const ParticleIndexSystem& indexSys, const FlagGrid& flags, const Grid<int>& index, LevelsetGrid& phi,
+                                  const Real radiusFactor = 1., const ParticleDataImpl<int>* ptype = NULL, const int exclude = 0) {       // :340
+	mpCheck(mp_union_particle_levelset(phi.getParent()->ctx(), parts.size(), parts.devPos(), indexSys.dev(), indexSys.size(), flags.dev(), index.dev(), phi.dev(), radiusFactor,
+	                                   detail::dp(ptype), exclude));
+	phi.markDeviceWritten();
+}
+inline void mapPartsToMAC(const FlagGrid& flags, MACGrid& vel, MACGrid& velOld, const BasicParticleSystem& parts, const ParticleDataImpl<Vec3>& partVel, Grid<Vec3>* weight = NULL,
+                          const ParticleDataImpl<int>* ptype = NULL, const int exclude = 0) {                                            // :573
+	mpCheck(mp_map_parts_to_mac(vel.getParent()->ctx(), flags.dev(), vel.dev(), velOld.dev(), parts.size(), parts.devPos(), parts.devFlag(), partVel.dev(),
+	                            weight ? weight->dev() : nullptr, detail::dp(ptype), exclude));
+	vel.markDeviceWritten(); velOld.markDeviceWritten(); if (weight) weight->markDeviceWritten();
+}
+inline void mapMACToParts(const FlagGrid& flags, const MACGrid& vel, const BasicParticleSystem& parts, ParticleDataImpl<Vec3>& partVel, const ParticleDataImpl<int>* ptype = NULL,
+                          const int exclude = 0) {                                                                                      // :651
+	mpCheck(mp_map_mac_to_parts(vel.getParent()->ctx(), flags.dev(), vel.dev(), parts.size(), parts.devPos(), parts.devFlag(), partVel.dev(), detail::dp(ptype), exclude));
+	if (parts.size()) partVel.markDeviceWritten();
+}
+inline void flipVelocityUpdate(const FlagGrid& flags, const MACGrid& vel, const MACGrid& velOld, const BasicParticleSystem& parts, ParticleDataImpl<Vec3>& partVel, const Real flipRatio,
+                               const ParticleDataImpl<int>* ptype = NULL, const int exclude = 0) {                                       // :669
+	mpCheck(mp_flip_velocity_update(vel.getParent()->ctx(), flags.dev(), vel.dev(), velOld.dev(), parts.size(), parts.devPos(), parts.devFlag(), partVel.dev(), flipRatio,
+	                                detail::dp(ptype), exclude));
+	if (parts.size()) partVel.markDeviceWritten();
+}
+inline void pushOutofObs(BasicParticleSystem& parts, const FlagGrid& flags, const Grid<Real>& phiObs, const Real shift = 0, const Real thresh = 0,
+                         const ParticleDataImpl<int>* ptype = NULL, const int exclude = 0) {                                             // :542
+	if (!parts.size()) return;
+	mpCheck(mp_push_out_of_obs(phiObs.getParent()->ctx(), parts.size(), parts.devPos(), parts.devFlag(), flags.dev(), phiObs.dev(), shift, thresh, detail::dp(ptype), exclude));
+	parts.markPosDeviceWritten();
 }
 
 }  // namespace Manta

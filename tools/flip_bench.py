@@ -41,6 +41,8 @@ vel, velOld, weight = s.create(mf.MACGrid), s.create(mf.MACGrid), s.create(mf.Ve
 phi, index = s.create(mf.LevelsetGrid), s.create(mf.IntGrid)
 pp = s.create(mf.BasicParticleSystem)
 pVel, pindex = pp.create(mf.PdataVec3), s.create(mf.ParticleIndexSystem)
+phiObs = mf.LevelsetGrid(s, np.minimum(np.minimum(np.minimum(i + 0.5 - 1, res - 1.5 - i), np.minimum(j + 0.5 - 1, res - 1.5 - j)), np.minimum(k + 0.5 - 1, res - 1.5 - k)).astype(np.float32))
+s.timestep = 0.5
 pp.setParticles(pos)
 pVel.copyFromArray(pvel)
 mf.markFluidCells(pp, F); s.synchronize()
@@ -60,6 +62,9 @@ rows = [   # name, call, minimum bytes
     ("mapPartsToMAC", lambda: mf.mapPartsToMAC(F, vel, velOld, pp, pVel), 28 * N + 24 * n),
     ("mapMACToParts", lambda: mf.mapMACToParts(F, vel, pp, pVel), 28 * N + 12 * n),
     ("flipVelocityUpdate", lambda: mf.flipVelocityUpdate(F, vel, velOld, pp, pVel, 0.97), 40 * N + 24 * n),
+    ("advectInGrid RK4", lambda: pp.advectInGrid(F, vel, mf.IntRK4, deleteInObstacle=False), 32 * N + 12 * n),
+    ("projectOutOfBnd", lambda: pp.projectOutOfBnd(F, 1.5), 28 * N),
+    ("pushOutofObs", lambda: mf.pushOutofObs(pp, F, phiObs, thresh=0.5), 28 * N + 4 * n),
     ("gridParticleIndex", lambda: mf.gridParticleIndex(pp, pindex, F, index), 20 * N + 8 * n),
     ("unionParticleLevelset", lambda: mf.unionParticleLevelset(pp, pindex, F, index, phi), 16 * N + 8 * n),
 ]
