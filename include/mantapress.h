@@ -271,6 +271,15 @@ int mp_push_out_of_obs(mp_context* ctx, long long np, mp_grid* pos, const mp_gri
                        const mp_grid* ptype, int exclude);
 int mp_parts_project_out_of_bnd(mp_context* ctx, const mp_grid* flags, long long np, mp_grid* pos, const mp_grid* pflag, double bnd, const char* plane,
                                 const mp_grid* ptype, int exclude);
+/* The Lagrangian-particle helpers of scenes/benchmark_dam.py:118-134: addForcePvel, updateVelocityFromDeltaPos, eulerStep, setPartType
+ * (plugin/ptsplugins.cpp:26-29,:38-41,:50-53,:62-65; dt of eulerStep = FluidSolver::getDt()), ParticleSystem::getPosPdata (particle.h:422-427),
+ * markIsolatedFluidCell (grid.cpp:885-890).  With them every plugin of that scene's main loop has a device version. */
+int mp_add_force_pvel(mp_context* ctx, long long np, mp_grid* vel, double ax, double ay, double az, double dt, const mp_grid* ptype, int exclude);
+int mp_update_velocity_from_delta_pos(mp_context* ctx, long long np, const mp_grid* pos, mp_grid* vel, const mp_grid* xPrev, double dt, const mp_grid* ptype, int exclude);
+int mp_euler_step(mp_context* ctx, long long np, mp_grid* pos, const mp_grid* vel, double dt, const mp_grid* ptype, int exclude);
+int mp_set_part_type(mp_context* ctx, long long np, const mp_grid* pos, mp_grid* ptype, int mark, int stype, const mp_grid* flags, int cflag);
+int mp_parts_get_pos_pdata(mp_context* ctx, long long np, const mp_grid* pos, mp_grid* target);
+int mp_mark_isolated_fluid_cell(mp_context* ctx, mp_grid* flags, int mark);
 int mp_mark_fluid_cells(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* flags, const mp_grid* phiObs, const mp_grid* ptype, int exclude);
 int mp_grid_particle_index(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* indexSys, const mp_grid* flags, mp_grid* index, long long* count);
 int mp_union_particle_levelset(mp_context* ctx, long long np, const mp_grid* pos, const mp_grid* indexSys, long long count, const mp_grid* flags, const mp_grid* index,

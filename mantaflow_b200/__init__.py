@@ -17,6 +17,7 @@ from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE
 from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, extrapolateLsSimple, extrapolateMACFromWeight, extrapolateMACSimple,
                    extrapolateVec3Simple, getCurvature, getLaplacian, lastGuidingIterations, releaseBlurPrecomp, setObstacleFlags, setWallBcs, updateFractions)
 from .particles import (PDELETE, PNEW, IntEuler, IntRK2, IntRK4, BasicParticleSystem, IntGrid, ParticleIndexSystem, PdataInt, PdataReal, PdataVec3, flipVelocityUpdate, gridParticleIndex, mapMACToParts,
-                        mapPartsToMAC, markFluidCells, pushOutofObs, unionParticleLevelset)
+                        mapPartsToMAC, markFluidCells, pushOutofObs, unionParticleLevelset, addForcePvel, updateVelocityFromDeltaPos, eulerStep, setPartType,
+                        markIsolatedFluidCell)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

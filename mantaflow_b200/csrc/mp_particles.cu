@@ -276,6 +276,80 @@ int mp_parts_project_out_of_bnd(mp_context* ctx, const mp_grid* flags, long long
 	return ex.parts(np, op);
 }
 
+// ---- plugin/ptsplugins.cpp:17-70, ParticleSystem::getPosPdata particle.h:422-427, markIsolatedFluidCell grid.cpp:866-890
+static int checkPdata(const char* who, mp_context* ctx, long long np, const mp_grid* a, const char* name, int kind, int prec) {
+	if (!ctx) MP_FAIL(MP_ERR_INVALID, "%s: NULL context", who);
+	if (np < 0 || np > 0x7fffffffLL) MP_FAIL(MP_ERR_INVALID, "%s: bad particle count %lld", who, np);
+	MP_TRY(checkArray(who, name, a, kind, prec, np, false));
+	MP_CUDA(cudaSetDevice(ctx->device));
+	return MP_OK;
+}
+int mp_add_force_pvel(mp_context* ctx, long long np, mp_grid* vel, double ax, double ay, double az, double dt, const mp_grid* ptype, int exclude)
+{
+	const int prec = vel ? vel->prec : 4;
+	MP_TRY(checkPdata("mp_add_force_pvel", ctx, np, vel, "vel", MP_GRID_MAC, prec)); MP_TRY(checkArray("mp_add_force_pvel", "ptype", ptype, MP_GRID_FLAGS, 4, np, true));
+	if (np == 0) return MP_OK;
+	CudaExec ex = { ctx };
+	const int* pt = ptype ? (const int*)ptype->d : nullptr;
+	if (prec == 4) { const float d = (float)dt; parts::AddForcePvel<float> op = { (float*)vel->d, { (float)ax * d, (float)ay * d, (float)az * d }, pt, exclude }; return ex.parts(np, op); }
+	parts::AddForcePvel<double> op = { (double*)vel->d, { ax * dt, ay * dt, az * dt }, pt, exclude };
+	return ex.parts(np, op);
+}
+int mp_update_velocity_from_delta_pos(mp_context* ctx, long long np, const mp_grid* pos, mp_grid* vel, const mp_grid* xPrev, double dt, const mp_grid* ptype, int exclude)
+{
+	const int prec = vel ? vel->prec : 4;
+	MP_TRY(checkPdata("mp_update_velocity_from_delta_pos", ctx, np, vel, "vel", MP_GRID_MAC, prec));
+	MP_TRY(checkArray("mp_update_velocity_from_delta_pos", "pos", pos, MP_GRID_MAC, prec, np, false)); MP_TRY(checkArray("mp_update_velocity_from_delta_pos", "x_prev", xPrev, MP_GRID_MAC, prec, np, false));
+	MP_TRY(checkArray("mp_update_velocity_from_delta_pos", "ptype", ptype, MP_GRID_FLAGS, 4, np, true));
+	if (np == 0) return MP_OK;
+	CudaExec ex = { ctx };
+	const int* pt = ptype ? (const int*)ptype->d : nullptr;
+	if (prec == 4) { parts::UpdateVelocityFromDeltaPos<float> op = { (const float*)pos->d, (float*)vel->d, (const float*)xPrev->d, (float)(1.0 / (double)(float)dt), pt, exclude }; return ex.parts(np, op); }
+	parts::UpdateVelocityFromDeltaPos<double> op = { (const double*)pos->d, (double*)vel->d, (const double*)xPrev->d, 1.0 / dt, pt, exclude };
+	return ex.parts(np, op);
+}
+int mp_euler_step(mp_context* ctx, long long np, mp_grid* pos, const mp_grid* vel, double dt, const mp_grid* ptype, int exclude)
+{
+	const int prec = pos ? pos->prec : 4;
+	MP_TRY(checkPdata("mp_euler_step", ctx, np, pos, "pos", MP_GRID_MAC, prec)); MP_TRY(checkArray("mp_euler_step", "vel", vel, MP_GRID_MAC, prec, np, false));
+	MP_TRY(checkArray("mp_euler_step", "ptype", ptype, MP_GRID_FLAGS, 4, np, true));
+	if (np == 0) return MP_OK;
+	CudaExec ex = { ctx };
+	const int* pt = ptype ? (const int*)ptype->d : nullptr;
+	if (prec == 4) { parts::StepEuler<float> op = { (float*)pos->d, (const float*)vel->d, (float)dt, pt, exclude }; return ex.parts(np, op); }
+	parts::StepEuler<double> op = { (double*)pos->d, (const double*)vel->d, dt, pt, exclude };
+	return ex.parts(np, op);
+}
+int mp_set_part_type(mp_context* ctx, long long np, const mp_grid* pos, mp_grid* ptype, int mark, int stype, const mp_grid* flags, int cflag)
+{
+	MP_TRY(checkCtx("mp_set_part_type", ctx, flags));
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "setPartType: flags is not a FlagGrid");
+	const int prec = pos ? pos->prec : 4;
+	MP_TRY(checkPdata("mp_set_part_type", ctx, np, pos, "pos", MP_GRID_MAC, prec)); MP_TRY(checkArray("mp_set_part_type", "ptype", ptype, MP_GRID_FLAGS, 4, np, false));
+	if (np == 0) return MP_OK;
+	CudaExec ex = { ctx };
+	const Dims d = dimsOf(flags);
+	if (prec == 4) { parts::SetPartType<float> op = { d, (const float*)pos->d, (int*)ptype->d, mark, stype, (const int*)flags->d, cflag }; return ex.parts(np, op); }
+	parts::SetPartType<double> op = { d, (const double*)pos->d, (int*)ptype->d, mark, stype, (const int*)flags->d, cflag };
+	return ex.parts(np, op);
+}
+int mp_parts_get_pos_pdata(mp_context* ctx, long long np, const mp_grid* pos, mp_grid* target)
+{
+	const int prec = pos ? pos->prec : 4;
+	MP_TRY(checkPdata("mp_parts_get_pos_pdata", ctx, np, pos, "pos", MP_GRID_MAC, prec)); MP_TRY(checkArray("mp_parts_get_pos_pdata", "target", target, MP_GRID_MAC, prec, np, false));
+	if (np == 0) return MP_OK;
+	MP_CUDA(cudaMemcpyAsync(target->d, pos->d, (size_t)np * 3 * prec, cudaMemcpyDeviceToDevice, ctx->stream));
+	return MP_OK;
+}
+int mp_mark_isolated_fluid_cell(mp_context* ctx, mp_grid* flags, int mark)
+{
+	MP_TRY(checkCtx("mp_mark_isolated_fluid_cell", ctx, flags));
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "markIsolatedFluidCell: flags is not a FlagGrid");
+	CudaExec ex = { ctx };
+	parts::MarkIsolatedFluidCell op = { (int*)flags->d, mark };
+	return ex.cells(dimsOf(flags), op);
+}
+
 int mp_map_mac_to_parts(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* partVel,
                         const mp_grid* ptype, int exclude)
 {

@@ -390,6 +390,41 @@ template <typename Real> struct ProjectOutOfBnd {
 	}
 };
 
+// ---------------------------------------------------------------- the Lagrangian-particle helpers of scenes/benchmark_dam.py:118-134
+// plugin/ptsplugins.cpp:17-70 (KnAddForcePvel, KnUpdateVelocityFromDeltaPos, KnStepEuler, KnSetPartType) and markIsolatedFluidCell
+// grid.cpp:866-890.  None of them looks at PDELETE; particles of an excluded type are skipped.
+template <typename Real> struct AddForcePvel {
+	Real* v; Real da[3]; const int* ptype; int exclude;
+	MP_HD void operator()(IndexInt idx) const { if (ptype && (ptype[idx] & exclude)) return; for (int c = 0; c < 3; c++) v[3 * idx + c] += da[c]; }
+};
+template <typename Real> struct UpdateVelocityFromDeltaPos {
+	const Real* pos; Real* v; const Real* xPrev; Real overDt; const int* ptype; int exclude;
+	MP_HD void operator()(IndexInt idx) const { if (ptype && (ptype[idx] & exclude)) return; for (int c = 0; c < 3; c++) v[3 * idx + c] = (pos[3 * idx + c] - xPrev[3 * idx + c]) * overDt; }
+};
+template <typename Real> struct StepEuler {
+	Real* pos; const Real* v; Real dt; const int* ptype; int exclude;
+	MP_HD void operator()(IndexInt idx) const { if (ptype && (ptype[idx] & exclude)) return; for (int c = 0; c < 3; c++) pos[3 * idx + c] += v[3 * idx + c] * dt; }
+};
+template <typename Real> struct SetPartType {
+	Dims d; const Real* pos; int* ptype; int mark, stype; const int* flags; int cflag;
+	MP_HD void operator()(IndexInt idx) const {
+		const int x = (int)pos[3 * idx], y = (int)pos[3 * idx + 1], z = (int)pos[3 * idx + 2];
+		if (inBounds0(d, x, y, z) && (flags[(IndexInt)x + d.Y * y + d.Z * z] & cflag) && (ptype[idx] & stype)) ptype[idx] = mark;
+	}
+};
+// A fluid cell without fluid neighbours takes `mark`.  In place: a cell that is rewritten has no fluid neighbour, so no cell that reads it can
+// change its own decision (the reference's parallel kernel relies on the same argument).  Fluid cells are interior cells.
+struct MarkIsolatedFluidCell {
+	static const bool kSplit = false;
+	int* flags; int mark;
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt p) const {
+		if (!(flags[p] & TypeFluid) || !liquid::interiorCell(d, i, j, k)) return;
+		if ((flags[p - 1] & TypeFluid) || (flags[p + 1] & TypeFluid) || (flags[p - d.Y] & TypeFluid) || (flags[p + d.Y] & TypeFluid)) return;
+		if (d.is3D && ((flags[p - d.Z] & TypeFluid) || (flags[p + d.Z] & TypeFluid))) return;
+		flags[p] = mark;
+	}
+};
+
 // ---------------------------------------------------------------- mapPartsToMAC
 // One thread per cell: its three faces gather from the particles bucketed (clamped) into the 3 x 3 (x 3) cells around it, visited in
 // ascending particle order, which is the order the reference's serial scatter adds them in.  A particle with bucket cell (kx, ky, kz)

@@ -193,6 +193,17 @@ class BasicParticleSystem:
                                                 None if ptype is None else ptype.dev(), C.c_int(exclude)))
         self._pos.markDeviceWritten()
 
+    def getPosPdata(self, target):
+        """ParticleSystem::getPosPdata particle.h:135,:422-427: a device-to-device copy of the positions"""
+        s = self.parent
+        _pdcheck(self, target, "target")
+        if self.size() == 0:
+            return
+        target._a._reserve(self.size())
+        target._a._hostDirty = False       # every entry in use is written
+        check(s.lib.mp_parts_get_pos_pdata(s._ctx, C.c_longlong(self.size()), self._pos.dev(), target._a._dev))
+        target.markDeviceWritten()
+
     def positions(self, writable=False): return self._pos.numpy(writable)
     def flags(self, writable=False): return self._flag.numpy(writable)
 
@@ -267,6 +278,53 @@ def pushOutofObs(parts, flags, phiObs, shift=0, thresh=0, ptype=None, exclude=0)
     n, pos, pflag = _ps(parts)
     check(s.lib.mp_push_out_of_obs(s._ctx, n, pos, pflag, _d(flags), phiObs.dev(), C.c_double(shift), C.c_double(thresh), _d(ptype), C.c_int(exclude)))
     parts._pos.markDeviceWritten()
+
+
+def addForcePvel(vel, a, dt, ptype, exclude):
+    """plugin/ptsplugins.cpp:26 (no defaults in the reference either)"""
+    s = vel.parent
+    if vel.size() == 0:
+        return
+    ax, ay, az = (float(c) for c in a)
+    check(s.lib.mp_add_force_pvel(s._ctx, C.c_longlong(vel.size()), vel.dev(), C.c_double(ax), C.c_double(ay), C.c_double(az), C.c_double(dt), _d(ptype), C.c_int(exclude)))
+    vel.markDeviceWritten()
+
+
+def updateVelocityFromDeltaPos(parts, vel, x_prev, dt, ptype, exclude):
+    """plugin/ptsplugins.cpp:38"""
+    s = vel.parent
+    _pdcheck(parts, vel, "vel"); _pdcheck(parts, x_prev, "x_prev"); _pdcheck(parts, ptype, "ptype")
+    if parts.size() == 0:
+        return
+    check(s.lib.mp_update_velocity_from_delta_pos(s._ctx, C.c_longlong(parts.size()), parts._pos.dev(), vel.dev(), x_prev.dev(), C.c_double(dt), _d(ptype), C.c_int(exclude)))
+    vel.markDeviceWritten()
+
+
+def eulerStep(parts, vel, ptype, exclude):
+    """plugin/ptsplugins.cpp:50 (dt = the solver's timestep)"""
+    s = parts.parent
+    _pdcheck(parts, vel, "vel"); _pdcheck(parts, ptype, "ptype")
+    if parts.size() == 0:
+        return
+    check(s.lib.mp_euler_step(s._ctx, C.c_longlong(parts.size()), parts._pos.dev(), vel.dev(), C.c_double(s.timestep), _d(ptype), C.c_int(exclude)))
+    parts._pos.markDeviceWritten()
+
+
+def setPartType(parts, ptype, mark, stype, flags, cflag):
+    """plugin/ptsplugins.cpp:62: particles of type `stype` in `cflag` cells become `mark`"""
+    s = flags.parent
+    _pdcheck(parts, ptype, "ptype")
+    if parts.size() == 0:
+        return
+    check(s.lib.mp_set_part_type(s._ctx, C.c_longlong(parts.size()), parts._pos.dev(), ptype.dev(), C.c_int(mark), C.c_int(stype), flags.dev(), C.c_int(cflag)))
+    ptype.markDeviceWritten()
+
+
+def markIsolatedFluidCell(flags, mark):
+    """grid.cpp:885-890"""
+    s = flags.parent
+    check(s.lib.mp_mark_isolated_fluid_cell(s._ctx, flags.dev(), C.c_int(mark)))
+    flags.markDeviceWritten()
 
 
 def mapPartsToMAC(flags, vel, velOld, parts, partVel, weight=None, ptype=None, exclude=0):

@@ -2356,3 +2356,45 @@ int mfo_project_out_of_bnd(int sx, int sy, int sz, long long np, Real* pos, cons
 	}
 	return 0;
 }
+
+/* The Lagrangian-particle helpers of scenes/benchmark_dam.py:118-134 (plugin/ptsplugins.cpp:17-70, ParticleSystem::getPosPdata particle.h:422-427,
+ * markIsolatedFluidCell grid.cpp:866-890).  None of them looks at the PDELETE flag; an excluded type is skipped. */
+#define T_SKIP(idx) (ptype && (ptype[idx] & exclude))
+int mfo_add_force_pvel(long long np, Real* pvel, double ax, double ay, double az, double dt_, const int* ptype, int exclude)
+{
+	const Real dt = (Real)dt_, da[3] = { (Real)ax * dt, (Real)ay * dt, (Real)az * dt };
+	for (long long idx = 0; idx < np; idx++) { if (T_SKIP(idx)) continue; for (int c = 0; c < 3; c++) pvel[3 * idx + c] += da[c]; }
+	return 0;
+}
+int mfo_update_velocity_from_delta_pos(long long np, const Real* pos, Real* pvel, const Real* xPrev, double dt_, const int* ptype, int exclude)
+{
+	const Real overDt = (Real)(1.0 / (double)(Real)dt_);
+	for (long long idx = 0; idx < np; idx++) { if (T_SKIP(idx)) continue; for (int c = 0; c < 3; c++) pvel[3 * idx + c] = (pos[3 * idx + c] - xPrev[3 * idx + c]) * overDt; }
+	return 0;
+}
+int mfo_euler_step(long long np, Real* pos, const Real* pvel, double dt_, const int* ptype, int exclude)
+{
+	const Real dt = (Real)dt_;
+	for (long long idx = 0; idx < np; idx++) { if (T_SKIP(idx)) continue; for (int c = 0; c < 3; c++) pos[3 * idx + c] += pvel[3 * idx + c] * dt; }
+	return 0;
+}
+int mfo_set_part_type(int sx, int sy, int sz, long long np, const Real* pos, int* ptype, int mark, int stype, const int* flags, int cflag)
+{
+	for (long long idx = 0; idx < np; idx++) {
+		const Real* x = pos + 3 * idx;
+		if (in_bounds_b(sx, sy, sz, x, 0) && (flags[(IndexInt)(int)x[0] + (IndexInt)sx * (int)x[1] + (sz > 1 ? (IndexInt)sx * sy * (int)x[2] : 0)] & cflag) && (ptype[idx] & stype)) ptype[idx] = mark;
+	}
+	return 0;
+}
+int mfo_mark_isolated_fluid_cell(int sx, int sy, int sz, int* flags, int mark)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	for (IndexInt q = 0; q < n; q++) {
+		if (!(flags[q] & TypeFluid)) continue;
+		if ((flags[q - X] & TypeFluid) || (flags[q + X] & TypeFluid) || (flags[q - Y] & TypeFluid) || (flags[q + Y] & TypeFluid)) continue;
+		if (IS3D && ((flags[q - Z] & TypeFluid) || (flags[q + Z] & TypeFluid))) continue;
+		flags[q] = mark;
+	}
+	return 0;
+}

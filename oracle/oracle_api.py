@@ -345,6 +345,31 @@ class Oracle:
         self._chk(self._f("project_out_of_bnd")(*self.dims(np.empty(shape, np.int8)), n, pp, pf, C.c_double(bnd), C.c_int(axis), pt, C.c_int(exclude)))
         return pos
 
+    # -- plugin/ptsplugins.cpp:17-70, grid.cpp:866-890: the Lagrangian-particle helpers of scenes/benchmark_dam.py; arrays updated in place and returned --
+    def _pt(self, ptype):
+        return None if ptype is None else _p(np.ascontiguousarray(ptype, np.int32))
+
+    def add_force_pvel(self, pvel, a, dt, ptype=None, exclude=0):
+        self._chk(self._f("add_force_pvel")(C.c_longlong(len(pvel)), _p(pvel), C.c_double(a[0]), C.c_double(a[1]), C.c_double(a[2]), C.c_double(dt), self._pt(ptype), C.c_int(exclude)))
+        return pvel
+
+    def update_velocity_from_delta_pos(self, pos, pvel, x_prev, dt, ptype=None, exclude=0):
+        self._chk(self._f("update_velocity_from_delta_pos")(C.c_longlong(len(pos)), _p(pos), _p(pvel), _p(self._r(x_prev)), C.c_double(dt), self._pt(ptype), C.c_int(exclude)))
+        return pvel
+
+    def euler_step(self, pos, pvel, dt, ptype=None, exclude=0):
+        self._chk(self._f("euler_step")(C.c_longlong(len(pos)), _p(pos), _p(self._r(pvel)), C.c_double(dt), self._pt(ptype), C.c_int(exclude)))
+        return pos
+
+    def set_part_type(self, flags, pos, ptype, mark, stype, cflag):
+        assert ptype.dtype == np.int32 and ptype.flags.c_contiguous
+        self._chk(self._f("set_part_type")(*self.dims(flags), C.c_longlong(len(pos)), _p(pos), _p(ptype), C.c_int(mark), C.c_int(stype), _p(flags), C.c_int(cflag)))
+        return ptype
+
+    def mark_isolated_fluid_cell(self, flags, mark):
+        self._chk(self._f("mark_isolated_fluid_cell")(*self.dims(flags), _p(flags), C.c_int(mark)))
+        return flags
+
     def grid_file(self, name, array, kind, load=False):
         """Grid<T>::save / load of the unmodified reference (grid.cpp:113-156; reference build only).
         kind: "real" | "mac" | "flags" | "levelset" | "vec3"; `array` is written to / filled from the file `name`."""

@@ -63,6 +63,11 @@ void releaseBlurPrecomp();
 void extrapolateMACSimple(FlagGrid& flags, MACGrid& vel, int distance, LevelsetGrid* phiObs, bool intoObs);
 void extrapolateLsSimple(Grid<Real>& phi, int distance, bool inside);
 void extrapolateMACFromWeight(MACGrid& vel, Grid<Vec3>& weight, int distance);
+void addForcePvel(ParticleDataImpl<Vec3>& vel, const Vec3& a, const Real dt, const ParticleDataImpl<int>* ptype, const int exclude);
+void updateVelocityFromDeltaPos(const BasicParticleSystem& parts, ParticleDataImpl<Vec3>& vel, const ParticleDataImpl<Vec3>& x_prev, const Real dt, const ParticleDataImpl<int>* ptype, const int exclude);
+void eulerStep(BasicParticleSystem& parts, const ParticleDataImpl<Vec3>& vel, const ParticleDataImpl<int>* ptype, const int exclude);
+void setPartType(const BasicParticleSystem& parts, ParticleDataImpl<int>& ptype, const int mark, const int stype, const FlagGrid& flags, const int cflag);
+void markIsolatedFluidCell(FlagGrid& flags, const int mark);
 void pushOutofObs(BasicParticleSystem& parts, const FlagGrid& flags, const Grid<Real>& phiObs, const Real shift, const Real thresh, const ParticleDataImpl<int>* ptype, const int exclude);
 void markFluidCells(const BasicParticleSystem& parts, FlagGrid& flags, const Grid<Real>* phiObs, const ParticleDataImpl<int>* ptype, const int exclude);
 void gridParticleIndex(const BasicParticleSystem& parts, ParticleIndexSystem& indexSys, const FlagGrid& flags, Grid<int>& index, Grid<int>* counter);
@@ -288,6 +293,52 @@ int ref_project_out_of_bnd(int sx, int sy, int sz, long long np, Real* pos, cons
 	  std::string plane; for (int q = 0; q < 6; q++) if (axis & (1 << q)) plane += "xXyYzZ"[q];
 	  P.pp.projectOutOfBnd(F, (Real)bnd, plane, P.pt, exclude);
 	  for (long long q = 0; q < np; q++) { pos[3 * q] = P.pp[q].pos.x; pos[3 * q + 1] = P.pp[q].pos.y; pos[3 * q + 2] = P.pp[q].pos.z; } }
+	delete s;
+  CATCH }
+
+// plugin/ptsplugins.cpp:17-70 and grid.cpp:866-890 through the unmodified plugins
+#define PV_OUT for (long long q = 0; q < np; q++) { pvel[3 * q] = (*P.pv)[q].x; pvel[3 * q + 1] = (*P.pv)[q].y; pvel[3 * q + 2] = (*P.pv)[q].z; }
+#define POS_OUT for (long long q = 0; q < np; q++) { pos[3 * q] = P.pp[q].pos.x; pos[3 * q + 1] = P.pp[q].pos.y; pos[3 * q + 2] = P.pp[q].pos.z; }
+int ref_add_force_pvel(long long np, Real* pvel, double ax, double ay, double az, double dt, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(4, 4, 4);
+	{ std::vector<Real> pos(3 * np, 1); std::vector<int> pf(np, 0);
+	  RefParts P(s, np, pos.data(), pf.data(), ptype, pvel);
+	  addForcePvel(*P.pv, Vec3((Real)ax, (Real)ay, (Real)az), (Real)dt, P.pt, exclude); PV_OUT }
+	delete s;
+  CATCH }
+int ref_update_velocity_from_delta_pos(long long np, const Real* pos, Real* pvel, const Real* xPrev, double dt, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(4, 4, 4);
+	{ std::vector<int> pf(np, 0);
+	  RefParts P(s, np, pos, pf.data(), ptype, pvel);
+	  ParticleDataImpl<Vec3> xp(s); P.pp.registerPdata(&xp); xp.resize(np);
+	  for (long long q = 0; q < np; q++) xp[q] = Vec3(xPrev[3 * q], xPrev[3 * q + 1], xPrev[3 * q + 2]);
+	  updateVelocityFromDeltaPos(P.pp, *P.pv, xp, (Real)dt, P.pt, exclude); PV_OUT }      // xp leaves the system in its destructor, before P goes
+	delete s;
+  CATCH }
+int ref_euler_step(long long np, Real* pos, const Real* pvel, double dt, const int* ptype, int exclude)
+{ TRY
+	FluidSolver* s = mkSolver(4, 4, 4); s->mDt = (Real)dt;
+	{ std::vector<int> pf(np, 0);
+	  RefParts P(s, np, pos, pf.data(), ptype, pvel);
+	  eulerStep(P.pp, *P.pv, P.pt, exclude); POS_OUT }
+	delete s;
+  CATCH }
+int ref_set_part_type(int sx, int sy, int sz, long long np, const Real* pos, int* ptype, int mark, int stype, const int* flags, int cflag)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ std::vector<int> pf(np, 0);
+	  RefParts P(s, np, pos, pf.data(), ptype, 0);
+	  FlagGrid F(s, (int*)flags);
+	  setPartType(P.pp, *P.pt, mark, stype, F, cflag);
+	  for (long long q = 0; q < np; q++) ptype[q] = (*P.pt)[q]; }
+	delete s;
+  CATCH }
+int ref_mark_isolated_fluid_cell(int sx, int sy, int sz, int* flags, int mark)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ FlagGrid F(s, flags); markIsolatedFluidCell(F, mark); }
 	delete s;
   CATCH }
 

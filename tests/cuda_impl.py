@@ -311,6 +311,48 @@ class CudaImpl:
         pos[...] = P.positions()
         return pos
 
+    # -- the Lagrangian-particle helpers (plugin/ptsplugins.cpp, grid.cpp:866-890); arrays updated in place and returned like the oracle's --
+    def _lag(self, pos, ptype=None, pvel=None):
+        s = self._solver(np.zeros((4, 4, 4), np.int32))
+        return (s,) + self._parts(s, pos, np.zeros(len(pos), np.int32), ptype, pvel)
+
+    def add_force_pvel(self, pvel, a, dt, ptype=None, exclude=0):
+        s, P, T, V = self._lag(np.zeros_like(pvel), ptype, pvel)
+        mf.addForcePvel(V, a, dt, T, exclude)
+        pvel[...] = V.numpy()
+        return pvel
+
+    def update_velocity_from_delta_pos(self, pos, pvel, x_prev, dt, ptype=None, exclude=0):
+        s, P, T, V = self._lag(pos, ptype, pvel)
+        X = P.create(mf.PdataVec3); X.copyFromArray(x_prev)
+        mf.updateVelocityFromDeltaPos(P, V, X, dt, T, exclude)
+        pvel[...] = V.numpy()
+        return pvel
+
+    def euler_step(self, pos, pvel, dt, ptype=None, exclude=0):
+        s, P, T, V = self._lag(pos, ptype, pvel)
+        s.timestep = dt
+        before = P.create(mf.PdataVec3)
+        P.getPosPdata(before)                       # ParticleSystem::getPosPdata on the way: the copy holds the old positions
+        mf.eulerStep(P, V, T, exclude)
+        assert np.array_equal(before.numpy(), pos)
+        pos[...] = P.positions()
+        return pos
+
+    def set_part_type(self, flags, pos, ptype, mark, stype, cflag):
+        s = self._solver(flags)
+        P, T, _ = self._parts(s, pos, np.zeros(len(pos), np.int32), ptype)
+        mf.setPartType(P, T, mark, stype, mf.FlagGrid(s, flags), cflag)
+        ptype[...] = T.numpy()
+        return ptype
+
+    def mark_isolated_fluid_cell(self, flags, mark):
+        s = self._solver(flags)
+        F = mf.FlagGrid(s, flags)
+        mf.markIsolatedFluidCell(F, mark)
+        flags[...] = F.numpy()
+        return flags
+
     def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
         s = self._solver(flags); s.timestep = dt
         U, Um, O = mf.RealGrid(s, ut), mf.RealGrid(s, utm1), mf.RealGrid(s)

@@ -120,6 +120,31 @@ template <typename Real> int advect(int order, const Dims& d, const int* flags, 
 }  // namespace
 
 extern "C" {
+int emu_add_force_pvel(int prec, int order, long long np, void* pvel, double ax, double ay, double az, double dt, const int* ptype, int exclude) {
+	HostExec ex = { order };
+	if (prec == 4) { const float d = (float)dt; parts::AddForcePvel<float> op = { (float*)pvel, { (float)ax * d, (float)ay * d, (float)az * d }, ptype, exclude }; return ex.parts(np, op); }
+	parts::AddForcePvel<double> op = { (double*)pvel, { ax * dt, ay * dt, az * dt }, ptype, exclude }; return ex.parts(np, op);
+}
+int emu_update_velocity_from_delta_pos(int prec, int order, long long np, const void* pos, void* pvel, const void* xPrev, double dt, const int* ptype, int exclude) {
+	HostExec ex = { order };
+	if (prec == 4) { parts::UpdateVelocityFromDeltaPos<float> op = { (const float*)pos, (float*)pvel, (const float*)xPrev, (float)(1.0 / (double)(float)dt), ptype, exclude }; return ex.parts(np, op); }
+	parts::UpdateVelocityFromDeltaPos<double> op = { (const double*)pos, (double*)pvel, (const double*)xPrev, 1.0 / dt, ptype, exclude }; return ex.parts(np, op);
+}
+int emu_euler_step(int prec, int order, long long np, void* pos, const void* pvel, double dt, const int* ptype, int exclude) {
+	HostExec ex = { order };
+	if (prec == 4) { parts::StepEuler<float> op = { (float*)pos, (const float*)pvel, (float)dt, ptype, exclude }; return ex.parts(np, op); }
+	parts::StepEuler<double> op = { (double*)pos, (const double*)pvel, dt, ptype, exclude }; return ex.parts(np, op);
+}
+int emu_set_part_type(int prec, int order, int sx, int sy, int sz, long long np, const void* pos, int* ptype, int mark, int stype, const int* flags, int cflag) {
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	if (prec == 4) { parts::SetPartType<float> op = { d, (const float*)pos, ptype, mark, stype, flags, cflag }; return ex.parts(np, op); }
+	parts::SetPartType<double> op = { d, (const double*)pos, ptype, mark, stype, flags, cflag }; return ex.parts(np, op);
+}
+int emu_mark_isolated_fluid_cell(int prec, int order, int sx, int sy, int sz, int* flags, int mark) {
+	(void)prec;
+	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
+	parts::MarkIsolatedFluidCell op = { flags, mark }; return ex.cells(d, op);
+}
 int emu_push_out_of_obs(int prec, int order, int sx, int sy, int sz, long long np, void* pos, const int* pflag, const void* phiObs, double shift, double thresh, const int* ptype, int exclude) {
 	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
 	if (prec == 4) { parts::PSet<float> ps = { (const float*)pos, pflag, ptype, exclude }; parts::PushOutOfObs<float> op = { d, (float*)pos, ps, (const float*)phiObs, (float)shift, (float)thresh }; return ex.parts(np, op); }

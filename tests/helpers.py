@@ -675,6 +675,18 @@ def run_advect_cases(I, name, prec):
     out["project_xY"] = I.project_out_of_bnd(flags.shape, moved.copy(), mflag, 2.25, plane="xY")
     out["push"] = I.push_out_of_obs(flags.shape, out["project"].copy(), mflag, phiObs, shift=0.0, thresh=0.5, ptype=ptype, exclude=4)
     out["push_shift"] = I.push_out_of_obs(flags.shape, moved.copy(), mflag, phiObs, shift=0.25, thresh=0.0)
+    # the Lagrangian-particle helpers of scenes/benchmark_dam.py:118-134 (plugin/ptsplugins.cpp, grid.cpp:866-890); type 4 plays the free particles
+    pv0 = (np.random.default_rng(31).random(pos.shape) * 2 - 1).astype(pos.dtype)
+    if sz == 1:
+        pv0[:, 2] = 0
+    out["lag_force"] = I.add_force_pvel(pv0.copy(), (0.0, -0.3, 0.1 if sz > 1 else 0.0), 0.8, ptype=ptype, exclude=1)
+    out["lag_force_all"] = I.add_force_pvel(pv0.copy(), (0.2, -0.3, 0.0), 0.7)
+    out["lag_euler"] = I.euler_step(pos.copy(), pv0, 0.8, ptype=ptype, exclude=1)
+    out["lag_delta"] = I.update_velocity_from_delta_pos(out["lag_euler"], pv0.copy(), pos, 0.8, ptype=ptype, exclude=1)
+    sparse = I.mark_fluid_cells(flags.copy(), np.ascontiguousarray(pos[::5]), np.ascontiguousarray(pflag[::5]))       # sparse particles leave isolated fluid cells
+    out["lag_type1"] = I.set_part_type(sparse, pos, ptype.copy(), 1, 4, 1)
+    out["lag_isolated"] = I.mark_isolated_fluid_cell(sparse.copy(), 4)
+    out["lag_type2"] = I.set_part_type(out["lag_isolated"], pos, out["lag_type1"].copy(), 4, 1, 4)
     return out
 
 

@@ -23,6 +23,8 @@ PLUGINS = {     # plugin -> reference file
     "updateFractions": "plugin/initplugins.cpp", "setObstacleFlags": "plugin/initplugins.cpp",
     "markFluidCells": "plugin/flip.cpp", "gridParticleIndex": "plugin/flip.cpp", "unionParticleLevelset": "plugin/flip.cpp", "mapPartsToMAC": "plugin/flip.cpp",
     "mapMACToParts": "plugin/flip.cpp", "flipVelocityUpdate": "plugin/flip.cpp", "pushOutofObs": "plugin/flip.cpp",
+    "addForcePvel": "plugin/ptsplugins.cpp", "updateVelocityFromDeltaPos": "plugin/ptsplugins.cpp", "eulerStep": "plugin/ptsplugins.cpp", "setPartType": "plugin/ptsplugins.cpp",
+    "markIsolatedFluidCell": "grid.cpp",
 }
 
 
