@@ -225,6 +225,18 @@ def flip_fixtures():
             print("%-34s %7.1f KiB  %d particles" % (os.path.basename(path), os.path.getsize(path) / 1024, len(fx["rk4_flip_flag"])))
 
 
+def dam_fixtures():
+    """step_dam_f{32,64}.npz: twelve passes of the main loop of scenes/benchmark_dam.py:100-134 through the unmodified reference (tests/helpers.py::run_dam_loop)"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import helpers
+    for prec in (4, 8):
+        fx = helpers.run_dam_loop(Oracle("reference", prec), prec)
+        path = os.path.join(HERE, "step_dam_f%d.npz" % (prec * 8))
+        np.savez_compressed(path, **fx)
+        print("%-34s %7.1f KiB  its %s  %d particles, %d typed FlagEmpty at the end" % (os.path.basename(path), os.path.getsize(path) / 1024, list(fx["iterations"]), len(fx["pos"]),
+                                                                                       int((fx["ptype"] == 4).sum())))
+
+
 def icp_fixtures():
     """icp_<scene>_f{32,64}.npz: the reference's IC(0) preconditioner (InitPreconditionIncompCholesky / ApplyPreconditionIncompCholesky,
     conjugategrad.cpp:26-63,:109-132) and a GridCg solve with PC_ICP on the systems of the 3-D kernels_* fixtures"""
@@ -261,6 +273,8 @@ def main():
         return flip_fixtures()
     if "--only-icp" in sys.argv:
         return icp_fixtures()
+    if "--only-dam" in sys.argv:
+        return dam_fixtures()
     if "--only-liquid" in sys.argv:
         return liquid_fixtures()
     if "--only-step" in sys.argv:
@@ -271,6 +285,7 @@ def main():
     flip_fixtures()
     io_fixtures()
     icp_fixtures()
+    dam_fixtures()
     for prec in (4, 8):
         R = Oracle("reference", prec)
         for name in KERNEL_SCENES:

@@ -701,3 +701,53 @@ def obstacle_levelset(shape, prec):
     cz = 0.5 * sz if sz > 1 else 0.5
     sphere = np.sqrt((x - 5 * sx / 12.0) ** 2 + (y - (1 + sy / 8.0)) ** 2 + ((z - cz) ** 2 if sz > 1 else 0)) - sx / 8.0
     return np.ascontiguousarray(np.minimum(d, sphere).astype(np.float32 if prec == 4 else np.float64))
+
+
+# ---------------------------------------------------------------- the main loop of scenes/benchmark_dam.py:100-134 (the reference's FLIP benchmark)
+def run_dam_loop(I, prec, steps=12, shape=(12, 20, 16)):
+    """every plugin call of that loop, in its order and with its arguments (ghost-fluid variant, `gfm`), on a small dam: particles typed
+    FlagFluid take part in the grid solve, particles typed FlagEmpty fly ballistically (the scene's `exclude` arguments)"""
+    from mantaflow_b200 import scenes
+    sz, sy, sx = shape
+    real = np.float32 if prec == 4 else np.float64
+    flags = scenes.closed_box_flags(sx, sy, sz)
+    rng = np.random.default_rng(11)
+    k, j, i = np.nonzero((flags & 2) == 0)
+    dam = (i < sx // 3) & (j < 2 * sy // 3)                                    # a column of liquid in one corner
+    base = np.repeat(np.stack([i[dam], j[dam], k[dam]], 1), 4, 0).astype(np.float64)
+    pos = np.ascontiguousarray((base + rng.random(base.shape)).astype(real))
+    spray = (np.array([sx // 2, 2 * sy // 3, sz // 3]) + rng.random((60, 3)) * np.array([sx // 3, sy // 5, sz // 3])).astype(real)      # free particles above the floor
+    pos = np.ascontiguousarray(np.concatenate([pos, spray]))
+    pflag = np.zeros(len(pos), np.int32)
+    ptype = np.full(len(pos), 1, np.int32)
+    ptype[-len(spray):] = 4
+    pvel = np.zeros_like(pos)
+    pvel[-len(spray):] = ((rng.random((len(spray), 3)) - 0.5) * 0.6).astype(real)
+    phiObs = obstacle_levelset(shape, prec)
+    dt, grav, dx = 0.8, -0.1, 1.0
+    flags = I.mark_fluid_cells(flags, pos, pflag, ptype=ptype)
+    its = []
+    for _ in range(steps):
+        vel, velOld = I.map_parts_to_mac(shape, pos, pflag, pvel, ptype=ptype, exclude=4)
+        I.add_gravity(flags, vel, (0, grav, 0), scale=False, dt=dt)
+        index, isys = I.grid_particle_index(shape, pos, pflag)
+        phi = I.union_particle_levelset(pos, index, isys, radiusFactor=1.0)
+        I.extrapolate_ls_simple(phi, distance=4, inside=True)
+        I.set_wall_bcs_obvel(flags, vel)
+        p, it, _ = I.solve_pressure(flags, vel, phi=phi, cgAccuracy=1e-5 if prec == 4 else 1e-10, cgMaxIterFac=3.0)
+        its.append(it)
+        I.set_wall_bcs_obvel(flags, vel)
+        I.extrapolate_mac_simple(flags, vel)
+        I.flip_velocity_update(vel, velOld, pos, pflag, pvel, 0.97, ptype=ptype, exclude=4)
+        I.add_force_pvel(pvel, (0, grav, 0), dt, ptype=ptype, exclude=1)
+        x_prev = pos.copy()                                                   # pp.getPosPdata(target=pVtmp)
+        I.advect_in_grid(flags, vel, pos, pflag, dt, integrationMode=2, deleteInObstacle=False, ptype=ptype, exclude=4)
+        I.euler_step(pos, pvel, dt, ptype=ptype, exclude=1)
+        I.project_out_of_bnd(shape, pos, pflag, 1 + dx * 0.5, plane="xXyYzZ", ptype=ptype)
+        I.push_out_of_obs(shape, pos, pflag, phiObs, thresh=dx * 0.5, ptype=ptype)
+        I.update_velocity_from_delta_pos(pos, pvel, x_prev, dt, ptype=ptype, exclude=1)
+        I.mark_fluid_cells(flags, pos, pflag, ptype=ptype)
+        I.set_part_type(flags, pos, ptype, 1, 4, 1)
+        I.mark_isolated_fluid_cell(flags, 4)
+        I.set_part_type(flags, pos, ptype, 4, 1, 4)
+    return dict(flags=flags, pos=pos, pvel=pvel, ptype=ptype, vel=vel, phi=phi, pressure=p, iterations=np.array(its))

@@ -44,11 +44,13 @@ class FlipEmulation(Oracle):
     kernels of mantaflow_b200/csrc/mp_particles.cu run, walked by host loops (the build container has no GPU)"""
     kind = "emulation"
 
-    def __init__(self, lib, prec, order):
-        self.lib, self.prec, self.order = lib, prec, order
+    def __init__(self, lib, prec, order, port=None):
+        self.lib, self.prec, self.order, self.port = lib, prec, order, port
         self.real = np.float32 if prec == 4 else np.float64
 
     def _f(self, name, restype=C.c_int):
+        if self.port is not None and not hasattr(self.lib, "emu_" + name):
+            return self.port._f(name, restype)          # what is not a particle kernel (the projection, the extrapolations) comes from the restatement
         f = getattr(self.lib, "emu_" + name)
         f.restype = restype
         return lambda *a: f(C.c_int(self.prec), C.c_int(self.order), *a)
@@ -132,3 +134,32 @@ def test_kernel_emulation_reproduces_advect_golden(name, prec, order, parts_emul
     out = helpers.run_advect_cases(FlipEmulation(parts_emul_lib, prec, order), name, prec)
     for key in g:
         assert np.array_equal(out[key], g[key]), (name, prec, order, key)
+
+
+# ---------------------------------------------------------------- the whole main loop of scenes/benchmark_dam.py:100-134
+@pytest.mark.parametrize("prec", [4, 8])
+def test_port_reproduces_the_benchmark_dam_loop(prec, port32, port64):
+    """twelve passes of the reference's FLIP benchmark loop (20 plugin calls per pass, ghost-fluid PcMIC solves included): the restatement ends with the
+    reference's particles, types, flags and fields -- bit for bit in float, within the reduction order in double"""
+    g = load_golden("step_dam", prec)
+    out = helpers.run_dam_loop(port32 if prec == 4 else port64, prec)
+    assert np.array_equal(out["iterations"], g["iterations"])
+    for key in ("flags", "ptype"):
+        assert np.array_equal(out[key], g[key]), key
+    for key in ("pos", "pvel", "vel", "phi", "pressure"):
+        if prec == 4:
+            assert np.array_equal(out[key], g[key]), key
+        else:
+            assert float(np.abs(out[key] - g[key]).max()) <= 1e-12, key
+    # not vacuous: the dam has collapsed along x, particles changed type in both directions
+    assert g["pos"][:, 0].max() > 10 and 0 < (g["ptype"] == 4).sum() < 60
+
+
+@pytest.mark.parametrize("order", [0, 3])
+def test_kernel_emulation_runs_the_benchmark_dam_loop(order, parts_emul_lib, port32):
+    """the same twelve passes with every particle kernel taken from the device code (host emulation) and the grid plugins from the restatement:
+    still the reference's bits at the end"""
+    g = load_golden("step_dam", 4)
+    out = helpers.run_dam_loop(FlipEmulation(parts_emul_lib, 4, order, port=port32), 4)
+    for key in g:
+        assert np.array_equal(out[key], g[key]), key
