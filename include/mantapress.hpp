@@ -195,6 +195,7 @@ public:
 	~DevArray() { if (mDev) mp_grid_destroy(mDev); }
 	DevArray(const DevArray&) = delete;
 	DevArray& operator=(const DevArray&) = delete;
+	FluidSolver* getParent() const { return mParent; }
 	long long size() const { return (long long)mData.size(); }
 	void resize(long long n) { syncToHost(); mData.resize((size_t)n); if (n) mHostDirty = true; }
 	const T& operator[](long long idx) const { syncToHost(); return mData[(size_t)idx]; }
@@ -443,6 +444,27 @@ inline void flipVelocityUpdate(const FlagGrid& flags, const MACGrid& vel, const 
 	mpCheck(mp_flip_velocity_update(vel.getParent()->ctx(), flags.dev(), vel.dev(), velOld.dev(), parts.size(), parts.devPos(), parts.devFlag(), partVel.dev(), flipRatio,
 	                                detail::dp(ptype), exclude));
 	if (parts.size()) partVel.markDeviceWritten();
+}
+// ---- the Lagrangian-particle helpers of scenes/benchmark_dam.py:118-134 (plugin/ptsplugins.cpp:26-65, grid.cpp:885-890)
+inline void addForcePvel(ParticleDataImpl<Vec3>& vel, const Vec3& a, const Real dt, const ParticleDataImpl<int>* ptype, const int exclude) {
+	if (!vel.size()) return;
+	mpCheck(mp_add_force_pvel(vel.getParent()->ctx(), vel.size(), vel.dev(), a.x, a.y, a.z, dt, detail::dp(ptype), exclude)); vel.markDeviceWritten();
+}
+inline void updateVelocityFromDeltaPos(const BasicParticleSystem& parts, ParticleDataImpl<Vec3>& vel, const ParticleDataImpl<Vec3>& x_prev, const Real dt, const ParticleDataImpl<int>* ptype,
+                                       const int exclude) {
+	if (!parts.size()) return;
+	mpCheck(mp_update_velocity_from_delta_pos(parts.getParent()->ctx(), parts.size(), parts.devPos(), vel.dev(), x_prev.dev(), dt, detail::dp(ptype), exclude)); vel.markDeviceWritten();
+}
+inline void eulerStep(BasicParticleSystem& parts, const ParticleDataImpl<Vec3>& vel, const ParticleDataImpl<int>* ptype, const int exclude) {
+	if (!parts.size()) return;
+	mpCheck(mp_euler_step(parts.getParent()->ctx(), parts.size(), parts.devPos(), vel.dev(), parts.getParent()->getDt(), detail::dp(ptype), exclude)); parts.markPosDeviceWritten();
+}
+inline void setPartType(const BasicParticleSystem& parts, ParticleDataImpl<int>& ptype, const int mark, const int stype, const FlagGrid& flags, const int cflag) {
+	if (!parts.size()) return;
+	mpCheck(mp_set_part_type(flags.getParent()->ctx(), parts.size(), parts.devPos(), ptype.dev(), mark, stype, flags.dev(), cflag)); ptype.markDeviceWritten();
+}
+inline void markIsolatedFluidCell(FlagGrid& flags, const int mark) {
+	mpCheck(mp_mark_isolated_fluid_cell(flags.getParent()->ctx(), flags.dev(), mark)); flags.markDeviceWritten();
 }
 inline void pushOutofObs(BasicParticleSystem& parts, const FlagGrid& flags, const Grid<Real>& phiObs, const Real shift = 0, const Real thresh = 0,
                          const ParticleDataImpl<int>* ptype = NULL, const int exclude = 0) {                                             // :542

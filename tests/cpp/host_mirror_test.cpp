@@ -49,7 +49,8 @@ int main(int argc, char** argv) {
 		void* p[] = { (void*)&computePressureRhs, (void*)&solvePressureSystem, (void*)&correctVelocity, (void*)&solvePressure, (void*)&releaseMG, (void*)&setWallBcs,
 		              (void*)&addGravity, (void*)&addGravityNoScale, (void*)&addBuoyancy, (void*)&advectSemiLagrange<Grid<Real> >, (void*)&advectSemiLagrange<MACGrid>,
 		              (void*)&extrapolateMACSimple, (void*)&extrapolateLsSimple, (void*)&extrapolateVec3Simple, (void*)&extrapolateMACFromWeight, (void*)&updateFractions, (void*)&setObstacleFlags, (void*)&getLaplacian, (void*)&getCurvature, (void*)&cgSolveDiffusion<Grid<Real> >, (void*)&cgSolveWE,
-		              (void*)&markFluidCells, (void*)&gridParticleIndex, (void*)&unionParticleLevelset, (void*)&mapPartsToMAC, (void*)&mapMACToParts, (void*)&flipVelocityUpdate, (void*)&pushOutofObs };
+		              (void*)&markFluidCells, (void*)&gridParticleIndex, (void*)&unionParticleLevelset, (void*)&mapPartsToMAC, (void*)&mapMACToParts, (void*)&flipVelocityUpdate, (void*)&pushOutofObs,
+		              (void*)&addForcePvel, (void*)&updateVelocityFromDeltaPos, (void*)&eulerStep, (void*)&setPartType, (void*)&markIsolatedFluidCell };
 		{ typedef void (BasicParticleSystem::*Adv)(const FlagGrid&, const MACGrid&, const int, const bool, const bool, const bool, const ParticleDataImpl<int>*, const int);
 		  Adv a = &BasicParticleSystem::advectInGrid; if (!a) return 1; }
 		std::printf("OK: %d plugins link\n", (int)(sizeof p / sizeof p[0]));
