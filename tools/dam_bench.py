@@ -89,7 +89,7 @@ s.synchronize()
 whole = 1e3 * (time.perf_counter() - t0) / reps
 total = sum(per.values()) / reps
 out = {"res": res, "particles": N, "step_ms": whole, "sum_of_plugins_ms": total, "plugins_ms": {k: v / reps for k, v in per.items()},
-       "last_solve": mf.lastSolveInfo().as_dict() if hasattr(mf.lastSolveInfo(), "as_dict") else None}
+       "last_solve": {k: v for k, v in dict(mf.lastSolveInfo() or {}).items() if isinstance(v, (int, float))}}
 print(f"# benchmark_dam loop, {res}^3 float, {N} particles, one B200: {whole:.2f} ms per step ({total:.2f} ms as the sum of synchronised plugins)")
 for name, ms in sorted(out["plugins_ms"].items(), key=lambda kv: -kv[1]):
     print(f"{name:32s} {ms:9.3f} ms  {100 * ms / total:5.1f} %")
