@@ -117,7 +117,7 @@ int   mp_host_free(void* p);
 
 /* ---- Grid<Real> reductions / BLAS-1 used by GridCg ---- */
 int mp_grid_dot(mp_context* ctx, const mp_grid* a, const mp_grid* b, double* out);        /* GridDotProduct conjugategrad.cpp:175-178 */
-int mp_grid_max_abs(mp_context* ctx, const mp_grid* a, double* out);                      /* Grid<Real>::getMaxAbs grid.cpp:319-323 */
+int mp_grid_max_abs(mp_context* ctx, const mp_grid* a, double* out);                      /* Grid<Real>::getMaxAbs grid.cpp:319-323; Vec3 / MAC grids: Grid<Vec3>::getMaxAbs :330-332 */
 int mp_grid_sum_sqr(mp_context* ctx, const mp_grid* a, double* out);                      /* GridSumSqr commonkernels.h:32-35 */
 int mp_grid_scaled_add(mp_context* ctx, mp_grid* me, const mp_grid* other, double factor);/* gridScaledAdd grid.h:478 */
 int mp_grid_add_const(mp_context* ctx, mp_grid* me, double value);                        /* Grid<T>::operator+=(S) grid.h:490 */

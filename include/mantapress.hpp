@@ -147,6 +147,7 @@ template <> inline void Grid<Real>::setBound(Real value, int w) { mpCheck(mp_gri
 template <> inline void Grid<int>::setBound(int value, int w) { mpCheck(mp_grid_set_bound(mParent->ctx(), dev(), value, value, value, w)); markDeviceWritten(); }
 template <> inline void Grid<Vec3>::setBound(Vec3 value, int w) { mpCheck(mp_grid_set_bound(mParent->ctx(), dev(), value.x, value.y, value.z, w)); markDeviceWritten(); }
 template <> inline Real Grid<Real>::getMaxAbs() const { double v = 0; mpCheck(mp_grid_max_abs(mParent->ctx(), dev(), &v)); return (Real)v; }
+template <> inline Real Grid<Vec3>::getMaxAbs() const { double v = 0; mpCheck(mp_grid_max_abs(mParent->ctx(), dev(), &v)); return (Real)v; }      // grid.cpp:330-332
 
 class LevelsetGrid : public Grid<Real> {             // levelset.h:25-60
 public:

@@ -244,6 +244,31 @@ __global__ void __launch_bounds__(256) k_add_const(Real* __restrict__ me, Real c
 	for (IndexInt i = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IndexInt)gridDim.x * blockDim.x) me[i] += c;
 }
 
+// Grid<Vec3>::getMaxAbs grid.cpp:330-332: sqrt(CompMaxVec) = the largest |v|; normSquare in Real, the maximum is order independent
+template <typename Real>
+__global__ void __launch_bounds__(256) k_reduce_vec_max(const Real* __restrict__ a, IndexInt n, double* partials, unsigned int* ticket, double* out) {
+	double v[1] = { -1.0 };
+	for (IndexInt i = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (IndexInt)gridDim.x * blockDim.x) {
+		const Real x = a[3 * i], y = a[3 * i + 1], z = a[3 * i + 2];
+		const Real s = x * x + y * y + z * z;
+		v[0] = fmax(v[0], (double)s);
+	}
+	const bool isMax[1] = { true };
+	double fin[1];
+	if (blockReduceFinal<1>(v, isMax, partials, ticket, fin) && threadIdx.x == 0) out[0] = fin[0];
+}
+static int vecMaxAbs(mp_context* ctx, const mp_grid* a, double* out) {
+	MP_CUDA(cudaSetDevice(ctx->device));
+	unsigned int blocks = gridFor(a->n, 256 * 8); if (blocks > (unsigned)ctx->smCount * 8) blocks = ctx->smCount * 8;
+	if (a->prec == 4) k_reduce_vec_max<float><<<blocks, 256, 0, ctx->stream>>>((const float*)a->d, a->n, ctx->partials, ctx->tickets + 0, ctx->dScal);
+	else              k_reduce_vec_max<double><<<blocks, 256, 0, ctx->stream>>>((const double*)a->d, a->n, ctx->partials, ctx->tickets + 0, ctx->dScal);
+	MP_CHECK_LAUNCH(ctx);
+	MP_CUDA(cudaMemcpyAsync(ctx->hScal, ctx->dScal, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	*out = a->prec == 4 ? (double)sqrtf((float)ctx->hScal[0]) : sqrt(ctx->hScal[0]);       // the maximum is a Real value: the cast back is exact
+	return MP_OK;
+}
+
 template <int MODE>
 static int reduceLaunch(mp_context* ctx, const mp_grid* a, const mp_grid* b, double* out) {
 	if (!a || a->kind != MP_GRID_REAL) MP_FAIL(MP_ERR_INVALID, "reduction: grid must be a Real grid");
@@ -260,7 +285,10 @@ static int reduceLaunch(mp_context* ctx, const mp_grid* a, const mp_grid* b, dou
 
 extern "C" {
 int mp_grid_dot(mp_context* ctx, const mp_grid* a, const mp_grid* b, double* out) { return reduceLaunch<0>(ctx, a, b, out); }
-int mp_grid_max_abs(mp_context* ctx, const mp_grid* a, double* out) { return reduceLaunch<1>(ctx, a, nullptr, out); }
+int mp_grid_max_abs(mp_context* ctx, const mp_grid* a, double* out) {
+	if (a && ctx && out && a->kind == MP_GRID_MAC) return vecMaxAbs(ctx, a, out);        // Grid<Vec3>::getMaxAbs (adaptTimestep(vel.getMaxAbs()) in the liquid scenes)
+	return reduceLaunch<1>(ctx, a, nullptr, out);
+}
 int mp_grid_sum_sqr(mp_context* ctx, const mp_grid* a, double* out) { return reduceLaunch<2>(ctx, a, nullptr, out); }
 int mp_grid_scaled_add(mp_context* ctx, mp_grid* me, const mp_grid* other, double factor) {
 	MP_TRY(mp_check_same(me, other, MP_GRID_REAL, "other", false));

@@ -28,6 +28,9 @@ class Solver:
         self.gridSize, self.dim, self.prec, self.name = gs, dim, prec, name
         self.real = np.float32 if prec == 4 else np.float64
         self.timestep = 1.0
+        # time stepping state, fluidsolver.cpp:107-110 (Python names of fluidsolver.h:58-69)
+        self.timeTotal, self.frame, self.cfl, self.timestepMin, self.timestepMax, self.frameLength, self.timePerFrame = 0.0, 0, 1000.0, 1.0, 1.0, 1.0, 0.0
+        self._lockDt = False
         self.lib = _lib.load()
         self._ctx = C.c_void_p()
         check(self.lib.mp_context_create(C.c_int(device), C.byref(self._ctx)))
@@ -41,6 +44,34 @@ class Solver:
 
     def is3D(self):
         return self.dim == 3
+
+    def step(self):
+        """FluidSolver::step fluidsolver.cpp:142-158 (the time bookkeeping; there is no GUI to update)"""
+        R = self.real
+        eps = 1e-6 if self.prec == 4 else 1e-10
+        self.timePerFrame = float(R(self.timePerFrame) + R(self.timestep))
+        self.timeTotal = float(R(self.timeTotal) + R(self.timestep))
+        if self.timePerFrame + eps > self.frameLength:
+            self.frame += 1
+            self.timeTotal = float(R(float(self.frame) * float(R(self.frameLength))))
+            self.timePerFrame = 0.0
+            self._lockDt = False
+
+    def adaptTimestep(self, maxVel):
+        """FluidSolver::adaptTimestep fluidsolver.cpp:176-196: CFL-limited step, clamped to [timestepMin, timestepMax] and fitted to the frame"""
+        R = self.real
+        dt, tpf, fl = R(self.timestep), R(self.timePerFrame), R(self.frameLength)
+        mvt = R(maxVel) * dt
+        if not self._lockDt:
+            dt = max(min(dt * R(float(R(self.cfl)) / (float(mvt) + 1e-05)), R(self.timestepMax)), R(self.timestepMin))
+            if float(tpf) + float(dt) * 1.05 > float(fl):
+                dt = R(float(fl - tpf) + 1e-04)
+            elif float(tpf + dt + R(self.timestepMin)) > float(fl) or float(tpf) + float(dt) * 1.25 > float(fl):
+                dt = R((float(fl - tpf) + 1e-04) * 0.5)
+                self._lockDt = True
+        if not float(dt) > self.timestepMin / 2.0:
+            raise _lib.MantaError(1, "Invalid dt encountered! Shouldnt happen...")
+        self.timestep = float(dt)
 
     def synchronize(self):
         check(self.lib.mp_context_synchronize(self._ctx))
@@ -176,6 +207,12 @@ class LevelsetGrid(RealGrid):
 class MACGrid(_GridBase):
     """MACGrid (grid.h:243-281), AoS Vec3"""
     KIND = MP_GRID_MAC
+
+    def getMaxAbs(self):
+        """Grid<Vec3>::getMaxAbs grid.cpp:330-332: the largest |v| (what the liquid scenes hand to adaptTimestep)"""
+        out = C.c_double(0)
+        check(self.parent.lib.mp_grid_max_abs(self.parent._ctx, self.dev(), C.byref(out)))
+        return out.value
 
 
 class VecGrid(MACGrid):

@@ -48,6 +48,7 @@ int mfo_set_debug_level(int l) { (void)l; return 0; }
 #define STRIDES const IndexInt X = 1, Y = sx, SZ = (sz > 1) ? (IndexInt)sx * sy : 0, Z = SZ; (void)X; (void)Y; (void)Z;
 
 static inline Real rmin(Real a, Real b) { return a < b ? a : b; }
+#define REAL_MAX_ (MF_REAL_IS_DOUBLE ? (Real)1.7976931348623157e308 : (Real)3.402823466e38f)
 static inline Real rmax(Real a, Real b) { return a > b ? a : b; }
 
 /* ---------------------------------------------------------------------------------------------
@@ -2396,5 +2397,15 @@ int mfo_mark_isolated_fluid_cell(int sx, int sy, int sz, int* flags, int mark)
 		if (IS3D && ((flags[q - Z] & TypeFluid) || (flags[q + Z] & TypeFluid))) continue;
 		flags[q] = mark;
 	}
+	return 0;
+}
+
+/* Grid<Vec3>::getMaxAbs grid.cpp:330-332 = sqrt(CompMaxVec :198-203) */
+int mfo_vec_max_abs(int sx, int sy, int sz, const Real* v, double* out)
+{
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	Real m = -REAL_MAX_;
+	for (IndexInt q = 0; q < n; q++) { const Real s = v[3 * q] * v[3 * q] + v[3 * q + 1] * v[3 * q + 1] + v[3 * q + 2] * v[3 * q + 2]; if (s > m) m = s; }
+	*out = (double)R_SQRT(m);
 	return 0;
 }

@@ -370,6 +370,12 @@ class Oracle:
         self._chk(self._f("mark_isolated_fluid_cell")(*self.dims(flags), _p(flags), C.c_int(mark)))
         return flags
 
+    def vec_max_abs(self, vel):
+        """Grid<Vec3>::getMaxAbs grid.cpp:330-332"""
+        out = C.c_double(0)
+        self._chk(self._f("vec_max_abs")(*self.dims(vel[..., 0]), _p(self._r(vel)), C.byref(out)))
+        return out.value
+
     def grid_file(self, name, array, kind, load=False):
         """Grid<T>::save / load of the unmodified reference (grid.cpp:113-156; reference build only).
         kind: "real" | "mac" | "flags" | "levelset" | "vec3"; `array` is written to / filled from the file `name`."""

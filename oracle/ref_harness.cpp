@@ -342,6 +342,13 @@ int ref_mark_isolated_fluid_cell(int sx, int sy, int sz, int* flags, int mark)
 	delete s;
   CATCH }
 
+int ref_vec_max_abs(int sx, int sy, int sz, const Real* v, double* out)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	{ MACGrid V(s, (Vec3*)v); *out = (double)V.getMaxAbs(); }
+	delete s;
+  CATCH }
+
 int ref_extrapolate_mac_from_weight(int sx, int sy, int sz, Real* vel, Real* weight, int distance)
 { TRY
 	FluidSolver* s = mkSolver(sx, sy, sz);

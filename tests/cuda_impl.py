@@ -353,6 +353,10 @@ class CudaImpl:
         flags[...] = F.numpy()
         return flags
 
+    def vec_max_abs(self, vel):
+        s = self._solver(vel[..., 0])
+        return mf.MACGrid(s, vel).getMaxAbs()
+
     def cg_solve_we(self, flags, ut, utm1, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5, cgAccuracy=1e-5, dt=1.0):
         s = self._solver(flags); s.timestep = dt
         U, Um, O = mf.RealGrid(s, ut), mf.RealGrid(s, utm1), mf.RealGrid(s)

@@ -171,3 +171,20 @@ def test_cuda_runs_the_benchmark_dam_loop(prec):
     assert close.mean() >= 0.99, close.mean()
     assert (out["flags"] == g["flags"]).mean() >= 0.995
     assert (out["ptype"] == g["ptype"]).mean() >= 0.99
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+def test_macgrid_get_max_abs(prec, port32, port64):
+    """Grid<Vec3>::getMaxAbs on the device: the maximum is order independent -> the reference's value exactly; Solver.adaptTimestep consumes it"""
+    import mantaflow_b200 as m
+    from cuda_impl import CudaImpl
+    vel = load_golden("step_dam", prec)["vel"]
+    want = (port32 if prec == 4 else port64).vec_max_abs(vel)
+    assert CudaImpl(prec).vec_max_abs(vel) == want
+    sz, sy, sx = vel.shape[:3]
+    s = m.Solver(gridSize=(sx, sy, sz), dim=3, prec=prec)
+    s.cfl, s.timestepMin, s.timestepMax, s.frameLength, s.timestep = 1.0, 0.2, 2.0, 4.0, 1.0
+    s.adaptTimestep(m.MACGrid(s, vel).getMaxAbs())
+    assert 0.2 <= s.timestep <= 2.0 and abs(s.timestep - 1.0 / (want + 1e-5)) < 1e-3
+    s.step()
+    assert abs(s.timePerFrame - s.timestep) < 1e-6 and s.frame == 0

@@ -163,3 +163,11 @@ def test_kernel_emulation_runs_the_benchmark_dam_loop(order, parts_emul_lib, por
     out = helpers.run_dam_loop(FlipEmulation(parts_emul_lib, 4, order, port=port32), 4)
     for key in g:
         assert np.array_equal(out[key], g[key]), key
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+def test_vec_max_abs_port_equals_reference(prec, port32, port64, ref32, ref64):
+    """Grid<Vec3>::getMaxAbs (grid.cpp:330-332), what the liquid scenes hand to adaptTimestep"""
+    P, R = (port32, ref32) if prec == 4 else (port64, ref64)
+    vel = load_golden("step_dam", prec)["vel"]
+    assert P.vec_max_abs(vel) == R.vec_max_abs(vel) > 1.0

@@ -43,7 +43,7 @@ FlagFluid, FlagEmpty = mf.FlagFluid, mf.FlagEmpty
 
 calls = [   # scenes/benchmark_dam.py:100-134, ghost-fluid variant
     ("mapPartsToMAC", lambda: mf.mapPartsToMAC(vel=vel, flags=flags, velOld=velOld, parts=pp, partVel=pV, ptype=pT, exclude=FlagEmpty)),
-    ("getMaxAbs (adaptTimestep)", lambda: vel.getMaxAbs() if hasattr(vel, "getMaxAbs") else None),
+    ("getMaxAbs (adaptTimestep)", lambda: vel.getMaxAbs()),
     ("addGravityNoScale", lambda: mf.addGravityNoScale(flags=flags, vel=vel, gravity=(0, grav, 0))),
     ("gridParticleIndex", lambda: mf.gridParticleIndex(parts=pp, flags=flags, indexSys=pindex, index=index)),
     ("unionParticleLevelset", lambda: mf.unionParticleLevelset(parts=pp, indexSys=pindex, flags=flags, index=index, phi=phi, radiusFactor=1.0)),
