@@ -53,6 +53,17 @@ def test_cuda_reproduces_advect_golden(name, prec):
         assert np.array_equal(out[key], g[key]), (name, prec, key)
 
 
+@pytest.mark.parametrize("prec", [4, 8])
+def test_cuda_particle_movers_equal_oracle_on_a_larger_scene(prec, port32, port64, monkeypatch):
+    """advectInGrid (all modes), projectOutOfBnd, pushOutofObs and the Lagrangian helpers on tens of thousands of particles (several blocks per launch)"""
+    from cuda_impl import CudaImpl
+    monkeypatch.setitem(helpers.FLIP_SCENES, "large", (36, 40, 150))
+    a, b = helpers.run_advect_cases(port32 if prec == 4 else port64, "large", prec), helpers.run_advect_cases(CudaImpl(prec), "large", prec)
+    assert len(a["rk4_flip_flag"]) > 20000
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+
+
 def test_map_parts_to_mac_is_reproducible(mf):
     """the same particles in the same order give the same bits on every call (a scatter with floating-point atomics would not)"""
     from cuda_impl import CudaImpl
