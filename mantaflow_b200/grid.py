@@ -149,15 +149,22 @@ class _GridBase:
     def is3D(self): return self.size[2] > 1
 
     def clear(self):
+        """Grid<T>::clear grid.cpp:93-96: both copies are zeroed, nothing crosses the bus"""
+        check(self.parent.lib.mp_grid_clear(self._dev))
         self._host[...] = 0
-        self._hostDirty, self._devDirty = True, False
+        self._hostDirty, self._devDirty = False, False
 
     def setConst(self, value):
         self._host[...] = value
         self._hostDirty, self._devDirty = True, False
 
     def copyFrom(self, other):
-        self.copyFromArray(other.numpy())
+        """Grid<T>::copyFrom grid.cpp:205-210: a device-to-device copy when both grids live in the same context"""
+        if other.parent is self.parent and other.KIND == self.KIND and other.size == self.size:
+            check(self.parent.lib.mp_grid_copy_from(self._dev, other.dev()))
+            self.markDeviceWritten()
+        else:
+            self.copyFromArray(other.numpy())
 
     def save(self, name):
         """Grid<T>::save grid.cpp:134-156 (.uni, .raw, .npz) from the device-resident grid"""

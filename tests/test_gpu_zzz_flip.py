@@ -199,3 +199,19 @@ def test_macgrid_get_max_abs(prec, port32, port64):
     assert 0.2 <= s.timestep <= 2.0 and abs(s.timestep - 1.0 / (want + 1e-5)) < 1e-3
     s.step()
     assert abs(s.timePerFrame - s.timestep) < 1e-6 and s.frame == 0
+
+
+def test_grid_copy_from_and_clear_stay_on_the_device(mf):
+    s = mf.Solver(gridSize=(9, 7, 5), dim=3, prec=4)
+    a = mf.MACGrid(s, np.arange(9 * 7 * 5 * 3, dtype=np.float32).reshape(5, 7, 9, 3))
+    b = s.create(mf.MACGrid)
+    b.copyFrom(a)
+    assert b._devDirty and not b._hostDirty and np.array_equal(b.numpy(), a.numpy())
+    b.clear()
+    assert not b._devDirty and not b._hostDirty and not b.numpy().any()
+    mf.addGravity(s.create(mf.FlagGrid), b, (0, 0, 0))          # touches the device copy: still zero there
+    assert not b.numpy().any()
+    t = mf.Solver(gridSize=(9, 7, 5), dim=3, prec=4)
+    c = t.create(mf.MACGrid)
+    c.copyFrom(a)                                                # another context: through the host
+    assert np.array_equal(c.numpy(), a.numpy())
