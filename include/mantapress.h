@@ -121,6 +121,12 @@ int mp_grid_max_abs(mp_context* ctx, const mp_grid* a, double* out);            
 int mp_grid_sum_sqr(mp_context* ctx, const mp_grid* a, double* out);                      /* GridSumSqr commonkernels.h:32-35 */
 int mp_grid_scaled_add(mp_context* ctx, mp_grid* me, const mp_grid* other, double factor);/* gridScaledAdd grid.h:478 */
 int mp_grid_add_const(mp_context* ctx, mp_grid* me, double value);                        /* Grid<T>::operator+=(S) grid.h:490 */
+/* Element-wise Grid<T> arithmetic on the device, grid.cpp:258-284 (Real, int and Vec3 / MAC grids): setConst, addConst, multConst, add, sub, mult,
+ * addScaled, clamp, stomp, safeDivide.  (x, y, z): the constant / factor / threshold -- x alone for Real and int grids, per component for Vec3 grids;
+ * clamp: x = min, y = max for every component (Grid<T>::clamp(Real min, Real max) builds T(min), T(max)).  `other` is NULL for the constant operations. */
+enum mp_grid_arith_op { MP_OP_SET_CONST = 0, MP_OP_ADD_CONST = 1, MP_OP_MULT_CONST = 2, MP_OP_ADD = 3, MP_OP_SUB = 4, MP_OP_MULT = 5, MP_OP_ADD_SCALED = 6,
+                        MP_OP_CLAMP = 7, MP_OP_STOMP = 8, MP_OP_SAFE_DIVIDE = 9 };
+int mp_grid_arith(mp_context* ctx, mp_grid* me, int op, const mp_grid* other, double x, double y, double z);
 
 /* ---- assembly kernels ---- */
 /* MakeRhs pressure.cpp:32-84 (+ the optional mean subtraction of computePressureRhs :297-298 is NOT

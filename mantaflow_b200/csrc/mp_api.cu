@@ -2,6 +2,7 @@
 // Reference: Grid<T> grid.cpp:47-96,:205-210; FluidSolver::GridStorage fluidsolver.cpp:33-50;
 // GridDotProduct conjugategrad.cpp:175-178; getMaxAbs grid.cpp:319-323; GridSumSqr commonkernels.h:32-35.
 #include "mp_common.cuh"
+#include "mp_gridops.cuh"
 #include <thread>
 #include <vector>
 #include <cstring>
@@ -283,7 +284,36 @@ static int reduceLaunch(mp_context* ctx, const mp_grid* a, const mp_grid* b, dou
 	*out = ctx->hScal[0]; return MP_OK;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) k_grid_arith(gridops::Op<T> f, IndexInt n) {
+	for (IndexInt e = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (IndexInt)gridDim.x * blockDim.x) f(e);
+}
+template <typename T>
+static int gridArith(mp_context* ctx, mp_grid* me, int op, const mp_grid* other, double x, double y, double z) {
+	gridops::Op<T> f;
+	f.me = (T*)me->d; f.other = other ? (const T*)other->d : nullptr; f.op = op; f.comps = me->comps();
+	const double c[3] = { x, me->comps() == 3 ? y : x, me->comps() == 3 ? z : x };
+	for (int q = 0; q < 3; q++) { f.c0[q] = (T)(op == MP_OP_CLAMP ? x : c[q]); f.c1[q] = (T)y; }
+	const IndexInt n = me->n * me->comps();
+	unsigned int blocks = gridFor(n, 256 * 4); if (blocks > (unsigned)ctx->smCount * 16) blocks = ctx->smCount * 16;
+	k_grid_arith<T><<<blocks, 256, 0, ctx->stream>>>(f, n);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
 extern "C" {
+int mp_grid_arith(mp_context* ctx, mp_grid* me, int op, const mp_grid* other, double x, double y, double z) {
+	if (!ctx || !me) MP_FAIL(MP_ERR_INVALID, "mp_grid_arith: NULL argument");
+	if (op < MP_OP_SET_CONST || op > MP_OP_SAFE_DIVIDE) MP_FAIL(MP_ERR_INVALID, "mp_grid_arith: unknown operation %d", op);
+	const bool binary = op == MP_OP_ADD || op == MP_OP_SUB || op == MP_OP_MULT || op == MP_OP_ADD_SCALED || op == MP_OP_SAFE_DIVIDE;
+	if (binary) { MP_TRY(mp_check_same(me, other, me->kind, "other", false)); if (other->d == me->d && op != MP_OP_ADD && op != MP_OP_MULT) MP_FAIL(MP_ERR_INVALID, "mp_grid_arith: other must be another grid"); }
+	else if (other) MP_FAIL(MP_ERR_INVALID, "mp_grid_arith: this operation takes no second grid");
+	if (ctx->dist && ctx->dist->active && me->sz > 1) MP_TRY(mp_dist_check_grid(me));       // element-wise: ghost planes included, nothing to exchange
+	MP_CUDA(cudaSetDevice(ctx->device));
+	if (me->kind == MP_GRID_FLAGS) return gridArith<int>(ctx, me, op, other, x, y, z);
+	if (me->prec == 4) return gridArith<float>(ctx, me, op, other, x, y, z);
+	return gridArith<double>(ctx, me, op, other, x, y, z);
+}
 int mp_grid_dot(mp_context* ctx, const mp_grid* a, const mp_grid* b, double* out) { return reduceLaunch<0>(ctx, a, b, out); }
 int mp_grid_max_abs(mp_context* ctx, const mp_grid* a, double* out) {
 	if (a && ctx && out && a->kind == MP_GRID_MAC) return vecMaxAbs(ctx, a, out);        // Grid<Vec3>::getMaxAbs (adaptTimestep(vel.getMaxAbs()) in the liquid scenes)

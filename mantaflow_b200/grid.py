@@ -154,9 +154,32 @@ class _GridBase:
         self._host[...] = 0
         self._hostDirty, self._devDirty = False, False
 
-    def setConst(self, value):
-        self._host[...] = value
-        self._hostDirty, self._devDirty = True, False
+    # ---- element-wise arithmetic on the device, grid.cpp:258-284 (constants: a scalar, or a 3-tuple for Vec3 grids) ----
+    _OPS = {"setConst": 0, "addConst": 1, "multConst": 2, "add": 3, "sub": 4, "mult": 5, "addScaled": 6, "clamp": 7, "stomp": 8, "safeDivide": 9}
+
+    def _arith(self, op, other=None, x=0.0, y=0.0, z=0.0):
+        check(self.parent.lib.mp_grid_arith(self.parent._ctx, self.dev(), C.c_int(self._OPS[op]), None if other is None else other.dev(),
+                                            C.c_double(x), C.c_double(y), C.c_double(z)))
+        self.markDeviceWritten()
+
+    @staticmethod
+    def _xyz(v):
+        try:
+            x, y, z = (float(c) for c in v)
+        except TypeError:
+            x = y = z = float(v)
+        return x, y, z
+
+    def setConst(self, value): self._arith("setConst", None, *self._xyz(value))
+    def addConst(self, value): self._arith("addConst", None, *self._xyz(value))
+    def multConst(self, value): self._arith("multConst", None, *self._xyz(value))
+    def add(self, a): self._arith("add", a)
+    def sub(self, a): self._arith("sub", a)
+    def mult(self, a): self._arith("mult", a)
+    def addScaled(self, a, factor): self._arith("addScaled", a, *self._xyz(factor))
+    def clamp(self, min, max): self._arith("clamp", None, float(min), float(max), 0.0)
+    def stomp(self, threshold): self._arith("stomp", None, *self._xyz(threshold))
+    def safeDivide(self, a): self._arith("safeDivide", a)
 
     def copyFrom(self, other):
         """Grid<T>::copyFrom grid.cpp:205-210: a device-to-device copy when both grids live in the same context"""

@@ -7,6 +7,7 @@
 // (particles) -- the passes are written so that any order gives the same result, which the tests assert.
 // Built by tests/test_oracle_flip.py:  g++ -O2 -ffp-contract=off -I/usr/local/cuda/include -shared -fPIC
 #include "../../mantaflow_b200/csrc/mp_particles_cells.cuh"
+#include "../../mantaflow_b200/csrc/mp_gridops.cuh"
 #include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
@@ -119,7 +120,22 @@ template <typename Real> int advect(int order, const Dims& d, const int* flags, 
 }
 }  // namespace
 
+template <typename T> int gridArith(int order, IndexInt n, int comps, void* me, int op, const void* other, double x, double y, double z) {
+	// the constants exactly as mp_api.cu::gridArith prepares them
+	gridops::Op<T> f;
+	f.me = (T*)me; f.other = (const T*)other; f.op = op; f.comps = comps;
+	const double c[3] = { x, comps == 3 ? y : x, comps == 3 ? z : x };
+	for (int q = 0; q < 3; q++) { f.c0[q] = (T)(op == MP_OP_CLAMP ? x : c[q]); f.c1[q] = (T)y; }
+	HostExec ex = { order };
+	return ex.parts(n * comps, f);
+}
 extern "C" {
+// elem: 0 int, 4 float, 8 double
+int emu_grid_arith(int elem, int order, long long n, int comps, void* me, int op, const void* other, double x, double y, double z) {
+	if (elem == 0) return gridArith<int>(order, n, comps, me, op, other, x, y, z);
+	if (elem == 4) return gridArith<float>(order, n, comps, me, op, other, x, y, z);
+	return gridArith<double>(order, n, comps, me, op, other, x, y, z);
+}
 int emu_add_force_pvel(int prec, int order, long long np, void* pvel, double ax, double ay, double az, double dt, const int* ptype, int exclude) {
 	HostExec ex = { order };
 	if (prec == 4) { const float d = (float)dt; parts::AddForcePvel<float> op = { (float*)pvel, { (float)ax * d, (float)ay * d, (float)az * d }, ptype, exclude }; return ex.parts(np, op); }

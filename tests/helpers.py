@@ -751,3 +751,30 @@ def run_dam_loop(I, prec, steps=12, shape=(12, 20, 16)):
         I.mark_isolated_fluid_cell(flags, 4)
         I.set_part_type(flags, pos, ptype, 4, 1, 4)
     return dict(flags=flags, pos=pos, pvel=pvel, ptype=ptype, vel=vel, phi=phi, pressure=p, iterations=np.array(its))
+
+
+# ---------------------------------------------------------------- element-wise Grid<T> arithmetic (grid.cpp:258-284, grid.h:472-480)
+GRID_OPS = ["setConst", "addConst", "multConst", "add", "sub", "mult", "addScaled", "clamp", "stomp", "safeDivide"]
+
+
+def grid_arith_case(op, dtype, comps, seed=3):
+    """inputs and the numpy restatement of one operation: (me, other | None, constant (x, y, z), expected)"""
+    rng = np.random.default_rng(seed + comps)
+    shape = (5, 6, 7) + ((3,) if comps == 3 else ())
+    if dtype == np.int32:
+        me, other = rng.integers(-9, 9, shape).astype(np.int32), rng.integers(-3, 3, shape).astype(np.int32)
+        c = (3.0, -2.0, 5.0)
+    else:
+        me, other = ((rng.random(shape) - 0.5) * 4).astype(dtype), ((rng.random(shape) - 0.5) * 4).astype(dtype)
+        other[rng.random(shape) < 0.2] = 0
+        c = (0.3, -1.7, 2.9)
+    cv = np.array(c[:3] if comps == 3 else c[:1], dtype=dtype)           # T(value): one constant per component
+    lo, hi = dtype(-1), dtype(1.25) if dtype != np.int32 else dtype(2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        safe_div = (me // other if dtype != np.int32 else (np.trunc(me / np.where(other == 0, 1, other))).astype(np.int32)) if dtype == np.int32 else me / other
+    want = {"setConst": np.broadcast_to(cv, shape).astype(dtype), "addConst": me + cv, "multConst": me * cv, "add": me + other, "sub": me - other, "mult": me * other,
+            "addScaled": me + cv * other, "clamp": np.minimum(np.maximum(me, lo), hi), "stomp": np.where(me < cv, dtype(0), me),
+            "safeDivide": np.where(other != 0, safe_div, me)}[op].astype(dtype)
+    binary = op in ("add", "sub", "mult", "addScaled", "safeDivide")
+    const = (float(lo), float(hi), 0.0) if op == "clamp" else c
+    return me, (other if binary else None), const, np.ascontiguousarray(want)

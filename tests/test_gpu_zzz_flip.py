@@ -215,3 +215,26 @@ def test_grid_copy_from_and_clear_stay_on_the_device(mf):
     c = t.create(mf.MACGrid)
     c.copyFrom(a)                                                # another context: through the host
     assert np.array_equal(c.numpy(), a.numpy())
+
+
+@pytest.mark.parametrize("comps", [1, 3])
+@pytest.mark.parametrize("dtype", [np.int32, np.float32, np.float64])
+@pytest.mark.parametrize("op", helpers.GRID_OPS)
+def test_grid_arithmetic_on_the_device(mf, op, dtype, comps):
+    """Grid.setConst / addConst / multConst / add / sub / mult / addScaled / clamp / stomp / safeDivide (grid.cpp:258-284) without leaving the device"""
+    if dtype == np.int32 and comps == 3:
+        pytest.skip("there are no Vec3i grids")
+    me, other, c, want = helpers.grid_arith_case(op, dtype, comps)
+    s = mf.Solver(gridSize=(7, 6, 5), dim=3, prec=8 if dtype == np.float64 else 4)
+    cls = mf.IntGrid if dtype == np.int32 else (mf.VecGrid if comps == 3 else mf.RealGrid)
+    G, O = cls(s, me), (None if other is None else cls(s, other))
+    const = c if comps == 3 else c[0]
+    if op in ("setConst", "addConst", "multConst", "stomp"):
+        getattr(G, op)(const)
+    elif op == "clamp":
+        G.clamp(c[0], c[1])
+    elif op == "addScaled":
+        G.addScaled(O, const)
+    else:
+        getattr(G, op)(O)
+    assert G._devDirty and np.array_equal(G.numpy(), want), (op, dtype, comps)

@@ -171,3 +171,19 @@ def test_vec_max_abs_port_equals_reference(prec, port32, port64, ref32, ref64):
     P, R = (port32, ref32) if prec == 4 else (port64, ref64)
     vel = load_golden("step_dam", prec)["vel"]
     assert P.vec_max_abs(vel) == R.vec_max_abs(vel) > 1.0
+
+
+# ---------------------------------------------------------------- element-wise Grid<T> arithmetic (grid.cpp:258-284)
+@pytest.mark.parametrize("comps", [1, 3])
+@pytest.mark.parametrize("dtype", [np.int32, np.float32, np.float64])
+@pytest.mark.parametrize("op", helpers.GRID_OPS)
+def test_kernel_emulation_grid_arithmetic(op, dtype, comps, parts_emul_lib):
+    """the element functor of mp_gridops.cuh (what k_grid_arith runs) against the numpy restatement of the reference's one-line kernels"""
+    if dtype == np.int32 and comps == 3:
+        pytest.skip("there are no Vec3i grids")
+    me, other, c, want = helpers.grid_arith_case(op, dtype, comps)
+    got = me.copy()
+    f = parts_emul_lib.emu_grid_arith
+    rc = f(C.c_int(0 if dtype == np.int32 else np.dtype(dtype).itemsize), C.c_int(2), C.c_longlong(me.size // comps), C.c_int(comps), got.ctypes.data_as(C.c_void_p),
+           C.c_int(helpers.GRID_OPS.index(op)), None if other is None else other.ctypes.data_as(C.c_void_p), C.c_double(c[0]), C.c_double(c[1]), C.c_double(c[2]))
+    assert rc == 0 and np.array_equal(got, want), (op, dtype, comps)
