@@ -137,10 +137,26 @@ public:
 	void syncToHost() const { if (mDevDirty) { mpCheck(mp_grid_download(mDev, (void*)mData.data())); mDevDirty = false; } }
 	void clear() { mpCheck(mp_grid_clear(mDev)); std::fill(mData.begin(), mData.end(), T()); mHostDirty = mDevDirty = false; }   // grid.cpp:93-96
 	void copyFrom(const Grid<T>& a) { mpCheck(mp_grid_copy_from(dev(), a.dev())); markDeviceWritten(); }                                      // grid.cpp:205-210
-	void setConst(T s) { syncToHost(); std::fill(mData.begin(), mData.end(), s); markHostWritten(); }
+	// element-wise arithmetic on the device, grid.cpp:258-284
+	void setConst(T s) { arith(MP_OP_SET_CONST, nullptr, s); }
+	void addConst(T s) { arith(MP_OP_ADD_CONST, nullptr, s); }
+	void multConst(T s) { arith(MP_OP_MULT_CONST, nullptr, s); }
+	void add(const Grid<T>& a) { arith(MP_OP_ADD, &a, T()); }
+	void sub(const Grid<T>& a) { arith(MP_OP_SUB, &a, T()); }
+	void mult(const Grid<T>& a) { arith(MP_OP_MULT, &a, T()); }
+	void addScaled(const Grid<T>& a, const T& factor) { arith(MP_OP_ADD_SCALED, &a, factor); }
+	void clamp(Real min, Real max) { mpCheck(mp_grid_arith(mParent->ctx(), dev(), MP_OP_CLAMP, nullptr, min, max, 0)); markDeviceWritten(); }
+	void stomp(const T& threshold) { arith(MP_OP_STOMP, nullptr, threshold); }
+	Grid<T>& safeDivide(const Grid<T>& a) { arith(MP_OP_SAFE_DIVIDE, &a, T()); return *this; }
 	void setBound(T value, int boundaryWidth = 1);                                                                                             // grid.cpp:591-593
 	Real getMaxAbs() const;                                                                                                                    // grid.cpp:319-323 (Grid<Real>)
 protected:
+	static void xyz(const Vec3& v, double (&c)[3]) { c[0] = v.x; c[1] = v.y; c[2] = v.z; }
+	template <class S> static void xyz(const S& v, double (&c)[3]) { c[0] = c[1] = c[2] = (double)v; }
+	void arith(int op, const Grid<T>* other, const T& value) {
+		double c[3]; xyz(value, c);
+		mpCheck(mp_grid_arith(mParent->ctx(), dev(), op, other ? other->dev() : nullptr, c[0], c[1], c[2])); markDeviceWritten();
+	}
 	mutable std::vector<T> mData;
 };
 template <> inline void Grid<Real>::setBound(Real value, int w) { mpCheck(mp_grid_set_bound(mParent->ctx(), dev(), value, value, value, w)); markDeviceWritten(); }
