@@ -187,3 +187,38 @@ def test_kernel_emulation_grid_arithmetic(op, dtype, comps, parts_emul_lib):
     rc = f(C.c_int(0 if dtype == np.int32 else np.dtype(dtype).itemsize), C.c_int(2), C.c_longlong(me.size // comps), C.c_int(comps), got.ctypes.data_as(C.c_void_p),
            C.c_int(helpers.GRID_OPS.index(op)), None if other is None else other.ctypes.data_as(C.c_void_p), C.c_double(c[0]), C.c_double(c[1]), C.c_double(c[2]))
     assert rc == 0 and np.array_equal(got, want), (op, dtype, comps)
+
+
+@pytest.mark.parametrize("trial", range(12))
+def test_kernel_emulation_fuzz_against_port(trial, parts_emul_lib, port32, port64):
+    """random tiny grids (down to two cells per axis, 2-D and 3-D), particles outside the domain on every side, on cell faces and centres exactly, deleted and
+    excluded ones, dozens per cell: the device code equals the restatement bit for bit in three cell / particle orders"""
+    rng = np.random.default_rng(100 + trial)
+    prec = 4 if trial % 2 == 0 else 8
+    real = np.float32 if prec == 4 else np.float64
+    shape = (1, int(rng.integers(3, 9)), int(rng.integers(3, 9))) if trial % 3 == 0 else tuple(int(v) for v in rng.integers(2, 7, 3))
+    sz, sy, sx = shape
+    n = int(rng.integers(1, 600))
+    pos = (rng.random((n, 3)) * (np.array([sx, sy, sz]) + 2) - 1).astype(real)
+    snap = rng.random(n) < 0.2
+    pos[snap] = np.round(pos[snap] * 2) / 2
+    if sz == 1:
+        pos[:, 2] = 0.5
+    pflag = np.where(rng.random(n) < 0.1, 1024, 0).astype(np.int32)
+    ptype = np.where(rng.random(n) < 0.2, 4, 1).astype(np.int32)
+    pvel = (rng.random((n, 3)) * 2 - 1).astype(real)
+    if sz == 1:
+        pvel[:, 2] = 0
+    P = port32 if prec == 4 else port64
+    a = P.map_parts_to_mac(shape, pos, pflag, pvel, want_weight=True, ptype=ptype, exclude=4)
+    ia, sa = P.grid_particle_index(shape, pos, pflag)
+    ua = P.union_particle_levelset(pos, ia, sa, 1.3, ptype=ptype, exclude=4)
+    fa = P.flip_velocity_update(a[0], a[1], pos, pflag, pvel.copy(), 0.9, ptype=ptype, exclude=4)
+    for order in (0, 2, 3):
+        E = FlipEmulation(parts_emul_lib, prec, order)
+        b = E.map_parts_to_mac(shape, pos, pflag, pvel, want_weight=True, ptype=ptype, exclude=4)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)), (shape, n, order)
+        ib, sb = E.grid_particle_index(shape, pos, pflag)
+        assert np.array_equal(ia, ib) and np.array_equal(sa, sb)
+        assert np.array_equal(ua, E.union_particle_levelset(pos, ib, sb, 1.3, ptype=ptype, exclude=4))
+        assert np.array_equal(fa, E.flip_velocity_update(a[0], a[1], pos, pflag, pvel.copy(), 0.9, ptype=ptype, exclude=4))
