@@ -222,3 +222,42 @@ def test_kernel_emulation_fuzz_against_port(trial, parts_emul_lib, port32, port6
         assert np.array_equal(ia, ib) and np.array_equal(sa, sb)
         assert np.array_equal(ua, E.union_particle_levelset(pos, ib, sb, 1.3, ptype=ptype, exclude=4))
         assert np.array_equal(fa, E.flip_velocity_update(a[0], a[1], pos, pflag, pvel.copy(), 0.9, ptype=ptype, exclude=4))
+
+
+@pytest.mark.parametrize("trial", range(10))
+def test_kernel_emulation_fuzz_particle_movers(trial, parts_emul_lib, port32, port64):
+    """random obstacle cells inside small boxes, fast velocity fields, every integration mode x obstacle policy, new / deleted / excluded particles:
+    advectInGrid, pushOutofObs, setPartType, markIsolatedFluidCell and markFluidCells(phiObs) of the device code equal the restatement bit for bit"""
+    from mantaflow_b200 import scenes
+    rng = np.random.default_rng(500 + trial)
+    prec = 4 if trial % 2 == 0 else 8
+    real = np.float32 if prec == 4 else np.float64
+    sx, sy, sz = (int(rng.integers(4, 12)), int(rng.integers(4, 12)), 1) if trial % 3 == 0 else tuple(int(v) for v in rng.integers(4, 10, 3))
+    flags = scenes.closed_box_flags(sx, sy, sz)
+    flags[((flags & 2) == 0) & (rng.random(flags.shape) < 0.15)] = 2
+    free = (flags & 2) == 0
+    flags[free] = np.where(rng.random(flags.shape) < 0.5, 1, 4)[free]
+    n, nd = int(rng.integers(1, 400)), (3 if sz > 1 else 2)
+    pos = np.full((n, 3), 0.5)
+    pos[:, :nd] = 1 + rng.random((n, nd)) * (np.array([sx, sy, sz])[:nd] - 2)
+    pos = pos.astype(real)
+    pflag = (np.where(rng.random(n) < 0.1, 1024, 0) | np.where(rng.random(n) < 0.2, 1, 0)).astype(np.int32)
+    ptype = np.where(rng.random(n) < 0.2, 4, 1).astype(np.int32)
+    vel = ((rng.random(flags.shape + (3,)) - 0.5) * 8).astype(real)
+    if sz == 1:
+        vel[..., 2] = 0
+    phiObs = (rng.random(flags.shape) * 3 - 1).astype(real)
+    P, E = (port32 if prec == 4 else port64), FlipEmulation(parts_emul_lib, prec, trial % 3)
+    for mode in (0, 1, 2):
+        for dele in (False, True):
+            for stop in (False, True):
+                kw = dict(integrationMode=mode, deleteInObstacle=dele, stopInObstacle=stop, skipNew=bool(trial & 1), ptype=ptype if trial % 4 else None, exclude=4)
+                a, b = P.advect_in_grid(flags, vel, pos.copy(), pflag.copy(), 0.7, **kw), E.advect_in_grid(flags, vel, pos.copy(), pflag.copy(), 0.7, **kw)
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (mode, dele, stop)
+    moved = P.advect_in_grid(flags, vel, pos.copy(), pflag.copy(), 0.7, integrationMode=1, deleteInObstacle=False, stopInObstacle=False)[0]
+    assert np.array_equal(P.push_out_of_obs(flags.shape, moved.copy(), pflag, phiObs, shift=0.1, thresh=0.4, ptype=ptype, exclude=4),
+                          E.push_out_of_obs(flags.shape, moved.copy(), pflag, phiObs, shift=0.1, thresh=0.4, ptype=ptype, exclude=4))
+    assert np.array_equal(P.set_part_type(flags, moved, ptype.copy(), 1, 4, 1), E.set_part_type(flags, moved, ptype.copy(), 1, 4, 1))
+    assert np.array_equal(P.mark_isolated_fluid_cell(flags.copy(), 4), E.mark_isolated_fluid_cell(flags.copy(), 4))
+    assert np.array_equal(P.mark_fluid_cells(flags.copy(), moved, pflag, phiObs=phiObs, ptype=ptype, exclude=4),
+                          E.mark_fluid_cells(flags.copy(), moved, pflag, phiObs=phiObs, ptype=ptype, exclude=4))
