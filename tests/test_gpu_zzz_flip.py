@@ -1,7 +1,12 @@
-"""GPU: the FLIP particle <-> grid plugins on the device (second slice: markFluidCells, gridParticleIndex, unionParticleLevelset,
-mapPartsToMAC, mapMACToParts, flipVelocityUpdate -- plugin/flip.cpp) through the Python mirror and the C-ABI: bit for bit the golden vectors
-of the unmodified reference, the oracle on larger scenes (mapPartsToMAC included: faces gather in particle order, no floating-point
-atomics), and the particle <-> grid part of a FLIP step (scenes/benchmark_dam.py:100-125) with every array resident on the device."""
+"""GPU: everything that was written after round 1's GPU minutes were spent and has therefore only run through the host emulations so far (collected last, see
+tests/conftest.py):
+
+* the FLIP particle <-> grid plugins (second slice: markFluidCells, gridParticleIndex, unionParticleLevelset, mapPartsToMAC, mapMACToParts,
+  flipVelocityUpdate -- plugin/flip.cpp), the particle movers (advectInGrid, projectOutOfBnd, pushOutofObs) and the Lagrangian helpers of plugin/ptsplugins.cpp,
+  through the Python mirror and the C-ABI: bit for bit the golden vectors of the unmodified reference, the oracle on larger scenes (mapPartsToMAC included: faces
+  gather in particle order, no floating-point atomics), a device-resident FLIP step and twelve passes of the main loop of scenes/benchmark_dam.py:100-134;
+* GridCg with PC_ICP (IC(0), conjugategrad.cpp:26-63,:109-132);
+* MACGrid.getMaxAbs, Grid.copyFrom / clear and the element-wise grid arithmetic of grid.cpp:258-284 on the device."""
 import numpy as np
 import pytest
 
