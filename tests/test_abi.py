@@ -77,3 +77,32 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert not bad.search(txt), os.path.join(dp, f)
+
+
+def test_python_mirror_passes_as_many_arguments_as_the_header_declares():
+    """ctypes does not check argument counts; the C-ABI calls of the Python mirror (and of the test adapter) are compared with the declarations in
+    include/mantapress.h.  Calls with a starred argument are counted with the three values a vector constant expands to."""
+    import ast
+    import glob
+    import re
+    from mantaflow_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "mantapress.h")).read(), flags=re.S)
+    declared = {}
+    for m in re.finditer(r"\b(mp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = m.group(2).strip()
+        declared[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    assert set(declared) >= set(_lib.declared_symbols())
+    checked, bad = 0, []
+    for f in glob.glob(os.path.join(root, "mantaflow_b200", "*.py")) + [os.path.join(root, "tests", "cuda_impl.py")]:
+        for node in ast.walk(ast.parse(open(f).read())):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr in declared:
+                n = sum(3 if isinstance(a, ast.Starred) and "xyz" in ast.dump(a) or isinstance(a, ast.Starred) and "_vec3" in ast.dump(a) else (None if isinstance(a, ast.Starred) else 1)
+                        for a in node.args) if not any(isinstance(a, ast.Starred) and "xyz" not in ast.dump(a) and "_vec3" not in ast.dump(a) for a in node.args) else None
+                if n is None:
+                    continue
+                checked += 1
+                if n != declared[node.func.attr]:
+                    bad.append((os.path.basename(f), node.lineno, node.func.attr, n, declared[node.func.attr]))
+    assert not bad, bad
+    assert checked > 80
