@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:k_liquid_cells -s 4 -c 6 -o $out/${tag}_ncu_liquid_passes -f \
     python tools/liquid_bench.py 512 > /dev/null 2>&1
 # 6. the FLIP particle plugins (never timed so far): timings at 256^3, a launch list, one full capture of the gather of mapPartsToMAC
-timeout 600 python tools/flip_bench.py 256 $out/${tag}_flip_bench.json > $out/${tag}_flip_bench.txt $out/${tag}_dam_bench.txt 2>&1
+timeout 600 python tools/flip_bench.py 256 $out/${tag}_flip_bench.json > $out/${tag}_flip_bench.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/${tag}_launches_flip_256.csv \
     python tools/flip_bench.py 128 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_parts_cells -c 4 -o $out/${tag}_ncu_flip_cells -f \
