@@ -852,6 +852,24 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 	return MP_OK;
 }
 
+// Fused loop: x lags one update behind (k_matvec_fused applies alpha_{k-1} s_{k-1} while forming s_k) and the live search vector
+// alternates between search / search2.  This brings the caller-visible state to what GridCg::iterate leaves behind
+// (conjugategrad.cpp:254-257,:283): x holds every update, and -- when `syncSearch` -- the caller's search grid holds the live vector.
+// k_flush_x clears xPending, so the next fused matvec adds alpha_prev = 0.
+static int cgFlushFused(mp_cg* cg, bool syncSearch) {
+	mp_context* ctx = cg->ctx;
+	const Dims d = dimsOf(cg->flags);
+	const IndexInt nOwn = d.i1 - d.i0;
+	DISPATCH_RV(cg->dst, {
+		k_flush_x<Real, V><<<streamBlocks(ctx, nOwn / V), 256, 0, ctx->stream>>>(nOwn, (Real*)cg->dst->d + d.i0, (const Real*)cg->search->d + d.i0,
+			(const Real*)cg->search2->d + d.i0, (CgScal<Real>*)cg->dSc, ctx->tickets + 8);
+		MP_CHECK_LAUNCH(ctx);
+	});
+	// enqueued iteration q (0-based) writes search2 when q is even: after an odd number of enqueues the live vector is in search2
+	if (syncSearch && (cg->fusedEnq & 1)) MP_CUDA(cudaMemcpyAsync(cg->search->d, cg->search2->d, cg->search->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	return MP_OK;
+}
+
 static int cgFinishCheck(mp_cg* cg) {
 	if (cg->diverged) MP_FAIL(MP_ERR_DIVERGED, "GridCg::iterate: The CG solver diverged, residual norm > 1e30, stopping.");
 	return MP_OK;
@@ -879,15 +897,7 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 		slot = other;
 	}
 	for (int q = 0; q < 2; q++) if (pending[q]) { MP_TRY(cgPollWait(cg, q)); pending[q] = false; }
-	if (cg->fused) {      // the x-update of the last executed iteration is still pending
-		const Dims d = dimsOf(cg->flags);
-		const IndexInt nOwn = d.i1 - d.i0;
-		DISPATCH_RV(cg->dst, {
-			k_flush_x<Real, V><<<streamBlocks(ctx, nOwn / V), 256, 0, ctx->stream>>>(nOwn, (Real*)cg->dst->d + d.i0, (const Real*)cg->search->d + d.i0,
-				(const Real*)cg->search2->d + d.i0, (CgScal<Real>*)cg->dSc, ctx->tickets + 8);
-			MP_CHECK_LAUNCH(ctx);
-		});
-	}
+	if (cg->fused) MP_TRY(cgFlushFused(cg, false));      // the x-update of the last executed iteration is still pending
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));      // the state after everything that was enqueued
 	MP_TRY(mp_dist_p2p_check(ctx));
 	if (cg->pcMethod == MP_CG_PC_MICP) MP_TRY(mp_mic_check_stall(ctx));
@@ -970,7 +980,9 @@ int mp_cg_iterate(mp_cg* cg, int* keepGoing) {
 	mp_context* ctx = cg->ctx;
 	MP_CUDA(cudaSetDevice(ctx->device));
 	if (!cg->inited) MP_TRY(cgDoInit(cg));
+	if (cg->finished) { if (keepGoing) *keepGoing = 0; return cgFinishCheck(cg); }     // converged: nothing is enqueued any more
 	MP_TRY(cgEnqueueIteration(cg));
+	if (cg->fused) MP_TRY(cgFlushFused(cg, true));          // stepwise callers read x (and own the search grid) after every call
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));
 	if (keepGoing) *keepGoing = cg->finished ? 0 : 1;      // once converged, further calls are no-ops returning false
 	return cgFinishCheck(cg);

@@ -218,6 +218,60 @@ def test_gridcg_iterate_stepwise(mf):
 
 
 @pytest.mark.parametrize("prec", [4, 8])
+def test_gridcg_iterate_state_after_every_call(mf, prec, monkeypatch):
+    """GridCg::iterate (conjugategrad.cpp:237-299) as solvePressureSystem (pressure.cpp:436-439) and the VIC solve drive it: after EVERY
+    call x holds all updates and the caller's search grid the live search vector.  The fused PcNone loop keeps x one update behind and
+    ping-pongs the search vector internally; mp_cg_iterate flushes both.  x after n calls == the oracle's x after maxIter = n (float:
+    bit for bit), and x / residual / search of the fused loop == those of the three-kernel loop, bit for bit, including a stop before
+    convergence and the calls after convergence."""
+    from mantaflow_b200 import cg
+    flags, vel, _ = SCENES["smoke24"](prec)
+    O = oracle(prec)
+    rhs_o, _, _ = O.compute_rhs(flags, vel)
+    A_o = O.make_matrix(flags)
+    acc = 1e-5 if prec == 4 else 1e-10
+    x_full, it_full, _ = O.cg_solve(flags, rhs_o, *A_o, pc=0, accuracy=acc, maxIter=3000)
+
+    def run(fused, ncalls):
+        monkeypatch.setenv("MP_CG_FUSED", "1" if fused else "0")
+        s = mk(mf, flags.shape, prec)
+        F = mf.FlagGrid(s, flags)
+        A = [mf.RealGrid(s, a) for a in A_o]
+        x, b, r, se, t = mf.RealGrid(s), mf.RealGrid(s, rhs_o), mf.RealGrid(s), mf.RealGrid(s), mf.RealGrid(s)
+        g = cg.GridCg(x, b, r, se, F, t, *A)
+        g.setAccuracy(acc)
+        g.setUseL2Norm(False)
+        out = []
+        for n in range(1, ncalls + 1):
+            more = g.iterate()
+            out.append((x.numpy().copy(), r.numpy().copy(), se.numpy().copy(), g.getIterations(), more))
+        return out
+
+    nfirst = 11
+    fused, plain = run(True, nfirst), run(False, nfirst)
+    for n in range(1, nfirst + 1):
+        xf, rf, sf, itf, moref = fused[n - 1]
+        xp, rp, sp, itp, morep = plain[n - 1]
+        assert itf == itp == n and moref and morep
+        assert np.array_equal(xf, xp) and np.array_equal(rf, rp) and np.array_equal(sf, sp), ("fused vs three-kernel loop after call", n)
+        x_o, it_o, _ = O.cg_solve(flags, rhs_o, *A_o, pc=0, accuracy=acc, maxIter=n)
+        assert it_o == n
+        if prec == 4:
+            assert np.array_equal(xf, x_o), ("x after iterate() call", n)
+        else:
+            assert rel_l2(xf, x_o) <= 1e-12
+    # to convergence and three calls beyond: x stays the converged solution, iterate() keeps returning False
+    tail = run(True, it_full + 3)
+    its = [t[3] for t in tail]
+    assert abs(its[-1] - it_full) <= 1 and its[-1] == its[-2] == its[-3]
+    assert not tail[-1][4] and not tail[-2][4]
+    assert rel_l2(tail[-1][0], x_full) <= (1e-5 if prec == 4 else 1e-9)
+    if its[-1] == it_full and prec == 4:
+        assert np.array_equal(tail[-1][0], x_full)
+    assert np.array_equal(tail[-1][0], tail[-3][0])
+
+
+@pytest.mark.parametrize("prec", [4, 8])
 @pytest.mark.parametrize("scene", ["smoke_vec", "liquid_vec", "smoke_ragged"])
 def test_solve_pressure_pcmic_warp_columns(mf, scene, prec, monkeypatch):
     """the whole PcMIC solve on the schedule large grids get by default (MP_MIC=4): same iteration count, float bit-identical"""
