@@ -212,12 +212,17 @@ def run_ours(args):
         peak, peak_src = load_peaks()
         bpc = bytes_per_cell(prec)
         mvk = prof.get("matvecKernel", 1)
-        mv_name = {0: "k_matvec_dot", 1: "k_matvec_zmarch", 2: "k_matvec_zmarch_masked", 3: "k_matvec_fused"}[mvk]
+        mv_name = {0: "k_matvec_dot", 1: "k_matvec_zmarch", 2: "k_matvec_zmarch_masked", 3: "k_matvec_fused", 4: "k_matvec_fused_tma"}[mvk]
         if mvk == 2:
             bpc["matvec"] = 4 + 3 * prec          # coupling-mask fast path: cmask 4 + A0 w + s w + t w
         ax_name, up_name = "k_axpy2_norm", "k_update_search"
         if mvk == 3:                              # fused PcNone iteration: R r, s_old, x, cmask, A0; W s, t, x  |  R r, t; W r
             bpc["matvec"] = 4 + 7 * prec
+            bpc["axpy"] = 3 * prec
+            bpc["update"] = 0
+            ax_name, up_name = "k_axpy1_norm", None
+        if mvk == 4:                              # the same iteration, staged by TMA, matrix as 2 bytes per cell: R r, s_old, x, mask16; W s, t, x
+            bpc["matvec"] = 2 + 6 * prec
             bpc["axpy"] = 3 * prec
             bpc["update"] = 0
             ax_name, up_name = "k_axpy1_norm", None

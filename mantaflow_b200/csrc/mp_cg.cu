@@ -67,6 +67,8 @@ __global__ void k_cg_combine(const double* __restrict__ gathered, int world, CgS
 	else cgFinZR<Real>(sc, a, stage == 3);
 }
 
+#include "mp_cg_tma.cuh"
+
 // ---------------------------------------------------------------- k_matvec_dot
 // ApplyMatrix / ApplyMatrix2D (conjugategrad.h:118-151) over ALL cells: identity rows on non-fluid cells,
 // same left-to-right summation order as the reference (bit-identical t with -fmad=false), fused with
@@ -196,8 +198,8 @@ __global__ void __launch_bounds__(256) k_matvec_zmarch(Dims d, int nvx, int chun
 // the result equals ApplyMatrix's value for value (signs of exact zeros aside).  Any other off-diagonal value (face
 // fractions) makes the mask invalid and the general kernel is used.
 template <typename Real>
-__global__ void __launch_bounds__(256) k_build_cmask(Dims d, const int* __restrict__ flags, const Real* __restrict__ Ai, const Real* __restrict__ Aj,
-	const Real* __restrict__ Ak, int* __restrict__ cmask, int* bad)
+__global__ void __launch_bounds__(256) k_build_cmask(Dims d, const int* __restrict__ flags, const Real* __restrict__ A0, const Real* __restrict__ Ai, const Real* __restrict__ Aj,
+	const Real* __restrict__ Ak, int* __restrict__ cmask, unsigned short* __restrict__ mask16, int pitch, int* bad)
 {
 	const IndexInt idx = d.i0 + (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= d.i1) return;
@@ -212,6 +214,17 @@ __global__ void __launch_bounds__(256) k_build_cmask(Dims d, const int* __restri
 		}
 	}
 	cmask[idx] = m;
+	if (mask16) {      // + the diagonal as a 3-bit code: 0..6 = that integer (the count of non-obstacle neighbours), 7 = read A0
+		int code = 0;
+		if (m) {
+			const Real a0 = A0[idx];
+			code = 7;
+			#pragma unroll
+			for (int q = 0; q < 7; q++) if (a0 == (Real)q) code = q;
+		}
+		const IndexInt k = idx / d.Z, rem = idx - k * d.Z; const IndexInt j = rem / d.Y, i = rem - j * d.Y;
+		mask16[(k * d.sy + j) * pitch + i] = (unsigned short)(m | (code << 7));
+	}
 }
 
 template <typename Real, int V>
@@ -651,7 +664,9 @@ struct mp_cg {
 	mp_grid* cmask;               // coupling mask of the fast matvec path, or NULL (general kernel)
 	bool fused;                   // PcNone on a masked matrix: two fused kernels per iteration, search vector ping-pongs between search / search2
 	mp_grid* search2; long long fusedEnq;
+	bool stepwise = false;           // driven through iterate(): x / residual / search are caller-visible after every call -> no fused loop
 	int fusedNvx, fusedChunk; dim3 fusedGrid;
+	FusedTma tma;                 // the TMA-staged persistent variant of the fused matvec (default when the grid qualifies)
 };
 
 template <typename Real>
@@ -696,6 +711,34 @@ static int cgHalo(mp_cg* cg, mp_grid* g) {       // one-plane ghost exchange of 
 	return mp_dist_halo(cg->ctx, g->d, (size_t)g->sx * g->sy * g->prec, g->sz);
 }
 
+// tensor maps over residual / search / search2 / x / mask16 and the item decomposition of k_matvec_fused_tma
+template <typename Real> static int cgFusedTmaSetupT(mp_cg* cg, const Dims& d) {
+	typedef FusedTmaGeom<Real> G;
+	mp_context* ctx = cg->ctx; FusedTma& t = cg->tma;
+	constexpr int NSTAGE = 6;
+	const CUtensorMapDataType dt = sizeof(Real) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+	const int es = (int)sizeof(Real);
+	MP_TRY(encodeMap3D(&t.mapR, cg->residual->d, es, dt, d.sx, d.sx, d.sy, d.sz, G::BX, G::BY));
+	MP_TRY(encodeMap3D(&t.mapS[0], cg->search->d, es, dt, d.sx, d.sx, d.sy, d.sz, G::BX, G::BY));
+	MP_TRY(encodeMap3D(&t.mapS[1], cg->search2->d, es, dt, d.sx, d.sx, d.sy, d.sz, G::BX, G::BY));
+	MP_TRY(encodeMap3D(&t.mapX, cg->dst->d, es, dt, d.sx, d.sx, d.sy, d.sz, G::TX, G::TY));
+	MP_TRY(encodeMap3D(&t.mapM, t.mask16->d, 2, CU_TENSOR_MAP_DATA_TYPE_UINT16, d.sx, t.pitch, d.sy, d.sz, G::TX, G::TY));
+	t.tilesX = (d.sx + G::TX - 1) / G::TX; t.tiles = t.tilesX * ((d.sy + G::TY - 1) / G::TY);
+	t.smemBytes = NSTAGE * G::stageBytes + 2 * NSTAGE * 8 + 128;
+	MP_CUDA(cudaFuncSetAttribute(k_matvec_fused_tma<Real, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smemBytes));
+	int perSm = 0;
+	MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_matvec_fused_tma<Real, NSTAGE>, kFusedThreads, t.smemBytes));
+	if (perSm < 1) { t.on = false; return MP_OK; }
+	const int G_ = ctx->smCount * perSm;
+	fusedTmaDecompose(t.tiles, d.ke - d.kb, G_, &t.chunk, &t.nitems);
+	t.ctas = t.nitems < G_ ? t.nitems : G_;
+	if (t.ctas > kMaxPartials) t.on = false;
+	return MP_OK;
+}
+static int cgFusedTmaSetup(mp_cg* cg, const Dims& d) {
+	return cg->dst->prec == 4 ? cgFusedTmaSetupT<float>(cg, d) : cgFusedTmaSetupT<double>(cg, d);
+}
+
 static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	mp_context* ctx = cg->ctx;
 	const Dims d = dimsOf(cg->flags);
@@ -722,8 +765,16 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 			int* bad = (int*)(ctx->dScal + 20);
 			MP_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
 			const unsigned int blocks = gridFor(d.i1 - d.i0, 256);
-			if (cg->dst->prec == 4) k_build_cmask<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)cg->flags->d, (const float*)cg->Ai->d, (const float*)cg->Aj->d, (const float*)cg->Ak->d, (int*)cg->cmask->d, bad);
-			else                    k_build_cmask<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)cg->flags->d, (const double*)cg->Ai->d, (const double*)cg->Aj->d, (const double*)cg->Ak->d, (int*)cg->cmask->d, bad);
+			// MP_CG_FUSED: 0 three-kernel loop, 1 fused matvec with plain loads, 2 (default) fused matvec staged by TMA
+			const int fusedMode = getenv("MP_CG_FUSED") ? atoi(getenv("MP_CG_FUSED")) : 2;     // read per solve: the parity tests run all loops in one process
+			unsigned short* m16 = nullptr; cg->tma.on = false; cg->tma.pitch = (cg->flags->sx + 7) / 8 * 8;
+			if (fusedMode >= 2 && cg->pcMethod == MP_CG_PC_NONE && !cg->stepwise && encodeTiledFn() && cg->tma.pitch <= 2 * cg->flags->sx) {
+				if (!cg->tma.mask16) MP_TRY(mp_grid_create(ctx, MP_GRID_FLAGS, 4, cg->flags->sx, cg->flags->sy, cg->flags->sz, &cg->tma.mask16));
+				else MP_CUDA(cudaMemsetAsync(cg->tma.mask16->d, 0, cg->tma.mask16->bytes, ctx->stream));
+				m16 = (unsigned short*)cg->tma.mask16->d; cg->tma.on = true;
+			}
+			if (cg->dst->prec == 4) k_build_cmask<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)cg->flags->d, (const float*)cg->A0->d, (const float*)cg->Ai->d, (const float*)cg->Aj->d, (const float*)cg->Ak->d, (int*)cg->cmask->d, m16, cg->tma.pitch, bad);
+			else                    k_build_cmask<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)cg->flags->d, (const double*)cg->A0->d, (const double*)cg->Ai->d, (const double*)cg->Aj->d, (const double*)cg->Ak->d, (int*)cg->cmask->d, m16, cg->tma.pitch, bad);
 			MP_CHECK_LAUNCH(ctx);
 			MP_CUDA(cudaMemcpyAsync(ctx->hScal + 20, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
 			MP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -733,7 +784,7 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 	{	// fused PcNone loop: same launch geometry as the masked z-marching matvec
 		const int useFused = getenv("MP_CG_FUSED") ? atoi(getenv("MP_CG_FUSED")) : 1;     // read per solve: the parity tests run both loops in one process
 		cg->fused = false; cg->fusedEnq = 0;
-		if (useFused && none && cg->cmask) {
+		if (useFused && none && cg->cmask && !cg->stepwise) {
 			const int Vw = vecWidth(cg->dst), nvx = d.sx / Vw, planes = d.ke - d.kb;
 			const int tiles = ((nvx + 31) / 32) * ((d.sy + 7) / 8);
 			int nchunk = (4 * 3 * ctx->smCount + tiles - 1) / tiles; if (nchunk < 1) nchunk = 1;
@@ -743,6 +794,7 @@ static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
 			if ((long long)grid.x * grid.y * grid.z <= kMaxPartials) {
 				cg->fused = true; cg->fusedNvx = nvx; cg->fusedChunk = chunk; cg->fusedGrid = grid;
 				if (!cg->search2) MP_TRY(mp_grid_create(ctx, MP_GRID_REAL, cg->dst->prec, cg->dst->sx, cg->dst->sy, cg->dst->sz, &cg->search2));
+				if (cg->tma.on) MP_TRY(cgFusedTmaSetup(cg, d));
 			}
 		}
 	}
@@ -795,10 +847,17 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 		if (p2pHalo) MP_TRY(mp_dist_p2p_halo_out(ctx, planeBytes, &ho));
 		DISPATCH_RV(cg->dst, {
 			CgScal<Real>* sc = (CgScal<Real>*)cg->dSc;
-			k_matvec_fused<Real, V><<<cg->fusedGrid, block, 0, ctx->stream>>>(d, cg->fusedNvx, cg->fusedChunk, (const int*)cg->cmask->d, (Real*)cg->tmp->d,
-				(const Real*)sOld->d, (Real*)sNew->d, (const Real*)cg->residual->d, (Real*)cg->dst->d, (const Real*)cg->A0->d, sc, ctx->partials, ctx->tickets + 2, dl);
+			if (cg->tma.on) {
+				const FusedTma& t = cg->tma;
+				k_matvec_fused_tma<Real, 6><<<t.ctas, kFusedThreads, t.smemBytes, ctx->stream>>>(t.mapR, t.mapS[even ? 0 : 1], t.mapX, t.mapM, d, t.tilesX, t.tiles, t.chunk, t.nitems,
+					(Real*)cg->tmp->d, (Real*)sNew->d, (Real*)cg->dst->d, (const Real*)cg->A0->d, sc, ctx->partials, ctx->tickets + 2, dl);
+				ctx->lastMatvecKernel = 4;
+			} else {
+				k_matvec_fused<Real, V><<<cg->fusedGrid, block, 0, ctx->stream>>>(d, cg->fusedNvx, cg->fusedChunk, (const int*)cg->cmask->d, (Real*)cg->tmp->d,
+					(const Real*)sOld->d, (Real*)sNew->d, (const Real*)cg->residual->d, (Real*)cg->dst->d, (const Real*)cg->A0->d, sc, ctx->partials, ctx->tickets + 2, dl);
+				ctx->lastMatvecKernel = 3;
+			}
 			MP_CHECK_LAUNCH(ctx);
-			ctx->lastMatvecKernel = 3;
 			if (dl) MP_TRY(cgCombine(ctx, cg->dst, cg->dSc, 0, 0));
 			PROF(1);
 			const unsigned int blocks = streamBlocks(ctx, nOwn / V);
@@ -852,11 +911,9 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 	return MP_OK;
 }
 
-// Fused loop: x lags one update behind (k_matvec_fused applies alpha_{k-1} s_{k-1} while forming s_k) and the live search vector
-// alternates between search / search2.  This brings the caller-visible state to what GridCg::iterate leaves behind
-// (conjugategrad.cpp:254-257,:283): x holds every update, and -- when `syncSearch` -- the caller's search grid holds the live vector.
-// k_flush_x clears xPending, so the next fused matvec adds alpha_prev = 0.
-static int cgFlushFused(mp_cg* cg, bool syncSearch) {
+// Fused loop: x lags one update behind (k_matvec_fused applies alpha_{k-1} s_{k-1} while forming s_k); k_flush_x applies the pending
+// update and clears xPending, so a following fused matvec adds alpha_prev = 0.
+static int cgFlushFused(mp_cg* cg) {
 	mp_context* ctx = cg->ctx;
 	const Dims d = dimsOf(cg->flags);
 	const IndexInt nOwn = d.i1 - d.i0;
@@ -865,8 +922,27 @@ static int cgFlushFused(mp_cg* cg, bool syncSearch) {
 			(const Real*)cg->search2->d + d.i0, (CgScal<Real>*)cg->dSc, ctx->tickets + 8);
 		MP_CHECK_LAUNCH(ctx);
 	});
-	// enqueued iteration q (0-based) writes search2 when q is even: after an odd number of enqueues the live vector is in search2
-	if (syncSearch && (cg->fusedEnq & 1)) MP_CUDA(cudaMemcpyAsync(cg->search->d, cg->search2->d, cg->search->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	return MP_OK;
+}
+// Stepwise callers (GridCg::iterate driven by solvePressureSystem pressure.cpp:436-439, cgSolveWE, the VIC solve) see x, residual and
+// the search grid after EVERY call.  The fused loop is one phase behind the reference there: it forms s_k = r_k + beta_k s_{k-1} at the
+// START of iteration k, the reference at the end of iteration k-1 (UpdateSearchVec conjugategrad.cpp:283).  Leaving the fused loop
+// therefore applies the pending x-update and that search-vector update into the caller's search grid (same operands, same bits); the
+// three-kernel loop continues from there.
+static int cgUnfuse(mp_cg* cg) {
+	mp_context* ctx = cg->ctx;
+	const Dims d = dimsOf(cg->flags);
+	const IndexInt nOwn = d.i1 - d.i0;
+	MP_TRY(cgFlushFused(cg));
+	// enqueued fused iteration q (0-based) wrote its search vector to search2 when q is even
+	if (cg->fusedEnq & 1) MP_CUDA(cudaMemcpyAsync(cg->search->d, cg->search2->d, cg->search->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	DISPATCH_RV(cg->dst, {
+		k_update_search<Real, V><<<streamBlocks(ctx, nOwn / V), 256, 0, ctx->stream>>>(nOwn, (Real*)cg->search->d + d.i0, (const Real*)cg->residual->d + d.i0,
+			(const CgScal<Real>*)cg->dSc, HaloOut(), (IndexInt)d.sx * d.sy);
+		MP_CHECK_LAUNCH(ctx);
+	});
+	if (d.world > 1) MP_TRY(cgHalo(cg, cg->search));
+	cg->fused = false;
 	return MP_OK;
 }
 
@@ -897,7 +973,7 @@ int mp_cg_run(mp_cg* cg, int maxIter) {
 		slot = other;
 	}
 	for (int q = 0; q < 2; q++) if (pending[q]) { MP_TRY(cgPollWait(cg, q)); pending[q] = false; }
-	if (cg->fused) MP_TRY(cgFlushFused(cg, false));      // the x-update of the last executed iteration is still pending
+	if (cg->fused) MP_TRY(cgFlushFused(cg));      // the x-update of the last executed iteration is still pending
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));      // the state after everything that was enqueued
 	MP_TRY(mp_dist_p2p_check(ctx));
 	if (cg->pcMethod == MP_CG_PC_MICP) MP_TRY(mp_mic_check_stall(ctx));
@@ -947,6 +1023,7 @@ int mp_cg_destroy(mp_cg* cg) {
 	cudaFree(cg->dSc); cudaFreeHost(cg->hSc); cudaEventDestroy(cg->pollEv[0]); cudaEventDestroy(cg->pollEv[1]);
 	if (cg->cmask) mp_grid_destroy(cg->cmask);
 	if (cg->search2) mp_grid_destroy(cg->search2);
+	if (cg->tma.mask16) mp_grid_destroy(cg->tma.mask16);
 	delete cg; return MP_OK;
 }
 int mp_cg_set_accuracy(mp_cg* cg, double accuracy) { cg->accuracy = accuracy; return MP_OK; }
@@ -974,15 +1051,15 @@ int mp_cg_set_mg_preconditioner(mp_cg* cg, int method, mp_mg* mg) {
 	if (!mg) MP_FAIL(MP_ERR_INVALID, "setMGPreconditioner: mg is NULL");
 	cg->pcMethod = method; cg->mg = mg; return MP_OK;
 }
-int mp_cg_force_reinit(mp_cg* cg) { cg->inited = false; cg->finished = false; return MP_OK; }
+int mp_cg_force_reinit(mp_cg* cg) { cg->inited = false; cg->finished = false; cg->stepwise = false; return MP_OK; }
 
 int mp_cg_iterate(mp_cg* cg, int* keepGoing) {
 	mp_context* ctx = cg->ctx;
 	MP_CUDA(cudaSetDevice(ctx->device));
-	if (!cg->inited) MP_TRY(cgDoInit(cg));
+	if (!cg->inited) { cg->stepwise = true; MP_TRY(cgDoInit(cg)); }      // stepwise from the start: three-kernel loop
 	if (cg->finished) { if (keepGoing) *keepGoing = 0; return cgFinishCheck(cg); }     // converged: nothing is enqueued any more
+	if (cg->fused) MP_TRY(cgUnfuse(cg));                                   // a solve() ran before: leave the fused loop's lagged state
 	MP_TRY(cgEnqueueIteration(cg));
-	if (cg->fused) MP_TRY(cgFlushFused(cg, true));          // stepwise callers read x (and own the search grid) after every call
 	MP_TRY(cgPollAsync(cg, 0)); MP_TRY(cgPollWait(cg, 0));
 	if (keepGoing) *keepGoing = cg->finished ? 0 : 1;      // once converged, further calls are no-ops returning false
 	return cgFinishCheck(cg);

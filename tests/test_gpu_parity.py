@@ -220,10 +220,11 @@ def test_gridcg_iterate_stepwise(mf):
 @pytest.mark.parametrize("prec", [4, 8])
 def test_gridcg_iterate_state_after_every_call(mf, prec, monkeypatch):
     """GridCg::iterate (conjugategrad.cpp:237-299) as solvePressureSystem (pressure.cpp:436-439) and the VIC solve drive it: after EVERY
-    call x holds all updates and the caller's search grid the live search vector.  The fused PcNone loop keeps x one update behind and
-    ping-pongs the search vector internally; mp_cg_iterate flushes both.  x after n calls == the oracle's x after maxIter = n (float:
-    bit for bit), and x / residual / search of the fused loop == those of the three-kernel loop, bit for bit, including a stop before
-    convergence and the calls after convergence."""
+    call x holds all updates, residual the current residual and the caller's search grid the NEXT search vector (UpdateSearchVec :283).
+    The fused PcNone loop of solve() keeps x one update behind and forms the search vector one phase later, so iterate() runs the
+    three-kernel loop and, after a solve(), first leaves the fused state (cgUnfuse).  Checked: x after n calls == the oracle's x after
+    maxIter = n (float: bit for bit); solve(5) + iterate() x 6 == iterate() x 11 for x, residual and search, bit for bit; a stop before
+    convergence; the calls after convergence are no-ops returning False."""
     from mantaflow_b200 import cg
     flags, vel, _ = SCENES["smoke24"](prec)
     O = oracle(prec)
@@ -232,7 +233,7 @@ def test_gridcg_iterate_state_after_every_call(mf, prec, monkeypatch):
     acc = 1e-5 if prec == 4 else 1e-10
     x_full, it_full, _ = O.cg_solve(flags, rhs_o, *A_o, pc=0, accuracy=acc, maxIter=3000)
 
-    def run(fused, ncalls):
+    def run(ncalls, solve_first=0, fused=True):
         monkeypatch.setenv("MP_CG_FUSED", "1" if fused else "0")
         s = mk(mf, flags.shape, prec)
         F = mf.FlagGrid(s, flags)
@@ -242,26 +243,37 @@ def test_gridcg_iterate_state_after_every_call(mf, prec, monkeypatch):
         g.setAccuracy(acc)
         g.setUseL2Norm(False)
         out = []
-        for n in range(1, ncalls + 1):
+        if solve_first:
+            g.solve(solve_first)          # the fused loop (when enabled), stopped by maxIter before convergence
+            assert g.getIterations() == solve_first
+            out.append((x.numpy().copy(), None, None, solve_first, True))
+        for n in range(ncalls):
             more = g.iterate()
             out.append((x.numpy().copy(), r.numpy().copy(), se.numpy().copy(), g.getIterations(), more))
         return out
 
     nfirst = 11
-    fused, plain = run(True, nfirst), run(False, nfirst)
+    plain = run(nfirst)
     for n in range(1, nfirst + 1):
-        xf, rf, sf, itf, moref = fused[n - 1]
         xp, rp, sp, itp, morep = plain[n - 1]
-        assert itf == itp == n and moref and morep
-        assert np.array_equal(xf, xp) and np.array_equal(rf, rp) and np.array_equal(sf, sp), ("fused vs three-kernel loop after call", n)
+        assert itp == n and morep
         x_o, it_o, _ = O.cg_solve(flags, rhs_o, *A_o, pc=0, accuracy=acc, maxIter=n)
         assert it_o == n
         if prec == 4:
-            assert np.array_equal(xf, x_o), ("x after iterate() call", n)
+            assert np.array_equal(xp, x_o), ("x after iterate() call", n)
         else:
-            assert rel_l2(xf, x_o) <= 1e-12
+            assert rel_l2(xp, x_o) <= 1e-12
+    for fused in (True, False):
+        mixed = run(nfirst - 5, solve_first=5, fused=fused)
+        # solve(5) alone: x complete (the fused loop's pending update flushed)
+        assert np.array_equal(mixed[0][0], plain[4][0]), ("x after solve(5)", fused)
+        for q in range(1, nfirst - 5 + 1):
+            xm, rm, sm, itm, morem = mixed[q]
+            xp, rp, sp, itp, morep = plain[4 + q]
+            assert itm == itp and morem
+            assert np.array_equal(xm, xp) and np.array_equal(rm, rp) and np.array_equal(sm, sp), ("solve(5) then iterate() vs iterate() only", fused, q)
     # to convergence and three calls beyond: x stays the converged solution, iterate() keeps returning False
-    tail = run(True, it_full + 3)
+    tail = run(it_full + 3)
     its = [t[3] for t in tail]
     assert abs(its[-1] - it_full) <= 1 and its[-1] == its[-2] == its[-3]
     assert not tail[-1][4] and not tail[-2][4]
@@ -415,8 +427,13 @@ def test_matvec_kernel_selection_and_agreement(mf, prec, monkeypatch):
     F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
     mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
     info = mf.lastSolveInfo()
-    assert info["matvecKernel"] == 3 and info["iterations"] == it_o      # PcNone on a 0/-1 matrix: the fused two-kernel iteration
+    assert info["matvecKernel"] == 4 and info["iterations"] == it_o      # PcNone on a 0/-1 matrix: the fused two-kernel iteration, TMA-staged
     p_fused = P.numpy().copy()
+    monkeypatch.setenv("MP_CG_FUSED", "1")                                # the fused iteration with plain loads
+    V.copyFromArray(vel)
+    mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
+    info = mf.lastSolveInfo()
+    assert info["matvecKernel"] == 3 and info["iterations"] == it_o and np.array_equal(P.numpy(), p_fused)
     monkeypatch.setenv("MP_CG_FUSED", "0")                                # the three-kernel loop with the coupling-mask matvec
     V.copyFromArray(vel)
     mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
@@ -436,6 +453,36 @@ def test_matvec_kernel_selection_and_agreement(mf, prec, monkeypatch):
     v2 = vel2.copy()
     p2, it2, _ = O.solve_pressure(flags2, v2, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0)
     assert abs(mf.lastSolveInfo()["iterations"] - it2) <= 1 and rel_l2(P2.numpy(), p2) <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("shape,liquid,fix", [((20, 24, 32), False, False), ((70, 41, 144), False, True), ((37, 19, 264), True, False),
+                                              ((90, 64, 128), True, True), ((12, 9, 8), False, False)])
+def test_fused_tma_matvec_equals_three_kernel_loop(mf, shape, liquid, fix, prec, monkeypatch):
+    """k_matvec_fused_tma (the TMA-staged persistent form of the fused PcNone iteration) against the three-kernel loop on the same
+    system: tiles cut by the grid in x and y, several tiles and z-chunks, the 2-byte matrix with integer diagonals (smoke) and with
+    ghost-fluid diagonals / a pinned cell read from A0 (liquid, zeroPressureFixing).  Same iteration count, pressure and velocity bit
+    for bit; iteration count within 1 of the oracle's."""
+    flags, vel, phi = random_domain(shape, prec, seed=shape[2] + 7 * prec, liquid=liquid)
+    O = oracle(prec)
+    acc = 1e-5 if prec == 4 else 1e-11
+    v_o = vel.copy()
+    p_o, it_o, _ = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0, zeroPressureFixing=fix)
+    s = mk(mf, flags.shape, prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+    PH = mf.RealGrid(s, phi) if phi is not None else None
+    res = {}
+    for mode, kernel in (("2", 4), ("1", 3), ("0", 2)):
+        monkeypatch.setenv("MP_CG_FUSED", mode)
+        V.copyFromArray(vel)
+        mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=0, zeroPressureFixing=fix)
+        info = mf.lastSolveInfo()
+        assert info["matvecKernel"] == kernel, (mode, info["matvecKernel"])
+        res[mode] = (info["iterations"], P.numpy().copy(), V.numpy().copy())
+    assert res["2"][0] == res["0"][0] == res["1"][0] and abs(res["2"][0] - it_o) <= 1
+    assert np.array_equal(res["2"][1], res["0"][1]) and np.array_equal(res["2"][2], res["0"][2])
+    assert np.array_equal(res["1"][1], res["0"][1])
+    assert rel_l2(res["2"][1], p_o) <= TOL[prec] and rel_l2(res["2"][2], v_o) <= TOL[prec]
 
 
 def random_domain(shape, prec, seed, liquid=False, outflow=False):
