@@ -712,10 +712,10 @@ static int cgHalo(mp_cg* cg, mp_grid* g) {       // one-plane ghost exchange of 
 }
 
 // tensor maps over residual / search / search2 / x / mask16 and the item decomposition of k_matvec_fused_tma
-template <typename Real> static int cgFusedTmaSetupT(mp_cg* cg, const Dims& d) {
-	typedef FusedTmaGeom<Real> G;
+static const int kFusedStages = 6;
+template <typename Real, int TY> static int cgFusedTmaSetupT(mp_cg* cg, const Dims& d) {
+	typedef FusedTmaGeom<Real, TY> G;
 	mp_context* ctx = cg->ctx; FusedTma& t = cg->tma;
-	constexpr int NSTAGE = 6;
 	const CUtensorMapDataType dt = sizeof(Real) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
 	const int es = (int)sizeof(Real);
 	MP_TRY(encodeMap3D(&t.mapR, cg->residual->d, es, dt, d.sx, d.sx, d.sy, d.sz, G::BX, G::BY));
@@ -723,12 +723,14 @@ template <typename Real> static int cgFusedTmaSetupT(mp_cg* cg, const Dims& d) {
 	MP_TRY(encodeMap3D(&t.mapS[1], cg->search2->d, es, dt, d.sx, d.sx, d.sy, d.sz, G::BX, G::BY));
 	MP_TRY(encodeMap3D(&t.mapX, cg->dst->d, es, dt, d.sx, d.sx, d.sy, d.sz, G::TX, G::TY));
 	MP_TRY(encodeMap3D(&t.mapM, t.mask16->d, 2, CU_TENSOR_MAP_DATA_TYPE_UINT16, d.sx, t.pitch, d.sy, d.sz, G::TX, G::TY));
+	t.ty = TY;
 	t.tilesX = (d.sx + G::TX - 1) / G::TX; t.tiles = t.tilesX * ((d.sy + G::TY - 1) / G::TY);
-	t.smemBytes = NSTAGE * G::stageBytes + 2 * NSTAGE * 8 + 128;
-	MP_CUDA(cudaFuncSetAttribute(k_matvec_fused_tma<Real, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smemBytes));
+	t.smemBytes = kFusedStages * G::stageBytes + 2 * kFusedStages * 8;
+	MP_CUDA(cudaFuncSetAttribute(k_matvec_fused_tma<Real, TY, kFusedStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smemBytes));
 	int perSm = 0;
-	MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_matvec_fused_tma<Real, NSTAGE>, kFusedThreads, t.smemBytes));
+	MP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_matvec_fused_tma<Real, TY, kFusedStages>, G::threads, t.smemBytes));
 	if (perSm < 1) { t.on = false; return MP_OK; }
+	if (perSm > G::ctasPerSm) perSm = G::ctasPerSm;
 	const int G_ = ctx->smCount * perSm;
 	fusedTmaDecompose(t.tiles, d.ke - d.kb, G_, &t.chunk, &t.nitems);
 	t.ctas = t.nitems < G_ ? t.nitems : G_;
@@ -736,7 +738,14 @@ template <typename Real> static int cgFusedTmaSetupT(mp_cg* cg, const Dims& d) {
 	return MP_OK;
 }
 static int cgFusedTmaSetup(mp_cg* cg, const Dims& d) {
-	return cg->dst->prec == 4 ? cgFusedTmaSetupT<float>(cg, d) : cgFusedTmaSetupT<double>(cg, d);
+	const int ty = getenv("MP_TMA_TY") ? atoi(getenv("MP_TMA_TY")) : 16;
+	if (cg->dst->prec == 4) return ty == 8 ? cgFusedTmaSetupT<float, 8>(cg, d) : cgFusedTmaSetupT<float, 16>(cg, d);
+	return ty == 8 ? cgFusedTmaSetupT<double, 8>(cg, d) : cgFusedTmaSetupT<double, 16>(cg, d);
+}
+template <typename Real, int TY> static void cgFusedTmaLaunch(mp_cg* cg, const Dims& d, bool even, Real* sNew, double* dl) {
+	mp_context* ctx = cg->ctx; const FusedTma& t = cg->tma;
+	k_matvec_fused_tma<Real, TY, kFusedStages><<<t.ctas, FusedTmaGeom<Real, TY>::threads, t.smemBytes, ctx->stream>>>(t.mapR, t.mapS[even ? 0 : 1], t.mapX, t.mapM, d,
+		t.tilesX, t.tiles, t.chunk, t.nitems, (Real*)cg->tmp->d, sNew, (Real*)cg->dst->d, (const Real*)cg->A0->d, (CgScal<Real>*)cg->dSc, ctx->partials, ctx->tickets + 2, dl);
 }
 
 static int cgDoInit(mp_cg* cg) {    // doInit conjugategrad.cpp:209-235
@@ -848,9 +857,7 @@ static int cgEnqueueIteration(mp_cg* cg, int iterIndex = -1) {   // iterate conj
 		DISPATCH_RV(cg->dst, {
 			CgScal<Real>* sc = (CgScal<Real>*)cg->dSc;
 			if (cg->tma.on) {
-				const FusedTma& t = cg->tma;
-				k_matvec_fused_tma<Real, 6><<<t.ctas, kFusedThreads, t.smemBytes, ctx->stream>>>(t.mapR, t.mapS[even ? 0 : 1], t.mapX, t.mapM, d, t.tilesX, t.tiles, t.chunk, t.nitems,
-					(Real*)cg->tmp->d, (Real*)sNew->d, (Real*)cg->dst->d, (const Real*)cg->A0->d, sc, ctx->partials, ctx->tickets + 2, dl);
+				if (cg->tma.ty == 8) cgFusedTmaLaunch<Real, 8>(cg, d, even, (Real*)sNew->d, dl); else cgFusedTmaLaunch<Real, 16>(cg, d, even, (Real*)sNew->d, dl);
 				ctx->lastMatvecKernel = 4;
 			} else {
 				k_matvec_fused<Real, V><<<cg->fusedGrid, block, 0, ctx->stream>>>(d, cg->fusedNvx, cg->fusedChunk, (const int*)cg->cmask->d, (Real*)cg->tmp->d,

@@ -23,9 +23,9 @@
 #include "mp_common.cuh"
 #include "mp_cg.cuh"
 
-template <typename Real> struct FusedTmaGeom {
+template <typename Real, int TY_> struct FusedTmaGeom {
 	static constexpr int V = 16 / (int)sizeof(Real);       // cells per 16-byte vector
-	static constexpr int TX = 32 * V, TY = 8;              // tile: one warp row of vectors x 8 rows
+	static constexpr int TX = 32 * V, TY = TY_;            // tile: one warp row of vectors x TY rows (one consumer warp per row)
 	static constexpr int HX = V;                           // x halo in cells (TMA boxes are 16-byte granular)
 	static constexpr int BX = TX + 2 * HX, BY = TY + 2;    // staged box of r / s_old
 	static constexpr int boxBytes = BX * BY * (int)sizeof(Real);
@@ -35,8 +35,9 @@ template <typename Real> struct FusedTmaGeom {
 	static constexpr int offS = boxPad, offX = 2 * boxPad, offM = 2 * boxPad + xBytes;
 	static constexpr int stageBytes = 2 * boxPad + xBytes + (mBytes + 127) / 128 * 128;
 	static constexpr int txEdge = 2 * boxBytes, txInterior = 2 * boxBytes + xBytes + mBytes;
+	static constexpr int consumers = 32 * TY, threads = consumers + 32;      // TY consumer warps + 1 producer warp
+	static constexpr int ctasPerSm = TY <= 8 ? 2 : 1;
 };
-static const int kFusedConsumers = 256, kFusedThreads = 288;       // 8 consumer warps + 1 producer warp
 
 // ---------------------------------------------------------------- PTX wrappers (mbarrier, TMA)
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,14 +59,14 @@ template <typename Real, int V> struct alignas(sizeof(Real) * V) TVec { Real v[V
 template <int V> struct alignas(2 * V) MVec { unsigned short v[V]; };
 
 // ---------------------------------------------------------------- the kernel
-template <typename Real, int NSTAGE>
-__global__ void __launch_bounds__(kFusedThreads, 2) k_matvec_fused_tma(
+template <typename Real, int TY, int NSTAGE>
+__global__ void __launch_bounds__((FusedTmaGeom<Real, TY>::threads), (FusedTmaGeom<Real, TY>::ctasPerSm)) k_matvec_fused_tma(
 	const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapM,
 	Dims d, int tilesX, int tiles, int chunk, int nitems,
 	Real* __restrict__ dst, Real* __restrict__ sNew, Real* __restrict__ x, const Real* __restrict__ A0,
 	CgScal<Real>* sc, double* partials, unsigned int* ticket, double* distLocal)
 {
-	typedef FusedTmaGeom<Real> G;
+	typedef FusedTmaGeom<Real, TY> G;
 	constexpr int V = G::V;
 	typedef TVec<Real, V> Vec;
 	if (sc->done) return;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_matvec_fused_tma(
 	uint64_t* const bars = (uint64_t*)(smem + (size_t)NSTAGE * G::stageBytes);      // full[NSTAGE], empty[NSTAGE]
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	if (tid == 0) {
-		for (int q = 0; q < NSTAGE; q++) { mbarInit(smemAddr(bars + q), 1); mbarInit(smemAddr(bars + NSTAGE + q), kFusedConsumers / 32); }
+		for (int q = 0; q < NSTAGE; q++) { mbarInit(smemAddr(bars + q), 1); mbarInit(smemAddr(bars + NSTAGE + q), G::consumers / 32); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_matvec_fused_tma(
 	const IndexInt Y = d.Y, Z = d.Z;
 	double acc = 0.0;
 
-	if (warp == kFusedConsumers / 32) {
+	if (warp == G::consumers / 32) {
 		// ------------------------------------------------ producer: one lane walks the same item / plane sequence as the consumers
 		if (lane == 0) {
 			int slot = 0; uint32_t phase = 0;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) k_matvec_fused_tma(
 		#undef RELEASE
 	}
 	double v[1] = { acc }; const bool isMax[1] = { false }; double fin[1];
-	if (blockReduceFinalL<1>(v, isMax, partials, ticket, fin, (unsigned)tid, kFusedThreads, blockIdx.x, gridDim.x) && tid == 0) {
+	if (blockReduceFinalL<1>(v, isMax, partials, ticket, fin, (unsigned)tid, G::threads, blockIdx.x, gridDim.x) && tid == 0) {
 		if (distLocal) distLocal[0] = fin[0]; else cgFinA<Real>(sc, fin[0]);
 	}
 }
@@ -217,7 +218,7 @@ struct FusedTma {
 	bool on = false;
 	CUtensorMap mapR, mapS[2], mapX, mapM;      // mapS[0]: the caller's search grid, mapS[1]: search2
 	mp_grid* mask16 = nullptr;                  // 2 bytes per cell, row pitch rounded up to 8 cells (backed by a pooled 4-byte grid)
-	int pitch = 0, tilesX = 0, tiles = 0, chunk = 0, nitems = 0, ctas = 0, smemBytes = 0;
+	int pitch = 0, ty = 16, tilesX = 0, tiles = 0, chunk = 0, nitems = 0, ctas = 0, smemBytes = 0;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,

@@ -1,0 +1,100 @@
+"""GPU: parity at BASELINE.json's OWN grid sizes, against the UNMODIFIED reference compiled into oracle/_ref (the C restatement only when
+_ref is absent): config 1 (scenes/simpleplume.py geometry 64x96x64, PcMIC / PcMGStatic), config 2 (scenes/benchmark_dam.py geometry
+88x83x33 liquid with the free surface as ghost-fluid Dirichlet cells, PcMIC / PcMGDynamic), config 3 (256^3 smoke plume with obstacle,
+PcNone vs PcMIC vs PcMGStatic, cgAccuracy 1e-4) and a 128^3 cut of it in both precisions.  Launch geometry is size dependent (z-chunks,
+TMA tile grid, MIC warp columns, the multigrid's level count), so the small parity grids of test_gpu_parity.py do not cover it.
+
+Per case: right-hand side and A0/Ai/Aj/Ak bit for bit in the same Real; iteration count within 1 (PcNone, PcMIC -- both are the
+reference's arithmetic in the reference's order) or within 1 (multigrid, same V-cycle); converged pressure within relative L2 1e-4
+(float) / 1e-10 (double); max |div| of the projected field at or below the reference's (north_star).
+The reference side costs ~70 s of host CPU at 256^3 on the GPU box's cores (profiles/r1_configs.md)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from mantaflow_b200 import scenes  # noqa: E402
+
+TOL = {4: 1e-4, 8: 1e-10}
+
+
+def _ref(prec):
+    from oracle.oracle_api import Oracle, available
+    return Oracle("reference" if available("reference", prec) else "port", prec)
+
+
+def rel_l2(a, b):
+    d = np.linalg.norm((a.astype(np.float64) - b.astype(np.float64)).ravel())
+    return float(d / max(np.linalg.norm(b.astype(np.float64).ravel()), 1e-300))
+
+
+def demean(p, flags):
+    fl = (flags & 1) != 0
+    q = p.astype(np.float64).copy()
+    q[fl] -= q[fl].mean()
+    return q
+
+
+CASES = {
+    # name: (scene builder -> flags, vel, phi), prec, [(preconditioner, cgAccuracy, cgMaxIterFac, zeroPressureFixing)]
+    "cfg1_64x96x64": (lambda prec: scenes.smoke_plume((64, 96, 64), prec, obstacle=False) + (None,), 4, [(1, 1e-3, 1.5, False), (3, 1e-3, 1.5, True)]),
+    "cfg2_88x83x33_phi": (lambda prec: scenes.liquid_basin((88, 83, 33), prec), 4, [(1, 1e-3, 1.5, False), (2, 1e-3, 1.5, False)]),
+    "smoke128_f32": (lambda prec: scenes.smoke_plume(128, prec) + (None,), 4, [(0, 1e-4, 99, False), (1, 1e-4, 99, False), (3, 1e-4, 99, True)]),
+    "smoke128_f64": (lambda prec: scenes.smoke_plume(128, prec) + (None,), 8, [(0, 1e-4, 99, False), (1, 1e-4, 99, False), (3, 1e-4, 99, True)]),
+    "cfg3_256_f32": (lambda prec: scenes.smoke_plume(256, prec) + (None,), 4, [(0, 1e-4, 99, False), (1, 1e-4, 99, False), (3, 1e-4, 99, True)]),
+}
+
+
+def _ref_solve(O, flags, vel, phi, pc, acc, fac, fix):
+    v = vel.copy()
+    if pc == 0:
+        # the reference plugin asserts on PcNone in 3-D: rhs + matrix + GridCg + correctVelocity driven directly
+        rhs, _, _ = O.compute_rhs(flags, v, phi=phi)
+        A = O.make_matrix(flags, phi=phi)
+        p, it, rn = O.cg_solve(flags, rhs, *A, pc=0, accuracy=acc, maxIter=int(np.float32(fac) * max(flags.shape)))
+        O.correct_velocity(flags, v, p, phi=phi)
+    else:
+        p, it, rn = O.solve_pressure(flags, v, phi=phi, cgAccuracy=acc, cgMaxIterFac=fac, preconditioner=pc, zeroPressureFixing=fix)
+    return p, v, it
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_baseline_config_against_reference(name):
+    import mantaflow_b200 as mf
+    from cuda_impl import CudaImpl
+    make, prec, runs = CASES[name]
+    flags, vel, phi = make(prec)
+    O, I = _ref(prec), CudaImpl(prec)
+    # assembly: bit for bit in the same Real
+    rhs_o, sum_o, cnt_o = O.compute_rhs(flags, vel, phi=phi)
+    rhs_g, sum_g, cnt_g = I.compute_rhs(flags, vel, phi=phi)
+    assert np.array_equal(rhs_g, rhs_o) and cnt_g == cnt_o, name
+    A_o, A_g = O.make_matrix(flags, phi=phi), I.make_matrix(flags, phi=phi)
+    for q, nm in enumerate(("A0", "Ai", "Aj", "Ak")):
+        assert np.array_equal(A_g[q], A_o[q]), (name, nm)
+    del A_o, A_g, rhs_o, rhs_g
+    sz, sy, sx = flags.shape
+    s = mf.Solver(gridSize=(sx, sy, sz), dim=3, prec=prec)
+    F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+    PH = mf.RealGrid(s, phi) if phi is not None else None
+    report = []
+    for pc, acc, fac, fix in runs:
+        p_o, v_o, it_o = _ref_solve(O, flags, vel, phi, pc, acc, fac, fix)
+        V.copyFromArray(vel)
+        mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=fac, preconditioner=pc, zeroPressureFixing=fix)
+        info = mf.lastSolveInfo()
+        p_g, v_g = P.numpy(), V.numpy()
+        div_o, div_g = scenes.max_divergence(flags, v_o), scenes.max_divergence(flags, v_g)
+        e = rel_l2(demean(p_g, flags), demean(p_o, flags)) if (fix or phi is None) else rel_l2(p_g, p_o)
+        report.append((pc, info["iterations"], it_o, e, div_g, div_o))
+        print("%s %s pc %d: iterations %d (reference %d) pressure rel-L2 %.2e max|div| %.3e (reference %.3e)" % (name, O.kind, pc, info["iterations"], it_o, e, div_g, div_o))
+        assert abs(info["iterations"] - it_o) <= 1, report[-1]
+        assert e <= TOL[prec], report[-1]
+        assert rel_l2(v_g, v_o) <= TOL[prec], report[-1]
+        if phi is None:
+            assert div_g <= div_o * (1 + 1e-3) + (1e-7 if prec == 4 else 1e-15), report[-1]
+        if prec == 4 and pc in (0, 1):
+            # float, reference arithmetic in the reference's order: the same bits
+            assert info["iterations"] == it_o and np.array_equal(p_g, p_o), report[-1]
+    mf.releaseMG(s)
+    s.close()
