@@ -13,8 +13,8 @@
 //                           monotone closure and therefore order independent: k_mg_select iterates it in parallel
 //                           to the fixed point.  If fine vertices with >= 2 free interpolation vertices remain
 //                           (isolated features), the order-dependent second phase is needed: that level is then
-//                           redone by the exact serial algorithm on the host (hostCoarsen) -- same result as the
-//                           reference in every case, fast in the common one.
+//                           redone serially on the host (mp_mg_coarsen.h: per-count stacks with lazy deletion give the
+//                           reference's visiting order) -- same result as the reference in every case, fast in the common one.
 //   k_mg_galerkin1/k_mg_galerkinN  knGenCoarseGridOperator :580-657 (one thread per stored stencil entry, the
 //                           reference's accumulation order per entry)
 // V-cycle (doVCycle :448-504)
@@ -23,6 +23,7 @@
 //   k_mg_restrict                   knRestrict :904-927          k_mg_interp_add  knInterpolate + knAddAssign :934-954,:445
 //   k_mg_coarse_cg                  solveCG :796-902 (double Jacobi-PCG, one CTA; block reductions in fixed order)
 #include "mp_common.cuh"
+#include "mp_mg_coarsen.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -128,63 +129,7 @@ __global__ void __launch_bounds__(256) k_mg_activate_coarse(signed char* t, int 
 	if (i < n) t[i] = (t[i] == vtZero) ? vtActive : vtInactive;
 }
 
-// exact serial algorithm (multigrid.cpp:59-203,:520-578) for levels where the parallel closure leaves work
-namespace {
-struct HEntry { int key, prev, next; };
-struct NKMinHeap {
-	int N, K, size, minKey; std::vector<HEntry> e;
-	NKMinHeap(int n, int k) : N(n), K(k), size(0), minKey(-1), e((size_t)n + k, HEntry{ -1, -1, -1 }) {}
-	int getKey(int id) const { return e[K + id].key; }
-	void setKey(int id, int key) {
-		const int kid = K + id;
-		if (e[kid].key == key) return;
-		if (e[kid].key != -1) {
-			const int pred = e[kid].prev, succ = e[kid].next;
-			e[pred].next = succ; if (succ != -1) e[succ].prev = pred;
-			const int removed = e[kid].key;
-			if (removed == minKey) { if (size == 1) minKey = -1; else for (; minKey < K; minKey++) if (e[minKey].next != -1) break; }
-			size--;
-		}
-		e[kid].key = key;
-		if (key == -1) { e[kid].next = e[kid].prev = -1; return; }
-		size++;
-		minKey = (minKey == -1) ? key : std::min(minKey, key);
-		const int tmp = e[key].next;
-		e[key].next = kid; e[kid].prev = key; e[kid].next = tmp; if (tmp != -1) e[tmp].prev = kid;
-	}
-	int popMin() {
-		const int kid = e[minKey].next, id = kid - K;
-		const int pred = e[kid].prev, succ = e[kid].next;
-		e[pred].next = succ; if (succ != -1) e[succ].prev = pred;
-		e[kid] = HEntry{ -1, -1, -1 }; size--;
-		if (size == 0) minKey = -1; else for (; minKey < K; minKey++) if (e[minKey].next != -1) break;
-		return id;
-	}
-};
-void hostCoarsen(const LvlGeom& gf, const LvlGeom& gc, bool is3D, const std::vector<signed char>& tf, std::vector<signed char>& tc) {
-	std::fill(tc.begin(), tc.end(), (signed char)vtFree);
-	NKMinHeap heap(gf.n, is3D ? 9 : 5);
-	for (int v = 0; v < gf.n; v++) if (tf[v] != vtInactive) { int x, y, z; vecIdx(gf, v, x, y, z); heap.setKey(v, 1 << ((x % 2) + (y % 2) + (z % 2))); }
-	while (heap.size > 0) {
-		const int v = heap.popMin();
-		int x, y, z; vecIdx(gf, v, x, y, z);
-		bool vdone = false;
-		for (int iz = z / 2; iz <= (z + 1) / 2; iz++) for (int iy = y / 2; iy <= (y + 1) / 2; iy++) for (int ix = x / 2; ix <= (x + 1) / 2; ix++) {
-			const int i = linIdx(gc, ix, iy, iz);
-			if (tc[i] != vtFree) continue;
-			if (vdone) tc[i] = vtRemoved; else { tc[i] = vtZero; vdone = true; }
-			for (int rz = std::max(0, iz * 2 - 1); rz <= std::min(gf.sz - 1, iz * 2 + 1); rz++)
-			for (int ry = std::max(0, iy * 2 - 1); ry <= std::min(gf.sy - 1, iy * 2 + 1); ry++)
-			for (int rx = std::max(0, ix * 2 - 1); rx <= std::min(gf.sx - 1, ix * 2 + 1); rx++) {
-				const int r = linIdx(gf, rx, ry, rz);
-				const int key = heap.getKey(r);
-				if (key > 1) heap.setKey(r, key - 1); else if (key > -1) heap.setKey(r, -1);
-			}
-		}
-	}
-	for (auto& t : tc) t = (t == vtZero) ? vtActive : vtInactive;
-}
-}
+// levels where the parallel closure leaves work: the serial, order-dependent selection (mp_mg_coarsen.h)
 
 // ---------------------------------------------------------------- setA: Galerkin operators
 // level 1 from the 7-point level 0 along the precomputed paths (V)<-R-(U)<-A-(W)<-I-(N); thread = (coarse vertex, sc)
@@ -601,7 +546,7 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 			// order-dependent phase needed: redo this level with the exact serial algorithm
 			std::vector<signed char> tf(gf.n), tc(gc.n);
 			MP_CUDA(cudaMemcpy(tf.data(), m->type[l - 1], gf.n, cudaMemcpyDeviceToHost));
-			hostCoarsen(gf, gc, m->is3D != 0, tf, tc);
+			mgcoarsen::selectCoarseVertices(mgcoarsen::Dim3i{ gf.sx, gf.sy, gf.sz }, mgcoarsen::Dim3i{ gc.sx, gc.sy, gc.sz }, m->is3D != 0, tf, tc);
 			MP_CUDA(cudaMemcpy(m->type[l], tc.data(), gc.n, cudaMemcpyHostToDevice));
 			m->hostCoarsenLevels++;
 		} else {
