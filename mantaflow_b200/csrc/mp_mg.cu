@@ -46,6 +46,7 @@ struct mp_mg {
 	int prec, is3D, dim, stencil, stencil0, nlev;
 	LvlGeom geom[MG_MAXLVL];
 	void *A[MG_MAXLVL], *x[MG_MAXLVL], *b[MG_MAXLVL], *r[MG_MAXLVL];
+	void* Afull[MG_MAXLVL];          // levels > 0: the whole 27-point (9-point) row of every vertex, colour-major (see k_mg_build_full)
 	signed char* type[MG_MAXLVL];
 	double* cg;                      // 4 * n_coarsest doubles
 	CoarseningPath* dPaths; int npaths; int pathStart[15];
@@ -322,6 +323,199 @@ __global__ void __launch_bounds__(128) k_mg_residual0(LvlGeom g, int is3D, const
 	r[v] = sum;
 }
 
+// ---------------------------------------------------------------- level 0, 16 bytes of cells per thread
+// Same arithmetic as k_mg_smooth0 / k_mg_residual0 / k_mg_interp_add / k_mg_restrict, cell for cell and term for term; what changes is
+// the shape of the work: a thread owns V consecutive x-cells (one 16-byte vector), a CTA of 32 x 4 threads an x-y tile, and each CTA
+// marches through `kchunk` z-planes, so level 0 of a 512^3 grid is 32 k fat CTAs instead of 1 M one-cell-per-thread ones and every
+// array is read with 16-byte loads.  Needs sx % V == 0 (every row starts on a 16-byte boundary).
+template <typename Real, int V> struct alignas(sizeof(Real) * V) RVec { Real v[V]; };
+template <int V> struct alignas(V) CVec { signed char v[V]; };
+template <typename Real, int V> __device__ __forceinline__ RVec<Real, V> ldR(const Real* p) { return *reinterpret_cast<const RVec<Real, V>*>(p); }
+template <int V> __device__ __forceinline__ CVec<V> ldC(const signed char* p) { return *reinterpret_cast<const CVec<V>*>(p); }
+
+// MODE 0: one colour of the smoother; MODE 1: the first colour on x == 0 (x = b / A0 on that colour, zeros elsewhere: writes EVERY
+// cell, so the caller needs no memset of x); MODE 2: residual r = b - A x
+template <typename Real, int V, int MODE>
+__global__ void __launch_bounds__(128) k_mg_l0_vec(LvlGeom g, int is3D, int color, int nvx, int kchunk, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
+	const signed char* __restrict__ type, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int m = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+	if (m >= nvx || j >= g.sy) return;
+	const int k0 = blockIdx.z * kchunk, k1 = min(g.sz, k0 + kchunk);
+	const size_t n = (size_t)g.n; const int Y = g.sx, Z = g.sx * g.sy;
+	const int i0 = m * V;
+	for (int k = k0; k < k1; k++) {
+		const int v = i0 + Y * j + Z * k;
+		const CVec<V> ty = ldC<V>(type + v);
+		bool mine[V]; bool any = false;
+		#pragma unroll
+		for (int q = 0; q < V; q++) { mine[q] = ty.v[q] != vtInactive && (MODE == 2 || ((i0 + q + j + k + color) & 1) == 0); any |= mine[q]; }
+		if (MODE == 1) {
+			RVec<Real, V> out;
+			#pragma unroll
+			for (int q = 0; q < V; q++) out.v[q] = (Real)0;
+			if (any) {
+				const RVec<Real, V> bv = ldR<Real, V>(b + v), a0 = ldR<Real, V>(A + v);
+				#pragma unroll
+				for (int q = 0; q < V; q++) if (mine[q]) {
+					Real sum = bv.v[q];
+					if (bscale != (Real)0 && ty.v[q] == vtActiveTrivial) sum *= bscale;
+					out.v[q] = sum / a0.v[q];
+				}
+			}
+			*reinterpret_cast<RVec<Real, V>*>(x + v) = out;
+			continue;
+		}
+		if (!any) {
+			if (MODE == 2) { RVec<Real, V> z; for (int q = 0; q < V; q++) z.v[q] = (Real)0; *reinterpret_cast<RVec<Real, V>*>(r + v) = z; }      // inactive vertices: r stays 0
+			continue;
+		}
+		const RVec<Real, V> bv = ldR<Real, V>(b + v), a0 = ldR<Real, V>(A + v), ai = ldR<Real, V>(A + n + v), aj = ldR<Real, V>(A + 2 * n + v);
+		RVec<Real, V> xc = ldR<Real, V>(x + v);
+		RVec<Real, V> ajm, xym, xyp, ak, akm, xzm, xzp;
+		#pragma unroll
+		for (int q = 0; q < V; q++) { ajm.v[q] = xym.v[q] = xyp.v[q] = ak.v[q] = akm.v[q] = xzm.v[q] = xzp.v[q] = (Real)0; }
+		if (j > 0) { ajm = ldR<Real, V>(A + 2 * n + v - Y); xym = ldR<Real, V>(x + v - Y); }
+		if (j < g.sy - 1) xyp = ldR<Real, V>(x + v + Y);
+		if (is3D) {
+			ak = ldR<Real, V>(A + 3 * n + v);
+			if (k > 0) { akm = ldR<Real, V>(A + 3 * n + v - Z); xzm = ldR<Real, V>(x + v - Z); }
+			if (k < g.sz - 1) xzp = ldR<Real, V>(x + v + Z);
+		}
+		Real aim0 = (Real)0, xm0 = (Real)0, xpL = (Real)0;
+		if (i0 > 0) { aim0 = A[n + v - 1]; xm0 = x[v - 1]; }
+		if (i0 + V < g.sx) xpL = x[v + V];
+		RVec<Real, V> out = xc;
+		if (MODE == 2) { for (int q = 0; q < V; q++) out.v[q] = (Real)0; }
+		#pragma unroll
+		for (int q = 0; q < V; q++) if (mine[q]) {
+			const int i = i0 + q;
+			Real sum = bv.v[q];
+			if (bscale != (Real)0 && ty.v[q] == vtActiveTrivial) sum *= bscale;
+			if (i > 0)        sum -= (q == 0 ? aim0 : ai.v[q - 1 < 0 ? 0 : q - 1]) * (q == 0 ? xm0 : xc.v[q - 1 < 0 ? 0 : q - 1]);
+			if (i < g.sx - 1) sum -= ai.v[q] * (q == V - 1 ? xpL : xc.v[q + 1 > V - 1 ? V - 1 : q + 1]);
+			if (j > 0)        sum -= ajm.v[q] * xym.v[q];
+			if (j < g.sy - 1) sum -= aj.v[q] * xyp.v[q];
+			if (is3D) {
+				if (k > 0)        sum -= akm.v[q] * xzm.v[q];
+				if (k < g.sz - 1) sum -= ak.v[q] * xzp.v[q];
+			}
+			if (MODE == 2) { sum -= a0.v[q] * xc.v[q]; out.v[q] = sum; }
+			else out.v[q] = sum / a0.v[q];
+		}
+		*reinterpret_cast<RVec<Real, V>*>((MODE == 2 ? r : x) + v) = out;
+	}
+}
+
+// knInterpolate + knAddAssign from level 1 into the level-0 iterate, V fine cells per thread
+template <typename Real, int V>
+__global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeom gc, int nvx, int kchunk, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+	const Real* __restrict__ xc, Real* __restrict__ xf, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int m = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y;
+	if (m >= nvx || y >= gf.sy) return;
+	const int k0 = blockIdx.z * kchunk, k1 = min(gf.sz, k0 + kchunk);
+	const int x0 = m * V, py = y & 1, cY = gc.sx, cZ = gc.sx * gc.sy;
+	for (int z = k0; z < k1; z++) {
+		const int v = x0 + gf.sx * (y + gf.sy * z);
+		const CVec<V> ty = ldC<V>(tf + v);
+		bool any = false;
+		#pragma unroll
+		for (int q = 0; q < V; q++) any |= ty.v[q] != vtInactive;
+		if (!any) continue;
+		const int pz = z & 1;
+		const int base = (x0 >> 1) + cY * (y >> 1) + cZ * (z >> 1);
+		// the V fine cells interpolate from the coarse vertices x0/2 .. x0/2 + V/2 of up to 4 coarse rows; values of inactive ones count as absent
+		Real pv[2][2][V / 2 + 1]; bool pa[2][2][V / 2 + 1];
+		#pragma unroll
+		for (int dz = 0; dz < 2; dz++)
+			#pragma unroll
+			for (int dy = 0; dy < 2; dy++)
+				#pragma unroll
+				for (int e = 0; e <= V / 2; e++) {
+					pa[dz][dy][e] = false; pv[dz][dy][e] = (Real)0;
+					if (dz <= pz && dy <= py && (x0 >> 1) + e < gc.sx) {
+						const int i = base + e + dy * cY + dz * cZ;
+						pa[dz][dy][e] = tc[i] != vtInactive;
+						if (pa[dz][dy][e]) pv[dz][dy][e] = xc[i];
+					}
+				}
+		RVec<Real, V> xv = ldR<Real, V>(xf + v);
+		#pragma unroll
+		for (int q = 0; q < V; q++) {
+			if (ty.v[q] == vtInactive) continue;
+			const int px = q & 1, e = q >> 1;                       // x0 is even: parity of x0 + q is that of q
+			Real sum = 0;
+			#pragma unroll
+			for (int dz = 0; dz < 2; dz++)
+				#pragma unroll
+				for (int dy = 0; dy < 2; dy++) {
+					if (dz > pz || dy > py) continue;
+					if (pa[dz][dy][e]) sum += pv[dz][dy][e];
+					if (px && pa[dz][dy][e + 1]) sum += pv[dz][dy][e + 1];
+				}
+			xv.v[q] += pow2weight<Real>(px + py + pz) * sum;
+		}
+		*reinterpret_cast<RVec<Real, V>*>(xf + v) = xv;
+	}
+}
+
+// knRestrict of the level-0 residual onto level 1 (and x1 = 0), V / 2 coarse vertices per thread: their 27 fine vertices are
+// one scalar + one 16-byte vector in each of 9 fine rows
+template <typename Real, int V>
+__global__ void __launch_bounds__(128) k_mg_restrict_l0_vec(LvlGeom gf, LvlGeom gc, int ncx, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+	const Real* __restrict__ src, Real* __restrict__ dst, Real* __restrict__ xc, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	constexpr int CW = V / 2;
+	const int t = blockIdx.x * 32 + threadIdx.x, vy = blockIdx.y * 4 + threadIdx.y, vz = blockIdx.z;
+	if (t >= ncx || vy >= gc.sy) return;
+	const int vx0 = t * CW;
+	bool act[CW]; bool any = false; Real sum[CW];
+	#pragma unroll
+	for (int c = 0; c < CW; c++) {
+		act[c] = false; sum[c] = (Real)0;
+		if (vx0 + c < gc.sx) { const int v = linIdx(gc, vx0 + c, vy, vz); xc[v] = (Real)0; act[c] = tc[v] != vtInactive; any |= act[c]; }
+	}
+	if (!any) return;
+	const int fx0 = 2 * vx0;                                         // multiple of V
+	const bool vecIn = fx0 < gf.sx;                                  // sx % V == 0: the vector is inside or outside as a whole
+	for (int rz = max(0, vz * 2 - 1); rz <= min(gf.sz - 1, vz * 2 + 1); rz++)
+	for (int ry = max(0, vy * 2 - 1); ry <= min(gf.sy - 1, vy * 2 + 1); ry++) {
+		const int row = gf.sx * (ry + gf.sy * rz);
+		const Real wyz = pow2weight<Real>((ry & 1) + (rz & 1));
+		// fine x = fx0 - 1 (scalar) and fx0 .. fx0 + V - 1 (vector); coarse vertex c takes fx0 + 2c - 1 .. fx0 + 2c + 1, ascending
+		Real f[V + 1]; bool fa[V + 1];
+		f[0] = (Real)0; fa[0] = false;
+		if (fx0 > 0) { fa[0] = tf[row + fx0 - 1] != vtInactive; if (fa[0]) f[0] = src[row + fx0 - 1]; }
+		if (vecIn) {
+			const CVec<V> tv = ldC<V>(tf + row + fx0); const RVec<Real, V> sv = ldR<Real, V>(src + row + fx0);
+			#pragma unroll
+			for (int q = 0; q < V; q++) { fa[q + 1] = tv.v[q] != vtInactive; f[q + 1] = sv.v[q]; }
+		} else {
+			#pragma unroll
+			for (int q = 0; q < V; q++) { fa[q + 1] = false; f[q + 1] = (Real)0; }
+		}
+		#pragma unroll
+		for (int c = 0; c < CW; c++) {
+			if (!act[c]) continue;
+			#pragma unroll
+			for (int e = 0; e < 3; e++) {                             // rx = fx0 + 2c - 1 + e
+				const int q = 2 * c + e;                             // index into f[]
+				const int rx = fx0 + 2 * c - 1 + e;
+				if (rx < 0 || rx >= gf.sx || !fa[q]) continue;
+				// weight 1 / 2^(#odd coordinates): rx is odd for e = 0, 2
+				const Real rw = (e == 1) ? wyz : wyz * (Real)0.5;
+				sum[c] += rw * f[q];
+			}
+		}
+	}
+	#pragma unroll
+	for (int c = 0; c < CW; c++) if (act[c]) dst[linIdx(gc, vx0 + c, vy, vz)] = sum[c];
+}
+
 // 27-point (9-point in 2-D) stencil application shared by smoother / residual / coarse CG on levels > 0
 template <typename Real, typename VecT, bool SKIPCENTER, bool IS3D>
 __device__ __forceinline__ VecT stencilSubT(const LvlGeom& g, const Real* __restrict__ A, const signed char* __restrict__ type,
@@ -377,6 +571,68 @@ __global__ void __launch_bounds__(128) k_mg_residualN(LvlGeom g, int is3D, int S
 	const int v = linIdx(g, vx, vy, vz);
 	if (type[v] == vtInactive) return;
 	r[v] = stencilSub<Real, Real, false>(g, is3D, S, A, type, x, v, vx, vy, vz, b[v]);
+}
+
+// ---------------------------------------------------------------- levels > 0, colour-major rows
+// The Galerkin operators are stored like the reference stores them: the 14 (5) "upper" entries per vertex, the lower half read from the
+// neighbour's row.  A colour sweep over that layout reads x-stride-2 and touches every sector of 27 coefficient arrays 8 times per
+// sweep (216 n B for 112 n B of coefficients).  For the sweeps -- and only for them -- setA also writes every vertex's WHOLE row, grouped by
+// colour (= parity of x,y,z, the smoother's colours multigrid.cpp:722):
+//     Afull[((c * NENT + s) * nc) + ci],   c = ox + 2 oy + 4 oz,  ci = (x>>1) + hbx ((y>>1) + hby (z>>1)),  s = stencil offset index 0..26
+// Entries towards vertices outside the grid or inactive ones are 0, so the sweep needs no neighbour tests: it subtracts 0 * x instead of
+// skipping (same value; an exact zero at worst changes sign).  One sweep then reads 108 n B of coefficients once, unit stride.
+template <typename Real, bool IS3D>
+__global__ void __launch_bounds__(128) k_mg_build_full(LvlGeom g, int hbx, int hby, int hbz, const Real* __restrict__ A, const signed char* __restrict__ type, Real* __restrict__ Afull)
+{
+	constexpr int S = IS3D ? 14 : 5, NENT = IS3D ? 27 : 9;
+	const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y, tzc = blockIdx.z;
+	if (tx >= hbx) return;
+	const int c = tzc / hbz, tz = tzc - c * hbz;
+	const int vx = 2 * tx + (c & 1), vy = 2 * ty + ((c >> 1) & 1), vz = 2 * tz + ((c >> 2) & 1);
+	const size_t nc = (size_t)hbx * hby * hbz, ci = tx + (size_t)hbx * (ty + (size_t)hby * tz);
+	Real* out = Afull + (size_t)c * NENT * nc + ci;
+	const bool live = inGrid(g, vx, vy, vz) && type[linIdx(g, vx, vy, vz)] != vtInactive;
+	const int v = live ? linIdx(g, vx, vy, vz) : 0;
+	#pragma unroll
+	for (int s = 0; s < NENT; s++) {
+		const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = IS3D ? s / 9 - 1 : 0;
+		Real val = (Real)0;
+		if (live && inGrid(g, vx + dx, vy + dy, vz + dz)) {
+			const int nb = v + dx + g.sx * (dy + g.sy * dz);
+			if (type[nb] != vtInactive) val = (s < S) ? A[(size_t)(S - 1 - s) * g.n + nb] : A[(size_t)(s - S + 1) * g.n + v];
+		}
+		out[(size_t)s * nc] = val;
+	}
+}
+
+// one colour of knSmoothColor (:668-711) / knCalcResidual (:739-771) over the colour-major rows; RESID: all colours in one launch
+template <typename Real, bool IS3D, bool RESID>
+__global__ void __launch_bounds__(128) k_mg_sweep_full(LvlGeom g, int hbx, int hby, int hbz, int color, const Real* __restrict__ Afull, const Real* __restrict__ b,
+	const signed char* __restrict__ type, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	constexpr int S = IS3D ? 14 : 5, NENT = IS3D ? 27 : 9;
+	const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y;
+	if (tx >= hbx) return;
+	int c = color, tz = blockIdx.z;
+	if (RESID) { c = blockIdx.z / hbz; tz = blockIdx.z - c * hbz; }
+	const int vx = 2 * tx + (c & 1), vy = 2 * ty + ((c >> 1) & 1), vz = 2 * tz + ((c >> 2) & 1);
+	if (!inGrid(g, vx, vy, vz)) return;
+	const int v = linIdx(g, vx, vy, vz);
+	if (type[v] == vtInactive) return;
+	const size_t nc = (size_t)hbx * hby * hbz;
+	const Real* a = Afull + (size_t)c * NENT * nc + (tx + (size_t)hbx * (ty + (size_t)hby * tz));
+	const bool interior = vx > 0 && vy > 0 && vx < g.sx - 1 && vy < g.sy - 1 && (!IS3D || (vz > 0 && vz < g.sz - 1));
+	Real sum = b[v];
+	#pragma unroll
+	for (int s = 0; s < NENT; s++) {
+		if (!RESID && s == S - 1) continue;
+		const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = IS3D ? s / 9 - 1 : 0;
+		int nb = v + dx + g.sx * (dy + g.sy * dz);
+		if (!interior && !inGrid(g, vx + dx, vy + dy, vz + dz)) nb = v;      // coefficient is 0 there
+		sum -= a[(size_t)s * nc] * x[nb];
+	}
+	if (RESID) r[v] = sum; else x[v] = sum / a[(size_t)(S - 1) * nc];
 }
 
 // knRestrict :904-927 (dst level = coarse), also zeroes x on the coarse level (knSet :472)
@@ -558,6 +814,13 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 		else if (l == 1) k_mg_galerkin1<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->dPaths, (const int*)(m->dFlags + 16), (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1]);
 		else        k_mg_galerkinN<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->A[l]);
 		MP_CHECK_LAUNCH(ctx);
+		if (m->Afull[l]) {
+			const int hbx = (gc.sx + 1) / 2, hby = (gc.sy + 1) / 2, hbz = m->is3D ? (gc.sz + 1) / 2 : 1, ncol = m->is3D ? 8 : 4;
+			const dim3 gr((unsigned)((hbx + 127) / 128), (unsigned)hby, (unsigned)(hbz * ncol));
+			if (m->is3D) k_mg_build_full<Real, true><<<gr, 128, 0, st>>>(gc, hbx, hby, hbz, (const Real*)m->A[l], m->type[l], (Real*)m->Afull[l]);
+			else         k_mg_build_full<Real, false><<<gr, 128, 0, st>>>(gc, hbx, hby, hbz, (const Real*)m->A[l], m->type[l], (Real*)m->Afull[l]);
+			MP_CHECK_LAUNCH(ctx);
+		}
 	}
 	m->isASet = true; m->isRhsSet = false;
 	return MP_OK;
@@ -566,6 +829,13 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 // level-0 vectors of the running V-cycle: x0 is the caller's dst grid (no copy at the end), b0 either the scaled copy made
 // by setRhs or the caller's rhs with trivial rows scaled on the fly (bscale != 0)
 template <typename Real> struct L0 { Real* x; const Real* b; Real bscale; };
+
+// level-0 kernels with 16 bytes of cells per thread: rows must start on 16-byte boundaries
+template <typename Real> static inline bool l0vec(const LvlGeom& g) {
+	const char* e = getenv("MP_MG_L0VEC");      // read per call: the parity tests run both forms in one process
+	return (!e || atoi(e)) && g.sx % (16 / (int)sizeof(Real)) == 0;
+}
+static inline int l0chunk(const LvlGeom& g) { return g.sz >= 64 ? 8 : (g.sz >= 8 ? 4 : 1); }
 
 template <typename Real>
 static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneFlag, const L0<Real>& l0)
@@ -576,6 +846,15 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 		const dim3 gr = grid3((g.sx + 1) / 2, g.sy, g.sz, 128);
 		for (int c = 0; c < 2; c++) {
 			const int color = reversed ? 1 - c : c;
+			if (l0vec<Real>(g)) {
+				constexpr int V = 16 / (int)sizeof(Real);
+				const int nvx = g.sx / V, kchunk = l0chunk(g);
+				const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((g.sy + 3) / 4), (unsigned)((g.sz + kchunk - 1) / kchunk)), blk(32, 4, 1);
+				if (zeroX && c == 0) k_mg_l0_vec<Real, V, 1><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
+				else                 k_mg_l0_vec<Real, V, 0><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
+				MP_CHECK_LAUNCH(ctx);
+				continue;
+			}
 			// with x == 0 on entry the first colour reduces to x = b / A0 (same arithmetic: the skipped products are exact zeros)
 			if (zeroX && c == 0) k_mg_smooth0<Real, true><<<gr, 128, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, doneFlag);
 			else                 k_mg_smooth0<Real, false><<<gr, 128, 0, st>>>(g, m->is3D, color, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, doneFlag);
@@ -588,6 +867,13 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 		const dim3 gr = grid3(hbx, (g.sy + 1) / 2, (g.sz + 1) / 2, bsz);
 		for (int c = 0; c < ncol; c++) {
 			const int color = reversed ? ncol - 1 - c : c;
+			if (m->Afull[l]) {
+				const int hby = (g.sy + 1) / 2, hbz = m->is3D ? (g.sz + 1) / 2 : 1;
+				if (m->is3D) k_mg_sweep_full<Real, true, false><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, color, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
+				else         k_mg_sweep_full<Real, false, false><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, color, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
+				MP_CHECK_LAUNCH(ctx);
+				continue;
+			}
 			k_mg_smoothN<Real><<<gr, bsz, 0, st>>>(g, m->is3D, m->stencil, color & 1, (color >> 1) & 1, (color >> 2) & 1,
 				(const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], doneFlag);
 			MP_CHECK_LAUNCH(ctx);
@@ -601,7 +887,20 @@ static int mgResidual(mp_mg* m, int l, const int* doneFlag, const L0<Real>& l0)
 {
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	const LvlGeom g = m->geom[l];
-	if (l == 0) k_mg_residual0<Real><<<grid3(g.sx, g.sy, g.sz, 128), 128, 0, st>>>(g, m->is3D, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], (const Real*)l0.x, (Real*)m->r[0], doneFlag);
+	if (l == 0 && l0vec<Real>(g)) {
+		constexpr int V = 16 / (int)sizeof(Real);
+		const int nvx = g.sx / V, kchunk = l0chunk(g);
+		const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((g.sy + 3) / 4), (unsigned)((g.sz + kchunk - 1) / kchunk)), blk(32, 4, 1);
+		k_mg_l0_vec<Real, V, 2><<<grv, blk, 0, st>>>(g, m->is3D, 0, nvx, kchunk, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, (Real*)m->r[0], doneFlag);
+	}
+	else if (l == 0) k_mg_residual0<Real><<<grid3(g.sx, g.sy, g.sz, 128), 128, 0, st>>>(g, m->is3D, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], (const Real*)l0.x, (Real*)m->r[0], doneFlag);
+	else if (m->Afull[l]) {
+		const int hbx = (g.sx + 1) / 2, hby = (g.sy + 1) / 2, hbz = m->is3D ? (g.sz + 1) / 2 : 1, ncol = m->is3D ? 8 : 4;
+		const int bsz = hbx >= 96 ? 128 : (hbx >= 48 ? 64 : 32);
+		const dim3 gr((unsigned)((hbx + bsz - 1) / bsz), (unsigned)hby, (unsigned)(hbz * ncol));
+		if (m->is3D) k_mg_sweep_full<Real, true, true><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, 0, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
+		else         k_mg_sweep_full<Real, false, true><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, 0, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
+	}
 	else        k_mg_residualN<Real><<<grid3(g.sx, g.sy, g.sz, g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32)), g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32), 0, st>>>(g, m->is3D, m->stencil, (const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (const Real*)m->x[l], (Real*)m->r[l], doneFlag);
 	MP_CHECK_LAUNCH(ctx);
 	return MP_OK;
@@ -622,6 +921,14 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 		for (int i = 0; i < m->numPre; i++) MP_TRY((mgSmooth<Real>(m, l, false, l == 0 && i == 0 && !xInit, doneFlag, l0)));
 		MP_TRY((mgResidual<Real>(m, l, doneFlag, l0)));
 		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
+		if (l == 0 && l0vec<Real>(gf)) {
+			constexpr int V = 16 / (int)sizeof(Real);
+			const int ncx = (gc.sx + V / 2 - 1) / (V / 2);
+			const dim3 grv((unsigned)((ncx + 31) / 32), (unsigned)((gc.sy + 3) / 4), (unsigned)gc.sz), blk(32, 4, 1);
+			k_mg_restrict_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, ncx, m->type[0], m->type[1], (const Real*)m->r[0], (Real*)m->b[1], (Real*)m->x[1], doneFlag);
+			MP_CHECK_LAUNCH(ctx);
+			continue;
+		}
 		k_mg_restrict<Real><<<grid3(gc.sx, gc.sy, gc.sz, gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32)), gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32), 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->r[l], (Real*)m->b[l + 1], (Real*)m->x[l + 1], doneFlag);
 		MP_CHECK_LAUNCH(ctx);
 	}
@@ -634,6 +941,13 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 	}
 	for (int l = maxLevel - 1; l >= 0; l--) {
 		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
+		if (l == 0 && l0vec<Real>(gf)) {
+			constexpr int V = 16 / (int)sizeof(Real);
+			const int nvx = gf.sx / V, kchunk = l0chunk(gf);
+			const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((gf.sy + 3) / 4), (unsigned)((gf.sz + kchunk - 1) / kchunk)), blk(32, 4, 1);
+			k_mg_interp_add_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, nvx, kchunk, m->type[0], m->type[1], (const Real*)m->x[1], l0.x, doneFlag);
+			MP_CHECK_LAUNCH(ctx);
+		} else
 		k_mg_interp_add<Real><<<grid3(gf.sx, gf.sy, gf.sz, gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32)), gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32), 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], l == 0 ? l0.x : (Real*)m->x[l], doneFlag);
 		MP_CHECK_LAUNCH(ctx);
 		for (int i = 0; i < m->numPost; i++) MP_TRY((mgSmooth<Real>(m, l, true, false, doneFlag, l0)));
@@ -703,6 +1017,12 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 		MP_CUDA(cudaMalloc(&m->A[l], n * S * prec)); MP_CUDA(cudaMalloc(&m->b[l], n * prec));
 		if (l > 0) MP_CUDA(cudaMalloc(&m->x[l], n * prec));        // the level-0 iterate lives in the caller's dst grid
 		MP_CUDA(cudaMalloc(&m->r[l], n * prec)); MP_CUDA(cudaMalloc((void**)&m->type[l], n));
+		const int useFull = getenv("MP_MG_FULL") ? atoi(getenv("MP_MG_FULL")) : 1;
+		if (l > 0 && useFull) {
+			const LvlGeom g = m->geom[l];
+			const size_t nc = (size_t)((g.sx + 1) / 2) * ((g.sy + 1) / 2) * (m->is3D ? (g.sz + 1) / 2 : 1);
+			MP_CUDA(cudaMalloc(&m->Afull[l], nc * (m->is3D ? 8 * 27 : 4 * 9) * prec));
+		}
 		MP_CUDA(cudaMemsetAsync(m->A[l], 0, n * S * prec, ctx->stream)); if (l > 0) MP_CUDA(cudaMemsetAsync(m->x[l], 0, n * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, n * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->type[l], 0, n, ctx->stream));
@@ -749,7 +1069,7 @@ int mp_mg_destroy(mp_mg* m)
 	if (!m) return MP_OK;
 	cudaSetDevice(m->ctx->device);
 	cudaStreamSynchronize(m->ctx->stream);
-	for (int l = 0; l < m->nlev; l++) { cudaFree(m->A[l]); cudaFree(m->x[l]); cudaFree(m->b[l]); cudaFree(m->r[l]); cudaFree(m->type[l]); }
+	for (int l = 0; l < m->nlev; l++) { cudaFree(m->A[l]); cudaFree(m->x[l]); cudaFree(m->b[l]); cudaFree(m->r[l]); cudaFree(m->type[l]); if (m->Afull[l]) cudaFree(m->Afull[l]); }
 	cudaFree(m->cg); cudaFree(m->dPaths); cudaFree(m->dFlags); cudaFreeHost(m->hFlags);
 	if (m->ctx->staticMg == m) m->ctx->staticMg = nullptr;
 	if (m->ctx->spareMg == m) m->ctx->spareMg = nullptr;

@@ -153,3 +153,38 @@ def test_static_mg_reuses_hierarchy_like_test_0110(mf):
         assert rel_l2(P.numpy(), p_o) <= 1e-4 and rel_l2(V.numpy(), v_o) <= 1e-4
     O.release_solver(key)
     mf.releaseMG(s)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("shape,liquid", [((24, 24, 24), False), ((40, 36, 64), False), ((33, 47, 72), True), ((1, 40, 48), False), ((70, 66, 132), False)])
+def test_vcycle_kernel_forms_agree_bit_for_bit(mf, shape, liquid, prec, monkeypatch):
+    """The V-cycle's bandwidth forms -- level 0 with 16 bytes of cells per thread (k_mg_l0_vec, k_mg_restrict_l0_vec, k_mg_interp_add_l0_vec)
+    and the colour-major full rows of levels > 0 (k_mg_build_full / k_mg_sweep_full) -- do the arithmetic of the one-cell-per-thread
+    kernels term for term: the iterate after two V-cycles is the same bit for bit (both are compared with the oracle elsewhere in this file)."""
+    from mantaflow_b200 import cg
+    from test_gpu_parity import random_domain
+    flags, vel, phi = random_domain(shape, prec, seed=shape[1], liquid=liquid)
+    O = oracle(prec)
+    rhs, _, _ = O.compute_rhs(flags, vel, phi=phi)
+    A_o = O.make_matrix(flags, phi=phi)
+    fix = O.choose_fix_cell(flags)
+    if fix >= 0:
+        O.fix_pressure(flags, fix, 0.0, rhs, *A_o)
+    out = {}
+    for full, vec in ((1, 1), (0, 0), (1, 0), (0, 1)):
+        monkeypatch.setenv("MP_MG_FULL", str(full)); monkeypatch.setenv("MP_MG_L0VEC", str(vec))
+        s = mk(mf, flags.shape, prec)
+        A = [mf.RealGrid(s, a) for a in A_o]
+        mg = cg.GridMg(s)
+        B, Z, Z2 = mf.RealGrid(s, rhs), mf.RealGrid(s), mf.RealGrid(s)
+        mg.setA(*A)
+        mg.setSmoothing(2, 1)
+        mg.setRhs(B)
+        r1 = mg.doVCycle(Z)
+        r2 = mg.doVCycle(Z2, Z)
+        out[(full, vec)] = (Z.numpy().copy(), Z2.numpy().copy(), r1, r2)
+        assert r2 < r1
+        mg.close(); s.close()
+    ref = out[(0, 0)]
+    for k, v in out.items():
+        assert np.array_equal(v[0], ref[0]) and np.array_equal(v[1], ref[1]), ("V-cycle forms differ", k)
