@@ -97,13 +97,42 @@ def make_scene(res, prec, n_slabs=1):
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_step(O, flags, vel, pc, max_iter, accuracy):
     """One bounded pass of the hot path on the CPU: rhs + matrix + GridCg capped at max_iter + correctVelocity.
-    GridCg is driven directly because solvePressure(PcNone) asserts in the reference."""
+    GridCg is driven directly because solvePressure(PcNone) asserts in the reference.  Returns (seconds, iterations)."""
     t0 = time.perf_counter()
     rhs, _, _ = O.compute_rhs(flags, vel)
     A = O.make_matrix(flags)
     x, it, rn = O.cg_solve(flags, rhs, *A, pc={0: 0, 1: 1, 2: 2, 3: 2}[pc], accuracy=accuracy, maxIter=max_iter)
     O.correct_velocity(flags, vel, x)
     return time.perf_counter() - t0, it
+
+
+def cpu_sample(O, flags, vel, pc, cap_lo, cap_hi):
+    """The reference's cost split into set-up and per-iteration parts from two capped passes over the same input:
+    a pass costs setup + iterations x per_iter, so per_iter = (t_hi - t_lo) / (it_hi - it_lo) and setup = t_lo - it_lo x per_iter
+    (rhs, matrix, GridCg::doInit, preconditioner set-up, correctVelocity).  A full solve takes the same number of iterations as ours
+    (same algorithm, same arithmetic: 1598 at 512^3 PcNone, tests/golden/fullsize_divergence.json), so the per-iteration rate is the
+    honest CPU figure for the Gcell-iter/s metric; the capped-sample rate (which amortises the set-up over a handful of iterations) is
+    kept beside it."""
+    t_lo, it_lo = cpu_step(O, flags, vel.copy(), pc, cap_lo, 1e-4)
+    t_hi, it_hi = cpu_step(O, flags, vel.copy(), pc, cap_hi, 1e-4)
+    if it_hi > it_lo:
+        per_iter = max((t_hi - t_lo) / (it_hi - it_lo), 1e-9)
+    else:                      # converged below the low cap (multigrid): nothing to separate
+        per_iter = t_hi / max(it_hi, 1)
+    setup = max(t_lo - it_lo * per_iter, 0.0)
+    return {"per_iter_s": per_iter, "setup_s": setup, "t_hi_s": t_hi, "it_hi": it_hi, "t_lo_s": t_lo, "it_lo": it_lo}
+
+
+def cpu_fields(smp, cells, cores, kind, what):
+    """the cpu_baseline object (and the reference line's extra keys) from one cpu_sample"""
+    per_iter_rate = cells / smp["per_iter_s"] / 1e9
+    capped_rate = cells * smp["it_hi"] / smp["t_hi_s"] / 1e9
+    return {"value": per_iter_rate, "unit": "Gcell-iter/s", "cores": cores, "kind": kind,
+            "value_is": "cells / per-iteration time (set-up excluded: the figure a full solve of ~3.1 x res iterations converges to)",
+            "ref_ms_per_iter": 1e3 * smp["per_iter_s"], "ref_setup_ms": 1e3 * smp["setup_s"],
+            "value_capped_sample": capped_rate,
+            "sample": "%s: two passes of rhs+matrix+GridCg+correctVelocity capped at %d and %d iterations (%.1f s + %.1f s)" % (
+                what, smp["it_lo"], smp["it_hi"], smp["t_lo_s"], smp["t_hi_s"])}
 
 
 def run_reference(args):
@@ -116,23 +145,30 @@ def run_reference(args):
     O = Oracle(kind, args.prec)
     flags, vel = make_scene(args.res, args.prec)
     cells = flags.size
-    cap = args.cpu_iters
-    times, its = [], 0
+    cap_hi = args.cpu_iters
+    cap_lo = max(2, cap_hi // 4)
+    smps = []
     for s in range(args.warmup + args.steps):
-        v = vel.copy()
-        dt, its = cpu_step(O, flags, v, args.pc, cap, 1e-4)
-        if s >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
-    value = cells * its / (ms * 1e-3) / 1e9
-    sample = "one %d^3 block of the workload (the per-GPU share), %s, rhs+matrix+GridCg capped at %d iterations+correctVelocity per step (a full %d^3 solve needs ~%d iterations)" % (
-        args.res, PC_NAMES[args.pc], cap, args.res, 3.2 * args.res)
+        # a warm-up pass is a short one (page faults, thread pool); every timed step is the bounded two-pass sample
+        if s < args.warmup:
+            cpu_step(O, flags, vel.copy(), args.pc, 2, 1e-4)
+        else:
+            smps.append(cpu_sample(O, flags, vel, args.pc, cap_lo, cap_hi))
+    smp = {k: float(np.mean([q[k] for q in smps])) for k in smps[0]}
+    smp["it_hi"], smp["it_lo"] = int(smps[0]["it_hi"]), int(smps[0]["it_lo"])
+    what = "one %d^3 block of the workload (the per-GPU share%s), %s" % (
+        args.res, "" if args.gpus == 1 else "; the global grid of the N-GPU arm does not fit the host, so for N > 1 this is a machine-vs-machine figure, not the same problem", PC_NAMES[args.pc])
+    cb = cpu_fields(smp, cells, cores, kind, what)
+    value = cb["value"]
     line = {"impl": "reference", "metric": "pressure-solve CG throughput (cells x iterations / s)", "value": value, "unit": "Gcell-iter/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (smp["t_lo_s"] + smp["t_hi_s"]),
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.prec == 4 else "f64", "data": "synthetic",
             "config": workload_config(args, args.gpus),
-            "cg_iter_per_s": its / (ms * 1e-3),
-            "cpu_baseline": {"value": value, "unit": "Gcell-iter/s", "cores": cores, "kind": kind, "sample": sample},
+            "cg_iter_per_s": 1.0 / smp["per_iter_s"],
+            "ref_ms_per_iter": cb["ref_ms_per_iter"], "ref_setup_ms": cb["ref_setup_ms"], "value_capped_sample": cb["value_capped_sample"],
+            "same_problem_as_repo_arm": args.gpus == 1,
+            "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "Gcell-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -246,11 +282,17 @@ def run_ours(args):
                 "kernel_frac_of_peak": {kn[k]: (gbs[k] / peak if gbs[k] else None) for k in kt},
                 "kernel_bytes_per_cell": {kn[k]: bpc[k] for k in kt},
                 "roofline": {"bound": "hbm", "kernel": kn[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": (achieved / peak) if achieved else None, "traffic": runner.ncu_traffic(kn[dom]), "peak_source": peak_src,
+                             "frac": (achieved / peak) if achieved else None, "traffic": runner.ncu_traffic(kn[dom]),
+                             "traffic_source": "ncu --set full capture of this kernel at this size (profiles/traffic.json), not this run", "peak_source": peak_src,
+                             "frac_of_nominal_8TBs": (achieved / 8000.0) if achieved else None,
                              "algorithmic_bytes_per_cell": bpc[dom]},
+                "exchange": runner.exchange(),
                 "e2e": {"value": cells * iters / (e2e_ms * 1e-3) / 1e9, "unit": "Gcell-iter/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_configs and args.pc == 0 and args.prec == 4:
+            runner.release()
+            line["configs"] = extra_configs(args, peak)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -313,6 +355,15 @@ class SingleBench:
         bo = self.h_vel.nbytes + self.h_p.nbytes
         return float(np.mean(ts)), bi, bo
 
+    def exchange(self):
+        return "none (1 GPU)"
+
+    def release(self):
+        """give the device memory of the timed workload back before the other configurations run"""
+        for g in (self.F, self.V0, self.V, self.P):
+            g.close()
+        self.s.close()
+
     def ncu_traffic(self, kernel):
         p = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(p):
@@ -330,11 +381,73 @@ def cpu_baseline(args):
     O = Oracle(kind, args.prec)
     res = args.cpu_res or args.res
     flags, vel = make_scene(res, args.prec)
-    cap = args.cpu_iters
     cpu_step(O, flags, vel.copy(), args.pc, 2, 1e-4)       # warm-up (page faults, thread pool)
-    dt, its = cpu_step(O, flags, vel.copy(), args.pc, cap, 1e-4)
-    return {"value": flags.size * its / dt / 1e9, "unit": "Gcell-iter/s", "cores": cores, "kind": kind,
-            "sample": "%d^3 %s, rhs+matrix+GridCg capped at %d iterations+correctVelocity, %.1f s" % (res, PC_NAMES[args.pc], its, dt)}
+    smp = cpu_sample(O, flags, vel, args.pc, max(2, args.cpu_iters // 4), args.cpu_iters)
+    return cpu_fields(smp, flags.size, cores, kind, "%d^3 %s" % (res, PC_NAMES[args.pc]))
+
+
+# ------------------------------------------------------------------------------------------------ the other configurations (N = 1)
+def extra_configs(args, peak):
+    """BASELINE.json's other configurations and preconditioners, each as device-resident solvePressure calls on this GPU: PcMIC / PcMGStatic
+    (cold = first solve incl. GridMg::setA, warm = hierarchy reused) / PcMGDynamic at the bench size, the double build, config 1
+    (64x96x64 smoke, PcMIC) and config 2 (88x83x33 liquid + phi, PcMIC / PcMGDynamic).  Not part of `value`; measured after the timed region."""
+    import mantaflow_b200 as mf
+    from mantaflow_b200 import scenes
+    res = args.res
+    out = {}
+
+    def run(name, flags, vel, phi, prec, pc, acc, fac, fix, reps):
+        sz, sy, sx = flags.shape
+        s = mf.Solver(gridSize=(sx, sy, sz), dim=3, prec=prec)
+        s.setProfiling(4 if pc else 16)
+        F, V0, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.MACGrid(s), mf.RealGrid(s)
+        PH = mf.RealGrid(s, phi) if phi is not None else None
+        F.dev(); V0.dev()
+        ms, info = [], None
+        for r in range(reps):
+            mf._lib.check(s.lib.mp_grid_copy_from(V.dev(), V0.dev()))
+            mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=fac, preconditioner=pc, zeroPressureFixing=fix)
+            info = mf.lastSolveInfo()
+            ms.append(info["msTotal"])
+        cells = flags.size
+        w = prec
+        row = {"grid": [sx, sy, sz], "dtype": "f32" if prec == 4 else "f64", "preconditioner": PC_NAMES[pc], "cgAccuracy": acc,
+               "iterations": info["iterations"], "solve_ms": min(ms[1:]) if len(ms) > 1 else ms[0], "solve_ms_cold": ms[0],
+               "ms_per_iteration": (min(ms[1:]) if len(ms) > 1 else ms[0]) / max(info["iterations"], 1), "exchange": "none (1 GPU)",
+               "kernel_ms": {"matvec": info["msMatvecAvg"], "axpy": info["msAxpyAvg"], "precond": info["msPrecondAvg"], "update": info["msUpdateAvg"]},
+               "matvecKernel": info["matvecKernel"], "mgLevels": info["mgLevels"]}
+        # dominant kernel of the iteration against its algorithmic bytes (DESIGN.md 3): MIC apply 12+12w, V-cycle ~(4+28w)+(3+55w)/7, matvec per kernel
+        mvb = {0: 4 + 6 * w, 1: 4 + 6 * w, 2: 4 + 3 * w, 3: 4 + 7 * w, 4: 2 + 6 * w}[info["matvecKernel"]]
+        cand = {"matvec": (info["msMatvecAvg"], mvb)}
+        if pc == 1:
+            cand["precond (MIC apply)"] = (info["msPrecondAvg"], 12 + 12 * w)
+        if pc >= 2:
+            cand["precond (GridMg V-cycle)"] = (info["msPrecondAvg"], (4 + 28 * w) + (3 + 55 * w) / 7.0)
+        dom = max(cand, key=lambda k: cand[k][0] or 0.0)
+        t, bpc = cand[dom]
+        if t and t > 0:
+            gbs = bpc * cells / (t * 1e-3) / 1e9
+            row["dominant_kernel"] = {"name": dom, "ms": t, "bytes_per_cell": bpc, "achieved_gbs": gbs, "frac_of_measured_peak": gbs / peak}
+        if pc == 3:
+            mf.releaseMG(s)
+        s.close()
+        out[name] = row
+
+    f32 = make_scene(res, 4)
+    run("pcmic_f32", f32[0], f32[1], None, 4, 1, 1e-4, 99, False, 2)
+    run("pcmgstatic_f32", f32[0], f32[1], None, 4, 3, 1e-4, 99, True, 3)
+    run("pcmgdynamic_f32", f32[0], f32[1], None, 4, 2, 1e-4, 99, True, 2)
+    del f32
+    f64 = make_scene(res, 8)
+    run("pcnone_f64", f64[0], f64[1], None, 8, 0, 1e-4, 99, False, 2)
+    run("pcmgstatic_f64", f64[0], f64[1], None, 8, 3, 1e-4, 99, True, 3)
+    del f64
+    c1 = scenes.smoke_plume((64, 96, 64), 4, obstacle=False)
+    run("cfg1_64x96x64_pcmic", c1[0], c1[1], None, 4, 1, 1e-3, 1.5, False, 3)
+    c2 = scenes.liquid_basin((88, 83, 33), 4)
+    run("cfg2_88x83x33_phi_pcmic", c2[0], c2[1], c2[2], 4, 1, 1e-3, 1.5, False, 3)
+    run("cfg2_88x83x33_phi_pcmgdynamic", c2[0], c2[1], c2[2], 4, 2, 1e-3, 1.5, False, 3)
+    return out
 
 
 def main():
@@ -349,6 +462,7 @@ def main():
     ap.add_argument("--cpu-res", type=int, default=0, help="grid of the bounded cpu_baseline sample in our arm (0 = --res)")
     ap.add_argument("--cpu-iters", type=int, default=24, help="GridCg iteration cap of a CPU step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (other preconditioners / precisions / BASELINE configs 1-2)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -79,7 +79,7 @@ typedef struct mp_solve_info {
 	/* per-kernel averages over sampled launches of the CG loop (mp_context_set_profiling), 0 when off */
 	float     msMatvecAvg, msAxpyAvg, msUpdateAvg, msPrecondAvg;
 	int       profSamples;
-	int       matvecKernel;       /* 0 k_matvec_dot (L2 reuse), 1 k_matvec_zmarch (4+6w B/cell), 2 k_matvec_zmarch_masked (4+3w), 3 k_matvec_fused (PcNone loop, 4+7w incl. the s and x updates) */
+	int       matvecKernel;       /* 0 k_matvec_dot (L2 reuse), 1 k_matvec_zmarch (4+6w B/cell), 2 k_matvec_zmarch_masked (4+3w), 3 k_matvec_fused (PcNone loop, 4+7w incl. the s and x updates), 4 k_matvec_fused_tma (the same loop staged by TMA, matrix as 2 B/cell: 2+6w) */
 } mp_solve_info;
 
 /* ---- library / errors ---- */
@@ -331,6 +331,9 @@ int mp_dist_slab(int sz_global, int rank, int world, int* k0, int* k1);
 int mp_dist_set_domain(mp_context* ctx, int sz_global);
 /* refresh the two ghost planes of a slab grid from the neighbouring ranks (NCCL send/recv on the context stream) */
 int mp_dist_exchange_halo(mp_context* ctx, mp_grid* g);
+/* how the per-iteration exchanges of the CG loop travel: 0 single GPU (none), 1 NCCL send/recv + all-gather,
+ * 2 peer memory (NVLink stores into the neighbours' CUDA-IPC mapped arenas + release/acquire flags) */
+int mp_dist_exchange_mode(const mp_context* ctx, int* mode);
 
 #ifdef __cplusplus
 }

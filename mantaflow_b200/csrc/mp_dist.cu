@@ -324,6 +324,13 @@ int mp_dist_shutdown(mp_context* ctx) {
 	return MP_OK;
 }
 
+int mp_dist_exchange_mode(const mp_context* ctx, int* mode) {
+	if (!ctx || !mode) MP_FAIL(MP_ERR_INVALID, "mp_dist_exchange_mode: NULL argument");
+	const DistState* ds = ctx->dist;
+	*mode = (!ds || ds->world <= 1) ? 0 : (ds->p2p ? 2 : 1);
+	return MP_OK;
+}
+
 int mp_dist_slab(int sz, int rank, int world, int* k0, int* k1) {
 	if (world < 1 || rank < 0 || rank >= world) MP_FAIL(MP_ERR_INVALID, "mp_dist_slab: bad rank %d / world %d", rank, world);
 	const int base = sz / world, rem = sz % world;

@@ -142,5 +142,12 @@ class ShardedBench:
         bo = (self.h_vel.nbytes + self.h_p.nbytes) * self.world
         return float(np.mean(ts)), bi, bo
 
+    def exchange(self):
+        """how the per-iteration halo planes and scalar partials travelled (mp_dist_exchange_mode)"""
+        mode = C.c_int(0)
+        check(self.s.lib.mp_dist_exchange_mode(self.s._ctx, C.byref(mode)))
+        return {0: "none (1 GPU)", 1: "nccl (send/recv halo planes + all-gather of the partials)",
+                2: "p2p (NVLink peer stores into CUDA-IPC mapped arenas + release/acquire flags; NCCL only carries the set-up)"}[mode.value]
+
     def ncu_traffic(self, kernel):
         return None

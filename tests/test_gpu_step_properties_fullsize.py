@@ -29,6 +29,7 @@ def test_projection_properties_512():
     import os
     from cuda_impl import CudaImpl
     # what the unmodified reference (oracle/_ref, 986 s on 6 host cores) left behind on this input: 1598 iterations, max |div| 3.62e-4
-    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_divergence.json")))["reference_512"]
-    its = check_projection_properties(CudaImpl(4), 512, 4, [0, 3], random_vel=False, reference={0: gold})
-    assert its[0] == gold["iterations"] and its[3] <= 12
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_divergence.json")))
+    # PcMGStatic on the same input in the reference: 6 iterations, the pinned cell alone above the tolerance
+    its = check_projection_properties(CudaImpl(4), 512, 4, [0, 3], random_vel=False, reference={0: gold["reference_512"], 3: gold["reference_512_pc3"]})
+    assert its[0] == gold["reference_512"]["iterations"] and its[3] == gold["reference_512_pc3"]["iterations"]

@@ -1,0 +1,10 @@
+#!/bin/bash
+tag=${1:-rX}
+out=gpurun_out
+mkdir -p $out
+timeout 1500 python -m pytest tests -m gpu -q -rf -x > $out/${tag}_pytest_gpu_x.txt 2>&1
+tail -6 $out/${tag}_pytest_gpu_x.txt
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
+cat $out/${tag}_bench_ref.json
+timeout 900 python bench.py > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
+cat $out/${tag}_bench_n1.json; tail -3 $out/${tag}_bench_n1.err
