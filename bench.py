@@ -433,6 +433,13 @@ def extra_configs(args, peak):
         s.close()
         out[name] = row
 
+    # CUDA loads kernels lazily: the first PcMIC / PcMG* solve of the process would pay ~1 s of module loading that has nothing to do with the
+    # hierarchy set-up the "cold" figure is about -- run every preconditioner once on a small grid in both precisions first
+    for wprec in (4, 8):
+        wflags, wvel = make_scene(32, wprec)
+        for wpc in (0, 1, 2, 3):
+            run("_warm", wflags, wvel, None, wprec, wpc, 1e-4, 99, wpc >= 2, 1)
+    out.pop("_warm", None)
     f32 = make_scene(res, 4)
     run("pcmic_f32", f32[0], f32[1], None, 4, 1, 1e-4, 99, False, 2)
     run("pcmgstatic_f32", f32[0], f32[1], None, 4, 3, 1e-4, 99, True, 3)
