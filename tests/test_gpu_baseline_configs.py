@@ -101,7 +101,7 @@ def test_baseline_config_against_reference(name):
         loose = prec == 8 and acc > 1e-9 and pc == 1         # see the comment at CASES["smoke128_f64"]
         assert abs(info["iterations"] - it_o) <= (4 if loose else 1), report[-1]
         assert e <= (1e-6 if loose else TOL[prec]), report[-1]
-        assert rel_l2(v_g, v_o) <= (1e-6 if loose else TOL[prec]), report[-1]
+        assert rel_l2(v_g, v_o) <= (1e-5 if loose else TOL[prec]), report[-1]      # the velocity correction is a difference of pressures: ~20x the pressure's relative spread
         if phi is None:
             # at or below the reference's; two double solves that stop a step apart both sit below cgAccuracy, either may be the smaller one
             assert div_g <= div_o * (1 + 1e-3) + (1e-7 if prec == 4 else 1e-15) or (prec == 8 and div_g <= acc), report[-1]
