@@ -23,6 +23,8 @@ struct NcclApi {
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
 	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
 	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
 	ncclResult_t (*GroupStart)();
 	ncclResult_t (*GroupEnd)();
 	const char* (*GetErrorString)(ncclResult_t);
@@ -37,7 +39,7 @@ int loadNccl(const char* path) {
 	if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
 	if (!h) MP_FAIL(MP_ERR_COMM, "mp_dist: cannot load NCCL (%s)", dlerror());
 	#define SYM(name) do { *(void**)(&g_nccl.name) = dlsym(h, "nccl" #name); if (!g_nccl.name) MP_FAIL(MP_ERR_COMM, "mp_dist: NCCL symbol nccl" #name " missing"); } while (0)
-	SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllGather); SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+	SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllGather); SYM(Send); SYM(Recv); SYM(Broadcast); SYM(AllReduce); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 	#undef SYM
 	g_nccl.handle = h;
 	return MP_OK;
@@ -254,6 +256,28 @@ __global__ void k_dist_pack(const double* src, int n, double* dLocal) { for (int
 __global__ void k_dist_sum(const double* gathered, int world, int n, double* out) {
 	for (int q = 0; q < n; q++) { double s = 0; for (int r = 0; r < world; r++) s += gathered[8 * r + q]; out[q] = s; }   // fixed rank order
 }
+// every rank's owned planes of a slab array (local layout: ghost, owned..., ghost) into one global array on every rank: one broadcast per
+// rank, grouped (the slabs of mp_dist_slab may differ by one plane, so this is not a fixed-count all-gather)
+int mp_dist_gather_planes(mp_context* ctx, const void* localBase, size_t planeBytes, void* globalBase) {
+	DistState* ds = ctx->dist;
+	if (!ds || !ds->active || ds->world == 1) MP_FAIL(MP_ERR_INVALID, "mp_dist_gather_planes: context is not in slab mode");
+	MP_NCCL(g_nccl.GroupStart());
+	for (int r = 0; r < ds->world; r++) {
+		int k0, k1; mp_dist_slab(ds->gsz, r, ds->world, &k0, &k1);
+		MP_NCCL(g_nccl.Broadcast((const char*)localBase + planeBytes, (char*)globalBase + planeBytes * (size_t)k0, planeBytes * (size_t)(k1 - k0), ncclChar, r,
+			(ncclComm_t)ds->comm, ctx->stream));
+	}
+	MP_NCCL(g_nccl.GroupEnd());
+	return MP_OK;
+}
+// in-place sum over the ranks of an array of Reals (every rank contributes zeros outside the part it computed, so the sum is exact)
+int mp_dist_allreduce_sum(mp_context* ctx, void* data, size_t count, int prec) {
+	DistState* ds = ctx->dist;
+	if (!ds || !ds->active || ds->world == 1) return MP_OK;
+	MP_NCCL(g_nccl.AllReduce(data, data, count, prec == 4 ? ncclFloat : ncclDouble, ncclSum, (ncclComm_t)ds->comm, ctx->stream));
+	return MP_OK;
+}
+
 // in-place global sum of n <= 8 doubles living at device pointer vals (same result, bit for bit, on every rank)
 int mp_dist_sum(mp_context* ctx, double* vals, int n) {
 	DistState* ds = ctx->dist;

@@ -55,6 +55,11 @@ struct mp_mg {
 	int* dFlags;                     // [0] changed, [1] leftovers, [2] nonZeroStencilSum, [3] trivialFound, [4] coarse iterations
 	int* hFlags;                     // pinned
 	int hostCoarsenLevels;           // how many levels needed the serial host path in the last setA
+	// z-slab mode (mp_dist.cu): the hierarchy is the GLOBAL one and lives on every rank; setA gathers the ranks' slabs of A0/Ai/Aj/Ak, the
+	// coarse levels (1/7 of the work) are computed redundantly, and the level-0 work of the V-cycle -- smoothing, residual, restriction,
+	// interpolation over this rank's planes [k0,k1) -- is sharded, with a one-plane halo exchange of the iterate after each colour.
+	// Same arithmetic on the same values as a single-GPU solve of the global grid: same V-cycle, same iteration count.
+	bool slab; int k0, k1, lsz;      // owned global planes, local planes incl. the two ghost planes
 };
 
 // ---------------------------------------------------------------- index helpers
@@ -79,8 +84,8 @@ template <typename Real> __device__ __forceinline__ Real pow2weight(int nOdd) {
 
 // ---------------------------------------------------------------- setA: level 0
 template <typename Real>
-__global__ void __launch_bounds__(256) k_mg_copy_activate(LvlGeom g, int is3D, Real trivialScale, const Real* __restrict__ A0, const Real* __restrict__ Ai,
-	const Real* __restrict__ Aj, const Real* __restrict__ Ak, Real* __restrict__ A, signed char* __restrict__ type, int* flagsOut)
+__global__ void __launch_bounds__(256) k_mg_copy_activate(LvlGeom g, int is3D, Real trivialScale, const Real* A0, const Real* Ai,
+	const Real* Aj, const Real* Ak, Real* A, signed char* __restrict__ type, int* flagsOut)      // slab mode runs it in place (A0 == A, Ai == A + n, ...): no restrict
 {
 	const int v = blockIdx.x * blockDim.x + threadIdx.x;
 	if (v >= g.n) return;
@@ -336,13 +341,13 @@ template <int V> __device__ __forceinline__ CVec<V> ldC(const signed char* p) { 
 // MODE 0: one colour of the smoother; MODE 1: the first colour on x == 0 (x = b / A0 on that colour, zeros elsewhere: writes EVERY
 // cell, so the caller needs no memset of x); MODE 2: residual r = b - A x
 template <typename Real, int V, int MODE>
-__global__ void __launch_bounds__(128) k_mg_l0_vec(LvlGeom g, int is3D, int color, int nvx, int kchunk, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
+__global__ void __launch_bounds__(128) k_mg_l0_vec(LvlGeom g, int is3D, int color, int nvx, int kchunk, int kb, int ke, const Real* __restrict__ A, const Real* __restrict__ b, Real bscale,
 	const signed char* __restrict__ type, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
 	const int m = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
 	if (m >= nvx || j >= g.sy) return;
-	const int k0 = blockIdx.z * kchunk, k1 = min(g.sz, k0 + kchunk);
+	const int k0 = kb + blockIdx.z * kchunk, k1 = min(ke, k0 + kchunk);      // [kb,ke): all planes, or this rank's slab (b, x, r are then shifted views of slab arrays)
 	const size_t n = (size_t)g.n; const int Y = g.sx, Z = g.sx * g.sy;
 	const int i0 = m * V;
 	for (int k = k0; k < k1; k++) {
@@ -410,13 +415,13 @@ __global__ void __launch_bounds__(128) k_mg_l0_vec(LvlGeom g, int is3D, int colo
 
 // knInterpolate + knAddAssign from level 1 into the level-0 iterate, V fine cells per thread
 template <typename Real, int V>
-__global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeom gc, int nvx, int kchunk, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+__global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeom gc, int nvx, int kchunk, int kb, int ke, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
 	const Real* __restrict__ xc, Real* __restrict__ xf, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
 	const int m = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y;
 	if (m >= nvx || y >= gf.sy) return;
-	const int k0 = blockIdx.z * kchunk, k1 = min(gf.sz, k0 + kchunk);
+	const int k0 = kb + blockIdx.z * kchunk, k1 = min(ke, k0 + kchunk);
 	const int x0 = m * V, py = y & 1, cY = gc.sx, cZ = gc.sx * gc.sy;
 	for (int z = k0; z < k1; z++) {
 		const int v = x0 + gf.sx * (y + gf.sy * z);
@@ -465,12 +470,12 @@ __global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeo
 // knRestrict of the level-0 residual onto level 1 (and x1 = 0), V / 2 coarse vertices per thread: their 27 fine vertices are
 // one scalar + one 16-byte vector in each of 9 fine rows
 template <typename Real, int V>
-__global__ void __launch_bounds__(128) k_mg_restrict_l0_vec(LvlGeom gf, LvlGeom gc, int ncx, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+__global__ void __launch_bounds__(128) k_mg_restrict_l0_vec(LvlGeom gf, LvlGeom gc, int ncx, int Kb, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
 	const Real* __restrict__ src, Real* __restrict__ dst, Real* __restrict__ xc, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
 	constexpr int CW = V / 2;
-	const int t = blockIdx.x * 32 + threadIdx.x, vy = blockIdx.y * 4 + threadIdx.y, vz = blockIdx.z;
+	const int t = blockIdx.x * 32 + threadIdx.x, vy = blockIdx.y * 4 + threadIdx.y, vz = Kb + blockIdx.z;      // coarse planes [Kb, Kb + gridDim.z)
 	if (t >= ncx || vy >= gc.sy) return;
 	const int vx0 = t * CW;
 	bool act[CW]; bool any = false; Real sum[CW];
@@ -783,6 +788,14 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	MP_CUDA(cudaMemsetAsync(m->dFlags, 0, 8 * sizeof(int), st));
 	const LvlGeom g0 = m->geom[0];
+	if (m->slab) {
+		// the ranks' owned planes of A0/Ai/Aj/Ak straight into the global struct-of-arrays copy, then types and trivial-row scaling in place
+		const size_t planeBytes = (size_t)g0.sx * g0.sy * sizeof(Real), n = (size_t)g0.n;
+		const mp_grid* src[4] = { A0, Ai, Aj, Ak };
+		for (int q = 0; q < 4; q++) MP_TRY(mp_dist_gather_planes(ctx, src[q]->d, planeBytes, (Real*)m->A[0] + q * n));
+		Real* A = (Real*)m->A[0];
+		k_mg_copy_activate<Real><<<nb(g0.n, 256), 256, 0, st>>>(g0, m->is3D, (Real)m->trivialScale, A, A + n, A + 2 * n, A + 3 * n, A, m->type[0], m->dFlags);
+	} else
 	k_mg_copy_activate<Real><<<nb(g0.n, 256), 256, 0, st>>>(g0, m->is3D, (Real)m->trivialScale, (const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d,
 		(const Real*)Ak->d, (Real*)m->A[0], m->type[0], m->dFlags);
 	MP_CHECK_LAUNCH(ctx);
@@ -828,7 +841,13 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 
 // level-0 vectors of the running V-cycle: x0 is the caller's dst grid (no copy at the end), b0 either the scaled copy made
 // by setRhs or the caller's rhs with trivial rows scaled on the fly (bscale != 0)
-template <typename Real> struct L0 { Real* x; const Real* b; Real bscale; };
+template <typename Real> struct L0 { Real* x; const Real* b; Real bscale; Real* xLocal; };      // xLocal: the slab array x is a shifted view of (slab mode)
+// slab mode: level-0 vectors are slab arrays (ghost, owned planes, ghost) while A[0] / type[0] are global; the kernels index everything with
+// the GLOBAL vertex index, so the slab arrays are passed as views shifted by the planes below the slab (only planes [k0-1, k1] are touched)
+template <typename Real> static inline Real* slabView(const mp_mg* m, Real* localBase) {
+	return m->slab ? localBase - (ptrdiff_t)(m->k0 - 1) * m->geom[0].sx * m->geom[0].sy : localBase;
+}
+template <typename Real> static inline Real* l0r(const mp_mg* m) { return slabView<Real>(m, (Real*)m->r[0]); }
 
 // level-0 kernels with 16 bytes of cells per thread: rows must start on 16-byte boundaries
 template <typename Real> static inline bool l0vec(const LvlGeom& g) {
@@ -838,7 +857,7 @@ template <typename Real> static inline bool l0vec(const LvlGeom& g) {
 static inline int l0chunk(const LvlGeom& g) { return g.sz >= 64 ? 8 : (g.sz >= 8 ? 4 : 1); }
 
 template <typename Real>
-static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneFlag, const L0<Real>& l0)
+static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneFlag, const L0<Real>& l0, bool skipLastHalo = false)
 {
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	const LvlGeom g = m->geom[l];
@@ -849,10 +868,13 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 			if (l0vec<Real>(g)) {
 				constexpr int V = 16 / (int)sizeof(Real);
 				const int nvx = g.sx / V, kchunk = l0chunk(g);
-				const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((g.sy + 3) / 4), (unsigned)((g.sz + kchunk - 1) / kchunk)), blk(32, 4, 1);
-				if (zeroX && c == 0) k_mg_l0_vec<Real, V, 1><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
-				else                 k_mg_l0_vec<Real, V, 0><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
+				const int kb = m->slab ? m->k0 : 0, ke = m->slab ? m->k1 : g.sz;
+				const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((g.sy + 3) / 4), (unsigned)((ke - kb + kchunk - 1) / kchunk)), blk(32, 4, 1);
+				if (zeroX && c == 0) k_mg_l0_vec<Real, V, 1><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, kb, ke, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
+				else                 k_mg_l0_vec<Real, V, 0><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, kb, ke, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
 				MP_CHECK_LAUNCH(ctx);
+				// slab mode: the neighbours' boundary planes of this colour before the next colour (or the residual) reads them
+				if (m->slab && !(skipLastHalo && c == 1)) MP_TRY(mp_dist_halo(ctx, l0.xLocal, (size_t)g.sx * g.sy * sizeof(Real), m->lsz));
 				continue;
 			}
 			// with x == 0 on entry the first colour reduces to x = b / A0 (same arithmetic: the skipped products are exact zeros)
@@ -890,8 +912,9 @@ static int mgResidual(mp_mg* m, int l, const int* doneFlag, const L0<Real>& l0)
 	if (l == 0 && l0vec<Real>(g)) {
 		constexpr int V = 16 / (int)sizeof(Real);
 		const int nvx = g.sx / V, kchunk = l0chunk(g);
-		const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((g.sy + 3) / 4), (unsigned)((g.sz + kchunk - 1) / kchunk)), blk(32, 4, 1);
-		k_mg_l0_vec<Real, V, 2><<<grv, blk, 0, st>>>(g, m->is3D, 0, nvx, kchunk, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, (Real*)m->r[0], doneFlag);
+		const int kb = m->slab ? m->k0 : 0, ke = m->slab ? m->k1 : g.sz;
+		const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((g.sy + 3) / 4), (unsigned)((ke - kb + kchunk - 1) / kchunk)), blk(32, 4, 1);
+		k_mg_l0_vec<Real, V, 2><<<grv, blk, 0, st>>>(g, m->is3D, 0, nvx, kchunk, kb, ke, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, l0r<Real>(m), doneFlag);
 	}
 	else if (l == 0) k_mg_residual0<Real><<<grid3(g.sx, g.sy, g.sz, 128), 128, 0, st>>>(g, m->is3D, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], (const Real*)l0.x, (Real*)m->r[0], doneFlag);
 	else if (m->Afull[l]) {
@@ -913,9 +936,11 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 {
 	mp_context* ctx = m->ctx; cudaStream_t st = ctx->stream;
 	const int maxLevel = m->nlev - 1;
-	L0<Real> l0; l0.x = dst; l0.b = rhsExt ? rhsExt : (const Real*)m->b[0]; l0.bscale = rhsExt ? (Real)m->trivialScale : (Real)0;
+	L0<Real> l0; l0.x = slabView<Real>(m, dst); l0.xLocal = dst; l0.b = rhsExt ? slabView<Real>(m, (Real*)rhsExt) : (const Real*)m->b[0]; l0.bscale = rhsExt ? (Real)m->trivialScale : (Real)0;
+	if (m->slab && !rhsExt) MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg on z-slabs runs as the preconditioner of GridCg only (rhs folded in)");
 	// knSet(x0, 0) :458.  (If a preconditioner call was skipped because the solve is done, dst simply keeps zeros.)
-	if (!xInit) MP_CUDA(cudaMemsetAsync(dst, 0, sizeof(Real) * (size_t)m->geom[0].n, st));
+	const size_t n0 = m->slab ? (size_t)m->geom[0].sx * m->geom[0].sy * m->lsz : (size_t)m->geom[0].n;
+	if (!xInit) MP_CUDA(cudaMemsetAsync(dst, 0, sizeof(Real) * n0, st));
 	for (int l = 0; l < maxLevel; l++) {
 		// with x == 0 on entry the first colour of the first sweep reduces to x = b / A0 (the skipped products are exact zeros)
 		for (int i = 0; i < m->numPre; i++) MP_TRY((mgSmooth<Real>(m, l, false, l == 0 && i == 0 && !xInit, doneFlag, l0)));
@@ -924,8 +949,22 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 		if (l == 0 && l0vec<Real>(gf)) {
 			constexpr int V = 16 / (int)sizeof(Real);
 			const int ncx = (gc.sx + V / 2 - 1) / (V / 2);
+			if (m->slab) {
+				// the residual's ghost planes, then this rank's coarse planes K with fine plane 2K owned (the last rank also takes the planes
+				// beyond the fine grid); the other planes of b1 stay zero and the sum over the ranks assembles b1 on every rank
+				MP_TRY(mp_dist_halo(ctx, m->r[0], (size_t)gf.sx * gf.sy * sizeof(Real), m->lsz));
+				MP_CUDA(cudaMemsetAsync(m->b[1], 0, sizeof(Real) * (size_t)gc.n, st)); MP_CUDA(cudaMemsetAsync(m->x[1], 0, sizeof(Real) * (size_t)gc.n, st));
+				const int Kb = (m->k0 + 1) / 2, Ke = (m->k1 == gf.sz) ? gc.sz : (m->k1 + 1) / 2;
+				if (Ke > Kb) {
+					const dim3 grs((unsigned)((ncx + 31) / 32), (unsigned)((gc.sy + 3) / 4), (unsigned)(Ke - Kb)), blk(32, 4, 1);
+					k_mg_restrict_l0_vec<Real, V><<<grs, blk, 0, st>>>(gf, gc, ncx, Kb, m->type[0], m->type[1], (const Real*)l0r<Real>(m), (Real*)m->b[1], (Real*)m->x[1], doneFlag);
+					MP_CHECK_LAUNCH(ctx);
+				}
+				MP_TRY(mp_dist_allreduce_sum(ctx, m->b[1], (size_t)gc.n, (int)sizeof(Real)));
+				continue;
+			}
 			const dim3 grv((unsigned)((ncx + 31) / 32), (unsigned)((gc.sy + 3) / 4), (unsigned)gc.sz), blk(32, 4, 1);
-			k_mg_restrict_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, ncx, m->type[0], m->type[1], (const Real*)m->r[0], (Real*)m->b[1], (Real*)m->x[1], doneFlag);
+			k_mg_restrict_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, ncx, 0, m->type[0], m->type[1], (const Real*)m->r[0], (Real*)m->b[1], (Real*)m->x[1], doneFlag);
 			MP_CHECK_LAUNCH(ctx);
 			continue;
 		}
@@ -944,13 +983,15 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 		if (l == 0 && l0vec<Real>(gf)) {
 			constexpr int V = 16 / (int)sizeof(Real);
 			const int nvx = gf.sx / V, kchunk = l0chunk(gf);
-			const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((gf.sy + 3) / 4), (unsigned)((gf.sz + kchunk - 1) / kchunk)), blk(32, 4, 1);
-			k_mg_interp_add_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, nvx, kchunk, m->type[0], m->type[1], (const Real*)m->x[1], l0.x, doneFlag);
+			const int kb = m->slab ? m->k0 : 0, ke = m->slab ? m->k1 : gf.sz;
+			const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((gf.sy + 3) / 4), (unsigned)((ke - kb + kchunk - 1) / kchunk)), blk(32, 4, 1);
+			k_mg_interp_add_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, nvx, kchunk, kb, ke, m->type[0], m->type[1], (const Real*)m->x[1], l0.x, doneFlag);
 			MP_CHECK_LAUNCH(ctx);
+			if (m->slab) MP_TRY(mp_dist_halo(ctx, l0.xLocal, (size_t)gf.sx * gf.sy * sizeof(Real), m->lsz));      // the post-smoother reads the neighbours' corrected planes
 		} else
 		k_mg_interp_add<Real><<<grid3(gf.sx, gf.sy, gf.sz, gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32)), gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32), 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], l == 0 ? l0.x : (Real*)m->x[l], doneFlag);
 		MP_CHECK_LAUNCH(ctx);
-		for (int i = 0; i < m->numPost; i++) MP_TRY((mgSmooth<Real>(m, l, true, false, doneFlag, l0)));
+		for (int i = 0; i < m->numPost; i++) MP_TRY((mgSmooth<Real>(m, l, true, false, doneFlag, l0, l == 0 && i == m->numPost - 1 && !wantNorm)));
 	}
 	if (wantNorm) MP_TRY((mgResidual<Real>(m, 0, doneFlag, l0)));      // calcResidual(0) only feeds the returned norm (:496-497)
 	return MP_OK;
@@ -968,7 +1009,9 @@ static int mgSetRhs(mp_mg* m, const Real* rhs, const int* doneFlag)
 }
 
 void mp_mg_invalidate(mp_mg* mg) { mg->isASet = false; mg->isRhsSet = false; mg->numPre = mg->numPost = 1; mg->coarsestAcc = (mg->prec == 4) ? (double)1E-8f : 1E-8; }
-bool mp_mg_matches(const mp_mg* mg, int prec, int sx, int sy, int sz) { return mg->prec == prec && mg->geom[0].sx == sx && mg->geom[0].sy == sy && mg->geom[0].sz == sz; }
+bool mp_mg_matches(const mp_mg* mg, int prec, int sx, int sy, int sz) {      // sz: the size of the caller's grids (the local slab in slab mode)
+	return mg->prec == prec && mg->geom[0].sx == sx && mg->geom[0].sy == sy && (mg->slab ? mg->lsz : mg->geom[0].sz) == sz;
+}
 
 // InitPreconditionMultigrid conjugategrad.cpp:100-106
 int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, double accuracy)
@@ -1000,6 +1043,17 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 	memset(m, 0, sizeof *m);
 	m->ctx = ctx; m->prec = prec;
 	m->numPre = m->numPost = 1; m->coarsestAcc = (prec == 4) ? (double)1E-8f : 1E-8; m->trivialScale = (prec == 4) ? (double)1E-6f : 1E-6;
+	// z-slab mode: `sz` is the local slab (owned planes + 2 ghost planes); the hierarchy is built for the global grid when the level-0
+	// kernels can run on 16-byte vectors (rows aligned), else every rank coarsens its own slab (block-Jacobi, more iterations)
+	{
+		const DistState* ds = ctx->dist;
+		const int wantGlobal = getenv("MP_MG_SLAB_GLOBAL") ? atoi(getenv("MP_MG_SLAB_GLOBAL")) : 1;
+		if (ds && ds->active && ds->world > 1 && sz > 1 && sz == ds->k1 - ds->k0 + 2 && wantGlobal && sx % (16 / prec) == 0
+		    && (long long)sx * sy * ds->gsz <= 2000000000LL) {
+			m->slab = true; m->k0 = ds->k0; m->k1 = ds->k1; m->lsz = sz;
+			sz = ds->gsz;
+		}
+	}
 	m->is3D = sz > 1; m->dim = m->is3D ? 3 : 2; m->stencil = m->is3D ? 14 : 5; m->stencil0 = m->is3D ? 4 : 3;
 	// levels: size_l = (size_{l-1}+2)/2 until all dims <= 5 or n <= 1000 (multigrid.cpp:256-263)
 	int l = 0; m->geom[0] = LvlGeom{ sx, sy, sz, sx * sy * sz };
@@ -1016,7 +1070,8 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 		const size_t n = (size_t)m->geom[l].n; const int S = l == 0 ? m->stencil0 : m->stencil;
 		MP_CUDA(cudaMalloc(&m->A[l], n * S * prec)); MP_CUDA(cudaMalloc(&m->b[l], n * prec));
 		if (l > 0) MP_CUDA(cudaMalloc(&m->x[l], n * prec));        // the level-0 iterate lives in the caller's dst grid
-		MP_CUDA(cudaMalloc(&m->r[l], n * prec)); MP_CUDA(cudaMalloc((void**)&m->type[l], n));
+		const size_t nr = (l == 0 && m->slab) ? (size_t)sx * sy * m->lsz : n;      // slab mode: the level-0 residual is a slab array
+		MP_CUDA(cudaMalloc(&m->r[l], nr * prec)); MP_CUDA(cudaMalloc((void**)&m->type[l], n));
 		const int useFull = getenv("MP_MG_FULL") ? atoi(getenv("MP_MG_FULL")) : 1;
 		if (l > 0 && useFull) {
 			const LvlGeom g = m->geom[l];
@@ -1024,7 +1079,7 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 			MP_CUDA(cudaMalloc(&m->Afull[l], nc * (m->is3D ? 8 * 27 : 4 * 9) * prec));
 		}
 		MP_CUDA(cudaMemsetAsync(m->A[l], 0, n * S * prec, ctx->stream)); if (l > 0) MP_CUDA(cudaMemsetAsync(m->x[l], 0, n * prec, ctx->stream));
-		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, n * prec, ctx->stream));
+		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, nr * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->type[l], 0, n, ctx->stream));
 	}
 	MP_CUDA(cudaMalloc((void**)&m->cg, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n));
@@ -1081,7 +1136,7 @@ int mp_mg_set_a(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid* A
 	if (!m || !A0 || !Ai || !Aj || !Ak) MP_FAIL(MP_ERR_INVALID, "mp_mg_set_a: NULL argument");
 	const mp_grid* gs[] = { A0, Ai, Aj, Ak };
 	for (const mp_grid* g : gs) {
-		if (g->kind != MP_GRID_REAL || g->prec != m->prec || g->sx != m->geom[0].sx || g->sy != m->geom[0].sy || g->sz != m->geom[0].sz)
+		if (g->kind != MP_GRID_REAL || g->prec != m->prec || g->sx != m->geom[0].sx || g->sy != m->geom[0].sy || g->sz != (m->slab ? m->lsz : m->geom[0].sz))
 			MP_FAIL(MP_ERR_INVALID, "mp_mg_set_a: grid does not match the GridMg size/precision");
 	}
 	MP_CUDA(cudaSetDevice(m->ctx->device));
@@ -1091,6 +1146,7 @@ int mp_mg_set_a(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid* A
 int mp_mg_set_rhs(mp_mg* m, const mp_grid* rhs)
 {
 	if (!m || !rhs) MP_FAIL(MP_ERR_INVALID, "mp_mg_set_rhs: NULL argument");
+	if (m->slab) MP_FAIL(MP_ERR_UNSUPPORTED, "mp_mg_set_rhs: on z-slabs GridMg runs as the preconditioner of GridCg only");
 	if (rhs->kind != MP_GRID_REAL || rhs->prec != m->prec || rhs->n != m->geom[0].n) MP_FAIL(MP_ERR_INVALID, "mp_mg_set_rhs: grid does not match the GridMg size/precision");
 	return m->prec == 4 ? mgSetRhs<float>(m, (const float*)rhs->d, nullptr) : mgSetRhs<double>(m, (const double*)rhs->d, nullptr);
 }
@@ -1101,6 +1157,7 @@ int mp_mg_do_vcycle(mp_mg* m, mp_grid* dst, const mp_grid* src, double* resNorm)
 {
 	if (!m || !dst) MP_FAIL(MP_ERR_INVALID, "mp_mg_do_vcycle: NULL argument");
 	if (!m->isASet || !m->isRhsSet) MP_FAIL(MP_ERR_NOT_SET, "GridMg::doVCycle Error: A and/or rhs have not been set.");   // :453
+	if (m->slab) MP_FAIL(MP_ERR_UNSUPPORTED, "mp_mg_do_vcycle: on z-slabs GridMg runs as the preconditioner of GridCg only");
 	if (dst->kind != MP_GRID_REAL || dst->prec != m->prec || dst->n != m->geom[0].n) MP_FAIL(MP_ERR_INVALID, "mp_mg_do_vcycle: dst does not match the GridMg size/precision");
 	mp_context* ctx = m->ctx;
 	MP_CUDA(cudaSetDevice(ctx->device));

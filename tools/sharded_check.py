@@ -53,8 +53,9 @@ for name, prec, extra in cases:
         good = abs(info["iterations"] - it_o) <= 1 and e_p <= (1e-4 if prec == 4 else 1e-10) and e_v <= (1e-4 if prec == 4 else 1e-10)
         print("sharded_check %-16s f%d world=%d iterations %d (oracle %d) relL2 p %.2e vel %.2e fixed %d %s" % (name, prec * 8, world, info["iterations"], it_o, e_p, e_v, info["fixedCell"], "OK" if good else "FAIL"), flush=True)
         ok = ok and good
-    # preconditioned solves: block-Jacobi MIC / GridMg over the slabs (different operator than the global preconditioner,
-    # same solution within the solver tolerance; iteration counts are reported, not asserted)
+    # preconditioned solves: PcMIC is block-Jacobi over the slabs (different operator than the global preconditioner, same solution within
+    # the solver tolerance; iteration counts are reported, not asserted); PcMG is the global hierarchy here (sx = 44: rows 16-byte aligned
+    # in float) -- asserted in the section below
     if name in ("smoke_pin", "liquid"):
         for pc in (1, 2):
             fixp = pc >= 2 or bool(extra.get("zeroPressureFixing"))
@@ -67,9 +68,40 @@ for name, prec, extra in cases:
                 p_o, it_o, rn_o = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=fixp)
                 e_p, e_v = rel(p_all, p_o), rel(v_all, v_o)
                 good = info["resNorm"] < acc and e_v <= 2e-3 and e_p <= 2e-3
-                print("sharded_check %-16s f%d world=%d %s block-Jacobi: iterations %d (global preconditioner %d) resNorm %.2e relL2 p %.2e vel %.2e %s"
+                print("sharded_check %-16s f%d world=%d %s on slabs: iterations %d (single-process oracle %d) resNorm %.2e relL2 p %.2e vel %.2e %s"
                       % (name, prec * 8, world, {1: "PcMIC", 2: "PcMGDynamic"}[pc], info["iterations"], it_o, info["resNorm"], e_p, e_v, "OK" if good else "FAIL"), flush=True)
                 ok = ok and good
+    s.close()
+
+# the global GridMg on z-slabs (rows aligned to 16 bytes): the hierarchy of the GLOBAL grid on every rank, level-0 work of the V-cycle sharded
+# with halo exchanges -- the same V-cycle as a single-GPU solve, so the iteration count is the oracle's and the float result its bits
+for name, prec, shape in [("smoke_pin", 4, (48, 36, 45)), ("liquid", 4, (64, 40, 44)), ("smoke_pin", 8, (48, 36, 45)), ("liquid", 8, (32, 30, 38))]      # (sx, sy, sz):
+    phi = None
+    if name == "liquid":
+        flags, vel, phi = scenes.liquid_basin(shape, prec)
+    else:
+        flags, vel = scenes.smoke_plume(shape, prec, random_vel=True)
+    acc = 1e-5 if prec == 4 else 1e-11
+    uid = sharded.exchange_unique_id(dist, rank)
+    s = sharded.ShardedSolver(shape, rank, world, uid, prec=prec, device=local)
+    F = mf.FlagGrid(s, sharded.local_slab(flags, rank, world)); V = mf.MACGrid(s, sharded.local_slab(vel, rank, world)); P = mf.RealGrid(s)
+    PH = mf.RealGrid(s, sharded.local_slab(phi, rank, world)) if phi is not None else None
+    if rank == 0:
+        O = Oracle("port", prec)
+    for pc in (3, 3, 2):          # PcMGStatic twice (second solve reuses the hierarchy), then PcMGDynamic
+        V.copyFromArray(sharded.local_slab(vel, rank, world))
+        mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=True)
+        info = mf.lastSolveInfo()
+        p_all, v_all = gather(P.numpy()), gather(V.numpy())
+        if rank == 0:
+            v_o = vel.copy()
+            p_o, it_o, rn_o = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=True)
+            e_p, e_v = rel(p_all, p_o), rel(v_all, v_o)
+            good = abs(info["iterations"] - it_o) <= 1 and e_p <= (1e-4 if prec == 4 else 1e-10) and e_v <= (1e-4 if prec == 4 else 1e-10)
+            print("sharded_check %-16s f%d world=%d %s GLOBAL GridMg on slabs: iterations %d (single-process oracle %d) levels %d relL2 p %.2e vel %.2e %s"
+                  % (name, prec * 8, world, {2: "PcMGDynamic", 3: "PcMGStatic"}[pc], info["iterations"], it_o, info["mgLevels"], e_p, e_v, "OK" if good else "FAIL"), flush=True)
+            ok = ok and good
+    mf.releaseMG(s)
     s.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, src=0)
