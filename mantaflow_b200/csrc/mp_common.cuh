@@ -124,6 +124,7 @@ static inline Dims dimsOf(const mp_grid* g) {
 int mp_dist_check_grid(const mp_grid* g);                                  // slab grids must have sz == k1-k0+2
 int mp_dist_halo(mp_context* ctx, void* base, size_t planeBytes, int szLocal);   // exchange the two ghost planes (no-op when world == 1)
 int mp_dist_allgather(mp_context* ctx, int nvals);
+int mp_dist_halo_range(mp_context* ctx, void* base, size_t planeBytes, int K0, int K1, int nplanes);          // boundary planes of a global-size array kept current on [K0,K1)
 int mp_dist_gather_planes(mp_context* ctx, const void* localBase, size_t planeBytes, void* globalBase);   // owned planes of every rank -> a global array on every rank
 int mp_dist_allreduce_sum(mp_context* ctx, void* data, size_t count, int prec);                          // in-place sum of a Real array over the ranks
 int mp_dist_p2p_prepare(mp_context* ctx, size_t searchBytes);                  // collective: (re)build the arena, exchange IPC handles

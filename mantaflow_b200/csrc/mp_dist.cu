@@ -73,6 +73,25 @@ int mp_dist_halo(mp_context* ctx, void* base, size_t planeBytes, int szLocal) {
 	return MP_OK;
 }
 
+// boundary planes of a GLOBAL-size array of which every rank keeps its planes [K0,K1) current: plane K0 goes to the rank below (which stores
+// it at the same place in its copy), plane K1-1 to the rank above; planes K0-1 and K1 arrive
+int mp_dist_halo_range(mp_context* ctx, void* base, size_t planeBytes, int K0, int K1, int nplanes) {
+	DistState* ds = ctx->dist;
+	if (!ds || !ds->active || ds->world == 1) return MP_OK;
+	char* b = (char*)base;
+	MP_NCCL(g_nccl.GroupStart());
+	if (ds->rank > 0 && K0 > 0 && K1 > K0) {
+		MP_NCCL(g_nccl.Send(b + planeBytes * (size_t)K0, planeBytes, ncclChar, ds->rank - 1, (ncclComm_t)ds->comm, ctx->stream));
+		MP_NCCL(g_nccl.Recv(b + planeBytes * (size_t)(K0 - 1), planeBytes, ncclChar, ds->rank - 1, (ncclComm_t)ds->comm, ctx->stream));
+	}
+	if (ds->rank < ds->world - 1 && K1 < nplanes && K1 > K0) {
+		MP_NCCL(g_nccl.Send(b + planeBytes * (size_t)(K1 - 1), planeBytes, ncclChar, ds->rank + 1, (ncclComm_t)ds->comm, ctx->stream));
+		MP_NCCL(g_nccl.Recv(b + planeBytes * (size_t)K1, planeBytes, ncclChar, ds->rank + 1, (ncclComm_t)ds->comm, ctx->stream));
+	}
+	MP_NCCL(g_nccl.GroupEnd());
+	return MP_OK;
+}
+
 int mp_dist_allgather(mp_context* ctx, int nvals) {
 	DistState* ds = ctx->dist;
 	(void)nvals;

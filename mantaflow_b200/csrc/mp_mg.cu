@@ -60,6 +60,10 @@ struct mp_mg {
 	// interpolation over this rank's planes [k0,k1) -- is sharded, with a one-plane halo exchange of the iterate after each colour.
 	// Same arithmetic on the same values as a single-GPU solve of the global grid: same V-cycle, same iteration count.
 	bool slab; int k0, k1, lsz;      // owned global planes, local planes incl. the two ghost planes
+	// The large coarse levels are sharded too: levels 0 .. nshard-1 are swept over this rank's planes [K0[l], K1[l]) of the (replicated,
+	// global-size) level arrays, with an exchange of the two boundary planes of x_l after every colour; coarse plane K belongs to the
+	// owner of fine plane 2K.  Level nshard and below are small and computed redundantly on every rank.
+	int nshard; int K0[MG_MAXLVL], K1[MG_MAXLVL];
 };
 
 // ---------------------------------------------------------------- index helpers
@@ -612,17 +616,18 @@ __global__ void __launch_bounds__(128) k_mg_build_full(LvlGeom g, int hbx, int h
 
 // one colour of knSmoothColor (:668-711) / knCalcResidual (:739-771) over the colour-major rows; RESID: all colours in one launch
 template <typename Real, bool IS3D, bool RESID>
-__global__ void __launch_bounds__(128) k_mg_sweep_full(LvlGeom g, int hbx, int hby, int hbz, int color, const Real* __restrict__ Afull, const Real* __restrict__ b,
+__global__ void __launch_bounds__(128) k_mg_sweep_full(LvlGeom g, int hbx, int hby, int hbz, int color, int tz0, int ntz, int Kb, int Ke, const Real* __restrict__ Afull, const Real* __restrict__ b,
 	const signed char* __restrict__ type, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
 	constexpr int S = IS3D ? 14 : 5, NENT = IS3D ? 27 : 9;
 	const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y;
 	if (tx >= hbx) return;
-	int c = color, tz = blockIdx.z;
-	if (RESID) { c = blockIdx.z / hbz; tz = blockIdx.z - c * hbz; }
+	// blockIdx.z walks the 2-plane blocks [tz0, tz0 + ntz) (all of them, or those that hold this rank's planes [Kb,Ke)); RESID: x all colours
+	int c = color, tz = tz0 + blockIdx.z;
+	if (RESID) { c = blockIdx.z / ntz; tz = tz0 + blockIdx.z - c * ntz; }
 	const int vx = 2 * tx + (c & 1), vy = 2 * ty + ((c >> 1) & 1), vz = 2 * tz + ((c >> 2) & 1);
-	if (!inGrid(g, vx, vy, vz)) return;
+	if (!inGrid(g, vx, vy, vz) || vz < Kb || vz >= Ke) return;
 	const int v = linIdx(g, vx, vy, vz);
 	if (type[v] == vtInactive) return;
 	const size_t nc = (size_t)hbx * hby * hbz;
@@ -642,12 +647,13 @@ __global__ void __launch_bounds__(128) k_mg_sweep_full(LvlGeom g, int hbx, int h
 
 // knRestrict :904-927 (dst level = coarse), also zeroes x on the coarse level (knSet :472)
 template <typename Real>
-__global__ void __launch_bounds__(128) k_mg_restrict(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+__global__ void __launch_bounds__(128) k_mg_restrict(LvlGeom gf, LvlGeom gc, int Kb, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
 	const Real* __restrict__ src, Real* __restrict__ dst, Real* __restrict__ xc, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
 	int vx, vy, vz;
 	if (!cell3(gc.sx, vx, vy, vz)) return;
+	vz += Kb;                                   // coarse planes [Kb, Kb + gridDim.z)
 	const int v = linIdx(gc, vx, vy, vz);
 	xc[v] = (Real)0;
 	if (tc[v] == vtInactive) return;
@@ -665,12 +671,13 @@ __global__ void __launch_bounds__(128) k_mg_restrict(LvlGeom gf, LvlGeom gc, con
 
 // knInterpolate :934-954 into r_l, then x_l += r_l (knAddAssign :445-446, over ALL vertices: inactive ones add their stale r)
 template <typename Real>
-__global__ void __launch_bounds__(128) k_mg_interp_add(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
+__global__ void __launch_bounds__(128) k_mg_interp_add(LvlGeom gf, LvlGeom gc, int kb, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
 	const Real* __restrict__ xc, Real* __restrict__ rf, Real* __restrict__ xf, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
 	int x, y, z;
 	if (!cell3(gf.sx, x, y, z)) return;
+	z += kb;                                    // fine planes [kb, kb + gridDim.z)
 	const int v = linIdx(gf, x, y, z);
 	// inactive vertices: the reference adds their r entry, which is never written and stays 0 -> nothing to do;
 	// the interpolated value itself (mr[l] in the reference) is a temporary and is not stored
@@ -856,6 +863,17 @@ template <typename Real> static inline bool l0vec(const LvlGeom& g) {
 }
 static inline int l0chunk(const LvlGeom& g) { return g.sz >= 64 ? 8 : (g.sz >= 8 ? 4 : 1); }
 
+// planes of level l this rank sweeps: its share on sharded levels, everything otherwise
+static inline void lvlRange(const mp_mg* m, int l, int* kb, int* ke) {
+	if (m->slab && l < m->nshard) { *kb = m->K0[l]; *ke = m->K1[l]; } else { *kb = 0; *ke = m->geom[l].sz; }
+}
+static inline bool lvlSharded(const mp_mg* m, int l) { return m->slab && l >= 1 && l < m->nshard; }
+// boundary planes of a sharded level array (levels >= 1: global-size arrays on every rank, each rank keeps its planes current)
+template <typename Real> static int lvlHalo(mp_mg* m, int l, void* base) {
+	const LvlGeom g = m->geom[l];
+	return mp_dist_halo_range(m->ctx, base, (size_t)g.sx * g.sy * sizeof(Real), m->K0[l], m->K1[l], g.sz);
+}
+
 template <typename Real>
 static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneFlag, const L0<Real>& l0, bool skipLastHalo = false)
 {
@@ -891,9 +909,13 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 			const int color = reversed ? ncol - 1 - c : c;
 			if (m->Afull[l]) {
 				const int hby = (g.sy + 1) / 2, hbz = m->is3D ? (g.sz + 1) / 2 : 1;
-				if (m->is3D) k_mg_sweep_full<Real, true, false><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, color, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
-				else         k_mg_sweep_full<Real, false, false><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, color, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
+				int Kb, Ke; lvlRange(m, l, &Kb, &Ke);
+				const int tz0 = m->is3D ? Kb / 2 : 0, ntz = m->is3D ? (Ke - 1) / 2 - tz0 + 1 : 1;
+				const dim3 grz(gr.x, gr.y, (unsigned)ntz);
+				if (m->is3D) k_mg_sweep_full<Real, true, false><<<grz, bsz, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
+				else         k_mg_sweep_full<Real, false, false><<<grz, bsz, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
 				MP_CHECK_LAUNCH(ctx);
+				if (lvlSharded(m, l)) MP_TRY(lvlHalo<Real>(m, l, m->x[l]));      // the next colour (or the residual / the interpolation) reads the neighbours' planes
 				continue;
 			}
 			k_mg_smoothN<Real><<<gr, bsz, 0, st>>>(g, m->is3D, m->stencil, color & 1, (color >> 1) & 1, (color >> 2) & 1,
@@ -920,9 +942,11 @@ static int mgResidual(mp_mg* m, int l, const int* doneFlag, const L0<Real>& l0)
 	else if (m->Afull[l]) {
 		const int hbx = (g.sx + 1) / 2, hby = (g.sy + 1) / 2, hbz = m->is3D ? (g.sz + 1) / 2 : 1, ncol = m->is3D ? 8 : 4;
 		const int bsz = hbx >= 96 ? 128 : (hbx >= 48 ? 64 : 32);
-		const dim3 gr((unsigned)((hbx + bsz - 1) / bsz), (unsigned)hby, (unsigned)(hbz * ncol));
-		if (m->is3D) k_mg_sweep_full<Real, true, true><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, 0, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
-		else         k_mg_sweep_full<Real, false, true><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, 0, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
+		int Kb, Ke; lvlRange(m, l, &Kb, &Ke);
+		const int tz0 = m->is3D ? Kb / 2 : 0, ntz = m->is3D ? (Ke - 1) / 2 - tz0 + 1 : 1;
+		const dim3 gr((unsigned)((hbx + bsz - 1) / bsz), (unsigned)hby, (unsigned)(ntz * ncol));
+		if (m->is3D) k_mg_sweep_full<Real, true, true><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
+		else         k_mg_sweep_full<Real, false, true><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
 	}
 	else        k_mg_residualN<Real><<<grid3(g.sx, g.sy, g.sz, g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32)), g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32), 0, st>>>(g, m->is3D, m->stencil, (const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (const Real*)m->x[l], (Real*)m->r[l], doneFlag);
 	MP_CHECK_LAUNCH(ctx);
@@ -953,14 +977,17 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 				// the residual's ghost planes, then this rank's coarse planes K with fine plane 2K owned (the last rank also takes the planes
 				// beyond the fine grid); the other planes of b1 stay zero and the sum over the ranks assembles b1 on every rank
 				MP_TRY(mp_dist_halo(ctx, m->r[0], (size_t)gf.sx * gf.sy * sizeof(Real), m->lsz));
-				MP_CUDA(cudaMemsetAsync(m->b[1], 0, sizeof(Real) * (size_t)gc.n, st)); MP_CUDA(cudaMemsetAsync(m->x[1], 0, sizeof(Real) * (size_t)gc.n, st));
-				const int Kb = (m->k0 + 1) / 2, Ke = (m->k1 == gf.sz) ? gc.sz : (m->k1 + 1) / 2;
+				const bool nextSharded = m->nshard > 1;
+				if (!nextSharded) MP_CUDA(cudaMemsetAsync(m->b[1], 0, sizeof(Real) * (size_t)gc.n, st));
+				MP_CUDA(cudaMemsetAsync(m->x[1], 0, sizeof(Real) * (size_t)gc.n, st));
+				const int Kb = m->K0[1], Ke = m->K1[1];
 				if (Ke > Kb) {
 					const dim3 grs((unsigned)((ncx + 31) / 32), (unsigned)((gc.sy + 3) / 4), (unsigned)(Ke - Kb)), blk(32, 4, 1);
 					k_mg_restrict_l0_vec<Real, V><<<grs, blk, 0, st>>>(gf, gc, ncx, Kb, m->type[0], m->type[1], (const Real*)l0r<Real>(m), (Real*)m->b[1], (Real*)m->x[1], doneFlag);
 					MP_CHECK_LAUNCH(ctx);
 				}
-				MP_TRY(mp_dist_allreduce_sum(ctx, m->b[1], (size_t)gc.n, (int)sizeof(Real)));
+				// level 1 sharded: every rank needs b1 on its own planes only, which it has just computed; else assemble b1 everywhere
+				if (!nextSharded) MP_TRY(mp_dist_allreduce_sum(ctx, m->b[1], (size_t)gc.n, (int)sizeof(Real)));
 				continue;
 			}
 			const dim3 grv((unsigned)((ncx + 31) / 32), (unsigned)((gc.sy + 3) / 4), (unsigned)gc.sz), blk(32, 4, 1);
@@ -968,7 +995,22 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 			MP_CHECK_LAUNCH(ctx);
 			continue;
 		}
-		k_mg_restrict<Real><<<grid3(gc.sx, gc.sy, gc.sz, gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32)), gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32), 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->r[l], (Real*)m->b[l + 1], (Real*)m->x[l + 1], doneFlag);
+		if (lvlSharded(m, l)) {
+			// sharded fine level: its residual's boundary planes, then this rank's coarse planes; a replicated coarse level is assembled by a sum
+			MP_TRY(lvlHalo<Real>(m, l, m->r[l]));
+			const bool nextSharded = l + 1 < m->nshard;
+			if (!nextSharded) MP_CUDA(cudaMemsetAsync(m->b[l + 1], 0, sizeof(Real) * (size_t)gc.n, st));
+			MP_CUDA(cudaMemsetAsync(m->x[l + 1], 0, sizeof(Real) * (size_t)gc.n, st));
+			const int Kb = (m->K0[l] + 1) / 2, Ke = (m->K1[l] == gf.sz) ? gc.sz : (m->K1[l] + 1) / 2;
+			if (Ke > Kb) {
+				const int bs = gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32);
+				k_mg_restrict<Real><<<grid3(gc.sx, gc.sy, Ke - Kb, bs), bs, 0, st>>>(gf, gc, Kb, m->type[l], m->type[l + 1], (const Real*)m->r[l], (Real*)m->b[l + 1], (Real*)m->x[l + 1], doneFlag);
+				MP_CHECK_LAUNCH(ctx);
+			}
+			if (!nextSharded) MP_TRY(mp_dist_allreduce_sum(ctx, m->b[l + 1], (size_t)gc.n, (int)sizeof(Real)));
+			continue;
+		}
+		k_mg_restrict<Real><<<grid3(gc.sx, gc.sy, gc.sz, gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32)), gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32), 0, st>>>(gf, gc, 0, m->type[l], m->type[l + 1], (const Real*)m->r[l], (Real*)m->b[l + 1], (Real*)m->x[l + 1], doneFlag);
 		MP_CHECK_LAUNCH(ctx);
 	}
 	{
@@ -988,9 +1030,13 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 			k_mg_interp_add_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, nvx, kchunk, kb, ke, m->type[0], m->type[1], (const Real*)m->x[1], l0.x, doneFlag);
 			MP_CHECK_LAUNCH(ctx);
 			if (m->slab) MP_TRY(mp_dist_halo(ctx, l0.xLocal, (size_t)gf.sx * gf.sy * sizeof(Real), m->lsz));      // the post-smoother reads the neighbours' corrected planes
-		} else
-		k_mg_interp_add<Real><<<grid3(gf.sx, gf.sy, gf.sz, gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32)), gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32), 0, st>>>(gf, gc, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], l == 0 ? l0.x : (Real*)m->x[l], doneFlag);
-		MP_CHECK_LAUNCH(ctx);
+		} else {
+			int kb, ke; lvlRange(m, l, &kb, &ke);
+			const int bs = gf.sx >= 96 ? 128 : (gf.sx >= 48 ? 64 : 32);
+			k_mg_interp_add<Real><<<grid3(gf.sx, gf.sy, ke - kb, bs), bs, 0, st>>>(gf, gc, kb, m->type[l], m->type[l + 1], (const Real*)m->x[l + 1], (Real*)m->r[l], l == 0 ? l0.x : (Real*)m->x[l], doneFlag);
+			MP_CHECK_LAUNCH(ctx);
+			if (lvlSharded(m, l)) MP_TRY(lvlHalo<Real>(m, l, m->x[l]));
+		}
 		for (int i = 0; i < m->numPost; i++) MP_TRY((mgSmooth<Real>(m, l, true, false, doneFlag, l0, l == 0 && i == m->numPost - 1 && !wantNorm)));
 	}
 	if (wantNorm) MP_TRY((mgResidual<Real>(m, 0, doneFlag, l0)));      // calcResidual(0) only feeds the returned norm (:496-497)
@@ -1054,6 +1100,7 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 			sz = ds->gsz;
 		}
 	}
+	const bool slabMode = m->slab;
 	m->is3D = sz > 1; m->dim = m->is3D ? 3 : 2; m->stencil = m->is3D ? 14 : 5; m->stencil0 = m->is3D ? 4 : 3;
 	// levels: size_l = (size_{l-1}+2)/2 until all dims <= 5 or n <= 1000 (multigrid.cpp:256-263)
 	int l = 0; m->geom[0] = LvlGeom{ sx, sy, sz, sx * sy * sz };
@@ -1065,6 +1112,24 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 		if (g.n <= 1000) break;
 		LvlGeom c; c.sx = (g.sx + 2) / 2; c.sy = (g.sy + 2) / 2; c.sz = (g.sz + 2) / 2; c.n = c.sx * c.sy * c.sz;
 		m->geom[++l] = c;
+	}
+	m->nshard = 0;
+	if (slabMode) {
+		// plane ranges: coarse plane K belongs to the owner of fine plane 2K (the last rank also takes the planes beyond the fine grid).
+		// A level is sharded while it is large (>= 4 M vertices) and every rank keeps >= 4 of its planes.
+		const DistState* ds = ctx->dist;
+		int maxShard = getenv("MP_MG_SHARD_LEVELS") ? atoi(getenv("MP_MG_SHARD_LEVELS")) : MG_MAXLVL;
+		const long long minN = getenv("MP_MG_SHARD_MIN_N") ? atoll(getenv("MP_MG_SHARD_MIN_N")) : (4ll << 20);      // the parity check shards small levels too
+		if (getenv("MP_MG_FULL") && !atoi(getenv("MP_MG_FULL"))) maxShard = 1;                                     // coarse levels are sharded through the colour-major rows only
+		int minPlanes = m->geom[0].sz;
+		for (int r = 0; r < ds->world; r++) { int a, b; mp_dist_slab(ds->gsz, r, ds->world, &a, &b); minPlanes = std::min(minPlanes, b - a); }
+		m->K0[0] = m->k0; m->K1[0] = m->k1; m->nshard = 1;
+		for (int q = 1; q < m->nlev; q++) {
+			m->K0[q] = (m->K0[q - 1] + 1) / 2;
+			m->K1[q] = (m->K1[q - 1] == m->geom[q - 1].sz) ? m->geom[q].sz : (m->K1[q - 1] + 1) / 2;
+			minPlanes /= 2;
+			if (m->nshard == q && q < maxShard && q < m->nlev - 1 && (long long)m->geom[q].n >= minN && minPlanes >= 4) m->nshard = q + 1;
+		}
 	}
 	for (l = 0; l < m->nlev; l++) {
 		const size_t n = (size_t)m->geom[l].n; const int S = l == 0 ? m->stencil0 : m->stencil;

@@ -75,7 +75,8 @@ for name, prec, extra in cases:
 
 # the global GridMg on z-slabs (rows aligned to 16 bytes): the hierarchy of the GLOBAL grid on every rank, level-0 work of the V-cycle sharded
 # with halo exchanges -- the same V-cycle as a single-GPU solve, so the iteration count is the oracle's and the float result its bits
-for name, prec, shape in [("smoke_pin", 4, (48, 36, 45)), ("liquid", 4, (64, 40, 44)), ("smoke_pin", 8, (48, 36, 45)), ("liquid", 8, (32, 30, 38))]      # (sx, sy, sz):
+# shapes are (sx, sy, sz)
+for name, prec, shape in [("smoke_pin", 4, (48, 36, 45)), ("liquid", 4, (64, 40, 44)), ("smoke_pin", 8, (48, 36, 45)), ("liquid", 8, (32, 30, 38))]:
     phi = None
     if name == "liquid":
         flags, vel, phi = scenes.liquid_basin(shape, prec)
@@ -88,7 +89,9 @@ for name, prec, shape in [("smoke_pin", 4, (48, 36, 45)), ("liquid", 4, (64, 40,
     PH = mf.RealGrid(s, sharded.local_slab(phi, rank, world)) if phi is not None else None
     if rank == 0:
         O = Oracle("port", prec)
-    for pc in (3, 3, 2):          # PcMGStatic twice (second solve reuses the hierarchy), then PcMGDynamic
+    for step, pc in enumerate((3, 3, 2, 2)):          # PcMGStatic twice (second solve reuses the hierarchy), then PcMGDynamic twice:
+        # the last solve shards every level that leaves each rank >= 4 planes (production shards levels of >= 4 M vertices only)
+        os.environ["MP_MG_SHARD_MIN_N"] = "1000" if step == 3 else str(4 << 20)
         V.copyFromArray(sharded.local_slab(vel, rank, world))
         mf.solvePressure(vel=V, pressure=P, flags=F, phi=PH, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=True)
         info = mf.lastSolveInfo()
@@ -98,8 +101,8 @@ for name, prec, shape in [("smoke_pin", 4, (48, 36, 45)), ("liquid", 4, (64, 40,
             p_o, it_o, rn_o = O.solve_pressure(flags, v_o, phi=phi, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=pc, zeroPressureFixing=True)
             e_p, e_v = rel(p_all, p_o), rel(v_all, v_o)
             good = abs(info["iterations"] - it_o) <= 1 and e_p <= (1e-4 if prec == 4 else 1e-10) and e_v <= (1e-4 if prec == 4 else 1e-10)
-            print("sharded_check %-16s f%d world=%d %s GLOBAL GridMg on slabs: iterations %d (single-process oracle %d) levels %d relL2 p %.2e vel %.2e %s"
-                  % (name, prec * 8, world, {2: "PcMGDynamic", 3: "PcMGStatic"}[pc], info["iterations"], it_o, info["mgLevels"], e_p, e_v, "OK" if good else "FAIL"), flush=True)
+            print("sharded_check %-16s f%d world=%d %s GLOBAL GridMg on slabs%s: iterations %d (single-process oracle %d) levels %d relL2 p %.2e vel %.2e %s"
+                  % (name, prec * 8, world, {2: "PcMGDynamic", 3: "PcMGStatic"}[pc], " (coarse levels sharded too)" if step == 3 else "", info["iterations"], it_o, info["mgLevels"], e_p, e_v, "OK" if good else "FAIL"), flush=True)
             ok = ok and good
     mf.releaseMG(s)
     s.close()
