@@ -243,6 +243,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item()
 
+    extra = None
+    if world > 1 and not args.no_configs and args.pc == 0:
+        extra = runner.extra_configs()          # collective
+        t = torch.tensor([extra["pcmgstatic"]["solve_ms"], extra["pcmgstatic"]["solve_ms_cold"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        extra["pcmgstatic"]["solve_ms"], extra["pcmgstatic"]["solve_ms_cold"] = t.tolist()
     if rank == 0:
         cells = res ** 3 * world          # = product of global_grid(res, world)
         peak, peak_src = load_peaks()
@@ -293,6 +299,8 @@ def run_ours(args):
         if world == 1 and not args.no_configs and args.pc == 0 and args.prec == 4:
             runner.release()
             line["configs"] = extra_configs(args, peak)
+        if extra is not None:
+            line["configs"] = extra
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)

@@ -142,6 +142,25 @@ class ShardedBench:
         bo = (self.h_vel.nbytes + self.h_p.nbytes) * self.world
         return float(np.mean(ts)), bi, bo
 
+    def extra_configs(self):
+        """PcMGStatic on the same sharded grid (collective: every rank calls it): the GLOBAL GridMg hierarchy on every rank, levels of >= 4 M
+        vertices swept over the rank's planes with boundary-plane exchanges -- first solve incl. setA (cold) and two with the hierarchy reused"""
+        mf = self.mf
+        kw = dict(self.kw)
+        kw.update(preconditioner=3, zeroPressureFixing=True)
+        ms, info = [], None
+        for _ in range(3):
+            check(self.s.lib.mp_grid_copy_from(self.V.dev(), self.V0.dev()))
+            mf.solvePressure(vel=self.V, pressure=self.P, flags=self.F, **kw)
+            info = mf.lastSolveInfo()
+            ms.append(info["msTotal"])
+        mf.releaseMG(self.s)
+        gx, gy, gz = self.s.globalGridSize
+        return {"pcmgstatic": {"grid": [gx, gy, gz], "preconditioner": "PcMGStatic", "cgAccuracy": kw["cgAccuracy"], "iterations": info["iterations"],
+                               "solve_ms": min(ms[1:]), "solve_ms_cold": ms[0], "mgLevels": info["mgLevels"],
+                               "kernel_ms": {"matvec": info["msMatvecAvg"], "axpy": info["msAxpyAvg"], "precond": info["msPrecondAvg"], "update": info["msUpdateAvg"]},
+                               "exchange": "CG loop: " + self.exchange() + "; V-cycle: NCCL send/recv of boundary planes per colour, one all-reduce at the first replicated level"}}
+
     def exchange(self):
         """how the per-iteration halo planes and scalar partials travelled (mp_dist_exchange_mode)"""
         mode = C.c_int(0)
