@@ -93,6 +93,9 @@ void        mp_pressure_params_default(mp_pressure_params* p);
 int   mp_context_create(int device, mp_context** out);
 int   mp_context_destroy(mp_context* ctx);
 int   mp_context_synchronize(mp_context* ctx);
+/* Freed grids are kept in a per-context pool (FluidSolver::GridStorage, fluidsolver.cpp:33-50) bounded by bytes (16 blocks of the
+ * largest size seen); this returns all of them to the driver. */
+int   mp_context_trim(mp_context* ctx);
 void* mp_context_stream(mp_context* ctx);                      /* cudaStream_t all work is enqueued on */
 int   mp_context_device(const mp_context* ctx);
 int   mp_context_sm_count(const mp_context* ctx);

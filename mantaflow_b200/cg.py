@@ -128,6 +128,7 @@ class GridMg:
         sx, sy, sz = solver.gridSize
         self._h = C.c_void_p()
         check(solver.lib.mp_mg_create(solver._ctx, C.c_int(solver.prec), C.c_int(sx), C.c_int(sy), C.c_int(sz), C.byref(self._h)))
+        solver._adopt(self)
 
     def setA(self, A0, Ai, Aj, Ak):
         check(self.solver.lib.mp_mg_set_a(self._h, A0.dev(), Ai.dev(), Aj.dev(), Ak.dev()))
@@ -176,9 +177,9 @@ class GridMg:
         return out
 
     def close(self):
-        if self._h:
+        if self._h and self.solver._ctx:          # the handle points into the context: once that is gone (Solver.close released us first) nothing is left to free
             self.solver.lib.mp_mg_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -198,6 +199,7 @@ class GridCg:
         self._h = C.c_void_p()
         check(s.lib.mp_cg_create(s._ctx, dst.dev(), rhs.dev(), residual.dev(), search.dev(), flags.dev(), tmp.dev(),
                                  A0.dev(), Ai.dev(), Aj.dev(), Ak.dev(), C.byref(self._h)))
+        s._adopt(self)
         self._keep = []
 
     def setAccuracy(self, v):
@@ -250,9 +252,9 @@ class GridCg:
     def getSigma(self): return self._get()[2]
 
     def close(self):
-        if self._h:
+        if self._h and self.solver._ctx:
             self.solver.lib.mp_cg_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

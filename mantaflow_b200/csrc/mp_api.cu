@@ -2,6 +2,7 @@
 // Reference: Grid<T> grid.cpp:47-96,:205-210; FluidSolver::GridStorage fluidsolver.cpp:33-50;
 // GridDotProduct conjugategrad.cpp:175-178; getMaxAbs grid.cpp:319-323; GridSumSqr commonkernels.h:32-35.
 #include "mp_common.cuh"
+#include <algorithm>
 #include "mp_gridops.cuh"
 #include <thread>
 #include <vector>
@@ -77,6 +78,15 @@ int mp_context_destroy(mp_context* c) {
 	cudaStreamDestroy(c->stream); cudaStreamDestroy(c->copyStream);
 	delete c; return MP_OK;
 }
+// give every pooled (currently unused) device block back to the driver, e.g. before another library on the same GPU needs the memory
+int mp_context_trim(mp_context* c) {
+	if (!c) MP_FAIL(MP_ERR_INVALID, "mp_context_trim: NULL context");
+	MP_CUDA(cudaSetDevice(c->device));
+	MP_CUDA(cudaStreamSynchronize(c->stream));
+	for (auto& pb : c->pool) cudaFree(pb.first);
+	c->pool.clear(); c->poolBytes = 0;
+	return MP_OK;
+}
 int mp_context_synchronize(mp_context* c) { MP_CUDA(cudaSetDevice(c->device)); MP_CUDA(cudaStreamSynchronize(c->stream)); return MP_OK; }
 void* mp_context_stream(mp_context* c) { return (void*)c->stream; }
 int mp_context_device(const mp_context* c) { return c->device; }
@@ -122,8 +132,17 @@ int mp_grid_destroy(mp_grid* g) {
 	if (g->owns) {
 		// stream-ordered reuse: every consumer of a pooled block runs on ctx->stream, so no synchronisation is needed
 		mp_context* ctx = g->ctx;
-		if (ctx->pool.size() < 64) { ctx->pool.push_back(std::make_pair(g->d, g->bytes)); ctx->poolBytes += g->bytes; }
-		else { cudaStreamSynchronize(ctx->stream); cudaFree(g->d); }
+		// the pool is bounded by BYTES: a solve parks ~12 grids, so room for 16 blocks of the largest size seen (at least 1 GiB) is kept and
+		// the oldest blocks go first -- a process that changes grid sizes (or grows particle arrays) does not pile up dead blocks
+		if (g->bytes > ctx->poolMaxBlock) ctx->poolMaxBlock = g->bytes;
+		const size_t cap = std::max((size_t)1 << 30, 16 * ctx->poolMaxBlock);
+		ctx->pool.push_back(std::make_pair(g->d, g->bytes)); ctx->poolBytes += g->bytes;
+		if (ctx->poolBytes > cap || ctx->pool.size() > 256) {
+			cudaStreamSynchronize(ctx->stream);
+			while (!ctx->pool.empty() && (ctx->poolBytes > cap || ctx->pool.size() > 256)) {
+				cudaFree(ctx->pool.front().first); ctx->poolBytes -= ctx->pool.front().second; ctx->pool.erase(ctx->pool.begin());
+			}
+		}
 	}
 	delete g; return MP_OK;
 }

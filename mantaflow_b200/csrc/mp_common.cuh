@@ -43,7 +43,7 @@ struct mp_context {
 	// FluidSolver::GridStorage analogue (fluidsolver.cpp:33-50): freed device blocks are kept for reuse so the
 	// ~12 temporary grids of a solve cost no cudaMalloc/cudaFree after the first call
 	std::vector<std::pair<void*, size_t>> pool;
-	size_t poolBytes = 0;
+	size_t poolBytes = 0, poolMaxBlock = 0;
 	// sampled per-kernel timing of the CG loop
 	int profPeriod = 0;
 	std::vector<cudaEvent_t> profEv;      // 5 events per sample: t0 | matvec | axpy | precond+dot | update

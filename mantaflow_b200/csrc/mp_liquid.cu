@@ -11,6 +11,41 @@ __global__ void __launch_bounds__(liquid::kThreads, 4) k_liquid_cells(Dims d, F 
 	liquid::threadCells(d, f, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);
 }
 
+// ---------------------------------------------------------------- frontier schedule of the extrapolation passes
+// A pass only changes unmarked cells next to a cell that carries the mark of that pass, and those cells were all marked by the pass
+// before.  So instead of sweeping the grid `distance` times (4 B/cell of marks through the L2 per sweep, seven loads per cell), the first
+// sweep also lists the cells it marks, and every further pass walks the six neighbours of the listed cells only -- the SAME per-cell
+// code (F::load / F::apply of mp_liquid_cells.cuh) on the few cells it can change, in any order (see the note on execution order there).
+// A candidate with several listed neighbours is taken by the one that comes first in the neighbour order +x -x +y -y +z -z; the
+// others leave it alone, so a cell is processed and listed once per pass and the lists hold at most one entry per cell.
+struct ListSink {
+	int* list; int* count;
+	__device__ __forceinline__ void operator()(IndexInt idx) const { list[atomicAdd(count, 1)] = (int)idx; }
+};
+template <typename F>
+__global__ void __launch_bounds__(liquid::kThreads, 4) k_liquid_cells_list(Dims d, F f, ListSink sink) {
+	liquid::threadCells(d, f, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x, sink);
+}
+template <typename F>
+__global__ void __launch_bounds__(256) k_liquid_frontier(Dims d, F f, const int* __restrict__ list, const int* __restrict__ countIn, ListSink out) {
+	const int nq = d.is3D ? 6 : 4;
+	const long long work = (long long)(*countIn) * nq;
+	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (long long)gridDim.x * blockDim.x) {
+		const int e = (int)(t / nq), q = (int)(t - (long long)e * nq);
+		const IndexInt nb = (IndexInt)list[e] + liquid::nbOffset(d, q);
+		const int k = d.is3D ? (int)(nb / d.Z) : 0; const IndexInt rem = nb - (IndexInt)k * d.Z;
+		const int j = (int)(rem / d.Y), i = (int)(rem - (IndexInt)j * d.Y);
+		const typename F::State s = f.load(d, i, j, k, nb);
+		if (!s.interior) continue;
+		// from the candidate's side the listed cell is neighbour q ^ 1: take it only if no earlier neighbour is listed too
+		const int mine = q ^ 1;
+		bool owner = f.reached(s.tn[mine]);
+		for (int qq = 0; qq < mine; qq++) owner = owner && !f.reached(s.tn[qq]);
+		if (!owner) continue;
+		if (f.apply(d, i, j, k, nb, s)) out(nb);
+	}
+}
+
 struct CudaExec {
 	mp_context* ctx;
 	template <typename F> int cells(const Dims& d, const F& f) {
@@ -35,12 +70,59 @@ int checkLiquid(const char* who, mp_context* ctx, const mp_grid* g) {
 }
 bool noInterior(const mp_grid* g) { return g->sx < 3 || g->sy < 3 || (g->sz > 1 && g->sz < 3); }
 
+static bool useFrontier(const mp_grid* g) {
+	const char* e = getenv("MP_LIQUID_FRONTIER");      // read per call: the tests run both schedules in one process
+	return (!e || atoi(e)) && g->n < ((IndexInt)1 << 31);
+}
+// two cell lists (one int per cell each, ping-pong) and their counters (ctx->dScal + 32 .. 35 as ints)
+struct Frontier {
+	Tmp a, b; int* cnt;
+	int init(mp_context* ctx, const mp_grid* like) {
+		MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_FLAGS, 4, like->sx, like->sy, like->sz, &a.g));
+		MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_FLAGS, 4, like->sx, like->sy, like->sz, &b.g));
+		cnt = (int*)(ctx->dScal + 32);
+		MP_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(int), ctx->stream));
+		return MP_OK;
+	}
+	int* list(int p) const { return (int*)((p & 1) ? b.g->d : a.g->d); }
+};
+template <typename F> static int cellsListed(mp_context* ctx, const Dims& d, const F& f, int* list, int* count) {
+	const liquid::LaunchGeom g = liquid::launchGeomOf(d);
+	ListSink sink = { list, count };
+	k_liquid_cells_list<F><<<dim3(g.gx, g.gy, g.gz), liquid::kThreads, 0, ctx->stream>>>(d, f, sink);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+template <typename F> static int frontierPass(mp_context* ctx, const Dims& d, const F& f, const int* listIn, const int* countIn, int* listOut, int* countOut) {
+	MP_CUDA(cudaMemsetAsync(countOut, 0, sizeof(int), ctx->stream));
+	ListSink sink = { listOut, countOut };
+	k_liquid_frontier<F><<<ctx->smCount * 4, 256, 0, ctx->stream>>>(d, f, listIn, countIn, sink);
+	MP_CHECK_LAUNCH(ctx);
+	return MP_OK;
+}
+
 template <typename Real>
 int macSimple(mp_context* ctx, const mp_grid* flags, mp_grid* vel, int distance, const mp_grid* phiObs, int intoObs) {
 	Tmp tmp, stage;
 	MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_FLAGS, vel->prec, vel->sx, vel->sy, vel->sz, &tmp.g));      // every cell written by MacMark
 	MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_MAC, vel->prec, vel->sx, vel->sy, vel->sz, &stage.g));       // only its outer layer is written and read
 	CudaExec ex = { ctx };
+	if (useFrontier(vel) && distance >= 2) {
+		// extrapolateMacSimple (mp_liquid_cells.cuh) with passes 2 .. distance on the cell lists
+		const Dims d = dimsOf(flags);
+		Frontier fr; MP_TRY(fr.init(ctx, vel));
+		Real* v = (Real*)vel->d; int* t = (int*)tmp.g->d;
+		{ liquid::MacMark<Real> op = { (const int*)flags->d, t, intoObs ? 1 : 0 }; MP_TRY(ex.cells(d, op)); }
+		{ liquid::MacExtrapolate<Real> op = { v, t, 1 }; MP_TRY(cellsListed(ctx, d, op, fr.list(2), fr.cnt + 0)); }      // pass 1 lists the cells it marks (mark 2)
+		for (int pass = 2; pass < 1 + distance; pass++) {
+			liquid::MacExtrapolate<Real> op = { v, t, pass };
+			MP_TRY(frontierPass(ctx, d, op, fr.list(pass), fr.cnt + (pass & 1), fr.list(pass + 1), fr.cnt + ((pass + 1) & 1)));
+		}
+		if (phiObs) { liquid::UnprojectNormal<Real> op = { v, (const Real*)phiObs->d, (Real)distance }; MP_TRY(ex.cells(d, op)); }
+		{ liquid::IntoBndStage<Real> op = { (const int*)flags->d, v, (Real*)stage.g->d }; MP_TRY(ex.cells(d, op)); }
+		{ liquid::IntoBndCopy<Real> op = { (const Real*)stage.g->d, v }; MP_TRY(ex.cells(d, op)); }
+		return MP_OK;
+	}
 	return liquid::extrapolateMacSimple<Real>(ex, dimsOf(flags), (const int*)flags->d, (Real*)vel->d, distance, phiObs ? (const Real*)phiObs->d : nullptr,
 	                                          intoObs != 0, (int*)tmp.g->d, (Real*)stage.g->d);
 }
@@ -51,6 +133,22 @@ int lsSimple(mp_context* ctx, mp_grid* val, const mp_grid* phi, int distance, in
 	MP_TRY(mp_grid_create_scratch(ctx, MP_GRID_FLAGS, val->prec, val->sx, val->sy, val->sz, &tmp.g));
 	CudaExec ex = { ctx };
 	const Dims d = dimsOf(val);
+	if (useFrontier(val) && distance >= 3) {
+		// extrapolateLs (mp_liquid_cells.cuh): the mark pass lists the first layer (mark 2), passes 2 .. distance run on the lists, the cells
+		// no pass reached get knSetRemaining's value in one sweep at the end
+		const Real direction = vec3 ? (Real)0 : (inside ? (Real)-1. : (Real)1.);
+		const Real remaining = vec3 ? (Real)0 : (Real)(direction * (distance + 2));
+		Frontier fr; MP_TRY(fr.init(ctx, val));
+		int* t = (int*)tmp.g->d;
+		{ liquid::LsMark<Real> op = { (const Real*)phi->d, t, inside ? 1 : 0 }; MP_TRY(cellsListed(ctx, d, op, fr.list(2), fr.cnt + 0)); }
+		for (int pass = 2; pass < 1 + distance; pass++) {
+			int* lin = fr.list(pass); int* cin = fr.cnt + (pass & 1); int* lout = fr.list(pass + 1); int* cout = fr.cnt + ((pass + 1) & 1);
+			if (vec3) { liquid::LsExtrapolate<Real, 3> op = { (Real*)val->d, t, pass, direction, 0, remaining }; MP_TRY(frontierPass(ctx, d, op, lin, cin, lout, cout)); }
+			else      { liquid::LsExtrapolate<Real, 1> op = { (Real*)val->d, t, pass, direction, 0, remaining }; MP_TRY(frontierPass(ctx, d, op, lin, cin, lout, cout)); }
+		}
+		if (vec3) { liquid::LsRemaining<Real, 3> op = { (Real*)val->d, t, remaining }; return ex.cells(d, op); }
+		liquid::LsRemaining<Real, 1> op = { (Real*)val->d, t, remaining }; return ex.cells(d, op);
+	}
 	if (vec3) return liquid::extrapolateLs<Real, 3>(ex, d, (Real*)val->d, (const Real*)phi->d, distance, inside != 0, (Real)0, (Real)0, (int*)tmp.g->d);
 	const Real direction = inside ? (Real)-1. : (Real)1.;
 	return liquid::extrapolateLs<Real, 1>(ex, d, (Real*)val->d, (const Real*)phi->d, distance, inside != 0, direction, (Real)(direction * (distance + 2)), (int*)tmp.g->d);

@@ -41,7 +41,8 @@ inline LaunchGeom launchGeomOf(const Dims& d) {
 // writes.  A thread first loads for all its kCols cells of a row and then applies -- the loads of several cells are in flight together
 // instead of one dependent round trip after the other (the passes are latency bound otherwise: 1 ms per pass at 512^3).  Any order of
 // loads and applies of different cells is as good as any other (see the note on execution order above).
-template <typename F> MP_HD void threadCells(const Dims& d, const F& f, int bx, int by, int bz, int tx) {
+struct NoSink { MP_HD void operator()(IndexInt) const {} };
+template <typename F, typename Sink = NoSink> MP_HD void threadCells(const Dims& d, const F& f, int bx, int by, int bz, int tx, const Sink& sink = Sink()) {
 	const IndexInt plane = (IndexInt)d.sx * d.sy * bz;
 	for (int r = 0; r < kRows; r++) {
 		const int j = by * kRows + r;
@@ -57,7 +58,7 @@ template <typename F> MP_HD void threadCells(const Dims& d, const F& f, int bx, 
 			#pragma unroll
 			for (int c = 0; c < kCols; c++) {
 				const int i = (bx * kCols + c) * kThreads + tx;
-				if (i < d.sx) f.apply(d, i, j, bz, (IndexInt)i + row, st[c]);
+				if (i < d.sx) { if (f.apply(d, i, j, bz, (IndexInt)i + row, st[c])) sink((IndexInt)i + row); }
 			}
 		} else {
 			for (int c = 0; c < kCols; c++) {
@@ -125,8 +126,9 @@ template <typename Real> struct MacExtrapolate {         // knExtrapolateMACSimp
 		s.tn[4] = tmp[idx + d.Z]; s.tn[5] = tmp[idx - d.Z];            // 2-D: Z == 0, the cell itself; not used
 		return s;
 	}
-	MP_HD void apply(const Dims& d, int, int, int, IndexInt idx, const State& s) const {
-		if (!s.interior) return;
+	MP_HD bool reached(int w) const { return (w & 255) == pass || ((w >> 8) & 255) == pass || ((w >> 16) & 255) == pass; }      // some component carries the mark of this pass
+	MP_HD bool apply(const Dims& d, int, int, int, IndexInt idx, const State& s) const {      // true: the cell got a new mark
+		if (!s.interior) return false;
 		const int dim = d.is3D ? 3 : 2;
 		const int t = s.t;
 		int tNew = t;
@@ -138,6 +140,7 @@ template <typename Real> struct MacExtrapolate {         // knExtrapolateMACSimp
 			if (nbs > 0) { tNew |= (pass + 1) << (8 * c); vel[3 * idx + c] = avgVel / (Real)nbs; }
 		}
 		if (tNew != t) tmp[idx] = tNew;
+		return tNew != t;
 	}
 };
 // normalize util/vectorbase.h:415-429: the comparison against 1. and the reciprocal are double expressions
@@ -261,7 +264,7 @@ template <typename Real> struct LsMark {                 // fastmarch.cpp:475-49
 		s.pn[4] = phi[idx + d.Z]; s.pn[5] = phi[idx - d.Z];
 		return s;
 	}
-	MP_HD void apply(const Dims& d, int i, int j, int k, IndexInt idx, const State& s) const {
+	MP_HD bool apply(const Dims& d, int i, int j, int k, IndexInt idx, const State& s) const {      // true: first layer next to the chosen side (mark 2)
 		int m = 0;
 		if (s.interior) {
 			if (on(s.p)) m = 1;
@@ -272,6 +275,7 @@ template <typename Real> struct LsMark {                 // fastmarch.cpp:475-49
 			}
 		}
 		tmp[idx] = m;
+		return m == 2;
 	}
 };
 // knExtrapolateLsSimple<S> fastmarch.cpp:439-460 (NC = 1: Real, 3: Vec3).  `last`: this is the final pass, so cells that stay unmarked
@@ -289,8 +293,9 @@ template <typename Real, int NC> struct LsExtrapolate {
 		s.tn[4] = tmp[idx + d.Z]; s.tn[5] = tmp[idx - d.Z];
 		return s;
 	}
-	MP_HD void apply(const Dims& d, int, int, int, IndexInt idx, const State& s) const {
-		if (!s.interior || s.t != 0) return;
+	MP_HD bool reached(int w) const { return w == pass; }
+	MP_HD bool apply(const Dims& d, int, int, int, IndexInt idx, const State& s) const {      // true: the cell got the mark pass + 1
+		if (!s.interior || s.t != 0) return false;
 		const int dim = d.is3D ? 3 : 2;
 		int nbs = 0;
 		Real avg[NC];
@@ -301,8 +306,9 @@ template <typename Real, int NC> struct LsExtrapolate {
 			for (int c = 0; c < NC; c++) avg[c] += val[NC * nb + c];
 			nbs++;
 		}
-		if (nbs > 0) { tmp[idx] = pass + 1; for (int c = 0; c < NC; c++) val[NC * idx + c] = avg[c] / (Real)nbs + direction; }
-		else if (last) for (int c = 0; c < NC; c++) val[NC * idx + c] = remaining;
+		if (nbs > 0) { tmp[idx] = pass + 1; for (int c = 0; c < NC; c++) val[NC * idx + c] = avg[c] / (Real)nbs + direction; return true; }
+		if (last) for (int c = 0; c < NC; c++) val[NC * idx + c] = remaining;
+		return false;
 	}
 };
 template <typename Real, int NC> struct LsRemaining {

@@ -1062,6 +1062,7 @@ bool mp_mg_matches(const mp_mg* mg, int prec, int sx, int sy, int sz) {      // 
 // InitPreconditionMultigrid conjugategrad.cpp:100-106
 int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, double accuracy)
 {
+	if (!mp_mg_matches(mg, A0->prec, A0->sx, A0->sy, A0->sz)) MP_FAIL(MP_ERR_INVALID, "GridMg preconditioner: the hierarchy was built for another grid size or precision");
 	if (!mg->isASet) MP_TRY(mp_mg_set_a(mg, A0, Ai, Aj, Ak));
 	// mAccuracy * 1E-4 is evaluated in double from a Real accuracy and narrowed to the Real member (multigrid.h:52)
 	mg->coarsestAcc = (mg->prec == 4) ? (double)(float)((double)(float)accuracy * 1E-4) : accuracy * 1E-4;
@@ -1072,6 +1073,8 @@ int mp_mg_precond_init(mp_mg* mg, const mp_grid* A0, const mp_grid* Ai, const mp
 int mp_mg_precond_apply(mp_mg* mg, mp_grid* dst, const mp_grid* rhs, const int* doneFlag)
 {
 	if (!mg->isASet) MP_FAIL(MP_ERR_NOT_SET, "GridMg::setRhs Error: A has not been set.");
+	if (!dst || !rhs || !mp_mg_matches(mg, dst->prec, dst->sx, dst->sy, dst->sz) || !mp_mg_matches(mg, rhs->prec, rhs->sx, rhs->sy, rhs->sz) || dst->kind != MP_GRID_REAL || rhs->kind != MP_GRID_REAL)
+		MP_FAIL(MP_ERR_INVALID, "GridMg preconditioner: dst / rhs do not match the size or precision the hierarchy was built for");
 	mg->isRhsSet = false;      // b0 is not materialised on this path (setRhs is folded into the level-0 kernels)
 	if (mg->prec == 4) return mgVCycle<float>(mg, (float*)dst->d, (const float*)rhs->d, false, false, doneFlag);
 	return mgVCycle<double>(mg, (double*)dst->d, (const double*)rhs->d, false, false, doneFlag);

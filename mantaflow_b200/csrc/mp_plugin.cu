@@ -152,6 +152,9 @@ int mp_solve_pressure_system(mp_context* ctx, mp_grid* rhs, mp_grid* vel, mp_gri
 		maxIter = 100;                                                            // :419
 		pmg = ctx->staticMg;
 		if (pmg && preconditioner == MP_PC_MG_DYNAMIC) { mp_release_mg(ctx); pmg = nullptr; }   // :423-426
+		// a kept hierarchy belongs to one grid size and precision (gMapMG is per FluidSolver, and a FluidSolver has one grid size): a caller
+		// that projects other grids in the same context gets a fresh hierarchy instead of V-cycles with the old geometry
+		if (pmg && !mp_mg_matches(pmg, prec, flags->sx, flags->sy, flags->sz)) { mp_release_mg(ctx); pmg = nullptr; }
 		if (!pmg) {
 			if (ctx->spareMg && mp_mg_matches(ctx->spareMg, prec, flags->sx, flags->sy, flags->sz)) { pmg = ctx->spareMg; ctx->spareMg = nullptr; }
 			else MP_TRY(mp_mg_create(ctx, prec, flags->sx, flags->sy, flags->sz, &pmg));

@@ -6,6 +6,7 @@ Two dirty bits keep them coherent lazily, so a sequence of pressure plugins neve
 Only what the pressure path and its callers need is here; scene construction helpers (initDomain, fillGrid, setConst) are
 the simple host loops of grid.cpp:732-861; updateFromLevelset and setBound, which liquid scenes call every step, run on the device."""
 import ctypes as C
+import weakref
 import numpy as np
 
 from . import _lib
@@ -34,6 +35,12 @@ class Solver:
         self.lib = _lib.load()
         self._ctx = C.c_void_p()
         check(self.lib.mp_context_create(C.c_int(device), C.byref(self._ctx)))
+        # everything that holds device memory or a handle of this context (grids, particle arrays, GridCg, GridMg): close() releases them
+        # BEFORE the context goes, so no handle outlives the mp_context it points into and no device block is leaked
+        self._children = weakref.WeakSet()
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     # solver.create(RealGrid) like the reference's Python API
     def create(self, cls, **kw):
@@ -73,6 +80,10 @@ class Solver:
             raise _lib.MantaError(1, "Invalid dt encountered! Shouldnt happen...")
         self.timestep = float(dt)
 
+    def trim(self):
+        """return the context's pooled (unused) device blocks to the driver (mp_context_trim)"""
+        check(self.lib.mp_context_trim(self._ctx))
+
     def synchronize(self):
         check(self.lib.mp_context_synchronize(self._ctx))
 
@@ -89,6 +100,13 @@ class Solver:
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx:
+            kids = list(getattr(self, "_children", ()))
+            # solvers before their operands: a GridCg / GridMg refers to grids
+            for c in sorted(kids, key=lambda c: 0 if type(c).__name__ in ("GridCg", "GridMg") else 1):
+                try:
+                    c.close()
+                except Exception:
+                    pass
             self.lib.mp_context_destroy(self._ctx)
             self._ctx = C.c_void_p()
 
@@ -115,6 +133,7 @@ class _GridBase:
         self._dev = C.c_void_p()
         check(parent.lib.mp_grid_create(parent._ctx, C.c_int(self.KIND), C.c_int(parent.prec), C.c_int(sx), C.c_int(sy), C.c_int(sz), C.byref(self._dev)))
         self._hostDirty = data is not None      # host holds newer data than the device
+        parent._adopt(self)
         self._devDirty = False                  # device holds newer data than the host
 
     # ---- coherence ----

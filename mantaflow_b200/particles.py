@@ -38,6 +38,7 @@ class _DevArray:
         self._host = np.zeros((n,) + self._tail, self.dtype)
         self._dev, self._cap = C.c_void_p(), 0
         self._hostDirty, self._devDirty = n > 0, False
+        solver._adopt(self)
 
     def __len__(self):
         return len(self._host)

@@ -48,6 +48,35 @@ def test_cuda_equals_oracle_on_larger_scenes(shape, prec):
 
 
 @pytest.mark.parametrize("prec", [4, 8])
+def test_extrapolation_schedules_agree(prec, monkeypatch):
+    """The extrapolation plugins run their passes 2 .. distance on lists of the cells the pass before marked (the frontier schedule of
+    mp_liquid.cu) instead of sweeping the grid per pass: the same per-cell code on the only cells a pass can change.  Both schedules give
+    the same grids bit for bit (3-D with rows longer than a block, 2-D, distances 2 .. 9), and both equal the oracle."""
+    from cuda_impl import CudaImpl
+    from oracle.oracle_api import Oracle
+    O, I = Oracle("port", prec), CudaImpl(prec)
+    for shape in ((37, 45, 150), (1, 70, 66)):
+        helpers.LIQUID_SCENES["sched"] = shape
+        try:
+            flags, vel, phi, phiObs = liquid_scene("sched", prec)
+        finally:
+            del helpers.LIQUID_SCENES["sched"]
+        for distance in (2, 3, 5, 9):
+            res = {}
+            for mode in ("1", "0"):
+                monkeypatch.setenv("MP_LIQUID_FRONTIER", mode)
+                res[mode] = (I.extrapolate_mac_simple(flags, vel.copy(), distance=distance), I.extrapolate_mac_simple(flags, vel.copy(), distance=distance, phiObs=phiObs, intoObs=True),
+                             I.extrapolate_ls_simple(phi.copy(), distance=distance), I.extrapolate_ls_simple(phi.copy(), distance=distance, inside=True),
+                             I.extrapolate_vec3_simple(vel.copy(), phi, distance=distance))
+            ref = (O.extrapolate_mac_simple(flags, vel.copy(), distance=distance), O.extrapolate_mac_simple(flags, vel.copy(), distance=distance, phiObs=phiObs, intoObs=True),
+                   O.extrapolate_ls_simple(phi.copy(), distance=distance), O.extrapolate_ls_simple(phi.copy(), distance=distance, inside=True),
+                   O.extrapolate_vec3_simple(vel.copy(), phi, distance=distance))
+            for q in range(5):
+                assert np.array_equal(res["1"][q], res["0"][q]), (shape, distance, q, "frontier vs sweeps")
+                assert np.array_equal(res["1"][q], ref[q]), (shape, distance, q, "vs the oracle")
+
+
+@pytest.mark.parametrize("prec", [4, 8])
 @pytest.mark.parametrize("name", list(FREESURFACE_SCENES))
 def test_freesurface_steps_match_the_reference(name, prec):
     """scenes/freesurface.py:54-84 through the adapter: identical fluid / empty cells after six steps, fields within the solver tolerance"""
