@@ -187,6 +187,9 @@ int mp_mg_num_levels(const mp_mg* mg, int* levels);
 int mp_mg_level_info(const mp_mg* mg, int level, int* sx, int* sy, int* sz, int* stencil);
 /* parity probes: copy one level's vertex types (int8) / operator (interleaved, multigrid.cpp:208-218) / x,b,r to the host */
 int mp_mg_download(const mp_mg* mg, int level, const char* what /* "type","a","x","b","r" */, void* host);
+/* 1 when level 0 of the V-cycle (doVCycle :458-466,:484-494 on level 0) runs as the fused single-pass kernels: the operator set by the last
+   setA is codable as 2 bytes per vertex (no face fractions), rows are 16-byte aligned, single GPU.  0: the per-colour kernels run. */
+int mp_mg_level0_fused(const mp_mg* mg, int* fused);
 
 /* ---- the plugins, device-resident grids (fields stay in HBM for the whole projection) ---- */
 /* releaseMG pressure.cpp:252-266 (the context plays the FluidSolver key of gMapMG) */

@@ -164,6 +164,12 @@ class GridMg:
         check(self.solver.lib.mp_mg_level_info(self._h, C.c_int(l), C.byref(a), C.byref(b), C.byref(c), C.byref(st)))
         return (a.value, b.value, c.value), st.value
 
+    def level0Fused(self):
+        """True when level 0 of the V-cycle runs as the fused single-pass kernels (mp_mg_level0_fused)"""
+        v = C.c_int(0)
+        check(self.solver.lib.mp_mg_level0_fused(self._h, C.byref(v)))
+        return bool(v.value)
+
     def download(self, what, l):
         (sx, sy, sz), st = self.levelInfo(l)
         n = sx * sy * sz

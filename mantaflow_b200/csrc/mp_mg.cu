@@ -24,6 +24,7 @@
 //   k_mg_coarse_cg                  solveCG :796-902 (double Jacobi-PCG, one CTA; block reductions in fixed order)
 #include "mp_common.cuh"
 #include "mp_mg_coarsen.h"
+#include "mp_mg_l0_fused.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -64,6 +65,8 @@ struct mp_mg {
 	// global-size) level arrays, with an exchange of the two boundary planes of x_l after every colour; coarse plane K belongs to the
 	// owner of fine plane 2K.  Level nshard and below are small and computed redundantly on every rank.
 	int nshard; int K0[MG_MAXLVL], K1[MG_MAXLVL];
+	// the level-0 operator as 2 bytes per vertex for the fused level-0 kernels (mp_mg_l0_fused.cuh); valid when every off-diagonal is 0 / -1
+	unsigned short* mask0; bool mask0Valid;
 };
 
 // ---------------------------------------------------------------- index helpers
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(128) k_mg_l0_vec(LvlGeom g, int is3D, int colo
 // knInterpolate + knAddAssign from level 1 into the level-0 iterate, V fine cells per thread
 template <typename Real, int V>
 __global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeom gc, int nvx, int kchunk, int kb, int ke, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
-	const Real* __restrict__ xc, Real* __restrict__ xf, const int* doneFlag)
+	const Real* __restrict__ xc, Real* xf, Real* xout, const int* doneFlag)      // xout == xf: in place; else every vertex of xout is written
 {
 	if (doneFlag && *doneFlag) return;
 	const int m = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeo
 		bool any = false;
 		#pragma unroll
 		for (int q = 0; q < V; q++) any |= ty.v[q] != vtInactive;
-		if (!any) continue;
+		if (!any) { if (xout != xf) *reinterpret_cast<RVec<Real, V>*>(xout + v) = ldR<Real, V>(xf + v); continue; }
 		const int pz = z & 1;
 		const int base = (x0 >> 1) + cY * (y >> 1) + cZ * (z >> 1);
 		// the V fine cells interpolate from the coarse vertices x0/2 .. x0/2 + V/2 of up to 4 coarse rows; values of inactive ones count as absent
@@ -467,7 +470,7 @@ __global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeo
 				}
 			xv.v[q] += pow2weight<Real>(px + py + pz) * sum;
 		}
-		*reinterpret_cast<RVec<Real, V>*>(xf + v) = xv;
+		*reinterpret_cast<RVec<Real, V>*>(xout + v) = xv;
 	}
 }
 
@@ -523,6 +526,52 @@ __global__ void __launch_bounds__(128) k_mg_restrict_l0_vec(LvlGeom gf, LvlGeom 
 	}
 	#pragma unroll
 	for (int c = 0; c < CW; c++) if (act[c]) dst[linIdx(gc, vx0 + c, vy, vz)] = sum[c];
+}
+
+// ---------------------------------------------------------------- level 0 fused (mp_mg_l0_fused.cuh)
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_build_mask0(LvlGeom g, int is3D, const Real* __restrict__ A, const signed char* __restrict__ type, unsigned short* __restrict__ mask, int* bad)
+{
+	int x, y, z;
+	if (!cell3(g.sx, x, y, z)) return;
+	const mgl0::Geom gg = { g.sx, g.sy, g.sz };
+	int b = 0;
+	mask[linIdx(g, x, y, z)] = mgl0::maskOf<Real>(gg, is3D, x, y, z, A, type, &b);
+	if (b) *bad = 1;
+}
+
+// MODE_DOWN: x = two colour sweeps (c0, then 1 - c0) over a zero iterate, r = b - A x.  MODE_SMOOTH: x = sweep (c0, then c1) over xin
+// (xin != xout: neighbouring CTAs read the halo of xin while this one writes its tile).
+template <typename Real, int MODE>
+__global__ void __launch_bounds__(mgl0::Tile<Real>::NTHR, 2) k_mg_l0_fused(mgl0::Geom g, int kchunk, int c0, int c1, const Real* __restrict__ A0, const Real* __restrict__ b, Real bscale,
+	const unsigned short* __restrict__ mask, const Real* __restrict__ xin, Real* __restrict__ xout, Real* __restrict__ rout, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	typedef mgl0::Tile<Real> T;
+	extern __shared__ __align__(16) unsigned char mgl0_smem[];
+	mgl0::Smem<Real>& s = *reinterpret_cast<mgl0::Smem<Real>*>(mgl0_smem);
+	const int tid = threadIdx.x;
+	const int x0 = blockIdx.x * T::TX, y0 = blockIdx.y * T::TY, k0 = blockIdx.z * kchunk, k1 = min(g.sz, k0 + kchunk);
+	const int cm = MODE == mgl0::MODE_DOWN ? 1 - c0 : c0;      // the colour completed one plane behind the staging
+	mgl0::Pre<Real> p;
+	for (int q = k0 - 2; q <= k0 + 1; q++) {
+		mgl0::issue<Real, MODE>(g, x0, y0, q, tid, b, xin, mask, p);
+		mgl0::stage<Real, MODE>(g, x0, y0, q, tid, bscale, A0, c0, p, s);
+	}
+	__syncthreads();
+	mgl0::mid<Real>(g, x0, y0, k0 - 1, tid, cm, A0, s);
+	mgl0::mid<Real>(g, x0, y0, k0, tid, cm, A0, s);
+	mgl0::issue<Real, MODE>(g, x0, y0, k0 + 2, tid, b, xin, mask, p);
+	__syncthreads();
+	for (int sp = k0; sp < k1; sp++) {
+		mgl0::stage<Real, MODE>(g, x0, y0, sp + 2, tid, bscale, A0, c0, p, s);
+		if (sp + 1 < k1) mgl0::issue<Real, MODE>(g, x0, y0, sp + 3, tid, b, xin, mask, p);      // in flight while this plane is computed
+		__syncthreads();
+		mgl0::mid<Real>(g, x0, y0, sp + 1, tid, cm, A0, s);
+		__syncthreads();
+		mgl0::last<Real, MODE>(g, x0, y0, sp, tid, c1, A0, s, xout, rout);
+		__syncthreads();
+	}
 }
 
 // 27-point (9-point in 2-D) stencil application shared by smoother / residual / coarse CG on levels > 0
@@ -806,6 +855,16 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 	k_mg_copy_activate<Real><<<nb(g0.n, 256), 256, 0, st>>>(g0, m->is3D, (Real)m->trivialScale, (const Real*)A0->d, (const Real*)Ai->d, (const Real*)Aj->d,
 		(const Real*)Ak->d, (Real*)m->A[0], m->type[0], m->dFlags);
 	MP_CHECK_LAUNCH(ctx);
+	m->mask0Valid = false;
+	if (m->mask0) {
+		// the operator as 2 bytes per vertex (mp_mg_l0_fused.cuh); dFlags[5] is raised when a row cannot be coded (face fractions)
+		const int bs = g0.sx >= 96 ? 128 : (g0.sx >= 48 ? 64 : 32);
+		k_mg_build_mask0<Real><<<grid3(g0.sx, g0.sy, g0.sz, bs), bs, 0, st>>>(g0, m->is3D, (const Real*)m->A[0], m->type[0], m->mask0, m->dFlags + 5);
+		MP_CHECK_LAUNCH(ctx);
+		MP_CUDA(cudaMemcpyAsync(m->hFlags + 5, m->dFlags + 5, sizeof(int), cudaMemcpyDeviceToHost, st));
+		MP_CUDA(cudaStreamSynchronize(st));
+		m->mask0Valid = m->hFlags[5] == 0;
+	}
 	m->hostCoarsenLevels = 0;
 	for (int l = 1; l < m->nlev; l++) {
 		const LvlGeom gf = m->geom[l - 1], gc = m->geom[l];
@@ -862,6 +921,40 @@ template <typename Real> static inline bool l0vec(const LvlGeom& g) {
 	return (!e || atoi(e)) && g.sx % (16 / (int)sizeof(Real)) == 0;
 }
 static inline int l0chunk(const LvlGeom& g) { return g.sz >= 64 ? 8 : (g.sz >= 8 ? 4 : 1); }
+
+// fused level-0 kernels (mp_mg_l0_fused.cuh): single GPU, rows on 16-byte boundaries, operator codable as the mask
+template <typename Real> static inline bool l0fused(const mp_mg* m) {
+	const char* e = getenv("MP_MG_L0FUSED");      // read per call: the parity tests run both forms in one process
+	return (!e || atoi(e)) && m->mask0 && m->mask0Valid && !m->slab && l0vec<Real>(m->geom[0]);
+}
+// planes per CTA: every chunk pays 4 planes of warm-up, and the CTAs should fill whole waves of 2 CTAs per SM
+template <typename Real> static inline int l0fusedChunk(const mp_mg* m) {
+	typedef mgl0::Tile<Real> T;
+	const LvlGeom g = m->geom[0];
+	const long long tiles = (long long)((g.sx + T::TX - 1) / T::TX) * ((g.sy + T::TY - 1) / T::TY), slots = 2ll * m->ctx->smCount;
+	int best = g.sz; long long bestCost = -1;
+	for (int nchunk = 1; nchunk <= std::max(1, g.sz / 8); nchunk++) {
+		const int chunk = (g.sz + nchunk - 1) / nchunk;
+		const long long ctas = tiles * ((g.sz + chunk - 1) / chunk), waves = (ctas + slots - 1) / slots;
+		const long long cost = waves * (chunk + 4);
+		if (bestCost < 0 || cost < bestCost) { bestCost = cost; best = chunk; }
+	}
+	return best;
+}
+template <typename Real, int MODE>
+static int l0fusedLaunch(mp_mg* m, int c0, int c1, const Real* b, Real bscale, const Real* xin, Real* xout, Real* rout, const int* doneFlag)
+{
+	typedef mgl0::Tile<Real> T;
+	const LvlGeom g = m->geom[0];
+	static bool attr = false;      // per instantiation
+	if (!attr) { MP_CUDA(cudaFuncSetAttribute(k_mg_l0_fused<Real, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(mgl0::Smem<Real>))); attr = true; }
+	const int chunk = l0fusedChunk<Real>(m);
+	const dim3 gr((unsigned)((g.sx + T::TX - 1) / T::TX), (unsigned)((g.sy + T::TY - 1) / T::TY), (unsigned)((g.sz + chunk - 1) / chunk));
+	const mgl0::Geom gg = { g.sx, g.sy, g.sz };
+	k_mg_l0_fused<Real, MODE><<<gr, T::NTHR, sizeof(mgl0::Smem<Real>), m->ctx->stream>>>(gg, chunk, c0, c1, (const Real*)m->A[0], b, bscale, m->mask0, xin, xout, rout, doneFlag);
+	MP_CHECK_LAUNCH(m->ctx);
+	return MP_OK;
+}
 
 // planes of level l this rank sweeps: its share on sharded levels, everything otherwise
 static inline void lvlRange(const mp_mg* m, int l, int* kb, int* ke) {
@@ -964,11 +1057,16 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 	if (m->slab && !rhsExt) MP_FAIL(MP_ERR_UNSUPPORTED, "GridMg on z-slabs runs as the preconditioner of GridCg only (rhs folded in)");
 	// knSet(x0, 0) :458.  (If a preconditioner call was skipped because the solve is done, dst simply keeps zeros.)
 	const size_t n0 = m->slab ? (size_t)m->geom[0].sx * m->geom[0].sy * m->lsz : (size_t)m->geom[0].n;
-	if (!xInit) MP_CUDA(cudaMemsetAsync(dst, 0, sizeof(Real) * n0, st));
+	const bool fusedDown = maxLevel > 0 && !xInit && m->numPre == 1 && l0fused<Real>(m);      // zero iterate + both colours + residual in one pass (writes every x)
+	const bool fusedUp = maxLevel > 0 && m->numPost == 1 && l0fused<Real>(m);
+	if (!xInit && !fusedDown) MP_CUDA(cudaMemsetAsync(dst, 0, sizeof(Real) * n0, st));
 	for (int l = 0; l < maxLevel; l++) {
+		if (l == 0 && fusedDown) MP_TRY((l0fusedLaunch<Real, mgl0::MODE_DOWN>(m, 0, 0, l0.b, l0.bscale, nullptr, l0.x, (Real*)m->r[0], doneFlag)));
+		else {
 		// with x == 0 on entry the first colour of the first sweep reduces to x = b / A0 (the skipped products are exact zeros)
 		for (int i = 0; i < m->numPre; i++) MP_TRY((mgSmooth<Real>(m, l, false, l == 0 && i == 0 && !xInit, doneFlag, l0)));
 		MP_TRY((mgResidual<Real>(m, l, doneFlag, l0)));
+		}
 		const LvlGeom gf = m->geom[l], gc = m->geom[l + 1];
 		if (l == 0 && l0vec<Real>(gf)) {
 			constexpr int V = 16 / (int)sizeof(Real);
@@ -1027,8 +1125,11 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 			const int nvx = gf.sx / V, kchunk = l0chunk(gf);
 			const int kb = m->slab ? m->k0 : 0, ke = m->slab ? m->k1 : gf.sz;
 			const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((gf.sy + 3) / 4), (unsigned)((ke - kb + kchunk - 1) / kchunk)), blk(32, 4, 1);
-			k_mg_interp_add_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, nvx, kchunk, kb, ke, m->type[0], m->type[1], (const Real*)m->x[1], l0.x, doneFlag);
+			// fused post-smoothing reads the corrected iterate from r0 (free since the restriction) and writes dst: neighbouring CTAs read each other's halos
+			Real* xcorr = fusedUp ? (Real*)m->r[0] : l0.x;
+			k_mg_interp_add_l0_vec<Real, V><<<grv, blk, 0, st>>>(gf, gc, nvx, kchunk, kb, ke, m->type[0], m->type[1], (const Real*)m->x[1], l0.x, xcorr, doneFlag);
 			MP_CHECK_LAUNCH(ctx);
+			if (fusedUp) { MP_TRY((l0fusedLaunch<Real, mgl0::MODE_SMOOTH>(m, 1, 0, l0.b, l0.bscale, xcorr, l0.x, nullptr, doneFlag))); continue; }
 			if (m->slab) MP_TRY(mp_dist_halo(ctx, l0.xLocal, (size_t)gf.sx * gf.sy * sizeof(Real), m->lsz));      // the post-smoother reads the neighbours' corrected planes
 		} else {
 			int kb, ke; lvlRange(m, l, &kb, &ke);
@@ -1150,6 +1251,7 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, nr * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->type[l], 0, n, ctx->stream));
 	}
+	if (!m->slab && sx % (16 / prec) == 0) MP_CUDA(cudaMalloc((void**)&m->mask0, sizeof(unsigned short) * (size_t)m->geom[0].n + 64));
 	MP_CUDA(cudaMalloc((void**)&m->cg, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n));
 	MP_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n, ctx->stream));
 	MP_CUDA(cudaMalloc((void**)&m->dFlags, 64 * sizeof(int)));
@@ -1193,7 +1295,7 @@ int mp_mg_destroy(mp_mg* m)
 	cudaSetDevice(m->ctx->device);
 	cudaStreamSynchronize(m->ctx->stream);
 	for (int l = 0; l < m->nlev; l++) { cudaFree(m->A[l]); cudaFree(m->x[l]); cudaFree(m->b[l]); cudaFree(m->r[l]); cudaFree(m->type[l]); if (m->Afull[l]) cudaFree(m->Afull[l]); }
-	cudaFree(m->cg); cudaFree(m->dPaths); cudaFree(m->dFlags); cudaFreeHost(m->hFlags);
+	cudaFree(m->cg); cudaFree(m->dPaths); cudaFree(m->dFlags); cudaFreeHost(m->hFlags); if (m->mask0) cudaFree(m->mask0);
 	if (m->ctx->staticMg == m) m->ctx->staticMg = nullptr;
 	if (m->ctx->spareMg == m) m->ctx->spareMg = nullptr;
 	delete m; return MP_OK;
@@ -1256,6 +1358,13 @@ int mp_mg_level_info(const mp_mg* m, int level, int* sx, int* sy, int* sz, int* 
 	if (level < 0 || level >= m->nlev) MP_FAIL(MP_ERR_INVALID, "mp_mg_level_info: level %d out of range", level);
 	if (sx) *sx = m->geom[level].sx; if (sy) *sy = m->geom[level].sy; if (sz) *sz = m->geom[level].sz;
 	if (stencil) *stencil = level == 0 ? m->stencil0 : m->stencil;
+	return MP_OK;
+}
+
+int mp_mg_level0_fused(const mp_mg* m, int* fused)
+{
+	if (!m || !fused) MP_FAIL(MP_ERR_INVALID, "mp_mg_level0_fused: NULL argument");
+	*fused = (m->isASet && (m->prec == 4 ? l0fused<float>(m) : l0fused<double>(m)) && m->nlev > 1) ? 1 : 0;
 	return MP_OK;
 }
 

@@ -188,3 +188,46 @@ def test_vcycle_kernel_forms_agree_bit_for_bit(mf, shape, liquid, prec, monkeypa
     ref = out[(0, 0)]
     for k, v in out.items():
         assert np.array_equal(v[0], ref[0]) and np.array_equal(v[1], ref[1]), ("V-cycle forms differ", k)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("shape,liquid", [((24, 24, 24), False), ((40, 36, 64), False), ((33, 47, 72), True), ((1, 40, 48), False), ((70, 66, 132), False), ((37, 50, 260), True)])
+def test_vcycle_level0_fused_agrees_bit_for_bit(mf, shape, liquid, prec, monkeypatch):
+    """Level 0 of the V-cycle as the fused single-pass kernels (mp_mg_l0_fused.cuh: zero iterate + both colours + residual in one pass on the
+    way down, both colours of the post-smoothing in one pass on the way up, the operator as 2 bytes per vertex) does the arithmetic of the
+    per-colour kernels term for term: iterates, residual norms and a PcMGStatic solve are the same bit for bit.  (The host walk of the same
+    phase functions is checked against numpy in tests/test_mg_l0_fused_emul.py.)"""
+    from mantaflow_b200 import cg
+    from test_gpu_parity import random_domain
+    flags, vel, phi = random_domain(shape, prec, seed=shape[1] + 1, liquid=liquid)
+    O = oracle(prec)
+    rhs, _, _ = O.compute_rhs(flags, vel, phi=phi)
+    A_o = O.make_matrix(flags, phi=phi)
+    fix = O.choose_fix_cell(flags)
+    if fix >= 0:
+        O.fix_pressure(flags, fix, 0.0, rhs, *A_o)
+    out = {}
+    for fused in (1, 0):
+        monkeypatch.setenv("MP_MG_L0FUSED", str(fused))
+        s = mk(mf, flags.shape, prec)
+        A = [mf.RealGrid(s, a) for a in A_o]
+        mg = cg.GridMg(s)
+        B, Z, Z2 = mf.RealGrid(s, rhs), mf.RealGrid(s), mf.RealGrid(s)
+        mg.setA(*A)
+        assert mg.level0Fused() == bool(fused)
+        mg.setRhs(B)
+        r1 = mg.doVCycle(Z)                     # fused down + fused up
+        r2 = mg.doVCycle(Z2, Z)                 # initial guess given: per-colour pre-smoothing, fused up
+        # the preconditioner path (rhs scaled on the fly, no residual norm)
+        F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+        PH = mf.RealGrid(s, phi) if phi is not None else None
+        mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=1e-5 if prec == 4 else 1e-9, phi=PH, preconditioner=mf.PcMGStatic, cgMaxIterFac=99,
+                         zeroPressureFixing=True)
+        out[fused] = (Z.numpy().copy(), Z2.numpy().copy(), r1, r2, P.numpy().copy(), V.numpy().copy(), mf.lastSolveInfo()["iterations"])
+        assert r2 < r1
+        mf.releaseMG(s)
+        mg.close(); s.close()
+    a, b = out[1], out[0]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), "fused level-0 V-cycle differs from the per-colour kernels"
+    assert a[2] == b[2] and a[3] == b[3]
+    assert a[6] == b[6] and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]), "PcMGStatic solve differs"
