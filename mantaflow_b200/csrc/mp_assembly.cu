@@ -31,7 +31,7 @@ template <typename Real> __device__ __forceinline__ bool ghostFluidWasClamped(In
 
 // interior test of KERNEL(bnd=1): kernel.cpp:21-30
 __device__ __forceinline__ bool interior(const Dims& d, IndexInt idx, int& i, int& j, int& k) {
-	i = (int)(idx % d.sx); const IndexInt t = idx / d.sx; j = (int)(t % d.sy); k = (int)(t / d.sy);
+	cellOf(d, idx, i, j, k);
 	if (i < 1 || i >= d.sx - 1 || j < 1 || j >= d.sy - 1) return false;
 	if (d.is3D) { const int kg = k + d.kOff; return k >= d.kb && k < d.ke && kg >= 1 && kg < d.gsz - 1; }   // owned plane, global interior
 	return true;

@@ -222,8 +222,8 @@ __global__ void __launch_bounds__(256) k_build_cmask(Dims d, const int* __restri
 			#pragma unroll
 			for (int q = 0; q < 7; q++) if (a0 == (Real)q) code = q;
 		}
-		const IndexInt k = idx / d.Z, rem = idx - k * d.Z; const IndexInt j = rem / d.Y, i = rem - j * d.Y;
-		mask16[(k * d.sy + j) * pitch + i] = (unsigned short)(m | (code << 7));
+		int i, j, k; cellOf(d, idx, i, j, k);
+		mask16[((size_t)k * d.sy + j) * pitch + i] = (unsigned short)(m | (code << 7));
 	}
 }
 

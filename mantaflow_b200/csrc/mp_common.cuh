@@ -110,6 +110,16 @@ struct Dims {
 	int kb, ke, kOff, gsz, world;
 	IndexInt i0, i1;         // owned linear range [kb*Z, ke*Z) (whole grid on a single GPU / in 2-D)
 };
+// linear index -> (i, j, k).  A 64-bit division costs ~100 instructions; every grid of one GPU has < 2^31 cells, so the common case takes
+// two 32-bit unsigned divisions (a warp-uniform branch).
+__host__ __device__ __forceinline__ void cellOf(const Dims& d, IndexInt idx, int& i, int& j, int& k) {
+	if (d.n <= 0x7fffffffLL) {
+		const unsigned u = (unsigned)idx, t = u / (unsigned)d.sx;
+		i = (int)(u - t * (unsigned)d.sx); k = (int)(t / (unsigned)d.sy); j = (int)(t - (unsigned)k * (unsigned)d.sy);
+	} else {
+		i = (int)(idx % d.sx); const IndexInt t = idx / d.sx; j = (int)(t % d.sy); k = (int)(t / d.sy);
+	}
+}
 static inline Dims dimsOf(const mp_grid* g) {
 	Dims d; d.sx = g->sx; d.sy = g->sy; d.sz = g->sz; d.is3D = g->sz > 1;
 	d.X = 1; d.Y = g->sx; d.Z = d.is3D ? (IndexInt)g->sx * g->sy : 0; d.n = (IndexInt)g->sx * g->sy * g->sz;

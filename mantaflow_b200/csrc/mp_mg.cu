@@ -420,6 +420,83 @@ __global__ void __launch_bounds__(128) k_mg_l0_vec(LvlGeom g, int is3D, int colo
 	}
 }
 
+// k_mg_l0_vec with the operator as the 2-byte mask of mp_mg_l0_fused.cuh instead of the type byte + four coefficient arrays: a pass
+// streams 2 + 3w bytes per cell (MODE 0), 2 + 2w (MODE 1), 2 + 4w (MODE 2) instead of 1 + 7w.  Same terms in the same order; a coupling
+// of -1 is added as `sum += x`, a coupling of +0 is skipped (signs of exact zeros aside, the same value).
+template <typename Real, int V, int MODE>
+__global__ void __launch_bounds__(128) k_mg_l0_vecm(LvlGeom g, int color, int nvx, int kchunk, int kb, int ke, const Real* __restrict__ A0, const unsigned short* __restrict__ mask,
+	const Real* __restrict__ b, Real bscale, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	const int m = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+	if (m >= nvx || j >= g.sy) return;
+	const int k0 = kb + blockIdx.z * kchunk, k1 = min(ke, k0 + kchunk);
+	const int Y = g.sx, Z = g.sx * g.sy;
+	const int i0 = m * V;
+	typedef mgl0::Vec<unsigned short, V> MVec;
+	for (int k = k0; k < k1; k++) {
+		const int v = i0 + Y * j + Z * k;
+		const MVec mv = *reinterpret_cast<const MVec*>(mask + v);
+		unsigned mine = 0, any7 = 0;
+		#pragma unroll
+		for (int q = 0; q < V; q++) {
+			if ((mv.v[q] & mgl0::mActive) && (MODE == 2 || ((i0 + q + j + k + color) & 1) == 0)) mine |= 1u << q;
+			any7 |= (unsigned)(((mv.v[q] >> 7) & 7) == 7) << q;
+		}
+		RVec<Real, V> out;
+		#pragma unroll
+		for (int q = 0; q < V; q++) out.v[q] = (Real)0;
+		if (!mine) {
+			if (MODE == 1) *reinterpret_cast<RVec<Real, V>*>(x + v) = out;
+			if (MODE == 2) *reinterpret_cast<RVec<Real, V>*>(r + v) = out;      // inactive vertices: r stays 0
+			continue;
+		}
+		RVec<Real, V> bv = ldR<Real, V>(b + v), a0;
+		#pragma unroll
+		for (int q = 0; q < V; q++) a0.v[q] = (Real)(int)((mv.v[q] >> 7) & 7);
+		if (any7 & mine) {      // ghost-fluid diagonals, trivial rows: the stored value
+			#pragma unroll
+			for (int q = 0; q < V; q++) if ((any7 >> q) & 1) a0.v[q] = A0[v + q];
+		}
+		if (bscale != (Real)0) {
+			#pragma unroll
+			for (int q = 0; q < V; q++) if (mv.v[q] & mgl0::mTrivial) bv.v[q] *= bscale;
+		}
+		if (MODE == 1) {
+			#pragma unroll
+			for (int q = 0; q < V; q++) if ((mine >> q) & 1) out.v[q] = bv.v[q] / a0.v[q];
+			*reinterpret_cast<RVec<Real, V>*>(x + v) = out;
+			continue;
+		}
+		const RVec<Real, V> xc = ldR<Real, V>(x + v);
+		RVec<Real, V> xym, xyp, xzm, xzp;
+		#pragma unroll
+		for (int q = 0; q < V; q++) { xym.v[q] = xyp.v[q] = xzm.v[q] = xzp.v[q] = (Real)0; }
+		if (j > 0) xym = ldR<Real, V>(x + v - Y);
+		if (j < g.sy - 1) xyp = ldR<Real, V>(x + v + Y);
+		if (k > 0) xzm = ldR<Real, V>(x + v - Z);
+		if (k < g.sz - 1) xzp = ldR<Real, V>(x + v + Z);
+		Real xm0 = (Real)0, xpL = (Real)0;
+		if (i0 > 0) xm0 = x[v - 1];
+		if (i0 + V < g.sx) xpL = x[v + V];
+		if (MODE == 0) out = xc;
+		#pragma unroll
+		for (int q = 0; q < V; q++) if ((mine >> q) & 1) {
+			const unsigned mm = mv.v[q];
+			Real sum = bv.v[q];
+			if (mm & 2u)  sum += (q == 0 ? xm0 : xc.v[q - 1 < 0 ? 0 : q - 1]);
+			if (mm & 4u)  sum += (q == V - 1 ? xpL : xc.v[q + 1 > V - 1 ? V - 1 : q + 1]);
+			if (mm & 8u)  sum += xym.v[q];
+			if (mm & 16u) sum += xyp.v[q];
+			if (mm & 32u) sum += xzm.v[q];
+			if (mm & 64u) sum += xzp.v[q];
+			if (MODE == 2) { sum -= a0.v[q] * xc.v[q]; out.v[q] = sum; }
+			else out.v[q] = sum / a0.v[q];
+		}
+		*reinterpret_cast<RVec<Real, V>*>((MODE == 2 ? r : x) + v) = out;
+	}
+}
+
 // knInterpolate + knAddAssign from level 1 into the level-0 iterate, V fine cells per thread
 template <typename Real, int V>
 __global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeom gc, int nvx, int kchunk, int kb, int ke, const signed char* __restrict__ tf, const signed char* __restrict__ tc,
@@ -550,26 +627,26 @@ __global__ void __launch_bounds__(mgl0::Tile<Real>::NTHR, 2) k_mg_l0_fused(mgl0:
 	typedef mgl0::Tile<Real> T;
 	extern __shared__ __align__(16) unsigned char mgl0_smem[];
 	mgl0::Smem<Real>& s = *reinterpret_cast<mgl0::Smem<Real>*>(mgl0_smem);
-	const int tid = threadIdx.x;
 	const int x0 = blockIdx.x * T::TX, y0 = blockIdx.y * T::TY, k0 = blockIdx.z * kchunk, k1 = min(g.sz, k0 + kchunk);
 	const int cm = MODE == mgl0::MODE_DOWN ? 1 - c0 : c0;      // the colour completed one plane behind the staging
+	const mgl0::Ctx<Real> c = mgl0::makeCtx<Real>(g, x0, y0, threadIdx.x);
 	mgl0::Pre<Real> p;
 	for (int q = k0 - 2; q <= k0 + 1; q++) {
-		mgl0::issue<Real, MODE>(g, x0, y0, q, tid, b, xin, mask, p);
-		mgl0::stage<Real, MODE>(g, x0, y0, q, tid, bscale, A0, c0, p, s);
+		mgl0::issue<Real, MODE>(g, c, q, b, xin, mask, p);
+		mgl0::stage<Real, MODE>(g, c, q, bscale, A0, c0, p, s);
 	}
 	__syncthreads();
-	mgl0::mid<Real>(g, x0, y0, k0 - 1, tid, cm, A0, s);
-	mgl0::mid<Real>(g, x0, y0, k0, tid, cm, A0, s);
-	mgl0::issue<Real, MODE>(g, x0, y0, k0 + 2, tid, b, xin, mask, p);
+	mgl0::mid<Real>(g, c, k0 - 1, cm, A0, s);
+	mgl0::mid<Real>(g, c, k0, cm, A0, s);
+	mgl0::issue<Real, MODE>(g, c, k0 + 2, b, xin, mask, p);
 	__syncthreads();
 	for (int sp = k0; sp < k1; sp++) {
-		mgl0::stage<Real, MODE>(g, x0, y0, sp + 2, tid, bscale, A0, c0, p, s);
-		if (sp + 1 < k1) mgl0::issue<Real, MODE>(g, x0, y0, sp + 3, tid, b, xin, mask, p);      // in flight while this plane is computed
+		mgl0::stage<Real, MODE>(g, c, sp + 2, bscale, A0, c0, p, s);
+		if (sp + 1 < k1) mgl0::issue<Real, MODE>(g, c, sp + 3, b, xin, mask, p);      // in flight while this plane is computed
 		__syncthreads();
-		mgl0::mid<Real>(g, x0, y0, sp + 1, tid, cm, A0, s);
+		mgl0::mid<Real>(g, c, sp + 1, cm, A0, s);
 		__syncthreads();
-		mgl0::last<Real, MODE>(g, x0, y0, sp, tid, c1, A0, s, xout, rout);
+		mgl0::last<Real, MODE>(g, c, sp, c1, A0, s, xout, rout);
 		__syncthreads();
 	}
 }
@@ -663,15 +740,19 @@ __global__ void __launch_bounds__(128) k_mg_build_full(LvlGeom g, int hbx, int h
 	}
 }
 
-// one colour of knSmoothColor (:668-711) / knCalcResidual (:739-771) over the colour-major rows; RESID: all colours in one launch
+// one colour of knSmoothColor (:668-711) / knCalcResidual (:739-771) over the colour-major rows; RESID: all colours in one launch.
+// Threads are numbered along the 2x2-block rows of a plane (no CTA is left with a one-vertex tail when a row is 128 k + 1 blocks long); a
+// thread first puts its whole row of coefficients and its neighbours' iterate in flight (streaming loads for the coefficients, which are
+// read once per sweep, so that the iterate -- re-read by every colour -- stays in L2), then accumulates in the reference's order.
 template <typename Real, bool IS3D, bool RESID>
-__global__ void __launch_bounds__(128) k_mg_sweep_full(LvlGeom g, int hbx, int hby, int hbz, int color, int tz0, int ntz, int Kb, int Ke, const Real* __restrict__ Afull, const Real* __restrict__ b,
+__global__ void __launch_bounds__(128, 6) k_mg_sweep_full(LvlGeom g, int hbx, int hby, int hbz, int color, int tz0, int ntz, int Kb, int Ke, const Real* __restrict__ Afull, const Real* __restrict__ b,
 	const signed char* __restrict__ type, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
 {
 	if (doneFlag && *doneFlag) return;
 	constexpr int S = IS3D ? 14 : 5, NENT = IS3D ? 27 : 9;
-	const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y;
-	if (tx >= hbx) return;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= hbx * hby) return;
+	const int ty = t / hbx, tx = t - ty * hbx;
 	// blockIdx.z walks the 2-plane blocks [tz0, tz0 + ntz) (all of them, or those that hold this rank's planes [Kb,Ke)); RESID: x all colours
 	int c = color, tz = tz0 + blockIdx.z;
 	if (RESID) { c = blockIdx.z / ntz; tz = tz0 + blockIdx.z - c * ntz; }
@@ -682,16 +763,23 @@ __global__ void __launch_bounds__(128) k_mg_sweep_full(LvlGeom g, int hbx, int h
 	const size_t nc = (size_t)hbx * hby * hbz;
 	const Real* a = Afull + (size_t)c * NENT * nc + (tx + (size_t)hbx * (ty + (size_t)hby * tz));
 	const bool interior = vx > 0 && vy > 0 && vx < g.sx - 1 && vy < g.sy - 1 && (!IS3D || (vz > 0 && vz < g.sz - 1));
+	Real av[NENT], xv[NENT];
+	#pragma unroll
+	for (int s = 0; s < NENT; s++) av[s] = __ldcs(a + (size_t)s * nc);
+	#pragma unroll
+	for (int s = 0; s < NENT; s++) {
+		const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = IS3D ? s / 9 - 1 : 0;
+		int nb = v + dx + g.sx * (dy + g.sy * dz);
+		if (!interior && !inGrid(g, vx + dx, vy + dy, vz + dz)) nb = v;      // coefficient is 0 there
+		xv[s] = x[nb];
+	}
 	Real sum = b[v];
 	#pragma unroll
 	for (int s = 0; s < NENT; s++) {
 		if (!RESID && s == S - 1) continue;
-		const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = IS3D ? s / 9 - 1 : 0;
-		int nb = v + dx + g.sx * (dy + g.sy * dz);
-		if (!interior && !inGrid(g, vx + dx, vy + dy, vz + dz)) nb = v;      // coefficient is 0 there
-		sum -= a[(size_t)s * nc] * x[nb];
+		sum -= av[s] * xv[s];
 	}
-	if (RESID) r[v] = sum; else x[v] = sum / a[(size_t)(S - 1) * nc];
+	if (RESID) r[v] = sum; else x[v] = sum / av[S - 1];
 }
 
 // knRestrict :904-927 (dst level = coarse), also zeroes x on the coarse level (knSet :472)
@@ -924,8 +1012,10 @@ static inline int l0chunk(const LvlGeom& g) { return g.sz >= 64 ? 8 : (g.sz >= 8
 
 // fused level-0 kernels (mp_mg_l0_fused.cuh): single GPU, rows on 16-byte boundaries, operator codable as the mask
 template <typename Real> static inline bool l0fused(const mp_mg* m) {
-	const char* e = getenv("MP_MG_L0FUSED");      // read per call: the parity tests run both forms in one process
-	return (!e || atoi(e)) && m->mask0 && m->mask0Valid && !m->slab && l0vec<Real>(m->geom[0]);
+	// read per call: the parity tests run both forms in one process.  Default: on in double, off in float -- measured at 512^3 (profiles/r2_mg_bench.txt):
+	// the fused pair is instruction bound (halo recomputation, three barriers per plane) and only beats the masked per-colour kernels in double
+	const char* e = getenv("MP_MG_L0FUSED");
+	return (e ? atoi(e) != 0 : sizeof(Real) == 8) && m->mask0 && m->mask0Valid && !m->slab && l0vec<Real>(m->geom[0]);
 }
 // planes per CTA: every chunk pays 4 planes of warm-up, and the CTAs should fill whole waves of 2 CTAs per SM
 template <typename Real> static inline int l0fusedChunk(const mp_mg* m) {
@@ -940,6 +1030,11 @@ template <typename Real> static inline int l0fusedChunk(const mp_mg* m) {
 		if (bestCost < 0 || cost < bestCost) { bestCost = cost; best = chunk; }
 	}
 	return best;
+}
+// the per-colour level-0 kernels with the operator mask (k_mg_l0_vecm)
+template <typename Real> static inline bool l0masked(const mp_mg* m) {
+	const char* e = getenv("MP_MG_L0MASK");      // read per call
+	return (!e || atoi(e)) && m->mask0 && m->mask0Valid && !m->slab && l0vec<Real>(m->geom[0]);
 }
 template <typename Real, int MODE>
 static int l0fusedLaunch(mp_mg* m, int c0, int c1, const Real* b, Real bscale, const Real* xin, Real* xout, Real* rout, const int* doneFlag)
@@ -981,7 +1076,11 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 				const int nvx = g.sx / V, kchunk = l0chunk(g);
 				const int kb = m->slab ? m->k0 : 0, ke = m->slab ? m->k1 : g.sz;
 				const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((g.sy + 3) / 4), (unsigned)((ke - kb + kchunk - 1) / kchunk)), blk(32, 4, 1);
-				if (zeroX && c == 0) k_mg_l0_vec<Real, V, 1><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, kb, ke, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
+				if (l0masked<Real>(m)) {
+					if (zeroX && c == 0) k_mg_l0_vecm<Real, V, 1><<<grv, blk, 0, st>>>(g, color, nvx, kchunk, kb, ke, (const Real*)m->A[0], m->mask0, l0.b, l0.bscale, l0.x, nullptr, doneFlag);
+					else                 k_mg_l0_vecm<Real, V, 0><<<grv, blk, 0, st>>>(g, color, nvx, kchunk, kb, ke, (const Real*)m->A[0], m->mask0, l0.b, l0.bscale, l0.x, nullptr, doneFlag);
+				}
+				else if (zeroX && c == 0) k_mg_l0_vec<Real, V, 1><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, kb, ke, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
 				else                 k_mg_l0_vec<Real, V, 0><<<grv, blk, 0, st>>>(g, m->is3D, color, nvx, kchunk, kb, ke, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, nullptr, doneFlag);
 				MP_CHECK_LAUNCH(ctx);
 				// slab mode: the neighbours' boundary planes of this colour before the next colour (or the residual) reads them
@@ -1004,9 +1103,10 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 				const int hby = (g.sy + 1) / 2, hbz = m->is3D ? (g.sz + 1) / 2 : 1;
 				int Kb, Ke; lvlRange(m, l, &Kb, &Ke);
 				const int tz0 = m->is3D ? Kb / 2 : 0, ntz = m->is3D ? (Ke - 1) / 2 - tz0 + 1 : 1;
-				const dim3 grz(gr.x, gr.y, (unsigned)ntz);
-				if (m->is3D) k_mg_sweep_full<Real, true, false><<<grz, bsz, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
-				else         k_mg_sweep_full<Real, false, false><<<grz, bsz, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
+				const int bszF = hbx * hby >= 4096 ? 128 : (hbx * hby >= 512 ? 64 : 32);
+				const dim3 grz((unsigned)((hbx * hby + bszF - 1) / bszF), 1u, (unsigned)ntz);
+				if (m->is3D) k_mg_sweep_full<Real, true, false><<<grz, bszF, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
+				else         k_mg_sweep_full<Real, false, false><<<grz, bszF, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
 				MP_CHECK_LAUNCH(ctx);
 				if (lvlSharded(m, l)) MP_TRY(lvlHalo<Real>(m, l, m->x[l]));      // the next colour (or the residual / the interpolation) reads the neighbours' planes
 				continue;
@@ -1029,7 +1129,8 @@ static int mgResidual(mp_mg* m, int l, const int* doneFlag, const L0<Real>& l0)
 		const int nvx = g.sx / V, kchunk = l0chunk(g);
 		const int kb = m->slab ? m->k0 : 0, ke = m->slab ? m->k1 : g.sz;
 		const dim3 grv((unsigned)((nvx + 31) / 32), (unsigned)((g.sy + 3) / 4), (unsigned)((ke - kb + kchunk - 1) / kchunk)), blk(32, 4, 1);
-		k_mg_l0_vec<Real, V, 2><<<grv, blk, 0, st>>>(g, m->is3D, 0, nvx, kchunk, kb, ke, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, l0r<Real>(m), doneFlag);
+		if (l0masked<Real>(m)) k_mg_l0_vecm<Real, V, 2><<<grv, blk, 0, st>>>(g, 0, nvx, kchunk, kb, ke, (const Real*)m->A[0], m->mask0, l0.b, l0.bscale, l0.x, l0r<Real>(m), doneFlag);
+		else k_mg_l0_vec<Real, V, 2><<<grv, blk, 0, st>>>(g, m->is3D, 0, nvx, kchunk, kb, ke, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], l0.x, l0r<Real>(m), doneFlag);
 	}
 	else if (l == 0) k_mg_residual0<Real><<<grid3(g.sx, g.sy, g.sz, 128), 128, 0, st>>>(g, m->is3D, (const Real*)m->A[0], l0.b, l0.bscale, m->type[0], (const Real*)l0.x, (Real*)m->r[0], doneFlag);
 	else if (m->Afull[l]) {
@@ -1037,9 +1138,10 @@ static int mgResidual(mp_mg* m, int l, const int* doneFlag, const L0<Real>& l0)
 		const int bsz = hbx >= 96 ? 128 : (hbx >= 48 ? 64 : 32);
 		int Kb, Ke; lvlRange(m, l, &Kb, &Ke);
 		const int tz0 = m->is3D ? Kb / 2 : 0, ntz = m->is3D ? (Ke - 1) / 2 - tz0 + 1 : 1;
-		const dim3 gr((unsigned)((hbx + bsz - 1) / bsz), (unsigned)hby, (unsigned)(ntz * ncol));
-		if (m->is3D) k_mg_sweep_full<Real, true, true><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
-		else         k_mg_sweep_full<Real, false, true><<<gr, bsz, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
+		const int bszF = hbx * hby >= 4096 ? 128 : (hbx * hby >= 512 ? 64 : 32);
+		const dim3 gr((unsigned)((hbx * hby + bszF - 1) / bszF), 1u, (unsigned)(ntz * ncol));
+		if (m->is3D) k_mg_sweep_full<Real, true, true><<<gr, bszF, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
+		else         k_mg_sweep_full<Real, false, true><<<gr, bszF, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
 	}
 	else        k_mg_residualN<Real><<<grid3(g.sx, g.sy, g.sz, g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32)), g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32), 0, st>>>(g, m->is3D, m->stencil, (const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (const Real*)m->x[l], (Real*)m->r[l], doneFlag);
 	MP_CHECK_LAUNCH(ctx);

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) k_diffusion_matrix(Dims d, const int* __r
 {
 	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= d.n) return;
-	const int i = (int)(idx % d.sx); const IndexInt t = idx / d.sx; const int j = (int)(t % d.sy), k = (int)(t / d.sy);
+	int i, j, k; cellOf(d, idx, i, j, k);
 	const bool interior = i >= 1 && i < d.sx - 1 && j >= 1 && j < d.sy - 1 && (!d.is3D || (k >= 1 && k < d.sz - 1));
 	Real a0 = 0, ai = 0, aj = 0, ak = 0;
 	if (interior) { a0 = d.is3D ? (Real)6 : (Real)4; ai = (Real)-1; aj = (Real)-1; if (d.is3D) ak = (Real)-1; }
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_we_setup(Dims d, Real s, Real* __restri
 {
 	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= d.n) return;
-	const int i = (int)(idx % d.sx); const IndexInt t = idx / d.sx; const int j = (int)(t % d.sy), k = (int)(t / d.sy);
+	int i, j, k; cellOf(d, idx, i, j, k);
 	Ai[idx] = Ai[idx] * s; Aj[idx] = Aj[idx] * s; Ak[idx] = Ak[idx] * s;
 	A0[idx] = (Real)((double)(A0[idx] * s) + 1.);
 	const bool interior = i >= 1 && i < d.sx - 1 && j >= 1 && j < d.sy - 1 && (!d.is3D || (k >= 1 && k < d.sz - 1));

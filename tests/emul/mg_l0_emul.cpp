@@ -27,24 +27,27 @@ static void run(int sx, int sy, int sz, int kchunk, int cFirst, int cSecond, con
 	const Geom g = { sx, sy, sz };
 	std::vector<Smem<Real>> smv(1); Smem<Real>& s = smv[0];
 	std::vector<Pre<Real>> pre(T::NTHR);
+	std::vector<Ctx<Real>> ctx(T::NTHR);
 	const int tilesX = (sx + T::TX - 1) / T::TX, tilesY = (sy + T::TY - 1) / T::TY, nchunk = (sz + kchunk - 1) / kchunk;
 	auto tidOf = [&](int t) { return order ? T::NTHR - 1 - t : t; };
+	const int cm = MODE == MODE_DOWN ? 1 - cFirst : cFirst;
 	for (int bz = 0; bz < nchunk; bz++) for (int by = 0; by < tilesY; by++) for (int bx = 0; bx < tilesX; bx++) {
 		// shared memory comes uninitialised
 		memset(&s, 0x7f, sizeof(s));
 		const int x0 = bx * T::TX, y0 = by * T::TY, k0 = bz * kchunk, k1 = std::min(sz, k0 + kchunk);
+		for (int t = 0; t < T::NTHR; t++) ctx[t] = makeCtx<Real>(g, x0, y0, t);
 		for (int q = k0 - 2; q <= k0 + 1; q++)
-			for (int t = 0; t < T::NTHR; t++) { const int tid = tidOf(t); issue<Real, MODE>(g, x0, y0, q, tid, b, xin, mask, pre[tid]); stage<Real, MODE>(g, x0, y0, q, tid, bscale, A0, cFirst, pre[tid], s); }
-		for (int t = 0; t < T::NTHR; t++) { const int tid = tidOf(t); mid<Real>(g, x0, y0, k0 - 1, tid, MODE == MODE_DOWN ? 1 - cFirst : cFirst, A0, s); mid<Real>(g, x0, y0, k0, tid, MODE == MODE_DOWN ? 1 - cFirst : cFirst, A0, s); }
-		for (int t = 0; t < T::NTHR; t++) { const int tid = tidOf(t); issue<Real, MODE>(g, x0, y0, k0 + 2, tid, b, xin, mask, pre[tid]); }
+			for (int t = 0; t < T::NTHR; t++) { const int tid = tidOf(t); issue<Real, MODE>(g, ctx[tid], q, b, xin, mask, pre[tid]); stage<Real, MODE>(g, ctx[tid], q, bscale, A0, cFirst, pre[tid], s); }
+		for (int t = 0; t < T::NTHR; t++) { const int tid = tidOf(t); mid<Real>(g, ctx[tid], k0 - 1, cm, A0, s); mid<Real>(g, ctx[tid], k0, cm, A0, s); }
+		for (int t = 0; t < T::NTHR; t++) { const int tid = tidOf(t); issue<Real, MODE>(g, ctx[tid], k0 + 2, b, xin, mask, pre[tid]); }
 		for (int sp = k0; sp < k1; sp++) {
 			for (int t = 0; t < T::NTHR; t++) {
 				const int tid = tidOf(t);
-				stage<Real, MODE>(g, x0, y0, sp + 2, tid, bscale, A0, cFirst, pre[tid], s);
-				if (sp + 1 < k1) issue<Real, MODE>(g, x0, y0, sp + 3, tid, b, xin, mask, pre[tid]);
+				stage<Real, MODE>(g, ctx[tid], sp + 2, bscale, A0, cFirst, pre[tid], s);
+				if (sp + 1 < k1) issue<Real, MODE>(g, ctx[tid], sp + 3, b, xin, mask, pre[tid]);
 			}
-			for (int t = 0; t < T::NTHR; t++) mid<Real>(g, x0, y0, sp + 1, tidOf(t), MODE == MODE_DOWN ? 1 - cFirst : cFirst, A0, s);
-			for (int t = 0; t < T::NTHR; t++) last<Real, MODE>(g, x0, y0, sp, tidOf(t), cSecond, A0, s, xout, rout);
+			for (int t = 0; t < T::NTHR; t++) mid<Real>(g, ctx[tidOf(t)], sp + 1, cm, A0, s);
+			for (int t = 0; t < T::NTHR; t++) last<Real, MODE>(g, ctx[tidOf(t)], sp, cSecond, A0, s, xout, rout);
 		}
 	}
 }

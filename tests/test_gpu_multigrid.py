@@ -193,7 +193,7 @@ def test_vcycle_kernel_forms_agree_bit_for_bit(mf, shape, liquid, prec, monkeypa
 @pytest.mark.parametrize("prec", [4, 8])
 @pytest.mark.parametrize("shape,liquid", [((24, 24, 24), False), ((40, 36, 64), False), ((33, 47, 72), True), ((1, 40, 48), False), ((70, 66, 132), False), ((37, 50, 260), True)])
 def test_vcycle_level0_fused_agrees_bit_for_bit(mf, shape, liquid, prec, monkeypatch):
-    """Level 0 of the V-cycle as the fused single-pass kernels (mp_mg_l0_fused.cuh: zero iterate + both colours + residual in one pass on the
+    """Level 0 of the V-cycle on the 2-byte operator mask -- per colour (k_mg_l0_vecm) and as the fused single-pass kernels (mp_mg_l0_fused.cuh: zero iterate + both colours + residual in one pass on the
     way down, both colours of the post-smoothing in one pass on the way up, the operator as 2 bytes per vertex) does the arithmetic of the
     per-colour kernels term for term: iterates, residual norms and a PcMGStatic solve are the same bit for bit.  (The host walk of the same
     phase functions is checked against numpy in tests/test_mg_l0_fused_emul.py.)"""
@@ -207,8 +207,8 @@ def test_vcycle_level0_fused_agrees_bit_for_bit(mf, shape, liquid, prec, monkeyp
     if fix >= 0:
         O.fix_pressure(flags, fix, 0.0, rhs, *A_o)
     out = {}
-    for fused in (1, 0):
-        monkeypatch.setenv("MP_MG_L0FUSED", str(fused))
+    for fused, masked in ((1, 1), (0, 1), (0, 0)):
+        monkeypatch.setenv("MP_MG_L0FUSED", str(fused)); monkeypatch.setenv("MP_MG_L0MASK", str(masked))
         s = mk(mf, flags.shape, prec)
         A = [mf.RealGrid(s, a) for a in A_o]
         mg = cg.GridMg(s)
@@ -223,11 +223,13 @@ def test_vcycle_level0_fused_agrees_bit_for_bit(mf, shape, liquid, prec, monkeyp
         PH = mf.RealGrid(s, phi) if phi is not None else None
         mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=1e-5 if prec == 4 else 1e-9, phi=PH, preconditioner=mf.PcMGStatic, cgMaxIterFac=99,
                          zeroPressureFixing=True)
-        out[fused] = (Z.numpy().copy(), Z2.numpy().copy(), r1, r2, P.numpy().copy(), V.numpy().copy(), mf.lastSolveInfo()["iterations"])
+        out[(fused, masked)] = (Z.numpy().copy(), Z2.numpy().copy(), r1, r2, P.numpy().copy(), V.numpy().copy(), mf.lastSolveInfo()["iterations"])
         assert r2 < r1
         mf.releaseMG(s)
         mg.close(); s.close()
-    a, b = out[1], out[0]
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), "fused level-0 V-cycle differs from the per-colour kernels"
-    assert a[2] == b[2] and a[3] == b[3]
-    assert a[6] == b[6] and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]), "PcMGStatic solve differs"
+    b = out[(0, 0)]      # the per-colour kernels on the coefficient arrays
+    for key in ((1, 1), (0, 1)):
+        a = out[key]
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), ("level-0 V-cycle form differs from the per-colour kernels", key)
+        assert a[2] == b[2] and a[3] == b[3], key
+        assert a[6] == b[6] and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]), ("PcMGStatic solve differs", key)

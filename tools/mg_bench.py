@@ -47,8 +47,9 @@ for prec in (4, 8):
     run(prec, 3, 1, 2); run(prec, 3, 0, 2)
 rows.clear(); res = _r
 for prec in (4, 8):
-    for fused in (1, 0):
-        run(prec, 3, fused, 4)
-run(4, 2, 1, 3)
+    run(prec, 3, 1, 4)
+    run(prec, 3, 0, 4)
+    run(prec, 3, 0, 4, {"MP_MG_L0MASK": "0"})
+run(4, 2, 0, 3)
 if out_path:
     json.dump(rows, open(out_path, "w"), indent=1)
