@@ -222,6 +222,15 @@ int mp_cg_solve_diffusion(mp_context* ctx, const mp_grid* flags, mp_grid* grid, 
 int mp_cg_solve_we(mp_context* ctx, const mp_grid* flags, mp_grid* ut, mp_grid* utm1, mp_grid* out, int crankNic, double cSqr, double cgMaxIterFac,
                    double cgAccuracy, double dt, mp_solve_info* info);
 
+/* The grid half of VICintegration plugin/vortexplugins.cpp:253-299 (the VIC Poisson solve): from the vorticity grid the Peskin
+ * kernel of :203-250 leaves (a centred Grid<Vec3>) to the velocity -- MakeLaplaceMatrix, CurlOp, then for each of the three components
+ * GetShiftedComponent (velIsMac != 0: vel is a MACGrid) or GetComponent, a GridCg<ApplyMatrix> solve with setUseL2Norm(true) and
+ * setICPreconditioner(PreconditionType(precondition)), solution *= scale, SetComponent.  precondition: 1 = PC_ICP, 2 = PC_mICP; as in the
+ * reference every other value (the plugin's default 0 included) fails with setICPreconditioner's message (conjugategrad.cpp:312).
+ * iterations: int[3], the GridCg iteration count per component (the plugin's debMsg line :295), may be NULL. */
+int mp_vic_poisson(mp_context* ctx, const mp_grid* flags, const mp_grid* vorticity, mp_grid* vel, int velIsMac, double cgMaxIterFac, double cgAccuracy,
+                   double scale, int precondition, int* iterations);
+
 /* ---- the steps either side of the projection, so that a whole smoke step keeps its fields in HBM ----
  * setWallBcs          plugin/extforces.cpp:186-218, :307-316  (KnSetWallBcs; with phiObs AND fractions the second-order variant KnSetWallBcsFrac :220-303)
  * addGravity          plugin/extforces.cpp:45-65              (scale != 0: divided by the grid's dx = 1/max(size))

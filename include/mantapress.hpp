@@ -11,7 +11,7 @@
 //     BasicParticleSystem, ParticleDataImpl<T>, ParticleIndexSystem (particle.h) and the FLIP plugins of plugin/flip.cpp (markFluidCells ... pushOutofObs)
 //     getLaplacian, getCurvature                                      plugin/flip.cpp:710-716
 //     updateFractions, setObstacleFlags                               plugin/initplugins.cpp:437-440,:473-475
-//     cgSolveDiffusion, cgSolveWE                                     conjugategrad.cpp:350, plugin/waves.cpp:86
+//     cgSolveDiffusion, cgSolveWE, vicPoisson                         conjugategrad.cpp:350, plugin/waves.cpp:86, plugin/vortexplugins.cpp:253
 // so that C++ callers of these plugins (e.g. plugin/fluidguiding.cpp:276-335) and tests written against the reference's headers compile
 // against this header unchanged.  Every grid owns a host array in the reference layout (grid.h:70) AND an mp_grid in HBM; two dirty
 // bits keep them coherent lazily, so a sequence of plugins never leaves the device.
@@ -423,6 +423,17 @@ inline void cgSolveWE(const FlagGrid& flags, Grid<Real>& ut, Grid<Real>& utm1, G
 	mpCheck(mp_cg_solve_we(flags.getParent()->ctx(), flags.dev(), ut.dev(), utm1.dev(), out.dev(), crankNic, cSqr, cgMaxIterFac, cgAccuracy, flags.getParent()->getDt(),
 	                       &detail::lastInfo()));
 	ut.markDeviceWritten(); utm1.markDeviceWritten(); out.markDeviceWritten();
+}
+
+// The grid half of VICintegration plugin/vortexplugins.cpp:253-299 (parameter names and defaults of the plugin :195-196; the mesh and its Peskin
+// mapping :203-250 stay with the caller): vorticity grid -> vel (MACGrid: shifted components, Grid<Vec3>: centred).  precondition: 1 PC_ICP,
+// 2 PC_mICP; the plugin's default 0 throws setICPreconditioner's error as in the reference (conjugategrad.cpp:312).
+inline void vicPoisson(Grid<Vec3>& vel, const FlagGrid& flags, const Grid<Vec3>& vorticity, Real cgMaxIterFac = 1.5, Real cgAccuracy = 1e-3, Real scale = 0.01,
+	int precondition = 0, int* iterations = NULL)
+{
+	mpCheck(mp_vic_poisson(flags.getParent()->ctx(), flags.dev(), vorticity.dev(), vel.dev(), (vel.getType() & GridBase::TypeMAC) ? 1 : 0, cgMaxIterFac, cgAccuracy, scale,
+	                       precondition, iterations));
+	vel.markDeviceWritten();
 }
 
 // ---- FLIP particle <-> grid plugins plugin/flip.cpp (second slice)

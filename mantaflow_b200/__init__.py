@@ -13,7 +13,7 @@ from .grid import (FlagEmpty, FlagFluid, FlagGrid, FlagInflow, FlagObstacle, Fla
                    LevelsetGrid, MACGrid, RealGrid, Solver, VecGrid)
 from .pressure import (computePressureRhs, correctVelocity, lastSolveInfo, releaseMG, solvePressure, solvePressureHost,
                        solvePressureSystem)
-from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE
+from .cg import GridCg, GridMg, cgSolveDiffusion, cgSolveWE, vicPoisson
 from .step import (PD_fluid_guiding, addBuoyancy, addGravity, addGravityNoScale, advectSemiLagrange, extrapolateLsSimple, extrapolateMACFromWeight, extrapolateMACSimple,
                    extrapolateVec3Simple, getCurvature, getLaplacian, lastGuidingIterations, releaseBlurPrecomp, setObstacleFlags, setWallBcs, updateFractions)
 from .particles import (PDELETE, PNEW, IntEuler, IntRK2, IntRK4, BasicParticleSystem, IntGrid, ParticleIndexSystem, PdataInt, PdataReal, PdataVec3, flipVelocityUpdate, gridParticleIndex, mapMACToParts,

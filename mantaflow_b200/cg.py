@@ -120,6 +120,20 @@ def cgSolveWE(flags, ut, utm1, out, crankNic=False, cSqr=0.25, cgMaxIterFac=1.5,
     return info.as_dict()
 
 
+def vicPoisson(vel, flags, vorticity, cgMaxIterFac=1.5, cgAccuracy=1e-3, scale=0.01, precondition=0):
+    """The grid half of VICintegration (plugin/vortexplugins.cpp:253-299; parameter names and defaults of the plugin :195-196): from the vorticity
+    grid the plugin's Peskin kernel leaves (:203-250) to `vel` (MACGrid: shifted components, VecGrid: centred) through three GridCg solves
+    preconditioned with PC_ICP (precondition=1) or PC_mICP (2).  precondition=0, the plugin's default, raises setICPreconditioner's error as it
+    does in the reference (conjugategrad.cpp:312).  Returns the three iteration counts."""
+    from .grid import VecGrid
+    s = flags.parent
+    its = (C.c_int * 3)()
+    check(s.lib.mp_vic_poisson(s._ctx, flags.dev(), vorticity.dev(), vel.dev(), C.c_int(0 if isinstance(vel, VecGrid) else 1), C.c_double(cgMaxIterFac),
+                               C.c_double(cgAccuracy), C.c_double(scale), C.c_int(precondition), its))
+    vel.markDeviceWritten()
+    return list(its)
+
+
 class GridMg:
     """multigrid.h:31-137"""
 

@@ -516,20 +516,18 @@ __global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeo
 		if (!any) { if (xout != xf) *reinterpret_cast<RVec<Real, V>*>(xout + v) = ldR<Real, V>(xf + v); continue; }
 		const int pz = z & 1;
 		const int base = (x0 >> 1) + cY * (y >> 1) + cZ * (z >> 1);
-		// the V fine cells interpolate from the coarse vertices x0/2 .. x0/2 + V/2 of up to 4 coarse rows; values of inactive ones count as absent
-		Real pv[2][2][V / 2 + 1]; bool pa[2][2][V / 2 + 1];
+		// the V fine cells interpolate from the coarse vertices x0/2 .. x0/2 + V/2 of up to 4 coarse rows.  The reference leaves inactive parents
+		// out; their iterate is an exact zero throughout the cycle (zeroed by the restriction, never smoothed or corrected), so adding it
+		// gives the same sum (signs of exact zeros aside) and the coarse types need not be read
+		Real pv[2][2][V / 2 + 1];
 		#pragma unroll
 		for (int dz = 0; dz < 2; dz++)
 			#pragma unroll
 			for (int dy = 0; dy < 2; dy++)
 				#pragma unroll
 				for (int e = 0; e <= V / 2; e++) {
-					pa[dz][dy][e] = false; pv[dz][dy][e] = (Real)0;
-					if (dz <= pz && dy <= py && (x0 >> 1) + e < gc.sx) {
-						const int i = base + e + dy * cY + dz * cZ;
-						pa[dz][dy][e] = tc[i] != vtInactive;
-						if (pa[dz][dy][e]) pv[dz][dy][e] = xc[i];
-					}
+					pv[dz][dy][e] = (Real)0;
+					if (dz <= pz && dy <= py && (x0 >> 1) + e < gc.sx) pv[dz][dy][e] = xc[base + e + dy * cY + dz * cZ];
 				}
 		RVec<Real, V> xv = ldR<Real, V>(xf + v);
 		#pragma unroll
@@ -542,8 +540,8 @@ __global__ void __launch_bounds__(128) k_mg_interp_add_l0_vec(LvlGeom gf, LvlGeo
 				#pragma unroll
 				for (int dy = 0; dy < 2; dy++) {
 					if (dz > pz || dy > py) continue;
-					if (pa[dz][dy][e]) sum += pv[dz][dy][e];
-					if (px && pa[dz][dy][e + 1]) sum += pv[dz][dy][e + 1];
+					sum += pv[dz][dy][e];
+					if (px) sum += pv[dz][dy][e + 1];
 				}
 			xv.v[q] += pow2weight<Real>(px + py + pz) * sum;
 		}
@@ -575,17 +573,19 @@ __global__ void __launch_bounds__(128) k_mg_restrict_l0_vec(LvlGeom gf, LvlGeom 
 	for (int ry = max(0, vy * 2 - 1); ry <= min(gf.sy - 1, vy * 2 + 1); ry++) {
 		const int row = gf.sx * (ry + gf.sy * rz);
 		const Real wyz = pow2weight<Real>((ry & 1) + (rz & 1));
-		// fine x = fx0 - 1 (scalar) and fx0 .. fx0 + V - 1 (vector); coarse vertex c takes fx0 + 2c - 1 .. fx0 + 2c + 1, ascending
-		Real f[V + 1]; bool fa[V + 1];
-		f[0] = (Real)0; fa[0] = false;
-		if (fx0 > 0) { fa[0] = tf[row + fx0 - 1] != vtInactive; if (fa[0]) f[0] = src[row + fx0 - 1]; }
+		// fine x = fx0 - 1 (scalar) and fx0 .. fx0 + V - 1 (vector); coarse vertex c takes fx0 + 2c - 1 .. fx0 + 2c + 1, ascending.  The reference
+		// leaves inactive fine vertices out; their residual is an exact zero (written by the residual kernel), so adding it gives the same sum
+		// (signs of exact zeros aside) and the fine types need not be read
+		Real f[V + 1];
+		f[0] = (Real)0;
+		if (fx0 > 0) f[0] = src[row + fx0 - 1];
 		if (vecIn) {
-			const CVec<V> tv = ldC<V>(tf + row + fx0); const RVec<Real, V> sv = ldR<Real, V>(src + row + fx0);
+			const RVec<Real, V> sv = ldR<Real, V>(src + row + fx0);
 			#pragma unroll
-			for (int q = 0; q < V; q++) { fa[q + 1] = tv.v[q] != vtInactive; f[q + 1] = sv.v[q]; }
+			for (int q = 0; q < V; q++) f[q + 1] = sv.v[q];
 		} else {
 			#pragma unroll
-			for (int q = 0; q < V; q++) { fa[q + 1] = false; f[q + 1] = (Real)0; }
+			for (int q = 0; q < V; q++) f[q + 1] = (Real)0;
 		}
 		#pragma unroll
 		for (int c = 0; c < CW; c++) {
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(128) k_mg_restrict_l0_vec(LvlGeom gf, LvlGeom 
 			for (int e = 0; e < 3; e++) {                             // rx = fx0 + 2c - 1 + e
 				const int q = 2 * c + e;                             // index into f[]
 				const int rx = fx0 + 2 * c - 1 + e;
-				if (rx < 0 || rx >= gf.sx || !fa[q]) continue;
+				if (rx < 0 || rx >= gf.sx) continue;
 				// weight 1 / 2^(#odd coordinates): rx is odd for e = 0, 2
 				const Real rw = (e == 1) ? wyz : wyz * (Real)0.5;
 				sum[c] += rw * f[q];

@@ -60,6 +60,47 @@ __global__ void __launch_bounds__(256) k_component(IndexInt n, Real* __restrict_
 	}
 }
 
+// VICintegration's grid half (plugin/vortexplugins.cpp:253-299): CurlOp commonkernels.h:38-47 (bnd = 1, 3-D) and GetShiftedComponent :104-108 /
+// GetComponent :111-113.  The factors 0.5 are exact in either precision, so `0.5 * Real` evaluated in double and narrowed equals the Real product.
+template <typename Real>
+__global__ void __launch_bounds__(256) k_vic_curl(Dims d, const Real* __restrict__ w, Real* __restrict__ curl)
+{
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n) return;
+	int i, j, k; cellOf(d, idx, i, j, k);
+	Real v0 = 0, v1 = 0, v2 = 0;
+	if (i >= 1 && i < d.sx - 1 && j >= 1 && j < d.sy - 1 && k >= 1 && k < d.sz - 1) {
+		const IndexInt X = 3, Y = 3 * d.Y, Z = 3 * d.Z; const Real* c = w + 3 * idx;
+		v2 = (Real)0.5 * ((c[X + 1] - c[-X + 1]) - (c[Y + 0] - c[-Y + 0]));
+		v0 = (Real)0.5 * ((c[Y + 2] - c[-Y + 2]) - (c[Z + 1] - c[-Z + 1]));
+		v1 = (Real)0.5 * ((c[Z + 0] - c[-Z + 0]) - (c[X + 2] - c[-X + 2]));
+	}
+	curl[3 * idx] = v0; curl[3 * idx + 1] = v1; curl[3 * idx + 2] = v2;        // outside bnd the fresh grid keeps its zeros
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) k_vic_rhs(Dims d, const Real* __restrict__ curl, Real* __restrict__ rhs, int c, int shifted)
+{
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= d.n) return;
+	if (!shifted) { rhs[idx] = curl[3 * idx + c]; return; }
+	int i, j, k; cellOf(d, idx, i, j, k);
+	Real r = 0;                                                               // bnd = 1: the border of the (fresh) rhs grid stays zero
+	if (i >= 1 && i < d.sx - 1 && j >= 1 && j < d.sy - 1 && k >= 1 && k < d.sz - 1) {
+		const IndexInt sh = c == 0 ? 1 : (c == 1 ? d.Y : d.Z);
+		r = (Real)0.5 * (curl[3 * idx + c] + curl[3 * (idx - sh) + c]);
+	}
+	rhs[idx] = r;
+}
+// solution *= scale; SetComponent(vel, solution, c) :297-298
+template <typename Real>
+__global__ void __launch_bounds__(256) k_vic_store(IndexInt n, Real* __restrict__ sol, Real* __restrict__ vel, Real scale, int c)
+{
+	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= n) return;
+	const Real v = sol[idx] * scale;
+	sol[idx] = v; vel[3 * idx + c] = v;
+}
+
 struct GridHolder {   // RAII for the temp grids of one call (the reference takes them from the FluidSolver pool, pressure.cpp:331-338)
 	std::vector<mp_grid*> gs;
 	~GridHolder() { for (mp_grid* g : gs) mp_grid_destroy(g); }
@@ -263,6 +304,57 @@ int mp_cg_solve_diffusion(mp_context* ctx, const mp_grid* flags, mp_grid* grid, 
 		}
 	}
 	if (info) { memset(info, 0, sizeof *info); info->fixedCell = -1; mp_cg_get(cg, &info->iterations, &info->resNorm, nullptr); info->maxIter = maxIter; info->matvecKernel = ctx->lastMatvecKernel; }
+	MP_CUDA(cudaStreamSynchronize(ctx->stream));
+	return MP_OK;
+}
+
+// The grid half of VICintegration plugin/vortexplugins.cpp:253-299 -- from the vorticity grid the Peskin kernel (:203-250, mesh code) leaves to
+// the velocity: MakeLaplaceMatrix, CurlOp, then per component rhs = (shifted) component of the curl, GridCg<ApplyMatrix> with the L2 stop test
+// and PreconditionType(precondition), solution *= scale, SetComponent.  As in the reference, setICPreconditioner accepts PC_ICP (1) and
+// PC_mICP (2) only (conjugategrad.cpp:312): the plugin's default precondition = 0 is an error there and here.
+int mp_vic_poisson(mp_context* ctx, const mp_grid* flags, const mp_grid* vorticity, mp_grid* vel, int velIsMac, double cgMaxIterFac, double cgAccuracy,
+                   double scale, int precondition, int* iterations)
+{
+	if (!ctx || !flags || !vorticity || !vel) MP_FAIL(MP_ERR_INVALID, "mp_vic_poisson: NULL argument");
+	if (flags->kind != MP_GRID_FLAGS) MP_FAIL(MP_ERR_INVALID, "mp_vic_poisson: flags is not a FlagGrid");
+	MP_TRY(mp_check_same(flags, vorticity, MP_GRID_MAC, "vorticity", false)); MP_TRY(mp_check_same(flags, vel, MP_GRID_MAC, "vel", false));
+	if (vorticity->prec != vel->prec) MP_FAIL(MP_ERR_INVALID, "mp_vic_poisson: vorticity and vel differ in precision");
+	if (vorticity == vel) MP_FAIL(MP_ERR_INVALID, "mp_vic_poisson: vorticity and vel must be two grids");
+	if (flags->sz <= 1) MP_FAIL(MP_ERR_UNSUPPORTED, "VICintegration: 3-D grids only (GridCg<ApplyMatrix>)");
+	if (precondition != MP_CG_PC_ICP && precondition != MP_CG_PC_MICP) MP_FAIL(MP_ERR_INVALID, "GridCg<APPLYMAT>::setICPreconditioner: Invalid method specified.");
+	if (ctx->dist && ctx->dist->active) MP_FAIL(MP_ERR_UNSUPPORTED, "mp_vic_poisson: not sharded across GPUs");
+	MP_CUDA(cudaSetDevice(ctx->device));
+	MP_TRY(mp_check_flags_interior(ctx, flags));
+	const int prec = vel->prec;
+	const Dims d = dimsOf(flags);
+	GridHolder tmp;
+	mp_grid *curl, *rhs, *sol, *residual, *search, *t, *A0, *Ai, *Aj, *Ak, *P0, *P1, *P2, *P3;
+	MP_TRY(tmp.make(ctx, MP_GRID_MAC, prec, flags, &curl));
+	mp_grid** reals[] = { &rhs, &sol, &residual, &search, &t, &A0, &Ai, &Aj, &Ak, &P0, &P1, &P2, &P3 };
+	for (mp_grid** g : reals) MP_TRY(tmp.make(ctx, MP_GRID_REAL, prec, flags, g));
+	MP_TRY(mp_make_laplace_matrix(ctx, flags, A0, Ai, Aj, Ak, nullptr));
+	const unsigned int blocks = gridFor(d.n, 256);
+	if (prec == 4) k_vic_curl<float><<<blocks, 256, 0, ctx->stream>>>(d, (const float*)vorticity->d, (float*)curl->d);
+	else           k_vic_curl<double><<<blocks, 256, 0, ctx->stream>>>(d, (const double*)vorticity->d, (double*)curl->d);
+	MP_CHECK_LAUNCH(ctx);
+	const int maxDim = std::max(flags->sx, std::max(flags->sy, flags->sz));
+	const int maxIter = prec == 4 ? (int)((float)cgMaxIterFac * (float)maxDim) : (int)(cgMaxIterFac * (double)maxDim);      // :273
+	for (int c = 0; c < 3; c++) {
+		if (prec == 4) k_vic_rhs<float><<<blocks, 256, 0, ctx->stream>>>(d, (const float*)curl->d, (float*)rhs->d, c, velIsMac ? 1 : 0);
+		else           k_vic_rhs<double><<<blocks, 256, 0, ctx->stream>>>(d, (const double*)curl->d, (double*)rhs->d, c, velIsMac ? 1 : 0);
+		MP_CHECK_LAUNCH(ctx);
+		mp_cg* cg = nullptr;                                                                       // a new GridCg per component :274
+		MP_TRY(mp_cg_create(ctx, sol, rhs, residual, search, flags, t, A0, Ai, Aj, Ak, &cg));
+		struct CgGuard { mp_cg* c; ~CgGuard() { mp_cg_destroy(c); } } guard{ cg };
+		mp_cg_set_accuracy(cg, prec == 4 ? (double)(float)cgAccuracy : cgAccuracy);
+		mp_cg_set_use_l2_norm(cg, 1);
+		MP_TRY(mp_cg_set_ic_preconditioner(cg, precondition, P0, P1, P2, P3));
+		MP_TRY(mp_cg_run(cg, maxIter));
+		if (iterations) mp_cg_get(cg, &iterations[c], nullptr, nullptr);
+		if (prec == 4) k_vic_store<float><<<blocks, 256, 0, ctx->stream>>>(d.n, (float*)sol->d, (float*)vel->d, (float)scale, c);
+		else           k_vic_store<double><<<blocks, 256, 0, ctx->stream>>>(d.n, (double*)sol->d, (double*)vel->d, scale, c);
+		MP_CHECK_LAUNCH(ctx);
+	}
 	MP_CUDA(cudaStreamSynchronize(ctx->stream));
 	return MP_OK;
 }

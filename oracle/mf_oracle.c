@@ -1024,6 +1024,52 @@ int mfo_cg_solve_diffusion(int sx, int sy, int sz, const int* flags, Real* data,
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * The grid half of VICintegration plugin/vortexplugins.cpp:253-299 (another GridCg caller): from the vorticity grid the Peskin
+ * kernel left (:203-250, mesh code, not restated) to the velocity -- MakeLaplaceMatrix, CurlOp commonkernels.h:38-47, per component
+ * GetShiftedComponent :104-108 (MAC target) / GetComponent :111-113, GridCg<ApplyMatrix> with the L2 stop test and the preconditioner
+ * PreconditionType(precondition) (1 PC_ICP, 2 PC_mICP; conjugategrad.h:30), solution *= scale, SetComponent :121-123.            */
+int mfo_vic_poisson(int sx, int sy, int sz, const int* flags, const Real* vort, Real* vel, int velIsMac, double cgMaxIterFac, double cgAccuracy,
+	double scale_, int precondition, int* iters)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	if (!IS3D) { snprintf(g_err, sizeof g_err, "VICintegration: 3-D grids only (GridCg<ApplyMatrix>)"); return 1; }
+	/* setICPreconditioner accepts PC_ICP and PC_mICP only (conjugategrad.cpp:312): the plugin's default precondition = 0 throws in the reference */
+	if (precondition != 1 && precondition != 2) { snprintf(g_err, sizeof g_err, "GridCg<APPLYMAT>::setICPreconditioner: Invalid method specified."); return 1; }
+	Real *A0 = (Real*)calloc((size_t)n, sizeof(Real)), *Ai = (Real*)calloc((size_t)n, sizeof(Real)), *Aj = (Real*)calloc((size_t)n, sizeof(Real)), *Ak = (Real*)calloc((size_t)n, sizeof(Real));
+	Real *curl = (Real*)calloc((size_t)n * 3, sizeof(Real)), *rhs = (Real*)calloc((size_t)n, sizeof(Real)), *sol = (Real*)calloc((size_t)n, sizeof(Real));
+	mfo_make_matrix(sx, sy, sz, flags, 0, 0, 0., A0, Ai, Aj, Ak);
+	#define W(i_, j_, k_, c_) vort[3 * ((IndexInt)(i_) + Y * (j_) + Z * (k_)) + (c_)]
+	for (int k = 1; k < sz - 1; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++) {                /* CurlOp, bnd = 1 */
+		Real* v = curl + 3 * ((IndexInt)i + Y * j + Z * k);
+		v[2] = (Real)(0.5 * (double)((W(i + 1, j, k, 1) - W(i - 1, j, k, 1)) - (W(i, j + 1, k, 0) - W(i, j - 1, k, 0))));
+		v[0] = (Real)(0.5 * (double)((W(i, j + 1, k, 2) - W(i, j - 1, k, 2)) - (W(i, j, k + 1, 1) - W(i, j, k - 1, 1))));
+		v[1] = (Real)(0.5 * (double)((W(i, j, k + 1, 0) - W(i, j, k - 1, 0)) - (W(i + 1, j, k, 2) - W(i - 1, j, k, 2))));
+	}
+	#undef W
+	const int maxDim = sx > sy ? (sx > sz ? sx : sz) : (sy > sz ? sy : sz);
+	const int maxIter = (int)((Real)cgMaxIterFac * maxDim);                                                            /* :273 */
+	const int pc = precondition == 1 ? 3 : 1;                                                                          /* cg_run: 3 = IC(0), 1 = MIC(0) */
+	const Real scale = (Real)scale_;
+	int rc = 0;
+	for (int c = 0; c < 3 && rc == 0; c++) {
+		if (velIsMac) {                                                                                                /* GetShiftedComponent, bnd = 1: the border of rhs keeps its zeros */
+			const IndexInt sh = c == 0 ? X : (c == 1 ? Y : Z);
+			for (int k = 1; k < sz - 1; k++) for (int j = 1; j < sy - 1; j++) for (int i = 1; i < sx - 1; i++) {
+				const IndexInt q = (IndexInt)i + Y * j + Z * k;
+				rhs[q] = (Real)(0.5 * (double)(curl[3 * q + c] + curl[3 * (q - sh) + c]));
+			}
+		} else for (IndexInt q = 0; q < n; q++) rhs[q] = curl[3 * q + c];
+		int its = 0;
+		rc = cg_run(sx, sy, sz, flags, rhs, sol, A0, Ai, Aj, Ak, pc, (Real)cgAccuracy, 1, maxIter, 0, &its, 0);
+		if (iters) iters[c] = its;
+		for (IndexInt q = 0; q < n; q++) { sol[q] *= scale; vel[3 * q + c] = sol[q]; }                                   /* solution *= scale; SetComponent */
+	}
+	free(A0); free(Ai); free(Aj); free(Ak); free(curl); free(rhs); free(sol);
+	return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------
  * correctVelocity plugin/pressure.cpp:455-476: knCorrectVelocity :87-109,
  * knCorrectVelocityGhostFluid :154-187, knReplaceClampedGhostFluidVels :198-214                 */
 int mfo_correct_velocity(int sx, int sy, int sz, const int* flags, Real* vel, const Real* pressure,

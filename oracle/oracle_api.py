@@ -117,6 +117,28 @@ class Oracle:
                                          C.c_double(cgMaxIterFac), C.c_double(cgAccuracy), C.c_double(dt)))
         return out
 
+    def vic_integration(self, flags, tri, triVort, sigma, vel, velIsMac=True, cgMaxIterFac=1.5, cgAccuracy=1e-3, scale=0.01, precondition=0):
+        """plugin/vortexplugins.cpp:195 VICintegration on a vortex sheet given as triangles (reference only: the mesh code is not restated);
+        returns (vorticity grid, vel, the three GridCg iteration counts)"""
+        assert self.kind == "reference"
+        tri, triVort = self._r(tri), self._r(triVort)
+        vel = np.array(vel, dtype=self.real, order="C")
+        vort = np.zeros(flags.shape + (3,), self.real)
+        its = (C.c_int * 3)()
+        self._chk(self._f("vic_integration")(*self.dims(flags), _p(flags), C.c_int(len(triVort)), _p(tri), _p(triVort), C.c_double(sigma), _p(vel), C.c_int(int(velIsMac)),
+                                             _p(vort), C.c_double(cgMaxIterFac), C.c_double(cgAccuracy), C.c_double(scale), C.c_int(precondition), its))
+        return vort, vel, list(its)
+
+    def vic_poisson(self, flags, vort, vel, velIsMac=True, cgMaxIterFac=1.5, cgAccuracy=1e-3, scale=0.01, precondition=0):
+        """the grid half of VICintegration (vortexplugins.cpp:253-299): vorticity grid -> velocity; returns (vel, iteration counts).  Port only."""
+        assert self.kind == "port"
+        vort = self._r(vort)
+        vel = np.array(vel, dtype=self.real, order="C")
+        its = (C.c_int * 3)()
+        self._chk(self._f("vic_poisson")(*self.dims(flags), _p(flags), _p(vort), _p(vel), C.c_int(int(velIsMac)), C.c_double(cgMaxIterFac), C.c_double(cgAccuracy),
+                                         C.c_double(scale), C.c_int(precondition), its))
+        return vel, list(its)
+
     def pd_fluid_guiding(self, flags, vel, velT, weight, blurRadius=5, theta=1.0, tau=1.0, sigma=1.0, epsRel=1e-3, epsAbs=1e-3, maxIters=200,
                          cgMaxIterFac=1.5, cgAccuracy=1e-3, preconditioner=1, zeroPressureFixing=False):
         """plugin/fluidguiding.cpp:294 PD_fluid_guiding; vel is replaced by the guided, divergence-free field; returns (pressure, iterations)"""

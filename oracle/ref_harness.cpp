@@ -48,6 +48,7 @@
 #include "commonkernels.h"
 #include "levelset.h"
 #include "particle.h"
+#include "vortexsheet.h"
 
 namespace Manta {
 // --- link stubs for the OpenVDB entry points referenced by grid.cpp (the .uni / .raw / .npz readers and writers are the reference's own, fileio/iogrids.cpp) ---
@@ -84,6 +85,7 @@ void extrapolateVec3Simple(Grid<Vec3>& vel, Grid<Real>& phi, int distance, bool 
 void addGravity(const FlagGrid& flags, MACGrid& vel, Vec3 gravity, const Grid<Real>* exclude, bool scale);
 void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGrid& vel, Vec3 gravity, Real coefficient, bool scale);
 void advectSemiLagrange(const FlagGrid* flags, const MACGrid* vel, GridBase* grid, int order, Real strength, int orderSpace, bool openBounds, int boundaryWidth, int clampMode, int orderTrace);
+void VICintegration(VortexSheetMesh& mesh, Real sigma, Grid<Vec3>& vel, const FlagGrid& flags, Grid<Vec3>* vorticity, Real cgMaxIterFac, Real cgAccuracy, Real scale, int precondition);
 void InitPreconditionIncompCholesky(const FlagGrid& flags, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak, Grid<Real>& orgA0, Grid<Real>& orgAi, Grid<Real>& orgAj, Grid<Real>& orgAk);
 void ApplyPreconditionIncompCholesky(Grid<Real>& dst, Grid<Real>& Var1, const FlagGrid& flags, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak, Grid<Real>& orgA0, Grid<Real>& orgAi, Grid<Real>& orgAj, Grid<Real>& orgAk);
 void InitPreconditionModifiedIncompCholesky2(const FlagGrid& flags, Grid<Real>& Aprecond, Grid<Real>& A0, Grid<Real>& Ai, Grid<Real>& Aj, Grid<Real>& Ak);
@@ -455,6 +457,46 @@ int ref_pd_fluid_guiding(int sx, int sy, int sz, const int* flags, Real* vel, co
   CATCH }
 
 // ut / utm1 are swapped by the plugin (not allowed for external data): solver-owned copies, results copied back
+// VICintegration plugin/vortexplugins.cpp:195-300 on a vortex sheet given as triangles (tri: [ntri][3 corners][3], vort: [ntri][3]); returns the
+// vorticity grid the Peskin kernel leaves (:203-250) and the velocity of the three Poisson solves (:253-299).  velIsMac: vel is a MACGrid
+// (GetShiftedComponent) or a centred Grid<Vec3> (GetComponent).  iters: the three GridCg iteration counts, parsed from the debMsg line :295.
+int ref_vic_integration(int sx, int sy, int sz, const int* flags, int ntri, const Real* tri, const Real* vort, double sigma, Real* vel, int velIsMac,
+	Real* vorticity, double cgMaxIterFac, double cgAccuracy, double scale, int precondition, int* iters)
+{ TRY
+	FluidSolver* s = mkSolver(sx, sy, sz);
+	const size_t n = (size_t)sx * sy * sz;
+	std::string log;
+	{ FlagGrid F(s, (int*)flags); Grid<Vec3> W(s);
+	  Grid<Vec3>* V = velIsMac ? new MACGrid(s) : new Grid<Vec3>(s);
+	  memcpy(&(*V)[0], vel, 3 * n * sizeof(Real));
+	  struct Sheet : VortexSheetMesh { Sheet(FluidSolver* p) : VortexSheetMesh(p) {} void sync() { rebuildChannels(); } } mesh(s);   // Mesh::load does the same after reading triangles
+	  for (int t = 0; t < ntri; t++) {
+		int c[3];
+		for (int q = 0; q < 3; q++) c[q] = mesh.addNode(Node(Vec3(tri[9 * t + 3 * q], tri[9 * t + 3 * q + 1], tri[9 * t + 3 * q + 2])));
+		mesh.addTri(Triangle(c[0], c[1], c[2]));
+	  }
+	  mesh.sync();
+	  for (int t = 0; t < ntri; t++) mesh.sheet(t).vorticity = Vec3(vort[3 * t], vort[3 * t + 1], vort[3 * t + 2]);
+	  const int dl = gDebugLevel; gDebugLevel = 1;
+	  { CoutCapture cap;
+	    VICintegration(mesh, (Real)sigma, *V, F, &W, (Real)cgMaxIterFac, (Real)cgAccuracy, (Real)scale, precondition);
+	    log = cap.ss.str(); }
+	  gDebugLevel = dl;
+	  memcpy(vel, &(*V)[0], 3 * n * sizeof(Real)); memcpy(vorticity, &W[0], 3 * n * sizeof(Real));
+	  delete V; }
+	delete s;
+	if (iters) {
+		size_t pos = 0;
+		for (int c = 0; c < 3; c++) {
+			iters[c] = -1;
+			pos = log.find("VICintegration CG iterations:", pos);
+			if (pos == std::string::npos) break;
+			pos += strlen("VICintegration CG iterations:");
+			iters[c] = atoi(log.c_str() + pos);
+		}
+	}
+  CATCH }
+
 int ref_cg_solve_we(int sx, int sy, int sz, const int* flags, Real* ut, Real* utm1, Real* out, int crankNic, double cSqr, double cgMaxIterFac, double cgAccuracy, double dt)
 { TRY
 	FluidSolver* s = mkSolver(sx, sy, sz); s->mDt = (Real)dt;

@@ -408,3 +408,10 @@ class CudaImpl:
         Z = mf.RealGrid(s)
         self._mg.doVCycle(Z)
         return Z.numpy().copy()
+
+    def vic_poisson(self, flags, vort, vel, velIsMac=True, cgMaxIterFac=1.5, cgAccuracy=1e-3, scale=0.01, precondition=0):
+        s = self._solver(flags)
+        F, W = mf.FlagGrid(s, flags), mf.VecGrid(s, vort)
+        V = (mf.MACGrid if velIsMac else mf.VecGrid)(s, vel)
+        its = cg.vicPoisson(V, F, W, cgMaxIterFac=cgMaxIterFac, cgAccuracy=cgAccuracy, scale=scale, precondition=precondition)
+        return V.numpy().copy(), its

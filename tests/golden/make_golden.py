@@ -251,6 +251,18 @@ def icp_fixtures():
             print("%-34s %7.1f KiB  PC_ICP %d its" % (os.path.basename(path), os.path.getsize(path) / 1024, int(fx["cg_ic_it"])))
 
 
+def vic_fixtures():
+    """vic_sheet24_f{32,64}.npz: VICintegration (plugin/vortexplugins.cpp:195-300) of the unmodified reference on helpers.vic_scene: the vorticity grid
+    of its Peskin kernel, and the velocity / iteration counts of its Poisson solves for MACGrid and Grid<Vec3> targets with PC_ICP and PC_mICP"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import helpers
+    for prec in (4, 8):
+        fx = helpers.run_vic_reference(Oracle("reference", prec), prec)
+        path = os.path.join(HERE, "vic_sheet24_f%d.npz" % (prec * 8))
+        np.savez_compressed(path, **fx)
+        print("%-34s %7.1f KiB  its %s" % (os.path.basename(path), os.path.getsize(path) / 1024, {k: list(v) for k, v in fx.items() if k.startswith("its_")}))
+
+
 def io_fixtures():
     """tests/golden/io/ref_<kind>_<2d|3d>_f{32,64}.uni: grid files written by the unmodified reference's Grid<T>::save (fileio/iogrids.cpp)
     from the seeded arrays of tests/test_fileio.py::sample"""
@@ -273,6 +285,8 @@ def main():
         return flip_fixtures()
     if "--only-icp" in sys.argv:
         return icp_fixtures()
+    if "--only-vic" in sys.argv:
+        return vic_fixtures()
     if "--only-dam" in sys.argv:
         return dam_fixtures()
     if "--only-liquid" in sys.argv:
@@ -285,6 +299,7 @@ def main():
     flip_fixtures()
     io_fixtures()
     icp_fixtures()
+    vic_fixtures()
     dam_fixtures()
     for prec in (4, 8):
         R = Oracle("reference", prec)

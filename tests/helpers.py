@@ -14,7 +14,7 @@ KERNEL_FIXTURES = ["smoke16", "liquid14", "smoke2d"]
 
 def load_golden(name, prec):
     """kernels_<name>_f<bits>.npz, or <name>_f<bits>.npz for the step_* / plume* fixtures"""
-    stem = name if name.startswith(("step_", "plume", "icp_")) else "kernels_" + name
+    stem = name if name.startswith(("step_", "plume", "icp_", "vic_")) else "kernels_" + name
     return dict(np.load(os.path.join(GOLDEN, "%s_f%d.npz" % (stem, prec * 8))))
 
 
@@ -795,3 +795,59 @@ def grid_arith_case(op, dtype, comps, seed=3):
     binary = op in ("add", "sub", "mult", "addScaled", "safeDivide")
     const = (float(lo), float(hi), 0.0) if op == "clamp" else c
     return me, (other if binary else None), const, np.ascontiguousarray(want)
+
+
+# ---------------------------------------------------------------------------------------------- VICintegration, grid half
+VIC_CASES = [(True, 1), (True, 2), (False, 1), (False, 2)]          # (vel is a MACGrid, precondition: 1 PC_ICP, 2 PC_mICP)
+
+
+def vic_scene(prec, res=24):
+    """a closed box whose top layers are empty (Dirichlet cells: the Poisson problem is regular) and a vortex sheet of 60 triangles kept so
+    far from every non-fluid cell that the curl vanishes there -- on non-fluid cells the reference's IC / MIC sweeps leave the stale content of
+    their output grid, and a right-hand side that is non-zero there stalls its preconditioned CG (measured: residual stuck at 0.059)"""
+    import mantaflow_b200.scenes as scenes
+    real = np.float32 if prec == 4 else np.float64
+    flags, vel = scenes.smoke_plume(res, prec, obstacle=False)
+    top = flags[:, -4:-1, 1:-1]
+    top[top == 1] = 4
+    rng = np.random.default_rng(1)
+    c = np.array([res * 0.5, res * 0.45, res * 0.5])
+    tri, vort = [], []
+    for _ in range(60):
+        a = rng.random(3) * res * 0.3 + res * 0.33
+        tri.append(np.stack([a, a + rng.random(3) * 2 - 1, a + rng.random(3) * 2 - 1]))
+        vort.append(np.cross(a - c, [0.3, 1.0, 0.2]) * 0.2)
+    return flags, np.zeros_like(vel), np.array(tri, real), np.array(vort, real)
+
+
+def vic_accuracy(prec):
+    return 1e-6 if prec == 4 else 1e-12
+
+
+def run_vic_reference(R, prec):
+    """the fixture: VICintegration of the UNMODIFIED reference on vic_scene -> the vorticity grid its Peskin kernel leaves and, per case, the velocity"""
+    flags, vel0, tri, tv = vic_scene(prec)
+    out = {"flags": flags}
+    for mac, pc in VIC_CASES:
+        vort, vel, its = R.vic_integration(flags, tri, tv, 2.0, vel0, velIsMac=mac, cgMaxIterFac=5, cgAccuracy=vic_accuracy(prec), scale=0.01, precondition=pc)
+        tag = "%s_pc%d" % ("mac" if mac else "vec", pc)
+        out["vorticity"] = vort
+        out["vel_" + tag] = vel
+        out["its_" + tag] = np.array(its)
+    return out
+
+
+def check_vic_against_golden(I, prec, exact_reductions):
+    """I.vic_poisson (the port, or the CUDA path) on the golden vorticity grid against the reference's velocity"""
+    g = load_golden("vic_sheet24", prec)
+    flags, vort = g["flags"], g["vorticity"]
+    for mac, pc in VIC_CASES:
+        tag = "%s_pc%d" % ("mac" if mac else "vec", pc)
+        vel, its = I.vic_poisson(flags, vort, np.zeros(flags.shape + (3,), vort.dtype), velIsMac=mac, cgMaxIterFac=5, cgAccuracy=vic_accuracy(prec), scale=0.01,
+                                 precondition=pc)
+        ref, rits = g["vel_" + tag], list(g["its_" + tag])
+        if exact_reductions:
+            assert its == rits and np.array_equal(vel, ref), tag
+        else:
+            assert all(abs(a - b) <= 1 for a, b in zip(its, rits)), (tag, its, rits)
+            assert rel_l2(vel, ref) <= (1e-4 if prec == 4 else 1e-10), (tag, rel_l2(vel, ref))

@@ -150,6 +150,25 @@ def test_empty_particle_system_and_invalid_arguments(mf):
         mf.flipVelocityUpdate(flags, vel, velOld, pp, short, 0.9)      # data field of another size
 
 
+# ---------------------------------------------------------------- VICintegration, grid half (the VIC Poisson solve)
+@pytest.mark.parametrize("prec", [4, 8])
+def test_cuda_reproduces_vic_golden(prec):
+    """mp_vic_poisson (plugin/vortexplugins.cpp:253-299 on the device) on the vorticity grid of the reference's own VICintegration run: velocity for a
+    MACGrid / Grid<Vec3> target with PC_ICP / PC_mICP, iteration counts within one, velocity within the solver tolerance of north_star"""
+    from cuda_impl import CudaImpl
+    helpers.check_vic_against_golden(CudaImpl(prec), prec, exact_reductions=False)
+
+
+def test_vic_default_precondition_is_the_reference_error(mf):
+    from mantaflow_b200 import cg
+    flags, vel0, _, _ = helpers.vic_scene(4)
+    s = mf.Solver(gridSize=flags.shape[::-1], dim=3, prec=4)
+    F, W, V = mf.FlagGrid(s, flags), mf.VecGrid(s), mf.MACGrid(s, vel0)
+    with pytest.raises(RuntimeError, match="setICPreconditioner: Invalid method"):
+        cg.vicPoisson(V, F, W)
+    s.close()
+
+
 # ---------------------------------------------------------------- IC(0) preconditioner PC_ICP (written in the same GPU-less session)
 @pytest.mark.parametrize("prec", [4, 8])
 @pytest.mark.parametrize("name", helpers.ICP_SCENES)
