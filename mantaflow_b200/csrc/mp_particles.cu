@@ -121,8 +121,19 @@ int mapParts(mp_context* ctx, mp_grid* vel, mp_grid* velOld, long long np, const
 	Tmp start, key, keyTmp, val, sorted;
 	MP_TRY(scratchInts(ctx, vel->n, start)); MP_TRY(scratchInts(ctx, np, key)); MP_TRY(scratchInts(ctx, np, keyTmp)); MP_TRY(scratchInts(ctx, np, val)); MP_TRY(scratchInts(ctx, np, sorted));
 	CudaExec ex = { ctx };
+	// the tree of 3-way merges (default; MP_MAPPARTS=0: the 27-way walk).  Its lists hold a particle 3 + 9 times: 96 + 24 bytes per particle
+	const char* e = getenv("MP_MAPPARTS");
+	const bool useTree = (!e || atoi(e)) && np > 0 && 9 * np <= 0x3fffffffLL;
+	if (!useTree)
+		return parts::mapPartsToMAC<Real>(ex, dimsOf(vel), (Real*)vel->d, (Real*)velOld->d, np, psetOf<Real>(pos, pflag, ptype, exclude), partVel ? (const Real*)partVel->d : nullptr,
+		                                  weight ? (Real*)weight->d : nullptr, start.ints(), key.ints(), keyTmp.ints(), val.ints(), sorted.ints());
+	Tmp off1, off2, e1, e2, posS, pvelS;
+	const IndexInt realInts = 3 * np * (IndexInt)(sizeof(Real) / 4);
+	MP_TRY(scratchInts(ctx, vel->n, off1)); MP_TRY(scratchInts(ctx, vel->n, off2)); MP_TRY(scratchInts(ctx, 2 * 3 * np, e1)); MP_TRY(scratchInts(ctx, 2 * 9 * np, e2));
+	MP_TRY(scratchInts(ctx, realInts, posS)); MP_TRY(scratchInts(ctx, realInts, pvelS));
+	const parts::MapPartsTreeScratch<Real> tree = { off1.ints(), off2.ints(), (parts::Ent*)e1.g->d, (parts::Ent*)e2.g->d, (Real*)posS.g->d, (Real*)pvelS.g->d };
 	return parts::mapPartsToMAC<Real>(ex, dimsOf(vel), (Real*)vel->d, (Real*)velOld->d, np, psetOf<Real>(pos, pflag, ptype, exclude), partVel ? (const Real*)partVel->d : nullptr,
-	                                  weight ? (Real*)weight->d : nullptr, start.ints(), key.ints(), keyTmp.ints(), val.ints(), sorted.ints());
+	                                  weight ? (Real*)weight->d : nullptr, start.ints(), key.ints(), keyTmp.ints(), val.ints(), sorted.ints(), &tree);
 }
 
 int flipUpdate(const char* who, mp_context* ctx, const mp_grid* vel, const mp_grid* velOld, long long np, const mp_grid* pos, const mp_grid* pflag, mp_grid* partVel,
@@ -199,8 +210,13 @@ int mp_union_particle_levelset(mp_context* ctx, long long np, const mp_grid* pos
 	const Dims d = dimsOf(phi);
 	const int* isys = indexSys ? (const int*)indexSys->d : nullptr;
 	const int* pt = ptype ? (const int*)ptype->d : nullptr;
-	if (phi->prec == 4) return parts::unionParticleLevelset<float>(ex, d, pos ? (const float*)pos->d : nullptr, (const int*)index->d, isys, count, (float*)phi->d, radiusFactor, pt, exclude);
-	return parts::unionParticleLevelset<double>(ex, d, pos ? (const double*)pos->d : nullptr, (const int*)index->d, isys, count, (double*)phi->d, radiusFactor, pt, exclude);
+	Tmp posS;      // positions in index order (MP_UNION_SORTED=0: read through indexSys)
+	const char* e = getenv("MP_UNION_SORTED");
+	if ((!e || atoi(e)) && count > 0) MP_TRY(scratchInts(ctx, 3 * count * (phi->prec / 4), posS));
+	if (phi->prec == 4) return parts::unionParticleLevelset<float>(ex, d, pos ? (const float*)pos->d : nullptr, (const int*)index->d, isys, count, (float*)phi->d, radiusFactor, pt, exclude,
+	                                                               posS.g ? (float*)posS.g->d : nullptr);
+	return parts::unionParticleLevelset<double>(ex, d, pos ? (const double*)pos->d : nullptr, (const int*)index->d, isys, count, (double*)phi->d, radiusFactor, pt, exclude,
+	                                            posS.g ? (double*)posS.g->d : nullptr);
 }
 
 int mp_map_parts_to_mac(mp_context* ctx, const mp_grid* flags, mp_grid* vel, mp_grid* velOld, long long np, const mp_grid* pos, const mp_grid* pflag, const mp_grid* partVel,

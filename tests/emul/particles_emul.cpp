@@ -101,7 +101,20 @@ template <typename Real> int mapParts(int order, const Dims& d, Real* vel, Real*
 	HostExec ex = { order };
 	int *start = scratchInts(d.n), *key = scratchInts(np), *keyTmp = scratchInts(np), *val = scratchInts(np), *sorted = scratchInts(np);
 	parts::PSet<Real> ps = { pos, pflag, ptype, exclude };
-	const int rc = parts::mapPartsToMAC<Real>(ex, d, vel, velOld, np, ps, pvel, weight, start, key, keyTmp, val, sorted);
+	// MP_MAPPARTS=0: the 27-way walk; default: the tree of 3-way merges (what mp_particles.cu launches) -- scratch comes uninitialised
+	const char* e = getenv("MP_MAPPARTS");
+	int rc;
+	if (e && !atoi(e)) rc = parts::mapPartsToMAC<Real>(ex, d, vel, velOld, np, ps, pvel, weight, start, key, keyTmp, val, sorted);
+	else {
+		const IndexInt n = np < 1 ? 1 : np;
+		parts::MapPartsTreeScratch<Real> t;
+		t.off1 = scratchInts(d.n); t.off2 = scratchInts(d.n);
+		t.e1 = (parts::Ent*)scratchInts(2 * 3 * n); t.e2 = (parts::Ent*)scratchInts(2 * 9 * n);
+		t.posS = (Real*)malloc(sizeof(Real) * 3 * (size_t)n); t.pvelS = (Real*)malloc(sizeof(Real) * 3 * (size_t)n);
+		memset(t.posS, 0x7f, sizeof(Real) * 3 * (size_t)n); memset(t.pvelS, 0x7f, sizeof(Real) * 3 * (size_t)n);
+		rc = parts::mapPartsToMAC<Real>(ex, d, vel, velOld, np, ps, pvel, weight, start, key, keyTmp, val, sorted, &t);
+		free(t.off1); free(t.off2); free(t.e1); free(t.e2); free(t.posS); free(t.pvelS);
+	}
 	free(start); free(key); free(keyTmp); free(val); free(sorted);
 	return rc;
 }
@@ -192,8 +205,14 @@ int emu_union_particle_levelset(int prec, int order, int sx, int sy, int sz, lon
                                 double radiusFactor, const int* ptype, int exclude) {
 	(void)np;
 	const Dims d = mkDims(sx, sy, sz); HostExec ex = { order };
-	return prec == 4 ? parts::unionParticleLevelset<float>(ex, d, (const float*)pos, index, indexSys, count, (float*)phi, radiusFactor, ptype, exclude)
-	                 : parts::unionParticleLevelset<double>(ex, d, (const double*)pos, index, indexSys, count, (double*)phi, radiusFactor, ptype, exclude);
+	// positions in index order, as mp_particles.cu runs it (MP_UNION_SORTED=0: through indexSys); the scratch comes uninitialised
+	const char* e = getenv("MP_UNION_SORTED");
+	void* scratch = ((!e || atoi(e)) && count > 0) ? malloc((size_t)prec * 3 * (size_t)count) : nullptr;
+	if (scratch) memset(scratch, 0x7f, (size_t)prec * 3 * (size_t)count);
+	const int rc = prec == 4 ? parts::unionParticleLevelset<float>(ex, d, (const float*)pos, index, indexSys, count, (float*)phi, radiusFactor, ptype, exclude, (float*)scratch)
+	                         : parts::unionParticleLevelset<double>(ex, d, (const double*)pos, index, indexSys, count, (double*)phi, radiusFactor, ptype, exclude, (double*)scratch);
+	free(scratch);
+	return rc;
 }
 int emu_map_parts_to_mac(int prec, int order, int sx, int sy, int sz, void* vel, void* velOld, long long np, const void* pos, const int* pflag, const void* pvel, void* weight,
                          const int* ptype, int exclude) {

@@ -88,6 +88,18 @@ def test_kernel_emulation_reproduces_flip_golden(name, prec, order, parts_emul_l
 
 
 @pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", list(FLIP_SCENES))
+def test_kernel_emulation_map_parts_27_way_walk(name, prec, parts_emul_lib, monkeypatch):
+    """mapPartsToMAC has two forms on the device: a tree of 3-way merges (default, used by every other test here) and the one-kernel 27-way walk
+    (MP_MAPPARTS=0) -- the same particles in the same order: both give the golden bits"""
+    monkeypatch.setenv("MP_MAPPARTS", "0")
+    g = load_golden("step_" + name, prec)
+    out = run_flip_plugins(FlipEmulation(parts_emul_lib, prec, 3), name, prec)
+    for key in g:
+        assert np.array_equal(out[key], g[key]), (name, prec, key)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
 @pytest.mark.parametrize("shape", [(6, 5, 7), (1, 9, 530)])
 def test_kernel_emulation_equals_port_on_other_scenes(shape, prec, parts_emul_lib, port32, port64, monkeypatch):
     """another seed, a row wider than one block's 4 x 128 cells, and no particles at all"""
