@@ -38,8 +38,10 @@ __device__ __forceinline__ bool interior(const Dims& d, IndexInt idx, int& i, in
 }
 
 // ---------------------------------------------------------------- MakeRhs
-template <typename Real>
-__global__ void __launch_bounds__(256) k_make_rhs(Dims d, const int* __restrict__ flags, Real* __restrict__ rhs, const Real* __restrict__ vel,
+// FULL = false: no face fractions, no surface tension -- the smoke / plain liquid case, compiled without those paths (the full kernel needs 113
+// registers and runs at a quarter of the occupancy; same cells per thread and same reduction order in both)
+template <typename Real, bool FULL>
+__global__ void __launch_bounds__(256, FULL ? 1 : 4) k_make_rhs(Dims d, const int* __restrict__ flags, Real* __restrict__ rhs, const Real* __restrict__ vel,
 	const Real* __restrict__ perCellCorr, const Real* __restrict__ fractions, const Real* __restrict__ obvel,
 	const Real* __restrict__ phi, const Real* __restrict__ curv, Real surfTens, Real gfClamp,
 	double* partials, unsigned int* ticket, double* out)
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) k_make_rhs(Dims d, const int* __restrict_
 			const IndexInt X = d.X, Y = d.Y, Z = d.Z;
 			const Real* c = vel + 3 * idx; const Real* cx = vel + 3 * (idx + X); const Real* cy = vel + 3 * (idx + Y); const Real* cz = vel + 3 * (idx + Z);
 			Real set;
-			if (!fractions) {
+			if (!FULL || !fractions) {
 				set = c[0] - cx[0] + c[1] - cy[1];
 				if (d.is3D) set += c[2] - cz[2];
 			} else {
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(256) k_make_rhs(Dims d, const int* __restrict_
 					if (d.is3D) set += (1 - f[2]) * o[2] - (1 - fz[2]) * oz[2];
 				}
 			}
-			if (phi && curv) {
+			if (FULL && phi && curv) {
 				if (flags[idx - X] & TypeEmpty) set += surfTensHelper<Real>(idx, -X, phi, curv, surfTens, gfClamp);
 				if (flags[idx + X] & TypeEmpty) set += surfTensHelper<Real>(idx, +X, phi, curv, surfTens, gfClamp);
 				if (flags[idx - Y] & TypeEmpty) set += surfTensHelper<Real>(idx, -Y, phi, curv, surfTens, gfClamp);
@@ -158,15 +160,24 @@ __global__ void __launch_bounds__(256) k_ghost_diag(Dims d, const int* __restric
 // slots: [0] #empty cells, [1] min linear index of an interior fluid cell, [2] #fluid cells on the outer layer
 __global__ void __launch_bounds__(256) k_scan_flags(Dims d, const int* __restrict__ flags, unsigned long long* slots)
 {
+	// a warp walks whole rows of the owned planes [kb, ke): (j, k) come from one division per row, not per cell
 	unsigned long long nEmpty = 0, nBad = 0, minFluid = ~0ull;
-	for (IndexInt idx = d.i0 + (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; idx < d.i1; idx += (IndexInt)gridDim.x * blockDim.x) {
-		const int f = flags[idx];
-		if (f & TypeEmpty) nEmpty++;
-		if (f & TypeFluid) {
-			int i, j, k;
-			const unsigned long long gidx = (unsigned long long)(idx + (IndexInt)d.kOff * d.Z);      // index in the global grid
-			if (interior(d, idx, i, j, k)) { if (gidx < minFluid) minFluid = gidx; }
-			else nBad++;
+	const int lane = threadIdx.x & 31, warpsPerBlock = blockDim.x >> 5;
+	const long long nrows = (long long)d.sy * (d.ke - d.kb), plane = (long long)d.sx * d.sy;
+	for (long long r = (long long)blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); r < nrows; r += (long long)gridDim.x * warpsPerBlock) {
+		const int k = d.kb + (int)(r / d.sy), j = (int)(r - (long long)(k - d.kb) * d.sy);
+		const int kg = k + d.kOff;
+		const bool rowInterior = j >= 1 && j < d.sy - 1 && (!d.is3D || (kg >= 1 && kg < d.gsz - 1));
+		const IndexInt row = (IndexInt)k * plane + (IndexInt)j * d.sx;
+		for (int i = lane; i < d.sx; i += 32) {
+			const int f = flags[row + i];
+			if (f & TypeEmpty) nEmpty++;
+			if (f & TypeFluid) {
+				if (rowInterior && i >= 1 && i < d.sx - 1) {
+					const unsigned long long gidx = (unsigned long long)(row + i + (IndexInt)d.kOff * plane);      // index in the global grid
+					if (gidx < minFluid) minFluid = gidx;
+				} else nBad++;
+			}
 		}
 	}
 	#pragma unroll
@@ -390,12 +401,18 @@ int mp_make_rhs(mp_context* ctx, const mp_grid* flags, mp_grid* rhs, const mp_gr
 	const Dims d = dimsOf(flags);
 	unsigned int blocks = gridFor(d.n, 256);
 	if (blocks > (unsigned)kMaxPartials) blocks = kMaxPartials;   // grid-stride beyond that
-	if (rhs->prec == 4)
-		k_make_rhs<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)rhs->d, (const float*)vel->d, dptr<float>(perCellCorr), dptr<float>(fractions),
+	const bool full = fractions || (phi && curv);
+	if (rhs->prec == 4) {
+		if (full) k_make_rhs<float, true><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)rhs->d, (const float*)vel->d, dptr<float>(perCellCorr), dptr<float>(fractions),
 			dptr<float>(obvel), dptr<float>(phi), dptr<float>(curv), (float)surfTens, (float)gfClamp, ctx->partials, ctx->tickets + 1, ctx->dScal + 2);
-	else
-		k_make_rhs<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)rhs->d, (const double*)vel->d, dptr<double>(perCellCorr), dptr<double>(fractions),
+		else k_make_rhs<float, false><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)rhs->d, (const float*)vel->d, dptr<float>(perCellCorr), nullptr,
+			nullptr, nullptr, nullptr, 0.f, (float)gfClamp, ctx->partials, ctx->tickets + 1, ctx->dScal + 2);
+	} else {
+		if (full) k_make_rhs<double, true><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)rhs->d, (const double*)vel->d, dptr<double>(perCellCorr), dptr<double>(fractions),
 			dptr<double>(obvel), dptr<double>(phi), dptr<double>(curv), surfTens, gfClamp, ctx->partials, ctx->tickets + 1, ctx->dScal + 2);
+		else k_make_rhs<double, false><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)rhs->d, (const double*)vel->d, dptr<double>(perCellCorr), nullptr,
+			nullptr, nullptr, nullptr, 0., gfClamp, ctx->partials, ctx->tickets + 1, ctx->dScal + 2);
+	}
 	MP_CHECK_LAUNCH(ctx);
 	MP_TRY(mp_dist_sum(ctx, ctx->dScal + 2, 2));          // slab mode: global sum / cnt
 	if (sum || cnt) {

@@ -1034,7 +1034,8 @@ template <typename Real> static inline int l0fusedChunk(const mp_mg* m) {
 // the per-colour level-0 kernels with the operator mask (k_mg_l0_vecm)
 template <typename Real> static inline bool l0masked(const mp_mg* m) {
 	const char* e = getenv("MP_MG_L0MASK");      // read per call
-	return (!e || atoi(e)) && m->mask0 && m->mask0Valid && !m->slab && l0vec<Real>(m->geom[0]);
+	// z-slabs: A[0] and the mask are those of the global grid on every rank (every rank takes the same decision), the kernels index them globally
+	return (!e || atoi(e)) && m->mask0 && m->mask0Valid && l0vec<Real>(m->geom[0]);
 }
 template <typename Real, int MODE>
 static int l0fusedLaunch(mp_mg* m, int c0, int c1, const Real* b, Real bscale, const Real* xin, Real* xout, Real* rout, const int* doneFlag)
@@ -1353,7 +1354,7 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, nr * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->type[l], 0, n, ctx->stream));
 	}
-	if (!m->slab && sx % (16 / prec) == 0) MP_CUDA(cudaMalloc((void**)&m->mask0, sizeof(unsigned short) * (size_t)m->geom[0].n + 64));
+	if (sx % (16 / prec) == 0) MP_CUDA(cudaMalloc((void**)&m->mask0, sizeof(unsigned short) * (size_t)m->geom[0].n + 64));
 	MP_CUDA(cudaMalloc((void**)&m->cg, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n));
 	MP_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n, ctx->stream));
 	MP_CUDA(cudaMalloc((void**)&m->dFlags, 64 * sizeof(int)));

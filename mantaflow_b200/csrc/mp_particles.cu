@@ -123,15 +123,16 @@ int mapParts(mp_context* ctx, mp_grid* vel, mp_grid* velOld, long long np, const
 	CudaExec ex = { ctx };
 	// the tree of 3-way merges (default; MP_MAPPARTS=0: the 27-way walk).  Its lists hold a particle 3 + 9 times: 96 + 24 bytes per particle
 	const char* e = getenv("MP_MAPPARTS");
-	const bool useTree = (!e || atoi(e)) && np > 0 && 9 * np <= 0x3fffffffLL;
+	const bool useTree = (!e || atoi(e)) && np > 0 && 2 * parts::treeEntries(vel->n, np, 9) <= 0x7fffffffLL;
 	if (!useTree)
 		return parts::mapPartsToMAC<Real>(ex, dimsOf(vel), (Real*)vel->d, (Real*)velOld->d, np, psetOf<Real>(pos, pflag, ptype, exclude), partVel ? (const Real*)partVel->d : nullptr,
 		                                  weight ? (Real*)weight->d : nullptr, start.ints(), key.ints(), keyTmp.ints(), val.ints(), sorted.ints());
-	Tmp off1, off2, e1, e2, posS, pvelS;
+	Tmp len1, off1, len2, off2, e1, e2, posS, pvelS;
 	const IndexInt realInts = 3 * np * (IndexInt)(sizeof(Real) / 4);
-	MP_TRY(scratchInts(ctx, vel->n, off1)); MP_TRY(scratchInts(ctx, vel->n, off2)); MP_TRY(scratchInts(ctx, 2 * 3 * np, e1)); MP_TRY(scratchInts(ctx, 2 * 9 * np, e2));
+	MP_TRY(scratchInts(ctx, vel->n, len1)); MP_TRY(scratchInts(ctx, vel->n, off1)); MP_TRY(scratchInts(ctx, vel->n, len2)); MP_TRY(scratchInts(ctx, vel->n, off2));
+	MP_TRY(scratchInts(ctx, 2 * parts::treeEntries(vel->n, np, 3), e1)); MP_TRY(scratchInts(ctx, 2 * parts::treeEntries(vel->n, np, 9), e2));
 	MP_TRY(scratchInts(ctx, realInts, posS)); MP_TRY(scratchInts(ctx, realInts, pvelS));
-	const parts::MapPartsTreeScratch<Real> tree = { off1.ints(), off2.ints(), (parts::Ent*)e1.g->d, (parts::Ent*)e2.g->d, (Real*)posS.g->d, (Real*)pvelS.g->d };
+	const parts::MapPartsTreeScratch<Real> tree = { len1.ints(), off1.ints(), len2.ints(), off2.ints(), (parts::Ent*)e1.g->d, (parts::Ent*)e2.g->d, (Real*)posS.g->d, (Real*)pvelS.g->d };
 	return parts::mapPartsToMAC<Real>(ex, dimsOf(vel), (Real*)vel->d, (Real*)velOld->d, np, psetOf<Real>(pos, pflag, ptype, exclude), partVel ? (const Real*)partVel->d : nullptr,
 	                                  weight ? (Real*)weight->d : nullptr, start.ints(), key.ints(), keyTmp.ints(), val.ints(), sorted.ints(), &tree);
 }

@@ -498,51 +498,89 @@ template <typename Real> struct MapPartsGather {
 // consumers; entries carry the particle id (the merge key) and its slot in bucket order, where copies of pos / partVel lie next to their
 // cell's neighbours.  Same particles in the same (ascending id) order through the same arithmetic: bit-identical to the 27-way walk.
 struct Ent { int id, slot; };
+struct alignas(16) Ent2 { Ent a, b; };
+enum : int { kNoId = 0x7fffffff };
 struct MergeAxis {                     // neighbours of cell (i, j, k) along `axis` that exist
 	static MP_HD bool lo(const Dims& d, int axis, int i, int j, int k) { return axis == 0 ? i > 0 : (axis == 1 ? j > 0 : (d.is3D && k > 0)); }
 	static MP_HD bool hi(const Dims& d, int axis, int i, int j, int k) { return axis == 0 ? i < d.sx - 1 : (axis == 1 ? j < d.sy - 1 : (d.is3D && k < d.sz - 1)); }
 	static MP_HD IndexInt stride(const Dims& d, int axis) { return axis == 0 ? 1 : (axis == 1 ? d.Y : d.Z); }
 };
-// number of entries of the merged list of a cell: start[] / count describe the input lists (start of cell c, total)
+// The lists of one level.  Level 0: ranges of `sorted` (start = first slot of a cell's bucket, lengths from the differences, entries are
+// (sorted[s], s)).  Levels >= 1: materialised Ent lists; every list starts on a 32-byte boundary (start[] counts entries and is a multiple
+// of 4, len[] holds the true lengths), so that a thread -- whose list is private to it and lies ~600 bytes from its neighbour lane's -- moves
+// whole 32-byte sectors: read element by element, every sector of a list crossed DRAM four times (measured: 23.7 GB for 5.6 GB of lists).
+struct Lists {
+	const int* start; const int* len; IndexInt count; const Ent* ent; const int* sorted;
+	MP_HD int first(IndexInt c) const { return start[c]; }
+	MP_HD int length(const Dims& d, IndexInt c) const { return len ? len[c] : ((c + 1 < d.n) ? start[c + 1] : (int)count) - start[c]; }
+};
+// reader of one ascending list: the head entry in b0, up to three more of its sector behind it in registers
+struct ListCur {
+	const Ent* ent; const int* sorted; int pos, end, have; Ent b0, b1, b2, b3;
+	MP_HD void fill() {
+		have = 0; b0.id = kNoId;
+		if (pos >= end) return;
+		if (!ent) { b0.id = sorted[pos]; b0.slot = pos; have = 1; return; }
+		const Ent2* q = reinterpret_cast<const Ent2*>(ent + pos);        // pos is a multiple of 4 here: two 16-byte loads of one sector
+		const Ent2 u = q[0], v = q[1];
+		b0 = u.a; b1 = u.b; b2 = v.a; b3 = v.b;
+		have = end - pos < 4 ? end - pos : 4;
+	}
+	MP_HD void open(const Dims& d, const Lists& l, IndexInt c) { ent = l.ent; sorted = l.sorted; pos = l.first(c); end = pos + l.length(d, c); fill(); }
+	MP_HD void close() { ent = nullptr; sorted = nullptr; pos = end = have = 0; b0.id = kNoId; }
+	MP_HD void pop() { pos++; if (--have > 0) { b0 = b1; b1 = b2; b2 = b3; } else fill(); }
+};
+// lengths of the merged lists: true length and, rounded up to whole sectors, what the exclusive scan turns into the list's first entry
 struct MergeLen {
 	static const bool kSplit = false;
-	const int* start; IndexInt count; int axis; int* len;
-	static MP_HD int lenOf(const Dims& d, const int* start, IndexInt count, IndexInt c) { return ((c + 1 < d.n) ? start[c + 1] : (int)count) - start[c]; }
+	Lists in; int axis; int* lenOut; int* offOut;
 	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		const IndexInt st = MergeAxis::stride(d, axis);
-		int n = lenOf(d, start, count, idx);
-		if (MergeAxis::lo(d, axis, i, j, k)) n += lenOf(d, start, count, idx - st);
-		if (MergeAxis::hi(d, axis, i, j, k)) n += lenOf(d, start, count, idx + st);
-		len[idx] = n;
+		int n = in.length(d, idx);
+		if (MergeAxis::lo(d, axis, i, j, k)) n += in.length(d, idx - st);
+		if (MergeAxis::hi(d, axis, i, j, k)) n += in.length(d, idx + st);
+		lenOut[idx] = n; offOut[idx] = (n + 3) & ~3;
 	}
 };
-// three ascending lists -> one; `visit(Ent)` is called in ascending id order.  in == NULL: level 0, the lists are ranges of `sorted`
+// three ascending lists -> one; `visit(Ent)` is called in ascending id order
 struct Merge3 {
-	const int* start; IndexInt count; const Ent* in; const int* sorted; int axis;
-	MP_HD Ent at(int s) const { if (in) return in[s]; Ent e = { sorted[s], s }; return e; }
+	Lists in; int axis;
 	template <typename V> MP_HD void walk(const Dims& d, int i, int j, int k, IndexInt idx, V& visit) const {
 		const IndexInt st = MergeAxis::stride(d, axis);
-		int a = 0, ae = 0, b = start[idx], be = b + MergeLen::lenOf(d, start, count, idx), c = 0, ce = 0;
-		if (MergeAxis::lo(d, axis, i, j, k)) { a = start[idx - st]; ae = a + MergeLen::lenOf(d, start, count, idx - st); }
-		if (MergeAxis::hi(d, axis, i, j, k)) { c = start[idx + st]; ce = c + MergeLen::lenOf(d, start, count, idx + st); }
-		const int none = 0x7fffffff;
-		Ent ea = { none, 0 }, eb = { none, 0 }, ec = { none, 0 };
-		if (a < ae) ea = at(a);
-		if (b < be) eb = at(b);
-		if (c < ce) ec = at(c);
+		ListCur a, b, c;
+		b.open(d, in, idx);
+		if (MergeAxis::lo(d, axis, i, j, k)) a.open(d, in, idx - st); else a.close();
+		if (MergeAxis::hi(d, axis, i, j, k)) c.open(d, in, idx + st); else c.close();
 		for (;;) {
-			if (ea.id < eb.id && ea.id < ec.id) { visit(ea); ea.id = none; if (++a < ae) ea = at(a); }        // ids are distinct: ties only among exhausted lists
-			else if (eb.id < ec.id) { visit(eb); eb.id = none; if (++b < be) eb = at(b); }
-			else if (ec.id != none) { visit(ec); ec.id = none; if (++c < ce) ec = at(c); }
-			else break;
+			// ids are distinct: the smallest head is unique until all three lists are exhausted.  One call site of visit(): lanes that take
+			// their entry from different lists stay converged through it
+			const int mab = a.b0.id < b.b0.id ? a.b0.id : b.b0.id, mn = mab < c.b0.id ? mab : c.b0.id;
+			if (mn == kNoId) break;
+			const bool ta = a.b0.id == mn, tb = b.b0.id == mn;
+			const Ent e = ta ? a.b0 : (tb ? b.b0 : c.b0);
+			visit(e);
+			if (ta) a.pop(); else if (tb) b.pop(); else c.pop();
 		}
 	}
 };
 struct MergeStore {
 	static const bool kSplit = false;
 	Merge3 m; const int* outStart; Ent* out;
-	struct Put { Ent* p; MP_HD void operator()(const Ent& e) { *p++ = e; } };
-	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const { Put put = { out + outStart[idx] }; m.walk(d, i, j, k, idx, put); }
+	struct Put {                       // four entries = one sector at a time; the tail of the last sector is padding no reader looks at
+		Ent* p; int n; Ent w0, w1, w2, w3;
+		MP_HD void flush() { Ent2* q = reinterpret_cast<Ent2*>(p); Ent2 u = { w0, w1 }, v = { w2, w3 }; q[0] = u; q[1] = v; p += 4; n = 0; }
+		MP_HD void operator()(const Ent& e) {
+			if (n == 0) w0 = e; else if (n == 1) w1 = e; else if (n == 2) w2 = e; else w3 = e;
+			if (++n == 4) flush();
+		}
+	};
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		const Ent z = { 0, 0 };
+		Put put = { out + outStart[idx], 0, z, z, z, z };
+		m.walk(d, i, j, k, idx, put);
+		if (put.n) flush(put);
+	}
+	static MP_HD void flush(Put& put) { put.flush(); }
 };
 // copies of pos / partVel in bucket order
 template <typename Real> struct GatherSlots {
@@ -579,12 +617,14 @@ template <typename Real> struct MapPartsGatherTree {
 	}
 };
 
-// scratch of the merge tree, provided by the caller (upper bounds: a particle enters 3 x-triples and 9 x-y blocks)
+// scratch of the merge tree, provided by the caller.  A particle enters 3 x-triples and 9 x-y blocks, and a non-empty list is padded by up to
+// three entries: e1 holds 3 np + 3 min(cells, 3 np) entries at most, e2 9 np + 3 min(cells, 9 np)  (treeEntries below)
 template <typename Real> struct MapPartsTreeScratch {
-	int* off1; int* off2;            // int[d.n] each
-	Ent* e1; Ent* e2;                // Ent[3 np], Ent[9 np]
-	Real* posS; Real* pvelS;         // Real[3 np] each
+	int* len1; int* off1; int* len2; int* off2;      // int[d.n] each
+	Ent* e1; Ent* e2;
+	Real* posS; Real* pvelS;                          // Real[3 np] each
 };
+inline IndexInt treeEntries(IndexInt cells, IndexInt np, int copies) { const IndexInt t = (IndexInt)copies * np; return t + 3 * (cells < t ? cells : t) + 4; }
 // start: scratch int[d.n]; key / keyTmp / val / sorted: scratch int[np]; tree == NULL: the 27-way walk
 template <typename Real, typename Exec>
 int mapPartsToMAC(Exec& ex, const Dims& d, Real* vel, Real* velOld, IndexInt np, const PSet<Real>& ps, const Real* pvel, Real* weight,
@@ -597,11 +637,14 @@ int mapPartsToMAC(Exec& ex, const Dims& d, Real* vel, Real* velOld, IndexInt np,
 	}
 	if (count > 0) { GatherSlots<Real> gs = { sorted, ps.pos, pvel, tree->posS, tree->pvelS }; MP_TRY(ex.parts(count, gs)); }
 	IndexInt n1 = 0, n2 = 0;
-	MergeLen l1 = { start, count, 0, tree->off1 }; MP_TRY(ex.cells(d, l1)); MP_TRY(ex.exclusiveScan(tree->off1, d.n, &n1));
-	MergeStore s1 = { { start, count, nullptr, sorted, 0 }, tree->off1, tree->e1 }; MP_TRY(ex.cells(d, s1));
-	MergeLen l2 = { tree->off1, n1, 1, tree->off2 }; MP_TRY(ex.cells(d, l2)); MP_TRY(ex.exclusiveScan(tree->off2, d.n, &n2));
-	MergeStore s2 = { { tree->off1, n1, tree->e1, nullptr, 1 }, tree->off2, tree->e2 }; MP_TRY(ex.cells(d, s2));
-	MapPartsGatherTree<Real> op = { { tree->off2, n2, tree->e2, nullptr, 2 }, tree->posS, tree->pvelS, vel, velOld, weight };
+	const Lists l0 = { start, nullptr, count, nullptr, sorted };
+	MergeLen m1 = { l0, 0, tree->len1, tree->off1 }; MP_TRY(ex.cells(d, m1)); MP_TRY(ex.exclusiveScan(tree->off1, d.n, &n1));
+	MergeStore s1 = { { l0, 0 }, tree->off1, tree->e1 }; MP_TRY(ex.cells(d, s1));
+	const Lists l1 = { tree->off1, tree->len1, n1, tree->e1, nullptr };
+	MergeLen m2 = { l1, 1, tree->len2, tree->off2 }; MP_TRY(ex.cells(d, m2)); MP_TRY(ex.exclusiveScan(tree->off2, d.n, &n2));
+	MergeStore s2 = { { l1, 1 }, tree->off2, tree->e2 }; MP_TRY(ex.cells(d, s2));
+	const Lists l2 = { tree->off2, tree->len2, n2, tree->e2, nullptr };
+	MapPartsGatherTree<Real> op = { { l2, 2 }, tree->posS, tree->pvelS, vel, velOld, weight };
 	return ex.cells(d, op);
 }
 

@@ -108,12 +108,16 @@ template <typename Real> int mapParts(int order, const Dims& d, Real* vel, Real*
 	else {
 		const IndexInt n = np < 1 ? 1 : np;
 		parts::MapPartsTreeScratch<Real> t;
-		t.off1 = scratchInts(d.n); t.off2 = scratchInts(d.n);
-		t.e1 = (parts::Ent*)scratchInts(2 * 3 * n); t.e2 = (parts::Ent*)scratchInts(2 * 9 * n);
+		t.len1 = scratchInts(d.n); t.off1 = scratchInts(d.n); t.len2 = scratchInts(d.n); t.off2 = scratchInts(d.n);
+		void *raw1 = nullptr, *raw2 = nullptr;      // 32-byte aligned like a device allocation; filled with garbage
+		const size_t b1 = sizeof(parts::Ent) * (size_t)parts::treeEntries(d.n, n, 3), b2 = sizeof(parts::Ent) * (size_t)parts::treeEntries(d.n, n, 9);
+		if (posix_memalign(&raw1, 64, b1) || posix_memalign(&raw2, 64, b2)) return MP_ERR_CUDA;
+		memset(raw1, 0x5a, b1); memset(raw2, 0x5a, b2);
+		t.e1 = (parts::Ent*)raw1; t.e2 = (parts::Ent*)raw2;
 		t.posS = (Real*)malloc(sizeof(Real) * 3 * (size_t)n); t.pvelS = (Real*)malloc(sizeof(Real) * 3 * (size_t)n);
 		memset(t.posS, 0x7f, sizeof(Real) * 3 * (size_t)n); memset(t.pvelS, 0x7f, sizeof(Real) * 3 * (size_t)n);
 		rc = parts::mapPartsToMAC<Real>(ex, d, vel, velOld, np, ps, pvel, weight, start, key, keyTmp, val, sorted, &t);
-		free(t.off1); free(t.off2); free(t.e1); free(t.e2); free(t.posS); free(t.pvelS);
+		free(t.len1); free(t.off1); free(t.len2); free(t.off2); free(t.e1); free(t.e2); free(t.posS); free(t.pvelS);
 	}
 	free(start); free(key); free(keyTmp); free(val); free(sorted);
 	return rc;

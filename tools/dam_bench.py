@@ -41,6 +41,8 @@ mf.markFluidCells(parts=pp, flags=flags, ptype=pT)
 grav, dx, bnd = -0.01, 1.0, 1
 FlagFluid, FlagEmpty = mf.FlagFluid, mf.FlagEmpty
 
+PC = int(os.environ.get("DAM_PC", "1"))          # the scene's own call takes the plugin's default PcMIC; DAM_PC=2: PcMGDynamic (BASELINE config 2 names PcMG)
+PC_NAME = {0: "PcNone", 1: "PcMIC", 2: "PcMGDynamic", 3: "PcMGStatic"}[PC]
 calls = [   # scenes/benchmark_dam.py:100-134, ghost-fluid variant
     ("mapPartsToMAC", lambda: mf.mapPartsToMAC(vel=vel, flags=flags, velOld=velOld, parts=pp, partVel=pV, ptype=pT, exclude=FlagEmpty)),
     ("getMaxAbs (adaptTimestep)", lambda: vel.getMaxAbs()),
@@ -49,7 +51,7 @@ calls = [   # scenes/benchmark_dam.py:100-134, ghost-fluid variant
     ("unionParticleLevelset", lambda: mf.unionParticleLevelset(parts=pp, indexSys=pindex, flags=flags, index=index, phi=phi, radiusFactor=1.0)),
     ("extrapolateLsSimple", lambda: mf.extrapolateLsSimple(phi=phi, distance=4, inside=True)),
     ("setWallBcs", lambda: mf.setWallBcs(flags=flags, vel=vel)),
-    ("solvePressure (PcMIC, phi)", lambda: mf.solvePressure(flags=flags, vel=vel, pressure=pressure, phi=phi, cgAccuracy=1e-3)),
+    ("solvePressure (%s, phi)" % PC_NAME, lambda: mf.solvePressure(flags=flags, vel=vel, pressure=pressure, phi=phi, cgAccuracy=1e-3, preconditioner=PC)),
     ("setWallBcs 2", lambda: mf.setWallBcs(flags=flags, vel=vel)),
     ("extrapolateMACSimple", lambda: mf.extrapolateMACSimple(flags=flags, vel=vel)),
     ("flipVelocityUpdate", lambda: mf.flipVelocityUpdate(vel=vel, velOld=velOld, flags=flags, parts=pp, partVel=pV, flipRatio=0.97, ptype=pT, exclude=FlagEmpty)),

@@ -68,6 +68,9 @@ rows = [   # name, call, minimum bytes
     ("gridParticleIndex", lambda: mf.gridParticleIndex(pp, pindex, F, index), 20 * N + 8 * n),
     ("unionParticleLevelset", lambda: mf.unionParticleLevelset(pp, pindex, F, index, phi), 16 * N + 8 * n),
 ]
+only = os.environ.get("FLIP_BENCH_ONLY")          # e.g. FLIP_BENCH_ONLY=mapPartsToMAC under ncu
+if only:
+    rows = [r for r in rows if r[0] == only]
 out = {"res": res, "prec": 4, "particles": N, "peak_gbs": PEAK, "plugins": {}}
 print(f"# {res}^3 float, {N} particles (8 per liquid cell, shuffled), one B200", flush=True)
 for name, fn, nbytes in rows:
