@@ -273,8 +273,9 @@ __global__ void k_fix_pressure(Dims d, const long long* pIdx, Real value, Real* 
 }
 
 // ---------------------------------------------------------------- correctVelocity
-template <typename Real>
-__global__ void __launch_bounds__(256) k_correct_velocity(Dims d, const int* __restrict__ flags, Real* __restrict__ vel, const Real* __restrict__ pressure,
+// GHOST = false: no level set -- compiled without the ghost-fluid / surface-tension paths (fewer registers, full occupancy)
+template <typename Real, bool GHOST>
+__global__ void __launch_bounds__(256, GHOST ? 4 : 8) k_correct_velocity(Dims d, const int* __restrict__ flags, Real* __restrict__ vel, const Real* __restrict__ pressure,
 	const Real* __restrict__ phi, const Real* __restrict__ curv, Real gfClamp, Real surfTens)
 {
 	const IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(256) k_correct_velocity(Dims d, const int* __r
 		if (d.is3D) { if (fz & TypeFluid) vz += pressure[idx - Z]; else vz = 0.f; }
 	}
 	// knCorrectVelocityGhostFluid :154-187 (touches only this cell's velocity -> fused)
-	if (phi) {
+	if (GHOST && phi) {
 		if (fl) {
 			if (fx & TypeEmpty) vx += p * ghostFluidHelper<Real>(idx, -X, phi, gfClamp);
 			if (fy & TypeEmpty) vy += p * ghostFluidHelper<Real>(idx, -Y, phi, gfClamp);
@@ -514,12 +515,14 @@ int mp_correct_velocity(mp_context* ctx, mp_grid* vel, const mp_grid* pressure, 
 	const size_t planeReal = (size_t)d.Z * pressure->prec;
 	if (d.world > 1) MP_TRY(mp_dist_halo(ctx, pressure->d, planeReal, pressure->sz));    // p(k-1) of the first owned plane
 	if (vel->prec == 4) {
-		k_correct_velocity<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, (const float*)pressure->d, dptr<float>(phi), dptr<float>(curv), (float)params->gfClamp, (float)params->surfTens);
+		if (phi) k_correct_velocity<float, true><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, (const float*)pressure->d, dptr<float>(phi), dptr<float>(curv), (float)params->gfClamp, (float)params->surfTens);
+		else     k_correct_velocity<float, false><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, (const float*)pressure->d, nullptr, nullptr, (float)params->gfClamp, 0.f);
 		MP_CHECK_LAUNCH(ctx);
 		if (phi && d.world > 1) MP_TRY(mp_dist_halo(ctx, vel->d, planeReal * 3, vel->sz));   // k_replace_clamped reads neighbours' updated velocity
 		if (phi) { k_replace_clamped<float><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (float*)vel->d, (const float*)phi->d, (float)params->gfClamp); MP_CHECK_LAUNCH(ctx); }
 	} else {
-		k_correct_velocity<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, (const double*)pressure->d, dptr<double>(phi), dptr<double>(curv), params->gfClamp, params->surfTens);
+		if (phi) k_correct_velocity<double, true><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, (const double*)pressure->d, dptr<double>(phi), dptr<double>(curv), params->gfClamp, params->surfTens);
+		else     k_correct_velocity<double, false><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, (const double*)pressure->d, nullptr, nullptr, params->gfClamp, 0.);
 		MP_CHECK_LAUNCH(ctx);
 		if (phi && d.world > 1) MP_TRY(mp_dist_halo(ctx, vel->d, planeReal * 3, vel->sz));
 		if (phi) { k_replace_clamped<double><<<blocks, 256, 0, ctx->stream>>>(d, (const int*)flags->d, (double*)vel->d, (const double*)phi->d, params->gfClamp); MP_CHECK_LAUNCH(ctx); }

@@ -20,7 +20,16 @@ __global__ void __launch_bounds__(liquid::kThreads, 4) k_liquid_cells(Dims d, F 
 // others leave it alone, so a cell is processed and listed once per pass and the lists hold at most one entry per cell.
 struct ListSink {
 	int* list; int* count;
-	__device__ __forceinline__ void operator()(IndexInt idx) const { list[atomicAdd(count, 1)] = (int)idx; }
+	// the lanes of a warp that list a cell in the same instruction share ONE atomic on the counter (a million single-address atomics made the
+	// listing pass of a 512^3 extrapolation 0.8 - 1.7 ms); the order of a list's entries is free (see above)
+	__device__ __forceinline__ void operator()(IndexInt idx) const {
+		const unsigned m = __activemask();
+		const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+		int base = 0;
+		if (lane == leader) base = atomicAdd(count, __popc(m));
+		base = __shfl_sync(m, base, leader);
+		list[base + __popc(m & ((1u << lane) - 1u))] = (int)idx;
+	}
 };
 template <typename F>
 __global__ void __launch_bounds__(liquid::kThreads, 4) k_liquid_cells_list(Dims d, F f, ListSink sink) {
@@ -33,8 +42,7 @@ __global__ void __launch_bounds__(256) k_liquid_frontier(Dims d, F f, const int*
 	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (long long)gridDim.x * blockDim.x) {
 		const int e = (int)(t / nq), q = (int)(t - (long long)e * nq);
 		const IndexInt nb = (IndexInt)list[e] + liquid::nbOffset(d, q);
-		const int k = d.is3D ? (int)(nb / d.Z) : 0; const IndexInt rem = nb - (IndexInt)k * d.Z;
-		const int j = (int)(rem / d.Y), i = (int)(rem - (IndexInt)j * d.Y);
+		int i, j, k; cellOf(d, nb, i, j, k);
 		const typename F::State s = f.load(d, i, j, k, nb);
 		if (!s.interior) continue;
 		// from the candidate's side the listed cell is neighbour q ^ 1: take it only if no earlier neighbour is listed too

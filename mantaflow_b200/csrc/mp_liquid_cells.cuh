@@ -127,10 +127,19 @@ template <typename Real> struct MacExtrapolate {         // knExtrapolateMACSimp
 		return s;
 	}
 	MP_HD bool reached(int w) const { return (w & 255) == pass || ((w >> 8) & 255) == pass || ((w >> 16) & 255) == pass; }      // some component carries the mark of this pass
+	// non-zero iff one of the three mark bytes of w equals `pass` (bytes of x = w ^ pass-in-every-byte that are zero; marks are < 128)
+	MP_HD unsigned reachedBits(int w) const { const unsigned x = ((unsigned)w ^ (0x010101u * (unsigned)pass)) & 0xffffffu; return (x - 0x010101u) & ~x & 0x808080u; }
 	MP_HD bool apply(const Dims& d, int, int, int, IndexInt idx, const State& s) const {      // true: the cell got a new mark
 		if (!s.interior) return false;
 		const int dim = d.is3D ? 3 : 2;
 		const int t = s.t;
+		// the bulk of the grid: every component already marked, or no neighbour reached in this pass -- nothing to do (one test instead of
+		// eighteen byte comparisons; the pass over all cells was instruction bound)
+		if (pass < 128) {
+			unsigned any = 0;
+			for (int q = 0; q < 2 * dim; q++) any |= reachedBits(s.tn[q]);
+			if (!any) return false;
+		}
 		int tNew = t;
 		for (int c = 0; c < dim; c++) {
 			if (((t >> (8 * c)) & 255) != 0) continue;
@@ -254,7 +263,7 @@ template <typename Real> struct LsMark {                 // fastmarch.cpp:475-49
 	static const bool kSplit = true;
 	const Real* phi; int* tmp; int inside;
 	struct State { Real p, pn[6]; bool interior; };
-	MP_HD bool on(Real p) const { return inside ? (p > 0.) : (p < 0.); }
+	MP_HD bool on(Real p) const { return inside ? (p > (Real)0) : (p < (Real)0); }      // the reference compares with the double 0.: same outcome for every Real
 	MP_HD State load(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		State s;
 		s.interior = interiorCell(d, i, j, k);
@@ -269,9 +278,11 @@ template <typename Real> struct LsMark {                 // fastmarch.cpp:475-49
 		if (s.interior) {
 			if (on(s.p)) m = 1;
 			else {
+				// cells of the outer layer carry no mark: neighbour q (+x -x +y -y +z -z) of an interior cell is interior iff it is not on the layer
+				const bool ok[6] = { i < d.sx - 2, i > 1, j < d.sy - 2, j > 1, k < d.sz - 2, k > 1 };
 				const int dim = d.is3D ? 3 : 2;
 				for (int q = 0; q < 2 * dim; q++)
-					if (nbInterior(d, q, i, j, k) && on(s.pn[q])) { m = 2; break; }      // cells of the outer layer carry no mark
+					if (ok[q] && on(s.pn[q])) { m = 2; break; }
 			}
 		}
 		tmp[idx] = m;

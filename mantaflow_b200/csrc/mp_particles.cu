@@ -127,12 +127,17 @@ int mapParts(mp_context* ctx, mp_grid* vel, mp_grid* velOld, long long np, const
 	if (!useTree)
 		return parts::mapPartsToMAC<Real>(ex, dimsOf(vel), (Real*)vel->d, (Real*)velOld->d, np, psetOf<Real>(pos, pflag, ptype, exclude), partVel ? (const Real*)partVel->d : nullptr,
 		                                  weight ? (Real*)weight->d : nullptr, start.ints(), key.ints(), keyTmp.ints(), val.ints(), sorted.ints());
-	Tmp len1, off1, len2, off2, e1, e2, posS, pvelS;
+	Tmp len1, off1, len2, off2, e1, e2, posS, pvelS, rec;
 	const IndexInt realInts = 3 * np * (IndexInt)(sizeof(Real) / 4);
+	// per-particle records (3-D; MP_MAPPARTS=2: evaluate the weights in the walk): 208 / 400 bytes per particle
+	const IndexInt recInts = np * (IndexInt)(sizeof(parts::PartRec<Real>) / 4);
+	const bool useRec = !(e && atoi(e) == 2) && vel->sz > 1 && vel->sx < 65536 && vel->sy < 65536 && vel->sz < 65536 && recInts <= 0x7fffffffLL;
+	if (useRec) MP_TRY(scratchInts(ctx, recInts, rec));
 	MP_TRY(scratchInts(ctx, vel->n, len1)); MP_TRY(scratchInts(ctx, vel->n, off1)); MP_TRY(scratchInts(ctx, vel->n, len2)); MP_TRY(scratchInts(ctx, vel->n, off2));
 	MP_TRY(scratchInts(ctx, 2 * parts::treeEntries(vel->n, np, 3), e1)); MP_TRY(scratchInts(ctx, 2 * parts::treeEntries(vel->n, np, 9), e2));
-	MP_TRY(scratchInts(ctx, realInts, posS)); MP_TRY(scratchInts(ctx, realInts, pvelS));
-	const parts::MapPartsTreeScratch<Real> tree = { len1.ints(), off1.ints(), len2.ints(), off2.ints(), (parts::Ent*)e1.g->d, (parts::Ent*)e2.g->d, (Real*)posS.g->d, (Real*)pvelS.g->d };
+	if (!useRec) { MP_TRY(scratchInts(ctx, realInts, posS)); MP_TRY(scratchInts(ctx, realInts, pvelS)); }
+	const parts::MapPartsTreeScratch<Real> tree = { len1.ints(), off1.ints(), len2.ints(), off2.ints(), (parts::Ent*)e1.g->d, (parts::Ent*)e2.g->d,
+	                                                posS.g ? (Real*)posS.g->d : nullptr, pvelS.g ? (Real*)pvelS.g->d : nullptr, rec.g ? (parts::PartRec<Real>*)rec.g->d : nullptr };
 	return parts::mapPartsToMAC<Real>(ex, dimsOf(vel), (Real*)vel->d, (Real*)velOld->d, np, psetOf<Real>(pos, pflag, ptype, exclude), partVel ? (const Real*)partVel->d : nullptr,
 	                                  weight ? (Real*)weight->d : nullptr, start.ints(), key.ints(), keyTmp.ints(), val.ints(), sorted.ints(), &tree);
 }

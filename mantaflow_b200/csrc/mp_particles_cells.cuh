@@ -590,6 +590,17 @@ template <typename Real> struct GatherSlots {
 		for (int c = 0; c < 3; c++) { posS[3 * s + c] = pos[3 * p + c]; pvelS[3 * s + c] = pvel[3 * p + c]; }
 	}
 };
+template <typename Real> MP_HD void finishFace(Real (&S)[3], Real (&R)[3], IndexInt idx, Real* vel, Real* velOld, Real* weight) {
+	// stomp(VECTOR_EPSILON), safeDivide, velOld.copyFrom(vel)   flip.cpp:590-594
+	const Real eps = sizeof(Real) == 8 ? (Real)1e-10 : (Real)1e-6f;
+	for (int c = 0; c < 3; c++) {
+		Real w = S[c];
+		if (w < eps) w = 0;
+		const Real r = w ? (R[c] / w) : R[c];
+		vel[3 * idx + c] = r; velOld[3 * idx + c] = r;
+		if (weight) weight[3 * idx + c] = w;
+	}
+}
 template <typename Real> struct MapPartsGatherTree {
 	static const bool kSplit = false;
 	Merge3 m; const Real* posS; const Real* pvelS; Real* vel; Real* velOld; Real* weight;
@@ -606,14 +617,56 @@ template <typename Real> struct MapPartsGatherTree {
 	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
 		Acc acc = { &d, i, j, k, posS, pvelS, { 0, 0, 0 }, { 0, 0, 0 } };
 		m.walk(d, i, j, k, idx, acc);
-		const Real eps = sizeof(Real) == 8 ? (Real)1e-10 : (Real)1e-6f;
-		for (int c = 0; c < 3; c++) {
-			Real w = acc.S[c];
-			if (w < eps) w = 0;
-			const Real r = w ? (acc.R[c] / w) : acc.R[c];
-			vel[3 * idx + c] = r; velOld[3 * idx + c] = r;
-			if (weight) weight[3 * idx + c] = w;
+		finishFace<Real>(acc.S, acc.R, idx, vel, velOld, weight);
+	}
+};
+// ---- 3-D, every axis < 65536 cells: the walk above evaluates the MAC weights of a particle once per visiting cell, 27 times (ncu: 13 G warp
+// instructions for 26 M particles, 15 of 32 lanes active).  Instead every particle gets a record, written once in bucket order: its three
+// face bases and, per component, the 8 products w = b (a c) and w v that setInterpolMAC adds to the faces base + {0,1}^3 (util/interpol.h:
+// 159-203).  A visiting cell looks its own pair up; S += w, R += w v are the reference's additions of the reference's products.
+template <typename Real> struct alignas(16) PartRec {
+	unsigned bx, by, bz, pad;          // shifted base | centred base << 16, per axis (bases are >= 0 and < 65536)
+	Real tab[3][8][2];                  // [component][di + 2 dj + 4 dk] -> { w, w v }
+};
+template <typename Real> struct BuildRecords {
+	Dims d; const int* sorted; const Real* pos; const Real* pvel; PartRec<Real>* rec;
+	MP_HD void operator()(IndexInt s) const {
+		const IndexInt p = sorted[s];
+		const MacWeights<Real> m(d, pos + 3 * p);
+		const Real* v = pvel + 3 * p;
+		PartRec<Real> r;
+		r.bx = (unsigned)m.sxi | ((unsigned)m.xi << 16); r.by = (unsigned)m.syi | ((unsigned)m.yi << 16); r.bz = (unsigned)m.szi | ((unsigned)m.zi << 16); r.pad = 0;
+		for (int dk = 0; dk < 2; dk++) for (int dj = 0; dj < 2; dj++) for (int di = 0; di < 2; di++) {
+			const int t = di + 2 * dj + 4 * dk;
+			Real w;
+			w = m.t[dj] * (m.ss[di] * m.f[dk]);  r.tab[0][t][0] = w; r.tab[0][t][1] = w * v[0];      // MapPartsGather::add with (a, b, c) = (x, y, z weights)
+			w = m.st[dj] * (m.s[di] * m.f[dk]);  r.tab[1][t][0] = w; r.tab[1][t][1] = w * v[1];
+			w = m.t[dj] * (m.s[di] * m.sf[dk]);  r.tab[2][t][0] = w; r.tab[2][t][1] = w * v[2];
 		}
+		rec[s] = r;
+	}
+};
+template <typename Real> struct MapPartsGatherRec {
+	static const bool kSplit = false;
+	Merge3 m; const PartRec<Real>* rec; Real* vel; Real* velOld; Real* weight;
+	struct Acc {
+		int i, j, k; const PartRec<Real>* rec; Real S[3], R[3];
+		MP_HD void one(const PartRec<Real>& r, int c, int bi, int bj, int bk) {
+			const unsigned di = (unsigned)(i - bi), dj = (unsigned)(j - bj), dk = (unsigned)(k - bk);
+			if (di < 2u && dj < 2u && dk < 2u) { const Real* q = r.tab[c][di + 2 * dj + 4 * dk]; S[c] += q[0]; R[c] += q[1]; }
+		}
+		MP_HD void operator()(const Ent& e) {
+			const PartRec<Real>& r = rec[e.slot];
+			const unsigned bx = r.bx, by = r.by, bz = r.bz;
+			one(r, 0, (int)(bx & 0xffffu), (int)(by >> 16), (int)(bz >> 16));        // x faces: shifted in x, centred in y, z
+			one(r, 1, (int)(bx >> 16), (int)(by & 0xffffu), (int)(bz >> 16));
+			one(r, 2, (int)(bx >> 16), (int)(by >> 16), (int)(bz & 0xffffu));
+		}
+	};
+	MP_HD void operator()(const Dims& d, int i, int j, int k, IndexInt idx) const {
+		Acc acc = { i, j, k, rec, { 0, 0, 0 }, { 0, 0, 0 } };
+		m.walk(d, i, j, k, idx, acc);
+		finishFace<Real>(acc.S, acc.R, idx, vel, velOld, weight);
 	}
 };
 
@@ -622,7 +675,8 @@ template <typename Real> struct MapPartsGatherTree {
 template <typename Real> struct MapPartsTreeScratch {
 	int* len1; int* off1; int* len2; int* off2;      // int[d.n] each
 	Ent* e1; Ent* e2;
-	Real* posS; Real* pvelS;                          // Real[3 np] each
+	Real* posS; Real* pvelS;                          // Real[3 np] each (used when rec == NULL)
+	PartRec<Real>* rec;                               // PartRec[np], or NULL: evaluate the weights in the walk (2-D, huge grids or particle counts)
 };
 inline IndexInt treeEntries(IndexInt cells, IndexInt np, int copies) { const IndexInt t = (IndexInt)copies * np; return t + 3 * (cells < t ? cells : t) + 4; }
 // start: scratch int[d.n]; key / keyTmp / val / sorted: scratch int[np]; tree == NULL: the 27-way walk
@@ -635,7 +689,11 @@ int mapPartsToMAC(Exec& ex, const Dims& d, Real* vel, Real* velOld, IndexInt np,
 		MapPartsGather<Real> op = { start, sorted, count, ps.pos, pvel, vel, velOld, weight };
 		return ex.cells(d, op);
 	}
-	if (count > 0) { GatherSlots<Real> gs = { sorted, ps.pos, pvel, tree->posS, tree->pvelS }; MP_TRY(ex.parts(count, gs)); }
+	const bool useRec = tree->rec && d.is3D && d.sx < 65536 && d.sy < 65536 && d.sz < 65536;
+	if (count > 0) {
+		if (useRec) { BuildRecords<Real> br = { d, sorted, ps.pos, pvel, tree->rec }; MP_TRY(ex.parts(count, br)); }
+		else { GatherSlots<Real> gs = { sorted, ps.pos, pvel, tree->posS, tree->pvelS }; MP_TRY(ex.parts(count, gs)); }
+	}
 	IndexInt n1 = 0, n2 = 0;
 	const Lists l0 = { start, nullptr, count, nullptr, sorted };
 	MergeLen m1 = { l0, 0, tree->len1, tree->off1 }; MP_TRY(ex.cells(d, m1)); MP_TRY(ex.exclusiveScan(tree->off1, d.n, &n1));
@@ -644,6 +702,7 @@ int mapPartsToMAC(Exec& ex, const Dims& d, Real* vel, Real* velOld, IndexInt np,
 	MergeLen m2 = { l1, 1, tree->len2, tree->off2 }; MP_TRY(ex.cells(d, m2)); MP_TRY(ex.exclusiveScan(tree->off2, d.n, &n2));
 	MergeStore s2 = { { l1, 1 }, tree->off2, tree->e2 }; MP_TRY(ex.cells(d, s2));
 	const Lists l2 = { tree->off2, tree->len2, n2, tree->e2, nullptr };
+	if (useRec) { MapPartsGatherRec<Real> op = { { l2, 2 }, tree->rec, vel, velOld, weight }; return ex.cells(d, op); }
 	MapPartsGatherTree<Real> op = { { l2, 2 }, tree->posS, tree->pvelS, vel, velOld, weight };
 	return ex.cells(d, op);
 }

@@ -116,7 +116,12 @@ template <typename Real> int mapParts(int order, const Dims& d, Real* vel, Real*
 		t.e1 = (parts::Ent*)raw1; t.e2 = (parts::Ent*)raw2;
 		t.posS = (Real*)malloc(sizeof(Real) * 3 * (size_t)n); t.pvelS = (Real*)malloc(sizeof(Real) * 3 * (size_t)n);
 		memset(t.posS, 0x7f, sizeof(Real) * 3 * (size_t)n); memset(t.pvelS, 0x7f, sizeof(Real) * 3 * (size_t)n);
+		// MP_MAPPARTS=2: the weights evaluated in the walk (what 2-D grids take anyway); default: per-particle records
+		void* rawRec = nullptr;
+		if (!(e && atoi(e) == 2)) { if (posix_memalign(&rawRec, 64, sizeof(parts::PartRec<Real>) * (size_t)n)) return MP_ERR_CUDA; memset(rawRec, 0x5a, sizeof(parts::PartRec<Real>) * (size_t)n); }
+		t.rec = (parts::PartRec<Real>*)rawRec;
 		rc = parts::mapPartsToMAC<Real>(ex, d, vel, velOld, np, ps, pvel, weight, start, key, keyTmp, val, sorted, &t);
+		free(rawRec);
 		free(t.len1); free(t.off1); free(t.len2); free(t.off2); free(t.e1); free(t.e2); free(t.posS); free(t.pvelS);
 	}
 	free(start); free(key); free(keyTmp); free(val); free(sorted);

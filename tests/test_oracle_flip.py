@@ -87,12 +87,14 @@ def test_kernel_emulation_reproduces_flip_golden(name, prec, order, parts_emul_l
         assert np.array_equal(out[key], g[key]), (name, prec, order, key)
 
 
+@pytest.mark.parametrize("mode", ["0", "2"])
 @pytest.mark.parametrize("prec", [4, 8])
 @pytest.mark.parametrize("name", list(FLIP_SCENES))
-def test_kernel_emulation_map_parts_27_way_walk(name, prec, parts_emul_lib, monkeypatch):
-    """mapPartsToMAC has two forms on the device: a tree of 3-way merges (default, used by every other test here) and the one-kernel 27-way walk
-    (MP_MAPPARTS=0) -- the same particles in the same order: both give the golden bits"""
-    monkeypatch.setenv("MP_MAPPARTS", "0")
+def test_kernel_emulation_map_parts_27_way_walk(name, prec, mode, parts_emul_lib, monkeypatch):
+    """mapPartsToMAC has three forms on the device: a tree of 3-way merges whose walk looks up per-particle records of the 24 (w, w v) pairs
+    (default in 3-D, used by every other test here), the same tree with the MAC weights evaluated in the walk (MP_MAPPARTS=2; what 2-D grids
+    take) and the one-kernel 27-way walk (MP_MAPPARTS=0) -- the same particles in the same order: all give the golden bits"""
+    monkeypatch.setenv("MP_MAPPARTS", mode)
     g = load_golden("step_" + name, prec)
     out = run_flip_plugins(FlipEmulation(parts_emul_lib, prec, 3), name, prec)
     for key in g:

@@ -31,6 +31,7 @@ def run(prec, pc, fused, reps, envs=None):
     p = P.numpy()
     row = {"res": res, "prec": prec, "pc": pc, "l0fused": fused, "env": envs or {}, "iterations": info["iterations"], "solve_ms_cold": ms[0], "solve_ms_warm": min(ms[1:]),
            "vcycle_ms": info["msPrecondAvg"], "matvec_ms": info["msMatvecAvg"], "axpy_ms": info["msAxpyAvg"], "update_ms": info["msUpdateAvg"],
+           "stage_ms": {k: info[k] for k in ("msRhs", "msMatrix", "msSolve", "msCorrect")},
            "pressure_checksum": float(abs(p).sum(dtype="float64"))}
     rows.append(row)
     print(json.dumps(row), flush=True)
