@@ -67,6 +67,9 @@ struct mp_mg {
 	int nshard; int K0[MG_MAXLVL], K1[MG_MAXLVL];
 	// the level-0 operator as 2 bytes per vertex for the fused level-0 kernels (mp_mg_l0_fused.cuh); valid when every off-diagonal is 0 / -1
 	unsigned short* mask0; bool mask0Valid;
+	// Galerkin products of regular vertices (setA): regular[l][v] = 1 when the whole neighbourhood a coarse row is built from is the unperturbed
+	// operator, so the row equals that of every other regular vertex of the level; cst = one such row per level (14 entries), first = its vertex
+	unsigned char* regular[MG_MAXLVL]; void* cst; int* first;
 };
 
 // ---------------------------------------------------------------- index helpers
@@ -179,11 +182,14 @@ __global__ void __launch_bounds__(256) k_mg_galerkin1(LvlGeom gf, LvlGeom gc, in
 // the sums are the same bit for bit as k_mg_galerkin1 / multigrid.cpp:594-614 -- with 189 instead of ~700 coefficient loads.
 template <typename Real>
 __global__ void __launch_bounds__(128) k_mg_galerkin1_v2(LvlGeom gf, LvlGeom gc, int is3D, const Real* __restrict__ Af,
-	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A)
+	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A, const unsigned char* __restrict__ skip, const int* __restrict__ only, size_t outStride)
 {
+	// skip: regular vertices are filled with the level's constant row afterwards.  only: compute the row of vertex *only alone, into A[e * outStride]
 	__shared__ Real acc[14][128];
-	const int v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= gc.n || tc[v] == vtInactive) return;
+	int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (only) { if (v != 0 || *only >= gc.n) return; v = *only; }
+	if (v >= gc.n || tc[v] == vtInactive || (skip && skip[v])) return;
+	const size_t vOut = only ? 0 : (size_t)v;
 	const int S = is3D ? 14 : 5, t = threadIdx.x;
 	for (int e = 0; e < S; e++) acc[e][t] = (Real)0;
 	int vx, vy, vz; vecIdx(gc, v, vx, vy, vz);
@@ -217,22 +223,24 @@ __global__ void __launch_bounds__(128) k_mg_galerkin1_v2(LvlGeom gf, LvlGeom gc,
 			}
 		}
 	}
-	if (is3D) { for (int e = 0; e < 14; e++) A[(size_t)e * gc.n + v] = acc[e][t]; }
+	if (is3D) { for (int e = 0; e < 14; e++) A[(size_t)e * outStride + vOut] = acc[e][t]; }
 	else {
 		// 2-D: stored entries sc = s-13 with nz == 1: s in {13,14,15,16,17} -> e = 0..4
-		for (int e = 0; e < 5; e++) A[(size_t)e * gc.n + v] = acc[e][t];
+		for (int e = 0; e < 5; e++) A[(size_t)e * outStride + vOut] = acc[e][t];
 	}
 }
 
 // levels > 1 from a 27-point fine level; thread = (coarse vertex, stored entry e = sc-13)
 template <typename Real>
 __global__ void __launch_bounds__(256) k_mg_galerkinN(LvlGeom gf, LvlGeom gc, int S, int is3D, const Real* __restrict__ Af,
-	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A)
+	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A, const unsigned char* __restrict__ skip, const int* __restrict__ only, size_t outStride)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= (long long)gc.n * S) return;
-	const int e = (int)(t / gc.n), v = (int)(t % gc.n);
-	if (tc[v] == vtInactive) return;
+	int e, v;
+	if (only) { if (t >= S || *only >= gc.n) return; e = (int)t; v = *only; }
+	else { if (t >= (long long)gc.n * S) return; e = (int)(t / gc.n); v = (int)(t % gc.n); }
+	if (tc[v] == vtInactive || (skip && skip[v])) return;
+	const size_t vOut = only ? 0 : (size_t)v;
 	int V[3]; vecIdx(gc, v, V[0], V[1], V[2]);
 	const int smaxz = is3D ? 1 : 0;
 	// stencil offset of entry e: sc = e + S - 1 ; SC = N - V + smax
@@ -266,7 +274,61 @@ __global__ void __launch_bounds__(256) k_mg_galerkinN(LvlGeom gf, LvlGeom gc, in
 			}
 		}
 	}
-	A[(size_t)e * gc.n + v] = acc;
+	A[(size_t)e * outStride + vOut] = acc;
+}
+
+// ---- regular vertices.  In the interior of the fluid the operator is the same at every vertex, and so is everything a coarse row is built
+// from; the Galerkin kernels above spend ~7 k instructions per coarse vertex on re-deriving the same 14 numbers (11 + 10 ms for levels 1 and 2 of
+// 512^3).  A coarse vertex is REGULAR when every fine vertex the product reads is in the grid, active and itself regular (level 0: operator mask
+// == 6 couplings of -1 and diagonal 6) and its 14 stored coarse neighbours are active.  The row of ONE regular vertex per level is computed by
+// the kernel above (`only`), the others copy it: the same arithmetic on the same values gives the same bits.  3-D only.
+__device__ __forceinline__ bool coarseNbFull(const LvlGeom& gc, const signed char* __restrict__ tc, int vx, int vy, int vz) {
+	for (int s = 13; s < 27; s++) {
+		const int nx = vx + s % 3 - 1, ny = vy + (s / 3) % 3 - 1, nz = vz + s / 9 - 1;
+		if (!inGrid(gc, nx, ny, nz) || tc[linIdx(gc, nx, ny, nz)] == vtInactive) return false;
+	}
+	return true;
+}
+__global__ void __launch_bounds__(128) k_mg_classify1(LvlGeom gf, LvlGeom gc, const unsigned short* __restrict__ mask, const signed char* __restrict__ tc,
+	unsigned char* __restrict__ reg, int* first)
+{
+	int vx, vy, vz;
+	if (!cell3(gc.sx, vx, vy, vz)) return;
+	const int v = linIdx(gc, vx, vy, vz);
+	const unsigned short kRegular = (unsigned short)(1u | 0x7eu | (6u << 7));      // mp_mg_l0_fused.cuh: active, six couplings of -1, diagonal 6
+	bool ok = tc[v] != vtInactive && vx > 0 && vy > 0 && vz > 0 && 2 * vx + 1 < gf.sx && 2 * vy + 1 < gf.sy && 2 * vz + 1 < gf.sz;
+	if (ok) {
+		for (int dz = -1; dz <= 1 && ok; dz++) for (int dy = -1; dy <= 1 && ok; dy++) for (int dx = -1; dx <= 1; dx++)
+			if (mask[linIdx(gf, 2 * vx + dx, 2 * vy + dy, 2 * vz + dz)] != kRegular) { ok = false; break; }
+	}
+	ok = ok && coarseNbFull(gc, tc, vx, vy, vz);
+	reg[v] = ok ? 1 : 0;
+	if (ok) atomicMin(first, v);
+}
+__global__ void __launch_bounds__(128) k_mg_classifyN(LvlGeom gf, LvlGeom gc, const unsigned char* __restrict__ regF, const signed char* __restrict__ tf,
+	const signed char* __restrict__ tc, unsigned char* __restrict__ reg, int* first)
+{
+	int vx, vy, vz;
+	if (!cell3(gc.sx, vx, vy, vz)) return;
+	const int v = linIdx(gc, vx, vy, vz);
+	// the product reads the rows of the fine vertices within 2 of 2V (U within 1, W within 1 of U)
+	bool ok = tc[v] != vtInactive && 2 * vx - 2 >= 0 && 2 * vy - 2 >= 0 && 2 * vz - 2 >= 0 && 2 * vx + 2 < gf.sx && 2 * vy + 2 < gf.sy && 2 * vz + 2 < gf.sz;
+	if (ok) {
+		for (int dz = -2; dz <= 2 && ok; dz++) for (int dy = -2; dy <= 2 && ok; dy++) for (int dx = -2; dx <= 2; dx++) {
+			const int u = linIdx(gf, 2 * vx + dx, 2 * vy + dy, 2 * vz + dz);
+			if (!regF[u] || tf[u] == vtInactive) { ok = false; break; }
+		}
+	}
+	ok = ok && coarseNbFull(gc, tc, vx, vy, vz);
+	reg[v] = ok ? 1 : 0;
+	if (ok) atomicMin(first, v);
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) k_mg_fill_regular(int n, int S, const unsigned char* __restrict__ reg, const Real* __restrict__ cst, Real* __restrict__ A)
+{
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n || !reg[v]) return;
+	for (int e = 0; e < S; e++) A[(size_t)e * n + v] = cst[e];
 }
 
 // ---------------------------------------------------------------- V-cycle kernels
@@ -954,6 +1016,7 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 		m->mask0Valid = m->hFlags[5] == 0;
 	}
 	m->hostCoarsenLevels = 0;
+	bool regularLevel[MG_MAXLVL] = {};
 	for (int l = 1; l < m->nlev; l++) {
 		const LvlGeom gf = m->geom[l - 1], gc = m->geom[l];
 		k_mg_fill_type<<<nb(gc.n, 256), 256, 0, st>>>(m->type[l], gc.n, vtFree); MP_CHECK_LAUNCH(ctx);
@@ -977,10 +1040,30 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 		}
 		const long long work = (long long)gc.n * m->stencil;
 		static const int g1variant = getenv("MP_MG_GALERKIN1") ? atoi(getenv("MP_MG_GALERKIN1")) : 2;
-		if (l == 1 && g1variant == 2) k_mg_galerkin1_v2<Real><<<nb(gc.n, 128), 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1]);
+		// regular vertices (see k_mg_classify1): classified first, skipped by the product, filled with the row of the level's first regular vertex
+		const char* eReg = getenv("MP_MG_REGULAR");      // read per call: the parity tests run both forms in one process
+		const bool prevOk = l == 1 ? (m->mask0 && m->mask0Valid) : regularLevel[l - 1];
+		regularLevel[l] = (!eReg || atoi(eReg)) && m->is3D && prevOk && m->regular[l] && (l > 1 || g1variant == 2) && gc.n >= 4096;
+		const unsigned char* skip = nullptr;
+		if (regularLevel[l]) {
+			const int bs = gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32);
+			MP_CUDA(cudaMemsetAsync(m->first, 0x7f, sizeof(int), st));
+			if (l == 1) k_mg_classify1<<<grid3(gc.sx, gc.sy, gc.sz, bs), bs, 0, st>>>(gf, gc, m->mask0, m->type[1], m->regular[1], m->first);
+			else        k_mg_classifyN<<<grid3(gc.sx, gc.sy, gc.sz, bs), bs, 0, st>>>(gf, gc, m->regular[l - 1], m->type[l - 1], m->type[l], m->regular[l], m->first);
+			MP_CHECK_LAUNCH(ctx);
+			skip = m->regular[l];
+		}
+		if (l == 1 && g1variant == 2) k_mg_galerkin1_v2<Real><<<nb(gc.n, 128), 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1], skip, nullptr, (size_t)gc.n);
 		else if (l == 1) k_mg_galerkin1<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->dPaths, (const int*)(m->dFlags + 16), (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1]);
-		else        k_mg_galerkinN<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->A[l]);
+		else        k_mg_galerkinN<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->A[l], skip, nullptr, (size_t)gc.n);
 		MP_CHECK_LAUNCH(ctx);
+		if (regularLevel[l]) {
+			if (l == 1) k_mg_galerkin1_v2<Real><<<1, 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->cst, nullptr, m->first, (size_t)1);
+			else        k_mg_galerkinN<Real><<<1, 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->cst, nullptr, m->first, (size_t)1);
+			MP_CHECK_LAUNCH(ctx);
+			k_mg_fill_regular<Real><<<nb(gc.n, 256), 256, 0, st>>>(gc.n, m->stencil, m->regular[l], (const Real*)m->cst, (Real*)m->A[l]);
+			MP_CHECK_LAUNCH(ctx);
+		}
 		if (m->Afull[l]) {
 			const int hbx = (gc.sx + 1) / 2, hby = (gc.sy + 1) / 2, hbz = m->is3D ? (gc.sz + 1) / 2 : 1, ncol = m->is3D ? 8 : 4;
 			const dim3 gr((unsigned)((hbx + 127) / 128), (unsigned)hby, (unsigned)(hbz * ncol));
@@ -1354,6 +1437,8 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, nr * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->type[l], 0, n, ctx->stream));
 	}
+	for (l = 1; l < m->nlev; l++) if (m->is3D && m->geom[l].n >= 4096) MP_CUDA(cudaMalloc((void**)&m->regular[l], (size_t)m->geom[l].n));
+	MP_CUDA(cudaMalloc(&m->cst, 16 * sizeof(double))); MP_CUDA(cudaMalloc((void**)&m->first, sizeof(int)));
 	if (sx % (16 / prec) == 0) MP_CUDA(cudaMalloc((void**)&m->mask0, sizeof(unsigned short) * (size_t)m->geom[0].n + 64));
 	MP_CUDA(cudaMalloc((void**)&m->cg, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n));
 	MP_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n, ctx->stream));
@@ -1399,6 +1484,8 @@ int mp_mg_destroy(mp_mg* m)
 	cudaStreamSynchronize(m->ctx->stream);
 	for (int l = 0; l < m->nlev; l++) { cudaFree(m->A[l]); cudaFree(m->x[l]); cudaFree(m->b[l]); cudaFree(m->r[l]); cudaFree(m->type[l]); if (m->Afull[l]) cudaFree(m->Afull[l]); }
 	cudaFree(m->cg); cudaFree(m->dPaths); cudaFree(m->dFlags); cudaFreeHost(m->hFlags); if (m->mask0) cudaFree(m->mask0);
+	for (int l = 0; l < m->nlev; l++) if (m->regular[l]) cudaFree(m->regular[l]);
+	cudaFree(m->cst); cudaFree(m->first);
 	if (m->ctx->staticMg == m) m->ctx->staticMg = nullptr;
 	if (m->ctx->spareMg == m) m->ctx->spareMg = nullptr;
 	delete m; return MP_OK;

@@ -233,3 +233,34 @@ def test_vcycle_level0_fused_agrees_bit_for_bit(mf, shape, liquid, prec, monkeyp
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), ("level-0 V-cycle form differs from the per-colour kernels", key)
         assert a[2] == b[2] and a[3] == b[3], key
         assert a[6] == b[6] and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]), ("PcMGStatic solve differs", key)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("res,liquid", [(48, False), (72, False), (64, True)])
+def test_galerkin_regular_vertices_copy_the_same_row(mf, res, liquid, prec, monkeypatch):
+    """setA's fast path: coarse vertices whose whole neighbourhood is the unperturbed operator (k_mg_classify1 / k_mg_classifyN) take the row of the
+    level's first regular vertex instead of recomputing it.  Every level's operator equals the one computed vertex by vertex (MP_MG_REGULAR=0),
+    bit for bit -- on a smoke plume with a sphere obstacle (mostly regular) and on a liquid basin (ghost-fluid diagonals along the surface)."""
+    from mantaflow_b200 import cg, scenes
+    if liquid:
+        flags, vel, phi = scenes.liquid_basin((res, res, res), prec)
+    else:
+        (flags, vel), phi = scenes.smoke_plume(res, prec), None
+    O = oracle(prec)
+    rhs, _, _ = O.compute_rhs(flags, vel, phi=phi)
+    A_o = O.make_matrix(flags, phi=phi)
+    fix = O.choose_fix_cell(flags)
+    if fix >= 0:
+        O.fix_pressure(flags, fix, 0.0, rhs, *A_o)
+    ops = {}
+    for regular in (1, 0):
+        monkeypatch.setenv("MP_MG_REGULAR", str(regular))
+        s = mk(mf, flags.shape, prec)
+        mg = cg.GridMg(s)
+        mg.setA(*[mf.RealGrid(s, a) for a in A_o])
+        ops[regular] = [mg.download("a", l) for l in range(mg.numLevels())]
+        mg.close(); s.close()
+    assert len(ops[1]) >= 3
+    for l, (a, b) in enumerate(zip(ops[1], ops[0])):
+        assert np.array_equal(a, b), "level %d operator differs with the regular-vertex fast path" % l
+    assert np.count_nonzero(ops[1][1]) > 0
