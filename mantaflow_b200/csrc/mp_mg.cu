@@ -70,6 +70,9 @@ struct mp_mg {
 	// Galerkin products of regular vertices (setA): regular[l][v] = 1 when the whole neighbourhood a coarse row is built from is the unperturbed
 	// operator, so the row equals that of every other regular vertex of the level; cst = one such row per level (14 entries), first = its vertex
 	unsigned char* regular[MG_MAXLVL]; void* cst; int* first;
+	// colour-major sweeps: rowreg[l][c * nc + ci] = 1 when the vertex's whole 27-entry row equals cstFull[l] (32 Reals per level), the full row of
+	// the level's first regular vertex -- such vertices take their coefficients from cstFull instead of streaming 108 bytes each
+	unsigned char* rowreg[MG_MAXLVL]; void* cstFull; bool rowregOn[MG_MAXLVL];
 };
 
 // ---------------------------------------------------------------- index helpers
@@ -125,10 +128,16 @@ __global__ void __launch_bounds__(256) k_mg_copy_activate(LvlGeom g, int is3D, R
 // ---------------------------------------------------------------- setA: coarse vertex selection (phase-1 closure of genCoarseGrid)
 __global__ void __launch_bounds__(256) k_mg_fill_type(signed char* t, int n, signed char v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) t[i] = v; }
 
-// one sweep: every active fine vertex with exactly one free interpolation vertex selects it.  mode 1: count leftovers.
-__global__ void __launch_bounds__(256) k_mg_select(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, signed char* tc, int* flagsOut, int mode)
+// one sweep: every active fine vertex with exactly one free interpolation vertex selects it.  The first sweep visits every fine vertex and lists
+// the undecided ones (>= 2 free interpolation vertices); the following sweeps visit the list of the sweep before only -- a vertex that is not
+// listed had at most one free interpolation vertex, took it, and the number of free ones never grows.  flagsOut: [0] changed, [1] undecided
+// vertices remain, [6] a list overflowed (the host then falls back to whole sweeps), [8 + parity] list lengths.
+__global__ void __launch_bounds__(256) k_mg_select(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, signed char* tc, int* flagsOut,
+	const int* __restrict__ listIn, const int* __restrict__ countIn, int* __restrict__ listOut, int* countOut, int cap)
 {
-	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	int v = t;
+	if (listIn) { if (t >= *countIn) return; v = listIn[t]; }
 	if (v >= gf.n || tf[v] == vtInactive) return;
 	int x, y, z; vecIdx(gf, v, x, y, z);
 	int nfree = 0, last = -1;
@@ -136,9 +145,28 @@ __global__ void __launch_bounds__(256) k_mg_select(LvlGeom gf, LvlGeom gc, const
 		const int i = linIdx(gc, ix, iy, iz);
 		if (tc[i] == vtFree) { nfree++; last = i; }
 	}
-	(void)mode;
 	if (nfree == 1) { tc[last] = vtZero; flagsOut[0] = 1; }       // changed
-	else if (nfree >= 2) flagsOut[1] = 1;                         // still undecided (final only in a sweep without changes)
+	else if (nfree >= 2) {
+		flagsOut[1] = 1;                                          // still undecided (final only in a sweep without changes)
+		if (listOut) {                                            // one atomic per warp
+			const unsigned m = __activemask();
+			const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+			int base = 0;
+			if (lane == leader) base = atomicAdd(countOut, __popc(m));
+			base = __shfl_sync(m, base, leader);
+			const int pos = base + __popc(m & ((1u << lane) - 1u));
+			if (pos < cap) listOut[pos] = v; else flagsOut[6] = 1;
+		}
+	}
+}
+// before the first sweep: an active fine vertex with even coordinates has one interpolation vertex, the coarse vertex at its place, and selects it
+// whatever the order -- done first, the first whole sweep finds the neighbours of those vertices decided instead of racing with them (without this
+// most of the fine level ended up on the undecided list of sweep 1)
+__global__ void __launch_bounds__(128) k_mg_select_even(LvlGeom gf, LvlGeom gc, const signed char* __restrict__ tf, signed char* __restrict__ tc)
+{
+	int x, y, z;
+	if (!cell3(gc.sx, x, y, z)) return;
+	if (2 * x < gf.sx && 2 * y < gf.sy && 2 * z < gf.sz && tf[linIdx(gf, 2 * x, 2 * y, 2 * z)] != vtInactive) tc[linIdx(gc, x, y, z)] = vtZero;
 }
 __global__ void __launch_bounds__(256) k_mg_activate_coarse(signed char* t, int n) {   // knActivateCoarseVertices :507-516
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,12 +210,14 @@ __global__ void __launch_bounds__(256) k_mg_galerkin1(LvlGeom gf, LvlGeom gc, in
 // the sums are the same bit for bit as k_mg_galerkin1 / multigrid.cpp:594-614 -- with 189 instead of ~700 coefficient loads.
 template <typename Real>
 __global__ void __launch_bounds__(128) k_mg_galerkin1_v2(LvlGeom gf, LvlGeom gc, int is3D, const Real* __restrict__ Af,
-	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A, const unsigned char* __restrict__ skip, const int* __restrict__ only, size_t outStride)
+	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A, const unsigned char* __restrict__ skip, const int* __restrict__ only, size_t outStride,
+	const int* __restrict__ list, int listCount)
 {
-	// skip: regular vertices are filled with the level's constant row afterwards.  only: compute the row of vertex *only alone, into A[e * outStride]
+	// list: the vertices to compute (the irregular ones).  skip: regular vertices are filled with the level's constant row afterwards.  only: compute the row of vertex *only alone, into A[e * outStride]
 	__shared__ Real acc[14][128];
 	int v = blockIdx.x * blockDim.x + threadIdx.x;
 	if (only) { if (v != 0 || *only >= gc.n) return; v = *only; }
+	else if (list) { if (v >= listCount) return; v = list[v]; }
 	if (v >= gc.n || tc[v] == vtInactive || (skip && skip[v])) return;
 	const size_t vOut = only ? 0 : (size_t)v;
 	const int S = is3D ? 14 : 5, t = threadIdx.x;
@@ -233,11 +263,13 @@ __global__ void __launch_bounds__(128) k_mg_galerkin1_v2(LvlGeom gf, LvlGeom gc,
 // levels > 1 from a 27-point fine level; thread = (coarse vertex, stored entry e = sc-13)
 template <typename Real>
 __global__ void __launch_bounds__(256) k_mg_galerkinN(LvlGeom gf, LvlGeom gc, int S, int is3D, const Real* __restrict__ Af,
-	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A, const unsigned char* __restrict__ skip, const int* __restrict__ only, size_t outStride)
+	const signed char* __restrict__ tf, const signed char* __restrict__ tc, Real* __restrict__ A, const unsigned char* __restrict__ skip, const int* __restrict__ only, size_t outStride,
+	const int* __restrict__ list, int listCount)
 {
 	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	int e, v;
 	if (only) { if (t >= S || *only >= gc.n) return; e = (int)t; v = *only; }
+	else if (list) { if (t >= (long long)listCount * S) return; e = (int)(t / listCount); v = list[(int)(t % listCount)]; }
 	else { if (t >= (long long)gc.n * S) return; e = (int)(t / gc.n); v = (int)(t % gc.n); }
 	if (tc[v] == vtInactive || (skip && skip[v])) return;
 	const size_t vOut = only ? 0 : (size_t)v;
@@ -282,6 +314,16 @@ __global__ void __launch_bounds__(256) k_mg_galerkinN(LvlGeom gf, LvlGeom gc, in
 // 512^3).  A coarse vertex is REGULAR when every fine vertex the product reads is in the grid, active and itself regular (level 0: operator mask
 // == 6 couplings of -1 and diagonal 6) and its 14 stored coarse neighbours are active.  The row of ONE regular vertex per level is computed by
 // the kernel above (`only`), the others copy it: the same arithmetic on the same values gives the same bits.  3-D only.
+// the irregular active vertices are listed (one atomic per warp) so that the product kernels run over full warps of them: walls are planes, and a
+// vertex-per-thread launch with the regular ones skipped leaves one busy lane per warp along an x wall
+__device__ __forceinline__ void listAppend(int* __restrict__ list, int* count, int v) {
+	const unsigned m = __activemask();
+	const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+	int base = 0;
+	if (lane == leader) base = atomicAdd(count, __popc(m));
+	base = __shfl_sync(m, base, leader);
+	list[base + __popc(m & ((1u << lane) - 1u))] = v;
+}
 __device__ __forceinline__ bool coarseNbFull(const LvlGeom& gc, const signed char* __restrict__ tc, int vx, int vy, int vz) {
 	for (int s = 13; s < 27; s++) {
 		const int nx = vx + s % 3 - 1, ny = vy + (s / 3) % 3 - 1, nz = vz + s / 9 - 1;
@@ -290,7 +332,7 @@ __device__ __forceinline__ bool coarseNbFull(const LvlGeom& gc, const signed cha
 	return true;
 }
 __global__ void __launch_bounds__(128) k_mg_classify1(LvlGeom gf, LvlGeom gc, const unsigned short* __restrict__ mask, const signed char* __restrict__ tc,
-	unsigned char* __restrict__ reg, int* first)
+	unsigned char* __restrict__ reg, int* first, int* __restrict__ irrList, int* irrCount)
 {
 	int vx, vy, vz;
 	if (!cell3(gc.sx, vx, vy, vz)) return;
@@ -304,9 +346,10 @@ __global__ void __launch_bounds__(128) k_mg_classify1(LvlGeom gf, LvlGeom gc, co
 	ok = ok && coarseNbFull(gc, tc, vx, vy, vz);
 	reg[v] = ok ? 1 : 0;
 	if (ok) atomicMin(first, v);
+	else if (tc[v] != vtInactive) listAppend(irrList, irrCount, v);
 }
 __global__ void __launch_bounds__(128) k_mg_classifyN(LvlGeom gf, LvlGeom gc, const unsigned char* __restrict__ regF, const signed char* __restrict__ tf,
-	const signed char* __restrict__ tc, unsigned char* __restrict__ reg, int* first)
+	const signed char* __restrict__ tc, unsigned char* __restrict__ reg, int* first, int* __restrict__ irrList, int* irrCount)
 {
 	int vx, vy, vz;
 	if (!cell3(gc.sx, vx, vy, vz)) return;
@@ -322,6 +365,7 @@ __global__ void __launch_bounds__(128) k_mg_classifyN(LvlGeom gf, LvlGeom gc, co
 	ok = ok && coarseNbFull(gc, tc, vx, vy, vz);
 	reg[v] = ok ? 1 : 0;
 	if (ok) atomicMin(first, v);
+	else if (tc[v] != vtInactive) listAppend(irrList, irrCount, v);
 }
 template <typename Real>
 __global__ void __launch_bounds__(256) k_mg_fill_regular(int n, int S, const unsigned char* __restrict__ reg, const Real* __restrict__ cst, Real* __restrict__ A)
@@ -779,17 +823,28 @@ __global__ void __launch_bounds__(128) k_mg_residualN(LvlGeom g, int is3D, int S
 // Entries towards vertices outside the grid or inactive ones are 0, so the sweep needs no neighbour tests: it subtracts 0 * x instead of
 // skipping (same value; an exact zero at worst changes sign).  One sweep then reads 108 n B of coefficients once, unit stride.
 template <typename Real, bool IS3D>
-__global__ void __launch_bounds__(128) k_mg_build_full(LvlGeom g, int hbx, int hby, int hbz, const Real* __restrict__ A, const signed char* __restrict__ type, Real* __restrict__ Afull)
+__global__ void __launch_bounds__(128) k_mg_build_full(LvlGeom g, int hbx, int hby, int hbz, const Real* __restrict__ A, const signed char* __restrict__ type, Real* __restrict__ Afull,
+	const int* __restrict__ only, Real* cstFull, unsigned char* __restrict__ rowreg)
 {
+	// only != NULL: one thread assembles the row of vertex *only into cstFull.  Otherwise, with rowreg != NULL, every row is compared with cstFull:
+	// rowreg = 1 where all 27 entries are the same numbers (the sweeps then take them from cstFull)
 	constexpr int S = IS3D ? 14 : 5, NENT = IS3D ? 27 : 9;
-	const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y, tzc = blockIdx.z;
-	if (tx >= hbx) return;
-	const int c = tzc / hbz, tz = tzc - c * hbz;
+	int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y, tzc = blockIdx.z;
+	int c, tz;
+	if (only) {
+		if (tx != 0 || ty != 0 || tzc != 0 || *only >= g.n) return;
+		int ox, oy, oz; vecIdx(g, *only, ox, oy, oz);
+		tx = ox >> 1; ty = oy >> 1; tz = oz >> 1; c = (ox & 1) | ((oy & 1) << 1) | ((oz & 1) << 2);
+	} else {
+		if (tx >= hbx) return;
+		c = tzc / hbz; tz = tzc - c * hbz;
+	}
 	const int vx = 2 * tx + (c & 1), vy = 2 * ty + ((c >> 1) & 1), vz = 2 * tz + ((c >> 2) & 1);
 	const size_t nc = (size_t)hbx * hby * hbz, ci = tx + (size_t)hbx * (ty + (size_t)hby * tz);
 	Real* out = Afull + (size_t)c * NENT * nc + ci;
 	const bool live = inGrid(g, vx, vy, vz) && type[linIdx(g, vx, vy, vz)] != vtInactive;
 	const int v = live ? linIdx(g, vx, vy, vz) : 0;
+	bool same = live;
 	#pragma unroll
 	for (int s = 0; s < NENT; s++) {
 		const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = IS3D ? s / 9 - 1 : 0;
@@ -798,8 +853,13 @@ __global__ void __launch_bounds__(128) k_mg_build_full(LvlGeom g, int hbx, int h
 			const int nb = v + dx + g.sx * (dy + g.sy * dz);
 			if (type[nb] != vtInactive) val = (s < S) ? A[(size_t)(S - 1 - s) * g.n + nb] : A[(size_t)(s - S + 1) * g.n + v];
 		}
-		out[(size_t)s * nc] = val;
+		if (only) cstFull[s] = val;
+		else {
+			out[(size_t)s * nc] = val;
+			if (rowreg) same = same && (val == cstFull[s]) && (val != (Real)0 || !signbit(val) == !signbit(cstFull[s]));      // the same number, zeros of the same sign
+		}
 	}
+	if (!only && rowreg) rowreg[(size_t)c * nc + ci] = same ? 1 : 0;
 }
 
 // one colour of knSmoothColor (:668-711) / knCalcResidual (:739-771) over the colour-major rows; RESID: all colours in one launch.
@@ -808,7 +868,7 @@ __global__ void __launch_bounds__(128) k_mg_build_full(LvlGeom g, int hbx, int h
 // read once per sweep, so that the iterate -- re-read by every colour -- stays in L2), then accumulates in the reference's order.
 template <typename Real, bool IS3D, bool RESID>
 __global__ void __launch_bounds__(128, 6) k_mg_sweep_full(LvlGeom g, int hbx, int hby, int hbz, int color, int tz0, int ntz, int Kb, int Ke, const Real* __restrict__ Afull, const Real* __restrict__ b,
-	const signed char* __restrict__ type, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag)
+	const signed char* __restrict__ type, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag, const unsigned char* __restrict__ rowreg, const Real* __restrict__ cstFull)
 {
 	if (doneFlag && *doneFlag) return;
 	constexpr int S = IS3D ? 14 : 5, NENT = IS3D ? 27 : 9;
@@ -826,8 +886,14 @@ __global__ void __launch_bounds__(128, 6) k_mg_sweep_full(LvlGeom g, int hbx, in
 	const Real* a = Afull + (size_t)c * NENT * nc + (tx + (size_t)hbx * (ty + (size_t)hby * tz));
 	const bool interior = vx > 0 && vy > 0 && vx < g.sx - 1 && vy < g.sy - 1 && (!IS3D || (vz > 0 && vz < g.sz - 1));
 	Real av[NENT], xv[NENT];
-	#pragma unroll
-	for (int s = 0; s < NENT; s++) av[s] = __ldcs(a + (size_t)s * nc);
+	// a row that equals the level's constant row (setA compared all 27 numbers) is taken from there: the interior of the fluid streams no coefficients
+	if (rowreg && rowreg[(size_t)c * nc + (tx + (size_t)hbx * (ty + (size_t)hby * tz))]) {
+		#pragma unroll
+		for (int s = 0; s < NENT; s++) av[s] = cstFull[s];
+	} else {
+		#pragma unroll
+		for (int s = 0; s < NENT; s++) av[s] = __ldcs(a + (size_t)s * nc);
+	}
 	#pragma unroll
 	for (int s = 0; s < NENT; s++) {
 		const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = IS3D ? s / 9 - 1 : 0;
@@ -856,12 +922,12 @@ __global__ void __launch_bounds__(128) k_mg_restrict(LvlGeom gf, LvlGeom gc, int
 	const int v = linIdx(gc, vx, vy, vz);
 	xc[v] = (Real)0;
 	if (tc[v] == vtInactive) return;
+	// the residual of an inactive fine vertex is an exact zero (no kernel writes it; setA leaves zeros): adding it is the reference's skip
 	Real sum = 0;
 	for (int rz = max(0, vz * 2 - 1); rz <= min(gf.sz - 1, vz * 2 + 1); rz++)
 	for (int ry = max(0, vy * 2 - 1); ry <= min(gf.sy - 1, vy * 2 + 1); ry++)
 	for (int rx = max(0, vx * 2 - 1); rx <= min(gf.sx - 1, vx * 2 + 1); rx++) {
 		const int r = linIdx(gf, rx, ry, rz);
-		if (tf[r] == vtInactive) continue;
 		const Real rw = pow2weight<Real>((rx & 1) + (ry & 1) + (rz & 1));
 		sum += rw * src[r];
 	}
@@ -884,11 +950,12 @@ __global__ void __launch_bounds__(128) k_mg_interp_add(LvlGeom gf, LvlGeom gc, i
 	// parents (x>>1 .. (x+1)>>1) x (y..) x (z..), summed in the reference's order (x fastest); y/z parity is warp-uniform
 	const int px = x & 1, py = y & 1, pz = z & 1;
 	const int base = linIdx(gc, x >> 1, y >> 1, z >> 1);
+	// the iterate of an inactive coarse vertex is an exact zero throughout the cycle: adding it is the reference's skip
 	Real sum = 0;
 	for (int dz = 0; dz <= pz; dz++) for (int dy = 0; dy <= py; dy++) {
 		const int i0 = base + dy * gc.sx + dz * gc.sx * gc.sy;
-		if (tc[i0] != vtInactive) sum += xc[i0];
-		if (px && tc[i0 + 1] != vtInactive) sum += xc[i0 + 1];
+		sum += xc[i0];
+		if (px) sum += xc[i0 + 1];
 	}
 	const Real iw = pow2weight<Real>(px + py + pz);
 	xf[v] += iw * sum;
@@ -1020,13 +1087,38 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 	for (int l = 1; l < m->nlev; l++) {
 		const LvlGeom gf = m->geom[l - 1], gc = m->geom[l];
 		k_mg_fill_type<<<nb(gc.n, 256), 256, 0, st>>>(m->type[l], gc.n, vtFree); MP_CHECK_LAUNCH(ctx);
-		// phase-1 closure to its fixed point: sweep until a sweep changes nothing; that sweep's "undecided" flag is then final
-		for (int sweep = 0; sweep < gf.sx + gf.sy + gf.sz + 8; sweep++) {
-			MP_CUDA(cudaMemsetAsync(m->dFlags, 0, 2 * sizeof(int), st));
-			k_mg_select<<<nb(gf.n, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, 0); MP_CHECK_LAUNCH(ctx);
-			MP_CUDA(cudaMemcpyAsync(m->hFlags, m->dFlags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-			MP_CUDA(cudaStreamSynchronize(st));
-			if (!m->hFlags[0]) break;
+		// phase-1 closure to its fixed point: sweep until a sweep changes nothing; that sweep's "undecided" flag is then final.  Sweeps after the
+		// first walk the list of vertices the sweep before left undecided (lists live in the level's b / r arrays, idle during setA)
+		{
+			int* lists[2] = { (int*)m->b[l - 1], (int*)m->r[l - 1] };
+			const long long capLL = (l == 1 && m->slab) ? (long long)gf.sx * gf.sy * m->lsz : (long long)gf.n;
+			const int cap = (int)std::min<long long>(capLL, gf.n);
+			bool useLists = !(getenv("MP_MG_SELECT_LISTS") && !atoi(getenv("MP_MG_SELECT_LISTS")));
+			int listed = 0, maxListed = 0;
+			{ const int bs = gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32); k_mg_select_even<<<grid3(gc.sx, gc.sy, gc.sz, bs), bs, 0, st>>>(gf, gc, m->type[l - 1], m->type[l]); MP_CHECK_LAUNCH(ctx); }
+			for (int sweep = 0; sweep < gf.sx + gf.sy + gf.sz + 8; sweep++) {
+				MP_CUDA(cudaMemsetAsync(m->dFlags, 0, 2 * sizeof(int), st));
+				const bool fromList = useLists && sweep > 0;
+				int* out = useLists ? lists[sweep & 1] : nullptr;
+				if (useLists) MP_CUDA(cudaMemsetAsync(m->dFlags + 8 + (sweep & 1), 0, sizeof(int), st));
+				const int work = fromList ? listed : gf.n;
+				if (work > 0) {
+					k_mg_select<<<nb(work, 256), 256, 0, st>>>(gf, gc, m->type[l - 1], m->type[l], m->dFlags, fromList ? lists[(sweep - 1) & 1] : nullptr,
+						fromList ? m->dFlags + 8 + ((sweep - 1) & 1) : nullptr, out, m->dFlags + 8 + (sweep & 1), cap);
+					MP_CHECK_LAUNCH(ctx);
+				}
+				MP_CUDA(cudaMemcpyAsync(m->hFlags, m->dFlags, 10 * sizeof(int), cudaMemcpyDeviceToHost, st));
+				MP_CUDA(cudaStreamSynchronize(st));
+				if (useLists && m->hFlags[6]) {      // a list overflowed (cannot happen with cap == n; slab-sized r0 only): start over with whole sweeps
+					useLists = false; MP_CUDA(cudaMemsetAsync(m->dFlags + 6, 0, sizeof(int), st));
+					continue;
+				}
+				listed = m->hFlags[8 + (sweep & 1)];
+				maxListed = std::max(maxListed, std::min(listed, cap));
+				if (!m->hFlags[0]) break;
+			}
+			// b / r of the level go back to zeros where the lists were (inactive vertices are never written by the V-cycle)
+			if (maxListed > 0) { MP_CUDA(cudaMemsetAsync(lists[0], 0, sizeof(int) * (size_t)maxListed, st)); MP_CUDA(cudaMemsetAsync(lists[1], 0, sizeof(int) * (size_t)maxListed, st)); }
 		}
 		if (m->hFlags[1]) {
 			// order-dependent phase needed: redo this level with the exact serial algorithm
@@ -1045,21 +1137,33 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 		const bool prevOk = l == 1 ? (m->mask0 && m->mask0Valid) : regularLevel[l - 1];
 		regularLevel[l] = (!eReg || atoi(eReg)) && m->is3D && prevOk && m->regular[l] && (l > 1 || g1variant == 2) && gc.n >= 4096;
 		const unsigned char* skip = nullptr;
+		int* irr = nullptr; int nIrr = 0;
 		if (regularLevel[l]) {
 			const int bs = gc.sx >= 96 ? 128 : (gc.sx >= 48 ? 64 : 32);
 			MP_CUDA(cudaMemsetAsync(m->first, 0x7f, sizeof(int), st));
-			if (l == 1) k_mg_classify1<<<grid3(gc.sx, gc.sy, gc.sz, bs), bs, 0, st>>>(gf, gc, m->mask0, m->type[1], m->regular[1], m->first);
-			else        k_mg_classifyN<<<grid3(gc.sx, gc.sy, gc.sz, bs), bs, 0, st>>>(gf, gc, m->regular[l - 1], m->type[l - 1], m->type[l], m->regular[l], m->first);
+			MP_CUDA(cudaMemsetAsync(m->dFlags + 10, 0, sizeof(int), st));
+			irr = (int*)m->x[l];      // the level's iterate is idle during setA (the restriction zeroes it in every V-cycle)
+			if (l == 1) k_mg_classify1<<<grid3(gc.sx, gc.sy, gc.sz, bs), bs, 0, st>>>(gf, gc, m->mask0, m->type[1], m->regular[1], m->first, irr, m->dFlags + 10);
+			else        k_mg_classifyN<<<grid3(gc.sx, gc.sy, gc.sz, bs), bs, 0, st>>>(gf, gc, m->regular[l - 1], m->type[l - 1], m->type[l], m->regular[l], m->first, irr, m->dFlags + 10);
 			MP_CHECK_LAUNCH(ctx);
+			MP_CUDA(cudaMemcpyAsync(m->hFlags + 10, m->dFlags + 10, sizeof(int), cudaMemcpyDeviceToHost, st));
+			MP_CUDA(cudaStreamSynchronize(st));
+			nIrr = m->hFlags[10];
 			skip = m->regular[l];
 		}
-		if (l == 1 && g1variant == 2) k_mg_galerkin1_v2<Real><<<nb(gc.n, 128), 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1], skip, nullptr, (size_t)gc.n);
+		if (regularLevel[l]) {      // the products of the listed (irregular) vertices only
+			if (nIrr > 0) {
+				if (l == 1) k_mg_galerkin1_v2<Real><<<nb(nIrr, 128), 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1], skip, nullptr, (size_t)gc.n, irr, nIrr);
+				else        k_mg_galerkinN<Real><<<nb((long long)nIrr * m->stencil, 256), 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->A[l], skip, nullptr, (size_t)gc.n, irr, nIrr);
+			}
+		}
+		else if (l == 1 && g1variant == 2) k_mg_galerkin1_v2<Real><<<nb(gc.n, 128), 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1], nullptr, nullptr, (size_t)gc.n, nullptr, 0);
 		else if (l == 1) k_mg_galerkin1<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->dPaths, (const int*)(m->dFlags + 16), (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->A[1]);
-		else        k_mg_galerkinN<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->A[l], skip, nullptr, (size_t)gc.n);
+		else        k_mg_galerkinN<Real><<<nb(work, 256), 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->A[l], nullptr, nullptr, (size_t)gc.n, nullptr, 0);
 		MP_CHECK_LAUNCH(ctx);
 		if (regularLevel[l]) {
-			if (l == 1) k_mg_galerkin1_v2<Real><<<1, 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->cst, nullptr, m->first, (size_t)1);
-			else        k_mg_galerkinN<Real><<<1, 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->cst, nullptr, m->first, (size_t)1);
+			if (l == 1) k_mg_galerkin1_v2<Real><<<1, 128, 0, st>>>(gf, gc, m->is3D, (const Real*)m->A[0], m->type[0], m->type[1], (Real*)m->cst, nullptr, m->first, (size_t)1, nullptr, 0);
+			else        k_mg_galerkinN<Real><<<1, 256, 0, st>>>(gf, gc, m->stencil, m->is3D, (const Real*)m->A[l - 1], m->type[l - 1], m->type[l], (Real*)m->cst, nullptr, m->first, (size_t)1, nullptr, 0);
 			MP_CHECK_LAUNCH(ctx);
 			k_mg_fill_regular<Real><<<nb(gc.n, 256), 256, 0, st>>>(gc.n, m->stencil, m->regular[l], (const Real*)m->cst, (Real*)m->A[l]);
 			MP_CHECK_LAUNCH(ctx);
@@ -1067,8 +1171,14 @@ static int mgSetA(mp_mg* m, const mp_grid* A0, const mp_grid* Ai, const mp_grid*
 		if (m->Afull[l]) {
 			const int hbx = (gc.sx + 1) / 2, hby = (gc.sy + 1) / 2, hbz = m->is3D ? (gc.sz + 1) / 2 : 1, ncol = m->is3D ? 8 : 4;
 			const dim3 gr((unsigned)((hbx + 127) / 128), (unsigned)hby, (unsigned)(hbz * ncol));
-			if (m->is3D) k_mg_build_full<Real, true><<<gr, 128, 0, st>>>(gc, hbx, hby, hbz, (const Real*)m->A[l], m->type[l], (Real*)m->Afull[l]);
-			else         k_mg_build_full<Real, false><<<gr, 128, 0, st>>>(gc, hbx, hby, hbz, (const Real*)m->A[l], m->type[l], (Real*)m->Afull[l]);
+			// rows equal to the full row of the level's first regular vertex are flagged for the sweeps (MP_MG_ROWREG=0: every row is streamed)
+			const char* eRow = getenv("MP_MG_ROWREG");
+			m->rowregOn[l] = regularLevel[l] && m->rowreg[l] && (!eRow || atoi(eRow));
+			Real* cf = (Real*)m->cstFull + 32 * l;
+			if (m->rowregOn[l]) { k_mg_build_full<Real, true><<<1, 1, 0, st>>>(gc, hbx, hby, hbz, (const Real*)m->A[l], m->type[l], (Real*)m->Afull[l], m->first, cf, nullptr); MP_CHECK_LAUNCH(ctx); }
+			unsigned char* rr = m->rowregOn[l] ? m->rowreg[l] : nullptr;
+			if (m->is3D) k_mg_build_full<Real, true><<<gr, 128, 0, st>>>(gc, hbx, hby, hbz, (const Real*)m->A[l], m->type[l], (Real*)m->Afull[l], nullptr, cf, rr);
+			else         k_mg_build_full<Real, false><<<gr, 128, 0, st>>>(gc, hbx, hby, hbz, (const Real*)m->A[l], m->type[l], (Real*)m->Afull[l], nullptr, cf, rr);
 			MP_CHECK_LAUNCH(ctx);
 		}
 	}
@@ -1188,9 +1298,10 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 				int Kb, Ke; lvlRange(m, l, &Kb, &Ke);
 				const int tz0 = m->is3D ? Kb / 2 : 0, ntz = m->is3D ? (Ke - 1) / 2 - tz0 + 1 : 1;
 				const int bszF = hbx * hby >= 4096 ? 128 : (hbx * hby >= 512 ? 64 : 32);
+				const unsigned char* rr = m->rowregOn[l] ? m->rowreg[l] : nullptr; const Real* cf = (const Real*)m->cstFull + 32 * l;
 				const dim3 grz((unsigned)((hbx * hby + bszF - 1) / bszF), 1u, (unsigned)ntz);
-				if (m->is3D) k_mg_sweep_full<Real, true, false><<<grz, bszF, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
-				else         k_mg_sweep_full<Real, false, false><<<grz, bszF, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag);
+				if (m->is3D) k_mg_sweep_full<Real, true, false><<<grz, bszF, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag, rr, cf);
+				else         k_mg_sweep_full<Real, false, false><<<grz, bszF, 0, st>>>(g, hbx, hby, hbz, color, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], nullptr, doneFlag, rr, cf);
 				MP_CHECK_LAUNCH(ctx);
 				if (lvlSharded(m, l)) MP_TRY(lvlHalo<Real>(m, l, m->x[l]));      // the next colour (or the residual / the interpolation) reads the neighbours' planes
 				continue;
@@ -1223,9 +1334,10 @@ static int mgResidual(mp_mg* m, int l, const int* doneFlag, const L0<Real>& l0)
 		int Kb, Ke; lvlRange(m, l, &Kb, &Ke);
 		const int tz0 = m->is3D ? Kb / 2 : 0, ntz = m->is3D ? (Ke - 1) / 2 - tz0 + 1 : 1;
 		const int bszF = hbx * hby >= 4096 ? 128 : (hbx * hby >= 512 ? 64 : 32);
+		const unsigned char* rr = m->rowregOn[l] ? m->rowreg[l] : nullptr; const Real* cf = (const Real*)m->cstFull + 32 * l;
 		const dim3 gr((unsigned)((hbx * hby + bszF - 1) / bszF), 1u, (unsigned)(ntz * ncol));
-		if (m->is3D) k_mg_sweep_full<Real, true, true><<<gr, bszF, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
-		else         k_mg_sweep_full<Real, false, true><<<gr, bszF, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag);
+		if (m->is3D) k_mg_sweep_full<Real, true, true><<<gr, bszF, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag, rr, cf);
+		else         k_mg_sweep_full<Real, false, true><<<gr, bszF, 0, st>>>(g, hbx, hby, hbz, 0, tz0, ntz, Kb, Ke, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag, rr, cf);
 	}
 	else        k_mg_residualN<Real><<<grid3(g.sx, g.sy, g.sz, g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32)), g.sx >= 96 ? 128 : (g.sx >= 48 ? 64 : 32), 0, st>>>(g, m->is3D, m->stencil, (const Real*)m->A[l], (const Real*)m->b[l], m->type[l], (const Real*)m->x[l], (Real*)m->r[l], doneFlag);
 	MP_CHECK_LAUNCH(ctx);
@@ -1432,6 +1544,7 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 			const LvlGeom g = m->geom[l];
 			const size_t nc = (size_t)((g.sx + 1) / 2) * ((g.sy + 1) / 2) * (m->is3D ? (g.sz + 1) / 2 : 1);
 			MP_CUDA(cudaMalloc(&m->Afull[l], nc * (m->is3D ? 8 * 27 : 4 * 9) * prec));
+			if (m->is3D && g.n >= 4096) MP_CUDA(cudaMalloc((void**)&m->rowreg[l], nc * 8));
 		}
 		MP_CUDA(cudaMemsetAsync(m->A[l], 0, n * S * prec, ctx->stream)); if (l > 0) MP_CUDA(cudaMemsetAsync(m->x[l], 0, n * prec, ctx->stream));
 		MP_CUDA(cudaMemsetAsync(m->b[l], 0, n * prec, ctx->stream)); MP_CUDA(cudaMemsetAsync(m->r[l], 0, nr * prec, ctx->stream));
@@ -1439,6 +1552,7 @@ int mp_mg_create(mp_context* ctx, int prec, int sx, int sy, int sz, mp_mg** out)
 	}
 	for (l = 1; l < m->nlev; l++) if (m->is3D && m->geom[l].n >= 4096) MP_CUDA(cudaMalloc((void**)&m->regular[l], (size_t)m->geom[l].n));
 	MP_CUDA(cudaMalloc(&m->cst, 16 * sizeof(double))); MP_CUDA(cudaMalloc((void**)&m->first, sizeof(int)));
+	MP_CUDA(cudaMalloc(&m->cstFull, 32 * MG_MAXLVL * sizeof(double))); MP_CUDA(cudaMemsetAsync(m->cstFull, 0, 32 * MG_MAXLVL * sizeof(double), ctx->stream));
 	if (sx % (16 / prec) == 0) MP_CUDA(cudaMalloc((void**)&m->mask0, sizeof(unsigned short) * (size_t)m->geom[0].n + 64));
 	MP_CUDA(cudaMalloc((void**)&m->cg, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n));
 	MP_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(double) * 4 * (size_t)m->geom[m->nlev - 1].n, ctx->stream));
@@ -1485,7 +1599,8 @@ int mp_mg_destroy(mp_mg* m)
 	for (int l = 0; l < m->nlev; l++) { cudaFree(m->A[l]); cudaFree(m->x[l]); cudaFree(m->b[l]); cudaFree(m->r[l]); cudaFree(m->type[l]); if (m->Afull[l]) cudaFree(m->Afull[l]); }
 	cudaFree(m->cg); cudaFree(m->dPaths); cudaFree(m->dFlags); cudaFreeHost(m->hFlags); if (m->mask0) cudaFree(m->mask0);
 	for (int l = 0; l < m->nlev; l++) if (m->regular[l]) cudaFree(m->regular[l]);
-	cudaFree(m->cst); cudaFree(m->first);
+	for (int l = 0; l < m->nlev; l++) if (m->rowreg[l]) cudaFree(m->rowreg[l]);
+	cudaFree(m->cst); cudaFree(m->first); cudaFree(m->cstFull);
 	if (m->ctx->staticMg == m) m->ctx->staticMg = nullptr;
 	if (m->ctx->spareMg == m) m->ctx->spareMg = nullptr;
 	delete m; return MP_OK;

@@ -264,3 +264,40 @@ def test_galerkin_regular_vertices_copy_the_same_row(mf, res, liquid, prec, monk
     for l, (a, b) in enumerate(zip(ops[1], ops[0])):
         assert np.array_equal(a, b), "level %d operator differs with the regular-vertex fast path" % l
     assert np.count_nonzero(ops[1][1]) > 0
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("res,liquid", [(72, False), (64, True)])
+def test_sweeps_with_constant_rows_agree_bit_for_bit(mf, res, liquid, prec, monkeypatch):
+    """levels > 0: vertices whose whole 27-entry row equals the row of the level's first regular vertex (compared number by number in setA) take
+    their coefficients from that constant row instead of streaming them (k_mg_sweep_full with rowreg).  Same numbers, same order: V-cycle iterates,
+    residual norms and a PcMGStatic solve are the same bit for bit with MP_MG_ROWREG=0."""
+    from mantaflow_b200 import cg, scenes
+    if liquid:
+        flags, vel, phi = scenes.liquid_basin((res, res, res), prec)
+    else:
+        (flags, vel), phi = scenes.smoke_plume(res, prec), None
+    O = oracle(prec)
+    rhs, _, _ = O.compute_rhs(flags, vel, phi=phi)
+    A_o = O.make_matrix(flags, phi=phi)
+    fix = O.choose_fix_cell(flags)
+    if fix >= 0:
+        O.fix_pressure(flags, fix, 0.0, rhs, *A_o)
+    out = {}
+    for rowreg in (1, 0):
+        monkeypatch.setenv("MP_MG_ROWREG", str(rowreg))
+        s = mk(mf, flags.shape, prec)
+        mg = cg.GridMg(s)
+        B, Z, Z2 = mf.RealGrid(s, rhs), mf.RealGrid(s), mf.RealGrid(s)
+        mg.setA(*[mf.RealGrid(s, a) for a in A_o])
+        mg.setRhs(B)
+        r1 = mg.doVCycle(Z)
+        r2 = mg.doVCycle(Z2, Z)
+        F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
+        PH = mf.RealGrid(s, phi) if phi is not None else None
+        mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=1e-5 if prec == 4 else 1e-9, phi=PH, preconditioner=mf.PcMGStatic, cgMaxIterFac=99, zeroPressureFixing=True)
+        out[rowreg] = (Z.numpy().copy(), Z2.numpy().copy(), r1, r2, P.numpy().copy(), mf.lastSolveInfo()["iterations"])
+        mf.releaseMG(s); mg.close(); s.close()
+    a, b = out[1], out[0]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
+    assert a[5] == b[5] and np.array_equal(a[4], b[4])
