@@ -867,17 +867,10 @@ __global__ void __launch_bounds__(128) k_mg_build_full(LvlGeom g, int hbx, int h
 // thread first puts its whole row of coefficients and its neighbours' iterate in flight (streaming loads for the coefficients, which are
 // read once per sweep, so that the iterate -- re-read by every colour -- stays in L2), then accumulates in the reference's order.
 template <typename Real, bool IS3D, bool RESID>
-__global__ void __launch_bounds__(128, 6) k_mg_sweep_full(LvlGeom g, int hbx, int hby, int hbz, int color, int tz0, int ntz, int Kb, int Ke, const Real* __restrict__ Afull, const Real* __restrict__ b,
-	const signed char* __restrict__ type, Real* __restrict__ x, Real* __restrict__ r, const int* doneFlag, const unsigned char* __restrict__ rowreg, const Real* __restrict__ cstFull)
+__device__ __forceinline__ void sweepVertex(const LvlGeom& g, int hbx, int hby, int hbz, int c, int tx, int ty, int tz, int Kb, int Ke, const Real* __restrict__ Afull,
+	const Real* __restrict__ b, const signed char* __restrict__ type, Real* x, Real* __restrict__ r, const unsigned char* __restrict__ rowreg, const Real* __restrict__ cstFull)
 {
-	if (doneFlag && *doneFlag) return;
 	constexpr int S = IS3D ? 14 : 5, NENT = IS3D ? 27 : 9;
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= hbx * hby) return;
-	const int ty = t / hbx, tx = t - ty * hbx;
-	// blockIdx.z walks the 2-plane blocks [tz0, tz0 + ntz) (all of them, or those that hold this rank's planes [Kb,Ke)); RESID: x all colours
-	int c = color, tz = tz0 + blockIdx.z;
-	if (RESID) { c = blockIdx.z / ntz; tz = tz0 + blockIdx.z - c * ntz; }
 	const int vx = 2 * tx + (c & 1), vy = 2 * ty + ((c >> 1) & 1), vz = 2 * tz + ((c >> 2) & 1);
 	if (!inGrid(g, vx, vy, vz) || vz < Kb || vz >= Ke) return;
 	const int v = linIdx(g, vx, vy, vz);
@@ -908,6 +901,42 @@ __global__ void __launch_bounds__(128, 6) k_mg_sweep_full(LvlGeom g, int hbx, in
 		sum -= av[s] * xv[s];
 	}
 	if (RESID) r[v] = sum; else x[v] = sum / av[S - 1];
+}
+template <typename Real, bool IS3D, bool RESID>
+__global__ void __launch_bounds__(128, 6) k_mg_sweep_full(LvlGeom g, int hbx, int hby, int hbz, int color, int tz0, int ntz, int Kb, int Ke, const Real* __restrict__ Afull, const Real* __restrict__ b,
+	const signed char* __restrict__ type, Real* x, Real* __restrict__ r, const int* doneFlag, const unsigned char* __restrict__ rowreg, const Real* __restrict__ cstFull)
+{
+	if (doneFlag && *doneFlag) return;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= hbx * hby) return;
+	const int ty = t / hbx, tx = t - ty * hbx;
+	// blockIdx.z walks the 2-plane blocks [tz0, tz0 + ntz) (all of them, or those that hold this rank's planes [Kb,Ke)); RESID: x all colours
+	int c = color, tz = tz0 + blockIdx.z;
+	if (RESID) { c = blockIdx.z / ntz; tz = tz0 + blockIdx.z - c * ntz; }
+	sweepVertex<Real, IS3D, RESID>(g, hbx, hby, hbz, c, tx, ty, tz, Kb, Ke, Afull, b, type, x, r, rowreg, cstFull);
+}
+// small levels (<= 40 k vertices, 3-D): all eight colours of a sweep -- and, if asked, the residual after it -- by ONE CTA with a barrier between the
+// colours, instead of eight (nine) launches of a few microseconds each; same per-vertex code, same order of the colours
+template <typename Real>
+__global__ void __launch_bounds__(512, 1) k_mg_sweep_cta(LvlGeom g, int hbx, int hby, int hbz, int reversed, int withResidual, const Real* __restrict__ Afull, const Real* __restrict__ b,
+	const signed char* __restrict__ type, Real* x, Real* __restrict__ r, const int* doneFlag, const unsigned char* __restrict__ rowreg, const Real* __restrict__ cstFull)
+{
+	if (doneFlag && *doneFlag) return;
+	const int nblk = hbx * hby * hbz, plane = hbx * hby;
+	for (int cc = 0; cc < 8; cc++) {
+		const int c = reversed ? 7 - cc : cc;
+		for (int t = threadIdx.x; t < nblk; t += blockDim.x) {
+			const int tz = t / plane, rem = t - tz * plane, ty = rem / hbx, tx = rem - ty * hbx;
+			sweepVertex<Real, true, false>(g, hbx, hby, hbz, c, tx, ty, tz, 0, g.sz, Afull, b, type, x, r, rowreg, cstFull);
+		}
+		__syncthreads();      // the next colour reads what this one wrote (one CTA: its own global writes are visible after the barrier)
+	}
+	if (withResidual) {
+		for (int t = threadIdx.x; t < 8 * nblk; t += blockDim.x) {
+			const int c = t / nblk, q = t - c * nblk, tz = q / plane, rem = q - tz * plane, ty = rem / hbx, tx = rem - ty * hbx;
+			sweepVertex<Real, true, true>(g, hbx, hby, hbz, c, tx, ty, tz, 0, g.sz, Afull, b, type, x, r, rowreg, cstFull);
+		}
+	}
 }
 
 // knRestrict :904-927 (dst level = coarse), also zeroes x on the coarse level (knSet :472)
@@ -1035,6 +1064,99 @@ __global__ void __launch_bounds__(1024) k_mg_coarse_cg(LvlGeom g, int is3D, int 
 		__syncthreads();
 	}
 	for (int v = threadIdx.x; v < n; v += blockDim.x) xr[v] = (Real)x[v];
+	if (threadIdx.x == 0) flagsOut[4] = iter;
+}
+
+// The same solve for a coarsest level of <= 1024 vertices with colour-major rows (the usual case): one vertex per thread, the four CG vectors in
+// shared memory, the operator applied through the whole-row layout (entries towards inactive or outside vertices are 0: no type tests, 27
+// independent coefficient loads), two sums per reduction pass.  Same operations on the same values in the same order per quantity as
+// k_mg_coarse_cg (an absent neighbour contributes 0 * 0 instead of being skipped).
+__device__ __forceinline__ void ctaSum2(double& a, double& b, double (*sh)[33]) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	a = warpSum(a); b = warpSum(b);
+	__syncthreads();
+	if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; }
+	__syncthreads();
+	double ta = (threadIdx.x < (blockDim.x >> 5)) ? sh[0][threadIdx.x] : 0.0, tb = (threadIdx.x < (blockDim.x >> 5)) ? sh[1][threadIdx.x] : 0.0;
+	if (warp == 0) { ta = warpSum(ta); tb = warpSum(tb); if (lane == 0) { sh[0][32] = ta; sh[1][32] = tb; } }
+	__syncthreads();
+	a = sh[0][32]; b = sh[1][32];
+}
+template <typename Real>
+__global__ void __launch_bounds__(1024, 1) k_mg_coarse_cg_rows(LvlGeom g, int hbx, int hby, int hbz, const Real* __restrict__ Afull, const Real* __restrict__ b,
+	const signed char* __restrict__ type, Real* __restrict__ xr, double accuracy, int* flagsOut, const int* doneFlag)
+{
+	if (doneFlag && *doneFlag) return;
+	constexpr int S = 14, NENT = 27;
+	__shared__ double sh[2][33];
+	__shared__ double X[1024], R[1024], P[1024], Z[1024];
+	const int n = g.n, v = threadIdx.x;
+	const bool in = v < n, act = in && type[v] != vtInactive;
+	X[v] = in ? (double)xr[v] : 0.0; R[v] = 0.0; P[v] = 0.0; Z[v] = 0.0;
+	// the row is re-read (L1) in every application: 27 registers more would spill at 1024 threads.  Neighbours outside the grid read the vertex
+	// itself (their coefficient is 0): bit s of `inside`
+	constexpr bool kRegs = false;
+	Real a[kRegs ? NENT : 1];
+	const Real* row = Afull;
+	unsigned inside = 0;
+	const size_t nc = (size_t)hbx * hby * hbz;
+	const int Y = g.sx, Zs = g.sx * g.sy;
+	if (act) {
+		int vx, vy, vz; vecIdx(g, v, vx, vy, vz);
+		const int c = (vx & 1) | ((vy & 1) << 1) | ((vz & 1) << 2);
+		row = Afull + (size_t)c * NENT * nc + ((vx >> 1) + (size_t)hbx * ((vy >> 1) + (size_t)hby * (vz >> 1)));
+		#pragma unroll
+		for (int s = 0; s < NENT; s++) {
+			const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = s / 9 - 1;
+			if (inGrid(g, vx + dx, vy + dy, vz + dz)) inside |= 1u << s;
+			if (kRegs) a[s] = row[(size_t)s * nc];
+		}
+	}
+	__syncthreads();
+	auto applyA = [&](const double* vec) -> double {      // -(0 - a0 x0 - a1 x1 ...) as stencilSub accumulates it
+		double sum = 0.0;
+		#pragma unroll
+		for (int s = 0; s < NENT; s++) {
+			const int dx = s % 3 - 1, dy = (s / 3) % 3 - 1, dz = s / 9 - 1;
+			const int nbv = ((inside >> s) & 1u) ? v + dx + Y * dy + Zs * dz : v;
+			const Real as = kRegs ? a[kRegs ? s : 0] : row[(size_t)s * nc];
+			sum -= (double)as * vec[nbv];
+		}
+		return -sum;
+	};
+	const double diag = act ? (double)row[(size_t)(S - 1) * nc] : 1.0;
+	double aTop = 0, res0 = 0;
+	if (act) {
+		const double rv = (double)b[v] - applyA(X);
+		const double zv = rv / diag;
+		R[v] = rv; Z[v] = zv; P[v] = zv;
+		res0 = rv * rv; aTop = rv * zv;
+	}
+	ctaSum2(aTop, res0, sh); res0 = sqrt(res0);
+	int iter = 0; const int maxIter = 10000;
+	for (; iter < maxIter && res0 > 1E-12; iter++) {
+		double aBot = 0, dummy = 0, zv = 0;
+		if (act) { zv = applyA(P); aBot = P[v] * zv; }
+		__syncthreads();                                   // every thread has read P / nothing reads Z of this iteration before it is written
+		if (act) Z[v] = zv;
+		ctaSum2(aBot, dummy, sh);
+		const double alpha = aTop / aBot;
+		double aTopNew = 0, res = 0;
+		if (act) {
+			X[v] += alpha * P[v];
+			const double rv = R[v] - alpha * Z[v];
+			R[v] = rv; res = rv * rv;
+			const double zn = rv / diag;
+			Z[v] = zn; aTopNew = rv * zn;
+		}
+		ctaSum2(aTopNew, res, sh); res = sqrt(res);
+		if (res / res0 < accuracy) break;
+		const double beta = aTopNew / aTop;
+		aTop = aTopNew;
+		if (act) P[v] = Z[v] + beta * P[v];
+		__syncthreads();
+	}
+	if (in) xr[v] = (Real)X[v];
 	if (threadIdx.x == 0) flagsOut[4] = iter;
 }
 
@@ -1291,6 +1413,15 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 		const int hbx = (g.sx + 1) / 2;
 		const int bsz = hbx >= 96 ? 128 : (hbx >= 48 ? 64 : 32);
 		const dim3 gr = grid3(hbx, (g.sy + 1) / 2, (g.sz + 1) / 2, bsz);
+		// small levels: the whole sweep in one launch of one CTA (MP_MG_SWEEP_CTA=0: one launch per colour)
+		static const int sweepCta = getenv("MP_MG_SWEEP_CTA") ? atoi(getenv("MP_MG_SWEEP_CTA")) : 1;
+		if (sweepCta && m->Afull[l] && m->is3D && g.n <= 40000 && !lvlSharded(m, l)) {
+			const int hby = (g.sy + 1) / 2, hbz = (g.sz + 1) / 2;
+			const unsigned char* rr = m->rowregOn[l] ? m->rowreg[l] : nullptr; const Real* cf = (const Real*)m->cstFull + 32 * l;
+			k_mg_sweep_cta<Real><<<1, 512, 0, st>>>(g, hbx, hby, hbz, reversed ? 1 : 0, 0, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag, rr, cf);
+			MP_CHECK_LAUNCH(ctx);
+			return MP_OK;
+		}
 		for (int c = 0; c < ncol; c++) {
 			const int color = reversed ? ncol - 1 - c : c;
 			if (m->Afull[l]) {
@@ -1412,6 +1543,11 @@ static int mgVCycle(mp_mg* m, Real* dst, const Real* rhsExt, bool xInit, bool wa
 	{
 		const LvlGeom g = m->geom[maxLevel];
 		const bool lvl0 = maxLevel == 0;
+		static const int cgRows = getenv("MP_MG_COARSE_ROWS") ? atoi(getenv("MP_MG_COARSE_ROWS")) : 1;
+		if (!lvl0 && cgRows && m->is3D && m->Afull[maxLevel] && g.n <= 1024)
+			k_mg_coarse_cg_rows<Real><<<1, 1024, 0, st>>>(g, (g.sx + 1) / 2, (g.sy + 1) / 2, (g.sz + 1) / 2, (const Real*)m->Afull[maxLevel], (const Real*)m->b[maxLevel], m->type[maxLevel],
+				(Real*)m->x[maxLevel], m->coarsestAcc, m->dFlags, doneFlag);
+		else
 		k_mg_coarse_cg<Real><<<1, 1024, 0, st>>>(g, m->is3D, m->stencil, lvl0 ? 1 : 0, (const Real*)m->A[maxLevel], lvl0 ? l0.b : (const Real*)m->b[maxLevel], m->type[maxLevel],
 			lvl0 ? l0.x : (Real*)m->x[maxLevel], m->cg, m->coarsestAcc, m->dFlags, doneFlag, lvl0 ? l0.bscale : (Real)0);
 		MP_CHECK_LAUNCH(ctx);
