@@ -915,7 +915,7 @@ __global__ void __launch_bounds__(128, 6) k_mg_sweep_full(LvlGeom g, int hbx, in
 	if (RESID) { c = blockIdx.z / ntz; tz = tz0 + blockIdx.z - c * ntz; }
 	sweepVertex<Real, IS3D, RESID>(g, hbx, hby, hbz, c, tx, ty, tz, Kb, Ke, Afull, b, type, x, r, rowreg, cstFull);
 }
-// small levels (<= 40 k vertices, 3-D): all eight colours of a sweep -- and, if asked, the residual after it -- by ONE CTA with a barrier between the
+// small levels (<= 6000 vertices, 3-D; a 33^3 level is already faster as eight launches over many SMs): all eight colours of a sweep -- and, if asked, the residual after it -- by ONE CTA with a barrier between the
 // colours, instead of eight (nine) launches of a few microseconds each; same per-vertex code, same order of the colours
 template <typename Real>
 __global__ void __launch_bounds__(512, 1) k_mg_sweep_cta(LvlGeom g, int hbx, int hby, int hbz, int reversed, int withResidual, const Real* __restrict__ Afull, const Real* __restrict__ b,
@@ -1415,7 +1415,7 @@ static int mgSmooth(mp_mg* m, int l, bool reversed, bool zeroX, const int* doneF
 		const dim3 gr = grid3(hbx, (g.sy + 1) / 2, (g.sz + 1) / 2, bsz);
 		// small levels: the whole sweep in one launch of one CTA (MP_MG_SWEEP_CTA=0: one launch per colour)
 		static const int sweepCta = getenv("MP_MG_SWEEP_CTA") ? atoi(getenv("MP_MG_SWEEP_CTA")) : 1;
-		if (sweepCta && m->Afull[l] && m->is3D && g.n <= 40000 && !lvlSharded(m, l)) {
+		if (sweepCta && m->Afull[l] && m->is3D && g.n <= 6000 && !lvlSharded(m, l)) {
 			const int hby = (g.sy + 1) / 2, hbz = (g.sz + 1) / 2;
 			const unsigned char* rr = m->rowregOn[l] ? m->rowreg[l] : nullptr; const Real* cf = (const Real*)m->cstFull + 32 * l;
 			k_mg_sweep_cta<Real><<<1, 512, 0, st>>>(g, hbx, hby, hbz, reversed ? 1 : 0, 0, (const Real*)m->Afull[l], (const Real*)m->b[l], m->type[l], (Real*)m->x[l], (Real*)m->r[l], doneFlag, rr, cf);
