@@ -235,14 +235,17 @@ int mp_vic_poisson(mp_context* ctx, const mp_grid* flags, const mp_grid* vortici
  * setWallBcs          plugin/extforces.cpp:186-218, :307-316  (KnSetWallBcs; with phiObs AND fractions the second-order variant KnSetWallBcsFrac :220-303)
  * addGravity          plugin/extforces.cpp:45-65              (scale != 0: divided by the grid's dx = 1/max(size))
  * addBuoyancy         plugin/extforces.cpp:75-90
- * advectSemiLagrange  plugin/advection.cpp:442-461            (grid: Real or MAC; order 1 | 2 (MacCormack), clampMode 1 | 2, convective outflow
- *                     boundary for MAC grids; orderSpace / orderTrace other than 1: MP_ERR_UNSUPPORTED).  dt = FluidSolver::getDt().
+ * advectSemiLagrange  plugin/advection.cpp:442-461            (grid: Real / Levelset or MAC, _vec3: a cell-centred Grid<Vec3> in MP_GRID_MAC storage;
+ *                     order 1 | 2 (MacCormack), clampMode 1 | 2, orderSpace 1 | 2 (cubic lookups, util/interpolHigh.h), orderTrace 1 | 2 (explicit
+ *                     midpoint, advection.cpp:32-37, :58-73), convective outflow boundary for MAC grids).  dt = FluidSolver::getDt().
  * Results are bit-identical to the reference's in both precisions. */
 int mp_set_wall_bcs(mp_context* ctx, const mp_grid* flags, mp_grid* vel, const mp_grid* obvel, const mp_grid* fractions, const mp_grid* phiObs, int boundaryWidth);
 int mp_add_gravity(mp_context* ctx, const mp_grid* flags, mp_grid* vel, double gx, double gy, double gz, const mp_grid* exclude, int scale, double dt);
 int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* density, mp_grid* vel, double gx, double gy, double gz, double coefficient, int scale, double dt);
 int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
                             int clampMode, int orderTrace, double dt);
+int mp_advect_semi_lagrange_vec3(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
+                                 int clampMode, int orderTrace, double dt);
 
 /* ---- liquid neighbours (first slice): with them the level-set free-surface loop of scenes/freesurface.py:54-84
  * (extrapolateLsSimple x2, extrapolateMACSimple, advect phi, phi.setBound, flags.updateFromLevelset, advect vel, addGravity, setWallBcs,

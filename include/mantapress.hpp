@@ -363,15 +363,14 @@ inline void addBuoyancy(const FlagGrid& flags, const Grid<Real>& density, MACGri
 	mpCheck(mp_add_buoyancy(flags.getParent()->ctx(), flags.dev(), density.dev(), vel.dev(), gravity.x, gravity.y, gravity.z, coefficient, scale, flags.getParent()->getDt()));
 	vel.markDeviceWritten();
 }
-template <class G>          // G: Grid<Real> (incl. LevelsetGrid) or MACGrid -- the reference takes a GridBase* and dispatches on its type (advection.cpp:447-459)
+template <class G>          // G: Grid<Real> (incl. LevelsetGrid), MACGrid or Grid<Vec3> -- the reference takes a GridBase* and dispatches on its type (advection.cpp:447-459)
 inline void advectSemiLagrange(const FlagGrid* flags, const MACGrid* vel, G* grid, int order = 1, Real strength = 1.0, int orderSpace = 1, bool openBounds = false,
 	int boundaryWidth = -1, int clampMode = 2, int orderTrace = 1)
 {
-	static_assert(!std::is_same<G, Grid<Vec3> >::value, "advectSemiLagrange: plain Grid<Vec3> advection is not built (only Grid<Real>, LevelsetGrid, MACGrid)");
 	(void)openBounds; (void)boundaryWidth;             // deprecated in the reference, no effect (advection.cpp:446)
 	if (order != 1 && order != 2) throw Error(MP_ERR_INVALID, "AdvectSemiLagrange: Only order 1 (regular SL) and 2 (MacCormack) supported");
-	mpCheck(mp_advect_semi_lagrange(flags->getParent()->ctx(), flags->dev(), vel->dev(), grid->dev(), order, strength, orderSpace, clampMode, orderTrace,
-	                                flags->getParent()->getDt()));
+	mpCheck((std::is_same<G, Grid<Vec3> >::value ? mp_advect_semi_lagrange_vec3 : mp_advect_semi_lagrange)(flags->getParent()->ctx(), flags->dev(), vel->dev(), grid->dev(),
+	        order, strength, orderSpace, clampMode, orderTrace, flags->getParent()->getDt()));
 	grid->markDeviceWritten();
 }
 

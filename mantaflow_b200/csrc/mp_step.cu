@@ -3,7 +3,8 @@
 //   addGravity          plugin/extforces.cpp:45-65               (KnApplyForce, additive)
 //   addBuoyancy         plugin/extforces.cpp:75-90               (KnAddBuoyancy)
 //   advectSemiLagrange  plugin/advection.cpp:25-58, :81-316, :323-461 (semi-Lagrange + MacCormack for Real and MAC grids,
-//                       orderSpace 1 / orderTrace 1, clamp modes 1 and 2, convective outflow boundary)
+//                       orderSpace 1 / 2 (cubic lookups, util/interpolHigh.h), orderTrace 1 / 2 (explicit-midpoint back-tracing),
+//                       clamp modes 1 and 2, convective outflow boundary)
 // One thread per cell, gathers only, every cell written by exactly one thread: any order of execution gives the serial result.
 // The per-cell arithmetic keeps the reference's evaluation (double literals promote, results narrow on assignment; -fmad=false),
 // so the fields are BIT-IDENTICAL to the reference's in both precisions (tests/test_gpu_step.py).
@@ -170,34 +171,147 @@ __device__ __forceinline__ V3<Real> macAt(const Dims& d, const Real* __restrict_
 }
 #undef VC
 
-// ---------------------------------------------------------------- SemiLagrange / SemiLagrangeMAC (advection.cpp:25-58, orderTrace 1)
-// Pass 1 of an advection: dst = src traced back along vel in the interior, 0 on the outer layer (the reference's fresh grid).
-template <typename Real>
-__device__ __forceinline__ Real slReal(const Dims& d, const Real* __restrict__ vel, const Real* __restrict__ src, Real dt, int i, int j, int k, IndexInt idx) {
-	const V3<Real> c = macCentered<Real>(d, vel, idx);
-	return interpol<Real, 1>(d, src, (i + 0.5f) - c.x * dt, (j + 0.5f) - c.y * dt, (k + 0.5f) - c.z * dt);
+// ---------------------------------------------------------------- higher-order lookups: orderSpace 2 (util/interpolHigh.h), orderTrace 2 (interpolMAC)
+// cubicInterp util/interpolHigh.h:22-39.  The reference instantiates it for Real and for Vec3: the Vec3 one narrows after every scalar * vector
+// product (vectorbase.h:272-279), the Real one forms the polynomial coefficients in double and narrows once.  In double both are the same arithmetic.
+template <typename Real, bool VEC>
+__device__ __forceinline__ Real cubicInterp(Real t, Real p0, Real p1, Real p2, Real p3) {
+	const Real d0 = (Real)((double)(p2 - p0) * 0.5), d1 = (Real)((double)(p3 - p1) * 0.5), dk = p2 - p1;
+	Real a2, a3;
+	if (VEC) { a2 = ((Real)(3.0 * (double)dk) - (Real)(2.0 * (double)d0)) - d1; a3 = ((Real)(-2.0 * (double)dk) + d0) + d1; }
+	else     { a2 = (Real)((3.0 * (double)dk - 2.0 * (double)d0) - (double)d1); a3 = (Real)((-2.0 * (double)dk + (double)d0) + (double)d1); }
+	const Real sq = t * t, cu = sq * t;
+	return ((a3 * cu + a2 * sq) + d0 * t) + p1;
 }
+// interpolCubic / interpolCubic2D util/interpolHigh.h:42-172: 4 x 4 (x 4) support, x first, then y, then z; within one cell of the border the
+// reference falls back to the linear lookup.  STRIDE 3 = one component of a Vec3 grid (the Vec3 instantiation of cubicInterp).
+template <typename Real, int STRIDE>
+__device__ Real interpolCubic(const Dims& d, const Real* __restrict__ a, Real posx, Real posy, Real posz) {
+	const Real px = posx - 0.5f, py = posy - 0.5f, pz = posz - 0.5f;
+	const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
+	const bool out = x1 < 1 || y1 < 1 || x1 + 2 >= d.sx || y1 + 2 >= d.sy || (d.is3D && (z1 < 1 || z1 + 2 >= d.sz));
+	if (out) return interpol<Real, STRIDE>(d, a, posx, posy, posz);
+	const Real tx = px - (Real)x1, ty = py - (Real)y1;
+	constexpr bool VEC = STRIDE == 3;
+	const int nz = d.is3D ? 4 : 1;
+	Real zp[4];
+	for (int c = 0; c < nz; c++) {
+		const Real* pl = a + ((IndexInt)(x1 - 1) + d.Y * (y1 - 1) + (d.is3D ? d.Z * (z1 - 1 + c) : (IndexInt)0)) * STRIDE;
+		Real yp[4];
+		#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			const Real* r = pl + d.Y * b * STRIDE;
+			yp[b] = cubicInterp<Real, VEC>(tx, r[0], r[STRIDE], r[2 * STRIDE], r[3 * STRIDE]);
+		}
+		zp[c] = cubicInterp<Real, VEC>(ty, yp[0], yp[1], yp[2], yp[3]);
+	}
+	if (!d.is3D) return zp[0];
+	return cubicInterp<Real, VEC>(pz - (Real)z1, zp[0], zp[1], zp[2], zp[3]);
+}
+// one axis of BUILD_INDEX / BUILD_INDEX_SHIFT util/interpol.h:50-66, :112-125
 template <typename Real>
-__device__ __forceinline__ V3<Real> slMAC(const Dims& d, const Real* __restrict__ vel, const Real* __restrict__ src, Real dt, int i, int j, int k, IndexInt idx) {
-	const V3<Real> mx = macAt<Real, 0>(d, vel, idx), my = macAt<Real, 1>(d, vel, idx), mz = macAt<Real, 2>(d, vel, idx);
+__device__ __forceinline__ void axisWeights(Real p, int size, bool clampHigh, int& i, Real& w0, Real& w1) {
+	i = (int)p; w1 = p - (Real)i; w0 = (Real)(1. - w1);
+	if (p < 0.) { i = 0; w0 = 1; w1 = 0; }
+	if (clampHigh && i >= size - 1) { i = size - 2; w0 = 0; w1 = 1; }
+}
+// MACGrid::getInterpolated = interpolMAC util/interpol.h:127-157: each component looked up on its own faces
+template <typename Real>
+__device__ V3<Real> interpolMACAt(const Dims& d, const Real* __restrict__ v, Real posx, Real posy, Real posz) {
+	int xi, yi, zi, sxi, syi, szi; Real s0, s1, t0, t1, f0, f1, ss0, ss1, st0, st1, sf0, sf1;
+	axisWeights<Real>(posx - 0.5f, d.sx, true, xi, s0, s1); axisWeights<Real>(posy - 0.5f, d.sy, true, yi, t0, t1); axisWeights<Real>(posz - 0.5f, d.sz, d.sz > 1, zi, f0, f1);
+	axisWeights<Real>(posx, d.sx, true, sxi, ss0, ss1); axisWeights<Real>(posy, d.sy, true, syi, st0, st1); axisWeights<Real>(posz, d.sz, d.sz > 1, szi, sf0, sf1);
+	const IndexInt X = 3, Y = 3 * d.Y, Z = 3 * d.Z;
 	V3<Real> o;
-	o.x = interpol<Real, 3>(d, src + 0, (i + 0.5f) - mx.x * dt, (j + 0.5f) - mx.y * dt, (k + 0.5f) - mx.z * dt);
-	o.y = interpol<Real, 3>(d, src + 1, (i + 0.5f) - my.x * dt, (j + 0.5f) - my.y * dt, (k + 0.5f) - my.z * dt);
-	o.z = interpol<Real, 3>(d, src + 2, (i + 0.5f) - mz.x * dt, (j + 0.5f) - mz.y * dt, (k + 0.5f) - mz.z * dt);
+	{ const Real* p = v + 3 * (((IndexInt)zi * d.sy + yi) * d.sx + sxi);
+	  o.x = f0 * ((p[0] * t0 + p[Y] * t1) * ss0 + (p[X] * t0 + p[X + Y] * t1) * ss1) + f1 * ((p[Z] * t0 + p[Z + Y] * t1) * ss0 + (p[X + Z] * t0 + p[X + Y + Z] * t1) * ss1); }
+	{ const Real* p = v + 3 * (((IndexInt)zi * d.sy + syi) * d.sx + xi) + 1;
+	  o.y = f0 * ((p[0] * st0 + p[Y] * st1) * s0 + (p[X] * st0 + p[X + Y] * st1) * s1) + f1 * ((p[Z] * st0 + p[Z + Y] * st1) * s0 + (p[X + Z] * st0 + p[X + Y + Z] * st1) * s1); }
+	{ const Real* p = v + 3 * (((IndexInt)szi * d.sy + yi) * d.sx + xi) + 2;
+	  o.z = sf0 * ((p[0] * t0 + p[Y] * t1) * s0 + (p[X] * t0 + p[X + Y] * t1) * s1) + sf1 * ((p[Z] * t0 + p[Z + Y] * t1) * s0 + (p[X + Z] * t0 + p[X + Y + Z] * t1) * s1); }
 	return o;
 }
-template <typename Real>
+// Grid<Real>::getInterpolatedHi (grid.h:146-151) and MACGrid::getInterpolatedComponentHi<C> (grid.h:268-273; the cubic one is
+// interpolCubicMAC(pos)[C], util/interpolHigh.h:174-181: the lookup position moved by half a cell along C, 0 for z in 2-D)
+template <typename Real, int OS>
+__device__ __forceinline__ Real lookupReal(const Dims& d, const Real* __restrict__ src, Real x, Real y, Real z) {
+	return OS == 1 ? interpol<Real, 1>(d, src, x, y, z) : interpolCubic<Real, 1>(d, src, x, y, z);
+}
+template <typename Real, int OS, int C>
+__device__ __forceinline__ Real lookupMAC(const Dims& d, const Real* __restrict__ src, Real x, Real y, Real z) {
+	if (OS == 1) return interpol<Real, 3>(d, src + C, x, y, z);
+	if (C == 2 && !d.is3D) return (Real)0;
+	return interpolCubic<Real, 3>(d, src + C, C == 0 ? x + (Real)0.5 : x + (Real)0, C == 1 ? y + (Real)0.5 : y + (Real)0, C == 2 ? z + (Real)0.5 : z + (Real)0);
+}
+
+// ---------------------------------------------------------------- SemiLagrange / SemiLagrangeMAC (advection.cpp:25-77)
+// Pass 1 of an advection: dst = src traced back along vel in the interior, 0 on the outer layer (the reference's fresh grid).
+// OT 2: explicit midpoint (:32-37); the MAC kernel takes its velocities from SRC there (:58-73), as the reference does.
+template <typename Real, int OS, int OT>
+__device__ __forceinline__ Real slReal(const Dims& d, const Real* __restrict__ vel, const Real* __restrict__ src, Real dt, int i, int j, int k, IndexInt idx) {
+	const V3<Real> c = macCentered<Real>(d, vel, idx);
+	if (OT == 1) return lookupReal<Real, OS>(d, src, (i + 0.5f) - c.x * dt, (j + 0.5f) - c.y * dt, (k + 0.5f) - c.z * dt);
+	const Real p0x = i + 0.5f, p0y = j + 0.5f, p0z = k + 0.5f;
+	const V3<Real> u = interpolMACAt<Real>(d, vel, p0x - (Real)((double)(c.x * dt) * 0.5), p0y - (Real)((double)(c.y * dt) * 0.5), p0z - (Real)((double)(c.z * dt) * 0.5));
+	return lookupReal<Real, OS>(d, src, p0x - u.x * dt, p0y - u.y * dt, p0z - u.z * dt);
+}
+template <typename Real, int OS, int OT, int C>
+__device__ __forceinline__ Real slMACc(const Dims& d, const Real* __restrict__ vel, const Real* __restrict__ src, Real dt, int i, int j, int k, IndexInt idx) {
+	if (OT == 1) {
+		const V3<Real> m = macAt<Real, C>(d, vel, idx);
+		return lookupMAC<Real, OS, C>(d, src, (i + 0.5f) - m.x * dt, (j + 0.5f) - m.y * dt, (k + 0.5f) - m.z * dt);
+	}
+	const V3<Real> m = macAt<Real, C>(d, src, idx);
+	const Real p0x = i + 0.5f, p0y = j + 0.5f, p0z = k + 0.5f;
+	const Real fx = C == 0 ? (Real)i : p0x, fy = C == 1 ? (Real)j : p0y, fz = C == 2 ? (Real)k : p0z;      // the face centre
+	const V3<Real> u = interpolMACAt<Real>(d, src, fx - (Real)((double)(m.x * dt) * 0.5), fy - (Real)((double)(m.y * dt) * 0.5), fz - (Real)((double)(m.z * dt) * 0.5));
+	return lookupMAC<Real, OS, C>(d, src, p0x - u.x * dt, p0y - u.y * dt, p0z - u.z * dt);
+}
+template <typename Real, int OS, int OT>
+__device__ __forceinline__ V3<Real> slMAC(const Dims& d, const Real* __restrict__ vel, const Real* __restrict__ src, Real dt, int i, int j, int k, IndexInt idx) {
+	V3<Real> o;
+	o.x = slMACc<Real, OS, OT, 0>(d, vel, src, dt, i, j, k, idx);
+	o.y = slMACc<Real, OS, OT, 1>(d, vel, src, dt, i, j, k, idx);
+	o.z = slMACc<Real, OS, OT, 2>(d, vel, src, dt, i, j, k, idx);
+	return o;
+}
+template <typename Real, int OS, int OT>
 __global__ void __launch_bounds__(128) k_semi_lagrange(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
-	dst[idx] = isInterior(d, i, j, k) ? slReal<Real>(d, vel, src, dt, i, j, k, idx) : (Real)0;
+	dst[idx] = isInterior(d, i, j, k) ? slReal<Real, OS, OT>(d, vel, src, dt, i, j, k, idx) : (Real)0;
 }
-template <typename Real>
+template <typename Real, int OS, int OT>
 __global__ void __launch_bounds__(128) k_semi_lagrange_mac(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
 	V3<Real> o; o.x = o.y = o.z = 0;
-	if (isInterior(d, i, j, k)) o = slMAC<Real>(d, vel, src, dt, i, j, k, idx);
+	if (isInterior(d, i, j, k)) o = slMAC<Real, OS, OT>(d, vel, src, dt, i, j, k, idx);
+	dst[3 * idx] = o.x; dst[3 * idx + 1] = o.y; dst[3 * idx + 2] = o.z;
+}
+
+// SemiLagrange<Vec3> (a cell-centred Grid<Vec3>): the position of slReal, one lookup per component (interpol<Vec3> / interpolCubic<Vec3> share the weights)
+template <typename Real, int OS, int OT>
+__device__ __forceinline__ V3<Real> slVec3(const Dims& d, const Real* __restrict__ vel, const Real* __restrict__ src, Real dt, int i, int j, int k, IndexInt idx) {
+	const V3<Real> c = macCentered<Real>(d, vel, idx);
+	Real px, py, pz;
+	if (OT == 1) { px = (i + 0.5f) - c.x * dt; py = (j + 0.5f) - c.y * dt; pz = (k + 0.5f) - c.z * dt; }
+	else {
+		const Real p0x = i + 0.5f, p0y = j + 0.5f, p0z = k + 0.5f;
+		const V3<Real> u = interpolMACAt<Real>(d, vel, p0x - (Real)((double)(c.x * dt) * 0.5), p0y - (Real)((double)(c.y * dt) * 0.5), p0z - (Real)((double)(c.z * dt) * 0.5));
+		px = p0x - u.x * dt; py = p0y - u.y * dt; pz = p0z - u.z * dt;
+	}
+	V3<Real> o;
+	if (OS == 1) { o.x = interpol<Real, 3>(d, src, px, py, pz); o.y = interpol<Real, 3>(d, src + 1, px, py, pz); o.z = interpol<Real, 3>(d, src + 2, px, py, pz); }
+	else { o.x = interpolCubic<Real, 3>(d, src, px, py, pz); o.y = interpolCubic<Real, 3>(d, src + 1, px, py, pz); o.z = interpolCubic<Real, 3>(d, src + 2, px, py, pz); }
+	return o;
+}
+template <typename Real, int OS, int OT>
+__global__ void __launch_bounds__(128) k_semi_lagrange_vec3(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx)) return;
+	V3<Real> o; o.x = o.y = o.z = 0;
+	if (isInterior(d, i, j, k)) o = slVec3<Real, OS, OT>(d, vel, src, dt, i, j, k, idx);
 	dst[3 * idx] = o.x; dst[3 * idx + 1] = o.y; dst[3 * idx + 2] = o.z;
 }
 
@@ -211,14 +325,14 @@ __device__ __forceinline__ bool checkFlag(const int* flags, IndexInt q) { return
 // Pass 2 of a MacCormack advection of a Real grid: the reference's backward trace (SemiLagrange with -dt on fwd), MacCormackCorrect and
 // MacCormackClamp only ever combine values of ONE cell (plus read-only neighbourhoods of fwd / orig), so they are one kernel here:
 // three full-grid round trips of bwd and the corrected grid never reach HBM.
-template <typename Real>
+template <typename Real, int OS, int OT>
 __global__ void __launch_bounds__(128) k_mc_rest(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
 	const Real* __restrict__ fwd, Real dt, Real strength, int clampMode) {
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
 	const bool in = isInterior(d, i, j, k);
 	const Real f = fwd[idx];
-	const Real bwd = in ? slReal<Real>(d, vel, fwd, -dt, i, j, k, idx) : (Real)0;
+	const Real bwd = in ? slReal<Real, OS, OT>(d, vel, fwd, -dt, i, j, k, idx) : (Real)0;
 	Real dval = f;                                                   // MacCormackCorrect :81-91 (all cells)
 	if (flags[idx] & TypeFluid) dval = (Real)((double)dval + ((double)strength * 0.5) * (double)(orig[idx] - bwd));
 	if (in) {                                                        // MacCormackClamp :241-267
@@ -257,6 +371,64 @@ __global__ void __launch_bounds__(128) k_mc_rest(Dims d, const int* __restrict__
 	dst[idx] = dval;
 }
 
+// Pass 2 for a cell-centred Grid<Vec3>: MacCormackCorrect<Vec3> (the correction is narrowed before it is added: double * Vec3, then Vec3 += Vec3) and
+// doClampComponent<Vec3> (:141-186): minimum / maximum per component over the flagged corners; clampMode 2 resets the WHOLE vector when one
+// component leaves its range (cmpMinMax<Vec3> :134-136), clampMode 1 clamps component by component (clamp<Vec3> vectorbase.h:605-609)
+template <typename Real, int OS, int OT>
+__global__ void __launch_bounds__(128) k_mc_rest_vec3(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
+	const Real* __restrict__ fwd, Real dt, Real strength, int clampMode) {
+	int i, j, k; IndexInt idx;
+	if (!cellOf(d, i, j, k, idx)) return;
+	const bool in = isInterior(d, i, j, k);
+	const Real f[3] = { fwd[3 * idx], fwd[3 * idx + 1], fwd[3 * idx + 2] };
+	V3<Real> bw; bw.x = bw.y = bw.z = 0;
+	if (in) bw = slVec3<Real, OS, OT>(d, vel, fwd, -dt, i, j, k, idx);
+	const Real b[3] = { bw.x, bw.y, bw.z };
+	Real dv[3] = { f[0], f[1], f[2] };
+	if (flags[idx] & TypeFluid) {
+		#pragma unroll
+		for (int c = 0; c < 3; c++) dv[c] = dv[c] + (Real)(((double)strength * 0.5) * (double)(orig[3 * idx + c] - b[c]));
+	}
+	if (in) {
+		const V3<Real> cv = macCentered<Real>(d, vel, idx);
+		const Real v[3] = { cv.x * dt, cv.y * dt, cv.z * dt }, pos[3] = { (Real)i, (Real)j, (Real)k };
+		Real minv[3] = { realMax<Real>(), realMax<Real>(), realMax<Real>() }, maxv[3] = { -realMax<Real>(), -realMax<Real>(), -realMax<Real>() };
+		bool haveFl = false;
+		const int numPos = clampMode == 1 ? 2 : 1;
+		for (int l = 0; l < numPos; l++) {
+			int cp[3];
+			#pragma unroll
+			for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
+			const int i0 = iclamp(cp[0], 0, d.sx - 2), j0 = iclamp(cp[1], 0, d.sy - 2), k0 = iclamp(cp[2], 0, d.is3D ? d.sz - 2 : 1);
+			const int k1 = d.is3D ? k0 + 1 : k0;
+			for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++) for (int bb = 0; bb < 2; bb++) for (int a = 0; a < 2; a++) {
+				const IndexInt q = (IndexInt)(i0 + a) + d.Y * (j0 + bb) + d.Z * (cc ? k1 : k0);
+				if (checkFlag(flags, q)) {
+					#pragma unroll
+					for (int c = 0; c < 3; c++) { const Real o = orig[3 * q + c]; if (o < minv[c]) minv[c] = o; if (o > maxv[c]) maxv[c] = o; }
+					haveFl = true;
+				}
+			}
+		}
+		if (!haveFl) { dv[0] = f[0]; dv[1] = f[1]; dv[2] = f[2]; }
+		else if (clampMode == 1) {
+			#pragma unroll
+			for (int c = 0; c < 3; c++) dv[c] = dv[c] < minv[c] ? minv[c] : (dv[c] > maxv[c] ? maxv[c] : dv[c]);
+		} else if (dv[0] < minv[0] || dv[0] > maxv[0] || dv[1] < minv[1] || dv[1] > maxv[1] || dv[2] < minv[2] || dv[2] > maxv[2]) { dv[0] = f[0]; dv[1] = f[1]; dv[2] = f[2]; }
+		if (clampMode == 1) {
+			int pf[3], pb[3];
+			#pragma unroll
+			for (int a = 0; a < 3; a++) { pf[a] = (int)((pos[a] + (Real)0.5) - v[a]); pb[a] = (int)((pos[a] + (Real)0.5) + v[a]); }
+			const int ux = d.sx - 1, uy = d.sy - 1, uz = d.sz - 1;
+			bool bad = pf[0] < 0 || pf[1] < 0 || pf[2] < 0 || pb[0] < 0 || pb[1] < 0 || pb[2] < 0 ||
+			           pf[0] > ux || pf[1] > uy || ((pf[2] > uz) && d.is3D) || pb[0] > ux || pb[1] > uy || ((pb[2] > uz) && d.is3D);
+			if (!bad) bad = (flags[(IndexInt)pf[0] + d.Y * pf[1] + d.Z * pf[2]] & TypeObstacle) || (flags[(IndexInt)pb[0] + d.Y * pb[1] + d.Z * pb[2]] & TypeObstacle);
+			if (bad) { dv[0] = f[0]; dv[1] = f[1]; dv[2] = f[2]; }
+		}
+	}
+	dst[3 * idx] = dv[0]; dst[3 * idx + 1] = dv[1]; dst[3 * idx + 2] = dv[2];
+}
+
 template <typename Real, int C>     // doClampComponentMAC<c> :191-235
 __device__ __forceinline__ Real clampComponentMAC(const Dims& d, const int* __restrict__ flags, Real dst, const Real* __restrict__ orig, Real fwd,
 	int i, int j, int k, IndexInt idx, V3<Real> vel, int clampMode) {
@@ -285,7 +457,7 @@ __device__ __forceinline__ Real clampComponentMAC(const Dims& d, const int* __re
 }
 // Pass 2 for a MAC grid: backward trace + MacCormackCorrectMAC (:94-117, all cells) + MacCormackClampMAC (:270-287, interior);
 // *anyOutflow is raised when the flags hold an outflow cell, so that the boundary pass can be skipped otherwise
-template <typename Real>
+template <typename Real, int OS, int OT>
 __global__ void __launch_bounds__(128) k_mc_rest_mac(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
 	const Real* __restrict__ fwd, Real dt, Real strength, int clampMode, int* anyOutflow) {
 	int i, j, k; IndexInt idx;
@@ -295,7 +467,7 @@ __global__ void __launch_bounds__(128) k_mc_rest_mac(Dims d, const int* __restri
 	if (fl & TypeOutflow) *anyOutflow = 1;
 	const Real f[3] = { fwd[3 * idx], fwd[3 * idx + 1], fwd[3 * idx + 2] };
 	V3<Real> bw; bw.x = bw.y = bw.z = 0;
-	if (in) bw = slMAC<Real>(d, vel, fwd, -dt, i, j, k, idx);
+	if (in) bw = slMAC<Real, OS, OT>(d, vel, fwd, -dt, i, j, k, idx);
 	const Real b[3] = { bw.x, bw.y, bw.z };
 	bool skip[3] = { false, false, false };
 	if (!(fl & TypeFluid)) skip[0] = skip[1] = skip[2] = true;
@@ -392,29 +564,32 @@ int adopt(mp_context* ctx, mp_grid* grid, mp_grid* neu) {
 
 // Two passes per advection: (1) the forward trace, (2, MacCormack only) backward trace + correction + clamping; the reference's
 // four kernels and three temporaries (fwd, bwd, newGrid) become two kernels and two temporaries, every cell written exactly once.
-template <typename Real>
-int advect(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int clampMode, double dt_) {
+template <typename Real, int OS, int OT>
+int advect(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int clampMode, double dt_, bool vec3) {
 	const Dims d = dimsOf(flags);
-	const bool mac = grid->kind == MP_GRID_MAC;
+	const bool mac = grid->kind == MP_GRID_MAC && !vec3;
 	const Real dt = (Real)dt_;
 	const dim3 cg = cellGrid(d);
 	const int* F = (const int*)flags->d; const Real* V = (const Real*)vel->d;
 	Tmp fwd; MP_TRY(mp_grid_create_scratch(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &fwd.g));
-	if (mac) k_semi_lagrange_mac<Real><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
-	else     k_semi_lagrange<Real><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	if (vec3)     k_semi_lagrange_vec3<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	else if (mac) k_semi_lagrange_mac<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	else          k_semi_lagrange<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
 	MP_CHECK_LAUNCH(ctx);
 	if (order == 1) {
 		if (mac) MP_TRY(applyOutflowBC<Real>(ctx, d, flags, fwd.g, grid, (double)dt, nullptr));
 		return adopt(ctx, grid, fwd.g);
 	}
 	Tmp neu; MP_TRY(mp_grid_create_scratch(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &neu.g));
-	if (mac) {
+	if (vec3) {
+		k_mc_rest_vec3<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode); MP_CHECK_LAUNCH(ctx);
+	} else if (mac) {
 		int* any = (int*)(ctx->dScal + 24);
 		MP_CUDA(cudaMemsetAsync(any, 0, sizeof(int), ctx->stream));
-		k_mc_rest_mac<Real><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode, any); MP_CHECK_LAUNCH(ctx);
+		k_mc_rest_mac<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode, any); MP_CHECK_LAUNCH(ctx);
 		MP_TRY(applyOutflowBC<Real>(ctx, d, flags, neu.g, grid, (double)dt, any));
 	} else {
-		k_mc_rest<Real><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode); MP_CHECK_LAUNCH(ctx);
+		k_mc_rest<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode); MP_CHECK_LAUNCH(ctx);
 	}
 	return adopt(ctx, grid, neu.g);
 }
@@ -487,18 +662,32 @@ int mp_add_buoyancy(mp_context* ctx, const mp_grid* flags, const mp_grid* densit
 	}
 }
 
-int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
-                            int clampMode, int orderTrace, double dt)
+static int advectEntry(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
+                       int clampMode, int orderTrace, double dt, bool vec3)
 {
 	MP_TRY(checkStep("mp_advect_semi_lagrange", ctx, flags, vel));
 	if (!grid) MP_FAIL(MP_ERR_INVALID, "mp_advect_semi_lagrange: NULL grid");
 	if (order != 1 && order != 2) MP_FAIL(MP_ERR_INVALID, "AdvectSemiLagrange: Only order 1 (regular SL) and 2 (MacCormack) supported");
-	if (orderSpace != 1 || orderTrace != 1) MP_FAIL(MP_ERR_UNSUPPORTED, "advectSemiLagrange: orderSpace %d / orderTrace %d are not built (only 1 / 1, the defaults)", orderSpace, orderTrace);
-	if (grid->kind != MP_GRID_REAL && grid->kind != MP_GRID_MAC) MP_FAIL(MP_ERR_INVALID, "AdvectSemiLagrange: Grid Type is not supported (only Real, MAC, Levelset)");
+	if (orderSpace != 1 && orderSpace != 2) MP_FAIL(MP_ERR_INVALID, "Unknown interpolation order %d", orderSpace);      // grid.h:150
+	if (orderTrace != 1 && orderTrace != 2) MP_FAIL(MP_ERR_INVALID, "Unknown backtracing order %d", orderTrace);        // advection.cpp:39
+	if (grid->kind != MP_GRID_REAL && grid->kind != MP_GRID_MAC) MP_FAIL(MP_ERR_INVALID, "AdvectSemiLagrange: Grid Type is not supported (only Real, Vec3, MAC, Levelset)");
+	if (vec3 && grid->kind != MP_GRID_MAC) MP_FAIL(MP_ERR_INVALID, "mp_advect_semi_lagrange_vec3: grid does not hold Vec3 cells");
 	MP_TRY(mp_check_same(flags, grid, grid->kind, "grid", false));
 	if (flags->sx < 3 || flags->sy < 3 || (flags->sz > 1 && flags->sz < 3)) return MP_OK;       // no interior cells
-	if (grid->prec == 4) return advect<float>(ctx, flags, vel, grid, order, strength, clampMode, dt);
-	return advect<double>(ctx, flags, vel, grid, order, strength, clampMode, dt);
+#define MP_ADV(R) (orderSpace == 1 ? (orderTrace == 1 ? advect<R, 1, 1> : advect<R, 1, 2>) : (orderTrace == 1 ? advect<R, 2, 1> : advect<R, 2, 2>))(ctx, flags, vel, grid, order, strength, clampMode, dt, vec3)
+	if (grid->prec == 4) return MP_ADV(float);
+	return MP_ADV(double);
+#undef MP_ADV
+}
+int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
+                            int clampMode, int orderTrace, double dt)
+{
+	return advectEntry(ctx, flags, vel, grid, order, strength, orderSpace, clampMode, orderTrace, dt, false);
+}
+int mp_advect_semi_lagrange_vec3(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,
+                                 int clampMode, int orderTrace, double dt)
+{
+	return advectEntry(ctx, flags, vel, grid, order, strength, orderSpace, clampMode, orderTrace, dt, true);
 }
 
 }

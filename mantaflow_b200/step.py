@@ -61,10 +61,10 @@ def advectSemiLagrange(flags, vel, grid, order=1, strength=1.0, orderSpace=1, op
     if order not in (1, 2):
         raise MantaError(1, "AdvectSemiLagrange: Only order 1 (regular SL) and 2 (MacCormack) supported")
     from .grid import VecGrid
-    if isinstance(grid, VecGrid):       # same storage as a MACGrid, but cell-centred: the MAC kernels would silently give a different field
-        raise MantaError(5, "advectSemiLagrange: plain Grid<Vec3> advection is not built (only Real, MAC, Levelset)")
-    check(s.lib.mp_advect_semi_lagrange(s._ctx, flags.dev(), vel.dev(), grid.dev(), C.c_int(order), C.c_double(strength), C.c_int(orderSpace),
-                                        C.c_int(clampMode), C.c_int(orderTrace), C.c_double(s.timestep)))
+    # a Grid<Vec3> has the storage of a MACGrid but is cell-centred: fnAdvectSemiLagrange<Grid<Vec3>> (advection.cpp:455-457), not the MAC kernels
+    fn = s.lib.mp_advect_semi_lagrange_vec3 if isinstance(grid, VecGrid) else s.lib.mp_advect_semi_lagrange
+    check(fn(s._ctx, flags.dev(), vel.dev(), grid.dev(), C.c_int(order), C.c_double(strength), C.c_int(orderSpace),
+             C.c_int(clampMode), C.c_int(orderTrace), C.c_double(s.timestep)))
     grid.markDeviceWritten()
 
 

@@ -1334,27 +1334,116 @@ static inline void mac_at(const Real* v, int sx, int sy, int sz, IndexInt idx, i
 #undef Vc
 }
 
-/* SemiLagrange (advection.cpp:25-41, orderTrace 1) and SemiLagrangeMAC (:44-58): dst interior only, rest stays as it was */
-static void semi_lagrange_real(int sx, int sy, int sz, const Real* vel, Real* dst, const Real* src, Real dt)
+/* ---- higher-order lookups: util/interpolHigh.h.  cubicInterp :22-39 is instantiated for Real and for Vec3; the Vec3 one narrows after every
+ * scalar * vector product (vectorbase.h:272-279), the Real one forms the coefficients in double and narrows once. */
+static inline Real cubic_interp(Real t, const Real* p, int vec)
+{
+	const Real d0 = (Real)((double)(p[2] - p[0]) * 0.5), d1 = (Real)((double)(p[3] - p[1]) * 0.5), dk = p[2] - p[1];
+	Real a2, a3;
+	if (vec) { const Real q = (Real)(3.0 * (double)dk), r = (Real)(2.0 * (double)d0), u = (Real)(-2.0 * (double)dk); a2 = (q - r) - d1; a3 = (u + d0) + d1; }
+	else     { a2 = (Real)((3.0 * (double)dk - 2.0 * (double)d0) - (double)d1); a3 = (Real)((-2.0 * (double)dk + (double)d0) + (double)d1); }
+	const Real sq = t * t, cu = sq * t;
+	return ((a3 * cu + a2 * sq) + d0 * t) + p[1];
+}
+/* interpolCubic :78-172 / interpolCubic2D :42-76; stride 3 = one component of a Vec3 grid */
+static Real interpol_cubic_s(const Real* d, int stride, int sx, int sy, int sz, const Real pos[3])
+{
+	const Real px = pos[0] - 0.5f, py = pos[1] - 0.5f, pz = pos[2] - 0.5f;
+	const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
+	const int is3 = sz > 1, vec = stride == 3;
+	if (x1 - 1 < 0 || y1 - 1 < 0 || x1 + 2 >= sx || y1 + 2 >= sy || (is3 && (z1 - 1 < 0 || z1 + 2 >= sz))) return interpol_s(d, stride, sx, sy, sz, pos);
+	const Real tx = px - x1, ty = py - y1, tz = pz - z1;
+	Real zp[4];
+	for (int c = 0; c < (is3 ? 4 : 1); c++) {
+		Real yp[4];
+		for (int b = 0; b < 4; b++) {
+			Real row[4];
+			for (int a = 0; a < 4; a++) row[a] = d[((IndexInt)(x1 - 1 + a) + (IndexInt)sx * (y1 - 1 + b) + (is3 ? (IndexInt)sx * sy * (z1 - 1 + c) : 0)) * stride];
+			yp[b] = cubic_interp(tx, row, vec);
+		}
+		zp[c] = cubic_interp(ty, yp, vec);
+	}
+	return is3 ? cubic_interp(tz, zp, vec) : zp[0];
+}
+/* Grid<Real>::getInterpolatedHi grid.h:146-151 */
+static inline Real lookup_real(const Real* src, int sx, int sy, int sz, const Real pos[3], int orderSpace)
+{
+	return orderSpace == 1 ? interpol_s(src, 1, sx, sy, sz, pos) : interpol_cubic_s(src, 1, sx, sy, sz, pos);
+}
+/* MACGrid::getInterpolatedComponentHi<c> grid.h:268-273; order 2 = interpolCubicMAC(pos)[c] util/interpolHigh.h:174-181 (position moved by half a cell along c) */
+static inline Real lookup_mac(const Real* src, int sx, int sy, int sz, const Real pos[3], int c, int orderSpace)
+{
+	if (orderSpace == 1) return interpol_s(src + c, 3, sx, sy, sz, pos);
+	if (c == 2 && sz <= 1) return 0;
+	Real q[3] = { pos[0] + (Real)0, pos[1] + (Real)0, pos[2] + (Real)0 };
+	q[c] = pos[c] + (Real)0.5;
+	return interpol_cubic_s(src + c, 3, sx, sy, sz, q);
+}
+static void interpol_mac(int sx, int sy, int sz, const Real* data, const Real* pos, Real out[3]);
+
+/* SemiLagrange (advection.cpp:25-41) and SemiLagrangeMAC (:44-77): dst interior only, rest stays as it was.  orderTrace 2 = explicit midpoint;
+ * the MAC kernel then takes its velocities from src (:60-71), as the reference does. */
+static void semi_lagrange_real(int sx, int sy, int sz, const Real* vel, Real* dst, const Real* src, Real dt, int orderSpace, int orderTrace)
 {
 	STRIDES
 	FOR_BND1 {
 		const IndexInt idx = IDX(i, j, k);
 		Real c[3]; mac_centered(vel, sx, sy, sz, idx, c);
-		const Real pos[3] = { (i + 0.5f) - c[0] * dt, (j + 0.5f) - c[1] * dt, (k + 0.5f) - c[2] * dt };
-		dst[idx] = interpol_s(src, 1, sx, sy, sz, pos);
+		if (orderTrace == 1) {
+			const Real pos[3] = { (i + 0.5f) - c[0] * dt, (j + 0.5f) - c[1] * dt, (k + 0.5f) - c[2] * dt };
+			dst[idx] = lookup_real(src, sx, sy, sz, pos, orderSpace);
+		} else {
+			const Real p0[3] = { i + 0.5f, j + 0.5f, k + 0.5f };
+			Real p1[3], u[3], p2[3];
+			for (int a = 0; a < 3; a++) p1[a] = p0[a] - (Real)((double)(c[a] * dt) * 0.5);
+			interpol_mac(sx, sy, sz, vel, p1, u);
+			for (int a = 0; a < 3; a++) p2[a] = p0[a] - u[a] * dt;
+			dst[idx] = lookup_real(src, sx, sy, sz, p2, orderSpace);
+		}
 	}
 }
-static void semi_lagrange_mac(int sx, int sy, int sz, const Real* vel, Real* dst, const Real* src, Real dt)
+static void semi_lagrange_mac(int sx, int sy, int sz, const Real* vel, Real* dst, const Real* src, Real dt, int orderSpace, int orderTrace)
 {
 	STRIDES
 	FOR_BND1 {
 		const IndexInt idx = IDX(i, j, k);
 		for (int c = 0; c < 3; c++) {
-			Real m[3]; mac_at(vel, sx, sy, sz, idx, c, m);      /* getAtMACZ is evaluated in 2-D too (:53); its z stride is 0 there */
-			const Real pos[3] = { (i + 0.5f) - m[0] * dt, (j + 0.5f) - m[1] * dt, (k + 0.5f) - m[2] * dt };
-			dst[3 * idx + c] = interpol_s(src + c, 3, sx, sy, sz, pos);
+			Real m[3];
+			if (orderTrace == 1) {
+				mac_at(vel, sx, sy, sz, idx, c, m);      /* getAtMACZ is evaluated in 2-D too (:53); its z stride is 0 there */
+				const Real pos[3] = { (i + 0.5f) - m[0] * dt, (j + 0.5f) - m[1] * dt, (k + 0.5f) - m[2] * dt };
+				dst[3 * idx + c] = lookup_mac(src, sx, sy, sz, pos, c, orderSpace);
+			} else {
+				mac_at(src, sx, sy, sz, idx, c, m);
+				const Real p0[3] = { i + 0.5f, j + 0.5f, k + 0.5f };
+				Real f0[3] = { p0[0], p0[1], p0[2] }, p1[3], u[3], p2[3];
+				f0[c] = (Real)(c == 0 ? i : (c == 1 ? j : k));
+				for (int a = 0; a < 3; a++) p1[a] = f0[a] - (Real)((double)(m[a] * dt) * 0.5);
+				interpol_mac(sx, sy, sz, src, p1, u);
+				for (int a = 0; a < 3; a++) p2[a] = p0[a] - u[a] * dt;
+				dst[3 * idx + c] = lookup_mac(src, sx, sy, sz, p2, c, orderSpace);
+			}
 		}
+	}
+}
+
+/* SemiLagrange<Vec3>: a cell-centred Grid<Vec3>; the position of the Real kernel, one lookup per component */
+static void semi_lagrange_vec3(int sx, int sy, int sz, const Real* vel, Real* dst, const Real* src, Real dt, int orderSpace, int orderTrace)
+{
+	STRIDES
+	FOR_BND1 {
+		const IndexInt idx = IDX(i, j, k);
+		Real c[3], pos[3]; mac_centered(vel, sx, sy, sz, idx, c);
+		if (orderTrace == 1) { pos[0] = (i + 0.5f) - c[0] * dt; pos[1] = (j + 0.5f) - c[1] * dt; pos[2] = (k + 0.5f) - c[2] * dt; }
+		else {
+			const Real p0[3] = { i + 0.5f, j + 0.5f, k + 0.5f };
+			Real p1[3], u[3];
+			for (int a = 0; a < 3; a++) p1[a] = p0[a] - (Real)((double)(c[a] * dt) * 0.5);
+			interpol_mac(sx, sy, sz, vel, p1, u);
+			for (int a = 0; a < 3; a++) pos[a] = p0[a] - u[a] * dt;
+		}
+		for (int a = 0; a < 3; a++)
+			dst[3 * idx + a] = orderSpace == 1 ? interpol_s(src + a, 3, sx, sy, sz, pos) : interpol_cubic_s(src + a, 3, sx, sy, sz, pos);
 	}
 }
 
@@ -1465,28 +1554,33 @@ static void apply_outflow_bc(int sx, int sy, int sz, const int* flags, Real* vel
 }
 
 /* advectSemiLagrange: advection.cpp:442-461, fnAdvectSemiLagrange :289-316 (Real) and :404-434 (MAC).
- * kind 0: Grid<Real> (density, level set), 1: MACGrid.  orderSpace 1 and orderTrace 1 only (the defaults). */
+ * kind 0: Grid<Real> (density, level set), 1: MACGrid, 2: cell-centred Grid<Vec3>.  orderSpace 1 / 2, orderTrace 1 / 2. */
 int mfo_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Real* vel, Real* grid, int kind,
                              int order, double strength_, int orderSpace, int clampMode, int orderTrace, double dt_)
 {
 	STRIDES
 	if (order != 1 && order != 2) { snprintf(g_err, sizeof g_err, "AdvectSemiLagrange: Only order 1 (regular SL) and 2 (MacCormack) supported"); return 1; }
-	if (orderSpace != 1 || orderTrace != 1) { snprintf(g_err, sizeof g_err, "oracle: only orderSpace 1 / orderTrace 1 are restated"); return 1; }
-	if (kind != 0 && kind != 1) { snprintf(g_err, sizeof g_err, "oracle: grid kind %d not restated", kind); return 1; }
+	if (orderSpace != 1 && orderSpace != 2) { snprintf(g_err, sizeof g_err, "Unknown interpolation order %d", orderSpace); return 1; }
+	if (orderTrace != 1 && orderTrace != 2) { snprintf(g_err, sizeof g_err, "Unknown backtracing order %d", orderTrace); return 1; }
+	if (kind != 0 && kind != 1 && kind != 2) { snprintf(g_err, sizeof g_err, "oracle: grid kind %d not restated", kind); return 1; }
 	const IndexInt n = (IndexInt)sx * sy * sz;
 	const int nc = kind == 0 ? 1 : 3;
 	const Real dt = (Real)dt_, strength = (Real)strength_;
 	Real* fwd = (Real*)calloc((size_t)n * nc, sizeof(Real));
-	if (kind == 0) semi_lagrange_real(sx, sy, sz, vel, fwd, grid, dt); else semi_lagrange_mac(sx, sy, sz, vel, fwd, grid, dt);
+	if (kind == 0) semi_lagrange_real(sx, sy, sz, vel, fwd, grid, dt, orderSpace, orderTrace);
+	else if (kind == 1) semi_lagrange_mac(sx, sy, sz, vel, fwd, grid, dt, orderSpace, orderTrace);
+	else semi_lagrange_vec3(sx, sy, sz, vel, fwd, grid, dt, orderSpace, orderTrace);
 	if (order == 1) {
-		if (kind == 1) apply_outflow_bc(sx, sy, sz, flags, fwd, grid, (double)dt);
+		if (kind == 1) apply_outflow_bc(sx, sy, sz, flags, fwd, grid, (double)dt);      /* MAC grids only */
 		memcpy(grid, fwd, sizeof(Real) * (size_t)n * nc);
 		free(fwd);
 		return 0;
 	}
 	Real* bwd = (Real*)calloc((size_t)n * nc, sizeof(Real));
 	Real* neu = (Real*)calloc((size_t)n * nc, sizeof(Real));
-	if (kind == 0) semi_lagrange_real(sx, sy, sz, vel, bwd, fwd, -dt); else semi_lagrange_mac(sx, sy, sz, vel, bwd, fwd, -dt);
+	if (kind == 0) semi_lagrange_real(sx, sy, sz, vel, bwd, fwd, -dt, orderSpace, orderTrace);
+	else if (kind == 1) semi_lagrange_mac(sx, sy, sz, vel, bwd, fwd, -dt, orderSpace, orderTrace);
+	else semi_lagrange_vec3(sx, sy, sz, vel, bwd, fwd, -dt, orderSpace, orderTrace);
 	const double half = (double)strength * 0.5;
 	if (kind == 0) {
 		/* MacCormackCorrect :81-91 (all cells) */
@@ -1511,6 +1605,47 @@ int mfo_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Rea
 				if (bad) dval = fwd[idx];
 			}
 			neu[idx] = dval;
+		}
+	} else if (kind == 2) {
+		/* MacCormackCorrect<Vec3> :81-91: the correction is narrowed before it is added (double * Vec3, then Vec3 += Vec3) */
+		for (IndexInt idx = 0; idx < n; idx++) for (int c = 0; c < 3; c++) {
+			const IndexInt q = 3 * idx + c;
+			neu[q] = fwd[q];
+			if (flags[idx] & TypeFluid) neu[q] = neu[q] + (Real)(half * (double)(grid[q] - bwd[q]));
+		}
+		/* MacCormackClamp<Vec3> :241-267 with doClampComponent<Vec3> :141-186 (getMinMax / cmpMinMax<Vec3> :119-136, clamp<Vec3> vectorbase.h:605-609) */
+		FOR_BND1 {
+			const IndexInt idx = IDX(i, j, k);
+			Real cv[3]; mac_centered(vel, sx, sy, sz, idx, cv);
+			const Real v[3] = { cv[0] * dt, cv[1] * dt, cv[2] * dt };
+			const Real pos[3] = { (Real)i, (Real)j, (Real)k };
+			Real minv[3] = { REAL_MAX_, REAL_MAX_, REAL_MAX_ }, maxv[3] = { -REAL_MAX_, -REAL_MAX_, -REAL_MAX_ };
+			int haveFl = 0;
+			for (int l = 0; l < (clampMode == 1 ? 2 : 1); l++) {
+				int cp[3];
+				for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
+				const int i0 = iclamp(cp[0], 0, sx - 2), j0 = iclamp(cp[1], 0, sy - 2), k0 = iclamp(cp[2], 0, IS3D ? sz - 2 : 1);
+				const int k1 = IS3D ? k0 + 1 : k0;
+				for (int cc = 0; cc < (IS3D ? 2 : 1); cc++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
+					const IndexInt q = IDX(i0 + a, j0 + b, cc ? k1 : k0);
+					if (!check_flag(flags, q)) continue;
+					for (int c = 0; c < 3; c++) { const Real o = grid[3 * q + c]; if (o < minv[c]) minv[c] = o; if (o > maxv[c]) maxv[c] = o; }
+					haveFl = 1;
+				}
+			}
+			Real* dv = neu + 3 * idx; const Real* f = fwd + 3 * idx;
+			if (!haveFl) { dv[0] = f[0]; dv[1] = f[1]; dv[2] = f[2]; }
+			else if (clampMode == 1) { for (int c = 0; c < 3; c++) dv[c] = dv[c] < minv[c] ? minv[c] : (dv[c] > maxv[c] ? maxv[c] : dv[c]); }
+			else if (dv[0] < minv[0] || dv[0] > maxv[0] || dv[1] < minv[1] || dv[1] > maxv[1] || dv[2] < minv[2] || dv[2] > maxv[2]) { dv[0] = f[0]; dv[1] = f[1]; dv[2] = f[2]; }
+			if (clampMode == 1) {
+				int pf[3], pb[3];
+				for (int d = 0; d < 3; d++) { pf[d] = (int)((pos[d] + (Real)0.5) - v[d]); pb[d] = (int)((pos[d] + (Real)0.5) + v[d]); }
+				const int ux = sx - 1, uy = sy - 1, uz = sz - 1;
+				int bad = pf[0] < 0 || pf[1] < 0 || pf[2] < 0 || pb[0] < 0 || pb[1] < 0 || pb[2] < 0 ||
+				          pf[0] > ux || pf[1] > uy || ((pf[2] > uz) && IS3D) || pb[0] > ux || pb[1] > uy || ((pb[2] > uz) && IS3D);
+				if (!bad) bad = (flags[IDX(pf[0], pf[1], pf[2])] & TypeObstacle) || (flags[IDX(pb[0], pb[1], pb[2])] & TypeObstacle);
+				if (bad) { dv[0] = f[0]; dv[1] = f[1]; dv[2] = f[2]; }
+			}
 		}
 	} else {
 		/* MacCormackCorrectMAC :94-117 (all cells, isMAC) */

@@ -101,10 +101,10 @@ class Oracle:
                                           C.c_double(coefficient), C.c_int(int(scale)), C.c_double(dt)))
         return vel
 
-    def advect_semi_lagrange(self, flags, vel, grid, order=1, strength=1.0, orderSpace=1, clampMode=2, orderTrace=1, dt=1.0):
-        """grid: (sz,sy,sx) Real grid or (sz,sy,sx,3) MAC grid, advected in place"""
+    def advect_semi_lagrange(self, flags, vel, grid, order=1, strength=1.0, orderSpace=1, clampMode=2, orderTrace=1, dt=1.0, vec3=False):
+        """grid: (sz,sy,sx) Real grid or (sz,sy,sx,3) MAC grid (vec3=True: a cell-centred Grid<Vec3>), advected in place"""
         assert grid.dtype == self.real and grid.flags.c_contiguous
-        kind = 1 if grid.ndim == 4 else 0
+        kind = (2 if vec3 else 1) if grid.ndim == 4 else 0
         self._chk(self._f("advect_semi_lagrange")(*self.dims(flags), _p(flags), _p(self._r(vel)), _p(grid), C.c_int(kind), C.c_int(order),
                                                   C.c_double(strength), C.c_int(orderSpace), C.c_int(clampMode), C.c_int(orderTrace), C.c_double(dt)))
         return grid

@@ -415,7 +415,7 @@ int ref_grid_file(int sx, int sy, int sz, int kind, void* data, const char* name
 	if (!ok) { gLastError = std::string("Grid::") + (load ? "load" : "save") + " returned 0 for " + name; return 1; }
   CATCH }
 
-// kind 0: Grid<Real>, 1: MACGrid.  The plugin swaps its result in, which the reference forbids for external data: work on solver-owned copies.
+// kind 0: Grid<Real>, 1: MACGrid, 2: Grid<Vec3>.  The plugin swaps its result in, which the reference forbids for external data: work on solver-owned copies.
 int ref_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Real* vel, Real* grid, int kind,
 	int order, double strength, int orderSpace, int clampMode, int orderTrace, double dt)
 { TRY
@@ -425,6 +425,9 @@ int ref_advect_semi_lagrange(int sx, int sy, int sz, const int* flags, const Rea
 	  if (kind == 0) { Grid<Real> G(s); memcpy(&G[0], grid, n * sizeof(Real));
 	    advectSemiLagrange(&F, &V, &G, order, (Real)strength, orderSpace, false, -1, clampMode, orderTrace);
 	    memcpy(grid, &G[0], n * sizeof(Real)); }
+	  else if (kind == 2) { Grid<Vec3> G(s); memcpy(&G[0], grid, n * sizeof(Vec3));
+	    advectSemiLagrange(&F, &V, &G, order, (Real)strength, orderSpace, false, -1, clampMode, orderTrace);
+	    memcpy(grid, &G[0], n * sizeof(Vec3)); }
 	  else { MACGrid G(s); memcpy(&G[0], grid, n * sizeof(Vec3));
 	    MACGrid Vc(s); memcpy(&Vc[0], vel, n * sizeof(Vec3));      // self-advection passes the same grid as vel and grid: keep that aliasing out of the harness
 	    advectSemiLagrange(&F, &Vc, &G, order, (Real)strength, orderSpace, false, -1, clampMode, orderTrace);

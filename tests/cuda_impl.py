@@ -151,10 +151,10 @@ class CudaImpl:
         vel[...] = V.numpy()
         return vel
 
-    def advect_semi_lagrange(self, flags, vel, grid, order=1, strength=1.0, orderSpace=1, clampMode=2, orderTrace=1, dt=1.0):
+    def advect_semi_lagrange(self, flags, vel, grid, order=1, strength=1.0, orderSpace=1, clampMode=2, orderTrace=1, dt=1.0, vec3=False):
         s = self._solver(flags); s.timestep = dt
         V = mf.MACGrid(s, vel)
-        G = V if grid is vel else (mf.RealGrid if grid.ndim == 3 else mf.MACGrid)(s, grid)      # self-advection: one grid, as in the scenes
+        G = V if grid is vel else (mf.RealGrid if grid.ndim == 3 else (mf.VecGrid if vec3 else mf.MACGrid))(s, grid)      # self-advection: one grid, as in the scenes
         mf.advectSemiLagrange(mf.FlagGrid(s, flags), V, G, order=order, strength=strength, orderSpace=orderSpace, clampMode=clampMode, orderTrace=orderTrace)
         grid[...] = G.numpy()
         return grid

@@ -160,6 +160,7 @@ def step_fixtures():
             path = os.path.join(HERE, "step_%s_f%d.npz" % (name, prec * 8))
             np.savez_compressed(path, **fx)
             print("%-34s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+        step_hi_fixtures(R, prec)
         for name in helpers.WE_SCENES:       # cgSolveWE: three implicit wave steps, plain and Crank-Nicolson
             fx = {}
             for cn in (False, True):
@@ -178,6 +179,23 @@ def step_fixtures():
         path = os.path.join(HERE, "plume%s_f32.npz" % tag)
         np.savez_compressed(path, density=dens, vel=vel, pressure=p, iterations=np.array(its))
         print("%-34s %7.1f KiB  its %s  max density %.3f" % (os.path.basename(path), os.path.getsize(path) / 1024, its, float(dens.max())))
+
+
+def step_hi_fixtures(R=None, prec=None):
+    """step_hi_<scene>_f{32,64}.npz: the reference's advectSemiLagrange with orderSpace 2 (cubic lookups) and / or orderTrace 2 (explicit midpoint),
+    Real and MAC grids, plain and MacCormack, on the seeded scenes of tests/helpers.py"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import helpers
+    for pr in ((4, 8) if prec is None else (prec,)):
+        Rr = Oracle("reference", pr) if R is None or prec is None else R
+        for name in helpers.STEP_HI_SCENES:
+            flags, vel, dens, obvel = helpers.step_scene(name, pr)
+            fx = dict(flags=flags, vel=vel)
+            for case in helpers.STEP_HI_CASES:
+                fx[case] = helpers.run_step_hi_case(Rr, case, flags, vel, dens, obvel)
+            path = os.path.join(HERE, "step_hi_%s_f%d.npz" % (name, pr * 8))
+            np.savez_compressed(path, **fx)
+            print("%-34s %7.1f KiB" % (os.path.basename(path), os.path.getsize(path) / 1024))
 
 
 def liquid_fixtures():
@@ -289,6 +307,8 @@ def main():
         return vic_fixtures()
     if "--only-dam" in sys.argv:
         return dam_fixtures()
+    if "--only-step-hi" in sys.argv:
+        return step_hi_fixtures()
     if "--only-liquid" in sys.argv:
         return liquid_fixtures()
     if "--only-step" in sys.argv:

@@ -193,6 +193,55 @@ def run_step_case(I, case, flags, vel, dens, obvel):
     raise KeyError(case)
 
 
+# advectSemiLagrange with cubic lookups (orderSpace 2, util/interpolHigh.h) and explicit-midpoint back-tracing (orderTrace 2, advection.cpp:32-37, :58-73)
+STEP_HI_SCENES = ["box3d", "box2d"]
+STEP_HI_ORDERS = [(2, 1), (1, 2), (2, 2)]          # (orderSpace, orderTrace)
+STEP_HI_KINDS = ["real_o1", "real_o2_c2", "real_o2_c1", "mac_o1", "mac_o2_c2", "mac_o2_c1", "self_o2", "vec3_o1", "vec3_o2_c2", "vec3_o2_c1"]
+# a cell-centred Grid<Vec3> (fnAdvectSemiLagrange<Grid<Vec3>>, advection.cpp:455-457) also with the default orders
+STEP_HI_CASES = (["advhi_%s_s%dt%d" % (k, os_, ot) for (os_, ot) in STEP_HI_ORDERS for k in STEP_HI_KINDS] +
+                 ["advhi_%s_s1t1" % k for k in STEP_HI_KINDS if k.startswith("vec3")])
+
+
+def run_step_hi_case(I, case, flags, vel, dens, obvel):
+    kind, orders = case[len("advhi_"):].rsplit("_", 1)
+    kw = dict(orderSpace=int(orders[1]), orderTrace=int(orders[3]))
+    if kind == "real_o1":
+        return I.advect_semi_lagrange(flags, vel, dens.copy(), order=1, dt=0.8, **kw)
+    if kind == "real_o2_c2":
+        return I.advect_semi_lagrange(flags, vel, dens.copy(), order=2, clampMode=2, dt=0.8, **kw)
+    if kind == "real_o2_c1":
+        return I.advect_semi_lagrange(flags, vel, dens.copy(), order=2, clampMode=1, strength=0.8, dt=0.8, **kw)
+    if kind == "mac_o1":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=1, dt=0.8, **kw)
+    if kind == "mac_o2_c2":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=2, clampMode=2, dt=0.8, **kw)
+    if kind == "mac_o2_c1":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=2, clampMode=1, dt=1.7, **kw)
+    if kind == "self_o2":
+        v = vel.copy()
+        return I.advect_semi_lagrange(flags, v, v, order=2, dt=0.8, **kw)
+    if kind == "vec3_o1":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=1, dt=0.8, vec3=True, **kw)
+    if kind == "vec3_o2_c2":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=2, clampMode=2, dt=0.8, vec3=True, **kw)
+    if kind == "vec3_o2_c1":
+        return I.advect_semi_lagrange(flags, vel, obvel.copy(), order=2, clampMode=1, strength=0.9, dt=1.3, vec3=True, **kw)
+    raise KeyError(case)
+
+
+def check_step_hi_against_golden(I, name, prec):
+    """the higher-order advection variants bit for bit against the reference's output on the same seeded inputs"""
+    g = load_golden("step_hi_" + name, prec)
+    flags, vel, dens, obvel = step_scene(name, prec)
+    assert np.array_equal(flags, g["flags"]) and np.array_equal(vel, g["vel"])
+    lin = run_step_case(I, "adv_real_o1", flags, vel, dens, obvel)
+    for case in STEP_HI_CASES:
+        out = run_step_hi_case(I, case, flags, vel, dens, obvel)
+        assert np.array_equal(out, g[case]), (name, prec, case, float(np.abs(out.astype(np.float64) - g[case]).max()))
+        if case.startswith("advhi_real_o1"):
+            assert not np.array_equal(out, lin), case           # the variant really takes another path than the defaults
+
+
 def check_step_against_golden(I, name, prec):
     """every step plugin bit for bit against the reference's output on the same seeded inputs"""
     g = load_golden("step_" + name, prec)

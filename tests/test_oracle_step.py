@@ -38,7 +38,17 @@ def test_unsupported_orders_are_errors(port32):
     with pytest.raises(OracleError):
         port32.advect_semi_lagrange(flags, vel, dens.copy(), order=3)
     with pytest.raises(OracleError):
-        port32.advect_semi_lagrange(flags, vel, dens.copy(), order=1, orderSpace=2)
+        port32.advect_semi_lagrange(flags, vel, dens.copy(), order=1, orderSpace=3)
+    with pytest.raises(OracleError):
+        port32.advect_semi_lagrange(flags, vel, dens.copy(), order=1, orderTrace=3)
+
+
+@pytest.mark.parametrize("prec", [4, 8])
+@pytest.mark.parametrize("name", ["box3d", "box2d"])
+def test_port_reproduces_higher_order_advection_golden(name, prec, port32, port64):
+    """orderSpace 2 (cubic lookups) / orderTrace 2 (explicit midpoint): the restatement against the reference's output, bit for bit"""
+    from helpers import check_step_hi_against_golden
+    check_step_hi_against_golden(port32 if prec == 4 else port64, name, prec)
 
 
 @pytest.mark.parametrize("prec", [4, 8])
