@@ -56,6 +56,10 @@ rows = [
     # two passes: forward trace (vel + src read, fwd written), then backward trace + correction + clamping (vel, fwd, orig, flags read, result written)
     ("advectSemiLagrange density order 2 (MacCormack)", lambda: mf.advectSemiLagrange(F, V, D, order=2), (3 * w + 2 * w) + (4 + 3 * w + 3 * w)),
     ("advectSemiLagrange vel order 2 (MacCormack)", lambda: mf.advectSemiLagrange(F, V, V, order=2), (3 * w + 3 * w + 3 * w) + (4 + 3 * w + 3 * w + 3 * w + 3 * w)),
+    # round 2: cubic lookups (64 reads per lookup, all from the neighbourhood of the traced position) and explicit-midpoint back-tracing
+    ("advectSemiLagrange density order 2, orderSpace 2", lambda: mf.advectSemiLagrange(F, V, D, order=2, orderSpace=2), (3 * w + 2 * w) + (4 + 3 * w + 3 * w)),
+    ("advectSemiLagrange density order 2, orderTrace 2", lambda: mf.advectSemiLagrange(F, V, D, order=2, orderTrace=2), (3 * w + 2 * w) + (4 + 3 * w + 3 * w)),
+    ("advectSemiLagrange vel order 2, orderSpace 2 orderTrace 2", lambda: mf.advectSemiLagrange(F, V, V, order=2, orderSpace=2, orderTrace=2), (3 * w + 3 * w + 3 * w) + (4 + 3 * w + 3 * w + 3 * w + 3 * w)),
 ]
 out = {"res": res, "prec": prec, "peak_gbs": PEAK, "plugins": {}}
 print(f"# {res}^3 float, one B200; algorithmic bytes = compulsory reads + writes of every pass of the plugin")
@@ -102,4 +106,4 @@ try:
 except Exception as e:      # the reference library is test infrastructure; the bench still reports the device numbers without it
     print("cpu leg skipped:", e)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r1_step_bench.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "step_bench.json"), "w"), indent=1)
