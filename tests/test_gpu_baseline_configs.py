@@ -99,7 +99,10 @@ def test_baseline_config_against_reference(name):
         report.append((pc, info["iterations"], it_o, e, div_g, div_o))
         print("%s %s pc %d: iterations %d (reference %d) pressure rel-L2 %.2e max|div| %.3e (reference %.3e)" % (name, O.kind, pc, info["iterations"], it_o, e, div_g, div_o))
         loose = prec == 8 and acc > 1e-9 and pc == 1         # see the comment at CASES["smoke128_f64"]
-        assert abs(info["iterations"] - it_o) <= (4 if loose else 1), report[-1]
+        # the iteration count of the reference's double PcMIC solve moves with the order of its own OpenMP reductions at either accuracy (78 / 81 at
+        # 1e-4; at 1e-10: 241 on one B200 box, 239-240 on others; this path: 239 every time), so its own spread is the bar there; the converged
+        # pressures are still held to 1e-10 below
+        assert abs(info["iterations"] - it_o) <= (4 if (prec == 8 and pc == 1) else 1), report[-1]
         assert e <= (1e-6 if loose else TOL[prec]), report[-1]
         assert rel_l2(v_g, v_o) <= (1e-5 if loose else TOL[prec]), report[-1]      # the velocity correction is a difference of pressures: ~20x the pressure's relative spread
         if phi is None:
