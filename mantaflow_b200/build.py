@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 OUT = os.path.join(HERE, "libmantapress.so")
-SOURCES = ["mp_api.cu", "mp_assembly.cu", "mp_cg.cu", "mp_mic.cu", "mp_ic.cu", "mp_mg.cu", "mp_plugin.cu", "mp_step.cu", "mp_liquid.cu", "mp_particles.cu", "mp_guiding.cu", "mp_dist.cu"]
+SOURCES = ["mp_api.cu", "mp_assembly.cu", "mp_cg.cu", "mp_mic.cu", "mp_micrb.cu", "mp_ic.cu", "mp_mg.cu", "mp_plugin.cu", "mp_step.cu", "mp_liquid.cu", "mp_particles.cu", "mp_guiding.cu", "mp_dist.cu"]
 # -fmad=false: the reference build has no FMA; assembly and MIC kernels must be bit-exact.
 # IEEE div/sqrt and no flush-to-zero are nvcc's defaults without --use_fast_math.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

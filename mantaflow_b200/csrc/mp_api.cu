@@ -68,6 +68,7 @@ int mp_context_destroy(mp_context* c) {
 	c->pool.clear();
 	for (auto& e : c->profEv) cudaEventDestroy(e);
 	for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	mp_micrb_release(c);
 	if (c->micProg) cudaFree(c->micProg);
 	if (c->micMask) cudaFree(c->micMask);
 	if (c->micOrder) cudaFree(c->micOrder);

@@ -23,6 +23,7 @@ void mp_set_error(const char* fmt, ...);
 
 // ---------------------------------------------------------------- context / grid
 struct DistState;   // below
+struct mp_micrb_state;
 
 struct mp_context {
 	int device = 0;
@@ -55,6 +56,8 @@ struct mp_context {
 	int* micStall = nullptr;                              // raised by a MIC sweep whose dependency wait ran out of budget
 	int* micOrder = nullptr; int micOrderCount = 0;       // dispatch order of the warp columns
 	int* micProg = nullptr; size_t micProgBytes = 0;     // per-column progress counters (+ stall flag) of the pipelined MIC sweeps
+	int micRb = 0, micRbTY = 0, micRbTZ = 0;             // mp_set_mic_ordering: 1 = block red-black ordering (mp_micrb.cu) with tiles of TY x TZ rows
+	struct mp_micrb_state* micRbState = nullptr;         // its byte mask and geometry
 	int lastMatvecKernel = 0;     // which matvec instantiation the last launch used (reported in mp_solve_info)
 };
 static const int kMaxPartials = 1 << 16;   // max blocks of a reducing kernel
@@ -228,3 +231,11 @@ __device__ __forceinline__ bool blockReduceFinal(double (&v)[NV], const bool (&i
 	return blockReduceFinalL<NV>(v, isMax, partials, ticket, fin, threadIdx.x, blockDim.x, blockIdx.x, gridDim.x);
 }
 #endif
+
+// MIC(0) in block red-black ordering (mp_micrb.cu)
+int  mp_micrb_prepare(mp_context* ctx, const mp_grid* flags, const mp_grid* P, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, bool* use);
+bool mp_micrb_active(const mp_context* ctx, const mp_grid* flags, const mp_grid* P);
+int  mp_micrb_init_launch(mp_context* ctx, mp_grid* P, const mp_grid* A0);
+int  mp_micrb_apply_launch(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* P, const int* doneFlag);
+void mp_micrb_release(mp_context* ctx);
+void mp_micrb_tiles(const mp_context* ctx, int* ty, int* tz);

@@ -745,6 +745,11 @@ int mp_mic_init_launch(mp_context* ctx, const mp_grid* flags, mp_grid* P, const 
 {
 	const Dims d = dimsOf(flags);
 	if (!d.is3D) MP_FAIL(MP_ERR_INVALID, "mICP only supports 3D grids so far");
+	{	// mp_set_mic_ordering(ctx, 1, ...): MIC(0) of the block red-black ordering (mp_micrb.cu) when the matrix allows it
+		bool rb = false;
+		MP_TRY(mp_micrb_prepare(ctx, flags, P, Ai, Aj, Ak, &rb));
+		if (rb) return mp_micrb_init_launch(ctx, P, A0);
+	}
 	MP_CUDA(cudaMemsetAsync(P->d, 0, P->bytes, ctx->stream));          // Aprecond.clear() :71
 	if (d.sx < 3 || d.sy < 3 || d.sz < 3) return MP_OK;
 	const int variant = micVariantFor(P);
@@ -774,6 +779,7 @@ int mp_mic_apply_launch(mp_context* ctx, mp_grid* dst, const mp_grid* var1, cons
 	const Dims d = dimsOf(flags);
 	if (!d.is3D) MP_FAIL(MP_ERR_INVALID, "mICP only supports 3D grids so far");
 	if (d.sx < 3 || d.sy < 3 || d.sz < 3) return MP_OK;
+	if (mp_micrb_active(ctx, flags, P)) return mp_micrb_apply_launch(ctx, dst, var1, P, doneFlag);     // the factor in P is the block red-black one
 	const int variant = micVariantFor(dst);
 	if (variant == 4) {
 		if (ctx->micMaskFor != flags || ctx->micMaskPrec != dst->prec) MP_TRY(micWarpPrepare(ctx, d, flags, dst->prec));

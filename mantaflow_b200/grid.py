@@ -80,6 +80,12 @@ class Solver:
             raise _lib.MantaError(1, "Invalid dt encountered! Shouldnt happen...")
         self.timestep = float(dt)
 
+    def setMicOrdering(self, mode=0, tileY=0, tileZ=0):
+        """the ordering MIC(0) (PcMIC, GridCg PC_mICP, Init/ApplyPreconditionModifiedIncompCholesky2) is formed in: 0 the reference's
+        lexicographic one (default, bit-identical to the reference), 1 block red-black with tiles of tileY x tileZ rows -- the reformulated,
+        bandwidth-bound preconditioner; more iterations, reported by lastSolveInfo() (mp_set_mic_ordering)"""
+        check(self.lib.mp_set_mic_ordering(self._ctx, int(mode), int(tileY), int(tileZ)))
+
     def trim(self):
         """return the context's pooled (unused) device blocks to the driver (mp_context_trim)"""
         check(self.lib.mp_context_trim(self._ctx))

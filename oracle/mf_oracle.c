@@ -367,6 +367,118 @@ int mfo_mic_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Rea
 	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
 { (void)A0; mic_apply(sx, sy, sz, flags, dst, src, P, Ai, Aj, Ak); return 0; }
 
+/* ---------------------------------------------------------------------------------------------
+ * MIC(0) in BLOCK RED-BLACK ordering -- the reformulated preconditioner north_star (4) allows ("level-scheduled or colored triangular
+ * solves", iteration counts reported).  NO REFERENCE COUNTERPART: this is the specification of the device kernels k_micrb<MODE>
+ * (csrc/mp_micrb.cu), pinned in two ways: (a) with one tile covering the grid the ordering is the reference's and factor and sweeps equal
+ * mic_init / mic_apply (conjugategrad.cpp:66-97, :135-159) bit for bit; (b) the factor of a small grid is checked against a dense
+ * incomplete Cholesky factorization of the permuted matrix (tests/test_micrb.py).
+ * Ordering: the grid is cut into tiles of T0 x T1 x T2 cells; tiles with even (tx+ty+tz) come first ("red"), then the odd ones ("black"),
+ * cells in lexicographic order inside a tile.  A 7-point stencil couples tiles through faces only, so tiles of one colour are independent.
+ * For a cell c and a face neighbour n: n precedes c iff (same tile and n is lexicographically earlier) or (other tile and n is red).
+ *   e_c = A_cc - sum_{n prec c} (A_cn P_n)^2 - tau * sum_{n prec c} A_cn * (sum_{s succ n, s != c} A_ns) * P_n^2,  P_c = 1/sqrt(e_c)
+ *   forward  z_c = P_c (r_c - sum_{n prec c} z_n A_cn P_n),  backward  z_c = P_c (z_c - sum_{s succ c} z_s A_cs P_c)
+ * with the reference's safety rule (e < sigma A_cc -> e = A_cc) and its mixed Real / double roundings.  Order of the terms: first the
+ * neighbours in OTHER tiles (direction order -x,-y,-z,+x,+y,+z), then the neighbours in the cell's own tile in the reference's order
+ * (-x,-y,-z forward and in the factor, +x,+y,+z backward) -- with one tile that is the reference's expression.                        */
+static int g_mic_tile[3] = { 1 << 30, 1 << 30, 1 << 30 };
+int mfo_set_mic_tiles(int t0, int t1, int t2) { g_mic_tile[0] = t0 > 0 ? t0 : 1 << 30; g_mic_tile[1] = t1 > 0 ? t1 : 1 << 30; g_mic_tile[2] = t2 > 0 ? t2 : 1 << 30; return 0; }
+static inline int rb_colour(int i, int j, int k) { return (i / g_mic_tile[0] + j / g_mic_tile[1] + k / g_mic_tile[2]) & 1; }
+/* direction q (0..5 = -x,-y,-z,+x,+y,+z) from cell (i,j,k): does it leave the cell's tile? */
+static inline int rb_leaves(int i, int j, int k, int q)
+{
+	const int c[3] = { i, j, k }; const int a = q % 3;
+	return c[a] / g_mic_tile[a] != (c[a] + (q >= 3 ? 1 : -1)) / g_mic_tile[a];
+}
+/* does the neighbour of cell (i,j,k) in direction q precede it?  (the neighbour must lie in the grid) */
+static inline int rb_prec(int i, int j, int k, int q)
+{
+	if (!rb_leaves(i, j, k, q)) return q < 3;
+	return rb_colour(i, j, k) == 1;                             /* the neighbour's tile has the other colour; red comes first */
+}
+static const int rb_di[6] = { -1, 0, 0, 1, 0, 0 }, rb_dj[6] = { 0, -1, 0, 0, 1, 0 }, rb_dk[6] = { 0, 0, -1, 0, 0, 1 };
+static void micrb_init(int sx, int sy, int sz, const int* flags, Real* P, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{
+	STRIDES
+	const IndexInt n = (IndexInt)sx * sy * sz;
+	memset(P, 0, sizeof(Real) * (size_t)n);
+	const Real tau = (Real)0.97, sigma = (Real)0.25;
+	const IndexInt off[6] = { -X, -Y, -Z, X, Y, Z };
+	const Real* Aq[3] = { Ai, Aj, Ak };
+	for (int colour = 0; colour < 2; colour++)
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		if (rb_colour(i, j, k) != colour) continue;
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		/* fluid cells are interior cells (mp_check_flags_interior / the reference's own assumption): all six neighbours exist */
+		Real e = A0[idx], inner = 0; int first = 1;
+		for (int pass = 0; pass < 2; pass++) for (int q = 0; q < 6; q++) {          /* pass 0: other tiles, pass 1: own tile */
+			if (rb_leaves(i, j, k, q) != (pass == 0) || !rb_prec(i, j, k, q)) continue;
+			const IndexInt nb = idx + off[q];
+			const Real a = Aq[q % 3][q < 3 ? nb : idx];                         /* the coupling of c and nb is stored at the lower cell */
+			const Real t = a * P[nb];
+			e = e - t * t;
+			/* couplings of nb to its successors other than c (sums of the entries in direction order) */
+			const int ni = i + rb_di[q], nj = j + rb_dj[q], nk = k + rb_dk[q];
+			Real ssum = 0; int sfirst = 1;
+			for (int r = 0; r < 6; r++) {
+				if (r == (q + 3) % 6) continue;                                  /* that is c */
+				const int si = ni + rb_di[r], sj = nj + rb_dj[r], sk = nk + rb_dk[r];
+				if (si < 0 || sj < 0 || sk < 0 || si >= sx || sj >= sy || sk >= sz) continue;
+				if (rb_prec(ni, nj, nk, r)) continue;                            /* a predecessor of nb */
+				const IndexInt sidx = nb + off[r];
+				const Real an = Aq[r % 3][r < 3 ? sidx : nb];
+				if (sfirst) { ssum = an; sfirst = 0; } else ssum = ssum + an;
+			}
+			const Real term = a * ssum * (P[nb] * P[nb]);
+			if (first) { inner = term; first = 0; } else inner = inner + term;
+		}
+		e = (Real)((double)e - (double)tau * ((double)inner + 0.));
+		if (e < sigma * A0[idx]) e = A0[idx];
+		P[idx] = (Real)(1. / (double)R_SQRT(e));
+	}
+}
+static void micrb_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src, const Real* P,
+	const Real* Ai, const Real* Aj, const Real* Ak)
+{
+	STRIDES
+	const IndexInt off[6] = { -X, -Y, -Z, X, Y, Z };
+	const Real* Aq[3] = { Ai, Aj, Ak };
+	for (int colour = 0; colour < 2; colour++)
+	for (int k = 0; k < sz; k++) for (int j = 0; j < sy; j++) for (int i = 0; i < sx; i++) {
+		if (rb_colour(i, j, k) != colour) continue;
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		Real acc = src[idx];
+		for (int pass = 0; pass < 2; pass++) for (int q = 0; q < 6; q++) {
+			if (rb_leaves(i, j, k, q) != (pass == 0) || !rb_prec(i, j, k, q)) continue;
+			const IndexInt nb = idx + off[q];
+			acc = acc - dst[nb] * Aq[q % 3][q < 3 ? nb : idx] * P[nb];
+		}
+		dst[idx] = P[idx] * acc;
+	}
+	for (int colour = 1; colour >= 0; colour--)
+	for (int k = sz - 1; k >= 0; k--) for (int j = sy - 1; j >= 0; j--) for (int i = sx - 1; i >= 0; i--) {
+		if (rb_colour(i, j, k) != colour) continue;
+		const IndexInt idx = IDX(i, j, k);
+		if (!(flags[idx] & TypeFluid)) continue;
+		const Real p = P[idx];
+		Real acc = dst[idx];
+		for (int pass = 0; pass < 2; pass++) for (int qq = 0; qq < 6; qq++) {
+			const int q = pass == 0 ? qq : (qq + 3) % 6;                         /* own tile: +x, +y, +z (the reference's order) */
+			if (rb_leaves(i, j, k, q) != (pass == 0) || rb_prec(i, j, k, q)) continue;
+			const IndexInt nb = idx + off[q];
+			acc = acc - dst[nb] * Aq[q % 3][q < 3 ? nb : idx] * p;
+		}
+		dst[idx] = p * acc;
+	}
+}
+int mfo_micrb_init(int sx, int sy, int sz, const int* flags, Real* P, const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ micrb_init(sx, sy, sz, flags, P, A0, Ai, Aj, Ak); return 0; }
+int mfo_micrb_apply(int sx, int sy, int sz, const int* flags, Real* dst, const Real* src, const Real* P,
+	const Real* A0, const Real* Ai, const Real* Aj, const Real* Ak)
+{ (void)A0; micrb_apply(sx, sy, sz, flags, dst, src, P, Ai, Aj, Ak); return 0; }
+
 /* =============================================================================================
  * GridMg  (multigrid.h:31-137, multigrid.cpp)                                                   */
 enum { vtInactive = 0, vtActive = 1, vtActiveTrivial = 2, vtRemoved = 3, vtZero = 4, vtFree = 5 };  /* multigrid.h:87-94 */
@@ -933,7 +1045,7 @@ static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Rea
 	Real* tmp = (Real*)calloc((size_t)n, sizeof(Real));
 	Real* P = 0; Real* Pc[3] = { 0, 0, 0 };
 	int rc = 0;
-	if ((pc == 1 || pc == 3) && !IS3D) pc = 0;                 /* setICPreconditioner :315-321 */
+	if ((pc == 1 || pc == 3 || pc == 4) && !IS3D) pc = 0;      /* setICPreconditioner :315-321 */
 	/* doInit */
 	memset(x, 0, sizeof(Real) * (size_t)n);
 	memcpy(residual, rhs, sizeof(Real) * (size_t)n);
@@ -941,6 +1053,10 @@ static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Rea
 		P = (Real*)calloc((size_t)n, sizeof(Real));
 		mic_init(sx, sy, sz, flags, P, A0, Ai, Aj, Ak);
 		mic_apply(sx, sy, sz, flags, tmp, residual, P, Ai, Aj, Ak);
+	} else if (pc == 4) {                                       /* MIC(0) in block red-black ordering (no reference counterpart, see micrb_init) */
+		P = (Real*)calloc((size_t)n, sizeof(Real));
+		micrb_init(sx, sy, sz, flags, P, A0, Ai, Aj, Ak);
+		micrb_apply(sx, sy, sz, flags, tmp, residual, P, Ai, Aj, Ak);
 	} else if (pc == 3) {
 		P = (Real*)calloc((size_t)n, sizeof(Real));
 		for (int c = 0; c < 3; c++) Pc[c] = (Real*)calloc((size_t)n, sizeof(Real));
@@ -964,6 +1080,7 @@ static int cg_run(int sx, int sy, int sz, const int* flags, const Real* rhs, Rea
 		scaled_add(x, search, alpha, n);
 		scaled_add(residual, tmp, -alpha, n);
 		if (pc == 1) mic_apply(sx, sy, sz, flags, tmp, residual, P, Ai, Aj, Ak);
+		else if (pc == 4) micrb_apply(sx, sy, sz, flags, tmp, residual, P, Ai, Aj, Ak);
 		else if (pc == 3) ic_apply(sx, sy, sz, flags, tmp, residual, P, Pc[0], Pc[1], Pc[2]);
 		else if (pc == 2) { mg_set_rhs(mg, residual); mg_vcycle(mg, tmp); }
 		else memcpy(tmp, residual, sizeof(Real) * (size_t)n);

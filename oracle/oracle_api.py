@@ -190,6 +190,24 @@ class Oracle:
         self._chk(self._f("mic_apply")(*self.dims(flags), _p(flags), _p(dst), _p(self._r(src)), _p(P), _p(A0), _p(Ai), _p(Aj), _p(Ak)))
         return dst
 
+    # -- MIC(0) in block red-black ordering: the reformulated preconditioner (no reference counterpart; mf_oracle.c micrb_*), port only.
+    #    cg_solve(pc=4) runs PCG with it.  tiles = (T0, T1, T2), 0 = the whole extent; (0, 0, 0) is the reference's ordering.
+    def set_mic_tiles(self, tiles):
+        assert self.kind == "port"
+        self._chk(self._f("set_mic_tiles")(*[C.c_int(int(t)) for t in tiles]))
+
+    def micrb_init(self, flags, A0, Ai, Aj, Ak, tiles):
+        self.set_mic_tiles(tiles)
+        P = np.zeros(flags.shape, self.real)
+        self._chk(self._f("micrb_init")(*self.dims(flags), _p(flags), _p(P), _p(A0), _p(Ai), _p(Aj), _p(Ak)))
+        return P
+
+    def micrb_apply(self, flags, src, P, A0, Ai, Aj, Ak, tiles, dst=None):
+        self.set_mic_tiles(tiles)
+        dst = np.zeros(flags.shape, self.real) if dst is None else dst
+        self._chk(self._f("micrb_apply")(*self.dims(flags), _p(flags), _p(dst), _p(self._r(src)), _p(P), _p(A0), _p(Ai), _p(Aj), _p(Ak)))
+        return dst
+
     def ic_init(self, flags, A0, Ai, Aj, Ak):
         """InitPreconditionIncompCholesky conjugategrad.cpp:26-63 (PC_ICP); returns the factor grids (P0, Pi, Pj, Pk)"""
         P = [np.zeros(flags.shape, self.real) for _ in range(4)]
