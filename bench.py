@@ -404,10 +404,12 @@ def extra_configs(args, peak):
     res = args.res
     out = {}
 
-    def run(name, flags, vel, phi, prec, pc, acc, fac, fix, reps):
+    def run(name, flags, vel, phi, prec, pc, acc, fac, fix, reps, mic_rb=False):
         sz, sy, sx = flags.shape
         s = mf.Solver(gridSize=(sx, sy, sz), dim=3, prec=prec)
         s.setProfiling(4 if pc else 16)
+        if mic_rb:                   # PcMIC reformulated: MIC(0) of the block red-black ordering, tile chosen from the grid (mp_set_mic_ordering)
+            s.setMicOrdering(1)
         F, V0, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.MACGrid(s), mf.RealGrid(s)
         PH = mf.RealGrid(s, phi) if phi is not None else None
         F.dev(); V0.dev()
@@ -437,7 +439,11 @@ def extra_configs(args, peak):
         # dominant kernel of the iteration against its algorithmic bytes: MIC apply 12+12w, V-cycle ~(4+28w)+(3+55w)/7, matvec per kernel
         mvb = {0: 4 + 6 * w, 1: 4 + 6 * w, 2: 4 + 3 * w, 3: 4 + 7 * w, 4: 2 + 6 * w}[info["matvecKernel"]]
         cand = {"matvec": (info["msMatvecAvg"], mvb)}
-        if pc == 1:
+        if pc == 1 and mic_rb:
+            mode, ty, tz = s.micOrdering()
+            row["preconditioner"] = "PcMIC, block red-black ordering (reformulated; %dx%d rows per tile)" % (ty, tz) if mode else "PcMIC (ordering request fell back to lexicographic)"
+            cand["precond (MIC apply, block red-black)"] = (info["msPrecondAvg"], 2 + 6 * w)       # 4 Real read + 2 written + 2 mask bytes per cell
+        elif pc == 1:
             cand["precond (MIC apply)"] = (info["msPrecondAvg"], 12 + 12 * w)
         if pc >= 2:
             cand["precond (GridMg V-cycle)"] = (info["msPrecondAvg"], (4 + 28 * w) + (3 + 55 * w) / 7.0)
@@ -460,6 +466,7 @@ def extra_configs(args, peak):
     out.pop("_warm", None)
     f32 = make_scene(res, 4)
     run("pcmic_f32", f32[0], f32[1], None, 4, 1, 1e-4, 99, False, 2)
+    run("pcmic_blockrb_f32", f32[0], f32[1], None, 4, 1, 1e-4, 99, False, 2, mic_rb=True)
     run("pcmgstatic_f32", f32[0], f32[1], None, 4, 3, 1e-4, 99, True, 3)
     run("pcmgdynamic_f32", f32[0], f32[1], None, 4, 2, 1e-4, 99, True, 2)
     del f32

@@ -156,10 +156,12 @@ int mp_apply_matrix(mp_context* ctx, const mp_grid* flags, mp_grid* dst, const m
 /* The ordering MIC(0) is formed in.  mode 0 (default): the reference's lexicographic ordering -- Aprecond and the sweeps are bit-identical to
  * conjugategrad.cpp:66-97,:135-159 and PcMIC keeps the reference's iteration counts, but the sweeps are a chain of sx+sy+sz dependent
  * hyperplanes.  mode 1: block red-black ordering, the reformulated ("coloured") triangular solves: tiles of tileY x tileZ rows (rounded up to
- * multiples of 8 and 4; 0 = 8 x 8), an exact MIC(0) of the permuted matrix, bandwidth-bound; more iterations (reported in mp_solve_info as usual).
+ * multiples of 8 and 4; 0 = chosen from the grid size), an exact MIC(0) of the permuted matrix, bandwidth-bound; more iterations (reported in mp_solve_info as usual).
  * Applies to mp_mic_init / mp_mic_apply, GridCg with PC_mICP and solvePressure with PcMIC on unsharded 3-D grids whose off-diagonals are 0 / -1
  * (no face fractions); other cases keep mode 0.  No reference counterpart: specified by the test oracle's restatement micrb_init / micrb_apply. */
 int mp_set_mic_ordering(mp_context* ctx, int mode, int tileY, int tileZ);
+/* what the last MIC(0) factorisation of the context used: mode 1 + its tile when it ran in block red-black ordering, else 0 / 0 / 0 */
+int mp_get_mic_ordering(const mp_context* ctx, int* mode, int* tileY, int* tileZ);
 int mp_mic_init(mp_context* ctx, const mp_grid* flags, mp_grid* Aprecond, const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);
 int mp_mic_apply(mp_context* ctx, mp_grid* dst, const mp_grid* var1, const mp_grid* flags, const mp_grid* Aprecond,
                  const mp_grid* A0, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak);

@@ -14,10 +14,15 @@
 // Schedule.  One warp per tile; a tile is walked in sub-blocks of 8 x 4 rows (lane (lj, lk) owns row (8 sa + lj, 4 sb + lk)), rows in
 // chunks of 32 bytes.  A lane trails its -y / -z neighbour lane by ONE CHUNK: in round T it works on chunk T - (lj + lk), takes the
 // neighbours' products of that chunk by warp shuffle (they were formed a round earlier) and runs the x-recurrence of its chunk on
-// registers -- no shared memory, no barrier, no mailbox.  Operands of round T+1 are requested in round T.  Rows next to another tile
-// (or to an earlier sub-block of the same tile) read the neighbour row's chunk from global memory.
+// registers -- no shared memory, no barrier, no mailbox.  Operands of round T+1 are requested in round T (two register sets).  Rows next
+// to another tile (or to an earlier sub-block of the same tile) read the neighbour row's chunk from global memory.
 // The matrix is the byte mask k_micrb_mask builds (every off-diagonal 0 or -1, verified on the arrays; anything else -- face
 // fractions -- keeps the lexicographic kernels): per cell and application 4 Real read + 2 written + 2 mask bytes + the edge rows.
+// Measured (512^3 float, one B200): 1.6-2.0 ms per application against 4.5 ms of the lexicographic sweeps, ~2 TB/s.
+// ncu: 350-400 instructions per warp and 8-cell round at 3.5 cycles per instruction (dependent ALU chain + selects on the mask bits) and a
+// third of the stall samples on the first use of the operands requested a round earlier.  Tried and dropped: L2 prefetch 2-4 rounds ahead
+// (slower), a register cap for 16 warps per SM (spills, slower), a cp.async ring in shared memory 3 rounds deep (long-scoreboard stalls gone,
+// but ~50 more instructions per round: 1.7-2.4 ms).
 #include "mp_common.cuh"
 #include <cstdlib>
 
@@ -175,96 +180,124 @@ __global__ void __launch_bounds__(32) k_micrb(RbGeom g, int colour, const unsign
 		Real oy[CH], oz[CH], oyS[CH], ozS[CH];     // handed to the next lanes: forward products, backward values, factor P (+ successor sums)
 		#pragma unroll
 		for (int s = 0; s < CH; s++) { oy[s] = oz[s] = (Real)0; oyS[s] = ozS[s] = (Real)0; }
+		// warp-uniform: does any lane of this sub-block read an edge row at all (red tiles of one sub-block never do in the forward sweep)
+		const bool anyY = __any_sync(FULL, ySide != 0), anyZ = __any_sync(FULL, zSide != 0);
 
-		// operands of a round, requested one round ahead
-		Real Pn[CH], Rn[CH], EYn[CH], EYPn[CH], EZn[CH], EZPn[CH]; unsigned long long Mn = 0, EYMn = 0, EZMn = 0;
-		auto request = [&](int c) {
+		// Operands of a round live in one of two register sets: round T computes on one while the loads of round T+1 land in the other.
+		struct Ops { Real P[CH], R[CH], EY[CH], EYP[CH], EZ[CH], EZP[CH]; unsigned long long M, EYM, EZM; };
+		auto request = [&](int c, Ops& o) {
 			const bool act = rowIn && (unsigned)c < (unsigned)g.nch;
-			#pragma unroll
-			for (int s = 0; s < CH; s++) { Pn[s] = Rn[s] = EYn[s] = EYPn[s] = EZn[s] = EZPn[s] = (Real)0; }
-			Mn = EYMn = EZMn = 0;
+			o.M = o.EYM = o.EZM = 0;                                // a round without fluid cells computes on stale operands and selects zeros
 			if (!act) return;
 			const int i0 = CH * (bwd ? g.nch - 1 - c : c);
-			Mn = ldMask<CH>(mrow, i0);
-			if (Mn == 0) return;                                    // no fluid cell in the chunk: nothing to read, nothing to write
-			if (MODE == 0) ldChunk<Real, CH, VEC>(A0 + rowOff, i0, g.sx, Rn);
-			else { ldChunk<Real, CH, VEC>(P + rowOff, i0, g.sx, Pn); ldChunk<Real, CH, VEC>((MODE == 1 ? src : (const Real*)dst) + rowOff, i0, g.sx, Rn); }
+			o.M = ldMask<CH>(mrow, i0);                             // (no test of the mask here: a branch on it would put its latency in front of the loads below)
+			if (MODE == 0) ldChunk<Real, CH, VEC>(A0 + rowOff, i0, g.sx, o.R);
+			else { ldChunk<Real, CH, VEC>(P + rowOff, i0, g.sx, o.P); ldChunk<Real, CH, VEC>((MODE == 1 ? src : (const Real*)dst) + rowOff, i0, g.sx, o.R); }
 			if (ySide) {
-				if (MODE == 0) { ldChunk<Real, CH, VEC>(P + eyOff, i0, g.sx, EYPn); EYMn = ldMask<CH>(eyM, i0); }
-				else { ldChunk<Real, CH, VEC>((const Real*)dst + eyOff, i0, g.sx, EYn); if (MODE == 1) ldChunk<Real, CH, VEC>(P + eyOff, i0, g.sx, EYPn); }
+				if (MODE == 0) { ldChunk<Real, CH, VEC>(P + eyOff, i0, g.sx, o.EYP); o.EYM = ldMask<CH>(eyM, i0); }
+				else { ldChunk<Real, CH, VEC>((const Real*)dst + eyOff, i0, g.sx, o.EY); if (MODE == 1) ldChunk<Real, CH, VEC>(P + eyOff, i0, g.sx, o.EYP); }
 			}
 			if (zSide) {
-				if (MODE == 0) { ldChunk<Real, CH, VEC>(P + ezOff, i0, g.sx, EZPn); EZMn = ldMask<CH>(ezM, i0); }
-				else { ldChunk<Real, CH, VEC>((const Real*)dst + ezOff, i0, g.sx, EZn); if (MODE == 1) ldChunk<Real, CH, VEC>(P + ezOff, i0, g.sx, EZPn); }
+				if (MODE == 0) { ldChunk<Real, CH, VEC>(P + ezOff, i0, g.sx, o.EZP); o.EZM = ldMask<CH>(ezM, i0); }
+				else { ldChunk<Real, CH, VEC>((const Real*)dst + ezOff, i0, g.sx, o.EZ); if (MODE == 1) ldChunk<Real, CH, VEC>(P + ezOff, i0, g.sx, o.EZP); }
 			}
 		};
-		__syncwarp();                        // rows of the sub-blocks before this one are written
-		request(-skew);
-		#pragma unroll 1
-		for (int T = 0; T < nRounds; T++) {
-			const int c = T - skew;
-			Real Pc[CH], Rc[CH], EY[CH], EYP[CH], EZ[CH], EZP[CH];
-			#pragma unroll
-			for (int s = 0; s < CH; s++) { Pc[s] = Pn[s]; Rc[s] = Rn[s]; EY[s] = EYn[s]; EYP[s] = EYPn[s]; EZ[s] = EZn[s]; EZP[s] = EZPn[s]; }
-			const unsigned long long M = Mn, EYM = EYMn, EZM = EZMn;
-			request(c + 1);
-			const bool act = rowIn && (unsigned)c < (unsigned)g.nch && M != 0;
+		// Arithmetic.  Every off-diagonal a is 0 or -1, so z a P is -(z P) or a zero and "acc - z a P" is "acc + z P" or acc: the products
+		// below are formed without the coefficient and added where the coupling bit is set -- the value the specification gets (signs of
+		// exact zeros aside, which no later value depends on).
+		auto compute = [&](int c, const Ops& o) {
+			const bool act = rowIn && (unsigned)c < (unsigned)g.nch && o.M != 0;
 			Real q[CH]; unsigned fluidBits = 0;
+			// edge rows: products of this round's cells, formed off the dependent chain; 0 where the row does not take part
+			Real ey[CH], ez[CH], sY[CH], sZ[CH];
+			#pragma unroll
+			for (int s = 0; s < CH; s++) { ey[s] = ez[s] = (Real)0; sY[s] = sZ[s] = (Real)0; }
+			if (anyY) {
+				#pragma unroll
+				for (int s = 0; s < CH; s++) {
+					const bool cp = ySide && (maskOf(o.M, s) & yBit);
+					if (MODE == 1) ey[s] = cp ? o.EY[s] * o.EYP[s] : (Real)0;
+					if (MODE == 2) ey[s] = cp ? o.EY[s] * o.P[s] : (Real)0;
+					if (MODE == 0) { ey[s] = cp ? o.EYP[s] : (Real)0; sY[s] = succSum<Real>(maskOf(o.EYM, s), eYymS, eYypS, eYzmS, eYzpS); }
+				}
+			}
+			if (anyZ) {
+				#pragma unroll
+				for (int s = 0; s < CH; s++) {
+					const bool cp = zSide && (maskOf(o.M, s) & zBit);
+					if (MODE == 1) ez[s] = cp ? o.EZ[s] * o.EZP[s] : (Real)0;
+					if (MODE == 2) ez[s] = cp ? o.EZ[s] * o.P[s] : (Real)0;
+					if (MODE == 0) { ez[s] = cp ? o.EZP[s] : (Real)0; sZ[s] = succSum<Real>(maskOf(o.EZM, s), eZymS, eZypS, eZzmS, eZzpS); }
+				}
+			}
 			#pragma unroll
 			for (int ss = 0; ss < CH; ss++) {
 				const int s = bwd ? CH - 1 - ss : ss;                    // processing order along the row
 				// the neighbour lanes' output for this cell (they worked on this chunk one round ago); every lane takes part
-				const Real iy = bwd ? __shfl_down_sync(FULL, oy[s], 1) : __shfl_up_sync(FULL, oy[s], 1);
-				const Real iz = bwd ? __shfl_down_sync(FULL, oz[s], 8) : __shfl_up_sync(FULL, oz[s], 8);
+				Real iy = bwd ? __shfl_down_sync(FULL, oy[s], 1) : __shfl_up_sync(FULL, oy[s], 1);
+				Real iz = bwd ? __shfl_down_sync(FULL, oz[s], 8) : __shfl_up_sync(FULL, oz[s], 8);
 				Real iyS = (Real)0, izS = (Real)0;
 				if (MODE == 0) { iyS = __shfl_up_sync(FULL, oyS[s], 1); izS = __shfl_up_sync(FULL, ozS[s], 8); }
-				const unsigned m = maskOf(M, s);
+				const unsigned m = maskOf(o.M, s);
 				const bool fl = act && (m & mFluid);
 				if (fl) fluidBits |= 1u << s;
 				Real out = (Real)0;
 				if (MODE == 1) {
-					const Real ey = ySide ? EY[s] * coup<Real>(m, yBit) * EYP[s] : (Real)0, ez = zSide ? EZ[s] * coup<Real>(m, zBit) * EZP[s] : (Real)0;
-					Real acc = Rc[s];
-					if (yOut && yFirst) acc = acc - ey;
-					if (zOut) acc = acc - ez;
-					if (yOut && !yFirst) acc = acc - ey;
-					acc = acc - tx;
-					if (inY) acc = acc - iy; else if (ySide && !yOut) acc = acc - ey;
-					if (inZ) acc = acc - iz; else if (zSide && !zOut) acc = acc - ez;
-					const Real p = Pc[s];
+					// iy / iz / tx arrive as z P of the neighbour, already zero where THAT cell has no coupling towards this one
+					if (!inY) iy = yOut ? (Real)0 : ey[s];
+					if (!inZ) iz = zOut ? (Real)0 : ez[s];
+					Real acc = o.R[s];
+					if (yOut && yFirst) acc = acc + ey[s];
+					if (zOut) acc = acc + ez[s];
+					if (yOut && !yFirst) acc = acc + ey[s];
+					acc = ((acc + tx) + iy) + iz;
+					const Real p = o.P[s];
 					out = fl ? p * acc : (Real)0;
-					tx = out * coup<Real>(m, mXp) * p; oy[s] = out * coup<Real>(m, mYp) * p; oz[s] = out * coup<Real>(m, mZp) * p;
+					const Real t = out * p;
+					tx = (m & mXp) ? t : (Real)0; oy[s] = (m & mYp) ? t : (Real)0; oz[s] = (m & mZp) ? t : (Real)0;
 				} else if (MODE == 2) {
-					const Real p = Pc[s];
-					const Real ey = ySide ? EY[s] * coup<Real>(m, yBit) * p : (Real)0, ez = zSide ? EZ[s] * coup<Real>(m, zBit) * p : (Real)0;
-					Real acc = Rc[s];
-					if (yOut && yFirst) acc = acc - ey;
-					if (zOut) acc = acc - ez;
-					if (yOut && !yFirst) acc = acc - ey;
-					acc = acc - tx * coup<Real>(m, mXp) * p;
-					if (inY) acc = acc - iy * coup<Real>(m, mYp) * p; else if (ySide && !yOut) acc = acc - ey;
-					if (inZ) acc = acc - iz * coup<Real>(m, mZp) * p; else if (zSide && !zOut) acc = acc - ez;
+					const Real p = o.P[s];
+					if (!inY) iy = (Real)0;
+					if (!inZ) iz = (Real)0;
+					const Real px = (m & mXp) ? tx * p : (Real)0;
+					const Real py = inY ? ((m & mYp) ? iy * p : (Real)0) : (yOut ? (Real)0 : ey[s]);
+					const Real pz = inZ ? ((m & mZp) ? iz * p : (Real)0) : (zOut ? (Real)0 : ez[s]);
+					Real acc = o.R[s];
+					if (yOut && yFirst) acc = acc + ey[s];
+					if (zOut) acc = acc + ez[s];
+					if (yOut && !yFirst) acc = acc + ey[s];
+					acc = ((acc + px) + py) + pz;
 					out = fl ? p * acc : (Real)0;
 					tx = out; oy[s] = out; oz[s] = out;
 				} else {
 					// factor: a predecessor n contributes (a P_n)^2 to e and a (S_n - a) P_n^2 to the bracket, S_n = sum over all successors of n
-					Real e = Rc[s], inner = (Real)0;
-					auto pred = [&](Real a, Real pn, Real sn) { const Real t = a * pn; e = e - t * t; inner = inner + a * (sn - a) * (pn * pn); };
-					const Real sY = ySide ? succSum<Real>(maskOf(EYM, s), eYymS, eYypS, eYzmS, eYzpS) : (Real)0;
-					const Real sZ = zSide ? succSum<Real>(maskOf(EZM, s), eZymS, eZypS, eZzmS, eZzpS) : (Real)0;
-					if (yOut && yFirst) pred(coup<Real>(m, yBit), EYP[s], sY);
-					if (zOut) pred(coup<Real>(m, zBit), EZP[s], sZ);
-					if (yOut && !yFirst) pred(coup<Real>(m, yBit), EYP[s], sY);
-					pred(coup<Real>(m, mXm), tx, txS);
-					if (inY) pred(coup<Real>(m, mYm), iy, iyS); else if (ySide && !yOut) pred(coup<Real>(m, yBit), EYP[s], sY);
-					if (inZ) pred(coup<Real>(m, mZm), iz, izS); else if (zSide && !zOut) pred(coup<Real>(m, zBit), EZP[s], sZ);
-					out = fl ? micrbFactorEnd<Real>(e, inner, Rc[s]) : (Real)0;
+					Real e = o.R[s], inner = (Real)0;
+					auto pred = [&](bool coupled, Real pn, Real sn) { if (coupled) { e = e - pn * pn; inner = inner + (Real)-1 * (sn - (Real)-1) * (pn * pn); } };
+					if (yOut && yFirst) pred(m & yBit, o.EYP[s], sY[s]);
+					if (zOut) pred(m & zBit, o.EZP[s], sZ[s]);
+					if (yOut && !yFirst) pred(m & yBit, o.EYP[s], sY[s]);
+					pred(m & mXm, tx, txS);
+					if (inY) pred(m & mYm, iy, iyS); else if (ySide && !yOut) pred(m & yBit, o.EYP[s], sY[s]);
+					if (inZ) pred(m & mZm, iz, izS); else if (zSide && !zOut) pred(m & zBit, o.EZP[s], sZ[s]);
+					out = fl ? micrbFactorEnd<Real>(e, inner, o.R[s]) : (Real)0;
 					const Real sn = fl ? succSum<Real>(m, ymS, ypS, zmS, zpS) : (Real)0;
 					tx = out; txS = sn; oy[s] = out; oyS[s] = sn; oz[s] = out; ozS[s] = sn;
 				}
 				q[s] = out;
 			}
 			if (fluidBits) stChunk<Real, CH, VEC>((MODE == 0 ? P : dst) + rowOff, CH * (bwd ? g.nch - 1 - c : c), fluidBits, q);
+		};
+		__syncwarp();                        // rows of the sub-blocks before this one are written
+		Ops A, B;
+		#pragma unroll
+		for (int s = 0; s < CH; s++) { A.P[s] = A.R[s] = A.EY[s] = A.EYP[s] = A.EZ[s] = A.EZP[s] = (Real)0; B.P[s] = B.R[s] = B.EY[s] = B.EYP[s] = B.EZ[s] = B.EZP[s] = (Real)0; }
+		request(-skew, A);
+		#pragma unroll 1
+		for (int T = 0; T < nRounds; T += 2) {
+			request(T + 1 - skew, B);
+			compute(T - skew, A);
+			request(T + 2 - skew, A);
+			compute(T + 1 - skew, B);
 		}
 	}
 	}
@@ -285,20 +318,30 @@ static int rbTiles(const mp_context* ctx, int& ty, int& tz) {
 	const char* e = getenv("MP_MIC_RB");          // "TY,TZ" switches the ordering on for every context (read per solve)
 	int on = ctx->micRb;
 	if (e && *e) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { on = 1; ty = a; tz = b; } else on = atoi(e) != 0; }
-	if (ty <= 0) ty = 8;
-	if (tz <= 0) tz = 8;
-	ty = (ty + 7) / 8 * 8; tz = (tz + 3) / 4 * 4;
+	ty = ty > 0 ? (ty + 7) / 8 * 8 : 0; tz = tz > 0 ? (tz + 3) / 4 * 4 : 0;     // 0: chosen from the grid (rbAutoTiles)
 	return on;
+}
+
+// Tile of a grid when none is given: larger tiles need fewer iterations (512^3: 612 / 571 / 483 with 8x4 / 8x8 / 16x8) but there is one warp per tile and
+// only half of the tiles run at a time, so the largest tile that still leaves ~900 warps per launch (measured: 16x8 at 512^3, 8x4 at 256^3).
+static void rbAutoTiles(const Dims& d, int& ty, int& tz) {
+	static const int cand[3][2] = { { 16, 8 }, { 8, 8 }, { 8, 4 } };
+	for (int q = 0; q < 3; q++) {
+		ty = cand[q][0]; tz = cand[q][1];
+		if ((long long)((d.sy + ty - 1) / ty) * ((d.sz + tz - 1) / tz) / 2 >= 900) return;
+	}
 }
 
 // Is the block red-black ordering selected, and can it run on this matrix?  Builds the byte mask on the way (once per factorisation).
 int mp_micrb_prepare(mp_context* ctx, const mp_grid* flags, const mp_grid* P, const mp_grid* Ai, const mp_grid* Aj, const mp_grid* Ak, bool* use)
 {
 	*use = false;
+	if (ctx->micRbState) ctx->micRbState->s.valid = false;       // a new factorisation: whatever the state said about an earlier factor is void
 	int ty, tz;
 	if (!rbTiles(ctx, ty, tz)) return MP_OK;
 	const Dims d = dimsOf(flags);
 	if (!d.is3D || d.world > 1 || d.sx < 3 || d.sy < 3 || d.sz < 3) return MP_OK;
+	if (ty == 0 || tz == 0) rbAutoTiles(d, ty, tz);
 	if (!ctx->micRbState) ctx->micRbState = new mp_micrb_state();
 	RbState& st = ctx->micRbState->s;
 	const int CH = 32 / P->prec;
@@ -379,13 +422,22 @@ int mp_micrb_apply_launch(mp_context* ctx, mp_grid* dst, const mp_grid* var1, co
 extern "C" {
 
 // mode 0: the reference's lexicographic ordering (default; bit-identical to conjugategrad.cpp:66-159), 1: block red-black ordering with tiles of
-// tileY x tileZ rows (rounded up to multiples of 8 and 4; 0 = the default 8 x 8).  Takes effect at the next factorisation.
+// tileY x tileZ rows (rounded up to multiples of 8 and 4; 0 = chosen from the grid size).  Takes effect at the next factorisation.
 int mp_set_mic_ordering(mp_context* ctx, int mode, int tileY, int tileZ)
 {
 	if (!ctx) MP_FAIL(MP_ERR_INVALID, "mp_set_mic_ordering: NULL context");
 	if (mode != 0 && mode != 1) MP_FAIL(MP_ERR_INVALID, "mp_set_mic_ordering: mode %d (0 lexicographic, 1 block red-black)", mode);
 	if (tileY < 0 || tileZ < 0) MP_FAIL(MP_ERR_INVALID, "mp_set_mic_ordering: negative tile size");
 	ctx->micRb = mode; ctx->micRbTY = tileY; ctx->micRbTZ = tileZ;
+	return MP_OK;
+}
+
+// what the last MIC(0) factorisation of this context used: *mode 1 and the tile when it ran in block red-black ordering, 0 / 0 / 0 otherwise
+int mp_get_mic_ordering(const mp_context* ctx, int* mode, int* tileY, int* tileZ)
+{
+	if (!ctx || !mode || !tileY || !tileZ) MP_FAIL(MP_ERR_INVALID, "mp_get_mic_ordering: NULL argument");
+	mp_micrb_tiles(ctx, tileY, tileZ);
+	*mode = *tileY > 0 ? 1 : 0;
 	return MP_OK;
 }
 

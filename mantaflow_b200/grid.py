@@ -86,6 +86,12 @@ class Solver:
         bandwidth-bound preconditioner; more iterations, reported by lastSolveInfo() (mp_set_mic_ordering)"""
         check(self.lib.mp_set_mic_ordering(self._ctx, int(mode), int(tileY), int(tileZ)))
 
+    def micOrdering(self):
+        """(mode, tileY, tileZ) of the last MIC(0) factorisation: (1, TY, TZ) in block red-black ordering, (0, 0, 0) in the reference's"""
+        m, ty, tz = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(self.lib.mp_get_mic_ordering(self._ctx, C.byref(m), C.byref(ty), C.byref(tz)))
+        return m.value, ty.value, tz.value
+
     def trim(self):
         """return the context's pooled (unused) device blocks to the driver (mp_context_trim)"""
         check(self.lib.mp_context_trim(self._ctx))

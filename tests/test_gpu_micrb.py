@@ -73,7 +73,7 @@ def test_factor_and_sweeps_bit_exact(mf, scene, prec, tile):
     # switched off again the same calls give the lexicographic factor
     s.setMicOrdering(0)
     cg.InitPreconditionModifiedIncompCholesky2(F, P, *A)
-    assert np.array_equal(P.numpy(), O.mic_init(flags, *A_o))
+    assert np.array_equal(P.numpy(), O.mic_init(flags, *A_o)) and s.micOrdering() == (0, 0, 0)
     s.close()
 
 
@@ -122,6 +122,7 @@ def test_solve_pressure_pcmic_reformulated(mf, prec):
     s.setMicOrdering(1, 8, 8)
     mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=mf.PcMIC)
     it_rb = mf.lastSolveInfo()["iterations"]
+    assert s.micOrdering() == (1, 8, 8)
     fl = (flags & 1) != 0
     pg, po = P.numpy().astype(np.float64), p_o.astype(np.float64)
     pg[fl] -= pg[fl].mean(); po[fl] -= po[fl].mean()
@@ -132,9 +133,14 @@ def test_solve_pressure_pcmic_reformulated(mf, prec):
     s.setMicOrdering(0)
     V.copyFromArray(vel)
     mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=mf.PcMIC)
-    assert abs(mf.lastSolveInfo()["iterations"] - it_o) <= (0 if prec == 4 else 1)
+    assert abs(mf.lastSolveInfo()["iterations"] - it_o) <= (0 if prec == 4 else 1) and s.micOrdering() == (0, 0, 0)
     if prec == 4:
         assert np.array_equal(P.numpy(), p_o)
+    # tile 0 x 0: chosen from the grid (8 x 4 on a grid this small)
+    s.setMicOrdering(1)
+    V.copyFromArray(vel)
+    mf.solvePressure(vel=V, pressure=P, flags=F, cgAccuracy=acc, cgMaxIterFac=99, preconditioner=mf.PcMIC)
+    assert s.micOrdering() == (1, 8, 4) and mf.lastSolveInfo()["iterations"] >= it_o
     s.close()
 
 
@@ -152,5 +158,5 @@ def test_face_fractions_keep_the_lexicographic_kernels(mf):
     A = [mf.RealGrid(s, a) for a in A_o]
     P = mf.RealGrid(s)
     cg.InitPreconditionModifiedIncompCholesky2(F, P, *A)
-    assert np.array_equal(P.numpy(), O.mic_init(flags, *A_o))
+    assert np.array_equal(P.numpy(), O.mic_init(flags, *A_o)) and s.micOrdering() == (0, 0, 0)
     s.close()

@@ -13,7 +13,7 @@ from mantaflow_b200 import scenes  # noqa: E402
 
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 prec = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-tiles = [tuple(int(v) for v in t.split("x")) for t in (sys.argv[3] if len(sys.argv) > 3 else "8x4,8x8,16x8,16x16").split(",")]
+tiles = [tuple(int(v) for v in t.split("x")) for t in (sys.argv[3] if len(sys.argv) > 3 else "0x0,8x4,8x8,16x8").split(",")]       # 0x0: chosen from the grid
 lex = os.environ.get("MICRB_SKIP_LEX", "0") != "1"
 flags, vel = scenes.smoke_plume((res, res, res), prec)
 s = mf.Solver(gridSize=(res, res, res), dim=3, prec=prec)
@@ -34,7 +34,7 @@ for t in ([None] if lex else []) + tiles:
         info = mf.lastSolveInfo()
         if best is None or info["msTotal"] < best["msTotal"]:
             best = info
-    name = "lexicographic (reference ordering)" if t is None else "block red-black %dx%d" % t
+    name = "lexicographic (reference ordering)" if t is None else "block red-black %dx%d" % s.micOrdering()[1:]
     # per application and cell: 4 Real read + 2 written + 2 mask bytes (+ the edge rows, not counted)
     bpc = 6 * prec + 2 if t is not None else 12 + 12 * prec
     gbs = bpc * cells / (best["msPrecondAvg"] * 1e-3) / 1e9 if best["msPrecondAvg"] > 0 else 0.0
