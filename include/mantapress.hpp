@@ -72,6 +72,8 @@ public:
 	mp_context* ctx() const { return mCtx; }
 	void synchronize() const { mpCheck(mp_context_synchronize(mCtx)); }
 	long long kernelLaunches() const { long long n = 0; mpCheck(mp_context_kernel_launches(mCtx, &n)); return n; }
+	// MIC(0) of PcMIC / PC_mICP in block red-black ordering (the reformulated preconditioner, no reference counterpart): mode 1 on, 0 the reference's ordering
+	void setMicOrdering(int mode = 1, int tileY = 0, int tileZ = 0) { mpCheck(mp_set_mic_ordering(mCtx, mode, tileY, tileZ)); }
 	Real mDt;                                        // timestep, public like the reference's Python-exposed member
 private:
 	Vec3i mGridSize; int mDim; mp_context* mCtx;

@@ -275,14 +275,16 @@ __device__ __forceinline__ V3<Real> slMAC(const Dims& d, const Real* __restrict_
 	o.z = slMACc<Real, OS, OT, 2>(d, vel, src, dt, i, j, k, idx);
 	return o;
 }
-template <typename Real, int OS, int OT>
-__global__ void __launch_bounds__(128) k_semi_lagrange(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+template <typename Real, int OS, int OT, bool D3>
+__global__ void __launch_bounds__(128) k_semi_lagrange(Dims d_, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+	Dims d = d_; if (D3) d.is3D = true;          // 3-D instantiation: the dimension tests fold, the corner loops unroll
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
 	dst[idx] = isInterior(d, i, j, k) ? slReal<Real, OS, OT>(d, vel, src, dt, i, j, k, idx) : (Real)0;
 }
-template <typename Real, int OS, int OT>
-__global__ void __launch_bounds__(128) k_semi_lagrange_mac(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+template <typename Real, int OS, int OT, bool D3>
+__global__ void __launch_bounds__(128) k_semi_lagrange_mac(Dims d_, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+	Dims d = d_; if (D3) d.is3D = true;          // 3-D instantiation: the dimension tests fold, the corner loops unroll
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
 	V3<Real> o; o.x = o.y = o.z = 0;
@@ -306,8 +308,9 @@ __device__ __forceinline__ V3<Real> slVec3(const Dims& d, const Real* __restrict
 	else { o.x = interpolCubic<Real, 3>(d, src, px, py, pz); o.y = interpolCubic<Real, 3>(d, src + 1, px, py, pz); o.z = interpolCubic<Real, 3>(d, src + 2, px, py, pz); }
 	return o;
 }
-template <typename Real, int OS, int OT>
-__global__ void __launch_bounds__(128) k_semi_lagrange_vec3(Dims d, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+template <typename Real, int OS, int OT, bool D3>
+__global__ void __launch_bounds__(128) k_semi_lagrange_vec3(Dims d_, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ src, Real dt) {
+	Dims d = d_; if (D3) d.is3D = true;          // 3-D instantiation: the dimension tests fold, the corner loops unroll
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
 	V3<Real> o; o.x = o.y = o.z = 0;
@@ -325,9 +328,10 @@ __device__ __forceinline__ bool checkFlag(const int* flags, IndexInt q) { return
 // Pass 2 of a MacCormack advection of a Real grid: the reference's backward trace (SemiLagrange with -dt on fwd), MacCormackCorrect and
 // MacCormackClamp only ever combine values of ONE cell (plus read-only neighbourhoods of fwd / orig), so they are one kernel here:
 // three full-grid round trips of bwd and the corrected grid never reach HBM.
-template <typename Real, int OS, int OT>
-__global__ void __launch_bounds__(128) k_mc_rest(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
+template <typename Real, int OS, int OT, bool D3>
+__global__ void __launch_bounds__(128) k_mc_rest(Dims d_, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
 	const Real* __restrict__ fwd, Real dt, Real strength, int clampMode) {
+	Dims d = d_; if (D3) d.is3D = true;          // 3-D instantiation: the dimension tests fold, the corner loops unroll
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
 	const bool in = isInterior(d, i, j, k);
@@ -348,7 +352,12 @@ __global__ void __launch_bounds__(128) k_mc_rest(Dims d, const int* __restrict__
 				for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
 				const int i0 = iclamp(cp[0], 0, d.sx - 2), j0 = iclamp(cp[1], 0, d.sy - 2), k0 = iclamp(cp[2], 0, d.is3D ? d.sz - 2 : 1);
 				const int k1 = d.is3D ? k0 + 1 : k0;
-				for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
+				#pragma unroll
+				for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++)
+				#pragma unroll
+				for (int b = 0; b < 2; b++)
+				#pragma unroll
+				for (int a = 0; a < 2; a++) {
 					const IndexInt q = (IndexInt)(i0 + a) + d.Y * (j0 + b) + d.Z * (cc ? k1 : k0);
 					if (checkFlag(flags, q)) { const Real o = orig[q]; if (o < minv) minv = o; if (o > maxv) maxv = o; haveFl = true; }
 				}
@@ -374,9 +383,10 @@ __global__ void __launch_bounds__(128) k_mc_rest(Dims d, const int* __restrict__
 // Pass 2 for a cell-centred Grid<Vec3>: MacCormackCorrect<Vec3> (the correction is narrowed before it is added: double * Vec3, then Vec3 += Vec3) and
 // doClampComponent<Vec3> (:141-186): minimum / maximum per component over the flagged corners; clampMode 2 resets the WHOLE vector when one
 // component leaves its range (cmpMinMax<Vec3> :134-136), clampMode 1 clamps component by component (clamp<Vec3> vectorbase.h:605-609)
-template <typename Real, int OS, int OT>
-__global__ void __launch_bounds__(128) k_mc_rest_vec3(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
+template <typename Real, int OS, int OT, bool D3>
+__global__ void __launch_bounds__(128) k_mc_rest_vec3(Dims d_, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
 	const Real* __restrict__ fwd, Real dt, Real strength, int clampMode) {
+	Dims d = d_; if (D3) d.is3D = true;          // 3-D instantiation: the dimension tests fold, the corner loops unroll
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
 	const bool in = isInterior(d, i, j, k);
@@ -401,7 +411,12 @@ __global__ void __launch_bounds__(128) k_mc_rest_vec3(Dims d, const int* __restr
 			for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
 			const int i0 = iclamp(cp[0], 0, d.sx - 2), j0 = iclamp(cp[1], 0, d.sy - 2), k0 = iclamp(cp[2], 0, d.is3D ? d.sz - 2 : 1);
 			const int k1 = d.is3D ? k0 + 1 : k0;
-			for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++) for (int bb = 0; bb < 2; bb++) for (int a = 0; a < 2; a++) {
+			#pragma unroll
+			for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++)
+			#pragma unroll
+			for (int bb = 0; bb < 2; bb++)
+			#pragma unroll
+			for (int a = 0; a < 2; a++) {
 				const IndexInt q = (IndexInt)(i0 + a) + d.Y * (j0 + bb) + d.Z * (cc ? k1 : k0);
 				if (checkFlag(flags, q)) {
 					#pragma unroll
@@ -445,8 +460,15 @@ __device__ __forceinline__ Real clampComponentMAC(const Dims& d, const int* __re
 		for (int a = 0; a < 3; a++) cp[a] = (int)(l == 0 ? pos[a] - v[a] : pos[a] + v[a]);
 		const int i0 = iclamp(cp[0], 0, d.sx - 2), j0 = iclamp(cp[1], 0, d.sy - 2), k0 = iclamp(cp[2], 0, d.is3D ? d.sz - 2 : 0);
 		const int k1 = d.is3D ? k0 + 1 : k0;
-		for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++) for (int b = 0; b < 2; b++) for (int a = 0; a < 2; a++) {
-			const Real o = orig[3 * ((IndexInt)(i0 + a) + d.Y * (j0 + b) + d.Z * (cc ? k1 : k0)) + C];
+		const Real* p = orig + 3 * ((IndexInt)i0 + d.Y * j0 + d.Z * k0) + C;       // the corner (i0, j0, k0); the others at fixed offsets from it
+		const IndexInt oY = 3 * d.Y, oZ = 3 * d.Z * (k1 - k0);
+		#pragma unroll
+		for (int cc = 0; cc < (d.is3D ? 2 : 1); cc++)
+		#pragma unroll
+		for (int b = 0; b < 2; b++)
+		#pragma unroll
+		for (int a = 0; a < 2; a++) {
+			const Real o = p[3 * a + (b ? oY : 0) + (cc ? oZ : 0)];
 			if (o < minv) minv = o;
 			if (o > maxv) maxv = o;
 		}
@@ -457,9 +479,10 @@ __device__ __forceinline__ Real clampComponentMAC(const Dims& d, const int* __re
 }
 // Pass 2 for a MAC grid: backward trace + MacCormackCorrectMAC (:94-117, all cells) + MacCormackClampMAC (:270-287, interior);
 // *anyOutflow is raised when the flags hold an outflow cell, so that the boundary pass can be skipped otherwise
-template <typename Real, int OS, int OT>
-__global__ void __launch_bounds__(128) k_mc_rest_mac(Dims d, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
+template <typename Real, int OS, int OT, bool D3>
+__global__ void __launch_bounds__(128) k_mc_rest_mac(Dims d_, const int* __restrict__ flags, const Real* __restrict__ vel, Real* __restrict__ dst, const Real* __restrict__ orig,
 	const Real* __restrict__ fwd, Real dt, Real strength, int clampMode, int* anyOutflow) {
+	Dims d = d_; if (D3) d.is3D = true;          // 3-D instantiation: the dimension tests fold, the corner loops unroll
 	int i, j, k; IndexInt idx;
 	if (!cellOf(d, i, j, k, idx)) return;
 	const bool in = isInterior(d, i, j, k);
@@ -564,7 +587,7 @@ int adopt(mp_context* ctx, mp_grid* grid, mp_grid* neu) {
 
 // Two passes per advection: (1) the forward trace, (2, MacCormack only) backward trace + correction + clamping; the reference's
 // four kernels and three temporaries (fwd, bwd, newGrid) become two kernels and two temporaries, every cell written exactly once.
-template <typename Real, int OS, int OT>
+template <typename Real, int OS, int OT, bool D3>
 int advect(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int clampMode, double dt_, bool vec3) {
 	const Dims d = dimsOf(flags);
 	const bool mac = grid->kind == MP_GRID_MAC && !vec3;
@@ -572,9 +595,9 @@ int advect(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* g
 	const dim3 cg = cellGrid(d);
 	const int* F = (const int*)flags->d; const Real* V = (const Real*)vel->d;
 	Tmp fwd; MP_TRY(mp_grid_create_scratch(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &fwd.g));
-	if (vec3)     k_semi_lagrange_vec3<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
-	else if (mac) k_semi_lagrange_mac<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
-	else          k_semi_lagrange<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	if (vec3)     k_semi_lagrange_vec3<Real, OS, OT, D3><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	else if (mac) k_semi_lagrange_mac<Real, OS, OT, D3><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
+	else          k_semi_lagrange<Real, OS, OT, D3><<<cg, 128, 0, ctx->stream>>>(d, V, (Real*)fwd.g->d, (const Real*)grid->d, dt);
 	MP_CHECK_LAUNCH(ctx);
 	if (order == 1) {
 		if (mac) MP_TRY(applyOutflowBC<Real>(ctx, d, flags, fwd.g, grid, (double)dt, nullptr));
@@ -582,14 +605,14 @@ int advect(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* g
 	}
 	Tmp neu; MP_TRY(mp_grid_create_scratch(ctx, grid->kind, grid->prec, grid->sx, grid->sy, grid->sz, &neu.g));
 	if (vec3) {
-		k_mc_rest_vec3<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode); MP_CHECK_LAUNCH(ctx);
+		k_mc_rest_vec3<Real, OS, OT, D3><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode); MP_CHECK_LAUNCH(ctx);
 	} else if (mac) {
 		int* any = (int*)(ctx->dScal + 24);
 		MP_CUDA(cudaMemsetAsync(any, 0, sizeof(int), ctx->stream));
-		k_mc_rest_mac<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode, any); MP_CHECK_LAUNCH(ctx);
+		k_mc_rest_mac<Real, OS, OT, D3><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode, any); MP_CHECK_LAUNCH(ctx);
 		MP_TRY(applyOutflowBC<Real>(ctx, d, flags, neu.g, grid, (double)dt, any));
 	} else {
-		k_mc_rest<Real, OS, OT><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode); MP_CHECK_LAUNCH(ctx);
+		k_mc_rest<Real, OS, OT, D3><<<cg, 128, 0, ctx->stream>>>(d, F, V, (Real*)neu.g->d, (const Real*)grid->d, (const Real*)fwd.g->d, dt, (Real)strength, clampMode); MP_CHECK_LAUNCH(ctx);
 	}
 	return adopt(ctx, grid, neu.g);
 }
@@ -674,9 +697,10 @@ static int advectEntry(mp_context* ctx, const mp_grid* flags, const mp_grid* vel
 	if (vec3 && grid->kind != MP_GRID_MAC) MP_FAIL(MP_ERR_INVALID, "mp_advect_semi_lagrange_vec3: grid does not hold Vec3 cells");
 	MP_TRY(mp_check_same(flags, grid, grid->kind, "grid", false));
 	if (flags->sx < 3 || flags->sy < 3 || (flags->sz > 1 && flags->sz < 3)) return MP_OK;       // no interior cells
-#define MP_ADV(R) (orderSpace == 1 ? (orderTrace == 1 ? advect<R, 1, 1> : advect<R, 1, 2>) : (orderTrace == 1 ? advect<R, 2, 1> : advect<R, 2, 2>))(ctx, flags, vel, grid, order, strength, clampMode, dt, vec3)
-	if (grid->prec == 4) return MP_ADV(float);
-	return MP_ADV(double);
+#define MP_ADV(R, D3) (orderSpace == 1 ? (orderTrace == 1 ? advect<R, 1, 1, D3> : advect<R, 1, 2, D3>) : (orderTrace == 1 ? advect<R, 2, 1, D3> : advect<R, 2, 2, D3>))(ctx, flags, vel, grid, order, strength, clampMode, dt, vec3)
+	const bool is3D = flags->sz > 1;
+	if (grid->prec == 4) return is3D ? MP_ADV(float, true) : MP_ADV(float, false);
+	return is3D ? MP_ADV(double, true) : MP_ADV(double, false);
 #undef MP_ADV
 }
 int mp_advect_semi_lagrange(mp_context* ctx, const mp_grid* flags, const mp_grid* vel, mp_grid* grid, int order, double strength, int orderSpace,

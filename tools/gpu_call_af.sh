@@ -6,4 +6,3 @@ timeout 900 python -m pytest tests/test_gpu_step.py tests/test_gpu_step_liquid.p
 tail -8 $out/${tag}_pytest_step.txt
 timeout 600 python tools/step_bench.py 512 128 > $out/${tag}_step_bench.txt 2>&1
 cat $out/${tag}_step_bench.txt | cut -c1-200
-MP_ADVECT_PLANES=0 timeout 600 python tools/step_bench.py 512 128 2>&1 | grep "vel order" | cut -c1-200
