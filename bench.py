@@ -476,6 +476,7 @@ def extra_configs(args, peak):
     del f64
     c1 = scenes.smoke_plume((64, 96, 64), 4, obstacle=False)
     run("cfg1_64x96x64_pcmic", c1[0], c1[1], None, 4, 1, 1e-3, 1.5, False, 3)
+    run("cfg1_64x96x64_pcmic_blockrb", c1[0], c1[1], None, 4, 1, 1e-3, 1.5, False, 3, mic_rb=True)
     c2 = scenes.liquid_basin((88, 83, 33), 4)
     run("cfg2_88x83x33_phi_pcmic", c2[0], c2[1], c2[2], 4, 1, 1e-3, 1.5, False, 3)
     run("cfg2_88x83x33_phi_pcmgdynamic", c2[0], c2[1], c2[2], 4, 2, 1e-3, 1.5, False, 3)

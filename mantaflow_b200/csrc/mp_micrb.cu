@@ -22,7 +22,8 @@
 // ncu: 350-400 instructions per warp and 8-cell round at 3.5 cycles per instruction (dependent ALU chain + selects on the mask bits) and a
 // third of the stall samples on the first use of the operands requested a round earlier.  Tried and dropped: L2 prefetch 2-4 rounds ahead
 // (slower), a register cap for 16 warps per SM (spills, slower), a cp.async ring in shared memory 3 rounds deep (long-scoreboard stalls gone,
-// but ~50 more instructions per round: 1.7-2.4 ms).
+// but ~50 more instructions per round: 1.7-2.4 ms), the ring plus a mask-free path for rounds whose chunks are all fluid and fully coupled
+// (1.7-2.3 ms: no pipe is busy -- ALU 37 %, FMA 10 %, LSU 13 % -- a warp simply issues every 3.5 cycles and there are 2-3 warps per scheduler).
 #include "mp_common.cuh"
 #include <cstdlib>
 
