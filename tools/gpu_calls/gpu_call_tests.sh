@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call: the whole GPU suite WITHOUT -x (every failure is listed, none hides the rest), then the default bench line and the
-# plugin timings of the liquid / FLIP neighbours.   usage: gpurun --timeout 1500 -- 'bash tools/gpu_call_tests.sh r2a'
+# plugin timings of the liquid / FLIP neighbours.   usage: gpurun --timeout 1500 -- 'bash tools/gpu_calls/gpu_call_tests.sh r2a'
 tag=${1:-rX}
 out=gpurun_out
 mkdir -p $out
