@@ -41,12 +41,47 @@ __device__ __forceinline__ bool interior(const Dims& d, IndexInt idx, int& i, in
 // FULL = false: no face fractions, no surface tension -- the smoke / plain liquid case, compiled without those paths (the full kernel needs 113
 // registers and runs at a quarter of the occupancy; same cells per thread and same reduction order in both)
 template <typename Real, bool FULL>
-__global__ void __launch_bounds__(256, FULL ? 1 : 4) k_make_rhs(Dims d, const int* __restrict__ flags, Real* __restrict__ rhs, const Real* __restrict__ vel,
+__global__ void __launch_bounds__(256, FULL ? 1 : 3) k_make_rhs(Dims d, const int* __restrict__ flags, Real* __restrict__ rhs, const Real* __restrict__ vel,
 	const Real* __restrict__ perCellCorr, const Real* __restrict__ fractions, const Real* __restrict__ obvel,
 	const Real* __restrict__ phi, const Real* __restrict__ curv, Real surfTens, Real gfClamp,
 	double* partials, unsigned int* ticket, double* out)
 {
 	double v[2] = { 0.0, 0.0 };
+	if (!FULL) {
+		// The plain case four cells at a time: a thread's cells are the same and are summed in the same order as in the loop below, but the
+		// flag and velocity loads of four cells are in flight together instead of two dependent round trips per cell (1.35 -> 0.5 ms at 512^3).
+		constexpr int U = 4;
+		const IndexInt stride = (IndexInt)gridDim.x * blockDim.x;
+		const IndexInt X = d.X, Y = d.Y, Z = d.Z;
+		for (IndexInt base = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; base < d.n; base += U * stride) {
+			bool in[U]; int fl[U]; Real c0[U], c1[U], c2[U], x0[U], y1[U], z2[U], pc[U];
+			#pragma unroll
+			for (int u = 0; u < U; u++) {
+				const IndexInt idx = base + u * stride;
+				int i, j, k;
+				in[u] = idx < d.n && interior(d, idx, i, j, k);
+				fl[u] = 0; c0[u] = c1[u] = c2[u] = x0[u] = y1[u] = z2[u] = pc[u] = (Real)0;
+				if (in[u]) {          // interior cells have all their plus neighbours: the velocity is requested before the flag is known
+					fl[u] = flags[idx];
+					const Real* c = vel + 3 * idx;
+					c0[u] = c[0]; c1[u] = c[1]; x0[u] = c[3 * X]; y1[u] = c[3 * Y + 1];
+					if (d.is3D) { c2[u] = c[2]; z2[u] = c[3 * Z + 2]; }
+					if (perCellCorr) pc[u] = perCellCorr[idx];
+				}
+			}
+			#pragma unroll
+			for (int u = 0; u < U; u++) {
+				if (!in[u]) continue;
+				const IndexInt idx = base + u * stride;
+				if (!(fl[u] & TypeFluid)) { rhs[idx] = 0; continue; }
+				Real set = c0[u] - x0[u] + c1[u] - y1[u];
+				if (d.is3D) set += c2[u] - z2[u];
+				if (perCellCorr) set += pc[u];
+				v[0] += (double)set; v[1] += 1.0;
+				rhs[idx] = set;
+			}
+		}
+	} else
 	for (IndexInt idx = (IndexInt)blockIdx.x * blockDim.x + threadIdx.x; idx < d.n; idx += (IndexInt)gridDim.x * blockDim.x) {
 		int i, j, k;
 		if (!interior(d, idx, i, j, k)) continue;
@@ -282,24 +317,26 @@ __global__ void __launch_bounds__(256, GHOST ? 4 : 8) k_correct_velocity(Dims d,
 	int i, j, k;
 	if (idx >= d.n || !interior(d, idx, i, j, k)) return;
 	const IndexInt X = d.X, Y = d.Y, Z = d.Z;
+	// an interior cell has its minus neighbours: everything is requested before the cell's own flag is known (one round trip instead of two)
 	const int f = flags[idx];
-	const bool fl = f & TypeFluid, em = (f & TypeEmpty) && !(f & TypeOutflow);
-	if (!fl && !em) return;
 	const int fx = flags[idx - X], fy = flags[idx - Y], fz = d.is3D ? flags[idx - Z] : 0;
 	Real vx = vel[3 * idx + 0], vy = vel[3 * idx + 1], vz = vel[3 * idx + 2];
 	const Real p = pressure[idx];
+	const Real pxm = pressure[idx - X], pym = pressure[idx - Y], pzm = d.is3D ? pressure[idx - Z] : (Real)0;
+	const bool fl = f & TypeFluid, em = (f & TypeEmpty) && !(f & TypeOutflow);
+	if (!fl && !em) return;
 	// knCorrectVelocity :87-109
 	if (fl) {
-		if (fx & TypeFluid) vx -= (p - pressure[idx - X]);
-		if (fy & TypeFluid) vy -= (p - pressure[idx - Y]);
-		if (d.is3D && (fz & TypeFluid)) vz -= (p - pressure[idx - Z]);
+		if (fx & TypeFluid) vx -= (p - pxm);
+		if (fy & TypeFluid) vy -= (p - pym);
+		if (d.is3D && (fz & TypeFluid)) vz -= (p - pzm);
 		if (fx & TypeEmpty) vx -= p;
 		if (fy & TypeEmpty) vy -= p;
 		if (d.is3D && (fz & TypeEmpty)) vz -= p;
 	} else {
-		if (fx & TypeFluid) vx += pressure[idx - X]; else vx = 0.f;
-		if (fy & TypeFluid) vy += pressure[idx - Y]; else vy = 0.f;
-		if (d.is3D) { if (fz & TypeFluid) vz += pressure[idx - Z]; else vz = 0.f; }
+		if (fx & TypeFluid) vx += pxm; else vx = 0.f;
+		if (fy & TypeFluid) vy += pym; else vy = 0.f;
+		if (d.is3D) { if (fz & TypeFluid) vz += pzm; else vz = 0.f; }
 	}
 	// knCorrectVelocityGhostFluid :154-187 (touches only this cell's velocity -> fused)
 	if (GHOST && phi) {
