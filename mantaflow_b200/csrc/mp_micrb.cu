@@ -370,7 +370,8 @@ int mp_micrb_prepare(mp_context* ctx, const mp_grid* flags, const mp_grid* P, co
 bool mp_micrb_active(const mp_context* ctx, const mp_grid* flags, const mp_grid* P) {
 	if (!ctx->micRbState) return false;
 	const RbState& st = ctx->micRbState->s;
-	return st.valid && st.forFlags == flags && st.forP == P && st.prec == P->prec;
+	(void)flags;                 // the factor grid identifies the factorisation; the mask built with it already holds what the sweeps need of the flags
+	return st.valid && st.forP == P && st.prec == P->prec && st.g.sx == P->sx && st.g.sy == P->sy && st.g.sz == P->sz;
 }
 void mp_micrb_release(mp_context* ctx) {
 	if (!ctx->micRbState) return;
