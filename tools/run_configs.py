@@ -31,9 +31,11 @@ def demean(p, flags):
     return q
 
 
-def gpu_solve(flags, vel, phi, prec, pc, acc, fac, fix, reps=2):
+def gpu_solve(flags, vel, phi, prec, pc, acc, fac, fix, reps=2, mic_rb=False):
     sz, sy, sx = flags.shape
     s = mf.Solver(gridSize=(sx, sy, sz), dim=3 if sz > 1 else 2, prec=prec)
+    if mic_rb:            # PcMIC reformulated: MIC(0) in block red-black ordering, tile chosen from the grid
+        s.setMicOrdering(1)
     F, V, P = mf.FlagGrid(s, flags), mf.MACGrid(s, vel), mf.RealGrid(s)
     PH = mf.RealGrid(s, phi) if phi is not None else None
     kw = dict(cgAccuracy=acc, cgMaxIterFac=fac, preconditioner=pc, zeroPressureFixing=fix)
@@ -52,8 +54,9 @@ def gpu_solve(flags, vel, phi, prec, pc, acc, fac, fix, reps=2):
     mf.solvePressureHost(s, hv, hp, flags, phi=phi, **kw)
     host_ms = 1e3 * (time.perf_counter() - t0)
     mf.releaseMG(s)
+    order = s.micOrdering() if mic_rb else (0, 0, 0)
     s.close()
-    return dict(iterations=best["iterations"], resNorm=best["resNorm"], ms=best["msTotal"], ms_cold=cold, ms_solve=best["msSolve"], host_ms=host_ms, p=p, v=v)
+    return dict(order=order, iterations=best["iterations"], resNorm=best["resNorm"], ms=best["msTotal"], ms_cold=cold, ms_solve=best["msSolve"], host_ms=host_ms, p=p, v=v)
 
 
 def cpu_solve(O, flags, vel, phi, pc, acc, fac, fix):
@@ -84,13 +87,13 @@ def main():
 
     cfgs = []
     # config 1: scenes/simpleplume.py geometry 64x96x64, PcMIC, cgAccuracy 1e-3 (scene defaults), float
-    cfgs.append(("1 simpleplume-like 64x96x64 smoke", lambda prec: scenes.smoke_plume((64, 96, 64), prec, obstacle=False) + (None,), 4, [(1, 1e-3, 1.5, False), (3, 1e-3, 1.5, True)]))
+    cfgs.append(("1 simpleplume-like 64x96x64 smoke", lambda prec: scenes.smoke_plume((64, 96, 64), prec, obstacle=False) + (None,), 4, [(1, 1e-3, 1.5, False), (1, 1e-3, 1.5, False, True), (3, 1e-3, 1.5, True)]))
     # config 2: benchmark_dam.py geometry 88x83x33 liquid with free surface (phi ghost fluid)
-    cfgs.append(("2 dam-like 88x83x33 liquid+phi", lambda prec: scenes.liquid_basin((88, 83, 33), prec), 4, [(1, 1e-3, 1.5, False), (2, 1e-3, 1.5, False)]))
+    cfgs.append(("2 dam-like 88x83x33 liquid+phi", lambda prec: scenes.liquid_basin((88, 83, 33), prec), 4, [(1, 1e-3, 1.5, False), (1, 1e-3, 1.5, False, True), (2, 1e-3, 1.5, False)]))
     # config 3: 256^3 smoke plume with obstacle, PcNone vs PcMIC vs PcMGStatic, cgAccuracy 1e-4
-    cfgs.append(("3 synthetic 256^3 smoke+obstacle", lambda prec: scenes.smoke_plume(256, prec) + (None,), 4, [(0, 1e-4, 99, False), (1, 1e-4, 99, False), (3, 1e-4, 99, True)]))
+    cfgs.append(("3 synthetic 256^3 smoke+obstacle", lambda prec: scenes.smoke_plume(256, prec) + (None,), 4, [(0, 1e-4, 99, False), (1, 1e-4, 99, False), (1, 1e-4, 99, False, True), (3, 1e-4, 99, True)]))
     # config 4: 512^3 single GPU, float and double
-    cfgs.append(("4 synthetic 512^3 smoke+obstacle", lambda prec: scenes.smoke_plume(512, prec) + (None,), 4, [(0, 1e-4, 99, False), (1, 1e-4, 99, False), (3, 1e-4, 99, True)]))
+    cfgs.append(("4 synthetic 512^3 smoke+obstacle", lambda prec: scenes.smoke_plume(512, prec) + (None,), 4, [(0, 1e-4, 99, False), (1, 1e-4, 99, False), (1, 1e-4, 99, False, True), (3, 1e-4, 99, True)]))
     cfgs.append(("4 synthetic 512^3 smoke+obstacle", lambda prec: scenes.smoke_plume(512, prec) + (None,), 8, [(0, 1e-4, 99, False), (3, 1e-4, 99, True)]))
     rows = []
     for name, make, prec, runs in cfgs:
@@ -101,12 +104,18 @@ def main():
         O = None
         if not a.skip_cpu and res <= a.max_cpu_res:
             O = Oracle("reference" if available("reference", prec) else "port", prec)
-        for pc, acc, fac, fix in runs:
-            g = gpu_solve(flags, vel, phi, prec, pc, acc, fac, fix)
-            row = dict(config=name, prec="f32" if prec == 4 else "f64", pc=PC[pc], cgAccuracy=acc, gpu_iterations=g["iterations"], gpu_resNorm=g["resNorm"],
+        cpu_cache = {}
+        for run in runs:
+            pc, acc, fac, fix = run[:4]
+            rb = len(run) > 4 and run[4]
+            g = gpu_solve(flags, vel, phi, prec, pc, acc, fac, fix, mic_rb=rb)
+            pcname = PC[pc] if not rb else "PcMIC reformulated (block red-black %dx%d; CPU column: the reference's PcMIC)" % g["order"][1:]
+            row = dict(config=name, prec="f32" if prec == 4 else "f64", pc=pcname, cgAccuracy=acc, gpu_iterations=g["iterations"], gpu_resNorm=g["resNorm"],
                        gpu_ms=g["ms"], gpu_ms_cold=g["ms_cold"], gpu_host_ms=g["host_ms"], max_div_after=scenes.max_divergence(flags, g["v"]) if phi is None else None)
             if O is not None:
-                c = cpu_solve(O, flags, vel, phi, pc, acc, fac, fix)
+                if (pc, acc, fac, fix) not in cpu_cache:
+                    cpu_cache[(pc, acc, fac, fix)] = cpu_solve(O, flags, vel, phi, pc, acc, fac, fix)
+                c = cpu_cache[(pc, acc, fac, fix)]
                 row.update(cpu_kind=O.kind, cpu_cores=cores, cpu_iterations=c["iterations"], cpu_ms=c["ms"], speedup_device=c["ms"] / g["ms"], speedup_plugin=c["ms"] / g["host_ms"],
                            p_rel_l2=rel_l2(g["p"], c["p"]), p_rel_l2_demeaned=rel_l2(demean(g["p"], flags), demean(c["p"], flags)), vel_rel_l2=rel_l2(g["v"], c["v"]),
                            cpu_max_div_after=scenes.max_divergence(flags, c["v"]) if phi is None else None)
