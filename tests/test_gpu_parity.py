@@ -552,7 +552,13 @@ def test_random_domains_all_preconditioners(mf, kind, prec, seed):
         # In the double build the reductions themselves round differently in every summation order (the reference's own
         # OpenMP order included), and on these randomly clamped ghost-fluid systems CG at 1e-11 amplifies that into a few
         # per cent of the iteration count; the converged fields still agree to 1e-9.
-        tol_it = 1 if prec == 4 else max(2, int(0.06 * it_o))
+        # measured (profiles/r2d_double_iteration_spread.txt): every preconditioned double solve within +-1; unpreconditioned CG (PcNone, and PcMIC
+        # in 2-D, which the reference runs without preconditioner) 0 / -1 on the smoke domains and up to -2.9 % (fewer iterations) on the liquid ones
+        plain_cg = pc == 0 or (pc == 1 and flags.shape[0] == 1)
+        tol_it = 1 if (prec == 4 or not plain_cg) else max(2, int(0.04 * it_o))
+        if prec == 8:       # the measured spread goes on record (pytest -s; profiles/r2d_double_iteration_spread.txt), the bar only catches a broken solver
+            print("double-build iterations %-15s seed %d pc %d: device %4d oracle %4d (%+d, %+.2f %%)" % (kind, seed, pc, info["iterations"], it_o, info["iterations"] - it_o,
+                                                                                                   100.0 * (info["iterations"] - it_o) / max(it_o, 1)))
         assert abs(info["iterations"] - it_o) <= tol_it, (kind, pc, info["iterations"], it_o)
         scale = max(1.0, float(np.abs(p_o).max()))
         assert np.abs(P.numpy().astype(np.float64) - p_o).max() <= (2e-4 if prec == 4 else 1e-9) * scale, (kind, pc)
